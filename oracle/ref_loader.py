@@ -1,0 +1,210 @@
+"""TEST INFRASTRUCTURE -- loads the reference's own MDP code behind stub modules.
+
+Only ``tests/`` (and ``tests/golden/make_golden.py``) may import this.  It needs
+``/root/reference`` and therefore works only in the build container; nothing that
+runs on the GPU box imports it.  The GPU box sees the committed fixtures under
+``tests/golden/`` that this loader produced.
+
+What it does (recipe from SURVEY.md Appendix D): registers stand-ins for
+``gymnasium``, ``isaaclab.*`` and ``zbot.assets`` in ``sys.modules`` and then executes
+``source/zbot/zbot/tasks/zbot6b_direct/zbot_direct_6dof_bipedal_env_v2.py`` *unmodified*
+via ``importlib``.  An instance is built with ``object.__new__`` (the real ``__init__``
+needs a live PhysX scene) and given plain CPU tensors for ``_robot.data``,
+``_contact_sensor.data`` and ``_terrain.env_origins``; the reference's unbound methods
+``_pre_physics_step / _get_dones / _get_rewards / _reset_idx / _get_observations``
+(``...env_v2.py:276-459``) are then called as-is.
+"""
+from __future__ import annotations
+
+import importlib.util
+import os
+import sys
+import types
+
+import torch
+
+REF_ROOT = os.environ.get("ZBOT_REFERENCE_ROOT", "/root/reference")
+REF_ENV_V2 = os.path.join(
+    REF_ROOT, "source/zbot/zbot/tasks/zbot6b_direct/zbot_direct_6dof_bipedal_env_v2.py"
+)
+
+
+def reference_available() -> bool:
+    return os.path.isfile(REF_ENV_V2)
+
+
+def _quat_apply(quat: torch.Tensor, vec: torch.Tensor) -> torch.Tensor:
+    # isaaclab.utils.math.quat_apply: wxyz, t = 2 q_xyz x v; v + w t + q_xyz x t
+    shape = vec.shape
+    quat = quat.reshape(-1, 4)
+    vec = vec.reshape(-1, 3)
+    xyz = quat[:, 1:]
+    t = xyz.cross(vec, dim=-1) * 2
+    return (vec + quat[:, 0:1] * t + xyz.cross(t, dim=-1)).view(shape)
+
+
+class _Cfg:
+    """kwargs-accepting dummy with ``replace`` (stands in for every ``*Cfg`` class)."""
+
+    def __init__(self, *a, **kw):
+        self.__dict__.update(kw)
+
+    def replace(self, **kw):
+        new = _Cfg(**self.__dict__)
+        new.__dict__.update(kw)
+        return new
+
+
+class _DirectRLEnv:
+    """Stand-in base: only the part of ``DirectRLEnv._reset_idx`` the subclass relies on
+    (``episode_length_buf[ids] = 0`` after scene/event/noise resets)."""
+
+    def _reset_idx(self, env_ids):
+        self.episode_length_buf[env_ids] = 0
+
+
+def _install_stubs():
+    def mod(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+
+    saved = {k: sys.modules.get(k) for k in (
+        "gymnasium", "gymnasium.spaces", "isaaclab", "isaaclab.sim", "isaaclab.utils",
+        "isaaclab.utils.math", "isaaclab.assets", "isaaclab.envs", "isaaclab.scene",
+        "isaaclab.sensors", "isaaclab.terrains", "zbot", "zbot.assets")}
+    spaces = mod("gymnasium.spaces", flatdim=lambda s: int(s))
+    mod("gymnasium", spaces=spaces)
+    sim = mod("isaaclab.sim", RigidBodyMaterialCfg=_Cfg, SimulationCfg=_Cfg, DomeLightCfg=_Cfg)
+    umath = mod("isaaclab.utils.math", quat_apply=_quat_apply)
+    utils = mod("isaaclab.utils", configclass=lambda c: c, math=umath)
+    assets = mod("isaaclab.assets", Articulation=object, ArticulationCfg=_Cfg)
+    envs = mod("isaaclab.envs", DirectRLEnv=_DirectRLEnv, DirectRLEnvCfg=object)
+    scene = mod("isaaclab.scene", InteractiveSceneCfg=_Cfg)
+    sensors = mod("isaaclab.sensors", ContactSensor=object, ContactSensorCfg=_Cfg)
+    terrains = mod("isaaclab.terrains", TerrainImporterCfg=_Cfg)
+    mod("isaaclab", sim=sim, utils=utils, assets=assets, envs=envs, scene=scene,
+        sensors=sensors, terrains=terrains)
+    zassets = mod("zbot.assets", ZBOT_6S_CFG=_Cfg())
+    mod("zbot", assets=zassets)
+    return saved
+
+
+def _restore(saved):
+    for k, v in saved.items():
+        if v is None:
+            sys.modules.pop(k, None)
+        else:
+            sys.modules[k] = v
+
+
+_REF_MODULE = None
+
+
+def load_reference_module():
+    """Execute the reference env_v2 file unmodified; returns the module."""
+    global _REF_MODULE
+    if _REF_MODULE is not None:
+        return _REF_MODULE
+    if not reference_available():
+        raise FileNotFoundError(REF_ENV_V2)
+    saved = _install_stubs()
+    try:
+        spec = importlib.util.spec_from_file_location("_zbot_ref_env_v2", REF_ENV_V2)
+        m = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(m)
+    finally:
+        _restore(saved)
+    _REF_MODULE = m
+    return m
+
+
+class _NS:
+    pass
+
+
+class _Recorder:
+    """no-op articulation recording the writes ``_reset_idx`` makes (…env_v2.py:416,431-433)."""
+
+    def __init__(self, n):
+        self.data = _NS()
+        self._ALL_INDICES = torch.arange(n, dtype=torch.long)
+        self.calls = []
+
+    def reset(self, env_ids):
+        self.calls.append(("reset", env_ids.clone()))
+
+    def write_root_pose_to_sim(self, pose, env_ids):
+        self.calls.append(("root_pose", pose.clone(), env_ids.clone()))
+
+    def write_root_velocity_to_sim(self, vel, env_ids):
+        self.calls.append(("root_vel", vel.clone(), env_ids.clone()))
+
+    def write_joint_state_to_sim(self, pos, vel, _ids, env_ids):
+        self.calls.append(("joint_state", pos.clone(), vel.clone(), env_ids.clone()))
+
+
+def make_reference_env(num_envs: int, *, feet_ids, undesired_ids, base_body_idx, feet_body_idx,
+                       default_joint_pos, default_root_state, env_origins):
+    """Build a ``ZbotDirectEnvV2`` (reference class) without its ``__init__``.
+
+    Mirrors the attribute set of ``…env_v2.py:211-257`` with plain CPU tensors.
+    ``reward_scales`` is a *copy* of the cfg dict scaled by step_dt once (SURVEY C-3).
+    """
+    ref = load_reference_module()
+    n = num_envs
+    env = object.__new__(ref.ZbotDirectEnvV2)
+    env.cfg = _NS()
+    env.cfg.termination_height = ref.ZbotDirectEnvCfgV2.termination_height
+    env.cfg.reward_cfg = ref.ZbotDirectEnvCfgV2.reward_cfg
+    env.num_envs = n
+    env.device = torch.device("cpu")
+    env.sim = _NS()
+    env.sim.device = "cpu"
+    env.step_dt = ref.ZbotDirectEnvCfgV2.decimation * (1 / 200.0)
+    env.max_episode_length = 1000
+    env.max_episode_length_s = ref.ZbotDirectEnvCfgV2.episode_length_s
+    env.extras = {}
+
+    env._robot = _Recorder(n)
+    d = env._robot.data
+    d.default_joint_pos = default_joint_pos.clone()
+    d.default_joint_vel = torch.zeros(n, 6)
+    d.default_root_state = default_root_state.clone()
+    d.GRAVITY_VEC_W = torch.tensor([0.0, 0.0, -1.0]).repeat(n, 1)
+    env._contact_sensor = _NS()
+    env._contact_sensor.data = _NS()
+    env._terrain = _NS()
+    env._terrain.env_origins = env_origins.clone()
+
+    env._feet_ids = list(feet_ids)
+    env._undesired_contact_body_ids = list(undesired_ids)
+    env.base_body_idx = list(base_body_idx)
+    env.feet_body_idx = list(feet_body_idx)
+
+    env._actions = torch.zeros(n, 6)
+    env._previous_actions = torch.zeros(n, 6)
+    env.feet_contact_forces_last = torch.zeros(n, 2)
+    env.feet_down_pos_last = torch.zeros(n, 2, 3)
+    env.feet_step_length = torch.zeros(n, 2)
+    env.feet_air_times = torch.zeros(n, 2)
+    env.feet_force_sum = torch.zeros(n)
+    env.base_heading_x_sum = torch.zeros(n)
+    env.base_pos_y_err_sum = torch.zeros(n)
+    env.joint_speed_limit = torch.ones(n, 1)
+    env.p_delta = torch.zeros(n, 6)
+    env.episode_length_buf = torch.zeros(n, dtype=torch.long)
+    env.reset_terminated = torch.zeros(n, dtype=torch.bool)
+    env.reset_time_outs = torch.zeros(n, dtype=torch.bool)
+
+    scales = dict(ref.ZbotDirectEnvCfgV2.reward_cfg["reward_scales"])
+    env.reward_scales = {k: v * env.step_dt for k, v in scales.items()}
+    env.reward_functions = {k: getattr(env, "_reward_" + k) for k in env.reward_scales}
+    env._episode_sums = {k: torch.zeros(n) for k in env.reward_scales}
+    return env
+
+
+def reference_reward_scales() -> dict:
+    """Unscaled term->weight dict, in the reference's insertion order (…env_v2.py:190-206)."""
+    return dict(load_reference_module().ZbotDirectEnvCfgV2.reward_cfg["reward_scales"])

@@ -1,0 +1,114 @@
+"""Deterministic synthetic inputs for the ``zbot-6b-walking-v2`` step.
+
+Used by the parity tests, ``tests/golden/make_golden.py`` and ``bench.py`` so that
+every consumer sees the same state for a given seed (SURVEY.md §8(d) "Synthetic inputs").
+Pure numpy; nothing here touches the GPU.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from ..assets import zbot_6s as Z
+
+F = np.float32
+
+
+def index_sets() -> dict:
+    """The four index lists of ``…env_v2.py:227-230`` resolved BY NAME:
+    sensor order for the contact sets, articulation order for the pose sets."""
+    feet_ids, _ = Z.find_bodies("foot.*", Z.SENSOR_BODY_NAMES)
+    undesired, _ = Z.find_bodies("base|a.*|b.*", Z.SENSOR_BODY_NAMES)
+    base_idx, _ = Z.find_bodies("base", Z.LINK_NAMES)
+    feet_idx, _ = Z.find_bodies("foot.*", Z.LINK_NAMES)
+    return {"feet_ids": feet_ids, "undesired_ids": undesired, "base_body_idx": base_idx,
+            "feet_body_idx": feet_idx}
+
+
+def reset_tables() -> dict:
+    """Default-pose link poses relative to the env origin (constant rows written on reset)."""
+    p, q = Z.default_link_poses()
+    return {"body_link_pos_local": p.astype(F), "body_link_quat": q.astype(F)}
+
+
+def env_origins_grid(num_envs: int, spacing: float = 4.0) -> np.ndarray:
+    """Plane-terrain env origins (Isaac Lab grid).  float32 (N,3)."""
+    n = int(num_envs)
+    num_rows = int(np.ceil(n / int(np.sqrt(n))))
+    num_cols = int(np.ceil(n / num_rows))
+    ii, jj = np.meshgrid(np.arange(num_rows), np.arange(num_cols), indexing="ij")
+    org = np.zeros((num_rows * num_cols, 3), dtype=F)
+    org[:, 0] = -(ii.flatten().astype(F) - F((num_rows - 1) / 2)) * F(spacing)
+    org[:, 1] = (jj.flatten().astype(F) - F((num_cols - 1) / 2)) * F(spacing)
+    return org[:n].copy()
+
+
+def synth_articulation_state(rng: np.random.Generator, n: int, origins: np.ndarray,
+                             die_frac: float = 0.08) -> dict:
+    """Synthetic end-of-physics articulation + contact-sensor state in the reference's
+    tensor layouts (``robot.data`` / ``contact_sensor.data``)."""
+    ids = index_sets()
+    pos = rng.normal(0.0, 0.12, (n, 12, 3)).astype(F)
+    pos[..., 2] += F(0.30)
+    base = ids["base_body_idx"][0]
+    pos[:, base, 2] = F(0.24) + np.abs(rng.normal(0, 0.03, n)).astype(F)
+    low = rng.random(n) < die_frac * 0.4
+    pos[low, base, 2] = F(0.2) - rng.random(int(low.sum())).astype(F) * F(0.05)
+    far = rng.random(n) < die_frac * 0.2
+    pos[far, base, 1] += F(0.7)
+    pos = pos + origins[:, None, :]
+    quat = rng.normal(size=(n, 12, 4)).astype(F)
+    quat /= np.linalg.norm(quat, axis=-1, keepdims=True)
+    vel = rng.normal(0.0, 0.3, (n, 12, 3)).astype(F)
+    jp = (np.asarray(Z.DEFAULT_JOINT_POS, F) + rng.uniform(-0.2, 0.2, (n, 6)).astype(F)).astype(F)
+    jv = rng.normal(0.0, 0.5, (n, 6)).astype(F)
+    tau = rng.normal(0.0, 5.0, (n, 6)).astype(F)
+    hist = np.abs(rng.normal(size=(n, 5, 12, 3))).astype(F) * np.array([0.3, 0.3, 8.0], F)
+    scale = np.full(12, 0.02, F)
+    scale[ids["feet_ids"]] = 1.0
+    hist = hist * scale[None, None, :, None]
+    # some feet in the air (forces below the 1 N / 10 N thresholds)
+    air = rng.random((n, 2)) < 0.3
+    for j, b in enumerate(ids["feet_ids"]):
+        hist[air[:, j], :, b, :] *= F(0.05)
+    hit = rng.random(n) < die_frac * 0.4
+    which = rng.integers(0, len(ids["undesired_ids"]), n)
+    for e in np.nonzero(hit)[0]:
+        hist[e, rng.integers(0, 5), ids["undesired_ids"][which[e]], :] = np.array([0.5, -0.4, 2.0], F)
+    return {
+        "body_link_pos_w": pos, "body_link_quat_w": quat.astype(F), "body_com_lin_vel_w": vel,
+        "joint_pos": jp, "joint_vel": jv, "applied_torque": tau,
+        "net_forces_w_history": hist.astype(F),
+        "last_air_time": rng.random((n, 12)).astype(F),
+        "current_contact_time": rng.random((n, 12)).astype(F),
+    }
+
+
+def synth_mdp_case(seed: int, n: int, steps: int, die_frac: float = 0.08) -> dict:
+    """A whole MDP-only parity case: initial state S0, per-step (actions, S1), initial
+    episode counters (some close to the 999-step truncation)."""
+    rng = np.random.default_rng(seed)
+    origins = env_origins_grid(n)
+    ep = rng.integers(0, 1000, n).astype(np.int64)
+    near = rng.random(n) < 0.1
+    ep[near] = 999 - rng.integers(1, max(2, steps), int(near.sum()))
+    case = {"origins": origins, "episode_length_buf0": ep,
+            "S0": synth_articulation_state(rng, n, origins, die_frac=0.0), "steps": []}
+    for _ in range(steps):
+        a = rng.normal(0.0, 1.0, (n, 6)).astype(F)
+        case["steps"].append((a, synth_articulation_state(rng, n, origins, die_frac)))
+    return case
+
+
+def synth_sim_state(rng: np.random.Generator, n: int) -> dict:
+    """Perturbed start state for the FULL fused step: default pose with
+    ``q += U(-0.2,0.2)``, ``qd = N(0,0.5)``, root ``z += U(0,0.02)``, root lin vel ``N(0,0.1)``.
+    Root position is env-LOCAL (relative to the env origin)."""
+    q = np.asarray(Z.DEFAULT_JOINT_POS, F) + rng.uniform(-0.2, 0.2, (n, 6)).astype(F)
+    qd = rng.normal(0, 0.5, (n, 6)).astype(F)
+    root_pos = np.tile(np.asarray(Z.DEFAULT_ROOT_POS, F), (n, 1))
+    root_pos[:, 2] += rng.uniform(0.0, 0.02, n).astype(F)
+    root_quat = np.tile(np.asarray(Z.DEFAULT_ROOT_QUAT, F), (n, 1))
+    root_lin = rng.normal(0, 0.1, (n, 3)).astype(F)
+    root_ang = np.zeros((n, 3), F)
+    return {"root_pos": root_pos, "root_quat": root_quat, "root_lin_vel": root_lin,
+            "root_ang_vel": root_ang, "joint_pos": q.astype(F), "joint_vel": qd}
