@@ -1,0 +1,197 @@
+/* zbot_b200.h -- C ABI of the B200-native batched environment step for the
+ * `zbot-6b-walking-v2` task (reference: crowznl/zbot_lab).
+ *
+ * The reference has no FFI: the path is Python (torch eager ops + Isaac Lab + PhysX).
+ * Each entry point below names the reference Python interface it stands in for
+ * (paths relative to /root/reference/source/zbot/zbot/).  The binding a maintainer
+ * would add on the reference side is a ctypes stub -- see INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a CUDA *device* pointer unless the
+ *     parameter name ends in `_host`.  All tensors are allocated and freed by the caller
+ *     (PyTorch); a handle owns only constants and a small reduction scratch.
+ *   - every call returns 0 on success, a negative ZBOT_E_* code otherwise; nothing throws
+ *     across the ABI.  zbot_last_error() returns a static, thread-local message.
+ *   - launches go to the caller's `stream` (a cudaStream_t passed as void*; NULL = legacy
+ *     default stream); no call synchronises or reads device memory on the host unless
+ *     documented ("_host").
+ *   - one handle per device; a handle is not re-entrant.
+ */
+#ifndef ZBOT_B200_H_
+#define ZBOT_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZBOT_ABI_VERSION 1
+
+#define ZBOT_OK 0
+#define ZBOT_E_INVALID (-1) /* bad argument / unsupported configuration */
+#define ZBOT_E_CUDA (-2)    /* a CUDA runtime call failed; see zbot_last_error() */
+#define ZBOT_E_UNBOUND (-3) /* zbot_bind() has not been called */
+
+#define ZBOT_NUM_ACTIONS 6
+#define ZBOT_NUM_OBS 23
+#define ZBOT_MAX_TERMS 16
+#define ZBOT_STATE_WORDS 80      /* fused-step state: 20 float4 per env, laid out [20][N][4] */
+#define ZBOT_MDP_STATE_WORDS 72  /* MDP-only state:   18 float4 per env, laid out [18][N][4] */
+#define ZBOT_STATS_WORDS 32
+#define ZBOT_NUM_LINKS 12
+#define ZBOT_HISTORY 5
+
+/* reward-term ids; names = the reference's `_reward_<name>` methods
+ * (tasks/zbot6b_direct/zbot_direct_6dof_bipedal_env_v2.py:461-571) */
+enum ZbotTerm {
+  ZBOT_TERM_BASE_VEL_FORWARD = 0,
+  ZBOT_TERM_FEET_DOWNWARD = 1,
+  ZBOT_TERM_FEET_FORWARD = 2,
+  ZBOT_TERM_BASE_HEADING_X = 3,
+  ZBOT_TERM_BASE_HEADING_X_SUM = 4,
+  ZBOT_TERM_STEP_LENGTH = 5,
+  ZBOT_TERM_AIRTIME_BALANCE = 6,
+  ZBOT_TERM_ACTION_RATE = 7,
+  ZBOT_TERM_TORQUES = 8,
+  ZBOT_TERM_FEET_SLIDE = 9,
+  ZBOT_TERM_BASE_POS_Y_ERR = 10,
+  ZBOT_TERM_BASE_POS_Y_ERR_SUM = 11,
+  ZBOT_TERM_AIRTIME_SUM = 12,
+  ZBOT_TERM_FEET_FORCE_DIFF = 13,
+  ZBOT_TERM_FEET_FORCE_SUM = 14
+};
+
+/* Static task parameters.  Replaces `ZbotDirectEnvCfgV2` (…env_v2.py:26-206), the actuator /
+ * init-state part of `ZBOT_6S_CFG` (assets/zbot_cfg.py:621-669) and the reward table built in
+ * `ZbotDirectEnvV2.__init__` (…env_v2.py:246-257). */
+typedef struct ZbotCfg {
+  int32_t abi_version; /* = ZBOT_ABI_VERSION */
+  int32_t num_envs;
+  int32_t decimation;         /* 4 (…env_v2.py:40); only 4 is supported (5-deep force history) */
+  int32_t max_episode_length; /* 1000 = ceil(20 s / 0.02 s) (…env_v2.py:39) */
+  float sim_dt;               /* 1/200 (…env_v2.py:48) */
+  float termination_height;   /* 0.22 (…env_v2.py:44) */
+  float y_err_limit;          /* 0.5  (…env_v2.py:407) */
+  float terminated_penalty;   /* 20.0 (…env_v2.py:380) */
+  float contact_died_force;   /* 1.0  (…env_v2.py:400) */
+  /* implicit PD actuator (assets/zbot_cfg.py:658-668) */
+  float kp, kd, effort_limit;
+  float gravity;
+  /* ground-contact model (ours; zbot_lab_b200/assets/zbot_6s.py) */
+  float contact_alpha, contact_erp, contact_vdep, contact_beta_max, contact_mu, contact_ramp,
+      contact_vt_eps, contact_margin;
+  /* reward table in cfg-dict order; weight already multiplied by step_dt (…env_v2.py:250-251) */
+  int32_t num_terms;
+  int32_t term_id[ZBOT_MAX_TERMS];
+  float term_weight[ZBOT_MAX_TERMS];
+} ZbotCfg;
+
+typedef struct ZbotHandle ZbotHandle;
+
+/* Library / build identification; usable without a GPU. */
+int zbot_abi_version(void);
+const char* zbot_build_info(void);
+const char* zbot_last_error(void);
+/* Fill `cfg` with the zbot-6b-walking-v2 defaults (13 active terms, …env_v2.py:190-206). */
+int zbot_default_cfg(ZbotCfg* cfg, int32_t num_envs);
+/* Word offset of a named field inside the 80-word fused state / 72-word MDP state
+ * (-1 = unknown).  Names: root_pos root_quat root_lin_vel root_ang_vel joint_pos joint_vel
+ * p_delta actions carry_feet_fz carry_mid_max current_air_time current_contact_time
+ * last_air_time last_contact_time feet_contact_forces_last feet_down_pos_last feet_step_length
+ * base_heading_x_sum base_pos_y_err_sum feet_force_sum joint_speed_limit episode_sums;
+ * MDP state adds: stale_base_pos stale_forward stale_feet_x stale_feet_z stale_feet_pos stale_v_fwd */
+int zbot_state_word(const char* field);
+int zbot_mdp_state_word(const char* field);
+
+/* Create / destroy.  Replaces `ZbotDirectEnvV2.__init__` + `DirectRLEnv.__init__` (…env_v2.py:211-257). */
+int zbot_create(const ZbotCfg* cfg, int device, ZbotHandle** out);
+int zbot_destroy(ZbotHandle* h);
+
+/* Bind caller-owned device buffers:
+ *   state          float [20][N][4]   fused-step state (AoSoA; see zbot_state_word)
+ *   episode_length int64 [N]          `episode_length_buf`
+ *   stats_ring     float [slots][32]  per-step reset statistics, one slot per step (slots >= 1) */
+int zbot_bind(ZbotHandle* h, float* state, int64_t* episode_length, float* stats_ring, int32_t stats_slots);
+
+/* One fused control step: `DirectRLEnv.step` for ZbotDirectEnvV2:
+ * _pre_physics_step (…env_v2.py:276-287), 4 x [_apply_action + implicit PD + articulation step +
+ * ContactSensor update], episode_length += 1, _get_dones (:384-411), _get_rewards (:371-382),
+ * partial _reset_idx (:413-459), _get_observations (:312-369) -- one kernel launch.
+ *   actions     float [N][6]   raw policy output (pre-tanh)
+ *   obs         float [N][23]
+ *   rew         float [N]
+ *   terminated / truncated  uint8 [N]
+ *   stats_slot  which ring slot receives this step's reset statistics:
+ *               [0..num_terms) sum over reset envs of the per-term episode sums,
+ *               [16] #reset, [17] #terminated among reset, [18] #timed out among reset,
+ *               [19] sum of rewards, [20] #terminated, [21] #truncated.
+ *               When no env reset this step words 0..18 are copied from `prev_slot` (the reference
+ *               keeps the last `extras["log"]`, …env_v2.py:450). prev_slot < 0: zeros. */
+int zbot_step(ZbotHandle* h, const float* actions, float* obs, float* rew, uint8_t* terminated,
+              uint8_t* truncated, int32_t stats_slot, int32_t prev_slot, void* stream);
+
+/* Same step, additionally exporting the articulation / contact-sensor view the MDP saw, in the
+ * reference's tensor layouts (`robot.data.*`, `contact_sensor.data.*`):
+ *   body_link_pos_w0/1 [N][12][3], body_link_quat_w0/1 [N][12][4], body_com_lin_vel_w0/1 [N][12][3]
+ *   (0 = start of step, 1 = end of physics, env-local), joint_pos1/joint_vel1/applied_torque1 [N][6],
+ *   net_forces_w_history1 [N][5][12][3] (sensor body order), last_air_time1/current_contact_time1 [N][12].
+ * Test hook (parity of the fused kernel's MDP against the pinned MDP oracle); not a hot path. */
+typedef struct ZbotExport {
+  float *body_link_pos_w0, *body_link_quat_w0, *body_com_lin_vel_w0;
+  float *body_link_pos_w1, *body_link_quat_w1, *body_com_lin_vel_w1;
+  float *joint_pos1, *joint_vel1, *applied_torque1;
+  float *net_forces_w_history1, *last_air_time1, *current_contact_time1;
+} ZbotExport;
+int zbot_step_export(ZbotHandle* h, const float* actions, float* obs, float* rew, uint8_t* terminated,
+                     uint8_t* truncated, int32_t stats_slot, int32_t prev_slot, const ZbotExport* ex,
+                     void* stream);
+
+/* `_reset_idx(env_ids)` (…env_v2.py:413-459) for an explicit id list; n < 0 or env_ids == NULL
+ * resets every env.  Does NOT draw the random episode lengths of the all-env case
+ * (…env_v2.py:418-422): that stays on the caller's torch generator.  `terminated` / `truncated`
+ * (uint8 [N], may be NULL) are `reset_terminated` / `reset_time_outs`, only counted into the
+ * statistics (…env_v2.py:453-458).  Statistics as in zbot_step (words 19..21 are zero). */
+int zbot_reset_idx(ZbotHandle* h, const int64_t* env_ids, int64_t n, const uint8_t* terminated,
+                   const uint8_t* truncated, int32_t stats_slot, void* stream);
+
+/* `_get_observations` (…env_v2.py:312-369) on the current state: obs float [N][23]. */
+int zbot_observe(ZbotHandle* h, float* obs, void* stream);
+
+/* Articulation view of the current state (`robot.data.body_link_pos_w` etc., env-local):
+ * any pointer may be NULL. */
+int zbot_articulation_view(ZbotHandle* h, float* body_link_pos, float* body_link_quat,
+                           float* body_com_lin_vel, void* stream);
+
+/* ---- MDP-only step (BASELINE.json configs[0]) ---------------------------------
+ * The reference's MDP code on caller-supplied articulation / contact state, i.e.
+ * _pre_physics_step + episode_length += 1 + _get_dones + _get_rewards + _reset_idx + _get_observations
+ * with `robot.data` / `contact_sensor.data` given as tensors in the reference's layouts. */
+typedef struct ZbotMdpInputs {
+  const float* body_link_pos_w;      /* [N][12][3] articulation body order */
+  const float* body_link_quat_w;     /* [N][12][4] wxyz */
+  const float* body_com_lin_vel_w;   /* [N][12][3] */
+  const float* joint_pos;            /* [N][6] */
+  const float* joint_vel;            /* [N][6] */
+  const float* applied_torque;       /* [N][6] */
+  const float* net_forces_w_history; /* [N][5][12][3] sensor body order, newest first */
+  const float* last_air_time;        /* [N][12] sensor body order */
+  const float* env_origins;          /* [N][3] */
+} ZbotMdpInputs;
+
+/* mdp_state float [18][N][4]; episode_length int64 [N]. */
+int zbot_mdp_bind(ZbotHandle* h, float* mdp_state, int64_t* episode_length, float* stats_ring,
+                  int32_t stats_slots);
+/* `_get_observations` only (fills the stale cache from `in`). */
+int zbot_mdp_observe(ZbotHandle* h, const ZbotMdpInputs* in, float* obs, void* stream);
+int zbot_mdp_step(ZbotHandle* h, const ZbotMdpInputs* in, const float* actions, float* obs, float* rew,
+                  uint8_t* terminated, uint8_t* truncated, int32_t stats_slot, int32_t prev_slot,
+                  void* stream);
+
+/* Number of kernel launches issued through this handle so far (host counter). */
+int64_t zbot_launch_count(const ZbotHandle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZBOT_B200_H_ */

@@ -1,0 +1,128 @@
+// TEST INFRASTRUCTURE / CPU BASELINE -- host build of the per-env step math.
+//
+// Compiles zbot_lab_b200/csrc/zbot_core.h (the same templates the sm_100a kernels
+// instantiate with T = float) for the CPU with T = float and T = double and loops over
+// envs with OpenMP.  Two uses, both outside the product path:
+//   1. tests/: lets the build box (no GPU) check the kernel's arithmetic against the
+//      independent float64 oracle (oracle/dyn_oracle.py) and the pinned MDP oracle;
+//   2. bench.py cpu_baseline / --impl reference: "the path on the host cores", standing in
+//      for the reference's torch + PhysX-CPU step (PhysX is closed and absent).
+// Nothing under zbot_lab_b200/ links or loads this file; the product fails loudly without
+// its CUDA library.  State layout: [N][ZBOT_STATE_WORDS] (AoS on the CPU).
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../zbot_lab_b200/csrc/zbot_layout.h"
+
+using namespace zbot;
+
+template <typename T>
+static void default_pose_constants(T feet_pos[2][3], T base_quat[4]) {
+  SimState<T> s;
+  sim_state_default(s);
+  LinkKin<T> k;
+  link_kinematics(s, k);
+  for (int j = 0; j < 2; ++j)
+    for (int i = 0; i < 3; ++i) feet_pos[j][i] = k.feet_pos[j][i];
+  for (int i = 0; i < 4; ++i) base_quat[i] = k.base_quat[i];
+}
+
+template <typename T>
+static int port_step(const ZbotCfg* cfg, T* state, int64_t* ep_len, const T* actions, T* obs, T* rew,
+                     uint8_t* term, uint8_t* trunc, T* reset_sums /*[N][16] or null*/,
+                     T* export_buf /*[N][EXPORT_WORDS] or null*/, int n) {
+  const char* why = nullptr;
+  if (cfg_validate(*cfg, &why) != ZBOT_OK) return ZBOT_E_INVALID;
+  Params<T> P;
+  params_from_cfg(*cfg, P);
+  T dfp[2][3], dbq[4];
+  default_pose_constants(dfp, dbq);
+#pragma omp parallel for schedule(static)
+  for (int e = 0; e < n; ++e) {
+    EnvState<T> es;
+    env_state_unpack(state + (size_t)e * ZBOT_STATE_WORDS, es);
+    StepOut<T> out;
+    T rs[MAX_TERMS];
+    for (int i = 0; i < MAX_TERMS; ++i) rs[i] = T(0);
+    StepExport<T> ex;
+    env_step(P, es, actions + (size_t)e * 6, ep_len[e], dfp, dbq, out, rs, export_buf ? &ex : (StepExport<T>*)nullptr);
+    env_state_pack(es, state + (size_t)e * ZBOT_STATE_WORDS);
+    for (int i = 0; i < 23; ++i) obs[(size_t)e * 23 + i] = out.obs[i];
+    rew[e] = out.reward;
+    term[e] = out.terminated ? 1 : 0;
+    trunc[e] = out.time_out ? 1 : 0;
+    if (reset_sums)
+      for (int i = 0; i < MAX_TERMS; ++i) reset_sums[(size_t)e * MAX_TERMS + i] = rs[i];
+    if (export_buf) memcpy(export_buf + (size_t)e * (sizeof(StepExport<T>) / sizeof(T)), &ex, sizeof(ex));
+  }
+  return ZBOT_OK;
+}
+
+// dynamics only: sim [N][25] (root_pos3 quat4 lin3 ang3 q6 qd6), target [N][6]
+// forces [N][7][3] (body 0 and 6 = applied foot forces, 1..5 = predictor), tau [N][6]
+template <typename T>
+static int port_substeps(const ZbotCfg* cfg, T* sim, const T* target, T* forces, T* tau, int n, int nsub) {
+  Params<T> P;
+  params_from_cfg(*cfg, P);
+#pragma omp parallel for schedule(static)
+  for (int e = 0; e < n; ++e) {
+    SimState<T> s;
+    T* w = sim + (size_t)e * 25;
+    for (int i = 0; i < 3; ++i) { s.p[i] = w[i]; s.v[i] = w[7 + i]; s.w[i] = w[10 + i]; }
+    for (int i = 0; i < 4; ++i) s.Q[i] = w[3 + i];
+    for (int i = 0; i < 6; ++i) { s.q[i] = w[13 + i]; s.qd[i] = w[19 + i]; }
+    SubstepOut<T> so;
+    for (int k = 0; k < nsub; ++k) physics_substep(P, s, target + (size_t)e * 6, so);
+    for (int i = 0; i < 3; ++i) { w[i] = s.p[i]; w[7 + i] = s.v[i]; w[10 + i] = s.w[i]; }
+    for (int i = 0; i < 4; ++i) w[3 + i] = s.Q[i];
+    for (int i = 0; i < 6; ++i) { w[13 + i] = s.q[i]; w[19 + i] = s.qd[i]; }
+    T* f = forces + (size_t)e * 21;
+    for (int i = 0; i < 3; ++i) { f[i] = so.foot_force[0][i]; f[18 + i] = so.foot_force[1][i]; }
+    for (int b = 0; b < 5; ++b)
+      for (int i = 0; i < 3; ++i) f[3 * (b + 1) + i] = so.mid_force[b][i];
+    for (int i = 0; i < 6; ++i) tau[(size_t)e * 6 + i] = so.applied_torque[i];
+  }
+  return ZBOT_OK;
+}
+
+template <typename T>
+static int port_link_view(const T* sim, T* pos, T* quat, T* vel, int n) {
+  for (int e = 0; e < n; ++e) {
+    SimState<T> s;
+    const T* w = sim + (size_t)e * 25;
+    for (int i = 0; i < 3; ++i) { s.p[i] = w[i]; s.v[i] = w[7 + i]; s.w[i] = w[10 + i]; }
+    for (int i = 0; i < 4; ++i) s.Q[i] = w[3 + i];
+    for (int i = 0; i < 6; ++i) { s.q[i] = w[13 + i]; s.qd[i] = w[19 + i]; }
+    all_link_kinematics(s, pos + (size_t)e * 36, quat + (size_t)e * 48, vel + (size_t)e * 36);
+  }
+  return 0;
+}
+
+extern "C" {
+int zbot_port_default_cfg(ZbotCfg* c, int n) { cfg_defaults(*c, n); return 0; }
+int zbot_port_export_words_f32(void) { return (int)(sizeof(StepExport<float>) / sizeof(float)); }
+int zbot_port_export_words_f64(void) { return (int)(sizeof(StepExport<double>) / sizeof(double)); }
+int zbot_port_state_word(const char* f) { return find_word(kStateFields, (int)(sizeof(kStateFields) / sizeof(kStateFields[0])), f); }
+
+int zbot_port_step_f32(const ZbotCfg* cfg, float* state, int64_t* ep_len, const float* actions, float* obs,
+                       float* rew, uint8_t* term, uint8_t* trunc, float* reset_sums, float* export_buf, int n) {
+  return port_step<float>(cfg, state, ep_len, actions, obs, rew, term, trunc, reset_sums, export_buf, n);
+}
+int zbot_port_step_f64(const ZbotCfg* cfg, double* state, int64_t* ep_len, const double* actions, double* obs,
+                       double* rew, uint8_t* term, uint8_t* trunc, double* reset_sums, double* export_buf, int n) {
+  return port_step<double>(cfg, state, ep_len, actions, obs, rew, term, trunc, reset_sums, export_buf, n);
+}
+int zbot_port_substeps_f32(const ZbotCfg* cfg, float* sim, const float* target, float* forces, float* tau, int n, int nsub) {
+  return port_substeps<float>(cfg, sim, target, forces, tau, n, nsub);
+}
+int zbot_port_substeps_f64(const ZbotCfg* cfg, double* sim, const double* target, double* forces, double* tau, int n, int nsub) {
+  return port_substeps<double>(cfg, sim, target, forces, tau, n, nsub);
+}
+int zbot_port_link_view_f64(const double* sim, double* pos, double* quat, double* vel, int n) {
+  return port_link_view<double>(sim, pos, quat, vel, n);
+}
+int zbot_port_link_view_f32(const float* sim, float* pos, float* quat, float* vel, int n) {
+  return port_link_view<float>(sim, pos, quat, vel, n);
+}
+}

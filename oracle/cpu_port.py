@@ -1,0 +1,137 @@
+"""TEST INFRASTRUCTURE / CPU BASELINE -- ctypes loader of ``oracle/cpu_port.cpp``.
+
+Builds ``oracle/_build/libzbot_cpu_port.so`` on demand with g++ (portable ``-march=x86-64-v3``)
+and exposes the float / double CPU instantiations of the per-env step math.  Only
+``tests/``, ``__graft_entry__`` and ``bench.py``'s cpu_baseline / reference legs import this.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from zbot_lab_b200.native import ZbotCfg, make_cfg  # noqa: F401  (struct definition only)
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+SO = os.path.join(HERE, "_build", "libzbot_cpu_port.so")
+SRCS = [os.path.join(HERE, "cpu_port.cpp"),
+        os.path.join(ROOT, "zbot_lab_b200", "csrc", "zbot_core.h"),
+        os.path.join(ROOT, "zbot_lab_b200", "csrc", "zbot_layout.h"),
+        os.path.join(ROOT, "zbot_lab_b200", "csrc", "zbot_model_constants.h"),
+        os.path.join(ROOT, "include", "zbot_b200.h")]
+
+
+def build(force: bool = False) -> str:
+    stale = force or not os.path.isfile(SO) or any(os.path.getmtime(s) > os.path.getmtime(SO) for s in SRCS)
+    if stale:
+        os.makedirs(os.path.dirname(SO), exist_ok=True)
+        cxx = "/usr/bin/g++" if os.access("/usr/bin/g++", os.X_OK) else "g++"
+        cmd = [cxx, "-O3", "-march=x86-64-v3", "-fopenmp", "-fPIC", "-std=c++17", "-ffp-contract=off",
+               "-shared", "-o", SO, SRCS[0]]
+        subprocess.run(cmd, check=True, cwd=HERE)
+    return SO
+
+
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        _LIB.zbot_port_state_word.argtypes = [C.c_char_p]
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class PortEnv:
+    """N envs stepped on the CPU with the kernel's own arithmetic (float32 or float64)."""
+
+    def __init__(self, n, dtype=np.float32, cfg: ZbotCfg | None = None):
+        self.n = n
+        self.dtype = np.dtype(dtype)
+        self.sfx = "f32" if self.dtype == np.float32 else "f64"
+        self.cfg = cfg or make_cfg(n)
+        self.state = np.zeros((n, 80), self.dtype)
+        self.ep_len = np.zeros(n, np.int64)
+        self.export_words = getattr(lib(), "zbot_port_export_words_" + self.sfx)()
+        self.reset_all()
+
+    def word(self, name):
+        w = lib().zbot_port_state_word(name.encode())
+        assert w >= 0, name
+        return w
+
+    def field(self, name, width):
+        w = self.word(name)
+        return self.state[:, w:w + width]
+
+    def reset_all(self):
+        from zbot_lab_b200.assets import zbot_6s as Z
+        self.state[:] = 0
+        self.field("root_pos", 3)[:] = Z.model_f32().default_root_pos
+        self.field("root_quat", 4)[:] = Z.DEFAULT_ROOT_QUAT
+        self.field("joint_pos", 6)[:] = Z.model_f32().default_joint_pos
+        self.field("joint_speed_limit", 1)[:] = 1.0
+        lp, _ = Z.default_link_poses()
+        self.field("feet_down_pos_last", 6)[:] = np.concatenate([lp[0], lp[11]])
+        self.ep_len[:] = 0
+
+    def set_sim_state(self, st):
+        for k, (name, w) in {"root_pos": ("root_pos", 3), "root_quat": ("root_quat", 4),
+                             "root_lin_vel": ("root_lin_vel", 3), "root_ang_vel": ("root_ang_vel", 3),
+                             "joint_pos": ("joint_pos", 6), "joint_vel": ("joint_vel", 6)}.items():
+            self.field(name, w)[:] = st[k]
+
+    def step(self, actions, export=False):
+        n = self.n
+        a = np.ascontiguousarray(actions, self.dtype)
+        obs = np.zeros((n, 23), self.dtype)
+        rew = np.zeros(n, self.dtype)
+        term = np.zeros(n, np.uint8)
+        trunc = np.zeros(n, np.uint8)
+        rs = np.zeros((n, 16), self.dtype)
+        ex = np.zeros((n, self.export_words), self.dtype) if export else None
+        fn = getattr(lib(), "zbot_port_step_" + self.sfx)
+        rc = fn(C.byref(self.cfg), _p(self.state), _p(self.ep_len), _p(a), _p(obs), _p(rew), _p(term),
+                _p(trunc), _p(rs), _p(ex), C.c_int(n))
+        assert rc == 0, rc
+        return obs, rew, term.astype(bool), trunc.astype(bool), rs, ex
+
+
+def substeps(sim: np.ndarray, target: np.ndarray, nsub: int, cfg: ZbotCfg | None = None):
+    """sim [N][25] (in/out), target [N][6] -> forces [N][7][3], applied torque [N][6]."""
+    n = sim.shape[0]
+    dt = sim.dtype
+    sfx = "f32" if dt == np.float32 else "f64"
+    cfg = cfg or make_cfg(n)
+    forces = np.zeros((n, 7, 3), dt)
+    tau = np.zeros((n, 6), dt)
+    target = np.ascontiguousarray(target, dt)
+    rc = getattr(lib(), "zbot_port_substeps_" + sfx)(C.byref(cfg), _p(sim), _p(target), _p(forces), _p(tau),
+                                                     C.c_int(n), C.c_int(nsub))
+    assert rc == 0
+    return forces, tau
+
+
+def link_view(sim: np.ndarray):
+    n = sim.shape[0]
+    dt = sim.dtype
+    sfx = "f32" if dt == np.float32 else "f64"
+    pos = np.zeros((n, 12, 3), dt)
+    quat = np.zeros((n, 12, 4), dt)
+    vel = np.zeros((n, 12, 3), dt)
+    getattr(lib(), "zbot_port_link_view_" + sfx)(_p(sim), _p(pos), _p(quat), _p(vel), C.c_int(n))
+    return pos, quat, vel
+
+
+def pack_sim(st: dict, dtype=np.float64) -> np.ndarray:
+    return np.ascontiguousarray(np.concatenate(
+        [st["root_pos"], st["root_quat"], st["root_lin_vel"], st["root_ang_vel"], st["joint_pos"],
+         st["joint_vel"]], axis=-1), dtype)

@@ -1,0 +1,144 @@
+"""CPU tests (no GPU): dynamics-oracle invariants, the float64 CPU instantiation of the kernel's
+own arithmetic against the independent oracle, and the composed full-step oracle."""
+import numpy as np
+import pytest
+
+from oracle.dyn_oracle import DynOracle, DynParams
+
+
+def test_fk_known_answers_from_reference_comments():
+    """…env_v2.py:403-404 and …env_v4.py:814-816 print these values at the default pose."""
+    o = DynOracle(1)
+    ls = o.link_state()
+    assert ls["body_link_pos"][0, 6, 2] == pytest.approx(0.2545, abs=5e-5)
+    assert np.allclose(ls["body_link_quat"][0, 6], [0.6003, -0.6003, -0.3735, -0.3739], atol=5e-5)
+    assert ls["body_link_pos"][0, 0, 2] == pytest.approx(0.0, abs=1e-9)
+    assert ls["body_link_pos"][0, 11, 2] == pytest.approx(5.3035e-2, abs=5e-7)
+
+
+def test_free_motion_conserves_energy_and_momentum_first_order():
+    """No gravity / contact / PD: drift must shrink ~linearly with dt (wrong bias terms give O(1))."""
+    drift = []
+    for dt in (2e-4, 1e-4):
+        rng = np.random.default_rng(0)
+        o = DynOracle(4, DynParams(gravity=0.0, contacts=False, pd=False, dt=dt))
+        o.root_pos[:, 2] += 1.0
+        o.root_ang_vel = rng.normal(0, 2, (4, 3))
+        o.root_lin_vel = rng.normal(0, 1, (4, 3))
+        o.qd = rng.normal(0, 3, (4, 6))
+        E0, P0, L0 = o.energy_momentum()
+        for _ in range(int(round(0.1 / dt))):
+            o.substep(o.q)
+        E1, P1, L1 = o.energy_momentum()
+        drift.append((np.abs((E1 - E0) / E0).max(), np.abs(P1 - P0).max(), np.abs(L1 - L0).max()))
+    for a, b in zip(drift[0], drift[1]):
+        assert b < 0.7 * a + 1e-9          # halving dt roughly halves the drift
+    assert drift[1][0] < 5e-4 and drift[1][1] < 1e-3 and drift[1][2] < 1e-3
+
+
+def test_free_fall_momentum():
+    o = DynOracle(2, DynParams(contacts=False, pd=False))
+    o.root_pos[:, 2] += 5
+    for _ in range(100):
+        o.substep(o.q)
+    _, P, _ = o.energy_momentum()
+    mass = o.m.body_mass.sum()
+    assert np.allclose(P[:, 2], -mass * o.P.gravity * 100 * o.P.dt, rtol=1e-9)
+    assert np.allclose(P[:, :2], 0, atol=1e-12)
+
+
+def test_static_stand_supports_weight_at_reference_height():
+    o = DynOracle(1)
+    for _ in range(600):
+        o.substep(o.m.default_joint_pos[None])
+    ls = o.link_state()
+    assert ls["body_link_pos"][0, 6, 2] == pytest.approx(0.2545, abs=5e-4)   # reference prints 0.2545
+    mg = o.m.body_mass.sum() * o.P.gravity
+    assert o.body_force[0, :, 2].sum() == pytest.approx(mg, rel=1e-3)
+    assert np.abs(o.body_force[0, 1:6]).max() == 0.0                         # only the feet touch
+    assert abs(o.body_force[0, 0, 2] - o.body_force[0, 6, 2]) < 0.2 * mg
+
+
+def test_port_f64_matches_independent_oracle():
+    """The kernel's arithmetic (zbot_core.h, T=double, ABA in spatial algebra) equals the dense
+    classical-Jacobian oracle to round-off, including contact and PD, over 40 substeps."""
+    from oracle import cpu_port
+    from zbot_lab_b200.utils import synthetic as syn
+    n = 48
+    rng = np.random.default_rng(3)
+    st = syn.synth_sim_state(rng, n)
+    st["root_ang_vel"] = rng.normal(0, 0.5, (n, 3)).astype(np.float32)
+    o = DynOracle(n)
+    o.set_state({k: v.astype(np.float64) for k, v in st.items()})
+    sim = cpu_port.pack_sim(st, np.float64)
+    tgt = o.m.default_joint_pos[None] + rng.uniform(-0.3, 0.3, (n, 6))
+    for i in range(40):
+        f, tau = cpu_port.substeps(sim, tgt, 1)
+        o.substep(tgt)
+        ref = np.concatenate([o.root_pos, o.root_quat, o.root_lin_vel, o.root_ang_vel, o.q, o.qd], -1)
+        if i < 10:
+            assert np.abs(sim - ref).max() < 1e-9, i
+            assert np.abs(f[:, [0, 6]] - o.body_force[:, [0, 6]]).max() < 1e-7
+            assert np.abs(tau - o.applied_torque).max() < 1e-9
+    assert np.abs(sim - ref).max() < 1e-5       # round-off amplified by contact dynamics only
+
+
+def test_port_mid_body_contact_matches_oracle():
+    """A robot lying on its side: the merged-body spheres touch the ground (termination path)."""
+    from oracle import cpu_port
+    n = 4
+    o = DynOracle(n)
+    st = {"root_pos": np.tile([0.0, 0.0, 0.051], (n, 1)), "root_quat": np.tile([0.7071067811865476, 0.0, 0.7071067811865476, 0.0], (n, 1)),
+          "root_lin_vel": np.zeros((n, 3)), "root_ang_vel": np.zeros((n, 3)),
+          "joint_pos": np.zeros((n, 6)), "joint_vel": np.zeros((n, 6))}
+    st["root_pos"][:, 2] += np.linspace(-0.002, 0.002, n)
+    o.set_state(st)
+    sim = cpu_port.pack_sim(st, np.float64)
+    tgt = np.zeros((n, 6))
+    touched = False
+    for i in range(20):
+        f, _ = cpu_port.substeps(sim, tgt, 1)
+        o.substep(tgt)
+        assert np.abs(f[:, 1:6] - o.body_force_pred[:, 1:6]).max() < 1e-6
+        touched |= bool(np.abs(f[:, 1:6]).max() > 1.0)
+        ref = np.concatenate([o.root_pos, o.root_quat, o.root_lin_vel, o.root_ang_vel, o.q, o.qd], -1)
+        assert np.abs(sim - ref).max() < 1e-8
+    assert touched
+
+
+def test_full_step_oracle_matches_port_f64_with_resets():
+    from oracle import cpu_port
+    from oracle.full_step_oracle import FullStepOracle
+    n = 24
+    rng = np.random.default_rng(0)
+    fo = FullStepOracle(n)
+    fo.reset_all()
+    pe = cpu_port.PortEnv(n, np.float64)
+    fo.mdp.episode_length_buf[:4] = 990
+    pe.ep_len[:4] = 990
+    resets = 0
+    for t in range(40):
+        a = rng.normal(0, 0.6, (n, 6)).astype(np.float32)
+        obs, rew, term, trunc, ids, log = fo.step(a)
+        o2, r2, t2, tr2, rs, _ = pe.step(a)
+        assert np.array_equal(term, t2) and np.array_equal(trunc, tr2)
+        assert np.array_equal(fo.mdp.episode_length_buf, pe.ep_len)
+        assert np.abs(obs - o2).max() < 5e-5 and np.abs(rew - r2).max() < 5e-5
+        resets += len(ids)
+    assert resets >= 4
+
+
+def test_port_f32_tracks_f64_over_50_steps():
+    """Stated horizon tolerance holds for the float32 instantiation on the CPU."""
+    from oracle import cpu_port
+    n = 256
+    rng = np.random.default_rng(5)
+    e32, e64 = cpu_port.PortEnv(n, np.float32), cpu_port.PortEnv(n, np.float64)
+    alive = np.ones(n, bool)
+    for t in range(50):
+        a = rng.normal(0, 0.3, (n, 6)).astype(np.float32)
+        _, _, t32, tr32, _, _ = e32.step(a)
+        _, _, t64, tr64, _, _ = e64.step(a)
+        alive &= ~(t32 | t64 | tr32 | tr64)
+    dq = np.abs(e32.field("joint_pos", 6) - e64.field("joint_pos", 6))[alive]
+    assert dq.max() < 5e-3 and np.median(dq.max(1)) < 1e-4

@@ -1,0 +1,340 @@
+"""GPU parity tests: every call goes through the C ABI (libzbot_b200.so) on cuda:0.
+
+  * MDP-only kernel  vs the reference's own outputs (tests/golden, bit-exact flags / 1e-5 floats)
+  * fused step MDP   vs the pinned MDP oracle, fed with the kernel's own exported physics
+  * fused step       vs the float64 full-step oracle (one-step teacher forcing + 50-step horizon)
+  * reset / stats / size-independent properties at BASELINE sizes (4096, 65536)
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN_CASES, load_golden, make_mdp_oracle, rel_err
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5  # north_star: float32 reward / observation terms within 1e-5 relative
+DEV = "cuda:0"
+
+
+def _stepper(n, **kw):
+    from zbot_lab_b200 import native
+    from zbot_lab_b200.stepper import NativeStepper
+    return NativeStepper(n, DEV, native.make_cfg(n, **kw) if kw else None)
+
+
+def _t(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def _S(S):
+    return {k: _t(v) for k, v in S.items()}
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_mdp_kernel_matches_reference_golden(name):
+    g, case = load_golden(name)
+    n, steps = int(g["n"]), int(g["steps"])
+    st = _stepper(n)
+    st.mdp_init()
+    org = _t(case["origins"])
+    st.mdp_episode_length_buf[:] = _t(case["episode_length_buf0"])
+    obs0 = st.mdp_observe(_S(case["S0"]), org).cpu().numpy()
+    assert rel_err(obs0, g["obs0"]) <= RTOL
+    names = ["p_delta", "actions", "feet_contact_forces_last", "feet_down_pos_last", "feet_step_length",
+             "base_heading_x_sum", "base_pos_y_err_sum"]
+    term_names = list(np.load(__import__("os").path.join(__import__("helpers").GOLDEN_DIR, "reward_scales_v2.npz"))["names"])
+    for t, (a, S1) in enumerate(case["steps"]):
+        k = t + 1
+        obs, rew, term, trunc = st.mdp_step(_S(S1), org, _t(a))
+        torch.cuda.synchronize()
+        # integer / index work: bit-exact
+        assert np.array_equal(term.cpu().numpy().astype(bool), g[f"terminated{k}"])
+        assert np.array_equal(trunc.cpu().numpy().astype(bool), g[f"truncated{k}"])
+        ids = torch.nonzero(term.bool() | trunc.bool()).squeeze(-1).cpu().numpy()
+        assert np.array_equal(ids, g[f"reset_ids{k}"])
+        assert np.array_equal(st.mdp_episode_length_buf.cpu().numpy(), g[f"state{k}/episode_length_buf"])
+        # float work
+        assert rel_err(obs.cpu().numpy(), g[f"obs{k}"]) <= RTOL
+        assert rel_err(rew.cpu().numpy(), g[f"rew{k}"]) <= RTOL
+        for nm in names:
+            got = st.mdp_state.get(nm).cpu().numpy().reshape(g[f"state{k}/{nm}"].shape)
+            assert rel_err(got, g[f"state{k}/{nm}"]) <= RTOL, nm
+        assert rel_err(st.mdp_state.get("actions").cpu().numpy(), g[f"state{k}/prev_actions"]) <= RTOL
+        eps = st.mdp_state.get("episode_sums").cpu().numpy()
+        for i, nm in enumerate(term_names):
+            assert rel_err(eps[:, i], g[f"state{k}/episode_sum/{nm}"]) <= RTOL, nm
+        # extras["log"] statistics (…env_v2.py:441-459)
+        stats = st.mdp_stats_ring[st._mdp_slot].cpu().numpy()
+        if len(ids) > 0:
+            assert stats[16] == len(ids)
+            assert stats[17] == g[f"log{k}/Episode_Termination/body_contact"]
+            assert stats[18] == g[f"log{k}/Episode_Termination/time_out"]
+            for i, nm in enumerate(term_names):
+                want = g[f"log{k}/Episode_Reward/{nm}"]
+                assert abs(stats[i] / stats[16] / 20.0 - want) <= 1e-5 * max(1.0, abs(want)), nm
+        assert abs(stats[19] - float(np.sum(g[f"rew{k}"], dtype=np.float64))) <= 1e-4 * max(1.0, abs(stats[19]))
+    st.close()
+
+
+def test_mdp_kernel_matches_oracle_random_sizes():
+    """Fresh seeds / ragged sizes (1 env, warp-straddling, multi-block) against the pinned oracle."""
+    from zbot_lab_b200.utils import synthetic as syn
+    for seed, n in ((11, 2), (12, 33), (13, 129), (14, 1000)):
+        case = syn.synth_mdp_case(seed, n, 3)
+        o = make_mdp_oracle(n, case["origins"])
+        o.episode_length_buf[:] = case["episode_length_buf0"]
+        st = _stepper(n)
+        st.mdp_init()
+        org = _t(case["origins"])
+        st.mdp_episode_length_buf[:] = _t(case["episode_length_buf0"])
+        o.observe(case["S0"])
+        st.mdp_observe(_S(case["S0"]), org)
+        for a, S1 in case["steps"]:
+            obs_o, rew_o, term_o, trunc_o, ids_o, _ = o.step(a, S1)
+            obs, rew, term, trunc = st.mdp_step(_S(S1), org, _t(a))
+            assert np.array_equal(term.cpu().numpy().astype(bool), term_o)
+            assert np.array_equal(trunc.cpu().numpy().astype(bool), trunc_o)
+            assert np.array_equal(st.mdp_episode_length_buf.cpu().numpy(), o.episode_length_buf)
+            assert rel_err(obs.cpu().numpy(), obs_o) <= RTOL
+            assert rel_err(rew.cpu().numpy(), rew_o) <= RTOL
+        st.close()
+
+
+# ---------------------------------------------------------------------------------------------
+def _export_to_S(ex, which):
+    if which == 0:
+        return {"body_link_pos_w": ex["body_link_pos_w0"], "body_link_quat_w": ex["body_link_quat_w0"],
+                "body_com_lin_vel_w": ex["body_com_lin_vel_w0"]}
+    return {"body_link_pos_w": ex["body_link_pos_w1"], "body_link_quat_w": ex["body_link_quat_w1"],
+            "body_com_lin_vel_w": ex["body_com_lin_vel_w1"], "joint_pos": ex["joint_pos1"],
+            "joint_vel": ex["joint_vel1"], "applied_torque": ex["applied_torque1"],
+            "net_forces_w_history": ex["net_forces_w_history1"], "last_air_time": ex["last_air_time1"],
+            "current_contact_time": ex["current_contact_time1"]}
+
+
+def test_fused_step_mdp_matches_pinned_oracle_on_exported_physics():
+    """The fused kernel's dones / rewards / resets / observations equal the reference-pinned MDP
+    oracle evaluated on the articulation + contact state the kernel itself produced."""
+    from zbot_lab_b200.utils import synthetic as syn
+    n = 192
+    rng = np.random.default_rng(21)
+    st = _stepper(n)
+    st.reset_idx(None)
+    st.set_sim_state({k: _t(v) for k, v in syn.synth_sim_state(rng, n).items()})
+    ep0 = rng.integers(0, 1000, n)
+    ep0[:8] = 996
+    st.episode_length_buf[:] = _t(ep0.astype(np.int64))
+    o = make_mdp_oracle(n, np.zeros((n, 3), np.float32))
+    o.episode_length_buf[:] = ep0
+    ex = st.alloc_export()
+    n_reset = 0
+    for t in range(30):
+        a = rng.normal(0, 1.0, (n, 6)).astype(np.float32)
+        obs, rew, term, trunc = st.step(_t(a), export=ex)
+        torch.cuda.synchronize()
+        exn = {k: v.cpu().numpy() for k, v in ex.items()}
+        if t == 0:
+            S0 = _export_to_S(exn, 0)
+            S0["joint_pos"] = np.zeros((n, 6), np.float32)
+            S0["joint_vel"] = np.zeros((n, 6), np.float32)
+            o.observe(S0)                       # fills the stale cache from the start-of-step view
+            o.actions[:] = 0
+        else:
+            # the oracle's stale cache must equal the kernel's start-of-step view for envs that did not reset
+            keep = ~last_reset
+            assert rel_err(o.base_pos_w[keep], exn["body_link_pos_w0"][keep][:, 6]) <= 1e-5
+        obs_o, rew_o, term_o, trunc_o, ids_o, _ = o.step(a, _export_to_S(exn, 1))
+        assert np.array_equal(term.cpu().numpy().astype(bool), term_o)
+        assert np.array_equal(trunc.cpu().numpy().astype(bool), trunc_o)
+        assert np.array_equal(st.episode_length_buf.cpu().numpy(), o.episode_length_buf)
+        assert rel_err(rew.cpu().numpy(), rew_o) <= RTOL
+        assert rel_err(obs.cpu().numpy(), obs_o, floor=1.0) <= 2e-5
+        last_reset = term_o | trunc_o
+        n_reset += int(last_reset.sum())
+        for nm in ("p_delta", "feet_contact_forces_last", "feet_step_length", "base_heading_x_sum",
+                   "base_pos_y_err_sum"):
+            want = getattr(o, nm)
+            assert rel_err(st.state.get(nm).cpu().numpy().reshape(want.shape), want) <= RTOL, nm
+    assert n_reset > 0
+    st.close()
+
+
+def _oracle_state_vec(d):
+    return np.concatenate([d.root_pos, d.root_quat, d.root_lin_vel, d.root_ang_vel, d.q, d.qd], -1)
+
+
+def _gpu_state_vec(st):
+    return torch.cat([st.state.get(k) for k in ("root_pos", "root_quat", "root_lin_vel", "root_ang_vel",
+                                                 "joint_pos", "joint_vel")], -1).cpu().numpy().astype(np.float64)
+
+
+def test_fused_step_dynamics_one_step_vs_float64_oracle():
+    """Teacher forcing: from identical states, ONE control step (4 substeps) of the float32 kernel
+    stays within 2e-4 (positions / angles) and 2e-2 (velocities) of the independent float64 oracle."""
+    from oracle.full_step_oracle import FullStepOracle
+    from zbot_lab_b200.utils import synthetic as syn
+    n = 256
+    rng = np.random.default_rng(5)
+    fo = FullStepOracle(n)
+    fo.reset_all()
+    st = _stepper(n)
+    st.reset_idx(None)
+    worst_q = worst_v = 0.0
+    for t in range(12):
+        if t % 4 == 0:
+            s0 = syn.synth_sim_state(rng, n)
+            fo.dyn.set_state({k: v.astype(np.float64) for k, v in s0.items()})
+        # teacher forcing: kernel starts from the oracle's float32-rounded state
+        vec = _oracle_state_vec(fo.dyn).astype(np.float32)
+        fo.dyn.set_state({"root_pos": vec[:, 0:3], "root_quat": vec[:, 3:7], "root_lin_vel": vec[:, 7:10],
+                          "root_ang_vel": vec[:, 10:13], "joint_pos": vec[:, 13:19], "joint_vel": vec[:, 19:25]})
+        st.set_sim_state({"root_pos": _t(vec[:, 0:3]), "root_quat": _t(vec[:, 3:7]), "root_lin_vel": _t(vec[:, 7:10]),
+                          "root_ang_vel": _t(vec[:, 10:13]), "joint_pos": _t(vec[:, 13:19]), "joint_vel": _t(vec[:, 19:25])})
+        st.state.set("p_delta", _t(fo.mdp.p_delta))
+        st.episode_length_buf[:] = 5
+        fo.mdp.episode_length_buf[:] = 5
+        a = rng.normal(0, 0.7, (n, 6)).astype(np.float32)
+        _, _, term_o, trunc_o, _, _ = fo.step(a)
+        _, _, term, trunc = st.step(_t(a))
+        ok = ~(term_o | trunc_o) & ~(term.cpu().numpy().astype(bool))
+        dv = np.abs(_gpu_state_vec(st) - _oracle_state_vec(fo.dyn))[ok]
+        worst_q = max(worst_q, dv[:, list(range(0, 7)) + list(range(13, 19))].max())
+        worst_v = max(worst_v, dv[:, list(range(7, 13)) + list(range(19, 25))].max())
+    assert worst_q <= 2e-4, worst_q
+    assert worst_v <= 2e-2, worst_v
+    st.close()
+
+
+def test_fused_step_50_step_horizon_vs_float64_oracle():
+    """north_star: dynamics within a STATED tolerance over a fixed 50-step horizon from identical
+    initial states.  Stated tolerance: joint positions 5e-3 rad and base position
+    5e-3 m (max over envs that neither side terminated), median <= 1e-4."""
+    from oracle.full_step_oracle import FullStepOracle
+    n = 256
+    rng = np.random.default_rng(9)
+    fo = FullStepOracle(n)
+    fo.reset_all()
+    st = _stepper(n)
+    st.reset_idx(None)
+    alive = np.ones(n, bool)
+    for t in range(50):
+        a = rng.normal(0, 0.3, (n, 6)).astype(np.float32)
+        _, rew_o, term_o, trunc_o, _, _ = fo.step(a)
+        _, rew, term, trunc = st.step(_t(a))
+        alive &= ~(term_o | trunc_o | term.cpu().numpy().astype(bool) | trunc.cpu().numpy().astype(bool))
+    assert alive.sum() > n // 2
+    dq = np.abs(st.state.get("joint_pos").cpu().numpy() - fo.dyn.q)[alive]
+    pos, _, _ = st.articulation_view()
+    ls = fo.dyn.link_state()
+    dbase = np.abs(pos.cpu().numpy()[:, 6] - ls["body_link_pos"][:, 6])[alive]
+    assert dq.max() <= 5e-3 and dbase.max() <= 5e-3, (dq.max(), dbase.max())
+    assert np.median(dq.max(1)) <= 1e-4
+    st.close()
+
+
+# ---------------------------------------------------------------------------------------------
+def test_reset_idx_bit_exact_and_partial():
+    n = 300
+    st = _stepper(n)
+    st.reset_idx(None)
+    rng = np.random.default_rng(2)
+    for _ in range(5):
+        st.step(_t(rng.normal(0, 1, (n, 6)).astype(np.float32)))
+    before = st.state.buf.clone()
+    ep_before = st.episode_length_buf.clone()
+    ids = torch.tensor([0, 7, 31, 32, 33, 128, 299], device=DEV)
+    st.reset_idx(ids)
+    torch.cuda.synchronize()
+    after = st.state.buf
+    mask = torch.zeros(n, dtype=torch.bool, device=DEV)
+    mask[ids] = True
+    assert torch.equal(after[:, ~mask], before[:, ~mask])           # untouched envs: bit-identical
+    assert torch.equal(st.episode_length_buf[~mask], ep_before[~mask])
+    assert torch.all(st.episode_length_buf[mask] == 0)
+    from zbot_lab_b200.assets import zbot_6s as Z
+    assert torch.allclose(st.state.get("joint_pos")[mask], torch.tensor(Z.DEFAULT_JOINT_POS, device=DEV).float())
+    for nm in ("joint_vel", "root_lin_vel", "root_ang_vel", "p_delta", "actions", "carry_feet_fz", "last_air_time",
+               "base_heading_x_sum", "base_pos_y_err_sum", "episode_sums"):
+        assert torch.all(st.state.get(nm)[mask] == 0), nm
+    # NOT reset in v2 (SURVEY C-5)
+    assert torch.equal(st.state.get("feet_step_length")[mask], st.state.get("feet_step_length")[mask])
+    lp, _ = Z.default_link_poses()
+    want = torch.tensor(np.concatenate([lp[0], lp[11]]), device=DEV).float()
+    assert torch.allclose(st.state.get("feet_down_pos_last")[mask], want.expand(int(mask.sum()), 6), atol=1e-6)
+    assert st.stats[16].item() == len(ids)
+    st.close()
+
+
+@pytest.mark.parametrize("n", [4096, 65536])
+def test_full_size_properties(n):
+    """Size-independent properties at BASELINE.json's sizes: identical envs stay identical
+    (determinism across threads/blocks), counters advance by one, truncation at step 999,
+    statistics equal torch reductions of the outputs, two runs are bit-identical."""
+    st = _stepper(n)
+    st.reset_idx(None)
+    st.episode_length_buf[:] = 990
+    g = torch.Generator(device=DEV).manual_seed(1234)
+    a_row = torch.randn(12, 1, 6, device=DEV, generator=g)
+    outs = []
+    for t in range(12):
+        a = a_row[t].expand(n, 6).contiguous()
+        obs, rew, term, trunc = st.step(a)
+        assert torch.equal(obs, obs[:1].expand_as(obs))
+        assert torch.equal(rew, rew[:1].expand_as(rew))
+        s = st.stats.clone()
+        assert s[19].item() == pytest.approx(rew.double().sum().item(), rel=1e-5, abs=1e-3)
+        assert s[20].item() == term.sum().item() and s[21].item() == trunc.sum().item()
+        assert s[16].item() == (term.bool() | trunc.bool()).sum().item()
+        if t < 8:
+            assert not trunc.any() or term.any()
+        if t == 8 and not term.any():
+            assert trunc.all()                      # 990 + 9 = 999 -> time_out (…env_v2.py:385)
+            assert torch.all(st.episode_length_buf == 0)
+        outs.append((obs.clone(), rew.clone()))
+    st2 = _stepper(n)
+    st2.reset_idx(None)
+    st2.episode_length_buf[:] = 990
+    for t in range(12):
+        obs, rew, _, _ = st2.step(a_row[t].expand(n, 6).contiguous())
+        assert torch.equal(obs, outs[t][0]) and torch.equal(rew, outs[t][1])
+    st.close()
+    st2.close()
+
+
+def test_random_actions_stay_finite_and_reset_consistently():
+    n = 8192
+    st = _stepper(n)
+    st.reset_idx(None)
+    g = torch.Generator(device=DEV).manual_seed(7)
+    st.episode_length_buf[:] = torch.randint(0, 1000, (n,), device=DEV, generator=g)
+    total_reset = 0
+    for t in range(100):
+        ep_prev = st.episode_length_buf.clone()
+        obs, rew, term, trunc = st.step(torch.randn(n, 6, device=DEV, generator=g))
+        done = term.bool() | trunc.bool()
+        assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
+        assert torch.isfinite(st.state.buf).all()
+        assert torch.equal(st.episode_length_buf[~done], ep_prev[~done] + 1)
+        assert torch.all(st.episode_length_buf[done] == 0)
+        assert torch.equal(trunc.bool(), ep_prev + 1 >= 999)
+        assert torch.all(rew[term.bool()] < -10.0)            # -20 termination penalty (…env_v2.py:380)
+        assert torch.all(obs[done, 16:22] == 0)               # _actions[env_ids] = 0 (…env_v2.py:423)
+        total_reset += int(done.sum())
+    assert total_reset > 0
+    st.close()
+
+
+def test_abi_error_paths():
+    import ctypes as C
+    from zbot_lab_b200 import native
+    lib = native.lib()
+    cfg = native.make_cfg(16)
+    cfg.decimation = 2
+    h = C.c_void_p()
+    assert lib.zbot_create(C.byref(cfg), 0, C.byref(h)) == -1
+    assert b"decimation" in lib.zbot_last_error()
+    cfg = native.make_cfg(16)
+    assert lib.zbot_create(C.byref(cfg), 0, C.byref(h)) == 0
+    assert lib.zbot_step(h, None, None, None, None, None, 0, -1, None) == -3   # unbound
+    assert lib.zbot_destroy(h) == 0

@@ -85,6 +85,25 @@ NUM_FOOT_POINTS = 4     # rim points per foot disc
 
 GRAVITY = 9.81
 
+# ---- ground-contact model (OUR choice; PhysX's is closed -- see DESIGN.md "Contact model") ----
+# Each contact point carries a linearly-implicit soft constraint  f = F0 - dt*K*a_point,
+# K = diag(beta, beta, gamma) in the world frame (ground normal = +z):
+#   normal : spring k = ALPHA*ERP/dt on the PREDICTED penetration (pen - dt*v_z'), force cap
+#            ALPHA*VDEP (max depenetration velocity, zbot_cfg.py:633), damper d = ALPHA*(1-ERP)
+#            ramped in over RAMP metres of penetration; active iff the predictor force > 0, so the
+#            law is continuous in position and velocity (no on/off jump at first touch)
+#   tangent: regularised Coulomb, viscous coefficient beta = min(BETA_MAX, MU*f_n0/|v_t|)
+CONTACT_ALPHA = 1000.0     # N s/m
+CONTACT_ERP = 0.2
+CONTACT_VDEP = 1.0         # m/s  (RigidBodyPropertiesCfg.max_depenetration_velocity)
+CONTACT_BETA_MAX = 3000.0  # N s/m
+CONTACT_MU = 1.0           # static = dynamic friction 1.0 x 1.0, "multiply" combine (env_v2.py:50-68)
+CONTACT_RAMP = 5.0e-4      # m
+CONTACT_VT_EPS = 1.0e-6    # m/s
+CONTACT_MARGIN = 0.02      # m: a point may activate speculatively (predicted penetration) within this gap
+SIM_DT = 1.0 / 200.0       # env_v2.py:48
+DECIMATION = 4             # env_v2.py:40
+
 
 # --------------------------------------------------------------------------- #
 # helpers
@@ -189,9 +208,17 @@ def build_model(dtype=np.float32) -> ZbotModel:
         return np.asarray(x, dtype=dtype).astype(np.float64)
 
     inertia = 0.5 * (inertia + inertia.transpose(0, 2, 1))
+    # CAD noise: |Ixy|, |Iyz| < 1e-10 kg m^2 and CoM_y = -5.1e-8 m are zeroed so the kernel can
+    # use the sparse (Ixx, Iyy, Izz, Ixz) / (cx, 0, cz) forms; oracle and kernel share this table.
+    inertia[:, 0, 1] = inertia[:, 1, 0] = 0.0
+    inertia[:, 1, 2] = inertia[:, 2, 1] = 0.0
+    com[:, 1] = 0.0
+    link_com[:, 1] = 0.0
     return ZbotModel(
         body_mass=r(mass), body_com=r(com), body_inertia=r(inertia),
-        joint_pos=r(jpos), joint_axis=r(jaxis), foot_points=r(foot_points),
+        # joint_axis is the UNIT vector (+-sqrt(1/2), 0, sqrt(1/2)): kept in double so the joint
+        # quaternions stay unit in the float64 instantiations; float code rounds it on use.
+        joint_pos=r(jpos), joint_axis=jaxis, foot_points=r(foot_points),
         sphere_centre=r(sphere_centre), sphere_radius=float(dtype(BODY_SPHERE_RADIUS)),
         link_offset=r(link_offset), link_com=r(link_com), link_body=link_body,
         default_joint_pos=r(DEFAULT_JOINT_POS), default_root_pos=r(DEFAULT_ROOT_POS),

@@ -1,0 +1,1008 @@
+// zbot_core.h -- per-environment math of the zbot-6b-walking-v2 control step.
+//
+// One environment = one call chain on scalars held in registers.  The header is
+// compiled by nvcc for the sm_100a kernels (T = float) and by g++ for the CPU port
+// under oracle/ (T = float or double), so the same arithmetic can be checked on the
+// build box (no GPU) against the independent float64 oracle (oracle/dyn_oracle.py).
+//
+// What it restates (reference = /root/reference/source/zbot/zbot/...):
+//   * tasks/zbot6b_direct/zbot_direct_6dof_bipedal_env_v2.py:276-287  action -> joint target
+//   * ...:384-411 terminations, :371-382 + :461-571 reward terms, :413-459 partial reset,
+//     :312-369 observation (mdp_* functions below)
+//   * assets/zbot_cfg.py:621-669 + zbot_6s_new.usd: the articulation that PhysX steps in the
+//     reference.  PhysX is closed, so the dynamics here are OUR model:
+//     7-body floating-base chain, articulated-body algorithm in world-aligned Pluecker
+//     coordinates about the root origin, implicit joint PD folded into the joint-space
+//     diagonal, linearly-implicit soft ground contact folded into the articulated inertia.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include "zbot_model_constants.h"
+
+#if defined(__CUDACC__)
+#define ZB_HD __host__ __device__ __forceinline__
+#define ZB_UNROLL _Pragma("unroll")
+#else
+#define ZB_HD inline __attribute__((always_inline))
+#define ZB_UNROLL
+#endif
+
+namespace zbot {
+
+// ------------------------------------------------------------------------------------
+// reward-term ids (names = reference method suffixes, ...env_v2.py:461-571)
+// ------------------------------------------------------------------------------------
+enum TermId : int {
+  TERM_BASE_VEL_FORWARD = 0,
+  TERM_FEET_DOWNWARD = 1,
+  TERM_FEET_FORWARD = 2,
+  TERM_BASE_HEADING_X = 3,
+  TERM_BASE_HEADING_X_SUM = 4,
+  TERM_STEP_LENGTH = 5,
+  TERM_AIRTIME_BALANCE = 6,
+  TERM_ACTION_RATE = 7,
+  TERM_TORQUES = 8,
+  TERM_FEET_SLIDE = 9,
+  TERM_BASE_POS_Y_ERR = 10,
+  TERM_BASE_POS_Y_ERR_SUM = 11,
+  TERM_AIRTIME_SUM = 12,
+  TERM_FEET_FORCE_DIFF = 13,  // defined but inactive in v2's scale dict (:563-565)
+  TERM_FEET_FORCE_SUM = 14,   // defined but inactive in v2's scale dict (:567-571)
+  NUM_TERM_IDS = 15
+};
+constexpr int MAX_TERMS = 16;
+
+// ------------------------------------------------------------------------------------
+// uniform parameters
+// ------------------------------------------------------------------------------------
+template <typename T>
+struct Params {
+  // dynamics
+  T dt, kp, kd, effort, arm;  // arm = dt*kd + dt*dt*kp
+  T gravity;
+  T c_k, c_d, c_fcap, c_beta_max, c_mu, c_inv_ramp, c_vt_eps, c_margin;  // contact law (zbot_6s.py)
+  int decimation;
+  // MDP
+  T step_dt;
+  T termination_height, y_limit, term_penalty, contact_died_threshold;
+  int max_episode_length;
+  int num_terms;
+  int term_id[MAX_TERMS];
+  T term_w[MAX_TERMS];  // weight * step_dt, rounded the way the reference rounds it
+};
+
+// ------------------------------------------------------------------------------------
+// math shims
+// ------------------------------------------------------------------------------------
+ZB_HD float zb_sqrt(float x) { return sqrtf(x); }
+ZB_HD double zb_sqrt(double x) { return sqrt(x); }
+ZB_HD float zb_tanh(float x) { return tanhf(x); }
+ZB_HD double zb_tanh(double x) { return tanh(x); }
+ZB_HD float zb_abs(float x) { return fabsf(x); }
+ZB_HD double zb_abs(double x) { return fabs(x); }
+ZB_HD float zb_min(float a, float b) { return fminf(a, b); }
+ZB_HD double zb_min(double a, double b) { return fmin(a, b); }
+ZB_HD float zb_max(float a, float b) { return fmaxf(a, b); }
+ZB_HD double zb_max(double a, double b) { return fmax(a, b); }
+ZB_HD void zb_sincos(float x, float* s, float* c) {
+#if defined(__CUDA_ARCH__)
+  sincosf(x, s, c);
+#else
+  *s = sinf(x);
+  *c = cosf(x);
+#endif
+}
+ZB_HD void zb_sincos(double x, double* s, double* c) {
+  *s = sin(x);
+  *c = cos(x);
+}
+template <typename T>
+ZB_HD T zb_clamp(T x, T lo, T hi) {
+  return zb_min(zb_max(x, lo), hi);
+}
+
+template <typename T>
+ZB_HD void cross3(const T* a, const T* b, T* o) {
+  T x = a[1] * b[2] - a[2] * b[1];
+  T y = a[2] * b[0] - a[0] * b[2];
+  T z = a[0] * b[1] - a[1] * b[0];
+  o[0] = x; o[1] = y; o[2] = z;
+}
+template <typename T>
+ZB_HD T dot3(const T* a, const T* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+
+// isaaclab.utils.math.quat_apply: wxyz; t = 2 (q_xyz x v); v + q_w t + q_xyz x t
+template <typename T>
+ZB_HD void quat_apply(const T* q, const T* v, T* o) {
+  T t[3], u[3];
+  cross3(q + 1, v, t);
+  t[0] *= T(2); t[1] *= T(2); t[2] *= T(2);
+  cross3(q + 1, t, u);
+  o[0] = v[0] + q[0] * t[0] + u[0];
+  o[1] = v[1] + q[0] * t[1] + u[1];
+  o[2] = v[2] + q[0] * t[2] + u[2];
+}
+
+// rotation matrix (row-major R[3*r+c]) of a unit quaternion wxyz
+template <typename T>
+ZB_HD void quat_to_mat(const T* q, T* R) {
+  T w = q[0], x = q[1], y = q[2], z = q[3];
+  T xx = x * x, yy = y * y, zz = z * z;
+  T xy = x * y, xz = x * z, yz = y * z, wx = w * x, wy = w * y, wz = w * z;
+  R[0] = T(1) - T(2) * (yy + zz); R[1] = T(2) * (xy - wz);        R[2] = T(2) * (xz + wy);
+  R[3] = T(2) * (xy + wz);        R[4] = T(1) - T(2) * (xx + zz); R[5] = T(2) * (yz - wx);
+  R[6] = T(2) * (xz - wy);        R[7] = T(2) * (yz + wx);        R[8] = T(1) - T(2) * (xx + yy);
+}
+
+// Q <- Q (x) (c, sx*s, 0, sz*s): child orientation after a revolute joint about (sx, 0, sz)
+template <typename T>
+ZB_HD void quat_mul_joint(T* Q, T c, T jx, T jz) {
+  T w1 = Q[0], x1 = Q[1], y1 = Q[2], z1 = Q[3];
+  Q[0] = w1 * c - x1 * jx - z1 * jz;
+  Q[1] = w1 * jx + x1 * c + y1 * jz;
+  Q[2] = -x1 * jz + y1 * c + z1 * jx;
+  Q[3] = w1 * jz - y1 * jx + z1 * c;
+}
+
+// ------------------------------------------------------------------------------------
+// simulation state of one environment (root pose is env-LOCAL: relative to the env origin)
+// ------------------------------------------------------------------------------------
+template <typename T>
+struct SimState {
+  T p[3];   // root (foot_0 link origin) position
+  T Q[4];   // root orientation wxyz
+  T v[3];   // root origin linear velocity (world frame)
+  T w[3];   // root angular velocity (world frame)
+  T q[6];   // joint positions
+  T qd[6];  // joint velocities
+};
+
+template <typename T>
+ZB_HD void sim_state_default(SimState<T>& s) {
+  s.p[0] = T(model::DEFAULT_ROOT_X); s.p[1] = T(model::DEFAULT_ROOT_Y); s.p[2] = T(model::DEFAULT_ROOT_Z);
+  s.Q[0] = T(1); s.Q[1] = T(0); s.Q[2] = T(0); s.Q[3] = T(0);
+  ZB_UNROLL for (int i = 0; i < 3; ++i) { s.v[i] = T(0); s.w[i] = T(0); }
+  s.q[0] = T(model::DQ0); s.q[1] = T(model::DQ1); s.q[2] = T(model::DQ2);
+  s.q[3] = T(model::DQ3); s.q[4] = T(model::DQ4); s.q[5] = T(model::DQ5);
+  ZB_UNROLL for (int i = 0; i < 6; ++i) s.qd[i] = T(0);
+}
+
+template <typename T>
+ZB_HD T default_joint_pos(int k) {
+  return k == 0 ? T(model::DQ0) : k == 1 ? T(model::DQ1) : k == 2 ? T(model::DQ2)
+       : k == 3 ? T(model::DQ3) : k == 4 ? T(model::DQ4) : T(model::DQ5);
+}
+
+// ------------------------------------------------------------------------------------
+// symmetric 6x6 articulated inertia  [[I, H], [H^T, M]]  (motion = (w; vO), force = (n; f))
+// ------------------------------------------------------------------------------------
+template <typename T>
+struct SpInertia {
+  T I[6];  // xx xy xz yy yz zz
+  T H[9];  // row-major
+  T M[6];  // xx xy xz yy yz zz
+};
+
+template <typename T>
+ZB_HD void sym3_mul(const T* S, const T* v, T* o) {
+  o[0] = S[0] * v[0] + S[1] * v[1] + S[2] * v[2];
+  o[1] = S[1] * v[0] + S[3] * v[1] + S[4] * v[2];
+  o[2] = S[2] * v[0] + S[4] * v[1] + S[5] * v[2];
+}
+
+// (top; bot) = IA * (a; m)
+template <typename T>
+ZB_HD void spi_mul(const SpInertia<T>& A, const T* a, const T* m, T* top, T* bot) {
+  T t0[3], t1[3];
+  sym3_mul(A.I, a, t0);
+  top[0] = t0[0] + A.H[0] * m[0] + A.H[1] * m[1] + A.H[2] * m[2];
+  top[1] = t0[1] + A.H[3] * m[0] + A.H[4] * m[1] + A.H[5] * m[2];
+  top[2] = t0[2] + A.H[6] * m[0] + A.H[7] * m[1] + A.H[8] * m[2];
+  sym3_mul(A.M, m, t1);
+  bot[0] = t1[0] + A.H[0] * a[0] + A.H[3] * a[1] + A.H[6] * a[2];
+  bot[1] = t1[1] + A.H[1] * a[0] + A.H[4] * a[1] + A.H[7] * a[2];
+  bot[2] = t1[2] + A.H[2] * a[0] + A.H[5] * a[1] + A.H[8] * a[2];
+}
+
+// A -= s * (ut; ub)(ut; ub)^T
+template <typename T>
+ZB_HD void spi_rank1_sub(SpInertia<T>& A, const T* ut, const T* ub, T s) {
+  T st[3] = {s * ut[0], s * ut[1], s * ut[2]};
+  T sb[3] = {s * ub[0], s * ub[1], s * ub[2]};
+  A.I[0] -= st[0] * ut[0]; A.I[1] -= st[0] * ut[1]; A.I[2] -= st[0] * ut[2];
+  A.I[3] -= st[1] * ut[1]; A.I[4] -= st[1] * ut[2]; A.I[5] -= st[2] * ut[2];
+  ZB_UNROLL for (int r = 0; r < 3; ++r)
+    ZB_UNROLL for (int c = 0; c < 3; ++c) A.H[3 * r + c] -= st[r] * ub[c];
+  A.M[0] -= sb[0] * ub[0]; A.M[1] -= sb[0] * ub[1]; A.M[2] -= sb[0] * ub[2];
+  A.M[3] -= sb[1] * ub[1]; A.M[4] -= sb[1] * ub[2]; A.M[5] -= sb[2] * ub[2];
+}
+
+// A += rigid body (mass m, world inertia about CoM Iw[6], CoM at c relative to O)
+template <typename T>
+ZB_HD void spi_add_rigid(SpInertia<T>& A, T m, const T* Iw, const T* c) {
+  T hx = m * c[0], hy = m * c[1], hz = m * c[2];
+  A.I[0] += Iw[0] + (hy * c[1] + hz * c[2]);
+  A.I[1] += Iw[1] - hx * c[1];
+  A.I[2] += Iw[2] - hx * c[2];
+  A.I[3] += Iw[3] + (hx * c[0] + hz * c[2]);
+  A.I[4] += Iw[4] - hy * c[2];
+  A.I[5] += Iw[5] + (hx * c[0] + hy * c[1]);
+  // H = skew(h)
+  A.H[1] -= hz; A.H[2] += hy;
+  A.H[3] += hz; A.H[5] -= hx;
+  A.H[6] -= hy; A.H[7] += hx;
+  A.M[0] += m; A.M[3] += m; A.M[5] += m;
+}
+
+// A += k * g g^T with g = (rho x e_j ; e_j), e_j the j-th world axis (sparse rank-1)
+template <typename T>
+ZB_HD void spi_add_contact(SpInertia<T>& A, const T* r, T kx, T ky, T kz) {
+  // g_x = ((0, rz, -ry); (1,0,0))
+  A.I[3] += kx * r[2] * r[2]; A.I[4] -= kx * r[2] * r[1]; A.I[5] += kx * r[1] * r[1];
+  A.H[3] += kx * r[2]; A.H[6] -= kx * r[1]; A.M[0] += kx;
+  // g_y = ((-rz, 0, rx); (0,1,0))
+  A.I[0] += ky * r[2] * r[2]; A.I[2] -= ky * r[2] * r[0]; A.I[5] += ky * r[0] * r[0];
+  A.H[1] -= ky * r[2]; A.H[7] += ky * r[0]; A.M[3] += ky;
+  // g_z = ((ry, -rx, 0); (0,0,1))
+  A.I[0] += kz * r[1] * r[1]; A.I[1] -= kz * r[1] * r[0]; A.I[3] += kz * r[0] * r[0];
+  A.H[2] += kz * r[1]; A.H[5] -= kz * r[0]; A.M[5] += kz;
+}
+
+// Solve the SPD system  A x = b  for the floating base (6x6 LDL^T, fully unrolled).
+template <typename T>
+ZB_HD void spi_solve(const SpInertia<T>& A, const T* bt, const T* bb, T* xt, T* xb) {
+  T a[6][6];
+  a[0][0] = A.I[0]; a[1][0] = A.I[1]; a[2][0] = A.I[2]; a[1][1] = A.I[3]; a[2][1] = A.I[4]; a[2][2] = A.I[5];
+  ZB_UNROLL for (int r = 0; r < 3; ++r)
+    ZB_UNROLL for (int c = 0; c < 3; ++c) a[3 + c][r] = A.H[3 * r + c];  // lower block = H^T
+  a[3][3] = A.M[0]; a[4][3] = A.M[1]; a[5][3] = A.M[2]; a[4][4] = A.M[3]; a[5][4] = A.M[4]; a[5][5] = A.M[5];
+  T x[6] = {bt[0], bt[1], bt[2], bb[0], bb[1], bb[2]};
+  T dinv[6];
+  ZB_UNROLL for (int j = 0; j < 6; ++j) {
+    T d = a[j][j];
+    ZB_UNROLL for (int k = 0; k < j; ++k) d -= a[j][k] * a[j][k] * a[k][k];
+    a[j][j] = d;  // D_j
+    dinv[j] = T(1) / d;
+    ZB_UNROLL for (int i = j + 1; i < 6; ++i) {
+      T s = a[i][j];
+      ZB_UNROLL for (int k = 0; k < j; ++k) s -= a[i][k] * a[j][k] * a[k][k];
+      a[i][j] = s * dinv[j];  // L_ij
+    }
+  }
+  ZB_UNROLL for (int i = 0; i < 6; ++i)
+    ZB_UNROLL for (int k = 0; k < i; ++k) x[i] -= a[i][k] * x[k];
+  ZB_UNROLL for (int i = 0; i < 6; ++i) x[i] *= dinv[i];
+  ZB_UNROLL for (int i = 5; i >= 0; --i)
+    ZB_UNROLL for (int k = i + 1; k < 6; ++k) x[i] -= a[k][i] * x[k];
+  xt[0] = x[0]; xt[1] = x[1]; xt[2] = x[2];
+  xb[0] = x[3]; xb[1] = x[4]; xb[2] = x[5];
+}
+
+// ------------------------------------------------------------------------------------
+// contact: one candidate point at rho (relative to O) on a body with spatial velocity (w; vO)
+// ------------------------------------------------------------------------------------
+template <typename T>
+struct ContactAgg {  // enough to evaluate  sum_c (F0_c - dt K_c (A_lin + A_ang x rho_c))  later
+  T F0[3];
+  T sb, sg;         // sum beta, sum gamma
+  T sbr[3];         // sum beta * rho
+  T sgrx, sgry;     // sum gamma * rho_x, rho_y
+};
+template <typename T>
+ZB_HD void contact_agg_zero(ContactAgg<T>& g) {
+  g.F0[0] = g.F0[1] = g.F0[2] = T(0);
+  g.sb = g.sg = T(0);
+  g.sbr[0] = g.sbr[1] = g.sbr[2] = T(0);
+  g.sgrx = g.sgry = T(0);
+}
+template <typename T>
+ZB_HD void contact_agg_force(const ContactAgg<T>& g, T dt, const T* At, const T* Ab, T* f) {
+  // K (A_lin + A_ang x rho), K = diag(beta, beta, gamma)
+  f[0] = g.F0[0] - dt * (g.sb * Ab[0] + At[1] * g.sbr[2] - At[2] * g.sbr[1]);
+  f[1] = g.F0[1] - dt * (g.sb * Ab[1] + At[2] * g.sbr[0] - At[0] * g.sbr[2]);
+  f[2] = g.F0[2] - dt * (g.sg * Ab[2] + At[0] * g.sgry - At[1] * g.sgrx);
+}
+
+// Returns true when the point is active.  Adds dt*J^T K J to IA, subtracts J^T F0 from pA.
+template <typename T>
+ZB_HD bool contact_point(const Params<T>& P, const T* rho, T height, const T* w, const T* vO,
+                         SpInertia<T>& IA, T* pAt, T* pAb, ContactAgg<T>* agg, T* f0out) {
+  T pen = -height;
+  if (!(pen > -P.c_margin)) return false;   // speculative margin: points this far above ground are skipped
+  T vp[3], wxv[3];
+  cross3(w, rho, vp);
+  vp[0] += vO[0]; vp[1] += vO[1]; vp[2] += vO[2];
+  cross3(w, vp, wxv);
+  T sx = vp[0] + P.dt * wxv[0], sy = vp[1] + P.dt * wxv[1], sz = vp[2] + P.dt * wxv[2];
+  T s = zb_clamp(pen * P.c_inv_ramp, T(0), T(1));
+  T fs = zb_min(P.c_k * pen, P.c_fcap);
+  T gamma = P.c_k * P.dt + P.c_d * s;
+  T fn0 = fs - gamma * sz;
+  if (!(fn0 > T(0))) return false;
+  T vt = zb_sqrt(sx * sx + sy * sy);
+  T beta = zb_min(P.c_beta_max, P.c_mu * fn0 / zb_max(vt, P.c_vt_eps));
+  T F0[3] = {-beta * sx, -beta * sy, fn0};
+  T n[3];
+  cross3(rho, F0, n);
+  pAt[0] -= n[0]; pAt[1] -= n[1]; pAt[2] -= n[2];
+  pAb[0] -= F0[0]; pAb[1] -= F0[1]; pAb[2] -= F0[2];
+  spi_add_contact(IA, rho, P.dt * beta, P.dt * beta, P.dt * gamma);
+  if (agg) {
+    agg->F0[0] += F0[0]; agg->F0[1] += F0[1]; agg->F0[2] += F0[2];
+    agg->sb += beta; agg->sg += gamma;
+    agg->sbr[0] += beta * rho[0]; agg->sbr[1] += beta * rho[1]; agg->sbr[2] += beta * rho[2];
+    agg->sgrx += gamma * rho[0]; agg->sgry += gamma * rho[1];
+  }
+  if (f0out) { f0out[0] = F0[0]; f0out[1] = F0[1]; f0out[2] = F0[2]; }
+  return true;
+}
+
+// ------------------------------------------------------------------------------------
+// per-body rigid terms: adds the body's spatial inertia about O and its bias force
+//   p = V x* (I V) - f_gravity
+// ------------------------------------------------------------------------------------
+template <typename T>
+ZB_HD void body_rigid_terms(const Params<T>& P, T mass, T cx, T cz, T ixx, T iyy, T izz, T ixz,
+                            const T* R, const T* r, const T* w, const T* vO,
+                            SpInertia<T>& IA, T* pAt, T* pAb) {
+  // CoM relative to O (body CoM_y == 0)
+  T c[3] = {r[0] + R[0] * cx + R[2] * cz, r[1] + R[3] * cx + R[5] * cz, r[2] + R[6] * cx + R[8] * cz};
+  // Iw = R diag/sparse R^T
+  T t0[3] = {ixx * R[0] + ixz * R[2], ixx * R[3] + ixz * R[5], ixx * R[6] + ixz * R[8]};
+  T t1[3] = {iyy * R[1], iyy * R[4], iyy * R[7]};
+  T t2[3] = {ixz * R[0] + izz * R[2], ixz * R[3] + izz * R[5], ixz * R[6] + izz * R[8]};
+  T Iw[6];
+  Iw[0] = t0[0] * R[0] + t1[0] * R[1] + t2[0] * R[2];
+  Iw[1] = t0[0] * R[3] + t1[0] * R[4] + t2[0] * R[5];
+  Iw[2] = t0[0] * R[6] + t1[0] * R[7] + t2[0] * R[8];
+  Iw[3] = t0[1] * R[3] + t1[1] * R[4] + t2[1] * R[5];
+  Iw[4] = t0[1] * R[6] + t1[1] * R[7] + t2[1] * R[8];
+  Iw[5] = t0[2] * R[6] + t1[2] * R[7] + t2[2] * R[8];
+  // momentum about O:  L = Iw w + c x (m vc),  Pl = m vc,  vc = vO + w x c
+  T wxc[3];
+  cross3(w, c, wxc);
+  T Pl[3] = {mass * (vO[0] + wxc[0]), mass * (vO[1] + wxc[1]), mass * (vO[2] + wxc[2])};
+  T L[3], cxP[3];
+  sym3_mul(Iw, w, L);
+  cross3(c, Pl, cxP);
+  L[0] += cxP[0]; L[1] += cxP[1]; L[2] += cxP[2];
+  // p = (w x L + vO x Pl ; w x Pl) - (c x m g ; m g),  g = (0,0,-G)
+  T a0[3], a1[3], a2[3];
+  cross3(w, L, a0);
+  cross3(vO, Pl, a1);
+  cross3(w, Pl, a2);
+  T mg = mass * P.gravity;
+  pAt[0] += a0[0] + a1[0] + mg * c[1];
+  pAt[1] += a0[1] + a1[1] - mg * c[0];
+  pAt[2] += a0[2] + a1[2];
+  pAb[0] += a2[0];
+  pAb[1] += a2[1];
+  pAb[2] += a2[2] + mg;
+  spi_add_rigid(IA, mass, Iw, c);
+}
+
+// ------------------------------------------------------------------------------------
+// one physics substep (dt = P.dt): implicit PD + contact + ABA + semi-implicit Euler
+// ------------------------------------------------------------------------------------
+template <typename T>
+struct SubstepOut {
+  T foot_force[2][3];  // net contact force on foot_0 / foot_1 (applied, world frame)
+  T mid_force2_max;    // max over bodies 1..5 of |predictor contact force|^2
+  T mid_force[5][3];   // predictor contact force of bodies 1..5 (export / debug)
+  T applied_torque[6]; // ImplicitActuator bookkeeping evaluated BEFORE this substep
+};
+
+template <typename T>
+ZB_HD void physics_substep(const Params<T>& P, SimState<T>& s, const T* target, SubstepOut<T>& out) {
+  using namespace model;
+  const T dt = P.dt;
+  // ---- forward kinematics sweep: keep only joint half-angle sin/cos, arrive at body 6 ----
+  T sn[6], cs[6];
+  ZB_UNROLL for (int k = 0; k < 6; ++k) zb_sincos(T(0.5) * s.q[k], &sn[k], &cs[k]);
+  T Q[4] = {s.Q[0], s.Q[1], s.Q[2], s.Q[3]};
+  T r[3] = {T(0), T(0), T(0)};               // body origin relative to O (= root origin)
+  T w[3] = {s.w[0], s.w[1], s.w[2]};         // spatial velocity of the current body about O
+  T vO[3] = {s.v[0], s.v[1], s.v[2]};
+  T Sa[6][3], Sm[6][3];                      // motion subspaces S_k = (a_k ; r_k x a_k)
+  ZB_UNROLL for (int k = 0; k < 6; ++k) {
+    T R[9];
+    quat_to_mat(Q, R);
+    const T jz = (k == 0) ? T(JOINT_Z_FIRST) : T(JOINT_Z_REST);
+    const T sg = (k & 1) ? T(-AXIS_S) : T(AXIS_S);
+    r[0] += jz * R[2]; r[1] += jz * R[5]; r[2] += jz * R[8];
+    Sa[k][0] = sg * R[0] + T(AXIS_S) * R[2];
+    Sa[k][1] = sg * R[3] + T(AXIS_S) * R[5];
+    Sa[k][2] = sg * R[6] + T(AXIS_S) * R[8];
+    cross3(r, Sa[k], Sm[k]);
+    ZB_UNROLL for (int i = 0; i < 3; ++i) { w[i] += Sa[k][i] * s.qd[k]; vO[i] += Sm[k][i] * s.qd[k]; }
+    quat_mul_joint(Q, cs[k], sg * sn[k], T(AXIS_S) * sn[k]);
+  }
+  // ---- PD (implicit part lives in P.arm) ----
+  T tau[6];
+  ZB_UNROLL for (int k = 0; k < 6; ++k) {
+    T e = target[k] - s.q[k];
+    out.applied_torque[k] = zb_clamp(P.kp * e - P.kd * s.qd[k], -P.effort, P.effort);
+    tau[k] = zb_clamp(P.kp * (e - dt * s.qd[k]) - P.kd * s.qd[k], -P.effort, P.effort);
+  }
+  // ---- backward sweep: body k terms, then eliminate joint k ----
+  SpInertia<T> IA;
+  ZB_UNROLL for (int i = 0; i < 6; ++i) { IA.I[i] = T(0); IA.M[i] = T(0); }
+  ZB_UNROLL for (int i = 0; i < 9; ++i) IA.H[i] = T(0);
+  T pAt[3] = {T(0), T(0), T(0)}, pAb[3] = {T(0), T(0), T(0)};
+  T Ut[6][3], Ub[6][3], Dinv[6], u[6];
+  ContactAgg<T> agg1;   // foot_1 (body 6)
+  contact_agg_zero(agg1);
+  T mid2 = T(0);
+  ZB_UNROLL for (int i = 0; i < 5; ++i) { out.mid_force[i][0] = out.mid_force[i][1] = out.mid_force[i][2] = T(0); }
+  ZB_UNROLL for (int k = 6; k >= 1; --k) {
+    T R[9];
+    quat_to_mat(Q, R);
+    if (k == 6) {
+      body_rigid_terms(P, T(FOOT1_MASS), T(FOOT1_COM_X), T(FOOT1_COM_Z), T(FOOT1_IXX), T(FOOT1_IYY),
+                       T(FOOT1_IZZ), T(FOOT1_IXZ), R, r, w, vO, IA, pAt, pAb);
+      ZB_UNROLL for (int j = 0; j < 4; ++j) {
+        const T lx = (j == 0) ? T(FOOT_R) : (j == 2) ? T(-FOOT_R) : T(0);
+        const T ly = (j == 1) ? T(FOOT_R) : (j == 3) ? T(-FOOT_R) : T(0);
+        T rho[3] = {r[0] + R[0] * lx + R[1] * ly + R[2] * T(FOOT1_SOLE_Z),
+                    r[1] + R[3] * lx + R[4] * ly + R[5] * T(FOOT1_SOLE_Z),
+                    r[2] + R[6] * lx + R[7] * ly + R[8] * T(FOOT1_SOLE_Z)};
+        contact_point(P, rho, s.p[2] + rho[2], w, vO, IA, pAt, pAb, &agg1, (T*)nullptr);
+      }
+    } else {
+      body_rigid_terms(P, T(MID_MASS), T(MID_COM_X), T(MID_COM_Z), T(MID_IXX), T(MID_IYY), T(MID_IZZ),
+                       T(MID_IXZ), R, r, w, vO, IA, pAt, pAb);
+      T rho[3] = {r[0] + R[2] * T(SPHERE_Z), r[1] + R[5] * T(SPHERE_Z), r[2] + R[8] * T(SPHERE_Z) - T(SPHERE_R)};
+      T f0[3];
+      if (contact_point(P, rho, s.p[2] + rho[2], w, vO, IA, pAt, pAb, (ContactAgg<T>*)nullptr, f0)) {
+        mid2 = zb_max(mid2, f0[0] * f0[0] + f0[1] * f0[1] + f0[2] * f0[2]);
+        out.mid_force[k - 1][0] = f0[0]; out.mid_force[k - 1][1] = f0[1]; out.mid_force[k - 1][2] = f0[2];
+      }
+    }
+    // joint k (index k-1): velocity-product term c = V x (S qd)
+    const int j = k - 1;
+    T sa[3] = {Sa[j][0] * s.qd[j], Sa[j][1] * s.qd[j], Sa[j][2] * s.qd[j]};
+    T sm[3] = {Sm[j][0] * s.qd[j], Sm[j][1] * s.qd[j], Sm[j][2] * s.qd[j]};
+    T ct[3], cb[3], tmp[3];
+    cross3(w, sa, ct);
+    cross3(w, sm, cb);
+    cross3(vO, sa, tmp);
+    cb[0] += tmp[0]; cb[1] += tmp[1]; cb[2] += tmp[2];
+    spi_mul(IA, Sa[j], Sm[j], Ut[j], Ub[j]);
+    T D = dot3(Sa[j], Ut[j]) + dot3(Sm[j], Ub[j]) + P.arm;
+    Dinv[j] = T(1) / D;
+    u[j] = tau[j] - (dot3(Sa[j], pAt) + dot3(Sm[j], pAb));
+    // pa = pA + IA c + U (u - U.c)/D   (== pA + Ia c + U u/D)
+    T Ict[3], Icb[3];
+    spi_mul(IA, ct, cb, Ict, Icb);
+    T g = (u[j] - (dot3(Ut[j], ct) + dot3(Ub[j], cb))) * Dinv[j];
+    ZB_UNROLL for (int i = 0; i < 3; ++i) {
+      pAt[i] += Ict[i] + Ut[j][i] * g;
+      pAb[i] += Icb[i] + Ub[j][i] * g;
+    }
+    spi_rank1_sub(IA, Ut[j], Ub[j], Dinv[j]);
+    // unwind kinematics to body k-1
+    ZB_UNROLL for (int i = 0; i < 3; ++i) { w[i] -= sa[i]; vO[i] -= sm[i]; }
+    const T sg = (j & 1) ? T(-AXIS_S) : T(AXIS_S);
+    quat_mul_joint(Q, cs[j], -sg * sn[j], -T(AXIS_S) * sn[j]);   // Q_{k-1} = Q_k (x) conj(qj)
+    const T jz = (j == 0) ? T(JOINT_Z_FIRST) : T(JOINT_Z_REST);
+    T Rp2[3] = {T(2) * (Q[1] * Q[3] + Q[0] * Q[2]), T(2) * (Q[2] * Q[3] - Q[0] * Q[1]),
+                T(1) - T(2) * (Q[1] * Q[1] + Q[2] * Q[2])};     // third column of R_{k-1}
+    r[0] -= jz * Rp2[0]; r[1] -= jz * Rp2[1]; r[2] -= jz * Rp2[2];
+  }
+  // ---- root body (foot_0): exact kinematics from the state (no unwinding round-off) ----
+  ContactAgg<T> agg0;
+  contact_agg_zero(agg0);
+  {
+    T R[9];
+    quat_to_mat(s.Q, R);
+    const T zero3[3] = {T(0), T(0), T(0)};
+    body_rigid_terms(P, T(FOOT0_MASS), T(FOOT0_COM_X), T(FOOT0_COM_Z), T(FOOT0_IXX), T(FOOT0_IYY),
+                     T(FOOT0_IZZ), T(FOOT0_IXZ), R, zero3, s.w, s.v, IA, pAt, pAb);
+    ZB_UNROLL for (int j = 0; j < 4; ++j) {
+      const T lx = (j == 0) ? T(FOOT_R) : (j == 2) ? T(-FOOT_R) : T(0);
+      const T ly = (j == 1) ? T(FOOT_R) : (j == 3) ? T(-FOOT_R) : T(0);
+      T rho[3] = {R[0] * lx + R[1] * ly + R[2] * T(FOOT0_SOLE_Z), R[3] * lx + R[4] * ly + R[5] * T(FOOT0_SOLE_Z),
+                  R[6] * lx + R[7] * ly + R[8] * T(FOOT0_SOLE_Z)};
+      contact_point(P, rho, s.p[2] + rho[2], s.w, s.v, IA, pAt, pAb, &agg0, (T*)nullptr);
+    }
+  }
+  // ---- floating base:  IA a0 = -pA ----
+  T At[3], Ab[3];
+  {
+    T nt[3] = {-pAt[0], -pAt[1], -pAt[2]}, nb[3] = {-pAb[0], -pAb[1], -pAb[2]};
+    spi_solve(IA, nt, nb, At, Ab);
+  }
+  contact_agg_force(agg0, dt, At, Ab, out.foot_force[0]);
+  // classical acceleration of the root origin = spatial + w x v
+  T wxv[3];
+  cross3(s.w, s.v, wxv);
+  T w0[3] = {s.w[0], s.w[1], s.w[2]}, v0[3] = {s.v[0], s.v[1], s.v[2]};
+  ZB_UNROLL for (int i = 0; i < 3; ++i) {
+    s.w[i] += dt * At[i];
+    s.v[i] += dt * (Ab[i] + wxv[i]);
+  }
+  // ---- forward sweep: joint accelerations ----
+  T wk[3] = {w0[0], w0[1], w0[2]}, vk[3] = {v0[0], v0[1], v0[2]};  // V_{k-1} (pre-update velocities)
+  ZB_UNROLL for (int j = 0; j < 6; ++j) {
+    T sa[3] = {Sa[j][0] * s.qd[j], Sa[j][1] * s.qd[j], Sa[j][2] * s.qd[j]};
+    T sm[3] = {Sm[j][0] * s.qd[j], Sm[j][1] * s.qd[j], Sm[j][2] * s.qd[j]};
+    T ct[3], cb[3], tmp[3];
+    cross3(wk, sa, ct);
+    cross3(wk, sm, cb);
+    cross3(vk, sa, tmp);
+    cb[0] += tmp[0]; cb[1] += tmp[1]; cb[2] += tmp[2];
+    ZB_UNROLL for (int i = 0; i < 3; ++i) { At[i] += ct[i]; Ab[i] += cb[i]; wk[i] += sa[i]; vk[i] += sm[i]; }
+    T qdd = (u[j] - (dot3(Ut[j], At) + dot3(Ub[j], Ab))) * Dinv[j];
+    ZB_UNROLL for (int i = 0; i < 3; ++i) { At[i] += Sa[j][i] * qdd; Ab[i] += Sm[j][i] * qdd; }
+    s.qd[j] += dt * qdd;
+    s.q[j] += dt * s.qd[j];
+  }
+  contact_agg_force(agg1, dt, At, Ab, out.foot_force[1]);
+  out.mid_force2_max = mid2;
+  // ---- root pose ----
+  ZB_UNROLL for (int i = 0; i < 3; ++i) s.p[i] += dt * s.v[i];
+  {
+    T h = T(0.5) * dt;
+    T qw = s.Q[0], qx = s.Q[1], qy = s.Q[2], qz = s.Q[3];
+    T nw = qw + h * (-s.w[0] * qx - s.w[1] * qy - s.w[2] * qz);
+    T nx = qx + h * (s.w[0] * qw + s.w[1] * qz - s.w[2] * qy);
+    T ny = qy + h * (-s.w[0] * qz + s.w[1] * qw + s.w[2] * qx);
+    T nz = qz + h * (s.w[0] * qy - s.w[1] * qx + s.w[2] * qw);
+    T inv = T(1) / zb_sqrt(nw * nw + nx * nx + ny * ny + nz * nz);
+    s.Q[0] = nw * inv; s.Q[1] = nx * inv; s.Q[2] = ny * inv; s.Q[3] = nz * inv;
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// kinematic quantities the MDP reads from robot.data (…env_v2.py:315-326, 554)
+// ------------------------------------------------------------------------------------
+template <typename T>
+struct LinkKin {
+  T base_pos[3], base_quat[4], base_com_vel[3];
+  T feet_pos[2][3], feet_quat[2][4], feet_com_vel[2][3];
+};
+
+template <typename T>
+ZB_HD void link_kinematics(const SimState<T>& s, LinkKin<T>& o) {
+  using namespace model;
+  T Q[4] = {s.Q[0], s.Q[1], s.Q[2], s.Q[3]};
+  T r[3] = {T(0), T(0), T(0)};
+  T w[3] = {s.w[0], s.w[1], s.w[2]};
+  T vO[3] = {s.v[0], s.v[1], s.v[2]};
+  {
+    T R[9];
+    quat_to_mat(Q, R);
+    T c[3] = {R[0] * T(A_COM_X) + R[2] * T(A_COM_Z), R[3] * T(A_COM_X) + R[5] * T(A_COM_Z),
+              R[6] * T(A_COM_X) + R[8] * T(A_COM_Z)};
+    T wxc[3];
+    cross3(w, c, wxc);
+    ZB_UNROLL for (int i = 0; i < 3; ++i) { o.feet_pos[0][i] = s.p[i]; o.feet_com_vel[0][i] = vO[i] + wxc[i]; }
+    ZB_UNROLL for (int i = 0; i < 4; ++i) o.feet_quat[0][i] = Q[i];
+  }
+  ZB_UNROLL for (int k = 0; k < 6; ++k) {
+    T R[9];
+    quat_to_mat(Q, R);
+    const T jz = (k == 0) ? T(JOINT_Z_FIRST) : T(JOINT_Z_REST);
+    const T sg = (k & 1) ? T(-AXIS_S) : T(AXIS_S);
+    r[0] += jz * R[2]; r[1] += jz * R[5]; r[2] += jz * R[8];
+    T a[3] = {sg * R[0] + T(AXIS_S) * R[2], sg * R[3] + T(AXIS_S) * R[5], sg * R[6] + T(AXIS_S) * R[8]};
+    T m[3];
+    cross3(r, a, m);
+    ZB_UNROLL for (int i = 0; i < 3; ++i) { w[i] += a[i] * s.qd[k]; vO[i] += m[i] * s.qd[k]; }
+    T sn, cs;
+    zb_sincos(T(0.5) * s.q[k], &sn, &cs);
+    quat_mul_joint(Q, cs, sg * sn, T(AXIS_S) * sn);
+    if (k == 2) {  // body 3 = b3 + base; base LINK origin = body origin + R (0,0,LINK_OFFSET_Z)
+      T Rb[9];
+      quat_to_mat(Q, Rb);
+      T lo[3] = {r[0] + Rb[2] * T(LINK_OFFSET_Z), r[1] + Rb[5] * T(LINK_OFFSET_Z), r[2] + Rb[8] * T(LINK_OFFSET_Z)};
+      T c[3] = {lo[0] + Rb[0] * T(A_COM_X) + Rb[2] * T(A_COM_Z), lo[1] + Rb[3] * T(A_COM_X) + Rb[5] * T(A_COM_Z),
+                lo[2] + Rb[6] * T(A_COM_X) + Rb[8] * T(A_COM_Z)};
+      T wxc[3];
+      cross3(w, c, wxc);
+      ZB_UNROLL for (int i = 0; i < 3; ++i) { o.base_pos[i] = s.p[i] + lo[i]; o.base_com_vel[i] = vO[i] + wxc[i]; }
+      ZB_UNROLL for (int i = 0; i < 4; ++i) o.base_quat[i] = Q[i];
+    }
+    if (k == 5) {  // body 6 = foot_1 (b-type link)
+      T Rb[9];
+      quat_to_mat(Q, Rb);
+      T c[3] = {r[0] + Rb[0] * T(B_COM_X) + Rb[2] * T(B_COM_Z), r[1] + Rb[3] * T(B_COM_X) + Rb[5] * T(B_COM_Z),
+                r[2] + Rb[6] * T(B_COM_X) + Rb[8] * T(B_COM_Z)};
+      T wxc[3];
+      cross3(w, c, wxc);
+      ZB_UNROLL for (int i = 0; i < 3; ++i) { o.feet_pos[1][i] = s.p[i] + r[i]; o.feet_com_vel[1][i] = vO[i] + wxc[i]; }
+      ZB_UNROLL for (int i = 0; i < 4; ++i) o.feet_quat[1][i] = Q[i];
+    }
+  }
+}
+
+// all 12 link poses + CoM velocities (articulation order) -- export / debug only
+template <typename T>
+ZB_HD void all_link_kinematics(const SimState<T>& s, T* pos /*12x3*/, T* quat /*12x4*/, T* comvel /*12x3*/) {
+  using namespace model;
+  T Q[4] = {s.Q[0], s.Q[1], s.Q[2], s.Q[3]};
+  T r[3] = {T(0), T(0), T(0)};
+  T w[3] = {s.w[0], s.w[1], s.w[2]};
+  T vO[3] = {s.v[0], s.v[1], s.v[2]};
+  for (int b = 0; b < 7; ++b) {
+    T R[9];
+    quat_to_mat(Q, R);
+    const int nl = (b == 0 || b == 6) ? 1 : 2;
+    for (int h = 0; h < nl; ++h) {
+      const int link = (b == 0) ? 0 : (b == 6) ? 11 : (2 * b - 1 + h);
+      const bool a_type = (b == 0) || (h == 1);
+      const T oz = (h == 1) ? T(LINK_OFFSET_Z) : T(0);
+      const T cx = a_type ? T(A_COM_X) : T(B_COM_X), cz = a_type ? T(A_COM_Z) : T(B_COM_Z);
+      T lo[3] = {r[0] + R[2] * oz, r[1] + R[5] * oz, r[2] + R[8] * oz};
+      T c[3] = {lo[0] + R[0] * cx + R[2] * cz, lo[1] + R[3] * cx + R[5] * cz, lo[2] + R[6] * cx + R[8] * cz};
+      T wxc[3];
+      cross3(w, c, wxc);
+      for (int i = 0; i < 3; ++i) { pos[3 * link + i] = s.p[i] + lo[i]; comvel[3 * link + i] = vO[i] + wxc[i]; }
+      for (int i = 0; i < 4; ++i) quat[4 * link + i] = Q[i];
+    }
+    if (b < 6) {
+      const int k = b;
+      const T jz = (k == 0) ? T(JOINT_Z_FIRST) : T(JOINT_Z_REST);
+      const T sg = (k & 1) ? T(-AXIS_S) : T(AXIS_S);
+      r[0] += jz * R[2]; r[1] += jz * R[5]; r[2] += jz * R[8];
+      T a[3] = {sg * R[0] + T(AXIS_S) * R[2], sg * R[3] + T(AXIS_S) * R[5], sg * R[6] + T(AXIS_S) * R[8]};
+      T m[3];
+      cross3(r, a, m);
+      for (int i = 0; i < 3; ++i) { w[i] += a[i] * s.qd[k]; vO[i] += m[i] * s.qd[k]; }
+      T sn, cs;
+      zb_sincos(T(0.5) * s.q[k], &sn, &cs);
+      quat_mul_joint(Q, cs, sg * sn, T(AXIS_S) * sn);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// MDP state carried between control steps (reference attributes, ...env_v2.py:215-245)
+// ------------------------------------------------------------------------------------
+template <typename T>
+struct MdpState {
+  T p_delta[6];
+  T actions[6];              // _actions == _previous_actions between steps (:313)
+  T feet_force_last[2];      // feet_contact_forces_last
+  T feet_down_pos_last[2][3];
+  T feet_step_length[2];
+  T heading_sum, y_err_sum, feet_force_sum;
+  T speed_limit;             // joint_speed_limit
+  T ep_sums[MAX_TERMS];      // _episode_sums in cfg dict order
+};
+
+// quantities cached by the PREVIOUS _get_observations (:315-345) -- "stale" (SURVEY C-1)
+template <typename T>
+struct StaleCache {
+  T base_pos[3];      // base_pos_w (world; fused path: env-local with origin 0)
+  T forward[3];       // base_dir_forward_w (NOT normalised, SURVEY C-2)
+  T feet_x[2][3], feet_z[2][3], feet_pos[2][3];
+  T v_fwd;            // base_lin_vel_forward_w
+};
+
+template <typename T>
+ZB_HD void stale_from_links(const T* base_pos, const T* base_quat, const T* base_com_vel,
+                            const T feet_pos[2][3], const T feet_quat[2][4], StaleCache<T>& c) {
+  const T ez[3] = {T(0), T(0), T(1)};
+  const T enz[3] = {T(0), T(0), T(-1)};
+  const T ex[3] = {T(1), T(0), T(0)};
+  T shoulder[3];
+  quat_apply(base_quat, ez, shoulder);                 // :322
+  const T grav[3] = {T(0), T(0), T(-1)};
+  cross3(grav, shoulder, c.forward);                   // :323
+  c.v_fwd = base_com_vel[0] * c.forward[0] + base_com_vel[1] * c.forward[1] + base_com_vel[2] * c.forward[2];  // :327
+  quat_apply(feet_quat[0], ez, c.feet_z[0]);           // :344  axis_z_feet = [[0,0,1],[0,0,-1]]
+  quat_apply(feet_quat[1], enz, c.feet_z[1]);
+  quat_apply(feet_quat[0], ex, c.feet_x[0]);           // :345
+  quat_apply(feet_quat[1], ex, c.feet_x[1]);
+  ZB_UNROLL for (int i = 0; i < 3; ++i) {
+    c.base_pos[i] = base_pos[i];
+    c.feet_pos[0][i] = feet_pos[0][i];
+    c.feet_pos[1][i] = feet_pos[1][i];
+  }
+}
+
+// fresh (end-of-physics) inputs of _get_dones/_get_rewards
+template <typename T>
+struct FreshInputs {
+  T feet_force[2];        // mean_t history[:, t, foot, z]  (:387-390)
+  T last_air_time[2];     // (:391)
+  T undesired_force_max;  // max_{t,b} |history[:, t, b, :]|  over the undesired bodies (:396-402)
+  T feet_vel_xy[2][2];    // body_com_lin_vel_w[:, feet, :2]  (:554)
+  T applied_torque[6];    // (:560)
+  T origin_y;             // env_origins[:, 1]  (0 in the fused path: env-local coordinates)
+};
+
+// …env_v2.py:276-287.  raw -> post-tanh actions, p_delta integration/clip, joint targets
+template <typename T>
+ZB_HD void mdp_pre_physics(const Params<T>& P, const T* raw, MdpState<T>& m, T* new_actions, T* target) {
+  const T pi = T(3.14159265358979323846);
+  ZB_UNROLL for (int k = 0; k < 6; ++k) {
+    T a = zb_tanh(raw[k]);
+    new_actions[k] = a;
+    T pd = m.p_delta[k] + pi * a * m.speed_limit * P.step_dt;
+    pd = zb_clamp(pd, -pi, pi);
+    m.p_delta[k] = pd;
+    target[k] = pd + default_joint_pos<T>(k);
+  }
+}
+
+// …env_v2.py:384-411 + 371-382 + 461-571.  `new_actions` = this step's post-tanh actions,
+// m.actions = previous step's.  Returns the reward; updates the stateful terms and ep_sums.
+template <typename T>
+ZB_HD T mdp_dones_rewards(const Params<T>& P, const StaleCache<T>& c, const FreshInputs<T>& f,
+                          const T* new_actions, MdpState<T>& m, int64_t ep_len, bool& terminated,
+                          bool& time_out) {
+  time_out = ep_len >= (int64_t)(P.max_episode_length - 1);                     // :385
+  bool died = f.undesired_force_max > P.contact_died_threshold;                  // :396-402
+  died |= c.base_pos[2] < P.termination_height;                                  // :405
+  const T y_err = c.base_pos[1] - f.origin_y;                                    // :406
+  died |= zb_abs(y_err) > P.y_limit;                                             // :407
+  terminated = died;
+  const T heading_err = -c.forward[1];                                           // :324
+  T reward = T(0);
+  for (int i = 0; i < P.num_terms; ++i) {
+    T val = T(0);
+    switch (P.term_id[i]) {
+      case TERM_BASE_VEL_FORWARD:                                                // :489-491
+        val = zb_tanh(T(10.0) * c.v_fwd / m.speed_limit);
+        break;
+      case TERM_FEET_DOWNWARD: {                                                 // :471-479
+        ZB_UNROLL for (int j = 0; j < 2; ++j) {
+          T dx = c.feet_z[j][0], dy = c.feet_z[j][1], dz = c.feet_z[j][2] - T(1);
+          val += zb_sqrt(dx * dx + dy * dy + dz * dz);
+        }
+      } break;
+      case TERM_FEET_FORWARD: {                                                  // :461-469
+        ZB_UNROLL for (int j = 0; j < 2; ++j) {
+          T dx = c.feet_x[j][0] - c.forward[0], dy = c.feet_x[j][1] - c.forward[1], dz = c.feet_x[j][2] - c.forward[2];
+          val += zb_sqrt(dx * dx + dy * dy + dz * dz);
+        }
+      } break;
+      case TERM_BASE_HEADING_X:                                                  // :481-482
+        val = zb_abs(heading_err);
+        break;
+      case TERM_BASE_HEADING_X_SUM:                                              // :484-487
+        m.heading_sum = zb_clamp(m.heading_sum + T(0.01) * heading_err, T(-1), T(1));
+        val = zb_abs(m.heading_sum);
+        break;
+      case TERM_STEP_LENGTH: {                                                   // :509-533
+        ZB_UNROLL for (int j = 0; j < 2; ++j) {
+          bool down = (f.feet_force[j] > T(10.0)) && (m.feet_force_last[j] < T(10.0));
+          if (down) {
+            T d[3] = {c.feet_pos[j][0] - m.feet_down_pos_last[j][0], c.feet_pos[j][1] - m.feet_down_pos_last[j][1],
+                      c.feet_pos[j][2] - m.feet_down_pos_last[j][2]};
+            m.feet_step_length[j] = d[0] * c.forward[0] + d[1] * c.forward[1] + d[2] * c.forward[2];
+            m.feet_down_pos_last[j][0] = c.feet_pos[j][0];
+            m.feet_down_pos_last[j][1] = c.feet_pos[j][1];
+            m.feet_down_pos_last[j][2] = c.feet_pos[j][2];
+          }
+          m.feet_force_last[j] = f.feet_force[j];
+        }
+        val = zb_tanh(T(15.0) * zb_min(m.feet_step_length[0], m.feet_step_length[1]));
+      } break;
+      case TERM_AIRTIME_BALANCE:                                                 // :535-539
+        val = zb_abs(f.last_air_time[0] - f.last_air_time[1]);
+        break;
+      case TERM_ACTION_RATE: {                                                   // :502-507
+        ZB_UNROLL for (int k = 0; k < 6; ++k) {
+          T d = new_actions[k] - m.actions[k];
+          val += d * d;
+        }
+      } break;
+      case TERM_TORQUES: {                                                       // :558-561
+        ZB_UNROLL for (int k = 0; k < 6; ++k) val += f.applied_torque[k] * f.applied_torque[k];
+      } break;
+      case TERM_FEET_SLIDE: {                                                    // :545-556
+        ZB_UNROLL for (int j = 0; j < 2; ++j) {
+          T sp = zb_sqrt(f.feet_vel_xy[j][0] * f.feet_vel_xy[j][0] + f.feet_vel_xy[j][1] * f.feet_vel_xy[j][1]);
+          val += (f.feet_force[j] > T(1.0)) ? sp : T(0);
+        }
+      } break;
+      case TERM_BASE_POS_Y_ERR:                                                  // :493-495
+        val = zb_abs(c.feet_pos[0][1] + c.feet_pos[1][1] - T(2.0) * f.origin_y) + zb_abs(c.base_pos[1] - f.origin_y);
+        break;
+      case TERM_BASE_POS_Y_ERR_SUM:                                              // :497-500
+        m.y_err_sum = zb_clamp(m.y_err_sum + T(0.01) * y_err, T(-1), T(1));
+        val = zb_abs(m.y_err_sum);
+        break;
+      case TERM_AIRTIME_SUM:                                                     // :541-543
+        val = zb_tanh(f.last_air_time[0] + f.last_air_time[1]);
+        break;
+      case TERM_FEET_FORCE_DIFF: {                                               // :563-565
+        T sgn = (m.feet_force_sum > T(0)) ? T(1) : (m.feet_force_sum < T(0)) ? T(-1) : T(0);
+        val = (f.feet_force[1] - f.feet_force[0]) * sgn;
+      } break;
+      case TERM_FEET_FORCE_SUM:                                                  // :567-571
+        m.feet_force_sum += T(0.001) * (f.feet_force[0] - f.feet_force[1]);
+        val = zb_abs(m.feet_force_sum);
+        break;
+      default:
+        break;
+    }
+    const T rew = val * P.term_w[i];                                             // :375
+    reward += rew;                                                               // :376
+    m.ep_sums[i] += rew;                                                         // :377
+  }
+  if (terminated) reward -= P.term_penalty;                                      // :379-380
+  return reward;
+}
+
+// local part of _reset_idx (:423-424, 435-439, 448); the caller resets the articulation /
+// sensor state and supplies the post-reset feet link positions (SURVEY C-5).
+template <typename T>
+ZB_HD void mdp_reset(MdpState<T>& m, const T feet_pos[2][3], int num_terms) {
+  ZB_UNROLL for (int k = 0; k < 6; ++k) { m.p_delta[k] = T(0); m.actions[k] = T(0); }
+  ZB_UNROLL for (int j = 0; j < 2; ++j)
+    ZB_UNROLL for (int i = 0; i < 3; ++i) m.feet_down_pos_last[j][i] = feet_pos[j][i];
+  m.feet_force_sum = T(0);
+  m.heading_sum = T(0);
+  m.y_err_sum = T(0);
+  for (int i = 0; i < num_terms; ++i) m.ep_sums[i] = T(0);
+  // NOT reset in v2 (SURVEY C-5): feet_force_last, feet_step_length
+}
+
+// :351-365   obs = [base_quat_w(4), q - q_default(6), qd(6), actions(6), joint_speed_limit(1)]
+template <typename T>
+ZB_HD void mdp_observation(const T* base_quat, const T* q, const T* qd, const T* actions, T speed_limit, T* obs) {
+  ZB_UNROLL for (int i = 0; i < 4; ++i) obs[i] = base_quat[i];
+  ZB_UNROLL for (int k = 0; k < 6; ++k) {
+    obs[4 + k] = q[k] - default_joint_pos<T>(k);
+    obs[10 + k] = qd[k];
+    obs[16 + k] = actions[k];
+  }
+  obs[22] = speed_limit;
+}
+
+// ------------------------------------------------------------------------------------
+// ContactSensor air/contact timers for one body, dt = physics dt
+// ------------------------------------------------------------------------------------
+template <typename T>
+struct ContactTimers {
+  T cur_air, cur_contact, last_air, last_contact;
+};
+template <typename T>
+ZB_HD void contact_timers_update(ContactTimers<T>& t, bool is_contact, T dt) {
+  const bool first_contact = (t.cur_air > T(0)) && is_contact;
+  const bool first_detached = (t.cur_contact > T(0)) && !is_contact;
+  t.last_air = first_contact ? (t.cur_air + dt) : t.last_air;
+  t.cur_air = (!is_contact) ? (t.cur_air + dt) : T(0);
+  t.last_contact = first_detached ? (t.cur_contact + dt) : t.last_contact;
+  t.cur_contact = is_contact ? (t.cur_contact + dt) : T(0);
+}
+
+// ------------------------------------------------------------------------------------
+// the whole control step of one environment (DirectRLEnv.step order)
+// ------------------------------------------------------------------------------------
+template <typename T>
+struct EnvState {
+  SimState<T> sim;
+  MdpState<T> mdp;
+  T carry_feet_fz[2];     // feet Fz of the LAST substep of the previous control step (history slot 4)
+  T carry_mid_max;        // max |F| over the undesired bodies in that substep
+  ContactTimers<T> timers[2];
+};
+
+template <typename T>
+struct StepOut {
+  T obs[23];
+  T reward;
+  bool terminated, time_out;
+};
+
+// optional export of the articulation/sensor view the MDP saw (test hook: feeds the pinned
+// MDP oracle with the kernel's own physics)
+template <typename T>
+struct StepExport {
+  LinkKin<T> k0, k1;
+  T pos0[36], quat0[48], vel0[36];  // all 12 links at the start of the step (articulation order)
+  T pos1[36], quat1[48], vel1[36];  // ... at the end of physics (before any reset)
+  T feet_force_hist[5][2][3];  // newest first
+  T mid_force_hist[5][5][3];   // newest first; slot 4 = carry (norm only: stored in [..][0])
+  T applied_torque[6];
+  T q1[6], qd1[6];
+  T last_air[2], cur_contact[2];
+};
+
+template <typename T>
+ZB_HD void env_reset(const Params<T>& P, EnvState<T>& e, const T default_feet_pos[2][3]) {
+  sim_state_default(e.sim);
+  mdp_reset(e.mdp, default_feet_pos, P.num_terms);
+  e.carry_feet_fz[0] = e.carry_feet_fz[1] = T(0);
+  e.carry_mid_max = T(0);
+  ZB_UNROLL for (int j = 0; j < 2; ++j) {
+    e.timers[j].cur_air = e.timers[j].cur_contact = e.timers[j].last_air = e.timers[j].last_contact = T(0);
+  }
+}
+
+template <typename T>
+ZB_HD void env_observe(const EnvState<T>& e, T* obs) {
+  LinkKin<T> k;
+  link_kinematics(e.sim, k);
+  mdp_observation(k.base_quat, e.sim.q, e.sim.qd, e.mdp.actions, e.mdp.speed_limit, obs);
+}
+
+template <typename T>
+ZB_HD void env_step(const Params<T>& P, EnvState<T>& e, const T* raw_actions, int64_t& ep_len,
+                    const T default_feet_pos[2][3], const T* default_base_quat, StepOut<T>& out,
+                    T* reset_ep_sums /*MAX_TERMS, valid when a reset happened*/, StepExport<T>* ex) {
+  // stale quantities = what _get_observations cached at the end of the previous step
+  StaleCache<T> stale;
+  {
+    LinkKin<T> k0;
+    link_kinematics(e.sim, k0);
+    stale_from_links(k0.base_pos, k0.base_quat, k0.base_com_vel, k0.feet_pos, k0.feet_quat, stale);
+    if (ex) { ex->k0 = k0; all_link_kinematics(e.sim, ex->pos0, ex->quat0, ex->vel0); }
+  }
+  T new_actions[6], target[6];
+  mdp_pre_physics(P, raw_actions, e.mdp, new_actions, target);
+  FreshInputs<T> f;
+  T fz[5][2];
+  fz[4][0] = e.carry_feet_fz[0];
+  fz[4][1] = e.carry_feet_fz[1];
+  T mid2 = e.carry_mid_max * e.carry_mid_max;
+  if (ex) {
+    ZB_UNROLL for (int b = 0; b < 5; ++b) { ex->mid_force_hist[4][b][0] = (b == 0) ? e.carry_mid_max : T(0);
+      ex->mid_force_hist[4][b][1] = T(0); ex->mid_force_hist[4][b][2] = T(0); }
+    ZB_UNROLL for (int j = 0; j < 2; ++j) { ex->feet_force_hist[4][j][0] = T(0); ex->feet_force_hist[4][j][1] = T(0);
+      ex->feet_force_hist[4][j][2] = e.carry_feet_fz[j]; }
+  }
+  SubstepOut<T> so;
+  for (int sub = 0; sub < P.decimation; ++sub) {
+    physics_substep(P, e.sim, target, so);
+    // ContactSensor.update
+    const int slot = P.decimation - 1 - sub;  // newest first
+    ZB_UNROLL for (int j = 0; j < 2; ++j) {
+      const T* ff = so.foot_force[j];
+      const T nrm = zb_sqrt(ff[0] * ff[0] + ff[1] * ff[1] + ff[2] * ff[2]);
+      contact_timers_update(e.timers[j], nrm > T(1.0), P.dt);
+      if (slot < 4) fz[slot][j] = ff[2];
+      if (ex && slot < 4) { ex->feet_force_hist[slot][j][0] = ff[0]; ex->feet_force_hist[slot][j][1] = ff[1];
+        ex->feet_force_hist[slot][j][2] = ff[2]; }
+    }
+    if (slot < 4) mid2 = zb_max(mid2, so.mid_force2_max);
+    if (ex && slot < 4) {
+      ZB_UNROLL for (int b = 0; b < 5; ++b)
+        ZB_UNROLL for (int i = 0; i < 3; ++i) ex->mid_force_hist[slot][b][i] = so.mid_force[b][i];
+    }
+  }
+  e.carry_feet_fz[0] = so.foot_force[0][2];
+  e.carry_feet_fz[1] = so.foot_force[1][2];
+  e.carry_mid_max = zb_sqrt(so.mid_force2_max);
+  ep_len += 1;                                             // DirectRLEnv.step
+  // fresh view
+  LinkKin<T> k1;
+  link_kinematics(e.sim, k1);
+  ZB_UNROLL for (int j = 0; j < 2; ++j) {
+    f.feet_force[j] = ((((fz[0][j] + fz[1][j]) + fz[2][j]) + fz[3][j]) + fz[4][j]) / T(5);
+    f.last_air_time[j] = e.timers[j].last_air;
+    f.feet_vel_xy[j][0] = k1.feet_com_vel[j][0];
+    f.feet_vel_xy[j][1] = k1.feet_com_vel[j][1];
+  }
+  f.undesired_force_max = zb_sqrt(mid2);
+  ZB_UNROLL for (int k = 0; k < 6; ++k) f.applied_torque[k] = so.applied_torque[k];
+  f.origin_y = T(0);
+  if (ex) {
+    ex->k1 = k1;
+    all_link_kinematics(e.sim, ex->pos1, ex->quat1, ex->vel1);
+    ZB_UNROLL for (int k = 0; k < 6; ++k) { ex->applied_torque[k] = so.applied_torque[k]; ex->q1[k] = e.sim.q[k]; ex->qd1[k] = e.sim.qd[k]; }
+    ZB_UNROLL for (int j = 0; j < 2; ++j) { ex->last_air[j] = e.timers[j].last_air; ex->cur_contact[j] = e.timers[j].cur_contact; }
+  }
+  bool terminated, time_out;
+  out.reward = mdp_dones_rewards(P, stale, f, new_actions, e.mdp, ep_len, terminated, time_out);
+  out.terminated = terminated;
+  out.time_out = time_out;
+  ZB_UNROLL for (int k = 0; k < 6; ++k) e.mdp.actions[k] = new_actions[k];   // :313 (next obs pass)
+  if (terminated || time_out) {
+    for (int i = 0; i < P.num_terms; ++i) reset_ep_sums[i] = e.mdp.ep_sums[i];
+    const T speed = e.mdp.speed_limit;
+    env_reset(P, e, default_feet_pos);
+    ep_len = 0;
+    mdp_observation(default_base_quat, e.sim.q, e.sim.qd, e.mdp.actions, speed, out.obs);
+  } else {
+    mdp_observation(k1.base_quat, e.sim.q, e.sim.qd, e.mdp.actions, e.mdp.speed_limit, out.obs);
+  }
+}
+
+}  // namespace zbot

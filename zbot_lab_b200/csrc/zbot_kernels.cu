@@ -1,0 +1,737 @@
+// zbot_kernels.cu -- sm_100a kernels + C ABI (include/zbot_b200.h) of the batched
+// zbot-6b-walking-v2 environment step.
+//
+// Layout / execution model:
+//   * one thread per environment; every per-env quantity lives in registers for the whole
+//     control step (4 physics substeps + MDP + partial reset), so state is read once and
+//     written once per step;
+//   * state in HBM is AoSoA `float4 state[20][N]`: thread e issues 20 independent 16-byte
+//     loads, a warp touches 512 contiguous bytes per load (fully coalesced);
+//   * the [N][23] observation rows (AoS, as the policy consumes them) are staged through
+//     shared memory and written back as contiguous float4 per block;
+//   * per-step reset statistics (`extras["log"]`) are reduced with warp shuffles -> shared
+//     memory -> one partial row per block -> fixed-order final pass by the last block
+//     (deterministic, no float atomics, no host sync).
+// No tensor cores: nothing here is a dense contraction.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "zbot_layout.h"
+
+using namespace zbot;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, const char* a = "") {
+  snprintf(g_err, sizeof(g_err), fmt, a);
+  return code;
+}
+#define ZB_CUDA(call)                                                                       \
+  do {                                                                                      \
+    cudaError_t e__ = (call);                                                               \
+    if (e__ != cudaSuccess) return fail(ZBOT_E_CUDA, #call ": %s", cudaGetErrorString(e__)); \
+  } while (0)
+
+struct DefaultPose {      // FK of the ZBOT_6S_CFG init state, computed ON THE DEVICE at create time
+  float feet_pos[2][3];   // env-local
+  float feet_quat[2][4];
+  float base_pos[3];
+  float base_quat[4];
+};
+
+constexpr int kStats = ZBOT_STATS_WORDS;   // 32
+constexpr int kStatUsed = 22;
+constexpr int S_NUM_RESET = 16, S_NUM_TERM_RESET = 17, S_NUM_TO_RESET = 18, S_REW_SUM = 19, S_NUM_TERM = 20,
+              S_NUM_TRUNC = 21;
+
+struct StatsCtx {
+  float* partials;        // [max_blocks][32]
+  unsigned int* ticket;   // last-block-done counter
+  float* ring;            // [slots][32]
+  int slot, prev_slot;
+};
+
+// ---------------------------------------------------------------------------------------------
+// deterministic block + grid reduction of the per-thread statistics vector
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// `vals[0..18]` are non-zero only for threads that reset this step; 19..21 for every thread.
+__device__ __forceinline__ void stats_reduce(float (&vals)[kStatUsed], bool did_reset, float* smem /*[32][kStatUsed]*/,
+                                             const StatsCtx& sc) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+  const bool any_reset = __any_sync(0xffffffffu, did_reset);
+#pragma unroll
+  for (int j = 0; j < kStatUsed; ++j) {
+    float v = 0.f;
+    if (j >= S_REW_SUM || any_reset) v = warp_sum(vals[j]);   // any_reset is warp-uniform
+    if (lane == 0) smem[warp * kStatUsed + j] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < kStatUsed) {
+    float acc = 0.f;
+    for (int w = 0; w < nwarps; ++w) acc += smem[w * kStatUsed + threadIdx.x];
+    sc.partials[(size_t)blockIdx.x * kStats + threadIdx.x] = acc;
+  }
+  __shared__ bool is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int t = atomicAdd(sc.ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  if (threadIdx.x < kStats) {
+    float acc = 0.f;
+    if (threadIdx.x < kStatUsed) {
+      const volatile float* p = sc.partials + threadIdx.x;
+      for (unsigned int b = 0; b < gridDim.x; ++b) acc += p[(size_t)b * kStats];
+    }
+    smem[threadIdx.x] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x < kStats) {
+    const float nreset = smem[S_NUM_RESET];
+    float v = smem[threadIdx.x];
+    // the reference only rewrites extras["log"] when something reset (…env_v2.py:450): keep the previous log
+    if (threadIdx.x < S_REW_SUM && !(nreset > 0.f))
+      v = (sc.prev_slot >= 0) ? sc.ring[(size_t)sc.prev_slot * kStats + threadIdx.x] : 0.f;
+    sc.ring[(size_t)sc.slot * kStats + threadIdx.x] = v;
+  }
+  if (threadIdx.x == 0) *sc.ticket = 0u;
+}
+
+// ---------------------------------------------------------------------------------------------
+// state load / store: 20 x float4 per thread, [quad][env] layout
+// ---------------------------------------------------------------------------------------------
+template <int NQ>
+__device__ __forceinline__ void load_words(const float4* __restrict__ st, int n, int e, float* w) {
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    const float4 v = __ldg(st + (size_t)q * n + e);
+    w[4 * q + 0] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+  }
+}
+template <int NQ>
+__device__ __forceinline__ void store_words(float4* __restrict__ st, int n, int e, const float* w) {
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) st[(size_t)q * n + e] = make_float4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+}
+
+// stage per-thread rows of ROW floats through shared memory, write the block's rows contiguously
+template <int ROW>
+__device__ __forceinline__ void store_rows_coalesced(float* __restrict__ dst, const float* row, int n, int e0,
+                                                     float* smem /*blockDim*ROW*/) {
+  const int e = e0 + threadIdx.x;
+#pragma unroll
+  for (int i = 0; i < ROW; ++i) smem[threadIdx.x * ROW + i] = row[i];   // ROW odd -> conflict-free
+  __syncthreads();
+  const int valid = min((int)blockDim.x, n - e0);
+  const int total = valid * ROW;
+  float* base = dst + (size_t)e0 * ROW;
+  if ((((size_t)e0 * ROW) & 3) == 0 && ((uintptr_t)dst & 15) == 0) {
+    const int nv = total >> 2;
+    for (int i = threadIdx.x; i < nv; i += blockDim.x)
+      reinterpret_cast<float4*>(base)[i] = reinterpret_cast<const float4*>(smem)[i];
+    for (int i = (nv << 2) + threadIdx.x; i < total; i += blockDim.x) base[i] = smem[i];
+  } else {
+    for (int i = threadIdx.x; i < total; i += blockDim.x) base[i] = smem[i];
+  }
+  (void)e;
+}
+
+struct ExportPtrs {
+  float *pos0, *quat0, *vel0, *pos1, *quat1, *vel1, *q1, *qd1, *tau1, *hist1, *last_air1, *cur_contact1;
+};
+
+// sensor-body index (USD prim order: b1 a2 b2 a3 b3 b4 a5 b5 a6 foot_0 foot_1 base) of the link a
+// merged body's sphere force is attributed to (the "a" half: a2 a3 base a5 a6)
+__device__ __constant__ int kMidSensorIdx[5] = {1, 3, 11, 6, 8};
+constexpr int kFoot0Sensor = 9, kFoot1Sensor = 10;
+
+// ---------------------------------------------------------------------------------------------
+// the fused control step
+// ---------------------------------------------------------------------------------------------
+template <bool kExport>
+__global__ void __launch_bounds__(128)
+zbot_step_kernel(const __grid_constant__ Params<float> P, const __grid_constant__ DefaultPose dp,
+                 float4* __restrict__ state, int64_t* __restrict__ ep_len_buf,
+                 const float* __restrict__ actions, float* __restrict__ obs, float* __restrict__ rew,
+                 uint8_t* __restrict__ terminated, uint8_t* __restrict__ truncated, int n, StatsCtx sc,
+                 ExportPtrs xp) {
+  extern __shared__ float smem[];   // max(blockDim*23, 32*kStatUsed) floats
+  const int e0 = blockIdx.x * blockDim.x;
+  const int e = e0 + threadIdx.x;
+  const bool live = e < n;
+  float stat[kStatUsed];
+#pragma unroll
+  for (int j = 0; j < kStatUsed; ++j) stat[j] = 0.f;
+  float obs_row[ZBOT_NUM_OBS];
+#pragma unroll
+  for (int i = 0; i < ZBOT_NUM_OBS; ++i) obs_row[i] = 0.f;
+  bool did_reset = false;
+  if (live) {
+    float w[ZBOT_STATE_WORDS];
+    load_words<ZBOT_STATE_WORDS / 4>(state, n, e, w);
+    EnvState<float> es;
+    env_state_unpack(w, es);
+    float raw[6];
+    {
+      const float2* a2 = reinterpret_cast<const float2*>(actions + (size_t)e * 6);
+      const float2 a0 = __ldg(a2), a1 = __ldg(a2 + 1), a2v = __ldg(a2 + 2);
+      raw[0] = a0.x; raw[1] = a0.y; raw[2] = a1.x; raw[3] = a1.y; raw[4] = a2v.x; raw[5] = a2v.y;
+    }
+    int64_t ep = ep_len_buf[e];
+    StepOut<float> out;
+    float rs[MAX_TERMS];
+#pragma unroll
+    for (int i = 0; i < MAX_TERMS; ++i) rs[i] = 0.f;
+    if (kExport) {
+      StepExport<float> ex;
+      env_step(P, es, raw, ep, dp.feet_pos, dp.base_quat, out, rs, &ex);
+      for (int i = 0; i < 36; ++i) { xp.pos0[(size_t)e * 36 + i] = ex.pos0[i]; xp.vel0[(size_t)e * 36 + i] = ex.vel0[i];
+                                     xp.pos1[(size_t)e * 36 + i] = ex.pos1[i]; xp.vel1[(size_t)e * 36 + i] = ex.vel1[i]; }
+      for (int i = 0; i < 48; ++i) { xp.quat0[(size_t)e * 48 + i] = ex.quat0[i]; xp.quat1[(size_t)e * 48 + i] = ex.quat1[i]; }
+      for (int i = 0; i < 6; ++i) { xp.q1[(size_t)e * 6 + i] = ex.q1[i]; xp.qd1[(size_t)e * 6 + i] = ex.qd1[i];
+                                    xp.tau1[(size_t)e * 6 + i] = ex.applied_torque[i]; }
+      float* h = xp.hist1 + (size_t)e * (5 * 12 * 3);
+      for (int i = 0; i < 5 * 12 * 3; ++i) h[i] = 0.f;
+      for (int t = 0; t < 5; ++t) {
+        for (int i = 0; i < 3; ++i) {
+          h[(t * 12 + kFoot0Sensor) * 3 + i] = ex.feet_force_hist[t][0][i];
+          h[(t * 12 + kFoot1Sensor) * 3 + i] = ex.feet_force_hist[t][1][i];
+          for (int b = 0; b < 5; ++b) h[(t * 12 + kMidSensorIdx[b]) * 3 + i] = ex.mid_force_hist[t][b][i];
+        }
+      }
+      for (int b = 0; b < 12; ++b) { xp.last_air1[(size_t)e * 12 + b] = 0.f; xp.cur_contact1[(size_t)e * 12 + b] = 0.f; }
+      xp.last_air1[(size_t)e * 12 + kFoot0Sensor] = ex.last_air[0];
+      xp.last_air1[(size_t)e * 12 + kFoot1Sensor] = ex.last_air[1];
+      xp.cur_contact1[(size_t)e * 12 + kFoot0Sensor] = ex.cur_contact[0];
+      xp.cur_contact1[(size_t)e * 12 + kFoot1Sensor] = ex.cur_contact[1];
+    } else {
+      env_step(P, es, raw, ep, dp.feet_pos, dp.base_quat, out, rs, (StepExport<float>*)nullptr);
+    }
+    env_state_pack(es, w);
+    store_words<ZBOT_STATE_WORDS / 4>(state, n, e, w);
+    ep_len_buf[e] = ep;
+    rew[e] = out.reward;
+    terminated[e] = out.terminated ? 1 : 0;
+    truncated[e] = out.time_out ? 1 : 0;
+#pragma unroll
+    for (int i = 0; i < ZBOT_NUM_OBS; ++i) obs_row[i] = out.obs[i];
+    did_reset = out.terminated || out.time_out;
+    if (did_reset) {
+#pragma unroll
+      for (int i = 0; i < MAX_TERMS; ++i) stat[i] = rs[i];
+      stat[S_NUM_RESET] = 1.f;
+      stat[S_NUM_TERM_RESET] = out.terminated ? 1.f : 0.f;
+      stat[S_NUM_TO_RESET] = out.time_out ? 1.f : 0.f;
+    }
+    stat[S_REW_SUM] = out.reward;
+    stat[S_NUM_TERM] = out.terminated ? 1.f : 0.f;
+    stat[S_NUM_TRUNC] = out.time_out ? 1.f : 0.f;
+  }
+  store_rows_coalesced<ZBOT_NUM_OBS>(obs, obs_row, n, e0, smem);
+  __syncthreads();
+  stats_reduce(stat, did_reset, smem, sc);
+}
+
+// ---------------------------------------------------------------------------------------------
+// reset / observe / articulation view / init
+// ---------------------------------------------------------------------------------------------
+__global__ void zbot_reset_kernel(const __grid_constant__ Params<float> P, const __grid_constant__ DefaultPose dp,
+                                  float4* __restrict__ state, int64_t* __restrict__ ep_len_buf,
+                                  const int64_t* __restrict__ ids, int64_t nids, const uint8_t* __restrict__ terminated,
+                                  const uint8_t* __restrict__ truncated, int n, StatsCtx sc) {
+  extern __shared__ float smem[];
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float stat[kStatUsed];
+#pragma unroll
+  for (int j = 0; j < kStatUsed; ++j) stat[j] = 0.f;
+  bool did = false;
+  if (i < nids) {
+    const int64_t e64 = ids ? ids[i] : i;
+    if (e64 >= 0 && e64 < n) {
+      const int e = (int)e64;
+      float w[ZBOT_STATE_WORDS];
+      load_words<ZBOT_STATE_WORDS / 4>(state, n, e, w);
+      EnvState<float> es;
+      env_state_unpack(w, es);
+#pragma unroll
+      for (int k = 0; k < MAX_TERMS; ++k) stat[k] = (k < P.num_terms) ? es.mdp.ep_sums[k] : 0.f;
+      stat[S_NUM_RESET] = 1.f;
+      stat[S_NUM_TERM_RESET] = (terminated && terminated[e]) ? 1.f : 0.f;
+      stat[S_NUM_TO_RESET] = (truncated && truncated[e]) ? 1.f : 0.f;
+      env_reset(P, es, dp.feet_pos);
+      env_state_pack(es, w);
+      store_words<ZBOT_STATE_WORDS / 4>(state, n, e, w);
+      ep_len_buf[e] = 0;
+      did = true;
+    }
+  }
+  stats_reduce(stat, did, smem, sc);
+}
+
+__global__ void zbot_observe_kernel(const float4* __restrict__ state, float* __restrict__ obs, int n) {
+  extern __shared__ float smem[];
+  const int e0 = blockIdx.x * blockDim.x;
+  const int e = e0 + threadIdx.x;
+  float row[ZBOT_NUM_OBS];
+#pragma unroll
+  for (int i = 0; i < ZBOT_NUM_OBS; ++i) row[i] = 0.f;
+  if (e < n) {
+    float w[ZBOT_STATE_WORDS];
+    load_words<ZBOT_STATE_WORDS / 4>(state, n, e, w);
+    EnvState<float> es;
+    env_state_unpack(w, es);
+    env_observe(es, row);
+  }
+  store_rows_coalesced<ZBOT_NUM_OBS>(obs, row, n, e0, smem);
+}
+
+__global__ void zbot_view_kernel(const float4* __restrict__ state, float* pos, float* quat, float* vel, int n) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  float w[ZBOT_STATE_WORDS];
+  load_words<ZBOT_STATE_WORDS / 4>(state, n, e, w);
+  EnvState<float> es;
+  env_state_unpack(w, es);
+  float p[36], q[48], v[36];
+  all_link_kinematics(es.sim, p, q, v);
+  if (pos) for (int i = 0; i < 36; ++i) pos[(size_t)e * 36 + i] = p[i];
+  if (quat) for (int i = 0; i < 48; ++i) quat[(size_t)e * 48 + i] = q[i];
+  if (vel) for (int i = 0; i < 36; ++i) vel[(size_t)e * 36 + i] = v[i];
+}
+
+__global__ void zbot_default_pose_kernel(DefaultPose* out) {
+  SimState<float> s;
+  sim_state_default(s);
+  LinkKin<float> k;
+  link_kinematics(s, k);
+  for (int j = 0; j < 2; ++j) {
+    for (int i = 0; i < 3; ++i) out->feet_pos[j][i] = k.feet_pos[j][i];
+    for (int i = 0; i < 4; ++i) out->feet_quat[j][i] = k.feet_quat[j][i];
+  }
+  for (int i = 0; i < 3; ++i) out->base_pos[i] = k.base_pos[i];
+  for (int i = 0; i < 4; ++i) out->base_quat[i] = k.base_quat[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// MDP-only step: the reference's MDP code on caller-supplied articulation / contact tensors
+// ---------------------------------------------------------------------------------------------
+struct MdpIn {
+  const float *pos, *quat, *vel, *q, *qd, *tau, *hist, *last_air, *origins;
+};
+constexpr int kHistRow = ZBOT_HISTORY * ZBOT_NUM_LINKS * 3;   // 180 floats = 45 float4 per env
+// articulation order: base = 6, feet = {0, 11}; sensor order: feet = {9, 10}, undesired = the other 10
+constexpr int kBaseLink = 6, kFoot0Link = 0, kFoot1Link = 11;
+
+__device__ __forceinline__ void mdp_load_links(const MdpIn& in, int e, float* base_pos, float* base_quat, float* base_vel,
+                                               float feet_pos[2][3], float feet_quat[2][4], float feet_vel[2][3]) {
+  const float* p = in.pos + (size_t)e * 36;
+  const float* q = in.quat + (size_t)e * 48;
+  const float* v = in.vel + (size_t)e * 36;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    base_pos[i] = __ldg(p + kBaseLink * 3 + i); base_vel[i] = __ldg(v + kBaseLink * 3 + i);
+    feet_pos[0][i] = __ldg(p + kFoot0Link * 3 + i); feet_pos[1][i] = __ldg(p + kFoot1Link * 3 + i);
+    feet_vel[0][i] = __ldg(v + kFoot0Link * 3 + i); feet_vel[1][i] = __ldg(v + kFoot1Link * 3 + i);
+  }
+  {
+    const float4 b = __ldg(reinterpret_cast<const float4*>(q + kBaseLink * 4));
+    const float4 f0 = __ldg(reinterpret_cast<const float4*>(q + kFoot0Link * 4));
+    const float4 f1 = __ldg(reinterpret_cast<const float4*>(q + kFoot1Link * 4));
+    base_quat[0] = b.x; base_quat[1] = b.y; base_quat[2] = b.z; base_quat[3] = b.w;
+    feet_quat[0][0] = f0.x; feet_quat[0][1] = f0.y; feet_quat[0][2] = f0.z; feet_quat[0][3] = f0.w;
+    feet_quat[1][0] = f1.x; feet_quat[1][1] = f1.y; feet_quat[1][2] = f1.z; feet_quat[1][3] = f1.w;
+  }
+}
+
+// kStep = false: `_get_observations` only (fills the stale cache)
+template <bool kStep>
+__global__ void __launch_bounds__(128)
+zbot_mdp_kernel(const __grid_constant__ Params<float> P, const __grid_constant__ DefaultPose dp, MdpIn in,
+                float4* __restrict__ mstate, int64_t* __restrict__ ep_len_buf, const float* __restrict__ actions,
+                float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ terminated,
+                uint8_t* __restrict__ truncated, int n, StatsCtx sc) {
+  extern __shared__ float smem[];   // [blockDim][180] history tile, reused for obs rows / stats
+  const int e0 = blockIdx.x * blockDim.x;
+  const int e = e0 + threadIdx.x;
+  const bool live = e < n;
+  const int valid = min((int)blockDim.x, n - e0);
+  float stat[kStatUsed];
+#pragma unroll
+  for (int j = 0; j < kStatUsed; ++j) stat[j] = 0.f;
+  float obs_row[ZBOT_NUM_OBS];
+#pragma unroll
+  for (int i = 0; i < ZBOT_NUM_OBS; ++i) obs_row[i] = 0.f;
+  bool did_reset = false;
+
+  FreshInputs<float> f;
+  if (kStep) {
+    // cooperative, coalesced copy of the block's contiguous history tile into shared memory
+    const float4* src = reinterpret_cast<const float4*>(in.hist + (size_t)e0 * kHistRow);
+    float4* dst = reinterpret_cast<float4*>(smem);
+    const int nv = valid * (kHistRow / 4);
+    for (int i = threadIdx.x; i < nv; i += blockDim.x) dst[i] = __ldg(src + i);
+    __syncthreads();
+    if (live) {
+      // per-thread pass over its own 45 float4 (conflict-free: row stride 45 float4 is odd)
+      const float4* row4 = reinterpret_cast<const float4*>(smem) + threadIdx.x * (kHistRow / 4);
+      float h[kHistRow];
+#pragma unroll
+      for (int i = 0; i < kHistRow / 4; ++i) {
+        const float4 v = row4[i];
+        h[4 * i] = v.x; h[4 * i + 1] = v.y; h[4 * i + 2] = v.z; h[4 * i + 3] = v.w;
+      }
+      float fz0 = 0.f, fz1 = 0.f, mx2 = 0.f;
+#pragma unroll
+      for (int t = 0; t < ZBOT_HISTORY; ++t) {
+        const float a = h[(t * 12 + kFoot0Sensor) * 3 + 2], b = h[(t * 12 + kFoot1Sensor) * 3 + 2];
+        fz0 = (t == 0) ? a : (fz0 + a);                      // (((h0+h1)+h2)+h3)+h4, newest first
+        fz1 = (t == 0) ? b : (fz1 + b);
+#pragma unroll
+        for (int b12 = 0; b12 < 12; ++b12) {
+          if (b12 == kFoot0Sensor || b12 == kFoot1Sensor) continue;
+          const float x = h[(t * 12 + b12) * 3], y = h[(t * 12 + b12) * 3 + 1], z = h[(t * 12 + b12) * 3 + 2];
+          mx2 = fmaxf(mx2, __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
+        }
+      }
+      f.feet_force[0] = fz0 / 5.0f;                            // torch.mean = sum / count (:387-390)
+      f.feet_force[1] = fz1 / 5.0f;
+      f.undesired_force_max = sqrtf(mx2);                      // max_t |F| > 1.0  (:396-402)
+    }
+    __syncthreads();   // the tile is dead; smem is reused below
+  }
+
+  if (live) {
+    float w[ZBOT_MDP_STATE_WORDS];
+    load_words<ZBOT_MDP_STATE_WORDS / 4>(mstate, n, e, w);
+    MdpState<float> m;
+    mdp_state_unpack(w, M_PDELTA, M_ACT, M_FLAST, M_FDPL, M_FSL, M_HSUM, M_YSUM, M_FFSUM, M_SPEED, M_EPSUM, m);
+    StaleCache<float> stale;
+    stale_unpack(w, stale);
+    float base_pos[3], base_quat[4], base_vel[3], feet_pos[2][3], feet_quat[2][4], feet_vel[2][3];
+    mdp_load_links(in, e, base_pos, base_quat, base_vel, feet_pos, feet_quat, feet_vel);
+    float q[6], qd[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { q[k] = __ldg(in.q + (size_t)e * 6 + k); qd[k] = __ldg(in.qd + (size_t)e * 6 + k); }
+    const float ox = __ldg(in.origins + (size_t)e * 3), oy = __ldg(in.origins + (size_t)e * 3 + 1),
+                oz = __ldg(in.origins + (size_t)e * 3 + 2);
+    if (kStep) {
+      float raw[6], new_actions[6], target[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) raw[k] = __ldg(actions + (size_t)e * 6 + k);
+      mdp_pre_physics(P, raw, m, new_actions, target);
+      int64_t ep = ep_len_buf[e] + 1;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) f.applied_torque[k] = __ldg(in.tau + (size_t)e * 6 + k);
+      f.last_air_time[0] = __ldg(in.last_air + (size_t)e * 12 + kFoot0Sensor);
+      f.last_air_time[1] = __ldg(in.last_air + (size_t)e * 12 + kFoot1Sensor);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) { f.feet_vel_xy[j][0] = feet_vel[j][0]; f.feet_vel_xy[j][1] = feet_vel[j][1]; }
+      f.origin_y = oy;
+      bool term, tout;
+      const float r = mdp_dones_rewards(P, stale, f, new_actions, m, ep, term, tout);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) m.actions[k] = new_actions[k];
+      did_reset = term || tout;
+      if (did_reset) {
+#pragma unroll
+        for (int i = 0; i < MAX_TERMS; ++i) stat[i] = (i < P.num_terms) ? m.ep_sums[i] : 0.f;
+        stat[S_NUM_RESET] = 1.f;
+        stat[S_NUM_TERM_RESET] = term ? 1.f : 0.f;
+        stat[S_NUM_TO_RESET] = tout ? 1.f : 0.f;
+        // post-reset articulation view = default pose + env origin (SURVEY C-5)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const float o = (i == 0) ? ox : (i == 1) ? oy : oz;
+          base_pos[i] = dp.base_pos[i] + o; base_vel[i] = 0.f;
+          feet_pos[0][i] = dp.feet_pos[0][i] + o; feet_pos[1][i] = dp.feet_pos[1][i] + o;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { base_quat[i] = dp.base_quat[i]; feet_quat[0][i] = dp.feet_quat[0][i]; feet_quat[1][i] = dp.feet_quat[1][i]; }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { q[k] = default_joint_pos<float>(k); qd[k] = 0.f; }
+        mdp_reset(m, feet_pos, P.num_terms);
+        ep = 0;
+      }
+      stat[S_REW_SUM] = r;
+      stat[S_NUM_TERM] = term ? 1.f : 0.f;
+      stat[S_NUM_TRUNC] = tout ? 1.f : 0.f;
+      ep_len_buf[e] = ep;
+      rew[e] = r;
+      terminated[e] = term ? 1 : 0;
+      truncated[e] = tout ? 1 : 0;
+    }
+    // _get_observations: refresh the stale cache from the (possibly reset) articulation view
+    stale_from_links(base_pos, base_quat, base_vel, feet_pos, feet_quat, stale);
+    mdp_observation(base_quat, q, qd, m.actions, m.speed_limit, obs_row);
+    mdp_state_pack(m, w, M_PDELTA, M_ACT, M_FLAST, M_FDPL, M_FSL, M_HSUM, M_YSUM, M_FFSUM, M_SPEED, M_EPSUM);
+    stale_pack(stale, w);
+    store_words<ZBOT_MDP_STATE_WORDS / 4>(mstate, n, e, w);
+  }
+  store_rows_coalesced<ZBOT_NUM_OBS>(obs, obs_row, n, e0, smem);
+  if (kStep) {
+    __syncthreads();
+    stats_reduce(stat, did_reset, smem, sc);
+  }
+}
+
+}  // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+struct ZbotHandle {
+  ZbotCfg cfg;
+  Params<float> P;
+  DefaultPose dp;
+  int device;
+  int num_sms;
+  float4* state;
+  int64_t* ep_len;
+  float* ring;
+  int ring_slots;
+  float4* mstate;
+  int64_t* m_ep_len;
+  float* m_ring;
+  int m_ring_slots;
+  float* partials;
+  unsigned int* ticket;
+  int max_blocks;
+  int64_t launches;
+};
+
+namespace {
+
+int pick_block(const ZbotHandle* h, int n) {
+  // fill the SMs first: the step is latency/issue bound, not bandwidth bound
+  int block = 128;
+  while (block > 32 && (n + block - 1) / block < 2 * h->num_sms) block >>= 1;
+  return block;
+}
+
+int check_slot(int slot, int prev, int slots) {
+  if (slot < 0 || slot >= slots) return fail(ZBOT_E_INVALID, "stats_slot out of range%s");
+  if (prev >= slots) return fail(ZBOT_E_INVALID, "prev_slot out of range%s");
+  return ZBOT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int zbot_abi_version(void) { return ZBOT_ABI_VERSION; }
+const char* zbot_build_info(void) { return "zbot_b200 sm_100a, nvcc " __DATE__ " " __TIME__; }
+const char* zbot_last_error(void) { return g_err; }
+
+int zbot_default_cfg(ZbotCfg* cfg, int32_t num_envs) {
+  if (!cfg) return fail(ZBOT_E_INVALID, "cfg is NULL%s");
+  cfg_defaults(*cfg, num_envs);
+  return ZBOT_OK;
+}
+int zbot_state_word(const char* f) { return find_word(kStateFields, (int)(sizeof(kStateFields) / sizeof(kStateFields[0])), f); }
+int zbot_mdp_state_word(const char* f) { return find_word(kMdpFields, (int)(sizeof(kMdpFields) / sizeof(kMdpFields[0])), f); }
+
+int zbot_create(const ZbotCfg* cfg, int device, ZbotHandle** out) {
+  if (!cfg || !out) return fail(ZBOT_E_INVALID, "cfg/out is NULL%s");
+  const char* why = "";
+  if (cfg_validate(*cfg, &why) != ZBOT_OK) return fail(ZBOT_E_INVALID, "%s", why);
+  int ndev = 0;
+  ZB_CUDA(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(ZBOT_E_INVALID, "no such CUDA device%s");
+  ZB_CUDA(cudaSetDevice(device));
+  ZbotHandle* h = new (std::nothrow) ZbotHandle();
+  if (!h) return fail(ZBOT_E_INVALID, "out of host memory%s");
+  memset(h, 0, sizeof(*h));
+  h->cfg = *cfg;
+  params_from_cfg(*cfg, h->P);
+  h->device = device;
+  cudaDeviceProp prop;
+  ZB_CUDA(cudaGetDeviceProperties(&prop, device));
+  h->num_sms = prop.multiProcessorCount;
+  h->max_blocks = (cfg->num_envs + 31) / 32 + 1;
+  ZB_CUDA(cudaMalloc(&h->partials, (size_t)h->max_blocks * kStats * sizeof(float)));
+  ZB_CUDA(cudaMalloc(&h->ticket, sizeof(unsigned int)));
+  ZB_CUDA(cudaMemset(h->ticket, 0, sizeof(unsigned int)));
+  DefaultPose* d_dp = nullptr;
+  ZB_CUDA(cudaMalloc(&d_dp, sizeof(DefaultPose)));
+  zbot_default_pose_kernel<<<1, 1>>>(d_dp);
+  ZB_CUDA(cudaGetLastError());
+  ZB_CUDA(cudaMemcpy(&h->dp, d_dp, sizeof(DefaultPose), cudaMemcpyDeviceToHost));
+  ZB_CUDA(cudaFree(d_dp));
+  ZB_CUDA(cudaFuncSetAttribute(zbot_mdp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * kHistRow * 4));
+  *out = h;
+  return ZBOT_OK;
+}
+
+int zbot_destroy(ZbotHandle* h) {
+  if (!h) return ZBOT_OK;
+  cudaSetDevice(h->device);
+  cudaFree(h->partials);
+  cudaFree(h->ticket);
+  delete h;
+  return ZBOT_OK;
+}
+
+int zbot_bind(ZbotHandle* h, float* state, int64_t* episode_length, float* stats_ring, int32_t stats_slots) {
+  if (!h || !state || !episode_length || !stats_ring || stats_slots < 1) return fail(ZBOT_E_INVALID, "zbot_bind: NULL buffer%s");
+  if (((uintptr_t)state & 15) != 0) return fail(ZBOT_E_INVALID, "state must be 16-byte aligned%s");
+  h->state = reinterpret_cast<float4*>(state);
+  h->ep_len = episode_length;
+  h->ring = stats_ring;
+  h->ring_slots = stats_slots;
+  return ZBOT_OK;
+}
+
+static int step_impl(ZbotHandle* h, const float* actions, float* obs, float* rew, uint8_t* terminated, uint8_t* truncated,
+                     int32_t slot, int32_t prev, const ZbotExport* ex, void* stream) {
+  if (!h) return fail(ZBOT_E_INVALID, "handle is NULL%s");
+  if (!h->state) return fail(ZBOT_E_UNBOUND, "zbot_bind has not been called%s");
+  if (!actions || !obs || !rew || !terminated || !truncated) return fail(ZBOT_E_INVALID, "zbot_step: NULL buffer%s");
+  if (((uintptr_t)actions & 7) != 0) return fail(ZBOT_E_INVALID, "actions must be 8-byte aligned%s");
+  if (int rc = check_slot(slot, prev, h->ring_slots)) return rc;
+  const int n = h->cfg.num_envs;
+  const int block = pick_block(h, n);
+  const int grid = (n + block - 1) / block;
+  const size_t smem = (size_t)((block * ZBOT_NUM_OBS > 32 * kStatUsed) ? block * ZBOT_NUM_OBS : 32 * kStatUsed) * sizeof(float);
+  StatsCtx sc{h->partials, h->ticket, h->ring, slot, prev};
+  cudaStream_t s = (cudaStream_t)stream;
+  ExportPtrs xp{};
+  if (ex) {
+    xp = ExportPtrs{ex->body_link_pos_w0, ex->body_link_quat_w0, ex->body_com_lin_vel_w0, ex->body_link_pos_w1,
+                    ex->body_link_quat_w1, ex->body_com_lin_vel_w1, ex->joint_pos1, ex->joint_vel1, ex->applied_torque1,
+                    ex->net_forces_w_history1, ex->last_air_time1, ex->current_contact_time1};
+    const float* const* pp = reinterpret_cast<const float* const*>(&xp);
+    for (int i = 0; i < 12; ++i)
+      if (!pp[i]) return fail(ZBOT_E_INVALID, "zbot_step_export: NULL export buffer%s");
+    zbot_step_kernel<true><<<grid, block, smem, s>>>(h->P, h->dp, h->state, h->ep_len, actions, obs, rew, terminated,
+                                                      truncated, n, sc, xp);
+  } else {
+    zbot_step_kernel<false><<<grid, block, smem, s>>>(h->P, h->dp, h->state, h->ep_len, actions, obs, rew, terminated,
+                                                       truncated, n, sc, xp);
+  }
+  ZB_CUDA(cudaGetLastError());
+  h->launches += 1;
+  return ZBOT_OK;
+}
+
+int zbot_step(ZbotHandle* h, const float* actions, float* obs, float* rew, uint8_t* terminated, uint8_t* truncated,
+              int32_t stats_slot, int32_t prev_slot, void* stream) {
+  return step_impl(h, actions, obs, rew, terminated, truncated, stats_slot, prev_slot, nullptr, stream);
+}
+
+int zbot_step_export(ZbotHandle* h, const float* actions, float* obs, float* rew, uint8_t* terminated, uint8_t* truncated,
+                     int32_t stats_slot, int32_t prev_slot, const ZbotExport* ex, void* stream) {
+  if (!ex) return fail(ZBOT_E_INVALID, "zbot_step_export: ex is NULL%s");
+  return step_impl(h, actions, obs, rew, terminated, truncated, stats_slot, prev_slot, ex, stream);
+}
+
+int zbot_reset_idx(ZbotHandle* h, const int64_t* env_ids, int64_t nids, const uint8_t* terminated, const uint8_t* truncated,
+                   int32_t stats_slot, void* stream) {
+  if (!h) return fail(ZBOT_E_INVALID, "handle is NULL%s");
+  if (!h->state) return fail(ZBOT_E_UNBOUND, "zbot_bind has not been called%s");
+  if (int rc = check_slot(stats_slot, -1, h->ring_slots)) return rc;
+  const int n = h->cfg.num_envs;
+  if (!env_ids || nids < 0) { env_ids = nullptr; nids = n; }
+  if (nids == 0) return ZBOT_OK;
+  if (nids > n) return fail(ZBOT_E_INVALID, "more env ids than envs%s");
+  const int block = 64;
+  const int grid = (int)((nids + block - 1) / block);
+  StatsCtx sc{h->partials, h->ticket, h->ring, stats_slot, -1};
+  zbot_reset_kernel<<<grid, block, 32 * kStatUsed * sizeof(float), (cudaStream_t)stream>>>(
+      h->P, h->dp, h->state, h->ep_len, env_ids, nids, terminated, truncated, n, sc);
+  ZB_CUDA(cudaGetLastError());
+  h->launches += 1;
+  return ZBOT_OK;
+}
+
+int zbot_observe(ZbotHandle* h, float* obs, void* stream) {
+  if (!h || !obs) return fail(ZBOT_E_INVALID, "zbot_observe: NULL argument%s");
+  if (!h->state) return fail(ZBOT_E_UNBOUND, "zbot_bind has not been called%s");
+  const int n = h->cfg.num_envs, block = 64, grid = (n + block - 1) / block;
+  zbot_observe_kernel<<<grid, block, block * ZBOT_NUM_OBS * sizeof(float), (cudaStream_t)stream>>>(h->state, obs, n);
+  ZB_CUDA(cudaGetLastError());
+  h->launches += 1;
+  return ZBOT_OK;
+}
+
+int zbot_articulation_view(ZbotHandle* h, float* pos, float* quat, float* vel, void* stream) {
+  if (!h) return fail(ZBOT_E_INVALID, "handle is NULL%s");
+  if (!h->state) return fail(ZBOT_E_UNBOUND, "zbot_bind has not been called%s");
+  const int n = h->cfg.num_envs, block = 64, grid = (n + block - 1) / block;
+  zbot_view_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(h->state, pos, quat, vel, n);
+  ZB_CUDA(cudaGetLastError());
+  h->launches += 1;
+  return ZBOT_OK;
+}
+
+int zbot_mdp_bind(ZbotHandle* h, float* mdp_state, int64_t* episode_length, float* stats_ring, int32_t stats_slots) {
+  if (!h || !mdp_state || !episode_length || !stats_ring || stats_slots < 1) return fail(ZBOT_E_INVALID, "zbot_mdp_bind: NULL buffer%s");
+  if (((uintptr_t)mdp_state & 15) != 0) return fail(ZBOT_E_INVALID, "mdp_state must be 16-byte aligned%s");
+  h->mstate = reinterpret_cast<float4*>(mdp_state);
+  h->m_ep_len = episode_length;
+  h->m_ring = stats_ring;
+  h->m_ring_slots = stats_slots;
+  return ZBOT_OK;
+}
+
+static int mdp_check(const ZbotHandle* h, const ZbotMdpInputs* in, bool step) {
+  if (!h || !in) return fail(ZBOT_E_INVALID, "zbot_mdp: NULL argument%s");
+  if (!h->mstate) return fail(ZBOT_E_UNBOUND, "zbot_mdp_bind has not been called%s");
+  if (!in->body_link_pos_w || !in->body_link_quat_w || !in->body_com_lin_vel_w || !in->joint_pos || !in->joint_vel ||
+      !in->env_origins)
+    return fail(ZBOT_E_INVALID, "zbot_mdp: NULL input tensor%s");
+  if (step && (!in->applied_torque || !in->net_forces_w_history || !in->last_air_time))
+    return fail(ZBOT_E_INVALID, "zbot_mdp_step: NULL input tensor%s");
+  if (((uintptr_t)in->body_link_quat_w & 15) != 0 || (step && ((uintptr_t)in->net_forces_w_history & 15) != 0))
+    return fail(ZBOT_E_INVALID, "quat / history tensors must be 16-byte aligned%s");
+  return ZBOT_OK;
+}
+
+int zbot_mdp_observe(ZbotHandle* h, const ZbotMdpInputs* in, float* obs, void* stream) {
+  if (int rc = mdp_check(h, in, false)) return rc;
+  if (!obs) return fail(ZBOT_E_INVALID, "obs is NULL%s");
+  const int n = h->cfg.num_envs, block = 128, grid = (n + block - 1) / block;
+  MdpIn mi{in->body_link_pos_w, in->body_link_quat_w, in->body_com_lin_vel_w, in->joint_pos, in->joint_vel,
+           in->applied_torque, in->net_forces_w_history, in->last_air_time, in->env_origins};
+  StatsCtx sc{h->partials, h->ticket, h->m_ring, 0, -1};
+  zbot_mdp_kernel<false><<<grid, block, block * ZBOT_NUM_OBS * sizeof(float), (cudaStream_t)stream>>>(
+      h->P, h->dp, mi, h->mstate, h->m_ep_len, nullptr, obs, nullptr, nullptr, nullptr, n, sc);
+  ZB_CUDA(cudaGetLastError());
+  h->launches += 1;
+  return ZBOT_OK;
+}
+
+int zbot_mdp_step(ZbotHandle* h, const ZbotMdpInputs* in, const float* actions, float* obs, float* rew, uint8_t* terminated,
+                  uint8_t* truncated, int32_t stats_slot, int32_t prev_slot, void* stream) {
+  if (int rc = mdp_check(h, in, true)) return rc;
+  if (!actions || !obs || !rew || !terminated || !truncated) return fail(ZBOT_E_INVALID, "zbot_mdp_step: NULL buffer%s");
+  if (int rc = check_slot(stats_slot, prev_slot, h->m_ring_slots)) return rc;
+  const int n = h->cfg.num_envs, block = 128, grid = (n + block - 1) / block;
+  MdpIn mi{in->body_link_pos_w, in->body_link_quat_w, in->body_com_lin_vel_w, in->joint_pos, in->joint_vel,
+           in->applied_torque, in->net_forces_w_history, in->last_air_time, in->env_origins};
+  StatsCtx sc{h->partials, h->ticket, h->m_ring, stats_slot, prev_slot};
+  zbot_mdp_kernel<true><<<grid, block, (size_t)block * kHistRow * sizeof(float), (cudaStream_t)stream>>>(
+      h->P, h->dp, mi, h->mstate, h->m_ep_len, actions, obs, rew, terminated, truncated, n, sc);
+  ZB_CUDA(cudaGetLastError());
+  h->launches += 1;
+  return ZBOT_OK;
+}
+
+int64_t zbot_launch_count(const ZbotHandle* h) { return h ? h->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,167 @@
+"""ctypes binding of the C-ABI shared library (``include/zbot_b200.h``).
+
+The library is built in-tree by ``__graft_entry__.build()`` /
+``python -m zbot_lab_b200.build`` into ``zbot_lab_b200/csrc/libzbot_b200.so``.
+There is NO fallback: if the library is missing, :func:`lib` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "csrc", "libzbot_b200.so")
+
+ZBOT_ABI_VERSION = 1
+MAX_TERMS = 16
+STATE_WORDS = 80
+MDP_STATE_WORDS = 72
+STATS_WORDS = 32
+NUM_OBS = 23
+NUM_ACTIONS = 6
+
+# stats slot words (zbot_b200.h: zbot_step)
+STAT_NUM_RESET = 16
+STAT_NUM_TERMINATED_RESET = 17
+STAT_NUM_TIMEOUT_RESET = 18
+STAT_REWARD_SUM = 19
+STAT_NUM_TERMINATED = 20
+STAT_NUM_TRUNCATED = 21
+
+TERM_IDS = {
+    "base_vel_forward": 0, "feet_downward": 1, "feet_forward": 2, "base_heading_x": 3,
+    "base_heading_x_sum": 4, "step_length": 5, "airtime_balance": 6, "action_rate": 7,
+    "torques": 8, "feet_slide": 9, "base_pos_y_err": 10, "base_pos_y_err_sum": 11,
+    "airtime_sum": 12, "feet_force_diff": 13, "feet_force_sum": 14,
+}
+
+
+class ZbotCfg(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("num_envs", C.c_int32), ("decimation", C.c_int32),
+        ("max_episode_length", C.c_int32), ("sim_dt", C.c_float), ("termination_height", C.c_float),
+        ("y_err_limit", C.c_float), ("terminated_penalty", C.c_float), ("contact_died_force", C.c_float),
+        ("kp", C.c_float), ("kd", C.c_float), ("effort_limit", C.c_float), ("gravity", C.c_float),
+        ("contact_alpha", C.c_float), ("contact_erp", C.c_float), ("contact_vdep", C.c_float),
+        ("contact_beta_max", C.c_float), ("contact_mu", C.c_float), ("contact_ramp", C.c_float),
+        ("contact_vt_eps", C.c_float), ("contact_margin", C.c_float),
+        ("num_terms", C.c_int32), ("term_id", C.c_int32 * MAX_TERMS), ("term_weight", C.c_float * MAX_TERMS),
+    ]
+
+
+class ZbotExport(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "body_link_pos_w0", "body_link_quat_w0", "body_com_lin_vel_w0",
+        "body_link_pos_w1", "body_link_quat_w1", "body_com_lin_vel_w1",
+        "joint_pos1", "joint_vel1", "applied_torque1",
+        "net_forces_w_history1", "last_air_time1", "current_contact_time1")]
+
+
+class ZbotMdpInputs(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "body_link_pos_w", "body_link_quat_w", "body_com_lin_vel_w", "joint_pos", "joint_vel",
+        "applied_torque", "net_forces_w_history", "last_air_time", "env_origins")]
+
+
+def make_cfg(num_envs: int, reward_scales: dict | None = None, step_dt: float | None = None,
+             **overrides) -> ZbotCfg:
+    """Build a ``ZbotCfg`` from the task constants (``zbot_lab_b200/assets/zbot_6s.py``) and a
+    reward-scale dict in cfg order (``…env_v2.py:190-206``); weights are multiplied by
+    ``step_dt`` here exactly once (the reference mutates its class-level dict, SURVEY C-3)."""
+    from .assets import zbot_6s as Z
+
+    cfg = ZbotCfg()
+    cfg.abi_version = ZBOT_ABI_VERSION
+    cfg.num_envs = int(num_envs)
+    cfg.decimation = Z.DECIMATION
+    cfg.max_episode_length = 1000
+    cfg.sim_dt = Z.SIM_DT
+    cfg.termination_height = 0.22
+    cfg.y_err_limit = 0.5
+    cfg.terminated_penalty = 20.0
+    cfg.contact_died_force = 1.0
+    cfg.kp, cfg.kd, cfg.effort_limit = Z.KP, Z.KD, Z.EFFORT_LIMIT
+    cfg.gravity = Z.GRAVITY
+    cfg.contact_alpha, cfg.contact_erp, cfg.contact_vdep = Z.CONTACT_ALPHA, Z.CONTACT_ERP, Z.CONTACT_VDEP
+    cfg.contact_beta_max, cfg.contact_mu = Z.CONTACT_BETA_MAX, Z.CONTACT_MU
+    cfg.contact_ramp, cfg.contact_vt_eps = Z.CONTACT_RAMP, Z.CONTACT_VT_EPS
+    cfg.contact_margin = Z.CONTACT_MARGIN
+    for k, v in overrides.items():
+        if not hasattr(cfg, k):
+            raise AttributeError(f"ZbotCfg has no field {k!r}")
+        setattr(cfg, k, v)
+    if reward_scales is None:
+        from .tasks.zbot6b_direct.walking_v2_cfg import REWARD_SCALES_V2
+        reward_scales = REWARD_SCALES_V2
+    if step_dt is None:
+        step_dt = cfg.decimation * Z.SIM_DT
+    if len(reward_scales) > MAX_TERMS:
+        raise ValueError(f"at most {MAX_TERMS} reward terms are supported")
+    cfg.num_terms = len(reward_scales)
+    for i, (name, w) in enumerate(reward_scales.items()):
+        if name not in TERM_IDS:
+            raise KeyError(f"unknown reward term {name!r}; known: {sorted(TERM_IDS)}")
+        cfg.term_id[i] = TERM_IDS[name]
+        cfg.term_weight[i] = float(w) * float(step_dt)
+    return cfg
+
+
+_LIB = None
+
+
+def _declare(lib):
+    vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
+    P = C.POINTER
+    lib.zbot_abi_version.restype = C.c_int
+    lib.zbot_build_info.restype = C.c_char_p
+    lib.zbot_last_error.restype = C.c_char_p
+    lib.zbot_default_cfg.argtypes = [P(ZbotCfg), i32]
+    lib.zbot_state_word.argtypes = [C.c_char_p]
+    lib.zbot_mdp_state_word.argtypes = [C.c_char_p]
+    lib.zbot_create.argtypes = [P(ZbotCfg), C.c_int, P(vp)]
+    lib.zbot_destroy.argtypes = [vp]
+    lib.zbot_bind.argtypes = [vp, vp, vp, vp, i32]
+    lib.zbot_step.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, vp]
+    lib.zbot_step_export.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, P(ZbotExport), vp]
+    lib.zbot_reset_idx.argtypes = [vp, vp, i64, vp, vp, i32, vp]
+    lib.zbot_observe.argtypes = [vp, vp, vp]
+    lib.zbot_articulation_view.argtypes = [vp, vp, vp, vp, vp]
+    lib.zbot_mdp_bind.argtypes = [vp, vp, vp, vp, i32]
+    lib.zbot_mdp_observe.argtypes = [vp, P(ZbotMdpInputs), vp, vp]
+    lib.zbot_mdp_step.argtypes = [vp, P(ZbotMdpInputs), vp, vp, vp, vp, vp, i32, i32, vp]
+    lib.zbot_launch_count.argtypes = [vp]
+    lib.zbot_launch_count.restype = i64
+    for name in ("zbot_default_cfg", "zbot_state_word", "zbot_mdp_state_word", "zbot_create", "zbot_destroy",
+                 "zbot_bind", "zbot_step", "zbot_step_export", "zbot_reset_idx", "zbot_observe",
+                 "zbot_articulation_view", "zbot_mdp_bind", "zbot_mdp_observe", "zbot_mdp_step"):
+        getattr(lib, name).restype = C.c_int
+
+
+EXPORTED_SYMBOLS = (
+    "zbot_abi_version", "zbot_build_info", "zbot_last_error", "zbot_default_cfg", "zbot_state_word",
+    "zbot_mdp_state_word", "zbot_create", "zbot_destroy", "zbot_bind", "zbot_step", "zbot_step_export",
+    "zbot_reset_idx", "zbot_observe", "zbot_articulation_view", "zbot_mdp_bind", "zbot_mdp_observe",
+    "zbot_mdp_step", "zbot_launch_count",
+)
+
+
+def lib():
+    """Load ``libzbot_b200.so``; raise (never fall back) when it is missing."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.isfile(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: the CUDA extension has not been built. Run "
+                "`python -c 'import __graft_entry__ as g; g.build()'` (or `python -m zbot_lab_b200.build`). "
+                "There is no CPU fallback.")
+        _LIB = C.CDLL(LIB_PATH)
+        _declare(_LIB)
+        if _LIB.zbot_abi_version() != ZBOT_ABI_VERSION:
+            raise RuntimeError("libzbot_b200.so ABI version mismatch; rebuild")
+    return _LIB
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = lib().zbot_last_error()
+        raise RuntimeError(f"{what or 'zbot call'} failed (rc={rc}): {msg.decode() if msg else ''}")

@@ -1,0 +1,231 @@
+"""Torch-side owner of the device buffers + handle of the fused step (thin over the C ABI).
+
+PyTorch is plumbing here: it allocates device memory and provides the current CUDA stream;
+every computation of the step happens inside ``libzbot_b200.so``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import native
+from .native import ZbotCfg, ZbotExport, ZbotMdpInputs
+
+STATS_SLOTS = 64
+
+#: (name, width) of every field of the 80-word fused state, see include/zbot_b200.h
+STATE_FIELDS = {
+    "root_pos": 3, "root_quat": 4, "root_lin_vel": 3, "root_ang_vel": 3, "joint_pos": 6, "joint_vel": 6,
+    "p_delta": 6, "actions": 6, "carry_feet_fz": 2, "carry_mid_max": 1, "current_air_time": 2,
+    "current_contact_time": 2, "last_air_time": 2, "last_contact_time": 2,
+    "feet_contact_forces_last": 2, "feet_down_pos_last": 6, "feet_step_length": 2,
+    "base_heading_x_sum": 1, "base_pos_y_err_sum": 1, "feet_force_sum": 1, "joint_speed_limit": 1,
+    "episode_sums": 16,
+}
+MDP_STATE_FIELDS = {
+    "p_delta": 6, "actions": 6, "feet_contact_forces_last": 2, "feet_down_pos_last": 6,
+    "feet_step_length": 2, "base_heading_x_sum": 1, "base_pos_y_err_sum": 1, "feet_force_sum": 1,
+    "joint_speed_limit": 1, "stale_base_pos": 3, "stale_forward": 3, "stale_feet_x": 6, "stale_feet_z": 6,
+    "stale_feet_pos": 6, "stale_v_fwd": 1, "episode_sums": 16,
+}
+
+
+def _ptr(t: torch.Tensor | None):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream(device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class _AoSoA:
+    """``[NQ][N][4]`` float buffer with named strided field views."""
+
+    def __init__(self, n, words, fields, word_fn, device):
+        self.n = n
+        self.buf = torch.zeros(words // 4, n, 4, dtype=torch.float32, device=device)
+        self._fields = fields
+        self._word = {k: word_fn(k.encode()) for k in fields}
+        for k, w in self._word.items():
+            if w < 0:
+                raise RuntimeError(f"library does not know state field {k!r}")
+
+    def get(self, name) -> torch.Tensor:
+        """(N, width) copy of a field."""
+        w0, width = self._word[name], self._fields[name]
+        cols = [self.buf[(w0 + i) // 4, :, (w0 + i) % 4] for i in range(width)]
+        return torch.stack(cols, dim=-1)
+
+    def set(self, name, value, ids=None):
+        w0, width = self._word[name], self._fields[name]
+        value = torch.as_tensor(value, dtype=torch.float32, device=self.buf.device)
+        if value.dim() == 0:
+            value = value.expand(width)
+        if value.dim() == 1 and value.shape[0] == width:
+            value = value.unsqueeze(0)
+        elif value.dim() == 1:
+            value = value.unsqueeze(-1)
+        sl = slice(None) if ids is None else ids
+        for i in range(width):
+            self.buf[(w0 + i) // 4, sl, (w0 + i) % 4] = value[..., i]
+
+    def column(self, name, i=0) -> torch.Tensor:
+        """strided (N,) VIEW of one word (writes go straight to the kernel's state)."""
+        w = self._word[name] + i
+        return self.buf[w // 4, :, w % 4]
+
+
+class NativeStepper:
+    """N envs of ``zbot-6b-walking-v2`` on one CUDA device."""
+
+    def __init__(self, num_envs: int, device, cfg: ZbotCfg | None = None):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("the zbot step has no CPU path: a CUDA device is required")
+        self.lib = native.lib()
+        self.n = int(num_envs)
+        self.cfg = cfg if cfg is not None else native.make_cfg(self.n)
+        if self.cfg.num_envs != self.n:
+            raise ValueError("cfg.num_envs mismatch")
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.dev_index = dev_index
+        self._h = C.c_void_p()
+        with torch.cuda.device(dev_index):
+            native.check(self.lib.zbot_create(C.byref(self.cfg), dev_index, C.byref(self._h)), "zbot_create")
+        self.state = _AoSoA(self.n, native.STATE_WORDS, STATE_FIELDS, self.lib.zbot_state_word, self.device)
+        self.episode_length_buf = torch.zeros(self.n, dtype=torch.int64, device=self.device)
+        self.stats_ring = torch.zeros(STATS_SLOTS, native.STATS_WORDS, dtype=torch.float32, device=self.device)
+        native.check(self.lib.zbot_bind(self._h, _ptr(self.state.buf), _ptr(self.episode_length_buf),
+                                        _ptr(self.stats_ring), STATS_SLOTS), "zbot_bind")
+        self.obs = torch.zeros(self.n, native.NUM_OBS, dtype=torch.float32, device=self.device)
+        self.rew = torch.zeros(self.n, dtype=torch.float32, device=self.device)
+        self.terminated = torch.zeros(self.n, dtype=torch.uint8, device=self.device)
+        self.truncated = torch.zeros(self.n, dtype=torch.uint8, device=self.device)
+        self._slot = -1
+        self.state.set("joint_speed_limit", 1.0)
+        self.mdp_state = None
+
+    # ------------------------------------------------------------------ lifecycle
+    def close(self):
+        if self._h:
+            self.lib.zbot_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.zbot_launch_count(self._h))
+
+    def _next_slot(self):
+        prev = self._slot
+        self._slot = (self._slot + 1) % STATS_SLOTS
+        return self._slot, prev
+
+    @property
+    def stats(self) -> torch.Tensor:
+        """(32,) view of the statistics of the most recent step / reset."""
+        return self.stats_ring[max(self._slot, 0)]
+
+    # ------------------------------------------------------------------ fused step
+    def step(self, actions: torch.Tensor, export: dict | None = None):
+        """One control step, in place.  ``actions`` (N,6) float32 contiguous on the device."""
+        if actions.dtype != torch.float32 or not actions.is_contiguous() or actions.device != self.obs.device:
+            actions = actions.to(device=self.device, dtype=torch.float32).contiguous()
+        if actions.shape != (self.n, 6):
+            raise ValueError(f"actions must be ({self.n}, 6), got {tuple(actions.shape)}")
+        slot, prev = self._next_slot()
+        if export is None:
+            rc = self.lib.zbot_step(self._h, _ptr(actions), _ptr(self.obs), _ptr(self.rew), _ptr(self.terminated),
+                                    _ptr(self.truncated), slot, prev, _stream(self.device))
+        else:
+            ex = ZbotExport(*[export[name].data_ptr() for name, _ in ZbotExport._fields_])
+            rc = self.lib.zbot_step_export(self._h, _ptr(actions), _ptr(self.obs), _ptr(self.rew),
+                                           _ptr(self.terminated), _ptr(self.truncated), slot, prev, C.byref(ex),
+                                           _stream(self.device))
+        native.check(rc, "zbot_step")
+        return self.obs, self.rew, self.terminated, self.truncated
+
+    def alloc_export(self) -> dict:
+        n, d = self.n, self.device
+        z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=d)
+        return {
+            "body_link_pos_w0": z(n, 12, 3), "body_link_quat_w0": z(n, 12, 4), "body_com_lin_vel_w0": z(n, 12, 3),
+            "body_link_pos_w1": z(n, 12, 3), "body_link_quat_w1": z(n, 12, 4), "body_com_lin_vel_w1": z(n, 12, 3),
+            "joint_pos1": z(n, 6), "joint_vel1": z(n, 6), "applied_torque1": z(n, 6),
+            "net_forces_w_history1": z(n, 5, 12, 3), "last_air_time1": z(n, 12), "current_contact_time1": z(n, 12),
+        }
+
+    def reset_idx(self, env_ids: torch.Tensor | None = None, terminated=None, truncated=None):
+        slot, _ = self._next_slot()
+        if env_ids is None:
+            rc = self.lib.zbot_reset_idx(self._h, None, -1, _ptr(terminated), _ptr(truncated), slot,
+                                         _stream(self.device))
+        else:
+            env_ids = env_ids.to(device=self.device, dtype=torch.int64).contiguous()
+            if env_ids.numel() == 0:
+                return
+            rc = self.lib.zbot_reset_idx(self._h, _ptr(env_ids), env_ids.numel(), _ptr(terminated), _ptr(truncated),
+                                         slot, _stream(self.device))
+        native.check(rc, "zbot_reset_idx")
+
+    def observe(self) -> torch.Tensor:
+        native.check(self.lib.zbot_observe(self._h, _ptr(self.obs), _stream(self.device)), "zbot_observe")
+        return self.obs
+
+    def articulation_view(self):
+        n, d = self.n, self.device
+        pos = torch.empty(n, 12, 3, device=d)
+        quat = torch.empty(n, 12, 4, device=d)
+        vel = torch.empty(n, 12, 3, device=d)
+        native.check(self.lib.zbot_articulation_view(self._h, _ptr(pos), _ptr(quat), _ptr(vel), _stream(self.device)),
+                     "zbot_articulation_view")
+        return pos, quat, vel
+
+    def set_sim_state(self, st: dict, ids=None):
+        for k in ("root_pos", "root_quat", "root_lin_vel", "root_ang_vel", "joint_pos", "joint_vel"):
+            self.state.set(k, st[k], ids)
+
+    # ------------------------------------------------------------------ MDP-only path
+    def mdp_init(self):
+        self.mdp_state = _AoSoA(self.n, native.MDP_STATE_WORDS, MDP_STATE_FIELDS, self.lib.zbot_mdp_state_word,
+                                self.device)
+        self.mdp_episode_length_buf = torch.zeros(self.n, dtype=torch.int64, device=self.device)
+        self.mdp_stats_ring = torch.zeros(STATS_SLOTS, native.STATS_WORDS, dtype=torch.float32, device=self.device)
+        self._mdp_slot = -1
+        native.check(self.lib.zbot_mdp_bind(self._h, _ptr(self.mdp_state.buf), _ptr(self.mdp_episode_length_buf),
+                                            _ptr(self.mdp_stats_ring), STATS_SLOTS), "zbot_mdp_bind")
+        self.mdp_state.set("joint_speed_limit", 1.0)
+
+    @staticmethod
+    def _mdp_inputs(S: dict, origins: torch.Tensor, step: bool) -> ZbotMdpInputs:
+        def p(k):
+            t = S.get(k)
+            if t is None:
+                return None
+            assert t.dtype == torch.float32 and t.is_contiguous()
+            return t.data_ptr()
+        return ZbotMdpInputs(p("body_link_pos_w"), p("body_link_quat_w"), p("body_com_lin_vel_w"), p("joint_pos"),
+                             p("joint_vel"), p("applied_torque") if step else None,
+                             p("net_forces_w_history") if step else None, p("last_air_time") if step else None,
+                             origins.data_ptr())
+
+    def mdp_observe(self, S: dict, origins: torch.Tensor) -> torch.Tensor:
+        mi = self._mdp_inputs(S, origins, False)
+        native.check(self.lib.zbot_mdp_observe(self._h, C.byref(mi), _ptr(self.obs), _stream(self.device)),
+                     "zbot_mdp_observe")
+        return self.obs
+
+    def mdp_step(self, S: dict, origins: torch.Tensor, actions: torch.Tensor):
+        mi = self._mdp_inputs(S, origins, True)
+        prev = self._mdp_slot
+        self._mdp_slot = (self._mdp_slot + 1) % STATS_SLOTS
+        native.check(self.lib.zbot_mdp_step(self._h, C.byref(mi), _ptr(actions), _ptr(self.obs), _ptr(self.rew),
+                                            _ptr(self.terminated), _ptr(self.truncated), self._mdp_slot, prev,
+                                            _stream(self.device)), "zbot_mdp_step")
+        return self.obs, self.rew, self.terminated, self.truncated
