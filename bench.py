@@ -1,0 +1,293 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s of the fused ``zbot-6b-walking-v2`` step on N B200s of one node.
+
+  python bench.py                         # N=1, 4096 envs (BASELINE.json configs[1])
+  torchrun ... bench.py --gpus 8 ...      # 65536 envs/GPU, env-sharded (configs[2]); NCCL only
+                                          # for the rollout statistics
+  python bench.py --impl reference        # the CPU path (oracle CPU port, all host threads)
+
+One "step" = one control step of every env (4 physics substeps + MDP + partial reset) = ONE
+kernel launch.  Prints one JSON line (rank 0).  Timing: CUDA events on the launching stream
+around every step, an L2 flush (256 MiB write) between timed steps, max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "env-steps/sec zbot-6b-walking-v2 fused step"
+UNIT = "env-steps/s"
+# algorithmic HBM bytes per env-step of the fused kernel: state 20 float4 read +
+# written (2 x 320), actions 24 read, obs 92 + reward 4 + flags 2 written, episode counter 8 + 8
+ALGO_BYTES_PER_ENV_STEP = 320 + 24 + 8 + 320 + 92 + 4 + 2 + 8
+ROLLOUT_STEPS = 24  # agents/rsl_rl_ppo_cfg.py:67 -- statistics are reduced once per rollout
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=200)
+    p.add_argument("--warmup", type=int, default=20)
+    p.add_argument("--envs", type=int, default=None, help="envs per GPU (default 4096 at N=1, 65536 at N>1)")
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--no-flush", action="store_true", help="back-to-back steps (state stays in L2)")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--cpu-sample-steps", type=int, default=None)
+    return p.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self._stop_evt = threading.Event()
+
+    def sample_once(self):
+        try:
+            out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                  "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+            f = [x.strip() for x in out.split(",")]
+            self.samples.append({"sm": float(f[0]), "max": float(f[1]), "power": float(f[2]),
+                                 "hw_slowdown": f[3], "hw_thermal": f[4], "sw_thermal": f[5], "sw_power_cap": f[6]})
+        except Exception:
+            pass
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            self.sample_once()
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=3)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(s["sm"] for s in self.samples)
+        reasons = sorted({k for s in self.samples for k in ("hw_slowdown", "hw_thermal", "sw_thermal", "sw_power_cap")
+                          if s[k].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.samples[0]["max"], "reasons": reasons,
+                "samples": len(self.samples), "power_w_max": max(s["power"] for s in self.samples)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_path(n_envs: int, steps: int, warmup: int, seed: int = 1234):
+    """The path on the host cores: oracle/cpu_port (float32, OpenMP over envs)."""
+    import numpy as np
+
+    from oracle import cpu_port
+    from zbot_lab_b200.utils import synthetic as syn
+
+    rng = np.random.default_rng(seed)
+    env = cpu_port.PortEnv(n_envs, np.float32)
+    env.set_sim_state(syn.synth_sim_state(rng, n_envs))
+    env.ep_len[:] = rng.integers(0, 1000, n_envs)
+    acts = rng.normal(0, 1, (8, n_envs, 6)).astype(np.float32)
+    for i in range(warmup):
+        env.step(acts[i % 8])
+    t0 = time.perf_counter()
+    for i in range(steps):
+        env.step(acts[i % 8])
+    dt = time.perf_counter() - t0
+    cores = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
+    return n_envs * steps / dt, dt, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_envs = args.envs or (4096 if args.gpus == 1 else 65536)
+    # bounded sample: the same workload shape, at most ~20 s of CPU work
+    steps = max(1, min(args.steps, 50))
+    warm = max(1, min(args.warmup, 3))
+    value, dt, cores = cpu_path(n_envs, steps, warm)
+    sample = f"{n_envs} envs x {steps} steps (oracle/cpu_port.cpp float32, OpenMP)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"zbot-6b-walking-v2 full step, {n_envs} envs, host CPU", "envs_per_gpu": n_envs},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference = torch eager MDP + Isaac Lab + PhysX (closed, not installable here); this arm times the "
+                "CPU port of the same step on all host threads (BASELINE.md §2)",
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from zbot_lab_b200.compat import gym_registry as gym
+    import zbot_lab_b200.tasks  # noqa: F401  (registers zbot-6b-walking-v2)
+    from zbot_lab_b200.utils import synthetic as syn
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the zbot step has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_envs = args.envs or (4096 if args.gpus == 1 else 65536)
+
+    # the public API: gym.make(task, cfg=...) exactly as scripts/rsl_rl/train.py:158
+    cfg = gym.load_cfg_from_registry("zbot-6b-walking-v2", "env_cfg_entry_point")
+    cfg.scene.num_envs = n_envs
+    cfg.sim.device = str(dev)
+    cfg.seed = 1234 + rank
+    env = gym.make("zbot-6b-walking-v2", cfg=cfg, render_mode=None)
+    st = env.unwrapped._stepper
+    env.reset()
+    rng = np.random.default_rng(1234 + rank)
+    st.set_sim_state({k: torch.from_numpy(v).to(dev) for k, v in syn.synth_sim_state(rng, n_envs).items()})
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    env.episode_length_buf = torch.randint(0, 1000, (n_envs,), device=dev, generator=g)
+    n_act = 16
+    actions = torch.randn(n_act, n_envs, 6, device=dev, generator=g)            # resident in HBM
+    flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    stats_acc = torch.zeros(32, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step(i):
+        st.step(actions[i % n_act])
+
+    for i in range(args.warmup):
+        one_step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.sample_once()
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches0 = st.launch_count
+    barrier()
+    t_wall0 = time.perf_counter()
+    for i in range(args.steps):
+        if flush is not None:
+            flush.fill_(i & 0xFF)                      # evict L2 (126 MB) -- outside the timed events
+        ev[i][0].record()
+        one_step(i)
+        ev[i][1].record()
+        if world > 1 and (i + 1) % ROLLOUT_STEPS == 0:
+            stats_acc.copy_(st.stats)
+            dist.all_reduce(stats_acc)                 # rollout statistics: the only collective on the path
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = st.launch_count - launches0
+    sampler.stop()
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = float(sum(step_ms))
+    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = world * n_envs * args.steps / (total_ms * 1e-3)
+
+    # end to end through the public API with HOST buffers: pinned actions -> H2D, env.step, D2H of the result
+    e2e = None
+    if not args.no_e2e:
+        h_act = [torch.randn(n_envs, 6).pin_memory() for _ in range(4)]
+        h_obs = torch.empty(n_envs, 23).pin_memory()
+        h_rew = torch.empty(n_envs).pin_memory()
+        h_term = torch.empty(n_envs, dtype=torch.bool).pin_memory()
+        h_trunc = torch.empty(n_envs, dtype=torch.bool).pin_memory()
+        d_act = torch.empty(n_envs, 6, device=dev)
+
+        def e2e_step(i):
+            d_act.copy_(h_act[i % 4], non_blocking=True)
+            obs, rew, term, trunc, _ = env.step(d_act)
+            h_obs.copy_(obs["policy"], non_blocking=True)
+            h_rew.copy_(rew, non_blocking=True)
+            h_term.copy_(term, non_blocking=True)
+            h_trunc.copy_(trunc, non_blocking=True)
+            torch.cuda.synchronize()
+
+        for i in range(max(3, args.warmup // 4)):
+            e2e_step(i)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            e2e_step(i)
+        barrier()
+        te = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * n_envs * args.steps / float(te.item()), "unit": UNIT,
+               "h2d_bytes_per_step": n_envs * 24, "d2h_bytes_per_step": n_envs * (92 + 4 + 1 + 1)}
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        kern_ms = total_ms / args.steps if world == 1 else float(sum(step_ms)) / args.steps
+        achieved = ALGO_BYTES_PER_ENV_STEP * n_envs / (kern_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"zbot-6b-walking-v2 full fused step (4 substeps + MDP + reset), {n_envs} envs/GPU",
+                       "envs_per_gpu": n_envs, "parallelism": f"env-sharded x{world}, no collective in the step",
+                       "l2": "flushed between timed steps (256 MiB write)" if flush is not None else "not flushed",
+                       "wall_s_incl_flush": t_wall},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "zbot_step_kernel<false>",
+                         "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP,
+                         "note": "the fused step is FP32-issue bound, not HBM bound (DESIGN.md §4)"},
+            "gpu_launches": int(launches), "clocks": sampler.summary(),
+        }
+        if e2e is not None:
+            line["e2e"] = e2e
+        if world == 1 and not args.no_cpu_baseline:
+            cs = args.cpu_sample_steps or 40
+            v, dt, cores = cpu_path(n_envs, cs, 2)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{n_envs} envs x {cs} steps, oracle/cpu_port.cpp float32 OpenMP, {dt:.1f} s"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

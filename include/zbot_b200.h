@@ -123,7 +123,8 @@ int zbot_bind(ZbotHandle* h, float* state, int64_t* episode_length, float* stats
  *   rew         float [N]
  *   terminated / truncated  uint8 [N]
  *   stats_slot  which ring slot receives this step's reset statistics:
- *               [0..num_terms) sum over reset envs of the per-term episode sums,
+ *               [0..num_terms) `Episode_Reward/<term>` = mean over the envs reset this step of the
+ *               per-term episodic sum, divided by max_episode_length_s (…env_v2.py:443-447),
  *               [16] #reset, [17] #terminated among reset, [18] #timed out among reset,
  *               [19] sum of rewards, [20] #terminated, [21] #truncated.
  *               When no env reset this step words 0..18 are copied from `prev_slot` (the reference

@@ -1,0 +1,94 @@
+"""GPU tests of the drop-in surface: registry -> gym.make -> ZbotDirectEnvV2 -> RslRlVecEnvWrapper."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _make(n, **over):
+    import zbot_lab_b200.tasks  # noqa: F401
+    from zbot_lab_b200.compat import gym_registry as gym
+    cfg = gym.load_cfg_from_registry("zbot-6b-walking-v2", "env_cfg_entry_point")
+    cfg.scene.num_envs = n
+    cfg.sim.device = "cuda:0"
+    cfg.seed = 3
+    for k, v in over.items():
+        setattr(cfg, k, v)
+    return gym.make("zbot-6b-walking-v2", cfg=cfg, render_mode=None), cfg
+
+
+def test_env_protocol_and_wrapper():
+    from zbot_lab_b200.envs.rsl_rl_wrapper import RslRlVecEnvWrapper
+    env, cfg = _make(64)
+    assert env.step_dt == pytest.approx(0.02) and env.max_episode_length == 1000
+    assert env.max_episode_length_s == 20.0 and env.num_envs == 64 and env.unwrapped is env
+    w = RslRlVecEnvWrapper(env, clip_actions=None)
+    assert w.num_actions == 6 and w.num_obs == 23
+    obs, extras = w.get_observations()
+    assert obs.shape == (64, 23) and obs.dtype == torch.float32 and "observations" in extras
+    # default pose known answers (…env_v2.py:403-404): base quat in obs[0:4], q - q_default = 0
+    assert torch.allclose(obs[0, :4], torch.tensor([0.6003, -0.6003, -0.3735, -0.3739], device="cuda:0"), atol=1e-4)
+    assert torch.all(obs[:, 4:22] == 0) and torch.all(obs[:, 22] == 1.0)
+    assert env.episode_length_buf.dtype == torch.int64
+    assert int(env.episode_length_buf.max()) < 1000 and int(env.episode_length_buf.max()) > 0   # randint spread
+    w.episode_length_buf = torch.randint_like(w.episode_length_buf, high=1000)                   # train.py:205 path
+    prev_obs = None
+    for t in range(40):
+        a = torch.randn(64, 6, device="cuda:0")
+        obs, rew, dones, extras = w.step(a)
+        assert obs.shape == (64, 23) and rew.shape == (64,) and dones.dtype == torch.long
+        assert extras["time_outs"].dtype == torch.bool and "log" in extras
+        assert set(extras["log"]) == {"Episode_Reward/" + k for k in cfg.reward_cfg["reward_scales"]} | {
+            "Episode_Termination/body_contact", "Episode_Termination/time_out"}
+        if prev_obs is not None:
+            assert prev_obs.data_ptr() != obs.data_ptr()       # outputs rotate, rsl_rl keeps obs_t alive
+        prev_obs = obs
+    assert env.common_step_counter == 40
+    # articulation view in world frame (origin added)
+    p = env._robot.data.body_link_pos_w
+    assert p.shape == (64, 12, 3)
+    assert torch.allclose((p[:, 6, 2]), p[:, 6, 2].clamp(0.0, 0.4))
+    w.close()
+
+
+def test_env_matches_bare_stepper_and_cfg_weights_drive_the_kernel():
+    from zbot_lab_b200.stepper import NativeStepper
+    env, cfg = _make(32, check_all_envs_reset=False)
+    st = NativeStepper(32, "cuda:0")
+    st.reset_idx(None)
+    env.reset()
+    env.episode_length_buf = torch.zeros(32, dtype=torch.int64)
+    g = torch.Generator(device="cuda:0").manual_seed(0)
+    for t in range(10):
+        a = torch.randn(32, 6, device="cuda:0", generator=g)
+        o1, r1, te1, tr1, _ = env.step(a)
+        o2, r2, te2, tr2 = st.step(a)
+        assert torch.equal(o1["policy"], o2) and torch.equal(r1, r2)
+        assert torch.equal(te1, te2.bool()) and torch.equal(tr1, tr2.bool())
+    # a cfg with a different term subset / order / weights (names drive the kernel's table)
+    env2, _ = _make(32, reward_cfg={"reward_scales": {"torques": -0.5, "base_vel_forward": 2.0}},
+                    check_all_envs_reset=False)
+    env2.reset()
+    _, r, _, _, ex = env2.step(torch.zeros(32, 6, device="cuda:0"))
+    assert set(ex["log"]) == {"Episode_Reward/torques", "Episode_Reward/base_vel_forward",
+                              "Episode_Termination/body_contact", "Episode_Termination/time_out"}
+    assert torch.isfinite(r).all()
+    with pytest.raises(KeyError):
+        _make(4, reward_cfg={"reward_scales": {"no_such_term": 1.0}})
+    env.close(); env2.close(); st.close()
+
+
+def test_all_envs_reset_spreads_episode_lengths_on_torch_generator():
+    """…env_v2.py:418-422: when every env resets in one step the counters are re-drawn with
+    torch.randint_like on the (device) torch generator -- bit-exact against the same call."""
+    env, _ = _make(16, check_all_envs_reset=True)
+    env.reset()
+    env.episode_length_buf = torch.full((16,), 998, dtype=torch.int64)
+    torch.manual_seed(123)
+    _, _, term, trunc, _ = env.step(torch.zeros(16, 6, device="cuda:0"))
+    assert trunc.all()
+    torch.manual_seed(123)
+    want = torch.randint_like(env.episode_length_buf, high=1000)
+    assert torch.equal(env.episode_length_buf, want)
+    env.close()

@@ -72,7 +72,7 @@ def test_mdp_kernel_matches_reference_golden(name):
             assert stats[18] == g[f"log{k}/Episode_Termination/time_out"]
             for i, nm in enumerate(term_names):
                 want = g[f"log{k}/Episode_Reward/{nm}"]
-                assert abs(stats[i] / stats[16] / 20.0 - want) <= 1e-5 * max(1.0, abs(want)), nm
+                assert abs(stats[i] - want) <= 1e-5 * max(1.0, abs(want)), nm
         assert abs(stats[19] - float(np.sum(g[f"rew{k}"], dtype=np.float64))) <= 1e-4 * max(1.0, abs(stats[19]))
     st.close()
 
@@ -125,6 +125,7 @@ def test_fused_step_mdp_matches_pinned_oracle_on_exported_physics():
     ep0 = rng.integers(0, 1000, n)
     ep0[:8] = 996
     st.episode_length_buf[:] = _t(ep0.astype(np.int64))
+    fdpl0 = st.state.get("feet_down_pos_last").cpu().numpy().reshape(n, 2, 3)   # post-reset default feet pos
     o = make_mdp_oracle(n, np.zeros((n, 3), np.float32))
     o.episode_length_buf[:] = ep0
     ex = st.alloc_export()
@@ -140,6 +141,7 @@ def test_fused_step_mdp_matches_pinned_oracle_on_exported_physics():
             S0["joint_vel"] = np.zeros((n, 6), np.float32)
             o.observe(S0)                       # fills the stale cache from the start-of-step view
             o.actions[:] = 0
+            o.feet_down_pos_last[:] = fdpl0
         else:
             # the oracle's stale cache must equal the kernel's start-of-step view for envs that did not reset
             keep = ~last_reset

@@ -55,6 +55,7 @@ struct StatsCtx {
   unsigned int* ticket;   // last-block-done counter
   float* ring;            // [slots][32]
   int slot, prev_slot;
+  float inv_episode_s;    // 1 / max_episode_length_s  (…env_v2.py:444-447)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -105,6 +106,9 @@ __device__ __forceinline__ void stats_reduce(float (&vals)[kStatUsed], bool did_
   if (threadIdx.x < kStats) {
     const float nreset = smem[S_NUM_RESET];
     float v = smem[threadIdx.x];
+    // words 0..15 leave the kernel as the reference's `Episode_Reward/<term>` values:
+    // mean over the reset envs of the episodic sum, divided by max_episode_length_s
+    if (threadIdx.x < MAX_TERMS && nreset > 0.f) v = (v / nreset) * sc.inv_episode_s;
     // the reference only rewrites extras["log"] when something reset (…env_v2.py:450): keep the previous log
     if (threadIdx.x < S_REW_SUM && !(nreset > 0.f))
       v = (sc.prev_slot >= 0) ? sc.ring[(size_t)sc.prev_slot * kStats + threadIdx.x] : 0.f;
@@ -513,6 +517,7 @@ struct ZbotHandle {
   unsigned int* ticket;
   int max_blocks;
   int64_t launches;
+  float inv_episode_s;
 };
 
 namespace {
@@ -560,6 +565,7 @@ int zbot_create(const ZbotCfg* cfg, int device, ZbotHandle** out) {
   h->cfg = *cfg;
   params_from_cfg(*cfg, h->P);
   h->device = device;
+  h->inv_episode_s = 1.0f / ((float)cfg->max_episode_length * cfg->sim_dt * (float)cfg->decimation);
   cudaDeviceProp prop;
   ZB_CUDA(cudaGetDeviceProperties(&prop, device));
   h->num_sms = prop.multiProcessorCount;
@@ -608,7 +614,7 @@ static int step_impl(ZbotHandle* h, const float* actions, float* obs, float* rew
   const int block = pick_block(h, n);
   const int grid = (n + block - 1) / block;
   const size_t smem = (size_t)((block * ZBOT_NUM_OBS > 32 * kStatUsed) ? block * ZBOT_NUM_OBS : 32 * kStatUsed) * sizeof(float);
-  StatsCtx sc{h->partials, h->ticket, h->ring, slot, prev};
+  StatsCtx sc{h->partials, h->ticket, h->ring, slot, prev, h->inv_episode_s};
   cudaStream_t s = (cudaStream_t)stream;
   ExportPtrs xp{};
   if (ex) {
@@ -651,7 +657,7 @@ int zbot_reset_idx(ZbotHandle* h, const int64_t* env_ids, int64_t nids, const ui
   if (nids > n) return fail(ZBOT_E_INVALID, "more env ids than envs%s");
   const int block = 64;
   const int grid = (int)((nids + block - 1) / block);
-  StatsCtx sc{h->partials, h->ticket, h->ring, stats_slot, -1};
+  StatsCtx sc{h->partials, h->ticket, h->ring, stats_slot, -1, h->inv_episode_s};
   zbot_reset_kernel<<<grid, block, 32 * kStatUsed * sizeof(float), (cudaStream_t)stream>>>(
       h->P, h->dp, h->state, h->ep_len, env_ids, nids, terminated, truncated, n, sc);
   ZB_CUDA(cudaGetLastError());
@@ -708,7 +714,7 @@ int zbot_mdp_observe(ZbotHandle* h, const ZbotMdpInputs* in, float* obs, void* s
   const int n = h->cfg.num_envs, block = 128, grid = (n + block - 1) / block;
   MdpIn mi{in->body_link_pos_w, in->body_link_quat_w, in->body_com_lin_vel_w, in->joint_pos, in->joint_vel,
            in->applied_torque, in->net_forces_w_history, in->last_air_time, in->env_origins};
-  StatsCtx sc{h->partials, h->ticket, h->m_ring, 0, -1};
+  StatsCtx sc{h->partials, h->ticket, h->m_ring, 0, -1, h->inv_episode_s};
   zbot_mdp_kernel<false><<<grid, block, block * ZBOT_NUM_OBS * sizeof(float), (cudaStream_t)stream>>>(
       h->P, h->dp, mi, h->mstate, h->m_ep_len, nullptr, obs, nullptr, nullptr, nullptr, n, sc);
   ZB_CUDA(cudaGetLastError());
@@ -724,7 +730,7 @@ int zbot_mdp_step(ZbotHandle* h, const ZbotMdpInputs* in, const float* actions, 
   const int n = h->cfg.num_envs, block = 128, grid = (n + block - 1) / block;
   MdpIn mi{in->body_link_pos_w, in->body_link_quat_w, in->body_com_lin_vel_w, in->joint_pos, in->joint_vel,
            in->applied_torque, in->net_forces_w_history, in->last_air_time, in->env_origins};
-  StatsCtx sc{h->partials, h->ticket, h->m_ring, stats_slot, prev_slot};
+  StatsCtx sc{h->partials, h->ticket, h->m_ring, stats_slot, prev_slot, h->inv_episode_s};
   zbot_mdp_kernel<true><<<grid, block, (size_t)block * kHistRow * sizeof(float), (cudaStream_t)stream>>>(
       h->P, h->dp, mi, h->mstate, h->m_ep_len, actions, obs, rew, terminated, truncated, n, sc);
   ZB_CUDA(cudaGetLastError());

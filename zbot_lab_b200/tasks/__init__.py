@@ -1,0 +1,2 @@
+"""Importing this package registers the task ids (reference: zbot/tasks/__init__.py:3-13)."""
+from . import zbot6b_direct  # noqa: F401

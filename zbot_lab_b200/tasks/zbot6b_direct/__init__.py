@@ -1,0 +1,17 @@
+"""Registers ``zbot-6b-walking-v2`` with the same id / kwargs keys as the reference
+(``/root/reference/source/zbot/zbot/tasks/zbot6b_direct/__init__.py:41-49``)."""
+from ...compat import gym_registry as gym
+from .walking_v2 import ZbotDirectEnvV2
+from .walking_v2_cfg import PPORunnerCfgV2, ZbotDirectEnvCfgV2
+
+gym.register(
+    id="zbot-6b-walking-v2",
+    entry_point="zbot_lab_b200.tasks.zbot6b_direct:ZbotDirectEnvV2",
+    disable_env_checker=True,
+    kwargs={
+        "env_cfg_entry_point": ZbotDirectEnvCfgV2,
+        "rsl_rl_cfg_entry_point": f"{__name__}.walking_v2_cfg:PPORunnerCfgV2",
+    },
+)
+
+__all__ = ["ZbotDirectEnvV2", "ZbotDirectEnvCfgV2", "PPORunnerCfgV2"]

@@ -1,0 +1,254 @@
+"""``ZbotDirectEnvV2`` -- drop-in for the reference task class of ``zbot-6b-walking-v2``
+(``/root/reference/source/zbot/zbot/tasks/zbot6b_direct/zbot_direct_6dof_bipedal_env_v2.py:208-605``)
+over the fused sm_100a step.  Same constructor signature, ``step`` 5-tuple, ``reset`` 2-tuple,
+attribute names and ``extras["log"]`` keys; the per-step work of the reference's
+``_pre_physics_step / _apply_action / _get_dones / _get_rewards / _reset_idx / _get_observations``
+plus Isaac Lab's articulation / contact-sensor stepping happens in ONE kernel launch.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from ... import native
+from ...assets import zbot_6s as Z
+from ...stepper import NativeStepper
+from ...utils import synthetic as syn
+from .walking_v2_cfg import ZbotDirectEnvCfgV2
+
+
+class _Box:
+    """Tiny stand-in for ``gymnasium.spaces.Box`` (only shape / bounds are ever read)."""
+
+    def __init__(self, shape, low=-math.inf, high=math.inf):
+        self.shape = tuple(shape)
+        self.low, self.high = low, high
+        self.dtype = "float32"
+
+    def __repr__(self):
+        return f"Box({self.low}, {self.high}, {self.shape}, float32)"
+
+
+class _ArticulationData:
+    """Lazy ``robot.data`` view (world frame = env-local + env origin), computed on demand by the
+    articulation-view kernel; names follow the call sites at …env_v2.py:315-326, 357-358, 554, 560."""
+
+    def __init__(self, env):
+        self._env = env
+        n, dev = env.num_envs, env.device
+        self.default_joint_pos = torch.tensor(Z.DEFAULT_JOINT_POS, dtype=torch.float32, device=dev).repeat(n, 1)
+        self.default_joint_vel = torch.zeros(n, 6, device=dev)
+        drs = torch.zeros(n, 13, device=dev)
+        drs[:, :3] = torch.tensor(Z.DEFAULT_ROOT_POS, device=dev)
+        drs[:, 3] = 1.0
+        self.default_root_state = drs
+        self.GRAVITY_VEC_W = torch.tensor([0.0, 0.0, -1.0], device=dev).repeat(n, 1)
+
+    def _view(self):
+        pos, quat, vel = self._env._stepper.articulation_view()
+        return pos + self._env._terrain.env_origins.unsqueeze(1), quat, vel
+
+    @property
+    def body_link_pos_w(self):
+        return self._view()[0]
+
+    @property
+    def body_link_quat_w(self):
+        return self._view()[1]
+
+    @property
+    def body_com_lin_vel_w(self):
+        return self._view()[2]
+
+    @property
+    def joint_pos(self):
+        return self._env._stepper.state.get("joint_pos")
+
+    @property
+    def joint_vel(self):
+        return self._env._stepper.state.get("joint_vel")
+
+
+class _Robot:
+    def __init__(self, env):
+        self.data = _ArticulationData(env)
+        self._ALL_INDICES = torch.arange(env.num_envs, dtype=torch.long, device=env.device)
+        self.body_names = list(Z.LINK_NAMES)
+        self.joint_names = list(Z.JOINT_NAMES)
+
+    def find_bodies(self, pattern):
+        return Z.find_bodies(pattern, Z.LINK_NAMES)
+
+
+class _Terrain:
+    def __init__(self, n, spacing, device):
+        self.env_origins = torch.from_numpy(syn.env_origins_grid(n, spacing)).to(device)
+
+
+class ZbotDirectEnvV2:
+    """``DirectRLEnv``-shaped vectorised env; all tensors live on ``cfg.sim.device``."""
+
+    metadata = {"render_modes": [None]}
+    cfg: ZbotDirectEnvCfgV2
+
+    def __init__(self, cfg: ZbotDirectEnvCfgV2 | None = None, render_mode: str | None = None, **kwargs):
+        self.cfg = cfg if cfg is not None else ZbotDirectEnvCfgV2()
+        if render_mode not in (None,):
+            raise NotImplementedError("rendering is out of scope of the B200 step (SURVEY.md §2 row 2)")
+        self.render_mode = render_mode
+        self.device = torch.device(self.cfg.sim.device)
+        self.num_envs = int(self.cfg.scene.num_envs)
+        if self.cfg.seed is not None:
+            self.seed(self.cfg.seed)
+        # timing
+        self.physics_dt = float(self.cfg.sim.dt)
+        self.step_dt = self.physics_dt * self.cfg.decimation
+        self.max_episode_length_s = float(self.cfg.episode_length_s)
+        self.max_episode_length = math.ceil(self.max_episode_length_s / self.step_dt)
+        # reward table: a COPY scaled once by step_dt (the reference scales its class dict in place, C-3)
+        self.reward_scales = {k: v * self.step_dt for k, v in self.cfg.reward_cfg["reward_scales"].items()}
+        c, a = self.cfg.contact, self.cfg.actuator
+        ncfg = native.make_cfg(
+            self.num_envs, reward_scales=self.cfg.reward_cfg["reward_scales"], step_dt=self.step_dt,
+            sim_dt=self.physics_dt, decimation=int(self.cfg.decimation),
+            max_episode_length=int(self.max_episode_length), termination_height=float(self.cfg.termination_height),
+            kp=a.stiffness, kd=a.damping, effort_limit=a.effort_limit,
+            gravity=-float(self.cfg.sim.gravity[2]),
+            contact_alpha=c.alpha, contact_erp=c.erp, contact_vdep=c.max_depenetration_velocity,
+            contact_beta_max=c.beta_max, contact_mu=c.friction, contact_ramp=c.ramp, contact_margin=c.margin)
+        self._stepper = NativeStepper(self.num_envs, self.device, ncfg)
+        self._terrain = _Terrain(self.num_envs, self.cfg.scene.env_spacing, self.device)
+        self._robot = _Robot(self)
+        # index sets, resolved by name exactly as …env_v2.py:227-230
+        self._feet_ids, _ = Z.find_bodies("foot.*", Z.SENSOR_BODY_NAMES)
+        self._undesired_contact_body_ids, _ = Z.find_bodies("base|a.*|b.*", Z.SENSOR_BODY_NAMES)
+        self.base_body_idx = Z.find_bodies("base", Z.LINK_NAMES)[0]
+        self.feet_body_idx = Z.find_bodies("foot.*", Z.LINK_NAMES)[0]
+        # spaces
+        self.single_observation_space = {"policy": _Box((self.cfg.observation_space,))}
+        self.single_action_space = _Box((self.cfg.action_space,))
+        self.observation_space = {"policy": _Box((self.num_envs, self.cfg.observation_space))}
+        self.action_space = _Box((self.num_envs, self.cfg.action_space))
+        # buffers the scripts / wrappers read
+        self.common_step_counter = 0
+        self.extras: dict = {}
+        self._term_names = list(self.cfg.reward_cfg["reward_scales"].keys())
+        ring = max(2, int(self.cfg.output_ring))
+        n, dev = self.num_envs, self.device
+        self._out = [(torch.zeros(n, 23, device=dev), torch.zeros(n, device=dev),
+                      torch.zeros(n, dtype=torch.uint8, device=dev), torch.zeros(n, dtype=torch.uint8, device=dev))
+                     for _ in range(ring)]
+        self._out_i = 0
+        self.reset_terminated = torch.zeros(n, dtype=torch.bool, device=dev)
+        self.reset_time_outs = torch.zeros(n, dtype=torch.bool, device=dev)
+        self.reset_buf = torch.zeros(n, dtype=torch.bool, device=dev)
+        chk = self.cfg.check_all_envs_reset
+        self._check_all_reset = (self.num_envs <= 256) if chk is None else bool(chk)
+        self._stepper.reset_idx(None)
+        self._sim_step_counter = 0
+
+    # ------------------------------------------------------------------ reference attribute surface
+    @property
+    def unwrapped(self):
+        return self
+
+    @property
+    def episode_length_buf(self) -> torch.Tensor:
+        return self._stepper.episode_length_buf
+
+    @episode_length_buf.setter
+    def episode_length_buf(self, value):
+        self._stepper.episode_length_buf.copy_(torch.as_tensor(value, device=self.device).to(torch.int64))
+
+    @property
+    def joint_speed_limit(self):
+        return self._stepper.state.get("joint_speed_limit")
+
+    @joint_speed_limit.setter
+    def joint_speed_limit(self, value):
+        self._stepper.state.set("joint_speed_limit", value)
+
+    @property
+    def p_delta(self):
+        return self._stepper.state.get("p_delta")
+
+    @property
+    def _actions(self):
+        return self._stepper.state.get("actions")
+
+    @property
+    def _previous_actions(self):
+        return self._stepper.state.get("actions")
+
+    @property
+    def _episode_sums(self) -> dict:
+        eps = self._stepper.state.get("episode_sums")
+        return {k: eps[:, i] for i, k in enumerate(self._term_names)}
+
+    def __getattr__(self, name):
+        # MDP state attributes of the reference (…env_v2.py:231-245), served from the kernel's state
+        fields = {"feet_contact_forces_last": 2, "feet_step_length": 2, "base_heading_x_sum": 1,
+                  "base_pos_y_err_sum": 1, "feet_force_sum": 1}
+        if name in fields and "_stepper" in self.__dict__:
+            v = self._stepper.state.get(name)
+            return v if fields[name] > 1 else v[:, 0]
+        if name == "feet_down_pos_last" and "_stepper" in self.__dict__:
+            return self._stepper.state.get(name).view(self.num_envs, 2, 3) + self._terrain.env_origins.unsqueeze(1)
+        raise AttributeError(name)
+
+    def seed(self, seed: int = -1) -> int:
+        if seed == -1:
+            seed = int(torch.randint(0, 10000, (1,)).item())
+        torch.manual_seed(seed)
+        if self.device.type == "cuda":
+            torch.cuda.manual_seed_all(seed)
+        return seed
+
+    # ------------------------------------------------------------------ log (…env_v2.py:441-459)
+    def _log_from_slot(self) -> dict:
+        s = self._stepper.stats          # 0-dim VIEWS into this step's statistics slot (no launch, no sync)
+        log = {"Episode_Reward/" + k: s[i] for i, k in enumerate(self._term_names)}
+        log["Episode_Termination/body_contact"] = s[native.STAT_NUM_TERMINATED_RESET]
+        log["Episode_Termination/time_out"] = s[native.STAT_NUM_TIMEOUT_RESET]
+        return log
+
+    # ------------------------------------------------------------------ gym API
+    def reset(self, seed: int | None = None, options=None):
+        """``DirectRLEnv.reset``: _reset_idx(all) -> observations."""
+        if seed is not None:
+            self.seed(seed)
+        self._stepper.reset_idx(None, self._out[self._out_i][2], self._out[self._out_i][3])
+        # all envs reset: spread the episode counters (…env_v2.py:418-422), on the torch generator
+        self.episode_length_buf = torch.randint_like(self._stepper.episode_length_buf, high=int(self.max_episode_length))
+        self.extras["log"] = self._log_from_slot()
+        obs = self._stepper.observe().clone()
+        return {"policy": obs}, self.extras
+
+    def step(self, actions: torch.Tensor):
+        """(obs_dict, rew, terminated, truncated, extras) -- one fused kernel launch."""
+        st = self._stepper
+        self._out_i = (self._out_i + 1) % len(self._out)
+        st.obs, st.rew, st.terminated, st.truncated = self._out[self._out_i]
+        obs, rew, term, trunc = st.step(actions.to(self.device))
+        self.common_step_counter += 1
+        self._sim_step_counter += self.cfg.decimation
+        self.reset_terminated = term.view(torch.bool)
+        self.reset_time_outs = trunc.view(torch.bool)
+        if self._check_all_reset:
+            # host sync, only for tiny env counts: the all-envs-reset RNG spread (…env_v2.py:418-422)
+            if int(st.stats[native.STAT_NUM_RESET].item()) == self.num_envs:
+                self.episode_length_buf = torch.randint_like(st.episode_length_buf, high=int(self.max_episode_length))
+        self.extras["log"] = self._log_from_slot()
+        return {"policy": obs}, rew, self.reset_terminated, self.reset_time_outs, self.extras
+
+    @property
+    def reset_buf_now(self):
+        return self.reset_terminated | self.reset_time_outs
+
+    def close(self):
+        if getattr(self, "_stepper", None) is not None:
+            self._stepper.close()
+
+    def render(self, recompute: bool = False):
+        return None
