@@ -127,7 +127,7 @@ int zbot_bind(ZbotHandle* h, float* state, int64_t* episode_length, float* stats
  *               per-term episodic sum, divided by max_episode_length_s (…env_v2.py:443-447),
  *               [16] #reset, [17] #terminated among reset, [18] #timed out among reset,
  *               [19] sum of rewards, [20] #terminated, [21] #truncated.
- *               When no env reset this step words 0..18 are copied from `prev_slot` (the reference
+ *               When no env reset this step words 0..15, 17, 18 are copied from `prev_slot` (the reference
  *               keeps the last `extras["log"]`, …env_v2.py:450). prev_slot < 0: zeros. */
 int zbot_step(ZbotHandle* h, const float* actions, float* obs, float* rew, uint8_t* terminated,
               uint8_t* truncated, int32_t stats_slot, int32_t prev_slot, void* stream);

@@ -46,7 +46,8 @@ static int port_step(const ZbotCfg* cfg, T* state, int64_t* ep_len, const T* act
     T rs[MAX_TERMS];
     for (int i = 0; i < MAX_TERMS; ++i) rs[i] = T(0);
     StepExport<T> ex;
-    env_step(P, es, actions + (size_t)e * 6, ep_len[e], dfp, dbq, out, rs, export_buf ? &ex : (StepExport<T>*)nullptr);
+    ArrayScratch<T> scr;
+    env_step(P, es, actions + (size_t)e * 6, ep_len[e], dfp, dbq, out, rs, export_buf ? &ex : (StepExport<T>*)nullptr, scr);
     env_state_pack(es, state + (size_t)e * ZBOT_STATE_WORDS);
     for (int i = 0; i < 23; ++i) obs[(size_t)e * 23 + i] = out.obs[i];
     rew[e] = out.reward;
@@ -73,14 +74,16 @@ static int port_substeps(const ZbotCfg* cfg, T* sim, const T* target, T* forces,
     for (int i = 0; i < 4; ++i) s.Q[i] = w[3 + i];
     for (int i = 0; i < 6; ++i) { s.q[i] = w[13 + i]; s.qd[i] = w[19 + i]; }
     SubstepOut<T> so;
-    for (int k = 0; k < nsub; ++k) physics_substep(P, s, target + (size_t)e * 6, so);
+    ArrayScratch<T> scr;
+    T midf[15];
+    for (int k = 0; k < nsub; ++k) physics_substep(P, s, target + (size_t)e * 6, so, scr, midf);
     for (int i = 0; i < 3; ++i) { w[i] = s.p[i]; w[7 + i] = s.v[i]; w[10 + i] = s.w[i]; }
     for (int i = 0; i < 4; ++i) w[3 + i] = s.Q[i];
     for (int i = 0; i < 6; ++i) { w[13 + i] = s.q[i]; w[19 + i] = s.qd[i]; }
     T* f = forces + (size_t)e * 21;
     for (int i = 0; i < 3; ++i) { f[i] = so.foot_force[0][i]; f[18 + i] = so.foot_force[1][i]; }
     for (int b = 0; b < 5; ++b)
-      for (int i = 0; i < 3; ++i) f[3 * (b + 1) + i] = so.mid_force[b][i];
+      for (int i = 0; i < 3; ++i) f[3 * (b + 1) + i] = midf[3 * b + i];
     for (int i = 0; i < 6; ++i) tau[(size_t)e * 6 + i] = so.applied_torque[i];
   }
   return ZBOT_OK;

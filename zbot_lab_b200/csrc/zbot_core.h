@@ -85,9 +85,29 @@ ZB_HD float zb_min(float a, float b) { return fminf(a, b); }
 ZB_HD double zb_min(double a, double b) { return fmin(a, b); }
 ZB_HD float zb_max(float a, float b) { return fmaxf(a, b); }
 ZB_HD double zb_max(double a, double b) { return fmax(a, b); }
+// sin/cos of a joint half-angle (|x| < ~8 rad): Cody-Waite reduction to [-pi/4, pi/4] + the classic
+// single-precision minimax polynomials (error ~1 ulp).  ~25 instructions, no slow path, no local
+// memory -- CUDA's sincosf() carries a Payne-Hanek fallback that cost ~1000 SASS instructions and a
+// stack frame per inlined call site.
 ZB_HD void zb_sincos(float x, float* s, float* c) {
 #if defined(__CUDA_ARCH__)
-  sincosf(x, s, c);
+  const float k = rintf(x * 0.63661977236758134f);
+  const int q = (int)k;
+  float r = fmaf(k, -1.57079601287841796875f, x);
+  r = fmaf(k, -3.1391647326017846353352069854736328125e-7f, r);
+  r = fmaf(k, -5.3903025299577647655e-15f, r);
+  const float r2 = r * r;
+  float sp = fmaf(r2, -1.9515295891e-4f, 8.3321608736e-3f);
+  sp = fmaf(sp, r2, -1.6666654611e-1f);
+  sp = fmaf(sp * r2, r, r);
+  float cp = fmaf(r2, 2.443315711809948e-5f, -1.388731625493765e-3f);
+  cp = fmaf(cp, r2, 4.166664568298827e-2f);
+  cp = fmaf(cp, r2, -0.5f);
+  cp = fmaf(cp, r2, 1.0f);
+  const float ss = (q & 1) ? cp : sp;
+  const float cc = (q & 1) ? sp : cp;
+  *s = (q & 2) ? -ss : ss;
+  *c = ((q + 1) & 2) ? -cc : cc;
 #else
   *s = sinf(x);
   *c = cosf(x);
@@ -383,129 +403,172 @@ ZB_HD void body_rigid_terms(const Params<T>& P, T mass, T cx, T cz, T ixx, T iyy
 }
 
 // ------------------------------------------------------------------------------------
+// per-thread scratch for the joint-indexed quantities of one substep.  The sweeps over the
+// chain are REAL loops (not unrolled: the fully unrolled step was ~160 KB of SASS and stalled
+// on instruction fetch), so everything indexed by the joint lives in indexable storage:
+// shared memory on the GPU ([slot][thread], conflict-free), a plain array on the CPU.
+// ------------------------------------------------------------------------------------
+constexpr int SCR_PER_JOINT = 18;
+constexpr int SCR_WORDS = 6 * SCR_PER_JOINT;   // 108 words per environment
+enum ScrSlot : int { SC_SA = 0, SC_SM = 3, SC_UT = 6, SC_UB = 9, SC_DINV = 12, SC_U = 13 /* tau, then u */,
+                     SC_SN = 14, SC_CS = 15, SC_Q = 16, SC_QD = 17 };
+
+template <typename T>
+struct ArrayScratch {
+  T a[SCR_WORDS];
+  ZB_HD T& operator()(int j, int slot) { return a[j * SCR_PER_JOINT + slot]; }
+};
+#if defined(__CUDACC__)
+struct SmemScratch {          // base points at this thread's column; consecutive slots are `stride` apart
+  float* base;
+  int stride;
+  __device__ __forceinline__ float& operator()(int j, int slot) { return base[(j * SCR_PER_JOINT + slot) * stride]; }
+};
+#endif
+
+// ------------------------------------------------------------------------------------
 // one physics substep (dt = P.dt): implicit PD + contact + ABA + semi-implicit Euler
 // ------------------------------------------------------------------------------------
 template <typename T>
 struct SubstepOut {
   T foot_force[2][3];  // net contact force on foot_0 / foot_1 (applied, world frame)
   T mid_force2_max;    // max over bodies 1..5 of |predictor contact force|^2
-  T mid_force[5][3];   // predictor contact force of bodies 1..5 (export / debug)
   T applied_torque[6]; // ImplicitActuator bookkeeping evaluated BEFORE this substep
 };
 
-template <typename T>
-ZB_HD void physics_substep(const Params<T>& P, SimState<T>& s, const T* target, SubstepOut<T>& out) {
+// mid_force_out: optional [5][3] predictor forces of bodies 1..5 (export / debug only)
+template <typename T, typename Scr>
+ZB_HD void physics_substep(const Params<T>& P, SimState<T>& s, const T* target, SubstepOut<T>& out, Scr& scr,
+                           T* mid_force_out) {
   using namespace model;
   const T dt = P.dt;
-  // ---- forward kinematics sweep: keep only joint half-angle sin/cos, arrive at body 6 ----
-  T sn[6], cs[6];
-  ZB_UNROLL for (int k = 0; k < 6; ++k) zb_sincos(T(0.5) * s.q[k], &sn[k], &cs[k]);
+  // ---- PD (implicit part lives in P.arm) + park q, qd (static indices: registers -> scratch) ----
+  ZB_UNROLL for (int k = 0; k < 6; ++k) {
+    const T e = target[k] - s.q[k];
+    out.applied_torque[k] = zb_clamp(P.kp * e - P.kd * s.qd[k], -P.effort, P.effort);
+    scr(k, SC_U) = zb_clamp(P.kp * (e - dt * s.qd[k]) - P.kd * s.qd[k], -P.effort, P.effort);
+    scr(k, SC_Q) = s.q[k];
+    scr(k, SC_QD) = s.qd[k];
+  }
+  // ---- forward kinematics sweep: motion subspaces S_k = (a_k ; r_k x a_k), arrive at body 6 ----
   T Q[4] = {s.Q[0], s.Q[1], s.Q[2], s.Q[3]};
   T r[3] = {T(0), T(0), T(0)};               // body origin relative to O (= root origin)
   T w[3] = {s.w[0], s.w[1], s.w[2]};         // spatial velocity of the current body about O
   T vO[3] = {s.v[0], s.v[1], s.v[2]};
-  T Sa[6][3], Sm[6][3];                      // motion subspaces S_k = (a_k ; r_k x a_k)
-  ZB_UNROLL for (int k = 0; k < 6; ++k) {
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
+  for (int k = 0; k < 6; ++k) {
     T R[9];
     quat_to_mat(Q, R);
     const T jz = (k == 0) ? T(JOINT_Z_FIRST) : T(JOINT_Z_REST);
     const T sg = (k & 1) ? T(-AXIS_S) : T(AXIS_S);
     r[0] += jz * R[2]; r[1] += jz * R[5]; r[2] += jz * R[8];
-    Sa[k][0] = sg * R[0] + T(AXIS_S) * R[2];
-    Sa[k][1] = sg * R[3] + T(AXIS_S) * R[5];
-    Sa[k][2] = sg * R[6] + T(AXIS_S) * R[8];
-    cross3(r, Sa[k], Sm[k]);
-    ZB_UNROLL for (int i = 0; i < 3; ++i) { w[i] += Sa[k][i] * s.qd[k]; vO[i] += Sm[k][i] * s.qd[k]; }
-    quat_mul_joint(Q, cs[k], sg * sn[k], T(AXIS_S) * sn[k]);
+    T a[3] = {sg * R[0] + T(AXIS_S) * R[2], sg * R[3] + T(AXIS_S) * R[5], sg * R[6] + T(AXIS_S) * R[8]};
+    T m[3];
+    cross3(r, a, m);
+    const T qd = scr(k, SC_QD);
+    T sn, cs;
+    zb_sincos(T(0.5) * scr(k, SC_Q), &sn, &cs);
+    ZB_UNROLL for (int i = 0; i < 3; ++i) {
+      scr(k, SC_SA + i) = a[i];
+      scr(k, SC_SM + i) = m[i];
+      w[i] += a[i] * qd;
+      vO[i] += m[i] * qd;
+    }
+    scr(k, SC_SN) = sn;
+    scr(k, SC_CS) = cs;
+    quat_mul_joint(Q, cs, sg * sn, T(AXIS_S) * sn);
   }
-  // ---- PD (implicit part lives in P.arm) ----
-  T tau[6];
-  ZB_UNROLL for (int k = 0; k < 6; ++k) {
-    T e = target[k] - s.q[k];
-    out.applied_torque[k] = zb_clamp(P.kp * e - P.kd * s.qd[k], -P.effort, P.effort);
-    tau[k] = zb_clamp(P.kp * (e - dt * s.qd[k]) - P.kd * s.qd[k], -P.effort, P.effort);
-  }
-  // ---- backward sweep: body k terms, then eliminate joint k ----
+  // ---- backward sweep over bodies 6..0: rigid + contact terms, then eliminate the joint above ----
   SpInertia<T> IA;
   ZB_UNROLL for (int i = 0; i < 6; ++i) { IA.I[i] = T(0); IA.M[i] = T(0); }
   ZB_UNROLL for (int i = 0; i < 9; ++i) IA.H[i] = T(0);
   T pAt[3] = {T(0), T(0), T(0)}, pAb[3] = {T(0), T(0), T(0)};
-  T Ut[6][3], Ub[6][3], Dinv[6], u[6];
-  ContactAgg<T> agg1;   // foot_1 (body 6)
+  ContactAgg<T> agg, agg1;   // running / foot_1 (body 6); after the sweep `agg` holds foot_0 (body 0)
   contact_agg_zero(agg1);
   T mid2 = T(0);
-  ZB_UNROLL for (int i = 0; i < 5; ++i) { out.mid_force[i][0] = out.mid_force[i][1] = out.mid_force[i][2] = T(0); }
-  ZB_UNROLL for (int k = 6; k >= 1; --k) {
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
+  for (int k = 6; k >= 0; --k) {
+    if (k == 0) {   // root: exact kinematics from the state (no unwinding round-off)
+      ZB_UNROLL for (int i = 0; i < 3; ++i) { r[i] = T(0); w[i] = s.w[i]; vO[i] = s.v[i]; }
+      ZB_UNROLL for (int i = 0; i < 4; ++i) Q[i] = s.Q[i];
+    }
     T R[9];
     quat_to_mat(Q, R);
-    if (k == 6) {
-      body_rigid_terms(P, T(FOOT1_MASS), T(FOOT1_COM_X), T(FOOT1_COM_Z), T(FOOT1_IXX), T(FOOT1_IYY),
-                       T(FOOT1_IZZ), T(FOOT1_IXZ), R, r, w, vO, IA, pAt, pAb);
-      ZB_UNROLL for (int j = 0; j < 4; ++j) {
-        const T lx = (j == 0) ? T(FOOT_R) : (j == 2) ? T(-FOOT_R) : T(0);
-        const T ly = (j == 1) ? T(FOOT_R) : (j == 3) ? T(-FOOT_R) : T(0);
-        T rho[3] = {r[0] + R[0] * lx + R[1] * ly + R[2] * T(FOOT1_SOLE_Z),
-                    r[1] + R[3] * lx + R[4] * ly + R[5] * T(FOOT1_SOLE_Z),
-                    r[2] + R[6] * lx + R[7] * ly + R[8] * T(FOOT1_SOLE_Z)};
-        contact_point(P, rho, s.p[2] + rho[2], w, vO, IA, pAt, pAb, &agg1, (T*)nullptr);
-      }
-    } else {
-      body_rigid_terms(P, T(MID_MASS), T(MID_COM_X), T(MID_COM_Z), T(MID_IXX), T(MID_IYY), T(MID_IZZ),
-                       T(MID_IXZ), R, r, w, vO, IA, pAt, pAb);
-      T rho[3] = {r[0] + R[2] * T(SPHERE_Z), r[1] + R[5] * T(SPHERE_Z), r[2] + R[8] * T(SPHERE_Z) - T(SPHERE_R)};
-      T f0[3];
-      if (contact_point(P, rho, s.p[2] + rho[2], w, vO, IA, pAt, pAb, (ContactAgg<T>*)nullptr, f0)) {
-        mid2 = zb_max(mid2, f0[0] * f0[0] + f0[1] * f0[1] + f0[2] * f0[2]);
-        out.mid_force[k - 1][0] = f0[0]; out.mid_force[k - 1][1] = f0[1]; out.mid_force[k - 1][2] = f0[2];
-      }
+    const bool foot1 = (k == 6), foot0 = (k == 0), foot = foot0 || foot1;
+    const T mass = foot ? T(FOOT0_MASS) : T(MID_MASS);
+    const T cx = foot0 ? T(FOOT0_COM_X) : foot1 ? T(FOOT1_COM_X) : T(MID_COM_X);
+    const T cz = foot0 ? T(FOOT0_COM_Z) : foot1 ? T(FOOT1_COM_Z) : T(MID_COM_Z);
+    const T ixx = foot0 ? T(FOOT0_IXX) : foot1 ? T(FOOT1_IXX) : T(MID_IXX);
+    const T iyy = foot0 ? T(FOOT0_IYY) : foot1 ? T(FOOT1_IYY) : T(MID_IYY);
+    const T izz = foot0 ? T(FOOT0_IZZ) : foot1 ? T(FOOT1_IZZ) : T(MID_IZZ);
+    const T ixz = foot0 ? T(FOOT0_IXZ) : foot1 ? T(FOOT1_IXZ) : T(MID_IXZ);
+    body_rigid_terms(P, mass, cx, cz, ixx, iyy, izz, ixz, R, r, w, vO, IA, pAt, pAb);
+    // contact candidates: 4 rim points of a foot sole, or the bottom of a merged body's sphere
+    contact_agg_zero(agg);
+    const int npts = foot ? 4 : 1;
+    const T lz = foot0 ? T(FOOT0_SOLE_Z) : foot1 ? T(FOOT1_SOLE_Z) : T(SPHERE_Z);
+    const T drop = foot ? T(0) : T(SPHERE_R);
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
+    for (int j = 0; j < npts; ++j) {
+      const T lx = !foot ? T(0) : (j == 0) ? T(FOOT_R) : (j == 2) ? T(-FOOT_R) : T(0);
+      const T ly = !foot ? T(0) : (j == 1) ? T(FOOT_R) : (j == 3) ? T(-FOOT_R) : T(0);
+      T rho[3] = {r[0] + R[0] * lx + R[1] * ly + R[2] * lz, r[1] + R[3] * lx + R[4] * ly + R[5] * lz,
+                  r[2] + R[6] * lx + R[7] * ly + R[8] * lz - drop};
+      contact_point(P, rho, s.p[2] + rho[2], w, vO, IA, pAt, pAb, &agg, (T*)nullptr);
     }
-    // joint k (index k-1): velocity-product term c = V x (S qd)
+    if (foot1) {
+      agg1 = agg;
+    } else if (!foot0) {
+      mid2 = zb_max(mid2, agg.F0[0] * agg.F0[0] + agg.F0[1] * agg.F0[1] + agg.F0[2] * agg.F0[2]);
+      if (mid_force_out) { mid_force_out[3 * (k - 1)] = agg.F0[0]; mid_force_out[3 * (k - 1) + 1] = agg.F0[1];
+                           mid_force_out[3 * (k - 1) + 2] = agg.F0[2]; }
+    }
+    if (k == 0) break;
+    // joint k (index j): velocity-product term c = V x (S qd), articulated-body elimination
     const int j = k - 1;
-    T sa[3] = {Sa[j][0] * s.qd[j], Sa[j][1] * s.qd[j], Sa[j][2] * s.qd[j]};
-    T sm[3] = {Sm[j][0] * s.qd[j], Sm[j][1] * s.qd[j], Sm[j][2] * s.qd[j]};
+    const T Sa[3] = {scr(j, SC_SA), scr(j, SC_SA + 1), scr(j, SC_SA + 2)};
+    const T Sm[3] = {scr(j, SC_SM), scr(j, SC_SM + 1), scr(j, SC_SM + 2)};
+    const T qd = scr(j, SC_QD);
+    T sa[3] = {Sa[0] * qd, Sa[1] * qd, Sa[2] * qd};
+    T sm[3] = {Sm[0] * qd, Sm[1] * qd, Sm[2] * qd};
     T ct[3], cb[3], tmp[3];
     cross3(w, sa, ct);
     cross3(w, sm, cb);
     cross3(vO, sa, tmp);
     cb[0] += tmp[0]; cb[1] += tmp[1]; cb[2] += tmp[2];
-    spi_mul(IA, Sa[j], Sm[j], Ut[j], Ub[j]);
-    T D = dot3(Sa[j], Ut[j]) + dot3(Sm[j], Ub[j]) + P.arm;
-    Dinv[j] = T(1) / D;
-    u[j] = tau[j] - (dot3(Sa[j], pAt) + dot3(Sm[j], pAb));
+    T Ut[3], Ub[3];
+    spi_mul(IA, Sa, Sm, Ut, Ub);
+    const T D = dot3(Sa, Ut) + dot3(Sm, Ub) + P.arm;
+    const T Dinv = T(1) / D;
+    const T u = scr(j, SC_U) - (dot3(Sa, pAt) + dot3(Sm, pAb));
     // pa = pA + IA c + U (u - U.c)/D   (== pA + Ia c + U u/D)
     T Ict[3], Icb[3];
     spi_mul(IA, ct, cb, Ict, Icb);
-    T g = (u[j] - (dot3(Ut[j], ct) + dot3(Ub[j], cb))) * Dinv[j];
+    const T g = (u - (dot3(Ut, ct) + dot3(Ub, cb))) * Dinv;
     ZB_UNROLL for (int i = 0; i < 3; ++i) {
-      pAt[i] += Ict[i] + Ut[j][i] * g;
-      pAb[i] += Icb[i] + Ub[j][i] * g;
+      pAt[i] += Ict[i] + Ut[i] * g;
+      pAb[i] += Icb[i] + Ub[i] * g;
+      scr(j, SC_UT + i) = Ut[i];
+      scr(j, SC_UB + i) = Ub[i];
     }
-    spi_rank1_sub(IA, Ut[j], Ub[j], Dinv[j]);
+    scr(j, SC_DINV) = Dinv;
+    scr(j, SC_U) = u;
+    spi_rank1_sub(IA, Ut, Ub, Dinv);
     // unwind kinematics to body k-1
     ZB_UNROLL for (int i = 0; i < 3; ++i) { w[i] -= sa[i]; vO[i] -= sm[i]; }
     const T sg = (j & 1) ? T(-AXIS_S) : T(AXIS_S);
-    quat_mul_joint(Q, cs[j], -sg * sn[j], -T(AXIS_S) * sn[j]);   // Q_{k-1} = Q_k (x) conj(qj)
+    const T sn = scr(j, SC_SN), cs = scr(j, SC_CS);
+    quat_mul_joint(Q, cs, -sg * sn, -T(AXIS_S) * sn);   // Q_{k-1} = Q_k (x) conj(qj)
     const T jz = (j == 0) ? T(JOINT_Z_FIRST) : T(JOINT_Z_REST);
     T Rp2[3] = {T(2) * (Q[1] * Q[3] + Q[0] * Q[2]), T(2) * (Q[2] * Q[3] - Q[0] * Q[1]),
                 T(1) - T(2) * (Q[1] * Q[1] + Q[2] * Q[2])};     // third column of R_{k-1}
     r[0] -= jz * Rp2[0]; r[1] -= jz * Rp2[1]; r[2] -= jz * Rp2[2];
-  }
-  // ---- root body (foot_0): exact kinematics from the state (no unwinding round-off) ----
-  ContactAgg<T> agg0;
-  contact_agg_zero(agg0);
-  {
-    T R[9];
-    quat_to_mat(s.Q, R);
-    const T zero3[3] = {T(0), T(0), T(0)};
-    body_rigid_terms(P, T(FOOT0_MASS), T(FOOT0_COM_X), T(FOOT0_COM_Z), T(FOOT0_IXX), T(FOOT0_IYY),
-                     T(FOOT0_IZZ), T(FOOT0_IXZ), R, zero3, s.w, s.v, IA, pAt, pAb);
-    ZB_UNROLL for (int j = 0; j < 4; ++j) {
-      const T lx = (j == 0) ? T(FOOT_R) : (j == 2) ? T(-FOOT_R) : T(0);
-      const T ly = (j == 1) ? T(FOOT_R) : (j == 3) ? T(-FOOT_R) : T(0);
-      T rho[3] = {R[0] * lx + R[1] * ly + R[2] * T(FOOT0_SOLE_Z), R[3] * lx + R[4] * ly + R[5] * T(FOOT0_SOLE_Z),
-                  R[6] * lx + R[7] * ly + R[8] * T(FOOT0_SOLE_Z)};
-      contact_point(P, rho, s.p[2] + rho[2], s.w, s.v, IA, pAt, pAb, &agg0, (T*)nullptr);
-    }
   }
   // ---- floating base:  IA a0 = -pA ----
   T At[3], Ab[3];
@@ -513,33 +576,42 @@ ZB_HD void physics_substep(const Params<T>& P, SimState<T>& s, const T* target, 
     T nt[3] = {-pAt[0], -pAt[1], -pAt[2]}, nb[3] = {-pAb[0], -pAb[1], -pAb[2]};
     spi_solve(IA, nt, nb, At, Ab);
   }
-  contact_agg_force(agg0, dt, At, Ab, out.foot_force[0]);
+  contact_agg_force(agg, dt, At, Ab, out.foot_force[0]);
   // classical acceleration of the root origin = spatial + w x v
   T wxv[3];
   cross3(s.w, s.v, wxv);
-  T w0[3] = {s.w[0], s.w[1], s.w[2]}, v0[3] = {s.v[0], s.v[1], s.v[2]};
+  T wk[3] = {s.w[0], s.w[1], s.w[2]}, vk[3] = {s.v[0], s.v[1], s.v[2]};  // V_{k-1} (pre-update velocities)
   ZB_UNROLL for (int i = 0; i < 3; ++i) {
     s.w[i] += dt * At[i];
     s.v[i] += dt * (Ab[i] + wxv[i]);
   }
   // ---- forward sweep: joint accelerations ----
-  T wk[3] = {w0[0], w0[1], w0[2]}, vk[3] = {v0[0], v0[1], v0[2]};  // V_{k-1} (pre-update velocities)
-  ZB_UNROLL for (int j = 0; j < 6; ++j) {
-    T sa[3] = {Sa[j][0] * s.qd[j], Sa[j][1] * s.qd[j], Sa[j][2] * s.qd[j]};
-    T sm[3] = {Sm[j][0] * s.qd[j], Sm[j][1] * s.qd[j], Sm[j][2] * s.qd[j]};
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
+  for (int j = 0; j < 6; ++j) {
+    const T Sa[3] = {scr(j, SC_SA), scr(j, SC_SA + 1), scr(j, SC_SA + 2)};
+    const T Sm[3] = {scr(j, SC_SM), scr(j, SC_SM + 1), scr(j, SC_SM + 2)};
+    const T Ut[3] = {scr(j, SC_UT), scr(j, SC_UT + 1), scr(j, SC_UT + 2)};
+    const T Ub[3] = {scr(j, SC_UB), scr(j, SC_UB + 1), scr(j, SC_UB + 2)};
+    T qd = scr(j, SC_QD);
+    T sa[3] = {Sa[0] * qd, Sa[1] * qd, Sa[2] * qd};
+    T sm[3] = {Sm[0] * qd, Sm[1] * qd, Sm[2] * qd};
     T ct[3], cb[3], tmp[3];
     cross3(wk, sa, ct);
     cross3(wk, sm, cb);
     cross3(vk, sa, tmp);
     cb[0] += tmp[0]; cb[1] += tmp[1]; cb[2] += tmp[2];
     ZB_UNROLL for (int i = 0; i < 3; ++i) { At[i] += ct[i]; Ab[i] += cb[i]; wk[i] += sa[i]; vk[i] += sm[i]; }
-    T qdd = (u[j] - (dot3(Ut[j], At) + dot3(Ub[j], Ab))) * Dinv[j];
-    ZB_UNROLL for (int i = 0; i < 3; ++i) { At[i] += Sa[j][i] * qdd; Ab[i] += Sm[j][i] * qdd; }
-    s.qd[j] += dt * qdd;
-    s.q[j] += dt * s.qd[j];
+    const T qdd = (scr(j, SC_U) - (dot3(Ut, At) + dot3(Ub, Ab))) * scr(j, SC_DINV);
+    ZB_UNROLL for (int i = 0; i < 3; ++i) { At[i] += Sa[i] * qdd; Ab[i] += Sm[i] * qdd; }
+    qd += dt * qdd;
+    scr(j, SC_QD) = qd;
+    scr(j, SC_Q) += dt * qd;
   }
   contact_agg_force(agg1, dt, At, Ab, out.foot_force[1]);
   out.mid_force2_max = mid2;
+  ZB_UNROLL for (int k = 0; k < 6; ++k) { s.q[k] = scr(k, SC_Q); s.qd[k] = scr(k, SC_QD); }
   // ---- root pose ----
   ZB_UNROLL for (int i = 0; i < 3; ++i) s.p[i] += dt * s.v[i];
   {
@@ -570,9 +642,12 @@ ZB_HD void link_kinematics(const SimState<T>& s, LinkKin<T>& o) {
   T r[3] = {T(0), T(0), T(0)};
   T w[3] = {s.w[0], s.w[1], s.w[2]};
   T vO[3] = {s.v[0], s.v[1], s.v[2]};
-  {
-    T R[9];
-    quat_to_mat(Q, R);
+  // park the joint state where a real (not unrolled) loop can index it
+  T qk[6], qdk[6];
+  ZB_UNROLL for (int k = 0; k < 6; ++k) { qk[k] = s.q[k]; qdk[k] = s.qd[k]; }
+  T R[9];
+  quat_to_mat(Q, R);
+  {  // body 0 = foot_0 (a-type link)
     T c[3] = {R[0] * T(A_COM_X) + R[2] * T(A_COM_Z), R[3] * T(A_COM_X) + R[5] * T(A_COM_Z),
               R[6] * T(A_COM_X) + R[8] * T(A_COM_Z)};
     T wxc[3];
@@ -580,39 +655,40 @@ ZB_HD void link_kinematics(const SimState<T>& s, LinkKin<T>& o) {
     ZB_UNROLL for (int i = 0; i < 3; ++i) { o.feet_pos[0][i] = s.p[i]; o.feet_com_vel[0][i] = vO[i] + wxc[i]; }
     ZB_UNROLL for (int i = 0; i < 4; ++i) o.feet_quat[0][i] = Q[i];
   }
-  ZB_UNROLL for (int k = 0; k < 6; ++k) {
-    T R[9];
-    quat_to_mat(Q, R);
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
+  for (int k = 0; k < 6; ++k) {
     const T jz = (k == 0) ? T(JOINT_Z_FIRST) : T(JOINT_Z_REST);
     const T sg = (k & 1) ? T(-AXIS_S) : T(AXIS_S);
     r[0] += jz * R[2]; r[1] += jz * R[5]; r[2] += jz * R[8];
     T a[3] = {sg * R[0] + T(AXIS_S) * R[2], sg * R[3] + T(AXIS_S) * R[5], sg * R[6] + T(AXIS_S) * R[8]};
     T m[3];
     cross3(r, a, m);
-    ZB_UNROLL for (int i = 0; i < 3; ++i) { w[i] += a[i] * s.qd[k]; vO[i] += m[i] * s.qd[k]; }
+    // select (not index) the joint state: keeps q/qd in registers
+    const T qv = (k == 0) ? qk[0] : (k == 1) ? qk[1] : (k == 2) ? qk[2] : (k == 3) ? qk[3] : (k == 4) ? qk[4] : qk[5];
+    const T qdv = (k == 0) ? qdk[0] : (k == 1) ? qdk[1] : (k == 2) ? qdk[2] : (k == 3) ? qdk[3] : (k == 4) ? qdk[4] : qdk[5];
+    ZB_UNROLL for (int i = 0; i < 3; ++i) { w[i] += a[i] * qdv; vO[i] += m[i] * qdv; }
     T sn, cs;
-    zb_sincos(T(0.5) * s.q[k], &sn, &cs);
+    zb_sincos(T(0.5) * qv, &sn, &cs);
     quat_mul_joint(Q, cs, sg * sn, T(AXIS_S) * sn);
-    if (k == 2) {  // body 3 = b3 + base; base LINK origin = body origin + R (0,0,LINK_OFFSET_Z)
-      T Rb[9];
-      quat_to_mat(Q, Rb);
-      T lo[3] = {r[0] + Rb[2] * T(LINK_OFFSET_Z), r[1] + Rb[5] * T(LINK_OFFSET_Z), r[2] + Rb[8] * T(LINK_OFFSET_Z)};
-      T c[3] = {lo[0] + Rb[0] * T(A_COM_X) + Rb[2] * T(A_COM_Z), lo[1] + Rb[3] * T(A_COM_X) + Rb[5] * T(A_COM_Z),
-                lo[2] + Rb[6] * T(A_COM_X) + Rb[8] * T(A_COM_Z)};
+    quat_to_mat(Q, R);
+    if (k == 2 || k == 5) {
+      // k == 2: body 3 = b3 + base; base LINK origin = body origin + R (0,0,LINK_OFFSET_Z), a-type CoM
+      // k == 5: body 6 = foot_1 (b-type link), link origin = body origin
+      const T oz = (k == 2) ? T(LINK_OFFSET_Z) : T(0);
+      const T cx = (k == 2) ? T(A_COM_X) : T(B_COM_X), cz = (k == 2) ? T(A_COM_Z) : T(B_COM_Z);
+      T lo[3] = {r[0] + R[2] * oz, r[1] + R[5] * oz, r[2] + R[8] * oz};
+      T c[3] = {lo[0] + R[0] * cx + R[2] * cz, lo[1] + R[3] * cx + R[5] * cz, lo[2] + R[6] * cx + R[8] * cz};
       T wxc[3];
       cross3(w, c, wxc);
-      ZB_UNROLL for (int i = 0; i < 3; ++i) { o.base_pos[i] = s.p[i] + lo[i]; o.base_com_vel[i] = vO[i] + wxc[i]; }
-      ZB_UNROLL for (int i = 0; i < 4; ++i) o.base_quat[i] = Q[i];
-    }
-    if (k == 5) {  // body 6 = foot_1 (b-type link)
-      T Rb[9];
-      quat_to_mat(Q, Rb);
-      T c[3] = {r[0] + Rb[0] * T(B_COM_X) + Rb[2] * T(B_COM_Z), r[1] + Rb[3] * T(B_COM_X) + Rb[5] * T(B_COM_Z),
-                r[2] + Rb[6] * T(B_COM_X) + Rb[8] * T(B_COM_Z)};
-      T wxc[3];
-      cross3(w, c, wxc);
-      ZB_UNROLL for (int i = 0; i < 3; ++i) { o.feet_pos[1][i] = s.p[i] + r[i]; o.feet_com_vel[1][i] = vO[i] + wxc[i]; }
-      ZB_UNROLL for (int i = 0; i < 4; ++i) o.feet_quat[1][i] = Q[i];
+      if (k == 2) {
+        ZB_UNROLL for (int i = 0; i < 3; ++i) { o.base_pos[i] = s.p[i] + lo[i]; o.base_com_vel[i] = vO[i] + wxc[i]; }
+        ZB_UNROLL for (int i = 0; i < 4; ++i) o.base_quat[i] = Q[i];
+      } else {
+        ZB_UNROLL for (int i = 0; i < 3; ++i) { o.feet_pos[1][i] = s.p[i] + lo[i]; o.feet_com_vel[1][i] = vO[i] + wxc[i]; }
+        ZB_UNROLL for (int i = 0; i < 4; ++i) o.feet_quat[1][i] = Q[i];
+      }
     }
   }
 }
@@ -923,10 +999,10 @@ ZB_HD void env_observe(const EnvState<T>& e, T* obs) {
   mdp_observation(k.base_quat, e.sim.q, e.sim.qd, e.mdp.actions, e.mdp.speed_limit, obs);
 }
 
-template <typename T>
+template <typename T, typename Scr>
 ZB_HD void env_step(const Params<T>& P, EnvState<T>& e, const T* raw_actions, int64_t& ep_len,
                     const T default_feet_pos[2][3], const T* default_base_quat, StepOut<T>& out,
-                    T* reset_ep_sums /*MAX_TERMS, valid when a reset happened*/, StepExport<T>* ex) {
+                    T* reset_ep_sums /*MAX_TERMS, valid when a reset happened*/, StepExport<T>* ex, Scr& scr) {
   // stale quantities = what _get_observations cached at the end of the previous step
   StaleCache<T> stale;
   {
@@ -950,7 +1026,8 @@ ZB_HD void env_step(const Params<T>& P, EnvState<T>& e, const T* raw_actions, in
   }
   SubstepOut<T> so;
   for (int sub = 0; sub < P.decimation; ++sub) {
-    physics_substep(P, e.sim, target, so);
+    T midf[15];
+    physics_substep(P, e.sim, target, so, scr, ex ? midf : (T*)nullptr);
     // ContactSensor.update
     const int slot = P.decimation - 1 - sub;  // newest first
     ZB_UNROLL for (int j = 0; j < 2; ++j) {
@@ -964,7 +1041,7 @@ ZB_HD void env_step(const Params<T>& P, EnvState<T>& e, const T* raw_actions, in
     if (slot < 4) mid2 = zb_max(mid2, so.mid_force2_max);
     if (ex && slot < 4) {
       ZB_UNROLL for (int b = 0; b < 5; ++b)
-        ZB_UNROLL for (int i = 0; i < 3; ++i) ex->mid_force_hist[slot][b][i] = so.mid_force[b][i];
+        ZB_UNROLL for (int i = 0; i < 3; ++i) ex->mid_force_hist[slot][b][i] = midf[3 * b + i];
     }
   }
   e.carry_feet_fz[0] = so.foot_force[0][2];

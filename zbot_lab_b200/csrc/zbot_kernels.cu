@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -110,7 +111,8 @@ __device__ __forceinline__ void stats_reduce(float (&vals)[kStatUsed], bool did_
     // mean over the reset envs of the episodic sum, divided by max_episode_length_s
     if (threadIdx.x < MAX_TERMS && nreset > 0.f) v = (v / nreset) * sc.inv_episode_s;
     // the reference only rewrites extras["log"] when something reset (…env_v2.py:450): keep the previous log
-    if (threadIdx.x < S_REW_SUM && !(nreset > 0.f))
+    // (word 16, the number of envs reset THIS step, is always the live count)
+    if (threadIdx.x < S_REW_SUM && threadIdx.x != S_NUM_RESET && !(nreset > 0.f))
       v = (sc.prev_slot >= 0) ? sc.ring[(size_t)sc.prev_slot * kStats + threadIdx.x] : 0.f;
     sc.ring[(size_t)sc.slot * kStats + threadIdx.x] = v;
   }
@@ -169,13 +171,13 @@ constexpr int kFoot0Sensor = 9, kFoot1Sensor = 10;
 // the fused control step
 // ---------------------------------------------------------------------------------------------
 template <bool kExport>
-__global__ void __launch_bounds__(128)
-zbot_step_kernel(const __grid_constant__ Params<float> P, const __grid_constant__ DefaultPose dp,
+__device__ __forceinline__ void
+zbot_step_body(const Params<float>& P, const DefaultPose& dp,
                  float4* __restrict__ state, int64_t* __restrict__ ep_len_buf,
                  const float* __restrict__ actions, float* __restrict__ obs, float* __restrict__ rew,
                  uint8_t* __restrict__ terminated, uint8_t* __restrict__ truncated, int n, StatsCtx sc,
                  ExportPtrs xp) {
-  extern __shared__ float smem[];   // max(blockDim*23, 32*kStatUsed) floats
+  extern __shared__ float smem[];   // blockDim*SCR_WORDS floats: substep scratch, then obs rows, then stats
   const int e0 = blockIdx.x * blockDim.x;
   const int e = e0 + threadIdx.x;
   const bool live = e < n;
@@ -202,9 +204,10 @@ zbot_step_kernel(const __grid_constant__ Params<float> P, const __grid_constant_
     float rs[MAX_TERMS];
 #pragma unroll
     for (int i = 0; i < MAX_TERMS; ++i) rs[i] = 0.f;
+    SmemScratch scr{smem + threadIdx.x, (int)blockDim.x};
     if (kExport) {
       StepExport<float> ex;
-      env_step(P, es, raw, ep, dp.feet_pos, dp.base_quat, out, rs, &ex);
+      env_step(P, es, raw, ep, dp.feet_pos, dp.base_quat, out, rs, &ex, scr);
       for (int i = 0; i < 36; ++i) { xp.pos0[(size_t)e * 36 + i] = ex.pos0[i]; xp.vel0[(size_t)e * 36 + i] = ex.vel0[i];
                                      xp.pos1[(size_t)e * 36 + i] = ex.pos1[i]; xp.vel1[(size_t)e * 36 + i] = ex.vel1[i]; }
       for (int i = 0; i < 48; ++i) { xp.quat0[(size_t)e * 48 + i] = ex.quat0[i]; xp.quat1[(size_t)e * 48 + i] = ex.quat1[i]; }
@@ -225,7 +228,7 @@ zbot_step_kernel(const __grid_constant__ Params<float> P, const __grid_constant_
       xp.cur_contact1[(size_t)e * 12 + kFoot0Sensor] = ex.cur_contact[0];
       xp.cur_contact1[(size_t)e * 12 + kFoot1Sensor] = ex.cur_contact[1];
     } else {
-      env_step(P, es, raw, ep, dp.feet_pos, dp.base_quat, out, rs, (StepExport<float>*)nullptr);
+      env_step(P, es, raw, ep, dp.feet_pos, dp.base_quat, out, rs, (StepExport<float>*)nullptr, scr);
     }
     env_state_pack(es, w);
     store_words<ZBOT_STATE_WORDS / 4>(state, n, e, w);
@@ -247,9 +250,30 @@ zbot_step_kernel(const __grid_constant__ Params<float> P, const __grid_constant_
     stat[S_NUM_TERM] = out.terminated ? 1.f : 0.f;
     stat[S_NUM_TRUNC] = out.time_out ? 1.f : 0.f;
   }
+  __syncthreads();   // every thread is done with its scratch column before the rows are staged
   store_rows_coalesced<ZBOT_NUM_OBS>(obs, obs_row, n, e0, smem);
   __syncthreads();
   stats_reduce(stat, did_reset, smem, sc);
+}
+
+#define ZB_STEP_ARGS                                                                                   \
+  const __grid_constant__ Params<float> P, const __grid_constant__ DefaultPose dp, float4 *__restrict__ state, \
+      int64_t *__restrict__ ep_len_buf, const float *__restrict__ actions, float *__restrict__ obs,      \
+      float *__restrict__ rew, uint8_t *__restrict__ terminated, uint8_t *__restrict__ truncated, int n, \
+      StatsCtx sc, ExportPtrs xp
+#define ZB_STEP_CALL P, dp, state, ep_len_buf, actions, obs, rew, terminated, truncated, n, sc, xp
+
+// register-budget variants of the same body (DESIGN.md §4 "occupancy"): kMinBlocks resident CTAs of
+// kMaxThreads threads per SM ...
+template <bool kExport, int kMaxThreads, int kMinBlocks>
+__global__ void __launch_bounds__(kMaxThreads, kMinBlocks) zbot_step_kernel(ZB_STEP_ARGS) {
+  zbot_step_body<kExport>(ZB_STEP_CALL);
+}
+// ... and an explicit per-thread register cap for one-warp CTAs (14 per SM at 144 registers:
+// 148 x 14 = 2072 resident warps >= the 2048 warps of 65536 envs -> a single wave, no tail)
+template <int kRegs>
+__global__ void __maxnreg__(kRegs) zbot_step_kernel_w1(ZB_STEP_ARGS) {
+  zbot_step_body<false>(ZB_STEP_CALL);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -518,12 +542,15 @@ struct ZbotHandle {
   int max_blocks;
   int64_t launches;
   float inv_episode_s;
+  int min_blocks;
+  int force_block;
 };
 
 namespace {
 
 int pick_block(const ZbotHandle* h, int n) {
   // fill the SMs first: the step is latency/issue bound, not bandwidth bound
+  if (h->force_block == 32 || h->force_block == 64 || h->force_block == 128) return h->force_block;
   int block = 128;
   while (block > 32 && (n + block - 1) / block < 2 * h->num_sms) block >>= 1;
   return block;
@@ -580,6 +607,17 @@ int zbot_create(const ZbotCfg* cfg, int device, ZbotHandle** out) {
   ZB_CUDA(cudaMemcpy(&h->dp, d_dp, sizeof(DefaultPose), cudaMemcpyDeviceToHost));
   ZB_CUDA(cudaFree(d_dp));
   ZB_CUDA(cudaFuncSetAttribute(zbot_mdp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * kHistRow * 4));
+  ZB_CUDA(cudaFuncSetAttribute(zbot_step_kernel<false, 128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_WORDS * 4));
+  ZB_CUDA(cudaFuncSetAttribute(zbot_step_kernel<false, 128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_WORDS * 4));
+  ZB_CUDA(cudaFuncSetAttribute(zbot_step_kernel<false, 128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_WORDS * 4));
+  ZB_CUDA(cudaFuncSetAttribute(zbot_step_kernel<true, 128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_WORDS * 4));
+  {
+    const char* mb = getenv("ZBOT_STEP_MIN_BLOCKS");   // tuning knob: resident 128-thread blocks per SM the
+    h->min_blocks = mb ? atoi(mb) : 2;                  // step kernel is compiled for (register budget)
+    if (h->min_blocks != 14 && (h->min_blocks < 2 || h->min_blocks > 4)) h->min_blocks = 2;
+    const char* bs = getenv("ZBOT_STEP_BLOCK");
+    h->force_block = bs ? atoi(bs) : 0;
+  }
   *out = h;
   return ZBOT_OK;
 }
@@ -611,9 +649,9 @@ static int step_impl(ZbotHandle* h, const float* actions, float* obs, float* rew
   if (((uintptr_t)actions & 7) != 0) return fail(ZBOT_E_INVALID, "actions must be 8-byte aligned%s");
   if (int rc = check_slot(slot, prev, h->ring_slots)) return rc;
   const int n = h->cfg.num_envs;
-  const int block = pick_block(h, n);
+  const int block = (h->min_blocks == 14) ? 32 : pick_block(h, n);
   const int grid = (n + block - 1) / block;
-  const size_t smem = (size_t)((block * ZBOT_NUM_OBS > 32 * kStatUsed) ? block * ZBOT_NUM_OBS : 32 * kStatUsed) * sizeof(float);
+  const size_t smem = (size_t)block * SCR_WORDS * sizeof(float);   // >= obs rows (23/thread) and stats (704 floats)
   StatsCtx sc{h->partials, h->ticket, h->ring, slot, prev, h->inv_episode_s};
   cudaStream_t s = (cudaStream_t)stream;
   ExportPtrs xp{};
@@ -624,11 +662,20 @@ static int step_impl(ZbotHandle* h, const float* actions, float* obs, float* rew
     const float* const* pp = reinterpret_cast<const float* const*>(&xp);
     for (int i = 0; i < 12; ++i)
       if (!pp[i]) return fail(ZBOT_E_INVALID, "zbot_step_export: NULL export buffer%s");
-    zbot_step_kernel<true><<<grid, block, smem, s>>>(h->P, h->dp, h->state, h->ep_len, actions, obs, rew, terminated,
-                                                      truncated, n, sc, xp);
+    zbot_step_kernel<true, 128, 2><<<grid, block, smem, s>>>(h->P, h->dp, h->state, h->ep_len, actions, obs, rew, terminated,
+                                                         truncated, n, sc, xp);
+  } else if (h->min_blocks == 2) {
+    zbot_step_kernel<false, 128, 2><<<grid, block, smem, s>>>(h->P, h->dp, h->state, h->ep_len, actions, obs, rew, terminated,
+                                                          truncated, n, sc, xp);
+  } else if (h->min_blocks == 3) {
+    zbot_step_kernel<false, 128, 3><<<grid, block, smem, s>>>(h->P, h->dp, h->state, h->ep_len, actions, obs, rew, terminated,
+                                                          truncated, n, sc, xp);
+  } else if (h->min_blocks == 4) {
+    zbot_step_kernel<false, 128, 4><<<grid, block, smem, s>>>(h->P, h->dp, h->state, h->ep_len, actions, obs, rew, terminated,
+                                                          truncated, n, sc, xp);
   } else {
-    zbot_step_kernel<false><<<grid, block, smem, s>>>(h->P, h->dp, h->state, h->ep_len, actions, obs, rew, terminated,
-                                                       truncated, n, sc, xp);
+    zbot_step_kernel_w1<144><<<grid, 32, smem, s>>>(h->P, h->dp, h->state, h->ep_len, actions, obs, rew, terminated,
+                                                    truncated, n, sc, xp);
   }
   ZB_CUDA(cudaGetLastError());
   h->launches += 1;
