@@ -12,7 +12,8 @@ from zbot_lab_b200.stepper import NativeStepper  # noqa: E402
 from zbot_lab_b200.utils import synthetic as syn  # noqa: E402
 
 
-def time_cfg(n, mb, block, steps=200, warm=30):
+def time_cfg(n, mb, block, steps=200, warm=30, two_pass=1):
+    os.environ["ZBOT_STATS_TWO_PASS"] = str(two_pass)
     os.environ["ZBOT_STEP_MIN_BLOCKS"] = str(mb)
     os.environ["ZBOT_STEP_BLOCK"] = str(block)
     st = NativeStepper(n, "cuda:0")
@@ -39,7 +40,8 @@ def time_cfg(n, mb, block, steps=200, warm=30):
 if __name__ == "__main__":
     sizes = [int(x) for x in sys.argv[1:]] or [4096, 65536]
     for n in sizes:
-        for mb, blocks in ((2, (64, 128)), (14, (32,))):
-            for block in blocks:
-                us = time_cfg(n, mb, block)
-                print(f"envs {n:6d} min_blocks {mb} block {block:3d}: {us:8.2f} us/step  {n / us:8.2f} M env-steps/s", flush=True)
+        for two_pass in (1,):
+            for mb, blocks in ((2, (64, 128)),):
+                for block in blocks:
+                    us = time_cfg(n, mb, block, two_pass=two_pass)
+                    print(f"envs {n:6d} two_pass {two_pass} min_blocks {mb} block {block:3d}: {us:8.2f} us/step  {n / us:8.2f} M env-steps/s", flush=True)

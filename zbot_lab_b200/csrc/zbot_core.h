@@ -67,6 +67,7 @@ struct Params {
   T step_dt;
   T termination_height, y_limit, term_penalty, contact_died_threshold;
   int max_episode_length;
+  int default_terms;   // 1: the table is exactly the 13 v2 terms in dict order (fast path)
   int num_terms;
   int term_id[MAX_TERMS];
   T term_w[MAX_TERMS];  // weight * step_dt, rounded the way the reference rounds it
@@ -804,6 +805,92 @@ ZB_HD void mdp_pre_physics(const Params<T>& P, const T* raw, MdpState<T>& m, T* 
   }
 }
 
+// One reward term (…env_v2.py:461-571).  `id` is a compile-time constant on the default-table fast
+// path (the switch folds away) and a runtime value on the generic path.
+template <typename T>
+ZB_HD T mdp_term_value(int id, const StaleCache<T>& c, const FreshInputs<T>& f, const T* new_actions,
+                       MdpState<T>& m, T heading_err, T y_err) {
+  T val = T(0);
+  switch (id) {
+    case TERM_BASE_VEL_FORWARD:                                                // :489-491
+      val = zb_tanh(T(10.0) * c.v_fwd / m.speed_limit);
+      break;
+    case TERM_FEET_DOWNWARD: {                                                 // :471-479
+      ZB_UNROLL for (int j = 0; j < 2; ++j) {
+        T dx = c.feet_z[j][0], dy = c.feet_z[j][1], dz = c.feet_z[j][2] - T(1);
+        val += zb_sqrt(dx * dx + dy * dy + dz * dz);
+      }
+    } break;
+    case TERM_FEET_FORWARD: {                                                  // :461-469
+      ZB_UNROLL for (int j = 0; j < 2; ++j) {
+        T dx = c.feet_x[j][0] - c.forward[0], dy = c.feet_x[j][1] - c.forward[1], dz = c.feet_x[j][2] - c.forward[2];
+        val += zb_sqrt(dx * dx + dy * dy + dz * dz);
+      }
+    } break;
+    case TERM_BASE_HEADING_X:                                                  // :481-482
+      val = zb_abs(heading_err);
+      break;
+    case TERM_BASE_HEADING_X_SUM:                                              // :484-487
+      m.heading_sum = zb_clamp(m.heading_sum + T(0.01) * heading_err, T(-1), T(1));
+      val = zb_abs(m.heading_sum);
+      break;
+    case TERM_STEP_LENGTH: {                                                   // :509-533
+      ZB_UNROLL for (int j = 0; j < 2; ++j) {
+        bool down = (f.feet_force[j] > T(10.0)) && (m.feet_force_last[j] < T(10.0));
+        if (down) {
+          T d[3] = {c.feet_pos[j][0] - m.feet_down_pos_last[j][0], c.feet_pos[j][1] - m.feet_down_pos_last[j][1],
+                    c.feet_pos[j][2] - m.feet_down_pos_last[j][2]};
+          m.feet_step_length[j] = d[0] * c.forward[0] + d[1] * c.forward[1] + d[2] * c.forward[2];
+          m.feet_down_pos_last[j][0] = c.feet_pos[j][0];
+          m.feet_down_pos_last[j][1] = c.feet_pos[j][1];
+          m.feet_down_pos_last[j][2] = c.feet_pos[j][2];
+        }
+        m.feet_force_last[j] = f.feet_force[j];
+      }
+      val = zb_tanh(T(15.0) * zb_min(m.feet_step_length[0], m.feet_step_length[1]));
+    } break;
+    case TERM_AIRTIME_BALANCE:                                                 // :535-539
+      val = zb_abs(f.last_air_time[0] - f.last_air_time[1]);
+      break;
+    case TERM_ACTION_RATE: {                                                   // :502-507
+      ZB_UNROLL for (int k = 0; k < 6; ++k) {
+        T d = new_actions[k] - m.actions[k];
+        val += d * d;
+      }
+    } break;
+    case TERM_TORQUES: {                                                       // :558-561
+      ZB_UNROLL for (int k = 0; k < 6; ++k) val += f.applied_torque[k] * f.applied_torque[k];
+    } break;
+    case TERM_FEET_SLIDE: {                                                    // :545-556
+      ZB_UNROLL for (int j = 0; j < 2; ++j) {
+        T sp = zb_sqrt(f.feet_vel_xy[j][0] * f.feet_vel_xy[j][0] + f.feet_vel_xy[j][1] * f.feet_vel_xy[j][1]);
+        val += (f.feet_force[j] > T(1.0)) ? sp : T(0);
+      }
+    } break;
+    case TERM_BASE_POS_Y_ERR:                                                  // :493-495
+      val = zb_abs(c.feet_pos[0][1] + c.feet_pos[1][1] - T(2.0) * f.origin_y) + zb_abs(c.base_pos[1] - f.origin_y);
+      break;
+    case TERM_BASE_POS_Y_ERR_SUM:                                              // :497-500
+      m.y_err_sum = zb_clamp(m.y_err_sum + T(0.01) * y_err, T(-1), T(1));
+      val = zb_abs(m.y_err_sum);
+      break;
+    case TERM_AIRTIME_SUM:                                                     // :541-543
+      val = zb_tanh(f.last_air_time[0] + f.last_air_time[1]);
+      break;
+    case TERM_FEET_FORCE_DIFF: {                                               // :563-565
+      T sgn = (m.feet_force_sum > T(0)) ? T(1) : (m.feet_force_sum < T(0)) ? T(-1) : T(0);
+      val = (f.feet_force[1] - f.feet_force[0]) * sgn;
+    } break;
+    case TERM_FEET_FORCE_SUM:                                                  // :567-571
+      m.feet_force_sum += T(0.001) * (f.feet_force[0] - f.feet_force[1]);
+      val = zb_abs(m.feet_force_sum);
+      break;
+    default:
+      break;
+  }
+  return val;
+}
+
 // …env_v2.py:384-411 + 371-382 + 461-571.  `new_actions` = this step's post-tanh actions,
 // m.actions = previous step's.  Returns the reward; updates the stateful terms and ep_sums.
 template <typename T>
@@ -818,88 +905,21 @@ ZB_HD T mdp_dones_rewards(const Params<T>& P, const StaleCache<T>& c, const Fres
   terminated = died;
   const T heading_err = -c.forward[1];                                           // :324
   T reward = T(0);
-  for (int i = 0; i < P.num_terms; ++i) {
-    T val = T(0);
-    switch (P.term_id[i]) {
-      case TERM_BASE_VEL_FORWARD:                                                // :489-491
-        val = zb_tanh(T(10.0) * c.v_fwd / m.speed_limit);
-        break;
-      case TERM_FEET_DOWNWARD: {                                                 // :471-479
-        ZB_UNROLL for (int j = 0; j < 2; ++j) {
-          T dx = c.feet_z[j][0], dy = c.feet_z[j][1], dz = c.feet_z[j][2] - T(1);
-          val += zb_sqrt(dx * dx + dy * dy + dz * dz);
-        }
-      } break;
-      case TERM_FEET_FORWARD: {                                                  // :461-469
-        ZB_UNROLL for (int j = 0; j < 2; ++j) {
-          T dx = c.feet_x[j][0] - c.forward[0], dy = c.feet_x[j][1] - c.forward[1], dz = c.feet_x[j][2] - c.forward[2];
-          val += zb_sqrt(dx * dx + dy * dy + dz * dz);
-        }
-      } break;
-      case TERM_BASE_HEADING_X:                                                  // :481-482
-        val = zb_abs(heading_err);
-        break;
-      case TERM_BASE_HEADING_X_SUM:                                              // :484-487
-        m.heading_sum = zb_clamp(m.heading_sum + T(0.01) * heading_err, T(-1), T(1));
-        val = zb_abs(m.heading_sum);
-        break;
-      case TERM_STEP_LENGTH: {                                                   // :509-533
-        ZB_UNROLL for (int j = 0; j < 2; ++j) {
-          bool down = (f.feet_force[j] > T(10.0)) && (m.feet_force_last[j] < T(10.0));
-          if (down) {
-            T d[3] = {c.feet_pos[j][0] - m.feet_down_pos_last[j][0], c.feet_pos[j][1] - m.feet_down_pos_last[j][1],
-                      c.feet_pos[j][2] - m.feet_down_pos_last[j][2]};
-            m.feet_step_length[j] = d[0] * c.forward[0] + d[1] * c.forward[1] + d[2] * c.forward[2];
-            m.feet_down_pos_last[j][0] = c.feet_pos[j][0];
-            m.feet_down_pos_last[j][1] = c.feet_pos[j][1];
-            m.feet_down_pos_last[j][2] = c.feet_pos[j][2];
-          }
-          m.feet_force_last[j] = f.feet_force[j];
-        }
-        val = zb_tanh(T(15.0) * zb_min(m.feet_step_length[0], m.feet_step_length[1]));
-      } break;
-      case TERM_AIRTIME_BALANCE:                                                 // :535-539
-        val = zb_abs(f.last_air_time[0] - f.last_air_time[1]);
-        break;
-      case TERM_ACTION_RATE: {                                                   // :502-507
-        ZB_UNROLL for (int k = 0; k < 6; ++k) {
-          T d = new_actions[k] - m.actions[k];
-          val += d * d;
-        }
-      } break;
-      case TERM_TORQUES: {                                                       // :558-561
-        ZB_UNROLL for (int k = 0; k < 6; ++k) val += f.applied_torque[k] * f.applied_torque[k];
-      } break;
-      case TERM_FEET_SLIDE: {                                                    // :545-556
-        ZB_UNROLL for (int j = 0; j < 2; ++j) {
-          T sp = zb_sqrt(f.feet_vel_xy[j][0] * f.feet_vel_xy[j][0] + f.feet_vel_xy[j][1] * f.feet_vel_xy[j][1]);
-          val += (f.feet_force[j] > T(1.0)) ? sp : T(0);
-        }
-      } break;
-      case TERM_BASE_POS_Y_ERR:                                                  // :493-495
-        val = zb_abs(c.feet_pos[0][1] + c.feet_pos[1][1] - T(2.0) * f.origin_y) + zb_abs(c.base_pos[1] - f.origin_y);
-        break;
-      case TERM_BASE_POS_Y_ERR_SUM:                                              // :497-500
-        m.y_err_sum = zb_clamp(m.y_err_sum + T(0.01) * y_err, T(-1), T(1));
-        val = zb_abs(m.y_err_sum);
-        break;
-      case TERM_AIRTIME_SUM:                                                     // :541-543
-        val = zb_tanh(f.last_air_time[0] + f.last_air_time[1]);
-        break;
-      case TERM_FEET_FORCE_DIFF: {                                               // :563-565
-        T sgn = (m.feet_force_sum > T(0)) ? T(1) : (m.feet_force_sum < T(0)) ? T(-1) : T(0);
-        val = (f.feet_force[1] - f.feet_force[0]) * sgn;
-      } break;
-      case TERM_FEET_FORCE_SUM:                                                  // :567-571
-        m.feet_force_sum += T(0.001) * (f.feet_force[0] - f.feet_force[1]);
-        val = zb_abs(m.feet_force_sum);
-        break;
-      default:
-        break;
+  if (P.default_terms) {
+    // the v2 table (…env_v2.py:190-206) in dict order: static indices, everything stays in registers
+    ZB_UNROLL for (int i = 0; i < 13; ++i) {
+      const T rew = mdp_term_value(i, c, f, new_actions, m, heading_err, y_err) * P.term_w[i];   // :375
+      reward += rew;                                                             // :376
+      m.ep_sums[i] += rew;                                                       // :377
     }
-    const T rew = val * P.term_w[i];                                             // :375
-    reward += rew;                                                               // :376
-    m.ep_sums[i] += rew;                                                         // :377
+  } else {
+    // any subset / order / weights of the 15 known terms (cfg-driven)
+    for (int i = 0; i < P.num_terms; ++i) {
+      const T rew = mdp_term_value(P.term_id[i], c, f, new_actions, m, heading_err, y_err) * P.term_w[i];
+      reward += rew;
+      // select, do not index: a dynamically indexed ep_sums[] would push the array to local memory
+      ZB_UNROLL for (int k = 0; k < MAX_TERMS; ++k) m.ep_sums[k] += (k == i) ? rew : T(0);
+    }
   }
   if (terminated) reward -= P.term_penalty;                                      // :379-380
   return reward;
@@ -915,7 +935,8 @@ ZB_HD void mdp_reset(MdpState<T>& m, const T feet_pos[2][3], int num_terms) {
   m.feet_force_sum = T(0);
   m.heading_sum = T(0);
   m.y_err_sum = T(0);
-  for (int i = 0; i < num_terms; ++i) m.ep_sums[i] = T(0);
+  (void)num_terms;
+  ZB_UNROLL for (int i = 0; i < MAX_TERMS; ++i) m.ep_sums[i] = T(0);   // slots >= num_terms are always 0
   // NOT reset in v2 (SURVEY C-5): feet_force_last, feet_step_length
 }
 
@@ -1025,6 +1046,9 @@ ZB_HD void env_step(const Params<T>& P, EnvState<T>& e, const T* raw_actions, in
       ex->feet_force_hist[4][j][2] = e.carry_feet_fz[j]; }
   }
   SubstepOut<T> so;
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
   for (int sub = 0; sub < P.decimation; ++sub) {
     T midf[15];
     physics_substep(P, e.sim, target, so, scr, ex ? midf : (T*)nullptr);
@@ -1034,7 +1058,7 @@ ZB_HD void env_step(const Params<T>& P, EnvState<T>& e, const T* raw_actions, in
       const T* ff = so.foot_force[j];
       const T nrm = zb_sqrt(ff[0] * ff[0] + ff[1] * ff[1] + ff[2] * ff[2]);
       contact_timers_update(e.timers[j], nrm > T(1.0), P.dt);
-      if (slot < 4) fz[slot][j] = ff[2];
+      ZB_UNROLL for (int k = 0; k < 4; ++k) fz[k][j] = (slot == k) ? ff[2] : fz[k][j];   // select, not index
       if (ex && slot < 4) { ex->feet_force_hist[slot][j][0] = ff[0]; ex->feet_force_hist[slot][j][1] = ff[1];
         ex->feet_force_hist[slot][j][2] = ff[2]; }
     }
@@ -1072,7 +1096,7 @@ ZB_HD void env_step(const Params<T>& P, EnvState<T>& e, const T* raw_actions, in
   out.time_out = time_out;
   ZB_UNROLL for (int k = 0; k < 6; ++k) e.mdp.actions[k] = new_actions[k];   // :313 (next obs pass)
   if (terminated || time_out) {
-    for (int i = 0; i < P.num_terms; ++i) reset_ep_sums[i] = e.mdp.ep_sums[i];
+    ZB_UNROLL for (int i = 0; i < MAX_TERMS; ++i) reset_ep_sums[i] = e.mdp.ep_sums[i];
     const T speed = e.mdp.speed_limit;
     env_reset(P, e, default_feet_pos);
     ep_len = 0;

@@ -10,8 +10,8 @@
 //   * the [N][23] observation rows (AoS, as the policy consumes them) are staged through
 //     shared memory and written back as contiguous float4 per block;
 //   * per-step reset statistics (`extras["log"]`) are reduced with warp shuffles -> shared
-//     memory -> one partial row per block -> fixed-order final pass by the last block
-//     (deterministic, no float atomics, no host sync).
+//     memory -> one partial row per block; a one-block finalize kernel sums the rows in a fixed
+//     order (deterministic, no float atomics, no host sync).
 // No tensor cores: nothing here is a dense contraction.
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -53,7 +53,6 @@ constexpr int S_NUM_RESET = 16, S_NUM_TERM_RESET = 17, S_NUM_TO_RESET = 18, S_RE
 
 struct StatsCtx {
   float* partials;        // [max_blocks][32]
-  unsigned int* ticket;   // last-block-done counter
   float* ring;            // [slots][32]
   int slot, prev_slot;
   float inv_episode_s;    // 1 / max_episode_length_s  (…env_v2.py:444-447)
@@ -68,9 +67,48 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// `vals[0..18]` are non-zero only for threads that reset this step; 19..21 for every thread.
-__device__ __forceinline__ void stats_reduce(float (&vals)[kStatUsed], bool did_reset, float* smem /*[32][kStatUsed]*/,
-                                             const StatsCtx& sc) {
+// Grid-level pass of the statistics: ONE block of 1024 threads.  Warp w sums the partial rows
+// b = w, w+32, ... (a row is 128 contiguous bytes: one coalesced load per warp) with four independent
+// accumulators so four L2 loads are in flight per thread; everything is combined in a fixed order, so the
+// result is bit-reproducible (no float atomics).
+__global__ void __launch_bounds__(1024) zbot_stats_finalize_kernel(StatsCtx sc, unsigned int nblocks) {
+  __shared__ float red[32][33];
+  const int j = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  const float* p = sc.partials + j;
+  unsigned int b = w;
+  for (; b + 96 < nblocks; b += 128) {
+    const float v0 = __ldcg(p + (size_t)b * kStats), v1 = __ldcg(p + (size_t)(b + 32) * kStats),
+                v2 = __ldcg(p + (size_t)(b + 64) * kStats), v3 = __ldcg(p + (size_t)(b + 96) * kStats);
+    a0 += v0; a1 += v1; a2 += v2; a3 += v3;
+  }
+  for (; b < nblocks; b += 32) a0 += __ldcg(p + (size_t)b * kStats);
+  red[w][j] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if (threadIdx.x < kStats) {
+    float acc = 0.f;
+#pragma unroll
+    for (int g = 0; g < 32; ++g) acc += red[g][threadIdx.x];
+    red[0][threadIdx.x] = (threadIdx.x < kStatUsed) ? acc : 0.f;
+  }
+  __syncthreads();
+  if (threadIdx.x < kStats) {
+    const float nreset = red[0][S_NUM_RESET];
+    float v = red[0][threadIdx.x];
+    // words 0..15 leave the kernel as the reference's `Episode_Reward/<term>` values:
+    // mean over the reset envs of the episodic sum, divided by max_episode_length_s
+    if (threadIdx.x < MAX_TERMS && nreset > 0.f) v = (v / nreset) * sc.inv_episode_s;
+    // the reference only rewrites extras["log"] when something reset (…env_v2.py:450): keep the previous log
+    // (word 16, the number of envs reset THIS step, is always the live count)
+    if (threadIdx.x < S_REW_SUM && threadIdx.x != S_NUM_RESET && !(nreset > 0.f))
+      v = (sc.prev_slot >= 0) ? sc.ring[(size_t)sc.prev_slot * kStats + threadIdx.x] : 0.f;
+    sc.ring[(size_t)sc.slot * kStats + threadIdx.x] = v;
+  }
+}
+
+// warp shuffles -> shared memory -> this block's partial row.  `vals[0..18]` are non-zero only for
+// threads that reset this step; 19..21 for every thread.
+__device__ __forceinline__ void stats_block_partial(float (&vals)[kStatUsed], bool did_reset, float* smem, const StatsCtx& sc) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
   const bool any_reset = __any_sync(0xffffffffu, did_reset);
 #pragma unroll
@@ -85,38 +123,6 @@ __device__ __forceinline__ void stats_reduce(float (&vals)[kStatUsed], bool did_
     for (int w = 0; w < nwarps; ++w) acc += smem[w * kStatUsed + threadIdx.x];
     sc.partials[(size_t)blockIdx.x * kStats + threadIdx.x] = acc;
   }
-  __shared__ bool is_last;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned int t = atomicAdd(sc.ticket, 1u);
-    is_last = (t == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (!is_last) return;
-  __threadfence();
-  if (threadIdx.x < kStats) {
-    float acc = 0.f;
-    if (threadIdx.x < kStatUsed) {
-      const volatile float* p = sc.partials + threadIdx.x;
-      for (unsigned int b = 0; b < gridDim.x; ++b) acc += p[(size_t)b * kStats];
-    }
-    smem[threadIdx.x] = acc;
-  }
-  __syncthreads();
-  if (threadIdx.x < kStats) {
-    const float nreset = smem[S_NUM_RESET];
-    float v = smem[threadIdx.x];
-    // words 0..15 leave the kernel as the reference's `Episode_Reward/<term>` values:
-    // mean over the reset envs of the episodic sum, divided by max_episode_length_s
-    if (threadIdx.x < MAX_TERMS && nreset > 0.f) v = (v / nreset) * sc.inv_episode_s;
-    // the reference only rewrites extras["log"] when something reset (…env_v2.py:450): keep the previous log
-    // (word 16, the number of envs reset THIS step, is always the live count)
-    if (threadIdx.x < S_REW_SUM && threadIdx.x != S_NUM_RESET && !(nreset > 0.f))
-      v = (sc.prev_slot >= 0) ? sc.ring[(size_t)sc.prev_slot * kStats + threadIdx.x] : 0.f;
-    sc.ring[(size_t)sc.slot * kStats + threadIdx.x] = v;
-  }
-  if (threadIdx.x == 0) *sc.ticket = 0u;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -253,7 +259,7 @@ zbot_step_body(const Params<float>& P, const DefaultPose& dp,
   __syncthreads();   // every thread is done with its scratch column before the rows are staged
   store_rows_coalesced<ZBOT_NUM_OBS>(obs, obs_row, n, e0, smem);
   __syncthreads();
-  stats_reduce(stat, did_reset, smem, sc);
+  stats_block_partial(stat, did_reset, smem, sc);
 }
 
 #define ZB_STEP_ARGS                                                                                   \
@@ -309,7 +315,7 @@ __global__ void zbot_reset_kernel(const __grid_constant__ Params<float> P, const
       did = true;
     }
   }
-  stats_reduce(stat, did, smem, sc);
+  stats_block_partial(stat, did, smem, sc);
 }
 
 __global__ void zbot_observe_kernel(const float4* __restrict__ state, float* __restrict__ obs, int n) {
@@ -387,6 +393,35 @@ __device__ __forceinline__ void mdp_load_links(const MdpIn& in, int e, float* ba
   }
 }
 
+// ---- 1-D bulk async copy (TMA) global -> shared, completion on an mbarrier ----------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+
+constexpr int kMdpTile = 64;   // envs (= threads) per CTA of the MDP step kernel: 45 KB history tile, 4 CTAs / SM
+                               // (32-env one-warp tiles measured 2x slower, 128-env tiles equal: profiles/r1_notes.md)
+
 // kStep = false: `_get_observations` only (fills the stale cache)
 template <bool kStep>
 __global__ void __launch_bounds__(128)
@@ -394,7 +429,7 @@ zbot_mdp_kernel(const __grid_constant__ Params<float> P, const __grid_constant__
                 float4* __restrict__ mstate, int64_t* __restrict__ ep_len_buf, const float* __restrict__ actions,
                 float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ terminated,
                 uint8_t* __restrict__ truncated, int n, StatsCtx sc) {
-  extern __shared__ float smem[];   // [blockDim][180] history tile, reused for obs rows / stats
+  extern __shared__ __align__(128) float smem[];   // [blockDim][180] history tile, reused for obs rows / stats
   const int e0 = blockIdx.x * blockDim.x;
   const int e = e0 + threadIdx.x;
   const bool live = e < n;
@@ -408,42 +443,18 @@ zbot_mdp_kernel(const __grid_constant__ Params<float> P, const __grid_constant__
   bool did_reset = false;
 
   FreshInputs<float> f;
+  __shared__ uint64_t tile_bar;
   if (kStep) {
-    // cooperative, coalesced copy of the block's contiguous history tile into shared memory
-    const float4* src = reinterpret_cast<const float4*>(in.hist + (size_t)e0 * kHistRow);
-    float4* dst = reinterpret_cast<float4*>(smem);
-    const int nv = valid * (kHistRow / 4);
-    for (int i = threadIdx.x; i < nv; i += blockDim.x) dst[i] = __ldg(src + i);
+    // the block's history tile is one contiguous span of valid*720 bytes: a single 1-D bulk async copy
+    // (TMA) brings it to shared memory while the threads issue their own global loads below
+    if (threadIdx.x == 0) mbar_init(&tile_bar, 1);
     __syncthreads();
-    if (live) {
-      // per-thread pass over its own 45 float4 (conflict-free: row stride 45 float4 is odd)
-      const float4* row4 = reinterpret_cast<const float4*>(smem) + threadIdx.x * (kHistRow / 4);
-      float h[kHistRow];
-#pragma unroll
-      for (int i = 0; i < kHistRow / 4; ++i) {
-        const float4 v = row4[i];
-        h[4 * i] = v.x; h[4 * i + 1] = v.y; h[4 * i + 2] = v.z; h[4 * i + 3] = v.w;
-      }
-      float fz0 = 0.f, fz1 = 0.f, mx2 = 0.f;
-#pragma unroll
-      for (int t = 0; t < ZBOT_HISTORY; ++t) {
-        const float a = h[(t * 12 + kFoot0Sensor) * 3 + 2], b = h[(t * 12 + kFoot1Sensor) * 3 + 2];
-        fz0 = (t == 0) ? a : (fz0 + a);                      // (((h0+h1)+h2)+h3)+h4, newest first
-        fz1 = (t == 0) ? b : (fz1 + b);
-#pragma unroll
-        for (int b12 = 0; b12 < 12; ++b12) {
-          if (b12 == kFoot0Sensor || b12 == kFoot1Sensor) continue;
-          const float x = h[(t * 12 + b12) * 3], y = h[(t * 12 + b12) * 3 + 1], z = h[(t * 12 + b12) * 3 + 2];
-          mx2 = fmaxf(mx2, __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
-        }
-      }
-      f.feet_force[0] = fz0 / 5.0f;                            // torch.mean = sum / count (:387-390)
-      f.feet_force[1] = fz1 / 5.0f;
-      f.undesired_force_max = sqrtf(mx2);                      // max_t |F| > 1.0  (:396-402)
+    if (threadIdx.x == 0) {
+      const uint32_t bytes = (uint32_t)valid * kHistRow * sizeof(float);
+      mbar_expect_tx(&tile_bar, bytes);
+      bulk_g2s(smem, in.hist + (size_t)e0 * kHistRow, bytes, &tile_bar);
     }
-    __syncthreads();   // the tile is dead; smem is reused below
   }
-
   if (live) {
     float w[ZBOT_MDP_STATE_WORDS];
     load_words<ZBOT_MDP_STATE_WORDS / 4>(mstate, n, e, w);
@@ -462,12 +473,40 @@ zbot_mdp_kernel(const __grid_constant__ Params<float> P, const __grid_constant__
       float raw[6], new_actions[6], target[6];
 #pragma unroll
       for (int k = 0; k < 6; ++k) raw[k] = __ldg(actions + (size_t)e * 6 + k);
-      mdp_pre_physics(P, raw, m, new_actions, target);
-      int64_t ep = ep_len_buf[e] + 1;
 #pragma unroll
       for (int k = 0; k < 6; ++k) f.applied_torque[k] = __ldg(in.tau + (size_t)e * 6 + k);
       f.last_air_time[0] = __ldg(in.last_air + (size_t)e * 12 + kFoot0Sensor);
       f.last_air_time[1] = __ldg(in.last_air + (size_t)e * 12 + kFoot1Sensor);
+      int64_t ep = ep_len_buf[e] + 1;
+      // ---- all global loads are in flight; now consume the history tile the TMA delivered ----
+      mbar_wait(&tile_bar, 0);
+      {
+        // per-thread pass over its own 45 float4 (conflict-free: row stride 45 float4 is odd)
+        const float4* row4 = reinterpret_cast<const float4*>(smem) + threadIdx.x * (kHistRow / 4);
+        float fz0 = 0.f, fz1 = 0.f, mx2 = 0.f;
+#pragma unroll
+        for (int t = 0; t < ZBOT_HISTORY; ++t) {
+          float h[36];
+#pragma unroll
+          for (int i = 0; i < 9; ++i) {
+            const float4 v = row4[t * 9 + i];
+            h[4 * i] = v.x; h[4 * i + 1] = v.y; h[4 * i + 2] = v.z; h[4 * i + 3] = v.w;
+          }
+          const float a = h[kFoot0Sensor * 3 + 2], b = h[kFoot1Sensor * 3 + 2];
+          fz0 = (t == 0) ? a : (fz0 + a);                      // (((h0+h1)+h2)+h3)+h4, newest first
+          fz1 = (t == 0) ? b : (fz1 + b);
+#pragma unroll
+          for (int b12 = 0; b12 < 12; ++b12) {
+            if (b12 == kFoot0Sensor || b12 == kFoot1Sensor) continue;
+            const float x = h[b12 * 3], y = h[b12 * 3 + 1], z = h[b12 * 3 + 2];
+            mx2 = fmaxf(mx2, __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
+          }
+        }
+        f.feet_force[0] = fz0 / 5.0f;                            // torch.mean = sum / count (:387-390)
+        f.feet_force[1] = fz1 / 5.0f;
+        f.undesired_force_max = sqrtf(mx2);                      // max_t |F| > 1.0  (:396-402)
+      }
+      mdp_pre_physics(P, raw, m, new_actions, target);
 #pragma unroll
       for (int j = 0; j < 2; ++j) { f.feet_vel_xy[j][0] = feet_vel[j][0]; f.feet_vel_xy[j][1] = feet_vel[j][1]; }
       f.origin_y = oy;
@@ -511,10 +550,11 @@ zbot_mdp_kernel(const __grid_constant__ Params<float> P, const __grid_constant__
     stale_pack(stale, w);
     store_words<ZBOT_MDP_STATE_WORDS / 4>(mstate, n, e, w);
   }
+  if (kStep) __syncthreads();   // every thread has consumed its history row: the tile is dead, smem is reused
   store_rows_coalesced<ZBOT_NUM_OBS>(obs, obs_row, n, e0, smem);
   if (kStep) {
     __syncthreads();
-    stats_reduce(stat, did_reset, smem, sc);
+    stats_block_partial(stat, did_reset, smem, sc);
   }
 }
 
@@ -538,12 +578,12 @@ struct ZbotHandle {
   float* m_ring;
   int m_ring_slots;
   float* partials;
-  unsigned int* ticket;
   int max_blocks;
   int64_t launches;
   float inv_episode_s;
   int min_blocks;
   int force_block;
+  int mdp_tile;
 };
 
 namespace {
@@ -598,8 +638,6 @@ int zbot_create(const ZbotCfg* cfg, int device, ZbotHandle** out) {
   h->num_sms = prop.multiProcessorCount;
   h->max_blocks = (cfg->num_envs + 31) / 32 + 1;
   ZB_CUDA(cudaMalloc(&h->partials, (size_t)h->max_blocks * kStats * sizeof(float)));
-  ZB_CUDA(cudaMalloc(&h->ticket, sizeof(unsigned int)));
-  ZB_CUDA(cudaMemset(h->ticket, 0, sizeof(unsigned int)));
   DefaultPose* d_dp = nullptr;
   ZB_CUDA(cudaMalloc(&d_dp, sizeof(DefaultPose)));
   zbot_default_pose_kernel<<<1, 1>>>(d_dp);
@@ -615,6 +653,9 @@ int zbot_create(const ZbotCfg* cfg, int device, ZbotHandle** out) {
     const char* mb = getenv("ZBOT_STEP_MIN_BLOCKS");   // tuning knob: resident 128-thread blocks per SM the
     h->min_blocks = mb ? atoi(mb) : 2;                  // step kernel is compiled for (register budget)
     if (h->min_blocks != 14 && (h->min_blocks < 2 || h->min_blocks > 4)) h->min_blocks = 2;
+    const char* mt = getenv("ZBOT_MDP_TILE");          // envs (= threads) per CTA of the MDP-only step kernel
+    h->mdp_tile = mt ? atoi(mt) : kMdpTile;
+    if (h->mdp_tile != 32 && h->mdp_tile != 64 && h->mdp_tile != 128) h->mdp_tile = kMdpTile;
     const char* bs = getenv("ZBOT_STEP_BLOCK");
     h->force_block = bs ? atoi(bs) : 0;
   }
@@ -626,7 +667,6 @@ int zbot_destroy(ZbotHandle* h) {
   if (!h) return ZBOT_OK;
   cudaSetDevice(h->device);
   cudaFree(h->partials);
-  cudaFree(h->ticket);
   delete h;
   return ZBOT_OK;
 }
@@ -652,7 +692,7 @@ static int step_impl(ZbotHandle* h, const float* actions, float* obs, float* rew
   const int block = (h->min_blocks == 14) ? 32 : pick_block(h, n);
   const int grid = (n + block - 1) / block;
   const size_t smem = (size_t)block * SCR_WORDS * sizeof(float);   // >= obs rows (23/thread) and stats (704 floats)
-  StatsCtx sc{h->partials, h->ticket, h->ring, slot, prev, h->inv_episode_s};
+  StatsCtx sc{h->partials, h->ring, slot, prev, h->inv_episode_s};
   cudaStream_t s = (cudaStream_t)stream;
   ExportPtrs xp{};
   if (ex) {
@@ -677,6 +717,9 @@ static int step_impl(ZbotHandle* h, const float* actions, float* obs, float* rew
     zbot_step_kernel_w1<144><<<grid, 32, smem, s>>>(h->P, h->dp, h->state, h->ep_len, actions, obs, rew, terminated,
                                                     truncated, n, sc, xp);
   }
+  ZB_CUDA(cudaGetLastError());
+  h->launches += 1;
+  zbot_stats_finalize_kernel<<<1, 1024, 0, s>>>(sc, (unsigned int)grid);
   ZB_CUDA(cudaGetLastError());
   h->launches += 1;
   return ZBOT_OK;
@@ -704,9 +747,12 @@ int zbot_reset_idx(ZbotHandle* h, const int64_t* env_ids, int64_t nids, const ui
   if (nids > n) return fail(ZBOT_E_INVALID, "more env ids than envs%s");
   const int block = 64;
   const int grid = (int)((nids + block - 1) / block);
-  StatsCtx sc{h->partials, h->ticket, h->ring, stats_slot, -1, h->inv_episode_s};
+  StatsCtx sc{h->partials, h->ring, stats_slot, -1, h->inv_episode_s};
   zbot_reset_kernel<<<grid, block, 32 * kStatUsed * sizeof(float), (cudaStream_t)stream>>>(
       h->P, h->dp, h->state, h->ep_len, env_ids, nids, terminated, truncated, n, sc);
+  ZB_CUDA(cudaGetLastError());
+  h->launches += 1;
+  zbot_stats_finalize_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(sc, (unsigned int)grid);
   ZB_CUDA(cudaGetLastError());
   h->launches += 1;
   return ZBOT_OK;
@@ -761,7 +807,7 @@ int zbot_mdp_observe(ZbotHandle* h, const ZbotMdpInputs* in, float* obs, void* s
   const int n = h->cfg.num_envs, block = 128, grid = (n + block - 1) / block;
   MdpIn mi{in->body_link_pos_w, in->body_link_quat_w, in->body_com_lin_vel_w, in->joint_pos, in->joint_vel,
            in->applied_torque, in->net_forces_w_history, in->last_air_time, in->env_origins};
-  StatsCtx sc{h->partials, h->ticket, h->m_ring, 0, -1, h->inv_episode_s};
+  StatsCtx sc{h->partials, h->m_ring, 0, -1, h->inv_episode_s};
   zbot_mdp_kernel<false><<<grid, block, block * ZBOT_NUM_OBS * sizeof(float), (cudaStream_t)stream>>>(
       h->P, h->dp, mi, h->mstate, h->m_ep_len, nullptr, obs, nullptr, nullptr, nullptr, n, sc);
   ZB_CUDA(cudaGetLastError());
@@ -774,12 +820,15 @@ int zbot_mdp_step(ZbotHandle* h, const ZbotMdpInputs* in, const float* actions, 
   if (int rc = mdp_check(h, in, true)) return rc;
   if (!actions || !obs || !rew || !terminated || !truncated) return fail(ZBOT_E_INVALID, "zbot_mdp_step: NULL buffer%s");
   if (int rc = check_slot(stats_slot, prev_slot, h->m_ring_slots)) return rc;
-  const int n = h->cfg.num_envs, block = 128, grid = (n + block - 1) / block;
+  const int n = h->cfg.num_envs, block = h->mdp_tile, grid = (n + block - 1) / block;
   MdpIn mi{in->body_link_pos_w, in->body_link_quat_w, in->body_com_lin_vel_w, in->joint_pos, in->joint_vel,
            in->applied_torque, in->net_forces_w_history, in->last_air_time, in->env_origins};
-  StatsCtx sc{h->partials, h->ticket, h->m_ring, stats_slot, prev_slot, h->inv_episode_s};
+  StatsCtx sc{h->partials, h->m_ring, stats_slot, prev_slot, h->inv_episode_s};
   zbot_mdp_kernel<true><<<grid, block, (size_t)block * kHistRow * sizeof(float), (cudaStream_t)stream>>>(
       h->P, h->dp, mi, h->mstate, h->m_ep_len, actions, obs, rew, terminated, truncated, n, sc);
+  ZB_CUDA(cudaGetLastError());
+  h->launches += 1;
+  zbot_stats_finalize_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(sc, (unsigned int)grid);
   ZB_CUDA(cudaGetLastError());
   h->launches += 1;
   return ZBOT_OK;

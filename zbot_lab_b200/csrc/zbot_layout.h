@@ -149,6 +149,8 @@ inline void params_from_cfg(const ZbotCfg& c, Params<T>& P) {
   P.max_episode_length = c.max_episode_length;
   P.num_terms = c.num_terms;
   for (int i = 0; i < MAX_TERMS; ++i) { P.term_id[i] = c.term_id[i]; P.term_w[i] = T(c.term_weight[i]); }
+  P.default_terms = (c.num_terms == 13);
+  for (int i = 0; i < 13 && P.default_terms; ++i) P.default_terms = (c.term_id[i] == i);
 }
 
 inline int cfg_validate(const ZbotCfg& c, const char** why) {
