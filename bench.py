@@ -29,6 +29,9 @@ UNIT = "env-steps/s"
 # algorithmic HBM bytes per env-step of the fused kernel: state 20 float4 read +
 # written (2 x 320), actions 24 read, obs 92 + reward 4 + flags 2 written, episode counter 8 + 8
 ALGO_BYTES_PER_ENV_STEP = 320 + 24 + 8 + 320 + 92 + 4 + 2 + 8
+# dram__bytes_read.sum + dram__bytes_write.sum of one zbot_step_kernel launch at 65536 envs (ncu --set full,
+# profiles/r1_step_ncu.md) per env: reads hit DRAM, most writes are still in the 126 MB L2 when the kernel ends
+NCU_TRAFFIC_BYTES_PER_ENV_STEP = 379
 ROLLOUT_STEPS = 24  # agents/rsl_rl_ppo_cfg.py:67 -- statistics are reduced once per rollout
 
 
@@ -42,6 +45,7 @@ def parse():
     p.add_argument("--no-flush", action="store_true", help="back-to-back steps (state stays in L2)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-mdp", action="store_true", help="skip the MDP-only kernel side measurement")
     p.add_argument("--cpu-sample-steps", type=int, default=None)
     return p.parse_args()
 
@@ -259,6 +263,22 @@ def main():
         e2e = {"value": world * n_envs * args.steps / float(te.item()), "unit": UNIT,
                "h2d_bytes_per_step": n_envs * 24, "d2h_bytes_per_step": n_envs * (92 + 4 + 1 + 1)}
 
+    mdp_only = None
+    if rank == 0 and world == 1 and not args.no_mdp:
+        # the HBM-bound first kernel (BASELINE.json configs[0] shape): MDP-only step on synthetic articulation state
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_mdp
+
+        peak_m, _ = measured_peak_gbs()
+        mdp_only = {}
+        for n_m in (65536, 262144):
+            ms = bench_mdp.bench_mdp(n_m, 30, 5)
+            gbs = bench_mdp.MDP_ALGO_BYTES * n_m / (ms * 1e-3) / 1e9
+            mdp_only[str(n_m)] = {"ms_per_step": ms, "env_steps_per_s": n_m / (ms * 1e-3), "achieved_gbs": gbs,
+                                  "frac_of_measured_hbm_peak": gbs / peak_m}
+        mdp_only["kernel"] = "zbot_mdp_kernel<true> + zbot_stats_finalize_kernel"
+        mdp_only["algorithmic_bytes_per_env_step"] = bench_mdp.MDP_ALGO_BYTES
+
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         kern_ms = total_ms / args.steps if world == 1 else float(sum(step_ms)) / args.steps
@@ -272,15 +292,22 @@ def main():
                        "l2": "flushed between timed steps (256 MiB write)" if flush is not None else "not flushed",
                        "wall_s_incl_flush": t_wall},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "zbot_step_kernel<false>",
+                         "traffic": NCU_TRAFFIC_BYTES_PER_ENV_STEP * n_envs, "peak_source": peak_src,
+                         "kernel": "zbot_step_kernel<false,128,2>",
+                         "traffic_note": "dram__bytes_read+write per launch from profiles/r1_step_ncu.md, scaled per env",
                          "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP,
                          "note": "the fused step is FP32-issue bound, not HBM bound (DESIGN.md §4)"},
             "gpu_launches": int(launches), "clocks": sampler.summary(),
         }
         if e2e is not None:
             line["e2e"] = e2e
+        if mdp_only is not None:
+            line["mdp_only_kernel"] = mdp_only
         if world == 1 and not args.no_cpu_baseline:
-            cs = args.cpu_sample_steps or 40
+            cs = args.cpu_sample_steps
+            if cs is None:   # bounded sample of the same workload: ~10 s of CPU work
+                _, dt0, _ = cpu_path(n_envs, 10, 1)
+                cs = int(max(20, min(20000, 10.0 / (dt0 / 10))))
             v, dt, cores = cpu_path(n_envs, cs, 2)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"{n_envs} envs x {cs} steps, oracle/cpu_port.cpp float32 OpenMP, {dt:.1f} s"}

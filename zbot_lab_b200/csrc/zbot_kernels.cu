@@ -419,8 +419,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
-constexpr int kMdpTile = 64;   // envs (= threads) per CTA of the MDP step kernel: 45 KB history tile, 4 CTAs / SM
-                               // (32-env one-warp tiles measured 2x slower, 128-env tiles equal: profiles/r1_notes.md)
+constexpr int kMdpTile = 128;  // envs (= threads) per CTA of the MDP step kernel: 90 KB history tile, 2 CTAs / SM (tile sweep: profiles/r1_notes.md)
 
 // kStep = false: `_get_observations` only (fills the stale cache)
 template <bool kStep>
