@@ -162,6 +162,7 @@ def main():
 
     from zbot_lab_b200.compat import gym_registry as gym
     import zbot_lab_b200.tasks  # noqa: F401  (registers zbot-6b-walking-v2)
+    from zbot_lab_b200 import distributed as zdist
     from zbot_lab_b200.utils import synthetic as syn
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -179,7 +180,7 @@ def main():
     cfg = gym.load_cfg_from_registry("zbot-6b-walking-v2", "env_cfg_entry_point")
     cfg.scene.num_envs = n_envs
     cfg.sim.device = str(dev)
-    cfg.seed = 1234 + rank
+    cfg.seed = zdist.rank_seed(1234, rank)
     env = gym.make("zbot-6b-walking-v2", cfg=cfg, render_mode=None)
     st = env.unwrapped._stepper
     env.reset()
@@ -217,8 +218,7 @@ def main():
         one_step(i)
         ev[i][1].record()
         if world > 1 and (i + 1) % ROLLOUT_STEPS == 0:
-            stats_acc.copy_(st.stats)
-            dist.all_reduce(stats_acc)                 # rollout statistics: the only collective on the path
+            stats_acc = zdist.reduce_rollout_stats(st.stats)   # rollout statistics: the only collective on the path
     barrier()
     t_wall = time.perf_counter() - t_wall0
     launches = st.launch_count - launches0
