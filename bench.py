@@ -111,6 +111,7 @@ def cpu_path(n_envs: int, steps: int, warmup: int, seed: int = 1234):
     from oracle import cpu_port
     from zbot_lab_b200.utils import synthetic as syn
 
+    cores = cpu_port.set_threads(None)          # all host threads, even under torchrun (OMP_NUM_THREADS=1)
     rng = np.random.default_rng(seed)
     env = cpu_port.PortEnv(n_envs, np.float32)
     env.set_sim_state(syn.synth_sim_state(rng, n_envs))
@@ -122,7 +123,6 @@ def cpu_path(n_envs: int, steps: int, warmup: int, seed: int = 1234):
     for i in range(steps):
         env.step(acts[i % 8])
     dt = time.perf_counter() - t0
-    cores = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
     return n_envs * steps / dt, dt, cores
 
 
@@ -130,6 +130,10 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to its workers; this arm must use every host thread.  libgomp reads
+    # these when it is first loaded (with oracle/_build/libzbot_cpu_port.so, below).
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+    os.environ.setdefault("OMP_WAIT_POLICY", "active")
     n_envs = args.envs or (4096 if args.gpus == 1 else 65536)
     # bounded sample: the same workload shape, at most ~20 s of CPU work
     steps = max(1, min(args.steps, 50))

@@ -9,6 +9,7 @@
 //      for the reference's torch + PhysX-CPU step (PhysX is closed and absent).
 // Nothing under zbot_lab_b200/ links or loads this file; the product fails loudly without
 // its CUDA library.  State layout: [N][ZBOT_STATE_WORDS] (AoS on the CPU).
+#include <omp.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -16,6 +17,9 @@
 #include "../zbot_lab_b200/csrc/zbot_layout.h"
 
 using namespace zbot;
+
+static int g_threads = 0;   // 0: OpenMP default
+static inline int port_threads() { return g_threads > 0 ? g_threads : omp_get_max_threads(); }
 
 template <typename T>
 static void default_pose_constants(T feet_pos[2][3], T base_quat[4]) {
@@ -38,7 +42,7 @@ static int port_step(const ZbotCfg* cfg, T* state, int64_t* ep_len, const T* act
   params_from_cfg(*cfg, P);
   T dfp[2][3], dbq[4];
   default_pose_constants(dfp, dbq);
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(port_threads())
   for (int e = 0; e < n; ++e) {
     EnvState<T> es;
     env_state_unpack(state + (size_t)e * ZBOT_STATE_WORDS, es);
@@ -66,7 +70,7 @@ template <typename T>
 static int port_substeps(const ZbotCfg* cfg, T* sim, const T* target, T* forces, T* tau, int n, int nsub) {
   Params<T> P;
   params_from_cfg(*cfg, P);
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(port_threads())
   for (int e = 0; e < n; ++e) {
     SimState<T> s;
     T* w = sim + (size_t)e * 25;
@@ -103,6 +107,8 @@ static int port_link_view(const T* sim, T* pos, T* quat, T* vel, int n) {
 }
 
 extern "C" {
+// torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU baseline must use all host threads
+int zbot_port_set_threads(int n) { if (n > 0) { g_threads = n; omp_set_num_threads(n); } return port_threads(); }
 int zbot_port_default_cfg(ZbotCfg* c, int n) { cfg_defaults(*c, n); return 0; }
 int zbot_port_export_words_f32(void) { return (int)(sizeof(StepExport<float>) / sizeof(float)); }
 int zbot_port_export_words_f64(void) { return (int)(sizeof(StepExport<double>) / sizeof(double)); }

@@ -46,6 +46,11 @@ def lib():
     return _LIB
 
 
+def set_threads(n: int | None = None) -> int:
+    """Use ``n`` OpenMP threads (default: every host core); returns the thread count in effect."""
+    return int(lib().zbot_port_set_threads(C.c_int(n if n else (os.cpu_count() or 1))))
+
+
 def _p(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
 
