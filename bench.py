@@ -130,10 +130,13 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # torchrun exports OMP_NUM_THREADS=1 to its workers; this arm must use every host thread.  libgomp reads
-    # these when it is first loaded (with oracle/_build/libzbot_cpu_port.so, below).
-    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
-    os.environ.setdefault("OMP_WAIT_POLICY", "active")
+    # torchrun exports OMP_NUM_THREADS=1 to its workers; this arm must use every host thread, and libgomp
+    # only behaves (thread pool, spinning) when it sees the final settings at process start: re-exec once.
+    want = str(os.cpu_count() or 1)
+    if os.environ.get("OMP_NUM_THREADS") != want and os.environ.get("ZBOT_BENCH_REEXEC") != "1":
+        env = dict(os.environ, OMP_NUM_THREADS=want, GOMP_SPINCOUNT="1000000", ZBOT_BENCH_REEXEC="1")
+        sys.stdout.flush()
+        os.execve(sys.executable, [sys.executable] + sys.argv, env)
     n_envs = args.envs or (4096 if args.gpus == 1 else 65536)
     # bounded sample: the same workload shape, at most ~20 s of CPU work
     steps = max(1, min(args.steps, 50))
