@@ -134,7 +134,7 @@ def run_reference(args):
     # only behaves (thread pool, spinning) when it sees the final settings at process start: re-exec once.
     want = str(os.cpu_count() or 1)
     if os.environ.get("OMP_NUM_THREADS") != want and os.environ.get("ZBOT_BENCH_REEXEC") != "1":
-        env = dict(os.environ, OMP_NUM_THREADS=want, GOMP_SPINCOUNT="1000000", ZBOT_BENCH_REEXEC="1")
+        env = dict(os.environ, OMP_NUM_THREADS=want, ZBOT_BENCH_REEXEC="1")
         sys.stdout.flush()
         os.execve(sys.executable, [sys.executable] + sys.argv, env)
     n_envs = args.envs or (4096 if args.gpus == 1 else 65536)
