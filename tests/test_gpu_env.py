@@ -92,3 +92,25 @@ def test_all_envs_reset_spreads_episode_lengths_on_torch_generator():
     want = torch.randint_like(env.episode_length_buf, high=1000)
     assert torch.equal(env.episode_length_buf, want)
     env.close()
+
+
+def test_ppo_runner_two_iterations_and_checkpoint(tmp_path):
+    """train.py flow: gym.make -> RslRlVecEnvWrapper -> OnPolicyRunner.learn (config 5 shape, tiny)."""
+    from zbot_lab_b200.compat import gym_registry as gym
+    from zbot_lab_b200.envs.rsl_rl_wrapper import RslRlVecEnvWrapper
+    from zbot_lab_b200.rl.ppo_runner import OnPolicyRunner
+    env, _ = _make(256)
+    agent_cfg = gym.load_cfg_from_registry("zbot-6b-walking-v2", "rsl_rl_cfg_entry_point")
+    w = RslRlVecEnvWrapper(env, clip_actions=agent_cfg.clip_actions)
+    r = OnPolicyRunner(w, agent_cfg.to_dict(), log_dir=str(tmp_path), device="cuda:0")
+    hist = r.learn(num_learning_iterations=2, init_at_random_ep_len=True)
+    assert len(hist) == 2 and all(np.isfinite(h["value_loss"]) for h in hist)
+    assert "Episode_Reward/base_vel_forward" in hist[-1] and "Episode_Termination/time_out" in hist[-1]
+    ck = tmp_path / "model_2.pt"
+    assert ck.exists()
+    r2 = OnPolicyRunner(w, agent_cfg.to_dict(), log_dir=None, device="cuda:0")
+    r2.load(str(ck))
+    pol = r2.get_inference_policy(device="cuda:0")
+    obs, _ = w.get_observations()
+    assert pol(obs).shape == (256, 6)
+    w.close()

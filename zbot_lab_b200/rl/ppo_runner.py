@@ -1,0 +1,245 @@
+"""Minimal on-policy PPO runner with the ``rsl_rl.runners.OnPolicyRunner`` surface the reference's
+training script uses (``scripts/rsl_rl/train.py:185-205``: ctor ``(env, cfg_dict, log_dir, device)``,
+``learn(num_learning_iterations, init_at_random_ep_len)``, ``load``, ``save``,
+``get_inference_policy``, ``add_git_repo_to_log``).  rsl_rl is not installed in this image; this is a
+from-scratch restatement of standard PPO with the hyper-parameters of ``PPORunnerCfgV2``
+(``agents/rsl_rl_ppo_cfg.py:65-91``): 24 steps/env, 3x128 ELU actor and critic, GAE(0.99, 0.95),
+clip 0.2, 5 epochs x 4 mini-batches, adaptive learning rate on KL 0.01, grad-norm 1.0.
+
+The policy network is plain PyTorch (cuBLAS GEMMs): it is not the hot path this repo accelerates.
+Multi-GPU: when ``torch.distributed`` is initialised, parameters are broadcast from rank 0 and the
+flattened gradients are all-reduced once per mini-batch (what rsl_rl does under ``--distributed``).
+"""
+from __future__ import annotations
+
+import json
+import os
+import time
+from collections import deque
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+
+def _mlp(inp, hidden, out, act):
+    layers, d = [], inp
+    for h in hidden:
+        layers += [nn.Linear(d, h), act()]
+        d = h
+    layers.append(nn.Linear(d, out))
+    return nn.Sequential(*layers)
+
+
+_ACT = {"elu": nn.ELU, "relu": nn.ReLU, "tanh": nn.Tanh, "selu": nn.SELU, "lrelu": nn.LeakyReLU}
+
+
+class ActorCritic(nn.Module):
+    def __init__(self, num_obs, num_actions, actor_hidden_dims=(128, 128, 128), critic_hidden_dims=(128, 128, 128),
+                 activation="elu", init_noise_std=1.0, **_):
+        super().__init__()
+        act = _ACT[activation]
+        self.actor = _mlp(num_obs, list(actor_hidden_dims), num_actions, act)
+        self.critic = _mlp(num_obs, list(critic_hidden_dims), 1, act)
+        self.std = nn.Parameter(init_noise_std * torch.ones(num_actions))
+
+    def dist(self, obs):
+        mean = self.actor(obs)
+        return torch.distributions.Normal(mean, self.std.clamp(min=1e-6).expand_as(mean))
+
+    def act_inference(self, obs):
+        return self.actor(obs)
+
+    def evaluate(self, obs):
+        return self.critic(obs).squeeze(-1)
+
+
+class OnPolicyRunner:
+    def __init__(self, env, train_cfg: dict, log_dir: str | None = None, device="cpu"):
+        self.env = env
+        self.cfg = train_cfg
+        self.alg_cfg = dict(train_cfg.get("algorithm", {}))
+        self.policy_cfg = dict(train_cfg.get("policy", {}))
+        self.device = torch.device(device)
+        self.log_dir = log_dir
+        self.num_steps = int(train_cfg.get("num_steps_per_env", 24))
+        self.save_interval = int(train_cfg.get("save_interval", 100))
+        obs, _ = env.get_observations()
+        self.num_obs, self.num_actions = obs.shape[1], env.num_actions
+        self.policy = ActorCritic(self.num_obs, self.num_actions, **{k: v for k, v in self.policy_cfg.items()
+                                                                   if k != "class_name"}).to(self.device)
+        self.lr = float(self.alg_cfg.get("learning_rate", 1e-3))
+        self.optimizer = torch.optim.Adam(self.policy.parameters(), lr=self.lr)
+        self.gamma, self.lam = float(self.alg_cfg.get("gamma", 0.99)), float(self.alg_cfg.get("lam", 0.95))
+        self.clip = float(self.alg_cfg.get("clip_param", 0.2))
+        self.epochs = int(self.alg_cfg.get("num_learning_epochs", 5))
+        self.minibatches = int(self.alg_cfg.get("num_mini_batches", 4))
+        self.value_coef = float(self.alg_cfg.get("value_loss_coef", 1.0))
+        self.entropy_coef = float(self.alg_cfg.get("entropy_coef", 0.0))
+        self.max_grad_norm = float(self.alg_cfg.get("max_grad_norm", 1.0))
+        self.desired_kl = self.alg_cfg.get("desired_kl", 0.01)
+        self.schedule = self.alg_cfg.get("schedule", "adaptive")
+        self.clipped_value = bool(self.alg_cfg.get("use_clipped_value_loss", True))
+        self.distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        if self.distributed:
+            for p in self.policy.parameters():
+                dist.broadcast(p.data, src=0)
+        self.current_learning_iteration = 0
+        self.history: list[dict] = []
+        self.git_status_repos: list[str] = []
+        n, T, dev = env.num_envs, self.num_steps, self.device
+        self.buf = {
+            "obs": torch.zeros(T, n, self.num_obs, device=dev), "act": torch.zeros(T, n, self.num_actions, device=dev),
+            "rew": torch.zeros(T, n, device=dev), "done": torch.zeros(T, n, device=dev),
+            "val": torch.zeros(T, n, device=dev), "logp": torch.zeros(T, n, device=dev),
+            "mu": torch.zeros(T, n, self.num_actions, device=dev), "sigma": torch.zeros(T, n, self.num_actions, device=dev),
+        }
+
+    # ------------------------------------------------------------------ rsl_rl surface
+    def add_git_repo_to_log(self, repo_file_path):
+        self.git_status_repos.append(repo_file_path)
+
+    def get_inference_policy(self, device=None):
+        self.policy.eval()
+        if device is not None:
+            self.policy.to(device)
+        return self.policy.act_inference
+
+    def save(self, path, infos=None):
+        torch.save({"model_state_dict": self.policy.state_dict(), "optimizer_state_dict": self.optimizer.state_dict(),
+                    "iter": self.current_learning_iteration, "infos": infos}, path)
+
+    def load(self, path, load_optimizer=True):
+        d = torch.load(path, map_location=self.device, weights_only=False)
+        self.policy.load_state_dict(d["model_state_dict"])
+        if load_optimizer and "optimizer_state_dict" in d:
+            self.optimizer.load_state_dict(d["optimizer_state_dict"])
+        self.current_learning_iteration = d.get("iter", 0)
+        return d.get("infos")
+
+    # ------------------------------------------------------------------ rollout + update
+    @torch.no_grad()
+    def collect_rollout(self, obs):
+        """``num_steps`` x (act -> env.step -> store); returns the last observation and episode infos."""
+        b, ep_infos = self.buf, []
+        for t in range(self.num_steps):
+            d = self.policy.dist(obs)
+            act = d.sample()
+            b["obs"][t], b["act"][t] = obs, act
+            b["val"][t], b["logp"][t] = self.policy.evaluate(obs), d.log_prob(act).sum(-1)
+            b["mu"][t], b["sigma"][t] = d.mean, d.stddev
+            obs, rew, dones, infos = self.env.step(act)
+            rew = rew.clone()
+            if "time_outs" in infos:   # bootstrap on truncation
+                rew += self.gamma * b["val"][t] * infos["time_outs"].to(rew.dtype)
+            b["rew"][t], b["done"][t] = rew, dones.to(rew.dtype)
+            if "log" in infos:
+                ep_infos.append(infos["log"])
+        return obs, ep_infos
+
+    def _returns(self, last_obs):
+        b, T = self.buf, self.num_steps
+        with torch.no_grad():
+            last_val = self.policy.evaluate(last_obs)
+        adv = torch.zeros_like(b["rew"])
+        gae = torch.zeros_like(last_val)
+        for t in reversed(range(T)):
+            nv = last_val if t == T - 1 else b["val"][t + 1]
+            nd = 1.0 - b["done"][t]
+            delta = b["rew"][t] + self.gamma * nv * nd - b["val"][t]
+            gae = delta + self.gamma * self.lam * nd * gae
+            adv[t] = gae
+        ret = adv + b["val"]
+        adv = (adv - adv.mean()) / (adv.std() + 1e-8)
+        return ret, adv
+
+    def update(self, last_obs):
+        b = self.buf
+        ret, adv = self._returns(last_obs)
+        flat = lambda x: x.reshape(-1, *x.shape[2:])
+        obs, act, logp_old, val_old = flat(b["obs"]), flat(b["act"]), flat(b["logp"]), flat(b["val"])
+        mu_old, sig_old, ret, adv = flat(b["mu"]), flat(b["sigma"]), flat(ret), flat(adv)
+        total = obs.shape[0]
+        mb = total // self.minibatches
+        stats = {"value_loss": 0.0, "surrogate_loss": 0.0, "kl": 0.0}
+        for _ in range(self.epochs):
+            perm = torch.randperm(total, device=self.device)
+            for i in range(self.minibatches):
+                idx = perm[i * mb:(i + 1) * mb]
+                d = self.policy.dist(obs[idx])
+                logp = d.log_prob(act[idx]).sum(-1)
+                value = self.policy.evaluate(obs[idx])
+                with torch.no_grad():
+                    kl = torch.sum(torch.log(d.stddev / sig_old[idx] + 1e-5)
+                                   + (sig_old[idx] ** 2 + (mu_old[idx] - d.mean) ** 2) / (2 * d.stddev ** 2) - 0.5, -1).mean()
+                    if self.distributed:
+                        dist.all_reduce(kl)
+                        kl /= dist.get_world_size()
+                    if self.schedule == "adaptive" and self.desired_kl is not None:
+                        if kl > 2.0 * self.desired_kl:
+                            self.lr = max(1e-5, self.lr / 1.5)
+                        elif 0.0 < kl < 0.5 * self.desired_kl:
+                            self.lr = min(1e-2, self.lr * 1.5)
+                        for g in self.optimizer.param_groups:
+                            g["lr"] = self.lr
+                ratio = torch.exp(logp - logp_old[idx])
+                surr = torch.max(-adv[idx] * ratio, -adv[idx] * ratio.clamp(1 - self.clip, 1 + self.clip)).mean()
+                if self.clipped_value:
+                    vc = val_old[idx] + (value - val_old[idx]).clamp(-self.clip, self.clip)
+                    vloss = torch.max((value - ret[idx]) ** 2, (vc - ret[idx]) ** 2).mean()
+                else:
+                    vloss = ((ret[idx] - value) ** 2).mean()
+                loss = surr + self.value_coef * vloss - self.entropy_coef * d.entropy().sum(-1).mean()
+                self.optimizer.zero_grad(set_to_none=True)
+                loss.backward()
+                if self.distributed:
+                    grads = [p.grad for p in self.policy.parameters() if p.grad is not None]
+                    flat_g = torch.cat([g.reshape(-1) for g in grads])
+                    dist.all_reduce(flat_g)
+                    flat_g /= dist.get_world_size()
+                    o = 0
+                    for g in grads:
+                        g.copy_(flat_g[o:o + g.numel()].view_as(g))
+                        o += g.numel()
+                nn.utils.clip_grad_norm_(self.policy.parameters(), self.max_grad_norm)
+                self.optimizer.step()
+                stats["value_loss"] += float(vloss.detach())
+                stats["surrogate_loss"] += float(surr.detach())
+                stats["kl"] += float(kl)
+        k = self.epochs * self.minibatches
+        return {n: v / k for n, v in stats.items()}
+
+    def learn(self, num_learning_iterations: int, init_at_random_ep_len: bool = False):
+        if init_at_random_ep_len:   # scripts/rsl_rl/train.py:205
+            self.env.episode_length_buf = torch.randint_like(self.env.episode_length_buf,
+                                                             high=int(self.env.max_episode_length))
+        obs, _ = self.env.get_observations()
+        obs = obs.to(self.device)
+        self.policy.train()
+        rewbuf, cur_rew = deque(maxlen=100), torch.zeros(self.env.num_envs, device=self.device)
+        if self.log_dir and (not self.distributed or dist.get_rank() == 0):
+            os.makedirs(self.log_dir, exist_ok=True)
+        start = self.current_learning_iteration
+        for it in range(start, start + num_learning_iterations):
+            t0 = time.perf_counter()
+            obs, ep_infos = self.collect_rollout(obs)
+            t1 = time.perf_counter()
+            losses = self.update(obs)
+            t2 = time.perf_counter()
+            self.current_learning_iteration = it + 1
+            rec = {"iteration": it, "collection_s": t1 - t0, "learn_s": t2 - t1,
+                   "fps": self.num_steps * self.env.num_envs / (t2 - t0),
+                   "mean_step_reward": float(self.buf["rew"].mean()), "lr": self.lr, **losses}
+            if ep_infos:   # average each key over the rollout, as rsl_rl's logger does
+                for key in ep_infos[0]:
+                    vals = [torch.as_tensor(e[key], dtype=torch.float32).reshape(-1).to(self.device) for e in ep_infos]
+                    rec[key] = float(torch.cat(vals).mean())
+            self.history.append(rec)
+            if self.log_dir and (not self.distributed or dist.get_rank() == 0):
+                with open(os.path.join(self.log_dir, "progress.jsonl"), "a") as f:
+                    f.write(json.dumps(rec) + "\n")
+                if (it + 1) % self.save_interval == 0:
+                    self.save(os.path.join(self.log_dir, f"model_{it + 1}.pt"))
+        if self.log_dir and (not self.distributed or dist.get_rank() == 0):
+            self.save(os.path.join(self.log_dir, f"model_{self.current_learning_iteration}.pt"))
+        return self.history
