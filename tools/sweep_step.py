@@ -41,7 +41,7 @@ if __name__ == "__main__":
     sizes = [int(x) for x in sys.argv[1:]] or [4096, 65536]
     for n in sizes:
         for two_pass in (1,):
-            for mb, blocks in ((2, (64, 128)),):
+            for mb, blocks in ((2, (64, 128)), (3, (64, 128)), (4, (64, 128))):
                 for block in blocks:
                     us = time_cfg(n, mb, block, two_pass=two_pass)
                     print(f"envs {n:6d} two_pass {two_pass} min_blocks {mb} block {block:3d}: {us:8.2f} us/step  {n / us:8.2f} M env-steps/s", flush=True)

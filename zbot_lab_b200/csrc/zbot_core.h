@@ -118,6 +118,25 @@ ZB_HD void zb_sincos(double x, double* s, double* c) {
   *s = sin(x);
   *c = cos(x);
 }
+// reciprocal / reciprocal square root for the DYNAMICS only (float on the GPU: one MUFU + one multiply,
+// ~2 ulp; the MDP terms keep IEEE division and sqrt for the 1e-5 parity with the reference)
+ZB_HD float zb_rcp(float x) {
+#if defined(__CUDA_ARCH__)
+  return __fdividef(1.0f, x);
+#else
+  return 1.0f / x;
+#endif
+}
+ZB_HD double zb_rcp(double x) { return 1.0 / x; }
+ZB_HD float zb_rsqrt(float x) {
+#if defined(__CUDA_ARCH__)
+  return rsqrtf(x);
+#else
+  return 1.0f / sqrtf(x);
+#endif
+}
+ZB_HD double zb_rsqrt(double x) { return 1.0 / sqrt(x); }
+
 template <typename T>
 ZB_HD T zb_clamp(T x, T lo, T hi) {
   return zb_min(zb_max(x, lo), hi);
@@ -284,7 +303,7 @@ ZB_HD void spi_solve(const SpInertia<T>& A, const T* bt, const T* bb, T* xt, T* 
     T d = a[j][j];
     ZB_UNROLL for (int k = 0; k < j; ++k) d -= a[j][k] * a[j][k] * a[k][k];
     a[j][j] = d;  // D_j
-    dinv[j] = T(1) / d;
+    dinv[j] = zb_rcp(d);
     ZB_UNROLL for (int i = j + 1; i < 6; ++i) {
       T s = a[i][j];
       ZB_UNROLL for (int k = 0; k < j; ++k) s -= a[i][k] * a[j][k] * a[k][k];
@@ -341,8 +360,8 @@ ZB_HD bool contact_point(const Params<T>& P, const T* rho, T height, const T* w,
   T gamma = P.c_k * P.dt + P.c_d * s;
   T fn0 = fs - gamma * sz;
   if (!(fn0 > T(0))) return false;
-  T vt = zb_sqrt(sx * sx + sy * sy);
-  T beta = zb_min(P.c_beta_max, P.c_mu * fn0 / zb_max(vt, P.c_vt_eps));
+  // beta = min(beta_max, mu fn0 / max(|v_t|, eps))
+  T beta = zb_min(P.c_beta_max, P.c_mu * fn0 * zb_rsqrt(zb_max(sx * sx + sy * sy, P.c_vt_eps * P.c_vt_eps)));
   T F0[3] = {-beta * sx, -beta * sy, fn0};
   T n[3];
   cross3(rho, F0, n);
@@ -409,10 +428,10 @@ ZB_HD void body_rigid_terms(const Params<T>& P, T mass, T cx, T cz, T ixx, T iyy
 // on instruction fetch), so everything indexed by the joint lives in indexable storage:
 // shared memory on the GPU ([slot][thread], conflict-free), a plain array on the CPU.
 // ------------------------------------------------------------------------------------
-constexpr int SCR_PER_JOINT = 18;
-constexpr int SCR_WORDS = 6 * SCR_PER_JOINT;   // 108 words per environment
+constexpr int SCR_PER_JOINT = 17;
+constexpr int SCR_WORDS = 6 * SCR_PER_JOINT;   // 102 words per environment
 enum ScrSlot : int { SC_SA = 0, SC_SM = 3, SC_UT = 6, SC_UB = 9, SC_DINV = 12, SC_U = 13 /* tau, then u */,
-                     SC_SN = 14, SC_CS = 15, SC_Q = 16, SC_QD = 17 };
+                     SC_SN = 14, SC_CS = 15, SC_QD = 16 };
 
 template <typename T>
 struct ArrayScratch {
@@ -420,10 +439,13 @@ struct ArrayScratch {
   ZB_HD T& operator()(int j, int slot) { return a[j * SCR_PER_JOINT + slot]; }
 };
 #if defined(__CUDACC__)
-struct SmemScratch {          // base points at this thread's column; consecutive slots are `stride` apart
-  float* base;
-  int stride;
-  __device__ __forceinline__ float& operator()(int j, int slot) { return base[(j * SCR_PER_JOINT + slot) * stride]; }
+// Each thread owns SCR_STRIDE consecutive words of shared memory.  SCR_STRIDE is odd, so the 32 lanes of a
+// warp hit 32 different banks for any (j, slot); `slot` is a compile-time constant at every use, so it folds
+// into the LDS/STS immediate and only `j * SCR_PER_JOINT` costs an instruction per loop iteration.
+constexpr int SCR_STRIDE = SCR_WORDS + 1;   // 103
+struct SmemScratch {
+  float* base;   // this thread's row
+  __device__ __forceinline__ float& operator()(int j, int slot) { return base[j * SCR_PER_JOINT + slot]; }
 };
 #endif
 
@@ -448,7 +470,6 @@ ZB_HD void physics_substep(const Params<T>& P, SimState<T>& s, const T* target, 
     const T e = target[k] - s.q[k];
     out.applied_torque[k] = zb_clamp(P.kp * e - P.kd * s.qd[k], -P.effort, P.effort);
     scr(k, SC_U) = zb_clamp(P.kp * (e - dt * s.qd[k]) - P.kd * s.qd[k], -P.effort, P.effort);
-    scr(k, SC_Q) = s.q[k];
     scr(k, SC_QD) = s.qd[k];
   }
   // ---- forward kinematics sweep: motion subspaces S_k = (a_k ; r_k x a_k), arrive at body 6 ----
@@ -470,7 +491,9 @@ ZB_HD void physics_substep(const Params<T>& P, SimState<T>& s, const T* target, 
     cross3(r, a, m);
     const T qd = scr(k, SC_QD);
     T sn, cs;
-    zb_sincos(T(0.5) * scr(k, SC_Q), &sn, &cs);
+    // select (not index) the joint angle: q stays in registers
+    const T qk = (k == 0) ? s.q[0] : (k == 1) ? s.q[1] : (k == 2) ? s.q[2] : (k == 3) ? s.q[3] : (k == 4) ? s.q[4] : s.q[5];
+    zb_sincos(T(0.5) * qk, &sn, &cs);
     ZB_UNROLL for (int i = 0; i < 3; ++i) {
       scr(k, SC_SA + i) = a[i];
       scr(k, SC_SM + i) = m[i];
@@ -546,7 +569,7 @@ ZB_HD void physics_substep(const Params<T>& P, SimState<T>& s, const T* target, 
     T Ut[3], Ub[3];
     spi_mul(IA, Sa, Sm, Ut, Ub);
     const T D = dot3(Sa, Ut) + dot3(Sm, Ub) + P.arm;
-    const T Dinv = T(1) / D;
+    const T Dinv = zb_rcp(D);
     const T u = scr(j, SC_U) - (dot3(Sa, pAt) + dot3(Sm, pAb));
     // pa = pA + IA c + U (u - U.c)/D   (== pA + Ia c + U u/D)
     T Ict[3], Icb[3];
@@ -608,11 +631,10 @@ ZB_HD void physics_substep(const Params<T>& P, SimState<T>& s, const T* target, 
     ZB_UNROLL for (int i = 0; i < 3; ++i) { At[i] += Sa[i] * qdd; Ab[i] += Sm[i] * qdd; }
     qd += dt * qdd;
     scr(j, SC_QD) = qd;
-    scr(j, SC_Q) += dt * qd;
   }
   contact_agg_force(agg1, dt, At, Ab, out.foot_force[1]);
   out.mid_force2_max = mid2;
-  ZB_UNROLL for (int k = 0; k < 6; ++k) { s.q[k] = scr(k, SC_Q); s.qd[k] = scr(k, SC_QD); }
+  ZB_UNROLL for (int k = 0; k < 6; ++k) { s.qd[k] = scr(k, SC_QD); s.q[k] += dt * s.qd[k]; }
   // ---- root pose ----
   ZB_UNROLL for (int i = 0; i < 3; ++i) s.p[i] += dt * s.v[i];
   {
@@ -622,7 +644,7 @@ ZB_HD void physics_substep(const Params<T>& P, SimState<T>& s, const T* target, 
     T nx = qx + h * (s.w[0] * qw + s.w[1] * qz - s.w[2] * qy);
     T ny = qy + h * (-s.w[0] * qz + s.w[1] * qw + s.w[2] * qx);
     T nz = qz + h * (s.w[0] * qy - s.w[1] * qx + s.w[2] * qw);
-    T inv = T(1) / zb_sqrt(nw * nw + nx * nx + ny * ny + nz * nz);
+    T inv = zb_rsqrt(nw * nw + nx * nx + ny * ny + nz * nz);
     s.Q[0] = nw * inv; s.Q[1] = nx * inv; s.Q[2] = ny * inv; s.Q[3] = nz * inv;
   }
 }
@@ -1020,25 +1042,26 @@ ZB_HD void env_observe(const EnvState<T>& e, T* obs) {
   mdp_observation(k.base_quat, e.sim.q, e.sim.qd, e.mdp.actions, e.mdp.speed_limit, obs);
 }
 
+// What the physics phase hands to the MDP phase (everything else the MDP needs is re-derivable
+// from the start-of-step state S0, which is still in global memory, and from the end state).
+template <typename T>
+struct PhysOut {
+  T fz[5][2];           // feet Fz history, newest first; slot 4 = last substep of the PREVIOUS step
+  T mid2;               // max over the 5 slots of |F|^2 on the undesired bodies
+  T applied_torque[6];  // ImplicitActuator bookkeeping before the last substep
+};
+
+// Phase B of the control step: _pre_physics_step (…env_v2.py:276-287) + decimation x (physics substep +
+// ContactSensor.update).  Touches only e.sim, e.mdp.p_delta / speed_limit and the contact carry /
+// timers, so a GPU thread can run it before the rest of the MDP state has even been loaded.
 template <typename T, typename Scr>
-ZB_HD void env_step(const Params<T>& P, EnvState<T>& e, const T* raw_actions, int64_t& ep_len,
-                    const T default_feet_pos[2][3], const T* default_base_quat, StepOut<T>& out,
-                    T* reset_ep_sums /*MAX_TERMS, valid when a reset happened*/, StepExport<T>* ex, Scr& scr) {
-  // stale quantities = what _get_observations cached at the end of the previous step
-  StaleCache<T> stale;
-  {
-    LinkKin<T> k0;
-    link_kinematics(e.sim, k0);
-    stale_from_links(k0.base_pos, k0.base_quat, k0.base_com_vel, k0.feet_pos, k0.feet_quat, stale);
-    if (ex) { ex->k0 = k0; all_link_kinematics(e.sim, ex->pos0, ex->quat0, ex->vel0); }
-  }
+ZB_HD void env_step_physics(const Params<T>& P, EnvState<T>& e, const T* raw_actions, PhysOut<T>& po, Scr& scr,
+                            StepExport<T>* ex) {
   T new_actions[6], target[6];
   mdp_pre_physics(P, raw_actions, e.mdp, new_actions, target);
-  FreshInputs<T> f;
-  T fz[5][2];
-  fz[4][0] = e.carry_feet_fz[0];
-  fz[4][1] = e.carry_feet_fz[1];
-  T mid2 = e.carry_mid_max * e.carry_mid_max;
+  po.fz[4][0] = e.carry_feet_fz[0];
+  po.fz[4][1] = e.carry_feet_fz[1];
+  po.mid2 = e.carry_mid_max * e.carry_mid_max;
   if (ex) {
     ZB_UNROLL for (int b = 0; b < 5; ++b) { ex->mid_force_hist[4][b][0] = (b == 0) ? e.carry_mid_max : T(0);
       ex->mid_force_hist[4][b][1] = T(0); ex->mid_force_hist[4][b][2] = T(0); }
@@ -1058,11 +1081,11 @@ ZB_HD void env_step(const Params<T>& P, EnvState<T>& e, const T* raw_actions, in
       const T* ff = so.foot_force[j];
       const T nrm = zb_sqrt(ff[0] * ff[0] + ff[1] * ff[1] + ff[2] * ff[2]);
       contact_timers_update(e.timers[j], nrm > T(1.0), P.dt);
-      ZB_UNROLL for (int k = 0; k < 4; ++k) fz[k][j] = (slot == k) ? ff[2] : fz[k][j];   // select, not index
+      ZB_UNROLL for (int k = 0; k < 4; ++k) po.fz[k][j] = (slot == k) ? ff[2] : po.fz[k][j];   // select, not index
       if (ex && slot < 4) { ex->feet_force_hist[slot][j][0] = ff[0]; ex->feet_force_hist[slot][j][1] = ff[1];
         ex->feet_force_hist[slot][j][2] = ff[2]; }
     }
-    if (slot < 4) mid2 = zb_max(mid2, so.mid_force2_max);
+    if (slot < 4) po.mid2 = zb_max(po.mid2, so.mid_force2_max);
     if (ex && slot < 4) {
       ZB_UNROLL for (int b = 0; b < 5; ++b)
         ZB_UNROLL for (int i = 0; i < 3; ++i) ex->mid_force_hist[slot][b][i] = midf[3 * b + i];
@@ -1071,23 +1094,44 @@ ZB_HD void env_step(const Params<T>& P, EnvState<T>& e, const T* raw_actions, in
   e.carry_feet_fz[0] = so.foot_force[0][2];
   e.carry_feet_fz[1] = so.foot_force[1][2];
   e.carry_mid_max = zb_sqrt(so.mid_force2_max);
+  ZB_UNROLL for (int k = 0; k < 6; ++k) po.applied_torque[k] = so.applied_torque[k];
+}
+
+// Phase C: episode counter, dones, rewards, partial reset, observation (DirectRLEnv.step steps 3-8,
+// SURVEY 3.2).  `s0` = articulation state at the START of the step: the quantities the reference caches in
+// _get_observations one step earlier ("stale", SURVEY C-1) are recomputed from it.  `raw_actions` again:
+// tanh is recomputed instead of carrying 6 registers across the physics phase.
+template <typename T>
+ZB_HD void env_step_finish(const Params<T>& P, EnvState<T>& e, const SimState<T>& s0, const T* raw_actions,
+                           const PhysOut<T>& po, int64_t& ep_len, const T default_feet_pos[2][3],
+                           const T* default_base_quat, StepOut<T>& out, T* reset_ep_sums, StepExport<T>* ex) {
+  StaleCache<T> stale;
+  {
+    LinkKin<T> k0;
+    link_kinematics(s0, k0);
+    stale_from_links(k0.base_pos, k0.base_quat, k0.base_com_vel, k0.feet_pos, k0.feet_quat, stale);
+    if (ex) { ex->k0 = k0; all_link_kinematics(s0, ex->pos0, ex->quat0, ex->vel0); }
+  }
+  T new_actions[6];
+  ZB_UNROLL for (int k = 0; k < 6; ++k) new_actions[k] = zb_tanh(raw_actions[k]);   // :278
   ep_len += 1;                                             // DirectRLEnv.step
   // fresh view
   LinkKin<T> k1;
   link_kinematics(e.sim, k1);
+  FreshInputs<T> f;
   ZB_UNROLL for (int j = 0; j < 2; ++j) {
-    f.feet_force[j] = ((((fz[0][j] + fz[1][j]) + fz[2][j]) + fz[3][j]) + fz[4][j]) / T(5);
+    f.feet_force[j] = ((((po.fz[0][j] + po.fz[1][j]) + po.fz[2][j]) + po.fz[3][j]) + po.fz[4][j]) / T(5);
     f.last_air_time[j] = e.timers[j].last_air;
     f.feet_vel_xy[j][0] = k1.feet_com_vel[j][0];
     f.feet_vel_xy[j][1] = k1.feet_com_vel[j][1];
   }
-  f.undesired_force_max = zb_sqrt(mid2);
-  ZB_UNROLL for (int k = 0; k < 6; ++k) f.applied_torque[k] = so.applied_torque[k];
+  f.undesired_force_max = zb_sqrt(po.mid2);
+  ZB_UNROLL for (int k = 0; k < 6; ++k) f.applied_torque[k] = po.applied_torque[k];
   f.origin_y = T(0);
   if (ex) {
     ex->k1 = k1;
     all_link_kinematics(e.sim, ex->pos1, ex->quat1, ex->vel1);
-    ZB_UNROLL for (int k = 0; k < 6; ++k) { ex->applied_torque[k] = so.applied_torque[k]; ex->q1[k] = e.sim.q[k]; ex->qd1[k] = e.sim.qd[k]; }
+    ZB_UNROLL for (int k = 0; k < 6; ++k) { ex->applied_torque[k] = po.applied_torque[k]; ex->q1[k] = e.sim.q[k]; ex->qd1[k] = e.sim.qd[k]; }
     ZB_UNROLL for (int j = 0; j < 2; ++j) { ex->last_air[j] = e.timers[j].last_air; ex->cur_contact[j] = e.timers[j].cur_contact; }
   }
   bool terminated, time_out;
@@ -1104,6 +1148,17 @@ ZB_HD void env_step(const Params<T>& P, EnvState<T>& e, const T* raw_actions, in
   } else {
     mdp_observation(k1.base_quat, e.sim.q, e.sim.qd, e.mdp.actions, e.mdp.speed_limit, out.obs);
   }
+}
+
+// the whole control step in one call (CPU port, export kernel)
+template <typename T, typename Scr>
+ZB_HD void env_step(const Params<T>& P, EnvState<T>& e, const T* raw_actions, int64_t& ep_len,
+                    const T default_feet_pos[2][3], const T* default_base_quat, StepOut<T>& out,
+                    T* reset_ep_sums /*MAX_TERMS, valid when a reset happened*/, StepExport<T>* ex, Scr& scr) {
+  const SimState<T> s0 = e.sim;
+  PhysOut<T> po;
+  env_step_physics(P, e, raw_actions, po, scr, ex);
+  env_step_finish(P, e, s0, raw_actions, po, ep_len, default_feet_pos, default_base_quat, out, reset_ep_sums, ex);
 }
 
 }  // namespace zbot

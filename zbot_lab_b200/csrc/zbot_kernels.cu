@@ -183,7 +183,7 @@ zbot_step_body(const Params<float>& P, const DefaultPose& dp,
                  const float* __restrict__ actions, float* __restrict__ obs, float* __restrict__ rew,
                  uint8_t* __restrict__ terminated, uint8_t* __restrict__ truncated, int n, StatsCtx sc,
                  ExportPtrs xp) {
-  extern __shared__ float smem[];   // blockDim*SCR_WORDS floats: substep scratch, then obs rows, then stats
+  extern __shared__ float smem[];   // blockDim*SCR_STRIDE floats: substep scratch, then obs rows, then stats
   const int e0 = blockIdx.x * blockDim.x;
   const int e = e0 + threadIdx.x;
   const bool live = e < n;
@@ -195,23 +195,21 @@ zbot_step_body(const Params<float>& P, const DefaultPose& dp,
   for (int i = 0; i < ZBOT_NUM_OBS; ++i) obs_row[i] = 0.f;
   bool did_reset = false;
   if (live) {
-    float w[ZBOT_STATE_WORDS];
-    load_words<ZBOT_STATE_WORDS / 4>(state, n, e, w);
     EnvState<float> es;
-    env_state_unpack(w, es);
-    float raw[6];
-    {
-      const float2* a2 = reinterpret_cast<const float2*>(actions + (size_t)e * 6);
-      const float2 a0 = __ldg(a2), a1 = __ldg(a2 + 1), a2v = __ldg(a2 + 2);
-      raw[0] = a0.x; raw[1] = a0.y; raw[2] = a1.x; raw[3] = a1.y; raw[4] = a2v.x; raw[5] = a2v.y;
-    }
-    int64_t ep = ep_len_buf[e];
     StepOut<float> out;
     float rs[MAX_TERMS];
 #pragma unroll
     for (int i = 0; i < MAX_TERMS; ++i) rs[i] = 0.f;
-    SmemScratch scr{smem + threadIdx.x, (int)blockDim.x};
+    SmemScratch scr{smem + threadIdx.x * SCR_STRIDE};
+    const float2* a2p = reinterpret_cast<const float2*>(actions + (size_t)e * 6);
+    int64_t ep;
     if (kExport) {
+      float w[ZBOT_STATE_WORDS];
+      load_words<ZBOT_STATE_WORDS / 4>(state, n, e, w);
+      env_state_unpack(w, es);
+      const float2 a0 = __ldg(a2p), a1 = __ldg(a2p + 1), a2v = __ldg(a2p + 2);
+      const float raw[6] = {a0.x, a0.y, a1.x, a1.y, a2v.x, a2v.y};
+      ep = ep_len_buf[e];
       StepExport<float> ex;
       env_step(P, es, raw, ep, dp.feet_pos, dp.base_quat, out, rs, &ex, scr);
       for (int i = 0; i < 36; ++i) { xp.pos0[(size_t)e * 36 + i] = ex.pos0[i]; xp.vel0[(size_t)e * 36 + i] = ex.vel0[i];
@@ -234,8 +232,38 @@ zbot_step_body(const Params<float>& P, const DefaultPose& dp,
       xp.cur_contact1[(size_t)e * 12 + kFoot0Sensor] = ex.cur_contact[0];
       xp.cur_contact1[(size_t)e * 12 + kFoot1Sensor] = ex.cur_contact[1];
     } else {
-      env_step(P, es, raw, ep, dp.feet_pos, dp.base_quat, out, rs, (StepExport<float>*)nullptr, scr);
+      // ---- phase A: only the 11 "early" quads (articulation state, p_delta, contact carry, timers) ----
+      {
+        float w[4 * EARLY_QUADS];
+        load_words<EARLY_QUADS>(state, n, e, w);
+        env_early_unpack(w, es);
+      }
+      PhysOut<float> po;
+      {
+        const float2 a0 = __ldg(a2p), a1 = __ldg(a2p + 1), a2v = __ldg(a2p + 2);
+        const float raw[6] = {a0.x, a0.y, a1.x, a1.y, a2v.x, a2v.y};
+        // ---- phase B: 4 physics substeps; the MDP state is not even loaded yet (register budget) ----
+        env_step_physics(P, es, raw, po, scr, (StepExport<float>*)nullptr);
+      }
+      // ---- phase C: the 9 "late" quads, the start-of-step state S0 again (still unmodified in global
+      //      memory -> L2 hit) for the one-step-stale quantities, the raw actions again, then the MDP ----
+      {
+        float w[ZBOT_STATE_WORDS - 4 * EARLY_QUADS];
+        load_words<ZBOT_STATE_WORDS / 4 - EARLY_QUADS>(state + (size_t)EARLY_QUADS * n, n, e, w);
+        env_late_unpack(w, es);
+      }
+      SimState<float> s0;
+      {
+        float w[4 * SIM_QUADS];
+        load_words<SIM_QUADS>(state, n, e, w);
+        sim_state_unpack(w, s0);
+      }
+      const float2 a0 = __ldg(a2p), a1 = __ldg(a2p + 1), a2v = __ldg(a2p + 2);
+      const float raw[6] = {a0.x, a0.y, a1.x, a1.y, a2v.x, a2v.y};
+      ep = ep_len_buf[e];
+      env_step_finish(P, es, s0, raw, po, ep, dp.feet_pos, dp.base_quat, out, rs, (StepExport<float>*)nullptr);
     }
+    float w[ZBOT_STATE_WORDS];
     env_state_pack(es, w);
     store_words<ZBOT_STATE_WORDS / 4>(state, n, e, w);
     ep_len_buf[e] = ep;
@@ -270,18 +298,11 @@ zbot_step_body(const Params<float>& P, const DefaultPose& dp,
 #define ZB_STEP_CALL P, dp, state, ep_len_buf, actions, obs, rew, terminated, truncated, n, sc, xp
 
 // register-budget variants of the same body (DESIGN.md §4 "occupancy"): kMinBlocks resident CTAs of
-// kMaxThreads threads per SM ...
+// kMaxThreads threads per SM
 template <bool kExport, int kMaxThreads, int kMinBlocks>
 __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) zbot_step_kernel(ZB_STEP_ARGS) {
   zbot_step_body<kExport>(ZB_STEP_CALL);
 }
-// ... and an explicit per-thread register cap for one-warp CTAs (14 per SM at 144 registers:
-// 148 x 14 = 2072 resident warps >= the 2048 warps of 65536 envs -> a single wave, no tail)
-template <int kRegs>
-__global__ void __maxnreg__(kRegs) zbot_step_kernel_w1(ZB_STEP_ARGS) {
-  zbot_step_body<false>(ZB_STEP_CALL);
-}
-
 // ---------------------------------------------------------------------------------------------
 // reset / observe / articulation view / init
 // ---------------------------------------------------------------------------------------------
@@ -644,14 +665,17 @@ int zbot_create(const ZbotCfg* cfg, int device, ZbotHandle** out) {
   ZB_CUDA(cudaMemcpy(&h->dp, d_dp, sizeof(DefaultPose), cudaMemcpyDeviceToHost));
   ZB_CUDA(cudaFree(d_dp));
   ZB_CUDA(cudaFuncSetAttribute(zbot_mdp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * kHistRow * 4));
-  ZB_CUDA(cudaFuncSetAttribute(zbot_step_kernel<false, 128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_WORDS * 4));
-  ZB_CUDA(cudaFuncSetAttribute(zbot_step_kernel<false, 128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_WORDS * 4));
-  ZB_CUDA(cudaFuncSetAttribute(zbot_step_kernel<false, 128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_WORDS * 4));
-  ZB_CUDA(cudaFuncSetAttribute(zbot_step_kernel<true, 128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_WORDS * 4));
+  ZB_CUDA(cudaFuncSetAttribute(zbot_step_kernel<false, 128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
+  ZB_CUDA(cudaFuncSetAttribute(zbot_step_kernel<false, 128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
+  ZB_CUDA(cudaFuncSetAttribute(zbot_step_kernel<false, 128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
+  ZB_CUDA(cudaFuncSetAttribute(zbot_step_kernel<true, 128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
   {
-    const char* mb = getenv("ZBOT_STEP_MIN_BLOCKS");   // tuning knob: resident 128-thread blocks per SM the
-    h->min_blocks = mb ? atoi(mb) : 2;                  // step kernel is compiled for (register budget)
-    if (h->min_blocks != 14 && (h->min_blocks < 2 || h->min_blocks > 4)) h->min_blocks = 2;
+    // register-budget variant of the step kernel = resident 128-thread CTAs per SM it is compiled for.
+    // Measured (profiles/r1_notes.md): 2 CTAs/SM (197 regs, no spill) is fastest while the grid fits two
+    // rounds of 2 x 148 CTAs; beyond that 3 CTAs/SM (168 regs) wins on throughput (+18 % at 131072 envs).
+    const char* mb = getenv("ZBOT_STEP_MIN_BLOCKS");   // tuning override
+    h->min_blocks = mb ? atoi(mb) : ((cfg->num_envs > 2 * 2 * 148 * 128) ? 3 : 2);
+    if (h->min_blocks < 2 || h->min_blocks > 4) h->min_blocks = 2;
     const char* mt = getenv("ZBOT_MDP_TILE");          // envs (= threads) per CTA of the MDP-only step kernel
     h->mdp_tile = mt ? atoi(mt) : kMdpTile;
     if (h->mdp_tile != 32 && h->mdp_tile != 64 && h->mdp_tile != 128) h->mdp_tile = kMdpTile;
@@ -688,9 +712,9 @@ static int step_impl(ZbotHandle* h, const float* actions, float* obs, float* rew
   if (((uintptr_t)actions & 7) != 0) return fail(ZBOT_E_INVALID, "actions must be 8-byte aligned%s");
   if (int rc = check_slot(slot, prev, h->ring_slots)) return rc;
   const int n = h->cfg.num_envs;
-  const int block = (h->min_blocks == 14) ? 32 : pick_block(h, n);
+  const int block = pick_block(h, n);
   const int grid = (n + block - 1) / block;
-  const size_t smem = (size_t)block * SCR_WORDS * sizeof(float);   // >= obs rows (23/thread) and stats (704 floats)
+  const size_t smem = (size_t)block * SCR_STRIDE * sizeof(float);   // >= obs rows (23/thread) and stats (704 floats)
   StatsCtx sc{h->partials, h->ring, slot, prev, h->inv_episode_s};
   cudaStream_t s = (cudaStream_t)stream;
   ExportPtrs xp{};
@@ -709,12 +733,9 @@ static int step_impl(ZbotHandle* h, const float* actions, float* obs, float* rew
   } else if (h->min_blocks == 3) {
     zbot_step_kernel<false, 128, 3><<<grid, block, smem, s>>>(h->P, h->dp, h->state, h->ep_len, actions, obs, rew, terminated,
                                                           truncated, n, sc, xp);
-  } else if (h->min_blocks == 4) {
+  } else {
     zbot_step_kernel<false, 128, 4><<<grid, block, smem, s>>>(h->P, h->dp, h->state, h->ep_len, actions, obs, rew, terminated,
                                                           truncated, n, sc, xp);
-  } else {
-    zbot_step_kernel_w1<144><<<grid, 32, smem, s>>>(h->P, h->dp, h->state, h->ep_len, actions, obs, rew, terminated,
-                                                    truncated, n, sc, xp);
   }
   ZB_CUDA(cudaGetLastError());
   h->launches += 1;

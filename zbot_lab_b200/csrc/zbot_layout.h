@@ -11,12 +11,15 @@ namespace zbot {
 
 // fused-step state (ZBOT_STATE_WORDS = 80)
 enum StateWord : int {
+  // "early" words (quads 0..10): everything the physics phase touches
   W_ROOT_POS = 0, W_ROOT_QUAT = 3, W_ROOT_LIN = 7, W_ROOT_ANG = 10, W_Q = 13, W_QD = 19,
-  W_PDELTA = 25, W_ACT = 31, W_CARRY_FZ = 37, W_CARRY_MID = 39,
-  W_CUR_AIR = 40, W_CUR_CONTACT = 42, W_LAST_AIR = 44, W_LAST_CONTACT = 46,
-  W_FLAST = 48, W_FDPL = 50, W_FSL = 56, W_HSUM = 58, W_YSUM = 59, W_FFSUM = 60, W_SPEED = 61,
+  W_PDELTA = 25, W_SPEED = 31, W_CARRY_FZ = 32, W_CARRY_MID = 34,
+  W_CUR_AIR = 36, W_CUR_CONTACT = 38, W_LAST_AIR = 40, W_LAST_CONTACT = 42,
+  // "late" words (quads 11..19): MDP state only needed after the physics
+  W_ACT = 44, W_FLAST = 50, W_FDPL = 52, W_FSL = 58, W_HSUM = 60, W_YSUM = 61, W_FFSUM = 62,
   W_EPSUM = 64
 };
+constexpr int EARLY_QUADS = 11, SIM_QUADS = 7;   // quads [0,11) early, [11,20) late; quads [0,7) hold the SimState
 // MDP-only state (ZBOT_MDP_STATE_WORDS = 72)
 enum MdpWord : int {
   M_PDELTA = 0, M_ACT = 6, M_FLAST = 12, M_FDPL = 14, M_FSL = 20, M_HSUM = 22, M_YSUM = 23, M_FFSUM = 24,
@@ -99,7 +102,39 @@ ZB_HD void env_state_pack(const EnvState<T>& e, T* w) {
     w[W_CUR_AIR + j] = e.timers[j].cur_air; w[W_CUR_CONTACT + j] = e.timers[j].cur_contact;
     w[W_LAST_AIR + j] = e.timers[j].last_air; w[W_LAST_CONTACT + j] = e.timers[j].last_contact;
   }
-  w[62] = T(0); w[63] = T(0);
+  w[35] = T(0); w[63] = T(0);
+}
+
+// --- split views of the same 80 words (GPU: load the early quads, run the physics, then load the rest) ---
+template <typename T>
+ZB_HD void sim_state_unpack(const T* w, SimState<T>& s) {
+  ZB_UNROLL for (int i = 0; i < 3; ++i) { s.p[i] = w[W_ROOT_POS + i]; s.v[i] = w[W_ROOT_LIN + i]; s.w[i] = w[W_ROOT_ANG + i]; }
+  ZB_UNROLL for (int i = 0; i < 4; ++i) s.Q[i] = w[W_ROOT_QUAT + i];
+  ZB_UNROLL for (int i = 0; i < 6; ++i) { s.q[i] = w[W_Q + i]; s.qd[i] = w[W_QD + i]; }
+}
+template <typename T>
+ZB_HD void env_early_unpack(const T* w /*first 44 words*/, EnvState<T>& e) {
+  sim_state_unpack(w, e.sim);
+  ZB_UNROLL for (int i = 0; i < 6; ++i) e.mdp.p_delta[i] = w[W_PDELTA + i];
+  e.mdp.speed_limit = w[W_SPEED];
+  e.carry_feet_fz[0] = w[W_CARRY_FZ]; e.carry_feet_fz[1] = w[W_CARRY_FZ + 1];
+  e.carry_mid_max = w[W_CARRY_MID];
+  ZB_UNROLL for (int j = 0; j < 2; ++j) {
+    e.timers[j].cur_air = w[W_CUR_AIR + j]; e.timers[j].cur_contact = w[W_CUR_CONTACT + j];
+    e.timers[j].last_air = w[W_LAST_AIR + j]; e.timers[j].last_contact = w[W_LAST_CONTACT + j];
+  }
+}
+template <typename T>
+ZB_HD void env_late_unpack(const T* w /*words 44..79, indexed from 0*/, EnvState<T>& e) {
+  constexpr int O = 4 * EARLY_QUADS;
+  ZB_UNROLL for (int i = 0; i < 6; ++i) e.mdp.actions[i] = w[W_ACT - O + i];
+  ZB_UNROLL for (int j = 0; j < 2; ++j) {
+    e.mdp.feet_force_last[j] = w[W_FLAST - O + j];
+    e.mdp.feet_step_length[j] = w[W_FSL - O + j];
+    ZB_UNROLL for (int i = 0; i < 3; ++i) e.mdp.feet_down_pos_last[j][i] = w[W_FDPL - O + 3 * j + i];
+  }
+  e.mdp.heading_sum = w[W_HSUM - O]; e.mdp.y_err_sum = w[W_YSUM - O]; e.mdp.feet_force_sum = w[W_FFSUM - O];
+  ZB_UNROLL for (int i = 0; i < MAX_TERMS; ++i) e.mdp.ep_sums[i] = w[W_EPSUM - O + i];
 }
 
 template <typename T>
