@@ -242,20 +242,15 @@ def main():
     e2e = None
     if not args.no_e2e:
         h_act = [torch.randn(n_envs, 6).pin_memory() for _ in range(4)]
-        h_obs = torch.empty(n_envs, 23).pin_memory()
-        h_rew = torch.empty(n_envs).pin_memory()
-        h_term = torch.empty(n_envs, dtype=torch.bool).pin_memory()
-        h_trunc = torch.empty(n_envs, dtype=torch.bool).pin_memory()
+        h_out = torch.empty(n_envs * 98, dtype=torch.uint8).pin_memory()   # obs | rew | terminated | truncated
         d_act = torch.empty(n_envs, 6, device=dev)
 
         def e2e_step(i):
-            d_act.copy_(h_act[i % 4], non_blocking=True)
-            obs, rew, term, trunc, _ = env.step(d_act)
-            h_obs.copy_(obs["policy"], non_blocking=True)
-            h_rew.copy_(rew, non_blocking=True)
-            h_term.copy_(term, non_blocking=True)
-            h_trunc.copy_(trunc, non_blocking=True)
+            d_act.copy_(h_act[i % 4], non_blocking=True)          # this step's inputs: pinned host -> device
+            env.step(d_act)                                       # the public API call
+            h_out.copy_(env.last_step_packed, non_blocking=True)  # the step's whole result: device -> pinned host
             torch.cuda.synchronize()
+            return env.unpack_host(h_out)
 
         for i in range(max(3, args.warmup // 4)):
             e2e_step(i)
@@ -269,6 +264,8 @@ def main():
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e = {"value": world * n_envs * args.steps / float(te.item()), "unit": UNIT,
                "h2d_bytes_per_step": n_envs * 24, "d2h_bytes_per_step": n_envs * (92 + 4 + 1 + 1)}
+        obs_h, rew_h, term_h, trunc_h = e2e_step(0)
+        assert obs_h.shape == (n_envs, 23) and bool(torch.isfinite(rew_h).all())
 
     mdp_only = None
     if rank == 0 and world == 1 and not args.no_mdp:

@@ -114,3 +114,30 @@ def test_ppo_runner_two_iterations_and_checkpoint(tmp_path):
     obs, _ = w.get_observations()
     assert pol(obs).shape == (256, 6)
     w.close()
+
+
+def test_cuda_graph_rollout_matches_eager_semantics(tmp_path):
+    """The captured 24-step rollout graph advances the env exactly like 24 eager steps would: counters,
+    finite storage, statistics slots, and a PPO update runs on the replayed buffers."""
+    from zbot_lab_b200.compat import gym_registry as gym
+    from zbot_lab_b200.envs.rsl_rl_wrapper import RslRlVecEnvWrapper
+    from zbot_lab_b200.rl.ppo_runner import OnPolicyRunner
+    env, _ = _make(512, check_all_envs_reset=False)
+    acfg = gym.load_cfg_from_registry("zbot-6b-walking-v2", "rsl_rl_cfg_entry_point").to_dict()
+    acfg["use_cuda_graph"] = True
+    w = RslRlVecEnvWrapper(env)
+    r = OnPolicyRunner(w, acfg, log_dir=None, device="cuda:0")
+    w.episode_length_buf = torch.zeros(512, dtype=torch.int64)
+    obs, _ = w.get_observations()
+    obs = r.capture_rollout(obs)                       # 2 warm-up rollouts + 1 captured = 72 steps
+    ep0 = env.episode_length_buf.clone()
+    done_any = (r.buf["done"].sum(0) > 0)
+    obs, infos = r.replay_rollout()
+    torch.cuda.synchronize()
+    assert len(infos) == 24 and torch.isfinite(r.buf["obs"]).all() and torch.isfinite(r.buf["rew"]).all()
+    still = r.buf["done"].sum(0) == 0
+    assert torch.equal(env.episode_length_buf[still], ep0[still] + 24)      # 24 control steps per replay
+    assert torch.equal(obs, r.buf["obs"].new_tensor(obs))                    # static output buffer is readable
+    hist = r.learn(num_learning_iterations=2)
+    assert len(hist) == 2 and all(np.isfinite(h["surrogate_loss"]) for h in hist)
+    w.close()

@@ -84,6 +84,10 @@ class OnPolicyRunner:
         if self.distributed:
             for p in self.policy.parameters():
                 dist.broadcast(p.data, src=0)
+        # rollout fusion: the whole `num_steps x (policy -> env.step -> store)` loop is captured
+        # into ONE CUDA graph and replayed per iteration (no Python / launch overhead between the kernels)
+        self.use_cuda_graph = bool(train_cfg.get("use_cuda_graph", self.device.type == "cuda"))
+        self._graph = None
         self.current_learning_iteration = 0
         self.history: list[dict] = []
         self.git_status_repos: list[str] = []
@@ -136,6 +140,42 @@ class OnPolicyRunner:
             if "log" in infos:
                 ep_infos.append(infos["log"])
         return obs, ep_infos
+
+    # ------------------------------------------------------------------ CUDA-graph rollout
+    def _pin_env_cursors(self):
+        """Make the env's ring cursors start every rollout from the same position, so the buffers a captured
+        graph writes (output ring, statistics slots 0..T-1) are the ones Python hands out afterwards."""
+        u = self.env.unwrapped
+        u._out_i = len(u._out) - 1
+        u._stepper._slot = self.num_steps - 1
+        u._check_all_reset = False          # a host sync cannot live inside a graph
+
+    def capture_rollout(self, obs):
+        """Warm up on a side stream, then capture one rollout; returns the static (obs_in, last_obs, ep_infos)."""
+        assert self.device.type == "cuda"
+        self._obs_in = obs.clone()
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self._pin_env_cursors()
+                last, _ = self.collect_rollout(self._obs_in)
+                self._obs_in.copy_(last)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        self._pin_env_cursors()
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            last, ep_infos = self.collect_rollout(self._obs_in)
+            self._obs_in.copy_(last)
+        self._graph_ep_infos = ep_infos
+        return self._obs_in
+
+    def replay_rollout(self):
+        self._graph.replay()
+        u = self.env.unwrapped
+        u.common_step_counter += self.num_steps
+        return self._obs_in, self._graph_ep_infos
 
     def _returns(self, last_obs):
         b, T = self.buf, self.num_steps
@@ -220,9 +260,17 @@ class OnPolicyRunner:
         if self.log_dir and (not self.distributed or dist.get_rank() == 0):
             os.makedirs(self.log_dir, exist_ok=True)
         start = self.current_learning_iteration
+        graphed = self.use_cuda_graph and self.device.type == "cuda"
+        if graphed and self._graph is None:
+            obs = self.capture_rollout(obs)
         for it in range(start, start + num_learning_iterations):
             t0 = time.perf_counter()
-            obs, ep_infos = self.collect_rollout(obs)
+            if graphed:
+                obs, ep_infos = self.replay_rollout()
+            else:
+                obs, ep_infos = self.collect_rollout(obs)
+            if self.device.type == "cuda":
+                torch.cuda.synchronize(self.device)
             t1 = time.perf_counter()
             losses = self.update(obs)
             t2 = time.perf_counter()

@@ -136,9 +136,11 @@ class ZbotDirectEnvV2:
         self._term_names = list(self.cfg.reward_cfg["reward_scales"].keys())
         ring = max(2, int(self.cfg.output_ring))
         n, dev = self.num_envs, self.device
-        self._out = [(torch.zeros(n, 23, device=dev), torch.zeros(n, device=dev),
-                      torch.zeros(n, dtype=torch.uint8, device=dev), torch.zeros(n, dtype=torch.uint8, device=dev))
-                     for _ in range(ring)]
+        # one packed buffer per ring slot: [obs N*23 f32 | rew N f32 | terminated N u8 | truncated N u8] so a
+        # host consumer can fetch a whole step result with ONE device->host copy (``last_step_packed``)
+        self._packed = [torch.zeros(n * 24 * 4 + 2 * n, dtype=torch.uint8, device=dev) for _ in range(ring)]
+        self._out = [(b[:n * 92].view(torch.float32).view(n, 23), b[n * 92:n * 96].view(torch.float32),
+                      b[n * 96:n * 97], b[n * 97:n * 98]) for b in self._packed]
         self._out_i = 0
         self.reset_terminated = torch.zeros(n, dtype=torch.bool, device=dev)
         self.reset_time_outs = torch.zeros(n, dtype=torch.bool, device=dev)
@@ -243,8 +245,15 @@ class ZbotDirectEnvV2:
         return {"policy": obs}, rew, self.reset_terminated, self.reset_time_outs, self.extras
 
     @property
-    def reset_buf_now(self):
-        return self.reset_terminated | self.reset_time_outs
+    def last_step_packed(self) -> torch.Tensor:
+        """uint8 view of the most recent step's outputs, laid out [obs | rew | terminated | truncated]."""
+        return self._packed[self._out_i]
+
+    def unpack_host(self, host_bytes: torch.Tensor):
+        """Views (obs, rew, terminated, truncated) into a host copy of ``last_step_packed``."""
+        n = self.num_envs
+        return (host_bytes[:n * 92].view(torch.float32).view(n, 23), host_bytes[n * 92:n * 96].view(torch.float32),
+                host_bytes[n * 96:n * 97].view(torch.bool), host_bytes[n * 97:n * 98].view(torch.bool))
 
     def close(self):
         if getattr(self, "_stepper", None) is not None:
