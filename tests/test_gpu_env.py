@@ -137,7 +137,7 @@ def test_cuda_graph_rollout_matches_eager_semantics(tmp_path):
     assert len(infos) == 24 and torch.isfinite(r.buf["obs"]).all() and torch.isfinite(r.buf["rew"]).all()
     still = r.buf["done"].sum(0) == 0
     assert torch.equal(env.episode_length_buf[still], ep0[still] + 24)      # 24 control steps per replay
-    assert torch.equal(obs, r.buf["obs"].new_tensor(obs))                    # static output buffer is readable
+    assert obs.shape == (512, 23) and torch.isfinite(obs).all()              # static output buffer is readable
     hist = r.learn(num_learning_iterations=2)
     assert len(hist) == 2 and all(np.isfinite(h["surrogate_loss"]) for h in hist)
     w.close()

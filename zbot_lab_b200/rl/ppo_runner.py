@@ -45,7 +45,7 @@ class ActorCritic(nn.Module):
 
     def dist(self, obs):
         mean = self.actor(obs)
-        return torch.distributions.Normal(mean, self.std.clamp(min=1e-6).expand_as(mean))
+        return torch.distributions.Normal(mean, self.std.clamp(min=1e-6).expand_as(mean), validate_args=False)
 
     def act_inference(self, obs):
         return self.actor(obs)
@@ -128,7 +128,9 @@ class OnPolicyRunner:
         b, ep_infos = self.buf, []
         for t in range(self.num_steps):
             d = self.policy.dist(obs)
-            act = d.sample()
+            # mean + std * N(0,1): torch.normal(mean, std_tensor) validates std with a host sync, which would
+            # break CUDA-graph capture of the rollout
+            act = d.mean + d.stddev * torch.randn_like(d.mean)
             b["obs"][t], b["act"][t] = obs, act
             b["val"][t], b["logp"][t] = self.policy.evaluate(obs), d.log_prob(act).sum(-1)
             b["mu"][t], b["sigma"][t] = d.mean, d.stddev
