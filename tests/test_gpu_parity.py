@@ -340,3 +340,58 @@ def test_abi_error_paths():
     assert lib.zbot_create(C.byref(cfg), 0, C.byref(h)) == 0
     assert lib.zbot_step(h, None, None, None, None, None, 0, -1, None) == -3   # unbound
     assert lib.zbot_destroy(h) == 0
+
+
+def test_no_out_of_bounds_writes_guard_bands():
+    """compute-sanitizer is not available on this pool: every output / state buffer is carved out of one
+    arena with canary gaps; after step, reset, observe, view and the MDP-only step (ragged N, tail blocks)
+    every canary must be intact."""
+    import ctypes as C
+    from zbot_lab_b200 import native
+    from zbot_lab_b200.utils import synthetic as syn
+    lib = native.lib()
+    for n in (1000, 129, 31):
+        cfg = native.make_cfg(n)
+        h = C.c_void_p()
+        native.check(lib.zbot_create(C.byref(cfg), 0, C.byref(h)))
+        sizes = {"state": 80 * n * 4, "ep": 8 * n, "ring": 4 * 32 * 4, "obs": 92 * n, "rew": 4 * n, "term": n, "trunc": n,
+                 "act": 24 * n, "mstate": 72 * n * 4, "mep": 8 * n, "mring": 4 * 32 * 4, "pos": 144 * n, "quat": 192 * n,
+                 "vel": 144 * n}
+        gap = 1024
+        total = sum((s + 255) // 256 * 256 + gap for s in sizes.values()) + gap
+        arena = torch.full((total,), 0xA5, dtype=torch.uint8, device=DEV)
+        off, views = gap, {}
+        for k, sz in sizes.items():
+            views[k] = arena[off:off + sz]
+            views[k].zero_()
+            off += (sz + 255) // 256 * 256 + gap
+        mask = torch.ones(total, dtype=torch.bool, device=DEV)
+        for v in views.values():
+            o = v.data_ptr() - arena.data_ptr()
+            mask[o:o + v.numel()] = False
+        p = lambda k: C.c_void_p(views[k].data_ptr())
+        native.check(lib.zbot_bind(h, p("state"), p("ep"), p("ring"), 4))
+        native.check(lib.zbot_reset_idx(h, None, -1, None, None, 0, None))
+        views["act"].view(torch.float32).normal_()
+        for t in range(6):
+            native.check(lib.zbot_step(h, p("act"), p("obs"), p("rew"), p("term"), p("trunc"), (t + 1) % 4, t % 4, None))
+        ids = torch.tensor([0, n - 1], device=DEV)
+        native.check(lib.zbot_reset_idx(h, C.c_void_p(ids.data_ptr()), 2, p("term"), p("trunc"), 1, None))
+        native.check(lib.zbot_observe(h, p("obs"), None))
+        native.check(lib.zbot_articulation_view(h, p("pos"), p("quat"), p("vel"), None))
+        # MDP-only path on synthetic inputs
+        rng = np.random.default_rng(n)
+        org = _t(syn.env_origins_grid(n))
+        S = _S(syn.synth_articulation_state(rng, n, org.cpu().numpy()))
+        mi = native.ZbotMdpInputs(*[S[k].data_ptr() for k in ("body_link_pos_w", "body_link_quat_w", "body_com_lin_vel_w",
+                                                              "joint_pos", "joint_vel", "applied_torque",
+                                                              "net_forces_w_history", "last_air_time")], org.data_ptr())
+        native.check(lib.zbot_mdp_bind(h, p("mstate"), p("mep"), p("mring"), 4))
+        native.check(lib.zbot_mdp_observe(h, C.byref(mi), p("obs"), None))
+        for t in range(3):
+            native.check(lib.zbot_mdp_step(h, C.byref(mi), p("act"), p("obs"), p("rew"), p("term"), p("trunc"),
+                                           (t + 1) % 4, t % 4, None))
+        torch.cuda.synchronize()
+        assert torch.all(arena[mask] == 0xA5), f"canary overwritten (n={n})"
+        assert torch.isfinite(views["obs"].view(torch.float32)).all()
+        lib.zbot_destroy(h)
