@@ -467,3 +467,21 @@ def test_yaw_and_translation_symmetry_of_the_fused_step():
     assert (res[0][0] - res[1][0])[both].abs().max() < 2e-3       # joint positions
     assert (res[0][2] - res[1][2])[both].abs().max() < 1e-3       # base height
     assert (res[0][0] - res[1][0])[both].abs().median() < 1e-5
+
+
+def test_single_env_and_empty_reset_list():
+    """Edge cases: one env (the reference's `.squeeze()` calls break at N = 1, SURVEY C-8; the kernel must
+    not), an empty reset id list (no launch, state untouched), out-of-range ids are ignored."""
+    st = _stepper(1)
+    st.reset_idx(None)
+    for t in range(5):
+        obs, rew, term, trunc = st.step(torch.zeros(1, 6, device=DEV))
+    assert obs.shape == (1, 23) and torch.isfinite(obs).all() and int(st.episode_length_buf[0]) == 5
+    before = st.state.buf.clone()
+    n0 = st.launch_count
+    st.reset_idx(torch.empty(0, dtype=torch.int64, device=DEV))
+    assert st.launch_count == n0 and torch.equal(st.state.buf, before)
+    st.reset_idx(torch.tensor([5, -1], device=DEV))          # not valid env ids: ignored
+    torch.cuda.synchronize()
+    assert torch.equal(st.state.buf, before) and int(st.episode_length_buf[0]) == 5
+    st.close()
