@@ -25,8 +25,8 @@ def test_env_protocol_and_wrapper():
     assert env.max_episode_length_s == 20.0 and env.num_envs == 64 and env.unwrapped is env
     w = RslRlVecEnvWrapper(env, clip_actions=None)
     assert w.num_actions == 6 and w.num_obs == 23
-    obs, extras = w.get_observations()
-    assert obs.shape == (64, 23) and obs.dtype == torch.float32 and "observations" in extras
+    obs = w.get_observations()["policy"]
+    assert obs.shape == (64, 23) and obs.dtype == torch.float32
     # default pose known answers (…env_v2.py:403-404): base quat in obs[0:4], q - q_default = 0
     assert torch.allclose(obs[0, :4], torch.tensor([0.6003, -0.6003, -0.3735, -0.3739], device="cuda:0"), atol=1e-4)
     assert torch.all(obs[:, 4:22] == 0) and torch.all(obs[:, 22] == 1.0)
@@ -37,6 +37,7 @@ def test_env_protocol_and_wrapper():
     for t in range(40):
         a = torch.randn(64, 6, device="cuda:0")
         obs, rew, dones, extras = w.step(a)
+        obs = obs["policy"]
         assert obs.shape == (64, 23) and rew.shape == (64,) and dones.dtype == torch.long
         assert extras["time_outs"].dtype == torch.bool and "log" in extras
         assert set(extras["log"]) == {"Episode_Reward/" + k for k in cfg.reward_cfg["reward_scales"]} | {
@@ -111,8 +112,8 @@ def test_ppo_runner_two_iterations_and_checkpoint(tmp_path):
     r2 = OnPolicyRunner(w, agent_cfg.to_dict(), log_dir=None, device="cuda:0")
     r2.load(str(ck))
     pol = r2.get_inference_policy(device="cuda:0")
-    obs, _ = w.get_observations()
-    assert pol(obs).shape == (256, 6)
+    obs = w.get_observations()
+    assert pol(obs).shape == (256, 6) and pol(obs["policy"]).shape == (256, 6)
     w.close()
 
 
@@ -128,7 +129,7 @@ def test_cuda_graph_rollout_matches_eager_semantics(tmp_path):
     w = RslRlVecEnvWrapper(env)
     r = OnPolicyRunner(w, acfg, log_dir=None, device="cuda:0")
     w.episode_length_buf = torch.zeros(512, dtype=torch.int64)
-    obs, _ = w.get_observations()
+    obs = w.get_observations()["policy"]
     obs = r.capture_rollout(obs)                       # 2 warm-up rollouts + 1 captured = 72 steps
     ep0 = env.episode_length_buf.clone()
     done_any = (r.buf["done"].sum(0) > 0)

@@ -55,7 +55,7 @@ def test_env_surface_on_cpu_double(shimmed):
     cfg.sim.device = "cpu"
     env = gym.make("zbot-6b-walking-v2", cfg=cfg, render_mode=None)
     w = RslRlVecEnvWrapper(env)
-    obs, _ = w.get_observations()
+    obs = w.get_observations()["policy"]
     assert obs.shape == (8, 23)
     w.episode_length_buf = torch.full((8,), 997, dtype=torch.int64)
     _, _, dones, ex = w.step(torch.zeros(8, 6))
@@ -64,3 +64,24 @@ def test_env_surface_on_cpu_double(shimmed):
     assert dones.all() and ex["time_outs"].all()                 # 997 + 2 = 999 -> truncation
     assert float(ex["log"]["Episode_Termination/time_out"]) == 8.0
     assert int(env.episode_length_buf.max()) < 1000               # all envs reset -> randint spread
+
+
+def test_reference_play_py_runs_unchanged(shimmed, monkeypatch):
+    """train (2 iterations) -> the reference's own play.py loads the checkpoint, exports the policy and
+    steps the env for a bounded number of iterations -- both scripts unmodified."""
+    monkeypatch.setattr(sys, "argv", ["train.py", "--task", "zbot-6b-walking-v2", "--num_envs", "8",
+                                      "--max_iterations", "1", "--headless", "--device", "cpu",
+                                      "agent.num_steps_per_env=4", "agent.device=cpu"])
+    runpy.run_path(os.path.join(REF_SCRIPTS, "train.py"), run_name="__main__")
+    for m in [k for k in sys.modules if k.split(".")[0] in ("cli_args",)]:
+        monkeypatch.delitem(sys.modules, m)
+    monkeypatch.setenv("ZBOT_PLAY_STEPS", "5")
+    monkeypatch.setattr(sys, "argv", ["play.py", "--task", "zbot-6b-walking-v2", "--num_envs", "4", "--headless",
+                                      "--device", "cpu", "agent.device=cpu"])
+    runpy.run_path(os.path.join(REF_SCRIPTS, "play.py"), run_name="__main__")
+    root = shimmed / "logs" / "rsl_rl" / "zbot_6b_flat_direct_v2"
+    run = root / os.listdir(root)[0]
+    assert (run / "exported" / "policy.pt").exists()
+    import torch
+    pol = torch.jit.load(str(run / "exported" / "policy.pt"))
+    assert pol(torch.zeros(3, 23)).shape == (3, 6)

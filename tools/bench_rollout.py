@@ -28,7 +28,7 @@ def make(n, device, graph):
 
 
 def time_rollouts(r, iters):
-    obs, _ = r.env.get_observations()
+    obs = r.env.get_observations()["policy"]
     if r.use_cuda_graph:
         obs = r.capture_rollout(obs)
     for _ in range(3):

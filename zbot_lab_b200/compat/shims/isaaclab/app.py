@@ -5,8 +5,18 @@ import os
 
 
 class _App:
+    """``simulation_app``: play.py loops ``while simulation_app.is_running()``.  With no GUI to close, the
+    loop length is bounded by ``ZBOT_PLAY_STEPS`` (default: run until interrupted)."""
+
+    def __init__(self):
+        n = os.environ.get("ZBOT_PLAY_STEPS")
+        self._left = int(n) if n else None
+
     def is_running(self):
-        return True
+        if self._left is None:
+            return True
+        self._left -= 1
+        return self._left >= 0
 
     def close(self):
         pass

@@ -6,6 +6,27 @@ from __future__ import annotations
 import torch
 
 
+class ObsDict(dict):
+    """Observation groups keyed by name -- the minimal ``TensorDict`` surface rsl_rl >= 3.0 relies on
+    (``obs["policy"]``, ``.to(device)``); ``tensordict`` is not installed in this image."""
+
+    def to(self, device):
+        return ObsDict({k: v.to(device) for k, v in self.items()})
+
+    @property
+    def batch_size(self):
+        return next(iter(self.values())).shape[:1]
+
+    @property
+    def device(self):
+        return next(iter(self.values())).device
+
+
+def policy_obs(obs) -> torch.Tensor:
+    """Accept both conventions: a plain tensor (rsl_rl 2.x) or an observation dict (rsl_rl >= 3.0)."""
+    return obs["policy"] if isinstance(obs, dict) else obs
+
+
 class RslRlVecEnvWrapper:
     def __init__(self, env, clip_actions: float | None = None):
         self.env = env
@@ -54,13 +75,13 @@ class RslRlVecEnvWrapper:
     def seed(self, seed: int = -1) -> int:
         return self.unwrapped.seed(seed)
 
-    def get_observations(self):
-        obs_dict = {"policy": self.unwrapped._stepper.observe().clone()}
-        return obs_dict["policy"], {"observations": obs_dict}
+    def get_observations(self) -> ObsDict:
+        """rsl_rl >= 3.0 convention (scripts/rsl_rl/train.py:59 requires 3.0.1): the observation groups."""
+        return ObsDict({"policy": self.unwrapped._stepper.observe().clone()})
 
     def reset(self):
-        obs_dict, _ = self.env.reset()
-        return obs_dict["policy"], {"observations": obs_dict}
+        obs_dict, extras = self.env.reset()
+        return ObsDict(obs_dict), extras
 
     def step(self, actions: torch.Tensor):
         if self.clip_actions is not None:
@@ -70,7 +91,7 @@ class RslRlVecEnvWrapper:
         extras["observations"] = obs_dict
         if not self.unwrapped.cfg.is_finite_horizon:
             extras["time_outs"] = truncated
-        return obs_dict["policy"], rew, dones, extras
+        return ObsDict(obs_dict), rew, dones, extras
 
     def close(self):
         return self.env.close()

@@ -17,9 +17,13 @@ import os
 import time
 from collections import deque
 
+import types
+
 import torch
 import torch.distributed as dist
 import torch.nn as nn
+
+from ..envs.rsl_rl_wrapper import policy_obs
 
 
 def _mlp(inp, hidden, out, act):
@@ -48,7 +52,7 @@ class ActorCritic(nn.Module):
         return torch.distributions.Normal(mean, self.std.clamp(min=1e-6).expand_as(mean), validate_args=False)
 
     def act_inference(self, obs):
-        return self.actor(obs)
+        return self.actor(policy_obs(obs))
 
     def evaluate(self, obs):
         return self.critic(obs).squeeze(-1)
@@ -64,12 +68,13 @@ class OnPolicyRunner:
         self.log_dir = log_dir
         self.num_steps = int(train_cfg.get("num_steps_per_env", 24))
         self.save_interval = int(train_cfg.get("save_interval", 100))
-        obs, _ = env.get_observations()
+        obs = policy_obs(env.get_observations())
         self.num_obs, self.num_actions = obs.shape[1], env.num_actions
         self.policy = ActorCritic(self.num_obs, self.num_actions, **{k: v for k, v in self.policy_cfg.items()
                                                                    if k != "class_name"}).to(self.device)
         self.lr = float(self.alg_cfg.get("learning_rate", 1e-3))
         self.optimizer = torch.optim.Adam(self.policy.parameters(), lr=self.lr)
+        self.alg = types.SimpleNamespace(policy=self.policy, optimizer=self.optimizer)   # `runner.alg.policy` (play.py:161)
         self.gamma, self.lam = float(self.alg_cfg.get("gamma", 0.99)), float(self.alg_cfg.get("lam", 0.95))
         self.clip = float(self.alg_cfg.get("clip_param", 0.2))
         self.epochs = int(self.alg_cfg.get("num_learning_epochs", 5))
@@ -135,6 +140,7 @@ class OnPolicyRunner:
             b["val"][t], b["logp"][t] = self.policy.evaluate(obs), d.log_prob(act).sum(-1)
             b["mu"][t], b["sigma"][t] = d.mean, d.stddev
             obs, rew, dones, infos = self.env.step(act)
+            obs = policy_obs(obs)
             rew = rew.clone()
             if "time_outs" in infos:   # bootstrap on truncation
                 rew += self.gamma * b["val"][t] * infos["time_outs"].to(rew.dtype)
@@ -255,8 +261,7 @@ class OnPolicyRunner:
         if init_at_random_ep_len:   # scripts/rsl_rl/train.py:205
             self.env.episode_length_buf = torch.randint_like(self.env.episode_length_buf,
                                                              high=int(self.env.max_episode_length))
-        obs, _ = self.env.get_observations()
-        obs = obs.to(self.device)
+        obs = policy_obs(self.env.get_observations()).to(self.device)
         self.policy.train()
         rewbuf, cur_rew = deque(maxlen=100), torch.zeros(self.env.num_envs, device=self.device)
         if self.log_dir and (not self.distributed or dist.get_rank() == 0):
