@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """bench.py -- env-steps/s of the fused ``zbot-6b-walking-v2`` step on N B200s of one node.
 
-  python bench.py                         # N=1, 4096 envs (BASELINE.json configs[1])
+  python bench.py                         # N=1: 65536 envs (headline `value`) + 4096 envs ("envs_4096",
+                                          # BASELINE.json configs[1]) + the MDP-only kernel side measurement
   torchrun ... bench.py --gpus 8 ...      # 65536 envs/GPU, env-sharded (configs[2]); NCCL only
                                           # for the rollout statistics
   python bench.py --impl reference        # the CPU path (oracle CPU port, all host threads)
@@ -32,6 +33,11 @@ ALGO_BYTES_PER_ENV_STEP = 320 + 24 + 8 + 320 + 92 + 4 + 2 + 8
 # dram__bytes_read.sum + dram__bytes_write.sum of one zbot_step_kernel launch at 65536 envs (ncu --set full,
 # profiles/r1_step_ncu.md) per env: reads hit DRAM, most writes are still in the 126 MB L2 when the kernel ends
 NCU_TRAFFIC_BYTES_PER_ENV_STEP = 379
+# Envs per GPU of the headline `value` at EVERY N (weak scaling: identical per-GPU work at N = 1, 2, 4, 8 so the
+# driver's scaling efficiency is meaningful).  65536 envs/GPU is the configuration BASELINE.json states the
+# multi-GPU target on (configs[2]); the 4096-env configuration (configs[1]) is measured in the same run at N = 1
+# and reported under "envs_4096".
+DEFAULT_ENVS_PER_GPU = 65536
 ROLLOUT_STEPS = 24  # agents/rsl_rl_ppo_cfg.py:67 -- statistics are reduced once per rollout
 
 
@@ -46,6 +52,7 @@ def parse():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-mdp", action="store_true", help="skip the MDP-only kernel side measurement")
+    p.add_argument("--no-small", action="store_true", help="skip the additional 4096-env measurement at N=1")
     p.add_argument("--cpu-sample-steps", type=int, default=None)
     return p.parse_args()
 
@@ -137,7 +144,7 @@ def run_reference(args):
         env = dict(os.environ, OMP_NUM_THREADS=want, ZBOT_BENCH_REEXEC="1")
         sys.stdout.flush()
         os.execve(sys.executable, [sys.executable] + sys.argv, env)
-    n_envs = args.envs or (4096 if args.gpus == 1 else 65536)
+    n_envs = args.envs or DEFAULT_ENVS_PER_GPU
     # bounded sample: the same workload shape, at most ~20 s of CPU work
     steps = max(1, min(args.steps, 50))
     warm = max(1, min(args.warmup, 3))
@@ -181,91 +188,105 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    n_envs = args.envs or (4096 if args.gpus == 1 else 65536)
-
-    # the public API: gym.make(task, cfg=...) exactly as scripts/rsl_rl/train.py:158
-    cfg = gym.load_cfg_from_registry("zbot-6b-walking-v2", "env_cfg_entry_point")
-    cfg.scene.num_envs = n_envs
-    cfg.sim.device = str(dev)
-    cfg.seed = zdist.rank_seed(1234, rank)
-    env = gym.make("zbot-6b-walking-v2", cfg=cfg, render_mode=None)
-    st = env.unwrapped._stepper
-    env.reset()
-    rng = np.random.default_rng(1234 + rank)
-    st.set_sim_state({k: torch.from_numpy(v).to(dev) for k, v in syn.synth_sim_state(rng, n_envs).items()})
-    g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    env.episode_length_buf = torch.randint(0, 1000, (n_envs,), device=dev, generator=g)
-    n_act = 16
-    actions = torch.randn(n_act, n_envs, 6, device=dev, generator=g)            # resident in HBM
-    flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    stats_acc = torch.zeros(32, device=dev)
+    n_envs = args.envs or DEFAULT_ENVS_PER_GPU
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def one_step(i):
-        st.step(actions[i % n_act])
+    def measure(n_envs, steps, warmup, with_e2e):
+        """Time `steps` control steps of `n_envs` envs on this rank; returns a dict (rank-local + max-reduced)."""
 
-    for i in range(args.warmup):
-        one_step(i)
-    barrier()
-    sampler = ClockSampler(local)
-    sampler.sample_once()
-    sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    launches0 = st.launch_count
-    barrier()
-    t_wall0 = time.perf_counter()
-    for i in range(args.steps):
-        if flush is not None:
-            flush.fill_(i & 0xFF)                      # evict L2 (126 MB) -- outside the timed events
-        ev[i][0].record()
-        one_step(i)
-        ev[i][1].record()
-        if world > 1 and (i + 1) % ROLLOUT_STEPS == 0:
-            stats_acc = zdist.reduce_rollout_stats(st.stats)   # rollout statistics: the only collective on the path
-    barrier()
-    t_wall = time.perf_counter() - t_wall0
-    launches = st.launch_count - launches0
-    sampler.stop()
-    step_ms = [a.elapsed_time(b) for a, b in ev]
-    total_ms = float(sum(step_ms))
-    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
-    value = world * n_envs * args.steps / (total_ms * 1e-3)
+        # the public API: gym.make(task, cfg=...) exactly as scripts/rsl_rl/train.py:158
+        cfg = gym.load_cfg_from_registry("zbot-6b-walking-v2", "env_cfg_entry_point")
+        cfg.scene.num_envs = n_envs
+        cfg.sim.device = str(dev)
+        cfg.seed = zdist.rank_seed(1234, rank)
+        env = gym.make("zbot-6b-walking-v2", cfg=cfg, render_mode=None)
+        st = env.unwrapped._stepper
+        env.reset()
+        rng = np.random.default_rng(1234 + rank)
+        st.set_sim_state({k: torch.from_numpy(v).to(dev) for k, v in syn.synth_sim_state(rng, n_envs).items()})
+        g = torch.Generator(device=dev).manual_seed(1234 + rank)
+        env.episode_length_buf = torch.randint(0, 1000, (n_envs,), device=dev, generator=g)
+        n_act = 16
+        actions = torch.randn(n_act, n_envs, 6, device=dev, generator=g)            # resident in HBM
+        flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        stats_acc = torch.zeros(32, device=dev)
 
-    # end to end through the public API with HOST buffers: pinned actions -> H2D, env.step, D2H of the result
-    e2e = None
-    if not args.no_e2e:
-        h_act = [torch.randn(n_envs, 6).pin_memory() for _ in range(4)]
-        h_out = torch.empty(n_envs * 98, dtype=torch.uint8).pin_memory()   # obs | rew | terminated | truncated
-        d_act = torch.empty(n_envs, 6, device=dev)
+        def one_step(i):
+            st.step(actions[i % n_act])
 
-        def e2e_step(i):
-            d_act.copy_(h_act[i % 4], non_blocking=True)          # this step's inputs: pinned host -> device
-            env.step(d_act)                                       # the public API call
-            h_out.copy_(env.last_step_packed, non_blocking=True)  # the step's whole result: device -> pinned host
-            torch.cuda.synchronize()
-            return env.unpack_host(h_out)
-
-        for i in range(max(3, args.warmup // 4)):
-            e2e_step(i)
+        for i in range(warmup):
+            one_step(i)
         barrier()
-        t0 = time.perf_counter()
-        for i in range(args.steps):
-            e2e_step(i)
+        sampler = ClockSampler(local)
+        sampler.sample_once()
+        sampler.start()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        launches0 = st.launch_count
         barrier()
-        te = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        t_wall0 = time.perf_counter()
+        for i in range(steps):
+            if flush is not None:
+                flush.fill_(i & 0xFF)                      # evict L2 (126 MB) -- outside the timed events
+            ev[i][0].record()
+            one_step(i)
+            ev[i][1].record()
+            if world > 1 and (i + 1) % ROLLOUT_STEPS == 0:
+                stats_acc = zdist.reduce_rollout_stats(st.stats)   # rollout statistics: the only collective on the path
+        barrier()
+        t_wall = time.perf_counter() - t_wall0
+        launches = st.launch_count - launches0
+        sampler.stop()
+        step_ms = [a.elapsed_time(b) for a, b in ev]
+        total_ms = float(sum(step_ms))
+        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
         if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * n_envs * args.steps / float(te.item()), "unit": UNIT,
-               "h2d_bytes_per_step": n_envs * 24, "d2h_bytes_per_step": n_envs * (92 + 4 + 1 + 1)}
-        obs_h, rew_h, term_h, trunc_h = e2e_step(0)
-        assert obs_h.shape == (n_envs, 23) and bool(torch.isfinite(rew_h).all())
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+        value = world * n_envs * steps / (total_ms * 1e-3)
+
+        # end to end through the public API with HOST buffers: pinned actions -> H2D, env.step, D2H of the result
+        e2e = None
+        if with_e2e:
+            h_act = [torch.randn(n_envs, 6).pin_memory() for _ in range(4)]
+            h_out = torch.empty(n_envs * 98, dtype=torch.uint8).pin_memory()   # obs | rew | terminated | truncated
+            d_act = torch.empty(n_envs, 6, device=dev)
+
+            def e2e_step(i):
+                d_act.copy_(h_act[i % 4], non_blocking=True)          # this step's inputs: pinned host -> device
+                env.step(d_act)                                       # the public API call
+                h_out.copy_(env.last_step_packed, non_blocking=True)  # the step's whole result: device -> pinned host
+                torch.cuda.synchronize()
+                return env.unpack_host(h_out)
+
+            for i in range(max(3, warmup // 4)):
+                e2e_step(i)
+            barrier()
+            t0 = time.perf_counter()
+            for i in range(steps):
+                e2e_step(i)
+            barrier()
+            te = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            e2e = {"value": world * n_envs * steps / float(te.item()), "unit": UNIT,
+                   "h2d_bytes_per_step": n_envs * 24, "d2h_bytes_per_step": n_envs * (92 + 4 + 1 + 1)}
+            obs_h, rew_h, term_h, trunc_h = e2e_step(0)
+            assert obs_h.shape == (n_envs, 23) and bool(torch.isfinite(rew_h).all())
+
+
+        env.close()
+        return {"n_envs": n_envs, "value": value, "total_ms": total_ms, "local_ms_per_step": float(sum(step_ms)) / steps,
+                "launches": int(launches), "e2e": e2e, "clocks": sampler.summary(), "wall": t_wall, "flushed": flush is not None}
+
+    main_m = measure(n_envs, args.steps, args.warmup, not args.no_e2e)
+    small_m = None
+    if world == 1 and args.envs is None and not args.no_small:
+        small_m = measure(4096, args.steps, args.warmup, not args.no_e2e)     # BASELINE.json configs[1]
+    value, total_ms, launches, e2e = main_m["value"], main_m["total_ms"], main_m["launches"], main_m["e2e"]
 
     mdp_only = None
     if rank == 0 and world == 1 and not args.no_mdp:
@@ -285,7 +306,7 @@ def main():
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
-        kern_ms = total_ms / args.steps if world == 1 else float(sum(step_ms)) / args.steps
+        kern_ms = main_m["local_ms_per_step"]
         achieved = ALGO_BYTES_PER_ENV_STEP * n_envs / (kern_ms * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -293,16 +314,21 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"zbot-6b-walking-v2 full fused step (4 substeps + MDP + reset), {n_envs} envs/GPU",
                        "envs_per_gpu": n_envs, "parallelism": f"env-sharded x{world}, no collective in the step",
-                       "l2": "flushed between timed steps (256 MiB write)" if flush is not None else "not flushed",
-                       "wall_s_incl_flush": t_wall},
+                       "l2": "flushed between timed steps (256 MiB write)" if main_m["flushed"] else "not flushed",
+                       "wall_s_incl_flush": main_m["wall"]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": NCU_TRAFFIC_BYTES_PER_ENV_STEP * n_envs, "peak_source": peak_src,
                          "kernel": "zbot_step_kernel<false,128,2>",
                          "traffic_note": "dram__bytes_read+write per launch from profiles/r1_step_ncu.md, scaled per env",
                          "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP,
                          "note": "the fused step is FP32-issue bound, not HBM bound (DESIGN.md §4)"},
-            "gpu_launches": int(launches), "clocks": sampler.summary(),
+            "gpu_launches": int(launches), "clocks": main_m["clocks"],
         }
+        if small_m is not None:
+            a4 = ALGO_BYTES_PER_ENV_STEP * 4096 / (small_m["local_ms_per_step"] * 1e-3) / 1e9
+            line["envs_4096"] = {"workload": "BASELINE.json configs[1]: full fused step, 4096 envs, 1 x B200",
+                                 "value": small_m["value"], "unit": UNIT, "ms_per_step": small_m["total_ms"] / args.steps,
+                                 "e2e": small_m["e2e"], "roofline_frac_hbm": a4 / peak, "gpu_launches": small_m["launches"]}
         if e2e is not None:
             line["e2e"] = e2e
         if mdp_only is not None:
