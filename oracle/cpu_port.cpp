@@ -67,7 +67,7 @@ static int port_step(const ZbotCfg* cfg, T* state, int64_t* ep_len, const T* act
 // dynamics only: sim [N][25] (root_pos3 quat4 lin3 ang3 q6 qd6), target [N][6]
 // forces [N][7][3] (body 0 and 6 = applied foot forces, 1..5 = predictor), tau [N][6]
 template <typename T>
-static int port_substeps(const ZbotCfg* cfg, T* sim, const T* target, T* forces, T* tau, int n, int nsub) {
+static int port_substeps(const ZbotCfg* cfg, T* sim, const T* target, T* forces, T* tau, int n, int nsub, bool snake = false) {
   Params<T> P;
   params_from_cfg(*cfg, P);
 #pragma omp parallel for schedule(static) num_threads(port_threads())
@@ -80,7 +80,10 @@ static int port_substeps(const ZbotCfg* cfg, T* sim, const T* target, T* forces,
     SubstepOut<T> so;
     ArrayScratch<T> scr;
     T midf[15];
-    for (int k = 0; k < nsub; ++k) physics_substep(P, s, target + (size_t)e * 6, so, scr, midf);
+    for (int k = 0; k < nsub; ++k) {
+      if (snake) physics_substep<ModelSnake>(P, s, target + (size_t)e * 6, so, scr, midf);
+      else physics_substep<ModelWalk>(P, s, target + (size_t)e * 6, so, scr, midf);
+    }
     for (int i = 0; i < 3; ++i) { w[i] = s.p[i]; w[7 + i] = s.v[i]; w[10 + i] = s.w[i]; }
     for (int i = 0; i < 4; ++i) w[3 + i] = s.Q[i];
     for (int i = 0; i < 6; ++i) { w[13 + i] = s.q[i]; w[19 + i] = s.qd[i]; }
@@ -127,6 +130,12 @@ int zbot_port_substeps_f32(const ZbotCfg* cfg, float* sim, const float* target, 
 }
 int zbot_port_substeps_f64(const ZbotCfg* cfg, double* sim, const double* target, double* forces, double* tau, int n, int nsub) {
   return port_substeps<double>(cfg, sim, target, forces, tau, n, nsub);
+}
+int zbot_port_substeps_snake_f32(const ZbotCfg* cfg, float* sim, const float* target, float* forces, float* tau, int n, int nsub) {
+  return port_substeps<float>(cfg, sim, target, forces, tau, n, nsub, true);
+}
+int zbot_port_substeps_snake_f64(const ZbotCfg* cfg, double* sim, const double* target, double* forces, double* tau, int n, int nsub) {
+  return port_substeps<double>(cfg, sim, target, forces, tau, n, nsub, true);
 }
 int zbot_port_link_view_f64(const double* sim, double* pos, double* quat, double* vel, int n) {
   return port_link_view<double>(sim, pos, quat, vel, n);

@@ -110,7 +110,7 @@ class PortEnv:
         return obs, rew, term.astype(bool), trunc.astype(bool), rs, ex
 
 
-def substeps(sim: np.ndarray, target: np.ndarray, nsub: int, cfg: ZbotCfg | None = None):
+def substeps(sim: np.ndarray, target: np.ndarray, nsub: int, cfg: ZbotCfg | None = None, snake: bool = False):
     """sim [N][25] (in/out), target [N][6] -> forces [N][7][3], applied torque [N][6]."""
     n = sim.shape[0]
     dt = sim.dtype
@@ -119,7 +119,7 @@ def substeps(sim: np.ndarray, target: np.ndarray, nsub: int, cfg: ZbotCfg | None
     forces = np.zeros((n, 7, 3), dt)
     tau = np.zeros((n, 6), dt)
     target = np.ascontiguousarray(target, dt)
-    rc = getattr(lib(), "zbot_port_substeps_" + sfx)(C.byref(cfg), _p(sim), _p(target), _p(forces), _p(tau),
+    rc = getattr(lib(), ("zbot_port_substeps_snake_" if snake else "zbot_port_substeps_") + sfx)(C.byref(cfg), _p(sim), _p(target), _p(forces), _p(tau),
                                                      C.c_int(n), C.c_int(nsub))
     assert rc == 0
     return forces, tau

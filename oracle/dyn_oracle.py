@@ -57,11 +57,12 @@ def _skew(v):
 
 
 class DynParams:
-    def __init__(self, **kw):
+    def __init__(self, model=None, **kw):
         f32 = lambda x: float(np.float32(x))  # the C ABI carries parameters as float32 (ZbotCfg)
+        model = model or Z.model_f32()
         self.dt = f32(Z.SIM_DT)
-        self.kp, self.kd, self.effort = f32(Z.KP), f32(Z.KD), f32(Z.EFFORT_LIMIT)
-        self.gravity = Z.model_f32().gravity
+        self.kp, self.kd, self.effort = f32(model.kp), f32(model.kd), f32(model.effort_limit)
+        self.gravity = model.gravity
         self.alpha, self.erp, self.vdep = f32(Z.CONTACT_ALPHA), f32(Z.CONTACT_ERP), f32(Z.CONTACT_VDEP)
         self.beta_max, self.mu, self.ramp = f32(Z.CONTACT_BETA_MAX), f32(Z.CONTACT_MU), f32(Z.CONTACT_RAMP)
         self.vt_eps = f32(Z.CONTACT_VT_EPS)
@@ -74,12 +75,12 @@ class DynParams:
 class DynOracle:
     """Batched (N envs) float64 state; positions are env-LOCAL."""
 
-    def __init__(self, n, params: DynParams | None = None):
+    def __init__(self, n, params: DynParams | None = None, model=None):
         self.n = n
-        self.P = params or DynParams()
-        self.m = Z.model_f32()
+        self.m = model or Z.model_f32()
+        self.P = params or DynParams(self.m)
         self.root_pos = np.tile(self.m.default_root_pos, (n, 1))
-        self.root_quat = np.tile(np.array(Z.DEFAULT_ROOT_QUAT, float), (n, 1))
+        self.root_quat = np.tile(np.asarray(self.m.default_root_quat, float), (n, 1))
         self.root_lin_vel = np.zeros((n, 3))
         self.root_ang_vel = np.zeros((n, 3))
         self.q = np.tile(self.m.default_joint_pos, (n, 1))
@@ -99,7 +100,7 @@ class DynOracle:
 
     def reset(self, ids):
         self.root_pos[ids] = self.m.default_root_pos
-        self.root_quat[ids] = np.array(Z.DEFAULT_ROOT_QUAT, float)
+        self.root_quat[ids] = np.asarray(self.m.default_root_quat, float)
         self.root_lin_vel[ids] = 0
         self.root_ang_vel[ids] = 0
         self.q[ids] = self.m.default_joint_pos
@@ -137,9 +138,16 @@ class DynOracle:
         b = m.link_body
         R = kin["R"][:, b]
         pos = kin["pos"][:, b] + np.einsum("nlij,lj->nli", R, m.link_offset)
-        com = pos + np.einsum("nlij,lj->nli", R, m.link_com)
+        lquat = Z.quat_mul(kin["quat"][:, b], np.broadcast_to(m.link_rot, kin["quat"][:, b].shape))
+        Rl = _quat_to_mat(lquat)
+        com = pos + np.einsum("nlij,lj->nli", Rl, m.link_com)
         vcom = kin["v"][:, b] + _cross(kin["w"][:, b], com - kin["pos"][:, b])
-        return {"body_link_pos": pos, "body_link_quat": kin["quat"][:, b], "body_com_lin_vel": vcom}
+        vlink = kin["v"][:, b] + _cross(kin["w"][:, b], pos - kin["pos"][:, b])
+        out = {"body_link_pos": pos, "body_link_quat": lquat, "body_com_lin_vel": vcom,
+               "body_link_lin_vel": vlink, "body_com_pos": com}
+        if m.link_centre is not None:
+            out["link_centre"] = kin["pos"][:, b] + np.einsum("nlij,lj->nli", R, m.link_centre)
+        return out
 
     # ------------------------------------------------------------------ Jacobians
     def _point_jac(self, kin, body, r):
@@ -175,12 +183,10 @@ class DynOracle:
         """List of (body, world position r) for every candidate contact point."""
         m = self.m
         pts = []
-        for f, b in ((0, 0), (1, 6)):
-            for j in range(m.foot_points.shape[1]):
-                pts.append((b, kin["pos"][:, b] + np.einsum("nij,j->ni", kin["R"][:, b], m.foot_points[f, j])))
-        for b in range(1, 6):
-            c = kin["pos"][:, b] + np.einsum("nij,j->ni", kin["R"][:, b], m.sphere_centre[b - 1])
-            pts.append((b, c - np.array([0.0, 0.0, m.sphere_radius])))
+        for row in m.contact_list:
+            b = int(row[0])
+            c = kin["pos"][:, b] + np.einsum("nij,j->ni", kin["R"][:, b], row[1:4])
+            pts.append((b, c - np.array([0.0, 0.0, row[4]])))
         return pts
 
     # ------------------------------------------------------------------ one substep

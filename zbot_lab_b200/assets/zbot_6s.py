@@ -164,6 +164,15 @@ class ZbotModel:
     kd: float
     effort_limit: float
     gravity: float
+    # generalisations shared with the snake robot (zbot_d_6s.py); defaults describe the v2 robot
+    name: str = "zbot_6s_new"
+    default_root_quat: np.ndarray = None   # (4,) wxyz
+    link_rot: np.ndarray = None            # (12,4) link-frame orientation relative to its body frame
+    contact_list: np.ndarray = None        # (P,5): body, local x,y,z, drop (world-z offset, = sphere radius)
+    link_names: tuple = LINK_NAMES
+    sensor_body_names: tuple = SENSOR_BODY_NAMES
+    self_pairs: tuple = ()                 # (link_i, link_j) pairs of the filtered self-contact sensors
+    link_centre: np.ndarray = None         # (12,3) sphere centre used for the self-contact check (body frame)
 
 
 def build_model(dtype=np.float32) -> ZbotModel:
@@ -214,7 +223,16 @@ def build_model(dtype=np.float32) -> ZbotModel:
     inertia[:, 1, 2] = inertia[:, 2, 1] = 0.0
     com[:, 1] = 0.0
     link_com[:, 1] = 0.0
+    contact_list = []
+    for f, b in ((0, 0), (1, 6)):
+        for j in range(P):
+            contact_list.append([b, *foot_points[f, j], 0.0])
+    for b in range(1, 6):
+        contact_list.append([b, *sphere_centre[b - 1], BODY_SPHERE_RADIUS])
+    link_rot = np.tile(np.array([1.0, 0.0, 0.0, 0.0]), (12, 1))
     return ZbotModel(
+        default_root_quat=np.array(DEFAULT_ROOT_QUAT, dtype=np.float64), link_rot=link_rot,
+        contact_list=r(np.array(contact_list)),
         body_mass=r(mass), body_com=r(com), body_inertia=r(inertia),
         # joint_axis is the UNIT vector (+-sqrt(1/2), 0, sqrt(1/2)): kept in double so the joint
         # quaternions stay unit in the float64 instantiations; float code rounds it on use.
@@ -300,7 +318,7 @@ def fk_links(root_pos, root_quat, joint_pos, model: ZbotModel | None = None):
     for i in range(12):
         b = int(m.link_body[i])
         lp.append(bpos[b] + quat_rotate(bquat[b], np.broadcast_to(m.link_offset[i], root_pos.shape)))
-        lq.append(bquat[b])
+        lq.append(quat_mul(bquat[b], np.broadcast_to(m.link_rot[i], bquat[b].shape)))
     return np.stack(lp, axis=-2), np.stack(lq, axis=-2)
 
 

@@ -198,21 +198,6 @@ struct SimState {
   T qd[6];  // joint velocities
 };
 
-template <typename T>
-ZB_HD void sim_state_default(SimState<T>& s) {
-  s.p[0] = T(model::DEFAULT_ROOT_X); s.p[1] = T(model::DEFAULT_ROOT_Y); s.p[2] = T(model::DEFAULT_ROOT_Z);
-  s.Q[0] = T(1); s.Q[1] = T(0); s.Q[2] = T(0); s.Q[3] = T(0);
-  ZB_UNROLL for (int i = 0; i < 3; ++i) { s.v[i] = T(0); s.w[i] = T(0); }
-  s.q[0] = T(model::DQ0); s.q[1] = T(model::DQ1); s.q[2] = T(model::DQ2);
-  s.q[3] = T(model::DQ3); s.q[4] = T(model::DQ4); s.q[5] = T(model::DQ5);
-  ZB_UNROLL for (int i = 0; i < 6; ++i) s.qd[i] = T(0);
-}
-
-template <typename T>
-ZB_HD T default_joint_pos(int k) {
-  return k == 0 ? T(model::DQ0) : k == 1 ? T(model::DQ1) : k == 2 ? T(model::DQ2)
-       : k == 3 ? T(model::DQ3) : k == 4 ? T(model::DQ4) : T(model::DQ5);
-}
 
 // ------------------------------------------------------------------------------------
 // symmetric 6x6 articulated inertia  [[I, H], [H^T, M]]  (motion = (w; vO), force = (n; f))
@@ -423,6 +408,94 @@ ZB_HD void body_rigid_terms(const Params<T>& P, T mass, T cx, T cz, T ixx, T iyy
 }
 
 // ------------------------------------------------------------------------------------
+// robot models: per-body mass tables, ground-contact candidate points, default pose.  The chain geometry
+// (joint positions / axes in the body frames) is common to both; a Model only supplies constants, selected
+// with compile-time-literal ternaries so they fold into FFMA immediates.
+// ------------------------------------------------------------------------------------
+struct ModelWalk {   // ZBOT_6S_CFG + zbot_6s_new.usd (zbot-6b-walking-*): stands on two foot discs
+  static constexpr int kTask = 0;
+  static constexpr bool kGroundForceSensor = true;   // feet: applied force; merged bodies: predictor force
+  template <typename T>
+  static ZB_HD void body(int k, T& mass, T& cx, T& cz, T& ixx, T& iyy, T& izz, T& ixz) {
+    using namespace model;
+    const bool foot0 = (k == 0), foot1 = (k == 6);
+    mass = (foot0 || foot1) ? T(FOOT0_MASS) : T(MID_MASS);
+    cx = foot0 ? T(FOOT0_COM_X) : foot1 ? T(FOOT1_COM_X) : T(MID_COM_X);
+    cz = foot0 ? T(FOOT0_COM_Z) : foot1 ? T(FOOT1_COM_Z) : T(MID_COM_Z);
+    ixx = foot0 ? T(FOOT0_IXX) : foot1 ? T(FOOT1_IXX) : T(MID_IXX);
+    iyy = foot0 ? T(FOOT0_IYY) : foot1 ? T(FOOT1_IYY) : T(MID_IYY);
+    izz = foot0 ? T(FOOT0_IZZ) : foot1 ? T(FOOT1_IZZ) : T(MID_IZZ);
+    ixz = foot0 ? T(FOOT0_IXZ) : foot1 ? T(FOOT1_IXZ) : T(MID_IXZ);
+  }
+  static ZB_HD int npts(int k) { return (k == 0 || k == 6) ? 4 : 1; }
+  // 4 rim points of a foot sole, or the bottom of a merged body's sphere (drop = world-z offset)
+  template <typename T>
+  static ZB_HD void point(int k, int j, T& lx, T& ly, T& lz, T& drop) {
+    using namespace model;
+    const bool foot0 = (k == 0), foot1 = (k == 6), foot = foot0 || foot1;
+    lx = !foot ? T(0) : (j == 0) ? T(FOOT_R) : (j == 2) ? T(-FOOT_R) : T(0);
+    ly = !foot ? T(0) : (j == 1) ? T(FOOT_R) : (j == 3) ? T(-FOOT_R) : T(0);
+    lz = foot0 ? T(FOOT0_SOLE_Z) : foot1 ? T(FOOT1_SOLE_Z) : T(SPHERE_Z);
+    drop = foot ? T(0) : T(SPHERE_R);
+  }
+  template <typename T>
+  static ZB_HD T default_q(int k) {
+    using namespace model;
+    return k == 0 ? T(DQ0) : k == 1 ? T(DQ1) : k == 2 ? T(DQ2) : k == 3 ? T(DQ3) : k == 4 ? T(DQ4) : T(DQ5);
+  }
+  template <typename T>
+  static ZB_HD void default_root(T* p, T* Q) {
+    p[0] = T(model::DEFAULT_ROOT_X); p[1] = T(model::DEFAULT_ROOT_Y); p[2] = T(model::DEFAULT_ROOT_Z);
+    Q[0] = T(1); Q[1] = T(0); Q[2] = T(0); Q[3] = T(0);
+  }
+};
+
+struct ModelSnake {  // ZBOT_D_6S_CFG + zbot_6s_v03.usd (zbot-6s-snake-v0): lies on the ground
+  static constexpr int kTask = 1;
+  static constexpr bool kGroundForceSensor = false;  // the task only senses filtered SELF contacts
+  template <typename T>
+  static ZB_HD void body(int k, T& mass, T& cx, T& cz, T& ixx, T& iyy, T& izz, T& ixz) {
+    using namespace model_snake;
+    const bool e0 = (k == 0), e6 = (k == 6), odd = (k & 1);
+    mass = (e0 || e6) ? T(A1_MASS) : T(MIDO_MASS);
+    cx = e0 ? T(A1_COM_X) : e6 ? T(B6_COM_X) : odd ? T(MIDO_COM_X) : T(MIDE_COM_X);
+    cz = e0 ? T(A1_COM_Z) : e6 ? T(B6_COM_Z) : T(MIDO_COM_Z);
+    ixx = e0 ? T(A1_IXX) : e6 ? T(B6_IXX) : T(MIDO_IXX);
+    iyy = e0 ? T(A1_IYY) : e6 ? T(B6_IYY) : T(MIDO_IYY);
+    izz = e0 ? T(A1_IZZ) : e6 ? T(B6_IZZ) : T(MIDO_IZZ);
+    ixz = e0 ? T(A1_IXZ) : e6 ? T(B6_IXZ) : odd ? T(MIDO_IXZ) : T(MIDE_IXZ);
+  }
+  // a line of r = 0.05 spheres on the chain axis: body origin (joint centre) and, except for a1, z = 0.053
+  static ZB_HD int npts(int k) { return (k == 0) ? 1 : 2; }
+  template <typename T>
+  static ZB_HD void point(int k, int j, T& lx, T& ly, T& lz, T& drop) {
+    (void)k;
+    lx = T(0); ly = T(0);
+    lz = (j == 0) ? T(0) : T(model_snake::LINK_Z);
+    drop = T(model_snake::SPHERE_R);
+  }
+  template <typename T>
+  static ZB_HD T default_q(int) { return T(0); }
+  template <typename T>
+  static ZB_HD void default_root(T* p, T* Q) {
+    using namespace model_snake;
+    p[0] = T(DEFAULT_ROOT_X); p[1] = T(DEFAULT_ROOT_Y); p[2] = T(DEFAULT_ROOT_Z);
+    Q[0] = T(DEFAULT_ROOT_QW); Q[1] = T(DEFAULT_ROOT_QX); Q[2] = T(DEFAULT_ROOT_QY); Q[3] = T(DEFAULT_ROOT_QZ);
+  }
+};
+
+template <typename Model, typename T>
+ZB_HD void sim_state_default(SimState<T>& s) {
+  Model::default_root(s.p, s.Q);
+  ZB_UNROLL for (int i = 0; i < 3; ++i) { s.v[i] = T(0); s.w[i] = T(0); }
+  ZB_UNROLL for (int i = 0; i < 6; ++i) { s.q[i] = Model::template default_q<T>(i); s.qd[i] = T(0); }
+}
+template <typename T>
+ZB_HD void sim_state_default(SimState<T>& s) { sim_state_default<ModelWalk>(s); }
+template <typename T>
+ZB_HD T default_joint_pos(int k) { return ModelWalk::default_q<T>(k); }
+
+// ------------------------------------------------------------------------------------
 // per-thread scratch for the joint-indexed quantities of one substep.  The sweeps over the
 // chain are REAL loops (not unrolled: the fully unrolled step was ~160 KB of SASS and stalled
 // on instruction fetch), so everything indexed by the joint lives in indexable storage:
@@ -460,7 +533,7 @@ struct SubstepOut {
 };
 
 // mid_force_out: optional [5][3] predictor forces of bodies 1..5 (export / debug only)
-template <typename T, typename Scr>
+template <typename Model, typename T, typename Scr>
 ZB_HD void physics_substep(const Params<T>& P, SimState<T>& s, const T* target, SubstepOut<T>& out, Scr& scr,
                            T* mid_force_out) {
   using namespace model;
@@ -522,36 +595,32 @@ ZB_HD void physics_substep(const Params<T>& P, SimState<T>& s, const T* target, 
     }
     T R[9];
     quat_to_mat(Q, R);
-    const bool foot1 = (k == 6), foot0 = (k == 0), foot = foot0 || foot1;
-    const T mass = foot ? T(FOOT0_MASS) : T(MID_MASS);
-    const T cx = foot0 ? T(FOOT0_COM_X) : foot1 ? T(FOOT1_COM_X) : T(MID_COM_X);
-    const T cz = foot0 ? T(FOOT0_COM_Z) : foot1 ? T(FOOT1_COM_Z) : T(MID_COM_Z);
-    const T ixx = foot0 ? T(FOOT0_IXX) : foot1 ? T(FOOT1_IXX) : T(MID_IXX);
-    const T iyy = foot0 ? T(FOOT0_IYY) : foot1 ? T(FOOT1_IYY) : T(MID_IYY);
-    const T izz = foot0 ? T(FOOT0_IZZ) : foot1 ? T(FOOT1_IZZ) : T(MID_IZZ);
-    const T ixz = foot0 ? T(FOOT0_IXZ) : foot1 ? T(FOOT1_IXZ) : T(MID_IXZ);
+    const bool foot1 = (k == 6), foot0 = (k == 0);
+    T mass, cx, cz, ixx, iyy, izz, ixz;
+    Model::body(k, mass, cx, cz, ixx, iyy, izz, ixz);
     body_rigid_terms(P, mass, cx, cz, ixx, iyy, izz, ixz, R, r, w, vO, IA, pAt, pAb);
-    // contact candidates: 4 rim points of a foot sole, or the bottom of a merged body's sphere
+    // ground-contact candidates of this body (Model::point)
     contact_agg_zero(agg);
-    const int npts = foot ? 4 : 1;
-    const T lz = foot0 ? T(FOOT0_SOLE_Z) : foot1 ? T(FOOT1_SOLE_Z) : T(SPHERE_Z);
-    const T drop = foot ? T(0) : T(SPHERE_R);
+    const int npts = Model::npts(k);
 #if defined(__CUDACC__)
 #pragma unroll 1
 #endif
     for (int j = 0; j < npts; ++j) {
-      const T lx = !foot ? T(0) : (j == 0) ? T(FOOT_R) : (j == 2) ? T(-FOOT_R) : T(0);
-      const T ly = !foot ? T(0) : (j == 1) ? T(FOOT_R) : (j == 3) ? T(-FOOT_R) : T(0);
+      T lx, ly, lz, drop;
+      Model::point(k, j, lx, ly, lz, drop);
       T rho[3] = {r[0] + R[0] * lx + R[1] * ly + R[2] * lz, r[1] + R[3] * lx + R[4] * ly + R[5] * lz,
                   r[2] + R[6] * lx + R[7] * ly + R[8] * lz - drop};
-      contact_point(P, rho, s.p[2] + rho[2], w, vO, IA, pAt, pAb, &agg, (T*)nullptr);
+      contact_point(P, rho, s.p[2] + rho[2], w, vO, IA, pAt, pAb,
+                    Model::kGroundForceSensor ? &agg : (ContactAgg<T>*)nullptr, (T*)nullptr);
     }
-    if (foot1) {
-      agg1 = agg;
-    } else if (!foot0) {
-      mid2 = zb_max(mid2, agg.F0[0] * agg.F0[0] + agg.F0[1] * agg.F0[1] + agg.F0[2] * agg.F0[2]);
-      if (mid_force_out) { mid_force_out[3 * (k - 1)] = agg.F0[0]; mid_force_out[3 * (k - 1) + 1] = agg.F0[1];
-                           mid_force_out[3 * (k - 1) + 2] = agg.F0[2]; }
+    if (Model::kGroundForceSensor) {
+      if (foot1) {
+        agg1 = agg;
+      } else if (!foot0) {
+        mid2 = zb_max(mid2, agg.F0[0] * agg.F0[0] + agg.F0[1] * agg.F0[1] + agg.F0[2] * agg.F0[2]);
+        if (mid_force_out) { mid_force_out[3 * (k - 1)] = agg.F0[0]; mid_force_out[3 * (k - 1) + 1] = agg.F0[1];
+                             mid_force_out[3 * (k - 1) + 2] = agg.F0[2]; }
+      }
     }
     if (k == 0) break;
     // joint k (index j): velocity-product term c = V x (S qd), articulated-body elimination
@@ -600,7 +669,7 @@ ZB_HD void physics_substep(const Params<T>& P, SimState<T>& s, const T* target, 
     T nt[3] = {-pAt[0], -pAt[1], -pAt[2]}, nb[3] = {-pAb[0], -pAb[1], -pAb[2]};
     spi_solve(IA, nt, nb, At, Ab);
   }
-  contact_agg_force(agg, dt, At, Ab, out.foot_force[0]);
+  if (Model::kGroundForceSensor) contact_agg_force(agg, dt, At, Ab, out.foot_force[0]);
   // classical acceleration of the root origin = spatial + w x v
   T wxv[3];
   cross3(s.w, s.v, wxv);
@@ -632,7 +701,7 @@ ZB_HD void physics_substep(const Params<T>& P, SimState<T>& s, const T* target, 
     qd += dt * qdd;
     scr(j, SC_QD) = qd;
   }
-  contact_agg_force(agg1, dt, At, Ab, out.foot_force[1]);
+  if (Model::kGroundForceSensor) contact_agg_force(agg1, dt, At, Ab, out.foot_force[1]);
   out.mid_force2_max = mid2;
   ZB_UNROLL for (int k = 0; k < 6; ++k) { s.qd[k] = scr(k, SC_QD); s.q[k] += dt * s.qd[k]; }
   // ---- root pose ----
@@ -814,16 +883,19 @@ struct FreshInputs {
 };
 
 // …env_v2.py:276-287.  raw -> post-tanh actions, p_delta integration/clip, joint targets
-template <typename T>
+template <typename Model, typename T>
 ZB_HD void mdp_pre_physics(const Params<T>& P, const T* raw, MdpState<T>& m, T* new_actions, T* target) {
   const T pi = T(3.14159265358979323846);
   ZB_UNROLL for (int k = 0; k < 6; ++k) {
     T a = zb_tanh(raw[k]);
     new_actions[k] = a;
-    T pd = m.p_delta[k] + pi * a * m.speed_limit * P.step_dt;
+    // walking: p_delta += pi * a * speed * dt (…env_v2.py:280-285); snake: p_delta += a * speed * dt, the pi lives
+    // in its per-env joint_speed_limit (zbot_direct_6dof_snake_v0.py:121, 162-166)
+    T pd = (Model::kTask == 0) ? (m.p_delta[k] + pi * a * m.speed_limit * P.step_dt)
+                               : (m.p_delta[k] + a * m.speed_limit * P.step_dt);
     pd = zb_clamp(pd, -pi, pi);
     m.p_delta[k] = pd;
-    target[k] = pd + default_joint_pos<T>(k);
+    target[k] = pd + Model::template default_q<T>(k);
   }
 }
 
@@ -1054,11 +1126,11 @@ struct PhysOut {
 // Phase B of the control step: _pre_physics_step (…env_v2.py:276-287) + decimation x (physics substep +
 // ContactSensor.update).  Touches only e.sim, e.mdp.p_delta / speed_limit and the contact carry /
 // timers, so a GPU thread can run it before the rest of the MDP state has even been loaded.
-template <typename T, typename Scr>
+template <typename Model, typename T, typename Scr>
 ZB_HD void env_step_physics(const Params<T>& P, EnvState<T>& e, const T* raw_actions, PhysOut<T>& po, Scr& scr,
                             StepExport<T>* ex) {
   T new_actions[6], target[6];
-  mdp_pre_physics(P, raw_actions, e.mdp, new_actions, target);
+  mdp_pre_physics<Model>(P, raw_actions, e.mdp, new_actions, target);
   po.fz[4][0] = e.carry_feet_fz[0];
   po.fz[4][1] = e.carry_feet_fz[1];
   po.mid2 = e.carry_mid_max * e.carry_mid_max;
@@ -1074,7 +1146,8 @@ ZB_HD void env_step_physics(const Params<T>& P, EnvState<T>& e, const T* raw_act
 #endif
   for (int sub = 0; sub < P.decimation; ++sub) {
     T midf[15];
-    physics_substep(P, e.sim, target, so, scr, ex ? midf : (T*)nullptr);
+    physics_substep<Model>(P, e.sim, target, so, scr, ex ? midf : (T*)nullptr);
+    if (!Model::kGroundForceSensor) continue;
     // ContactSensor.update
     const int slot = P.decimation - 1 - sub;  // newest first
     ZB_UNROLL for (int j = 0; j < 2; ++j) {
@@ -1091,9 +1164,11 @@ ZB_HD void env_step_physics(const Params<T>& P, EnvState<T>& e, const T* raw_act
         ZB_UNROLL for (int i = 0; i < 3; ++i) ex->mid_force_hist[slot][b][i] = midf[3 * b + i];
     }
   }
-  e.carry_feet_fz[0] = so.foot_force[0][2];
-  e.carry_feet_fz[1] = so.foot_force[1][2];
-  e.carry_mid_max = zb_sqrt(so.mid_force2_max);
+  if (Model::kGroundForceSensor) {
+    e.carry_feet_fz[0] = so.foot_force[0][2];
+    e.carry_feet_fz[1] = so.foot_force[1][2];
+    e.carry_mid_max = zb_sqrt(so.mid_force2_max);
+  }
   ZB_UNROLL for (int k = 0; k < 6; ++k) po.applied_torque[k] = so.applied_torque[k];
 }
 
@@ -1157,7 +1232,7 @@ ZB_HD void env_step(const Params<T>& P, EnvState<T>& e, const T* raw_actions, in
                     T* reset_ep_sums /*MAX_TERMS, valid when a reset happened*/, StepExport<T>* ex, Scr& scr) {
   const SimState<T> s0 = e.sim;
   PhysOut<T> po;
-  env_step_physics(P, e, raw_actions, po, scr, ex);
+  env_step_physics<ModelWalk>(P, e, raw_actions, po, scr, ex);
   env_step_finish(P, e, s0, raw_actions, po, ep_len, default_feet_pos, default_base_quat, out, reset_ep_sums, ex);
 }
 

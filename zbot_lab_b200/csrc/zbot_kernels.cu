@@ -243,7 +243,7 @@ zbot_step_body(const Params<float>& P, const DefaultPose& dp,
         const float2 a0 = __ldg(a2p), a1 = __ldg(a2p + 1), a2v = __ldg(a2p + 2);
         const float raw[6] = {a0.x, a0.y, a1.x, a1.y, a2v.x, a2v.y};
         // ---- phase B: 4 physics substeps; the MDP state is not even loaded yet (register budget) ----
-        env_step_physics(P, es, raw, po, scr, (StepExport<float>*)nullptr);
+        env_step_physics<ModelWalk>(P, es, raw, po, scr, (StepExport<float>*)nullptr);
       }
       // ---- phase C: the 9 "late" quads, the start-of-step state S0 again (still unmodified in global
       //      memory -> L2 hit) for the one-step-stale quantities, the raw actions again, then the MDP ----
@@ -526,7 +526,7 @@ zbot_mdp_kernel(const __grid_constant__ Params<float> P, const __grid_constant__
         f.feet_force[1] = fz1 / 5.0f;
         f.undesired_force_max = sqrtf(mx2);                      // max_t |F| > 1.0  (:396-402)
       }
-      mdp_pre_physics(P, raw, m, new_actions, target);
+      mdp_pre_physics<ModelWalk>(P, raw, m, new_actions, target);
 #pragma unroll
       for (int j = 0; j < 2; ++j) { f.feet_vel_xy[j][0] = feet_vel[j][0]; f.feet_vel_xy[j][1] = feet_vel[j][1]; }
       f.origin_y = oy;
