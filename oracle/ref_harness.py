@@ -95,3 +95,70 @@ class RefMdpHarness:
         for k, v in e._episode_sums.items():
             out["episode_sum/" + k] = v
         return {k: v.clone() for k, v in out.items()}
+
+
+SNAKE_SENSOR_WIDTHS = (5, 4, 3, 2)   # filter bodies per sensor (zbot_direct_6dof_snake_v0.py:23-48)
+
+
+class RefSnakeHarness:
+    """Same protocol as :class:`RefMdpHarness` for the reference snake task (``ZbotDirectEnvV0``)."""
+
+    ROBOT_KEYS = ("body_link_pos_w", "body_link_quat_w", "body_link_vel_w", "body_com_pos_w", "joint_pos",
+                  "joint_vel", "applied_torque")
+
+    def __init__(self, num_envs, env_origins, reset_tables, default_root_state, joint_speed_limit):
+        self.n = num_envs
+        self.reset_tables = {k: torch.as_tensor(v).clone() for k, v in reset_tables.items()}
+        self.env = ref_loader.make_reference_snake_env(num_envs, default_root_state=default_root_state,
+                                                       env_origins=env_origins, joint_speed_limit=joint_speed_limit)
+        rob = self.env._robot
+        harness = self
+        rob.write_root_pose_to_sim = lambda pose, env_ids: harness._apply_reset_rows(env_ids)
+        rob.write_root_velocity_to_sim = lambda vel, env_ids: None
+        rob.write_joint_state_to_sim = lambda p, v, _i, env_ids: None
+
+    def attach(self, S: dict):
+        d = self.env._robot.data
+        for k in self.ROBOT_KEYS:
+            setattr(d, k, torch.as_tensor(S[k]).clone())
+        for i in (1, 2, 3, 4):
+            getattr(self.env, f"_contact_sensor_{i}").data.force_matrix_w = torch.as_tensor(S[f"force_matrix_w_{i}"]).clone()
+
+    def _apply_reset_rows(self, env_ids):
+        d, t = self.env._robot.data, self.reset_tables
+        org = self.env._terrain.env_origins[env_ids]
+        d.body_link_pos_w[env_ids] = t["body_link_pos_local"].unsqueeze(0) + org.unsqueeze(1)
+        d.body_link_quat_w[env_ids] = t["body_link_quat"].unsqueeze(0).expand(len(env_ids), -1, -1)
+        d.body_com_pos_w[env_ids] = t["body_com_pos_local"].unsqueeze(0) + org.unsqueeze(1)
+        d.body_link_vel_w[env_ids] = 0.0
+        d.joint_pos[env_ids] = 0.0
+        d.joint_vel[env_ids] = 0.0
+        d.applied_torque[env_ids] = 0.0
+        for i in (1, 2, 3, 4):
+            getattr(self.env, f"_contact_sensor_{i}").data.force_matrix_w[env_ids] = 0.0
+
+    def observe(self):
+        return self.env._get_observations()["policy"]
+
+    def step(self, actions, S1):
+        e = self.env
+        e._pre_physics_step(torch.as_tensor(actions))
+        self.attach(S1)
+        e.episode_length_buf += 1
+        e.reset_terminated, e.reset_time_outs = e._get_dones()
+        rew = e._get_rewards()
+        ids = (e.reset_terminated | e.reset_time_outs).nonzero(as_tuple=False).squeeze(-1)
+        log = None
+        if len(ids) > 0:
+            e._reset_idx(ids)
+            log = dict(e.extras["log"])
+        obs = e._get_observations()["policy"]
+        return obs, rew, e.reset_terminated.clone(), e.reset_time_outs.clone(), ids, log
+
+    def mdp_state(self) -> dict:
+        e = self.env
+        out = {"p_delta": e.p_delta, "actions": e._actions, "base_heading_y_sum": e.base_heading_y_sum,
+               "base_pos_x_err_sum": e.base_pos_x_err_sum, "episode_length_buf": e.episode_length_buf}
+        for k, v in e._episode_sums.items():
+            out["episode_sum/" + k] = v
+        return {k: v.clone() for k, v in out.items()}

@@ -27,6 +27,7 @@ REF_ROOT = os.environ.get("ZBOT_REFERENCE_ROOT", "/root/reference")
 REF_ENV_V2 = os.path.join(
     REF_ROOT, "source/zbot/zbot/tasks/zbot6b_direct/zbot_direct_6dof_bipedal_env_v2.py"
 )
+REF_ENV_SNAKE = os.path.join(REF_ROOT, "source/zbot/zbot/tasks/zbot6_direct/zbot_direct_6dof_snake_v0.py")
 
 
 def reference_available() -> bool:
@@ -86,7 +87,7 @@ def _install_stubs():
     terrains = mod("isaaclab.terrains", TerrainImporterCfg=_Cfg)
     mod("isaaclab", sim=sim, utils=utils, assets=assets, envs=envs, scene=scene,
         sensors=sensors, terrains=terrains)
-    zassets = mod("zbot.assets", ZBOT_6S_CFG=_Cfg())
+    zassets = mod("zbot.assets", ZBOT_6S_CFG=_Cfg(), ZBOT_D_6S_CFG=_Cfg())
     mod("zbot", assets=zassets)
     return saved
 
@@ -99,24 +100,24 @@ def _restore(saved):
             sys.modules[k] = v
 
 
-_REF_MODULE = None
+_REF_MODULES = {}
 
 
-def load_reference_module():
-    """Execute the reference env_v2 file unmodified; returns the module."""
-    global _REF_MODULE
-    if _REF_MODULE is not None:
-        return _REF_MODULE
-    if not reference_available():
-        raise FileNotFoundError(REF_ENV_V2)
+def load_reference_module(path: str = REF_ENV_V2):
+    """Execute a reference task file unmodified behind the stubs; returns the module."""
+    if path in _REF_MODULES:
+        return _REF_MODULES[path]
+    if not os.path.isfile(path):
+        raise FileNotFoundError(path)
     saved = _install_stubs()
     try:
-        spec = importlib.util.spec_from_file_location("_zbot_ref_env_v2", REF_ENV_V2)
+        name = "_zbot_ref_" + os.path.splitext(os.path.basename(path))[0]
+        spec = importlib.util.spec_from_file_location(name, path)
         m = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(m)
     finally:
         _restore(saved)
-    _REF_MODULE = m
+    _REF_MODULES[path] = m
     return m
 
 
@@ -208,3 +209,53 @@ def make_reference_env(num_envs: int, *, feet_ids, undesired_ids, base_body_idx,
 def reference_reward_scales() -> dict:
     """Unscaled term->weight dict, in the reference's insertion order (…env_v2.py:190-206)."""
     return dict(load_reference_module().ZbotDirectEnvCfgV2.reward_cfg["reward_scales"])
+
+
+def make_reference_snake_env(num_envs: int, *, default_root_state, env_origins, joint_speed_limit):
+    """Build the reference ``ZbotDirectEnvV0`` (snake task, zbot_direct_6dof_snake_v0.py:102-146) without its
+    ``__init__``; attribute set mirrors that ``__init__`` with plain CPU tensors."""
+    ref = load_reference_module(REF_ENV_SNAKE)
+    n = num_envs
+    cfgc = ref.ZbotDirectEnvCfgV0
+    env = object.__new__(ref.ZbotDirectEnvV0)
+    env.cfg = _NS()
+    env.cfg.reward_cfg = cfgc.reward_cfg
+    env.num_envs = n
+    env.device = torch.device("cpu")
+    env.sim = _NS()
+    env.sim.device = "cpu"
+    env.step_dt = cfgc.decimation * (1 / 200.0)
+    env.max_episode_length_s = cfgc.episode_length_s
+    env.max_episode_length = int(round(cfgc.episode_length_s / env.step_dt))
+    env.extras = {}
+    env._robot = _Recorder(n)
+    d = env._robot.data
+    d.default_joint_pos = torch.zeros(n, 6)
+    d.default_joint_vel = torch.zeros(n, 6)
+    d.default_root_state = default_root_state.clone()
+    for i in (1, 2, 3, 4):
+        sensor = _NS()
+        sensor.data = _NS()
+        setattr(env, f"_contact_sensor_{i}", sensor)
+    env._terrain = _NS()
+    env._terrain.env_origins = env_origins.clone()
+    env._actions = torch.zeros(n, 6)
+    env._previous_actions = torch.zeros(n, 6)
+    env.heading_vec = torch.tensor([0, -1, 0], dtype=torch.float32).repeat((n, 1))
+    env.up_vec = torch.tensor([-1, 0, 0], dtype=torch.float32).repeat((n, 1))
+    env.base_heading_y_sum = torch.zeros(n)
+    env.base_pos_x_err_sum = torch.zeros(n)
+    env.joint_speed_limit = joint_speed_limit.clone().reshape(n, 1)
+    env.p_delta = torch.zeros(n, 6)
+    env.episode_length_buf = torch.zeros(n, dtype=torch.long)
+    env.reset_terminated = torch.zeros(n, dtype=torch.bool)
+    env.reset_time_outs = torch.zeros(n, dtype=torch.bool)
+    scales = dict(cfgc.reward_cfg["reward_scales"])
+    env.reward_scales = {k: v * env.step_dt for k, v in scales.items()}
+    env.reward_functions = {k: getattr(env, "_reward_" + k) for k in env.reward_scales}
+    env._episode_sums = {k: torch.zeros(n) for k in env.reward_scales}
+    return env
+
+
+def reference_snake_reward_scales() -> dict:
+    return dict(load_reference_module(REF_ENV_SNAKE).ZbotDirectEnvCfgV0.reward_cfg["reward_scales"])

@@ -52,8 +52,48 @@ def run_case(seed, n, steps):
     return out
 
 
+SNAKE_CASES = [("snake_v0_n64", 10, 64, 5), ("snake_v0_n9", 11, 9, 4)]
+
+
+def run_snake_case(seed, n, steps):
+    """BASELINE.json configs[3] (snake task) -- the MDP of the reference's own ZbotDirectEnvV0."""
+    from oracle.ref_harness import RefSnakeHarness
+    from zbot_lab_b200.assets import zbot_d_6s as S
+    torch.set_num_threads(1)
+    case = syn.synth_snake_case(seed, n, steps)
+    m = S.model_f32()
+    drs = torch.zeros(n, 13)
+    drs[:, :3] = torch.tensor(m.default_root_pos, dtype=torch.float32)
+    drs[:, 3:7] = torch.tensor(m.default_root_quat, dtype=torch.float32)
+    h = RefSnakeHarness(n, torch.from_numpy(case["origins"]), syn.snake_reset_tables(), drs,
+                        torch.from_numpy(case["joint_speed_limit"]))
+    h.env.episode_length_buf[:] = torch.from_numpy(case["episode_length_buf0"])
+    out = {"seed": seed, "n": n, "steps": steps}
+    h.attach(case["S0"])
+    out["obs0"] = h.observe().numpy()
+    for t, (a, S1) in enumerate(case["steps"]):
+        obs, rew, term, trunc, ids, log = h.step(torch.from_numpy(a), S1)
+        out[f"obs{t + 1}"], out[f"rew{t + 1}"] = obs.numpy(), rew.numpy()
+        out[f"terminated{t + 1}"], out[f"truncated{t + 1}"] = term.numpy(), trunc.numpy()
+        out[f"reset_ids{t + 1}"] = ids.numpy()
+        if log is not None:
+            for k, v in log.items():
+                out[f"log{t + 1}/{k}"] = np.float32(v)
+        for k, v in h.mdp_state().items():
+            out[f"state{t + 1}/{k}"] = v.numpy()
+    return out
+
+
 def main():
     here = os.path.dirname(os.path.abspath(__file__))
+    for name, seed, n, steps in SNAKE_CASES:
+        out = run_snake_case(seed, n, steps)
+        np.savez_compressed(os.path.join(here, name + ".npz"), **out)
+        print(name, "resets:", sum(len(out[f"reset_ids{t + 1}"]) for t in range(steps)),
+              "terminated:", sum(int(out[f"terminated{t + 1}"].sum()) for t in range(steps)))
+    sc = ref_loader.reference_snake_reward_scales()
+    np.savez(os.path.join(here, "reward_scales_snake.npz"), names=np.array(list(sc.keys())),
+             values=np.array(list(sc.values()), dtype=np.float64))
     for name, seed, n, steps in CASES:
         out = run_case(seed, n, steps)
         np.savez_compressed(os.path.join(here, name + ".npz"), **out)

@@ -59,3 +59,53 @@ def test_goldens_reproducible_from_reference_if_present():
     g = np.load(os.path.join(GOLDEN_DIR, "mdp_v2_n7.npz"))
     for k, v in out.items():
         assert np.array_equal(np.asarray(v), g[k]), k
+
+
+SNAKE_GOLDEN = ["snake_v0_n64", "snake_v0_n9"]
+
+
+def _snake_oracle(n, case):
+    from oracle.snake_mdp_oracle import SnakeMdpOracle
+    from zbot_lab_b200.utils import synthetic as syn
+    return SnakeMdpOracle(n, case["origins"], syn.snake_reset_tables(), case["joint_speed_limit"])
+
+
+@pytest.mark.parametrize("name", SNAKE_GOLDEN)
+def test_snake_mdp_oracle_matches_reference_golden(name):
+    """BASELINE.json configs[3]: the snake task's MDP restatement against the reference's own code."""
+    import os
+    from helpers import GOLDEN_DIR
+    from zbot_lab_b200.utils import synthetic as syn
+    g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    n, steps = int(g["n"]), int(g["steps"])
+    case = syn.synth_snake_case(int(g["seed"]), n, steps)
+    o = _snake_oracle(n, case)
+    o.episode_length_buf[:] = case["episode_length_buf0"]
+    assert rel_err(o.observe(case["S0"]), g["obs0"]) <= RTOL
+    for t, (a, S1) in enumerate(case["steps"]):
+        obs, rew, term, trunc, ids, log = o.step(a, S1)
+        k = t + 1
+        assert np.array_equal(term, g[f"terminated{k}"]) and np.array_equal(trunc, g[f"truncated{k}"])
+        assert np.array_equal(ids, g[f"reset_ids{k}"])
+        assert np.array_equal(o.episode_length_buf, g[f"state{k}/episode_length_buf"])
+        assert rel_err(obs, g[f"obs{k}"]) <= RTOL and rel_err(rew, g[f"rew{k}"]) <= RTOL
+        for key, v in o.mdp_state().items():
+            if key != "episode_length_buf":
+                assert rel_err(v, g[f"state{k}/{key}"]) <= RTOL, key
+        if log is not None:
+            for key, v in log.items():
+                assert rel_err(np.float32(v), g[f"log{k}/{key}"]) <= RTOL, key
+
+
+def test_snake_geometry_known_answers():
+    """The reference hard-codes 0.318 (middle link x offset) and 0.636 (sum of the end-link CoM x) for the
+    lying snake (zbot_direct_6dof_snake_v0.py:236, 333): the decoded model must reproduce them, and its
+    `up_vec` / `heading_vec` conventions (:118-119) must map to world +z / +y at the default pose."""
+    from zbot_lab_b200.assets import zbot_6s as Z, zbot_d_6s as S
+    m = S.model_f32()
+    lp, lq = Z.fk_links(m.default_root_pos, m.default_root_quat, m.default_joint_pos, m)
+    assert abs(lp[6, 0] + 0.318) < 1e-6 and np.allclose(lp[:, 2], 0.05, atol=1e-6)
+    com = lp + Z.quat_rotate(lq, m.link_com)
+    assert abs(com[0, 0] + com[11, 0] + 0.636) < 1e-5
+    assert np.allclose(Z.quat_rotate(lq[6], np.array([-1.0, 0, 0])), [0, 0, 1], atol=1e-7)
+    assert np.allclose(Z.quat_rotate(lq[6], np.array([0, -1.0, 0])), [0, 1, 0], atol=1e-7)

@@ -112,3 +112,56 @@ def synth_sim_state(rng: np.random.Generator, n: int) -> dict:
     root_ang = np.zeros((n, 3), F)
     return {"root_pos": root_pos, "root_quat": root_quat, "root_lin_vel": root_lin,
             "root_ang_vel": root_ang, "joint_pos": q.astype(F), "joint_vel": qd}
+
+
+# ------------------------------------------------------------------------------------------------ snake task
+SNAKE_SENSOR_WIDTHS = (5, 4, 3, 2)   # filter bodies of the four self-contact sensors (snake_v0.py:23-48)
+
+
+def snake_reset_tables() -> dict:
+    """Default-pose link poses / CoM positions of the snake robot, relative to the env origin."""
+    from ..assets import zbot_d_6s as S
+
+    m = S.model_f32()
+    p, q = Z.fk_links(m.default_root_pos, m.default_root_quat, m.default_joint_pos, m)
+    com = p + Z.quat_rotate(q, m.link_com)
+    return {"body_link_pos_local": p.astype(F), "body_link_quat": q.astype(F), "body_com_pos_local": com.astype(F)}
+
+
+def synth_snake_state(rng: np.random.Generator, n: int, origins: np.ndarray, die_frac: float = 0.06) -> dict:
+    """Synthetic end-of-physics state in the tensor layouts the reference snake task reads."""
+    t = snake_reset_tables()
+    pos = t["body_link_pos_local"][None] + rng.normal(0, 0.03, (n, 12, 3)).astype(F)
+    far = rng.random(n) < die_frac * 0.5
+    pos[far, 6, 0] += F(0.3)
+    pos = (pos + origins[:, None, :]).astype(F)
+    com = (t["body_com_pos_local"][None] + rng.normal(0, 0.03, (n, 12, 3)).astype(F) + origins[:, None, :]).astype(F)
+    quat = rng.normal(size=(n, 12, 4)).astype(F)
+    quat /= np.linalg.norm(quat, axis=-1, keepdims=True)
+    out = {
+        "body_link_pos_w": pos, "body_link_quat_w": quat.astype(F), "body_com_pos_w": com,
+        "body_link_vel_w": rng.normal(0, 0.3, (n, 12, 6)).astype(F),
+        "joint_pos": rng.uniform(-1.0, 1.0, (n, 6)).astype(F), "joint_vel": rng.normal(0, 0.5, (n, 6)).astype(F),
+        "applied_torque": rng.normal(0, 3.0, (n, 6)).astype(F),
+    }
+    hit = rng.random(n) < die_frac * 0.5
+    for i, w in enumerate(SNAKE_SENSOR_WIDTHS, start=1):
+        fm = (np.abs(rng.normal(size=(n, 1, w, 3))) * 0.1).astype(F)
+        sel = hit & (rng.integers(0, 4, n) == i - 1)
+        fm[sel, 0, rng.integers(0, w), :] = np.array([0.9, -0.8, 0.7], F)
+        out[f"force_matrix_w_{i}"] = fm
+    return out
+
+
+def synth_snake_case(seed: int, n: int, steps: int) -> dict:
+    rng = np.random.default_rng(seed)
+    origins = env_origins_grid(n)
+    ep = rng.integers(0, 800, n).astype(np.int64)
+    near = rng.random(n) < 0.1
+    ep[near] = 799 - rng.integers(1, max(2, steps), int(near.sum()))
+    speed = ((rng.random(n) * 1.8 + 0.2) * np.pi).astype(F)          # snake_v0.py:121
+    case = {"origins": origins, "episode_length_buf0": ep, "joint_speed_limit": speed,
+            "S0": synth_snake_state(rng, n, origins, 0.0), "steps": []}
+    for _ in range(steps):
+        case["steps"].append((rng.normal(0, 1, (n, 6)).astype(F), synth_snake_state(rng, n, origins)))
+    return case
