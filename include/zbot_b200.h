@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define ZBOT_ABI_VERSION 1
+#define ZBOT_ABI_VERSION 2
 
 #define ZBOT_OK 0
 #define ZBOT_E_INVALID (-1) /* bad argument / unsupported configuration */
@@ -59,14 +59,26 @@ enum ZbotTerm {
   ZBOT_TERM_BASE_POS_Y_ERR_SUM = 11,
   ZBOT_TERM_AIRTIME_SUM = 12,
   ZBOT_TERM_FEET_FORCE_DIFF = 13,
-  ZBOT_TERM_FEET_FORCE_SUM = 14
+  ZBOT_TERM_FEET_FORCE_SUM = 14,
+  /* snake task `_reward_<name>` (tasks/zbot6_direct/zbot_direct_6dof_snake_v0.py:300-350);
+   * base_vel_forward / action_rate / torques share ids 0 / 7 / 8 */
+  ZBOT_TERM_SNAKE_BASE_UP_Z = 15,
+  ZBOT_TERM_SNAKE_BASE_HEADING_Y = 16,
+  ZBOT_TERM_SNAKE_BASE_HEADING_Y_SUM = 17,
+  ZBOT_TERM_SNAKE_BASE_POS_X_ERR = 18,
+  ZBOT_TERM_SNAKE_BASE_POS_X_ERR_SUM = 19
 };
+
+/* tasks sharing the fused step (same 7-body chain, different robot cfg / USD frames / MDP) */
+#define ZBOT_TASK_WALKING_V2 0 /* zbot-6b-walking-v2: ZbotDirectEnvV2 + ZBOT_6S_CFG */
+#define ZBOT_TASK_SNAKE_V0 1   /* zbot-6s-snake-v0:  ZbotDirectEnvV0 (zbot6_direct) + ZBOT_D_6S_CFG */
 
 /* Static task parameters.  Replaces `ZbotDirectEnvCfgV2` (…env_v2.py:26-206), the actuator /
  * init-state part of `ZBOT_6S_CFG` (assets/zbot_cfg.py:621-669) and the reward table built in
  * `ZbotDirectEnvV2.__init__` (…env_v2.py:246-257). */
 typedef struct ZbotCfg {
   int32_t abi_version; /* = ZBOT_ABI_VERSION */
+  int32_t task;        /* ZBOT_TASK_* */
   int32_t num_envs;
   int32_t decimation;         /* 4 (…env_v2.py:40); only 4 is supported (5-deep force history) */
   int32_t max_episode_length; /* 1000 = ceil(20 s / 0.02 s) (…env_v2.py:39) */
@@ -147,6 +159,14 @@ typedef struct ZbotExport {
 int zbot_step_export(ZbotHandle* h, const float* actions, float* obs, float* rew, uint8_t* terminated,
                      uint8_t* truncated, int32_t stats_slot, int32_t prev_slot, const ZbotExport* ex,
                      void* stream);
+
+/* Snake task only: the same fused step, additionally exporting what its MDP saw -- per env 41 floats
+ * [base_pos0 3, base_quat0 4, base_vel0 3, base_pos1 3, base_quat1 4, base_vel1 3, com_x1 2, self_force1 1,
+ *  joint_pos1 6, joint_vel1 6, applied_torque1 6] (0 = start of step, 1 = end of physics; `base` = link a4,
+ * `com_x` = CoM x of the end links a1 / b6, `self_force` = filtered self-contact force proxy).  Test hook. */
+int zbot_snake_step_export(ZbotHandle* h, const float* actions, float* obs, float* rew, uint8_t* terminated,
+                           uint8_t* truncated, int32_t stats_slot, int32_t prev_slot, float* export41,
+                           void* stream);
 
 /* `_reset_idx(env_ids)` (…env_v2.py:413-459) for an explicit id list; n < 0 or env_ids == NULL
  * resets every env.  Does NOT draw the random episode lengths of the all-env case

@@ -64,6 +64,41 @@ static int port_step(const ZbotCfg* cfg, T* state, int64_t* ep_len, const T* act
   return ZBOT_OK;
 }
 
+// snake task: whole control step
+template <typename T>
+static int port_snake_step(const ZbotCfg* cfg, T* state, int64_t* ep_len, const T* actions, T* obs, T* rew,
+                           uint8_t* term, uint8_t* trunc, T* reset_sums, T* export_buf, int n) {
+  const char* why = nullptr;
+  if (cfg_validate(*cfg, &why) != ZBOT_OK) return ZBOT_E_INVALID;
+  Params<T> P;
+  params_from_cfg(*cfg, P);
+  SimState<T> sd;
+  sim_state_default<ModelSnake>(sd);
+  SnakeKin<T> kd;
+  snake_kinematics(sd, kd, false);
+#pragma omp parallel for schedule(static) num_threads(port_threads())
+  for (int e = 0; e < n; ++e) {
+    EnvState<T> es;
+    env_state_unpack(state + (size_t)e * ZBOT_STATE_WORDS, es);
+    StepOut<T> out;
+    T rs[MAX_TERMS];
+    for (int i = 0; i < MAX_TERMS; ++i) rs[i] = T(0);
+    SnakeExport<T> ex;
+    ArrayScratch<T> scr;
+    snake_env_step(P, es, actions + (size_t)e * 6, ep_len[e], kd.base_quat, out, rs,
+                   export_buf ? &ex : (SnakeExport<T>*)nullptr, scr);
+    env_state_pack(es, state + (size_t)e * ZBOT_STATE_WORDS);
+    for (int i = 0; i < 23; ++i) obs[(size_t)e * 23 + i] = out.obs[i];
+    rew[e] = out.reward;
+    term[e] = out.terminated ? 1 : 0;
+    trunc[e] = out.time_out ? 1 : 0;
+    if (reset_sums)
+      for (int i = 0; i < MAX_TERMS; ++i) reset_sums[(size_t)e * MAX_TERMS + i] = rs[i];
+    if (export_buf) memcpy(export_buf + (size_t)e * (sizeof(SnakeExport<T>) / sizeof(T)), &ex, sizeof(ex));
+  }
+  return ZBOT_OK;
+}
+
 // dynamics only: sim [N][25] (root_pos3 quat4 lin3 ang3 q6 qd6), target [N][6]
 // forces [N][7][3] (body 0 and 6 = applied foot forces, 1..5 = predictor), tau [N][6]
 template <typename T>
@@ -124,6 +159,15 @@ int zbot_port_step_f32(const ZbotCfg* cfg, float* state, int64_t* ep_len, const 
 int zbot_port_step_f64(const ZbotCfg* cfg, double* state, int64_t* ep_len, const double* actions, double* obs,
                        double* rew, uint8_t* term, uint8_t* trunc, double* reset_sums, double* export_buf, int n) {
   return port_step<double>(cfg, state, ep_len, actions, obs, rew, term, trunc, reset_sums, export_buf, n);
+}
+int zbot_port_snake_export_words(void) { return (int)(sizeof(SnakeExport<float>) / sizeof(float)); }
+int zbot_port_snake_step_f32(const ZbotCfg* cfg, float* state, int64_t* ep_len, const float* actions, float* obs,
+                             float* rew, uint8_t* term, uint8_t* trunc, float* reset_sums, float* export_buf, int n) {
+  return port_snake_step<float>(cfg, state, ep_len, actions, obs, rew, term, trunc, reset_sums, export_buf, n);
+}
+int zbot_port_snake_step_f64(const ZbotCfg* cfg, double* state, int64_t* ep_len, const double* actions, double* obs,
+                             double* rew, uint8_t* term, uint8_t* trunc, double* reset_sums, double* export_buf, int n) {
+  return port_snake_step<double>(cfg, state, ep_len, actions, obs, rew, term, trunc, reset_sums, export_buf, n);
 }
 int zbot_port_substeps_f32(const ZbotCfg* cfg, float* sim, const float* target, float* forces, float* tau, int n, int nsub) {
   return port_substeps<float>(cfg, sim, target, forces, tau, n, nsub);

@@ -63,9 +63,11 @@ class PortEnv:
         self.dtype = np.dtype(dtype)
         self.sfx = "f32" if self.dtype == np.float32 else "f64"
         self.cfg = cfg or make_cfg(n)
+        self.snake = (self.cfg.task == 1)
         self.state = np.zeros((n, 80), self.dtype)
         self.ep_len = np.zeros(n, np.int64)
-        self.export_words = getattr(lib(), "zbot_port_export_words_" + self.sfx)()
+        self.export_words = (lib().zbot_port_snake_export_words() if self.snake
+                             else getattr(lib(), "zbot_port_export_words_" + self.sfx)())
         self.reset_all()
 
     def word(self, name):
@@ -79,6 +81,15 @@ class PortEnv:
 
     def reset_all(self):
         from zbot_lab_b200.assets import zbot_6s as Z
+        if self.snake:
+            from zbot_lab_b200.assets import zbot_d_6s as S
+            m = S.model_f32()
+            self.state[:] = 0
+            self.field("root_pos", 3)[:] = m.default_root_pos
+            self.field("root_quat", 4)[:] = m.default_root_quat
+            self.field("joint_speed_limit", 1)[:] = np.pi
+            self.ep_len[:] = 0
+            return
         self.state[:] = 0
         self.field("root_pos", 3)[:] = Z.model_f32().default_root_pos
         self.field("root_quat", 4)[:] = Z.DEFAULT_ROOT_QUAT
@@ -103,7 +114,7 @@ class PortEnv:
         trunc = np.zeros(n, np.uint8)
         rs = np.zeros((n, 16), self.dtype)
         ex = np.zeros((n, self.export_words), self.dtype) if export else None
-        fn = getattr(lib(), "zbot_port_step_" + self.sfx)
+        fn = getattr(lib(), ("zbot_port_snake_step_" if self.snake else "zbot_port_step_") + self.sfx)
         rc = fn(C.byref(self.cfg), _p(self.state), _p(self.ep_len), _p(a), _p(obs), _p(rew), _p(term),
                 _p(trunc), _p(rs), _p(ex), C.c_int(n))
         assert rc == 0, rc

@@ -246,23 +246,26 @@ class DynOracle:
                 fs = np.minimum(k_n * pen, P.alpha * P.vdep)
                 gamma = k_n * dt + d_n * s
                 fn0 = fs - gamma * vs[:, 2]
-                active = (pen > -P.margin) & (fn0 > 0)
+                # continuous activation: the implicit normal stiffness ramps in over fn0 in [-fband, 0]
+                # (DESIGN.md §3); predictor force = max(fn0, 0)
+                fband = 0.25 * k_n * P.ramp
+                act = np.clip(fn0 / fband + 1.0, 0.0, 1.0) * (pen > -P.margin)
+                fn0 = np.maximum(fn0, 0.0) * (pen > -P.margin)
                 vt = np.sqrt(vs[:, 0] ** 2 + vs[:, 1] ** 2)
                 beta = np.minimum(P.beta_max, P.mu * fn0 / np.maximum(vt, P.vt_eps))
-                gamma = np.where(active, gamma, 0.0)
-                beta = np.where(active, beta, 0.0)
-                fs = np.where(active, fs, 0.0)
+                gamma = act * gamma
                 K = np.stack([beta, beta, gamma], -1)                    # (N,3) diagonal
-                # f = [0,0,fs] - K*(vs) - dt*K*(J nu_dot + a_vp - w x vc)
+                # f = Fp - dt*K*(J nu_dot + a_vp - w x vc), Fp = (-beta v*_x, -beta v*_y, max(fn0, 0))
                 #   = F0 - dt*K*J nu_dot   with F0 using the kernel's split (vs already has dt*w x vc)
                 a_rest = a_vp - _cross(w, vc)
-                F0 = np.stack([np.zeros(n), np.zeros(n), fs], -1) - K * (vs + dt * a_rest)
+                Fp = np.stack([-beta * vs[:, 0], -beta * vs[:, 1], fn0], -1)
+                F0 = Fp - dt * K * a_rest
                 M += dt * np.einsum("nki,nk,nkj->nij", J, K, J)
                 rhs += np.einsum("nki,nk->ni", J, F0)
                 clist.append((body, J, K, F0))
                 # predictor force (what the kernel reports for the mid bodies): F0 without the
-                # velocity-product part, i.e. [0,0,fs] - K v*
-                pred[:, body] += np.stack([np.zeros(n), np.zeros(n), fs], -1) - K * vs
+                # velocity-product part
+                pred[:, body] += Fp
 
         nud = np.linalg.solve(M, rhs[..., None])[..., 0]
 

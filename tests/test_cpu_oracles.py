@@ -142,3 +142,58 @@ def test_port_f32_tracks_f64_over_50_steps():
         alive &= ~(t32 | t64 | tr32 | tr64)
     dq = np.abs(e32.field("joint_pos", 6) - e64.field("joint_pos", 6))[alive]
     assert dq.max() < 5e-3 and np.median(dq.max(1)) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------ snake task
+def _snake_speed(rng, n):
+    return ((rng.random(n) * 1.8 + 0.2) * np.pi).astype(np.float32)        # snake_v0.py:121
+
+
+def test_snake_full_step_oracle_matches_port_f64_with_resets():
+    """BASELINE.json configs[3]: composed oracle (independent float64 dynamics of the snake model + the
+    reference-pinned snake MDP restatement) against the kernel's own arithmetic compiled for the host."""
+    from oracle import cpu_port
+    from oracle.full_step_oracle import SnakeFullStepOracle
+    from zbot_lab_b200 import native
+    n = 24
+    rng = np.random.default_rng(0)
+    speed = _snake_speed(rng, n)
+    fo = SnakeFullStepOracle(n, speed)
+    fo.reset_all()
+    pe = cpu_port.PortEnv(n, np.float64, native.make_cfg(n, task=native.TASK_SNAKE_V0))
+    pe.field("joint_speed_limit", 1)[:, 0] = speed
+    fo.mdp.episode_length_buf[:4] = 790
+    pe.ep_len[:4] = 790
+    resets = 0
+    for t in range(30):
+        a = rng.normal(0, 1.0, (n, 6)).astype(np.float32)
+        obs, rew, term, trunc, ids, _ = fo.step(a)
+        o2, r2, t2, tr2, _, _ = pe.step(a)
+        assert np.array_equal(term, t2) and np.array_equal(trunc, tr2)
+        assert np.array_equal(fo.mdp.episode_length_buf, pe.ep_len)
+        assert np.abs(obs - o2).max() < 1e-4 and np.abs(rew - r2).max() < 1e-5
+        assert np.all(o2[:, 22] == speed)                       # survives resets
+        resets += len(ids)
+    assert resets >= 4
+
+
+def test_snake_self_contact_and_x_drift_terminate():
+    """Curl the chain so the end links overlap (filtered self-contact proxy > 1 N), and push the base off
+    x = -0.318 m by more than 0.2 m: both terminations of snake_v0.py:222-240 fire, with the -20 penalty."""
+    from oracle import cpu_port
+    from zbot_lab_b200 import native
+    n = 4
+    pe = cpu_port.PortEnv(n, np.float64, native.make_cfg(n, task=native.TASK_SNAKE_V0))
+    pe.field("joint_speed_limit", 1)[:] = np.pi
+    pe.field("root_pos", 3)[1, 0] += 0.35                       # env 1: base_pos_x_err = 0.35
+    a = np.zeros((n, 6), np.float32)
+    _, rew, term, trunc, _, _ = pe.step(a)                      # stale base_pos is the START-of-step one
+    assert term.tolist() == [False, True, False, False] and not trunc.any()
+    assert rew[1] < -19.0 and abs(rew[0]) < 1.0
+    # env 2: q = 3 rad on every joint folds the chain onto itself (sphere centres 0.04 m apart)
+    pe.field("joint_pos", 6)[2] = 3.0
+    pe.field("p_delta", 6)[2] = 3.0                             # PD target = the folded pose
+    pe.field("root_pos", 3)[2, 2] += 0.3
+    _, _, term, _, _, ex = pe.step(a, export=True)
+    assert term[2] and not term[0]
+    assert ex[2, 22] > 1.0 and ex[0, 22] == 0.0                 # exported self-contact force proxy

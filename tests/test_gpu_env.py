@@ -142,3 +142,35 @@ def test_cuda_graph_rollout_matches_eager_semantics(tmp_path):
     hist = r.learn(num_learning_iterations=2)
     assert len(hist) == 2 and all(np.isfinite(h["surrogate_loss"]) for h in hist)
     w.close()
+
+
+def test_snake_env_registry_protocol_and_log_keys():
+    """zbot-6s-snake-v0 through the registry: reference id / entry-point keys (zbot6_direct/__init__.py:25-33),
+    episode length 800 (16 s / 0.02 s), per-env joint_speed_limit in ((0.2..2.0) * pi) as the last observation
+    column, log keys of snake_v0.py:277-293."""
+    import zbot_lab_b200.tasks  # noqa: F401
+    from zbot_lab_b200.compat import gym_registry as gym
+    from zbot_lab_b200.envs.rsl_rl_wrapper import RslRlVecEnvWrapper
+    cfg = gym.load_cfg_from_registry("zbot-6s-snake-v0", "env_cfg_entry_point")
+    agent = gym.load_cfg_from_registry("zbot-6s-snake-v0", "rsl_rl_cfg_entry_point")
+    assert agent.num_steps_per_env == 16 and agent.policy.actor_hidden_dims == [256, 256, 128]
+    cfg.scene.num_envs = 128
+    cfg.sim.device = "cuda:0"
+    cfg.seed = 5
+    env = gym.make("zbot-6s-snake-v0", cfg=cfg, render_mode=None)
+    assert env.max_episode_length == 800 and env.step_dt == pytest.approx(0.02)
+    w = RslRlVecEnvWrapper(env, clip_actions=None)
+    obs = w.get_observations()["policy"]
+    sp = obs[:, 22]
+    assert float(sp.min()) >= 0.2 * np.pi - 1e-6 and float(sp.max()) <= 2.0 * np.pi + 1e-6 and float(sp.std()) > 0.5
+    # default pose: base link a4 = root orientation (x) Rz(180): (0.707,0,-0.707,0)(x)(0,0,0,1) = (0,-0.707,0,0.707)
+    assert torch.allclose(obs[0, :4].abs(), torch.tensor([0.0, 0.70710678, 0.0, 0.70710678], device="cuda:0"), atol=1e-5)
+    assert torch.all(obs[:, 4:22] == 0)
+    for t in range(30):
+        obs, rew, dones, extras = w.step(torch.randn(128, 6, device="cuda:0"))
+        assert torch.isfinite(obs["policy"]).all() and torch.isfinite(rew).all()
+        assert torch.equal(obs["policy"][:, 22], sp)
+        assert set(extras["log"]) == {"Episode_Reward/" + k for k in cfg.reward_cfg["reward_scales"]} | {
+            "Episode_Termination/died", "Episode_Termination/time_out"}
+    assert env.base_heading_y_sum.shape == (128,)
+    w.close()

@@ -485,3 +485,171 @@ def test_single_env_and_empty_reset_list():
     torch.cuda.synchronize()
     assert torch.equal(st.state.buf, before) and int(st.episode_length_buf[0]) == 5
     st.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# snake task (BASELINE.json configs[3]: zbot-6s-snake-v0, 16384 envs, contact-heavy ground model)
+# ---------------------------------------------------------------------------------------------
+def _snake_stepper(n, speed):
+    from zbot_lab_b200 import native
+    from zbot_lab_b200.stepper import NativeStepper
+    st = NativeStepper(n, DEV, native.make_cfg(n, task=native.TASK_SNAKE_V0))
+    st.reset_idx(None)
+    st.state.set("joint_speed_limit", _t(speed.reshape(n, 1)))
+    return st
+
+
+def _snake_S(ex, which, n):
+    """Tensors the reference snake task reads (snake_v0.py:175-240, 329-335), from the kernel's export row."""
+    from zbot_lab_b200.stepper import SNAKE_EXPORT as E
+    from zbot_lab_b200.utils import synthetic as syn
+    col = lambda k: ex[:, E[k][0]:E[k][1]]
+    t = syn.snake_reset_tables()
+    S = {"body_link_pos_w": np.tile(t["body_link_pos_local"][None], (n, 1, 1)),
+         "body_link_quat_w": np.tile(t["body_link_quat"][None], (n, 1, 1)),
+         "body_com_pos_w": np.tile(t["body_com_pos_local"][None], (n, 1, 1)),
+         "body_link_vel_w": np.zeros((n, 12, 6), np.float32)}
+    S["body_link_pos_w"][:, 6] = col(f"base_pos{which}")
+    S["body_link_quat_w"][:, 6] = col(f"base_quat{which}")
+    S["body_link_vel_w"][:, 6, :3] = col(f"base_vel{which}")
+    if which == 0:
+        S.update(joint_pos=np.zeros((n, 6), np.float32), joint_vel=np.zeros((n, 6), np.float32),
+                 applied_torque=np.zeros((n, 6), np.float32))
+    else:
+        S["body_com_pos_w"][:, 0, 0] = ex[:, E["com_x1"][0]]
+        S["body_com_pos_w"][:, 11, 0] = ex[:, E["com_x1"][0] + 1]
+        S.update(joint_pos=col("joint_pos1").copy(), joint_vel=col("joint_vel1").copy(),
+                 applied_torque=col("applied_torque1").copy())
+    for i, w in enumerate(syn.SNAKE_SENSOR_WIDTHS, start=1):
+        fm = np.zeros((n, 1, w, 3), np.float32)
+        if which == 1 and i == 1:
+            fm[:, 0, 0, 0] = ex[:, E["self_force1"][0]]       # the proxy's max over the 14 pairs, in one slot
+        S[f"force_matrix_w_{i}"] = fm
+    return S
+
+
+def test_snake_fused_step_mdp_matches_pinned_oracle_on_exported_physics():
+    """The snake kernel's dones / rewards / resets / observations equal the reference-pinned snake MDP oracle
+    (tests/golden/snake_v0_*.npz) evaluated on the base pose / velocity / CoM / torque view the kernel itself
+    exported: flags, reset ids and counters bit-exact, float32 terms within 1e-5 relative."""
+    from oracle.snake_mdp_oracle import SnakeMdpOracle
+    from zbot_lab_b200.utils import synthetic as syn
+    n = 200
+    rng = np.random.default_rng(77)
+    speed = ((rng.random(n) * 1.8 + 0.2) * np.pi).astype(np.float32)
+    st = _snake_stepper(n, speed)
+    ep0 = rng.integers(0, 800, n)
+    ep0[:8] = 796
+    st.episode_length_buf[:] = _t(ep0.astype(np.int64))
+    # a few envs start folded (self-contact termination) or displaced in x (drift termination)
+    q0 = np.zeros((n, 6), np.float32)
+    q0[8:12] = 3.0
+    st.state.set("joint_pos", _t(q0))
+    st.state.set("p_delta", _t(q0))
+    rp = st.state.get("root_pos").cpu().numpy()
+    rp[12:16, 0] += 0.3
+    rp[8:12, 2] += 0.3
+    st.state.set("root_pos", _t(rp))
+    o = SnakeMdpOracle(n, np.zeros((n, 3), np.float32), syn.snake_reset_tables(), speed)
+    o.episode_length_buf[:] = ep0
+    o.p_delta[:] = q0
+    ex_t = torch.zeros(n, 41, device=DEV)
+    n_term = n_to = 0
+    for t in range(30):
+        a = rng.normal(0, 1.0, (n, 6)).astype(np.float32)
+        obs, rew, term, trunc = st.step(_t(a), export=ex_t)
+        torch.cuda.synchronize()
+        ex = ex_t.cpu().numpy()
+        if t == 0:
+            o.observe(_snake_S(ex, 0, n))
+            o.actions[:] = 0
+        else:
+            keep = ~last_reset
+            assert rel_err(o.base_pos_w[keep], ex[keep, 0:3]) <= 1e-5      # stale cache == start-of-step view
+        obs_o, rew_o, term_o, trunc_o, ids_o, log_o = o.step(a, _snake_S(ex, 1, n))
+        assert np.array_equal(term.cpu().numpy().astype(bool), term_o)
+        assert np.array_equal(trunc.cpu().numpy().astype(bool), trunc_o)
+        ids = torch.nonzero(term.bool() | trunc.bool()).squeeze(-1).cpu().numpy()
+        assert np.array_equal(ids, ids_o)
+        assert np.array_equal(st.episode_length_buf.cpu().numpy(), o.episode_length_buf)
+        assert rel_err(rew.cpu().numpy(), rew_o) <= RTOL
+        assert rel_err(obs.cpu().numpy(), obs_o) <= 2e-5
+        assert rel_err(st.state.get("p_delta").cpu().numpy(), o.p_delta) <= RTOL
+        assert rel_err(st.state.get("base_heading_x_sum").cpu().numpy()[:, 0], o.base_heading_y_sum) <= RTOL
+        eps = st.state.get("episode_sums").cpu().numpy()
+        for i, nm in enumerate(o.episode_sums):
+            assert rel_err(eps[:, i], o.episode_sums[nm]) <= RTOL, nm
+        if len(ids) > 0:
+            s = st.stats.cpu().numpy()
+            assert s[16] == len(ids) and s[17] == log_o["Episode_Termination/died"]
+            assert s[18] == log_o["Episode_Termination/time_out"]
+            for i, nm in enumerate(o.episode_sums):
+                want = float(log_o["Episode_Reward/" + nm])
+                assert abs(s[i] - want) <= 1e-5 * max(1.0, abs(want)), nm
+        last_reset = term_o | trunc_o
+        n_term += int(term_o.sum())
+        n_to += int(trunc_o.sum())
+    assert n_term >= 8 and n_to >= 8
+    assert np.all(st.state.get("joint_speed_limit").cpu().numpy()[:, 0] == speed)   # survives resets
+    st.close()
+
+
+def test_snake_fused_step_vs_float64_oracle_one_step_and_horizon():
+    """Snake dynamics (12 ground spheres in contact, kp 20 / kd 0.5) against the independent float64 oracle:
+    one control step from identical states within 2e-4 / 2e-2, and a free-running 50-step horizon within the
+    stated 5e-3 rad / 5e-3 m."""
+    from oracle.full_step_oracle import SnakeFullStepOracle
+    n = 256
+    rng = np.random.default_rng(6)
+    speed = ((rng.random(n) * 1.8 + 0.2) * np.pi).astype(np.float32)
+    fo = SnakeFullStepOracle(n, speed)
+    fo.reset_all()
+    st = _snake_stepper(n, speed)
+    alive = np.ones(n, bool)
+    for t in range(50):
+        a = rng.normal(0, 0.5, (n, 6)).astype(np.float32)
+        _, rew_o, term_o, trunc_o, _, _ = fo.step(a)
+        _, rew, term, trunc = st.step(_t(a))
+        alive &= ~(term_o | trunc_o | term.cpu().numpy().astype(bool) | trunc.cpu().numpy().astype(bool))
+        if t == 0:
+            d = np.abs(_gpu_state_vec(st) - _oracle_state_vec(fo.dyn))
+            assert d[:, list(range(0, 7)) + list(range(13, 19))].max() <= 2e-4
+            assert d[:, list(range(7, 13)) + list(range(19, 25))].max() <= 2e-2
+    assert alive.sum() > n // 2
+    dq = np.abs(st.state.get("joint_pos").cpu().numpy() - fo.dyn.q)[alive]
+    dp = np.abs(st.state.get("root_pos").cpu().numpy() - fo.dyn.root_pos)[alive]
+    assert dq.max() <= 5e-3 and dp.max() <= 5e-3, (dq.max(), dp.max())
+    assert np.median(dq.max(1)) <= 1e-4
+    st.close()
+
+
+def test_snake_full_size_properties_16384():
+    """BASELINE.json configs[3] size: identical envs stay identical, time-out at step 799 of 800, statistics
+    equal torch reductions, two runs are bit-identical, state stays finite under random actions."""
+    n = 16384
+    speed = np.full(n, np.pi, np.float32)
+    outs = []
+    for rep in range(2):
+        st = _snake_stepper(n, speed)
+        st.episode_length_buf[:] = 790
+        g = torch.Generator(device=DEV).manual_seed(99)
+        rec = []
+        for t in range(12):
+            a = torch.randn(1, 6, device=DEV, generator=g).expand(n, 6).contiguous()
+            obs, rew, term, trunc = st.step(a)
+            assert torch.equal(obs, obs[:1].expand_as(obs)) and torch.equal(rew, rew[:1].expand_as(rew))
+            s = st.stats.clone()
+            assert s[19].item() == pytest.approx(rew.double().sum().item(), rel=1e-5, abs=1e-3)
+            assert s[20].item() == term.sum().item() and s[21].item() == trunc.sum().item()
+            if t == 8 and not term.any():
+                assert trunc.all() and torch.all(st.episode_length_buf == 0)      # 790 + 9 = 799 (snake_v0.py:223)
+            rec.append((obs.clone(), rew.clone()))
+        outs.append(rec)
+        if rep == 1:
+            for (o0, r0), (o1, r1) in zip(outs[0], outs[1]):
+                assert torch.equal(o0, o1) and torch.equal(r0, r1)
+            for t in range(60):
+                obs, rew, term, trunc = st.step(torch.randn(n, 6, device=DEV, generator=g))
+                assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
+            assert torch.isfinite(st.state.buf).all()
+        st.close()

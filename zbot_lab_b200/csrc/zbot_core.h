@@ -49,7 +49,14 @@ enum TermId : int {
   TERM_AIRTIME_SUM = 12,
   TERM_FEET_FORCE_DIFF = 13,  // defined but inactive in v2's scale dict (:563-565)
   TERM_FEET_FORCE_SUM = 14,   // defined but inactive in v2's scale dict (:567-571)
-  NUM_TERM_IDS = 15
+  // snake task (tasks/zbot6_direct/zbot_direct_6dof_snake_v0.py:300-350); "base_vel_forward", "action_rate"
+  // and "torques" share ids 0, 7, 8 with the walking task
+  TERM_SNAKE_BASE_UP_Z = 15,
+  TERM_SNAKE_BASE_HEADING_Y = 16,
+  TERM_SNAKE_BASE_HEADING_Y_SUM = 17,
+  TERM_SNAKE_BASE_POS_X_ERR = 18,
+  TERM_SNAKE_BASE_POS_X_ERR_SUM = 19,  // defined but inactive in the snake scale dict
+  NUM_TERM_IDS = 20
 };
 constexpr int MAX_TERMS = 16;
 
@@ -61,7 +68,7 @@ struct Params {
   // dynamics
   T dt, kp, kd, effort, arm;  // arm = dt*kd + dt*dt*kp
   T gravity;
-  T c_k, c_d, c_fcap, c_beta_max, c_mu, c_inv_ramp, c_vt_eps, c_margin;  // contact law (zbot_6s.py)
+  T c_k, c_d, c_fcap, c_beta_max, c_mu, c_inv_ramp, c_vt_eps, c_margin, c_inv_fband;  // contact law (zbot_6s.py)
   int decimation;
   // MDP
   T step_dt;
@@ -344,7 +351,14 @@ ZB_HD bool contact_point(const Params<T>& P, const T* rho, T height, const T* w,
   T fs = zb_min(P.c_k * pen, P.c_fcap);
   T gamma = P.c_k * P.dt + P.c_d * s;
   T fn0 = fs - gamma * sz;
-  if (!(fn0 > T(0))) return false;
+  // Activation is CONTINUOUS in the state: the implicit normal stiffness ramps in over a band of predictor
+  // force [-fband, 0] (there F0 = 0 and only -dt*act*gamma*a_n acts: an added-mass term, PSD), so a point
+  // sitting exactly on the threshold (a snake at rest on the plane: all 12 spheres at pen = 0) does not flip a
+  // coin on float round-off.  Full stiffness for fn0 >= 0 as before.
+  const T act = zb_clamp(fn0 * P.c_inv_fband + T(1), T(0), T(1));
+  if (!(act > T(0))) return false;
+  fn0 = zb_max(fn0, T(0));
+  gamma *= act;
   // beta = min(beta_max, mu fn0 / max(|v_t|, eps))
   T beta = zb_min(P.c_beta_max, P.c_mu * fn0 * zb_rsqrt(zb_max(sx * sx + sy * sy, P.c_vt_eps * P.c_vt_eps)));
   T F0[3] = {-beta * sx, -beta * sy, fn0};
@@ -847,6 +861,7 @@ struct StaleCache {
   T forward[3];       // base_dir_forward_w (NOT normalised, SURVEY C-2)
   T feet_x[2][3], feet_z[2][3], feet_pos[2][3];
   T v_fwd;            // base_lin_vel_forward_w
+  T aux;              // snake task: base_up_w.y (snake_v0.py:181); `forward` then holds base_heading_w
 };
 
 template <typename T>
@@ -880,6 +895,7 @@ struct FreshInputs {
   T feet_vel_xy[2][2];    // body_com_lin_vel_w[:, feet, :2]  (:554)
   T applied_torque[6];    // (:560)
   T origin_y;             // env_origins[:, 1]  (0 in the fused path: env-local coordinates)
+  T com_x_sum;            // snake task: body_com_pos_w[:, 0, 0] + body_com_pos_w[:, 11, 0] - 2 origin_x (snake_v0.py:330-333)
 };
 
 // …env_v2.py:276-287.  raw -> post-tanh actions, p_delta integration/clip, joint targets
@@ -979,11 +995,33 @@ ZB_HD T mdp_term_value(int id, const StaleCache<T>& c, const FreshInputs<T>& f, 
       m.feet_force_sum += T(0.001) * (f.feet_force[0] - f.feet_force[1]);
       val = zb_abs(m.feet_force_sum);
       break;
+    // ---- snake task (zbot_direct_6dof_snake_v0.py); heading_err = -base_heading_w.x, y_err = base_pos_x_err ----
+    case TERM_SNAKE_BASE_UP_Z:                                                 // snake :304-305
+      val = zb_abs(c.aux);
+      break;
+    case TERM_SNAKE_BASE_HEADING_Y:                                            // snake :307-308
+      val = zb_abs(heading_err);
+      break;
+    case TERM_SNAKE_BASE_HEADING_Y_SUM:                                        // snake :310-313
+      m.heading_sum = zb_clamp(m.heading_sum + T(0.01) * heading_err, T(-1), T(1));
+      val = zb_abs(m.heading_sum);
+      break;
+    case TERM_SNAKE_BASE_POS_X_ERR:                                            // snake :329-335 -- only the first
+      val = zb_abs(f.com_x_sum + T(0.636));                                    // abs(): the second is a dangling statement (SURVEY C-9)
+      break;
+    case TERM_SNAKE_BASE_POS_X_ERR_SUM:                                        // snake :337-340
+      m.y_err_sum = zb_clamp(m.y_err_sum + T(0.01) * y_err, T(-1), T(1));
+      val = zb_abs(m.y_err_sum);
+      break;
     default:
       break;
   }
   return val;
 }
+
+template <typename T>
+ZB_HD T mdp_reward_sum(const Params<T>& P, const StaleCache<T>& c, const FreshInputs<T>& f, const T* new_actions,
+                       MdpState<T>& m, T heading_err, T y_err, bool terminated);
 
 // …env_v2.py:384-411 + 371-382 + 461-571.  `new_actions` = this step's post-tanh actions,
 // m.actions = previous step's.  Returns the reward; updates the stateful terms and ep_sums.
@@ -998,6 +1036,13 @@ ZB_HD T mdp_dones_rewards(const Params<T>& P, const StaleCache<T>& c, const Fres
   died |= zb_abs(y_err) > P.y_limit;                                             // :407
   terminated = died;
   const T heading_err = -c.forward[1];                                           // :324
+  return mdp_reward_sum(P, c, f, new_actions, m, heading_err, y_err, terminated);
+}
+
+// sum_k term_k * scale_k in cfg-dict order, episode sums, -penalty when terminated (…env_v2.py:371-382)
+template <typename T>
+ZB_HD T mdp_reward_sum(const Params<T>& P, const StaleCache<T>& c, const FreshInputs<T>& f, const T* new_actions,
+                       MdpState<T>& m, T heading_err, T y_err, bool terminated) {
   T reward = T(0);
   if (P.default_terms) {
     // the v2 table (…env_v2.py:190-206) in dict order: static indices, everything stays in registers
@@ -1223,6 +1268,176 @@ ZB_HD void env_step_finish(const Params<T>& P, EnvState<T>& e, const SimState<T>
   } else {
     mdp_observation(k1.base_quat, e.sim.q, e.sim.qd, e.mdp.actions, e.mdp.speed_limit, out.obs);
   }
+}
+
+// ------------------------------------------------------------------------------------
+// snake task (zbot-6s-snake-v0): per-link quantities its MDP reads (snake_v0.py:175-208, 222-240, 329-335)
+// ------------------------------------------------------------------------------------
+template <typename T>
+struct SnakeKin {
+  T base_pos[3], base_quat[4], base_vel[3];   // link 6 = a4: body_link_pos_w / quat_w / body_link_vel_w[:, 6, :3]
+  T com_x[2];                                 // body_com_pos_w[:, 0, 0] and [:, 11, 0] (a1 and b6)
+  T self_pen_max;                             // max sphere overlap over the 14 filtered self-contact pairs
+};
+
+template <typename T>
+ZB_HD void snake_kinematics(const SimState<T>& s, SnakeKin<T>& o, bool want_self) {
+  using namespace model_snake;
+  T Q[4] = {s.Q[0], s.Q[1], s.Q[2], s.Q[3]};
+  T r[3] = {T(0), T(0), T(0)};
+  T w[3] = {s.w[0], s.w[1], s.w[2]};
+  T vO[3] = {s.v[0], s.v[1], s.v[2]};
+  T ctr[12][3];   // self-contact sphere centres, articulation order a1 b1 a2 b2 a3 b3 a4 b4 a5 b5 a6 b6
+  ZB_UNROLL for (int b = 0; b < 7; ++b) {
+    T R[9];
+    quat_to_mat(Q, R);
+    // sphere centres lie on the body's z axis: origin + z * R[:,2]
+    if (b == 0) {
+      ZB_UNROLL for (int i = 0; i < 3; ++i) ctr[0][i] = r[i] + R[3 * i + 2] * T(CENTRE_A_Z);
+      o.com_x[0] = s.p[0] + r[0] + R[0] * T(A1_COM_X) + R[2] * T(A1_COM_Z);
+    } else if (b == 6) {
+      ZB_UNROLL for (int i = 0; i < 3; ++i) ctr[11][i] = r[i] + R[3 * i + 2] * T(CENTRE_B_Z);
+      o.com_x[1] = s.p[0] + r[0] + R[0] * T(B6_COM_X) + R[2] * T(B6_COM_Z);
+    } else {
+      ZB_UNROLL for (int i = 0; i < 3; ++i) {
+        ctr[2 * b - 1][i] = r[i] + R[3 * i + 2] * T(CENTRE_B_Z);
+        ctr[2 * b][i] = r[i] + R[3 * i + 2] * (T(LINK_Z) + T(CENTRE_A_Z));
+      }
+    }
+    if (b == 3) {   // a4 = second link of body 3: origin + (0,0,LINK_Z), frame rotated 180 deg about z
+      T lo[3] = {r[0] + R[2] * T(LINK_Z), r[1] + R[5] * T(LINK_Z), r[2] + R[8] * T(LINK_Z)};
+      T wxl[3];
+      cross3(w, lo, wxl);
+      ZB_UNROLL for (int i = 0; i < 3; ++i) { o.base_pos[i] = s.p[i] + lo[i]; o.base_vel[i] = vO[i] + wxl[i]; }
+      o.base_quat[0] = -Q[3]; o.base_quat[1] = Q[2]; o.base_quat[2] = -Q[1]; o.base_quat[3] = Q[0];   // Q (x) (0,0,0,1)
+    }
+    if (b < 6) {
+      const T jz = (b == 0) ? T(model::JOINT_Z_FIRST) : T(model::JOINT_Z_REST);
+      const T sg = (b & 1) ? T(-model::AXIS_S) : T(model::AXIS_S);
+      r[0] += jz * R[2]; r[1] += jz * R[5]; r[2] += jz * R[8];
+      T a[3] = {sg * R[0] + T(model::AXIS_S) * R[2], sg * R[3] + T(model::AXIS_S) * R[5], sg * R[6] + T(model::AXIS_S) * R[8]};
+      T m[3];
+      cross3(r, a, m);
+      ZB_UNROLL for (int i = 0; i < 3; ++i) { w[i] += a[i] * s.qd[b]; vO[i] += m[i] * s.qd[b]; }
+      T sn, cs;
+      zb_sincos(T(0.5) * s.q[b], &sn, &cs);
+      quat_mul_joint(Q, cs, sg * sn, T(model::AXIS_S) * sn);
+    }
+  }
+  o.self_pen_max = T(0);
+  if (want_self) {
+    // filtered contact sensors (snake_v0.py:23-48): a1|{b4 a5 b5 a6 b6}, b6|{a3 b2 a2 b1}, b1|{a5 b5 a6}, a6|{b2 a2}
+    const int pa[14] = {0, 0, 0, 0, 0, 11, 11, 11, 11, 1, 1, 1, 10, 10};
+    const int pb[14] = {7, 8, 9, 10, 11, 4, 3, 2, 1, 8, 9, 10, 3, 2};
+    T pen = T(0);
+    ZB_UNROLL for (int k = 0; k < 14; ++k) {
+      const T dx = ctr[pa[k]][0] - ctr[pb[k]][0], dy = ctr[pa[k]][1] - ctr[pb[k]][1], dz = ctr[pa[k]][2] - ctr[pb[k]][2];
+      pen = zb_max(pen, T(2) * T(SPHERE_R) - zb_sqrt(dx * dx + dy * dy + dz * dz));
+    }
+    o.self_pen_max = pen;
+  }
+}
+
+template <typename Model, typename T>
+ZB_HD void env_reset_model(const Params<T>& P, EnvState<T>& e, const T default_feet_pos[2][3]) {
+  sim_state_default<Model>(e.sim);
+  mdp_reset(e.mdp, default_feet_pos, P.num_terms);
+  e.carry_feet_fz[0] = e.carry_feet_fz[1] = T(0);
+  e.carry_mid_max = T(0);
+  ZB_UNROLL for (int j = 0; j < 2; ++j) {
+    e.timers[j].cur_air = e.timers[j].cur_contact = e.timers[j].last_air = e.timers[j].last_contact = T(0);
+  }
+}
+
+template <typename T>
+ZB_HD void snake_observe(const EnvState<T>& e, T* obs) {
+  SnakeKin<T> k;
+  snake_kinematics(e.sim, k, false);
+  ZB_UNROLL for (int i = 0; i < 4; ++i) obs[i] = k.base_quat[i];
+  ZB_UNROLL for (int j = 0; j < 6; ++j) { obs[4 + j] = e.sim.q[j]; obs[10 + j] = e.sim.qd[j]; obs[16 + j] = e.mdp.actions[j]; }
+  obs[22] = e.mdp.speed_limit;
+}
+
+// self-contact proxy exported for the parity test: what the MDP saw
+template <typename T>
+struct SnakeExport {
+  T base_pos0[3], base_quat0[4], base_vel0[3];
+  T base_pos1[3], base_quat1[4], base_vel1[3];
+  T com_x1[2], self_force1;
+  T q1[6], qd1[6], tau1[6];
+};
+
+// Phase C of the snake task's control step (same ordering as the walking task)
+template <typename T>
+ZB_HD void snake_step_finish(const Params<T>& P, EnvState<T>& e, const SimState<T>& s0, const T* raw_actions,
+                             const PhysOut<T>& po, int64_t& ep_len, const T* default_base_quat, StepOut<T>& out,
+                             T* reset_ep_sums, SnakeExport<T>* ex) {
+  StaleCache<T> stale;
+  SnakeKin<T> k0;
+  snake_kinematics(s0, k0, false);
+  {
+    const T heading_vec[3] = {T(0), T(-1), T(0)}, up_vec[3] = {T(-1), T(0), T(0)};   // snake_v0.py:118-119
+    T up[3];
+    quat_apply(k0.base_quat, heading_vec, stale.forward);                            // base_heading_w (:180)
+    quat_apply(k0.base_quat, up_vec, up);                                            // base_up_w (:181)
+    stale.aux = up[1];
+    ZB_UNROLL for (int i = 0; i < 3; ++i) stale.base_pos[i] = k0.base_pos[i];
+    stale.v_fwd = k0.base_vel[0] * stale.forward[0] + k0.base_vel[1] * stale.forward[1] + k0.base_vel[2] * stale.forward[2];  // :184
+  }
+  T new_actions[6];
+  ZB_UNROLL for (int k = 0; k < 6; ++k) new_actions[k] = zb_tanh(raw_actions[k]);
+  ep_len += 1;
+  SnakeKin<T> k1;
+  snake_kinematics(e.sim, k1, true);
+  FreshInputs<T> f;
+  f.feet_force[0] = f.feet_force[1] = T(0);
+  f.last_air_time[0] = f.last_air_time[1] = T(0);
+  f.feet_vel_xy[0][0] = f.feet_vel_xy[0][1] = f.feet_vel_xy[1][0] = f.feet_vel_xy[1][1] = T(0);
+  // filtered self-contact force proxy: contact spring x sphere overlap (not fed back into the dynamics)
+  f.undesired_force_max = P.c_k * k1.self_pen_max;
+  ZB_UNROLL for (int k = 0; k < 6; ++k) f.applied_torque[k] = po.applied_torque[k];
+  f.origin_y = T(0);
+  f.com_x_sum = k1.com_x[0] + k1.com_x[1];                                           // env-local: origin_x = 0
+  if (ex) {
+    ZB_UNROLL for (int i = 0; i < 3; ++i) { ex->base_pos0[i] = k0.base_pos[i]; ex->base_vel0[i] = k0.base_vel[i];
+                                            ex->base_pos1[i] = k1.base_pos[i]; ex->base_vel1[i] = k1.base_vel[i]; }
+    ZB_UNROLL for (int i = 0; i < 4; ++i) { ex->base_quat0[i] = k0.base_quat[i]; ex->base_quat1[i] = k1.base_quat[i]; }
+    ex->com_x1[0] = k1.com_x[0]; ex->com_x1[1] = k1.com_x[1]; ex->self_force1 = f.undesired_force_max;
+    ZB_UNROLL for (int k = 0; k < 6; ++k) { ex->q1[k] = e.sim.q[k]; ex->qd1[k] = e.sim.qd[k]; ex->tau1[k] = po.applied_torque[k]; }
+  }
+  const bool time_out = ep_len >= (int64_t)(P.max_episode_length - 1);               // snake :223
+  const T x_err = stale.base_pos[0] + T(0.318);                                      // snake :236 (origin_x = 0)
+  const bool died = (f.undesired_force_max > P.contact_died_threshold) || (zb_abs(x_err) > T(0.2));   // :228-239
+  const T heading_err = -stale.forward[0];                                           // snake :182
+  out.reward = mdp_reward_sum(P, stale, f, new_actions, e.mdp, heading_err, x_err, died);
+  out.terminated = died;
+  out.time_out = time_out;
+  ZB_UNROLL for (int k = 0; k < 6; ++k) e.mdp.actions[k] = new_actions[k];
+  if (died || time_out) {
+    ZB_UNROLL for (int i = 0; i < MAX_TERMS; ++i) reset_ep_sums[i] = e.mdp.ep_sums[i];
+    const T speed = e.mdp.speed_limit;
+    const T zero_feet[2][3] = {{T(0), T(0), T(0)}, {T(0), T(0), T(0)}};
+    env_reset_model<ModelSnake>(P, e, zero_feet);
+    e.mdp.speed_limit = speed;
+    ep_len = 0;
+    ZB_UNROLL for (int i = 0; i < 4; ++i) out.obs[i] = default_base_quat[i];
+    ZB_UNROLL for (int j = 0; j < 6; ++j) { out.obs[4 + j] = e.sim.q[j]; out.obs[10 + j] = e.sim.qd[j]; out.obs[16 + j] = e.mdp.actions[j]; }
+    out.obs[22] = speed;
+  } else {
+    ZB_UNROLL for (int i = 0; i < 4; ++i) out.obs[i] = k1.base_quat[i];
+    ZB_UNROLL for (int j = 0; j < 6; ++j) { out.obs[4 + j] = e.sim.q[j]; out.obs[10 + j] = e.sim.qd[j]; out.obs[16 + j] = e.mdp.actions[j]; }
+    out.obs[22] = e.mdp.speed_limit;
+  }
+}
+
+// whole snake control step in one call (CPU port, export kernel)
+template <typename T, typename Scr>
+ZB_HD void snake_env_step(const Params<T>& P, EnvState<T>& e, const T* raw_actions, int64_t& ep_len,
+                          const T* default_base_quat, StepOut<T>& out, T* reset_ep_sums, SnakeExport<T>* ex, Scr& scr) {
+  const SimState<T> s0 = e.sim;
+  PhysOut<T> po;
+  env_step_physics<ModelSnake>(P, e, raw_actions, po, scr, (StepExport<T>*)nullptr);
+  snake_step_finish(P, e, s0, raw_actions, po, ep_len, default_base_quat, out, reset_ep_sums, ex);
 }
 
 // the whole control step in one call (CPU port, export kernel)

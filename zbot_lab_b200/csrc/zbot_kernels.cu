@@ -304,8 +304,98 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) zbot_step_kernel(ZB_S
   zbot_step_body<kExport>(ZB_STEP_CALL);
 }
 // ---------------------------------------------------------------------------------------------
+// snake task (zbot-6s-snake-v0): same state layout, same physics substep (ModelSnake), its own MDP.
+// Phased like the walking kernel: early quads -> 4 substeps -> late quads + S0 re-read (L2) -> MDP.
+// ---------------------------------------------------------------------------------------------
+constexpr int kSnakeExportWords = (int)(sizeof(SnakeExport<float>) / sizeof(float));   // 41
+
+template <bool kExport>
+__global__ void __launch_bounds__(128, 2)
+zbot_snake_step_kernel(const __grid_constant__ Params<float> P, const __grid_constant__ DefaultPose dp,
+                       float4* __restrict__ state, int64_t* __restrict__ ep_len_buf, const float* __restrict__ actions,
+                       float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ terminated,
+                       uint8_t* __restrict__ truncated, int n, StatsCtx sc, float* __restrict__ export_buf) {
+  extern __shared__ float smem[];
+  const int e0 = blockIdx.x * blockDim.x;
+  const int e = e0 + threadIdx.x;
+  const bool live = e < n;
+  float stat[kStatUsed];
+#pragma unroll
+  for (int j = 0; j < kStatUsed; ++j) stat[j] = 0.f;
+  float obs_row[ZBOT_NUM_OBS];
+#pragma unroll
+  for (int i = 0; i < ZBOT_NUM_OBS; ++i) obs_row[i] = 0.f;
+  bool did_reset = false;
+  if (live) {
+    EnvState<float> es;
+    StepOut<float> out;
+    float rs[MAX_TERMS];
+#pragma unroll
+    for (int i = 0; i < MAX_TERMS; ++i) rs[i] = 0.f;
+    SmemScratch scr{smem + threadIdx.x * SCR_STRIDE};
+    const float2* a2p = reinterpret_cast<const float2*>(actions + (size_t)e * 6);
+    {
+      float w[4 * EARLY_QUADS];
+      load_words<EARLY_QUADS>(state, n, e, w);
+      env_early_unpack(w, es);
+    }
+    PhysOut<float> po;
+    {
+      const float2 a0 = __ldg(a2p), a1 = __ldg(a2p + 1), a2v = __ldg(a2p + 2);
+      const float raw[6] = {a0.x, a0.y, a1.x, a1.y, a2v.x, a2v.y};
+      env_step_physics<ModelSnake>(P, es, raw, po, scr, (StepExport<float>*)nullptr);
+    }
+    {
+      float w[ZBOT_STATE_WORDS - 4 * EARLY_QUADS];
+      load_words<ZBOT_STATE_WORDS / 4 - EARLY_QUADS>(state + (size_t)EARLY_QUADS * n, n, e, w);
+      env_late_unpack(w, es);
+    }
+    SimState<float> s0;
+    {
+      float w[4 * SIM_QUADS];
+      load_words<SIM_QUADS>(state, n, e, w);
+      sim_state_unpack(w, s0);
+    }
+    const float2 a0 = __ldg(a2p), a1 = __ldg(a2p + 1), a2v = __ldg(a2p + 2);
+    const float raw[6] = {a0.x, a0.y, a1.x, a1.y, a2v.x, a2v.y};
+    int64_t ep = ep_len_buf[e];
+    SnakeExport<float> ex;
+    snake_step_finish(P, es, s0, raw, po, ep, dp.base_quat, out, rs, kExport ? &ex : (SnakeExport<float>*)nullptr);
+    if (kExport) {
+      const float* src = reinterpret_cast<const float*>(&ex);
+      for (int i = 0; i < kSnakeExportWords; ++i) export_buf[(size_t)e * kSnakeExportWords + i] = src[i];
+    }
+    float w[ZBOT_STATE_WORDS];
+    env_state_pack(es, w);
+    store_words<ZBOT_STATE_WORDS / 4>(state, n, e, w);
+    ep_len_buf[e] = ep;
+    rew[e] = out.reward;
+    terminated[e] = out.terminated ? 1 : 0;
+    truncated[e] = out.time_out ? 1 : 0;
+#pragma unroll
+    for (int i = 0; i < ZBOT_NUM_OBS; ++i) obs_row[i] = out.obs[i];
+    did_reset = out.terminated || out.time_out;
+    if (did_reset) {
+#pragma unroll
+      for (int i = 0; i < MAX_TERMS; ++i) stat[i] = rs[i];
+      stat[S_NUM_RESET] = 1.f;
+      stat[S_NUM_TERM_RESET] = out.terminated ? 1.f : 0.f;
+      stat[S_NUM_TO_RESET] = out.time_out ? 1.f : 0.f;
+    }
+    stat[S_REW_SUM] = out.reward;
+    stat[S_NUM_TERM] = out.terminated ? 1.f : 0.f;
+    stat[S_NUM_TRUNC] = out.time_out ? 1.f : 0.f;
+  }
+  __syncthreads();
+  store_rows_coalesced<ZBOT_NUM_OBS>(obs, obs_row, n, e0, smem);
+  __syncthreads();
+  stats_block_partial(stat, did_reset, smem, sc);
+}
+
+// ---------------------------------------------------------------------------------------------
 // reset / observe / articulation view / init
 // ---------------------------------------------------------------------------------------------
+template <bool kSnake>
 __global__ void zbot_reset_kernel(const __grid_constant__ Params<float> P, const __grid_constant__ DefaultPose dp,
                                   float4* __restrict__ state, int64_t* __restrict__ ep_len_buf,
                                   const int64_t* __restrict__ ids, int64_t nids, const uint8_t* __restrict__ terminated,
@@ -329,7 +419,13 @@ __global__ void zbot_reset_kernel(const __grid_constant__ Params<float> P, const
       stat[S_NUM_RESET] = 1.f;
       stat[S_NUM_TERM_RESET] = (terminated && terminated[e]) ? 1.f : 0.f;
       stat[S_NUM_TO_RESET] = (truncated && truncated[e]) ? 1.f : 0.f;
-      env_reset(P, es, dp.feet_pos);
+      if (kSnake) {
+        const float speed = es.mdp.speed_limit;       // per-env random constant of the snake task: survives resets
+        env_reset_model<ModelSnake>(P, es, dp.feet_pos);
+        es.mdp.speed_limit = speed;
+      } else {
+        env_reset(P, es, dp.feet_pos);
+      }
       env_state_pack(es, w);
       store_words<ZBOT_STATE_WORDS / 4>(state, n, e, w);
       ep_len_buf[e] = 0;
@@ -339,6 +435,7 @@ __global__ void zbot_reset_kernel(const __grid_constant__ Params<float> P, const
   stats_block_partial(stat, did, smem, sc);
 }
 
+template <bool kSnake>
 __global__ void zbot_observe_kernel(const float4* __restrict__ state, float* __restrict__ obs, int n) {
   extern __shared__ float smem[];
   const int e0 = blockIdx.x * blockDim.x;
@@ -351,7 +448,7 @@ __global__ void zbot_observe_kernel(const float4* __restrict__ state, float* __r
     load_words<ZBOT_STATE_WORDS / 4>(state, n, e, w);
     EnvState<float> es;
     env_state_unpack(w, es);
-    env_observe(es, row);
+    if (kSnake) snake_observe(es, row); else env_observe(es, row);
   }
   store_rows_coalesced<ZBOT_NUM_OBS>(obs, row, n, e0, smem);
 }
@@ -370,8 +467,20 @@ __global__ void zbot_view_kernel(const float4* __restrict__ state, float* pos, f
   if (vel) for (int i = 0; i < 36; ++i) vel[(size_t)e * 36 + i] = v[i];
 }
 
-__global__ void zbot_default_pose_kernel(DefaultPose* out) {
+__global__ void zbot_default_pose_kernel(DefaultPose* out, int task) {
   SimState<float> s;
+  if (task == ZBOT_TASK_SNAKE_V0) {
+    sim_state_default<ModelSnake>(s);
+    SnakeKin<float> k;
+    snake_kinematics(s, k, false);
+    for (int j = 0; j < 2; ++j) {
+      for (int i = 0; i < 3; ++i) out->feet_pos[j][i] = 0.f;   // the snake MDP has no feet (mdp_reset zeroes the slots)
+      for (int i = 0; i < 4; ++i) out->feet_quat[j][i] = (i == 0) ? 1.f : 0.f;
+    }
+    for (int i = 0; i < 3; ++i) out->base_pos[i] = k.base_pos[i];
+    for (int i = 0; i < 4; ++i) out->base_quat[i] = k.base_quat[i];
+    return;
+  }
   sim_state_default(s);
   LinkKin<float> k;
   link_kinematics(s, k);
@@ -660,7 +769,7 @@ int zbot_create(const ZbotCfg* cfg, int device, ZbotHandle** out) {
   ZB_CUDA(cudaMalloc(&h->partials, (size_t)h->max_blocks * kStats * sizeof(float)));
   DefaultPose* d_dp = nullptr;
   ZB_CUDA(cudaMalloc(&d_dp, sizeof(DefaultPose)));
-  zbot_default_pose_kernel<<<1, 1>>>(d_dp);
+  zbot_default_pose_kernel<<<1, 1>>>(d_dp, cfg->task);
   ZB_CUDA(cudaGetLastError());
   ZB_CUDA(cudaMemcpy(&h->dp, d_dp, sizeof(DefaultPose), cudaMemcpyDeviceToHost));
   ZB_CUDA(cudaFree(d_dp));
@@ -669,6 +778,8 @@ int zbot_create(const ZbotCfg* cfg, int device, ZbotHandle** out) {
   ZB_CUDA(cudaFuncSetAttribute(zbot_step_kernel<false, 128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
   ZB_CUDA(cudaFuncSetAttribute(zbot_step_kernel<false, 128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
   ZB_CUDA(cudaFuncSetAttribute(zbot_step_kernel<true, 128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
+  ZB_CUDA(cudaFuncSetAttribute(zbot_snake_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
+  ZB_CUDA(cudaFuncSetAttribute(zbot_snake_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
   {
     // register-budget variant of the step kernel = resident 128-thread CTAs per SM it is compiled for.
     // Measured (profiles/r1_notes.md): 2 CTAs/SM (197 regs, no spill) is fastest while the grid fits two
@@ -705,7 +816,7 @@ int zbot_bind(ZbotHandle* h, float* state, int64_t* episode_length, float* stats
 }
 
 static int step_impl(ZbotHandle* h, const float* actions, float* obs, float* rew, uint8_t* terminated, uint8_t* truncated,
-                     int32_t slot, int32_t prev, const ZbotExport* ex, void* stream) {
+                     int32_t slot, int32_t prev, const ZbotExport* ex, void* stream, float* snake_export = nullptr) {
   if (!h) return fail(ZBOT_E_INVALID, "handle is NULL%s");
   if (!h->state) return fail(ZBOT_E_UNBOUND, "zbot_bind has not been called%s");
   if (!actions || !obs || !rew || !terminated || !truncated) return fail(ZBOT_E_INVALID, "zbot_step: NULL buffer%s");
@@ -718,7 +829,17 @@ static int step_impl(ZbotHandle* h, const float* actions, float* obs, float* rew
   StatsCtx sc{h->partials, h->ring, slot, prev, h->inv_episode_s};
   cudaStream_t s = (cudaStream_t)stream;
   ExportPtrs xp{};
-  if (ex) {
+  if (h->cfg.task == ZBOT_TASK_SNAKE_V0) {
+    if (ex) return fail(ZBOT_E_INVALID, "zbot_step_export is a walking-task hook; use zbot_snake_step_export%s");
+    if (snake_export)
+      zbot_snake_step_kernel<true><<<grid, block, smem, s>>>(h->P, h->dp, h->state, h->ep_len, actions, obs, rew, terminated,
+                                                         truncated, n, sc, snake_export);
+    else
+      zbot_snake_step_kernel<false><<<grid, block, smem, s>>>(h->P, h->dp, h->state, h->ep_len, actions, obs, rew, terminated,
+                                                          truncated, n, sc, nullptr);
+  } else if (snake_export) {
+    return fail(ZBOT_E_INVALID, "zbot_snake_step_export needs a handle created with task = ZBOT_TASK_SNAKE_V0%s");
+  } else if (ex) {
     xp = ExportPtrs{ex->body_link_pos_w0, ex->body_link_quat_w0, ex->body_com_lin_vel_w0, ex->body_link_pos_w1,
                     ex->body_link_quat_w1, ex->body_com_lin_vel_w1, ex->joint_pos1, ex->joint_vel1, ex->applied_torque1,
                     ex->net_forces_w_history1, ex->last_air_time1, ex->current_contact_time1};
@@ -756,6 +877,12 @@ int zbot_step_export(ZbotHandle* h, const float* actions, float* obs, float* rew
   return step_impl(h, actions, obs, rew, terminated, truncated, stats_slot, prev_slot, ex, stream);
 }
 
+int zbot_snake_step_export(ZbotHandle* h, const float* actions, float* obs, float* rew, uint8_t* terminated,
+                           uint8_t* truncated, int32_t stats_slot, int32_t prev_slot, float* export41, void* stream) {
+  if (!export41) return fail(ZBOT_E_INVALID, "zbot_snake_step_export: export41 is NULL%s");
+  return step_impl(h, actions, obs, rew, terminated, truncated, stats_slot, prev_slot, nullptr, stream, export41);
+}
+
 int zbot_reset_idx(ZbotHandle* h, const int64_t* env_ids, int64_t nids, const uint8_t* terminated, const uint8_t* truncated,
                    int32_t stats_slot, void* stream) {
   if (!h) return fail(ZBOT_E_INVALID, "handle is NULL%s");
@@ -768,8 +895,12 @@ int zbot_reset_idx(ZbotHandle* h, const int64_t* env_ids, int64_t nids, const ui
   const int block = 64;
   const int grid = (int)((nids + block - 1) / block);
   StatsCtx sc{h->partials, h->ring, stats_slot, -1, h->inv_episode_s};
-  zbot_reset_kernel<<<grid, block, 32 * kStatUsed * sizeof(float), (cudaStream_t)stream>>>(
-      h->P, h->dp, h->state, h->ep_len, env_ids, nids, terminated, truncated, n, sc);
+  if (h->cfg.task == ZBOT_TASK_SNAKE_V0)
+    zbot_reset_kernel<true><<<grid, block, 32 * kStatUsed * sizeof(float), (cudaStream_t)stream>>>(
+        h->P, h->dp, h->state, h->ep_len, env_ids, nids, terminated, truncated, n, sc);
+  else
+    zbot_reset_kernel<false><<<grid, block, 32 * kStatUsed * sizeof(float), (cudaStream_t)stream>>>(
+        h->P, h->dp, h->state, h->ep_len, env_ids, nids, terminated, truncated, n, sc);
   ZB_CUDA(cudaGetLastError());
   h->launches += 1;
   zbot_stats_finalize_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(sc, (unsigned int)grid);
@@ -782,7 +913,10 @@ int zbot_observe(ZbotHandle* h, float* obs, void* stream) {
   if (!h || !obs) return fail(ZBOT_E_INVALID, "zbot_observe: NULL argument%s");
   if (!h->state) return fail(ZBOT_E_UNBOUND, "zbot_bind has not been called%s");
   const int n = h->cfg.num_envs, block = 64, grid = (n + block - 1) / block;
-  zbot_observe_kernel<<<grid, block, block * ZBOT_NUM_OBS * sizeof(float), (cudaStream_t)stream>>>(h->state, obs, n);
+  if (h->cfg.task == ZBOT_TASK_SNAKE_V0)
+    zbot_observe_kernel<true><<<grid, block, block * ZBOT_NUM_OBS * sizeof(float), (cudaStream_t)stream>>>(h->state, obs, n);
+  else
+    zbot_observe_kernel<false><<<grid, block, block * ZBOT_NUM_OBS * sizeof(float), (cudaStream_t)stream>>>(h->state, obs, n);
   ZB_CUDA(cudaGetLastError());
   h->launches += 1;
   return ZBOT_OK;
@@ -791,6 +925,7 @@ int zbot_observe(ZbotHandle* h, float* obs, void* stream) {
 int zbot_articulation_view(ZbotHandle* h, float* pos, float* quat, float* vel, void* stream) {
   if (!h) return fail(ZBOT_E_INVALID, "handle is NULL%s");
   if (!h->state) return fail(ZBOT_E_UNBOUND, "zbot_bind has not been called%s");
+  if (h->cfg.task != ZBOT_TASK_WALKING_V2) return fail(ZBOT_E_INVALID, "zbot_articulation_view: walking task only%s");
   const int n = h->cfg.num_envs, block = 64, grid = (n + block - 1) / block;
   zbot_view_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(h->state, pos, quat, vel, n);
   ZB_CUDA(cudaGetLastError());
@@ -810,6 +945,7 @@ int zbot_mdp_bind(ZbotHandle* h, float* mdp_state, int64_t* episode_length, floa
 
 static int mdp_check(const ZbotHandle* h, const ZbotMdpInputs* in, bool step) {
   if (!h || !in) return fail(ZBOT_E_INVALID, "zbot_mdp: NULL argument%s");
+  if (h->cfg.task != ZBOT_TASK_WALKING_V2) return fail(ZBOT_E_INVALID, "zbot_mdp_*: walking task only%s");
   if (!h->mstate) return fail(ZBOT_E_UNBOUND, "zbot_mdp_bind has not been called%s");
   if (!in->body_link_pos_w || !in->body_link_quat_w || !in->body_com_lin_vel_w || !in->joint_pos || !in->joint_vel ||
       !in->env_origins)

@@ -175,6 +175,7 @@ inline void params_from_cfg(const ZbotCfg& c, Params<T>& P) {
   P.c_inv_ramp = T(1) / T(c.contact_ramp);
   P.c_vt_eps = T(c.contact_vt_eps);
   P.c_margin = T(c.contact_margin);
+  P.c_inv_fband = T(1) / (T(0.25) * P.c_k * T(c.contact_ramp));   // activation band: 5 N at the defaults
   P.decimation = c.decimation;
   P.step_dt = T(c.sim_dt * (float)c.decimation);
   P.termination_height = T(c.termination_height);
@@ -184,13 +185,14 @@ inline void params_from_cfg(const ZbotCfg& c, Params<T>& P) {
   P.max_episode_length = c.max_episode_length;
   P.num_terms = c.num_terms;
   for (int i = 0; i < MAX_TERMS; ++i) { P.term_id[i] = c.term_id[i]; P.term_w[i] = T(c.term_weight[i]); }
-  P.default_terms = (c.num_terms == 13);
+  P.default_terms = (c.num_terms == 13) && (c.task == ZBOT_TASK_WALKING_V2);
   for (int i = 0; i < 13 && P.default_terms; ++i) P.default_terms = (c.term_id[i] == i);
 }
 
 inline int cfg_validate(const ZbotCfg& c, const char** why) {
   if (c.abi_version != ZBOT_ABI_VERSION) { *why = "ZbotCfg.abi_version mismatch"; return ZBOT_E_INVALID; }
   if (c.num_envs < 1) { *why = "num_envs must be >= 1"; return ZBOT_E_INVALID; }
+  if (c.task != ZBOT_TASK_WALKING_V2 && c.task != ZBOT_TASK_SNAKE_V0) { *why = "unknown task"; return ZBOT_E_INVALID; }
   if (c.decimation != 4) { *why = "only decimation == 4 is supported (5-deep contact history)"; return ZBOT_E_INVALID; }
   if (c.num_terms < 0 || c.num_terms > ZBOT_MAX_TERMS) { *why = "num_terms out of range"; return ZBOT_E_INVALID; }
   for (int i = 0; i < c.num_terms; ++i)
@@ -202,6 +204,7 @@ inline int cfg_validate(const ZbotCfg& c, const char** why) {
 inline void cfg_defaults(ZbotCfg& c, int num_envs) {
   memset(&c, 0, sizeof(c));
   c.abi_version = ZBOT_ABI_VERSION;
+  c.task = ZBOT_TASK_WALKING_V2;
   c.num_envs = num_envs;
   c.decimation = 4;
   c.max_episode_length = 1000;

@@ -12,7 +12,8 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libzbot_b200.so")
 
-ZBOT_ABI_VERSION = 1
+ZBOT_ABI_VERSION = 2
+TASK_WALKING_V2, TASK_SNAKE_V0 = 0, 1
 MAX_TERMS = 16
 STATE_WORDS = 80
 MDP_STATE_WORDS = 72
@@ -34,11 +35,16 @@ TERM_IDS = {
     "torques": 8, "feet_slide": 9, "base_pos_y_err": 10, "base_pos_y_err_sum": 11,
     "airtime_sum": 12, "feet_force_diff": 13, "feet_force_sum": 14,
 }
+#: snake task (zbot-6s-snake-v0): its own name -> id table (three names are shared with the walking task)
+SNAKE_TERM_IDS = {
+    "base_vel_forward": 0, "action_rate": 7, "torques": 8, "base_up_z": 15, "base_heading_y": 16,
+    "base_heading_y_sum": 17, "base_pos_x_err": 18, "base_pos_x_err_sum": 19,
+}
 
 
 class ZbotCfg(C.Structure):
     _fields_ = [
-        ("abi_version", C.c_int32), ("num_envs", C.c_int32), ("decimation", C.c_int32),
+        ("abi_version", C.c_int32), ("task", C.c_int32), ("num_envs", C.c_int32), ("decimation", C.c_int32),
         ("max_episode_length", C.c_int32), ("sim_dt", C.c_float), ("termination_height", C.c_float),
         ("y_err_limit", C.c_float), ("terminated_penalty", C.c_float), ("contact_died_force", C.c_float),
         ("kp", C.c_float), ("kd", C.c_float), ("effort_limit", C.c_float), ("gravity", C.c_float),
@@ -64,7 +70,7 @@ class ZbotMdpInputs(C.Structure):
 
 
 def make_cfg(num_envs: int, reward_scales: dict | None = None, step_dt: float | None = None,
-             **overrides) -> ZbotCfg:
+             task: int = TASK_WALKING_V2, **overrides) -> ZbotCfg:
     """Build a ``ZbotCfg`` from the task constants (``zbot_lab_b200/assets/zbot_6s.py``) and a
     reward-scale dict in cfg order (``…env_v2.py:190-206``); weights are multiplied by
     ``step_dt`` here exactly once (the reference mutates its class-level dict, SURVEY C-3)."""
@@ -72,15 +78,19 @@ def make_cfg(num_envs: int, reward_scales: dict | None = None, step_dt: float | 
 
     cfg = ZbotCfg()
     cfg.abi_version = ZBOT_ABI_VERSION
+    cfg.task = int(task)
     cfg.num_envs = int(num_envs)
     cfg.decimation = Z.DECIMATION
-    cfg.max_episode_length = 1000
+    cfg.max_episode_length = 1000 if task == TASK_WALKING_V2 else 800
     cfg.sim_dt = Z.SIM_DT
     cfg.termination_height = 0.22
     cfg.y_err_limit = 0.5
     cfg.terminated_penalty = 20.0
     cfg.contact_died_force = 1.0
     cfg.kp, cfg.kd, cfg.effort_limit = Z.KP, Z.KD, Z.EFFORT_LIMIT
+    if task == TASK_SNAKE_V0:
+        from .assets import zbot_d_6s as S
+        cfg.kp, cfg.kd, cfg.effort_limit = S.KP, S.KD, S.EFFORT_LIMIT
     cfg.gravity = Z.GRAVITY
     cfg.contact_alpha, cfg.contact_erp, cfg.contact_vdep = Z.CONTACT_ALPHA, Z.CONTACT_ERP, Z.CONTACT_VDEP
     cfg.contact_beta_max, cfg.contact_mu = Z.CONTACT_BETA_MAX, Z.CONTACT_MU
@@ -90,18 +100,21 @@ def make_cfg(num_envs: int, reward_scales: dict | None = None, step_dt: float | 
         if not hasattr(cfg, k):
             raise AttributeError(f"ZbotCfg has no field {k!r}")
         setattr(cfg, k, v)
+    term_ids = TERM_IDS if task == TASK_WALKING_V2 else SNAKE_TERM_IDS
     if reward_scales is None:
-        from .tasks.zbot6b_direct.walking_v2_cfg import REWARD_SCALES_V2
-        reward_scales = REWARD_SCALES_V2
+        if task == TASK_WALKING_V2:
+            from .tasks.zbot6b_direct.walking_v2_cfg import REWARD_SCALES_V2 as reward_scales
+        else:
+            from .tasks.zbot6_direct.snake_v0_cfg import REWARD_SCALES_SNAKE_V0 as reward_scales
     if step_dt is None:
         step_dt = cfg.decimation * Z.SIM_DT
     if len(reward_scales) > MAX_TERMS:
         raise ValueError(f"at most {MAX_TERMS} reward terms are supported")
     cfg.num_terms = len(reward_scales)
     for i, (name, w) in enumerate(reward_scales.items()):
-        if name not in TERM_IDS:
-            raise KeyError(f"unknown reward term {name!r}; known: {sorted(TERM_IDS)}")
-        cfg.term_id[i] = TERM_IDS[name]
+        if name not in term_ids:
+            raise KeyError(f"unknown reward term {name!r}; known: {sorted(term_ids)}")
+        cfg.term_id[i] = term_ids[name]
         cfg.term_weight[i] = float(w) * float(step_dt)
     return cfg
 
@@ -123,6 +136,7 @@ def _declare(lib):
     lib.zbot_bind.argtypes = [vp, vp, vp, vp, i32]
     lib.zbot_step.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, vp]
     lib.zbot_step_export.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, P(ZbotExport), vp]
+    lib.zbot_snake_step_export.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, vp, vp]
     lib.zbot_reset_idx.argtypes = [vp, vp, i64, vp, vp, i32, vp]
     lib.zbot_observe.argtypes = [vp, vp, vp]
     lib.zbot_articulation_view.argtypes = [vp, vp, vp, vp, vp]
@@ -132,7 +146,7 @@ def _declare(lib):
     lib.zbot_launch_count.argtypes = [vp]
     lib.zbot_launch_count.restype = i64
     for name in ("zbot_default_cfg", "zbot_state_word", "zbot_mdp_state_word", "zbot_create", "zbot_destroy",
-                 "zbot_bind", "zbot_step", "zbot_step_export", "zbot_reset_idx", "zbot_observe",
+                 "zbot_bind", "zbot_step", "zbot_step_export", "zbot_snake_step_export", "zbot_reset_idx", "zbot_observe",
                  "zbot_articulation_view", "zbot_mdp_bind", "zbot_mdp_observe", "zbot_mdp_step"):
         getattr(lib, name).restype = C.c_int
 
@@ -140,7 +154,7 @@ def _declare(lib):
 EXPORTED_SYMBOLS = (
     "zbot_abi_version", "zbot_build_info", "zbot_last_error", "zbot_default_cfg", "zbot_state_word",
     "zbot_mdp_state_word", "zbot_create", "zbot_destroy", "zbot_bind", "zbot_step", "zbot_step_export",
-    "zbot_reset_idx", "zbot_observe", "zbot_articulation_view", "zbot_mdp_bind", "zbot_mdp_observe",
+    "zbot_snake_step_export", "zbot_reset_idx", "zbot_observe", "zbot_articulation_view", "zbot_mdp_bind", "zbot_mdp_observe",
     "zbot_mdp_step", "zbot_launch_count",
 )
 

@@ -76,8 +76,15 @@ class _AoSoA:
         return self.buf[w // 4, :, w % 4]
 
 
+#: column map of the snake task's (N, 41) export row (SnakeExport in csrc/zbot_core.h)
+SNAKE_EXPORT = {"base_pos0": (0, 3), "base_quat0": (3, 7), "base_vel0": (7, 10), "base_pos1": (10, 13),
+                "base_quat1": (13, 17), "base_vel1": (17, 20), "com_x1": (20, 22), "self_force1": (22, 23),
+                "joint_pos1": (23, 29), "joint_vel1": (29, 35), "applied_torque1": (35, 41)}
+
+
 class NativeStepper:
-    """N envs of ``zbot-6b-walking-v2`` on one CUDA device."""
+    """N envs of ``zbot-6b-walking-v2`` (or, with ``cfg.task = TASK_SNAKE_V0``, ``zbot-6s-snake-v0``) on one
+    CUDA device."""
 
     def __init__(self, num_envs: int, device, cfg: ZbotCfg | None = None):
         self.device = torch.device(device)
@@ -103,7 +110,8 @@ class NativeStepper:
         self.terminated = torch.zeros(self.n, dtype=torch.uint8, device=self.device)
         self.truncated = torch.zeros(self.n, dtype=torch.uint8, device=self.device)
         self._slot = -1
-        self.state.set("joint_speed_limit", 1.0)
+        # walking: joint_speed_limit = 1 (…env_v2.py:243); snake: per-env, set by the task class (snake_v0.py:121)
+        self.state.set("joint_speed_limit", 1.0 if self.cfg.task == native.TASK_WALKING_V2 else 3.14159265)
         self.mdp_state = None
 
     # ------------------------------------------------------------------ lifecycle
@@ -140,7 +148,12 @@ class NativeStepper:
         if actions.shape != (self.n, 6):
             raise ValueError(f"actions must be ({self.n}, 6), got {tuple(actions.shape)}")
         slot, prev = self._next_slot()
-        if export is None:
+        if export is not None and self.cfg.task == native.TASK_SNAKE_V0:
+            # snake task: `export` is one (N, 41) float32 tensor (include/zbot_b200.h: zbot_snake_step_export)
+            rc = self.lib.zbot_snake_step_export(self._h, _ptr(actions), _ptr(self.obs), _ptr(self.rew),
+                                                 _ptr(self.terminated), _ptr(self.truncated), slot, prev,
+                                                 _ptr(export), _stream(self.device))
+        elif export is None:
             rc = self.lib.zbot_step(self._h, _ptr(actions), _ptr(self.obs), _ptr(self.rew), _ptr(self.terminated),
                                     _ptr(self.truncated), slot, prev, _stream(self.device))
         else:

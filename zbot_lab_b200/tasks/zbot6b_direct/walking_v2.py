@@ -108,23 +108,9 @@ class ZbotDirectEnvV2:
         self.max_episode_length = math.ceil(self.max_episode_length_s / self.step_dt)
         # reward table: a COPY scaled once by step_dt (the reference scales its class dict in place, C-3)
         self.reward_scales = {k: v * self.step_dt for k, v in self.cfg.reward_cfg["reward_scales"].items()}
-        c, a = self.cfg.contact, self.cfg.actuator
-        ncfg = native.make_cfg(
-            self.num_envs, reward_scales=self.cfg.reward_cfg["reward_scales"], step_dt=self.step_dt,
-            sim_dt=self.physics_dt, decimation=int(self.cfg.decimation),
-            max_episode_length=int(self.max_episode_length), termination_height=float(self.cfg.termination_height),
-            kp=a.stiffness, kd=a.damping, effort_limit=a.effort_limit,
-            gravity=-float(self.cfg.sim.gravity[2]),
-            contact_alpha=c.alpha, contact_erp=c.erp, contact_vdep=c.max_depenetration_velocity,
-            contact_beta_max=c.beta_max, contact_mu=c.friction, contact_ramp=c.ramp, contact_margin=c.margin)
-        self._stepper = NativeStepper(self.num_envs, self.device, ncfg)
+        self._stepper = NativeStepper(self.num_envs, self.device, self._native_cfg())
         self._terrain = _Terrain(self.num_envs, self.cfg.scene.env_spacing, self.device)
-        self._robot = _Robot(self)
-        # index sets, resolved by name exactly as …env_v2.py:227-230
-        self._feet_ids, _ = Z.find_bodies("foot.*", Z.SENSOR_BODY_NAMES)
-        self._undesired_contact_body_ids, _ = Z.find_bodies("base|a.*|b.*", Z.SENSOR_BODY_NAMES)
-        self.base_body_idx = Z.find_bodies("base", Z.LINK_NAMES)[0]
-        self.feet_body_idx = Z.find_bodies("foot.*", Z.LINK_NAMES)[0]
+        self._setup_scene()
         # spaces
         self.single_observation_space = {"policy": _Box((self.cfg.observation_space,))}
         self.single_action_space = _Box((self.cfg.action_space,))
@@ -149,6 +135,30 @@ class ZbotDirectEnvV2:
         self._check_all_reset = (self.num_envs <= 256) if chk is None else bool(chk)
         self._stepper.reset_idx(None)
         self._sim_step_counter = 0
+
+    # ------------------------------------------------------------------ task hooks (overridden by the snake task)
+    _TASK = native.TASK_WALKING_V2
+    _DIED_LOG_KEY = "Episode_Termination/body_contact"     # …env_v2.py:453
+
+    def _native_cfg(self) -> native.ZbotCfg:
+        c, a = self.cfg.contact, self.cfg.actuator
+        extra = {"termination_height": float(self.cfg.termination_height)} if hasattr(self.cfg, "termination_height") else {}
+        return native.make_cfg(
+            self.num_envs, reward_scales=self.cfg.reward_cfg["reward_scales"], step_dt=self.step_dt, task=self._TASK,
+            sim_dt=self.physics_dt, decimation=int(self.cfg.decimation),
+            max_episode_length=int(self.max_episode_length),
+            kp=a.stiffness, kd=a.damping, effort_limit=a.effort_limit,
+            gravity=-float(self.cfg.sim.gravity[2]),
+            contact_alpha=c.alpha, contact_erp=c.erp, contact_vdep=c.max_depenetration_velocity,
+            contact_beta_max=c.beta_max, contact_mu=c.friction, contact_ramp=c.ramp, contact_margin=c.margin, **extra)
+
+    def _setup_scene(self):
+        self._robot = _Robot(self)
+        # index sets, resolved by name exactly as …env_v2.py:227-230
+        self._feet_ids, _ = Z.find_bodies("foot.*", Z.SENSOR_BODY_NAMES)
+        self._undesired_contact_body_ids, _ = Z.find_bodies("base|a.*|b.*", Z.SENSOR_BODY_NAMES)
+        self.base_body_idx = Z.find_bodies("base", Z.LINK_NAMES)[0]
+        self.feet_body_idx = Z.find_bodies("foot.*", Z.LINK_NAMES)[0]
 
     # ------------------------------------------------------------------ reference attribute surface
     @property
@@ -211,7 +221,7 @@ class ZbotDirectEnvV2:
     def _log_from_slot(self) -> dict:
         s = self._stepper.stats          # 0-dim VIEWS into this step's statistics slot (no launch, no sync)
         log = {"Episode_Reward/" + k: s[i] for i, k in enumerate(self._term_names)}
-        log["Episode_Termination/body_contact"] = s[native.STAT_NUM_TERMINATED_RESET]
+        log[self._DIED_LOG_KEY] = s[native.STAT_NUM_TERMINATED_RESET]
         log["Episode_Termination/time_out"] = s[native.STAT_NUM_TIMEOUT_RESET]
         return log
 
