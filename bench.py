@@ -253,14 +253,20 @@ def main():
         if with_e2e:
             h_act = [torch.randn(n_envs, 6).pin_memory() for _ in range(4)]
             h_out = torch.empty(n_envs * 98, dtype=torch.uint8).pin_memory()   # obs | rew | terminated | truncated
+            h_rows = torch.empty(n_envs, 25).pin_memory()                      # step_host rows: obs | rew | flags
             d_act = torch.empty(n_envs, 6, device=dev)
 
-            def e2e_step(i):
+            def e2e_step_staged(i):
                 d_act.copy_(h_act[i % 4], non_blocking=True)          # this step's inputs: pinned host -> device
                 env.step(d_act)                                       # the public API call
                 h_out.copy_(env.last_step_packed, non_blocking=True)  # the step's whole result: device -> pinned host
                 torch.cuda.synchronize()
                 return env.unpack_host(h_out)
+
+            def e2e_step(i):
+                # the host-facing public API call: pinned actions in, packed result out, both zero-copy over PCIe
+                # inside the one kernel launch; returns after the stream is synchronised (result owned by the host)
+                return env.step_host(h_act[i % 4], h_rows)
 
             for i in range(max(3, warmup // 4)):
                 e2e_step(i)
@@ -273,9 +279,24 @@ def main():
             if world > 1:
                 dist.all_reduce(te, op=dist.ReduceOp.MAX)
             e2e = {"value": world * n_envs * steps / float(te.item()), "unit": UNIT,
-                   "h2d_bytes_per_step": n_envs * 24, "d2h_bytes_per_step": n_envs * (92 + 4 + 1 + 1)}
+                   "h2d_bytes_per_step": n_envs * 24, "d2h_bytes_per_step": n_envs * 100,
+                   "path": "env.step_host -> zbot_step_host: pinned host actions in, (N,25) pinned host rows "
+                           "(obs | reward | flags) out, both zero-copy over PCIe inside the one fused-kernel launch; "
+                           "synchronous (stream synchronised every step)"}
             obs_h, rew_h, term_h, trunc_h = e2e_step(0)
             assert obs_h.shape == (n_envs, 23) and bool(torch.isfinite(rew_h).all())
+            # the staged variant (explicit H2D copy, device-resident step, one packed D2H copy) for comparison
+            for i in range(3):
+                e2e_step_staged(i)
+            barrier()
+            t0 = time.perf_counter()
+            for i in range(steps):
+                e2e_step_staged(i)
+            barrier()
+            ts = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+            e2e["staged_copies_value"] = world * n_envs * steps / float(ts.item())
 
 
         env.close()

@@ -160,6 +160,18 @@ int zbot_step_export(ZbotHandle* h, const float* actions, float* obs, float* rew
                      uint8_t* truncated, int32_t stats_slot, int32_t prev_slot, const ZbotExport* ex,
                      void* stream);
 
+/* The control step for a HOST-resident caller (the reference's CPU consumers: a host policy, a logger, a
+ * replay writer).  `host_actions` ([N][6] f32) and `host_rows` ([N][ZBOT_HOST_ROW_WORDS] f32, 16-byte aligned)
+ * are PINNED (page-locked, mapped) host buffers -- cudaHostAlloc / cudaHostRegister / torch pin_memory.
+ * Result row of env e: words 0..22 = observation, word 23 = reward, word 24 = flags as uint32 (bit 0
+ * terminated, bit 8 truncated: bytes 96 / 97 of the row, little endian).  One kernel launch: actions are read
+ * and rows written straight over PCIe from inside the fused kernel (zero-copy), no staging copies.
+ * Ordered after the work already queued on `stream`; SYNCHRONOUS: when it returns the result is complete in
+ * host memory.  Walking task. */
+#define ZBOT_HOST_ROW_WORDS 25
+int zbot_step_host(ZbotHandle* h, const float* host_actions, float* host_rows, int32_t stats_slot, int32_t prev_slot,
+                   void* stream);
+
 /* Snake task only: the same fused step, additionally exporting what its MDP saw -- per env 41 floats
  * [base_pos0 3, base_quat0 4, base_vel0 3, base_pos1 3, base_quat1 4, base_vel1 3, com_x1 2, self_force1 1,
  *  joint_pos1 6, joint_vel1 6, applied_torque1 6] (0 = start of step, 1 = end of physics; `base` = link a4,

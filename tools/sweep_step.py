@@ -12,10 +12,11 @@ from zbot_lab_b200.stepper import NativeStepper  # noqa: E402
 from zbot_lab_b200.utils import synthetic as syn  # noqa: E402
 
 
-def time_cfg(n, mb, block, steps=200, warm=30, two_pass=1):
-    os.environ["ZBOT_STATS_TWO_PASS"] = str(two_pass)
-    os.environ["ZBOT_STEP_MIN_BLOCKS"] = str(mb)
-    os.environ["ZBOT_STEP_BLOCK"] = str(block)
+VARIANTS = ["128x2", "128x3", "128x4", "64x5", "32x10", "32x11", "64x6", "32x12", "32x13", "32x14", "64x7", "32x16"]
+
+
+def time_cfg(n, variant, steps=200, warm=30):
+    os.environ["ZBOT_STEP_VARIANT"] = variant
     st = NativeStepper(n, "cuda:0")
     st.reset_idx(None)
     rng = np.random.default_rng(0)
@@ -40,8 +41,6 @@ def time_cfg(n, mb, block, steps=200, warm=30, two_pass=1):
 if __name__ == "__main__":
     sizes = [int(x) for x in sys.argv[1:]] or [4096, 65536]
     for n in sizes:
-        for two_pass in (1,):
-            for mb, blocks in ((2, (64, 128)), (3, (64, 128)), (4, (64, 128))):
-                for block in blocks:
-                    us = time_cfg(n, mb, block, two_pass=two_pass)
-                    print(f"envs {n:6d} two_pass {two_pass} min_blocks {mb} block {block:3d}: {us:8.2f} us/step  {n / us:8.2f} M env-steps/s", flush=True)
+        for v in VARIANTS:
+            us = min(time_cfg(n, v) for _ in range(2))
+            print(f"envs {n:6d} variant {v:>6s}: {us:8.2f} us/step  {n / us:8.2f} M env-steps/s", flush=True)

@@ -529,7 +529,8 @@ struct ArrayScratch {
 // Each thread owns SCR_STRIDE consecutive words of shared memory.  SCR_STRIDE is odd, so the 32 lanes of a
 // warp hit 32 different banks for any (j, slot); `slot` is a compile-time constant at every use, so it folds
 // into the LDS/STS immediate and only `j * SCR_PER_JOINT` costs an instruction per loop iteration.
-constexpr int SCR_STRIDE = SCR_WORDS + 1;   // 103
+constexpr int SCR_RAW_ACT = SCR_WORDS;       // 6 words: this step's raw actions, parked across the physics phase
+constexpr int SCR_STRIDE = SCR_WORDS + 7;   // 109 (odd)
 struct SmemScratch {
   float* base;   // this thread's row
   __device__ __forceinline__ float& operator()(int j, int slot) { return base[j * SCR_PER_JOINT + slot]; }

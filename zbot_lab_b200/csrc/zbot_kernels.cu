@@ -56,6 +56,7 @@ struct StatsCtx {
   float* ring;            // [slots][32]
   int slot, prev_slot;
   float inv_episode_s;    // 1 / max_episode_length_s  (…env_v2.py:444-447)
+  int block_offset;       // env-range launches (zbot_step_host): index of this launch's first partial row
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -121,7 +122,7 @@ __device__ __forceinline__ void stats_block_partial(float (&vals)[kStatUsed], bo
   if (threadIdx.x < kStatUsed) {
     float acc = 0.f;
     for (int w = 0; w < nwarps; ++w) acc += smem[w * kStatUsed + threadIdx.x];
-    sc.partials[(size_t)blockIdx.x * kStats + threadIdx.x] = acc;
+    sc.partials[(size_t)(blockIdx.x + sc.block_offset) * kStats + threadIdx.x] = acc;
   }
 }
 
@@ -176,23 +177,27 @@ constexpr int kFoot0Sensor = 9, kFoot1Sensor = 10;
 // ---------------------------------------------------------------------------------------------
 // the fused control step
 // ---------------------------------------------------------------------------------------------
-template <bool kExport>
+// kPacked: host-facing output layout -- ONE row of 25 words per env [obs 23 | reward | flags word
+// (terminated | truncated << 8)] written to `obs` ([N][25]); `rew` / `terminated` / `truncated` are not touched.
+template <bool kExport, bool kPacked = false>
 __device__ __forceinline__ void
 zbot_step_body(const Params<float>& P, const DefaultPose& dp,
                  float4* __restrict__ state, int64_t* __restrict__ ep_len_buf,
                  const float* __restrict__ actions, float* __restrict__ obs, float* __restrict__ rew,
-                 uint8_t* __restrict__ terminated, uint8_t* __restrict__ truncated, int n, StatsCtx sc,
-                 ExportPtrs xp) {
+                 uint8_t* __restrict__ terminated, uint8_t* __restrict__ truncated, int n, int e_begin, int e_end,
+                 StatsCtx sc, ExportPtrs xp) {
   extern __shared__ float smem[];   // blockDim*SCR_STRIDE floats: substep scratch, then obs rows, then stats
-  const int e0 = blockIdx.x * blockDim.x;
+  // this launch covers envs [e_begin, e_end) of the n-env state (whole range: 0, n)
+  const int e0 = e_begin + blockIdx.x * blockDim.x;
   const int e = e0 + threadIdx.x;
-  const bool live = e < n;
+  const bool live = e < e_end;
   float stat[kStatUsed];
 #pragma unroll
   for (int j = 0; j < kStatUsed; ++j) stat[j] = 0.f;
-  float obs_row[ZBOT_NUM_OBS];
+  constexpr int kRow = kPacked ? ZBOT_HOST_ROW_WORDS : ZBOT_NUM_OBS;
+  float obs_row[kRow];
 #pragma unroll
-  for (int i = 0; i < ZBOT_NUM_OBS; ++i) obs_row[i] = 0.f;
+  for (int i = 0; i < kRow; ++i) obs_row[i] = 0.f;
   bool did_reset = false;
   if (live) {
     EnvState<float> es;
@@ -242,6 +247,10 @@ zbot_step_body(const Params<float>& P, const DefaultPose& dp,
       {
         const float2 a0 = __ldg(a2p), a1 = __ldg(a2p + 1), a2v = __ldg(a2p + 2);
         const float raw[6] = {a0.x, a0.y, a1.x, a1.y, a2v.x, a2v.y};
+        // read ONCE (the buffer may be pinned host memory: zero-copy over PCIe) and parked in this thread's
+        // shared-memory row for phase C
+#pragma unroll
+        for (int k = 0; k < 6; ++k) scr.base[SCR_RAW_ACT + k] = raw[k];
         // ---- phase B: 4 physics substeps; the MDP state is not even loaded yet (register budget) ----
         env_step_physics<ModelWalk>(P, es, raw, po, scr, (StepExport<float>*)nullptr);
       }
@@ -258,8 +267,9 @@ zbot_step_body(const Params<float>& P, const DefaultPose& dp,
         load_words<SIM_QUADS>(state, n, e, w);
         sim_state_unpack(w, s0);
       }
-      const float2 a0 = __ldg(a2p), a1 = __ldg(a2p + 1), a2v = __ldg(a2p + 2);
-      const float raw[6] = {a0.x, a0.y, a1.x, a1.y, a2v.x, a2v.y};
+      float raw[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) raw[k] = scr.base[SCR_RAW_ACT + k];
       ep = ep_len_buf[e];
       env_step_finish(P, es, s0, raw, po, ep, dp.feet_pos, dp.base_quat, out, rs, (StepExport<float>*)nullptr);
     }
@@ -267,9 +277,14 @@ zbot_step_body(const Params<float>& P, const DefaultPose& dp,
     env_state_pack(es, w);
     store_words<ZBOT_STATE_WORDS / 4>(state, n, e, w);
     ep_len_buf[e] = ep;
-    rew[e] = out.reward;
-    terminated[e] = out.terminated ? 1 : 0;
-    truncated[e] = out.time_out ? 1 : 0;
+    if (kPacked) {
+      obs_row[ZBOT_NUM_OBS] = out.reward;
+      obs_row[ZBOT_NUM_OBS + 1] = __uint_as_float((out.terminated ? 1u : 0u) | (out.time_out ? 0x100u : 0u));
+    } else {
+      rew[e] = out.reward;
+      terminated[e] = out.terminated ? 1 : 0;
+      truncated[e] = out.time_out ? 1 : 0;
+    }
 #pragma unroll
     for (int i = 0; i < ZBOT_NUM_OBS; ++i) obs_row[i] = out.obs[i];
     did_reset = out.terminated || out.time_out;
@@ -285,7 +300,7 @@ zbot_step_body(const Params<float>& P, const DefaultPose& dp,
     stat[S_NUM_TRUNC] = out.time_out ? 1.f : 0.f;
   }
   __syncthreads();   // every thread is done with its scratch column before the rows are staged
-  store_rows_coalesced<ZBOT_NUM_OBS>(obs, obs_row, n, e0, smem);
+  store_rows_coalesced<kRow>(obs, obs_row, e_end, e0, smem);
   __syncthreads();
   stats_block_partial(stat, did_reset, smem, sc);
 }
@@ -294,14 +309,24 @@ zbot_step_body(const Params<float>& P, const DefaultPose& dp,
   const __grid_constant__ Params<float> P, const __grid_constant__ DefaultPose dp, float4 *__restrict__ state, \
       int64_t *__restrict__ ep_len_buf, const float *__restrict__ actions, float *__restrict__ obs,      \
       float *__restrict__ rew, uint8_t *__restrict__ terminated, uint8_t *__restrict__ truncated, int n, \
-      StatsCtx sc, ExportPtrs xp
-#define ZB_STEP_CALL P, dp, state, ep_len_buf, actions, obs, rew, terminated, truncated, n, sc, xp
+      int e_begin, int e_end, StatsCtx sc, ExportPtrs xp
+#define ZB_STEP_CALL P, dp, state, ep_len_buf, actions, obs, rew, terminated, truncated, n, e_begin, e_end, sc, xp
 
 // register-budget variants of the same body (DESIGN.md §4 "occupancy"): kMinBlocks resident CTAs of
 // kMaxThreads threads per SM
 template <bool kExport, int kMaxThreads, int kMinBlocks>
 __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) zbot_step_kernel(ZB_STEP_ARGS) {
   zbot_step_body<kExport>(ZB_STEP_CALL);
+}
+// host-facing output layout (zbot_step_host): one 25-word row per env
+__global__ void __launch_bounds__(128, 2) zbot_step_packed_kernel(ZB_STEP_ARGS) {
+  zbot_step_body<false, true>(ZB_STEP_CALL);
+}
+// same body, register cap given directly (ptxas snaps __launch_bounds__ caps to a few occupancy steps:
+// 197 -> 168 -> 128; __maxnreg__ gives the steps in between)
+template <int kMaxRegs>
+__global__ void __maxnreg__(kMaxRegs) zbot_step_kernel_r(ZB_STEP_ARGS) {
+  zbot_step_body<false>(ZB_STEP_CALL);
 }
 // ---------------------------------------------------------------------------------------------
 // snake task (zbot-6s-snake-v0): same state layout, same physics substep (ModelSnake), its own MDP.
@@ -343,6 +368,8 @@ zbot_snake_step_kernel(const __grid_constant__ Params<float> P, const __grid_con
     {
       const float2 a0 = __ldg(a2p), a1 = __ldg(a2p + 1), a2v = __ldg(a2p + 2);
       const float raw[6] = {a0.x, a0.y, a1.x, a1.y, a2v.x, a2v.y};
+#pragma unroll
+      for (int k = 0; k < 6; ++k) scr.base[SCR_RAW_ACT + k] = raw[k];
       env_step_physics<ModelSnake>(P, es, raw, po, scr, (StepExport<float>*)nullptr);
     }
     {
@@ -356,8 +383,9 @@ zbot_snake_step_kernel(const __grid_constant__ Params<float> P, const __grid_con
       load_words<SIM_QUADS>(state, n, e, w);
       sim_state_unpack(w, s0);
     }
-    const float2 a0 = __ldg(a2p), a1 = __ldg(a2p + 1), a2v = __ldg(a2p + 2);
-    const float raw[6] = {a0.x, a0.y, a1.x, a1.y, a2v.x, a2v.y};
+    float raw[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) raw[k] = scr.base[SCR_RAW_ACT + k];
     int64_t ep = ep_len_buf[e];
     SnakeExport<float> ex;
     snake_step_finish(P, es, s0, raw, po, ep, dp.base_quat, out, rs, kExport ? &ex : (SnakeExport<float>*)nullptr);
@@ -710,19 +738,41 @@ struct ZbotHandle {
   int max_blocks;
   int64_t launches;
   float inv_episode_s;
-  int min_blocks;
+  int variant;      // index into kStepVariants
   int force_block;
   int mdp_tile;
 };
 
 namespace {
 
+// Register-budget / CTA-shape variants of the walking step kernel: (threads per CTA, resident CTAs per SM the
+// kernel is compiled for).  The register cap follows from 65536 / (threads * ctas); smaller CTAs give a finer
+// occupancy grid (e.g. 5 x 64 threads = 10 warps/SM at the full 197 registers).
+typedef void (*StepFn)(Params<float>, DefaultPose, float4*, int64_t*, const float*, float*, float*, uint8_t*, uint8_t*, int,
+                       int, int, StatsCtx, ExportPtrs);
+struct StepVariant { int threads, ctas; StepFn fn; };
+const StepVariant kStepVariants[] = {
+    {128, 2, zbot_step_kernel<false, 128, 2>}, {128, 3, zbot_step_kernel<false, 128, 3>},
+    {128, 4, zbot_step_kernel<false, 128, 4>},
+    {64, 5, zbot_step_kernel_r<200>},  {32, 10, zbot_step_kernel_r<200>}, {32, 11, zbot_step_kernel_r<184>},
+    {64, 6, zbot_step_kernel<false, 64, 6>}, {32, 12, zbot_step_kernel<false, 32, 12>},
+    {32, 13, zbot_step_kernel_r<152>}, {32, 14, zbot_step_kernel_r<144>}, {64, 7, zbot_step_kernel_r<144>},
+    {32, 16, zbot_step_kernel<false, 32, 16>},
+};
+constexpr int kNumStepVariants = (int)(sizeof(kStepVariants) / sizeof(kStepVariants[0]));
+
 int pick_block(const ZbotHandle* h, int n) {
   // fill the SMs first: the step is latency/issue bound, not bandwidth bound
-  if (h->force_block == 32 || h->force_block == 64 || h->force_block == 128) return h->force_block;
-  int block = 128;
+  int block = kStepVariants[h->variant].threads;
+  if (h->force_block == 32 || h->force_block == 64 || h->force_block == 128) block = min(block, h->force_block);
   while (block > 32 && (n + block - 1) / block < 2 * h->num_sms) block >>= 1;
   return block;
+}
+
+int find_variant(int threads, int ctas) {
+  for (int v = 0; v < kNumStepVariants; ++v)
+    if (kStepVariants[v].threads == threads && kStepVariants[v].ctas == ctas) return v;
+  return -1;
 }
 
 int check_slot(int slot, int prev, int slots) {
@@ -774,19 +824,22 @@ int zbot_create(const ZbotCfg* cfg, int device, ZbotHandle** out) {
   ZB_CUDA(cudaMemcpy(&h->dp, d_dp, sizeof(DefaultPose), cudaMemcpyDeviceToHost));
   ZB_CUDA(cudaFree(d_dp));
   ZB_CUDA(cudaFuncSetAttribute(zbot_mdp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * kHistRow * 4));
-  ZB_CUDA(cudaFuncSetAttribute(zbot_step_kernel<false, 128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
-  ZB_CUDA(cudaFuncSetAttribute(zbot_step_kernel<false, 128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
-  ZB_CUDA(cudaFuncSetAttribute(zbot_step_kernel<false, 128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
+  for (int v = 0; v < kNumStepVariants; ++v)
+    ZB_CUDA(cudaFuncSetAttribute((const void*)kStepVariants[v].fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 128 * SCR_STRIDE * 4));
   ZB_CUDA(cudaFuncSetAttribute(zbot_step_kernel<true, 128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
+  ZB_CUDA(cudaFuncSetAttribute(zbot_step_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
   ZB_CUDA(cudaFuncSetAttribute(zbot_snake_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
   ZB_CUDA(cudaFuncSetAttribute(zbot_snake_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
   {
     // register-budget variant of the step kernel = resident 128-thread CTAs per SM it is compiled for.
     // Measured (profiles/r1_notes.md): 2 CTAs/SM (197 regs, no spill) is fastest while the grid fits two
     // rounds of 2 x 148 CTAs; beyond that 3 CTAs/SM (168 regs) wins on throughput (+18 % at 131072 envs).
-    const char* mb = getenv("ZBOT_STEP_MIN_BLOCKS");   // tuning override
-    h->min_blocks = mb ? atoi(mb) : ((cfg->num_envs > 2 * 2 * 148 * 128) ? 3 : 2);
-    if (h->min_blocks < 2 || h->min_blocks > 4) h->min_blocks = 2;
+    const char* sv = getenv("ZBOT_STEP_VARIANT");      // tuning override, "<threads>x<ctas>", e.g. 64x5
+    int vt = 0, vc = 0;
+    h->variant = -1;
+    if (sv && sscanf(sv, "%dx%d", &vt, &vc) == 2) h->variant = find_variant(vt, vc);
+    if (h->variant < 0) h->variant = find_variant(128, (cfg->num_envs > 2 * 2 * 148 * 128) ? 3 : 2);
     const char* mt = getenv("ZBOT_MDP_TILE");          // envs (= threads) per CTA of the MDP-only step kernel
     h->mdp_tile = mt ? atoi(mt) : kMdpTile;
     if (h->mdp_tile != 32 && h->mdp_tile != 64 && h->mdp_tile != 128) h->mdp_tile = kMdpTile;
@@ -826,7 +879,7 @@ static int step_impl(ZbotHandle* h, const float* actions, float* obs, float* rew
   const int block = pick_block(h, n);
   const int grid = (n + block - 1) / block;
   const size_t smem = (size_t)block * SCR_STRIDE * sizeof(float);   // >= obs rows (23/thread) and stats (704 floats)
-  StatsCtx sc{h->partials, h->ring, slot, prev, h->inv_episode_s};
+  StatsCtx sc{h->partials, h->ring, slot, prev, h->inv_episode_s, 0};
   cudaStream_t s = (cudaStream_t)stream;
   ExportPtrs xp{};
   if (h->cfg.task == ZBOT_TASK_SNAKE_V0) {
@@ -847,16 +900,10 @@ static int step_impl(ZbotHandle* h, const float* actions, float* obs, float* rew
     for (int i = 0; i < 12; ++i)
       if (!pp[i]) return fail(ZBOT_E_INVALID, "zbot_step_export: NULL export buffer%s");
     zbot_step_kernel<true, 128, 2><<<grid, block, smem, s>>>(h->P, h->dp, h->state, h->ep_len, actions, obs, rew, terminated,
-                                                         truncated, n, sc, xp);
-  } else if (h->min_blocks == 2) {
-    zbot_step_kernel<false, 128, 2><<<grid, block, smem, s>>>(h->P, h->dp, h->state, h->ep_len, actions, obs, rew, terminated,
-                                                          truncated, n, sc, xp);
-  } else if (h->min_blocks == 3) {
-    zbot_step_kernel<false, 128, 3><<<grid, block, smem, s>>>(h->P, h->dp, h->state, h->ep_len, actions, obs, rew, terminated,
-                                                          truncated, n, sc, xp);
+                                                         truncated, n, 0, n, sc, xp);
   } else {
-    zbot_step_kernel<false, 128, 4><<<grid, block, smem, s>>>(h->P, h->dp, h->state, h->ep_len, actions, obs, rew, terminated,
-                                                          truncated, n, sc, xp);
+    kStepVariants[h->variant].fn<<<grid, block, smem, s>>>(h->P, h->dp, h->state, h->ep_len, actions, obs, rew, terminated,
+                                                        truncated, n, 0, n, sc, xp);
   }
   ZB_CUDA(cudaGetLastError());
   h->launches += 1;
@@ -877,6 +924,53 @@ int zbot_step_export(ZbotHandle* h, const float* actions, float* obs, float* rew
   return step_impl(h, actions, obs, rew, terminated, truncated, stats_slot, prev_slot, ex, stream);
 }
 
+// Whole control step for a HOST-resident caller (DESIGN.md §4 "end to end").  ONE launch of the fused kernel with
+// pinned-host pointers: each thread reads its 24 B of actions straight from host memory (once -- they are parked in
+// shared memory for the MDP phase) and each CTA writes its envs' result rows [obs 23 | reward | flags] as one
+// contiguous run of float4 stores straight to host memory, so both directions cross PCIe inside the kernel,
+// overlapped with the other CTAs' compute, with no DMA operation at all.  Measured against the alternatives on
+// B200 / PCIe 5 x16 (tools/probe_host_step.py, 65536 envs): H2D + kernel + D2H back to back 297 us, four env
+// ranges pipelined on streams with one DMA each way per range 219 us (a DMA op costs ~5 us however small), this
+// 196 us.  Returns when the result is complete in host memory.
+int zbot_step_host(ZbotHandle* h, const float* host_actions, float* host_rows, int32_t stats_slot, int32_t prev_slot,
+                   void* stream) {
+  if (!h) return fail(ZBOT_E_INVALID, "handle is NULL%s");
+  if (!h->state) return fail(ZBOT_E_UNBOUND, "zbot_bind has not been called%s");
+  if (h->cfg.task != ZBOT_TASK_WALKING_V2) return fail(ZBOT_E_INVALID, "zbot_step_host: walking task only%s");
+  if (!host_actions || !host_rows) return fail(ZBOT_E_INVALID, "zbot_step_host: NULL buffer%s");
+  if (((uintptr_t)host_actions & 7) != 0 || ((uintptr_t)host_rows & 15) != 0)
+    return fail(ZBOT_E_INVALID, "zbot_step_host: host_actions must be 8-byte and host_rows 16-byte aligned%s");
+  if (int rc = check_slot(stats_slot, prev_slot, h->ring_slots)) return rc;
+  {
+    // the buffers must be device-accessible (pinned + mapped: cudaHostAlloc / cudaHostRegister / torch pin_memory)
+    const void *da = nullptr, *dr = nullptr;
+    if (cudaHostGetDevicePointer((void**)&da, (void*)host_actions, 0) != cudaSuccess ||
+        cudaHostGetDevicePointer((void**)&dr, (void*)host_rows, 0) != cudaSuccess) {
+      cudaGetLastError();
+      return fail(ZBOT_E_INVALID, "zbot_step_host: buffers must be pinned (page-locked, mapped) host memory%s");
+    }
+    host_actions = static_cast<const float*>(da);
+    host_rows = static_cast<float*>(const_cast<void*>(dr));
+  }
+  const int n = h->cfg.num_envs;
+  int block = 128;
+  while (block > 32 && (n + block - 1) / block < 2 * h->num_sms) block >>= 1;
+  const int grid = (n + block - 1) / block;
+  const size_t smem = (size_t)block * SCR_STRIDE * sizeof(float);
+  cudaStream_t s = (cudaStream_t)stream;
+  StatsCtx sc{h->partials, h->ring, stats_slot, prev_slot, h->inv_episode_s, 0};
+  ExportPtrs xp{};
+  zbot_step_packed_kernel<<<grid, block, smem, s>>>(h->P, h->dp, h->state, h->ep_len, host_actions, host_rows, nullptr, nullptr,
+                                                  nullptr, n, 0, n, sc, xp);
+  ZB_CUDA(cudaGetLastError());
+  h->launches += 1;
+  zbot_stats_finalize_kernel<<<1, 1024, 0, s>>>(sc, (unsigned int)grid);
+  ZB_CUDA(cudaGetLastError());
+  h->launches += 1;
+  ZB_CUDA(cudaStreamSynchronize(s));
+  return ZBOT_OK;
+}
+
 int zbot_snake_step_export(ZbotHandle* h, const float* actions, float* obs, float* rew, uint8_t* terminated,
                            uint8_t* truncated, int32_t stats_slot, int32_t prev_slot, float* export41, void* stream) {
   if (!export41) return fail(ZBOT_E_INVALID, "zbot_snake_step_export: export41 is NULL%s");
@@ -894,7 +988,7 @@ int zbot_reset_idx(ZbotHandle* h, const int64_t* env_ids, int64_t nids, const ui
   if (nids > n) return fail(ZBOT_E_INVALID, "more env ids than envs%s");
   const int block = 64;
   const int grid = (int)((nids + block - 1) / block);
-  StatsCtx sc{h->partials, h->ring, stats_slot, -1, h->inv_episode_s};
+  StatsCtx sc{h->partials, h->ring, stats_slot, -1, h->inv_episode_s, 0};
   if (h->cfg.task == ZBOT_TASK_SNAKE_V0)
     zbot_reset_kernel<true><<<grid, block, 32 * kStatUsed * sizeof(float), (cudaStream_t)stream>>>(
         h->P, h->dp, h->state, h->ep_len, env_ids, nids, terminated, truncated, n, sc);
@@ -963,7 +1057,7 @@ int zbot_mdp_observe(ZbotHandle* h, const ZbotMdpInputs* in, float* obs, void* s
   const int n = h->cfg.num_envs, block = 128, grid = (n + block - 1) / block;
   MdpIn mi{in->body_link_pos_w, in->body_link_quat_w, in->body_com_lin_vel_w, in->joint_pos, in->joint_vel,
            in->applied_torque, in->net_forces_w_history, in->last_air_time, in->env_origins};
-  StatsCtx sc{h->partials, h->m_ring, 0, -1, h->inv_episode_s};
+  StatsCtx sc{h->partials, h->m_ring, 0, -1, h->inv_episode_s, 0};
   zbot_mdp_kernel<false><<<grid, block, block * ZBOT_NUM_OBS * sizeof(float), (cudaStream_t)stream>>>(
       h->P, h->dp, mi, h->mstate, h->m_ep_len, nullptr, obs, nullptr, nullptr, nullptr, n, sc);
   ZB_CUDA(cudaGetLastError());
@@ -979,7 +1073,7 @@ int zbot_mdp_step(ZbotHandle* h, const ZbotMdpInputs* in, const float* actions, 
   const int n = h->cfg.num_envs, block = h->mdp_tile, grid = (n + block - 1) / block;
   MdpIn mi{in->body_link_pos_w, in->body_link_quat_w, in->body_com_lin_vel_w, in->joint_pos, in->joint_vel,
            in->applied_torque, in->net_forces_w_history, in->last_air_time, in->env_origins};
-  StatsCtx sc{h->partials, h->m_ring, stats_slot, prev_slot, h->inv_episode_s};
+  StatsCtx sc{h->partials, h->m_ring, stats_slot, prev_slot, h->inv_episode_s, 0};
   zbot_mdp_kernel<true><<<grid, block, (size_t)block * kHistRow * sizeof(float), (cudaStream_t)stream>>>(
       h->P, h->dp, mi, h->mstate, h->m_ep_len, actions, obs, rew, terminated, truncated, n, sc);
   ZB_CUDA(cudaGetLastError());

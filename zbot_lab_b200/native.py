@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(HERE, "csrc", "libzbot_b200.so")
 ZBOT_ABI_VERSION = 2
 TASK_WALKING_V2, TASK_SNAKE_V0 = 0, 1
 MAX_TERMS = 16
+HOST_ROW_WORDS = 25   # zbot_step_host result row: obs 23 | reward | flags word
 STATE_WORDS = 80
 MDP_STATE_WORDS = 72
 STATS_WORDS = 32
@@ -137,6 +138,7 @@ def _declare(lib):
     lib.zbot_step.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, vp]
     lib.zbot_step_export.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, P(ZbotExport), vp]
     lib.zbot_snake_step_export.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, vp, vp]
+    lib.zbot_step_host.argtypes = [vp, vp, vp, i32, i32, vp]
     lib.zbot_reset_idx.argtypes = [vp, vp, i64, vp, vp, i32, vp]
     lib.zbot_observe.argtypes = [vp, vp, vp]
     lib.zbot_articulation_view.argtypes = [vp, vp, vp, vp, vp]
@@ -146,7 +148,8 @@ def _declare(lib):
     lib.zbot_launch_count.argtypes = [vp]
     lib.zbot_launch_count.restype = i64
     for name in ("zbot_default_cfg", "zbot_state_word", "zbot_mdp_state_word", "zbot_create", "zbot_destroy",
-                 "zbot_bind", "zbot_step", "zbot_step_export", "zbot_snake_step_export", "zbot_reset_idx", "zbot_observe",
+                 "zbot_bind", "zbot_step", "zbot_step_export", "zbot_snake_step_export", "zbot_step_host", "zbot_reset_idx",
+                 "zbot_observe",
                  "zbot_articulation_view", "zbot_mdp_bind", "zbot_mdp_observe", "zbot_mdp_step"):
         getattr(lib, name).restype = C.c_int
 
@@ -154,7 +157,7 @@ def _declare(lib):
 EXPORTED_SYMBOLS = (
     "zbot_abi_version", "zbot_build_info", "zbot_last_error", "zbot_default_cfg", "zbot_state_word",
     "zbot_mdp_state_word", "zbot_create", "zbot_destroy", "zbot_bind", "zbot_step", "zbot_step_export",
-    "zbot_snake_step_export", "zbot_reset_idx", "zbot_observe", "zbot_articulation_view", "zbot_mdp_bind", "zbot_mdp_observe",
+    "zbot_snake_step_export", "zbot_step_host", "zbot_reset_idx", "zbot_observe", "zbot_articulation_view", "zbot_mdp_bind", "zbot_mdp_observe",
     "zbot_mdp_step", "zbot_launch_count",
 )
 

@@ -113,6 +113,7 @@ class NativeStepper:
         # walking: joint_speed_limit = 1 (…env_v2.py:243); snake: per-env, set by the task class (snake_v0.py:121)
         self.state.set("joint_speed_limit", 1.0 if self.cfg.task == native.TASK_WALKING_V2 else 3.14159265)
         self.mdp_state = None
+        self._host_ok: set = set()
 
     # ------------------------------------------------------------------ lifecycle
     def close(self):
@@ -125,6 +126,9 @@ class NativeStepper:
             self.close()
         except Exception:
             pass
+
+    def _stream_arg(self) -> C.c_void_p:
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     @property
     def launch_count(self) -> int:
@@ -163,6 +167,28 @@ class NativeStepper:
                                            _stream(self.device))
         native.check(rc, "zbot_step")
         return self.obs, self.rew, self.terminated, self.truncated
+
+    def step_host(self, host_actions: torch.Tensor, host_rows: torch.Tensor):
+        """One control step for HOST buffers (``zbot_step_host``): ``host_actions`` pinned (N,6) f32 in, one
+        25-word row per env ``[obs 23 | reward | flags]`` into the pinned ``host_rows`` ((N,25) f32).  One kernel
+        launch; actions and rows cross PCIe zero-copy from inside the kernel.  Synchronous: the host owns the
+        result when this returns."""
+        n = self.n
+        pa, pr = host_actions.data_ptr(), host_rows.data_ptr()
+        if (pa, pr) not in self._host_ok:     # validate a buffer pair once (is_pinned() is a driver query)
+            if not (host_actions.is_pinned() and host_rows.is_pinned()):
+                raise ValueError("step_host needs pinned host tensors (torch.Tensor.pin_memory())")
+            if host_actions.dtype != torch.float32 or tuple(host_actions.shape) != (n, 6) or not host_actions.is_contiguous():
+                raise ValueError(f"host_actions must be contiguous float32 ({n}, 6)")
+            if host_rows.dtype != torch.float32 or tuple(host_rows.shape) != (n, native.HOST_ROW_WORDS) \
+                    or not host_rows.is_contiguous():
+                raise ValueError(f"host_rows must be contiguous float32 ({n}, {native.HOST_ROW_WORDS})")
+            if len(self._host_ok) > 64:
+                self._host_ok.clear()
+            self._host_ok.add((pa, pr))
+        slot, prev = self._next_slot()
+        rc = self.lib.zbot_step_host(self._h, C.c_void_p(pa), C.c_void_p(pr), slot, prev, self._stream_arg())
+        native.check(rc, "zbot_step_host")
 
     def alloc_export(self) -> dict:
         n, d = self.n, self.device

@@ -120,6 +120,8 @@ class ZbotDirectEnvV2:
         self.common_step_counter = 0
         self.extras: dict = {}
         self._term_names = list(self.cfg.reward_cfg["reward_scales"].keys())
+        self._log_cache: dict = {}
+        self._host_views: dict = {}
         ring = max(2, int(self.cfg.output_ring))
         n, dev = self.num_envs, self.device
         # one packed buffer per ring slot: [obs N*23 f32 | rew N f32 | terminated N u8 | truncated N u8] so a
@@ -219,10 +221,16 @@ class ZbotDirectEnvV2:
 
     # ------------------------------------------------------------------ log (…env_v2.py:441-459)
     def _log_from_slot(self) -> dict:
-        s = self._stepper.stats          # 0-dim VIEWS into this step's statistics slot (no launch, no sync)
-        log = {"Episode_Reward/" + k: s[i] for i, k in enumerate(self._term_names)}
-        log[self._DIED_LOG_KEY] = s[native.STAT_NUM_TERMINATED_RESET]
-        log["Episode_Termination/time_out"] = s[native.STAT_NUM_TIMEOUT_RESET]
+        # 0-dim VIEWS into this step's statistics slot (no launch, no sync); the dict of a ring slot is built once
+        # and reused (the views alias the slot, the kernel refreshes the values)
+        slot = max(self._stepper._slot, 0)
+        log = self._log_cache.get(slot)
+        if log is None:
+            s = self._stepper.stats_ring[slot]
+            log = {"Episode_Reward/" + k: s[i] for i, k in enumerate(self._term_names)}
+            log[self._DIED_LOG_KEY] = s[native.STAT_NUM_TERMINATED_RESET]
+            log["Episode_Termination/time_out"] = s[native.STAT_NUM_TIMEOUT_RESET]
+            self._log_cache[slot] = log
         return log
 
     # ------------------------------------------------------------------ gym API
@@ -253,6 +261,28 @@ class ZbotDirectEnvV2:
                 self.episode_length_buf = torch.randint_like(st.episode_length_buf, high=int(self.max_episode_length))
         self.extras["log"] = self._log_from_slot()
         return {"policy": obs}, rew, self.reset_terminated, self.reset_time_outs, self.extras
+
+    def alloc_host_buffers(self):
+        """Pinned host buffers for ``step_host``: ``(actions (N,6) f32, rows (N,25) f32)``."""
+        return (torch.zeros(self.num_envs, 6).pin_memory(),
+                torch.zeros(self.num_envs, native.HOST_ROW_WORDS).pin_memory())
+
+    def step_host(self, host_actions: torch.Tensor, host_rows: torch.Tensor):
+        """``step`` for a HOST-resident consumer: pinned ``host_actions`` (N,6) in, the whole step result in the
+        pinned ``host_rows`` ((N,25) f32: obs | reward | flags).  One C-ABI call (``zbot_step_host``) = one launch
+        of the fused kernel reading / writing the pinned buffers directly over PCIe.  Synchronous.  Returns
+        zero-copy host views ``(obs (N,23), rew (N,), terminated (N,) bool, truncated (N,) bool)`` into
+        ``host_rows``; ``extras["log"]`` as in ``step``."""
+        self._stepper.step_host(host_actions, host_rows)
+        self.common_step_counter += 1
+        self._sim_step_counter += self.cfg.decimation
+        self.extras["log"] = self._log_from_slot()
+        views = self._host_views.get(host_rows.data_ptr())
+        if views is None:
+            flags = host_rows.view(torch.uint8).view(self.num_envs, native.HOST_ROW_WORDS * 4)
+            views = (host_rows[:, :23], host_rows[:, 23], flags[:, 96].view(torch.bool), flags[:, 97].view(torch.bool))
+            self._host_views = {host_rows.data_ptr(): views}
+        return views
 
     @property
     def last_step_packed(self) -> torch.Tensor:
