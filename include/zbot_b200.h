@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define ZBOT_ABI_VERSION 2
+#define ZBOT_ABI_VERSION 3
 
 #define ZBOT_OK 0
 #define ZBOT_E_INVALID (-1) /* bad argument / unsupported configuration */
@@ -66,12 +66,32 @@ enum ZbotTerm {
   ZBOT_TERM_SNAKE_BASE_HEADING_Y = 16,
   ZBOT_TERM_SNAKE_BASE_HEADING_Y_SUM = 17,
   ZBOT_TERM_SNAKE_BASE_POS_X_ERR = 18,
-  ZBOT_TERM_SNAKE_BASE_POS_X_ERR_SUM = 19
+  ZBOT_TERM_SNAKE_BASE_POS_X_ERR_SUM = 19,
+  /* zbot-6b-walking-v4 `_reward_<name>` (…/zbot_direct_6dof_bipedal_env_v4.py:1013-1199); feet_downward /
+   * feet_forward / action_rate / torques / feet_slide share ids 1 / 2 / 7 / 8 / 9 */
+  ZBOT_TERM_V4_TRACK_LIN_VEL_X = 20,
+  ZBOT_TERM_V4_TRACK_HEADING_YAW = 21,
+  ZBOT_TERM_V4_LIN_VEL_Y = 22,
+  ZBOT_TERM_V4_JOINT_VEL = 23,
+  ZBOT_TERM_V4_JOINT_ACC = 24,
+  ZBOT_TERM_V4_STEP_LENGTH = 25,
+  ZBOT_TERM_V4_FEET_AIR_TIME_BIPED = 26,
+  ZBOT_TERM_V4_AIRTIME_VARIANCE = 27,
+  ZBOT_TERM_V4_FEET_HARMONY = 28,
+  ZBOT_TERM_V4_FEET_CLOSE = 29,
+  ZBOT_TERM_V4_LIN_VEL_X = 30,
+  ZBOT_TERM_V4_AIRTIME_SUM = 31,
+  ZBOT_TERM_V4_FEET_HEIGHT = 32,
+  ZBOT_TERM_V4_BASE_HEIGHT = 33
 };
 
 /* tasks sharing the fused step (same 7-body chain, different robot cfg / USD frames / MDP) */
 #define ZBOT_TASK_WALKING_V2 0 /* zbot-6b-walking-v2: ZbotDirectEnvV2 + ZBOT_6S_CFG */
 #define ZBOT_TASK_SNAKE_V0 1   /* zbot-6s-snake-v0:  ZbotDirectEnvV0 (zbot6_direct) + ZBOT_D_6S_CFG */
+#define ZBOT_TASK_WALKING_V4 2 /* zbot-6b-walking-v4: Zbot6SEnvV4 + ZBOT_6S_CFG, commands + events */
+#define ZBOT_V4_NUM_OBS 24
+#define ZBOT_V4_NUM_RAND 10    /* uniforms per env-step, see zbot_v4_step */
+#define ZBOT_V4_EXPORT_WORDS 69
 
 /* Static task parameters.  Replaces `ZbotDirectEnvCfgV2` (…env_v2.py:26-206), the actuator /
  * init-state part of `ZBOT_6S_CFG` (assets/zbot_cfg.py:621-669) and the reward table built in
@@ -97,6 +117,16 @@ typedef struct ZbotCfg {
   int32_t num_terms;
   int32_t term_id[ZBOT_MAX_TERMS];
   float term_weight[ZBOT_MAX_TERMS];
+  /* zbot-6b-walking-v4 only.  Event parameters (`EventCfg`, …env_v4.py:331-418): `reset_command_resample` and
+   * `interval_command_resample` params (the reference's curricula always set both to the same values),
+   * `reset_base` pose ranges (x, y, yaw), `interval_range_s`.  term_weight holds the BARE weight for this task
+   * (the reference multiplies by step_dt at evaluation time, :857).  rng_seed seeds the in-kernel counter-based
+   * generator used when zbot_v4_step is given no random numbers. */
+  float ev_vel_lo, ev_vel_hi, ev_yaw_lo, ev_yaw_hi, ev_offset, ev_prob_pos;
+  int32_t ev_dual_sign;
+  float ev_pose_lo[3], ev_pose_hi[3];
+  float ev_interval_lo, ev_interval_hi;
+  uint64_t rng_seed;
 } ZbotCfg;
 
 typedef struct ZbotHandle ZbotHandle;
@@ -171,6 +201,28 @@ int zbot_step_export(ZbotHandle* h, const float* actions, float* obs, float* rew
 #define ZBOT_HOST_ROW_WORDS 25
 int zbot_step_host(ZbotHandle* h, const float* host_actions, float* host_rows, int32_t stats_slot, int32_t prev_slot,
                    void* stream);
+
+/* zbot-6b-walking-v4: one fused control step of `Zbot6SEnvV4` (…env_v4.py:776-976 + EventManager reset /
+ * interval modes): the v2 pipeline with FRESH MDP inputs, 3-deep contact history, command resampling and the
+ * randomised reset pose, all in the one kernel.
+ *   obs   float [N][24]   [base_quat 4, q - q0 6, qd 6, actions 6, commands[0], heading_err]
+ *   rand  float [N][ZBOT_V4_NUM_RAND] uniforms in [0,1) for this step, or NULL = in-kernel generator
+ *         (seed, call counter, env).  Slots: 0..2 reset pose x / y / yaw, 3..5 reset-mode resample
+ *         (bernoulli, velocity, yaw), 6 interval re-arm time, 7..9 interval-mode resample.  An env consumes a
+ *         slot only when the corresponding event fires for it, so the resample MASKS are a pure function of
+ *         the state (bit-exact vs the reference), the values follow the caller's generator.
+ * State slots reused (zbot_state_word names): carry_feet_fz = commands[0..1], carry_mid_max =
+ * target_heading_yaw, base_heading_x_sum = current_yaw, base_pos_y_err_sum = interval time_left.
+ * Statistics words 0..15 = mean over the reset envs of episodic sum / actual episode seconds (:893-901).
+ * `export` (zbot_v4_step_export, test hook): [N][ZBOT_V4_EXPORT_WORDS] view the MDP saw (V4Export). */
+int zbot_v4_step(ZbotHandle* h, const float* actions, const float* rand, float* obs, float* rew, uint8_t* terminated,
+                 uint8_t* truncated, int32_t stats_slot, int32_t prev_slot, void* stream);
+int zbot_v4_step_export(ZbotHandle* h, const float* actions, const float* rand, float* obs, float* rew,
+                        uint8_t* terminated, uint8_t* truncated, int32_t stats_slot, int32_t prev_slot,
+                        float* export_buf, void* stream);
+/* Replace the reward weights / event parameters of a live handle (host-side curricula, …env_v4.py:138-265);
+ * num_envs, task and the dynamics parameters must be unchanged. */
+int zbot_update_cfg(ZbotHandle* h, const ZbotCfg* cfg);
 
 /* Snake task only: the same fused step, additionally exporting what its MDP saw -- per env 41 floats
  * [base_pos0 3, base_quat0 4, base_vel0 3, base_pos1 3, base_quat1 4, base_vel1 3, com_x1 2, self_force1 1,

@@ -99,6 +99,36 @@ static int port_snake_step(const ZbotCfg* cfg, T* state, int64_t* ep_len, const 
   return ZBOT_OK;
 }
 
+// zbot-6b-walking-v4: whole control step; rnd [N][V4_NUM_RAND] uniforms, obs [N][24]
+template <typename T>
+static int port_v4_step(const ZbotCfg* cfg, T* state, int64_t* ep_len, const T* actions, const T* rnd, T* obs, T* rew,
+                        uint8_t* term, uint8_t* trunc, T* reset_sums, T* export_buf, int n) {
+  const char* why = nullptr;
+  if (cfg_validate(*cfg, &why) != ZBOT_OK || cfg->task != ZBOT_TASK_WALKING_V4) return ZBOT_E_INVALID;
+  Params<T> P;
+  params_from_cfg(*cfg, P);
+#pragma omp parallel for schedule(static) num_threads(port_threads())
+  for (int e = 0; e < n; ++e) {
+    EnvState<T> es;
+    env_state_unpack(state + (size_t)e * ZBOT_STATE_WORDS, es);
+    StepOut<T> out;
+    T rs[MAX_TERMS];
+    for (int i = 0; i < MAX_TERMS; ++i) rs[i] = T(0);
+    V4Export<T> ex;
+    ArrayScratch<T> scr;
+    v4_env_step(P, es, actions + (size_t)e * 6, ep_len[e], rnd + (size_t)e * V4_NUM_RAND, obs + (size_t)e * ZBOT_V4_NUM_OBS, out,
+                rs, export_buf ? &ex : (V4Export<T>*)nullptr, scr);
+    env_state_pack(es, state + (size_t)e * ZBOT_STATE_WORDS);
+    rew[e] = out.reward;
+    term[e] = out.terminated ? 1 : 0;
+    trunc[e] = out.time_out ? 1 : 0;
+    if (reset_sums)
+      for (int i = 0; i < MAX_TERMS; ++i) reset_sums[(size_t)e * MAX_TERMS + i] = rs[i];
+    if (export_buf) memcpy(export_buf + (size_t)e * ZBOT_V4_EXPORT_WORDS, &ex, sizeof(ex));
+  }
+  return ZBOT_OK;
+}
+
 // dynamics only: sim [N][25] (root_pos3 quat4 lin3 ang3 q6 qd6), target [N][6]
 // forces [N][7][3] (body 0 and 6 = applied foot forces, 1..5 = predictor), tau [N][6]
 template <typename T>
@@ -159,6 +189,14 @@ int zbot_port_step_f32(const ZbotCfg* cfg, float* state, int64_t* ep_len, const 
 int zbot_port_step_f64(const ZbotCfg* cfg, double* state, int64_t* ep_len, const double* actions, double* obs,
                        double* rew, uint8_t* term, uint8_t* trunc, double* reset_sums, double* export_buf, int n) {
   return port_step<double>(cfg, state, ep_len, actions, obs, rew, term, trunc, reset_sums, export_buf, n);
+}
+int zbot_port_v4_step_f32(const ZbotCfg* cfg, float* state, int64_t* ep_len, const float* actions, const float* rnd,
+                          float* obs, float* rew, uint8_t* term, uint8_t* trunc, float* reset_sums, float* export_buf, int n) {
+  return port_v4_step<float>(cfg, state, ep_len, actions, rnd, obs, rew, term, trunc, reset_sums, export_buf, n);
+}
+int zbot_port_v4_step_f64(const ZbotCfg* cfg, double* state, int64_t* ep_len, const double* actions, const double* rnd,
+                          double* obs, double* rew, uint8_t* term, uint8_t* trunc, double* reset_sums, double* export_buf, int n) {
+  return port_v4_step<double>(cfg, state, ep_len, actions, rnd, obs, rew, term, trunc, reset_sums, export_buf, n);
 }
 int zbot_port_snake_export_words(void) { return (int)(sizeof(SnakeExport<float>) / sizeof(float)); }
 int zbot_port_snake_step_f32(const ZbotCfg* cfg, float* state, int64_t* ep_len, const float* actions, float* obs,

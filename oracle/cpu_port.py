@@ -64,9 +64,10 @@ class PortEnv:
         self.sfx = "f32" if self.dtype == np.float32 else "f64"
         self.cfg = cfg or make_cfg(n)
         self.snake = (self.cfg.task == 1)
+        self.v4 = (self.cfg.task == 2)
         self.state = np.zeros((n, 80), self.dtype)
         self.ep_len = np.zeros(n, np.int64)
-        self.export_words = (lib().zbot_port_snake_export_words() if self.snake
+        self.export_words = (lib().zbot_port_snake_export_words() if self.snake else 69 if self.v4
                              else getattr(lib(), "zbot_port_export_words_" + self.sfx)())
         self.reset_all()
 
@@ -105,9 +106,21 @@ class PortEnv:
                              "joint_pos": ("joint_pos", 6), "joint_vel": ("joint_vel", 6)}.items():
             self.field(name, w)[:] = st[k]
 
-    def step(self, actions, export=False):
+    def step(self, actions, export=False, rnd=None):
         n = self.n
         a = np.ascontiguousarray(actions, self.dtype)
+        if self.v4:
+            obs = np.zeros((n, 24), self.dtype)
+            rew, term, trunc = np.zeros(n, self.dtype), np.zeros(n, np.uint8), np.zeros(n, np.uint8)
+            rs = np.zeros((n, 16), self.dtype)
+            ex = np.zeros((n, self.export_words), self.dtype) if export else None
+            r = np.ascontiguousarray(rnd, self.dtype)
+            assert r.shape == (n, 10)
+            rc = getattr(lib(), "zbot_port_v4_step_" + self.sfx)(
+                C.byref(self.cfg), _p(self.state), _p(self.ep_len), _p(a), _p(r), _p(obs), _p(rew), _p(term), _p(trunc),
+                _p(rs), _p(ex), C.c_int(n))
+            assert rc == 0, rc
+            return obs, rew, term.astype(bool), trunc.astype(bool), rs, ex
         obs = np.zeros((n, 23), self.dtype)
         rew = np.zeros(n, self.dtype)
         term = np.zeros(n, np.uint8)

@@ -162,3 +162,147 @@ class RefSnakeHarness:
         for k, v in e._episode_sums.items():
             out["episode_sum/" + k] = v
         return {k: v.clone() for k, v in out.items()}
+
+
+class RefV4Harness:
+    """The reference ``Zbot6SEnvV4`` driven in ``DirectRLEnv.step`` order, including the EventManager's "reset" and
+    "interval" modes ([IL-upstream] ``DirectRLEnv._reset_idx`` / ``step`` and ``EventManager.apply``): the
+    reference's OWN ``reset_root_state_uniform`` / ``my_curriculum`` / ``range_curriculum`` / ``resample_commands``
+    (…env_v4.py:59-265) are called in cfg order.  Random numbers: ``torch.rand`` / ``torch.bernoulli`` are patched
+    for the duration of each event call so that env e consumes ``rnd[e, slot]`` (slot map: V4RandSlot in
+    csrc/zbot_core.h) -- bernoulli(p) := (u < p)."""
+
+    ROBOT_KEYS = ("body_link_pos_w", "body_link_quat_w", "body_link_lin_vel_w", "body_com_lin_vel_w", "joint_pos",
+                  "joint_vel", "joint_acc", "applied_torque")
+    SENSOR_KEYS = ("net_forces_w_history", "last_air_time", "last_contact_time", "current_air_time", "current_contact_time")
+
+    def __init__(self, num_envs, env_origins, index_sets, default_joint_pos, default_root_state, interval_time_left):
+        from zbot_lab_b200.assets import zbot_6s as Z
+        self.Z = Z
+        self.n = num_envs
+        self.ref = ref_loader.load_reference_module(ref_loader.REF_ENV_V4)
+        self.env = ref_loader.make_reference_v4_env(num_envs, default_joint_pos=default_joint_pos,
+                                                    default_root_state=default_root_state, env_origins=env_origins,
+                                                    **index_sets)
+        self.time_left = torch.as_tensor(interval_time_left, dtype=torch.float32).clone()
+        self.rnd = None
+        rob = self.env._robot
+        harness = self
+        rob.write_root_pose_to_sim = lambda pose, env_ids: harness._write_root_pose(pose, env_ids)
+        rob.write_root_velocity_to_sim = lambda vel, env_ids: None
+        rob.write_joint_state_to_sim = lambda p, v, _i, env_ids: None
+        self.env._ref_reset_events = self._reset_events
+
+    # -- RNG plumbing ------------------------------------------------------------------
+    class _Patched:
+        def __init__(self, queue):
+            self.queue = list(queue)
+
+        def __enter__(self):
+            self._rand, self._bern = torch.rand, torch.bernoulli
+            q = self.queue
+
+            def rand(*size, **kw):
+                u = q.pop(0)
+                want = tuple(size[0]) if len(size) == 1 and isinstance(size[0], (tuple, list)) else tuple(size)
+                assert tuple(u.shape) == want, (u.shape, want)
+                return u.clone()
+
+            def bernoulli(p, **kw):
+                u = q.pop(0)
+                return (u < p).to(p.dtype)
+
+            torch.rand, torch.bernoulli = rand, bernoulli
+            return self
+
+        def __exit__(self, *a):
+            torch.rand, torch.bernoulli = self._rand, self._bern
+            assert not self.queue, "event drew fewer random tensors than queued"
+
+    # -- framework half ----------------------------------------------------------------
+    def attach(self, S: dict):
+        d = self.env._robot.data
+        for k in self.ROBOT_KEYS:
+            setattr(d, k, torch.as_tensor(S[k]).clone())
+        c = self.env._contact_sensor.data
+        for k in self.SENSOR_KEYS:
+            setattr(c, k, torch.as_tensor(S[k]).clone())
+
+    def _write_root_pose(self, pose, env_ids):
+        """CPU-PhysX semantics (SURVEY C-5): link poses follow the root write; joints = default; sensors reset."""
+        d, c = self.env._robot.data, self.env._contact_sensor.data
+        import numpy as np
+        for row, e in enumerate(env_ids.tolist()):
+            p, q = self.Z.fk_links(pose[row, :3].double().numpy(), pose[row, 3:7].double().numpy(),
+                                   np.asarray(self.Z.DEFAULT_JOINT_POS, np.float64))
+            d.body_link_pos_w[e] = torch.from_numpy(p).float()
+            d.body_link_quat_w[e] = torch.from_numpy(q).float()
+        d.body_link_lin_vel_w[env_ids] = 0.0
+        d.body_com_lin_vel_w[env_ids] = 0.0
+        d.joint_pos[env_ids] = d.default_joint_pos[env_ids]
+        d.joint_vel[env_ids] = 0.0
+        d.joint_acc[env_ids] = 0.0
+        d.applied_torque[env_ids] = 0.0
+        for k in self.SENSOR_KEYS:
+            getattr(c, k)[env_ids] = 0.0
+
+    def _reset_events(self, env_ids):
+        e, ev, r = self.env, self.env.cfg.events, self.rnd
+        k = len(env_ids)
+        pose = torch.full((k, 6), 0.5)
+        pose[:, 0], pose[:, 1], pose[:, 5] = r[env_ids, 0], r[env_ids, 1], r[env_ids, 2]
+        with self._Patched([pose, torch.full((k, 6), 0.5)]):
+            ev.reset_base.func(e, env_ids, **ev.reset_base.params)
+        ev.my_curric.func(e, env_ids)
+        ev.vel_range.func(e, env_ids, **ev.vel_range.params)
+        p = ev.reset_command_resample.params
+        with self._Patched(([r[env_ids, 3]] if p["dual_sign"] else []) + [r[env_ids, 4], r[env_ids, 5]]):
+            ev.reset_command_resample.func(e, env_ids, **p)
+
+    def _interval_events(self):
+        e, ev, r = self.env, self.env.cfg.events, self.rnd
+        term = ev.interval_command_resample
+        self.time_left -= e.step_dt
+        ids = (self.time_left < 1e-6).nonzero().flatten()
+        if len(ids) > 0:
+            lower, upper = term.interval_range_s
+            with self._Patched([r[ids, 6]]):
+                self.time_left[ids] = torch.rand(len(ids)) * (upper - lower) + lower
+            p = term.params
+            with self._Patched(([r[ids, 7]] if p["dual_sign"] else []) + [r[ids, 8], r[ids, 9]]):
+                term.func(e, ids, **p)
+        return ids
+
+    # -- protocol ----------------------------------------------------------------------
+    def observe(self):
+        self.env._compute_intermediate_values()
+        return self.env._get_observations()["policy"]
+
+    def step(self, actions, S1, rnd):
+        e = self.env
+        self.rnd = torch.as_tensor(rnd)
+        e._pre_physics_step(torch.as_tensor(actions))
+        self.attach(S1)
+        e.episode_length_buf += 1
+        e.common_step_counter += 1
+        e.reset_terminated, e.reset_time_outs = e._get_dones()
+        rew = e._get_rewards()
+        ids = (e.reset_terminated | e.reset_time_outs).nonzero(as_tuple=False).squeeze(-1)
+        log = None
+        if len(ids) > 0:
+            e._reset_idx(ids)
+            log = dict(e.extras["log"])
+        interval_ids = self._interval_events()
+        obs = e._get_observations()["policy"]
+        return obs, rew, e.reset_terminated.clone(), e.reset_time_outs.clone(), ids, interval_ids, log
+
+    def mdp_state(self) -> dict:
+        e = self.env
+        out = {"p_delta": e.p_delta, "actions": e._actions, "commands": e.commands,
+               "target_heading_yaw": e.target_heading_yaw, "current_yaw": e.current_yaw,
+               "feet_contact_forces_last": e.feet_contact_forces_last, "feet_down_pos_last": e.feet_down_pos_last,
+               "feet_step_length": e.feet_step_length, "episode_length_buf": e.episode_length_buf,
+               "interval_time_left": self.time_left}
+        for k, v in e._episode_sums.items():
+            out["episode_sum/" + k] = v
+        return {k: v.clone() for k, v in out.items()}

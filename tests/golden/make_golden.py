@@ -84,8 +84,50 @@ def run_snake_case(seed, n, steps):
     return out
 
 
+V4_CASES = [("v4_n64", 20, 64, 6), ("v4_n11", 21, 11, 5)]
+
+
+def run_v4_case(seed, n, steps):
+    """zbot-6b-walking-v4: the MDP + events of the reference's own Zbot6SEnvV4."""
+    from oracle.ref_harness import RefV4Harness
+    torch.set_num_threads(1)
+    case = syn.synth_v4_case(seed, n, steps)
+    dj = torch.tensor(Z.DEFAULT_JOINT_POS, dtype=torch.float32).repeat(n, 1)
+    drs = torch.zeros(n, 13)
+    drs[:, :3] = torch.tensor(Z.DEFAULT_ROOT_POS)
+    drs[:, 3] = 1.0
+    h = RefV4Harness(n, torch.from_numpy(case["origins"]), syn.index_sets(), dj, drs, case["interval_time_left0"])
+    h.env.episode_length_buf[:] = torch.from_numpy(case["episode_length_buf0"])
+    h.env.commands[:] = torch.from_numpy(case["commands0"])
+    h.env.target_heading_yaw[:] = torch.from_numpy(case["target_heading_yaw0"])
+    out = {"seed": seed, "n": n, "steps": steps}
+    h.attach(case["S0"])
+    out["obs0"] = h.observe().numpy()
+    for t, (a, S1, rnd) in enumerate(case["steps"]):
+        obs, rew, term, trunc, ids, iv_ids, log = h.step(torch.from_numpy(a), S1, rnd)
+        out[f"obs{t + 1}"], out[f"rew{t + 1}"] = obs.numpy(), rew.numpy()
+        out[f"terminated{t + 1}"], out[f"truncated{t + 1}"] = term.numpy(), trunc.numpy()
+        out[f"reset_ids{t + 1}"] = ids.numpy()
+        out[f"interval_ids{t + 1}"] = iv_ids.numpy()
+        if log is not None:
+            for k, v in log.items():
+                out[f"log{t + 1}/{k}"] = np.float32(v)
+        for k, v in h.mdp_state().items():
+            out[f"state{t + 1}/{k}"] = v.numpy()
+    return out
+
+
 def main():
     here = os.path.dirname(os.path.abspath(__file__))
+    for name, seed, n, steps in V4_CASES:
+        out = run_v4_case(seed, n, steps)
+        np.savez_compressed(os.path.join(here, name + ".npz"), **out)
+        print(name, "resets:", sum(len(out[f"reset_ids{t + 1}"]) for t in range(steps)),
+              "terminated:", sum(int(out[f"terminated{t + 1}"].sum()) for t in range(steps)),
+              "interval resamples:", sum(len(out[f"interval_ids{t + 1}"]) for t in range(steps)))
+    sc = ref_loader.reference_v4_reward_scales()
+    np.savez(os.path.join(here, "reward_scales_v4.npz"), names=np.array(list(sc.keys())),
+             values=np.array(list(sc.values()), dtype=np.float64))
     for name, seed, n, steps in SNAKE_CASES:
         out = run_snake_case(seed, n, steps)
         np.savez_compressed(os.path.join(here, name + ".npz"), **out)

@@ -197,3 +197,80 @@ def test_snake_self_contact_and_x_drift_terminate():
     _, _, term, _, _, ex = pe.step(a, export=True)
     assert term[2] and not term[0]
     assert ex[2, 22] > 1.0 and ex[0, 22] == 0.0                 # exported self-contact force proxy
+
+
+# ------------------------------------------------------------------------------------------------ walking v4
+def _v4_port(n, dtype, rng):
+    from oracle import cpu_port
+    from zbot_lab_b200 import native
+    pe = cpu_port.PortEnv(n, dtype, native.make_cfg(n, task=native.TASK_WALKING_V4))
+    pe.field("feet_contact_forces_last", 2)[:] = 15.0                                   # …env_v4.py:637
+    pe.field("carry_feet_fz", 2)[:] = np.stack([rng.uniform(-0.3, 0.3, n), rng.uniform(-0.1, 0.1, n)], -1)   # commands
+    pe.field("carry_mid_max", 1)[:, 0] = rng.uniform(-3, 3, n)                          # target_heading_yaw
+    tl = rng.uniform(3.0, 6.0, n)
+    tl[: n // 4] = rng.integers(1, 12, n // 4) * 0.02 - 0.01                            # interval events inside the test
+    pe.field("base_pos_y_err_sum", 1)[:, 0] = tl
+    return pe
+
+
+def test_v4_full_step_port_matches_pinned_oracle_on_exported_physics():
+    """the v4 step's dones / rewards / command resampling / randomised resets / observations (kernel
+    arithmetic, host build, float32) equal the reference-pinned v4 oracle evaluated on the articulation + contact
+    view the step itself produced.  Resample masks, reset ids, counters bit-exact; floats <= 1e-5 relative."""
+    from helpers import make_v4_oracle, v4_check_step
+    n = 96
+    rng = np.random.default_rng(42)
+    pe = _v4_port(n, np.float32, rng)
+    ep0 = rng.integers(0, 1000, n)
+    ep0[:6] = 995
+    pe.ep_len[:] = ep0
+    o = make_v4_oracle(n, np.zeros((n, 3), np.float32))
+    o.episode_length_buf[:] = ep0
+    o.commands[:] = pe.field("carry_feet_fz", 2)
+    o.target_heading_yaw[:] = pe.field("carry_mid_max", 1)[:, 0]
+    o.interval_time_left[:] = pe.field("base_pos_y_err_sum", 1)[:, 0]
+    o.feet_down_pos_last[:] = pe.field("feet_down_pos_last", 6).reshape(n, 2, 3)
+    n_reset = n_int = n_term = 0
+    for t in range(40):
+        a = rng.normal(0, 1.0, (n, 6)).astype(np.float32)
+        rnd = rng.random((n, 10)).astype(np.float32)
+        obs, rew, term, trunc, rs, ex = pe.step(a, export=True, rnd=rnd)
+        ids, iv, log = v4_check_step(o, a, rnd, ex, obs, rew, term, trunc, pe.ep_len,
+                                     lambda k: pe.field(k, {"carry_feet_fz": 2, "carry_mid_max": 1, "base_pos_y_err_sum": 1,
+                                                            "p_delta": 6, "feet_step_length": 2, "feet_contact_forces_last": 2,
+                                                            "feet_down_pos_last": 6, "episode_sums": 16}[k]))
+        if len(ids) > 0:
+            for i, nm in enumerate(o.episode_sums):
+                want = float(log["Episode_Reward/" + nm])
+                got = float(np.mean(rs[ids, i], dtype=np.float32))
+                assert abs(got - want) <= 1e-5 * max(1.0, abs(want)), nm
+        n_reset += len(ids)
+        n_int += len(iv)
+        n_term += int(term.sum())
+    assert n_reset >= 6 and n_int >= n // 4 and n_term > 0
+
+
+def test_v4_port_f32_tracks_f64_and_resets_randomise_the_pose():
+    n = 128
+    rng = np.random.default_rng(7)
+    e32, e64 = _v4_port(n, np.float32, np.random.default_rng(1)), _v4_port(n, np.float64, np.random.default_rng(1))
+    for e in (e32, e64):
+        e.ep_len[:8] = 990
+    alive = np.ones(n, bool)
+    for t in range(30):
+        a = rng.normal(0, 0.3, (n, 6)).astype(np.float32)
+        rnd = rng.random((n, 10)).astype(np.float32)
+        _, _, t32, tr32, _, _ = e32.step(a, rnd=rnd)
+        _, _, t64, tr64, _, _ = e64.step(a, rnd=rnd)
+        assert np.array_equal(tr32, tr64)
+        if t == 8:                                    # 990 + 9 = 999: the first 8 envs time out and get a random pose
+            assert tr32[:8].all()
+            p = e32.field("root_pos", 3)[:8]
+            want = np.array([0.0, -0.06]) + (rnd[:8, :2] - 0.5)
+            assert np.allclose(p[:, :2], want, atol=1e-6)
+            yaw = rnd[:8, 2] * 6.28 - 3.14
+            assert np.allclose(e32.field("root_quat", 4)[:8, 0], np.cos(yaw / 2), atol=1e-6)
+            assert np.allclose(e32.field("base_heading_x_sum", 1)[:8, 0], yaw, atol=1e-6)        # current_yaw
+        alive &= ~(t32 | t64 | tr32 | tr64)
+    dq = np.abs(e32.field("joint_pos", 6) - e64.field("joint_pos", 6))[alive]
+    assert alive.sum() > n // 3 and dq.max() < 5e-3

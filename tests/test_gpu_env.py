@@ -193,3 +193,43 @@ def test_step_host_zero_copy_equals_device_step():
     assert torch.equal(a_env._stepper.state.buf, b_env._stepper.state.buf)
     a_env.close()
     b_env.close()
+
+
+def test_v4_env_registry_protocol_curriculum_and_log_keys():
+    """zbot-6b-walking-v4 through the registry (reference id / kwargs keys, zbot6b_direct/__init__.py:91-99):
+    24-wide observation, commands inside the cfg ranges, log keys of …env_v4.py:893-933, and the host curricula
+    (my_curriculum thresholds, …env_v4.py:138-198) re-weighting the live kernel."""
+    import zbot_lab_b200.tasks  # noqa: F401
+    from zbot_lab_b200.compat import gym_registry as gym
+    from zbot_lab_b200.envs.rsl_rl_wrapper import RslRlVecEnvWrapper
+    cfg = gym.load_cfg_from_registry("zbot-6b-walking-v4", "env_cfg_entry_point")
+    agent = gym.load_cfg_from_registry("zbot-6b-walking-v4", "rsl_rl_cfg_entry_point")
+    assert agent.experiment_name == "zbot_6b_flat_direct_v4" and agent.policy.actor_hidden_dims == [256, 256, 128]
+    cfg.scene.num_envs = 256
+    cfg.sim.device = "cuda:0"
+    cfg.seed = 9
+    env = gym.make("zbot-6b-walking-v4", cfg=cfg, render_mode=None)
+    w = RslRlVecEnvWrapper(env, clip_actions=None)
+    assert w.num_obs == 24 and w.num_actions == 6 and env.max_episode_length == 1000
+    obs = w.get_observations()["policy"]
+    assert obs.shape == (256, 24) and torch.isfinite(obs).all()
+    assert torch.allclose(obs[:, 22], torch.full((256,), 0.3, device="cuda:0"))          # velocity_range (0.3, 0.3), prob_pos 1
+    assert float(obs[:, 23].abs().max()) <= 0.1 + 1e-5                                     # heading_err = commanded relative yaw
+    assert float(obs[:, 0].std()) > 0.05                                                   # random yaw at reset
+    for t in range(30):
+        obs, rew, dones, extras = w.step(torch.randn(256, 6, device="cuda:0"))
+        assert obs["policy"].shape == (256, 24) and torch.isfinite(obs["policy"]).all() and torch.isfinite(rew).all()
+    assert set(extras["log"]) == {"Episode_Reward/" + k for k in cfg.reward_cfg["reward_scales"]} | {
+        "Episode_Termination/died", "Episode_Termination/time_out", "Curriculum/curriculum_stage",
+        "Curriculum/vel_lower_bound", "Curriculum/vel_upper_bound", "Curriculum/yaw_bound"}
+    # my_curriculum stage 0 -> 1 at 12 episodes' worth of steps: new weights reach the kernel
+    env.common_step_counter = 12 * env.max_episode_length - 1
+    w.step(torch.zeros(256, 6, device="cuda:0"))
+    assert env.curriculum_stage == 1 and env.reward_scales["airtime_variance"] == -10.0
+    ids = [env._stepper.cfg.term_id[i] for i in range(env._stepper.cfg.num_terms)]
+    from zbot_lab_b200 import native
+    assert abs(env._stepper.cfg.term_weight[ids.index(native.V4_TERM_IDS["airtime_variance"])] + 10.0) < 1e-6
+    env.common_step_counter = 24 * env.max_episode_length - 1
+    w.step(torch.zeros(256, 6, device="cuda:0"))
+    assert env.curriculum_stage == 2 and abs(env._stepper.cfg.ev_prob_pos - 0.8) < 1e-6
+    w.close()

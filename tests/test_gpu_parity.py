@@ -653,3 +653,108 @@ def test_snake_full_size_properties_16384():
                 assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
             assert torch.isfinite(st.state.buf).all()
         st.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# zbot-6b-walking-v4: commands, reset / interval resampling, randomised resets, fresh rewards
+# ---------------------------------------------------------------------------------------------
+def _v4_stepper(n, rng, **kw):
+    from zbot_lab_b200 import native
+    from zbot_lab_b200.stepper import NativeStepper
+    st = NativeStepper(n, DEV, native.make_cfg(n, task=native.TASK_WALKING_V4, **kw))
+    st.reset_idx_v4(None, rand=torch.full((n, 6), 0.5, device=DEV))     # default pose: x = y = yaw = mid-range = 0
+    st.state.set("carry_feet_fz", _t(np.stack([rng.uniform(-0.3, 0.3, n), rng.uniform(-0.1, 0.1, n)], -1).astype(np.float32)))
+    st.state.set("carry_mid_max", _t(rng.uniform(-3, 3, (n, 1)).astype(np.float32)))
+    tl = rng.uniform(3.0, 6.0, n).astype(np.float32)
+    tl[: n // 4] = (rng.integers(1, 12, n // 4) * 0.02 - 0.01).astype(np.float32)
+    st.state.set("base_pos_y_err_sum", _t(tl.reshape(n, 1)))
+    return st
+
+
+def test_v4_fused_step_matches_pinned_oracle_on_exported_physics():
+    """The v4 kernel's dones / rewards / command resampling (reset + interval masks) / randomised resets /
+    24-wide observations equal the reference-pinned v4 oracle (tests/golden/v4_*.npz) evaluated on the
+    articulation + contact view the kernel itself exported, with the same per-env uniforms."""
+    from helpers import make_v4_oracle, v4_check_step
+    n = 200
+    rng = np.random.default_rng(52)
+    st = _v4_stepper(n, rng)
+    ep0 = rng.integers(0, 1000, n)
+    ep0[:8] = 994
+    st.episode_length_buf[:] = _t(ep0.astype(np.int64))
+    o = make_v4_oracle(n, np.zeros((n, 3), np.float32))
+    o.episode_length_buf[:] = ep0
+    g = lambda k: st.state.get(k).cpu().numpy()
+    o.commands[:] = g("carry_feet_fz")
+    o.target_heading_yaw[:] = g("carry_mid_max")[:, 0]
+    o.interval_time_left[:] = g("base_pos_y_err_sum")[:, 0]
+    o.feet_down_pos_last[:] = g("feet_down_pos_last").reshape(n, 2, 3)
+    ex_t = torch.zeros(n, 69, device=DEV)
+    n_reset = n_int = n_term = 0
+    for t in range(40):
+        a = rng.normal(0, 1.0, (n, 6)).astype(np.float32)
+        rnd = rng.random((n, 10)).astype(np.float32)
+        obs, rew, term, trunc = st.step(_t(a), export=ex_t, rand=_t(rnd))
+        torch.cuda.synchronize()
+        ids, iv, log = v4_check_step(o, a, rnd, ex_t.cpu().numpy(), obs.cpu().numpy(), rew.cpu().numpy(),
+                                     term.cpu().numpy(), trunc.cpu().numpy(), st.episode_length_buf.cpu().numpy(), g)
+        if len(ids) > 0:
+            s = st.stats.cpu().numpy()
+            assert s[16] == len(ids) and s[17] == log["Episode_Termination/died"] and s[18] == log["Episode_Termination/time_out"]
+            for i, nm in enumerate(o.episode_sums):
+                want = float(log["Episode_Reward/" + nm])
+                assert abs(s[i] - want) <= 1e-5 * max(1.0, abs(want)), nm
+        n_reset += len(ids)
+        n_int += len(iv)
+        n_term += int(term.sum())
+    assert n_reset >= 8 and n_int >= n // 4 and n_term > 0
+    st.close()
+
+
+def test_v4_kernel_equals_host_build_and_internal_rng_properties():
+    """(1) GPU kernel vs the same arithmetic compiled for the host (float32): one control step from identical states
+    and uniforms agrees to float32 round-off.  (2) With rand = NULL the in-kernel generator drives the events:
+    reset poses fall inside the cfg ranges and are spread out, commands inside their ranges, every env's interval
+    timer re-arms into [3, 6] s, two handles with the same seed are bit-identical, another seed differs."""
+    from oracle import cpu_port
+    from zbot_lab_b200 import native
+    n = 512
+    rng = np.random.default_rng(3)
+    st = _v4_stepper(n, rng)
+    pe = cpu_port.PortEnv(n, np.float32, native.make_cfg(n, task=native.TASK_WALKING_V4))
+    from zbot_lab_b200.stepper import STATE_FIELDS
+    for k, w in STATE_FIELDS.items():
+        pe.field(k, w)[:] = st.state.get(k).cpu().numpy()
+    for t in range(3):
+        a = rng.normal(0, 0.5, (n, 6)).astype(np.float32)
+        rnd = rng.random((n, 10)).astype(np.float32)
+        obs, rew, term, trunc = st.step(_t(a), rand=_t(rnd))
+        o2, r2, t2, tr2, _, _ = pe.step(a, rnd=rnd)
+        assert np.array_equal(term.cpu().numpy().astype(bool), t2) and np.array_equal(trunc.cpu().numpy().astype(bool), tr2)
+        assert np.abs(obs.cpu().numpy() - o2).max() < 2e-3 and np.abs(rew.cpu().numpy() - r2).max() < 2e-3
+        for k, w in STATE_FIELDS.items():                       # re-synchronise: a ONE-step comparison each time
+            pe.field(k, w)[:] = st.state.get(k).cpu().numpy()
+        pe.ep_len[:] = st.episode_length_buf.cpu().numpy()
+    st.close()
+    outs = []
+    for seed in (11, 11, 12):
+        s2 = _v4_stepper(n, np.random.default_rng(4), rng_seed=seed)
+        s2.episode_length_buf[:] = 990
+        g = torch.Generator(device=DEV).manual_seed(5)
+        for t in range(12):
+            obs, rew, term, trunc = s2.step(torch.randn(n, 6, device=DEV, generator=g) * 0.3)
+            if t == 8:
+                assert trunc.all()                               # every env timed out -> randomised reset, in-kernel RNG
+                p = s2.state.get("root_pos").cpu().numpy()
+                assert np.all(np.abs(p[:, 0]) <= 0.5 + 1e-6) and np.all(np.abs(p[:, 1] + 0.06) <= 0.5 + 1e-6)
+                assert p[:, 0].std() > 0.2 and p[:, 1].std() > 0.2
+                yaw = s2.state.get("base_heading_x_sum").cpu().numpy()[:, 0]
+                assert np.all(np.abs(yaw) <= 3.14 + 1e-6) and yaw.std() > 1.0
+                cmd = s2.state.get("carry_feet_fz").cpu().numpy()
+                assert np.allclose(cmd[:, 0], 0.3, atol=1e-6) and np.all(np.abs(cmd[:, 1]) <= 0.1 + 1e-6)
+        tl = s2.state.get("base_pos_y_err_sum").cpu().numpy()[:, 0]
+        assert np.all(tl > 2.7) and np.all(tl <= 6.0)
+        outs.append((s2.state.buf.clone(), obs.clone()))
+        s2.close()
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert not torch.equal(outs[0][0], outs[2][0])

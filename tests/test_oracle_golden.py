@@ -1,9 +1,12 @@
 """Pins ``oracle/mdp_oracle.py`` to the reference: the golden .npz files hold the outputs
 of the reference's own unmodified code (tests/golden/make_golden.py)."""
+import os
+
 import numpy as np
 import pytest
 
-from helpers import GOLDEN_CASES, load_golden, make_mdp_oracle, rel_err
+from helpers import GOLDEN_CASES, GOLDEN_DIR, load_golden, make_mdp_oracle, rel_err
+from zbot_lab_b200.utils import synthetic as syn
 
 RTOL = 1e-5  # BASELINE.json north_star: float32 reward/observation terms within 1e-5 relative
 
@@ -109,3 +112,52 @@ def test_snake_geometry_known_answers():
     assert abs(com[0, 0] + com[11, 0] + 0.636) < 1e-5
     assert np.allclose(Z.quat_rotate(lq[6], np.array([-1.0, 0, 0])), [0, 0, 1], atol=1e-7)
     assert np.allclose(Z.quat_rotate(lq[6], np.array([0, -1.0, 0])), [0, 1, 0], atol=1e-7)
+
+
+# ------------------------------------------------------------------------------------------------ walking v4
+V4_GOLDEN = ["v4_n64", "v4_n11"]
+
+
+from helpers import make_v4_oracle  # noqa: E402
+
+
+@pytest.mark.parametrize("name", V4_GOLDEN)
+def test_v4_mdp_oracle_matches_reference_golden(name):
+    """SURVEY §8 f1 (zbot-6b-walking-v4: commands, reset / interval resampling, randomised reset pose, 15 fresh
+    reward terms): the numpy restatement against the outputs of the reference's own Zbot6SEnvV4 code.
+    Flags, reset ids, interval-resample ids (the resample MASKS) and counters bit-exact; floats <= 1e-5."""
+    g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    n, steps = int(g["n"]), int(g["steps"])
+    case = syn.synth_v4_case(int(g["seed"]), n, steps)
+    o = make_v4_oracle(n, case["origins"])
+    o.episode_length_buf[:] = case["episode_length_buf0"]
+    o.commands[:] = case["commands0"]
+    o.target_heading_yaw[:] = case["target_heading_yaw0"]
+    o.interval_time_left[:] = case["interval_time_left0"]
+    assert rel_err(o.observe(case["S0"]), g["obs0"]) <= 1e-5
+    names = list(np.load(os.path.join(GOLDEN_DIR, "reward_scales_v4.npz"))["names"])
+    assert names == list(o.reward_scales)
+    n_reset = n_int = 0
+    for t, (a, S1, rnd) in enumerate(case["steps"]):
+        k = t + 1
+        obs, rew, term, trunc, ids, iv, log = o.step(a, S1, rnd)
+        assert np.array_equal(term, g[f"terminated{k}"]) and np.array_equal(trunc, g[f"truncated{k}"])
+        assert np.array_equal(ids, g[f"reset_ids{k}"]) and np.array_equal(iv, g[f"interval_ids{k}"])
+        assert np.array_equal(o.episode_length_buf, g[f"state{k}/episode_length_buf"])
+        assert rel_err(rew, g[f"rew{k}"]) <= 1e-5
+        assert rel_err(obs, g[f"obs{k}"]) <= 1e-5
+        st = o.mdp_state()
+        for nm in ("p_delta", "actions", "commands", "target_heading_yaw", "current_yaw", "feet_contact_forces_last",
+                   "feet_down_pos_last", "feet_step_length", "interval_time_left"):
+            assert rel_err(st[nm], g[f"state{k}/{nm}"]) <= 1e-5, (k, nm)
+        for nm in names:
+            assert rel_err(st["episode_sum/" + nm], g[f"state{k}/episode_sum/{nm}"]) <= 1e-5, nm
+        if len(ids) > 0:
+            for nm in names:
+                want = float(g[f"log{k}/Episode_Reward/{nm}"])
+                assert abs(float(log["Episode_Reward/" + nm]) - want) <= 1e-5 * max(1.0, abs(want)), nm
+            assert log["Episode_Termination/died"] == g[f"log{k}/Episode_Termination/died"]
+            assert log["Episode_Termination/time_out"] == g[f"log{k}/Episode_Termination/time_out"]
+        n_reset += len(ids)
+        n_int += len(iv)
+    assert n_reset > 0 and n_int > 0

@@ -56,7 +56,23 @@ enum TermId : int {
   TERM_SNAKE_BASE_HEADING_Y_SUM = 17,
   TERM_SNAKE_BASE_POS_X_ERR = 18,
   TERM_SNAKE_BASE_POS_X_ERR_SUM = 19,  // defined but inactive in the snake scale dict
-  NUM_TERM_IDS = 20
+  // zbot-6b-walking-v4 (tasks/zbot6b_direct/zbot_direct_6dof_bipedal_env_v4.py:1013-1199); "feet_downward",
+  // "feet_forward", "action_rate", "torques", "feet_slide" share ids 1, 2, 7, 8, 9 (same formulas, FRESH inputs)
+  TERM_V4_TRACK_LIN_VEL_X = 20,
+  TERM_V4_TRACK_HEADING_YAW = 21,
+  TERM_V4_LIN_VEL_Y = 22,
+  TERM_V4_JOINT_VEL = 23,
+  TERM_V4_JOINT_ACC = 24,
+  TERM_V4_STEP_LENGTH = 25,
+  TERM_V4_FEET_AIR_TIME_BIPED = 26,
+  TERM_V4_AIRTIME_VARIANCE = 27,
+  TERM_V4_FEET_HARMONY = 28,
+  TERM_V4_FEET_CLOSE = 29,
+  TERM_V4_LIN_VEL_X = 30,      // defined, not in the default v4 table
+  TERM_V4_AIRTIME_SUM = 31,    // defined, not in the default v4 table
+  TERM_V4_FEET_HEIGHT = 32,    // defined, not in the default v4 table
+  TERM_V4_BASE_HEIGHT = 33,    // defined, not in the default v4 table
+  NUM_TERM_IDS = 34
 };
 constexpr int MAX_TERMS = 16;
 
@@ -77,7 +93,12 @@ struct Params {
   int default_terms;   // 1: the table is exactly the 13 v2 terms in dict order (fast path)
   int num_terms;
   int term_id[MAX_TERMS];
-  T term_w[MAX_TERMS];  // weight * step_dt, rounded the way the reference rounds it
+  T term_w[MAX_TERMS];  // weight * step_dt, rounded the way the reference rounds it (v4: the bare weight)
+  // zbot-6b-walking-v4 event parameters (EventCfg, …env_v4.py:331-418; curriculum-adjusted by the host)
+  T ev_vel_lo, ev_vel_hi, ev_yaw_lo, ev_yaw_hi, ev_offset, ev_prob_pos;
+  int ev_dual_sign;
+  T ev_pose_lo[3], ev_pose_hi[3];     // reset_base pose_range x, y, yaw
+  T ev_interval_lo, ev_interval_hi;   // interval_range_s of interval_command_resample
 };
 
 // ------------------------------------------------------------------------------------
@@ -87,6 +108,16 @@ ZB_HD float zb_sqrt(float x) { return sqrtf(x); }
 ZB_HD double zb_sqrt(double x) { return sqrt(x); }
 ZB_HD float zb_tanh(float x) { return tanhf(x); }
 ZB_HD double zb_tanh(double x) { return tanh(x); }
+ZB_HD float zb_exp(float x) { return expf(x); }
+ZB_HD double zb_exp(double x) { return exp(x); }
+ZB_HD float zb_atan2(float y, float x) { return atan2f(y, x); }
+ZB_HD double zb_atan2(double y, double x) { return atan2(y, x); }
+ZB_HD float zb_sin(float x) { return sinf(x); }
+ZB_HD double zb_sin(double x) { return sin(x); }
+ZB_HD float zb_cos(float x) { return cosf(x); }
+ZB_HD double zb_cos(double x) { return cos(x); }
+ZB_HD float zb_fmod(float a, float b) { return fmodf(a, b); }
+ZB_HD double zb_fmod(double a, double b) { return fmod(a, b); }
 ZB_HD float zb_abs(float x) { return fabsf(x); }
 ZB_HD double zb_abs(double x) { return fabs(x); }
 ZB_HD float zb_min(float a, float b) { return fminf(a, b); }
@@ -464,6 +495,10 @@ struct ModelWalk {   // ZBOT_6S_CFG + zbot_6s_new.usd (zbot-6b-walking-*): stand
   }
 };
 
+struct ModelWalkV4 : ModelWalk {   // zbot-6b-walking-v4: same robot, 3-deep force history, FRESH MDP inputs
+  static constexpr int kTask = 2;
+};
+
 struct ModelSnake {  // ZBOT_D_6S_CFG + zbot_6s_v03.usd (zbot-6s-snake-v0): lies on the ground
   static constexpr int kTask = 1;
   static constexpr bool kGroundForceSensor = false;  // the task only senses filtered SELF contacts
@@ -740,6 +775,7 @@ template <typename T>
 struct LinkKin {
   T base_pos[3], base_quat[4], base_com_vel[3];
   T feet_pos[2][3], feet_quat[2][4], feet_com_vel[2][3];
+  T base_link_vel[3];   // body_link_lin_vel_w[:, base] (velocity of the LINK origin; v4 reads this, …env_v4.py:812)
 };
 
 template <typename T>
@@ -790,6 +826,9 @@ ZB_HD void link_kinematics(const SimState<T>& s, LinkKin<T>& o) {
       T wxc[3];
       cross3(w, c, wxc);
       if (k == 2) {
+        T wxl[3];
+        cross3(w, lo, wxl);
+        ZB_UNROLL for (int i = 0; i < 3; ++i) o.base_link_vel[i] = vO[i] + wxl[i];
         ZB_UNROLL for (int i = 0; i < 3; ++i) { o.base_pos[i] = s.p[i] + lo[i]; o.base_com_vel[i] = vO[i] + wxc[i]; }
         ZB_UNROLL for (int i = 0; i < 4; ++i) o.base_quat[i] = Q[i];
       } else {
@@ -908,7 +947,7 @@ ZB_HD void mdp_pre_physics(const Params<T>& P, const T* raw, MdpState<T>& m, T* 
     new_actions[k] = a;
     // walking: p_delta += pi * a * speed * dt (…env_v2.py:280-285); snake: p_delta += a * speed * dt, the pi lives
     // in its per-env joint_speed_limit (zbot_direct_6dof_snake_v0.py:121, 162-166)
-    T pd = (Model::kTask == 0) ? (m.p_delta[k] + pi * a * m.speed_limit * P.step_dt)
+    T pd = (Model::kTask != 1) ? (m.p_delta[k] + pi * a * m.speed_limit * P.step_dt)
                                : (m.p_delta[k] + a * m.speed_limit * P.step_dt);
     pd = zb_clamp(pd, -pi, pi);
     m.p_delta[k] = pd;
@@ -1167,6 +1206,8 @@ struct PhysOut {
   T fz[5][2];           // feet Fz history, newest first; slot 4 = last substep of the PREVIOUS step
   T mid2;               // max over the 5 slots of |F|^2 on the undesired bodies
   T applied_torque[6];  // ImplicitActuator bookkeeping before the last substep
+  T mid2_h3;            // v4 (history_length = 3): max over the LAST THREE substeps only
+  T qd_prev[6];         // v4: joint velocities before the last substep (joint_acc finite difference)
 };
 
 // Phase B of the control step: _pre_physics_step (…env_v2.py:276-287) + decimation x (physics substep +
@@ -1177,9 +1218,10 @@ ZB_HD void env_step_physics(const Params<T>& P, EnvState<T>& e, const T* raw_act
                             StepExport<T>* ex) {
   T new_actions[6], target[6];
   mdp_pre_physics<Model>(P, raw_actions, e.mdp, new_actions, target);
-  po.fz[4][0] = e.carry_feet_fz[0];
-  po.fz[4][1] = e.carry_feet_fz[1];
-  po.mid2 = e.carry_mid_max * e.carry_mid_max;
+  // (v4 keeps its commands in the carry slots: 3-deep history needs no carry-over from the previous step)
+  po.fz[4][0] = (Model::kTask == 2) ? T(0) : e.carry_feet_fz[0];
+  po.fz[4][1] = (Model::kTask == 2) ? T(0) : e.carry_feet_fz[1];
+  po.mid2 = (Model::kTask == 2) ? T(0) : e.carry_mid_max * e.carry_mid_max;
   if (ex) {
     ZB_UNROLL for (int b = 0; b < 5; ++b) { ex->mid_force_hist[4][b][0] = (b == 0) ? e.carry_mid_max : T(0);
       ex->mid_force_hist[4][b][1] = T(0); ex->mid_force_hist[4][b][2] = T(0); }
@@ -1187,11 +1229,15 @@ ZB_HD void env_step_physics(const Params<T>& P, EnvState<T>& e, const T* raw_act
       ex->feet_force_hist[4][j][2] = e.carry_feet_fz[j]; }
   }
   SubstepOut<T> so;
+  if (Model::kTask == 2) po.mid2_h3 = T(0);
 #if defined(__CUDACC__)
 #pragma unroll 1
 #endif
   for (int sub = 0; sub < P.decimation; ++sub) {
     T midf[15];
+    if (Model::kTask == 2) {
+      if (sub == P.decimation - 1) { ZB_UNROLL for (int k = 0; k < 6; ++k) po.qd_prev[k] = e.sim.qd[k]; }
+    }
     physics_substep<Model>(P, e.sim, target, so, scr, ex ? midf : (T*)nullptr);
     if (!Model::kGroundForceSensor) continue;
     // ContactSensor.update
@@ -1205,12 +1251,13 @@ ZB_HD void env_step_physics(const Params<T>& P, EnvState<T>& e, const T* raw_act
         ex->feet_force_hist[slot][j][2] = ff[2]; }
     }
     if (slot < 4) po.mid2 = zb_max(po.mid2, so.mid_force2_max);
+    if (Model::kTask == 2) { if (slot < 3) po.mid2_h3 = zb_max(po.mid2_h3, so.mid_force2_max); }
     if (ex && slot < 4) {
       ZB_UNROLL for (int b = 0; b < 5; ++b)
         ZB_UNROLL for (int i = 0; i < 3; ++i) ex->mid_force_hist[slot][b][i] = midf[3 * b + i];
     }
   }
-  if (Model::kGroundForceSensor) {
+  if (Model::kGroundForceSensor && Model::kTask != 2) {
     e.carry_feet_fz[0] = so.foot_force[0][2];
     e.carry_feet_fz[1] = so.foot_force[1][2];
     e.carry_mid_max = zb_sqrt(so.mid_force2_max);
@@ -1439,6 +1486,278 @@ ZB_HD void snake_env_step(const Params<T>& P, EnvState<T>& e, const T* raw_actio
   PhysOut<T> po;
   env_step_physics<ModelSnake>(P, e, raw_actions, po, scr, (StepExport<T>*)nullptr);
   snake_step_finish(P, e, s0, raw_actions, po, ep_len, default_base_quat, out, reset_ep_sums, ex);
+}
+
+// ------------------------------------------------------------------------------------
+// zbot-6b-walking-v4 (tasks/zbot6b_direct/zbot_direct_6dof_bipedal_env_v4.py): velocity / heading commands with
+// reset- and interval-mode resampling, randomised reset pose, 24-wide observation, 15 reward terms on FRESH
+// (end-of-physics) quantities, 3-deep contact history.  Same robot, actuator and physics substep as v2.
+// State reuse inside the 80-word layout: carry_feet_fz[0..1] = commands[0..1], carry_mid_max = target_heading_yaw,
+// heading_sum = current_yaw (what the last observation used), y_err_sum = interval_command_resample time_left.
+// ------------------------------------------------------------------------------------
+constexpr int V4_NUM_RAND = 10;
+// uniform [0,1) numbers of one env-step: the draws the reference makes through torch.rand / torch.bernoulli
+enum V4RandSlot : int { VR_POSE_X = 0, VR_POSE_Y = 1, VR_POSE_YAW = 2,          // reset_root_state_uniform (:84-86)
+                        VR_RESET_SIGN = 3, VR_RESET_VEL = 4, VR_RESET_YAW = 5,  // resample_commands, mode "reset"
+                        VR_INT_TIME = 6,                                        // EventManager interval re-arm
+                        VR_INT_SIGN = 7, VR_INT_VEL = 8, VR_INT_YAW = 9 };      // resample_commands, mode "interval"
+
+// isaaclab.utils.math.wrap_to_pi: ((a + pi) mod 2 pi) - pi with python-style modulo, +pi kept for a > 0
+template <typename T>
+ZB_HD T v4_wrap_to_pi(T a) {
+  const T pi = T(3.14159265358979323846), two_pi = T(2) * T(3.14159265358979323846);
+  T r = zb_fmod(a + pi, two_pi);
+  if (r != T(0) && r < T(0)) r += two_pi;
+  return (r == T(0) && a > T(0)) ? pi : (r - pi);
+}
+
+// resample_commands (…env_v4.py:109-135)
+template <typename T>
+ZB_HD void v4_resample_commands(const Params<T>& P, T u_sign, T u_vel, T u_yaw, T current_yaw, T& cmd0, T& cmd1,
+                                T& target_yaw) {
+  const T low = P.ev_vel_lo;
+  if (P.ev_dual_sign) {
+    const T vel_sign = ((u_sign < P.ev_prob_pos) ? T(1) : T(0)) * T(2) - T(1);   // torch.bernoulli(prob_pos) * 2 - 1
+    const T high = P.ev_vel_hi + P.ev_offset * (vel_sign - T(1));               // :126
+    cmd0 = (u_vel * (high - low) + low) * vel_sign;                              // :127
+  } else {
+    cmd0 = u_vel * (P.ev_vel_hi - low) + low;                                    // :129
+  }
+  cmd1 = u_yaw * (P.ev_yaw_hi - P.ev_yaw_lo) + P.ev_yaw_lo;                      // :133-134
+  target_yaw = v4_wrap_to_pi(current_yaw + cmd1);                                // :136
+}
+
+template <typename T>
+struct V4Fresh {   // _compute_intermediate_values (…env_v4.py:792-826) + the sensor / articulation reads of the terms
+  T forward[3], shoulder[3], current_yaw, heading_err, v_fwd, vel_y;
+  T feet_pos[2][3], feet_force[2];
+  T last_air[2], last_contact[2], cur_air[2], cur_contact[2];
+  T joint_vel2, joint_acc2, base_height;
+};
+
+template <typename T>
+ZB_HD T v4_term_value(int id, const StaleCache<T>& c, const FreshInputs<T>& f, const V4Fresh<T>& v, const T* new_actions,
+                      MdpState<T>& m, T cmd0) {
+  T val = T(0);
+  switch (id) {
+    case TERM_V4_TRACK_LIN_VEL_X: {                                              // :1013-1016
+      const T d = cmd0 - v.v_fwd;
+      val = zb_exp(-(d * d) / T(0.25));
+    } break;
+    case TERM_V4_TRACK_HEADING_YAW:                                              // :1018-1020
+      val = zb_exp(-(v.heading_err * v.heading_err) / T(0.25));
+      break;
+    case TERM_V4_LIN_VEL_X:                                                      // :1022-1024
+      val = v.v_fwd * v.v_fwd;
+      break;
+    case TERM_V4_LIN_VEL_Y:                                                      // :1026-1030
+      val = v.vel_y * v.vel_y;
+      break;
+    case TERM_V4_JOINT_VEL:                                                      // :1168-1171
+      val = v.joint_vel2;
+      break;
+    case TERM_V4_JOINT_ACC:                                                      // :1173-1176
+      val = v.joint_acc2;
+      break;
+    case TERM_V4_STEP_LENGTH: {                                                  // :1056-1079
+      const T sgn = (cmd0 > T(0)) ? T(1) : (cmd0 < T(0)) ? T(-1) : T(0);
+      bool down[2];
+      ZB_UNROLL for (int j = 0; j < 2; ++j) {
+        down[j] = (f.feet_force[j] > T(10.0)) && (m.feet_force_last[j] < T(10.0));
+        if (down[j]) {
+          const T d[3] = {v.feet_pos[j][0] - m.feet_down_pos_last[j][0], v.feet_pos[j][1] - m.feet_down_pos_last[j][1],
+                          v.feet_pos[j][2] - m.feet_down_pos_last[j][2]};
+          m.feet_step_length[j] = (d[0] * v.forward[0] + d[1] * v.forward[1] + d[2] * v.forward[2]) * sgn;
+        }
+      }
+      const T rew_len = zb_min(m.feet_step_length[0], m.feet_step_length[1]);
+      ZB_UNROLL for (int j = 0; j < 2; ++j) {
+        m.feet_step_length[j] *= T(0.99);                                        // decay (:1073)
+        if (down[j]) { ZB_UNROLL for (int i = 0; i < 3; ++i) m.feet_down_pos_last[j][i] = v.feet_pos[j][i]; }
+        m.feet_force_last[j] = f.feet_force[j];
+      }
+      val = zb_tanh(T(15.0) * rew_len);
+    } break;
+    case TERM_V4_FEET_AIR_TIME_BIPED: {                                          // :1110-1124
+      const bool c0 = v.cur_contact[0] > T(0), c1 = v.cur_contact[1] > T(0);
+      const T t0 = c0 ? v.cur_contact[0] : v.cur_air[0], t1 = c1 ? v.cur_contact[1] : v.cur_air[1];
+      const bool single = (c0 != c1);
+      val = zb_min(zb_min(single ? t0 : T(0), single ? t1 : T(0)), T(2.0));
+    } break;
+    case TERM_V4_AIRTIME_VARIANCE: {                                             // :1081-1087 (torch.var, unbiased, n = 2)
+      const T a0 = zb_min(v.last_air[0], T(0.5)), a1 = zb_min(v.last_air[1], T(0.5));
+      const T b0 = zb_min(v.last_contact[0], T(0.5)), b1 = zb_min(v.last_contact[1], T(0.5));
+      const T ma = (a0 + a1) * T(0.5), mb = (b0 + b1) * T(0.5);
+      val = ((a0 - ma) * (a0 - ma) + (a1 - ma) * (a1 - ma)) + ((b0 - mb) * (b0 - mb) + (b1 - mb) * (b1 - mb));
+    } break;
+    case TERM_V4_AIRTIME_SUM:                                                    // :1089-1093
+      val = zb_min(v.last_air[0] + v.last_air[1], T(2.0));
+      break;
+    case TERM_V4_FEET_HARMONY:                                                   // :1139-1144
+      val = (v.last_air[0] + v.last_air[1]) - T(3.0) * zb_abs(v.last_air[0] - v.last_air[1]);
+      break;
+    case TERM_V4_FEET_CLOSE: {                                                   // :1146-1151
+      const T dx = v.feet_pos[0][0] - v.feet_pos[1][0], dy = v.feet_pos[0][1] - v.feet_pos[1][1];
+      val = zb_max(T(0.115) - zb_sqrt(dx * dx + dy * dy), T(0));
+    } break;
+    case TERM_V4_FEET_HEIGHT:                                                    // :1178-1183
+      val = v.feet_pos[0][2] + (v.feet_pos[1][2] - T(0.053));
+      break;
+    case TERM_V4_BASE_HEIGHT:                                                    // :1185-1187 (env-local: origin z = 0)
+      val = v.base_height - T(0.25);
+      break;
+    default:   // feet_downward, feet_forward, action_rate, torques, feet_slide: the v2 formulas on fresh inputs
+      val = mdp_term_value(id, c, f, new_actions, m, T(0), T(0));
+      break;
+  }
+  return val;
+}
+
+template <typename T>
+struct V4Export {   // what the v4 MDP saw at the end of physics (test hook), 60 words
+  T base_pos[3], base_quat[4], base_link_vel[3];
+  T feet_pos[2][3], feet_quat[2][4], feet_com_vel[2][3];
+  T feet_fz_hist[3][2];       // newest first
+  T undesired_max;            // max_t,b |F| over the 3-deep history
+  T last_air[2], last_contact[2], cur_air[2], cur_contact[2];
+  T q1[6], qd1[6], tau1[6], joint_acc1[6];
+};
+
+// Phase C of the v4 control step.  `rnd` = this env-step's V4_NUM_RAND uniforms.  obs has 24 entries.
+template <typename T>
+ZB_HD void v4_step_finish(const Params<T>& P, EnvState<T>& e, const T* raw_actions, const PhysOut<T>& po, int64_t& ep_len,
+                          const T* rnd, T* obs24, StepOut<T>& out, T* reset_ep_sums, V4Export<T>* ex) {
+  T& cmd0 = e.carry_feet_fz[0];
+  T& cmd1 = e.carry_feet_fz[1];
+  T& target_yaw = e.carry_mid_max;
+  T& time_left = e.mdp.y_err_sum;
+  T new_actions[6];
+  ZB_UNROLL for (int k = 0; k < 6; ++k) new_actions[k] = zb_tanh(raw_actions[k]);
+  ep_len += 1;
+  // ---- _compute_intermediate_values (:792-826): everything FRESH ----
+  LinkKin<T> k1;
+  link_kinematics(e.sim, k1);
+  StaleCache<T> c;     // the v2 container, filled with fresh values (feet_x / feet_z / forward / feet_pos)
+  stale_from_links(k1.base_pos, k1.base_quat, k1.base_link_vel, k1.feet_pos, k1.feet_quat, c);
+  V4Fresh<T> v;
+  {
+    const T ez[3] = {T(0), T(0), T(1)};
+    quat_apply(k1.base_quat, ez, v.shoulder);
+    ZB_UNROLL for (int i = 0; i < 3; ++i) v.forward[i] = c.forward[i];
+    v.current_yaw = zb_atan2(v.forward[1], v.forward[0]);                         // :806
+    const T diff = target_yaw - v.current_yaw;
+    v.heading_err = zb_atan2(zb_sin(diff), zb_cos(diff));                         // :809
+    v.v_fwd = c.v_fwd;                                                            // :812-813 (link velocity . forward)
+    v.vel_y = k1.base_link_vel[0] * v.shoulder[0] + k1.base_link_vel[1] * v.shoulder[1] + k1.base_link_vel[2] * v.shoulder[2];
+    v.base_height = k1.base_pos[2];
+    v.joint_vel2 = T(0); v.joint_acc2 = T(0);
+    const T inv_dt = T(1) / P.dt;
+    ZB_UNROLL for (int k = 0; k < 6; ++k) {
+      v.joint_vel2 += e.sim.qd[k] * e.sim.qd[k];
+      const T acc = (e.sim.qd[k] - po.qd_prev[k]) * inv_dt;
+      v.joint_acc2 += acc * acc;
+    }
+  }
+  FreshInputs<T> f;
+  ZB_UNROLL for (int j = 0; j < 2; ++j) {
+    f.feet_force[j] = ((po.fz[0][j] + po.fz[1][j]) + po.fz[2][j]) / T(3);         // mean over history_length = 3 (:822-825)
+    f.last_air_time[j] = e.timers[j].last_air;
+    f.feet_vel_xy[j][0] = k1.feet_com_vel[j][0];
+    f.feet_vel_xy[j][1] = k1.feet_com_vel[j][1];
+    v.feet_force[j] = f.feet_force[j];
+    v.last_air[j] = e.timers[j].last_air; v.last_contact[j] = e.timers[j].last_contact;
+    v.cur_air[j] = e.timers[j].cur_air; v.cur_contact[j] = e.timers[j].cur_contact;
+    ZB_UNROLL for (int i = 0; i < 3; ++i) v.feet_pos[j][i] = k1.feet_pos[j][i];
+  }
+  f.undesired_force_max = zb_sqrt(po.mid2_h3);
+  ZB_UNROLL for (int k = 0; k < 6; ++k) f.applied_torque[k] = po.applied_torque[k];
+  f.origin_y = T(0);
+  f.com_x_sum = T(0);
+  if (ex) {
+    ZB_UNROLL for (int i = 0; i < 3; ++i) { ex->base_pos[i] = k1.base_pos[i]; ex->base_link_vel[i] = k1.base_link_vel[i]; }
+    ZB_UNROLL for (int i = 0; i < 4; ++i) ex->base_quat[i] = k1.base_quat[i];
+    ZB_UNROLL for (int j = 0; j < 2; ++j) {
+      ZB_UNROLL for (int i = 0; i < 3; ++i) { ex->feet_pos[j][i] = k1.feet_pos[j][i]; ex->feet_com_vel[j][i] = k1.feet_com_vel[j][i]; }
+      ZB_UNROLL for (int i = 0; i < 4; ++i) ex->feet_quat[j][i] = k1.feet_quat[j][i];
+      ZB_UNROLL for (int t = 0; t < 3; ++t) ex->feet_fz_hist[t][j] = po.fz[t][j];
+      ex->last_air[j] = v.last_air[j]; ex->last_contact[j] = v.last_contact[j];
+      ex->cur_air[j] = v.cur_air[j]; ex->cur_contact[j] = v.cur_contact[j];
+    }
+    ex->undesired_max = f.undesired_force_max;
+    ZB_UNROLL for (int k = 0; k < 6; ++k) {
+      ex->q1[k] = e.sim.q[k]; ex->qd1[k] = e.sim.qd[k]; ex->tau1[k] = po.applied_torque[k];
+      ex->joint_acc1[k] = (e.sim.qd[k] - po.qd_prev[k]) * (T(1) / P.dt);
+    }
+  }
+  // ---- _get_dones (:868-886) ----
+  const bool time_out = ep_len >= (int64_t)(P.max_episode_length - 1);
+  const bool died = (f.undesired_force_max > P.contact_died_threshold) || (k1.base_pos[2] < P.termination_height);
+  // ---- _get_rewards (:853-866): rew = f() * scale * step_dt, in cfg-dict order ----
+  T reward = T(0);
+  for (int i = 0; i < P.num_terms; ++i) {
+    const T rew = v4_term_value(P.term_id[i], c, f, v, new_actions, e.mdp, cmd0) * P.term_w[i] * P.step_dt;
+    reward += rew;
+    ZB_UNROLL for (int k = 0; k < MAX_TERMS; ++k) e.mdp.ep_sums[k] += (k == i) ? rew : T(0);
+  }
+  if (died) reward -= P.term_penalty;
+  out.reward = reward;
+  out.terminated = died;
+  out.time_out = time_out;
+  ZB_UNROLL for (int k = 0; k < 6; ++k) e.mdp.actions[k] = new_actions[k];
+  T current_yaw = v.current_yaw;
+  // ---- _reset_idx (:888-976) ----
+  if (died || time_out) {
+    // log: episodic sum per second of the ACTUAL episode duration (:893-901)
+    const T dur = zb_max(T(ep_len) * P.step_dt, P.step_dt);
+    ZB_UNROLL for (int i = 0; i < MAX_TERMS; ++i) reset_ep_sums[i] = e.mdp.ep_sums[i] / dur;
+    // EventManager mode "reset", cfg order: reset_base (:84-106), [curricula: host], reset_command_resample
+    sim_state_default<ModelWalk>(e.sim);
+    const T yaw = rnd[VR_POSE_YAW] * (P.ev_pose_hi[2] - P.ev_pose_lo[2]) + P.ev_pose_lo[2];
+    e.sim.p[0] += rnd[VR_POSE_X] * (P.ev_pose_hi[0] - P.ev_pose_lo[0]) + P.ev_pose_lo[0];
+    e.sim.p[1] += rnd[VR_POSE_Y] * (P.ev_pose_hi[1] - P.ev_pose_lo[1]) + P.ev_pose_lo[1];
+    // quat_mul(default (1,0,0,0), quat_from_euler_xyz(0, 0, yaw)) = (cos(yaw/2), 0, 0, sin(yaw/2))
+    e.sim.Q[0] = zb_cos(yaw * T(0.5)); e.sim.Q[1] = T(0); e.sim.Q[2] = T(0); e.sim.Q[3] = zb_sin(yaw * T(0.5));
+    current_yaw = yaw;                                                            // env.current_yaw[env_ids] = rand yaw (:88)
+    v4_resample_commands(P, rnd[VR_RESET_SIGN], rnd[VR_RESET_VEL], rnd[VR_RESET_YAW], current_yaw, cmd0, cmd1, target_yaw);
+    ep_len = 0;
+    ZB_UNROLL for (int k = 0; k < 6; ++k) { e.mdp.p_delta[k] = T(0); e.mdp.actions[k] = T(0); }
+    ZB_UNROLL for (int j = 0; j < 2; ++j) {
+      e.timers[j].cur_air = e.timers[j].cur_contact = e.timers[j].last_air = e.timers[j].last_contact = T(0);
+      e.mdp.feet_force_last[j] = T(15.0);                                         // :966
+      e.mdp.feet_step_length[j] = T(0);                                           // :970
+    }
+    e.mdp.feet_force_sum = T(0);
+    ZB_UNROLL for (int i = 0; i < MAX_TERMS; ++i) e.mdp.ep_sums[i] = T(0);
+    link_kinematics(e.sim, k1);                                                   // post-reset view
+    ZB_UNROLL for (int j = 0; j < 2; ++j)
+      ZB_UNROLL for (int i = 0; i < 3; ++i) e.mdp.feet_down_pos_last[j][i] = k1.feet_pos[j][i];   // :967-969
+  }
+  // ---- EventManager mode "interval" (per-env timer, [IL-upstream] EventManager.apply) ----
+  time_left -= P.step_dt;
+  if (time_left < T(1e-6)) {
+    time_left = rnd[VR_INT_TIME] * (P.ev_interval_hi - P.ev_interval_lo) + P.ev_interval_lo;
+    v4_resample_commands(P, rnd[VR_INT_SIGN], rnd[VR_INT_VEL], rnd[VR_INT_YAW], current_yaw, cmd0, cmd1, target_yaw);
+  }
+  e.mdp.heading_sum = current_yaw;
+  // ---- _get_observations (:828-851) ----
+  const T diff = target_yaw - current_yaw;
+  ZB_UNROLL for (int i = 0; i < 4; ++i) obs24[i] = k1.base_quat[i];
+  ZB_UNROLL for (int k = 0; k < 6; ++k) {
+    obs24[4 + k] = e.sim.q[k] - default_joint_pos<T>(k);
+    obs24[10 + k] = e.sim.qd[k];
+    obs24[16 + k] = e.mdp.actions[k];
+  }
+  obs24[22] = cmd0;
+  obs24[23] = zb_atan2(zb_sin(diff), zb_cos(diff));
+}
+
+// whole v4 control step in one call (CPU port)
+template <typename T, typename Scr>
+ZB_HD void v4_env_step(const Params<T>& P, EnvState<T>& e, const T* raw_actions, int64_t& ep_len, const T* rnd, T* obs24,
+                       StepOut<T>& out, T* reset_ep_sums, V4Export<T>* ex, Scr& scr) {
+  PhysOut<T> po;
+  env_step_physics<ModelWalkV4>(P, e, raw_actions, po, scr, (StepExport<T>*)nullptr);
+  v4_step_finish(P, e, raw_actions, po, ep_len, rnd, obs24, out, reset_ep_sums, ex);
 }
 
 // the whole control step in one call (CPU port, export kernel)

@@ -421,6 +421,108 @@ zbot_snake_step_kernel(const __grid_constant__ Params<float> P, const __grid_con
 }
 
 // ---------------------------------------------------------------------------------------------
+// zbot-6b-walking-v4: same phased structure; all MDP inputs are FRESH, so the start-of-step state is not
+// re-read.  Random numbers: caller-supplied [N][10] uniforms, or a counter-based generator
+// (splitmix64 finaliser of seed / call counter / env / slot -> 24-bit mantissa, like torch.rand's float32).
+// ---------------------------------------------------------------------------------------------
+static_assert(sizeof(V4Export<float>) / sizeof(float) == ZBOT_V4_EXPORT_WORDS, "V4Export layout");
+
+__device__ __forceinline__ float v4_uniform(uint64_t seed, uint64_t call, uint32_t env, uint32_t slot) {
+  uint64_t z = seed + 0x9E3779B97F4A7C15ull * (call * 0x100000000ull + env) + 0xD1B54A32D192ED03ull * (slot + 1);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (float)(uint32_t)(z >> 40) * (1.0f / 16777216.0f);
+}
+
+template <bool kExport>
+__global__ void __launch_bounds__(128, 2)
+zbot_v4_step_kernel(const __grid_constant__ Params<float> P, float4* __restrict__ state, int64_t* __restrict__ ep_len_buf,
+                    const float* __restrict__ actions, const float* __restrict__ rand, uint64_t seed, uint64_t call,
+                    float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ terminated,
+                    uint8_t* __restrict__ truncated, int n, StatsCtx sc, float* __restrict__ export_buf) {
+  extern __shared__ float smem[];
+  const int e0 = blockIdx.x * blockDim.x;
+  const int e = e0 + threadIdx.x;
+  const bool live = e < n;
+  float stat[kStatUsed];
+#pragma unroll
+  for (int j = 0; j < kStatUsed; ++j) stat[j] = 0.f;
+  float obs_row[ZBOT_V4_NUM_OBS];
+#pragma unroll
+  for (int i = 0; i < ZBOT_V4_NUM_OBS; ++i) obs_row[i] = 0.f;
+  bool did_reset = false;
+  if (live) {
+    EnvState<float> es;
+    StepOut<float> out;
+    float rs[MAX_TERMS];
+#pragma unroll
+    for (int i = 0; i < MAX_TERMS; ++i) rs[i] = 0.f;
+    SmemScratch scr{smem + threadIdx.x * SCR_STRIDE};
+    const float2* a2p = reinterpret_cast<const float2*>(actions + (size_t)e * 6);
+    {
+      float w[4 * EARLY_QUADS];
+      load_words<EARLY_QUADS>(state, n, e, w);
+      env_early_unpack(w, es);
+    }
+    PhysOut<float> po;
+    {
+      const float2 a0 = __ldg(a2p), a1 = __ldg(a2p + 1), a2v = __ldg(a2p + 2);
+      const float raw[6] = {a0.x, a0.y, a1.x, a1.y, a2v.x, a2v.y};
+#pragma unroll
+      for (int k = 0; k < 6; ++k) scr.base[SCR_RAW_ACT + k] = raw[k];
+      env_step_physics<ModelWalkV4>(P, es, raw, po, scr, (StepExport<float>*)nullptr);
+    }
+    {
+      float w[ZBOT_STATE_WORDS - 4 * EARLY_QUADS];
+      load_words<ZBOT_STATE_WORDS / 4 - EARLY_QUADS>(state + (size_t)EARLY_QUADS * n, n, e, w);
+      env_late_unpack(w, es);
+    }
+    float raw[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) raw[k] = scr.base[SCR_RAW_ACT + k];
+    float rnd[V4_NUM_RAND];
+    if (rand) {
+      const float2* rp = reinterpret_cast<const float2*>(rand + (size_t)e * V4_NUM_RAND);
+#pragma unroll
+      for (int i = 0; i < V4_NUM_RAND / 2; ++i) { const float2 v = __ldg(rp + i); rnd[2 * i] = v.x; rnd[2 * i + 1] = v.y; }
+    } else {
+#pragma unroll
+      for (int i = 0; i < V4_NUM_RAND; ++i) rnd[i] = v4_uniform(seed, call, (uint32_t)e, (uint32_t)i);
+    }
+    int64_t ep = ep_len_buf[e];
+    V4Export<float> ex;
+    v4_step_finish(P, es, raw, po, ep, rnd, obs_row, out, rs, kExport ? &ex : (V4Export<float>*)nullptr);
+    if (kExport) {
+      const float* src = reinterpret_cast<const float*>(&ex);
+      for (int i = 0; i < ZBOT_V4_EXPORT_WORDS; ++i) export_buf[(size_t)e * ZBOT_V4_EXPORT_WORDS + i] = src[i];
+    }
+    float w[ZBOT_STATE_WORDS];
+    env_state_pack(es, w);
+    store_words<ZBOT_STATE_WORDS / 4>(state, n, e, w);
+    ep_len_buf[e] = ep;
+    rew[e] = out.reward;
+    terminated[e] = out.terminated ? 1 : 0;
+    truncated[e] = out.time_out ? 1 : 0;
+    did_reset = out.terminated || out.time_out;
+    if (did_reset) {
+#pragma unroll
+      for (int i = 0; i < MAX_TERMS; ++i) stat[i] = rs[i];
+      stat[S_NUM_RESET] = 1.f;
+      stat[S_NUM_TERM_RESET] = out.terminated ? 1.f : 0.f;
+      stat[S_NUM_TO_RESET] = out.time_out ? 1.f : 0.f;
+    }
+    stat[S_REW_SUM] = out.reward;
+    stat[S_NUM_TERM] = out.terminated ? 1.f : 0.f;
+    stat[S_NUM_TRUNC] = out.time_out ? 1.f : 0.f;
+  }
+  __syncthreads();
+  store_rows_coalesced<ZBOT_V4_NUM_OBS>(obs, obs_row, n, e0, smem);
+  __syncthreads();
+  stats_block_partial(stat, did_reset, smem, sc);
+}
+
+// ---------------------------------------------------------------------------------------------
 // reset / observe / articulation view / init
 // ---------------------------------------------------------------------------------------------
 template <bool kSnake>
@@ -740,6 +842,7 @@ struct ZbotHandle {
   float inv_episode_s;
   int variant;      // index into kStepVariants
   int force_block;
+  uint64_t v4_calls;   // zbot_v4_step call counter (stream position of the in-kernel generator)
   int mdp_tile;
 };
 
@@ -812,6 +915,7 @@ int zbot_create(const ZbotCfg* cfg, int device, ZbotHandle** out) {
   params_from_cfg(*cfg, h->P);
   h->device = device;
   h->inv_episode_s = 1.0f / ((float)cfg->max_episode_length * cfg->sim_dt * (float)cfg->decimation);
+  if (cfg->task == ZBOT_TASK_WALKING_V4) h->inv_episode_s = 1.0f;   // v4 logs sum / ACTUAL duration, per env, in the kernel
   cudaDeviceProp prop;
   ZB_CUDA(cudaGetDeviceProperties(&prop, device));
   h->num_sms = prop.multiProcessorCount;
@@ -831,6 +935,8 @@ int zbot_create(const ZbotCfg* cfg, int device, ZbotHandle** out) {
   ZB_CUDA(cudaFuncSetAttribute(zbot_step_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
   ZB_CUDA(cudaFuncSetAttribute(zbot_snake_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
   ZB_CUDA(cudaFuncSetAttribute(zbot_snake_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
+  ZB_CUDA(cudaFuncSetAttribute(zbot_v4_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
+  ZB_CUDA(cudaFuncSetAttribute(zbot_v4_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
   {
     // register-budget variant of the step kernel = resident 128-thread CTAs per SM it is compiled for.
     // Measured (profiles/r1_notes.md): 2 CTAs/SM (197 regs, no spill) is fastest while the grid fits two
@@ -882,6 +988,7 @@ static int step_impl(ZbotHandle* h, const float* actions, float* obs, float* rew
   StatsCtx sc{h->partials, h->ring, slot, prev, h->inv_episode_s, 0};
   cudaStream_t s = (cudaStream_t)stream;
   ExportPtrs xp{};
+  if (h->cfg.task == ZBOT_TASK_WALKING_V4) return fail(ZBOT_E_INVALID, "task zbot-6b-walking-v4 steps through zbot_v4_step%s");
   if (h->cfg.task == ZBOT_TASK_SNAKE_V0) {
     if (ex) return fail(ZBOT_E_INVALID, "zbot_step_export is a walking-task hook; use zbot_snake_step_export%s");
     if (snake_export)
@@ -971,6 +1078,60 @@ int zbot_step_host(ZbotHandle* h, const float* host_actions, float* host_rows, i
   return ZBOT_OK;
 }
 
+static int v4_step_impl(ZbotHandle* h, const float* actions, const float* rand, float* obs, float* rew, uint8_t* terminated,
+                        uint8_t* truncated, int32_t slot, int32_t prev, float* export_buf, void* stream) {
+  if (!h) return fail(ZBOT_E_INVALID, "handle is NULL%s");
+  if (h->cfg.task != ZBOT_TASK_WALKING_V4) return fail(ZBOT_E_INVALID, "zbot_v4_step needs task = ZBOT_TASK_WALKING_V4%s");
+  if (!h->state) return fail(ZBOT_E_UNBOUND, "zbot_bind has not been called%s");
+  if (!actions || !obs || !rew || !terminated || !truncated) return fail(ZBOT_E_INVALID, "zbot_v4_step: NULL buffer%s");
+  if (((uintptr_t)actions & 7) != 0 || ((uintptr_t)rand & 7) != 0)
+    return fail(ZBOT_E_INVALID, "actions / rand must be 8-byte aligned%s");
+  if (int rc = check_slot(slot, prev, h->ring_slots)) return rc;
+  const int n = h->cfg.num_envs;
+  int block = 128;
+  while (block > 32 && (n + block - 1) / block < 2 * h->num_sms) block >>= 1;
+  const int grid = (n + block - 1) / block;
+  const size_t smem = (size_t)block * SCR_STRIDE * sizeof(float);
+  StatsCtx sc{h->partials, h->ring, slot, prev, h->inv_episode_s, 0};
+  cudaStream_t s = (cudaStream_t)stream;
+  const uint64_t call = h->v4_calls++;
+  if (export_buf)
+    zbot_v4_step_kernel<true><<<grid, block, smem, s>>>(h->P, h->state, h->ep_len, actions, rand, h->cfg.rng_seed, call, obs, rew,
+                                                    terminated, truncated, n, sc, export_buf);
+  else
+    zbot_v4_step_kernel<false><<<grid, block, smem, s>>>(h->P, h->state, h->ep_len, actions, rand, h->cfg.rng_seed, call, obs, rew,
+                                                     terminated, truncated, n, sc, nullptr);
+  ZB_CUDA(cudaGetLastError());
+  h->launches += 1;
+  zbot_stats_finalize_kernel<<<1, 1024, 0, s>>>(sc, (unsigned int)grid);
+  ZB_CUDA(cudaGetLastError());
+  h->launches += 1;
+  return ZBOT_OK;
+}
+
+int zbot_v4_step(ZbotHandle* h, const float* actions, const float* rand, float* obs, float* rew, uint8_t* terminated,
+                 uint8_t* truncated, int32_t stats_slot, int32_t prev_slot, void* stream) {
+  return v4_step_impl(h, actions, rand, obs, rew, terminated, truncated, stats_slot, prev_slot, nullptr, stream);
+}
+
+int zbot_v4_step_export(ZbotHandle* h, const float* actions, const float* rand, float* obs, float* rew, uint8_t* terminated,
+                        uint8_t* truncated, int32_t stats_slot, int32_t prev_slot, float* export_buf, void* stream) {
+  if (!export_buf) return fail(ZBOT_E_INVALID, "zbot_v4_step_export: export_buf is NULL%s");
+  return v4_step_impl(h, actions, rand, obs, rew, terminated, truncated, stats_slot, prev_slot, export_buf, stream);
+}
+
+int zbot_update_cfg(ZbotHandle* h, const ZbotCfg* cfg) {
+  if (!h || !cfg) return fail(ZBOT_E_INVALID, "zbot_update_cfg: NULL argument%s");
+  const char* why = "";
+  if (cfg_validate(*cfg, &why) != ZBOT_OK) return fail(ZBOT_E_INVALID, "%s", why);
+  if (cfg->num_envs != h->cfg.num_envs || cfg->task != h->cfg.task || cfg->sim_dt != h->cfg.sim_dt ||
+      cfg->max_episode_length != h->cfg.max_episode_length)
+    return fail(ZBOT_E_INVALID, "zbot_update_cfg: num_envs / task / sim_dt / max_episode_length must not change%s");
+  h->cfg = *cfg;
+  params_from_cfg(*cfg, h->P);
+  return ZBOT_OK;
+}
+
 int zbot_snake_step_export(ZbotHandle* h, const float* actions, float* obs, float* rew, uint8_t* terminated,
                            uint8_t* truncated, int32_t stats_slot, int32_t prev_slot, float* export41, void* stream) {
   if (!export41) return fail(ZBOT_E_INVALID, "zbot_snake_step_export: export41 is NULL%s");
@@ -982,6 +1143,8 @@ int zbot_reset_idx(ZbotHandle* h, const int64_t* env_ids, int64_t nids, const ui
   if (!h) return fail(ZBOT_E_INVALID, "handle is NULL%s");
   if (!h->state) return fail(ZBOT_E_UNBOUND, "zbot_bind has not been called%s");
   if (int rc = check_slot(stats_slot, -1, h->ring_slots)) return rc;
+  if (h->cfg.task == ZBOT_TASK_WALKING_V4)
+    return fail(ZBOT_E_INVALID, "zbot_reset_idx: the v4 task's randomised reset is written by the caller (state words)%s");
   const int n = h->cfg.num_envs;
   if (!env_ids || nids < 0) { env_ids = nullptr; nids = n; }
   if (nids == 0) return ZBOT_OK;
@@ -1005,6 +1168,7 @@ int zbot_reset_idx(ZbotHandle* h, const int64_t* env_ids, int64_t nids, const ui
 
 int zbot_observe(ZbotHandle* h, float* obs, void* stream) {
   if (!h || !obs) return fail(ZBOT_E_INVALID, "zbot_observe: NULL argument%s");
+  if (h->cfg.task == ZBOT_TASK_WALKING_V4) return fail(ZBOT_E_INVALID, "zbot_observe: v2 / snake observation layout only%s");
   if (!h->state) return fail(ZBOT_E_UNBOUND, "zbot_bind has not been called%s");
   const int n = h->cfg.num_envs, block = 64, grid = (n + block - 1) / block;
   if (h->cfg.task == ZBOT_TASK_SNAKE_V0)
@@ -1019,7 +1183,7 @@ int zbot_observe(ZbotHandle* h, float* obs, void* stream) {
 int zbot_articulation_view(ZbotHandle* h, float* pos, float* quat, float* vel, void* stream) {
   if (!h) return fail(ZBOT_E_INVALID, "handle is NULL%s");
   if (!h->state) return fail(ZBOT_E_UNBOUND, "zbot_bind has not been called%s");
-  if (h->cfg.task != ZBOT_TASK_WALKING_V2) return fail(ZBOT_E_INVALID, "zbot_articulation_view: walking task only%s");
+  if (h->cfg.task == ZBOT_TASK_SNAKE_V0) return fail(ZBOT_E_INVALID, "zbot_articulation_view: walking tasks only%s");
   const int n = h->cfg.num_envs, block = 64, grid = (n + block - 1) / block;
   zbot_view_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(h->state, pos, quat, vel, n);
   ZB_CUDA(cudaGetLastError());

@@ -185,6 +185,10 @@ inline void params_from_cfg(const ZbotCfg& c, Params<T>& P) {
   P.max_episode_length = c.max_episode_length;
   P.num_terms = c.num_terms;
   for (int i = 0; i < MAX_TERMS; ++i) { P.term_id[i] = c.term_id[i]; P.term_w[i] = T(c.term_weight[i]); }
+  P.ev_vel_lo = T(c.ev_vel_lo); P.ev_vel_hi = T(c.ev_vel_hi); P.ev_yaw_lo = T(c.ev_yaw_lo); P.ev_yaw_hi = T(c.ev_yaw_hi);
+  P.ev_offset = T(c.ev_offset); P.ev_prob_pos = T(c.ev_prob_pos); P.ev_dual_sign = c.ev_dual_sign;
+  for (int i = 0; i < 3; ++i) { P.ev_pose_lo[i] = T(c.ev_pose_lo[i]); P.ev_pose_hi[i] = T(c.ev_pose_hi[i]); }
+  P.ev_interval_lo = T(c.ev_interval_lo); P.ev_interval_hi = T(c.ev_interval_hi);
   P.default_terms = (c.num_terms == 13) && (c.task == ZBOT_TASK_WALKING_V2);
   for (int i = 0; i < 13 && P.default_terms; ++i) P.default_terms = (c.term_id[i] == i);
 }
@@ -192,7 +196,9 @@ inline void params_from_cfg(const ZbotCfg& c, Params<T>& P) {
 inline int cfg_validate(const ZbotCfg& c, const char** why) {
   if (c.abi_version != ZBOT_ABI_VERSION) { *why = "ZbotCfg.abi_version mismatch"; return ZBOT_E_INVALID; }
   if (c.num_envs < 1) { *why = "num_envs must be >= 1"; return ZBOT_E_INVALID; }
-  if (c.task != ZBOT_TASK_WALKING_V2 && c.task != ZBOT_TASK_SNAKE_V0) { *why = "unknown task"; return ZBOT_E_INVALID; }
+  if (c.task != ZBOT_TASK_WALKING_V2 && c.task != ZBOT_TASK_SNAKE_V0 && c.task != ZBOT_TASK_WALKING_V4) {
+    *why = "unknown task"; return ZBOT_E_INVALID;
+  }
   if (c.decimation != 4) { *why = "only decimation == 4 is supported (5-deep contact history)"; return ZBOT_E_INVALID; }
   if (c.num_terms < 0 || c.num_terms > ZBOT_MAX_TERMS) { *why = "num_terms out of range"; return ZBOT_E_INVALID; }
   for (int i = 0; i < c.num_terms; ++i)

@@ -12,8 +12,9 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libzbot_b200.so")
 
-ZBOT_ABI_VERSION = 2
-TASK_WALKING_V2, TASK_SNAKE_V0 = 0, 1
+ZBOT_ABI_VERSION = 3
+TASK_WALKING_V2, TASK_SNAKE_V0, TASK_WALKING_V4 = 0, 1, 2
+V4_NUM_OBS, V4_NUM_RAND, V4_EXPORT_WORDS = 24, 10, 69
 MAX_TERMS = 16
 HOST_ROW_WORDS = 25   # zbot_step_host result row: obs 23 | reward | flags word
 STATE_WORDS = 80
@@ -43,6 +44,15 @@ SNAKE_TERM_IDS = {
 }
 
 
+#: zbot-6b-walking-v4: its own name -> id table (…env_v4.py:1013-1199)
+V4_TERM_IDS = {
+    "track_lin_vel_x": 20, "track_heading_yaw": 21, "lin_vel_y": 22, "action_rate": 7, "torques": 8, "joint_vel": 23,
+    "joint_acc": 24, "feet_downward": 1, "feet_forward": 2, "step_length": 25, "feet_air_time_biped": 26,
+    "airtime_variance": 27, "feet_slide": 9, "feet_harmony": 28, "feet_close": 29, "lin_vel_x": 30, "airtime_sum": 31,
+    "feet_height": 32, "base_height": 33,
+}
+
+
 class ZbotCfg(C.Structure):
     _fields_ = [
         ("abi_version", C.c_int32), ("task", C.c_int32), ("num_envs", C.c_int32), ("decimation", C.c_int32),
@@ -53,6 +63,10 @@ class ZbotCfg(C.Structure):
         ("contact_beta_max", C.c_float), ("contact_mu", C.c_float), ("contact_ramp", C.c_float),
         ("contact_vt_eps", C.c_float), ("contact_margin", C.c_float),
         ("num_terms", C.c_int32), ("term_id", C.c_int32 * MAX_TERMS), ("term_weight", C.c_float * MAX_TERMS),
+        ("ev_vel_lo", C.c_float), ("ev_vel_hi", C.c_float), ("ev_yaw_lo", C.c_float), ("ev_yaw_hi", C.c_float),
+        ("ev_offset", C.c_float), ("ev_prob_pos", C.c_float), ("ev_dual_sign", C.c_int32),
+        ("ev_pose_lo", C.c_float * 3), ("ev_pose_hi", C.c_float * 3),
+        ("ev_interval_lo", C.c_float), ("ev_interval_hi", C.c_float), ("rng_seed", C.c_uint64),
     ]
 
 
@@ -82,12 +96,12 @@ def make_cfg(num_envs: int, reward_scales: dict | None = None, step_dt: float | 
     cfg.task = int(task)
     cfg.num_envs = int(num_envs)
     cfg.decimation = Z.DECIMATION
-    cfg.max_episode_length = 1000 if task == TASK_WALKING_V2 else 800
+    cfg.max_episode_length = 800 if task == TASK_SNAKE_V0 else 1000
     cfg.sim_dt = Z.SIM_DT
-    cfg.termination_height = 0.22
+    cfg.termination_height = 0.20 if task == TASK_WALKING_V4 else 0.22       # …env_v4.py:520 / …env_v2.py:44
     cfg.y_err_limit = 0.5
     cfg.terminated_penalty = 20.0
-    cfg.contact_died_force = 1.0
+    cfg.contact_died_force = 0.5 if task == TASK_WALKING_V4 else 1.0          # …env_v4.py:880 / …env_v2.py:400
     cfg.kp, cfg.kd, cfg.effort_limit = Z.KP, Z.KD, Z.EFFORT_LIMIT
     if task == TASK_SNAKE_V0:
         from .assets import zbot_d_6s as S
@@ -97,14 +111,26 @@ def make_cfg(num_envs: int, reward_scales: dict | None = None, step_dt: float | 
     cfg.contact_beta_max, cfg.contact_mu = Z.CONTACT_BETA_MAX, Z.CONTACT_MU
     cfg.contact_ramp, cfg.contact_vt_eps = Z.CONTACT_RAMP, Z.CONTACT_VT_EPS
     cfg.contact_margin = Z.CONTACT_MARGIN
+    if task == TASK_WALKING_V4:
+        # EventCfg (…env_v4.py:331-418): reset_base pose ranges, reset / interval command resampling
+        cfg.ev_vel_lo, cfg.ev_vel_hi, cfg.ev_yaw_lo, cfg.ev_yaw_hi = 0.3, 0.3, -0.1, 0.1
+        cfg.ev_offset, cfg.ev_prob_pos, cfg.ev_dual_sign = 0.0, 1.0, 1
+        cfg.ev_pose_lo[:] = (-0.5, -0.5, -3.14)
+        cfg.ev_pose_hi[:] = (0.5, 0.5, 3.14)
+        cfg.ev_interval_lo, cfg.ev_interval_hi = 3.0, 6.0
     for k, v in overrides.items():
         if not hasattr(cfg, k):
             raise AttributeError(f"ZbotCfg has no field {k!r}")
-        setattr(cfg, k, v)
-    term_ids = TERM_IDS if task == TASK_WALKING_V2 else SNAKE_TERM_IDS
+        if isinstance(v, (tuple, list)):
+            getattr(cfg, k)[:] = v
+        else:
+            setattr(cfg, k, v)
+    term_ids = {TASK_WALKING_V2: TERM_IDS, TASK_SNAKE_V0: SNAKE_TERM_IDS, TASK_WALKING_V4: V4_TERM_IDS}[task]
     if reward_scales is None:
         if task == TASK_WALKING_V2:
             from .tasks.zbot6b_direct.walking_v2_cfg import REWARD_SCALES_V2 as reward_scales
+        elif task == TASK_WALKING_V4:
+            from .tasks.zbot6b_direct.walking_v4_cfg import REWARD_SCALES_V4 as reward_scales
         else:
             from .tasks.zbot6_direct.snake_v0_cfg import REWARD_SCALES_SNAKE_V0 as reward_scales
     if step_dt is None:
@@ -116,7 +142,8 @@ def make_cfg(num_envs: int, reward_scales: dict | None = None, step_dt: float | 
         if name not in term_ids:
             raise KeyError(f"unknown reward term {name!r}; known: {sorted(term_ids)}")
         cfg.term_id[i] = term_ids[name]
-        cfg.term_weight[i] = float(w) * float(step_dt)
+        # v4 multiplies by step_dt at evaluation time (…env_v4.py:857): the kernel gets the bare weight
+        cfg.term_weight[i] = float(w) if task == TASK_WALKING_V4 else float(w) * float(step_dt)
     return cfg
 
 
@@ -139,6 +166,9 @@ def _declare(lib):
     lib.zbot_step_export.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, P(ZbotExport), vp]
     lib.zbot_snake_step_export.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, vp, vp]
     lib.zbot_step_host.argtypes = [vp, vp, vp, i32, i32, vp]
+    lib.zbot_v4_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, vp]
+    lib.zbot_v4_step_export.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp]
+    lib.zbot_update_cfg.argtypes = [vp, P(ZbotCfg)]
     lib.zbot_reset_idx.argtypes = [vp, vp, i64, vp, vp, i32, vp]
     lib.zbot_observe.argtypes = [vp, vp, vp]
     lib.zbot_articulation_view.argtypes = [vp, vp, vp, vp, vp]
@@ -148,7 +178,8 @@ def _declare(lib):
     lib.zbot_launch_count.argtypes = [vp]
     lib.zbot_launch_count.restype = i64
     for name in ("zbot_default_cfg", "zbot_state_word", "zbot_mdp_state_word", "zbot_create", "zbot_destroy",
-                 "zbot_bind", "zbot_step", "zbot_step_export", "zbot_snake_step_export", "zbot_step_host", "zbot_reset_idx",
+                 "zbot_bind", "zbot_step", "zbot_step_export", "zbot_snake_step_export", "zbot_step_host", "zbot_v4_step",
+                 "zbot_v4_step_export", "zbot_update_cfg", "zbot_reset_idx",
                  "zbot_observe",
                  "zbot_articulation_view", "zbot_mdp_bind", "zbot_mdp_observe", "zbot_mdp_step"):
         getattr(lib, name).restype = C.c_int
@@ -157,7 +188,7 @@ def _declare(lib):
 EXPORTED_SYMBOLS = (
     "zbot_abi_version", "zbot_build_info", "zbot_last_error", "zbot_default_cfg", "zbot_state_word",
     "zbot_mdp_state_word", "zbot_create", "zbot_destroy", "zbot_bind", "zbot_step", "zbot_step_export",
-    "zbot_snake_step_export", "zbot_step_host", "zbot_reset_idx", "zbot_observe", "zbot_articulation_view", "zbot_mdp_bind", "zbot_mdp_observe",
+    "zbot_snake_step_export", "zbot_step_host", "zbot_v4_step", "zbot_v4_step_export", "zbot_update_cfg", "zbot_reset_idx", "zbot_observe", "zbot_articulation_view", "zbot_mdp_bind", "zbot_mdp_observe",
     "zbot_mdp_step", "zbot_launch_count",
 )
 

@@ -105,13 +105,15 @@ class NativeStepper:
         self.stats_ring = torch.zeros(STATS_SLOTS, native.STATS_WORDS, dtype=torch.float32, device=self.device)
         native.check(self.lib.zbot_bind(self._h, _ptr(self.state.buf), _ptr(self.episode_length_buf),
                                         _ptr(self.stats_ring), STATS_SLOTS), "zbot_bind")
-        self.obs = torch.zeros(self.n, native.NUM_OBS, dtype=torch.float32, device=self.device)
+        self.v4 = (self.cfg.task == native.TASK_WALKING_V4)
+        self.num_obs = native.V4_NUM_OBS if self.v4 else native.NUM_OBS
+        self.obs = torch.zeros(self.n, self.num_obs, dtype=torch.float32, device=self.device)
         self.rew = torch.zeros(self.n, dtype=torch.float32, device=self.device)
         self.terminated = torch.zeros(self.n, dtype=torch.uint8, device=self.device)
         self.truncated = torch.zeros(self.n, dtype=torch.uint8, device=self.device)
         self._slot = -1
         # walking: joint_speed_limit = 1 (…env_v2.py:243); snake: per-env, set by the task class (snake_v0.py:121)
-        self.state.set("joint_speed_limit", 1.0 if self.cfg.task == native.TASK_WALKING_V2 else 3.14159265)
+        self.state.set("joint_speed_limit", 3.14159265 if self.cfg.task == native.TASK_SNAKE_V0 else 1.0)
         self.mdp_state = None
         self._host_ok: set = set()
 
@@ -145,13 +147,28 @@ class NativeStepper:
         return self.stats_ring[max(self._slot, 0)]
 
     # ------------------------------------------------------------------ fused step
-    def step(self, actions: torch.Tensor, export: dict | None = None):
+    def step(self, actions: torch.Tensor, export=None, rand: torch.Tensor | None = None):
         """One control step, in place.  ``actions`` (N,6) float32 contiguous on the device."""
         if actions.dtype != torch.float32 or not actions.is_contiguous() or actions.device != self.obs.device:
             actions = actions.to(device=self.device, dtype=torch.float32).contiguous()
         if actions.shape != (self.n, 6):
             raise ValueError(f"actions must be ({self.n}, 6), got {tuple(actions.shape)}")
         slot, prev = self._next_slot()
+        if self.v4:
+            # zbot-6b-walking-v4: `rand` = (N,10) uniforms for this step or None (in-kernel generator);
+            # `export` = one (N, 69) float32 tensor (V4Export)
+            if rand is not None and (rand.dtype != torch.float32 or tuple(rand.shape) != (self.n, native.V4_NUM_RAND)
+                                     or not rand.is_contiguous() or rand.device != self.obs.device):
+                raise ValueError(f"rand must be a contiguous float32 ({self.n}, {native.V4_NUM_RAND}) tensor on the device")
+            if export is None:
+                rc = self.lib.zbot_v4_step(self._h, _ptr(actions), _ptr(rand), _ptr(self.obs), _ptr(self.rew),
+                                           _ptr(self.terminated), _ptr(self.truncated), slot, prev, _stream(self.device))
+            else:
+                rc = self.lib.zbot_v4_step_export(self._h, _ptr(actions), _ptr(rand), _ptr(self.obs), _ptr(self.rew),
+                                                  _ptr(self.terminated), _ptr(self.truncated), slot, prev, _ptr(export),
+                                                  _stream(self.device))
+            native.check(rc, "zbot_v4_step")
+            return self.obs, self.rew, self.terminated, self.truncated
         if export is not None and self.cfg.task == native.TASK_SNAKE_V0:
             # snake task: `export` is one (N, 41) float32 tensor (include/zbot_b200.h: zbot_snake_step_export)
             rc = self.lib.zbot_snake_step_export(self._h, _ptr(actions), _ptr(self.obs), _ptr(self.rew),
@@ -200,7 +217,58 @@ class NativeStepper:
             "net_forces_w_history1": z(n, 5, 12, 3), "last_air_time1": z(n, 12), "current_contact_time1": z(n, 12),
         }
 
+    def update_cfg(self):
+        """Push the (mutated) ``self.cfg`` reward weights / event parameters to the live handle (host curricula)."""
+        native.check(self.lib.zbot_update_cfg(self._h, C.byref(self.cfg)), "zbot_update_cfg")
+
+    def reset_idx_v4(self, env_ids: torch.Tensor | None = None, rand: torch.Tensor | None = None):
+        """``_reset_idx`` of the v4 task for an explicit id list (construction / ``env.reset()``; NOT the per-step
+        partial reset, which the step kernel does itself): reset_base pose randomisation, command resampling and
+        the local state resets of …env_v4.py:59-136, 888-976, written into the kernel's state words."""
+        from .assets import zbot_6s as Z
+        dev, c = self.device, self.cfg
+        ids = torch.arange(self.n, device=dev) if env_ids is None else env_ids.to(device=dev, dtype=torch.int64)
+        k = ids.numel()
+        if k == 0:
+            return
+        u = torch.rand(k, 6, device=dev) if rand is None else rand.to(dev)
+        lo = torch.tensor(list(c.ev_pose_lo), device=dev)
+        hi = torch.tensor(list(c.ev_pose_hi), device=dev)
+        smp = u[:, :3] * (hi - lo) + lo
+        pos = torch.tensor(Z.DEFAULT_ROOT_POS, dtype=torch.float32, device=dev).repeat(k, 1)
+        pos[:, :2] += smp[:, :2]
+        yaw = smp[:, 2]
+        quat = torch.stack([torch.cos(yaw * 0.5), torch.zeros_like(yaw), torch.zeros_like(yaw), torch.sin(yaw * 0.5)], -1)
+        z = lambda w: torch.zeros(k, w, device=dev)
+        st = self.state
+        st.set("root_pos", pos, ids)
+        st.set("root_quat", quat, ids)
+        for name, w in (("root_lin_vel", 3), ("root_ang_vel", 3), ("joint_vel", 6), ("p_delta", 6), ("actions", 6),
+                        ("current_air_time", 2), ("current_contact_time", 2), ("last_air_time", 2), ("last_contact_time", 2),
+                        ("feet_step_length", 2), ("feet_force_sum", 1), ("episode_sums", 16)):
+            st.set(name, z(w), ids)
+        st.set("joint_pos", torch.tensor(Z.DEFAULT_JOINT_POS, dtype=torch.float32, device=dev).repeat(k, 1), ids)
+        st.set("feet_contact_forces_last", torch.full((k, 2), 15.0, device=dev), ids)
+        # resample_commands (mode "reset")
+        if c.ev_dual_sign:
+            sign = (u[:, 3] < c.ev_prob_pos).float() * 2.0 - 1.0
+            high = c.ev_vel_hi + c.ev_offset * (sign - 1.0)
+            cmd0 = (u[:, 4] * (high - c.ev_vel_lo) + c.ev_vel_lo) * sign
+        else:
+            cmd0 = u[:, 4] * (c.ev_vel_hi - c.ev_vel_lo) + c.ev_vel_lo
+        cmd1 = u[:, 5] * (c.ev_yaw_hi - c.ev_yaw_lo) + c.ev_yaw_lo
+        wrapped = torch.remainder(yaw + cmd1 + torch.pi, 2 * torch.pi)
+        target = torch.where((wrapped == 0) & (yaw + cmd1 > 0), torch.full_like(wrapped, torch.pi), wrapped - torch.pi)
+        st.set("carry_feet_fz", torch.stack([cmd0, cmd1], -1), ids)       # commands
+        st.set("carry_mid_max", target.unsqueeze(-1), ids)                # target_heading_yaw
+        st.set("base_heading_x_sum", yaw.unsqueeze(-1), ids)              # current_yaw
+        self.episode_length_buf[ids] = 0
+        posl, _, _ = self.articulation_view()                             # post-reset feet link positions (env-local)
+        st.set("feet_down_pos_last", posl[ids][:, [0, 11]].reshape(k, 6), ids)
+
     def reset_idx(self, env_ids: torch.Tensor | None = None, terminated=None, truncated=None):
+        if self.v4:
+            return self.reset_idx_v4(env_ids)
         slot, _ = self._next_slot()
         if env_ids is None:
             rc = self.lib.zbot_reset_idx(self._h, None, -1, _ptr(terminated), _ptr(truncated), slot,
@@ -214,6 +282,18 @@ class NativeStepper:
         native.check(rc, "zbot_reset_idx")
 
     def observe(self) -> torch.Tensor:
+        if self.v4:
+            # `_get_observations` of the v4 task (…env_v4.py:828-851) from the state words -- reset / query path only
+            # (the step kernel writes its own observation)
+            from .assets import zbot_6s as Z
+            _, quat, _ = self.articulation_view()
+            g = self.state.get
+            diff = g("carry_mid_max")[:, 0] - g("base_heading_x_sum")[:, 0]
+            heading_err = torch.atan2(torch.sin(diff), torch.cos(diff))
+            q0 = torch.tensor(Z.DEFAULT_JOINT_POS, dtype=torch.float32, device=self.device)
+            self.obs.copy_(torch.cat([quat[:, 6], g("joint_pos") - q0, g("joint_vel"), g("actions"),
+                                      g("carry_feet_fz")[:, 0:1], heading_err.unsqueeze(-1)], dim=-1))
+            return self.obs
         native.check(self.lib.zbot_observe(self._h, _ptr(self.obs), _stream(self.device)), "zbot_observe")
         return self.obs
 

@@ -126,16 +126,18 @@ class ZbotDirectEnvV2:
         n, dev = self.num_envs, self.device
         # one packed buffer per ring slot: [obs N*23 f32 | rew N f32 | terminated N u8 | truncated N u8] so a
         # host consumer can fetch a whole step result with ONE device->host copy (``last_step_packed``)
-        self._packed = [torch.zeros(n * 24 * 4 + 2 * n, dtype=torch.uint8, device=dev) for _ in range(ring)]
-        self._out = [(b[:n * 92].view(torch.float32).view(n, 23), b[n * 92:n * 96].view(torch.float32),
-                      b[n * 96:n * 97], b[n * 97:n * 98]) for b in self._packed]
+        no = self._num_obs = int(self.cfg.observation_space)
+        self._packed = [torch.zeros(n * (no + 1) * 4 + 2 * n, dtype=torch.uint8, device=dev) for _ in range(ring)]
+        self._out = [(b[:n * no * 4].view(torch.float32).view(n, no), b[n * no * 4:n * (no + 1) * 4].view(torch.float32),
+                      b[n * (no + 1) * 4:n * (no + 1) * 4 + n], b[n * (no + 1) * 4 + n:n * (no + 1) * 4 + 2 * n])
+                     for b in self._packed]
         self._out_i = 0
         self.reset_terminated = torch.zeros(n, dtype=torch.bool, device=dev)
         self.reset_time_outs = torch.zeros(n, dtype=torch.bool, device=dev)
         self.reset_buf = torch.zeros(n, dtype=torch.bool, device=dev)
         chk = self.cfg.check_all_envs_reset
         self._check_all_reset = (self.num_envs <= 256) if chk is None else bool(chk)
-        self._stepper.reset_idx(None)
+        self._initial_reset()
         self._sim_step_counter = 0
 
     # ------------------------------------------------------------------ task hooks (overridden by the snake task)
@@ -153,6 +155,9 @@ class ZbotDirectEnvV2:
             gravity=-float(self.cfg.sim.gravity[2]),
             contact_alpha=c.alpha, contact_erp=c.erp, contact_vdep=c.max_depenetration_velocity,
             contact_beta_max=c.beta_max, contact_mu=c.friction, contact_ramp=c.ramp, contact_margin=c.margin, **extra)
+
+    def _initial_reset(self):
+        self._stepper.reset_idx(None)
 
     def _setup_scene(self):
         self._robot = _Robot(self)
@@ -291,9 +296,10 @@ class ZbotDirectEnvV2:
 
     def unpack_host(self, host_bytes: torch.Tensor):
         """Views (obs, rew, terminated, truncated) into a host copy of ``last_step_packed``."""
-        n = self.num_envs
-        return (host_bytes[:n * 92].view(torch.float32).view(n, 23), host_bytes[n * 92:n * 96].view(torch.float32),
-                host_bytes[n * 96:n * 97].view(torch.bool), host_bytes[n * 97:n * 98].view(torch.bool))
+        n, no = self.num_envs, self._num_obs
+        o1 = n * no * 4
+        return (host_bytes[:o1].view(torch.float32).view(n, no), host_bytes[o1:o1 + 4 * n].view(torch.float32),
+                host_bytes[o1 + 4 * n:o1 + 5 * n].view(torch.bool), host_bytes[o1 + 5 * n:o1 + 6 * n].view(torch.bool))
 
     def close(self):
         if getattr(self, "_stepper", None) is not None:

@@ -165,3 +165,50 @@ def synth_snake_case(seed: int, n: int, steps: int) -> dict:
     for _ in range(steps):
         case["steps"].append((rng.normal(0, 1, (n, 6)).astype(F), synth_snake_state(rng, n, origins)))
     return case
+
+
+# ------------------------------------------------------------------------------------------------ walking v4
+def synth_v4_state(rng: np.random.Generator, n: int, origins: np.ndarray, die_frac: float = 0.06) -> dict:
+    """Synthetic end-of-physics state in the tensor layouts ``Zbot6SEnvV4`` reads (3-deep force history, all four
+    contact timers, link AND CoM velocities, joint accelerations)."""
+    S = synth_articulation_state(rng, n, origins, die_frac=0.0)
+    ids = index_sets()
+    base = ids["base_body_idx"][0]
+    low = rng.random(n) < die_frac * 0.5
+    S["body_link_pos_w"][low, base, 2] = F(0.19) - rng.random(int(low.sum())).astype(F) * F(0.05)
+    # feet close together for some envs (feet_close term)
+    close = rng.random(n) < 0.3
+    f0, f1 = ids["feet_body_idx"]
+    S["body_link_pos_w"][close, f1, :2] = S["body_link_pos_w"][close, f0, :2] + rng.normal(0, 0.05, (int(close.sum()), 2)).astype(F)
+    hist = S.pop("net_forces_w_history")[:, :3].copy()
+    hist[:, :, ids["undesired_ids"], :] *= F(0.5)
+    hit = rng.random(n) < die_frac * 0.5
+    which = rng.integers(0, len(ids["undesired_ids"]), n)
+    for e in np.nonzero(hit)[0]:
+        hist[e, rng.integers(0, 3), ids["undesired_ids"][which[e]], :] = np.array([0.3, -0.3, 0.4], F)
+    S["net_forces_w_history"] = hist
+    S["body_link_lin_vel_w"] = rng.normal(0.0, 0.3, (n, 12, 3)).astype(F)
+    S["joint_acc"] = rng.normal(0.0, 30.0, (n, 6)).astype(F)
+    S["last_contact_time"] = rng.random((n, 12)).astype(F)
+    S["current_air_time"] = (rng.random((n, 12)) * (rng.random((n, 12)) < 0.5)).astype(F)
+    S["current_contact_time"] = np.where(S["current_air_time"] > 0, F(0), rng.random((n, 12)).astype(F)).astype(F)
+    return S
+
+
+def synth_v4_case(seed: int, n: int, steps: int) -> dict:
+    rng = np.random.default_rng(seed)
+    origins = env_origins_grid(n)
+    ep = rng.integers(0, 1000, n).astype(np.int64)
+    near = rng.random(n) < 0.1
+    ep[near] = 999 - rng.integers(1, max(2, steps), int(near.sum()))
+    time_left = rng.uniform(3.0, 6.0, n).astype(F)
+    soon = rng.random(n) < 0.25
+    time_left[soon] = (rng.integers(1, max(2, steps + 1), int(soon.sum())) * 0.02 - 0.01).astype(F)   # fire within the case
+    case = {"origins": origins, "episode_length_buf0": ep, "interval_time_left0": time_left,
+            "commands0": np.stack([rng.uniform(-0.3, 0.3, n), rng.uniform(-0.1, 0.1, n)], -1).astype(F),
+            "target_heading_yaw0": rng.uniform(-3.0, 3.0, n).astype(F),
+            "S0": synth_v4_state(rng, n, origins, 0.0), "steps": []}
+    for _ in range(steps):
+        case["steps"].append((rng.normal(0, 1, (n, 6)).astype(F), synth_v4_state(rng, n, origins),
+                              rng.random((n, 10)).astype(F)))
+    return case
