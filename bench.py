@@ -53,6 +53,7 @@ def parse():
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-mdp", action="store_true", help="skip the MDP-only kernel side measurement")
     p.add_argument("--no-small", action="store_true", help="skip the additional 4096-env measurement at N=1")
+    p.add_argument("--no-tasks", action="store_true", help="skip the snake / v4 / PPO-rollout side measurements at N=1")
     p.add_argument("--cpu-sample-steps", type=int, default=None)
     return p.parse_args()
 
@@ -325,6 +326,62 @@ def main():
         mdp_only["kernel"] = "zbot_mdp_kernel<true> + zbot_stats_finalize_kernel"
         mdp_only["algorithmic_bytes_per_env_step"] = bench_mdp.MDP_ALGO_BYTES
 
+    other_tasks = None
+    if rank == 0 and world == 1 and args.envs is None and not args.no_tasks:
+        # the other BASELINE.json configs, device-resident, back to back after warm-up (CUDA events around the loop)
+        from zbot_lab_b200 import native
+        from zbot_lab_b200.stepper import NativeStepper
+
+        def time_task(task, n_t, steps_t=100):
+            st_t = NativeStepper(n_t, dev, native.make_cfg(n_t, task=task))
+            if task == native.TASK_WALKING_V4:
+                st_t.reset_idx_v4(None)
+                st_t.state.set("base_pos_y_err_sum", torch.rand(n_t, 1, device=dev) * 3.0 + 3.0)
+            else:
+                st_t.reset_idx(None)
+            gt = torch.Generator(device=dev).manual_seed(7)
+            st_t.episode_length_buf[:] = torch.randint(0, 790, (n_t,), device=dev, generator=gt)
+            if task == native.TASK_SNAKE_V0:
+                st_t.state.set("joint_speed_limit", (torch.rand(n_t, 1, device=dev, generator=gt) * 1.8 + 0.2) * 3.14159265)
+            acts_t = torch.randn(8, n_t, 6, device=dev, generator=gt)
+            for i in range(20):
+                st_t.step(acts_t[i % 8])
+            torch.cuda.synchronize()
+            a_ev, b_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            l0 = st_t.launch_count
+            a_ev.record()
+            for i in range(steps_t):
+                st_t.step(acts_t[i % 8])
+            b_ev.record()
+            torch.cuda.synchronize()
+            ms = a_ev.elapsed_time(b_ev) / steps_t
+            out_t = {"envs": n_t, "ms_per_step": ms, "value": n_t / (ms * 1e-3), "unit": UNIT,
+                     "gpu_launches": int(st_t.launch_count - l0), "l2": "not flushed (back to back)"}
+            st_t.close()
+            return out_t
+
+        other_tasks = {
+            "snake_16384": dict(time_task(native.TASK_SNAKE_V0, 16384),
+                                workload="BASELINE.json configs[3]: zbot-6s-snake-v0 fused step, 16384 envs, "
+                                         "12 ground spheres in contact per env"),
+            "walking_v4_4096": dict(time_task(native.TASK_WALKING_V4, 4096),
+                                    workload="zbot-6b-walking-v4 fused step (commands + event resampling, in-kernel RNG), 4096 envs"),
+            "walking_v4_65536": dict(time_task(native.TASK_WALKING_V4, 65536),
+                                     workload="zbot-6b-walking-v4 fused step, 65536 envs"),
+        }
+        try:   # BASELINE.json configs[4]: PPO rollout 24 steps x 4096 envs, policy MLP + env step + storage, one CUDA graph
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bench_rollout
+            r = bench_rollout.make(4096, str(dev), True)
+            sec = bench_rollout.time_rollouts(r, 30)
+            other_tasks["ppo_rollout_24x4096"] = {
+                "workload": "BASELINE.json configs[4]: rollout of 24 steps x 4096 envs (actor + critic MLP 3x128 ELU, "
+                            "fused env step, storage) replayed as one CUDA graph",
+                "ms_per_rollout": 1e3 * sec, "value": 24 * 4096 / sec, "unit": UNIT}
+            r.env.close()
+        except Exception as exc:   # the side measurement must never break the headline line
+            other_tasks["ppo_rollout_24x4096"] = {"error": repr(exc)}
+
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         kern_ms = main_m["local_ms_per_step"]
@@ -354,6 +411,8 @@ def main():
             line["e2e"] = e2e
         if mdp_only is not None:
             line["mdp_only_kernel"] = mdp_only
+        if other_tasks is not None:
+            line["other_tasks"] = other_tasks
         if world == 1 and not args.no_cpu_baseline:
             cs = args.cpu_sample_steps
             if cs is None:   # bounded sample of the same workload: ~10 s of CPU work

@@ -12,7 +12,7 @@ from zbot_lab_b200.stepper import NativeStepper  # noqa: E402
 from zbot_lab_b200.utils import synthetic as syn  # noqa: E402
 
 
-VARIANTS = ["128x2", "128x3", "128x4", "64x5", "32x10", "32x11", "64x6", "32x12", "32x13", "32x14", "64x7", "32x16"]
+VARIANTS = (os.environ.get("SWEEP_VARIANTS") or "128x2,128x3,128x4,64x5,32x10,32x11,64x6,32x12,32x13,32x14,64x7,32x16").split(",")
 
 
 def time_cfg(n, variant, steps=200, warm=30):

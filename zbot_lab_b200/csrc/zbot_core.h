@@ -20,6 +20,9 @@
 
 #include "zbot_model_constants.h"
 
+#ifndef ZB_PIPELINED_SWEEP
+#define ZB_PIPELINED_SWEEP 1   // software-pipelined backward sweep (physics_substep); 0 = the plain loop
+#endif
 #if defined(__CUDACC__)
 #define ZB_HD __host__ __device__ __forceinline__
 #define ZB_UNROLL _Pragma("unroll")
@@ -635,6 +638,119 @@ ZB_HD void physics_substep(const Params<T>& P, SimState<T>& s, const T* target, 
   ContactAgg<T> agg, agg1;   // running / foot_1 (body 6); after the sweep `agg` holds foot_0 (body 0)
   contact_agg_zero(agg1);
   T mid2 = T(0);
+#if ZB_PIPELINED_SWEEP
+  // Software-pipelined form: the articulated-body elimination of joint k-1 is one long dependent chain
+  // (IA S -> D -> 1/D -> rank-1 update); the kinematics, world inertia and bias force of the NEXT body (k-1) do not
+  // depend on it.  Both are issued in the same basic block, into separate accumulators (IB, pB), so the scheduler
+  // interleaves two instruction streams per thread (DESIGN.md §4 "ILP"); IA += IB afterwards.
+  {
+    T R[9];
+    quat_to_mat(Q, R);
+    T mass, cx, cz, ixx, iyy, izz, ixz;
+    Model::body(6, mass, cx, cz, ixx, iyy, izz, ixz);
+    body_rigid_terms(P, mass, cx, cz, ixx, iyy, izz, ixz, R, r, w, vO, IA, pAt, pAb);
+    contact_agg_zero(agg);
+    const int npts = Model::npts(6);
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
+    for (int j = 0; j < npts; ++j) {
+      T lx, ly, lz, drop;
+      Model::point(6, j, lx, ly, lz, drop);
+      T rho[3] = {r[0] + R[0] * lx + R[1] * ly + R[2] * lz, r[1] + R[3] * lx + R[4] * ly + R[5] * lz,
+                  r[2] + R[6] * lx + R[7] * ly + R[8] * lz - drop};
+      contact_point(P, rho, s.p[2] + rho[2], w, vO, IA, pAt, pAb,
+                    Model::kGroundForceSensor ? &agg : (ContactAgg<T>*)nullptr, (T*)nullptr);
+    }
+    if (Model::kGroundForceSensor) agg1 = agg;
+  }
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
+  for (int k = 6; k >= 1; --k) {
+    const int j = k - 1;          // joint between body k and body k-1
+    const T Sa[3] = {scr(j, SC_SA), scr(j, SC_SA + 1), scr(j, SC_SA + 2)};
+    const T Sm[3] = {scr(j, SC_SM), scr(j, SC_SM + 1), scr(j, SC_SM + 2)};
+    const T qd = scr(j, SC_QD);
+    const T sn = scr(j, SC_SN), cs = scr(j, SC_CS);
+    const T sa[3] = {Sa[0] * qd, Sa[1] * qd, Sa[2] * qd};
+    const T sm[3] = {Sm[0] * qd, Sm[1] * qd, Sm[2] * qd};
+    // ---- stream B: kinematics + rigid terms of body k-1 (independent of IA) ----
+    T wn[3], vn[3], Qn[4], rn[3], Rn[9];
+    {
+      const T sg = (j & 1) ? T(-AXIS_S) : T(AXIS_S);
+      ZB_UNROLL for (int i = 0; i < 4; ++i) Qn[i] = Q[i];
+      quat_mul_joint(Qn, cs, -sg * sn, -T(AXIS_S) * sn);   // Q_{k-1} = Q_k (x) conj(qj)
+      const bool root = (j == 0);                          // root: exact kinematics from the state
+      ZB_UNROLL for (int i = 0; i < 4; ++i) Qn[i] = root ? s.Q[i] : Qn[i];
+      quat_to_mat(Qn, Rn);
+      const T jz = root ? T(JOINT_Z_FIRST) : T(JOINT_Z_REST);
+      ZB_UNROLL for (int i = 0; i < 3; ++i) {
+        rn[i] = root ? T(0) : (r[i] - jz * Rn[3 * i + 2]);
+        wn[i] = root ? s.w[i] : (w[i] - sa[i]);
+        vn[i] = root ? s.v[i] : (vO[i] - sm[i]);
+      }
+    }
+    SpInertia<T> IB;
+    ZB_UNROLL for (int i = 0; i < 6; ++i) { IB.I[i] = T(0); IB.M[i] = T(0); }
+    ZB_UNROLL for (int i = 0; i < 9; ++i) IB.H[i] = T(0);
+    T pBt[3] = {T(0), T(0), T(0)}, pBb[3] = {T(0), T(0), T(0)};
+    {
+      T mass, cx, cz, ixx, iyy, izz, ixz;
+      Model::body(k - 1, mass, cx, cz, ixx, iyy, izz, ixz);
+      body_rigid_terms(P, mass, cx, cz, ixx, iyy, izz, ixz, Rn, rn, wn, vn, IB, pBt, pBb);
+    }
+    // ---- stream A: velocity-product term c = V x (S qd), articulated-body elimination of joint j ----
+    T ct[3], cb[3], tmp[3];
+    cross3(w, sa, ct);
+    cross3(w, sm, cb);
+    cross3(vO, sa, tmp);
+    cb[0] += tmp[0]; cb[1] += tmp[1]; cb[2] += tmp[2];
+    T Ut[3], Ub[3];
+    spi_mul(IA, Sa, Sm, Ut, Ub);
+    const T D = dot3(Sa, Ut) + dot3(Sm, Ub) + P.arm;
+    const T Dinv = zb_rcp(D);
+    const T u = scr(j, SC_U) - (dot3(Sa, pAt) + dot3(Sm, pAb));
+    T Ict[3], Icb[3];
+    spi_mul(IA, ct, cb, Ict, Icb);
+    const T g = (u - (dot3(Ut, ct) + dot3(Ub, cb))) * Dinv;
+    ZB_UNROLL for (int i = 0; i < 3; ++i) {
+      pAt[i] += Ict[i] + Ut[i] * g;
+      pAb[i] += Icb[i] + Ub[i] * g;
+      scr(j, SC_UT + i) = Ut[i];
+      scr(j, SC_UB + i) = Ub[i];
+    }
+    scr(j, SC_DINV) = Dinv;
+    scr(j, SC_U) = u;
+    spi_rank1_sub(IA, Ut, Ub, Dinv);
+    // ---- merge, then the ground contacts of body k-1 ----
+    ZB_UNROLL for (int i = 0; i < 6; ++i) { IA.I[i] += IB.I[i]; IA.M[i] += IB.M[i]; }
+    ZB_UNROLL for (int i = 0; i < 9; ++i) IA.H[i] += IB.H[i];
+    ZB_UNROLL for (int i = 0; i < 3; ++i) { pAt[i] += pBt[i]; pAb[i] += pBb[i]; }
+    ZB_UNROLL for (int i = 0; i < 3; ++i) { r[i] = rn[i]; w[i] = wn[i]; vO[i] = vn[i]; }
+    ZB_UNROLL for (int i = 0; i < 4; ++i) Q[i] = Qn[i];
+    contact_agg_zero(agg);
+    const int npts = Model::npts(k - 1);
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
+    for (int c = 0; c < npts; ++c) {
+      T lx, ly, lz, drop;
+      Model::point(k - 1, c, lx, ly, lz, drop);
+      T rho[3] = {r[0] + Rn[0] * lx + Rn[1] * ly + Rn[2] * lz, r[1] + Rn[3] * lx + Rn[4] * ly + Rn[5] * lz,
+                  r[2] + Rn[6] * lx + Rn[7] * ly + Rn[8] * lz - drop};
+      contact_point(P, rho, s.p[2] + rho[2], w, vO, IA, pAt, pAb,
+                    Model::kGroundForceSensor ? &agg : (ContactAgg<T>*)nullptr, (T*)nullptr);
+    }
+    if (Model::kGroundForceSensor) {
+      if (k - 1 != 0) {
+        mid2 = zb_max(mid2, agg.F0[0] * agg.F0[0] + agg.F0[1] * agg.F0[1] + agg.F0[2] * agg.F0[2]);
+        if (mid_force_out) { mid_force_out[3 * (k - 2)] = agg.F0[0]; mid_force_out[3 * (k - 2) + 1] = agg.F0[1];
+                             mid_force_out[3 * (k - 2) + 2] = agg.F0[2]; }
+      }
+    }
+  }
+#else
 #if defined(__CUDACC__)
 #pragma unroll 1
 #endif
@@ -713,6 +829,7 @@ ZB_HD void physics_substep(const Params<T>& P, SimState<T>& s, const T* target, 
                 T(1) - T(2) * (Q[1] * Q[1] + Q[2] * Q[2])};     // third column of R_{k-1}
     r[0] -= jz * Rp2[0]; r[1] -= jz * Rp2[1]; r[2] -= jz * Rp2[2];
   }
+#endif   // ZB_PIPELINED_SWEEP
   // ---- floating base:  IA a0 = -pA ----
   T At[3], Ab[3];
   {
