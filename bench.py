@@ -31,8 +31,8 @@ UNIT = "env-steps/s"
 # written (2 x 320), actions 24 read, obs 92 + reward 4 + flags 2 written, episode counter 8 + 8
 ALGO_BYTES_PER_ENV_STEP = 320 + 24 + 8 + 320 + 92 + 4 + 2 + 8
 # dram__bytes_read.sum + dram__bytes_write.sum of one zbot_step_kernel launch at 65536 envs (ncu --set full,
-# profiles/r1_step_ncu.md) per env: reads hit DRAM, most writes are still in the 126 MB L2 when the kernel ends
-NCU_TRAFFIC_BYTES_PER_ENV_STEP = 379
+# profiles/r1_ncu_raw_tables_session2.md: 23.14 MB read + 0 written) per env: reads hit DRAM, most writes are still in the 126 MB L2 when the kernel ends
+NCU_TRAFFIC_BYTES_PER_ENV_STEP = 353
 # Envs per GPU of the headline `value` at EVERY N (weak scaling: identical per-GPU work at N = 1, 2, 4, 8 so the
 # driver's scaling efficiency is meaningful).  65536 envs/GPU is the configuration BASELINE.json states the
 # multi-GPU target on (configs[2]); the 4096-env configuration (configs[1]) is measured in the same run at N = 1
@@ -397,7 +397,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": NCU_TRAFFIC_BYTES_PER_ENV_STEP * n_envs, "peak_source": peak_src,
                          "kernel": "zbot_step_kernel<false,128,2>",
-                         "traffic_note": "dram__bytes_read+write per launch from profiles/r1_step_ncu.md, scaled per env",
+                         "traffic_note": "dram__bytes_read+write per launch at 65536 envs (profiles/r1_ncu_raw_tables_session2.md), scaled per env",
                          "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP,
                          "note": "the fused step is FP32-issue bound, not HBM bound (DESIGN.md §4)"},
             "gpu_launches": int(launches), "clocks": main_m["clocks"],
