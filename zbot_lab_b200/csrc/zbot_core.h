@@ -20,15 +20,26 @@
 
 #include "zbot_model_constants.h"
 
+#ifndef ZB_LINKKIN_NOINLINE
+#define ZB_LINKKIN_NOINLINE 0   // 1 = link_kinematics as a real device function (smaller SASS).  Measured slower: the
+#endif                          // by-reference structs go through a 680 B stack frame; 34.9 -> 37.0 us @4096, 86.4 -> 93.8 @65536
 #ifndef ZB_PIPELINED_SWEEP
 #define ZB_PIPELINED_SWEEP 1   // software-pipelined backward sweep (physics_substep); 0 = the plain loop
 #endif
 #if defined(__CUDACC__)
+#define ZB_HD_NOINLINE __host__ __device__ __noinline__
 #define ZB_HD __host__ __device__ __forceinline__
 #define ZB_UNROLL _Pragma("unroll")
 #else
+#define ZB_HD_NOINLINE inline
 #define ZB_HD inline __attribute__((always_inline))
 #define ZB_UNROLL
+#endif
+
+#if ZB_LINKKIN_NOINLINE
+#define ZB_LINKKIN_ATTR ZB_HD_NOINLINE
+#else
+#define ZB_LINKKIN_ATTR ZB_HD
 #endif
 
 namespace zbot {
@@ -896,7 +907,7 @@ struct LinkKin {
 };
 
 template <typename T>
-ZB_HD void link_kinematics(const SimState<T>& s, LinkKin<T>& o) {
+ZB_LINKKIN_ATTR void link_kinematics(const SimState<T>& s, LinkKin<T>& o) {
   using namespace model;
   T Q[4] = {s.Q[0], s.Q[1], s.Q[2], s.Q[3]};
   T r[3] = {T(0), T(0), T(0)};
