@@ -758,3 +758,107 @@ def test_v4_kernel_equals_host_build_and_internal_rng_properties():
         s2.close()
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
     assert not torch.equal(outs[0][0], outs[2][0])
+
+
+def test_abi_error_paths_of_the_task_entry_points():
+    """Wrong-task calls, unbound handles, non-pinned host buffers and bad cfg updates return error codes with a
+    message (never a crash, never a silent fallback)."""
+    import ctypes as C
+    from zbot_lab_b200 import native
+    lib = native.lib()
+    vp = C.c_void_p
+    n = 64
+    buf = torch.zeros(n * 128, device=DEV)
+    p = vp(buf.data_ptr())
+    hs = {}
+    for task in (native.TASK_WALKING_V2, native.TASK_SNAKE_V0, native.TASK_WALKING_V4):
+        h = vp()
+        cfg = native.make_cfg(n, task=task)
+        native.check(lib.zbot_create(C.byref(cfg), 0, C.byref(h)))
+        hs[task] = (h, cfg)
+    h2, h1, h4 = hs[native.TASK_WALKING_V2][0], hs[native.TASK_SNAKE_V0][0], hs[native.TASK_WALKING_V4][0]
+    assert lib.zbot_v4_step(h4, p, None, p, p, p, p, 0, -1, None) == -3 and b"zbot_bind" in lib.zbot_last_error()
+    st, ep, ring = torch.zeros(20, n, 4, device=DEV), torch.zeros(n, dtype=torch.int64, device=DEV), torch.zeros(4, 32, device=DEV)
+    for h in (h2, h1, h4):
+        native.check(lib.zbot_bind(h, vp(st.data_ptr()), vp(ep.data_ptr()), vp(ring.data_ptr()), 4))
+    assert lib.zbot_v4_step(h2, p, None, p, p, p, p, 0, -1, None) == -1 and b"WALKING_V4" in lib.zbot_last_error()
+    assert lib.zbot_step(h4, p, p, p, p, p, 0, -1, None) == -1 and b"zbot_v4_step" in lib.zbot_last_error()
+    assert lib.zbot_snake_step_export(h2, p, p, p, p, p, 0, -1, p, None) == -1
+    assert lib.zbot_step_export(h1, p, p, p, p, p, 0, -1, C.byref(native.ZbotExport()), None) == -1
+    assert lib.zbot_step_host(h1, p, p, 0, -1, None) == -1
+    pageable = torch.zeros(n, 25)                               # not pinned: must be refused, not dereferenced
+    assert lib.zbot_step_host(h2, vp(pageable.data_ptr()), vp(pageable.data_ptr()), 0, -1, None) == -1
+    assert b"pinned" in lib.zbot_last_error()
+    assert lib.zbot_v4_step(h4, p, vp(buf.data_ptr() + 4), p, p, p, p, 0, -1, None) == -1      # misaligned rand
+    assert lib.zbot_step(h2, p, p, p, p, p, 7, -1, None) == -1 and b"slot" in lib.zbot_last_error()
+    bad = native.make_cfg(n + 1, task=native.TASK_WALKING_V4)
+    assert lib.zbot_update_cfg(h4, C.byref(bad)) == -1
+    bad = native.make_cfg(n, task=native.TASK_WALKING_V2)
+    assert lib.zbot_update_cfg(h4, C.byref(bad)) == -1
+    ok = native.make_cfg(n, task=native.TASK_WALKING_V4, ev_prob_pos=0.25)
+    assert lib.zbot_update_cfg(h4, C.byref(ok)) == 0
+    assert lib.zbot_reset_idx(h4, None, -1, None, None, 0, None) == -1
+    for h, _ in hs.values():
+        assert lib.zbot_destroy(h) == 0
+
+
+def test_no_out_of_bounds_writes_snake_v4_and_host_rows():
+    """Guard bands around every buffer the snake, v4 and host-row kernels write (ragged N, tail blocks)."""
+    import ctypes as C
+    from zbot_lab_b200 import native
+    lib = native.lib()
+    vp = C.c_void_p
+    for n in (1000, 129, 31):
+        for task in (native.TASK_SNAKE_V0, native.TASK_WALKING_V4, native.TASK_WALKING_V2):
+            nobs = 24 if task == native.TASK_WALKING_V4 else 23
+            cfg = native.make_cfg(n, task=task)
+            h = vp()
+            native.check(lib.zbot_create(C.byref(cfg), 0, C.byref(h)))
+            sizes = {"state": 80 * n * 4, "ep": 8 * n, "ring": 4 * 32 * 4, "obs": 4 * nobs * n, "rew": 4 * n, "term": n,
+                     "trunc": n, "act": 24 * n, "rand": 40 * n, "ex": 4 * 69 * n}
+            gap = 1024
+            total = sum((s + 255) // 256 * 256 + gap for s in sizes.values()) + gap
+            arena = torch.full((total,), 0xA5, dtype=torch.uint8, device=DEV)
+            off, views = gap, {}
+            for k, sz in sizes.items():
+                views[k] = arena[off:off + sz]
+                views[k].zero_()
+                off += (sz + 255) // 256 * 256 + gap
+            mask = torch.ones(total, dtype=torch.bool, device=DEV)
+            for v in views.values():
+                o = v.data_ptr() - arena.data_ptr()
+                mask[o:o + v.numel()] = False
+            p = lambda k: vp(views[k].data_ptr())
+            native.check(lib.zbot_bind(h, p("state"), p("ep"), p("ring"), 4))
+            # a valid start state: default pose written through the state words
+            stv = views["state"].view(torch.float32).view(20, n, 4)
+            w = lib.zbot_state_word(b"root_quat")
+            stv[w // 4, :, w % 4] = 1.0
+            w = lib.zbot_state_word(b"root_pos") + 2
+            stv[w // 4, :, w % 4] = 0.05
+            w = lib.zbot_state_word(b"joint_speed_limit")
+            stv[w // 4, :, w % 4] = 1.0
+            views["act"].view(torch.float32).normal_()
+            views["rand"].view(torch.float32).uniform_()
+            views["ep"].view(torch.int64)[:] = 990
+            for t in range(12):
+                if task == native.TASK_WALKING_V4:
+                    native.check(lib.zbot_v4_step_export(h, p("act"), p("rand") if t % 2 else None, p("obs"), p("rew"), p("term"),
+                                                         p("trunc"), (t + 1) % 4, t % 4, p("ex"), None))
+                elif task == native.TASK_SNAKE_V0:
+                    native.check(lib.zbot_snake_step_export(h, p("act"), p("obs"), p("rew"), p("term"), p("trunc"),
+                                                            (t + 1) % 4, t % 4, p("ex"), None))
+                else:
+                    native.check(lib.zbot_step(h, p("act"), p("obs"), p("rew"), p("term"), p("trunc"), (t + 1) % 4, t % 4, None))
+            torch.cuda.synchronize()
+            if task == native.TASK_WALKING_V2:        # host rows: canaries around the pinned result as well
+                h_act = torch.randn(n, 6).pin_memory()
+                h_big = torch.full((n * 25 + 64,), -7.0).pin_memory()
+                rows = h_big[32:32 + n * 25].view(n, 25)
+                native.check(lib.zbot_step_host(h, vp(h_act.data_ptr()), vp(rows.data_ptr()), 1, 0, None))
+                assert torch.all(h_big[:32] == -7.0) and torch.all(h_big[32 + n * 25:] == -7.0)
+                assert torch.isfinite(rows[:, :24]).all()
+            assert torch.all(arena[mask] == 0xA5), f"canary overwritten (n={n}, task={task})"
+            assert torch.isfinite(views["obs"].view(torch.float32)).all()
+            assert torch.isfinite(views["state"].view(torch.float32)).all()
+            lib.zbot_destroy(h)
