@@ -15,6 +15,7 @@
 #include <string.h>
 
 #include "../zbot_lab_b200/csrc/zbot_layout.h"
+#include "../zbot_lab_b200/csrc/zbot_pair.h"
 
 using namespace zbot;
 
@@ -161,6 +162,44 @@ static int port_substeps(const ZbotCfg* cfg, T* sim, const T* target, T* forces,
   return ZBOT_OK;
 }
 
+// the same substeps with TWO envs per call chain (T = F2, the packed GPU kernel's instantiation): envs (2i, 2i+1)
+static int port_substeps_pair(const ZbotCfg* cfg, float* sim, const float* target, float* forces, float* tau, int n, int nsub,
+                              bool snake) {
+  Params<float> P;
+  params_from_cfg(*cfg, P);
+  if (n & 1) return ZBOT_E_INVALID;
+#pragma omp parallel for schedule(static) num_threads(port_threads())
+  for (int e = 0; e < n; e += 2) {
+    SimState<F2> s;
+    float *w0 = sim + (size_t)e * 25, *w1 = w0 + 25;
+    for (int i = 0; i < 3; ++i) { s.p[i] = F2(w0[i], w1[i]); s.v[i] = F2(w0[7 + i], w1[7 + i]); s.w[i] = F2(w0[10 + i], w1[10 + i]); }
+    for (int i = 0; i < 4; ++i) s.Q[i] = F2(w0[3 + i], w1[3 + i]);
+    for (int i = 0; i < 6; ++i) { s.q[i] = F2(w0[13 + i], w1[13 + i]); s.qd[i] = F2(w0[19 + i], w1[19 + i]); }
+    F2 tgt[6];
+    for (int i = 0; i < 6; ++i) tgt[i] = F2(target[(size_t)e * 6 + i], target[(size_t)(e + 1) * 6 + i]);
+    SubstepOut<F2> so;
+    ArrayScratch<F2> scr;
+    F2 midf[15];
+    for (int k = 0; k < nsub; ++k) {
+      if (snake) physics_substep<ModelSnake>(P, s, tgt, so, scr, midf);
+      else physics_substep<ModelWalk>(P, s, tgt, so, scr, midf);
+    }
+    for (int l = 0; l < 2; ++l) {
+      float* w = l ? w1 : w0;
+      auto L = [l](F2 v) { return l ? v.y : v.x; };
+      for (int i = 0; i < 3; ++i) { w[i] = L(s.p[i]); w[7 + i] = L(s.v[i]); w[10 + i] = L(s.w[i]); }
+      for (int i = 0; i < 4; ++i) w[3 + i] = L(s.Q[i]);
+      for (int i = 0; i < 6; ++i) { w[13 + i] = L(s.q[i]); w[19 + i] = L(s.qd[i]); }
+      float* f = forces + (size_t)(e + l) * 21;
+      for (int i = 0; i < 3; ++i) { f[i] = L(so.foot_force[0][i]); f[18 + i] = L(so.foot_force[1][i]); }
+      for (int b = 0; b < 5; ++b)
+        for (int i = 0; i < 3; ++i) f[3 * (b + 1) + i] = L(midf[3 * b + i]);
+      for (int i = 0; i < 6; ++i) tau[(size_t)(e + l) * 6 + i] = L(so.applied_torque[i]);
+    }
+  }
+  return ZBOT_OK;
+}
+
 template <typename T>
 static int port_link_view(const T* sim, T* pos, T* quat, T* vel, int n) {
   for (int e = 0; e < n; ++e) {
@@ -206,6 +245,9 @@ int zbot_port_snake_step_f32(const ZbotCfg* cfg, float* state, int64_t* ep_len, 
 int zbot_port_snake_step_f64(const ZbotCfg* cfg, double* state, int64_t* ep_len, const double* actions, double* obs,
                              double* rew, uint8_t* term, uint8_t* trunc, double* reset_sums, double* export_buf, int n) {
   return port_snake_step<double>(cfg, state, ep_len, actions, obs, rew, term, trunc, reset_sums, export_buf, n);
+}
+int zbot_port_substeps_pair_f32(const ZbotCfg* cfg, float* sim, const float* target, float* forces, float* tau, int n, int nsub, int snake) {
+  return port_substeps_pair(cfg, sim, target, forces, tau, n, nsub, snake != 0);
 }
 int zbot_port_substeps_f32(const ZbotCfg* cfg, float* sim, const float* target, float* forces, float* tau, int n, int nsub) {
   return port_substeps<float>(cfg, sim, target, forces, tau, n, nsub);

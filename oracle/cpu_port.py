@@ -149,6 +149,20 @@ def substeps(sim: np.ndarray, target: np.ndarray, nsub: int, cfg: ZbotCfg | None
     return forces, tau
 
 
+def substeps_pair(sim: np.ndarray, target: np.ndarray, nsub: int, cfg: ZbotCfg | None = None, snake: bool = False):
+    """float32 substeps through the two-lane instantiation (T = F2, csrc/zbot_pair.h): envs (2i, 2i+1) share a call chain."""
+    n = sim.shape[0]
+    assert sim.dtype == np.float32
+    cfg = cfg or make_cfg(n)
+    forces = np.zeros((n, 7, 3), np.float32)
+    tau = np.zeros((n, 6), np.float32)
+    target = np.ascontiguousarray(target, np.float32)
+    rc = lib().zbot_port_substeps_pair_f32(C.byref(cfg), _p(sim), _p(target), _p(forces), _p(tau), C.c_int(n), C.c_int(nsub),
+                                           C.c_int(1 if snake else 0))
+    assert rc == 0
+    return forces, tau
+
+
 def link_view(sim: np.ndarray):
     n = sim.shape[0]
     dt = sim.dtype

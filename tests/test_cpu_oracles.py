@@ -274,3 +274,36 @@ def test_v4_port_f32_tracks_f64_and_resets_randomise_the_pose():
         alive &= ~(t32 | t64 | tr32 | tr64)
     dq = np.abs(e32.field("joint_pos", 6) - e64.field("joint_pos", 6))[alive]
     assert alive.sum() > n // 3 and dq.max() < 5e-3
+
+
+def test_two_lane_instantiation_equals_scalar_bit_for_bit():
+    """physics_substep instantiated with T = F2 (two environments per call chain, the packed GPU kernel's arithmetic;
+    csrc/zbot_pair.h) gives, lane by lane, exactly the scalar float32 result on the host -- walking and snake models,
+    contacts included (the lane-generic contact law contributes exact zeros for an inactive lane)."""
+    from oracle import cpu_port
+    from zbot_lab_b200 import native
+    from zbot_lab_b200.assets import zbot_d_6s as S
+    from zbot_lab_b200.utils import synthetic as syn
+    n = 64
+    rng = np.random.default_rng(3)
+    st = syn.synth_sim_state(rng, n)
+    st["root_ang_vel"] = rng.normal(0, 0.5, (n, 3)).astype(np.float32)
+    st["root_pos"][:8, 2] += 0.3                       # some pairs have one lane airborne, one in contact
+    a = cpu_port.pack_sim(st, np.float32)
+    b = a.copy()
+    tgt = (np.asarray([0.312, 0.837, -2.02, 2.02, -0.837, -0.312], np.float32)[None] + rng.uniform(-0.3, 0.3, (n, 6))).astype(np.float32)
+    for _ in range(24):
+        f1, t1 = cpu_port.substeps(a, tgt, 1)
+        f2, t2 = cpu_port.substeps_pair(b, tgt, 1)
+        assert np.array_equal(a, b) and np.array_equal(f1, f2) and np.array_equal(t1, t2)
+    m = S.model_f32()
+    cfg = native.make_cfg(n, task=native.TASK_SNAKE_V0)
+    sim = np.zeros((n, 25), np.float32)
+    sim[:, 0:3], sim[:, 3:7] = m.default_root_pos, m.default_root_quat
+    sim[:, 13:19], sim[:, 19:25] = rng.uniform(-0.5, 0.5, (n, 6)), rng.normal(0, 1, (n, 6))
+    a, b = sim.copy(), sim.copy()
+    tgt = rng.uniform(-1, 1, (n, 6)).astype(np.float32)
+    for _ in range(24):
+        cpu_port.substeps(a, tgt, 1, cfg, snake=True)
+        cpu_port.substeps_pair(b, tgt, 1, cfg, snake=True)
+        assert np.array_equal(a, b)

@@ -862,3 +862,45 @@ def test_no_out_of_bounds_writes_snake_v4_and_host_rows():
             assert torch.isfinite(views["obs"].view(torch.float32)).all()
             assert torch.isfinite(views["state"].view(torch.float32)).all()
             lib.zbot_destroy(h)
+
+
+def test_packed_two_env_variant_agrees_with_the_default_kernel(monkeypatch):
+    """The opt-in two-environments-per-thread kernel (packed FFMA2 arithmetic, ZBOT_STEP_VARIANT=p128x2) computes the
+    same control step as the default kernel up to float32 round-off: one step from identical states (ragged N, so the
+    dead second lane of the tail thread is exercised), flags / counters equal, positions within 2e-4 and velocities within 2e-2 (the one-step bounds of DESIGN.md §6)."""
+    from zbot_lab_b200.utils import synthetic as syn
+    n = 1000 + 37
+    rng = np.random.default_rng(8)
+    s0 = syn.synth_sim_state(rng, n)
+    ep0 = rng.integers(0, 1000, n).astype(np.int64)
+    ep0[:5] = 998
+    a = rng.normal(0, 0.5, (3, n, 6)).astype(np.float32)
+    res = []
+    for variant in ("128x2", "p128x2"):
+        monkeypatch.setenv("ZBOT_STEP_VARIANT", variant)
+        st = _stepper(n)
+        st.reset_idx(None)
+        st.set_sim_state({k: _t(v) for k, v in s0.items()})
+        st.episode_length_buf[:] = _t(ep0)
+        outs = []
+        for t in range(3):
+            obs, rew, term, trunc = st.step(_t(a[t]))
+            outs.append((obs.clone(), rew.clone(), term.clone(), trunc.clone(), st.state.buf.clone(), st.episode_length_buf.clone(),
+                         st.stats.clone()))
+            if variant == "p128x2":       # re-synchronise to the default kernel's state: a ONE-step comparison each time
+                st.state.buf.copy_(res[0][t][4])
+                st.episode_length_buf.copy_(res[0][t][5])
+        res.append(outs)
+        st.close()
+    for t in range(3):
+        o0, r0, te0, tr0, s0_, ep0_, st0 = res[0][t]
+        o1, r1, te1, tr1, s1_, ep1_, st1 = res[1][t]
+        same = (te0 == te1) & (tr0 == tr1)
+        assert torch.equal(tr0, tr1) and float(same.float().mean()) >= 0.995
+        assert torch.equal(ep0_[same], ep1_[same])
+        d = (o0 - o1)[same].abs()
+        assert float(d[:, :10].max()) <= 2e-4 and float(d[:, 16:].max()) <= 2e-4     # base quat, joint positions, actions
+        assert float(d[:, 10:16].max()) <= 2e-2                                      # joint velocities (DESIGN.md §6 bounds)
+        assert float((r0 - r1)[same].abs().max()) <= 1e-2
+        if bool(same.all()):
+            assert float((st0 - st1).abs().max()) <= 1e-2 * max(1.0, float(st0.abs().max()))

@@ -189,6 +189,13 @@ ZB_HD float zb_rsqrt(float x) {
 }
 ZB_HD double zb_rsqrt(double x) { return 1.0 / sqrt(x); }
 
+// predicate helpers: generic code that must also run with T = F2 (two lanes, zbot_pair.h) uses these instead of `if`
+ZB_HD bool zb_gt(float a, float b) { return a > b; }
+ZB_HD bool zb_gt(double a, double b) { return a > b; }
+ZB_HD bool zb_any(bool m) { return m; }
+ZB_HD float zb_sel(bool m, float a, float b) { return m ? a : b; }
+ZB_HD double zb_sel(bool m, double a, double b) { return m ? a : b; }
+
 template <typename T>
 ZB_HD T zb_clamp(T x, T lo, T hi) {
   return zb_min(zb_max(x, lo), hi);
@@ -381,37 +388,42 @@ ZB_HD void contact_agg_force(const ContactAgg<T>& g, T dt, const T* At, const T*
   f[2] = g.F0[2] - dt * (g.sg * Ab[2] + At[0] * g.sgry - At[1] * g.sgrx);
 }
 
-// Returns true when the point is active.  Adds dt*J^T K J to IA, subtracts J^T F0 from pA.
-template <typename T>
-ZB_HD bool contact_point(const Params<T>& P, const T* rho, T height, const T* w, const T* vO,
+// Adds dt*J^T K J to IA, subtracts J^T F0 from pA.  Branch-free per lane (T may be F2: two environments): a lane
+// outside the speculative margin, or below the activation band, contributes exact zeros; the early-outs only fire when
+// EVERY lane is out.  PS = scalar type of the uniform parameters.
+template <typename PS, typename T>
+ZB_HD void contact_point(const Params<PS>& P, const T* rho, T height, const T* w, const T* vO,
                          SpInertia<T>& IA, T* pAt, T* pAb, ContactAgg<T>* agg, T* f0out) {
-  T pen = -height;
-  if (!(pen > -P.c_margin)) return false;   // speculative margin: points this far above ground are skipped
+  const T pen = -height;
+  const auto in_margin = zb_gt(pen, T(-P.c_margin));   // speculative margin: points this far above ground are skipped
+  if (!zb_any(in_margin)) return;
   T vp[3], wxv[3];
   cross3(w, rho, vp);
   vp[0] += vO[0]; vp[1] += vO[1]; vp[2] += vO[2];
   cross3(w, vp, wxv);
-  T sx = vp[0] + P.dt * wxv[0], sy = vp[1] + P.dt * wxv[1], sz = vp[2] + P.dt * wxv[2];
-  T s = zb_clamp(pen * P.c_inv_ramp, T(0), T(1));
-  T fs = zb_min(P.c_k * pen, P.c_fcap);
-  T gamma = P.c_k * P.dt + P.c_d * s;
+  const T dt = T(P.dt);
+  T sx = vp[0] + dt * wxv[0], sy = vp[1] + dt * wxv[1], sz = vp[2] + dt * wxv[2];
+  T s = zb_clamp(pen * T(P.c_inv_ramp), T(0), T(1));
+  T fs = zb_min(T(P.c_k) * pen, T(P.c_fcap));
+  T gamma = T(P.c_k * P.dt) + T(P.c_d) * s;
   T fn0 = fs - gamma * sz;
   // Activation is CONTINUOUS in the state: the implicit normal stiffness ramps in over a band of predictor
   // force [-fband, 0] (there F0 = 0 and only -dt*act*gamma*a_n acts: an added-mass term, PSD), so a point
   // sitting exactly on the threshold (a snake at rest on the plane: all 12 spheres at pen = 0) does not flip a
   // coin on float round-off.  Full stiffness for fn0 >= 0 as before.
-  const T act = zb_clamp(fn0 * P.c_inv_fband + T(1), T(0), T(1));
-  if (!(act > T(0))) return false;
-  fn0 = zb_max(fn0, T(0));
+  T act = zb_clamp(fn0 * T(P.c_inv_fband) + T(1), T(0), T(1));
+  act = zb_sel(in_margin, act, T(0));
+  if (!zb_any(zb_gt(act, T(0)))) return;
+  fn0 = zb_sel(in_margin, zb_max(fn0, T(0)), T(0));
   gamma *= act;
   // beta = min(beta_max, mu fn0 / max(|v_t|, eps))
-  T beta = zb_min(P.c_beta_max, P.c_mu * fn0 * zb_rsqrt(zb_max(sx * sx + sy * sy, P.c_vt_eps * P.c_vt_eps)));
-  T F0[3] = {-beta * sx, -beta * sy, fn0};
+  T beta = zb_min(T(P.c_beta_max), T(P.c_mu) * fn0 * zb_rsqrt(zb_max(sx * sx + sy * sy, T(P.c_vt_eps * P.c_vt_eps))));
+  T F0[3] = {-(beta * sx), -(beta * sy), fn0};
   T n[3];
   cross3(rho, F0, n);
   pAt[0] -= n[0]; pAt[1] -= n[1]; pAt[2] -= n[2];
   pAb[0] -= F0[0]; pAb[1] -= F0[1]; pAb[2] -= F0[2];
-  spi_add_contact(IA, rho, P.dt * beta, P.dt * beta, P.dt * gamma);
+  spi_add_contact(IA, rho, dt * beta, dt * beta, dt * gamma);
   if (agg) {
     agg->F0[0] += F0[0]; agg->F0[1] += F0[1]; agg->F0[2] += F0[2];
     agg->sb += beta; agg->sg += gamma;
@@ -419,15 +431,14 @@ ZB_HD bool contact_point(const Params<T>& P, const T* rho, T height, const T* w,
     agg->sgrx += gamma * rho[0]; agg->sgry += gamma * rho[1];
   }
   if (f0out) { f0out[0] = F0[0]; f0out[1] = F0[1]; f0out[2] = F0[2]; }
-  return true;
 }
 
 // ------------------------------------------------------------------------------------
 // per-body rigid terms: adds the body's spatial inertia about O and its bias force
 //   p = V x* (I V) - f_gravity
 // ------------------------------------------------------------------------------------
-template <typename T>
-ZB_HD void body_rigid_terms(const Params<T>& P, T mass, T cx, T cz, T ixx, T iyy, T izz, T ixz,
+template <typename PS, typename T>
+ZB_HD void body_rigid_terms(const Params<PS>& P, T mass, T cx, T cz, T ixx, T iyy, T izz, T ixz,
                             const T* R, const T* r, const T* w, const T* vO,
                             SpInertia<T>& IA, T* pAt, T* pAb) {
   // CoM relative to O (body CoM_y == 0)
@@ -456,7 +467,7 @@ ZB_HD void body_rigid_terms(const Params<T>& P, T mass, T cx, T cz, T ixx, T iyy
   cross3(w, L, a0);
   cross3(vO, Pl, a1);
   cross3(w, Pl, a2);
-  T mg = mass * P.gravity;
+  T mg = mass * T(P.gravity);
   pAt[0] += a0[0] + a1[0] + mg * c[1];
   pAt[1] += a0[1] + a1[1] - mg * c[0];
   pAt[2] += a0[2] + a1[2];
@@ -597,16 +608,16 @@ struct SubstepOut {
 };
 
 // mid_force_out: optional [5][3] predictor forces of bodies 1..5 (export / debug only)
-template <typename Model, typename T, typename Scr>
-ZB_HD void physics_substep(const Params<T>& P, SimState<T>& s, const T* target, SubstepOut<T>& out, Scr& scr,
+template <typename Model, bool kPipe = (ZB_PIPELINED_SWEEP != 0), typename PS, typename T, typename Scr>
+ZB_HD void physics_substep(const Params<PS>& P, SimState<T>& s, const T* target, SubstepOut<T>& out, Scr& scr,
                            T* mid_force_out) {
   using namespace model;
-  const T dt = P.dt;
+  const T dt = T(P.dt);
   // ---- PD (implicit part lives in P.arm) + park q, qd (static indices: registers -> scratch) ----
   ZB_UNROLL for (int k = 0; k < 6; ++k) {
     const T e = target[k] - s.q[k];
-    out.applied_torque[k] = zb_clamp(P.kp * e - P.kd * s.qd[k], -P.effort, P.effort);
-    scr(k, SC_U) = zb_clamp(P.kp * (e - dt * s.qd[k]) - P.kd * s.qd[k], -P.effort, P.effort);
+    out.applied_torque[k] = zb_clamp(T(P.kp) * e - T(P.kd) * s.qd[k], T(-P.effort), T(P.effort));
+    scr(k, SC_U) = zb_clamp(T(P.kp) * (e - dt * s.qd[k]) - T(P.kd) * s.qd[k], T(-P.effort), T(P.effort));
     scr(k, SC_QD) = s.qd[k];
   }
   // ---- forward kinematics sweep: motion subspaces S_k = (a_k ; r_k x a_k), arrive at body 6 ----
@@ -649,7 +660,7 @@ ZB_HD void physics_substep(const Params<T>& P, SimState<T>& s, const T* target, 
   ContactAgg<T> agg, agg1;   // running / foot_1 (body 6); after the sweep `agg` holds foot_0 (body 0)
   contact_agg_zero(agg1);
   T mid2 = T(0);
-#if ZB_PIPELINED_SWEEP
+  if constexpr (kPipe) {
   // Software-pipelined form: the articulated-body elimination of joint k-1 is one long dependent chain
   // (IA S -> D -> 1/D -> rank-1 update); the kinematics, world inertia and bias force of the NEXT body (k-1) do not
   // depend on it.  Both are issued in the same basic block, into separate accumulators (IB, pB), so the scheduler
@@ -719,7 +730,7 @@ ZB_HD void physics_substep(const Params<T>& P, SimState<T>& s, const T* target, 
     cb[0] += tmp[0]; cb[1] += tmp[1]; cb[2] += tmp[2];
     T Ut[3], Ub[3];
     spi_mul(IA, Sa, Sm, Ut, Ub);
-    const T D = dot3(Sa, Ut) + dot3(Sm, Ub) + P.arm;
+    const T D = dot3(Sa, Ut) + dot3(Sm, Ub) + T(P.arm);
     const T Dinv = zb_rcp(D);
     const T u = scr(j, SC_U) - (dot3(Sa, pAt) + dot3(Sm, pAb));
     T Ict[3], Icb[3];
@@ -761,7 +772,7 @@ ZB_HD void physics_substep(const Params<T>& P, SimState<T>& s, const T* target, 
       }
     }
   }
-#else
+  } else {
 #if defined(__CUDACC__)
 #pragma unroll 1
 #endif
@@ -814,7 +825,7 @@ ZB_HD void physics_substep(const Params<T>& P, SimState<T>& s, const T* target, 
     cb[0] += tmp[0]; cb[1] += tmp[1]; cb[2] += tmp[2];
     T Ut[3], Ub[3];
     spi_mul(IA, Sa, Sm, Ut, Ub);
-    const T D = dot3(Sa, Ut) + dot3(Sm, Ub) + P.arm;
+    const T D = dot3(Sa, Ut) + dot3(Sm, Ub) + T(P.arm);
     const T Dinv = zb_rcp(D);
     const T u = scr(j, SC_U) - (dot3(Sa, pAt) + dot3(Sm, pAb));
     // pa = pA + IA c + U (u - U.c)/D   (== pA + Ia c + U u/D)
@@ -840,7 +851,7 @@ ZB_HD void physics_substep(const Params<T>& P, SimState<T>& s, const T* target, 
                 T(1) - T(2) * (Q[1] * Q[1] + Q[2] * Q[2])};     // third column of R_{k-1}
     r[0] -= jz * Rp2[0]; r[1] -= jz * Rp2[1]; r[2] -= jz * Rp2[2];
   }
-#endif   // ZB_PIPELINED_SWEEP
+  }   // kPipe
   // ---- floating base:  IA a0 = -pA ----
   T At[3], Ab[3];
   {

@@ -22,6 +22,7 @@
 #include <new>
 
 #include "zbot_layout.h"
+#include "zbot_pair.h"
 
 using namespace zbot;
 
@@ -318,6 +319,110 @@ template <bool kExport, int kMaxThreads, int kMinBlocks>
 __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) zbot_step_kernel(ZB_STEP_ARGS) {
   zbot_step_body<kExport>(ZB_STEP_CALL);
 }
+// ---------------------------------------------------------------------------------------------
+// the fused control step, TWO ENVIRONMENTS PER THREAD: the four physics substeps run once per thread with T = F2
+// (packed FFMA2 / FMUL2 / FADD2: every FP32 instruction of the articulated-body recursion serves both envs); the MDP
+// phase runs scalar, once per lane.  A CTA of B threads owns 2B consecutive envs: lane 0 = env e0 + t, lane 1 =
+// env e0 + B + t, so every state load / store is as coalesced as in the one-env kernel.
+// ---------------------------------------------------------------------------------------------
+template <int kMaxThreads, int kMinBlocks>
+__global__ void __launch_bounds__(kMaxThreads, kMinBlocks) zbot_step2_kernel(ZB_STEP_ARGS) {
+  extern __shared__ float smem[];   // blockDim * SCR_STRIDE float2: substep scratch, then obs rows, then stats
+  const int B = blockDim.x;
+  const int e0 = e_begin + blockIdx.x * 2 * B;
+  const int ea_i = e0 + threadIdx.x, eb_i = e0 + B + threadIdx.x;
+  const bool live_a = ea_i < e_end, live_b = eb_i < e_end;
+  const int eb_ld = live_b ? eb_i : ea_i;          // a dead lane shadows lane 0 (never stored)
+  float stat[kStatUsed];
+#pragma unroll
+  for (int j = 0; j < kStatUsed; ++j) stat[j] = 0.f;
+  float obs_a[ZBOT_NUM_OBS], obs_b[ZBOT_NUM_OBS];
+#pragma unroll
+  for (int i = 0; i < ZBOT_NUM_OBS; ++i) { obs_a[i] = 0.f; obs_b[i] = 0.f; }
+  bool did_reset = false;
+  if (live_a) {
+    EnvState<float> es_a, es_b;
+    PhysOut<float> po_a, po_b;
+    SmemScratch2 scr{reinterpret_cast<float2*>(smem) + threadIdx.x * SCR_STRIDE};
+    {
+      float w[4 * EARLY_QUADS];
+      load_words<EARLY_QUADS>(state, n, ea_i, w);
+      env_early_unpack(w, es_a);
+      load_words<EARLY_QUADS>(state, n, eb_ld, w);
+      env_early_unpack(w, es_b);
+    }
+    {
+      const float2* pa = reinterpret_cast<const float2*>(actions + (size_t)ea_i * 6);
+      const float2* pb = reinterpret_cast<const float2*>(actions + (size_t)eb_ld * 6);
+      const float2 a0 = __ldg(pa), a1 = __ldg(pa + 1), a2v = __ldg(pa + 2);
+      const float2 b0 = __ldg(pb), b1 = __ldg(pb + 1), b2v = __ldg(pb + 2);
+      const float raw_a[6] = {a0.x, a0.y, a1.x, a1.y, a2v.x, a2v.y};
+      const float raw_b[6] = {b0.x, b0.y, b1.x, b1.y, b2v.x, b2v.y};
+#pragma unroll
+      for (int k = 0; k < 6; ++k) scr.base[SCR_RAW_ACT + k] = make_float2(raw_a[k], raw_b[k]);
+      env_step_physics2<ModelWalk>(P, es_a, es_b, raw_a, raw_b, po_a, po_b, scr);
+    }
+    // ---- phase C, once per lane (scalar) ----
+#pragma unroll 1
+    for (int l = 0; l < 2; ++l) {
+      const bool live = l ? live_b : true;
+      if (!live) break;
+      const int e = l ? eb_i : ea_i;
+      // one code instance of the MDP phase: lane 1's physics results are moved into the lane-0 structs after lane 0 is
+      // done (register moves; a run-time choice between two structs would push both into local memory)
+      if (l) { es_a = es_b; po_a = po_b; }
+      EnvState<float>& es = es_a;
+      const PhysOut<float>& po = po_a;
+      {
+        float w[ZBOT_STATE_WORDS - 4 * EARLY_QUADS];
+        load_words<ZBOT_STATE_WORDS / 4 - EARLY_QUADS>(state + (size_t)EARLY_QUADS * n, n, e, w);
+        env_late_unpack(w, es);
+      }
+      SimState<float> s0;
+      {
+        float w[4 * SIM_QUADS];
+        load_words<SIM_QUADS>(state, n, e, w);
+        sim_state_unpack(w, s0);
+      }
+      float raw[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) { const float2 v = scr.base[SCR_RAW_ACT + k]; raw[k] = l ? v.y : v.x; }
+      int64_t ep = ep_len_buf[e];
+      StepOut<float> out;
+      float rs[MAX_TERMS];
+#pragma unroll
+      for (int i = 0; i < MAX_TERMS; ++i) rs[i] = 0.f;
+      env_step_finish(P, es, s0, raw, po, ep, dp.feet_pos, dp.base_quat, out, rs, (StepExport<float>*)nullptr);
+      float w[ZBOT_STATE_WORDS];
+      env_state_pack(es, w);
+      store_words<ZBOT_STATE_WORDS / 4>(state, n, e, w);
+      ep_len_buf[e] = ep;
+      rew[e] = out.reward;
+      terminated[e] = out.terminated ? 1 : 0;
+      truncated[e] = out.time_out ? 1 : 0;
+#pragma unroll
+      for (int i = 0; i < ZBOT_NUM_OBS; ++i) { if (l) obs_b[i] = out.obs[i]; else obs_a[i] = out.obs[i]; }
+      if (out.terminated || out.time_out) {
+        did_reset = true;
+#pragma unroll
+        for (int i = 0; i < MAX_TERMS; ++i) stat[i] += rs[i];
+        stat[S_NUM_RESET] += 1.f;
+        stat[S_NUM_TERM_RESET] += out.terminated ? 1.f : 0.f;
+        stat[S_NUM_TO_RESET] += out.time_out ? 1.f : 0.f;
+      }
+      stat[S_REW_SUM] += out.reward;
+      stat[S_NUM_TERM] += out.terminated ? 1.f : 0.f;
+      stat[S_NUM_TRUNC] += out.time_out ? 1.f : 0.f;
+    }
+  }
+  __syncthreads();   // every thread is done with its scratch row before the rows are staged
+  store_rows_coalesced<ZBOT_NUM_OBS>(obs, obs_a, e_end, e0, smem);
+  __syncthreads();
+  if (e0 + B < e_end) store_rows_coalesced<ZBOT_NUM_OBS>(obs, obs_b, e_end, e0 + B, smem);   // block-uniform condition
+  __syncthreads();
+  stats_block_partial(stat, did_reset, smem, sc);
+}
+
 // host-facing output layout (zbot_step_host): one 25-word row per env
 __global__ void __launch_bounds__(128, 2) zbot_step_packed_kernel(ZB_STEP_ARGS) {
   zbot_step_body<false, true>(ZB_STEP_CALL);
@@ -853,22 +958,27 @@ namespace {
 // occupancy grid (e.g. 5 x 64 threads = 10 warps/SM at the full 197 registers).
 typedef void (*StepFn)(Params<float>, DefaultPose, float4*, int64_t*, const float*, float*, float*, uint8_t*, uint8_t*, int,
                        int, int, StatsCtx, ExportPtrs);
-struct StepVariant { int threads, ctas; StepFn fn; };
+struct StepVariant { int threads, ctas; StepFn fn; int envs_per_thread; };
 const StepVariant kStepVariants[] = {
-    {128, 2, zbot_step_kernel<false, 128, 2>}, {128, 3, zbot_step_kernel<false, 128, 3>},
-    {128, 4, zbot_step_kernel<false, 128, 4>},
-    {64, 5, zbot_step_kernel_r<200>},  {32, 10, zbot_step_kernel_r<200>}, {32, 11, zbot_step_kernel_r<184>},
-    {64, 6, zbot_step_kernel<false, 64, 6>}, {32, 12, zbot_step_kernel<false, 32, 12>},
-    {32, 13, zbot_step_kernel_r<152>}, {32, 14, zbot_step_kernel_r<144>}, {64, 7, zbot_step_kernel_r<144>},
-    {32, 16, zbot_step_kernel<false, 32, 16>},
+    {128, 2, zbot_step_kernel<false, 128, 2>, 1}, {128, 3, zbot_step_kernel<false, 128, 3>, 1},
+    {128, 4, zbot_step_kernel<false, 128, 4>, 1},
+    {64, 5, zbot_step_kernel_r<200>, 1},  {32, 10, zbot_step_kernel_r<200>, 1}, {32, 11, zbot_step_kernel_r<184>, 1},
+    {64, 6, zbot_step_kernel<false, 64, 6>, 1}, {32, 12, zbot_step_kernel<false, 32, 12>, 1},
+    {32, 13, zbot_step_kernel_r<152>, 1}, {32, 14, zbot_step_kernel_r<144>, 1}, {64, 7, zbot_step_kernel_r<144>, 1},
+    {32, 16, zbot_step_kernel<false, 32, 16>, 1},
+    // EXPERIMENTAL, opt-in (ZBOT_STEP_VARIANT=p128x2): two envs per thread, packed FP32 (zbot_step2_kernel).  31 % fewer
+    // warp instructions per env, but 255 registers + spills at 1.7 warps per sub-partition: 84.0 vs 86.4 us at 65536 envs,
+    // 59 vs 35 us at 4096 (profiles/r1_notes.md).
+    {1128, 2, zbot_step2_kernel<128, 2>, 2},
 };
 constexpr int kNumStepVariants = (int)(sizeof(kStepVariants) / sizeof(kStepVariants[0]));
 
 int pick_block(const ZbotHandle* h, int n) {
   // fill the SMs first: the step is latency/issue bound, not bandwidth bound
-  int block = kStepVariants[h->variant].threads;
+  const StepVariant& v = kStepVariants[h->variant];
+  int block = v.threads % 1000;
   if (h->force_block == 32 || h->force_block == 64 || h->force_block == 128) block = min(block, h->force_block);
-  while (block > 32 && (n + block - 1) / block < 2 * h->num_sms) block >>= 1;
+  while (block > 32 && (n + block * v.envs_per_thread - 1) / (block * v.envs_per_thread) < 2 * h->num_sms) block >>= 1;
   return block;
 }
 
@@ -930,7 +1040,7 @@ int zbot_create(const ZbotCfg* cfg, int device, ZbotHandle** out) {
   ZB_CUDA(cudaFuncSetAttribute(zbot_mdp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * kHistRow * 4));
   for (int v = 0; v < kNumStepVariants; ++v)
     ZB_CUDA(cudaFuncSetAttribute((const void*)kStepVariants[v].fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 128 * SCR_STRIDE * 4));
+                                 128 * SCR_STRIDE * 4 * kStepVariants[v].envs_per_thread));
   ZB_CUDA(cudaFuncSetAttribute(zbot_step_kernel<true, 128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
   ZB_CUDA(cudaFuncSetAttribute(zbot_step_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
   ZB_CUDA(cudaFuncSetAttribute(zbot_snake_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
@@ -944,7 +1054,8 @@ int zbot_create(const ZbotCfg* cfg, int device, ZbotHandle** out) {
     const char* sv = getenv("ZBOT_STEP_VARIANT");      // tuning override, "<threads>x<ctas>", e.g. 64x5
     int vt = 0, vc = 0;
     h->variant = -1;
-    if (sv && sscanf(sv, "%dx%d", &vt, &vc) == 2) h->variant = find_variant(vt, vc);
+    if (sv && sv[0] == 'p' && sscanf(sv + 1, "%dx%d", &vt, &vc) == 2) h->variant = find_variant(1000 + vt, vc);
+    else if (sv && sscanf(sv, "%dx%d", &vt, &vc) == 2) h->variant = find_variant(vt, vc);
     if (h->variant < 0) h->variant = find_variant(128, (cfg->num_envs > 2 * 2 * 148 * 128) ? 3 : 2);
     const char* mt = getenv("ZBOT_MDP_TILE");          // envs (= threads) per CTA of the MDP-only step kernel
     h->mdp_tile = mt ? atoi(mt) : kMdpTile;
@@ -982,9 +1093,12 @@ static int step_impl(ZbotHandle* h, const float* actions, float* obs, float* rew
   if (((uintptr_t)actions & 7) != 0) return fail(ZBOT_E_INVALID, "actions must be 8-byte aligned%s");
   if (int rc = check_slot(slot, prev, h->ring_slots)) return rc;
   const int n = h->cfg.num_envs;
-  const int block = pick_block(h, n);
-  const int grid = (n + block - 1) / block;
-  const size_t smem = (size_t)block * SCR_STRIDE * sizeof(float);   // >= obs rows (23/thread) and stats (704 floats)
+  const bool walk = (h->cfg.task == ZBOT_TASK_WALKING_V2) && !ex;
+  const int ept = walk ? kStepVariants[h->variant].envs_per_thread : 1;
+  int block = pick_block(h, n);
+  if (!walk) { block = 128; while (block > 32 && (n + block - 1) / block < 2 * h->num_sms) block >>= 1; }
+  const int grid = (n + block * ept - 1) / (block * ept);
+  const size_t smem = (size_t)block * SCR_STRIDE * sizeof(float) * ept;   // >= obs rows (23/thread) and stats (704 floats)
   StatsCtx sc{h->partials, h->ring, slot, prev, h->inv_episode_s, 0};
   cudaStream_t s = (cudaStream_t)stream;
   ExportPtrs xp{};
