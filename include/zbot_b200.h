@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define ZBOT_ABI_VERSION 3
+#define ZBOT_ABI_VERSION 4
 
 #define ZBOT_OK 0
 #define ZBOT_E_INVALID (-1) /* bad argument / unsupported configuration */
@@ -127,6 +127,12 @@ typedef struct ZbotCfg {
   float ev_pose_lo[3], ev_pose_hi[3];
   float ev_interval_lo, ev_interval_hi;
   uint64_t rng_seed;
+  /* Additive uniform observation noise, ObservationManager semantics of the manager-based task
+   * (`zbotlab_manager/zbotlab_env_cfg.py` PolicyCfg: `noise=Unoise(n_min, n_max)`, `enable_corruption`):
+   * emitted obs[i] += U(obs_noise_lo[i], obs_noise_hi[i]) per env per step, drawn by the in-kernel counter-based
+   * generator (rng_seed); the stored state and the rewards never see it.  All tasks; off by default. */
+  int32_t obs_noise_enable;
+  float obs_noise_lo[24], obs_noise_hi[24];
 } ZbotCfg;
 
 typedef struct ZbotHandle ZbotHandle;

@@ -233,3 +233,36 @@ def test_v4_env_registry_protocol_curriculum_and_log_keys():
     w.step(torch.zeros(256, 6, device="cuda:0"))
     assert env.curriculum_stage == 2 and abs(env._stepper.cfg.ev_prob_pos - 0.8) < 1e-6
     w.close()
+
+
+def test_observation_noise_is_additive_uniform_and_touches_nothing_else():
+    """Opt-in ObservationManager-style corruption (manager-based task's PolicyCfg: base_quat +-0.01, joint_pos +-0.01,
+    joint_vel +-1.5, zbotlab_manager/zbotlab_env_cfg.py): emitted obs = clean obs + U(n_min, n_max) per element; rewards,
+    flags and the simulation state are bit-identical to the run without noise; the draw is reproducible per seed."""
+    n = 4096
+    noise = {"base_quat": (-0.01, 0.01), "joint_pos": (-0.01, 0.01), "joint_vel": (-1.5, 1.5)}
+    clean, _ = _make(n, check_all_envs_reset=False)
+    noisy, _ = _make(n, check_all_envs_reset=False, observation_noise=noise)
+    noisy2, _ = _make(n, check_all_envs_reset=False, observation_noise=noise)
+    for e in (noisy, noisy2):
+        e.episode_length_buf = clean.episode_length_buf.clone()
+    g = torch.Generator(device="cuda:0").manual_seed(2)
+    for t in range(6):
+        a = torch.randn(n, 6, device="cuda:0", generator=g)
+        o0, r0, te0, tr0, _ = clean.step(a)
+        o1, r1, te1, tr1, _ = noisy.step(a)
+        o2, _, _, _, _ = noisy2.step(a)
+        assert torch.equal(r0, r1) and torch.equal(te0, te1) and torch.equal(tr0, tr1)
+        assert torch.equal(o1["policy"], o2["policy"])                       # same seed, same stream position
+        d = o1["policy"] - o0["policy"]
+        assert torch.all(d[:, 16:] == 0)                                     # actions, joint_speed_limit: no noise term
+        for sl, w in ((slice(0, 10), 0.01), (slice(10, 16), 1.5)):
+            x = d[:, sl]
+            assert float(x.abs().max()) <= w * (1 + 1e-5) and abs(float(x.mean())) < 0.05 * w
+            assert abs(float(x.std()) - w / 3 ** 0.5) < 0.05 * w             # uniform on [-w, w]: std = w / sqrt(3)
+        if t > 0:
+            assert not torch.equal(d, d_prev)                                # fresh draw every step
+        d_prev = d.clone()
+    assert torch.equal(clean._stepper.state.buf, noisy._stepper.state.buf)
+    for e in (clean, noisy, noisy2):
+        e.close()

@@ -113,6 +113,10 @@ struct Params {
   int ev_dual_sign;
   T ev_pose_lo[3], ev_pose_hi[3];     // reset_base pose_range x, y, yaw
   T ev_interval_lo, ev_interval_hi;   // interval_range_s of interval_command_resample
+  // additive uniform observation noise (ObservationManager `Unoise`); applied to the EMITTED row only
+  int obs_noise_enable;
+  T obs_noise_lo[24], obs_noise_w[24];   // lower bound, width (hi - lo)
+  unsigned long long rng_seed;
 };
 
 // ------------------------------------------------------------------------------------

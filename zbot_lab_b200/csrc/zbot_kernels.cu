@@ -58,6 +58,8 @@ struct StatsCtx {
   int slot, prev_slot;
   float inv_episode_s;    // 1 / max_episode_length_s  (…env_v2.py:444-447)
   int block_offset;       // env-range launches (zbot_step_host): index of this launch's first partial row
+  unsigned long long call; // launch counter of the handle: stream position of the in-kernel generator (obs noise)
+  int packed_rows;         // 1: host-facing output layout (zbot_step_host), see zbot_step_body
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -67,6 +69,24 @@ __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
+}
+
+__device__ __forceinline__ float v4_uniform(uint64_t seed, uint64_t call, uint32_t env, uint32_t slot) {
+  uint64_t z = seed + 0x9E3779B97F4A7C15ull * (call * 0x100000000ull + env) + 0xD1B54A32D192ED03ull * (slot + 1);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (float)(uint32_t)(z >> 40) * (1.0f / 16777216.0f);
+}
+
+// ObservationManager-style corruption of the emitted observation row: obs[i] += lo[i] + u * (hi[i] - lo[i]), one
+// counter-based uniform per (launch, env, column).  Slots 32.. keep clear of the v4 event slots 0..9.
+template <int kCols>
+__device__ __forceinline__ void obs_add_noise(const Params<float>& P, uint64_t call, int e, float* row) {
+  if (!P.obs_noise_enable) return;
+#pragma unroll
+  for (int i = 0; i < kCols; ++i)
+    row[i] = fmaf(v4_uniform(P.rng_seed, call, (uint32_t)e, 32u + (uint32_t)i), P.obs_noise_w[i], row[i] + P.obs_noise_lo[i]);
 }
 
 // Grid-level pass of the statistics: ONE block of 1024 threads.  Warp w sums the partial rows
@@ -178,9 +198,10 @@ constexpr int kFoot0Sensor = 9, kFoot1Sensor = 10;
 // ---------------------------------------------------------------------------------------------
 // the fused control step
 // ---------------------------------------------------------------------------------------------
-// kPacked: host-facing output layout -- ONE row of 25 words per env [obs 23 | reward | flags word
+// sc.packed_rows: host-facing output layout -- ONE row of 25 words per env [obs 23 | reward | flags word
 // (terminated | truncated << 8)] written to `obs` ([N][25]); `rew` / `terminated` / `truncated` are not touched.
-template <bool kExport, bool kPacked = false>
+// A run-time flag of the SAME kernel (not a second instantiation), so step_host and step are bit-identical.
+template <bool kExport>
 __device__ __forceinline__ void
 zbot_step_body(const Params<float>& P, const DefaultPose& dp,
                  float4* __restrict__ state, int64_t* __restrict__ ep_len_buf,
@@ -195,10 +216,10 @@ zbot_step_body(const Params<float>& P, const DefaultPose& dp,
   float stat[kStatUsed];
 #pragma unroll
   for (int j = 0; j < kStatUsed; ++j) stat[j] = 0.f;
-  constexpr int kRow = kPacked ? ZBOT_HOST_ROW_WORDS : ZBOT_NUM_OBS;
-  float obs_row[kRow];
+  const bool kPacked = !kExport && sc.packed_rows != 0;
+  float obs_row[ZBOT_HOST_ROW_WORDS];
 #pragma unroll
-  for (int i = 0; i < kRow; ++i) obs_row[i] = 0.f;
+  for (int i = 0; i < ZBOT_HOST_ROW_WORDS; ++i) obs_row[i] = 0.f;
   bool did_reset = false;
   if (live) {
     EnvState<float> es;
@@ -288,6 +309,7 @@ zbot_step_body(const Params<float>& P, const DefaultPose& dp,
     }
 #pragma unroll
     for (int i = 0; i < ZBOT_NUM_OBS; ++i) obs_row[i] = out.obs[i];
+    obs_add_noise<ZBOT_NUM_OBS>(P, sc.call, e, obs_row);
     did_reset = out.terminated || out.time_out;
     if (did_reset) {
 #pragma unroll
@@ -301,7 +323,8 @@ zbot_step_body(const Params<float>& P, const DefaultPose& dp,
     stat[S_NUM_TRUNC] = out.time_out ? 1.f : 0.f;
   }
   __syncthreads();   // every thread is done with its scratch column before the rows are staged
-  store_rows_coalesced<kRow>(obs, obs_row, e_end, e0, smem);
+  if (kPacked) store_rows_coalesced<ZBOT_HOST_ROW_WORDS>(obs, obs_row, e_end, e0, smem);   // block-uniform branch
+  else store_rows_coalesced<ZBOT_NUM_OBS>(obs, obs_row, e_end, e0, smem);
   __syncthreads();
   stats_block_partial(stat, did_reset, smem, sc);
 }
@@ -401,6 +424,8 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) zbot_step2_kernel(ZB_
       terminated[e] = out.terminated ? 1 : 0;
       truncated[e] = out.time_out ? 1 : 0;
 #pragma unroll
+      obs_add_noise<ZBOT_NUM_OBS>(P, sc.call, e, out.obs);
+#pragma unroll
       for (int i = 0; i < ZBOT_NUM_OBS; ++i) { if (l) obs_b[i] = out.obs[i]; else obs_a[i] = out.obs[i]; }
       if (out.terminated || out.time_out) {
         did_reset = true;
@@ -423,10 +448,6 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) zbot_step2_kernel(ZB_
   stats_block_partial(stat, did_reset, smem, sc);
 }
 
-// host-facing output layout (zbot_step_host): one 25-word row per env
-__global__ void __launch_bounds__(128, 2) zbot_step_packed_kernel(ZB_STEP_ARGS) {
-  zbot_step_body<false, true>(ZB_STEP_CALL);
-}
 // same body, register cap given directly (ptxas snaps __launch_bounds__ caps to a few occupancy steps:
 // 197 -> 168 -> 128; __maxnreg__ gives the steps in between)
 template <int kMaxRegs>
@@ -507,6 +528,7 @@ zbot_snake_step_kernel(const __grid_constant__ Params<float> P, const __grid_con
     truncated[e] = out.time_out ? 1 : 0;
 #pragma unroll
     for (int i = 0; i < ZBOT_NUM_OBS; ++i) obs_row[i] = out.obs[i];
+    obs_add_noise<ZBOT_NUM_OBS>(P, sc.call, e, obs_row);
     did_reset = out.terminated || out.time_out;
     if (did_reset) {
 #pragma unroll
@@ -531,14 +553,6 @@ zbot_snake_step_kernel(const __grid_constant__ Params<float> P, const __grid_con
 // (splitmix64 finaliser of seed / call counter / env / slot -> 24-bit mantissa, like torch.rand's float32).
 // ---------------------------------------------------------------------------------------------
 static_assert(sizeof(V4Export<float>) / sizeof(float) == ZBOT_V4_EXPORT_WORDS, "V4Export layout");
-
-__device__ __forceinline__ float v4_uniform(uint64_t seed, uint64_t call, uint32_t env, uint32_t slot) {
-  uint64_t z = seed + 0x9E3779B97F4A7C15ull * (call * 0x100000000ull + env) + 0xD1B54A32D192ED03ull * (slot + 1);
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z ^= z >> 31;
-  return (float)(uint32_t)(z >> 40) * (1.0f / 16777216.0f);
-}
 
 template <bool kExport>
 __global__ void __launch_bounds__(128, 2)
@@ -598,6 +612,7 @@ zbot_v4_step_kernel(const __grid_constant__ Params<float> P, float4* __restrict_
     int64_t ep = ep_len_buf[e];
     V4Export<float> ex;
     v4_step_finish(P, es, raw, po, ep, rnd, obs_row, out, rs, kExport ? &ex : (V4Export<float>*)nullptr);
+    obs_add_noise<ZBOT_V4_NUM_OBS>(P, call, e, obs_row);
     if (kExport) {
       const float* src = reinterpret_cast<const float*>(&ex);
       for (int i = 0; i < ZBOT_V4_EXPORT_WORDS; ++i) export_buf[(size_t)e * ZBOT_V4_EXPORT_WORDS + i] = src[i];
@@ -1042,7 +1057,6 @@ int zbot_create(const ZbotCfg* cfg, int device, ZbotHandle** out) {
     ZB_CUDA(cudaFuncSetAttribute((const void*)kStepVariants[v].fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  128 * SCR_STRIDE * 4 * kStepVariants[v].envs_per_thread));
   ZB_CUDA(cudaFuncSetAttribute(zbot_step_kernel<true, 128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
-  ZB_CUDA(cudaFuncSetAttribute(zbot_step_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
   ZB_CUDA(cudaFuncSetAttribute(zbot_snake_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
   ZB_CUDA(cudaFuncSetAttribute(zbot_snake_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
   ZB_CUDA(cudaFuncSetAttribute(zbot_v4_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
@@ -1099,7 +1113,7 @@ static int step_impl(ZbotHandle* h, const float* actions, float* obs, float* rew
   if (!walk) { block = 128; while (block > 32 && (n + block - 1) / block < 2 * h->num_sms) block >>= 1; }
   const int grid = (n + block * ept - 1) / (block * ept);
   const size_t smem = (size_t)block * SCR_STRIDE * sizeof(float) * ept;   // >= obs rows (23/thread) and stats (704 floats)
-  StatsCtx sc{h->partials, h->ring, slot, prev, h->inv_episode_s, 0};
+  StatsCtx sc{h->partials, h->ring, slot, prev, h->inv_episode_s, 0, (unsigned long long)h->launches, 0};
   cudaStream_t s = (cudaStream_t)stream;
   ExportPtrs xp{};
   if (h->cfg.task == ZBOT_TASK_WALKING_V4) return fail(ZBOT_E_INVALID, "task zbot-6b-walking-v4 steps through zbot_v4_step%s");
@@ -1174,15 +1188,17 @@ int zbot_step_host(ZbotHandle* h, const float* host_actions, float* host_rows, i
     host_rows = static_cast<float*>(const_cast<void*>(dr));
   }
   const int n = h->cfg.num_envs;
-  int block = 128;
+  // the SAME kernel instantiation and CTA shape `zbot_step` uses for this handle (bit-identical results)
+  const int vi = (kStepVariants[h->variant].envs_per_thread == 1) ? h->variant : find_variant(128, 2);
+  int block = kStepVariants[vi].threads;
   while (block > 32 && (n + block - 1) / block < 2 * h->num_sms) block >>= 1;
   const int grid = (n + block - 1) / block;
   const size_t smem = (size_t)block * SCR_STRIDE * sizeof(float);
   cudaStream_t s = (cudaStream_t)stream;
-  StatsCtx sc{h->partials, h->ring, stats_slot, prev_slot, h->inv_episode_s, 0};
+  StatsCtx sc{h->partials, h->ring, stats_slot, prev_slot, h->inv_episode_s, 0, (unsigned long long)h->launches, 1};
   ExportPtrs xp{};
-  zbot_step_packed_kernel<<<grid, block, smem, s>>>(h->P, h->dp, h->state, h->ep_len, host_actions, host_rows, nullptr, nullptr,
-                                                  nullptr, n, 0, n, sc, xp);
+  kStepVariants[vi].fn<<<grid, block, smem, s>>>(h->P, h->dp, h->state, h->ep_len, host_actions, host_rows, nullptr, nullptr,
+                                                   nullptr, n, 0, n, sc, xp);
   ZB_CUDA(cudaGetLastError());
   h->launches += 1;
   zbot_stats_finalize_kernel<<<1, 1024, 0, s>>>(sc, (unsigned int)grid);
@@ -1206,7 +1222,7 @@ static int v4_step_impl(ZbotHandle* h, const float* actions, const float* rand, 
   while (block > 32 && (n + block - 1) / block < 2 * h->num_sms) block >>= 1;
   const int grid = (n + block - 1) / block;
   const size_t smem = (size_t)block * SCR_STRIDE * sizeof(float);
-  StatsCtx sc{h->partials, h->ring, slot, prev, h->inv_episode_s, 0};
+  StatsCtx sc{h->partials, h->ring, slot, prev, h->inv_episode_s, 0, (unsigned long long)h->launches, 0};
   cudaStream_t s = (cudaStream_t)stream;
   const uint64_t call = h->v4_calls++;
   if (export_buf)
@@ -1265,7 +1281,7 @@ int zbot_reset_idx(ZbotHandle* h, const int64_t* env_ids, int64_t nids, const ui
   if (nids > n) return fail(ZBOT_E_INVALID, "more env ids than envs%s");
   const int block = 64;
   const int grid = (int)((nids + block - 1) / block);
-  StatsCtx sc{h->partials, h->ring, stats_slot, -1, h->inv_episode_s, 0};
+  StatsCtx sc{h->partials, h->ring, stats_slot, -1, h->inv_episode_s, 0, (unsigned long long)h->launches, 0};
   if (h->cfg.task == ZBOT_TASK_SNAKE_V0)
     zbot_reset_kernel<true><<<grid, block, 32 * kStatUsed * sizeof(float), (cudaStream_t)stream>>>(
         h->P, h->dp, h->state, h->ep_len, env_ids, nids, terminated, truncated, n, sc);
@@ -1335,7 +1351,7 @@ int zbot_mdp_observe(ZbotHandle* h, const ZbotMdpInputs* in, float* obs, void* s
   const int n = h->cfg.num_envs, block = 128, grid = (n + block - 1) / block;
   MdpIn mi{in->body_link_pos_w, in->body_link_quat_w, in->body_com_lin_vel_w, in->joint_pos, in->joint_vel,
            in->applied_torque, in->net_forces_w_history, in->last_air_time, in->env_origins};
-  StatsCtx sc{h->partials, h->m_ring, 0, -1, h->inv_episode_s, 0};
+  StatsCtx sc{h->partials, h->m_ring, 0, -1, h->inv_episode_s, 0, (unsigned long long)h->launches, 0};
   zbot_mdp_kernel<false><<<grid, block, block * ZBOT_NUM_OBS * sizeof(float), (cudaStream_t)stream>>>(
       h->P, h->dp, mi, h->mstate, h->m_ep_len, nullptr, obs, nullptr, nullptr, nullptr, n, sc);
   ZB_CUDA(cudaGetLastError());
@@ -1351,7 +1367,7 @@ int zbot_mdp_step(ZbotHandle* h, const ZbotMdpInputs* in, const float* actions, 
   const int n = h->cfg.num_envs, block = h->mdp_tile, grid = (n + block - 1) / block;
   MdpIn mi{in->body_link_pos_w, in->body_link_quat_w, in->body_com_lin_vel_w, in->joint_pos, in->joint_vel,
            in->applied_torque, in->net_forces_w_history, in->last_air_time, in->env_origins};
-  StatsCtx sc{h->partials, h->m_ring, stats_slot, prev_slot, h->inv_episode_s, 0};
+  StatsCtx sc{h->partials, h->m_ring, stats_slot, prev_slot, h->inv_episode_s, 0, (unsigned long long)h->launches, 0};
   zbot_mdp_kernel<true><<<grid, block, (size_t)block * kHistRow * sizeof(float), (cudaStream_t)stream>>>(
       h->P, h->dp, mi, h->mstate, h->m_ep_len, actions, obs, rew, terminated, truncated, n, sc);
   ZB_CUDA(cudaGetLastError());

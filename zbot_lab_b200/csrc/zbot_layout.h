@@ -189,6 +189,9 @@ inline void params_from_cfg(const ZbotCfg& c, Params<T>& P) {
   P.ev_offset = T(c.ev_offset); P.ev_prob_pos = T(c.ev_prob_pos); P.ev_dual_sign = c.ev_dual_sign;
   for (int i = 0; i < 3; ++i) { P.ev_pose_lo[i] = T(c.ev_pose_lo[i]); P.ev_pose_hi[i] = T(c.ev_pose_hi[i]); }
   P.ev_interval_lo = T(c.ev_interval_lo); P.ev_interval_hi = T(c.ev_interval_hi);
+  P.obs_noise_enable = c.obs_noise_enable;
+  for (int i = 0; i < 24; ++i) { P.obs_noise_lo[i] = T(c.obs_noise_lo[i]); P.obs_noise_w[i] = T(c.obs_noise_hi[i]) - T(c.obs_noise_lo[i]); }
+  P.rng_seed = c.rng_seed;
   P.default_terms = (c.num_terms == 13) && (c.task == ZBOT_TASK_WALKING_V2);
   for (int i = 0; i < 13 && P.default_terms; ++i) P.default_terms = (c.term_id[i] == i);
 }

@@ -12,7 +12,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libzbot_b200.so")
 
-ZBOT_ABI_VERSION = 3
+ZBOT_ABI_VERSION = 4
 TASK_WALKING_V2, TASK_SNAKE_V0, TASK_WALKING_V4 = 0, 1, 2
 V4_NUM_OBS, V4_NUM_RAND, V4_EXPORT_WORDS = 24, 10, 69
 MAX_TERMS = 16
@@ -67,6 +67,7 @@ class ZbotCfg(C.Structure):
         ("ev_offset", C.c_float), ("ev_prob_pos", C.c_float), ("ev_dual_sign", C.c_int32),
         ("ev_pose_lo", C.c_float * 3), ("ev_pose_hi", C.c_float * 3),
         ("ev_interval_lo", C.c_float), ("ev_interval_hi", C.c_float), ("rng_seed", C.c_uint64),
+        ("obs_noise_enable", C.c_int32), ("obs_noise_lo", C.c_float * 24), ("obs_noise_hi", C.c_float * 24),
     ]
 
 
@@ -82,6 +83,26 @@ class ZbotMdpInputs(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "body_link_pos_w", "body_link_quat_w", "body_com_lin_vel_w", "joint_pos", "joint_vel",
         "applied_torque", "net_forces_w_history", "last_air_time", "env_origins")]
+
+
+#: observation columns per term, in concatenation order (…env_v2.py:351-366 / …env_v4.py:835-847 / snake_v0.py:189-206)
+OBS_TERMS = {"base_quat": (0, 4), "joint_pos": (4, 10), "joint_vel": (10, 16), "actions": (16, 22), "extra": (22, 24)}
+
+
+def set_obs_noise(cfg: "ZbotCfg", noise: dict | None):
+    """``noise`` = {term: (n_min, n_max)} over OBS_TERMS -- additive uniform corruption of the emitted observation
+    (ObservationManager ``Unoise`` semantics, zbotlab_manager/zbotlab_env_cfg.py PolicyCfg); None / {} disables it."""
+    for i in range(24):
+        cfg.obs_noise_lo[i] = cfg.obs_noise_hi[i] = 0.0
+    cfg.obs_noise_enable = 0
+    for term, (lo, hi) in (noise or {}).items():
+        if term not in OBS_TERMS:
+            raise KeyError(f"unknown observation term {term!r}; known: {sorted(OBS_TERMS)}")
+        a, b = OBS_TERMS[term]
+        for i in range(a, b):
+            cfg.obs_noise_lo[i], cfg.obs_noise_hi[i] = float(lo), float(hi)
+        cfg.obs_noise_enable = 1
+    return cfg
 
 
 def make_cfg(num_envs: int, reward_scales: dict | None = None, step_dt: float | None = None,

@@ -41,6 +41,10 @@ class ZbotDirectEnvCfgV0(Cfg):
     seed = None
     log_dir = None
     is_finite_horizon = False
+    # additive uniform observation noise {term: (n_min, n_max)} over base_quat / joint_pos / joint_vel / actions / extra
+    # (ObservationManager `Unoise` semantics of the manager-based task, zbotlab_manager/zbotlab_env_cfg.py PolicyCfg:
+    # base_quat +-0.01, joint_pos +-0.01, joint_vel +-1.5); None = the direct tasks' behaviour (no corruption)
+    observation_noise = None
     check_all_envs_reset = None
     output_ring = 4
 

@@ -147,14 +147,17 @@ class ZbotDirectEnvV2:
     def _native_cfg(self) -> native.ZbotCfg:
         c, a = self.cfg.contact, self.cfg.actuator
         extra = {"termination_height": float(self.cfg.termination_height)} if hasattr(self.cfg, "termination_height") else {}
-        return native.make_cfg(
+        if getattr(self.cfg, "observation_noise", None):
+            extra["rng_seed"] = int(self.cfg.seed if self.cfg.seed is not None else torch.initial_seed() & 0x7FFFFFFF)
+        return native.set_obs_noise(native.make_cfg(
             self.num_envs, reward_scales=self.cfg.reward_cfg["reward_scales"], step_dt=self.step_dt, task=self._TASK,
             sim_dt=self.physics_dt, decimation=int(self.cfg.decimation),
             max_episode_length=int(self.max_episode_length),
             kp=a.stiffness, kd=a.damping, effort_limit=a.effort_limit,
             gravity=-float(self.cfg.sim.gravity[2]),
             contact_alpha=c.alpha, contact_erp=c.erp, contact_vdep=c.max_depenetration_velocity,
-            contact_beta_max=c.beta_max, contact_mu=c.friction, contact_ramp=c.ramp, contact_margin=c.margin, **extra)
+            contact_beta_max=c.beta_max, contact_mu=c.friction, contact_ramp=c.ramp, contact_margin=c.margin, **extra),
+            getattr(self.cfg, "observation_noise", None))
 
     def _initial_reset(self):
         self._stepper.reset_idx(None)

@@ -46,7 +46,7 @@ class Zbot6SEnvV4(ZbotDirectEnvV2):
         hi = [pr.get(k, (0.0, 0.0))[1] for k in ("x", "y", "yaw")]
         p = self.event_params
         seed = self.cfg.seed if self.cfg.seed is not None else int(torch.initial_seed() & 0x7FFFFFFF)
-        return native.make_cfg(
+        return native.set_obs_noise(native.make_cfg(
             self.num_envs, reward_scales=self._live_scales, step_dt=self.step_dt, task=self._TASK,
             sim_dt=self.physics_dt, decimation=int(self.cfg.decimation), max_episode_length=int(self.max_episode_length),
             termination_height=float(self.cfg.termination_height), kp=a.stiffness, kd=a.damping,
@@ -56,7 +56,8 @@ class Zbot6SEnvV4(ZbotDirectEnvV2):
             ev_vel_lo=p["velocity_range"][0], ev_vel_hi=p["velocity_range"][1], ev_yaw_lo=p["yaw_range"][0],
             ev_yaw_hi=p["yaw_range"][1], ev_offset=p["offset"], ev_prob_pos=p["prob_pos"], ev_dual_sign=int(p["dual_sign"]),
             ev_pose_lo=lo, ev_pose_hi=hi, ev_interval_lo=float(ev.command_resample.interval_range_s[0]),
-            ev_interval_hi=float(ev.command_resample.interval_range_s[1]), rng_seed=int(seed))
+            ev_interval_hi=float(ev.command_resample.interval_range_s[1]), rng_seed=int(seed)),
+            getattr(self.cfg, "observation_noise", None))
 
     def _push_cfg(self):
         """Re-derive the kernel's weight table / event parameters after a curriculum changed them."""
