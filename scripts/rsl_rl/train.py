@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Train ``zbot-6b-walking-v2`` with PPO on the B200 step.
+"""Train a ZBOT task (``zbot-6b-walking-v2`` / ``-v4`` / ``zbot-6s-snake-v0``) with PPO on the B200 step.
 
 Same flow and flags as the reference's ``scripts/rsl_rl/train.py`` (task lookup in the gym registry
 -> cfg overrides from the CLI -> ``gym.make(task, cfg=env_cfg)`` -> ``RslRlVecEnvWrapper`` ->
@@ -31,7 +31,19 @@ parser.add_argument("--run_name", type=str, default=None)
 parser.add_argument("--resume", action="store_true", default=False)
 parser.add_argument("--checkpoint", type=str, default=None, help="Checkpoint file to resume from.")
 parser.add_argument("--log_root", type=str, default="logs/rsl_rl")
-args_cli = parser.parse_args()
+parser.add_argument("--load_run", type=str, default=None, help="Name of the run folder to resume from.")
+parser.add_argument("--logger", type=str, default=None, choices={"wandb", "tensorboard", "neptune"})
+parser.add_argument("--log_project_name", type=str, default=None)
+# flags of the reference command lines that have no effect here (no simulator app, no renderer):
+# AppLauncher.add_app_launcher_args (train.py:37) and the video options (train.py:20-22, 33)
+parser.add_argument("--headless", action="store_true", default=False, help="accepted for compatibility (always headless)")
+parser.add_argument("--enable_cameras", action="store_true", default=False, help="accepted for compatibility")
+parser.add_argument("--livestream", type=int, default=0, help="accepted for compatibility")
+parser.add_argument("--video", action="store_true", default=False, help="accepted; rendering is out of scope (no video is recorded)")
+parser.add_argument("--video_length", type=int, default=200)
+parser.add_argument("--video_interval", type=int, default=2000)
+parser.add_argument("--export_io_descriptors", action="store_true", default=False)
+args_cli, hydra_overrides = parser.parse_known_args()   # the reference forwards the rest to Hydra (train.py:44-45)
 
 import torch  # noqa: E402
 
@@ -45,6 +57,25 @@ from zbot_lab_b200.rl.ppo_runner import OnPolicyRunner  # noqa: E402
 def main():
     env_cfg = gym.load_cfg_from_registry(args_cli.task, "env_cfg_entry_point")
     agent_cfg = gym.load_cfg_from_registry(args_cli.task, args_cli.agent)
+    # Hydra-style overrides of the reference CLI ("env.scene.num_envs=64 agent.max_iterations=10", train.py:109)
+    for ov in hydra_overrides:
+        if "=" not in ov or not ov.split(".", 1)[0] in ("env", "agent"):
+            raise SystemExit(f"unrecognized argument: {ov}")
+        path, val = ov.split("=", 1)
+        obj = env_cfg if path.startswith("env.") else agent_cfg
+        *parents, leaf = path.split(".")[1:]
+        for part in parents:
+            obj = obj[part] if isinstance(obj, dict) else getattr(obj, part)
+        try:
+            val = __import__("ast").literal_eval(val)
+        except (ValueError, SyntaxError):
+            pass
+        if isinstance(obj, dict):
+            obj[leaf] = val
+        else:
+            setattr(obj, leaf, val)
+    if args_cli.video:
+        print("[WARN] --video: rendering is out of scope of the B200 step; training without recording.")
     if args_cli.seed is not None:
         agent_cfg.seed = args_cli.seed
     if args_cli.experiment_name:
