@@ -176,16 +176,17 @@ def test_snake_env_registry_protocol_and_log_keys():
     w.close()
 
 
-def test_step_host_zero_copy_equals_device_step():
+@pytest.mark.parametrize("n", [1000, 19001])   # 19001 > 148 * 128: the unroll-2 instantiation (one more variant family)
+def test_step_host_zero_copy_equals_device_step(n):
     """env.step_host (pinned host actions in, packed host result out, zero-copy inside the kernel launch) returns
     bit-for-bit what env.step returns on the device for the same state and actions."""
-    a_env, _ = _make(1000, check_all_envs_reset=False)
-    b_env, _ = _make(1000, check_all_envs_reset=False)
+    a_env, _ = _make(n, check_all_envs_reset=False)
+    b_env, _ = _make(n, check_all_envs_reset=False)
     b_env.episode_length_buf = a_env.episode_length_buf.clone()
     g = torch.Generator().manual_seed(4)
     _, h_out = b_env.alloc_host_buffers()
     for t in range(25):
-        h_act = torch.randn(1000, 6, generator=g).pin_memory()
+        h_act = torch.randn(n, 6, generator=g).pin_memory()
         obs_h, rew_h, term_h, trunc_h = b_env.step_host(h_act, h_out)
         obs, rew, term, trunc, _ = a_env.step(h_act.to("cuda:0"))
         assert torch.equal(obs["policy"].cpu(), obs_h) and torch.equal(rew.cpu(), rew_h)

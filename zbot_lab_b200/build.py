@@ -41,7 +41,7 @@ def is_stale() -> bool:
 def build_native(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return OUT
-    cmd = [nvcc_path(), *NVCC_FLAGS, "-o", OUT, *SOURCES]
+    cmd = [nvcc_path(), *NVCC_FLAGS, *os.environ.get("ZBOT_NVCC_EXTRA", "").split(), "-o", OUT, *SOURCES]
     env = dict(os.environ)
     # the image exports CC/CXX pointing at a wrapper without libgomp specs; nvcc only needs a host g++
     if os.access("/usr/bin/g++", os.X_OK):

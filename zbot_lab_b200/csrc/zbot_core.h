@@ -612,7 +612,10 @@ struct SubstepOut {
 };
 
 // mid_force_out: optional [5][3] predictor forces of bodies 1..5 (export / debug only)
-template <typename Model, bool kPipe = (ZB_PIPELINED_SWEEP != 0), typename PS, typename T, typename Scr>
+// kUnroll: unroll factor of the three sweeps over the chain (FK, backward, forward).  1 = smallest code (best for a lone
+// warp per SM: instruction fetch is 11 % of its time); 2 halves the loop-carried register shuffles (MOV was 8.5 % of the
+// executed instructions) and wins ~4 % once two or more warps share a sub-partition (profiles/r1_notes.md).
+template <typename Model, bool kPipe = (ZB_PIPELINED_SWEEP != 0), int kUnroll = 1, typename PS, typename T, typename Scr>
 ZB_HD void physics_substep(const Params<PS>& P, SimState<T>& s, const T* target, SubstepOut<T>& out, Scr& scr,
                            T* mid_force_out) {
   using namespace model;
@@ -630,7 +633,7 @@ ZB_HD void physics_substep(const Params<PS>& P, SimState<T>& s, const T* target,
   T w[3] = {s.w[0], s.w[1], s.w[2]};         // spatial velocity of the current body about O
   T vO[3] = {s.v[0], s.v[1], s.v[2]};
 #if defined(__CUDACC__)
-#pragma unroll 1
+#pragma unroll kUnroll
 #endif
   for (int k = 0; k < 6; ++k) {
     T R[9];
@@ -691,7 +694,7 @@ ZB_HD void physics_substep(const Params<PS>& P, SimState<T>& s, const T* target,
     if (Model::kGroundForceSensor) agg1 = agg;
   }
 #if defined(__CUDACC__)
-#pragma unroll 1
+#pragma unroll kUnroll
 #endif
   for (int k = 6; k >= 1; --k) {
     const int j = k - 1;          // joint between body k and body k-1
@@ -873,7 +876,7 @@ ZB_HD void physics_substep(const Params<PS>& P, SimState<T>& s, const T* target,
   }
   // ---- forward sweep: joint accelerations ----
 #if defined(__CUDACC__)
-#pragma unroll 1
+#pragma unroll kUnroll
 #endif
   for (int j = 0; j < 6; ++j) {
     const T Sa[3] = {scr(j, SC_SA), scr(j, SC_SA + 1), scr(j, SC_SA + 2)};
@@ -1356,7 +1359,7 @@ struct PhysOut {
 // Phase B of the control step: _pre_physics_step (…env_v2.py:276-287) + decimation x (physics substep +
 // ContactSensor.update).  Touches only e.sim, e.mdp.p_delta / speed_limit and the contact carry /
 // timers, so a GPU thread can run it before the rest of the MDP state has even been loaded.
-template <typename Model, typename T, typename Scr>
+template <typename Model, int kUnroll = 1, typename T, typename Scr>
 ZB_HD void env_step_physics(const Params<T>& P, EnvState<T>& e, const T* raw_actions, PhysOut<T>& po, Scr& scr,
                             StepExport<T>* ex) {
   T new_actions[6], target[6];
@@ -1381,7 +1384,7 @@ ZB_HD void env_step_physics(const Params<T>& P, EnvState<T>& e, const T* raw_act
     if (Model::kTask == 2) {
       if (sub == P.decimation - 1) { ZB_UNROLL for (int k = 0; k < 6; ++k) po.qd_prev[k] = e.sim.qd[k]; }
     }
-    physics_substep<Model>(P, e.sim, target, so, scr, ex ? midf : (T*)nullptr);
+    physics_substep<Model, (ZB_PIPELINED_SWEEP != 0), kUnroll>(P, e.sim, target, so, scr, ex ? midf : (T*)nullptr);
     if (!Model::kGroundForceSensor) continue;
     // ContactSensor.update
     const int slot = P.decimation - 1 - sub;  // newest first

@@ -201,7 +201,7 @@ constexpr int kFoot0Sensor = 9, kFoot1Sensor = 10;
 // sc.packed_rows: host-facing output layout -- ONE row of 25 words per env [obs 23 | reward | flags word
 // (terminated | truncated << 8)] written to `obs` ([N][25]); `rew` / `terminated` / `truncated` are not touched.
 // A run-time flag of the SAME kernel (not a second instantiation), so step_host and step are bit-identical.
-template <bool kExport>
+template <bool kExport, int kUnroll = 1>
 __device__ __forceinline__ void
 zbot_step_body(const Params<float>& P, const DefaultPose& dp,
                  float4* __restrict__ state, int64_t* __restrict__ ep_len_buf,
@@ -274,7 +274,7 @@ zbot_step_body(const Params<float>& P, const DefaultPose& dp,
 #pragma unroll
         for (int k = 0; k < 6; ++k) scr.base[SCR_RAW_ACT + k] = raw[k];
         // ---- phase B: 4 physics substeps; the MDP state is not even loaded yet (register budget) ----
-        env_step_physics<ModelWalk>(P, es, raw, po, scr, (StepExport<float>*)nullptr);
+        env_step_physics<ModelWalk, kUnroll>(P, es, raw, po, scr, (StepExport<float>*)nullptr);
       }
       // ---- phase C: the 9 "late" quads, the start-of-step state S0 again (still unmodified in global
       //      memory -> L2 hit) for the one-step-stale quantities, the raw actions again, then the MDP ----
@@ -448,6 +448,11 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) zbot_step2_kernel(ZB_
   stats_block_partial(stat, did_reset, smem, sc);
 }
 
+// chain sweeps unrolled by two (large N: two or more warps per sub-partition)
+template <int kMaxThreads, int kMinBlocks>
+__global__ void __launch_bounds__(kMaxThreads, kMinBlocks) zbot_step_u2_kernel(ZB_STEP_ARGS) {
+  zbot_step_body<false, 2>(ZB_STEP_CALL);
+}
 // same body, register cap given directly (ptxas snaps __launch_bounds__ caps to a few occupancy steps:
 // 197 -> 168 -> 128; __maxnreg__ gives the steps in between)
 template <int kMaxRegs>
@@ -460,7 +465,7 @@ __global__ void __maxnreg__(kMaxRegs) zbot_step_kernel_r(ZB_STEP_ARGS) {
 // ---------------------------------------------------------------------------------------------
 constexpr int kSnakeExportWords = (int)(sizeof(SnakeExport<float>) / sizeof(float));   // 41
 
-template <bool kExport>
+template <bool kExport, int kUnroll = 1>
 __global__ void __launch_bounds__(128, 2)
 zbot_snake_step_kernel(const __grid_constant__ Params<float> P, const __grid_constant__ DefaultPose dp,
                        float4* __restrict__ state, int64_t* __restrict__ ep_len_buf, const float* __restrict__ actions,
@@ -496,7 +501,7 @@ zbot_snake_step_kernel(const __grid_constant__ Params<float> P, const __grid_con
       const float raw[6] = {a0.x, a0.y, a1.x, a1.y, a2v.x, a2v.y};
 #pragma unroll
       for (int k = 0; k < 6; ++k) scr.base[SCR_RAW_ACT + k] = raw[k];
-      env_step_physics<ModelSnake>(P, es, raw, po, scr, (StepExport<float>*)nullptr);
+      env_step_physics<ModelSnake, kUnroll>(P, es, raw, po, scr, (StepExport<float>*)nullptr);
     }
     {
       float w[ZBOT_STATE_WORDS - 4 * EARLY_QUADS];
@@ -554,7 +559,7 @@ zbot_snake_step_kernel(const __grid_constant__ Params<float> P, const __grid_con
 // ---------------------------------------------------------------------------------------------
 static_assert(sizeof(V4Export<float>) / sizeof(float) == ZBOT_V4_EXPORT_WORDS, "V4Export layout");
 
-template <bool kExport>
+template <bool kExport, int kUnroll = 1>
 __global__ void __launch_bounds__(128, 2)
 zbot_v4_step_kernel(const __grid_constant__ Params<float> P, float4* __restrict__ state, int64_t* __restrict__ ep_len_buf,
                     const float* __restrict__ actions, const float* __restrict__ rand, uint64_t seed, uint64_t call,
@@ -590,7 +595,7 @@ zbot_v4_step_kernel(const __grid_constant__ Params<float> P, float4* __restrict_
       const float raw[6] = {a0.x, a0.y, a1.x, a1.y, a2v.x, a2v.y};
 #pragma unroll
       for (int k = 0; k < 6; ++k) scr.base[SCR_RAW_ACT + k] = raw[k];
-      env_step_physics<ModelWalkV4>(P, es, raw, po, scr, (StepExport<float>*)nullptr);
+      env_step_physics<ModelWalkV4, kUnroll>(P, es, raw, po, scr, (StepExport<float>*)nullptr);
     }
     {
       float w[ZBOT_STATE_WORDS - 4 * EARLY_QUADS];
@@ -948,6 +953,7 @@ struct ZbotHandle {
   DefaultPose dp;
   int device;
   int num_sms;
+  bool unroll2;    // chain sweeps unrolled by two (more than one warp per scheduler)
   float4* state;
   int64_t* ep_len;
   float* ring;
@@ -981,6 +987,8 @@ const StepVariant kStepVariants[] = {
     {64, 6, zbot_step_kernel<false, 64, 6>, 1}, {32, 12, zbot_step_kernel<false, 32, 12>, 1},
     {32, 13, zbot_step_kernel_r<152>, 1}, {32, 14, zbot_step_kernel_r<144>, 1}, {64, 7, zbot_step_kernel_r<144>, 1},
     {32, 16, zbot_step_kernel<false, 32, 16>, 1},
+    // chain sweeps unrolled by two: "u128x2" / "u128x3"
+    {2128, 2, zbot_step_u2_kernel<128, 2>, 1}, {2128, 3, zbot_step_u2_kernel<128, 3>, 1},
     // EXPERIMENTAL, opt-in (ZBOT_STEP_VARIANT=p128x2): two envs per thread, packed FP32 (zbot_step2_kernel).  31 % fewer
     // warp instructions per env, but 255 registers + spills at 1.7 warps per sub-partition: 84.0 vs 86.4 us at 65536 envs,
     // 59 vs 35 us at 4096 (profiles/r1_notes.md).
@@ -1061,6 +1069,8 @@ int zbot_create(const ZbotCfg* cfg, int device, ZbotHandle** out) {
   ZB_CUDA(cudaFuncSetAttribute(zbot_snake_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
   ZB_CUDA(cudaFuncSetAttribute(zbot_v4_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
   ZB_CUDA(cudaFuncSetAttribute(zbot_v4_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
+  ZB_CUDA(cudaFuncSetAttribute(zbot_snake_step_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
+  ZB_CUDA(cudaFuncSetAttribute(zbot_v4_step_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
   {
     // register-budget variant of the step kernel = resident 128-thread CTAs per SM it is compiled for.
     // Measured (profiles/r1_notes.md): 2 CTAs/SM (197 regs, no spill) is fastest while the grid fits two
@@ -1069,8 +1079,14 @@ int zbot_create(const ZbotCfg* cfg, int device, ZbotHandle** out) {
     int vt = 0, vc = 0;
     h->variant = -1;
     if (sv && sv[0] == 'p' && sscanf(sv + 1, "%dx%d", &vt, &vc) == 2) h->variant = find_variant(1000 + vt, vc);
+    else if (sv && sv[0] == 'u' && sscanf(sv + 1, "%dx%d", &vt, &vc) == 2) h->variant = find_variant(2000 + vt, vc);
     else if (sv && sscanf(sv, "%dx%d", &vt, &vc) == 2) h->variant = find_variant(vt, vc);
-    if (h->variant < 0) h->variant = find_variant(128, (cfg->num_envs > 2 * 2 * 148 * 128) ? 3 : 2);
+    // default: 2 CTAs/SM (197 registers) up to 75776 envs, 3 CTAs/SM (168) above; the sweeps unrolled by two as soon as a
+    // scheduler holds more than one warp (N > 148 * 4 * 32), measured -2.3 us at 32768, -3.3 us at 65536 envs
+    h->unroll2 = cfg->num_envs > 4 * 32 * h->num_sms;
+    if (const char* su = getenv("ZBOT_SWEEP_UNROLL")) h->unroll2 = (atoi(su) == 2);   // test / tuning override, all tasks
+    if (h->variant < 0)
+      h->variant = find_variant((h->unroll2 ? 2000 : 0) + 128, (cfg->num_envs > 2 * 2 * 148 * 128) ? 3 : 2);
     const char* mt = getenv("ZBOT_MDP_TILE");          // envs (= threads) per CTA of the MDP-only step kernel
     h->mdp_tile = mt ? atoi(mt) : kMdpTile;
     if (h->mdp_tile != 32 && h->mdp_tile != 64 && h->mdp_tile != 128) h->mdp_tile = kMdpTile;
@@ -1122,6 +1138,9 @@ static int step_impl(ZbotHandle* h, const float* actions, float* obs, float* rew
     if (snake_export)
       zbot_snake_step_kernel<true><<<grid, block, smem, s>>>(h->P, h->dp, h->state, h->ep_len, actions, obs, rew, terminated,
                                                          truncated, n, sc, snake_export);
+    else if (h->unroll2)   // more than one warp per scheduler: sweeps unrolled by two (see zbot_create)
+      zbot_snake_step_kernel<false, 2><<<grid, block, smem, s>>>(h->P, h->dp, h->state, h->ep_len, actions, obs, rew,
+                                                             terminated, truncated, n, sc, nullptr);
     else
       zbot_snake_step_kernel<false><<<grid, block, smem, s>>>(h->P, h->dp, h->state, h->ep_len, actions, obs, rew, terminated,
                                                           truncated, n, sc, nullptr);
@@ -1190,7 +1209,7 @@ int zbot_step_host(ZbotHandle* h, const float* host_actions, float* host_rows, i
   const int n = h->cfg.num_envs;
   // the SAME kernel instantiation and CTA shape `zbot_step` uses for this handle (bit-identical results)
   const int vi = (kStepVariants[h->variant].envs_per_thread == 1) ? h->variant : find_variant(128, 2);
-  int block = kStepVariants[vi].threads;
+  int block = kStepVariants[vi].threads % 1000;
   while (block > 32 && (n + block - 1) / block < 2 * h->num_sms) block >>= 1;
   const int grid = (n + block - 1) / block;
   const size_t smem = (size_t)block * SCR_STRIDE * sizeof(float);
@@ -1228,6 +1247,9 @@ static int v4_step_impl(ZbotHandle* h, const float* actions, const float* rand, 
   if (export_buf)
     zbot_v4_step_kernel<true><<<grid, block, smem, s>>>(h->P, h->state, h->ep_len, actions, rand, h->cfg.rng_seed, call, obs, rew,
                                                     terminated, truncated, n, sc, export_buf);
+  else if (h->unroll2)
+    zbot_v4_step_kernel<false, 2><<<grid, block, smem, s>>>(h->P, h->state, h->ep_len, actions, rand, h->cfg.rng_seed, call, obs,
+                                                        rew, terminated, truncated, n, sc, nullptr);
   else
     zbot_v4_step_kernel<false><<<grid, block, smem, s>>>(h->P, h->state, h->ep_len, actions, rand, h->cfg.rng_seed, call, obs, rew,
                                                      terminated, truncated, n, sc, nullptr);
