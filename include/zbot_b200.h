@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define ZBOT_ABI_VERSION 4
+#define ZBOT_ABI_VERSION 5
 
 #define ZBOT_OK 0
 #define ZBOT_E_INVALID (-1) /* bad argument / unsupported configuration */
@@ -82,13 +82,29 @@ enum ZbotTerm {
   ZBOT_TERM_V4_LIN_VEL_X = 30,
   ZBOT_TERM_V4_AIRTIME_SUM = 31,
   ZBOT_TERM_V4_FEET_HEIGHT = 32,
-  ZBOT_TERM_V4_BASE_HEIGHT = 33
+  ZBOT_TERM_V4_BASE_HEIGHT = 33,
+  /* zbot-6b-walking-m-v0 RewTerm functions (tasks/zbotlab_manager/mdp/rewards.py; isaaclab.envs.mdp [IL-upstream]).
+   * joint_torques_l2 / joint_acc_l2 / action_rate_l2 / foot_downward / foot_forward / air_time_balance_penalty /
+   * air_time_variance_penalty share ids 8 / 24 / 7 / 1 / 2 / 6 / 27.  term_param[slot] = the RewTerm's params. */
+  ZBOT_TERM_M_TRACK_LIN_VEL_XY_EXP = 34, /* params {std^2} */
+  ZBOT_TERM_M_TRACK_ANG_VEL_Z_EXP = 35,  /* params {std^2} */
+  ZBOT_TERM_M_FOOT_STEP_LENGTH = 36,
+  ZBOT_TERM_M_GAIT = 37,                 /* params {period, offset[0], offset[1], threshold} */
+  ZBOT_TERM_M_FEET_SLIDE = 38,
+  ZBOT_TERM_M_FEET_CLEARANCE = 39,       /* params {std, tanh_mult, target_height} */
+  ZBOT_TERM_M_FEET_AIR_TIME_BIPED = 40,  /* params {threshold} */
+  ZBOT_TERM_M_BASE_VEL_FORWARD = 41,     /* params {which_forward} */
+  ZBOT_TERM_M_FEET_FORCE_PATTERN = 42
 };
 
 /* tasks sharing the fused step (same 7-body chain, different robot cfg / USD frames / MDP) */
 #define ZBOT_TASK_WALKING_V2 0 /* zbot-6b-walking-v2: ZbotDirectEnvV2 + ZBOT_6S_CFG */
 #define ZBOT_TASK_SNAKE_V0 1   /* zbot-6s-snake-v0:  ZbotDirectEnvV0 (zbot6_direct) + ZBOT_D_6S_CFG */
 #define ZBOT_TASK_WALKING_V4 2 /* zbot-6b-walking-v4: Zbot6SEnvV4 + ZBOT_6S_CFG, commands + events */
+#define ZBOT_TASK_WALKING_M 3  /* zbot-6b-walking-m-v0: ManagerBasedRLEnv + Zbot6BFlatEnvCfg + ZBOT_6S_V2_CFG */
+#define ZBOT_M_NUM_OBS 25
+#define ZBOT_M_NUM_RAND 13     /* uniforms per env-step, see zbot_m_step */
+#define ZBOT_M_EXPORT_WORDS 67
 #define ZBOT_V4_NUM_OBS 24
 #define ZBOT_V4_NUM_RAND 10    /* uniforms per env-step, see zbot_v4_step */
 #define ZBOT_V4_EXPORT_WORDS 69
@@ -133,6 +149,18 @@ typedef struct ZbotCfg {
    * generator (rng_seed); the stored state and the rewards never see it.  All tasks; off by default. */
   int32_t obs_noise_enable;
   float obs_noise_lo[24], obs_noise_hi[24];
+  /* zbot-6b-walking-m-v0 only (zbotlab_manager/zbotlab_env_cfg.py).  term_weight holds the BARE RewTerm weight
+   * (RewardManager multiplies by step_dt at evaluation time), term_param the RewTerm params of the same slot;
+   * `CommandsCfg.base_velocity` ranges / rel_standing_envs / resampling_time_range (:99-117); `ActionsCfg.joint_pos`
+   * scale and symmetric clip (:124-130); DoneTerms: termination_height = base_height.minimum_height, feet_close
+   * minimum_distance (<= 0: absent); is_terminated_weight = weight of RewTerm termination_penalty (0: absent).
+   * reset_base pose ranges reuse ev_pose_lo / ev_pose_hi; per-env friction lives in the state word `joint_speed_limit`. */
+  float term_param[ZBOT_MAX_TERMS][4];
+  float cmd_lo[3], cmd_hi[3];
+  float cmd_rel_standing, cmd_resample_lo, cmd_resample_hi;
+  float act_scale, act_clip;
+  float feet_close_min;
+  float is_terminated_weight;
 } ZbotCfg;
 
 typedef struct ZbotHandle ZbotHandle;
@@ -226,6 +254,25 @@ int zbot_v4_step(ZbotHandle* h, const float* actions, const float* rand, float* 
 int zbot_v4_step_export(ZbotHandle* h, const float* actions, const float* rand, float* obs, float* rew,
                         uint8_t* terminated, uint8_t* truncated, int32_t stats_slot, int32_t prev_slot,
                         float* export_buf, void* stream);
+/* zbot-6b-walking-m-v0: one fused control step of the manager-based task in ManagerBasedRLEnv.step order
+ * ([IL-upstream]; terms from zbotlab_manager/zbotlab_env_cfg.py + mdp/*.py): RelativeJointPositionAction applied at every
+ * substep, 4 x (implicit PD + articulation + ContactSensor, history 3), TerminationManager (time_out, base_height,
+ * feet_close), RewardManager (cfg-order term table), reset of the done envs (reset_base, reset_robot_joints,
+ * reset_my_data, command resample), CommandManager.compute, ObservationManager with additive uniform noise.
+ *   actions float [N][6]   raw policy output, Isaac Lab joint order (joint1, joint7, joint2, joint8, joint3, joint9)
+ *   obs     float [N][25]  [root_quat_w 4, velocity_commands 3, joint_pos_rel 6, joint_vel_rel 6, last_action 6]
+ *   rand    float [N][ZBOT_M_NUM_RAND] uniforms in [0,1) or NULL = in-kernel generator.  Slots: 0..2 reset pose x / y /
+ *           yaw, 3..7 command resample at reset (time, vx, vy, wz, standing), 8..12 the same at timer expiry.
+ * State slots reused (zbot_state_word names): carry_feet_fz = command lin_vel x / y, carry_mid_max = command ang_vel z,
+ * base_heading_x_sum = is_standing_env, base_pos_y_err_sum = command time_left, joint_speed_limit = friction
+ * coefficient of the env, actions = last raw action.  Statistics words 0..num_terms-1 = Episode_Reward/<term>; when
+ * num_terms <= 14, words 14 / 15 = (#base_height, #feet_close among the reset envs) / #reset * (1 / episode seconds).
+ * `export` (zbot_m_step_export, test hook): [N][ZBOT_M_EXPORT_WORDS] view the terms saw (MExport). */
+int zbot_m_step(ZbotHandle* h, const float* actions, const float* rand, float* obs, float* rew, uint8_t* terminated,
+                uint8_t* truncated, int32_t stats_slot, int32_t prev_slot, void* stream);
+int zbot_m_step_export(ZbotHandle* h, const float* actions, const float* rand, float* obs, float* rew,
+                       uint8_t* terminated, uint8_t* truncated, int32_t stats_slot, int32_t prev_slot,
+                       float* export_buf, void* stream);
 /* Replace the reward weights / event parameters of a live handle (host-side curricula, …env_v4.py:138-265);
  * num_envs, task and the dynamics parameters must be unchanged. */
 int zbot_update_cfg(ZbotHandle* h, const ZbotCfg* cfg);

@@ -130,10 +130,41 @@ static int port_v4_step(const ZbotCfg* cfg, T* state, int64_t* ep_len, const T* 
   return ZBOT_OK;
 }
 
+// zbot-6b-walking-m-v0: whole control step; rnd [N][M_NUM_RAND] uniforms, obs [N][25] (no observation noise here)
+template <typename T>
+static int port_m_step(const ZbotCfg* cfg, T* state, int64_t* ep_len, const T* actions, const T* rnd, T* obs, T* rew,
+                       uint8_t* term, uint8_t* trunc, T* reset_sums, T* export_buf, int n) {
+  const char* why = nullptr;
+  if (cfg_validate(*cfg, &why) != ZBOT_OK || cfg->task != ZBOT_TASK_WALKING_M) return ZBOT_E_INVALID;
+  Params<T> P;
+  params_from_cfg(*cfg, P);
+#pragma omp parallel for schedule(static) num_threads(port_threads())
+  for (int e = 0; e < n; ++e) {
+    EnvState<T> es;
+    env_state_unpack(state + (size_t)e * ZBOT_STATE_WORDS, es);
+    StepOut<T> out;
+    T rs[MAX_TERMS];
+    for (int i = 0; i < MAX_TERMS; ++i) rs[i] = T(0);
+    MExport<T> ex;
+    ArrayScratch<T> scr;
+    m_env_step(P, es, actions + (size_t)e * 6, ep_len[e], rnd + (size_t)e * M_NUM_RAND, obs + (size_t)e * M_NUM_OBS, out,
+               rs, export_buf ? &ex : (MExport<T>*)nullptr, scr);
+    env_state_pack(es, state + (size_t)e * ZBOT_STATE_WORDS);
+    rew[e] = out.reward;
+    term[e] = out.terminated ? 1 : 0;
+    trunc[e] = out.time_out ? 1 : 0;
+    if (reset_sums)
+      for (int i = 0; i < MAX_TERMS; ++i) reset_sums[(size_t)e * MAX_TERMS + i] = rs[i];
+    if (export_buf) memcpy(export_buf + (size_t)e * ZBOT_M_EXPORT_WORDS, &ex, sizeof(ex));
+  }
+  return ZBOT_OK;
+}
+
 // dynamics only: sim [N][25] (root_pos3 quat4 lin3 ang3 q6 qd6), target [N][6]
 // forces [N][7][3] (body 0 and 6 = applied foot forces, 1..5 = predictor), tau [N][6]
 template <typename T>
-static int port_substeps(const ZbotCfg* cfg, T* sim, const T* target, T* forces, T* tau, int n, int nsub, bool snake = false) {
+static int port_substeps(const ZbotCfg* cfg, T* sim, const T* target, T* forces, T* tau, int n, int nsub, int model = 0) {
+  const bool snake = (model == 1);
   Params<T> P;
   params_from_cfg(*cfg, P);
 #pragma omp parallel for schedule(static) num_threads(port_threads())
@@ -146,9 +177,13 @@ static int port_substeps(const ZbotCfg* cfg, T* sim, const T* target, T* forces,
     SubstepOut<T> so;
     ArrayScratch<T> scr;
     T midf[15];
+    T tgt7[7];
+    for (int i = 0; i < 6; ++i) tgt7[i] = target[(size_t)e * 6 + i];
+    tgt7[6] = T(cfg->contact_mu);     // ModelWalkM reads its friction coefficient per env
     for (int k = 0; k < nsub; ++k) {
-      if (snake) physics_substep<ModelSnake>(P, s, target + (size_t)e * 6, so, scr, midf);
-      else physics_substep<ModelWalk>(P, s, target + (size_t)e * 6, so, scr, midf);
+      if (snake) physics_substep<ModelSnake>(P, s, tgt7, so, scr, midf);
+      else if (model == 2) physics_substep<ModelWalkM>(P, s, tgt7, so, scr, midf);
+      else physics_substep<ModelWalk>(P, s, tgt7, so, scr, midf);
     }
     for (int i = 0; i < 3; ++i) { w[i] = s.p[i]; w[7 + i] = s.v[i]; w[10 + i] = s.w[i]; }
     for (int i = 0; i < 4; ++i) w[3 + i] = s.Q[i];
@@ -256,10 +291,24 @@ int zbot_port_substeps_f64(const ZbotCfg* cfg, double* sim, const double* target
   return port_substeps<double>(cfg, sim, target, forces, tau, n, nsub);
 }
 int zbot_port_substeps_snake_f32(const ZbotCfg* cfg, float* sim, const float* target, float* forces, float* tau, int n, int nsub) {
-  return port_substeps<float>(cfg, sim, target, forces, tau, n, nsub, true);
+  return port_substeps<float>(cfg, sim, target, forces, tau, n, nsub, 1);
 }
 int zbot_port_substeps_snake_f64(const ZbotCfg* cfg, double* sim, const double* target, double* forces, double* tau, int n, int nsub) {
-  return port_substeps<double>(cfg, sim, target, forces, tau, n, nsub, true);
+  return port_substeps<double>(cfg, sim, target, forces, tau, n, nsub, 1);
+}
+int zbot_port_substeps_m_f32(const ZbotCfg* cfg, float* sim, const float* target, float* forces, float* tau, int n, int nsub) {
+  return port_substeps<float>(cfg, sim, target, forces, tau, n, nsub, 2);
+}
+int zbot_port_substeps_m_f64(const ZbotCfg* cfg, double* sim, const double* target, double* forces, double* tau, int n, int nsub) {
+  return port_substeps<double>(cfg, sim, target, forces, tau, n, nsub, 2);
+}
+int zbot_port_m_step_f32(const ZbotCfg* cfg, float* state, int64_t* ep_len, const float* actions, const float* rnd,
+                         float* obs, float* rew, uint8_t* term, uint8_t* trunc, float* reset_sums, float* export_buf, int n) {
+  return port_m_step<float>(cfg, state, ep_len, actions, rnd, obs, rew, term, trunc, reset_sums, export_buf, n);
+}
+int zbot_port_m_step_f64(const ZbotCfg* cfg, double* state, int64_t* ep_len, const double* actions, const double* rnd,
+                         double* obs, double* rew, uint8_t* term, uint8_t* trunc, double* reset_sums, double* export_buf, int n) {
+  return port_m_step<double>(cfg, state, ep_len, actions, rnd, obs, rew, term, trunc, reset_sums, export_buf, n);
 }
 int zbot_port_link_view_f64(const double* sim, double* pos, double* quat, double* vel, int n) {
   return port_link_view<double>(sim, pos, quat, vel, n);

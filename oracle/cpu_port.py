@@ -65,9 +65,10 @@ class PortEnv:
         self.cfg = cfg or make_cfg(n)
         self.snake = (self.cfg.task == 1)
         self.v4 = (self.cfg.task == 2)
+        self.mtask = (self.cfg.task == 3)
         self.state = np.zeros((n, 80), self.dtype)
         self.ep_len = np.zeros(n, np.int64)
-        self.export_words = (lib().zbot_port_snake_export_words() if self.snake else 69 if self.v4
+        self.export_words = (lib().zbot_port_snake_export_words() if self.snake else 69 if self.v4 else 67 if self.mtask
                              else getattr(lib(), "zbot_port_export_words_" + self.sfx)())
         self.reset_all()
 
@@ -91,6 +92,18 @@ class PortEnv:
             self.field("joint_speed_limit", 1)[:] = np.pi
             self.ep_len[:] = 0
             return
+        if self.mtask:
+            from zbot_lab_b200.assets import zbot_6s_v2 as V
+            m = V.model_f32()
+            self.state[:] = 0
+            self.field("root_pos", 3)[:] = m.default_root_pos
+            self.field("root_quat", 4)[:] = m.default_root_quat
+            self.field("joint_pos", 6)[:] = m.default_joint_pos
+            self.field("joint_speed_limit", 1)[:] = self.cfg.contact_mu      # per-env friction coefficient
+            lp, _ = V.default_link_poses()
+            self.field("feet_down_pos_last", 6)[:] = np.concatenate([lp[V.link_index("foot0")], lp[V.link_index("foot1")]])
+            self.ep_len[:] = 0
+            return
         self.state[:] = 0
         self.field("root_pos", 3)[:] = Z.model_f32().default_root_pos
         self.field("root_quat", 4)[:] = Z.DEFAULT_ROOT_QUAT
@@ -109,6 +122,18 @@ class PortEnv:
     def step(self, actions, export=False, rnd=None):
         n = self.n
         a = np.ascontiguousarray(actions, self.dtype)
+        if self.mtask:
+            obs = np.zeros((n, 25), self.dtype)
+            rew, term, trunc = np.zeros(n, self.dtype), np.zeros(n, np.uint8), np.zeros(n, np.uint8)
+            rs = np.zeros((n, 16), self.dtype)
+            ex = np.zeros((n, self.export_words), self.dtype) if export else None
+            r = np.ascontiguousarray(rnd, self.dtype)
+            assert r.shape == (n, 13)
+            rc = getattr(lib(), "zbot_port_m_step_" + self.sfx)(
+                C.byref(self.cfg), _p(self.state), _p(self.ep_len), _p(a), _p(r), _p(obs), _p(rew), _p(term), _p(trunc),
+                _p(rs), _p(ex), C.c_int(n))
+            assert rc == 0, rc
+            return obs, rew, term.astype(bool), trunc.astype(bool), rs, ex
         if self.v4:
             obs = np.zeros((n, 24), self.dtype)
             rew, term, trunc = np.zeros(n, self.dtype), np.zeros(n, np.uint8), np.zeros(n, np.uint8)
@@ -134,7 +159,8 @@ class PortEnv:
         return obs, rew, term.astype(bool), trunc.astype(bool), rs, ex
 
 
-def substeps(sim: np.ndarray, target: np.ndarray, nsub: int, cfg: ZbotCfg | None = None, snake: bool = False):
+def substeps(sim: np.ndarray, target: np.ndarray, nsub: int, cfg: ZbotCfg | None = None, snake: bool = False,
+             model: str | None = None):
     """sim [N][25] (in/out), target [N][6] -> forces [N][7][3], applied torque [N][6]."""
     n = sim.shape[0]
     dt = sim.dtype
@@ -143,7 +169,8 @@ def substeps(sim: np.ndarray, target: np.ndarray, nsub: int, cfg: ZbotCfg | None
     forces = np.zeros((n, 7, 3), dt)
     tau = np.zeros((n, 6), dt)
     target = np.ascontiguousarray(target, dt)
-    rc = getattr(lib(), ("zbot_port_substeps_snake_" if snake else "zbot_port_substeps_") + sfx)(C.byref(cfg), _p(sim), _p(target), _p(forces), _p(tau),
+    name = "zbot_port_substeps_m_" if model == "m" else "zbot_port_substeps_snake_" if snake else "zbot_port_substeps_"
+    rc = getattr(lib(), name + sfx)(C.byref(cfg), _p(sim), _p(target), _p(forces), _p(tau),
                                                      C.c_int(n), C.c_int(nsub))
     assert rc == 0
     return forces, tau

@@ -9,6 +9,7 @@ state.  Used by ``tests/golden/make_golden.py`` (build container only).
 """
 from __future__ import annotations
 
+import numpy as np
 import torch
 
 from . import ref_loader
@@ -306,3 +307,86 @@ class RefV4Harness:
         for k, v in e._episode_sums.items():
             out["episode_sum/" + k] = v
         return {k: v.clone() for k, v in out.items()}
+
+
+class RefMHarness:
+    """The reference's OWN manager-task term functions (``zbotlab_manager/mdp/rewards.py``, ``mdp/terminations.py``),
+    loaded unmodified behind the stub modules and called on a fake ``env`` whose ``scene`` / ``command_manager`` hand out
+    plain CPU tensors.  ``call(func_name, view, params)`` evaluates ONE term exactly as RewardManager would
+    (``func(env, **params)``); the per-env attributes of ``init_my_data`` (rewards.py:29-35) live on ``self.env`` and are
+    mutated by the reference code itself.  Isaac Lab functions that are not in the reference tree are not here (they are
+    restated, flagged [IL-upstream], in ``oracle/m_mdp_oracle.py``)."""
+
+    FEET_IDS = [10, 11]          # articulation indices of foot0 / foot1 (assets/zbot_6s_v2.py LINK_NAMES)
+
+    def __init__(self, n, step_dt=0.02):
+        import os
+        self.rew = ref_loader.load_reference_module(os.path.join(ref_loader.REF_M_MDP_DIR, "rewards.py"))
+        self.term = ref_loader.load_reference_module(os.path.join(ref_loader.REF_M_MDP_DIR, "terminations.py"))
+        self.n = n
+        NS = ref_loader._NS
+        env = NS()
+        env.num_envs, env.device, env.step_dt = n, torch.device("cpu"), step_dt
+        env.sim = NS()
+        env.sim.device = "cpu"
+        env.episode_length_buf = torch.zeros(n, dtype=torch.long)
+        self.asset, self.sensor = NS(), NS()
+        self.asset.data, self.sensor.data, self.sensor.cfg = NS(), NS(), NS()
+        self.sensor.cfg.track_air_time = True
+
+        class Scene(dict):
+            pass
+        scene = Scene(robot=self.asset)
+        scene.sensors = {"contact_forces": self.sensor}
+        env.scene = scene
+        env.command_manager = NS()
+        self.command = torch.zeros(n, 3)
+        env.command_manager.get_command = lambda name: self.command
+        self.env = env
+        self.rew.init_my_data(env, None)                                  # rewards.py:29-35
+        cfg = ref_loader._Cfg
+        self.asset_cfg = cfg(name="robot", body_ids=self.FEET_IDS)
+        self.sensor_cfg = cfg(name="contact_forces", body_ids=self.FEET_IDS)
+
+    def attach(self, view: dict):
+        """Scatter a view (oracle.m_mdp_oracle.synth_m_views layout) into robot.data / contact sensor tensors."""
+        n, t = self.n, lambda a: torch.from_numpy(np.ascontiguousarray(a, np.float32))
+        d, sd = self.asset.data, self.sensor.data
+        pos, quat, vel = torch.zeros(n, 12, 3), torch.zeros(n, 12, 4), torch.zeros(n, 12, 3)
+        quat[..., 0] = 1.0
+        pos[:, self.FEET_IDS], quat[:, self.FEET_IDS], vel[:, self.FEET_IDS] = t(view["feet_pos"]), t(view["feet_quat"]), t(view["feet_com_vel"])
+        pos[:, 0], quat[:, 0] = t(view["root_pos"]), t(view["root_quat"])
+        d.body_link_pos_w = d.body_pos_w = pos
+        d.body_link_quat_w = quat
+        d.body_lin_vel_w = vel                                             # CoM velocity [IL-upstream naming]
+        d.root_quat_w = t(view["root_quat"])
+        d.root_link_lin_vel_w = t(view["root_lin_vel"])
+        d.root_link_ang_vel_w = t(view["root_ang_vel"])
+        d.GRAVITY_VEC_W = torch.tensor([0.0, 0.0, -1.0]).repeat(n, 1)
+        hist = torch.zeros(n, 3, 12, 3)
+        hist[:, :, self.FEET_IDS] = t(view["feet_force_hist"])
+        sd.net_forces_w_history = hist
+        for name, key in (("last_air_time", "last_air"), ("last_contact_time", "last_contact"),
+                          ("current_air_time", "cur_air"), ("current_contact_time", "cur_contact")):
+            full = torch.zeros(n, 12)
+            full[:, self.FEET_IDS] = t(view[key])
+            setattr(sd, name, full)
+
+    def call(self, func: str, params: dict) -> torch.Tensor:
+        kw = dict(params)
+        fn = getattr(self.rew, func)
+        import inspect
+        sig = inspect.signature(fn).parameters
+        if "asset_cfg" in sig and func != "base_vel_forward" and not func.startswith("track_"):
+            kw["asset_cfg"] = self.asset_cfg
+        if "sensor_cfg" in sig:
+            kw["sensor_cfg"] = self.sensor_cfg
+        if func in ("base_vel_forward", "track_lin_vel_xy_yaw_frame_exp", "track_ang_vel_z_world_exp"):
+            kw["asset_cfg"] = ref_loader._Cfg(name="robot")
+        return fn(self.env, **kw)
+
+    def feet_close(self, minimum_distance: float) -> torch.Tensor:
+        return self.term.feet_close(self.env, minimum_distance, self.asset_cfg)
+
+    def reset_my_data(self, env_ids: torch.Tensor):
+        self.rew.reset_my_data(self.env, env_ids, self.asset_cfg)

@@ -29,6 +29,7 @@ REF_ENV_V2 = os.path.join(
 )
 REF_ENV_SNAKE = os.path.join(REF_ROOT, "source/zbot/zbot/tasks/zbot6_direct/zbot_direct_6dof_snake_v0.py")
 REF_ENV_V4 = os.path.join(REF_ROOT, "source/zbot/zbot/tasks/zbot6b_direct/zbot_direct_6dof_bipedal_env_v4.py")
+REF_M_MDP_DIR = os.path.join(REF_ROOT, "source/zbot/zbot/tasks/zbotlab_manager/mdp")      # rewards.py, terminations.py, curriculums.py
 
 
 def reference_available() -> bool:
@@ -74,6 +75,29 @@ def _quat_mul(q1, q2):
 def _wrap_to_pi(angles):
     wrapped = (angles + torch.pi) % (2 * torch.pi)
     return torch.where((wrapped == 0) & (angles > 0), torch.pi, wrapped - torch.pi)
+
+
+def _quat_apply_inverse(quat, vec):
+    # isaaclab.utils.math.quat_apply_inverse [IL-upstream]: v - w t + q_xyz x t, t = 2 q_xyz x v
+    shape = vec.shape
+    quat = quat.reshape(-1, 4)
+    vec = vec.reshape(-1, 3)
+    xyz = quat[:, 1:]
+    t = xyz.cross(vec, dim=-1) * 2
+    return (vec - quat[:, 0:1] * t + xyz.cross(t, dim=-1)).view(shape)
+
+
+def _yaw_quat(quat):
+    # isaaclab.utils.math.yaw_quat [IL-upstream]
+    shape = quat.shape
+    q = quat.view(-1, 4)
+    qw, qx, qy, qz = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    yaw = torch.atan2(2 * (qw * qz + qx * qy), 1 - 2 * (qy * qy + qz * qz))
+    out = torch.zeros_like(q)
+    out[:, 3] = torch.sin(yaw / 2)
+    out[:, 0] = torch.cos(yaw / 2)
+    out = torch.nn.functional.normalize(out, p=2.0, dim=-1)
+    return out.view(shape)
 
 
 def _sample_uniform(lower, upper, size, device=None):
@@ -124,9 +148,10 @@ def _install_stubs():
     mod("gymnasium", spaces=spaces)
     sim = mod("isaaclab.sim", RigidBodyMaterialCfg=_Cfg, SimulationCfg=_Cfg, DomeLightCfg=_Cfg)
     umath = mod("isaaclab.utils.math", quat_apply=_quat_apply, quat_from_euler_xyz=_quat_from_euler_xyz,
-                quat_mul=_quat_mul, wrap_to_pi=_wrap_to_pi, sample_uniform=_sample_uniform)
+                quat_mul=_quat_mul, wrap_to_pi=_wrap_to_pi, sample_uniform=_sample_uniform,
+                quat_apply_inverse=_quat_apply_inverse, yaw_quat=_yaw_quat)
     utils = mod("isaaclab.utils", configclass=lambda c: c, math=umath)
-    assets = mod("isaaclab.assets", Articulation=object, ArticulationCfg=_Cfg)
+    assets = mod("isaaclab.assets", Articulation=object, ArticulationCfg=_Cfg, RigidObject=object)
     envs_mdp = mod("isaaclab.envs.mdp")
     envs = mod("isaaclab.envs", DirectRLEnv=_DirectRLEnv, DirectRLEnvCfg=object, mdp=envs_mdp)
     managers = mod("isaaclab.managers", EventTermCfg=_Cfg, SceneEntityCfg=_Cfg)
@@ -135,7 +160,7 @@ def _install_stubs():
     markers = mod("isaaclab.markers", VisualizationMarkers=object, VisualizationMarkersCfg=_Cfg, config=markers_cfg)
     scene = mod("isaaclab.scene", InteractiveSceneCfg=_Cfg)
     sensors = mod("isaaclab.sensors", ContactSensor=object, ContactSensorCfg=_Cfg)
-    terrains = mod("isaaclab.terrains", TerrainImporterCfg=_Cfg)
+    terrains = mod("isaaclab.terrains", TerrainImporterCfg=_Cfg, TerrainImporter=object)
     mod("isaaclab", sim=sim, utils=utils, assets=assets, envs=envs, scene=scene,
         sensors=sensors, terrains=terrains, managers=managers, markers=markers)
     zassets = mod("zbot.assets", ZBOT_6S_CFG=_Cfg(), ZBOT_D_6S_CFG=_Cfg())

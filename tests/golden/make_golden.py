@@ -146,5 +146,70 @@ def main():
              values=np.array(list(scales.values()), dtype=np.float64))
 
 
+# ---- zbot-6b-walking-m-v0 (manager-based task): the reference's own RewTerm / DoneTerm functions ------------------
+M_CASES = [("m_v0_n64", 30, 64, 5), ("m_v0_n7", 31, 7, 4)]
+#: every RewTerm function of zbotlab_manager/mdp/rewards.py that the cfg can name, with the cfg's params
+#: (zbotlab_env_cfg.py:240-352)
+M_FUNCS = [
+    ("track_lin_vel_xy_yaw_frame_exp", {"command_name": "base_velocity", "std": 0.5}),
+    ("track_ang_vel_z_world_exp", {"command_name": "base_velocity", "std": 0.5}),
+    ("foot_step_length", {"command_name": None}),
+    ("foot_downward", {}),
+    ("foot_forward", {}),
+    ("feet_gait", {"period": 2.0, "offset": [0.0, 0.5], "threshold": 0.55, "command_name": "base_velocity"}),
+    ("feet_slide", {}),
+    ("foot_clearance_reward", {"std": 0.05, "tanh_mult": 2.0, "target_height": 0.01}),
+    ("feet_air_time_positive_biped", {"command_name": "base_velocity", "threshold": 0.3}),
+    ("air_time_variance_penalty", {}),
+    ("air_time_balance_penalty", {}),
+    ("base_vel_forward", {"which_forward": 1}),
+    ("feet_force_pattern", {}),
+]
+
+
+def run_m_case(seed, n, steps):
+    from oracle.ref_harness import RefMHarness
+    from oracle.m_mdp_oracle import synth_m_views
+    torch.set_num_threads(1)
+    h = RefMHarness(n)
+    rng = np.random.default_rng(seed + 1000)
+    out = {"seed": seed, "n": n, "steps": steps}
+    h.env.feet_contact_forces_last[:] = torch.from_numpy(rng.uniform(0, 20, (n, 2)).astype(np.float32))
+    h.env.feet_down_pos_last[:] = torch.from_numpy(rng.normal(0, 0.3, (n, 2, 3)).astype(np.float32))
+    h.env.feet_force_sum[:] = torch.from_numpy(rng.normal(0, 0.05, n).astype(np.float32))
+    out["state0/feet_contact_forces_last"] = h.env.feet_contact_forces_last.numpy().copy()
+    out["state0/feet_down_pos_last"] = h.env.feet_down_pos_last.numpy().copy()
+    out["state0/feet_force_sum"] = h.env.feet_force_sum.numpy().copy()
+    for t, (view, _a, _r) in enumerate(synth_m_views(seed, n, steps)):
+        cmd = np.stack([rng.uniform(-0.3, 0.3, n), rng.uniform(-0.2, 0.2, n), rng.uniform(-0.2, 0.2, n)], -1).astype(np.float32)
+        cmd[rng.random(n) < 0.2] = 0.0
+        ep = rng.integers(0, 1000, n)
+        h.attach(view)
+        h.command[:] = torch.from_numpy(cmd)
+        h.env.episode_length_buf[:] = torch.from_numpy(ep)
+        out[f"cmd{t}"], out[f"ep{t}"] = cmd, ep
+        for func, params in M_FUNCS:
+            out[f"val{t}/{func}"] = h.call(func, params).numpy().astype(np.float32).copy()
+        out[f"feet_close{t}"] = h.feet_close(0.12).numpy().copy()
+        for k in ("feet_contact_forces_last", "feet_down_pos_last", "feet_step_length", "feet_force_sum"):
+            out[f"state{t + 1}/{k}"] = getattr(h.env, k).numpy().copy()
+        if t == steps - 1:                                                  # reset_my_data on a few envs (rewards.py:37-43)
+            ids = torch.from_numpy(np.sort(rng.choice(n, max(1, n // 4), replace=False)))
+            h.reset_my_data(ids)
+            out["reset_ids"] = ids.numpy()
+            for k in ("feet_contact_forces_last", "feet_down_pos_last", "feet_step_length", "feet_force_sum"):
+                out[f"state_reset/{k}"] = getattr(h.env, k).numpy().copy()
+    return out
+
+
+def make_m():
+    here = os.path.dirname(os.path.abspath(__file__))
+    for name, seed, n, steps in M_CASES:
+        np.savez_compressed(os.path.join(here, name + ".npz"), **run_m_case(seed, n, steps))
+        print("wrote", name)
+
+
 if __name__ == "__main__":
-    main()
+    if "--m" not in sys.argv:
+        main()
+    make_m()

@@ -93,3 +93,97 @@ def v4_check_step(o, a, rnd, ex, obs, rew, term, trunc, ep_len, state_get, rtol=
     for i, nm in enumerate(o.episode_sums):
         assert rel_err(eps[:, i], o.episode_sums[nm]) <= rtol, nm
     return ids_o, iv_o, log_o
+
+
+# ---------------------------------------------------------------------------------------------
+# zbot-6b-walking-m-v0 (manager-based task)
+# ---------------------------------------------------------------------------------------------
+#: every RewTerm the fused step knows, with the reference cfg's params (zbotlab_env_cfg.py:240-352): 16 slots + is_terminated
+M_ALL_TERMS = [
+    ("track_lin_vel_xy_exp", "track_lin_vel_xy_yaw_frame_exp", 1.0, {"std": 0.5}),
+    ("track_ang_vel_z_exp", "track_ang_vel_z_world_exp", 0.5, {"std": 0.5}),
+    ("termination_penalty", "is_terminated", -200.0, {}),
+    ("dof_torques_l2", "joint_torques_l2", -1.0e-5, {}),
+    ("dof_acc_l2", "joint_acc_l2", -2.5e-7, {}),
+    ("action_rate_l2", "action_rate_l2", -0.01, {}),
+    ("foot_step_length", "foot_step_length", 2.0, {"command_name": None}),
+    ("foot_downward", "foot_downward", -1.0, {}),
+    ("foot_forward", "foot_forward", -0.5, {}),
+    ("gait", "feet_gait", 0.5, {"period": 2.0, "offset": [0.0, 0.5], "threshold": 0.55, "command_name": "base_velocity"}),
+    ("feet_slide", "feet_slide", -0.2, {}),
+    ("feet_clearance", "foot_clearance_reward", 1.0, {"std": 0.05, "tanh_mult": 2.0, "target_height": 0.01}),
+    ("feet_air_time", "feet_air_time_positive_biped", 2.5, {"command_name": "base_velocity", "threshold": 0.3}),
+    ("air_time_variance", "air_time_balance_penalty", -1.0, {}),
+    ("air_time_variance2", "air_time_variance_penalty", -1.0, {}),
+    ("base_vel_forward", "base_vel_forward", 1.0, {"which_forward": 1}),
+    ("feet_force_pattern", "feet_force_pattern", 1.0, {}),
+]
+M_PARAMS = {"minimum_height": 0.2, "feet_close_min": 0.12, "cmd_ranges": ((-0.3, 0.3), (-0.1, 0.1), (-0.2, 0.2)),
+            "rel_standing_envs": 0.1, "resampling_time_range": (0.1, 0.3), "pose_range": ((-0.5, 0.5), (-0.5, 0.5), (-3.14, 3.14)),
+            "max_episode_length": 1000, "step_dt": 0.02}
+
+
+def m_native_cfg(n, terms, P=M_PARAMS, **kw):
+    from zbot_lab_b200 import native
+    slot = [(f, w, p) for _, f, w, p in terms if f != "is_terminated"]
+    wt = [w for _, f, w, _ in terms if f == "is_terminated"]
+    return native.make_m_cfg(n, slot, is_terminated_weight=wt[0] if wt else 0.0, minimum_height=P["minimum_height"],
+                             feet_close_min=P["feet_close_min"], cmd_ranges=P["cmd_ranges"],
+                             rel_standing_envs=P["rel_standing_envs"], resampling_time_range=P["resampling_time_range"],
+                             pose_range=P["pose_range"], act_clip=0.04 * np.pi, **kw)
+
+
+def m_make_oracle(n, terms, state_get, ep_len, P=M_PARAMS):
+    """MMdpOracle initialised from the step implementation's own state words (``state_get(name, width)``)."""
+    from oracle.m_mdp_oracle import MMdpOracle
+    o = MMdpOracle(n, terms, P)
+    o.s["episode_length_buf"] = np.asarray(ep_len, np.int64).copy()
+    c2, c1 = state_get("carry_feet_fz", 2), state_get("carry_mid_max", 1)
+    o.cmd[:] = np.concatenate([c2, c1], 1)
+    o.standing[:] = state_get("base_heading_x_sum", 1)[:, 0] != 0
+    o.time_left[:] = state_get("base_pos_y_err_sum", 1)[:, 0]
+    o.s["feet_down_pos_last"][:] = state_get("feet_down_pos_last", 6).reshape(n, 2, 3)
+    o.s["feet_contact_forces_last"][:] = state_get("feet_contact_forces_last", 2)
+    o.s["feet_step_length"][:] = state_get("feet_step_length", 2)
+    o.s["feet_force_sum"][:] = state_get("feet_force_sum", 1)[:, 0]
+    o.s["action"][:] = state_get("actions", 6)
+    return o
+
+
+def m_check_step(o, a, rnd, ex, obs, rew, term, trunc, ep_len, state_get, rs=None, rtol=1e-5):
+    """One step of the manager task: the implementation's outputs / state words against the reference-pinned oracle
+    evaluated on the view the implementation exported.  Integer work bit-exact, floats <= rtol."""
+    from oracle.m_mdp_oracle import split_view
+    n = o.n
+    view = split_view(np.asarray(ex, np.float32))
+    view["qd_chain"] = np.asarray(state_get("joint_vel", 6), np.float32)       # reset envs are zeroed by the oracle anyway
+    r = o.step(view, a, rnd)
+    assert np.array_equal(r["terminated"], np.asarray(term, bool)), "terminated flags"
+    assert np.array_equal(r["time_outs"], np.asarray(trunc, bool)), "time-out flags"
+    assert np.array_equal(o.s["episode_length_buf"], np.asarray(ep_len)), "episode counters"
+    assert rel_err(rew, r["reward"], 1.0) <= rtol, ("reward", rel_err(rew, r["reward"], 1.0))
+    assert np.abs(np.asarray(obs) - r["obs"]).max() <= 5e-6, ("obs", np.abs(np.asarray(obs) - r["obs"]).max(0))
+    cmd = np.concatenate([state_get("carry_feet_fz", 2), state_get("carry_mid_max", 1)], 1)
+    assert np.abs(cmd - o.cmd).max() <= 1e-6, "commands"
+    assert np.array_equal(state_get("base_heading_x_sum", 1)[:, 0] != 0, o.standing), "standing envs"
+    assert np.abs(state_get("base_pos_y_err_sum", 1)[:, 0] - o.time_left).max() <= 1e-5, "command time_left"
+    for k, w in (("feet_step_length", 2), ("feet_contact_forces_last", 2), ("feet_down_pos_last", 6)):
+        assert np.abs(state_get(k, w).reshape(n, -1) - o.s[k].reshape(n, -1)).max() <= 2e-5, k
+    assert np.abs(state_get("feet_force_sum", 1)[:, 0] - o.s["feet_force_sum"]).max() <= 1e-6
+    assert np.abs(state_get("actions", 6) - o.s["action"]).max() == 0
+    sums = state_get("episode_sums", 16)
+    for i, (name, v) in enumerate(o.ep_sums.items()) if False else []:
+        pass
+    slot_names = [nm for nm, f, w, p in o.terms if f != "is_terminated" and float(w) != 0.0]
+    for i, nm in enumerate(slot_names):
+        assert rel_err(sums[:, i], o.ep_sums[nm], 1e-2) <= 20 * rtol, ("episode sum", nm)
+    ids = r["reset_ids"]
+    if rs is not None and len(ids):
+        for i, nm in enumerate(slot_names):
+            want = r["log"][nm] * (o.P["max_episode_length"] * o.P["step_dt"])     # mean episodic sum over the reset envs
+            got = float(np.mean(np.asarray(rs)[ids, i], dtype=np.float32))
+            assert abs(got - want) <= 20 * rtol * max(1e-2, abs(want)), ("log", nm, got, want)
+        if len(slot_names) <= 14:
+            assert int(np.asarray(rs)[ids, 14].sum()) == r["log"]["#base_height"]
+            assert int(np.asarray(rs)[ids, 15].sum()) == r["log"]["#feet_close"]
+    return r

@@ -307,3 +307,122 @@ def test_two_lane_instantiation_equals_scalar_bit_for_bit():
         cpu_port.substeps(a, tgt, 1, cfg, snake=True)
         cpu_port.substeps_pair(b, tgt, 1, cfg, snake=True)
         assert np.array_equal(a, b)
+
+
+# ------------------------------------------------------------------------------------------------ manager-based task
+def _m_port(n, dtype, rng, terms):
+    from helpers import m_native_cfg
+    from oracle import cpu_port
+    pe = cpu_port.PortEnv(n, dtype, m_native_cfg(n, terms))
+    pe.field("carry_feet_fz", 2)[:] = np.stack([rng.uniform(-0.3, 0.3, n), rng.uniform(-0.1, 0.1, n)], -1)
+    pe.field("carry_mid_max", 1)[:, 0] = rng.uniform(-0.2, 0.2, n)
+    pe.field("base_pos_y_err_sum", 1)[:, 0] = rng.uniform(0.05, 0.3, n)          # command time_left
+    pe.field("joint_speed_limit", 1)[:, 0] = rng.uniform(0.3, 1.0, n)           # per-env friction
+    pe.field("joint_pos", 6)[:] += rng.uniform(-0.1, 0.1, (n, 6))
+    return pe
+
+
+@pytest.mark.parametrize("which", ["flat", "all"])
+def test_m_full_step_port_matches_pinned_oracle_on_exported_physics(which):
+    """the manager task's terminations / rewards / command resampling / randomised resets / observations
+    (kernel arithmetic, host build, float32) equal the reference-pinned oracle evaluated on the view the step itself
+    produced.  Flags, reset ids, counters, standing masks bit-exact; floats <= 1e-5 relative.  `flat` = the 11 terms of
+    Zbot6BFlatEnvCfg, `all` = every RewTerm function the reference's rewards.py defines (16 slots + is_terminated)."""
+    from helpers import M_ALL_TERMS, m_check_step, m_make_oracle
+    from zbot_lab_b200 import native
+    terms = M_ALL_TERMS if which == "all" else native.M_FLAT_TERMS
+    n = 96
+    rng = np.random.default_rng(42)
+    pe = _m_port(n, np.float32, rng, terms)
+    ep0 = rng.integers(0, 990, n)
+    ep0[:6] = 996
+    pe.ep_len[:] = ep0
+    get = lambda k, w: pe.field(k, w).copy()
+    o = m_make_oracle(n, terms, get, ep0)
+    n_reset = n_term = n_res = 0
+    for t in range(40):
+        a = rng.normal(0, 1.5, (n, 6)).astype(np.float32)
+        rnd = rng.random((n, 13)).astype(np.float32)
+        obs, rew, term, trunc, rs, ex = pe.step(a, export=True, rnd=rnd)
+        r = m_check_step(o, a, rnd, ex, obs, rew, term, trunc, pe.ep_len, get, rs)
+        n_reset += len(r["reset_ids"])
+        n_term += int(term.sum())
+        n_res += len(r["resample_ids"])
+    assert n_reset >= 6 and n_term > 0 and n_res >= n
+
+
+def test_m_port_f32_tracks_f64_and_the_robot_stands():
+    """float32 vs float64 host builds of the manager step over 50 control steps of small random actions; with zero
+    actions the biped stands at the cfg's init height carrying m g on its two soles."""
+    from zbot_lab_b200 import native
+    n = 64
+    rng = np.random.default_rng(5)
+    e32, e64 = (_m_port(n, dt, np.random.default_rng(1), native.M_FLAT_TERMS) for dt in (np.float32, np.float64))
+    for e in (e32, e64):
+        e.field("base_pos_y_err_sum", 1)[:] = 100.0
+        e.cfg.feet_close_min = 0.0          # the init stance is 0.12002 m wide against the 0.12 m limit: keep the horizon alive
+    alive = np.ones(n, bool)
+    for t in range(50):
+        a = rng.normal(0, 0.3, (n, 6)).astype(np.float32)
+        rnd = rng.random((n, 13)).astype(np.float32)
+        _, _, t32, tr32, _, _ = e32.step(a, rnd=rnd)
+        _, _, t64, tr64, _, _ = e64.step(a, rnd=rnd)
+        alive &= ~(t32 | t64 | tr32 | tr64)
+    dq = np.abs(e32.field("joint_pos", 6) - e64.field("joint_pos", 6))[alive]
+    # kp 20 / kd 0.5 (ZBOT_6S_V2_CFG) is a softer, less damped drive than the direct tasks' 50 / 5: round-off grows faster
+    assert alive.sum() > n // 3 and dq.max() < 5e-2 and np.median(dq) < 1e-4 and np.quantile(dq, 0.9) < 2e-3
+    from oracle import cpu_port
+    from oracle.m_mdp_oracle import split_view
+    pe = cpu_port.PortEnv(4, np.float64, e64.cfg.__class__.from_buffer_copy(e64.cfg))
+    pe.cfg.num_envs = 4
+    pe.field("base_pos_y_err_sum", 1)[:] = 100.0
+    for t in range(40):
+        obs, rew, term, trunc, rs, ex = pe.step(np.zeros((4, 6)), export=True, rnd=np.full((4, 13), 0.5))
+    v = split_view(ex)
+    assert abs(v["root_pos"][0, 2] - 0.2545) < 1e-3 and abs(v["root_quat"][0, 0]) > 0.99999
+    assert np.abs(v["feet_fz_hist"][0] - 0.5 * 3.00504 * 9.81).max() < 0.05          # each sole carries m g / 2
+
+
+def test_m_model_known_answers_and_independent_dynamics():
+    """ZBOT_6S_V2_CFG (assets/zbot_cfg.py:959-1005) on the decoded zbot_6s_v09.usd: with the base link at (0, 0, 0.2545),
+    identity rotation, and the cfg's joint angles both soles lie flat on the ground (known answer: the init height),
+    the feet's link y axes point up / down and x forward (the axes rewards.py:113-115, 134-136 hard-code); the full-inertia
+    ABA of the kernel (host build, double) equals the dense classical-Jacobian oracle to round-off with contact, PD and
+    friction 0.7."""
+    from oracle import cpu_port
+    from oracle.dyn_oracle import DynOracle, DynParams
+    from helpers import m_native_cfg
+    from zbot_lab_b200 import native
+    from zbot_lab_b200.assets import zbot_6s as Z
+    from zbot_lab_b200.assets import zbot_6s_v2 as V
+    m = V.model_f32()
+    lp, lq = V.default_link_poses()
+    ib, i0, i1 = (V.link_index(k) for k in ("base", "foot0", "foot1"))
+    assert np.allclose(lp[ib], [0, 0, 0.2545], atol=1e-6) and np.allclose(np.abs(lq[ib]), [1, 0, 0, 0], atol=1e-6)
+    R0 = Z.quat_to_mat(m.default_root_quat)
+    assert abs(m.default_root_pos[2]) < 2e-4 and R0[2, 2] > 0.99999                       # foot0 sole on the ground, flat
+    up0, up1 = Z.quat_rotate(lq[i0], np.array([0.0, 1, 0])), Z.quat_rotate(lq[i1], np.array([0.0, -1, 0]))
+    assert up0[2] > 0.99999 and up1[2] > 0.99999
+    assert Z.quat_rotate(lq[i0], np.array([1.0, 0, 0]))[0] > 0.99999 and Z.quat_rotate(lq[i1], np.array([1.0, 0, 0]))[0] > 0.99999
+    assert abs(lp[i0][1] + 0.06) < 1e-4 and abs(lp[i1][1] - 0.06) < 1e-4 and abs(lp[i1][2] - lp[i0][2]) < 1e-6
+    assert abs(m.body_mass.sum() - 12 * 0.25042) < 1e-6
+    n = 48
+    rng = np.random.default_rng(3)
+    cfg = m_native_cfg(n, native.M_FLAT_TERMS, friction=0.7)
+    st = {"root_pos": np.tile(m.default_root_pos, (n, 1)) + np.c_[np.zeros((n, 2)), rng.uniform(0, 0.02, n)],
+          "root_lin_vel": rng.normal(0, 0.1, (n, 3)), "root_ang_vel": rng.normal(0, 0.5, (n, 3)),
+          "joint_pos": m.default_joint_pos[None] + rng.uniform(-0.2, 0.2, (n, 6)), "joint_vel": rng.normal(0, 0.5, (n, 6))}
+    yaw = rng.uniform(-np.pi, np.pi, n)
+    st["root_quat"] = Z.quat_mul(np.stack([np.cos(yaw / 2), 0 * yaw, 0 * yaw, np.sin(yaw / 2)], -1), np.tile(m.default_root_quat, (n, 1)))
+    st = {k: np.float32(v).astype(np.float64) for k, v in st.items()}
+    o = DynOracle(n, DynParams(m, mu=float(np.float32(0.7))), model=m)
+    o.set_state(st)
+    sim = cpu_port.pack_sim(st, np.float64)
+    tgt = m.default_joint_pos[None] + rng.uniform(-0.3, 0.3, (n, 6))
+    for i in range(30):
+        f, tau = cpu_port.substeps(sim, tgt, 1, cfg, model="m")
+        o.substep(tgt)
+        ref = np.concatenate([o.root_pos, o.root_quat, o.root_lin_vel, o.root_ang_vel, o.q, o.qd], -1)
+        if i < 10:
+            assert np.abs(sim - ref).max() < 1e-9 and np.abs(f[:, [0, 6]] - o.body_force[:, [0, 6]]).max() < 1e-7
+    assert np.abs(sim - ref).max() < 1e-5

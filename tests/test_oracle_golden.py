@@ -1,6 +1,7 @@
 """Pins ``oracle/mdp_oracle.py`` to the reference: the golden .npz files hold the outputs
 of the reference's own unmodified code (tests/golden/make_golden.py)."""
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -161,3 +162,55 @@ def test_v4_mdp_oracle_matches_reference_golden(name):
         n_reset += len(ids)
         n_int += len(iv)
     assert n_reset > 0 and n_int > 0
+
+
+# ---------------------------------------------------------------------------------------------
+# zbot-6b-walking-m-v0: every RewTerm / DoneTerm function of the reference's zbotlab_manager/mdp
+# ---------------------------------------------------------------------------------------------
+M_GOLDEN = ["m_v0_n64", "m_v0_n7"]
+
+
+def _m_funcs():
+    src = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "make_golden.py")).read()
+    ns = {}
+    exec(src[src.index("M_FUNCS = ["):src.index("def run_m_case")], ns)
+    return ns["M_FUNCS"]
+
+
+@pytest.mark.parametrize("name", M_GOLDEN)
+def test_m_oracle_terms_match_the_references_own_functions(name):
+    """oracle/m_mdp_oracle.MTerms against tests/golden/m_v0_*.npz = outputs of the reference's unmodified
+    zbotlab_manager/mdp/rewards.py functions (13 RewTerm functions) and terminations.py:feet_close on seeded synthetic data:
+    values <= 1e-5 relative, the stateful terms' env attributes (feet_step_length, feet_down_pos_last,
+    feet_contact_forces_last, feet_force_sum) and the feet_close mask exact."""
+    from oracle.m_mdp_oracle import MTerms, synth_m_views
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+    n, steps, seed = int(g["n"]), int(g["steps"]), int(g["seed"])
+    s = {"feet_contact_forces_last": g["state0/feet_contact_forces_last"].copy(), "feet_down_pos_last": g["state0/feet_down_pos_last"].copy(),
+         "feet_force_sum": g["state0/feet_force_sum"].copy(), "feet_step_length": np.zeros((n, 2), np.float32), "step_dt": 0.02}
+    for t, (view, _a, _r) in enumerate(synth_m_views(seed, n, steps)):
+        s["episode_length_buf"] = g[f"ep{t}"]
+        cmd = g[f"cmd{t}"]
+        for func, p in _m_funcs():
+            val, ref = getattr(MTerms, func)(view, s, cmd, p), g[f"val{t}/{func}"]
+            assert (np.abs(val - ref) / np.maximum(np.abs(ref), 1.0)).max() <= 1e-5, func
+        close = np.linalg.norm(view["feet_pos"][:, 0] - view["feet_pos"][:, 1], axis=-1) < np.float32(0.12)
+        assert np.array_equal(close, g[f"feet_close{t}"])
+        for k in ("feet_contact_forces_last", "feet_down_pos_last", "feet_force_sum"):
+            assert np.array_equal(s[k], g[f"state{t + 1}/{k}"]), k
+        assert np.abs(s["feet_step_length"] - g[f"state{t + 1}/feet_step_length"]).max() <= 1e-6
+    assert any(g[f"feet_close{t}"].any() for t in range(steps)) and any((g[f"val{t}/feet_gait"] > 0).any() for t in range(steps))
+
+
+def test_m_goldens_regenerate_from_the_reference():
+    """Build container only: re-run the reference's functions and compare with the committed fixtures."""
+    from oracle import ref_loader
+    if not ref_loader.reference_available():
+        pytest.skip("/root/reference is not present (GPU box)")
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_golden
+    for name, seed, n, steps in make_golden.M_CASES:
+        new = make_golden.run_m_case(seed, n, steps)
+        old = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+        for k in old.files:
+            assert np.array_equal(np.asarray(new[k]), old[k]), (name, k)

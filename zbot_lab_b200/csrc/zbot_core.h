@@ -86,7 +86,19 @@ enum TermId : int {
   TERM_V4_AIRTIME_SUM = 31,    // defined, not in the default v4 table
   TERM_V4_FEET_HEIGHT = 32,    // defined, not in the default v4 table
   TERM_V4_BASE_HEIGHT = 33,    // defined, not in the default v4 table
-  NUM_TERM_IDS = 34
+  // zbot-6b-walking-m-v0 (tasks/zbotlab_manager/mdp/rewards.py + isaaclab.envs.mdp [IL-upstream]).  RewTerm functions with
+  // a twin above reuse its id on FRESH inputs: joint_torques_l2 = 8, joint_acc_l2 = 24, action_rate_l2 = 7 (raw actions),
+  // foot_downward = 1, foot_forward = 2, air_time_balance_penalty = 6, air_time_variance_penalty = 27
+  TERM_M_TRACK_LIN_VEL_XY_EXP = 34,   // track_lin_vel_xy_yaw_frame_exp (rewards.py:286-297); par = {std^2}
+  TERM_M_TRACK_ANG_VEL_Z_EXP = 35,    // track_ang_vel_z_world_exp (:300-309); par = {std^2}
+  TERM_M_FOOT_STEP_LENGTH = 36,       // foot_step_length (:45-107), command_name = None
+  TERM_M_GAIT = 37,                   // feet_gait (:155-186); par = {period, offset0, offset1, threshold}
+  TERM_M_FEET_SLIDE = 38,             // feet_slide (:247-262)
+  TERM_M_FEET_CLEARANCE = 39,         // foot_clearance_reward (:143-153); par = {std, tanh_mult, target_height}
+  TERM_M_FEET_AIR_TIME_BIPED = 40,    // feet_air_time_positive_biped (:211-230); par = {threshold}
+  TERM_M_BASE_VEL_FORWARD = 41,       // base_vel_forward (:264-274); par = {which_forward}
+  TERM_M_FEET_FORCE_PATTERN = 42,     // feet_force_pattern (:276-284)
+  NUM_TERM_IDS = 43
 };
 constexpr int MAX_TERMS = 16;
 
@@ -117,6 +129,14 @@ struct Params {
   int obs_noise_enable;
   T obs_noise_lo[24], obs_noise_w[24];   // lower bound, width (hi - lo)
   unsigned long long rng_seed;
+  // zbot-6b-walking-m-v0 (manager-based task): RewTerm params, command term, action term, termination terms
+  T term_par[MAX_TERMS][4];             // RewTerm `params` of the term in the same slot (meaning per TermId)
+  T cmd_lo[3], cmd_hi[3];               // UniformVelocityCommandCfg.ranges lin_vel_x / lin_vel_y / ang_vel_z
+  T cmd_rel_standing;                   // rel_standing_envs
+  T cmd_resample_lo, cmd_resample_hi;   // resampling_time_range
+  T act_scale, act_clip;                // RelativeJointPositionActionCfg scale, symmetric clip of the processed action
+  T feet_close_min;                     // DoneTerm feet_close minimum_distance (<= 0: term absent)
+  T term_penalty_w;                     // RewTerm is_terminated: weight * step_dt (0: term absent)
 };
 
 // ------------------------------------------------------------------------------------
@@ -396,7 +416,7 @@ ZB_HD void contact_agg_force(const ContactAgg<T>& g, T dt, const T* At, const T*
 // outside the speculative margin, or below the activation band, contributes exact zeros; the early-outs only fire when
 // EVERY lane is out.  PS = scalar type of the uniform parameters.
 template <typename PS, typename T>
-ZB_HD void contact_point(const Params<PS>& P, const T* rho, T height, const T* w, const T* vO,
+ZB_HD void contact_point(const Params<PS>& P, T mu, const T* rho, T height, const T* w, const T* vO,
                          SpInertia<T>& IA, T* pAt, T* pAb, ContactAgg<T>* agg, T* f0out) {
   const T pen = -height;
   const auto in_margin = zb_gt(pen, T(-P.c_margin));   // speculative margin: points this far above ground are skipped
@@ -421,7 +441,7 @@ ZB_HD void contact_point(const Params<PS>& P, const T* rho, T height, const T* w
   fn0 = zb_sel(in_margin, zb_max(fn0, T(0)), T(0));
   gamma *= act;
   // beta = min(beta_max, mu fn0 / max(|v_t|, eps))
-  T beta = zb_min(T(P.c_beta_max), T(P.c_mu) * fn0 * zb_rsqrt(zb_max(sx * sx + sy * sy, T(P.c_vt_eps * P.c_vt_eps))));
+  T beta = zb_min(T(P.c_beta_max), mu * fn0 * zb_rsqrt(zb_max(sx * sx + sy * sy, T(P.c_vt_eps * P.c_vt_eps))));
   T F0[3] = {-(beta * sx), -(beta * sy), fn0};
   T n[3];
   cross3(rho, F0, n);
@@ -481,6 +501,62 @@ ZB_HD void body_rigid_terms(const Params<PS>& P, T mass, T cx, T cz, T ixx, T iy
   spi_add_rigid(IA, mass, Iw, c);
 }
 
+// Same terms for a body with a full CoM vector c_b and a full symmetric inertia Ib = (xx, xy, xz, yy, yz, zz) in its body
+// frame (the manager-based biped, whose authored mass properties sit off the chain's plane).
+template <typename PS, typename T>
+ZB_HD void body_rigid_terms_full(const Params<PS>& P, T mass, const T* cb, const T* Ib,
+                                 const T* R, const T* r, const T* w, const T* vO,
+                                 SpInertia<T>& IA, T* pAt, T* pAb) {
+  T c[3] = {r[0] + R[0] * cb[0] + R[1] * cb[1] + R[2] * cb[2], r[1] + R[3] * cb[0] + R[4] * cb[1] + R[5] * cb[2],
+            r[2] + R[6] * cb[0] + R[7] * cb[1] + R[8] * cb[2]};
+  // t_i = Ib * (row i of R)  ->  Iw = R Ib R^T
+  T t0[3], t1[3], t2[3];
+  sym3_mul(Ib, R + 0, t0);
+  sym3_mul(Ib, R + 3, t1);
+  sym3_mul(Ib, R + 6, t2);
+  T Iw[6];
+  Iw[0] = R[0] * t0[0] + R[1] * t0[1] + R[2] * t0[2];
+  Iw[1] = R[0] * t1[0] + R[1] * t1[1] + R[2] * t1[2];
+  Iw[2] = R[0] * t2[0] + R[1] * t2[1] + R[2] * t2[2];
+  Iw[3] = R[3] * t1[0] + R[4] * t1[1] + R[5] * t1[2];
+  Iw[4] = R[3] * t2[0] + R[4] * t2[1] + R[5] * t2[2];
+  Iw[5] = R[6] * t2[0] + R[7] * t2[1] + R[8] * t2[2];
+  T wxc[3];
+  cross3(w, c, wxc);
+  T Pl[3] = {mass * (vO[0] + wxc[0]), mass * (vO[1] + wxc[1]), mass * (vO[2] + wxc[2])};
+  T L[3], cxP[3];
+  sym3_mul(Iw, w, L);
+  cross3(c, Pl, cxP);
+  L[0] += cxP[0]; L[1] += cxP[1]; L[2] += cxP[2];
+  T a0[3], a1[3], a2[3];
+  cross3(w, L, a0);
+  cross3(vO, Pl, a1);
+  cross3(w, Pl, a2);
+  T mg = mass * T(P.gravity);
+  pAt[0] += a0[0] + a1[0] + mg * c[1];
+  pAt[1] += a0[1] + a1[1] - mg * c[0];
+  pAt[2] += a0[2] + a1[2];
+  pAb[0] += a2[0];
+  pAb[1] += a2[1];
+  pAb[2] += a2[2] + mg;
+  spi_add_rigid(IA, mass, Iw, c);
+}
+
+// rigid terms of body k of `Model` (sparse xz-symmetric table, or the full one)
+template <typename Model, typename PS, typename T>
+ZB_HD void model_body_terms(const Params<PS>& P, int k, const T* R, const T* r, const T* w, const T* vO,
+                            SpInertia<T>& IA, T* pAt, T* pAb) {
+  if constexpr (Model::kFullInertia) {
+    T mass, cb[3], Ib[6];
+    Model::body_full(k, mass, cb, Ib);
+    body_rigid_terms_full(P, mass, cb, Ib, R, r, w, vO, IA, pAt, pAb);
+  } else {
+    T mass, cx, cz, ixx, iyy, izz, ixz;
+    Model::body(k, mass, cx, cz, ixx, iyy, izz, ixz);
+    body_rigid_terms(P, mass, cx, cz, ixx, iyy, izz, ixz, R, r, w, vO, IA, pAt, pAb);
+  }
+}
+
 // ------------------------------------------------------------------------------------
 // robot models: per-body mass tables, ground-contact candidate points, default pose.  The chain geometry
 // (joint positions / axes in the body frames) is common to both; a Model only supplies constants, selected
@@ -488,6 +564,9 @@ ZB_HD void body_rigid_terms(const Params<PS>& P, T mass, T cx, T cz, T ixx, T iy
 // ------------------------------------------------------------------------------------
 struct ModelWalk {   // ZBOT_6S_CFG + zbot_6s_new.usd (zbot-6b-walking-*): stands on two foot discs
   static constexpr int kTask = 0;
+  static constexpr bool kFullInertia = false;      // bodies symmetric about the chain's xz plane
+  static constexpr bool kPerEnvFriction = false;
+  static constexpr bool kFresh = false;            // MDP reads one-step-stale quantities, 5-deep force history
   static constexpr bool kGroundForceSensor = true;   // feet: applied force; merged bodies: predictor force
   template <typename T>
   static ZB_HD void body(int k, T& mass, T& cx, T& cz, T& ixx, T& iyy, T& izz, T& ixz) {
@@ -526,10 +605,14 @@ struct ModelWalk {   // ZBOT_6S_CFG + zbot_6s_new.usd (zbot-6b-walking-*): stand
 
 struct ModelWalkV4 : ModelWalk {   // zbot-6b-walking-v4: same robot, 3-deep force history, FRESH MDP inputs
   static constexpr int kTask = 2;
+  static constexpr bool kFresh = true;             // MDP reads end-of-physics quantities, 3-deep force history
 };
 
 struct ModelSnake {  // ZBOT_D_6S_CFG + zbot_6s_v03.usd (zbot-6s-snake-v0): lies on the ground
   static constexpr int kTask = 1;
+  static constexpr bool kFullInertia = false;
+  static constexpr bool kPerEnvFriction = false;
+  static constexpr bool kFresh = false;
   static constexpr bool kGroundForceSensor = false;  // the task only senses filtered SELF contacts
   template <typename T>
   static ZB_HD void body(int k, T& mass, T& cx, T& cz, T& ixx, T& iyy, T& izz, T& ixz) {
@@ -561,6 +644,49 @@ struct ModelSnake {  // ZBOT_D_6S_CFG + zbot_6s_v03.usd (zbot-6s-snake-v0): lies
     Q[0] = T(DEFAULT_ROOT_QW); Q[1] = T(DEFAULT_ROOT_QX); Q[2] = T(DEFAULT_ROOT_QY); Q[3] = T(DEFAULT_ROOT_QZ);
   }
 };
+
+struct ModelWalkM : ModelWalk {   // ZBOT_6S_V2_CFG + zbot_6s_v09.usd (zbot-6b-walking-m-v0): same chain, authored mass tables
+  static constexpr int kTask = 3;
+  static constexpr bool kFullInertia = true;       // CoM / inertia sit off the chain's plane (assets/zbot_6s_v2.py)
+  static constexpr bool kPerEnvFriction = true;    // EventCfg.physics_material: per-env friction drawn at startup
+  static constexpr bool kFresh = true;             // ManagerBasedRLEnv: every term reads end-of-physics data; history_length = 3
+  template <typename T>
+  static ZB_HD void body_full(int k, T& mass, T* c, T* I) {
+    using namespace model_m;
+    const bool f0 = (k == 0), f1 = (k == 6), b3 = (k == 3), lo = (k < 3);   // bodies 1,2 = MIDA, 4,5 = MIDB
+    mass = (f0 || f1) ? T(FOOT0_MASS) : T(MIDA_MASS);
+    c[0] = f0 ? T(FOOT0_CX) : f1 ? T(FOOT1_CX) : b3 ? T(BASE_CX) : T(MIDA_CX);
+    c[1] = f0 ? T(FOOT0_CY) : f1 ? T(FOOT1_CY) : b3 ? T(BASE_CY) : T(MIDA_CY);
+    c[2] = f0 ? T(FOOT0_CZ) : f1 ? T(FOOT1_CZ) : b3 ? T(BASE_CZ) : lo ? T(MIDA_CZ) : T(MIDB_CZ);
+    I[0] = (f0 || f1) ? T(FOOT0_IXX) : b3 ? T(BASE_IXX) : T(MIDA_IXX);
+    I[1] = (f0 || f1) ? T(FOOT0_IXY) : b3 ? T(BASE_IXY) : T(MIDA_IXY);
+    I[2] = (f0 || f1) ? T(FOOT0_IXZ) : b3 ? T(BASE_IXZ) : lo ? T(MIDA_IXZ) : T(MIDB_IXZ);
+    I[3] = (f0 || f1) ? T(FOOT0_IYY) : b3 ? T(BASE_IYY) : T(MIDA_IYY);
+    I[4] = (f0 || f1) ? T(FOOT0_IYZ) : b3 ? T(BASE_IYZ) : lo ? T(MIDA_IYZ) : T(MIDB_IYZ);
+    I[5] = (f0 || f1) ? T(FOOT0_IZZ) : b3 ? T(BASE_IZZ) : T(MIDA_IZZ);
+  }
+  template <typename T>
+  static ZB_HD T default_q(int k) {
+    using namespace model_m;
+    return k == 0 ? T(DQ0) : k == 1 ? T(DQ1) : k == 2 ? T(DQ2) : k == 3 ? T(DQ3) : k == 4 ? T(DQ4) : T(DQ5);
+  }
+  template <typename T>
+  static ZB_HD void default_root(T* p, T* Q) {
+    using namespace model_m;
+    p[0] = T(DEFAULT_ROOT_X); p[1] = T(DEFAULT_ROOT_Y); p[2] = T(DEFAULT_ROOT_Z);
+    Q[0] = T(DEFAULT_ROOT_QW); Q[1] = T(DEFAULT_ROOT_QX); Q[2] = T(DEFAULT_ROOT_QY); Q[3] = T(DEFAULT_ROOT_QZ);
+  }
+  // Isaac Lab joint order (joint1, joint7, joint2, joint8, joint3, joint9) <-> chain joints (joint3, 2, 1, 7, 8, 9)
+  static ZB_HD int il_col(int chain_k) { return chain_k == 0 ? 4 : chain_k == 1 ? 2 : chain_k == 2 ? 0 : chain_k == 3 ? 1 : chain_k == 4 ? 3 : 5; }
+};
+static_assert(model_m::FOOT1_MASS == model_m::FOOT0_MASS && model_m::MIDB_MASS == model_m::MIDA_MASS &&
+              model_m::BASE_MASS == model_m::MIDA_MASS && model_m::FOOT1_IXX == model_m::FOOT0_IXX &&
+              model_m::FOOT1_IXY == model_m::FOOT0_IXY && model_m::FOOT1_IXZ == model_m::FOOT0_IXZ &&
+              model_m::FOOT1_IYY == model_m::FOOT0_IYY && model_m::FOOT1_IYZ == model_m::FOOT0_IYZ &&
+              model_m::FOOT1_IZZ == model_m::FOOT0_IZZ && model_m::MIDB_IXX == model_m::MIDA_IXX &&
+              model_m::MIDB_IXY == model_m::MIDA_IXY && model_m::MIDB_IYY == model_m::MIDA_IYY &&
+              model_m::MIDB_IZZ == model_m::MIDA_IZZ && model_m::MIDB_CX == model_m::MIDA_CX &&
+              model_m::MIDB_CY == model_m::MIDA_CY, "ModelWalkM::body_full shares table entries between bodies");
 
 template <typename Model, typename T>
 ZB_HD void sim_state_default(SimState<T>& s) {
@@ -620,6 +746,8 @@ ZB_HD void physics_substep(const Params<PS>& P, SimState<T>& s, const T* target,
                            T* mid_force_out) {
   using namespace model;
   const T dt = T(P.dt);
+  // friction coefficient: the uniform cfg value, or per env (`target[6]`) for models with randomised materials
+  const T mu = Model::kPerEnvFriction ? target[6] : T(P.c_mu);
   // ---- PD (implicit part lives in P.arm) + park q, qd (static indices: registers -> scratch) ----
   ZB_UNROLL for (int k = 0; k < 6; ++k) {
     const T e = target[k] - s.q[k];
@@ -675,9 +803,7 @@ ZB_HD void physics_substep(const Params<PS>& P, SimState<T>& s, const T* target,
   {
     T R[9];
     quat_to_mat(Q, R);
-    T mass, cx, cz, ixx, iyy, izz, ixz;
-    Model::body(6, mass, cx, cz, ixx, iyy, izz, ixz);
-    body_rigid_terms(P, mass, cx, cz, ixx, iyy, izz, ixz, R, r, w, vO, IA, pAt, pAb);
+    model_body_terms<Model>(P, 6, R, r, w, vO, IA, pAt, pAb);
     contact_agg_zero(agg);
     const int npts = Model::npts(6);
 #if defined(__CUDACC__)
@@ -688,7 +814,7 @@ ZB_HD void physics_substep(const Params<PS>& P, SimState<T>& s, const T* target,
       Model::point(6, j, lx, ly, lz, drop);
       T rho[3] = {r[0] + R[0] * lx + R[1] * ly + R[2] * lz, r[1] + R[3] * lx + R[4] * ly + R[5] * lz,
                   r[2] + R[6] * lx + R[7] * ly + R[8] * lz - drop};
-      contact_point(P, rho, s.p[2] + rho[2], w, vO, IA, pAt, pAb,
+      contact_point(P, mu, rho, s.p[2] + rho[2], w, vO, IA, pAt, pAb,
                     Model::kGroundForceSensor ? &agg : (ContactAgg<T>*)nullptr, (T*)nullptr);
     }
     if (Model::kGroundForceSensor) agg1 = agg;
@@ -724,11 +850,7 @@ ZB_HD void physics_substep(const Params<PS>& P, SimState<T>& s, const T* target,
     ZB_UNROLL for (int i = 0; i < 6; ++i) { IB.I[i] = T(0); IB.M[i] = T(0); }
     ZB_UNROLL for (int i = 0; i < 9; ++i) IB.H[i] = T(0);
     T pBt[3] = {T(0), T(0), T(0)}, pBb[3] = {T(0), T(0), T(0)};
-    {
-      T mass, cx, cz, ixx, iyy, izz, ixz;
-      Model::body(k - 1, mass, cx, cz, ixx, iyy, izz, ixz);
-      body_rigid_terms(P, mass, cx, cz, ixx, iyy, izz, ixz, Rn, rn, wn, vn, IB, pBt, pBb);
-    }
+    model_body_terms<Model>(P, k - 1, Rn, rn, wn, vn, IB, pBt, pBb);
     // ---- stream A: velocity-product term c = V x (S qd), articulated-body elimination of joint j ----
     T ct[3], cb[3], tmp[3];
     cross3(w, sa, ct);
@@ -768,7 +890,7 @@ ZB_HD void physics_substep(const Params<PS>& P, SimState<T>& s, const T* target,
       Model::point(k - 1, c, lx, ly, lz, drop);
       T rho[3] = {r[0] + Rn[0] * lx + Rn[1] * ly + Rn[2] * lz, r[1] + Rn[3] * lx + Rn[4] * ly + Rn[5] * lz,
                   r[2] + Rn[6] * lx + Rn[7] * ly + Rn[8] * lz - drop};
-      contact_point(P, rho, s.p[2] + rho[2], w, vO, IA, pAt, pAb,
+      contact_point(P, mu, rho, s.p[2] + rho[2], w, vO, IA, pAt, pAb,
                     Model::kGroundForceSensor ? &agg : (ContactAgg<T>*)nullptr, (T*)nullptr);
     }
     if (Model::kGroundForceSensor) {
@@ -791,9 +913,7 @@ ZB_HD void physics_substep(const Params<PS>& P, SimState<T>& s, const T* target,
     T R[9];
     quat_to_mat(Q, R);
     const bool foot1 = (k == 6), foot0 = (k == 0);
-    T mass, cx, cz, ixx, iyy, izz, ixz;
-    Model::body(k, mass, cx, cz, ixx, iyy, izz, ixz);
-    body_rigid_terms(P, mass, cx, cz, ixx, iyy, izz, ixz, R, r, w, vO, IA, pAt, pAb);
+    model_body_terms<Model>(P, k, R, r, w, vO, IA, pAt, pAb);
     // ground-contact candidates of this body (Model::point)
     contact_agg_zero(agg);
     const int npts = Model::npts(k);
@@ -805,7 +925,7 @@ ZB_HD void physics_substep(const Params<PS>& P, SimState<T>& s, const T* target,
       Model::point(k, j, lx, ly, lz, drop);
       T rho[3] = {r[0] + R[0] * lx + R[1] * ly + R[2] * lz, r[1] + R[3] * lx + R[4] * ly + R[5] * lz,
                   r[2] + R[6] * lx + R[7] * ly + R[8] * lz - drop};
-      contact_point(P, rho, s.p[2] + rho[2], w, vO, IA, pAt, pAb,
+      contact_point(P, mu, rho, s.p[2] + rho[2], w, vO, IA, pAt, pAb,
                     Model::kGroundForceSensor ? &agg : (ContactAgg<T>*)nullptr, (T*)nullptr);
     }
     if (Model::kGroundForceSensor) {
@@ -1354,6 +1474,7 @@ struct PhysOut {
   T applied_torque[6];  // ImplicitActuator bookkeeping before the last substep
   T mid2_h3;            // v4 (history_length = 3): max over the LAST THREE substeps only
   T qd_prev[6];         // v4: joint velocities before the last substep (joint_acc finite difference)
+  T fn2_h3[2];          // manager task: max over the last three substeps of |F_foot|^2 (feet_slide, rewards.py:256)
 };
 
 // Phase B of the control step: _pre_physics_step (…env_v2.py:276-287) + decimation x (physics substep +
@@ -1362,12 +1483,25 @@ struct PhysOut {
 template <typename Model, int kUnroll = 1, typename T, typename Scr>
 ZB_HD void env_step_physics(const Params<T>& P, EnvState<T>& e, const T* raw_actions, PhysOut<T>& po, Scr& scr,
                             StepExport<T>* ex) {
-  T new_actions[6], target[6];
-  mdp_pre_physics<Model>(P, raw_actions, e.mdp, new_actions, target);
+  T new_actions[6], target[7], proc[6];
+  if constexpr (Model::kTask == 3) {
+    // RelativeJointPositionAction [IL-upstream]: processed = clip(raw * scale); applied at EVERY substep as
+    // processed + the joint position of that moment.  Action columns are in Isaac Lab joint order.
+    ZB_UNROLL for (int k = 0; k < 6; ++k) {
+      proc[k] = zb_clamp(raw_actions[Model::il_col(k)] * P.act_scale, -P.act_clip, P.act_clip);
+      new_actions[k] = T(0); target[k] = T(0);
+    }
+    target[6] = e.mdp.speed_limit;      // per-env friction coefficient (startup material randomisation)
+    po.fn2_h3[0] = po.fn2_h3[1] = T(0);
+  } else {
+    mdp_pre_physics<Model>(P, raw_actions, e.mdp, new_actions, target);
+    target[6] = T(0);
+    ZB_UNROLL for (int k = 0; k < 6; ++k) proc[k] = T(0);
+  }
   // (v4 keeps its commands in the carry slots: 3-deep history needs no carry-over from the previous step)
-  po.fz[4][0] = (Model::kTask == 2) ? T(0) : e.carry_feet_fz[0];
-  po.fz[4][1] = (Model::kTask == 2) ? T(0) : e.carry_feet_fz[1];
-  po.mid2 = (Model::kTask == 2) ? T(0) : e.carry_mid_max * e.carry_mid_max;
+  po.fz[4][0] = (Model::kFresh) ? T(0) : e.carry_feet_fz[0];
+  po.fz[4][1] = (Model::kFresh) ? T(0) : e.carry_feet_fz[1];
+  po.mid2 = (Model::kFresh) ? T(0) : e.carry_mid_max * e.carry_mid_max;
   if (ex) {
     ZB_UNROLL for (int b = 0; b < 5; ++b) { ex->mid_force_hist[4][b][0] = (b == 0) ? e.carry_mid_max : T(0);
       ex->mid_force_hist[4][b][1] = T(0); ex->mid_force_hist[4][b][2] = T(0); }
@@ -1375,15 +1509,16 @@ ZB_HD void env_step_physics(const Params<T>& P, EnvState<T>& e, const T* raw_act
       ex->feet_force_hist[4][j][2] = e.carry_feet_fz[j]; }
   }
   SubstepOut<T> so;
-  if (Model::kTask == 2) po.mid2_h3 = T(0);
+  if (Model::kFresh) po.mid2_h3 = T(0);
 #if defined(__CUDACC__)
 #pragma unroll 1
 #endif
   for (int sub = 0; sub < P.decimation; ++sub) {
     T midf[15];
-    if (Model::kTask == 2) {
+    if (Model::kFresh) {
       if (sub == P.decimation - 1) { ZB_UNROLL for (int k = 0; k < 6; ++k) po.qd_prev[k] = e.sim.qd[k]; }
     }
+    if constexpr (Model::kTask == 3) { ZB_UNROLL for (int k = 0; k < 6; ++k) target[k] = proc[k] + e.sim.q[k]; }
     physics_substep<Model, (ZB_PIPELINED_SWEEP != 0), kUnroll>(P, e.sim, target, so, scr, ex ? midf : (T*)nullptr);
     if (!Model::kGroundForceSensor) continue;
     // ContactSensor.update
@@ -1392,18 +1527,19 @@ ZB_HD void env_step_physics(const Params<T>& P, EnvState<T>& e, const T* raw_act
       const T* ff = so.foot_force[j];
       const T nrm = zb_sqrt(ff[0] * ff[0] + ff[1] * ff[1] + ff[2] * ff[2]);
       contact_timers_update(e.timers[j], nrm > T(1.0), P.dt);
+      if constexpr (Model::kTask == 3) { if (slot < 3) po.fn2_h3[j] = zb_max(po.fn2_h3[j], nrm * nrm); }
       ZB_UNROLL for (int k = 0; k < 4; ++k) po.fz[k][j] = (slot == k) ? ff[2] : po.fz[k][j];   // select, not index
       if (ex && slot < 4) { ex->feet_force_hist[slot][j][0] = ff[0]; ex->feet_force_hist[slot][j][1] = ff[1];
         ex->feet_force_hist[slot][j][2] = ff[2]; }
     }
     if (slot < 4) po.mid2 = zb_max(po.mid2, so.mid_force2_max);
-    if (Model::kTask == 2) { if (slot < 3) po.mid2_h3 = zb_max(po.mid2_h3, so.mid_force2_max); }
+    if (Model::kFresh) { if (slot < 3) po.mid2_h3 = zb_max(po.mid2_h3, so.mid_force2_max); }
     if (ex && slot < 4) {
       ZB_UNROLL for (int b = 0; b < 5; ++b)
         ZB_UNROLL for (int i = 0; i < 3; ++i) ex->mid_force_hist[slot][b][i] = midf[3 * b + i];
     }
   }
-  if (Model::kGroundForceSensor && Model::kTask != 2) {
+  if (Model::kGroundForceSensor && !Model::kFresh) {
     e.carry_feet_fz[0] = so.foot_force[0][2];
     e.carry_feet_fz[1] = so.foot_force[1][2];
     e.carry_mid_max = zb_sqrt(so.mid_force2_max);
@@ -1904,6 +2040,381 @@ ZB_HD void v4_env_step(const Params<T>& P, EnvState<T>& e, const T* raw_actions,
   PhysOut<T> po;
   env_step_physics<ModelWalkV4>(P, e, raw_actions, po, scr, (StepExport<T>*)nullptr);
   v4_step_finish(P, e, raw_actions, po, ep_len, rnd, obs24, out, reset_ep_sums, ex);
+}
+
+// ------------------------------------------------------------------------------------
+// zbot-6b-walking-m-v0: the manager-based task (tasks/zbotlab_manager/zbotlab_env_cfg.py:82-452, config/zbot6b_manager/
+// flat_env_cfg.py, mdp/rewards.py, mdp/terminations.py) in ManagerBasedRLEnv.step order [IL-upstream]: action term ->
+// decimation x (apply action, physics, sensor update) -> episode_length += 1 -> TerminationManager -> RewardManager ->
+// reset of the done envs (EventManager mode "reset", then the managers' own reset: the command term resamples) ->
+// CommandManager.compute -> ObservationManager (25 columns, additive uniform noise applied by the caller).
+// Robot = ModelWalkM.  State reuse inside the 80-word layout: carry_feet_fz[0..1] = command lin_vel x / y, carry_mid_max =
+// command ang_vel z, heading_sum = is_standing_env, y_err_sum = command time_left, speed_limit = per-env friction,
+// actions = last RAW action (ActionManager.action, Isaac Lab joint order); p_delta is unused.
+// ------------------------------------------------------------------------------------
+constexpr int M_NUM_OBS = 25;
+constexpr int M_NUM_RAND = 13;
+// uniforms of one env-step, in the order the reference would draw them for that env
+enum MRandSlot : int { MR_POSE_X = 0, MR_POSE_Y = 1, MR_POSE_YAW = 2,                       // reset_root_state_uniform
+                       MR_RESET_TIME = 3, MR_RESET_VX = 4, MR_RESET_VY = 5, MR_RESET_WZ = 6, MR_RESET_STAND = 7,   // CommandTerm.reset
+                       MR_INT_TIME = 8, MR_INT_VX = 9, MR_INT_VY = 10, MR_INT_WZ = 11, MR_INT_STAND = 12 };        // CommandTerm.compute
+
+template <typename T>
+ZB_HD void quat_mul(const T* a, const T* b, T* o) {
+  o[0] = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
+  o[1] = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
+  o[2] = a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1];
+  o[3] = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0];
+}
+
+template <typename T>
+struct MKin {   // what the manager terms read from `robot.data` (root = LINK `base`, feet = LINKS foot0 / foot1)
+  T root_pos[3], root_quat[4], root_lin_vel[3], root_ang_vel[3], shoulder[3];   // shoulder = root_quat applied to (0,1,0)
+  T feet_pos[2][3], feet_up[2][3], feet_x[2][3], feet_com_vel[2][3];           // feet_up = link (0,+-1,0), feet_x = link (1,0,0)
+  T feet_bq[2][4];                                                             // BODY (chain-frame) quaternions of the feet
+};
+
+// Link axes in the body (chain) frame: x_link = -x_c, y_link = z_c, z_link = y_c (assets/zbot_6s_v2.py); `base` differs
+// from that by a rotation about its own y axis, which leaves the shoulder axis y_link = z_c in place.
+template <typename T>
+ZB_HD void m_kinematics(const SimState<T>& s, MKin<T>& o) {
+  using namespace model;
+  T Q[4] = {s.Q[0], s.Q[1], s.Q[2], s.Q[3]};
+  T r[3] = {T(0), T(0), T(0)};
+  T w[3] = {s.w[0], s.w[1], s.w[2]};
+  T vO[3] = {s.v[0], s.v[1], s.v[2]};
+  T qk[6], qdk[6];
+  ZB_UNROLL for (int k = 0; k < 6; ++k) { qk[k] = s.q[k]; qdk[k] = s.qd[k]; }
+  T R[9];
+  quat_to_mat(Q, R);
+  {  // body 0 = foot0: link origin at (0,0,FOOT0_LINK_Z), CoM = body CoM
+    const T lz = T(model_m::FOOT0_LINK_Z);
+    const T cx = T(model_m::FOOT0_CX), cy = T(model_m::FOOT0_CY), cz = T(model_m::FOOT0_CZ);
+    T c[3] = {R[0] * cx + R[1] * cy + R[2] * cz, R[3] * cx + R[4] * cy + R[5] * cz, R[6] * cx + R[7] * cy + R[8] * cz};
+    T wxc[3];
+    cross3(w, c, wxc);
+    ZB_UNROLL for (int i = 0; i < 3; ++i) {
+      o.feet_pos[0][i] = s.p[i] + R[3 * i + 2] * lz;
+      o.feet_com_vel[0][i] = vO[i] + wxc[i];
+      o.feet_up[0][i] = R[3 * i + 2];
+      o.feet_x[0][i] = -R[3 * i];
+    }
+    ZB_UNROLL for (int i = 0; i < 4; ++i) o.feet_bq[0][i] = Q[i];
+  }
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
+  for (int k = 0; k < 6; ++k) {
+    const T jz = (k == 0) ? T(JOINT_Z_FIRST) : T(JOINT_Z_REST);
+    const T sg = (k & 1) ? T(-AXIS_S) : T(AXIS_S);
+    r[0] += jz * R[2]; r[1] += jz * R[5]; r[2] += jz * R[8];
+    T a[3] = {sg * R[0] + T(AXIS_S) * R[2], sg * R[3] + T(AXIS_S) * R[5], sg * R[6] + T(AXIS_S) * R[8]};
+    T m[3];
+    cross3(r, a, m);
+    const T qv = (k == 0) ? qk[0] : (k == 1) ? qk[1] : (k == 2) ? qk[2] : (k == 3) ? qk[3] : (k == 4) ? qk[4] : qk[5];
+    const T qdv = (k == 0) ? qdk[0] : (k == 1) ? qdk[1] : (k == 2) ? qdk[2] : (k == 3) ? qdk[3] : (k == 4) ? qdk[4] : qdk[5];
+    ZB_UNROLL for (int i = 0; i < 3; ++i) { w[i] += a[i] * qdv; vO[i] += m[i] * qdv; }
+    T sn, cs;
+    zb_sincos(T(0.5) * qv, &sn, &cs);
+    quat_mul_joint(Q, cs, sg * sn, T(AXIS_S) * sn);
+    quat_to_mat(Q, R);
+    if (k == 2) {   // body 3 = base + a7: `base` link origin at (0,0,BASE_LINK_Z)
+      const T lz = T(model_m::BASE_LINK_Z);
+      T lo[3] = {r[0] + R[2] * lz, r[1] + R[5] * lz, r[2] + R[8] * lz};
+      T wxl[3];
+      cross3(w, lo, wxl);
+      const T lq[4] = {T(model_m::BASE_LQW), T(model_m::BASE_LQX), T(model_m::BASE_LQY), T(model_m::BASE_LQZ)};
+      quat_mul(Q, lq, o.root_quat);
+      ZB_UNROLL for (int i = 0; i < 3; ++i) {
+        o.root_pos[i] = s.p[i] + lo[i];
+        o.root_lin_vel[i] = vO[i] + wxl[i];
+        o.root_ang_vel[i] = w[i];
+        o.shoulder[i] = R[3 * i + 2];
+      }
+    }
+    if (k == 5) {   // body 6 = foot1: link origin = body origin
+      const T cx = T(model_m::FOOT1_CX), cy = T(model_m::FOOT1_CY), cz = T(model_m::FOOT1_CZ);
+      T c[3] = {r[0] + R[0] * cx + R[1] * cy + R[2] * cz, r[1] + R[3] * cx + R[4] * cy + R[5] * cz,
+                r[2] + R[6] * cx + R[7] * cy + R[8] * cz};
+      T wxc[3];
+      cross3(w, c, wxc);
+      ZB_UNROLL for (int i = 0; i < 3; ++i) {
+        o.feet_pos[1][i] = s.p[i] + r[i];
+        o.feet_com_vel[1][i] = vO[i] + wxc[i];
+        o.feet_up[1][i] = -R[3 * i + 2];
+        o.feet_x[1][i] = -R[3 * i];
+      }
+      ZB_UNROLL for (int i = 0; i < 4; ++i) o.feet_bq[1][i] = Q[i];
+    }
+  }
+}
+
+// UniformVelocityCommand._resample [IL-upstream]: time_left, lin_vel_x / y, ang_vel_z ~ U(range); standing ~ U(0,1) <= rel
+template <typename T>
+ZB_HD void m_resample_command(const Params<T>& P, T u_time, T ux, T uy, T uw, T u_stand, T& cmd0, T& cmd1, T& cmd2,
+                              T& standing, T& time_left) {
+  time_left = u_time * (P.cmd_resample_hi - P.cmd_resample_lo) + P.cmd_resample_lo;
+  cmd0 = ux * (P.cmd_hi[0] - P.cmd_lo[0]) + P.cmd_lo[0];
+  cmd1 = uy * (P.cmd_hi[1] - P.cmd_lo[1]) + P.cmd_lo[1];
+  cmd2 = uw * (P.cmd_hi[2] - P.cmd_lo[2]) + P.cmd_lo[2];
+  standing = (u_stand <= P.cmd_rel_standing) ? T(1) : T(0);
+}
+
+template <typename T>
+struct MFresh {
+  T cmd[3], forward[3];
+  T root_lin_vel[3], root_ang_z, yaw_c, yaw_s;   // (cos, sin) of the root yaw
+  T feet_pos[2][3], feet_force[2], feet_fnorm_max[2];
+  T cur_air[2], cur_contact[2];
+  T phase_time;                                  // episode_length_buf * step_dt (float32 product)
+};
+
+template <typename T>
+ZB_HD T m_term_value(int id, const T* par, const StaleCache<T>& c, const FreshInputs<T>& f, const V4Fresh<T>& v4,
+                     const MFresh<T>& v, const T* new_actions, MdpState<T>& m) {
+  T val = T(0);
+  switch (id) {
+    case TERM_M_TRACK_LIN_VEL_XY_EXP: {                                          // rewards.py:286-297
+      const T vx = v.yaw_c * v.root_lin_vel[0] + v.yaw_s * v.root_lin_vel[1];   // quat_apply_inverse(yaw_quat(root_quat_w), v)
+      const T vy = v.yaw_c * v.root_lin_vel[1] - v.yaw_s * v.root_lin_vel[0];
+      const T dx = v.cmd[0] - vx, dy = v.cmd[1] - vy;
+      val = zb_exp(-(dx * dx + dy * dy) / par[0]);
+    } break;
+    case TERM_M_TRACK_ANG_VEL_Z_EXP: {                                           // :300-309
+      const T d = v.cmd[2] - v.root_ang_z;
+      val = zb_exp(-(d * d) / par[0]);
+    } break;
+    case TERM_M_FOOT_STEP_LENGTH: {                                              // :45-107 (command_name = None)
+      const T inv = T(1) / (zb_sqrt(v.forward[0] * v.forward[0] + v.forward[1] * v.forward[1] + v.forward[2] * v.forward[2]) + T(1e-6));
+      const T fw[3] = {v.forward[0] * inv, v.forward[1] * inv, v.forward[2] * inv};
+      bool down[2];
+      ZB_UNROLL for (int j = 0; j < 2; ++j) {
+        down[j] = (v.feet_force[j] > T(10.0)) && (m.feet_force_last[j] < T(10.0));
+        if (down[j]) {
+          const T d[3] = {v.feet_pos[j][0] - m.feet_down_pos_last[j][0], v.feet_pos[j][1] - m.feet_down_pos_last[j][1],
+                          v.feet_pos[j][2] - m.feet_down_pos_last[j][2]};
+          m.feet_step_length[j] = zb_abs(d[0] * fw[0] + d[1] * fw[1] + d[2] * fw[2]);
+        }
+      }
+      const T rew_len = zb_min(m.feet_step_length[0], m.feet_step_length[1]);
+      ZB_UNROLL for (int j = 0; j < 2; ++j) {
+        if (down[j]) { ZB_UNROLL for (int i = 0; i < 3; ++i) m.feet_down_pos_last[j][i] = v.feet_pos[j][i]; }
+        m.feet_force_last[j] = v.feet_force[j];
+      }
+      val = zb_tanh(T(15.0) * rew_len);
+    } break;
+    case TERM_M_GAIT: {                                                          // :155-186, par = period, offsets, threshold
+      const T g = zb_fmod(v.phase_time, par[0]) / par[0];
+      ZB_UNROLL for (int j = 0; j < 2; ++j) {
+        const T ph = zb_fmod(g + par[1 + j], T(1.0));
+        const bool stance = ph < par[3], contact = v.cur_contact[j] > T(0);
+        val += (stance == contact) ? T(1) : T(0);
+      }
+      const T n = zb_sqrt(v.cmd[0] * v.cmd[0] + v.cmd[1] * v.cmd[1] + v.cmd[2] * v.cmd[2]);
+      val = (n > T(0.05)) ? val : T(0);
+    } break;
+    case TERM_M_FEET_SLIDE:                                                      // :247-262
+      ZB_UNROLL for (int j = 0; j < 2; ++j) {
+        const T sp = zb_sqrt(f.feet_vel_xy[j][0] * f.feet_vel_xy[j][0] + f.feet_vel_xy[j][1] * f.feet_vel_xy[j][1]);
+        val += (v.feet_fnorm_max[j] > T(1.0)) ? sp : T(0);
+      }
+      break;
+    case TERM_M_FEET_CLEARANCE: {                                                // :143-153, par = std, tanh_mult, target
+      T acc = T(0);
+      ZB_UNROLL for (int j = 0; j < 2; ++j) {
+        const T dz = v.feet_pos[j][2] - par[2];
+        const T sp = zb_sqrt(f.feet_vel_xy[j][0] * f.feet_vel_xy[j][0] + f.feet_vel_xy[j][1] * f.feet_vel_xy[j][1]);
+        acc += (dz * dz) * zb_tanh(par[1] * sp);
+      }
+      val = zb_exp(-acc / par[0]);
+    } break;
+    case TERM_M_FEET_AIR_TIME_BIPED: {                                           // :211-230, par = threshold
+      const bool c0 = v.cur_contact[0] > T(0), c1 = v.cur_contact[1] > T(0);
+      const T t0 = c0 ? v.cur_contact[0] : v.cur_air[0], t1 = c1 ? v.cur_contact[1] : v.cur_air[1];
+      const bool single = (c0 != c1);
+      val = zb_min(zb_min(single ? t0 : T(0), single ? t1 : T(0)), par[0]);
+      val = (zb_sqrt(v.cmd[0] * v.cmd[0] + v.cmd[1] * v.cmd[1]) > T(0.1)) ? val : T(0);
+    } break;
+    case TERM_M_BASE_VEL_FORWARD:                                                // :264-274, par = which_forward
+      val = par[0] * (v.root_lin_vel[0] * v.forward[0] + v.root_lin_vel[1] * v.forward[1] + v.root_lin_vel[2] * v.forward[2]);
+      break;
+    case TERM_M_FEET_FORCE_PATTERN: {                                            // :276-284
+      const T sg = (m.feet_force_sum > T(0)) ? T(1) : (m.feet_force_sum < T(0)) ? T(-1) : T(0);
+      const T diff = (v.feet_force[1] - v.feet_force[0]) * sg;
+      m.feet_force_sum += T(0.001) * (v.feet_force[0] - v.feet_force[1]);
+      val = T(0.5) * diff - T(0.1) * zb_abs(m.feet_force_sum);
+    } break;
+    default:   // ids shared with the direct tasks (torques, joint_acc, action_rate, foot_downward / forward, air-time terms)
+      val = v4_term_value(id, c, f, v4, new_actions, m, T(0));
+      break;
+  }
+  return val;
+}
+
+template <typename T>
+struct MExport {   // what the manager terms saw at the end of physics (test hook), 67 words; feet_quat = LINK quaternions
+  T root_pos[3], root_quat[4], root_lin_vel[3], root_ang_vel[3];
+  T feet_pos[2][3], feet_quat[2][4], feet_com_vel[2][3];
+  T feet_fz_hist[3][2], feet_fnorm_max[2];
+  T last_air[2], last_contact[2], cur_air[2], cur_contact[2];
+  T q1[6], tau1[6], joint_acc1[6];     // chain joint order
+};
+constexpr int M_EXPORT_WORDS = 13 + 20 + 8 + 8 + 18;
+
+// Phase C of the manager task's control step.  `rnd` = this env-step's M_NUM_RAND uniforms; obs25 = the clean row.
+template <typename T>
+ZB_HD void m_step_finish(const Params<T>& P, EnvState<T>& e, const T* raw_actions, const PhysOut<T>& po, int64_t& ep_len,
+                         const T* rnd, T* obs25, StepOut<T>& out, T* reset_ep_sums, MExport<T>* ex) {
+  T& cmd0 = e.carry_feet_fz[0];
+  T& cmd1 = e.carry_feet_fz[1];
+  T& cmd2 = e.carry_mid_max;
+  T& standing = e.mdp.heading_sum;
+  T& time_left = e.mdp.y_err_sum;
+  ep_len += 1;
+  MKin<T> k1;
+  m_kinematics(e.sim, k1);
+  // ---- the shared containers of the direct tasks, filled with this task's fresh values ----
+  StaleCache<T> c;
+  FreshInputs<T> f;
+  V4Fresh<T> v4;
+  MFresh<T> v;
+  {
+    const T grav[3] = {T(0), T(0), T(-1)};
+    cross3(grav, k1.shoulder, v.forward);                                       // cross(GRAVITY_VEC_W, R (0,1,0)), not normalised
+    const T qw = k1.root_quat[0], qx = k1.root_quat[1], qy = k1.root_quat[2], qz = k1.root_quat[3];
+    const T sy = T(2) * (qw * qz + qx * qy), cy = T(1) - T(2) * (qy * qy + qz * qz);   // yaw_quat [IL-upstream]
+    const T inv = zb_rsqrt(zb_max(sy * sy + cy * cy, T(1e-30)));
+    v.yaw_c = cy * inv; v.yaw_s = sy * inv;
+    v.cmd[0] = cmd0; v.cmd[1] = cmd1; v.cmd[2] = cmd2;
+    v.root_ang_z = k1.root_ang_vel[2];
+    v.phase_time = T(ep_len) * P.step_dt;
+    v4.joint_vel2 = T(0); v4.joint_acc2 = T(0);
+    const T inv_dt = T(1) / P.dt;
+    ZB_UNROLL for (int k = 0; k < 6; ++k) {
+      const T acc = (e.sim.qd[k] - po.qd_prev[k]) * inv_dt;                      // ArticulationData.joint_acc [IL-upstream]
+      v4.joint_vel2 += e.sim.qd[k] * e.sim.qd[k];
+      v4.joint_acc2 += acc * acc;
+      f.applied_torque[k] = po.applied_torque[k];
+    }
+    ZB_UNROLL for (int i = 0; i < 3; ++i) { v.root_lin_vel[i] = k1.root_lin_vel[i]; c.forward[i] = v.forward[i]; c.base_pos[i] = k1.root_pos[i]; }
+    ZB_UNROLL for (int j = 0; j < 2; ++j) {
+      v.feet_force[j] = ((po.fz[0][j] + po.fz[1][j]) + po.fz[2][j]) / T(3);      // mean over history_length = 3
+      v.feet_fnorm_max[j] = zb_sqrt(po.fn2_h3[j]);
+      v.cur_air[j] = e.timers[j].cur_air; v.cur_contact[j] = e.timers[j].cur_contact;
+      v4.last_air[j] = e.timers[j].last_air; v4.last_contact[j] = e.timers[j].last_contact;
+      v4.cur_air[j] = v.cur_air[j]; v4.cur_contact[j] = v.cur_contact[j];
+      f.feet_force[j] = v.feet_force[j];
+      f.last_air_time[j] = e.timers[j].last_air;
+      f.feet_vel_xy[j][0] = k1.feet_com_vel[j][0]; f.feet_vel_xy[j][1] = k1.feet_com_vel[j][1];
+      v4.feet_force[j] = v.feet_force[j];
+      ZB_UNROLL for (int i = 0; i < 3; ++i) {
+        v.feet_pos[j][i] = k1.feet_pos[j][i]; v4.feet_pos[j][i] = k1.feet_pos[j][i]; c.feet_pos[j][i] = k1.feet_pos[j][i];
+        c.feet_z[j][i] = k1.feet_up[j][i]; c.feet_x[j][i] = k1.feet_x[j][i];
+      }
+    }
+    ZB_UNROLL for (int i = 0; i < 3; ++i) { v4.forward[i] = v.forward[i]; v4.shoulder[i] = k1.shoulder[i]; }
+    v4.current_yaw = T(0); v4.heading_err = T(0); v4.v_fwd = T(0); v4.vel_y = T(0); v4.base_height = k1.root_pos[2];
+    c.v_fwd = T(0); c.aux = T(0);
+    f.undesired_force_max = zb_sqrt(po.mid2_h3);
+    f.origin_y = T(0); f.com_x_sum = T(0);
+  }
+  if (ex) {
+    ZB_UNROLL for (int i = 0; i < 3; ++i) { ex->root_pos[i] = k1.root_pos[i]; ex->root_lin_vel[i] = k1.root_lin_vel[i]; ex->root_ang_vel[i] = k1.root_ang_vel[i]; }
+    ZB_UNROLL for (int i = 0; i < 4; ++i) ex->root_quat[i] = k1.root_quat[i];
+    ZB_UNROLL for (int j = 0; j < 2; ++j) {
+      ZB_UNROLL for (int i = 0; i < 3; ++i) { ex->feet_pos[j][i] = k1.feet_pos[j][i]; ex->feet_com_vel[j][i] = k1.feet_com_vel[j][i]; }
+      const T lq[4] = {T(model_m::LINK_LQW), T(model_m::LINK_LQX), T(model_m::LINK_LQY), T(model_m::LINK_LQZ)};
+      quat_mul(k1.feet_bq[j], lq, ex->feet_quat[j]);
+      ZB_UNROLL for (int t = 0; t < 3; ++t) ex->feet_fz_hist[t][j] = po.fz[t][j];
+      ex->feet_fnorm_max[j] = v.feet_fnorm_max[j];
+      ex->last_air[j] = v4.last_air[j]; ex->last_contact[j] = v4.last_contact[j];
+      ex->cur_air[j] = v.cur_air[j]; ex->cur_contact[j] = v.cur_contact[j];
+    }
+    ZB_UNROLL for (int k = 0; k < 6; ++k) { ex->q1[k] = e.sim.q[k]; ex->tau1[k] = po.applied_torque[k];
+                                            ex->joint_acc1[k] = (e.sim.qd[k] - po.qd_prev[k]) * (T(1) / P.dt); }
+  }
+  // ---- TerminationManager.compute (TerminationsCfg, zbotlab_env_cfg.py:371-393; base_contact is None for this robot) ----
+  const bool time_out = ep_len >= (int64_t)P.max_episode_length;                 // mdp.time_out [IL-upstream]: >= max_episode_length
+  const bool low = k1.root_pos[2] < P.termination_height;                        // root_height_below_minimum
+  bool close = false;
+  if (P.feet_close_min > T(0)) {                                                 // terminations.py:55-60
+    const T dx = k1.feet_pos[0][0] - k1.feet_pos[1][0], dy = k1.feet_pos[0][1] - k1.feet_pos[1][1], dz = k1.feet_pos[0][2] - k1.feet_pos[1][2];
+    close = zb_sqrt(dx * dx + dy * dy + dz * dz) < P.feet_close_min;
+  }
+  const bool died = low || close;
+  // ---- RewardManager.compute: value = func(env) * weight * dt, in cfg order; raw actions are the action term's `action` ----
+  T reward = T(0);
+  for (int i = 0; i < P.num_terms; ++i) {
+    const T par[4] = {P.term_par[i][0], P.term_par[i][1], P.term_par[i][2], P.term_par[i][3]};
+    const T rew = m_term_value(P.term_id[i], par, c, f, v4, v, raw_actions, e.mdp) * P.term_w[i] * P.step_dt;
+    reward += rew;
+    ZB_UNROLL for (int k = 0; k < MAX_TERMS; ++k) e.mdp.ep_sums[k] += (k == i) ? rew : T(0);
+  }
+  if (died) reward += P.term_penalty_w;                                          // RewTerm is_terminated
+  out.reward = reward;
+  out.terminated = died;
+  out.time_out = time_out;
+  ZB_UNROLL for (int k = 0; k < 6; ++k) e.mdp.actions[k] = raw_actions[k];      // ActionManager.action (prev_action next step)
+  // ---- _reset_idx of the done envs ----
+  if (died || time_out) {
+    ZB_UNROLL for (int i = 0; i < MAX_TERMS; ++i) reset_ep_sums[i] = e.mdp.ep_sums[i];
+    if (P.num_terms <= MAX_TERMS - 2) { reset_ep_sums[MAX_TERMS - 2] = low ? T(1) : T(0); reset_ep_sums[MAX_TERMS - 1] = close ? T(1) : T(0); }
+    // EventManager mode "reset": reset_base (reset_root_state_uniform on the root LINK `base`), reset_robot_joints
+    // (default * U(1,1)), reset_my_data (rewards.py:37-43)
+    sim_state_default<ModelWalkM>(e.sim);
+    {
+      using namespace model_m;
+      const T yaw = rnd[MR_POSE_YAW] * (P.ev_pose_hi[2] - P.ev_pose_lo[2]) + P.ev_pose_lo[2];
+      const T bx = T(BASE_DEFAULT_X) + (rnd[MR_POSE_X] * (P.ev_pose_hi[0] - P.ev_pose_lo[0]) + P.ev_pose_lo[0]);
+      const T by = T(BASE_DEFAULT_Y) + (rnd[MR_POSE_Y] * (P.ev_pose_hi[1] - P.ev_pose_lo[1]) + P.ev_pose_lo[1]);
+      const T cyw = zb_cos(yaw), syw = zb_sin(yaw);
+      const T ox = T(DEFAULT_ROOT_X - BASE_DEFAULT_X), oy = T(DEFAULT_ROOT_Y - BASE_DEFAULT_Y);   // chain root relative to `base`
+      e.sim.p[0] = bx + (cyw * ox - syw * oy);
+      e.sim.p[1] = by + (syw * ox + cyw * oy);
+      const T qz[4] = {zb_cos(yaw * T(0.5)), T(0), T(0), zb_sin(yaw * T(0.5))};
+      const T q0[4] = {e.sim.Q[0], e.sim.Q[1], e.sim.Q[2], e.sim.Q[3]};
+      quat_mul(qz, q0, e.sim.Q);
+    }
+    ep_len = 0;
+    ZB_UNROLL for (int k = 0; k < 6; ++k) { e.mdp.p_delta[k] = T(0); e.mdp.actions[k] = T(0); }   // ActionManager.reset
+    ZB_UNROLL for (int j = 0; j < 2; ++j) {
+      e.timers[j].cur_air = e.timers[j].cur_contact = e.timers[j].last_air = e.timers[j].last_contact = T(0);
+      e.mdp.feet_force_last[j] = T(0);
+      e.mdp.feet_step_length[j] = T(0);
+    }
+    e.mdp.feet_force_sum = T(0);
+    ZB_UNROLL for (int i = 0; i < MAX_TERMS; ++i) e.mdp.ep_sums[i] = T(0);
+    m_kinematics(e.sim, k1);                                                     // post-reset view
+    ZB_UNROLL for (int j = 0; j < 2; ++j)
+      ZB_UNROLL for (int i = 0; i < 3; ++i) e.mdp.feet_down_pos_last[j][i] = k1.feet_pos[j][i];
+    // CommandManager.reset -> UniformVelocityCommand._resample
+    m_resample_command(P, rnd[MR_RESET_TIME], rnd[MR_RESET_VX], rnd[MR_RESET_VY], rnd[MR_RESET_WZ], rnd[MR_RESET_STAND],
+                       cmd0, cmd1, cmd2, standing, time_left);
+  }
+  // ---- CommandManager.compute(dt): timer, resample, standing envs get a zero command ----
+  time_left -= P.step_dt;
+  if (time_left <= T(0))
+    m_resample_command(P, rnd[MR_INT_TIME], rnd[MR_INT_VX], rnd[MR_INT_VY], rnd[MR_INT_WZ], rnd[MR_INT_STAND],
+                       cmd0, cmd1, cmd2, standing, time_left);
+  if (standing != T(0)) { cmd0 = T(0); cmd1 = T(0); cmd2 = T(0); }
+  // ---- ObservationManager: base_quat, velocity_commands, joint_pos_rel, joint_vel_rel, last_action (Isaac Lab joint order) ----
+  ZB_UNROLL for (int i = 0; i < 4; ++i) obs25[i] = k1.root_quat[i];
+  obs25[4] = cmd0; obs25[5] = cmd1; obs25[6] = cmd2;
+  ZB_UNROLL for (int k = 0; k < 6; ++k) {
+    const int col = ModelWalkM::il_col(k);
+    obs25[7 + col] = e.sim.q[k] - ModelWalkM::default_q<T>(k);
+    obs25[13 + col] = e.sim.qd[k];
+    obs25[19 + k] = e.mdp.actions[k];
+  }
+}
+
+// whole manager-task control step in one call (CPU port)
+template <typename T, typename Scr>
+ZB_HD void m_env_step(const Params<T>& P, EnvState<T>& e, const T* raw_actions, int64_t& ep_len, const T* rnd, T* obs25,
+                      StepOut<T>& out, T* reset_ep_sums, MExport<T>* ex, Scr& scr) {
+  PhysOut<T> po;
+  env_step_physics<ModelWalkM>(P, e, raw_actions, po, scr, (StepExport<T>*)nullptr);
+  m_step_finish(P, e, raw_actions, po, ep_len, rnd, obs25, out, reset_ep_sums, ex);
 }
 
 // the whole control step in one call (CPU port, export kernel)

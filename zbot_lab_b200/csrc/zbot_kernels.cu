@@ -648,6 +648,106 @@ zbot_v4_step_kernel(const __grid_constant__ Params<float> P, float4* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------------
+// zbot-6b-walking-m-v0 (manager-based task): same phased structure as the v4 kernel -- early quads, 4 substeps with the
+// relative joint-position action re-targeted at every substep, late quads, manager-ordered MDP -- on ModelWalkM (full
+// inertia tables, per-env friction).  Random numbers: caller-supplied [N][13] uniforms or the counter-based generator.
+// ---------------------------------------------------------------------------------------------
+static_assert(sizeof(MExport<float>) / sizeof(float) == ZBOT_M_EXPORT_WORDS && M_EXPORT_WORDS == ZBOT_M_EXPORT_WORDS, "MExport layout");
+static_assert(M_NUM_OBS == ZBOT_M_NUM_OBS && M_NUM_RAND == ZBOT_M_NUM_RAND, "manager task widths");
+
+template <bool kExport, int kUnroll = 1>
+__global__ void __launch_bounds__(128, 2)
+zbot_m_step_kernel(const __grid_constant__ Params<float> P, float4* __restrict__ state, int64_t* __restrict__ ep_len_buf,
+                   const float* __restrict__ actions, const float* __restrict__ rand, uint64_t seed, uint64_t call,
+                   float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ terminated,
+                   uint8_t* __restrict__ truncated, int n, StatsCtx sc, float* __restrict__ export_buf) {
+  extern __shared__ float smem[];
+  const int e0 = blockIdx.x * blockDim.x;
+  const int e = e0 + threadIdx.x;
+  const bool live = e < n;
+  float stat[kStatUsed];
+#pragma unroll
+  for (int j = 0; j < kStatUsed; ++j) stat[j] = 0.f;
+  float obs_row[M_NUM_OBS];
+#pragma unroll
+  for (int i = 0; i < M_NUM_OBS; ++i) obs_row[i] = 0.f;
+  bool did_reset = false;
+  if (live) {
+    EnvState<float> es;
+    StepOut<float> out;
+    float rs[MAX_TERMS];
+#pragma unroll
+    for (int i = 0; i < MAX_TERMS; ++i) rs[i] = 0.f;
+    SmemScratch scr{smem + threadIdx.x * SCR_STRIDE};
+    const float2* a2p = reinterpret_cast<const float2*>(actions + (size_t)e * 6);
+    {
+      float w[4 * EARLY_QUADS];
+      load_words<EARLY_QUADS>(state, n, e, w);
+      env_early_unpack(w, es);
+    }
+    PhysOut<float> po;
+    {
+      const float2 a0 = __ldg(a2p), a1 = __ldg(a2p + 1), a2v = __ldg(a2p + 2);
+      const float raw[6] = {a0.x, a0.y, a1.x, a1.y, a2v.x, a2v.y};
+#pragma unroll
+      for (int k = 0; k < 6; ++k) scr.base[SCR_RAW_ACT + k] = raw[k];
+      env_step_physics<ModelWalkM, kUnroll>(P, es, raw, po, scr, (StepExport<float>*)nullptr);
+    }
+    {
+      float w[ZBOT_STATE_WORDS - 4 * EARLY_QUADS];
+      load_words<ZBOT_STATE_WORDS / 4 - EARLY_QUADS>(state + (size_t)EARLY_QUADS * n, n, e, w);
+      env_late_unpack(w, es);
+    }
+    float raw[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) raw[k] = scr.base[SCR_RAW_ACT + k];
+    float rnd[M_NUM_RAND];
+    if (rand) {
+#pragma unroll
+      for (int i = 0; i < M_NUM_RAND; ++i) rnd[i] = __ldg(rand + (size_t)e * M_NUM_RAND + i);
+    } else {
+#pragma unroll
+      for (int i = 0; i < M_NUM_RAND; ++i) rnd[i] = v4_uniform(seed, call, (uint32_t)e, (uint32_t)i);
+    }
+    int64_t ep = ep_len_buf[e];
+    MExport<float> ex;
+    m_step_finish(P, es, raw, po, ep, rnd, obs_row, out, rs, kExport ? &ex : (MExport<float>*)nullptr);
+    // ObservationManager corruption (PolicyCfg: base_quat +-0.01, joint_pos +-0.01, joint_vel +-1.5); columns 0..23
+    if (P.obs_noise_enable) {
+#pragma unroll
+      for (int i = 0; i < 24; ++i)
+        obs_row[i] = fmaf(v4_uniform(P.rng_seed, call, (uint32_t)e, 32u + (uint32_t)i), P.obs_noise_w[i], obs_row[i] + P.obs_noise_lo[i]);
+    }
+    if (kExport) {
+      const float* src = reinterpret_cast<const float*>(&ex);
+      for (int i = 0; i < ZBOT_M_EXPORT_WORDS; ++i) export_buf[(size_t)e * ZBOT_M_EXPORT_WORDS + i] = src[i];
+    }
+    float w[ZBOT_STATE_WORDS];
+    env_state_pack(es, w);
+    store_words<ZBOT_STATE_WORDS / 4>(state, n, e, w);
+    ep_len_buf[e] = ep;
+    rew[e] = out.reward;
+    terminated[e] = out.terminated ? 1 : 0;
+    truncated[e] = out.time_out ? 1 : 0;
+    did_reset = out.terminated || out.time_out;
+    if (did_reset) {
+#pragma unroll
+      for (int i = 0; i < MAX_TERMS; ++i) stat[i] = rs[i];
+      stat[S_NUM_RESET] = 1.f;
+      stat[S_NUM_TERM_RESET] = out.terminated ? 1.f : 0.f;
+      stat[S_NUM_TO_RESET] = out.time_out ? 1.f : 0.f;
+    }
+    stat[S_REW_SUM] = out.reward;
+    stat[S_NUM_TERM] = out.terminated ? 1.f : 0.f;
+    stat[S_NUM_TRUNC] = out.time_out ? 1.f : 0.f;
+  }
+  __syncthreads();
+  store_rows_coalesced<M_NUM_OBS>(obs, obs_row, n, e0, smem);
+  __syncthreads();
+  stats_block_partial(stat, did_reset, smem, sc);
+}
+
+// ---------------------------------------------------------------------------------------------
 // reset / observe / articulation view / init
 // ---------------------------------------------------------------------------------------------
 template <bool kSnake>
@@ -1071,6 +1171,9 @@ int zbot_create(const ZbotCfg* cfg, int device, ZbotHandle** out) {
   ZB_CUDA(cudaFuncSetAttribute(zbot_v4_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
   ZB_CUDA(cudaFuncSetAttribute(zbot_snake_step_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
   ZB_CUDA(cudaFuncSetAttribute(zbot_v4_step_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
+  ZB_CUDA(cudaFuncSetAttribute(zbot_m_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
+  ZB_CUDA(cudaFuncSetAttribute(zbot_m_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
+  ZB_CUDA(cudaFuncSetAttribute(zbot_m_step_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
   {
     // register-budget variant of the step kernel = resident 128-thread CTAs per SM it is compiled for.
     // Measured (profiles/r1_notes.md): 2 CTAs/SM (197 regs, no spill) is fastest while the grid fits two
@@ -1133,6 +1236,7 @@ static int step_impl(ZbotHandle* h, const float* actions, float* obs, float* rew
   cudaStream_t s = (cudaStream_t)stream;
   ExportPtrs xp{};
   if (h->cfg.task == ZBOT_TASK_WALKING_V4) return fail(ZBOT_E_INVALID, "task zbot-6b-walking-v4 steps through zbot_v4_step%s");
+  if (h->cfg.task == ZBOT_TASK_WALKING_M) return fail(ZBOT_E_INVALID, "task zbot-6b-walking-m-v0 steps through zbot_m_step%s");
   if (h->cfg.task == ZBOT_TASK_SNAKE_V0) {
     if (ex) return fail(ZBOT_E_INVALID, "zbot_step_export is a walking-task hook; use zbot_snake_step_export%s");
     if (snake_export)
@@ -1272,6 +1376,50 @@ int zbot_v4_step_export(ZbotHandle* h, const float* actions, const float* rand, 
   return v4_step_impl(h, actions, rand, obs, rew, terminated, truncated, stats_slot, prev_slot, export_buf, stream);
 }
 
+static int m_step_impl(ZbotHandle* h, const float* actions, const float* rand, float* obs, float* rew, uint8_t* terminated,
+                       uint8_t* truncated, int32_t slot, int32_t prev, float* export_buf, void* stream) {
+  if (!h) return fail(ZBOT_E_INVALID, "handle is NULL%s");
+  if (h->cfg.task != ZBOT_TASK_WALKING_M) return fail(ZBOT_E_INVALID, "zbot_m_step needs task = ZBOT_TASK_WALKING_M%s");
+  if (!h->state) return fail(ZBOT_E_UNBOUND, "zbot_bind has not been called%s");
+  if (!actions || !obs || !rew || !terminated || !truncated) return fail(ZBOT_E_INVALID, "zbot_m_step: NULL buffer%s");
+  if (((uintptr_t)actions & 7) != 0) return fail(ZBOT_E_INVALID, "actions must be 8-byte aligned%s");
+  if (int rc = check_slot(slot, prev, h->ring_slots)) return rc;
+  const int n = h->cfg.num_envs;
+  int block = 128;
+  while (block > 32 && (n + block - 1) / block < 2 * h->num_sms) block >>= 1;
+  const int grid = (n + block - 1) / block;
+  const size_t smem = (size_t)block * SCR_STRIDE * sizeof(float);
+  StatsCtx sc{h->partials, h->ring, slot, prev, h->inv_episode_s, 0, (unsigned long long)h->launches, 0};
+  cudaStream_t s = (cudaStream_t)stream;
+  const uint64_t call = h->v4_calls++;
+  if (export_buf)
+    zbot_m_step_kernel<true><<<grid, block, smem, s>>>(h->P, h->state, h->ep_len, actions, rand, h->cfg.rng_seed, call, obs, rew,
+                                                   terminated, truncated, n, sc, export_buf);
+  else if (h->unroll2)
+    zbot_m_step_kernel<false, 2><<<grid, block, smem, s>>>(h->P, h->state, h->ep_len, actions, rand, h->cfg.rng_seed, call, obs,
+                                                       rew, terminated, truncated, n, sc, nullptr);
+  else
+    zbot_m_step_kernel<false><<<grid, block, smem, s>>>(h->P, h->state, h->ep_len, actions, rand, h->cfg.rng_seed, call, obs, rew,
+                                                    terminated, truncated, n, sc, nullptr);
+  ZB_CUDA(cudaGetLastError());
+  h->launches += 1;
+  zbot_stats_finalize_kernel<<<1, 1024, 0, s>>>(sc, (unsigned int)grid);
+  ZB_CUDA(cudaGetLastError());
+  h->launches += 1;
+  return ZBOT_OK;
+}
+
+int zbot_m_step(ZbotHandle* h, const float* actions, const float* rand, float* obs, float* rew, uint8_t* terminated,
+                uint8_t* truncated, int32_t stats_slot, int32_t prev_slot, void* stream) {
+  return m_step_impl(h, actions, rand, obs, rew, terminated, truncated, stats_slot, prev_slot, nullptr, stream);
+}
+
+int zbot_m_step_export(ZbotHandle* h, const float* actions, const float* rand, float* obs, float* rew, uint8_t* terminated,
+                       uint8_t* truncated, int32_t stats_slot, int32_t prev_slot, float* export_buf, void* stream) {
+  if (!export_buf) return fail(ZBOT_E_INVALID, "zbot_m_step_export: export_buf is NULL%s");
+  return m_step_impl(h, actions, rand, obs, rew, terminated, truncated, stats_slot, prev_slot, export_buf, stream);
+}
+
 int zbot_update_cfg(ZbotHandle* h, const ZbotCfg* cfg) {
   if (!h || !cfg) return fail(ZBOT_E_INVALID, "zbot_update_cfg: NULL argument%s");
   const char* why = "";
@@ -1295,8 +1443,8 @@ int zbot_reset_idx(ZbotHandle* h, const int64_t* env_ids, int64_t nids, const ui
   if (!h) return fail(ZBOT_E_INVALID, "handle is NULL%s");
   if (!h->state) return fail(ZBOT_E_UNBOUND, "zbot_bind has not been called%s");
   if (int rc = check_slot(stats_slot, -1, h->ring_slots)) return rc;
-  if (h->cfg.task == ZBOT_TASK_WALKING_V4)
-    return fail(ZBOT_E_INVALID, "zbot_reset_idx: the v4 task's randomised reset is written by the caller (state words)%s");
+  if (h->cfg.task == ZBOT_TASK_WALKING_V4 || h->cfg.task == ZBOT_TASK_WALKING_M)
+    return fail(ZBOT_E_INVALID, "zbot_reset_idx: the v4 / manager tasks' randomised reset is written by the caller (state words)%s");
   const int n = h->cfg.num_envs;
   if (!env_ids || nids < 0) { env_ids = nullptr; nids = n; }
   if (nids == 0) return ZBOT_OK;
@@ -1320,7 +1468,8 @@ int zbot_reset_idx(ZbotHandle* h, const int64_t* env_ids, int64_t nids, const ui
 
 int zbot_observe(ZbotHandle* h, float* obs, void* stream) {
   if (!h || !obs) return fail(ZBOT_E_INVALID, "zbot_observe: NULL argument%s");
-  if (h->cfg.task == ZBOT_TASK_WALKING_V4) return fail(ZBOT_E_INVALID, "zbot_observe: v2 / snake observation layout only%s");
+  if (h->cfg.task == ZBOT_TASK_WALKING_V4 || h->cfg.task == ZBOT_TASK_WALKING_M)
+    return fail(ZBOT_E_INVALID, "zbot_observe: v2 / snake observation layout only%s");
   if (!h->state) return fail(ZBOT_E_UNBOUND, "zbot_bind has not been called%s");
   const int n = h->cfg.num_envs, block = 64, grid = (n + block - 1) / block;
   if (h->cfg.task == ZBOT_TASK_SNAKE_V0)

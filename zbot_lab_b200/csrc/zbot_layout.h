@@ -192,6 +192,14 @@ inline void params_from_cfg(const ZbotCfg& c, Params<T>& P) {
   P.obs_noise_enable = c.obs_noise_enable;
   for (int i = 0; i < 24; ++i) { P.obs_noise_lo[i] = T(c.obs_noise_lo[i]); P.obs_noise_w[i] = T(c.obs_noise_hi[i]) - T(c.obs_noise_lo[i]); }
   P.rng_seed = c.rng_seed;
+  for (int i = 0; i < MAX_TERMS; ++i)
+    for (int j = 0; j < 4; ++j) P.term_par[i][j] = T(c.term_param[i][j]);
+  for (int i = 0; i < 3; ++i) { P.cmd_lo[i] = T(c.cmd_lo[i]); P.cmd_hi[i] = T(c.cmd_hi[i]); }
+  P.cmd_rel_standing = T(c.cmd_rel_standing);
+  P.cmd_resample_lo = T(c.cmd_resample_lo); P.cmd_resample_hi = T(c.cmd_resample_hi);
+  P.act_scale = T(c.act_scale); P.act_clip = T(c.act_clip);
+  P.feet_close_min = T(c.feet_close_min);
+  P.term_penalty_w = T(c.is_terminated_weight) * P.step_dt;       // value * weight * dt with value = 1 (RewardManager)
   P.default_terms = (c.num_terms == 13) && (c.task == ZBOT_TASK_WALKING_V2);
   for (int i = 0; i < 13 && P.default_terms; ++i) P.default_terms = (c.term_id[i] == i);
 }
@@ -199,7 +207,8 @@ inline void params_from_cfg(const ZbotCfg& c, Params<T>& P) {
 inline int cfg_validate(const ZbotCfg& c, const char** why) {
   if (c.abi_version != ZBOT_ABI_VERSION) { *why = "ZbotCfg.abi_version mismatch"; return ZBOT_E_INVALID; }
   if (c.num_envs < 1) { *why = "num_envs must be >= 1"; return ZBOT_E_INVALID; }
-  if (c.task != ZBOT_TASK_WALKING_V2 && c.task != ZBOT_TASK_SNAKE_V0 && c.task != ZBOT_TASK_WALKING_V4) {
+  if (c.task != ZBOT_TASK_WALKING_V2 && c.task != ZBOT_TASK_SNAKE_V0 && c.task != ZBOT_TASK_WALKING_V4 &&
+      c.task != ZBOT_TASK_WALKING_M) {
     *why = "unknown task"; return ZBOT_E_INVALID;
   }
   if (c.decimation != 4) { *why = "only decimation == 4 is supported (5-deep contact history)"; return ZBOT_E_INVALID; }

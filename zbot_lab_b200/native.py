@@ -12,8 +12,9 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libzbot_b200.so")
 
-ZBOT_ABI_VERSION = 4
-TASK_WALKING_V2, TASK_SNAKE_V0, TASK_WALKING_V4 = 0, 1, 2
+ZBOT_ABI_VERSION = 5
+TASK_WALKING_V2, TASK_SNAKE_V0, TASK_WALKING_V4, TASK_WALKING_M = 0, 1, 2, 3
+M_NUM_OBS, M_NUM_RAND, M_EXPORT_WORDS = 25, 13, 67
 V4_NUM_OBS, V4_NUM_RAND, V4_EXPORT_WORDS = 24, 10, 69
 MAX_TERMS = 16
 HOST_ROW_WORDS = 25   # zbot_step_host result row: obs 23 | reward | flags word
@@ -68,6 +69,10 @@ class ZbotCfg(C.Structure):
         ("ev_pose_lo", C.c_float * 3), ("ev_pose_hi", C.c_float * 3),
         ("ev_interval_lo", C.c_float), ("ev_interval_hi", C.c_float), ("rng_seed", C.c_uint64),
         ("obs_noise_enable", C.c_int32), ("obs_noise_lo", C.c_float * 24), ("obs_noise_hi", C.c_float * 24),
+        ("term_param", (C.c_float * 4) * MAX_TERMS), ("cmd_lo", C.c_float * 3), ("cmd_hi", C.c_float * 3),
+        ("cmd_rel_standing", C.c_float), ("cmd_resample_lo", C.c_float), ("cmd_resample_hi", C.c_float),
+        ("act_scale", C.c_float), ("act_clip", C.c_float), ("feet_close_min", C.c_float),
+        ("is_terminated_weight", C.c_float),
     ]
 
 
@@ -189,6 +194,8 @@ def _declare(lib):
     lib.zbot_step_host.argtypes = [vp, vp, vp, i32, i32, vp]
     lib.zbot_v4_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, vp]
     lib.zbot_v4_step_export.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp]
+    lib.zbot_m_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, vp]
+    lib.zbot_m_step_export.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp]
     lib.zbot_update_cfg.argtypes = [vp, P(ZbotCfg)]
     lib.zbot_reset_idx.argtypes = [vp, vp, i64, vp, vp, i32, vp]
     lib.zbot_observe.argtypes = [vp, vp, vp]
@@ -200,7 +207,7 @@ def _declare(lib):
     lib.zbot_launch_count.restype = i64
     for name in ("zbot_default_cfg", "zbot_state_word", "zbot_mdp_state_word", "zbot_create", "zbot_destroy",
                  "zbot_bind", "zbot_step", "zbot_step_export", "zbot_snake_step_export", "zbot_step_host", "zbot_v4_step",
-                 "zbot_v4_step_export", "zbot_update_cfg", "zbot_reset_idx",
+                 "zbot_v4_step_export", "zbot_m_step", "zbot_m_step_export", "zbot_update_cfg", "zbot_reset_idx",
                  "zbot_observe",
                  "zbot_articulation_view", "zbot_mdp_bind", "zbot_mdp_observe", "zbot_mdp_step"):
         getattr(lib, name).restype = C.c_int
@@ -209,7 +216,8 @@ def _declare(lib):
 EXPORTED_SYMBOLS = (
     "zbot_abi_version", "zbot_build_info", "zbot_last_error", "zbot_default_cfg", "zbot_state_word",
     "zbot_mdp_state_word", "zbot_create", "zbot_destroy", "zbot_bind", "zbot_step", "zbot_step_export",
-    "zbot_snake_step_export", "zbot_step_host", "zbot_v4_step", "zbot_v4_step_export", "zbot_update_cfg", "zbot_reset_idx", "zbot_observe", "zbot_articulation_view", "zbot_mdp_bind", "zbot_mdp_observe",
+    "zbot_snake_step_export", "zbot_step_host", "zbot_v4_step", "zbot_v4_step_export", "zbot_m_step", "zbot_m_step_export",
+    "zbot_update_cfg", "zbot_reset_idx", "zbot_observe", "zbot_articulation_view", "zbot_mdp_bind", "zbot_mdp_observe",
     "zbot_mdp_step", "zbot_launch_count",
 )
 
@@ -234,3 +242,111 @@ def check(rc: int, what: str = ""):
     if rc != 0:
         msg = lib().zbot_last_error()
         raise RuntimeError(f"{what or 'zbot call'} failed (rc={rc}): {msg.decode() if msg else ''}")
+
+
+# --------------------------------------------------------------------------------------------------------------
+# zbot-6b-walking-m-v0 (manager-based task): RewTerm function name -> (term id, params -> term_param row)
+# (reference: tasks/zbotlab_manager/mdp/rewards.py; joint_torques_l2 / joint_acc_l2 / action_rate_l2 / is_terminated are
+# isaaclab.envs.mdp functions [IL-upstream])
+# --------------------------------------------------------------------------------------------------------------
+def _need(cond, msg):
+    if not cond:
+        raise NotImplementedError(msg)
+
+
+def _gait_params(p):
+    _need(p.get("command_name") is not None, "feet_gait without command gating is not built")
+    off = list(p["offset"])
+    _need(len(off) == 2, "feet_gait: two feet")
+    return [p["period"], off[0], off[1], p.get("threshold", 0.5)]
+
+
+def _step_length_params(p):
+    _need(p.get("command_name") is None, "foot_step_length(command_name=...) (in-place command overwrite, rewards.py:79-80) is not built")
+    return []
+
+
+M_REWARD_FUNCS = {
+    "track_lin_vel_xy_yaw_frame_exp": (34, lambda p: [p["std"] ** 2]),
+    "track_ang_vel_z_world_exp": (35, lambda p: [p["std"] ** 2]),
+    "joint_torques_l2": (8, lambda p: []),
+    "joint_acc_l2": (24, lambda p: []),
+    "action_rate_l2": (7, lambda p: []),
+    "foot_step_length": (36, _step_length_params),
+    "foot_downward": (1, lambda p: []),
+    "foot_forward": (2, lambda p: []),
+    "feet_gait": (37, _gait_params),
+    "feet_slide": (38, lambda p: []),
+    "foot_clearance_reward": (39, lambda p: [p["std"], p["tanh_mult"], p["target_height"]]),
+    "feet_air_time_positive_biped": (40, lambda p: [p["threshold"]]),
+    "air_time_balance_penalty": (6, lambda p: []),
+    "air_time_variance_penalty": (27, lambda p: []),
+    "base_vel_forward": (41, lambda p: [float(p.get("which_forward", 1))]),
+    "feet_force_pattern": (42, lambda p: []),
+}
+
+
+def make_m_cfg(num_envs: int, terms, *, is_terminated_weight: float = 0.0, minimum_height: float = 0.2,
+               feet_close_min: float = 0.12, cmd_ranges=((-0.1, 0.1), (0.0, 0.0), (0.0, 0.0)), rel_standing_envs: float = 0.02,
+               resampling_time_range=(10.0, 10.0), act_scale: float = 0.04 * 3.141592653589793, act_clip: float | None = None,
+               pose_range=((-0.5, 0.5), (-0.5, 0.5), (-3.14, 3.14)), episode_length_s: float = 20.0, friction: float = 1.0,
+               rng_seed: int = 0, **overrides) -> ZbotCfg:
+    """``ZbotCfg`` of the manager-based task.  ``terms`` = [(func_name, weight, params_dict), ...] in cfg order
+    (zero-weight terms are skipped, as RewardManager does); the defaults are ``Zbot6BFlatEnvCfg``
+    (config/zbot6b_manager/flat_env_cfg.py) over ``ZbotLabRoughEnvCfg`` (zbotlab_env_cfg.py:99-452)."""
+    from .assets import zbot_6s as Z
+    from .assets import zbot_6s_v2 as V
+
+    cfg = make_cfg(num_envs, reward_scales={}, task=TASK_WALKING_V2)
+    cfg.task = TASK_WALKING_M
+    cfg.kp, cfg.kd, cfg.effort_limit = V.KP, V.KD, V.EFFORT_LIMIT
+    cfg.max_episode_length = int(-(-episode_length_s // (Z.SIM_DT * Z.DECIMATION)))
+    cfg.termination_height = float(minimum_height)
+    cfg.feet_close_min = float(feet_close_min) if feet_close_min else 0.0
+    cfg.is_terminated_weight = float(is_terminated_weight)
+    cfg.contact_mu = float(friction)
+    for i in range(3):
+        cfg.cmd_lo[i], cfg.cmd_hi[i] = float(cmd_ranges[i][0]), float(cmd_ranges[i][1])
+        cfg.ev_pose_lo[i], cfg.ev_pose_hi[i] = float(pose_range[i][0]), float(pose_range[i][1])
+    cfg.cmd_rel_standing = float(rel_standing_envs)
+    cfg.cmd_resample_lo, cfg.cmd_resample_hi = float(resampling_time_range[0]), float(resampling_time_range[1])
+    cfg.act_scale = float(act_scale)
+    cfg.act_clip = float(act_clip if act_clip is not None else 3.0e38)
+    cfg.rng_seed = int(rng_seed)
+    active = [(f, w, p) for f, w, p in terms if float(w) != 0.0]
+    if len(active) > MAX_TERMS - 0:
+        raise ValueError(f"at most {MAX_TERMS} weighted reward terms are supported (termination_penalty excluded)")
+    cfg.num_terms = len(active)
+    for i, (func, w, p) in enumerate(active):
+        if func not in M_REWARD_FUNCS:
+            raise NotImplementedError(f"reward function {func!r} is not built into the fused step; known: {sorted(M_REWARD_FUNCS)}")
+        tid, par = M_REWARD_FUNCS[func]
+        cfg.term_id[i] = tid
+        cfg.term_weight[i] = float(w)            # bare weight: RewardManager multiplies by dt per evaluation
+        row = [float(x) for x in par(dict(p or {}))]
+        for j in range(4):
+            cfg.term_param[i][j] = row[j] if j < len(row) else 0.0
+    for k, v in overrides.items():
+        if not hasattr(cfg, k):
+            raise AttributeError(f"ZbotCfg has no field {k!r}")
+        if isinstance(v, (tuple, list)):
+            getattr(cfg, k)[:] = v
+        else:
+            setattr(cfg, k, v)
+    return cfg
+
+
+#: Zbot6BFlatEnvCfg's active RewTerms in cfg order (zbotlab_env_cfg.py:240-352 with flat_env_cfg.py:96-112 applied)
+M_FLAT_TERMS = [
+    ("track_lin_vel_xy_exp", "track_lin_vel_xy_yaw_frame_exp", 1.0, {"std": 0.5}),
+    ("track_ang_vel_z_exp", "track_ang_vel_z_world_exp", 0.5, {"std": 0.5}),
+    ("termination_penalty", "is_terminated", -200.0, {}),
+    ("dof_torques_l2", "joint_torques_l2", -1.0e-5, {}),
+    ("dof_acc_l2", "joint_acc_l2", -2.5e-7, {}),
+    ("action_rate_l2", "action_rate_l2", -0.01, {}),
+    ("foot_step_length", "foot_step_length", 5.0, {"command_name": None}),
+    ("foot_downward", "foot_downward", -1.0, {}),
+    ("foot_forward", "foot_forward", -0.5, {}),
+    ("feet_slide", "feet_slide", -6.5, {}),
+    ("air_time_variance", "air_time_balance_penalty", -15.0, {}),
+]
