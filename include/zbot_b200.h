@@ -266,7 +266,8 @@ int zbot_v4_step_export(ZbotHandle* h, const float* actions, const float* rand, 
  * State slots reused (zbot_state_word names): carry_feet_fz = command lin_vel x / y, carry_mid_max = command ang_vel z,
  * base_heading_x_sum = is_standing_env, base_pos_y_err_sum = command time_left, joint_speed_limit = friction
  * coefficient of the env, actions = last raw action.  Statistics words 0..num_terms-1 = Episode_Reward/<term>; when
- * num_terms <= 14, words 14 / 15 = (#base_height, #feet_close among the reset envs) / #reset * (1 / episode seconds).
+ * num_terms <= 13, word 13 = Episode_Reward of the is_terminated term and words 14 / 15 = the number of reset envs that
+ * tripped base_height / feet_close (raw counts).
  * `export` (zbot_m_step_export, test hook): [N][ZBOT_M_EXPORT_WORDS] view the terms saw (MExport). */
 int zbot_m_step(ZbotHandle* h, const float* actions, const float* rand, float* obs, float* rew, uint8_t* terminated,
                 uint8_t* truncated, int32_t stats_slot, int32_t prev_slot, void* stream);

@@ -183,7 +183,11 @@ def m_check_step(o, a, rnd, ex, obs, rew, term, trunc, ep_len, state_get, rs=Non
             want = r["log"][nm] * (o.P["max_episode_length"] * o.P["step_dt"])     # mean episodic sum over the reset envs
             got = float(np.mean(np.asarray(rs)[ids, i], dtype=np.float32))
             assert abs(got - want) <= 20 * rtol * max(1e-2, abs(want)), ("log", nm, got, want)
-        if len(slot_names) <= 14:
+        if len(slot_names) <= 13:
+            pen = [nm for nm, f, w, p in o.terms if f == "is_terminated"]
+            if pen:
+                want = r["log"][pen[0]] * (o.P["max_episode_length"] * o.P["step_dt"])
+                assert abs(float(np.mean(np.asarray(rs)[ids, 13], dtype=np.float32)) - want) <= 1e-5 * max(1e-2, abs(want))
             assert int(np.asarray(rs)[ids, 14].sum()) == r["log"]["#base_height"]
             assert int(np.asarray(rs)[ids, 15].sum()) == r["log"]["#feet_close"]
     return r

@@ -267,3 +267,76 @@ def test_observation_noise_is_additive_uniform_and_touches_nothing_else():
     assert torch.equal(clean._stepper.state.buf, noisy._stepper.state.buf)
     for e in (clean, noisy, noisy2):
         e.close()
+
+
+def test_manager_env_registry_protocol_noise_friction_curriculum_and_ppo(tmp_path):
+    """zbot-6b-walking-m-v0 through the registry (reference id / kwargs keys, zbotlab_manager/config/zbot6b_manager/
+    __init__.py:14-22): ManagerBasedRLEnv over the fused step -- 25-wide policy group, standing robot at the cfg's init
+    pose, per-env friction from the startup material event (64 buckets in [0.3, 1.0]), commands inside the ranges,
+    the managers' log keys, the lin_vel_cmd_levels curriculum widening the live kernel's ranges, and a PPO iteration
+    through the rsl_rl wrapper."""
+    import zbot_lab_b200.tasks  # noqa: F401
+    from zbot_lab_b200.compat import gym_registry as gym
+    from zbot_lab_b200.envs.rsl_rl_wrapper import RslRlVecEnvWrapper
+    from zbot_lab_b200.rl.ppo_runner import OnPolicyRunner
+    cfg = gym.load_cfg_from_registry("zbot-6b-walking-m-v0", "env_cfg_entry_point")
+    cfg.scene.num_envs = 256
+    cfg.sim.device = "cuda:0"
+    cfg.seed = 9
+    env = gym.make("zbot-6b-walking-m-v0", cfg=cfg, render_mode=None)
+    w = RslRlVecEnvWrapper(env, clip_actions=None)
+    assert w.num_obs == 25 and w.num_actions == 6 and env.max_episode_length == 1000 and abs(env.step_dt - 0.02) < 1e-12
+    mu = env.friction
+    assert float(mu.min()) >= 0.3 and float(mu.max()) <= 1.0 and len(torch.unique(mu)) <= 64 and len(torch.unique(mu)) > 8
+    obs = w.get_observations()["policy"]
+    assert obs.shape == (256, 25) and torch.isfinite(obs).all()
+    assert float(obs[:, 1:3].abs().max()) < 2e-3 and float(obs[:, 0].std()) > 0.05             # yaw-only random root pose
+    assert float(obs[:, 4].abs().max()) <= 0.1 + 1e-6 and float(obs[:, 5:7].abs().max()) == 0   # ranges lin_vel_x (-0.1, 0.1)
+    assert float(obs[:, 7:19].abs().max()) < 1e-5                                               # default joints, at rest
+    stood = []
+    for t in range(30):
+        obs, rew, dones, extras = w.step(torch.zeros(256, 6, device="cuda:0"))
+        assert obs["policy"].shape == (256, 25) and torch.isfinite(obs["policy"]).all() and torch.isfinite(rew).all()
+        stood.append(int(dones.sum()))
+    # zero actions = hold the current joint positions: the biped stands; what ends episodes here is the cfg's own margin --
+    # the init stance is 0.12002 m wide against feet_close's 0.12 m, so a few hundredths of a millimetre of settling trip it
+    assert sum(stood[:5]) == 0 and sum(stood) < 256 * 3
+    want = {"Episode_Reward/" + k for k in ("track_lin_vel_xy_exp", "track_ang_vel_z_exp", "termination_penalty", "dof_torques_l2",
+                                            "dof_acc_l2", "action_rate_l2", "foot_step_length", "foot_downward", "foot_forward",
+                                            "feet_slide", "air_time_variance")}
+    want |= {"Episode_Termination/time_out", "Episode_Termination/base_height", "Episode_Termination/feet_close",
+             "Curriculum/lin_vel_cmd_levels"}
+    assert set(extras["log"]) == want
+    # random actions make envs fall; the log counts are consistent with the flags
+    g = torch.Generator(device="cuda:0").manual_seed(3)
+    n_term = 0
+    for t in range(40):
+        obs, rew, dones, extras = w.step(torch.randn(256, 6, device="cuda:0", generator=g) * 3.0)
+        k = int(env.reset_terminated.sum())
+        if k:
+            lg = extras["log"]
+            tot = float(lg["Episode_Termination/base_height"]) + float(lg["Episode_Termination/feet_close"])
+            assert tot >= k - 1e-3 and tot <= 2 * k + 1e-3           # an env may trip both terms in one step
+            assert abs(float(lg["Episode_Reward/termination_penalty"]) - (k / float(dones.sum())) * (-200.0 * 0.02 / 20.0)) < 1e-6
+        n_term += k
+    assert n_term > 0
+    # lin_vel_cmd_levels (mdp/curriculums.py:57-83): at a multiple of max_episode_length, tracking reward above 80 % of
+    # its weight widens lin_vel_x by 0.1 on both sides (clamped to limit_ranges)
+    i = env._term_names.index("track_lin_vel_xy_exp")
+    env._stepper.stats_ring[:, i] = 0.95
+    env.common_step_counter = env.max_episode_length - 1
+    env._stepper.stats_ring[(env._stepper._slot + 1) % 64, i] = 0.95
+    w.step(torch.zeros(256, 6, device="cuda:0"))
+    env._stepper.stats_ring[env._stepper._slot, i] = 0.95
+    env.common_step_counter = 2 * env.max_episode_length - 1
+    w.step(torch.zeros(256, 6, device="cuda:0"))
+    assert tuple(round(v, 6) for v in cfg.commands.base_velocity.ranges.lin_vel_x) in ((-0.2, 0.2), (-0.3, 0.3))
+    assert abs(env._stepper.cfg.cmd_hi[0] - cfg.commands.base_velocity.ranges.lin_vel_x[1]) < 1e-6
+    assert extras["log"]["Curriculum/lin_vel_cmd_levels"] in (0.1, 0.2, 0.3)
+    # PPO through the wrapper (agent cfg of the registry)
+    acfg = gym.load_cfg_from_registry("zbot-6b-walking-m-v0", "rsl_rl_cfg_entry_point").to_dict()
+    r = OnPolicyRunner(w, acfg, log_dir=str(tmp_path), device="cuda:0")
+    hist = r.learn(num_learning_iterations=2, init_at_random_ep_len=True)
+    assert len(hist) == 2 and all(np.isfinite(h["value_loss"]) for h in hist)
+    assert "Episode_Reward/foot_step_length" in hist[-1]
+    w.close()

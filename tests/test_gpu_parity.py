@@ -906,7 +906,7 @@ def test_packed_two_env_variant_agrees_with_the_default_kernel(monkeypatch):
             assert float((st0 - st1).abs().max()) <= 1e-2 * max(1.0, float(st0.abs().max()))
 
 
-@pytest.mark.parametrize("task", ["walk", "snake", "v4"])
+@pytest.mark.parametrize("task", ["walk", "snake", "v4", "m"])
 def test_unrolled_chain_sweeps_agree_with_the_rolled_kernel(monkeypatch, task):
     """Above one warp per scheduler the library launches the instantiation whose chain sweeps are unrolled by two
     (ZBOT_SWEEP_UNROLL overrides the choice).  Same arithmetic, but nvcc contracts multiply-adds differently in the
@@ -927,6 +927,9 @@ def test_unrolled_chain_sweeps_agree_with_the_rolled_kernel(monkeypatch, task):
             st.set_sim_state({k: _t(v) for k, v in syn.synth_sim_state(r, n).items()})
         elif task == "snake":
             st = _snake_stepper(n, r.uniform(0.2, 2.0, n).astype(np.float32) * np.pi)
+        elif task == "m":
+            from zbot_lab_b200 import native
+            st = _m_stepper(n, r, native.M_FLAT_TERMS, rng_seed=3)
         else:
             st = _v4_stepper(n, r)
         st.episode_length_buf[:] = _t(r.integers(0, 790, n).astype(np.int64))
@@ -947,8 +950,157 @@ def test_unrolled_chain_sweeps_agree_with_the_rolled_kernel(monkeypatch, task):
         assert torch.equal(tr0, tr1) and float(same.float().mean()) >= 0.995
         assert torch.equal(ep0[same], ep1[same])
         d = (o0[same] - o1[same]).abs()
-        assert float(d[:, :10].max()) <= 2e-4 and float(d[:, 10:16].max()) <= 2e-2      # quat + joint pos | joint vel
-        assert float(d[:, 16:].max()) <= 1e-6                                           # actions, commands / speed limit
+        if task == "m":    # [quat 4 | command 3 | joint pos 6 | joint vel 6 | last action 6]
+            assert float(d[:, :4].max()) <= 2e-4 and float(d[:, 7:13].max()) <= 2e-4 and float(d[:, 13:19].max()) <= 5e-2
+            assert float(d[:, 4:7].max()) <= 1e-6 and float(d[:, 19:].max()) <= 1e-6
+        else:
+            assert float(d[:, :10].max()) <= 2e-4 and float(d[:, 10:16].max()) <= 2e-2      # quat + joint pos | joint vel
+            assert float(d[:, 16:23].max()) <= 1e-6                                         # actions, command / speed limit
+            if task == "v4":
+                assert float(d[:, 23].max()) <= 2e-4                                        # heading error (a yaw angle)
         assert float((r0[same] - r1[same]).abs().max()) <= 2e-3
         worst = max(worst, float(d.max()))
     print(f"unroll-2 vs rolled ({task}): worst one-step observation difference {worst:.3e}")
+
+
+# ---------------------------------------------------------------------------------------------
+# zbot-6b-walking-m-v0: the manager-based task on the fused step
+# ---------------------------------------------------------------------------------------------
+def _m_stepper(n, rng, terms, **kw):
+    from helpers import m_native_cfg
+    from zbot_lab_b200.stepper import NativeStepper
+    st = NativeStepper(n, DEV, m_native_cfg(n, terms, **kw))
+    u = torch.full((n, 8), 0.5, device=DEV)                                  # default pose (mid-range = 0)
+    st.reset_idx_m(None, rand=u)
+    st.state.set("carry_feet_fz", _t(np.stack([rng.uniform(-0.3, 0.3, n), rng.uniform(-0.1, 0.1, n)], -1).astype(np.float32)))
+    st.state.set("carry_mid_max", _t(rng.uniform(-0.2, 0.2, (n, 1)).astype(np.float32)))
+    st.state.set("base_pos_y_err_sum", _t(rng.uniform(0.05, 0.3, (n, 1)).astype(np.float32)))      # command time_left
+    st.state.set("joint_speed_limit", _t(rng.uniform(0.3, 1.0, (n, 1)).astype(np.float32)))        # per-env friction
+    st.state.set("joint_pos", st.state.get("joint_pos") + _t(rng.uniform(-0.1, 0.1, (n, 6)).astype(np.float32)))
+    return st
+
+
+@pytest.mark.parametrize("which", ["flat", "all"])
+def test_m_fused_step_matches_pinned_oracle_on_exported_physics(which):
+    """The manager-task kernel's terminations / rewards / command resampling / randomised resets / 25-wide observations
+    equal the reference-pinned oracle (tests/golden/m_v0_*.npz pins its term functions to the reference's own rewards.py)
+    evaluated on the view the kernel itself exported, with the same per-env uniforms; Episode_Reward statistics of the
+    ring slot equal the oracle's log.  `flat` = Zbot6BFlatEnvCfg's 11 terms, `all` = all 17 built terms."""
+    from helpers import M_ALL_TERMS, m_check_step, m_make_oracle
+    from zbot_lab_b200 import native
+    terms = M_ALL_TERMS if which == "all" else native.M_FLAT_TERMS
+    n = 200
+    rng = np.random.default_rng(52)
+    st = _m_stepper(n, rng, terms)
+    ep0 = rng.integers(0, 990, n)
+    ep0[:8] = 995
+    st.episode_length_buf[:] = _t(ep0.astype(np.int64))
+    get = lambda k, w: st.state.get(k).cpu().numpy()
+    o = m_make_oracle(n, terms, get, ep0)
+    ex_t = torch.zeros(n, 67, device=DEV)
+    n_reset = n_term = n_res = 0
+    for t in range(40):
+        a = rng.normal(0, 1.5, (n, 6)).astype(np.float32)
+        rnd = rng.random((n, 13)).astype(np.float32)
+        obs, rew, term, trunc = st.step(_t(a), export=ex_t, rand=_t(rnd))
+        torch.cuda.synchronize()
+        r = m_check_step(o, a, rnd, ex_t.cpu().numpy(), obs.cpu().numpy(), rew.cpu().numpy(), term.cpu().numpy(),
+                         trunc.cpu().numpy(), st.episode_length_buf.cpu().numpy(), get)
+        ids = r["reset_ids"]
+        if len(ids) > 0:
+            s = st.stats.cpu().numpy()
+            assert s[16] == len(ids) and s[17] == int(r["terminated"][ids].sum()) and s[18] == r["log"]["#time_out"]
+            slot_names = [nm for nm, f, w, p in terms if f != "is_terminated"]
+            for i, nm in enumerate(slot_names):
+                want = r["log"][nm]
+                assert abs(s[i] - want) <= 2e-4 * max(1e-3, abs(want)), (nm, s[i], want)
+            if len(slot_names) <= 13:                                         # spare slots: penalty term's log, DoneTerm counts
+                assert s[14] == r["log"]["#base_height"] and s[15] == r["log"]["#feet_close"]
+                want = r["log"]["termination_penalty"]
+                assert abs(s[13] - want) <= 2e-4 * max(1e-3, abs(want))
+        n_reset += len(ids)
+        n_term += int(term.sum())
+        n_res += len(r["resample_ids"])
+    assert n_reset >= 8 and n_term > 0 and n_res >= n
+    st.close()
+
+
+def test_m_kernel_equals_host_build_noise_and_internal_rng():
+    """(1) GPU kernel vs the same arithmetic compiled for the host (float32): one control step from identical states and
+    uniforms agrees to round-off.  (2) ObservationManager corruption (PolicyCfg: base_quat / joint_pos +-0.01, joint_vel
+    +-1.5): only the noisy columns move, inside their bands, state / reward / flags untouched.  (3) rand = NULL: resets
+    land inside the pose range, commands inside the cfg ranges, same seed -> bit-identical, other seed -> different."""
+    from helpers import m_native_cfg
+    from oracle import cpu_port
+    from zbot_lab_b200 import native
+    from zbot_lab_b200.stepper import STATE_FIELDS
+    n = 512
+    rng = np.random.default_rng(3)
+    terms = native.M_FLAT_TERMS
+    st = _m_stepper(n, rng, terms)
+    pe = cpu_port.PortEnv(n, np.float32, m_native_cfg(n, terms))
+    for k, w in STATE_FIELDS.items():
+        pe.field(k, w)[:] = st.state.get(k).cpu().numpy()
+    for t in range(3):
+        a = rng.normal(0, 0.5, (n, 6)).astype(np.float32)
+        rnd = rng.random((n, 13)).astype(np.float32)
+        obs, rew, term, trunc = st.step(_t(a), rand=_t(rnd))
+        o2, r2, t2, tr2, _, _ = pe.step(a, rnd=rnd)
+        same = (term.cpu().numpy().astype(bool) == t2)
+        assert np.array_equal(trunc.cpu().numpy().astype(bool), tr2) and same.mean() >= 0.995
+        d = np.abs(obs.cpu().numpy() - o2)[same]
+        # one-step bounds: 1e-3 on quaternion / joint positions, 5e-2 rad/s on joint velocities (kp 20 / kd 0.5 drive)
+        assert d[:, :13].max() < 1e-3 and d[:, 13:19].max() < 5e-2 and d[:, 19:].max() == 0
+        assert np.abs(rew.cpu().numpy() - r2)[same].max() < 2e-3
+        for k, w in STATE_FIELDS.items():
+            pe.field(k, w)[:] = st.state.get(k).cpu().numpy()
+        pe.ep_len[:] = st.episode_length_buf.cpu().numpy()
+    st.close()
+    # (2) noise
+    outs = []
+    for noise in (False, True):
+        s2 = _m_stepper(n, np.random.default_rng(4), terms, rng_seed=9)
+        if noise:
+            native.set_obs_noise(s2.cfg, None)
+            for a0, b0, lo, hi in ((0, 4, -0.01, 0.01), (7, 13, -0.01, 0.01), (13, 19, -1.5, 1.5)):
+                for i in range(a0, b0):
+                    s2.cfg.obs_noise_lo[i], s2.cfg.obs_noise_hi[i] = lo, hi
+            s2.cfg.obs_noise_enable = 1
+            s2.update_cfg()
+        g = torch.Generator(device=DEV).manual_seed(5)
+        rec = []
+        for t in range(4):
+            u = torch.rand(n, 13, device=DEV, generator=g)
+            o_, r_, te_, tr_ = s2.step(torch.randn(n, 6, device=DEV, generator=g) * 0.3, rand=u)
+            rec.append((o_.clone(), r_.clone(), te_.clone(), tr_.clone(), s2.state.buf.clone()))
+        outs.append(rec)
+        s2.close()
+    for (o0, r0, te0, tr0, b0), (o1, r1, te1, tr1, b1) in zip(*outs):
+        assert torch.equal(r0, r1) and torch.equal(te0, te1) and torch.equal(tr0, tr1) and torch.equal(b0, b1)
+        d = (o1 - o0).cpu().numpy()
+        assert np.all(d[:, 4:7] == 0) and np.all(d[:, 19:] == 0)
+        assert np.abs(d[:, :4]).max() <= 0.01 + 1e-6 and np.abs(d[:, 7:13]).max() <= 0.01 + 1e-6 and np.abs(d[:, 13:19]).max() <= 1.5 + 1e-5
+        assert d[:, :4].std() > 0.004 and d[:, 13:19].std() > 0.6
+    # (3) in-kernel generator
+    res = []
+    for seed in (11, 11, 12):
+        s3 = _m_stepper(n, np.random.default_rng(4), terms, rng_seed=seed)
+        s3.episode_length_buf[:] = 995
+        g = torch.Generator(device=DEV).manual_seed(5)
+        alive = torch.ones(n, dtype=torch.bool, device=DEV)
+        for t in range(8):
+            o_, r_, te_, tr_ = s3.step(torch.randn(n, 6, device=DEV, generator=g) * 0.3)
+            if t == 4:
+                assert tr_.bool()[alive].all() and int(alive.sum()) > n // 8   # 995 + 5 = 1000 = max_episode_length
+                now = (tr_ | te_).bool()
+                p = s3.state.get("root_pos").cpu().numpy()                    # every env has been through a reset by now
+                assert np.all(np.abs(p[:, :2]) <= 0.5 + 0.12) and p[:, 0].std() > 0.2 and p[:, 1].std() > 0.2
+                cmd = np.concatenate([s3.state.get("carry_feet_fz").cpu().numpy(), s3.state.get("carry_mid_max").cpu().numpy()], 1)
+                assert np.all(np.abs(cmd[:, 0]) <= 0.3 + 1e-6) and np.all(np.abs(cmd[:, 1]) <= 0.1 + 1e-6) and cmd[:, 0].std() > 0.1
+                assert torch.all(s3.episode_length_buf[now] == 0)
+                q = o_[now].cpu().numpy()
+                assert np.abs(np.linalg.norm(q[:, :4], axis=1) - 1).max() < 1e-5 and np.abs(q[:, 1:3]).max() < 1e-3     # yaw-only root
+            alive &= ~(tr_ | te_).bool()
+        res.append((s3.state.buf.clone(), o_.clone()))
+        s3.close()
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1]) and not torch.equal(res[0][0], res[2][0])

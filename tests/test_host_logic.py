@@ -5,6 +5,7 @@ import os
 import re
 
 import numpy as np
+import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -84,3 +85,62 @@ def test_no_cuda_means_loud_failure():
     from zbot_lab_b200.stepper import NativeStepper
     with pytest.raises(RuntimeError):
         NativeStepper(4, "cpu")
+
+
+def test_manager_cfg_compiles_into_the_kernel_term_table_and_unknown_terms_fail_loudly():
+    """zbot-6b-walking-m-v0: the cfg tree mirrors the reference (registry id / kwargs keys of
+    zbotlab_manager/config/zbot6b_manager/__init__.py:14-22, term names / weights / params of zbotlab_env_cfg.py:240-393
+    with the flat overrides); ManagerBasedRLEnv compiles it term by term into ZbotCfg; editing a weight, enabling a
+    commented-out term or removing one is reflected; a term the kernel does not implement raises."""
+    import zbot_lab_b200.tasks  # noqa: F401
+    from zbot_lab_b200 import native
+    from zbot_lab_b200.compat import gym_registry as gym
+    from zbot_lab_b200.tasks.zbotlab_manager import mdp
+    from zbot_lab_b200.tasks.zbotlab_manager.manager_env import ManagerBasedRLEnv
+
+    spec = gym.spec("zbot-6b-walking-m-v0")
+    assert set(spec.kwargs) == {"env_cfg_entry_point", "rsl_rl_cfg_entry_point"}
+    agent = gym.load_cfg_from_registry("zbot-6b-walking-m-v0", "rsl_rl_cfg_entry_point")
+    assert agent.num_steps_per_env == 24 and agent.policy.actor_hidden_dims == [128, 128, 128] and agent.algorithm.entropy_coef == 0.01
+
+    def compile_(cfg, n=8):
+        e = object.__new__(ManagerBasedRLEnv)
+        e.cfg, e.num_envs, e.physics_dt, e.step_dt = cfg, n, 0.005, 0.02
+        e.max_episode_length_s, e.max_episode_length = 20.0, 1000
+        e._compile_cfg()
+        return e, e._native_cfg()
+
+    cfg = gym.load_cfg_from_registry("zbot-6b-walking-m-v0", "env_cfg_entry_point")
+    e, c = compile_(cfg)
+    assert c.task == native.TASK_WALKING_M and c.num_terms == 10 and c.max_episode_length == 1000
+    assert list(c.term_id)[:10] == [34, 35, 8, 24, 7, 36, 1, 2, 38, 6]
+    assert [round(w, 9) for w in list(c.term_weight)[:10]] == [1.0, 0.5, -1e-05, -2.5e-07, -0.01, 5.0, -1.0, -0.5, -6.5, -15.0]
+    assert c.is_terminated_weight == -200.0 and abs(c.term_param[0][0] - 0.25) < 1e-7
+    assert abs(c.kp - 20.0) < 1e-6 and abs(c.kd - 0.5) < 1e-6 and abs(c.termination_height - 0.2) < 1e-6 and abs(c.feet_close_min - 0.12) < 1e-6
+    assert abs(c.act_scale - 0.04 * np.pi) < 1e-6 and abs(c.act_clip - 0.04 * np.pi) < 1e-6
+    assert list(c.cmd_lo) == [np.float32(-0.1), 0.0, 0.0] and abs(c.cmd_rel_standing - 0.02) < 1e-7
+    assert c.obs_noise_enable == 1 and c.obs_noise_hi[0] == np.float32(0.01) and c.obs_noise_hi[4] == 0.0 and c.obs_noise_hi[13] == 1.5
+    # the reference's toggles: a weight edit, a commented-out term switched back on, a term removed
+    cfg.rewards.feet_slide.weight = -0.2
+    cfg.rewards.gait = mdp.RewardTermCfg(func=mdp.feet_gait, weight=0.5, params={
+        "period": 2.0, "offset": [0.0, 0.5], "threshold": 0.55, "command_name": "base_velocity"})
+    cfg.rewards.foot_forward = None
+    cfg.observations.policy.enable_corruption = False
+    e, c = compile_(cfg)
+    ids = list(c.term_id)[:c.num_terms]
+    assert 37 in ids and 2 not in ids and c.obs_noise_enable == 0
+    assert abs(c.term_weight[ids.index(38)] + 0.2) < 1e-7 and list(c.term_param[ids.index(37)]) == [2.0, 0.0, 0.5, np.float32(0.55)]
+    play = gym.load_cfg_from_registry("zbot-6b-walking-m-play-v0", "env_cfg_entry_point")
+    e, c = compile_(play, 64)
+    assert play.scene.num_envs == 64 and c.obs_noise_enable == 0 and list(c.cmd_hi)[0] == np.float32(0.3)
+    # not built -> loud
+    bad = gym.load_cfg_from_registry("zbot-6b-walking-m-v0", "env_cfg_entry_point")
+    bad.rewards.undesired_contacts = mdp.RewardTermCfg(func=mdp.undesired_contacts, weight=-1.0, params={"threshold": 1.0})
+    with pytest.raises(NotImplementedError):
+        compile_(bad)
+    bad = gym.load_cfg_from_registry("zbot-6b-walking-m-v0", "env_cfg_entry_point")
+    bad.terminations.base_contact = mdp.TerminationTermCfg(func=mdp.illegal_contact, params={"threshold": 1.0})
+    with pytest.raises(NotImplementedError):
+        compile_(bad)
+    with pytest.raises(RuntimeError):
+        mdp.feet_gait(None)

@@ -10,8 +10,8 @@ class DirectMARLEnvCfg:
     pass
 
 
-class ManagerBasedRLEnvCfg:
-    pass
+from zbot_lab_b200.tasks.zbotlab_manager.env_cfg import ManagerBasedRLEnvCfg  # noqa: E402,F401
+from zbot_lab_b200.tasks.zbotlab_manager.manager_env import ManagerBasedRLEnv  # noqa: E402,F401
 
 
 def multi_agent_to_single_agent(env):

@@ -2358,7 +2358,11 @@ ZB_HD void m_step_finish(const Params<T>& P, EnvState<T>& e, const T* raw_action
   // ---- _reset_idx of the done envs ----
   if (died || time_out) {
     ZB_UNROLL for (int i = 0; i < MAX_TERMS; ++i) reset_ep_sums[i] = e.mdp.ep_sums[i];
-    if (P.num_terms <= MAX_TERMS - 2) { reset_ep_sums[MAX_TERMS - 2] = low ? T(1) : T(0); reset_ep_sums[MAX_TERMS - 1] = close ? T(1) : T(0); }
+    if (P.num_terms <= MAX_TERMS - 3) {   // spare slots: the termination_penalty term's episodic sum and the per-DoneTerm counts
+      reset_ep_sums[MAX_TERMS - 3] = died ? P.term_penalty_w : T(0);
+      reset_ep_sums[MAX_TERMS - 2] = low ? T(1) : T(0);
+      reset_ep_sums[MAX_TERMS - 1] = close ? T(1) : T(0);
+    }
     // EventManager mode "reset": reset_base (reset_root_state_uniform on the root LINK `base`), reset_robot_joints
     // (default * U(1,1)), reset_my_data (rewards.py:37-43)
     sim_state_default<ModelWalkM>(e.sim);

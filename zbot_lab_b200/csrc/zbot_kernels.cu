@@ -60,6 +60,7 @@ struct StatsCtx {
   int block_offset;       // env-range launches (zbot_step_host): index of this launch's first partial row
   unsigned long long call; // launch counter of the handle: stream position of the in-kernel generator (obs noise)
   int packed_rows;         // 1: host-facing output layout (zbot_step_host), see zbot_step_body
+  int raw_tail;            // this many trailing term slots (…, 14, 15) hold raw counts: summed, not normalised (manager task)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -119,7 +120,7 @@ __global__ void __launch_bounds__(1024) zbot_stats_finalize_kernel(StatsCtx sc, 
     float v = red[0][threadIdx.x];
     // words 0..15 leave the kernel as the reference's `Episode_Reward/<term>` values:
     // mean over the reset envs of the episodic sum, divided by max_episode_length_s
-    if (threadIdx.x < MAX_TERMS && nreset > 0.f) v = (v / nreset) * sc.inv_episode_s;
+    if (threadIdx.x < MAX_TERMS - sc.raw_tail && nreset > 0.f) v = (v / nreset) * sc.inv_episode_s;
     // the reference only rewrites extras["log"] when something reset (…env_v2.py:450): keep the previous log
     // (word 16, the number of envs reset THIS step, is always the live count)
     if (threadIdx.x < S_REW_SUM && threadIdx.x != S_NUM_RESET && !(nreset > 0.f))
@@ -1389,7 +1390,8 @@ static int m_step_impl(ZbotHandle* h, const float* actions, const float* rand, f
   while (block > 32 && (n + block - 1) / block < 2 * h->num_sms) block >>= 1;
   const int grid = (n + block - 1) / block;
   const size_t smem = (size_t)block * SCR_STRIDE * sizeof(float);
-  StatsCtx sc{h->partials, h->ring, slot, prev, h->inv_episode_s, 0, (unsigned long long)h->launches, 0};
+  StatsCtx sc{h->partials, h->ring, slot, prev, h->inv_episode_s, 0, (unsigned long long)h->launches, 0,
+              (h->cfg.num_terms <= MAX_TERMS - 3) ? 2 : 0};
   cudaStream_t s = (cudaStream_t)stream;
   const uint64_t call = h->v4_calls++;
   if (export_buf)

@@ -106,14 +106,16 @@ class NativeStepper:
         native.check(self.lib.zbot_bind(self._h, _ptr(self.state.buf), _ptr(self.episode_length_buf),
                                         _ptr(self.stats_ring), STATS_SLOTS), "zbot_bind")
         self.v4 = (self.cfg.task == native.TASK_WALKING_V4)
-        self.num_obs = native.V4_NUM_OBS if self.v4 else native.NUM_OBS
+        self.mtask = (self.cfg.task == native.TASK_WALKING_M)
+        self.num_obs = native.V4_NUM_OBS if self.v4 else native.M_NUM_OBS if self.mtask else native.NUM_OBS
         self.obs = torch.zeros(self.n, self.num_obs, dtype=torch.float32, device=self.device)
         self.rew = torch.zeros(self.n, dtype=torch.float32, device=self.device)
         self.terminated = torch.zeros(self.n, dtype=torch.uint8, device=self.device)
         self.truncated = torch.zeros(self.n, dtype=torch.uint8, device=self.device)
         self._slot = -1
         # walking: joint_speed_limit = 1 (…env_v2.py:243); snake: per-env, set by the task class (snake_v0.py:121)
-        self.state.set("joint_speed_limit", 3.14159265 if self.cfg.task == native.TASK_SNAKE_V0 else 1.0)
+        self.state.set("joint_speed_limit", 3.14159265 if self.cfg.task == native.TASK_SNAKE_V0 else
+                       float(self.cfg.contact_mu) if self.mtask else 1.0)      # manager task: per-env friction coefficient
         self.mdp_state = None
         self._host_ok: set = set()
 
@@ -154,6 +156,20 @@ class NativeStepper:
         if actions.shape != (self.n, 6):
             raise ValueError(f"actions must be ({self.n}, 6), got {tuple(actions.shape)}")
         slot, prev = self._next_slot()
+        if self.mtask:
+            # zbot-6b-walking-m-v0: `rand` = (N,13) uniforms or None (in-kernel generator); `export` = (N,67) float32 (MExport)
+            if rand is not None and (rand.dtype != torch.float32 or tuple(rand.shape) != (self.n, native.M_NUM_RAND)
+                                     or not rand.is_contiguous() or rand.device != self.obs.device):
+                raise ValueError(f"rand must be a contiguous float32 ({self.n}, {native.M_NUM_RAND}) tensor on the device")
+            if export is None:
+                rc = self.lib.zbot_m_step(self._h, _ptr(actions), _ptr(rand), _ptr(self.obs), _ptr(self.rew),
+                                          _ptr(self.terminated), _ptr(self.truncated), slot, prev, _stream(self.device))
+            else:
+                rc = self.lib.zbot_m_step_export(self._h, _ptr(actions), _ptr(rand), _ptr(self.obs), _ptr(self.rew),
+                                                 _ptr(self.terminated), _ptr(self.truncated), slot, prev, _ptr(export),
+                                                 _stream(self.device))
+            native.check(rc, "zbot_m_step")
+            return self.obs, self.rew, self.terminated, self.truncated
         if self.v4:
             # zbot-6b-walking-v4: `rand` = (N,10) uniforms for this step or None (in-kernel generator);
             # `export` = one (N, 69) float32 tensor (V4Export)
@@ -266,9 +282,56 @@ class NativeStepper:
         posl, _, _ = self.articulation_view()                             # post-reset feet link positions (env-local)
         st.set("feet_down_pos_last", posl[ids][:, [0, 11]].reshape(k, 6), ids)
 
+    def reset_idx_m(self, env_ids: torch.Tensor | None = None, rand: torch.Tensor | None = None):
+        """``ManagerBasedRLEnv._reset_idx`` of the manager task for an explicit id list (construction / ``env.reset()``;
+        the per-step reset of done envs happens inside the step kernel): reset_base on the root link `base`
+        (zbotlab_env_cfg.py:207-222), default joints, reset_my_data (mdp/rewards.py:37-43), command resample, written
+        into the kernel's state words.  ``rand`` = (K, 8) uniforms: pose x / y / yaw, command time / vx / vy / wz / standing."""
+        from .assets import zbot_6s as Z
+        from .assets import zbot_6s_v2 as V
+        dev, c = self.device, self.cfg
+        ids = torch.arange(self.n, device=dev) if env_ids is None else env_ids.to(device=dev, dtype=torch.int64)
+        k = ids.numel()
+        if k == 0:
+            return
+        u = torch.rand(k, 8, device=dev) if rand is None else rand.to(dev)
+        m = V.model_f32()
+        lo = torch.tensor(list(c.ev_pose_lo), device=dev)
+        hi = torch.tensor(list(c.ev_pose_hi), device=dev)
+        smp = u[:, :3] * (hi - lo) + lo
+        yaw = smp[:, 2]
+        f32 = lambda a: torch.tensor(a, dtype=torch.float32, device=dev)
+        base0, root0, q0 = f32(V.DEFAULT_ROOT_POS), f32(m.default_root_pos), f32(m.default_root_quat)
+        rel = root0 - base0                                               # chain root (foot0 sole) relative to `base`
+        cy, sy = torch.cos(yaw), torch.sin(yaw)
+        pos = torch.stack([base0[0] + smp[:, 0] + cy * rel[0] - sy * rel[1],
+                           base0[1] + smp[:, 1] + sy * rel[0] + cy * rel[1], root0[2].expand(k)], -1)
+        ch, sh = torch.cos(yaw * 0.5), torch.sin(yaw * 0.5)              # (ch,0,0,sh) o q0
+        quat = torch.stack([ch * q0[0] - sh * q0[3], ch * q0[1] - sh * q0[2], ch * q0[2] + sh * q0[1], ch * q0[3] + sh * q0[0]], -1)
+        z = lambda w: torch.zeros(k, w, device=dev)
+        st = self.state
+        st.set("root_pos", pos, ids)
+        st.set("root_quat", quat, ids)
+        for name, w in (("root_lin_vel", 3), ("root_ang_vel", 3), ("joint_vel", 6), ("p_delta", 6), ("actions", 6),
+                        ("current_air_time", 2), ("current_contact_time", 2), ("last_air_time", 2), ("last_contact_time", 2),
+                        ("feet_step_length", 2), ("feet_contact_forces_last", 2), ("feet_force_sum", 1), ("episode_sums", 16)):
+            st.set(name, z(w), ids)
+        st.set("joint_pos", f32(m.default_joint_pos).repeat(k, 1), ids)
+        rng = lambda i: float(c.cmd_hi[i]) - float(c.cmd_lo[i])
+        cmd = torch.stack([u[:, 4 + i] * rng(i) + float(c.cmd_lo[i]) for i in range(3)], -1)
+        st.set("carry_feet_fz", cmd[:, :2], ids)
+        st.set("carry_mid_max", cmd[:, 2:3], ids)
+        st.set("base_heading_x_sum", (u[:, 7] <= c.cmd_rel_standing).float().unsqueeze(-1), ids)
+        st.set("base_pos_y_err_sum", (u[:, 3] * (c.cmd_resample_hi - c.cmd_resample_lo) + c.cmd_resample_lo).unsqueeze(-1), ids)
+        self.episode_length_buf[ids] = 0
+        posl, _, _ = self.articulation_view()         # chain view: link 1 = joint3 location = foot0 LINK origin, 11 = foot1
+        st.set("feet_down_pos_last", posl[ids][:, [1, 11]].reshape(k, 6), ids)
+
     def reset_idx(self, env_ids: torch.Tensor | None = None, terminated=None, truncated=None):
         if self.v4:
             return self.reset_idx_v4(env_ids)
+        if self.mtask:
+            return self.reset_idx_m(env_ids)
         slot, _ = self._next_slot()
         if env_ids is None:
             rc = self.lib.zbot_reset_idx(self._h, None, -1, _ptr(terminated), _ptr(truncated), slot,
@@ -282,6 +345,25 @@ class NativeStepper:
         native.check(rc, "zbot_reset_idx")
 
     def observe(self) -> torch.Tensor:
+        if self.mtask:
+            # ObservationManager.compute of the manager task from the state words (reset / query path only)
+            from .assets import zbot_6s_v2 as V
+            m = V.model_f32()
+            _, quat, _ = self.articulation_view()
+            g = self.state.get
+            lq = torch.tensor(m.link_rot[V.link_index("base")], dtype=torch.float32, device=self.device)
+            a, b = quat[:, 6], lq                                      # body 3 chain quaternion o (chain -> base link)
+            rq = torch.stack([a[:, 0] * b[0] - a[:, 1] * b[1] - a[:, 2] * b[2] - a[:, 3] * b[3],
+                              a[:, 0] * b[1] + a[:, 1] * b[0] + a[:, 2] * b[3] - a[:, 3] * b[2],
+                              a[:, 0] * b[2] - a[:, 1] * b[3] + a[:, 2] * b[0] + a[:, 3] * b[1],
+                              a[:, 0] * b[3] + a[:, 1] * b[2] - a[:, 2] * b[1] + a[:, 3] * b[0]], -1)
+            il = list(V.CHAIN_TO_IL)
+            q0 = torch.tensor(m.default_joint_pos, dtype=torch.float32, device=self.device)
+            qrel, qd = torch.zeros(self.n, 6, device=self.device), torch.zeros(self.n, 6, device=self.device)
+            qrel[:, il] = g("joint_pos") - q0
+            qd[:, il] = g("joint_vel")
+            self.obs.copy_(torch.cat([rq, g("carry_feet_fz"), g("carry_mid_max"), qrel, qd, g("actions")], dim=-1))
+            return self.obs
         if self.v4:
             # `_get_observations` of the v4 task (…env_v4.py:828-851) from the state words -- reset / query path only
             # (the step kernel writes its own observation)
