@@ -323,16 +323,23 @@ def test_manager_env_registry_protocol_noise_friction_curriculum_and_ppo(tmp_pat
     # lin_vel_cmd_levels (mdp/curriculums.py:57-83): at a multiple of max_episode_length, tracking reward above 80 % of
     # its weight widens lin_vel_x by 0.1 on both sides (clamped to limit_ranges)
     i = env._term_names.index("track_lin_vel_xy_exp")
-    env._stepper.stats_ring[:, i] = 0.95
-    env.common_step_counter = env.max_episode_length - 1
-    env._stepper.stats_ring[(env._stepper._slot + 1) % 64, i] = 0.95
-    w.step(torch.zeros(256, 6, device="cuda:0"))
-    env._stepper.stats_ring[env._stepper._slot, i] = 0.95
-    env.common_step_counter = 2 * env.max_episode_length - 1
-    w.step(torch.zeros(256, 6, device="cuda:0"))
-    assert tuple(round(v, 6) for v in cfg.commands.base_velocity.ranges.lin_vel_x) in ((-0.2, 0.2), (-0.3, 0.3))
-    assert abs(env._stepper.cfg.cmd_hi[0] - cfg.commands.base_velocity.ranges.lin_vel_x[1]) < 1e-6
-    assert extras["log"]["Curriculum/lin_vel_cmd_levels"] in (0.1, 0.2, 0.3)
+    env.common_step_counter = 3 * env.max_episode_length
+    env._stepper.stats_ring[max(env._stepper._slot, 0), i] = 0.5          # below 80 % of the weight: nothing moves
+    env._lin_vel_cmd_levels()
+    assert tuple(cfg.commands.base_velocity.ranges.lin_vel_x) == (-0.1, 0.1)
+    env._stepper.stats_ring[max(env._stepper._slot, 0), i] = 0.95
+    env.common_step_counter += 1                                           # not a multiple of max_episode_length
+    env._lin_vel_cmd_levels()
+    assert tuple(cfg.commands.base_velocity.ranges.lin_vel_x) == (-0.1, 0.1)
+    env.common_step_counter = 4 * env.max_episode_length
+    env._lin_vel_cmd_levels()
+    assert tuple(round(v, 6) for v in cfg.commands.base_velocity.ranges.lin_vel_x) == (-0.2, 0.2)
+    assert abs(env._stepper.cfg.cmd_hi[0] - 0.2) < 1e-6 and abs(env._stepper.cfg.cmd_lo[0] + 0.2) < 1e-6
+    for _ in range(3):                                                     # clamped to limit_ranges (-0.3, 0.3)
+        env._lin_vel_cmd_levels()
+    assert tuple(round(v, 6) for v in cfg.commands.base_velocity.ranges.lin_vel_x) == (-0.3, 0.3)
+    obs, rew, dones, extras = w.step(torch.zeros(256, 6, device="cuda:0"))
+    assert extras["log"]["Curriculum/lin_vel_cmd_levels"] == 0.3
     # PPO through the wrapper (agent cfg of the registry)
     acfg = gym.load_cfg_from_registry("zbot-6b-walking-m-v0", "rsl_rl_cfg_entry_point").to_dict()
     r = OnPolicyRunner(w, acfg, log_dir=str(tmp_path), device="cuda:0")
