@@ -333,8 +333,15 @@ def main():
         from zbot_lab_b200.stepper import NativeStepper
 
         def time_task(task, n_t, steps_t=100):
-            st_t = NativeStepper(n_t, dev, native.make_cfg(n_t, task=task))
-            if task == native.TASK_WALKING_V4:
+            if task == native.TASK_WALKING_M:
+                terms = [(f, w, p) for _, f, w, p in native.M_FLAT_TERMS if f != "is_terminated"]
+                st_t = NativeStepper(n_t, dev, native.make_m_cfg(n_t, terms, is_terminated_weight=-200.0, act_clip=0.04 * 3.141592653589793))
+            else:
+                st_t = NativeStepper(n_t, dev, native.make_cfg(n_t, task=task))
+            if task == native.TASK_WALKING_M:
+                st_t.reset_idx_m(None)
+                st_t.state.set("joint_speed_limit", torch.rand(n_t, 1, device=dev) * 0.7 + 0.3)      # friction 0.3 .. 1.0
+            elif task == native.TASK_WALKING_V4:
                 st_t.reset_idx_v4(None)
                 st_t.state.set("base_pos_y_err_sum", torch.rand(n_t, 1, device=dev) * 3.0 + 3.0)
             else:
@@ -368,6 +375,11 @@ def main():
                                     workload="zbot-6b-walking-v4 fused step (commands + event resampling, in-kernel RNG), 4096 envs"),
             "walking_v4_65536": dict(time_task(native.TASK_WALKING_V4, 65536),
                                      workload="zbot-6b-walking-v4 fused step, 65536 envs"),
+            "walking_m_4096": dict(time_task(native.TASK_WALKING_M, 4096),
+                                   workload="zbot-6b-walking-m-v0 (manager-based task, Zbot6BFlatEnvCfg terms, full-inertia robot, "
+                                            "per-env friction, in-kernel RNG) fused step, 4096 envs"),
+            "walking_m_65536": dict(time_task(native.TASK_WALKING_M, 65536),
+                                    workload="zbot-6b-walking-m-v0 fused step, 65536 envs"),
         }
         try:   # BASELINE.json configs[4]: PPO rollout 24 steps x 4096 envs, policy MLP + env step + storage, one CUDA graph
             sys.path.insert(0, os.path.join(ROOT, "tools"))
@@ -396,7 +408,7 @@ def main():
                        "wall_s_incl_flush": main_m["wall"]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": NCU_TRAFFIC_BYTES_PER_ENV_STEP * n_envs, "peak_source": peak_src,
-                         "kernel": "zbot_step_kernel<false,128,2>",
+                         "kernel": "zbot_step_u2_kernel<128,2>" if n_envs > 148 * 128 else "zbot_step_kernel<false,128,2>",
                          "traffic_note": "dram__bytes_read+write per launch at 65536 envs (profiles/r1_ncu_raw_tables_session2.md), scaled per env",
                          "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP,
                          "note": "the fused step is FP32-issue bound, not HBM bound (DESIGN.md §4)"},

@@ -14,9 +14,16 @@ from zbot_lab_b200.utils import synthetic as syn  # noqa: E402
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 12
 task = sys.argv[3] if len(sys.argv) > 3 else "walk"
-tid = {"walk": native.TASK_WALKING_V2, "snake": native.TASK_SNAKE_V0, "v4": native.TASK_WALKING_V4}[task]
-st = NativeStepper(n, "cuda:0", native.make_cfg(n, task=tid))
-if task == "v4":
+tid = {"walk": native.TASK_WALKING_V2, "snake": native.TASK_SNAKE_V0, "v4": native.TASK_WALKING_V4, "m": native.TASK_WALKING_M}[task]
+if task == "m":
+    terms = [(f, w, p) for _, f, w, p in native.M_FLAT_TERMS if f != "is_terminated"]
+    st = NativeStepper(n, "cuda:0", native.make_m_cfg(n, terms, is_terminated_weight=-200.0, act_clip=0.04 * np.pi))
+else:
+    st = NativeStepper(n, "cuda:0", native.make_cfg(n, task=tid))
+if task == "m":
+    st.reset_idx_m(None)
+    st.state.set("joint_speed_limit", torch.rand(n, 1, device="cuda:0") * 0.7 + 0.3)
+elif task == "v4":
     st.reset_idx_v4(None)
     st.state.set("base_pos_y_err_sum", torch.rand(n, 1, device="cuda:0") * 3 + 3)
 else:

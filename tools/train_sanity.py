@@ -14,12 +14,15 @@ from zbot_lab_b200.envs.rsl_rl_wrapper import RslRlVecEnvWrapper  # noqa: E402
 from zbot_lab_b200.rl.ppo_runner import OnPolicyRunner  # noqa: E402
 
 iters = int(sys.argv[1]) if len(sys.argv) > 1 else 300
+tasks = sys.argv[2:] or ["zbot-6b-walking-v2", "zbot-6b-walking-v4", "zbot-6s-snake-v0", "zbot-6b-walking-m-v0"]
 out = {}
-for task in ("zbot-6b-walking-v2", "zbot-6b-walking-v4", "zbot-6s-snake-v0"):
+for task in tasks:
     cfg = gym.load_cfg_from_registry(task, "env_cfg_entry_point")
     cfg.scene.num_envs, cfg.sim.device, cfg.seed = 4096, "cuda:0", 42
-    if hasattr(cfg, "events"):
+    if hasattr(cfg, "events") and hasattr(cfg.events, "my_curric"):
         cfg.events.my_curric = False          # fixed reward table for the comparison
+    if hasattr(cfg, "curriculum"):
+        cfg.curriculum.lin_vel_cmd_levels = None
     env = RslRlVecEnvWrapper(gym.make(task, cfg=cfg, render_mode=None))
     acfg = gym.load_cfg_from_registry(task, "rsl_rl_cfg_entry_point").to_dict()
     r = OnPolicyRunner(env, acfg, log_dir=None, device="cuda:0")
