@@ -1104,3 +1104,79 @@ def test_m_kernel_equals_host_build_noise_and_internal_rng():
         res.append((s3.state.buf.clone(), o_.clone()))
         s3.close()
     assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1]) and not torch.equal(res[0][0], res[2][0])
+
+
+def test_m_abi_error_paths_and_guard_bands():
+    """zbot_m_step: wrong-task / unbound / NULL / misaligned calls return error codes with a message; guard bands around
+    every buffer the manager kernel writes stay intact at ragged N (tail blocks, export rows of 67 words, 25-wide rows)."""
+    import ctypes as C
+    from helpers import m_native_cfg
+    from zbot_lab_b200 import native
+    lib = native.lib()
+    vp = C.c_void_p
+    n = 64
+    buf = torch.zeros(n * 128, device=DEV)
+    p0 = vp(buf.data_ptr())
+    hm, hw = vp(), vp()
+    cm, cw = m_native_cfg(n, native.M_FLAT_TERMS), native.make_cfg(n)
+    native.check(lib.zbot_create(C.byref(cm), 0, C.byref(hm)))
+    native.check(lib.zbot_create(C.byref(cw), 0, C.byref(hw)))
+    assert lib.zbot_m_step(hm, p0, None, p0, p0, p0, p0, 0, -1, None) == -3 and b"zbot_bind" in lib.zbot_last_error()
+    st, ep, ring = torch.zeros(20, n, 4, device=DEV), torch.zeros(n, dtype=torch.int64, device=DEV), torch.zeros(4, 32, device=DEV)
+    for h in (hm, hw):
+        native.check(lib.zbot_bind(h, vp(st.data_ptr()), vp(ep.data_ptr()), vp(ring.data_ptr()), 4))
+    assert lib.zbot_m_step(hw, p0, None, p0, p0, p0, p0, 0, -1, None) == -1 and b"WALKING_M" in lib.zbot_last_error()
+    assert lib.zbot_step(hm, p0, p0, p0, p0, p0, 0, -1, None) == -1 and b"zbot_m_step" in lib.zbot_last_error()
+    assert lib.zbot_v4_step(hm, p0, None, p0, p0, p0, p0, 0, -1, None) == -1
+    assert lib.zbot_m_step(hm, None, None, p0, p0, p0, p0, 0, -1, None) == -1 and b"NULL" in lib.zbot_last_error()
+    assert lib.zbot_m_step(hm, vp(buf.data_ptr() + 4), None, p0, p0, p0, p0, 0, -1, None) == -1
+    assert lib.zbot_m_step_export(hm, p0, None, p0, p0, p0, p0, 0, -1, None, None) == -1
+    assert lib.zbot_m_step(hm, p0, None, p0, p0, p0, p0, 9, -1, None) == -1 and b"slot" in lib.zbot_last_error()
+    assert lib.zbot_reset_idx(hm, None, -1, None, None, 0, None) == -1 and lib.zbot_observe(hm, p0, None) == -1
+    bad = m_native_cfg(n, native.M_FLAT_TERMS)
+    bad.term_id[0] = 999
+    assert lib.zbot_update_cfg(hm, C.byref(bad)) == -1
+    assert lib.zbot_destroy(hm) == 0 and lib.zbot_destroy(hw) == 0
+    for n in (1000, 129, 31):
+        cfg = m_native_cfg(n, native.M_FLAT_TERMS)
+        h = vp()
+        native.check(lib.zbot_create(C.byref(cfg), 0, C.byref(h)))
+        sizes = {"state": 80 * n * 4, "ep": 8 * n, "ring": 4 * 32 * 4, "obs": 4 * 25 * n, "rew": 4 * n, "term": n, "trunc": n,
+                 "act": 24 * n, "rand": 52 * n, "ex": 4 * 67 * n}
+        gap = 1024
+        total = sum((s + 255) // 256 * 256 + gap for s in sizes.values()) + gap
+        arena = torch.full((total,), 0xA5, dtype=torch.uint8, device=DEV)
+        off, views = gap, {}
+        for k, sz in sizes.items():
+            views[k] = arena[off:off + sz]
+            views[k].zero_()
+            off += (sz + 255) // 256 * 256 + gap
+        mask = torch.ones(total, dtype=torch.bool, device=DEV)
+        for v in views.values():
+            o = v.data_ptr() - arena.data_ptr()
+            mask[o:o + v.numel()] = False
+        p = lambda k: vp(views[k].data_ptr())
+        native.check(lib.zbot_bind(h, p("state"), p("ep"), p("ring"), 4))
+        from zbot_lab_b200.assets import zbot_6s_v2 as V
+        m = V.model_f32()
+        stv = views["state"].view(torch.float32).view(20, n, 4)
+        for name, vals in (("root_pos", m.default_root_pos), ("root_quat", m.default_root_quat), ("joint_pos", m.default_joint_pos),
+                           ("joint_speed_limit", [0.8]), ("base_pos_y_err_sum", [0.05])):
+            w0 = lib.zbot_state_word(name.encode())
+            for i, val in enumerate(vals):
+                stv[(w0 + i) // 4, :, (w0 + i) % 4] = float(val)
+        views["act"].view(torch.float32).normal_()
+        views["rand"].view(torch.float32).uniform_()
+        views["ep"].view(torch.int64)[:] = 992
+        for t in range(12):
+            if t % 3 == 0:
+                native.check(lib.zbot_m_step_export(h, p("act"), p("rand"), p("obs"), p("rew"), p("term"), p("trunc"),
+                                                    (t + 1) % 4, t % 4, p("ex"), None))
+            else:
+                native.check(lib.zbot_m_step(h, p("act"), p("rand") if t % 2 else None, p("obs"), p("rew"), p("term"), p("trunc"),
+                                             (t + 1) % 4, t % 4, None))
+        torch.cuda.synchronize()
+        assert torch.all(arena[mask] == 0xA5), f"canary overwritten (n={n})"
+        assert torch.isfinite(views["obs"].view(torch.float32)).all() and torch.isfinite(views["state"].view(torch.float32)).all()
+        assert int(views["trunc"].sum()) + int(views["term"].sum()) >= 0 and int(views["ep"].view(torch.int64).max()) < 1000
+        lib.zbot_destroy(h)
