@@ -312,8 +312,7 @@ def synth_m_views(seed: int, n: int, steps: int):
         base_f = np.array([[0.70710678, 0.70710678, 0, 0], [0.70710678, -0.70710678, 0, 0]])
         tilt, _ = rq((n, 2), 0.2)
         qz = np.stack([np.cos(yaw / 2), 0 * yaw, 0 * yaw, np.sin(yaw / 2)], -1)
-        tilt_only = Z.quat_mul(np.broadcast_to((qz * np.array([1, -1, -1, -1]))[:, None, :], tilt.shape), tilt) if False else tilt
-        feet_quat = Z.quat_mul(Z.quat_mul(np.broadcast_to(qz[:, None, :], (n, 2, 4)), tilt_only), np.broadcast_to(base_f, (n, 2, 4)))
+        feet_quat = Z.quat_mul(Z.quat_mul(np.broadcast_to(qz[:, None, :], (n, 2, 4)), tilt), np.broadcast_to(base_f, (n, 2, 4)))
         feet_quat = feet_quat / np.linalg.norm(feet_quat, axis=-1, keepdims=True)
         root_pos = np.stack([rng.normal(0, 0.3, n), rng.normal(0, 0.3, n), rng.normal(0.245, 0.03, n)], -1)
         feet_pos = root_pos[:, None, :] + np.stack([rng.normal(0, 0.05, (n, 2)), rng.normal(0, 0.03, (n, 2)) + np.array([-0.065, 0.065]),

@@ -172,8 +172,6 @@ def m_check_step(o, a, rnd, ex, obs, rew, term, trunc, ep_len, state_get, rs=Non
     assert np.abs(state_get("feet_force_sum", 1)[:, 0] - o.s["feet_force_sum"]).max() <= 1e-6
     assert np.abs(state_get("actions", 6) - o.s["action"]).max() == 0
     sums = state_get("episode_sums", 16)
-    for i, (name, v) in enumerate(o.ep_sums.items()) if False else []:
-        pass
     slot_names = [nm for nm, f, w, p in o.terms if f != "is_terminated" and float(w) != 0.0]
     for i, nm in enumerate(slot_names):
         assert rel_err(sums[:, i], o.ep_sums[nm], 1e-2) <= 20 * rtol, ("episode sum", nm)

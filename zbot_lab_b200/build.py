@@ -38,23 +38,26 @@ def is_stale() -> bool:
     return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
 
 
-def build_native(force: bool = False, verbose: bool = False) -> str:
-    if not force and not is_stale():
+def build_native(force: bool = False, verbose: bool = False, out: str | None = None, extra: list | None = None) -> str:
+    """``out`` / ``extra``: tuning builds (a differently-flagged copy next to the product library, loaded with
+    ``ZBOT_B200_LIB=<path>``, see ``native.lib``); the product build uses neither."""
+    if out is None and not force and not is_stale():
         return OUT
-    cmd = [nvcc_path(), *NVCC_FLAGS, *os.environ.get("ZBOT_NVCC_EXTRA", "").split(), "-o", OUT, *SOURCES]
+    out = out or OUT
+    cmd = [nvcc_path(), *NVCC_FLAGS, *os.environ.get("ZBOT_NVCC_EXTRA", "").split(), *(extra or []), "-o", out, *SOURCES]
     env = dict(os.environ)
     # the image exports CC/CXX pointing at a wrapper without libgomp specs; nvcc only needs a host g++
     if os.access("/usr/bin/g++", os.X_OK):
         cmd[1:1] = ["-ccbin", "/usr/bin/g++"]
     r = subprocess.run(cmd, cwd=CSRC, env=env, capture_output=True, text=True)
     log = r.stdout + r.stderr
-    with open(os.path.join(CSRC, "build.log"), "w") as f:
+    with open(os.path.join(CSRC, "build.log" if out == OUT else os.path.basename(out) + ".log"), "w") as f:
         f.write(" ".join(cmd) + "\n" + log)
     if verbose or r.returncode != 0:
         print(log)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed; see zbot_lab_b200/csrc/build.log")
-    return OUT
+    return out
 
 
 if __name__ == "__main__":

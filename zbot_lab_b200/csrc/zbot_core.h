@@ -741,6 +741,19 @@ struct SubstepOut {
 // kUnroll: unroll factor of the three sweeps over the chain (FK, backward, forward).  1 = smallest code (best for a lone
 // warp per SM: instruction fetch is 11 % of its time); 2 halves the loop-carried register shuffles (MOV was 8.5 % of the
 // executed instructions) and wins ~4 % once two or more warps share a sub-partition (profiles/r1_notes.md).
+// per-sweep unroll factors (tuning builds override them with -D; profiles/r1_notes.md "third session"): the backward and
+// forward sweeps follow kUnroll, the short kinematics sweep is always fully unrolled
+#define ZB_DO_PRAGMA(x) _Pragma(#x)
+#define ZB_PRAGMA_UNROLL(n) ZB_DO_PRAGMA(unroll n)
+#ifndef ZB_UNROLL_FK
+#define ZB_UNROLL_FK 6   // kinematics sweep fully unrolled in every instantiation: 35.8 -> 34.9 us at 4096 envs, 84.0 -> 82.0 at 65536
+#endif
+#ifndef ZB_UNROLL_BWD
+#define ZB_UNROLL_BWD kUnroll
+#endif
+#ifndef ZB_UNROLL_FWD
+#define ZB_UNROLL_FWD kUnroll
+#endif
 template <typename Model, bool kPipe = (ZB_PIPELINED_SWEEP != 0), int kUnroll = 1, typename PS, typename T, typename Scr>
 ZB_HD void physics_substep(const Params<PS>& P, SimState<T>& s, const T* target, SubstepOut<T>& out, Scr& scr,
                            T* mid_force_out) {
@@ -761,7 +774,7 @@ ZB_HD void physics_substep(const Params<PS>& P, SimState<T>& s, const T* target,
   T w[3] = {s.w[0], s.w[1], s.w[2]};         // spatial velocity of the current body about O
   T vO[3] = {s.v[0], s.v[1], s.v[2]};
 #if defined(__CUDACC__)
-#pragma unroll kUnroll
+ZB_PRAGMA_UNROLL(ZB_UNROLL_FK)
 #endif
   for (int k = 0; k < 6; ++k) {
     T R[9];
@@ -820,7 +833,7 @@ ZB_HD void physics_substep(const Params<PS>& P, SimState<T>& s, const T* target,
     if (Model::kGroundForceSensor) agg1 = agg;
   }
 #if defined(__CUDACC__)
-#pragma unroll kUnroll
+ZB_PRAGMA_UNROLL(ZB_UNROLL_BWD)
 #endif
   for (int k = 6; k >= 1; --k) {
     const int j = k - 1;          // joint between body k and body k-1
@@ -996,7 +1009,7 @@ ZB_HD void physics_substep(const Params<PS>& P, SimState<T>& s, const T* target,
   }
   // ---- forward sweep: joint accelerations ----
 #if defined(__CUDACC__)
-#pragma unroll kUnroll
+ZB_PRAGMA_UNROLL(ZB_UNROLL_FWD)
 #endif
   for (int j = 0; j < 6; ++j) {
     const T Sa[3] = {scr(j, SC_SA), scr(j, SC_SA + 1), scr(j, SC_SA + 2)};

@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libzbot_b200.so")
+# ZBOT_B200_LIB: load a tuning build of the SAME sources instead (tools/sweep_step.py); never a different implementation
+LIB_PATH = os.environ.get("ZBOT_B200_LIB") or os.path.join(HERE, "csrc", "libzbot_b200.so")
 
 ZBOT_ABI_VERSION = 5
 TASK_WALKING_V2, TASK_SNAKE_V0, TASK_WALKING_V4, TASK_WALKING_M = 0, 1, 2, 3
