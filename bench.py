@@ -33,6 +33,11 @@ ALGO_BYTES_PER_ENV_STEP = 320 + 24 + 8 + 320 + 92 + 4 + 2 + 8
 # dram__bytes_read.sum + dram__bytes_write.sum of one zbot_step_kernel launch at 65536 envs (ncu --set full,
 # profiles/r1_ncu_raw_tables_session2.md: 23.14 MB read + 0 written) per env: reads hit DRAM, most writes are still in the 126 MB L2 when the kernel ends
 NCU_TRAFFIC_BYTES_PER_ENV_STEP = 353
+# Warp instructions one launch of the throughput instantiation executes per ENV (smsp__inst_executed.sum / envs at 65536 envs,
+# profiles/r1_ncu_raw_tables_session3.md: 47.98 M / 65536 x 32 lanes ... kept per warp of 32 envs: 23.43 k) and the measured issue
+# ceiling of one SM sub-partition at this kernel's occupancy (2 warps: 0.73 instructions / clock; tools/micro/ffma2_probe.cu)
+WARP_INSTRUCTIONS_PER_32_ENVS = 47.98e6 / (65536 / 32)
+ISSUE_CEILING_INST_PER_CLK_PER_SMSP = 0.73
 # Envs per GPU of the headline `value` at EVERY N (weak scaling: identical per-GPU work at N = 1, 2, 4, 8 so the
 # driver's scaling efficiency is meaningful).  65536 envs/GPU is the configuration BASELINE.json states the
 # multi-GPU target on (configs[2]); the 4096-env configuration (configs[1]) is measured in the same run at N = 1
@@ -411,7 +416,17 @@ def main():
                          "kernel": "zbot_step_u2_kernel<128,2>" if n_envs > 148 * 128 else "zbot_step_kernel<false,128,2>",
                          "traffic_note": "dram__bytes_read+write per launch at 65536 envs (profiles/r1_ncu_raw_tables_session2.md), scaled per env",
                          "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP,
-                         "note": "the fused step is FP32-issue bound, not HBM bound (DESIGN.md §4)"},
+                         "note": "the fused step is FP32-issue bound, not HBM bound (DESIGN.md §4); see fp32_issue"},
+            # the bound that actually applies (not an HBM / tensor roofline, hence a separate object): warp instructions
+            # issued per clock per SM sub-partition against the measured ceiling at this occupancy
+            "fp32_issue": (lambda clk_hz: {
+                "achieved_inst_per_clk_per_smsp": WARP_INSTRUCTIONS_PER_32_ENVS * (n_envs / 32) / (148 * 4) / (kern_ms * 1e-3 * clk_hz),
+                "ceiling_at_2_warps": ISSUE_CEILING_INST_PER_CLK_PER_SMSP, "nominal": 1.0,
+                "frac_of_ceiling": WARP_INSTRUCTIONS_PER_32_ENVS * (n_envs / 32) / (148 * 4) / (kern_ms * 1e-3 * clk_hz) / ISSUE_CEILING_INST_PER_CLK_PER_SMSP,
+                "fp32_share_of_instructions": 0.76, "sm_clock_mhz": clk_hz / 1e6,
+                "source": "smsp__inst_executed.sum of profiles/r1_ncu_raw_tables_session3.md (65536 envs) / live kernel time; "
+                          "ceiling from tools/micro/ffma2_probe.cu (profiles/r1_notes.md)"})(
+                    1e6 * float((main_m["clocks"] or {}).get("sm_mhz") or 1965.0)),
             "gpu_launches": int(launches), "clocks": main_m["clocks"],
         }
         if small_m is not None:

@@ -930,6 +930,7 @@ zbot_mdp_kernel(const __grid_constant__ Params<float> P, const __grid_constant__
                 float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ terminated,
                 uint8_t* __restrict__ truncated, int n, StatsCtx sc) {
   extern __shared__ __align__(128) float smem[];   // [blockDim][180] history tile, reused for obs rows / stats
+  pdl_wait();
   const int e0 = blockIdx.x * blockDim.x;
   const int e = e0 + threadIdx.x;
   const bool live = e < n;
@@ -1575,12 +1576,10 @@ int zbot_mdp_step(ZbotHandle* h, const ZbotMdpInputs* in, const float* actions, 
   MdpIn mi{in->body_link_pos_w, in->body_link_quat_w, in->body_com_lin_vel_w, in->joint_pos, in->joint_vel,
            in->applied_torque, in->net_forces_w_history, in->last_air_time, in->env_origins};
   StatsCtx sc{h->partials, h->m_ring, stats_slot, prev_slot, h->inv_episode_s, 0, (unsigned long long)h->launches, 0};
-  zbot_mdp_kernel<true><<<grid, block, (size_t)block * kHistRow * sizeof(float), (cudaStream_t)stream>>>(
-      h->P, h->dp, mi, h->mstate, h->m_ep_len, actions, obs, rew, terminated, truncated, n, sc);
-  ZB_CUDA(cudaGetLastError());
+  ZB_CUDA(launch_pdl(zbot_mdp_kernel<true>, dim3(grid), dim3(block), (size_t)block * kHistRow * sizeof(float), (cudaStream_t)stream,
+                     h->pdl, h->P, h->dp, mi, h->mstate, h->m_ep_len, actions, obs, rew, terminated, truncated, n, sc));
   h->launches += 1;
-  zbot_stats_finalize_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(sc, (unsigned int)grid);
-  ZB_CUDA(cudaGetLastError());
+  ZB_CUDA(launch_pdl(zbot_stats_finalize_kernel, dim3(1), dim3(1024), 0, (cudaStream_t)stream, h->pdl, sc, (unsigned int)grid));
   h->launches += 1;
   return ZBOT_OK;
 }
