@@ -110,3 +110,46 @@ class FakeStepper:
 
     def close(self):
         pass
+
+
+class FakeMStepper(FakeStepper):
+    """CPU double of the manager task's stepper (``zbot-6b-walking-m-v0``): the kernel's arithmetic compiled for the host
+    behind the same methods; ``reset_idx_m`` / ``observe`` are the shipped host code of ``NativeStepper`` itself."""
+
+    def __init__(self, num_envs, device, cfg=None):
+        assert cfg is not None and cfg.task == native.TASK_WALKING_M
+        super().__init__(num_envs, device, cfg)
+        self.mtask, self.v4 = True, False
+        self.num_obs = native.M_NUM_OBS
+        self.obs = torch.zeros(self.n, native.M_NUM_OBS)
+        self._rng = np.random.default_rng(int(cfg.rng_seed) + 1)
+
+    from zbot_lab_b200.stepper import NativeStepper as _NS
+    reset_idx_m = _NS.reset_idx_m
+    observe = _NS.observe
+    del _NS
+
+    def reset_idx(self, env_ids=None, terminated=None, truncated=None):
+        return self.reset_idx_m(env_ids)
+
+    def update_cfg(self):
+        pass          # the port reads self.cfg on every step
+
+    def step(self, actions, export=None, rand=None):
+        rnd = self._rng.random((self.n, native.M_NUM_RAND)).astype(np.float32) if rand is None else rand.numpy()
+        obs, rew, term, trunc, rs, _ = self.port.step(actions.detach().cpu().numpy(), rnd=rnd)
+        if self.cfg.obs_noise_enable:
+            lo, hi = np.zeros(25, np.float32), np.zeros(25, np.float32)
+            lo[:24], hi[:24] = list(self.cfg.obs_noise_lo), list(self.cfg.obs_noise_hi)
+            obs = obs + (self._rng.random(obs.shape).astype(np.float32) * (hi - lo) + lo)
+        self.obs.copy_(torch.from_numpy(obs))
+        self.rew.copy_(torch.from_numpy(rew))
+        self.terminated.copy_(torch.from_numpy(term.astype(np.uint8)))
+        self.truncated.copy_(torch.from_numpy(trunc.astype(np.uint8)))
+        mask = term | trunc
+        self._write_stats(mask, rs, term, trunc, rew)
+        if mask.any() and self.cfg.num_terms <= 13:      # raw-count tail slots (include/zbot_b200.h: zbot_m_step)
+            self.stats_ring[self._slot][14] = float(rs[mask][:, 14].sum())
+            self.stats_ring[self._slot][15] = float(rs[mask][:, 15].sum())
+        self.launch_count += 2
+        return self.obs, self.rew, self.terminated, self.truncated

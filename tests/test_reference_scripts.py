@@ -85,3 +85,56 @@ def test_reference_play_py_runs_unchanged(shimmed, monkeypatch):
     import torch
     pol = torch.jit.load(str(run / "exported" / "policy.pt"))
     assert pol(torch.zeros(3, 23)).shape == (3, 6)
+
+
+def test_reference_train_py_runs_unchanged_on_the_manager_task(shimmed, monkeypatch):
+    """``--task zbot-6b-walking-m-v0``: the reference's own train.py resolves the id (registered by ``import zbot.tasks``)
+    to ``isaaclab.envs:ManagerBasedRLEnv``-shaped env + ``Zbot6BFlatEnvCfg`` + the flat PPO cfg, trains two iterations
+    and writes its run directory (CPU double of the stepper; the cfg -> term-table compilation, the startup friction
+    event, reset, logging and the wrapper are the shipped host code)."""
+    import zbot_lab_b200.tasks.zbotlab_manager.manager_env as me
+    from fake_stepper import FakeMStepper
+    monkeypatch.setattr(me, "NativeStepper", FakeMStepper)
+    monkeypatch.setattr(sys, "argv", ["train.py", "--task", "zbot-6b-walking-m-v0", "--num_envs", "16",
+                                      "--max_iterations", "2", "--headless", "--device", "cpu", "--seed", "7",
+                                      "agent.num_steps_per_env=6", "agent.device=cpu"])
+    runpy.run_path(os.path.join(REF_SCRIPTS, "train.py"), run_name="__main__")
+    root = shimmed / "logs" / "rsl_rl" / "zbot_6b_flat_mana_v1"
+    runs = os.listdir(root)
+    assert len(runs) == 1
+    run = root / runs[0]
+    assert (run / "params" / "env.yaml").exists() and (run / "model_2.pt").exists()
+    import json
+    recs = [json.loads(l) for l in open(run / "progress.jsonl")]
+    assert len(recs) == 2 and "Episode_Reward/foot_step_length" in recs[-1] and "Curriculum/lin_vel_cmd_levels" in recs[-1]
+
+
+def test_manager_env_surface_on_cpu_double(shimmed, monkeypatch):
+    """Host logic of ManagerBasedRLEnv + wrapper on the CPU double: 25-wide group, time-out at max_episode_length,
+    log keys, command inside the ranges, friction buckets, PLAY cfg."""
+    import torch
+    import zbot_lab_b200.tasks.zbotlab_manager.manager_env as me
+    from fake_stepper import FakeMStepper
+    monkeypatch.setattr(me, "NativeStepper", FakeMStepper)
+    import zbot_lab_b200.tasks  # noqa: F401
+    from zbot_lab_b200.compat import gym_registry as gym
+    from zbot_lab_b200.envs.rsl_rl_wrapper import RslRlVecEnvWrapper
+    cfg = gym.load_cfg_from_registry("zbot-6b-walking-m-play-v0", "env_cfg_entry_point")
+    cfg.scene.num_envs = 8
+    cfg.sim.device = "cpu"
+    cfg.seed = 3
+    cfg.terminations.feet_close = None          # the init stance sits on that term's margin; keep this test about time-outs
+    env = gym.make("zbot-6b-walking-m-play-v0", cfg=cfg, render_mode=None)
+    w = RslRlVecEnvWrapper(env)
+    obs = w.get_observations()["policy"]
+    assert obs.shape == (8, 25) and float(obs[:, 4].abs().max()) <= 0.3 + 1e-6 and float(obs[:, 7:19].abs().max()) < 1e-5
+    assert float(env.friction.min()) >= 0.3 and float(env.friction.max()) <= 1.0
+    w.episode_length_buf = torch.full((8,), 998, dtype=torch.int64)
+    _, _, dones, ex = w.step(torch.zeros(8, 6))
+    assert dones.sum() == 0
+    obs2, _, dones, ex = w.step(torch.zeros(8, 6))
+    assert dones.all() and ex["time_outs"].all()                 # 998 + 2 = 1000 = max_episode_length (mdp.time_out)
+    assert float(ex["log"]["Episode_Termination/time_out"]) == 8.0 and float(ex["log"]["Episode_Termination/base_height"]) == 0.0
+    assert "Episode_Termination/feet_close" not in ex["log"] and "Episode_Reward/track_lin_vel_xy_exp" in ex["log"]
+    assert int(env.episode_length_buf.max()) == 0 and float(obs2["policy"][:, 19:].abs().max()) == 0
+    assert env.command.shape == (8, 3)
