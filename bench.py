@@ -34,9 +34,9 @@ ALGO_BYTES_PER_ENV_STEP = 320 + 24 + 8 + 320 + 92 + 4 + 2 + 8
 # profiles/r1_ncu_raw_tables_session2.md: 23.14 MB read + 0 written) per env: reads hit DRAM, most writes are still in the 126 MB L2 when the kernel ends
 NCU_TRAFFIC_BYTES_PER_ENV_STEP = 353
 # Warp instructions one launch of the throughput instantiation executes per ENV (smsp__inst_executed.sum / envs at 65536 envs,
-# profiles/r1_ncu_raw_tables_session3.md: 47.98 M / 65536 x 32 lanes ... kept per warp of 32 envs: 23.43 k) and the measured issue
+# profiles/r1_ncu_raw_tables_session3.md: 46.14 M per launch = 22.5 k per warp of 32 envs) and the measured issue
 # ceiling of one SM sub-partition at this kernel's occupancy (2 warps: 0.73 instructions / clock; tools/micro/ffma2_probe.cu)
-WARP_INSTRUCTIONS_PER_32_ENVS = 47.98e6 / (65536 / 32)
+WARP_INSTRUCTIONS_PER_32_ENVS = 46.14e6 / (65536 / 32)
 ISSUE_CEILING_INST_PER_CLK_PER_SMSP = 0.73
 # Envs per GPU of the headline `value` at EVERY N (weak scaling: identical per-GPU work at N = 1, 2, 4, 8 so the
 # driver's scaling efficiency is meaningful).  65536 envs/GPU is the configuration BASELINE.json states the
