@@ -372,7 +372,34 @@ def main():
             st_t.close()
             return out_t
 
+        def time_no_termination(n_t, steps_t=100):
+            """the same fused step with zero actions from the default stance -- nobody falls, nobody resets
+            (episode counters start at 0): separates the cost of the reset path from the steady-state step."""
+            st_t = NativeStepper(n_t, dev, native.make_cfg(n_t, task=native.TASK_WALKING_V2))
+            st_t.reset_idx(None)
+            acts_t = torch.zeros(n_t, 6, device=dev)
+            for i in range(20):
+                st_t.step(acts_t)
+            torch.cuda.synchronize()
+            a_ev, b_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_ev.record()
+            resets = 0.0
+            for i in range(steps_t):
+                st_t.step(acts_t)
+            b_ev.record()
+            torch.cuda.synchronize()
+            resets = float(st_t.stats_ring[:, native.STAT_NUM_RESET].sum())
+            ms = a_ev.elapsed_time(b_ev) / steps_t
+            st_t.close()
+            return {"envs": n_t, "ms_per_step": ms, "value": n_t / (ms * 1e-3), "unit": UNIT, "resets_in_last_64_steps": resets,
+                    "l2": "not flushed (back to back)",
+                    "workload": "zbot-6b-walking-v2 fused step, zero actions from the default stance (no terminations, no resets)"}
+
         other_tasks = {
+            "walking_v2_65536_no_termination": time_no_termination(65536),
+            "walking_v2_65536_random_actions": dict(time_task(native.TASK_WALKING_V2, 65536),
+                                                    workload="zbot-6b-walking-v2 fused step, random actions (falls and resets "
+                                                             "every step), back to back"),
             "snake_16384": dict(time_task(native.TASK_SNAKE_V0, 16384),
                                 workload="BASELINE.json configs[3]: zbot-6s-snake-v0 fused step, 16384 envs, "
                                          "12 ground spheres in contact per env"),
