@@ -1180,3 +1180,67 @@ def test_m_abi_error_paths_and_guard_bands():
         assert torch.isfinite(views["obs"].view(torch.float32)).all() and torch.isfinite(views["state"].view(torch.float32)).all()
         assert int(views["trunc"].sum()) + int(views["term"].sum()) >= 0 and int(views["ep"].view(torch.int64).max()) < 1000
         lib.zbot_destroy(h)
+
+
+def test_m_full_size_properties_65536():
+    """Manager task at BASELINE size (65536 envs, the unrolled instantiation): identical envs stay identical (same
+    uniforms), statistics equal torch reductions, two runs bit-identical, state stays finite under random actions."""
+    from zbot_lab_b200 import native
+    n = 65536
+    outs = []
+    for rep in range(2):
+        st = _m_stepper(n, np.random.default_rng(1), native.M_FLAT_TERMS, rng_seed=5)
+        for k in ("carry_feet_fz", "carry_mid_max", "base_pos_y_err_sum", "joint_speed_limit", "joint_pos"):
+            st.state.set(k, st.state.get(k)[:1].expand(n, -1).contiguous())
+        st.episode_length_buf[:] = 994
+        g = torch.Generator(device=DEV).manual_seed(99)
+        rec = []
+        for t in range(10):
+            a = torch.randn(1, 6, device=DEV, generator=g).expand(n, 6).contiguous()
+            u = torch.rand(1, 13, device=DEV, generator=g).expand(n, 13).contiguous()
+            obs, rew, term, trunc = st.step(a, rand=u)
+            assert torch.equal(obs, obs[:1].expand_as(obs)) and torch.equal(rew, rew[:1].expand_as(rew))
+            s = st.stats.clone()
+            assert s[19].item() == pytest.approx(rew.double().sum().item(), rel=1e-5, abs=1e-2)
+            assert s[20].item() == term.sum().item() and s[21].item() == trunc.sum().item()
+            if t == 5 and not term.any():
+                assert trunc.all() and torch.all(st.episode_length_buf == 0)      # 994 + 6 = 1000 = max_episode_length
+            rec.append((obs.clone(), rew.clone()))
+        outs.append(rec)
+        if rep == 1:
+            for (o0, r0), (o1, r1) in zip(outs[0], outs[1]):
+                assert torch.equal(o0, o1) and torch.equal(r0, r1)
+            for t in range(40):
+                obs, rew, term, trunc = st.step(torch.randn(n, 6, device=DEV, generator=g) * 2.0)
+                assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
+            assert torch.isfinite(st.state.buf).all()
+        st.close()
+
+
+def test_register_budget_follows_the_wave_count():
+    """The library picks 3 CTAs/SM exactly when that needs fewer waves than 2 CTAs/SM; both instantiations compute the
+    same step to round-off (one step from identical states at 49152 envs, the size where the choice matters most)."""
+    from zbot_lab_b200.utils import synthetic as syn
+    n = 49152
+    rng = np.random.default_rng(2)
+    s0 = {k: _t(v) for k, v in syn.synth_sim_state(rng, n).items()}
+    a = _t(rng.normal(0, 0.5, (n, 6)).astype(np.float32))
+    res = []
+    import os
+    for variant in (None, "u128x2"):
+        if variant:
+            os.environ["ZBOT_STEP_VARIANT"] = variant
+        try:
+            st = _stepper(n)
+        finally:
+            os.environ.pop("ZBOT_STEP_VARIANT", None)
+        st.reset_idx(None)
+        st.set_sim_state(s0)
+        st.episode_length_buf[:] = 100
+        obs, rew, term, trunc = st.step(a)
+        res.append((obs.clone(), term.clone(), trunc.clone()))
+        st.close()
+    same = res[0][1] == res[1][1]
+    assert float(same.float().mean()) >= 0.995 and torch.equal(res[0][2], res[1][2])
+    d = (res[0][0][same] - res[1][0][same]).abs()
+    assert float(d[:, :10].max()) <= 2e-4 and float(d[:, 10:16].max()) <= 2e-2

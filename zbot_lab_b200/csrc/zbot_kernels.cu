@@ -1214,15 +1214,21 @@ int zbot_create(const ZbotCfg* cfg, int device, ZbotHandle** out) {
     if (sv && sv[0] == 'p' && sscanf(sv + 1, "%dx%d", &vt, &vc) == 2) h->variant = find_variant(1000 + vt, vc);
     else if (sv && sv[0] == 'u' && sscanf(sv + 1, "%dx%d", &vt, &vc) == 2) h->variant = find_variant(2000 + vt, vc);
     else if (sv && sscanf(sv, "%dx%d", &vt, &vc) == 2) h->variant = find_variant(vt, vc);
-    // default: 2 CTAs/SM (197 registers) up to 75776 envs, 3 CTAs/SM (168) above; the sweeps unrolled by two as soon as a
+    // default register budget: by wave count, below; the sweeps unrolled by two as soon as a
     // scheduler holds more than one warp (N > 148 * 4 * 32), measured -2.3 us at 32768, -3.3 us at 65536 envs
     // programmatic dependent launch: the statistics kernel and the next step kernel are scheduled while their predecessor
     // drains (34.9 -> 30.9 us per step at 4096 envs, 80.0 -> 76.7 at 65536); ZBOT_PDL=0 restores plain launches
     { const char* sp = getenv("ZBOT_PDL"); h->pdl = sp ? (atoi(sp) != 0) : true; }
     h->unroll2 = cfg->num_envs > 4 * 32 * h->num_sms;
     if (const char* su = getenv("ZBOT_SWEEP_UNROLL")) h->unroll2 = (atoi(su) == 2);   // test / tuning override, all tasks
-    if (h->variant < 0)
-      h->variant = find_variant((h->unroll2 ? 2000 : 0) + 128, (cfg->num_envs > 2 * 2 * 148 * 128) ? 3 : 2);
+    if (h->variant < 0) {
+      // 3 CTAs/SM (168 registers, 8 B spill) exactly when it needs FEWER waves than 2 CTAs/SM (208-218 registers, no spill):
+      // 49152 envs = one wave of three (59.4 us) against two waves of two (83.9 us); 65536 envs = two waves either way
+      // (80.0 us with two, 90.4 us with three); 131072 envs = three waves against four (143 us vs 154 us)
+      const int cap2 = 2 * h->num_sms * 128, cap3 = 3 * h->num_sms * 128;
+      const int w2 = (cfg->num_envs + cap2 - 1) / cap2, w3 = (cfg->num_envs + cap3 - 1) / cap3;
+      h->variant = find_variant((h->unroll2 ? 2000 : 0) + 128, (w3 < w2) ? 3 : 2);
+    }
     const char* mt = getenv("ZBOT_MDP_TILE");          // envs (= threads) per CTA of the MDP-only step kernel
     h->mdp_tile = mt ? atoi(mt) : kMdpTile;
     if (h->mdp_tile != 32 && h->mdp_tile != 64 && h->mdp_tile != 128) h->mdp_tile = kMdpTile;
