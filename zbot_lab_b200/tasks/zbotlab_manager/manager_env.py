@@ -18,7 +18,6 @@ import math
 import torch
 
 from ... import native
-from ...assets import zbot_6s_v2 as V
 from ...stepper import NativeStepper
 from ..zbot6b_direct.walking_v2 import ZbotDirectEnvV2, _Box, _Terrain
 from .env_cfg import Zbot6BFlatEnvCfg
