@@ -925,7 +925,7 @@ ZB_PRAGMA_UNROLL(ZB_UNROLL_PTS)
   }
   } else {
 #if defined(__CUDACC__)
-#pragma unroll 1
+ZB_PRAGMA_UNROLL(ZB_UNROLL_BWD)
 #endif
   for (int k = 6; k >= 0; --k) {
     if (k == 0) {   // root: exact kinematics from the state (no unwinding round-off)
@@ -940,7 +940,7 @@ ZB_PRAGMA_UNROLL(ZB_UNROLL_PTS)
     contact_agg_zero(agg);
     const int npts = Model::npts(k);
 #if defined(__CUDACC__)
-#pragma unroll 1
+ZB_PRAGMA_UNROLL(ZB_UNROLL_PTS)
 #endif
     for (int j = 0; j < npts; ++j) {
       T lx, ly, lz, drop;

@@ -9,6 +9,9 @@
 // The operators below use the round-to-nearest pair intrinsics; ptxas contracts a * b + c into one FFMA2 (checked in
 // SASS).  On the host (CPU port, tests) F2 is two plain floats with the same per-lane semantics.
 #pragma once
+#ifndef ZB_PACKED_UNROLL
+#define ZB_PACKED_UNROLL 1   // sweep unroll factor of the packed (two envs per thread) instantiation; tuning builds override
+#endif
 #include "zbot_core.h"
 
 namespace zbot {
@@ -92,7 +95,7 @@ ZB_HD void env_step_physics2(const Params<float>& P, EnvState<float>& ea, EnvSta
 #pragma unroll 1
 #endif
   for (int sub = 0; sub < P.decimation; ++sub) {
-    physics_substep<Model, false>(P, s, target, so, scr, (F2*)nullptr);   // plain sweep: the pipelined one needs 2 x 27 more registers
+    physics_substep<Model, false, ZB_PACKED_UNROLL>(P, s, target, so, scr, (F2*)nullptr);   // plain sweep: the pipelined one needs 2 x 27 more registers
     const int slot = P.decimation - 1 - sub;   // newest first
     ZB_UNROLL for (int l = 0; l < 2; ++l) {
       EnvState<float>& e = l ? eb : ea;
