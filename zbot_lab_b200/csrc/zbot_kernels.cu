@@ -466,6 +466,11 @@ template <int kMaxThreads, int kMinBlocks>
 __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) zbot_step_u2_kernel(ZB_STEP_ARGS) {
   zbot_step_body<false, 2>(ZB_STEP_CALL);
 }
+// unrolled sweeps under a direct register cap (single-wave experiments: 14 warps/SM hold 65536 envs at <= 146 registers)
+template <int kMaxRegs>
+__global__ void __maxnreg__(kMaxRegs) zbot_step_u2_kernel_r(ZB_STEP_ARGS) {
+  zbot_step_body<false, 2>(ZB_STEP_CALL);
+}
 // same body, register cap given directly (ptxas snaps __launch_bounds__ caps to a few occupancy steps:
 // 197 -> 168 -> 128; __maxnreg__ gives the steps in between)
 template <int kMaxRegs>
@@ -1107,6 +1112,7 @@ const StepVariant kStepVariants[] = {
     {32, 16, zbot_step_kernel<false, 32, 16>, 1},
     // chain sweeps unrolled by two: "u128x2" / "u128x3"
     {2128, 2, zbot_step_u2_kernel<128, 2>, 1}, {2128, 3, zbot_step_u2_kernel<128, 3>, 1},
+    {2064, 7, zbot_step_u2_kernel_r<144>, 1}, {2032, 14, zbot_step_u2_kernel_r<144>, 1},   // "u64x7" / "u32x14": one wave at 65536 envs
     // EXPERIMENTAL, opt-in (ZBOT_STEP_VARIANT=p128x2): two envs per thread, packed FP32 (zbot_step2_kernel).  31 % fewer
     // warp instructions per env, but 255 registers + spills at 1.7 warps per sub-partition: 84.0 vs 86.4 us at 65536 envs,
     // 59 vs 35 us at 4096 (profiles/r1_notes.md).
