@@ -184,7 +184,9 @@ def test_step_host_zero_copy_equals_device_step(n):
     b_env, _ = _make(n, check_all_envs_reset=False)
     b_env.episode_length_buf = a_env.episode_length_buf.clone()
     g = torch.Generator().manual_seed(4)
-    _, h_out = b_env.alloc_host_buffers()
+    # the rows live inside a larger pinned buffer with canaries on both sides (ragged tail CTA, 25-word rows)
+    big = torch.full((n * 25 + 128,), -7.0).pin_memory()
+    h_out = big[64:64 + n * 25].view(n, 25)
     for t in range(25):
         h_act = torch.randn(n, 6, generator=g).pin_memory()
         obs_h, rew_h, term_h, trunc_h = b_env.step_host(h_act, h_out)
@@ -192,6 +194,8 @@ def test_step_host_zero_copy_equals_device_step(n):
         assert torch.equal(obs["policy"].cpu(), obs_h) and torch.equal(rew.cpu(), rew_h)
         assert torch.equal(term.cpu(), term_h) and torch.equal(trunc.cpu(), trunc_h)
     assert torch.equal(a_env._stepper.state.buf, b_env._stepper.state.buf)
+    assert torch.all(big[:64] == -7.0) and torch.all(big[64 + n * 25:] == -7.0)
+    assert torch.equal(a_env._stepper.stats.cpu()[:22], b_env._stepper.stats.cpu()[:22])
     a_env.close()
     b_env.close()
 
