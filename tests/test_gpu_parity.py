@@ -1244,3 +1244,37 @@ def test_register_budget_follows_the_wave_count():
     assert float(same.float().mean()) >= 0.995 and torch.equal(res[0][2], res[1][2])
     d = (res[0][0][same] - res[1][0][same]).abs()
     assert float(d[:, :10].max()) <= 2e-4 and float(d[:, 10:16].max()) <= 2e-2
+
+
+def test_v4_full_size_properties_65536():
+    """zbot-6b-walking-v4 at 65536 envs (the unrolled instantiation): identical envs with identical uniforms stay identical,
+    statistics equal torch reductions, time-out at step 999, two runs bit-identical, finite state under random actions."""
+    n = 65536
+    outs = []
+    for rep in range(2):
+        st = _v4_stepper(n, np.random.default_rng(1), rng_seed=5)
+        for k in ("carry_feet_fz", "carry_mid_max", "base_pos_y_err_sum"):
+            st.state.set(k, st.state.get(k)[:1].expand(n, -1).contiguous())
+        st.episode_length_buf[:] = 993
+        g = torch.Generator(device=DEV).manual_seed(99)
+        rec = []
+        for t in range(10):
+            a = torch.randn(1, 6, device=DEV, generator=g).expand(n, 6).contiguous()
+            u = torch.rand(1, 10, device=DEV, generator=g).expand(n, 10).contiguous()
+            obs, rew, term, trunc = st.step(a, rand=u)
+            assert torch.equal(obs, obs[:1].expand_as(obs)) and torch.equal(rew, rew[:1].expand_as(rew))
+            s = st.stats.clone()
+            assert s[19].item() == pytest.approx(rew.double().sum().item(), rel=1e-5, abs=1e-2)
+            assert s[20].item() == term.sum().item() and s[21].item() == trunc.sum().item()
+            if t == 5 and not term.any():
+                assert trunc.all() and torch.all(st.episode_length_buf == 0)      # 993 + 6 = 999 (…env_v4.py:868-870)
+            rec.append((obs.clone(), rew.clone()))
+        outs.append(rec)
+        if rep == 1:
+            for (o0, r0), (o1, r1) in zip(outs[0], outs[1]):
+                assert torch.equal(o0, o1) and torch.equal(r0, r1)
+            for t in range(40):
+                obs, rew, term, trunc = st.step(torch.randn(n, 6, device=DEV, generator=g))
+                assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
+            assert torch.isfinite(st.state.buf).all()
+        st.close()
