@@ -918,8 +918,13 @@ def test_unrolled_chain_sweeps_agree_with_the_rolled_kernel(monkeypatch, task):
     rng = np.random.default_rng(21)
     a = rng.normal(0, 0.7, (4, n, 6)).astype(np.float32)
     res = []
-    for unroll in ("1", "2"):
+    # rolled; unrolled with 2 CTAs/SM; unrolled with 3 CTAs/SM (168 registers: the instantiation the wave rule picks e.g. at
+    # 49152 or 131072 envs; for the walking task that is ZBOT_STEP_VARIANT=u128x3)
+    for unroll, ctas3 in (("1", "0"), ("2", "0"), ("2", "1")):
         monkeypatch.setenv("ZBOT_SWEEP_UNROLL", unroll)
+        monkeypatch.setenv("ZBOT_CTAS3", ctas3)
+        if task == "walk" and ctas3 == "1":
+            monkeypatch.setenv("ZBOT_STEP_VARIANT", "u128x3")
         r = np.random.default_rng(5)
         if task == "walk":
             st = _stepper(n)
@@ -942,10 +947,11 @@ def test_unrolled_chain_sweeps_agree_with_the_rolled_kernel(monkeypatch, task):
                 st.episode_length_buf.copy_(res[0][t][5])
         res.append(outs)
         st.close()
+    monkeypatch.delenv("ZBOT_STEP_VARIANT", raising=False)
     worst = 0.0
-    for t in range(4):
+    for t, other in [(t, other) for other in (1, 2) for t in range(4)]:
         o0, r0, te0, tr0, s0, ep0 = res[0][t]
-        o1, r1, te1, tr1, s1, ep1 = res[1][t]
+        o1, r1, te1, tr1, s1, ep1 = res[other][t]
         same = te0 == te1
         assert torch.equal(tr0, tr1) and float(same.float().mean()) >= 0.995
         assert torch.equal(ep0[same], ep1[same])

@@ -483,8 +483,8 @@ __global__ void __maxnreg__(kMaxRegs) zbot_step_kernel_r(ZB_STEP_ARGS) {
 // ---------------------------------------------------------------------------------------------
 constexpr int kSnakeExportWords = (int)(sizeof(SnakeExport<float>) / sizeof(float));   // 41
 
-template <bool kExport, int kUnroll = 1>
-__global__ void __launch_bounds__(128, 2)
+template <bool kExport, int kUnroll = 1, int kMinBlocks = 2>
+__global__ void __launch_bounds__(128, kMinBlocks)
 zbot_snake_step_kernel(const __grid_constant__ Params<float> P, const __grid_constant__ DefaultPose dp,
                        float4* __restrict__ state, int64_t* __restrict__ ep_len_buf, const float* __restrict__ actions,
                        float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ terminated,
@@ -578,8 +578,8 @@ zbot_snake_step_kernel(const __grid_constant__ Params<float> P, const __grid_con
 // ---------------------------------------------------------------------------------------------
 static_assert(sizeof(V4Export<float>) / sizeof(float) == ZBOT_V4_EXPORT_WORDS, "V4Export layout");
 
-template <bool kExport, int kUnroll = 1>
-__global__ void __launch_bounds__(128, 2)
+template <bool kExport, int kUnroll = 1, int kMinBlocks = 2>
+__global__ void __launch_bounds__(128, kMinBlocks)
 zbot_v4_step_kernel(const __grid_constant__ Params<float> P, float4* __restrict__ state, int64_t* __restrict__ ep_len_buf,
                     const float* __restrict__ actions, const float* __restrict__ rand, uint64_t seed, uint64_t call,
                     float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ terminated,
@@ -675,8 +675,8 @@ zbot_v4_step_kernel(const __grid_constant__ Params<float> P, float4* __restrict_
 static_assert(sizeof(MExport<float>) / sizeof(float) == ZBOT_M_EXPORT_WORDS && M_EXPORT_WORDS == ZBOT_M_EXPORT_WORDS, "MExport layout");
 static_assert(M_NUM_OBS == ZBOT_M_NUM_OBS && M_NUM_RAND == ZBOT_M_NUM_RAND, "manager task widths");
 
-template <bool kExport, int kUnroll = 1>
-__global__ void __launch_bounds__(128, 2)
+template <bool kExport, int kUnroll = 1, int kMinBlocks = 2>
+__global__ void __launch_bounds__(128, kMinBlocks)
 zbot_m_step_kernel(const __grid_constant__ Params<float> P, float4* __restrict__ state, int64_t* __restrict__ ep_len_buf,
                    const float* __restrict__ actions, const float* __restrict__ rand, uint64_t seed, uint64_t call,
                    float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ terminated,
@@ -1077,6 +1077,7 @@ struct ZbotHandle {
   int num_sms;
   bool unroll2;    // chain sweeps unrolled by two (more than one warp per scheduler)
   bool pdl;        // launch the step / statistics kernels with programmatic stream serialization
+  bool ctas3;      // 3 CTAs/SM need fewer waves than 2 at this N (the register-budget rule of zbot_create)
   float4* state;
   int64_t* ep_len;
   float* ring;
@@ -1210,6 +1211,9 @@ int zbot_create(const ZbotCfg* cfg, int device, ZbotHandle** out) {
   ZB_CUDA(cudaFuncSetAttribute(zbot_m_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
   ZB_CUDA(cudaFuncSetAttribute(zbot_m_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
   ZB_CUDA(cudaFuncSetAttribute(zbot_m_step_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
+  ZB_CUDA(cudaFuncSetAttribute(zbot_snake_step_kernel<false, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
+  ZB_CUDA(cudaFuncSetAttribute(zbot_v4_step_kernel<false, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
+  ZB_CUDA(cudaFuncSetAttribute(zbot_m_step_kernel<false, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
   {
     // register-budget variant of the step kernel = resident 128-thread CTAs per SM it is compiled for.
     // Measured (profiles/r1_notes.md): 2 CTAs/SM (197 regs, no spill) is fastest while the grid fits two
@@ -1234,6 +1238,11 @@ int zbot_create(const ZbotCfg* cfg, int device, ZbotHandle** out) {
       const int cap2 = 2 * h->num_sms * 128, cap3 = 3 * h->num_sms * 128;
       const int w2 = (cfg->num_envs + cap2 - 1) / cap2, w3 = (cfg->num_envs + cap3 - 1) / cap3;
       h->variant = find_variant((h->unroll2 ? 2000 : 0) + 128, (w3 < w2) ? 3 : 2);
+    }
+    {
+      const int cap2 = 2 * h->num_sms * 128, cap3 = 3 * h->num_sms * 128;
+      h->ctas3 = (cfg->num_envs + cap3 - 1) / cap3 < (cfg->num_envs + cap2 - 1) / cap2;
+      if (const char* sc3 = getenv("ZBOT_CTAS3")) h->ctas3 = (atoi(sc3) != 0);   // tuning override (snake / v4 / manager kernels)
     }
     const char* mt = getenv("ZBOT_MDP_TILE");          // envs (= threads) per CTA of the MDP-only step kernel
     h->mdp_tile = mt ? atoi(mt) : kMdpTile;
@@ -1287,6 +1296,9 @@ static int step_impl(ZbotHandle* h, const float* actions, float* obs, float* rew
     if (snake_export)
       ZB_CUDA_LAUNCH(zbot_snake_step_kernel<true>, h->P, h->dp, h->state, h->ep_len, actions, obs, rew, terminated,
                                                          truncated, n, sc, snake_export);
+    else if (h->unroll2 && h->ctas3)   // more than one warp per scheduler: sweeps unrolled by two (see zbot_create)
+      ZB_CUDA_LAUNCH((zbot_snake_step_kernel<false, 2, 3>), h->P, h->dp, h->state, h->ep_len, actions, obs, rew,
+                                                             terminated, truncated, n, sc, nullptr);
     else if (h->unroll2)   // more than one warp per scheduler: sweeps unrolled by two (see zbot_create)
       ZB_CUDA_LAUNCH((zbot_snake_step_kernel<false, 2>), h->P, h->dp, h->state, h->ep_len, actions, obs, rew,
                                                              terminated, truncated, n, sc, nullptr);
@@ -1401,6 +1413,9 @@ static int v4_step_impl(ZbotHandle* h, const float* actions, const float* rand, 
   if (export_buf)
     ZB_CUDA_LAUNCH(zbot_v4_step_kernel<true>, h->P, h->state, h->ep_len, actions, rand, h->cfg.rng_seed, call, obs, rew,
                                                     terminated, truncated, n, sc, export_buf);
+  else if (h->unroll2 && h->ctas3)
+    ZB_CUDA_LAUNCH((zbot_v4_step_kernel<false, 2, 3>), h->P, h->state, h->ep_len, actions, rand, h->cfg.rng_seed, call, obs,
+                                                        rew, terminated, truncated, n, sc, nullptr);
   else if (h->unroll2)
     ZB_CUDA_LAUNCH((zbot_v4_step_kernel<false, 2>), h->P, h->state, h->ep_len, actions, rand, h->cfg.rng_seed, call, obs,
                                                         rew, terminated, truncated, n, sc, nullptr);
@@ -1445,6 +1460,9 @@ static int m_step_impl(ZbotHandle* h, const float* actions, const float* rand, f
   if (export_buf)
     ZB_CUDA_LAUNCH(zbot_m_step_kernel<true>, h->P, h->state, h->ep_len, actions, rand, h->cfg.rng_seed, call, obs, rew,
                                                    terminated, truncated, n, sc, export_buf);
+  else if (h->unroll2 && h->ctas3)
+    ZB_CUDA_LAUNCH((zbot_m_step_kernel<false, 2, 3>), h->P, h->state, h->ep_len, actions, rand, h->cfg.rng_seed, call, obs,
+                                                       rew, terminated, truncated, n, sc, nullptr);
   else if (h->unroll2)
     ZB_CUDA_LAUNCH((zbot_m_step_kernel<false, 2>), h->P, h->state, h->ep_len, actions, rand, h->cfg.rng_seed, call, obs,
                                                        rew, terminated, truncated, n, sc, nullptr);
