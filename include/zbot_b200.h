@@ -165,8 +165,10 @@ typedef struct ZbotCfg {
 
 typedef struct ZbotHandle ZbotHandle;
 
-/* Library / build identification; usable without a GPU. */
+/* Library / build identification; usable without a GPU.  zbot_cfg_sizeof() = sizeof(ZbotCfg) as the library was compiled: a
+ * binding checks it against its own mirror of the struct before the first call. */
 int zbot_abi_version(void);
+int zbot_cfg_sizeof(void);
 const char* zbot_build_info(void);
 const char* zbot_last_error(void);
 /* Fill `cfg` with the zbot-6b-walking-v2 defaults (13 active terms, …env_v2.py:190-206). */

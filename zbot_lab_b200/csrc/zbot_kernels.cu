@@ -1159,6 +1159,7 @@ int check_slot(int slot, int prev, int slots) {
 extern "C" {
 
 int zbot_abi_version(void) { return ZBOT_ABI_VERSION; }
+int zbot_cfg_sizeof(void) { return (int)sizeof(ZbotCfg); }
 const char* zbot_build_info(void) { return "zbot_b200 sm_100a, nvcc " __DATE__ " " __TIME__; }
 const char* zbot_last_error(void) { return g_err; }
 

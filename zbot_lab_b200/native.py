@@ -181,6 +181,7 @@ def _declare(lib):
     vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
     P = C.POINTER
     lib.zbot_abi_version.restype = C.c_int
+    lib.zbot_cfg_sizeof.restype = C.c_int
     lib.zbot_build_info.restype = C.c_char_p
     lib.zbot_last_error.restype = C.c_char_p
     lib.zbot_default_cfg.argtypes = [P(ZbotCfg), i32]
@@ -215,7 +216,7 @@ def _declare(lib):
 
 
 EXPORTED_SYMBOLS = (
-    "zbot_abi_version", "zbot_build_info", "zbot_last_error", "zbot_default_cfg", "zbot_state_word",
+    "zbot_abi_version", "zbot_cfg_sizeof", "zbot_build_info", "zbot_last_error", "zbot_default_cfg", "zbot_state_word",
     "zbot_mdp_state_word", "zbot_create", "zbot_destroy", "zbot_bind", "zbot_step", "zbot_step_export",
     "zbot_snake_step_export", "zbot_step_host", "zbot_v4_step", "zbot_v4_step_export", "zbot_m_step", "zbot_m_step_export",
     "zbot_update_cfg", "zbot_reset_idx", "zbot_observe", "zbot_articulation_view", "zbot_mdp_bind", "zbot_mdp_observe",
@@ -236,6 +237,9 @@ def lib():
         _declare(_LIB)
         if _LIB.zbot_abi_version() != ZBOT_ABI_VERSION:
             raise RuntimeError("libzbot_b200.so ABI version mismatch; rebuild")
+        if _LIB.zbot_cfg_sizeof() != C.sizeof(ZbotCfg):
+            raise RuntimeError(f"libzbot_b200.so was built with sizeof(ZbotCfg) = {_LIB.zbot_cfg_sizeof()}, the binding has "
+                               f"{C.sizeof(ZbotCfg)}: stale library, rebuild")
     return _LIB
 
 
