@@ -31,7 +31,7 @@ UNIT = "env-steps/s"
 # written (2 x 320), actions 24 read, obs 92 + reward 4 + flags 2 written, episode counter 8 + 8
 ALGO_BYTES_PER_ENV_STEP = 320 + 24 + 8 + 320 + 92 + 4 + 2 + 8
 # dram__bytes_read.sum + dram__bytes_write.sum of one zbot_step_kernel launch at 65536 envs (ncu --set full,
-# profiles/r1_ncu_raw_tables_session2.md: 23.14 MB read + 0 written) per env: reads hit DRAM, most writes are still in the 126 MB L2 when the kernel ends
+# profiles/r1_ncu_raw_tables_session3.md: 23.16 MB read + 0 written) per env: reads hit DRAM, most writes are still in the 126 MB L2 when the kernel ends
 NCU_TRAFFIC_BYTES_PER_ENV_STEP = 353
 # Warp instructions one launch of the throughput instantiation executes per ENV (smsp__inst_executed.sum / envs at 65536 envs,
 # profiles/r1_ncu_raw_tables_session3.md: 46.14 M per launch = 22.5 k per warp of 32 envs) and the measured issue
@@ -441,7 +441,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": NCU_TRAFFIC_BYTES_PER_ENV_STEP * n_envs, "peak_source": peak_src,
                          "kernel": "zbot_step_u2_kernel<128,2>" if n_envs > 148 * 128 else "zbot_step_kernel<false,128,2>",
-                         "traffic_note": "dram__bytes_read+write per launch at 65536 envs (profiles/r1_ncu_raw_tables_session2.md), scaled per env",
+                         "traffic_note": "dram__bytes_read+write per launch at 65536 envs (profiles/r1_ncu_raw_tables_session3.md: 23.16 MB read + 0 written), scaled per env",
                          "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP,
                          "note": "the fused step is FP32-issue bound, not HBM bound (DESIGN.md §4); see fp32_issue"},
             # the bound that actually applies (not an HBM / tensor roofline, hence a separate object): warp instructions
