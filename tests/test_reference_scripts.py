@@ -138,3 +138,27 @@ def test_manager_env_surface_on_cpu_double(shimmed, monkeypatch):
     assert "Episode_Termination/feet_close" not in ex["log"] and "Episode_Reward/track_lin_vel_xy_exp" in ex["log"]
     assert int(env.episode_length_buf.max()) == 0 and float(obs2["policy"][:, 19:].abs().max()) == 0
     assert env.command.shape == (8, 3)
+
+
+def test_reference_play_py_runs_unchanged_on_the_manager_task(shimmed, monkeypatch):
+    """train one iteration of ``zbot-6b-walking-m-v0`` -> the reference's own play.py with the PLAY id loads the checkpoint,
+    exports the 25-input policy and steps the 64-env PLAY cfg (no observation corruption, commands from the limit ranges)."""
+    import zbot_lab_b200.tasks.zbotlab_manager.manager_env as me
+    from fake_stepper import FakeMStepper
+    monkeypatch.setattr(me, "NativeStepper", FakeMStepper)
+    monkeypatch.setattr(sys, "argv", ["train.py", "--task", "zbot-6b-walking-m-v0", "--num_envs", "8",
+                                      "--max_iterations", "1", "--headless", "--device", "cpu",
+                                      "agent.num_steps_per_env=4", "agent.device=cpu"])
+    runpy.run_path(os.path.join(REF_SCRIPTS, "train.py"), run_name="__main__")
+    for m in [k for k in sys.modules if k.split(".")[0] in ("cli_args",)]:
+        monkeypatch.delitem(sys.modules, m)
+    monkeypatch.setenv("ZBOT_PLAY_STEPS", "5")
+    monkeypatch.setattr(sys, "argv", ["play.py", "--task", "zbot-6b-walking-m-play-v0", "--num_envs", "4", "--headless",
+                                      "--device", "cpu", "agent.device=cpu"])
+    runpy.run_path(os.path.join(REF_SCRIPTS, "play.py"), run_name="__main__")
+    root = shimmed / "logs" / "rsl_rl" / "zbot_6b_flat_mana_v1"
+    run = root / os.listdir(root)[0]
+    assert (run / "exported" / "policy.pt").exists()
+    import torch
+    pol = torch.jit.load(str(run / "exported" / "policy.pt"))
+    assert pol(torch.zeros(3, 25)).shape == (3, 6)
