@@ -51,7 +51,7 @@ def parse():
     p.add_argument("--gpus", type=int, default=1)
     p.add_argument("--steps", type=int, default=200)
     p.add_argument("--warmup", type=int, default=20)
-    p.add_argument("--envs", type=int, default=None, help="envs per GPU (default 4096 at N=1, 65536 at N>1)")
+    p.add_argument("--envs", type=int, default=None, help="envs per GPU (default 65536 at every N)")
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--no-flush", action="store_true", help="back-to-back steps (state stays in L2)")
     p.add_argument("--no-cpu-baseline", action="store_true")
