@@ -303,6 +303,27 @@ def main():
             if world > 1:
                 dist.all_reduce(ts, op=dist.ReduceOp.MAX)
             e2e["staged_copies_value"] = world * n_envs * steps / float(ts.item())
+            # context only (NOT the headline): a device-resident consumer, as in the reference's own RL loop where the policy
+            # lives on the GPU -- pinned host actions -> device every step, env.step, and a device -> host read of ONE scalar
+            # (the step's reward sum from the statistics slot); shows how much of `value` -> `e2e` is the 100 B/env of results
+            # crossing PCIe
+            def e2e_metric_only(i):
+                d_act.copy_(h_act[i % 4], non_blocking=True)
+                env.step(d_act)
+                return float(st.stats[19].item())
+            for i in range(3):
+                e2e_metric_only(i)
+            barrier()
+            t0 = time.perf_counter()
+            for i in range(steps):
+                e2e_metric_only(i)
+            barrier()
+            tm = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            e2e["metric_only_value"] = world * n_envs * steps / float(tm.item())
+            e2e["metric_only_note"] = ("context: H2D of the actions + env.step + D2H of one scalar per step (device-resident "
+                                       "observations, as with a GPU policy); h2d %d B, d2h 4 B per step" % (n_envs * 24))
 
 
         env.close()
