@@ -426,3 +426,69 @@ def test_m_model_known_answers_and_independent_dynamics():
         if i < 10:
             assert np.abs(sim - ref).max() < 1e-9 and np.abs(f[:, [0, 6]] - o.body_force[:, [0, 6]]).max() < 1e-7
     assert np.abs(sim - ref).max() < 1e-5
+
+
+def test_model_constants_match_the_references_usd_files():
+    """Build container only: the constants embedded in assets/zbot_6s.py / zbot_6s_v2.py against the reference's binary USD
+    crates, decoded with tools/usdc_dump.py -- link masses / CoMs / principal inertias, link placements, joint frames and axes,
+    articulation roots (zbot_6s_new.usd: SURVEY App. A; zbot_6s_v09.usd: the manager-task robot)."""
+    import os
+    import sys
+    ref = "/root/reference/source/zbot/zbot/assets/zbot_assets"
+    if not os.path.isfile(os.path.join(ref, "zbot_6s_v09.usd")):
+        pytest.skip("/root/reference is not present (GPU box)")
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import usdc_dump as U
+    from zbot_lab_b200.assets import zbot_6s as Z
+    from zbot_lab_b200.assets import zbot_6s_v2 as V
+
+    def load(name):
+        c = U.Crate(os.path.join(ref, name))
+        specs = {p: fs for p, fs, st in c.specs}
+        return c, (lambda path, field="default": c.value(c.spec_fields(specs[path])[field]))
+
+    # ---- zbot_6s_new.usd (walking robot)
+    c, val = load("zbot_6s_new.usd")
+    assert "PhysicsArticulationRootAPI" in val("/zbot/foot_0", "apiSchemas")["explicit"]
+    for k, name in enumerate(Z.LINK_NAMES):
+        assert np.allclose(val(f"/zbot/{name}.xformOp:translate"), (0, 0, Z.LINK_SPACING * k), atol=1e-6)
+        assert abs(val(f"/zbot/{name}.physics:mass") - Z.LINK_MASS) < 1e-6
+        com, diag, axes = (Z.A_COM, Z.A_DIAG_INERTIA, Z.A_PRINCIPAL_AXES) if name in Z.A_TYPE_LINKS else (Z.B_COM, Z.B_DIAG_INERTIA, Z.B_PRINCIPAL_AXES)
+        assert np.allclose(val(f"/zbot/{name}.physics:centerOfMass"), com, atol=1e-7)
+        assert np.allclose(val(f"/zbot/{name}.physics:diagonalInertia"), diag, rtol=1e-5)
+        assert np.allclose(val(f"/zbot/{name}.physics:principalAxes"), axes, atol=1e-6)
+    parents = ("foot_0", "a2", "a3", "base", "a5", "a6")
+    for k, (par, sgn) in enumerate(zip(parents, Z.JOINT_AXIS_SIGN)):
+        j = f"/zbot/{par}/joint{k + 1}"
+        assert val(j + ".physics:axis") == "Z" and np.allclose(val(j + ".physics:localPos0"), (0, 0, 0.053), atol=1e-6)
+        axis = Z.quat_rotate(np.array(val(j + ".physics:localRot0"), float), np.array([0.0, 0, 1]))
+        assert np.allclose(axis, (sgn * Z.SIN45, 0, Z.SIN45), atol=1e-6)
+    # ---- zbot_6s_v09.usd (manager-task robot)
+    c, val = load("zbot_6s_v09.usd")
+    assert "PhysicsArticulationRootAPI" in val("/zbot/base", "apiSchemas")["explicit"]
+    usd_name = {n: n for n in V.LINK_NAMES}
+    for name in V.LINK_NAMES:
+        assert np.allclose(val(f"/zbot/{name}.xformOp:translate"), (0, V.LINK_Y[name], 0), atol=1e-6)
+        q = np.array(val(f"/zbot/{name}.xformOp:orient"), float)
+        want = np.array(V.BASE_LINK_QUAT) if name == "base" else np.array([1.0, 0, 0, 0])
+        assert np.allclose(q, want, atol=2e-6)
+        com, diag = (Z.A_COM, Z.A_DIAG_INERTIA) if name in V.A_TYPE_LINKS else (Z.B_COM, Z.B_DIAG_INERTIA)
+        assert np.allclose(val(f"/zbot/{name}.physics:centerOfMass"), com, atol=1e-7)
+        assert np.allclose(val(f"/zbot/{name}.physics:diagonalInertia"), diag, rtol=1e-5)
+        assert abs(val(f"/zbot/{name}.physics:mass") - Z.LINK_MASS) < 1e-6
+    # joints: position on the y axis, axis = joint-frame Y rotated by localRot1 (the child link frames are identity-oriented)
+    joint_parent = {"joint1": "base", "joint2": "a2", "joint3": "a3", "joint7": "a7", "joint8": "a8", "joint9": "a9"}
+    C = V.CHAIN_IN_WORLD
+    m = V.model_f32()
+    for k, jn in enumerate(V.CHAIN_JOINTS):
+        j = f"/zbot/{joint_parent[jn]}/{jn}"
+        assert val(j + ".physics:axis") == "Y"
+        child = val(j + ".physics:body1", "targetPaths")["explicit"][0].split("/")[-1]
+        assert abs(V.LINK_Y[child] - V.JOINT_Y[k]) < 1e-6 and np.allclose(val(j + ".physics:localPos1"), 0, atol=1e-7)
+        axis_w = Z.quat_rotate(np.array(val(j + ".physics:localRot1"), float), np.array([0.0, 1, 0]))   # in the child = world frame
+        axis_c = C.T @ axis_w
+        # the three joints below the base are traversed child -> parent by the chain: the axis vector flips, the angle does not
+        flip = -1.0 if jn in ("joint1", "joint2", "joint3") else 1.0
+        assert np.allclose(flip * axis_c, m.joint_axis[k], atol=1e-6), (jn, axis_c, m.joint_axis[k])
+        for lim in ("lowerLimit", "upperLimit"):
+            assert abs(abs(val(j + ".physics:" + lim)) - 360.0) < 1e-6
