@@ -492,3 +492,37 @@ def test_model_constants_match_the_references_usd_files():
         assert np.allclose(flip * axis_c, m.joint_axis[k], atol=1e-6), (jn, axis_c, m.joint_axis[k])
         for lim in ("lowerLimit", "upperLimit"):
             assert abs(abs(val(j + ".physics:" + lim)) - 360.0) < 1e-6
+
+
+def test_snake_model_constants_match_the_references_usd_file():
+    """Build container only: assets/zbot_d_6s.py (derived from the ASCII sibling zbot_6s_v04.usda) against the binary
+    zbot_6s_v03.usd the snake task actually names (assets/zbot_cfg.py:109-168): root a1, link placements and the link-frame
+    rotations that the per-body mass tables are rotated with, revolute frames, mass properties."""
+    import os
+    import sys
+    ref = "/root/reference/source/zbot/zbot/assets/zbot_assets"
+    if not os.path.isfile(os.path.join(ref, "zbot_6s_v03.usd")):
+        pytest.skip("/root/reference is not present (GPU box)")
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import usdc_dump as U
+    from zbot_lab_b200.assets import zbot_6s as Z
+    from zbot_lab_b200.assets import zbot_d_6s as S
+    c = U.Crate(os.path.join(ref, "zbot_6s_v03.usd"))
+    specs = {p: fs for p, fs, st in c.specs}
+    val = lambda path, field="default": c.value(c.spec_fields(specs[path])[field])
+    assert "PhysicsArticulationRootAPI" in val("/zbot/a1", "apiSchemas")["explicit"]
+    for name in S.LINK_NAMES:
+        k = int(name[1])
+        z = 0.106 * (k - 1) + (0.053 if name[0] == "b" else 0.0)
+        assert np.allclose(val(f"/zbot/{name}.xformOp:translate"), (0, 0, z), atol=1e-6), name
+        q, want = np.array(val(f"/zbot/{name}.xformOp:orient"), float), S._link_rot(name)
+        assert min(np.abs(q - want).max(), np.abs(q + want).max()) < 2e-6, (name, q, want)
+        com, diag = (Z.A_COM, Z.A_DIAG_INERTIA) if name[0] == "a" else (Z.B_COM, Z.B_DIAG_INERTIA)
+        assert np.allclose(val(f"/zbot/{name}.physics:centerOfMass"), com, atol=1e-7)
+        assert np.allclose(val(f"/zbot/{name}.physics:diagonalInertia"), diag, rtol=1e-5)
+        assert abs(val(f"/zbot/{name}.physics:mass") - Z.LINK_MASS) < 1e-6
+    for k in range(1, 7):
+        j = f"/zbot/a{k}/joint{k}"
+        assert val(j + ".physics:axis") == "Z" and np.allclose(val(j + ".physics:localPos0"), (0, 0, 0.053), atol=1e-6)
+        assert np.allclose(val(j + ".physics:localRot0"), (0.92388, 0, 0.38268, 0), atol=2e-6)
+        assert val(j + ".physics:body1", "targetPaths")["explicit"] == [f"/zbot/b{k}"]
