@@ -526,3 +526,46 @@ def test_snake_model_constants_match_the_references_usd_file():
         assert val(j + ".physics:axis") == "Z" and np.allclose(val(j + ".physics:localPos0"), (0, 0, 0.053), atol=1e-6)
         assert np.allclose(val(j + ".physics:localRot0"), (0.92388, 0, 0.38268, 0), atol=2e-6)
         assert val(j + ".physics:body1", "targetPaths")["explicit"] == [f"/zbot/b{k}"]
+
+
+def test_sole_geometry_matches_the_collision_meshes():
+    """Build container only: the foot soles of the contact model (flat disc, radius 0.05 m, at the link-frame offsets the
+    models use) against the flat faces of the reference's convex-hull collision meshes (`/zbot/<foot>/collisions.points`
+    transformed by the mesh xform): zbot_6s_new.usd foot_0 z = 0 / foot_1 z = +0.053, zbot_6s_v09.usd foot0 y = -0.053 /
+    foot1 y = +0.053."""
+    import os
+    import struct
+    import sys
+    ref = "/root/reference/source/zbot/zbot/assets/zbot_assets"
+    if not os.path.isfile(os.path.join(ref, "zbot_6s_v09.usd")):
+        pytest.skip("/root/reference is not present (GPU box)")
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import usdc_dump as U
+    from zbot_lab_b200.assets import zbot_6s as Z
+    from zbot_lab_b200.assets import zbot_6s_v2 as V
+
+    def flat_faces(fname, link):
+        c = U.Crate(os.path.join(ref, fname))
+        specs = {p: fs for p, fs, st in c.specs}
+        rep = c.spec_fields(specs[f"/zbot/{link}/collisions.points"])["default"]
+        off = rep & ((1 << 48) - 1)
+        (n,) = struct.unpack_from("<Q", c.d, off)
+        P = np.frombuffer(c.d, dtype="<f4", count=3 * n, offset=off + 8).reshape(n, 3).astype(np.float64)
+        q = c.value(c.spec_fields(specs[f"/zbot/{link}/collisions.xformOp:orient"])["default"])
+        Q = P @ Z.quat_to_mat(q).T
+        out = []
+        for ax in range(3):
+            for v in (Q[:, ax].min(), Q[:, ax].max()):
+                sel = np.abs(Q[:, ax] - v) < 1e-4
+                if sel.sum() > 50:
+                    pts = Q[sel]
+                    out.append((ax, float(v), float(np.linalg.norm(pts - pts.mean(0), axis=1).max())))
+        return out
+
+    for fname, link, ax, pos in (("zbot_6s_new.usd", "foot_0", 2, Z.FOOT0_SOLE_Z), ("zbot_6s_new.usd", "foot_1", 2, Z.FOOT1_SOLE_Z),
+                                 ("zbot_6s_v09.usd", "foot0", 1, V.SOLE_Y[0] - V.LINK_Y["foot0"]),
+                                 ("zbot_6s_v09.usd", "foot1", 1, V.SOLE_Y[1] - V.LINK_Y["foot1"])):
+        faces = flat_faces(fname, link)
+        assert len(faces) == 1, (fname, link, faces)                 # each half-module has exactly one flat circular end
+        a, v, r = faces[0]
+        assert a == ax and abs(v - pos) < 2e-4 and abs(r - Z.FOOT_DISC_RADIUS) < 1.5e-3, (fname, link, faces)
