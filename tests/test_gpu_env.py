@@ -328,6 +328,7 @@ def test_manager_env_registry_protocol_noise_friction_curriculum_and_ppo(tmp_pat
     # its weight widens lin_vel_x by 0.1 on both sides (clamped to limit_ranges)
     i = env._term_names.index("track_lin_vel_xy_exp")
     env.common_step_counter = 3 * env.max_episode_length
+    env._stepper.stats_ring[max(env._stepper._slot, 0), 16] = 3.0         # some envs reset in that step
     env._stepper.stats_ring[max(env._stepper._slot, 0), i] = 0.5          # below 80 % of the weight: nothing moves
     env._lin_vel_cmd_levels()
     assert tuple(cfg.commands.base_velocity.ranges.lin_vel_x) == (-0.1, 0.1)
@@ -336,6 +337,10 @@ def test_manager_env_registry_protocol_noise_friction_curriculum_and_ppo(tmp_pat
     env._lin_vel_cmd_levels()
     assert tuple(cfg.commands.base_velocity.ranges.lin_vel_x) == (-0.1, 0.1)
     env.common_step_counter = 4 * env.max_episode_length
+    env._stepper.stats_ring[max(env._stepper._slot, 0), 16] = 0.0         # nobody reset in that step: the term is not evaluated
+    env._lin_vel_cmd_levels()
+    assert tuple(cfg.commands.base_velocity.ranges.lin_vel_x) == (-0.1, 0.1)
+    env._stepper.stats_ring[max(env._stepper._slot, 0), 16] = 3.0
     env._lin_vel_cmd_levels()
     assert tuple(round(v, 6) for v in cfg.commands.base_velocity.ranges.lin_vel_x) == (-0.2, 0.2)
     assert abs(env._stepper.cfg.cmd_hi[0] - 0.2) < 1e-6 and abs(env._stepper.cfg.cmd_lo[0] + 0.2) < 1e-6

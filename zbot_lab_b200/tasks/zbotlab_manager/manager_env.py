@@ -221,7 +221,9 @@ class ManagerBasedRLEnv(ZbotDirectEnvV2):
         if "track_lin_vel_xy_exp" not in names:
             return
         i = names.index("track_lin_vel_xy_exp")
-        s = self._stepper.stats_ring[max(self._stepper._slot, 0)]
+        s = self._stepper.stats_ring[max(self._stepper._slot, 0)].cpu()       # one host read per max_episode_length steps
+        if float(s[native.STAT_NUM_RESET]) == 0:                 # CurriculumManager.compute runs inside _reset_idx: no reset, no update
+            return
         reward = float(s[i])                                     # mean episodic sum of the reset envs / episode seconds
         weight = self._reward_terms[i][2]
         if reward > weight * 0.8:
