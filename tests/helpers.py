@@ -128,7 +128,7 @@ def m_native_cfg(n, terms, P=M_PARAMS, **kw):
     slot = [(f, w, p) for _, f, w, p in terms if f != "is_terminated"]
     wt = [w for _, f, w, _ in terms if f == "is_terminated"]
     return native.make_m_cfg(n, slot, is_terminated_weight=wt[0] if wt else 0.0, minimum_height=P["minimum_height"],
-                             feet_close_min=P["feet_close_min"], cmd_ranges=P["cmd_ranges"],
+                             feet_close_min=kw.pop("feet_close_min", P["feet_close_min"]), cmd_ranges=P["cmd_ranges"],
                              rel_standing_envs=P["rel_standing_envs"], resampling_time_range=P["resampling_time_range"],
                              pose_range=P["pose_range"], act_clip=0.04 * np.pi, **kw)
 

@@ -1284,3 +1284,36 @@ def test_v4_full_size_properties_65536():
                 assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
             assert torch.isfinite(st.state.buf).all()
         st.close()
+
+
+def test_m_fused_step_50_step_horizon_vs_float64_host_build():
+    """Manager task, free-running 50-step horizon from identical states and uniforms: the sm_100a kernel (float32, fast
+    reciprocals) against the float64 host build of the same arithmetic (which equals the independent dense-Jacobian oracle to
+    1e-12 per substep, test_m_model_known_answers_and_independent_dynamics).  Stated tolerance for this softer drive (kp 20 /
+    kd 0.5): joint positions median <= 1e-4 rad, 90 % <= 2e-3, max <= 5e-2 over the envs neither side reset."""
+    from helpers import m_native_cfg
+    from oracle import cpu_port
+    from zbot_lab_b200 import native
+    from zbot_lab_b200.stepper import STATE_FIELDS
+    n = 256
+    rng = np.random.default_rng(11)
+    st = _m_stepper(n, rng, native.M_FLAT_TERMS, feet_close_min=0.0)
+    st.state.set("base_pos_y_err_sum", torch.full((n, 1), 100.0, device=DEV))              # no command resample in the horizon
+    cfg = m_native_cfg(n, native.M_FLAT_TERMS, feet_close_min=0.0)
+    pe = cpu_port.PortEnv(n, np.float64, cfg)
+    for k, w in STATE_FIELDS.items():
+        pe.field(k, w)[:] = st.state.get(k).cpu().numpy()
+    pe.ep_len[:] = st.episode_length_buf.cpu().numpy()
+    alive = np.ones(n, bool)
+    for t in range(50):
+        a = rng.normal(0, 0.3, (n, 6)).astype(np.float32)
+        rnd = rng.random((n, 13)).astype(np.float32)
+        obs, rew, term, trunc = st.step(_t(a), rand=_t(rnd))
+        _, _, t2, tr2, _, _ = pe.step(a, rnd=rnd)
+        alive &= ~(term.cpu().numpy().astype(bool) | trunc.cpu().numpy().astype(bool) | t2 | tr2)
+    dq = np.abs(st.state.get("joint_pos").cpu().numpy() - pe.field("joint_pos", 6))[alive]
+    dp = np.abs(st.state.get("root_pos").cpu().numpy() - pe.field("root_pos", 3))[alive]
+    assert alive.sum() > n // 2
+    assert np.median(dq) <= 1e-4 and np.quantile(dq, 0.9) <= 2e-3 and dq.max() <= 5e-2, (np.median(dq), np.quantile(dq, 0.9), dq.max())
+    assert np.median(dp) <= 1e-4 and dp.max() <= 2e-2, (np.median(dp), dp.max())
+    st.close()
