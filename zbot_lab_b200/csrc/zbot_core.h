@@ -705,10 +705,16 @@ ZB_HD T default_joint_pos(int k) { return ModelWalk::default_q<T>(k); }
 // on instruction fetch), so everything indexed by the joint lives in indexable storage:
 // shared memory on the GPU ([slot][thread], conflict-free), a plain array on the CPU.
 // ------------------------------------------------------------------------------------
-constexpr int SCR_PER_JOINT = 17;
-constexpr int SCR_WORDS = 6 * SCR_PER_JOINT;   // 102 words per environment
+// ZB_STORE_Q: the kinematics sweep parks each body's quaternion (4 words per joint) and the backward sweep reloads it
+// instead of unwinding the joint rotation from (sin, cos) (2 words): 16 instructions and one link of the dependent chain less
+// per joint, 12 words more scratch per thread.
+#ifndef ZB_STORE_Q
+#define ZB_STORE_Q 0
+#endif
+constexpr int SCR_PER_JOINT = ZB_STORE_Q ? 19 : 17;
+constexpr int SCR_WORDS = 6 * SCR_PER_JOINT;   // 102 (114) words per environment
 enum ScrSlot : int { SC_SA = 0, SC_SM = 3, SC_UT = 6, SC_UB = 9, SC_DINV = 12, SC_U = 13 /* tau, then u */,
-                     SC_SN = 14, SC_CS = 15, SC_QD = 16 };
+                     SC_SN = 14, SC_CS = 15, SC_QJ = 14 /* ZB_STORE_Q: body quaternion, 4 words */, SC_QD = ZB_STORE_Q ? 18 : 16 };
 
 template <typename T>
 struct ArrayScratch {
@@ -805,8 +811,8 @@ ZB_PRAGMA_UNROLL(ZB_UNROLL_FK)
       w[i] += a[i] * qd;
       vO[i] += m[i] * qd;
     }
-    scr(k, SC_SN) = sn;
-    scr(k, SC_CS) = cs;
+    if (ZB_STORE_Q) { ZB_UNROLL for (int i = 0; i < 4; ++i) scr(k, SC_QJ + i) = Q[i]; }      // body k, before joint k turns it
+    else { scr(k, SC_SN) = sn; scr(k, SC_CS) = cs; }
     quat_mul_joint(Q, cs, sg * sn, T(AXIS_S) * sn);
   }
   // ---- backward sweep over bodies 6..0: rigid + contact terms, then eliminate the joint above ----
@@ -849,17 +855,21 @@ ZB_PRAGMA_UNROLL(ZB_UNROLL_BWD)
     const T Sa[3] = {scr(j, SC_SA), scr(j, SC_SA + 1), scr(j, SC_SA + 2)};
     const T Sm[3] = {scr(j, SC_SM), scr(j, SC_SM + 1), scr(j, SC_SM + 2)};
     const T qd = scr(j, SC_QD);
-    const T sn = scr(j, SC_SN), cs = scr(j, SC_CS);
     const T sa[3] = {Sa[0] * qd, Sa[1] * qd, Sa[2] * qd};
     const T sm[3] = {Sm[0] * qd, Sm[1] * qd, Sm[2] * qd};
     // ---- stream B: kinematics + rigid terms of body k-1 (independent of IA) ----
     T wn[3], vn[3], Qn[4], rn[3], Rn[9];
     {
-      const T sg = (j & 1) ? T(-AXIS_S) : T(AXIS_S);
-      ZB_UNROLL for (int i = 0; i < 4; ++i) Qn[i] = Q[i];
-      quat_mul_joint(Qn, cs, -sg * sn, -T(AXIS_S) * sn);   // Q_{k-1} = Q_k (x) conj(qj)
       const bool root = (j == 0);                          // root: exact kinematics from the state
-      ZB_UNROLL for (int i = 0; i < 4; ++i) Qn[i] = root ? s.Q[i] : Qn[i];
+      if (ZB_STORE_Q) {
+        ZB_UNROLL for (int i = 0; i < 4; ++i) Qn[i] = scr(j, SC_QJ + i);   // parked by the kinematics sweep (j == 0: s.Q itself)
+      } else {
+        const T sg = (j & 1) ? T(-AXIS_S) : T(AXIS_S);
+        const T sn = scr(j, SC_SN), cs = scr(j, SC_CS);
+        ZB_UNROLL for (int i = 0; i < 4; ++i) Qn[i] = Q[i];
+        quat_mul_joint(Qn, cs, -sg * sn, -T(AXIS_S) * sn);   // Q_{k-1} = Q_k (x) conj(qj)
+        ZB_UNROLL for (int i = 0; i < 4; ++i) Qn[i] = root ? s.Q[i] : Qn[i];
+      }
       quat_to_mat(Qn, Rn);
       const T jz = root ? T(JOINT_Z_FIRST) : T(JOINT_Z_REST);
       ZB_UNROLL for (int i = 0; i < 3; ++i) {
@@ -992,9 +1002,13 @@ ZB_PRAGMA_UNROLL(ZB_UNROLL_PTS)
     spi_rank1_sub(IA, Ut, Ub, Dinv);
     // unwind kinematics to body k-1
     ZB_UNROLL for (int i = 0; i < 3; ++i) { w[i] -= sa[i]; vO[i] -= sm[i]; }
-    const T sg = (j & 1) ? T(-AXIS_S) : T(AXIS_S);
-    const T sn = scr(j, SC_SN), cs = scr(j, SC_CS);
-    quat_mul_joint(Q, cs, -sg * sn, -T(AXIS_S) * sn);   // Q_{k-1} = Q_k (x) conj(qj)
+    if (ZB_STORE_Q) {
+      ZB_UNROLL for (int i = 0; i < 4; ++i) Q[i] = scr(j, SC_QJ + i);
+    } else {
+      const T sg = (j & 1) ? T(-AXIS_S) : T(AXIS_S);
+      const T sn = scr(j, SC_SN), cs = scr(j, SC_CS);
+      quat_mul_joint(Q, cs, -sg * sn, -T(AXIS_S) * sn);   // Q_{k-1} = Q_k (x) conj(qj)
+    }
     const T jz = (j == 0) ? T(JOINT_Z_FIRST) : T(JOINT_Z_REST);
     T Rp2[3] = {T(2) * (Q[1] * Q[3] + Q[0] * Q[2]), T(2) * (Q[2] * Q[3] - Q[0] * Q[1]),
                 T(1) - T(2) * (Q[1] * Q[1] + Q[2] * Q[2])};     // third column of R_{k-1}
