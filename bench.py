@@ -27,23 +27,57 @@ if ROOT not in sys.path:
 
 METRIC = "env-steps/sec zbot-6b-walking-v2 fused step"
 UNIT = "env-steps/s"
-# algorithmic HBM bytes per env-step of the fused kernel: state 20 float4 read +
-# written (2 x 320), actions 24 read, obs 92 + reward 4 + flags 2 written, episode counter 8 + 8
-ALGO_BYTES_PER_ENV_STEP = 320 + 24 + 8 + 320 + 92 + 4 + 2 + 8
-# dram__bytes_read.sum + dram__bytes_write.sum of one zbot_step_kernel launch at 65536 envs (ncu --set full,
-# profiles/r1_ncu_raw_tables_session3.md: 23.16 MB read + 0 written) per env: reads hit DRAM, most writes are still in the 126 MB L2 when the kernel ends
-NCU_TRAFFIC_BYTES_PER_ENV_STEP = 353
-# Warp instructions one launch of the throughput instantiation executes per ENV (smsp__inst_executed.sum / envs at 65536 envs,
-# profiles/r1_ncu_raw_tables_session3.md: 46.14 M per launch = 22.5 k per warp of 32 envs) and the measured issue
-# ceiling of one SM sub-partition at this kernel's occupancy (2 warps: 0.73 instructions / clock; tools/micro/ffma2_probe.cu)
-WARP_INSTRUCTIONS_PER_32_ENVS = 46.14e6 / (65536 / 32)
-ISSUE_CEILING_INST_PER_CLK_PER_SMSP = 0.73
+# ALGORITHMIC HBM bytes per env-step of the fused step: SURVEY.md §8(d) (read 336 B + write 394 B of SoA f32 state,
+# actions, observation, reward, flags) -- the figure `roofline.achieved` / `roofline.frac` are computed with.  The bytes
+# the kernel's actual LAYOUT moves (80-word padded state read + written, int64 episode counter) are
+# reported next to it as `layout_bytes_per_env_step` / `frac_layout_bytes`.
+ALGO_BYTES_PER_ENV_STEP = 730
+LAYOUT_BYTES_PER_ENV_STEP = 320 + 24 + 8 + 320 + 92 + 4 + 2 + 8
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12     # 148 SMs x 128 FP32 lanes x 2 FLOP (FMA) x 1.965 GHz = 74.4
 # Envs per GPU of the headline `value` at EVERY N (weak scaling: identical per-GPU work at N = 1, 2, 4, 8 so the
 # driver's scaling efficiency is meaningful).  65536 envs/GPU is the configuration BASELINE.json states the
 # multi-GPU target on (configs[2]); the 4096-env configuration (configs[1]) is measured in the same run at N = 1
 # and reported under "envs_4096".
 DEFAULT_ENVS_PER_GPU = 65536
 ROLLOUT_STEPS = 24  # agents/rsl_rl_ppo_cfg.py:67 -- statistics are reduced once per rollout
+# One bench "step" = a BLOCK of this many control steps (each one launch of the fused kernel; the L2 is flushed before
+# every one of them, outside the timed events), so the driver's `--steps 20` times 1000 control steps (>= 50 ms of
+# kernel time) instead of 1.7 ms.  `value` counts every control step: env-steps/s is unaffected by the block size.
+CONTROL_STEPS_PER_STEP = 50
+
+
+def workload_name(n_envs: int) -> str:
+    """The ONE workload string both arms (`--impl ours` / `--impl reference`) print in `config.workload`."""
+    return f"zbot-6b-walking-v2 full control step (4 physics substeps + MDP + partial reset), {n_envs} envs/GPU"
+
+
+def csrc_hash() -> str:
+    """Content hash of the sources the library is built from: a committed ncu summary (profiles/step_<N>.json) is only
+    used when it was captured on exactly these sources."""
+    import glob
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted(glob.glob(os.path.join(ROOT, "zbot_lab_b200", "csrc", "*.cu")) +
+                    glob.glob(os.path.join(ROOT, "zbot_lab_b200", "csrc", "*.h"))) + [os.path.join(ROOT, "include", "zbot_b200.h")]:
+        h.update(os.path.basename(f).encode())
+        h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
+
+
+def load_step_profile(n_envs: int):
+    """profiles/step_<N>.json (written by tools/ncu_profile_json.py from one `ncu --set full --clock-control none` capture
+    of the step kernel at N envs): instruction counts, DRAM bytes, duration.  Returns (dict | None, note)."""
+    p = os.path.join(ROOT, "profiles", f"step_{n_envs}.json")
+    if not os.path.isfile(p):
+        return None, f"no committed ncu summary for {n_envs} envs (profiles/step_{n_envs}.json)"
+    try:
+        prof = json.load(open(p))
+    except Exception as exc:
+        return None, f"unreadable {p}: {exc!r}"
+    if prof.get("source_hash") != csrc_hash():
+        return None, (f"profiles/step_{n_envs}.json was captured on other kernel sources (hash {prof.get('source_hash')} != "
+                      f"{csrc_hash()}): stale, not used")
+    return prof, "profiles/step_%d.json (%s)" % (n_envs, prof.get("captured_with", "ncu"))
 
 
 def parse():
@@ -151,21 +185,31 @@ def run_reference(args):
         sys.stdout.flush()
         os.execve(sys.executable, [sys.executable] + sys.argv, env)
     n_envs = args.envs or DEFAULT_ENVS_PER_GPU
-    # bounded sample: the same workload shape, at most ~20 s of CPU work
-    steps = max(1, min(args.steps, 50))
-    warm = max(1, min(args.warmup, 3))
-    value, dt, cores = cpu_path(n_envs, steps, warm)
-    sample = f"{n_envs} envs x {steps} steps (oracle/cpu_port.cpp float32, OpenMP)"
+    # Same metric / config / steps / warm-up as the GPU arm.  One bench step is a block of control steps; the block is
+    # the "bounded sample": CONTROL_STEPS_PER_STEP control steps when the whole run then fits ~2 minutes of CPU time,
+    # fewer otherwise (env-steps/s is a rate: the block length does not enter `value`).
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    _, dt_probe, cores = cpu_path(n_envs, 2, 1)
+    per_ctrl = dt_probe / 2
+    block = int(max(1, min(CONTROL_STEPS_PER_STEP, 120.0 / (per_ctrl * (steps + warm)))))
+    value, dt, cores = cpu_path(n_envs, steps * block, warm * block)
+    sample = (f"{n_envs} envs x {steps} bench steps x {block} control steps (+ {warm} x {block} warm-up), "
+              f"oracle/cpu_port.cpp float32, OpenMP, {dt:.1f} s")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warm, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"zbot-6b-walking-v2 full step, {n_envs} envs, host CPU", "envs_per_gpu": n_envs},
+        "config": {"workload": workload_name(n_envs), "envs_per_gpu": n_envs},
+        "timing": {"control_steps_per_step": block, "runs_on": f"host CPU, {cores} threads", "wall_s": dt},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "note": "reference = torch eager MDP + Isaac Lab + PhysX (closed, not installable here); this arm times the "
-                "CPU port of the same step on all host threads (BASELINE.md §2)",
+        "note": "kind = port: the reference's step is torch eager MDP + Isaac Lab + PhysX (closed, not installable here or on "
+                "the GPU box), so this arm times the C++ CPU port of the SAME control step (oracle/cpu_port.cpp = "
+                "csrc/zbot_core.h compiled for the host, OpenMP over envs, all host threads) -- NOT the reference's own "
+                "torch / PhysX CPU path, and a faster baseline than it (the reference's torch MDP alone, without physics, "
+                "ran at 1.3e6 env-steps/s on 8 vCPU: BASELINE.md §1; see cpu_baseline_torch_mdp in the GPU arm's line when "
+                "a reference tree is present)",
     }
     print(json.dumps(line))
 
@@ -224,35 +268,47 @@ def main():
         def one_step(i):
             st.step(actions[i % n_act])
 
-        for i in range(warmup):
+        blk = CONTROL_STEPS_PER_STEP
+        ctrl_steps, ctrl_warm = steps * blk, warmup * blk
+        for i in range(ctrl_warm):
             one_step(i)
         barrier()
         sampler = ClockSampler(local)
         sampler.sample_once()
         sampler.start()
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(ctrl_steps)]
+        # the only collective on the path: the rollout statistics, all-reduced once per rollout (24 control steps) -- inside
+        # the timed region, with its own events (N > 1 only)
+        n_red = ctrl_steps // ROLLOUT_STEPS if world > 1 else 0
+        ev_red = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_red)]
         launches0 = st.launch_count
         barrier()
         t_wall0 = time.perf_counter()
-        for i in range(steps):
+        k_red = 0
+        for i in range(ctrl_steps):
             if flush is not None:
                 flush.fill_(i & 0xFF)                      # evict L2 (126 MB) -- outside the timed events
             ev[i][0].record()
             one_step(i)
             ev[i][1].record()
-            if world > 1 and (i + 1) % ROLLOUT_STEPS == 0:
-                stats_acc = zdist.reduce_rollout_stats(st.stats)   # rollout statistics: the only collective on the path
+            if k_red < n_red and (i + 1) % ROLLOUT_STEPS == 0:
+                ev_red[k_red][0].record()
+                stats_acc = zdist.reduce_rollout_stats(st.stats)
+                ev_red[k_red][1].record()
+                k_red += 1
         barrier()
         t_wall = time.perf_counter() - t_wall0
         launches = st.launch_count - launches0
         sampler.stop()
         step_ms = [a.elapsed_time(b) for a, b in ev]
-        total_ms = float(sum(step_ms))
+        red_ms = [a.elapsed_time(b) for a, b in ev_red]
+        total_ms = float(sum(step_ms)) + float(sum(red_ms))
         t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
-        value = world * n_envs * steps / (total_ms * 1e-3)
+        value = world * n_envs * ctrl_steps / (total_ms * 1e-3)
+        steps_e2e = ctrl_steps
 
         # end to end through the public API with HOST buffers: pinned actions -> H2D, env.step, D2H of the result
         e2e = None
@@ -274,17 +330,17 @@ def main():
                 # inside the one kernel launch; returns after the stream is synchronised (result owned by the host)
                 return env.step_host(h_act[i % 4], h_rows)
 
-            for i in range(max(3, warmup // 4)):
+            for i in range(max(3, ctrl_warm // 4)):
                 e2e_step(i)
             barrier()
             t0 = time.perf_counter()
-            for i in range(steps):
+            for i in range(steps_e2e):
                 e2e_step(i)
             barrier()
             te = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
             if world > 1:
                 dist.all_reduce(te, op=dist.ReduceOp.MAX)
-            e2e = {"value": world * n_envs * steps / float(te.item()), "unit": UNIT,
+            e2e = {"value": world * n_envs * steps_e2e / float(te.item()), "unit": UNIT,
                    "h2d_bytes_per_step": n_envs * 24, "d2h_bytes_per_step": n_envs * 100,
                    "path": "env.step_host -> zbot_step_host: pinned host actions in, (N,25) pinned host rows "
                            "(obs | reward | flags) out, both zero-copy over PCIe inside the one fused-kernel launch; "
@@ -296,13 +352,13 @@ def main():
                 e2e_step_staged(i)
             barrier()
             t0 = time.perf_counter()
-            for i in range(steps):
+            for i in range(steps_e2e):
                 e2e_step_staged(i)
             barrier()
             ts = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
             if world > 1:
                 dist.all_reduce(ts, op=dist.ReduceOp.MAX)
-            e2e["staged_copies_value"] = world * n_envs * steps / float(ts.item())
+            e2e["staged_copies_value"] = world * n_envs * steps_e2e / float(ts.item())
             # context only (NOT the headline): a device-resident consumer, as in the reference's own RL loop where the policy
             # lives on the GPU -- pinned host actions -> device every step, env.step, and a device -> host read of ONE scalar
             # (the step's reward sum from the statistics slot); shows how much of `value` -> `e2e` is the 100 B/env of results
@@ -315,22 +371,28 @@ def main():
                 e2e_metric_only(i)
             barrier()
             t0 = time.perf_counter()
-            for i in range(steps):
+            for i in range(steps_e2e):
                 e2e_metric_only(i)
             barrier()
             tm = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
             if world > 1:
                 dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-            e2e["metric_only_value"] = world * n_envs * steps / float(tm.item())
+            e2e["metric_only_value"] = world * n_envs * steps_e2e / float(tm.item())
             e2e["metric_only_note"] = ("context: H2D of the actions + env.step + D2H of one scalar per step (device-resident "
                                        "observations, as with a GPU policy); h2d %d B, d2h 4 B per step" % (n_envs * 24))
 
 
+        kernel_name = st.kernel_name
         env.close()
-        return {"n_envs": n_envs, "value": value, "total_ms": total_ms, "local_ms_per_step": float(sum(step_ms)) / steps,
+        return {"n_envs": n_envs, "value": value, "total_ms": total_ms, "ctrl_steps": ctrl_steps, "kernel": kernel_name,
+                "local_ms_per_ctrl_step": float(sum(step_ms)) / ctrl_steps,
+                "stats_allreduce": ({"count": len(red_ms), "avg_us": 1e3 * float(sum(red_ms)) / len(red_ms),
+                                     "every_control_steps": ROLLOUT_STEPS, "words": int(stats_acc.numel()),
+                                     "included_in_value": True} if red_ms else None),
                 "launches": int(launches), "e2e": e2e, "clocks": sampler.summary(), "wall": t_wall, "flushed": flush is not None}
 
     main_m = measure(n_envs, args.steps, args.warmup, not args.no_e2e)
+    step_kernel_name = main_m["kernel"]
     small_m = None
     if world == 1 and args.envs is None and not args.no_small:
         small_m = measure(4096, args.steps, args.warmup, not args.no_e2e)     # BASELINE.json configs[1]
@@ -449,38 +511,50 @@ def main():
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
-        kern_ms = main_m["local_ms_per_step"]
+        kern_ms = main_m["local_ms_per_ctrl_step"]          # one control step = one launch of the step kernel (+ statistics kernel)
         achieved = ALGO_BYTES_PER_ENV_STEP * n_envs / (kern_ms * 1e-3) / 1e9
+        achieved_layout = LAYOUT_BYTES_PER_ENV_STEP * n_envs / (kern_ms * 1e-3) / 1e9
+        prof, prof_note = load_step_profile(n_envs)
+        clk_hz = 1e6 * float((main_m["clocks"] or {}).get("sm_mhz") or 1965.0)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"zbot-6b-walking-v2 full fused step (4 substeps + MDP + reset), {n_envs} envs/GPU",
-                       "envs_per_gpu": n_envs, "parallelism": f"env-sharded x{world}, no collective in the step",
-                       "l2": "flushed between timed steps (256 MiB write)" if main_m["flushed"] else "not flushed",
-                       "wall_s_incl_flush": main_m["wall"]},
+            "config": {"workload": workload_name(n_envs), "envs_per_gpu": n_envs},
+            "timing": {"control_steps_per_step": CONTROL_STEPS_PER_STEP, "ms_per_control_step": total_ms / main_m["ctrl_steps"],
+                       "timed_control_steps": main_m["ctrl_steps"], "timed_region_ms": total_ms,
+                       "parallelism": f"env-sharded x{world}, no collective in the step",
+                       "l2": "flushed before every control step (256 MiB write, outside the timed events)" if main_m["flushed"] else "not flushed",
+                       "wall_s_incl_flush": main_m["wall"], "stats_allreduce": main_m["stats_allreduce"]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": NCU_TRAFFIC_BYTES_PER_ENV_STEP * n_envs, "peak_source": peak_src,
-                         "kernel": "zbot_step_u2_kernel<128,2>" if n_envs > 148 * 128 else "zbot_step_kernel<false,128,2>",
-                         "traffic_note": "dram__bytes_read+write per launch at 65536 envs (profiles/r1_ncu_raw_tables_session3.md: 23.16 MB read + 0 written), scaled per env",
+                         "traffic": (prof["dram_bytes_read"] + prof["dram_bytes_write"]) if prof else None,
+                         "peak_source": peak_src, "kernel": step_kernel_name,
                          "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP,
-                         "note": "the fused step is FP32-issue bound, not HBM bound (DESIGN.md §4); see fp32_issue"},
-            # the bound that actually applies (not an HBM / tensor roofline, hence a separate object): warp instructions
-            # issued per clock per SM sub-partition against the measured ceiling at this occupancy
-            "fp32_issue": (lambda clk_hz: {
-                "achieved_inst_per_clk_per_smsp": WARP_INSTRUCTIONS_PER_32_ENVS * (n_envs / 32) / (148 * 4) / (kern_ms * 1e-3 * clk_hz),
-                "ceiling_at_2_warps": ISSUE_CEILING_INST_PER_CLK_PER_SMSP, "nominal": 1.0,
-                "frac_of_ceiling": WARP_INSTRUCTIONS_PER_32_ENVS * (n_envs / 32) / (148 * 4) / (kern_ms * 1e-3 * clk_hz) / ISSUE_CEILING_INST_PER_CLK_PER_SMSP,
-                "fp32_share_of_instructions": 0.76, "sm_clock_mhz": clk_hz / 1e6,
-                "source": "smsp__inst_executed.sum of profiles/r1_ncu_raw_tables_session3.md (65536 envs) / live kernel time; "
-                          "ceiling from tools/micro/ffma2_probe.cu (profiles/r1_notes.md)"})(
-                    1e6 * float((main_m["clocks"] or {}).get("sm_mhz") or 1965.0)),
+                         "layout_bytes_per_env_step": LAYOUT_BYTES_PER_ENV_STEP, "achieved_layout_bytes": achieved_layout,
+                         "frac_layout_bytes": achieved_layout / peak, "profile": prof_note,
+                         "note": "algorithmic bytes = SURVEY.md §8(d) x envs per launch / CUDA-event time of the launch; traffic = "
+                                 "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture (null when the committed "
+                                 "summary is stale).  The fused step is FP32-issue bound, not HBM bound (DESIGN.md §4): see fp32_issue"},
             "gpu_launches": int(launches), "clocks": main_m["clocks"],
         }
+        if prof:
+            # the bound that actually applies: warp instructions issued per clock per SM sub-partition, and the FP32 FLOP rate
+            # (2 x FFMA + FMUL + FADD thread instructions of the committed capture / live kernel time) against the FP32 peak
+            inst = float(prof["smsp_inst_executed"])
+            flop = 32.0 * (2.0 * prof["ffma"] + prof["fmul"] + prof["fadd"])
+            line["fp32_issue"] = {
+                "achieved_inst_per_clk_per_smsp": inst / (148 * 4) / (kern_ms * 1e-3 * clk_hz), "nominal": 1.0,
+                "warp_instructions_per_launch": inst, "fp32_share_of_instructions": (prof["ffma"] + prof["fmul"] + prof["fadd"]) / inst,
+                "fp32_tflops": flop / (kern_ms * 1e-3) / 1e12, "fp32_peak_tflops": FP32_PEAK_TFLOPS,
+                "fp32_peak_frac": flop / (kern_ms * 1e-3) / 1e12 / FP32_PEAK_TFLOPS, "sm_clock_mhz": clk_hz / 1e6,
+                "registers_per_thread": prof.get("registers"), "warps_per_scheduler": prof.get("warps_per_scheduler"),
+                "source": prof_note + ": instruction counts of the committed capture / live CUDA-event kernel time"}
+        else:
+            line["fp32_issue"] = {"unavailable": prof_note}
         if small_m is not None:
-            a4 = ALGO_BYTES_PER_ENV_STEP * 4096 / (small_m["local_ms_per_step"] * 1e-3) / 1e9
+            a4 = ALGO_BYTES_PER_ENV_STEP * 4096 / (small_m["local_ms_per_ctrl_step"] * 1e-3) / 1e9
             line["envs_4096"] = {"workload": "BASELINE.json configs[1]: full fused step, 4096 envs, 1 x B200",
-                                 "value": small_m["value"], "unit": UNIT, "ms_per_step": small_m["total_ms"] / args.steps,
+                                 "value": small_m["value"], "unit": UNIT, "ms_per_control_step": small_m["total_ms"] / small_m["ctrl_steps"],
                                  "e2e": small_m["e2e"], "roofline_frac_hbm": a4 / peak, "gpu_launches": small_m["launches"]}
         if e2e is not None:
             line["e2e"] = e2e
@@ -495,7 +569,41 @@ def main():
                 cs = int(max(20, min(20000, 10.0 / (dt0 / 10))))
             v, dt, cores = cpu_path(n_envs, cs, 2)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"{n_envs} envs x {cs} steps, oracle/cpu_port.cpp float32 OpenMP, {dt:.1f} s"}
+                                    "sample": f"{n_envs} envs x {cs} control steps, oracle/cpu_port.cpp float32 OpenMP, {dt:.1f} s",
+                                    "note": "C++ port of the same control step on all host threads -- NOT the reference's torch / PhysX "
+                                            "path (closed); a harder baseline than it"}
+            # the reference's OWN torch MDP (no physics) on the host cores -- only where a reference tree exists
+            # (ZBOT_REFERENCE_ROOT; never on the stock GPU box): north_star "reference's torch ... CPU path timed beside it"
+            try:
+                from oracle import ref_torch_bench
+                if ref_torch_bench.available():
+                    line["cpu_baseline_torch_mdp"] = ref_torch_bench.time_reference_torch_mdp(n_envs, 10, 2)
+                else:
+                    line["cpu_baseline_torch_mdp"] = {"unavailable": "no reference tree on this box (ZBOT_REFERENCE_ROOT); measured in the "
+                                                      "build container: see profiles/r2_notes.md"}
+            except Exception as exc:
+                line["cpu_baseline_torch_mdp"] = {"error": repr(exc)}
+            # BASELINE.json configs[4] comparator: the same 24 x 4096 rollout (CPU port of the env step + the same MLP) on the host cores
+            if other_tasks is not None and "ms_per_rollout" in other_tasks.get("ppo_rollout_24x4096", {}):
+                try:
+                    import bench_rollout
+                    import zbot_lab_b200.tasks.zbot6b_direct.walking_v2 as w2
+                    sys.path.insert(0, os.path.join(ROOT, "tests"))
+                    from fake_stepper import FakeStepper
+                    real = w2.NativeStepper
+                    w2.NativeStepper = FakeStepper
+                    try:
+                        torch.set_num_threads(os.cpu_count() or 1)
+                        rc = bench_rollout.make(4096, "cpu", False)
+                        sec = bench_rollout.time_rollouts(rc, 3)
+                    finally:
+                        w2.NativeStepper = real
+                    r = other_tasks["ppo_rollout_24x4096"]
+                    r["cpu_path"] = {"ms_per_rollout": 1e3 * sec, "value": 24 * 4096 / sec, "unit": UNIT, "threads": torch.get_num_threads(),
+                                     "what": "CPU port of the env step (oracle/cpu_port.cpp) + the same actor / critic MLP in CPU torch"}
+                    r["speedup_vs_cpu_path"] = sec / (r["ms_per_rollout"] * 1e-3)
+                except Exception as exc:
+                    other_tasks["ppo_rollout_24x4096"]["cpu_path"] = {"error": repr(exc)}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

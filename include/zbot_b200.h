@@ -276,6 +276,15 @@ int zbot_m_step(ZbotHandle* h, const float* actions, const float* rand, float* o
 int zbot_m_step_export(ZbotHandle* h, const float* actions, const float* rand, float* obs, float* rew,
                        uint8_t* terminated, uint8_t* truncated, int32_t stats_slot, int32_t prev_slot,
                        float* export_buf, void* stream);
+/* All-envs-reset spread of the episode counters, on the device.  The reference's `_reset_idx` does
+ * `episode_length_buf[:] = torch.randint_like(episode_length_buf, high=max_episode_length)` when EVERY env resets in one
+ * step (zbot_direct_6dof_bipedal_env_v2.py:418-422, ..._env_v4.py:972, zbot_direct_6dof_snake_v0.py:275) -- a host
+ * decision on a device count.  With `enable` the statistics kernel that follows each step kernel makes that decision
+ * (it holds the reset count) and writes the counters itself: no host sync, and no work unless the event fires.  The values
+ * come from the in-kernel counter-based generator, not from torch's (a host-synchronised caller that wants torch's
+ * stream leaves this off and does the spread itself, as `ZbotDirectEnvV2.step` does for N <= 256). */
+int zbot_set_all_reset_spread(ZbotHandle* h, int32_t enable);
+
 /* Replace the reward weights / event parameters of a live handle (host-side curricula, …env_v4.py:138-265);
  * num_envs, task and the dynamics parameters must be unchanged. */
 int zbot_update_cfg(ZbotHandle* h, const ZbotCfg* cfg);
@@ -331,6 +340,9 @@ int zbot_mdp_step(ZbotHandle* h, const ZbotMdpInputs* in, const float* actions, 
 
 /* Number of kernel launches issued through this handle so far (host counter). */
 int64_t zbot_launch_count(const ZbotHandle* h);
+/* Name of the step-kernel instantiation `zbot_step` (or the task's step entry) launches for this handle, as it appears in
+ * an ncu / nsys launch list (the library picks the register budget / sweep unroll from num_envs). */
+const char* zbot_step_kernel_name(const ZbotHandle* h);
 
 #ifdef __cplusplus
 }

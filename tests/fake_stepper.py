@@ -45,6 +45,9 @@ class FakeStepper:
     def stats(self):
         return self.stats_ring[max(self._slot, 0)]
 
+    def set_all_reset_spread(self, enable):
+        self.spread_all_reset = bool(enable)
+
     def _write_stats(self, reset_mask, rs, term, trunc, rew):
         prev = self._slot
         self._slot = (self._slot + 1) % 64

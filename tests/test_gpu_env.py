@@ -95,6 +95,75 @@ def test_all_envs_reset_spreads_episode_lengths_on_torch_generator():
     env.close()
 
 
+def test_all_envs_reset_spread_on_the_device_for_large_env_counts():
+    """Same event for N > 256 (default cfg): no host sync -- the statistics kernel sees `#reset == N` and writes the
+    counters itself (in-kernel generator): spread over [0, max_episode_length), different per env, deterministic per
+    seed, and a PARTIAL reset leaves the counters of the other envs at +1 / the reset ones at 0."""
+    n = 1024
+    outs = []
+    for rep in range(2):
+        env, _ = _make(n)
+        assert not env._check_all_reset
+        env.reset()
+        env.episode_length_buf = torch.full((n,), 998, dtype=torch.int64)
+        _, _, term, trunc, _ = env.step(torch.zeros(n, 6, device="cuda:0"))
+        assert trunc.all()
+        ep = env.episode_length_buf.clone()
+        assert int(ep.min()) >= 0 and int(ep.max()) < 1000
+        assert ep.unique().numel() > n // 3 and abs(float(ep.float().mean()) - 500.0) < 40.0
+        outs.append(ep)
+        # partial reset: only env 0 times out -> plain zero for it, +1 for the others
+        before = env.episode_length_buf.clone()
+        before[0] = 998
+        env.episode_length_buf = before
+        _, _, term, trunc, _ = env.step(torch.zeros(n, 6, device="cuda:0"))
+        after = env.episode_length_buf
+        done = term | trunc
+        assert bool(trunc[0]) and not bool(done.all())
+        assert torch.equal(after[~done], before[~done] + 1) and torch.all(after[done] == 0)
+        env.close()
+    assert torch.equal(outs[0], outs[1])
+
+
+def test_in_kernel_generator_advances_under_cuda_graph_replay():
+    """the stream position of the in-kernel generator lives in device memory (read by the step kernel,
+    bumped by the statistics kernel), so replays of ONE captured graph draw fresh uniforms: the v4 task's randomised
+    reset poses / resampled commands and the observation noise differ from replay to replay."""
+    import zbot_lab_b200.tasks  # noqa: F401
+    from zbot_lab_b200 import native
+    from zbot_lab_b200.stepper import NativeStepper
+    n = 512
+    st = NativeStepper(n, "cuda:0", native.set_obs_noise(native.make_cfg(n, task=native.TASK_WALKING_V4, rng_seed=11),
+                                                          {"joint_pos": (-0.01, 0.01)}))
+    st.reset_idx_v4(None)
+    a = torch.zeros(n, 6, device="cuda:0")
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            st._slot = -1
+            st.step(a)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    st._slot = -1
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        st.step(a)
+    seen_obs, seen_cmd, seen_pos = [], [], []
+    for rep in range(3):
+        st.episode_length_buf[:] = 998          # every env times out in the replayed step -> reset pose + commands re-drawn
+        g.replay()
+        torch.cuda.synchronize()
+        seen_obs.append(st.obs.clone())
+        seen_cmd.append(st.state.get("carry_feet_fz").clone())
+        seen_pos.append(st.state.get("root_pos").clone())
+    for i in range(2):
+        assert not torch.equal(seen_cmd[i], seen_cmd[i + 1])
+        assert not torch.equal(seen_pos[i], seen_pos[i + 1])
+        assert not torch.equal(seen_obs[i][:, 4:10], seen_obs[i + 1][:, 4:10])      # noise on the joint_pos columns
+    st.close()
+
+
 def test_ppo_runner_two_iterations_and_checkpoint(tmp_path):
     """train.py flow: gym.make -> RslRlVecEnvWrapper -> OnPolicyRunner.learn (config 5 shape, tiny)."""
     from zbot_lab_b200.compat import gym_registry as gym

@@ -144,3 +144,72 @@ def test_manager_cfg_compiles_into_the_kernel_term_table_and_unknown_terms_fail_
         compile_(bad)
     with pytest.raises(RuntimeError):
         mdp.feet_gait(None)
+
+
+def test_graph_replay_runs_host_curricula_and_recaptures_on_change():
+    """`env.step`'s Python does not run while a captured rollout graph is replayed, so
+    `OnPolicyRunner.replay_rollout` must advance the step counter, evaluate the env's host curricula for the replayed
+    steps, refresh the python-float `Curriculum/*` log entries and drop the graph when kernel parameters changed."""
+    import torch
+    from zbot_lab_b200.rl.ppo_runner import OnPolicyRunner
+
+    class Env:
+        num_envs, num_actions, max_episode_length = 4, 6, 1000
+        def __init__(self):
+            self.unwrapped = self
+            self.common_step_counter = 0
+            self.stage = 0
+        def get_observations(self):
+            return {"policy": torch.zeros(4, 23)}
+        def advance_host_curricula(self, steps):
+            before = self.stage
+            for _ in range(steps):
+                self.common_step_counter += 1
+                if self.common_step_counter == 30:
+                    self.stage = 1
+            return self.stage != before
+        def curriculum_log(self):
+            return {"Curriculum/curriculum_stage": self.stage}
+
+    class Graph:
+        replays = 0
+        def replay(self):
+            Graph.replays += 1
+
+    env = Env()
+    r = OnPolicyRunner(env, {"num_steps_per_env": 24, "use_cuda_graph": False}, device="cpu")
+    r._graph, r._obs_in = Graph(), torch.zeros(4, 23)
+    r._graph_ep_infos = [{"Curriculum/curriculum_stage": 0} for _ in range(24)]
+    r.replay_rollout()
+    assert env.common_step_counter == 24 and r._graph is not None and r._graph_ep_infos[0]["Curriculum/curriculum_stage"] == 0
+    r.replay_rollout()                              # step 30 falls inside this rollout: parameters changed
+    assert env.common_step_counter == 48 and r._graph is None
+    assert all(e["Curriculum/curriculum_stage"] == 1 for e in r._graph_ep_infos) and Graph.replays == 2
+
+
+def test_runner_statistics_ring_guard():
+    """log scalars are views into a 64-slot ring; rollouts longer than the ring clone them, and the
+    captured graph (which needs slots T..2T-1) is only used when 2T fits."""
+    import warnings
+    import torch
+    from zbot_lab_b200.rl.ppo_runner import OnPolicyRunner
+
+    class St:
+        stats_ring = torch.zeros(64, 32)
+
+    class Env:
+        num_envs, num_actions, max_episode_length = 4, 6, 1000
+        _stepper = St()
+        def __init__(self):
+            self.unwrapped = self
+        def get_observations(self):
+            return {"policy": torch.zeros(4, 23)}
+
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        r = OnPolicyRunner(Env(), {"num_steps_per_env": 40, "use_cuda_graph": True}, device="cpu")
+    assert not r.use_cuda_graph and not r._clone_logs and any("statistics slots" in str(x.message) for x in w)
+    r = OnPolicyRunner(Env(), {"num_steps_per_env": 24, "use_cuda_graph": True}, device="cpu")
+    assert r.use_cuda_graph and not r._clone_logs
+    r = OnPolicyRunner(Env(), {"num_steps_per_env": 100, "use_cuda_graph": False}, device="cpu")
+    assert r._clone_logs

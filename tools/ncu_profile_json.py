@@ -1,0 +1,81 @@
+"""Turn one `ncu --set full --clock-control none` capture of the step kernel into the tracked summary bench.py reads.
+
+    python tools/ncu_profile_json.py gpurun_out/prof_step65536.ncu-rep 65536 [kernel-name-substring]
+        -> profiles/step_65536.json
+
+The summary carries the source hash of the kernel sources (bench.csrc_hash), so bench.py refuses it when the kernel has
+changed since the capture (VERDICT r1 "measurement hygiene": no typed-in profile constants).  Per-launch values are the
+MEDIAN over the captured launches of the selected kernel.
+"""
+import csv
+import json
+import os
+import statistics
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+_SCALE = {"": 1.0, "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12,
+          "nsecond": 1e-3, "ns": 1e-3, "usecond": 1.0, "us": 1.0, "msecond": 1e3, "ms": 1e3, "second": 1e6, "s": 1e6,
+          "cycle/nsecond": 1e3, "cycle/usecond": 1.0, "Ghz": 1e3, "GHz": 1e3, "Mhz": 1.0, "MHz": 1.0}
+
+
+def raw_rows(rep):
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    return rows[0], rows[1], rows[2:]
+
+
+def main():
+    rep, n_envs = sys.argv[1], int(sys.argv[2])
+    want = sys.argv[3] if len(sys.argv) > 3 else "zbot_step"
+    hdr, units, rows = raw_rows(rep)
+    col = {h: i for i, h in enumerate(hdr)}
+    sel = [r for r in rows if want in r[col["Kernel Name"]]]
+    if not sel:
+        raise SystemExit(f"no launch of a kernel matching {want!r} in {rep}")
+    names = sorted({r[col["Kernel Name"]] for r in sel})
+
+    def med(name, scale_by_unit=False):
+        i = col[name]
+        vals = [float(r[i].replace(",", "")) for r in sel]
+        v = statistics.median(vals)
+        if scale_by_unit:
+            v *= _SCALE.get(units[i], 1.0)
+        return v
+
+    cycles = med("sm__cycles_elapsed.max") if "sm__cycles_elapsed.max" in col else med("sm__cycles_elapsed.avg")
+    def thread_ops(op):
+        return med(f"smsp__sass_thread_inst_executed_op_{op}_pred_on.sum.per_cycle_elapsed") * cycles
+    import bench
+    prof = {
+        "kernel": names[0].split("(")[0].replace("void ", "").replace("<unnamed>::", ""),
+        "envs": n_envs, "launches_in_capture": len(sel), "source_hash": bench.csrc_hash(),
+        "captured_with": "ncu --set full --clock-control none (cold cache, serialised launches)",
+        "report": os.path.basename(rep),
+        "gpu_time_duration_us": med("gpu__time_duration.sum", True),
+        "sm_clock_mhz": med("sm__cycles_elapsed.avg.per_second", True),
+        "smsp_inst_executed": med("smsp__inst_executed.sum"),
+        # warp-level counts (thread instructions / 32) of the three FP32 arithmetic opcodes
+        "ffma": thread_ops("ffma") / 32.0, "fmul": thread_ops("fmul") / 32.0, "fadd": thread_ops("fadd") / 32.0,
+        "dram_bytes_read": med("dram__bytes_read.sum", True), "dram_bytes_write": med("dram__bytes_write.sum", True),
+        "registers": int(med("launch__registers_per_thread")), "block": int(med("launch__block_size")),
+        "grid": int(med("launch__grid_size")), "warps_per_scheduler": med("smsp__warps_active.avg.per_cycle_active"),
+        "issue_active_pct": med("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+        "stall_no_instruction_per_issue": med("smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio"),
+        "stall_wait_per_issue": med("smsp__average_warps_issue_stalled_wait_per_issue_active.ratio"),
+        "stall_long_scoreboard_per_issue": med("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio"),
+        "stall_not_selected_per_issue": med("smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio"),
+    }
+    out = os.path.join(ROOT, "profiles", f"step_{n_envs}.json")
+    with open(out, "w") as f:
+        json.dump(prof, f, indent=1)
+        f.write("\n")
+    print(json.dumps(prof, indent=1))
+    print("wrote", out)
+
+
+if __name__ == "__main__":
+    main()

@@ -14,8 +14,15 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(CSRC, "libzbot_b200.so")
 SOURCES = ["zbot_kernels.cu"]
-DEPS = ["zbot_kernels.cu", "zbot_core.h", "zbot_layout.h", "zbot_model_constants.h",
-        os.path.join("..", "..", "include", "zbot_b200.h")]
+
+
+def deps() -> list:
+    """Every source the library is built from: all of csrc/*.cu|*.h (globbed, so a new header cannot be forgotten)
+    plus the C-ABI header."""
+    import glob
+    return sorted(glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.h"))) + [
+        os.path.join(HERE, "..", "include", "zbot_b200.h")]
+
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -35,7 +42,7 @@ def is_stale() -> bool:
     if not os.path.isfile(OUT):
         return True
     t = os.path.getmtime(OUT)
-    return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
+    return any(os.path.getmtime(d) > t for d in deps())
 
 
 def build_native(force: bool = False, verbose: bool = False, out: str | None = None, extra: list | None = None) -> str:

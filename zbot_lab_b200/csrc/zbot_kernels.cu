@@ -61,9 +61,19 @@ struct StatsCtx {
   int slot, prev_slot;
   float inv_episode_s;    // 1 / max_episode_length_s  (…env_v2.py:444-447)
   int block_offset;       // env-range launches (zbot_step_host): index of this launch's first partial row
-  unsigned long long call; // launch counter of the handle: stream position of the in-kernel generator (obs noise)
+  const unsigned long long* rng_ctr;  // DEVICE counter = stream position of the in-kernel generator (v4 / manager events,
+                                      // observation noise).  Read by the step kernel, bumped by the statistics kernel that
+                                      // follows it, so it also advances when a captured CUDA graph is replayed (a host
+                                      // counter passed by value is frozen at capture: every replay would re-draw the same
+                                      // uniforms)
   int packed_rows;         // 1: host-facing output layout (zbot_step_host), see zbot_step_body
   int raw_tail;            // this many trailing term slots (…, 14, 15) hold raw counts: summed, not normalised (manager task)
+  // all-envs-reset spread (…env_v2.py:418-422: `episode_length_buf[:] = randint_like(high=max_episode_length)` when EVERY env
+  // reset in this step): done on the device by the statistics kernel, which holds the reset count -- no host sync, no work
+  // unless the (rare) event fires.  Values come from the in-kernel counter generator (slot 64), not from torch's.
+  int64_t* spread_ep_len;  // nullptr: off
+  int spread_n, spread_high;
+  unsigned long long spread_seed;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -81,6 +91,8 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+__device__ __forceinline__ uint64_t rng_position(const StatsCtx& sc) { return sc.rng_ctr ? __ldcg(sc.rng_ctr) : 0ull; }
+
 __device__ __forceinline__ float v4_uniform(uint64_t seed, uint64_t call, uint32_t env, uint32_t slot) {
   uint64_t z = seed + 0x9E3779B97F4A7C15ull * (call * 0x100000000ull + env) + 0xD1B54A32D192ED03ull * (slot + 1);
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
@@ -92,8 +104,9 @@ __device__ __forceinline__ float v4_uniform(uint64_t seed, uint64_t call, uint32
 // ObservationManager-style corruption of the emitted observation row: obs[i] += lo[i] + u * (hi[i] - lo[i]), one
 // counter-based uniform per (launch, env, column).  Slots 32.. keep clear of the v4 event slots 0..9.
 template <int kCols>
-__device__ __forceinline__ void obs_add_noise(const Params<float>& P, uint64_t call, int e, float* row) {
+__device__ __forceinline__ void obs_add_noise(const Params<float>& P, const StatsCtx& sc, int e, float* row) {
   if (!P.obs_noise_enable) return;
+  const uint64_t call = rng_position(sc);
 #pragma unroll
   for (int i = 0; i < kCols; ++i)
     row[i] = fmaf(v4_uniform(P.rng_seed, call, (uint32_t)e, 32u + (uint32_t)i), P.obs_noise_w[i], row[i] + P.obs_noise_lo[i]);
@@ -138,6 +151,17 @@ __global__ void __launch_bounds__(1024) zbot_stats_finalize_kernel(StatsCtx sc, 
       v = (sc.prev_slot >= 0) ? sc.ring[(size_t)sc.prev_slot * kStats + threadIdx.x] : 0.f;
     sc.ring[(size_t)sc.slot * kStats + threadIdx.x] = v;
   }
+  if (sc.spread_ep_len && red[0][S_NUM_RESET] == (float)sc.spread_n) {   // block-uniform: every env reset in this step
+    const uint64_t call = rng_position(sc);
+    for (int i = threadIdx.x; i < sc.spread_n; i += blockDim.x) {
+      const float u = v4_uniform(sc.spread_seed, call, (uint32_t)i, 64u);
+      sc.spread_ep_len[i] = min((int)(u * (float)sc.spread_high), sc.spread_high - 1);
+    }
+    __syncthreads();                                                     // all reads of the position precede the bump
+  }
+  // advance the in-kernel generator's stream position: the step kernel of this control step has completed (pdl_wait
+  // above), the next one reads it only after this grid has completed (its own pdl_wait / stream order)
+  if (threadIdx.x == 0 && sc.rng_ctr) *const_cast<unsigned long long*>(sc.rng_ctr) = *sc.rng_ctr + 1ull;
 }
 
 // warp shuffles -> shared memory -> this block's partial row.  `vals[0..18]` are non-zero only for
@@ -220,6 +244,30 @@ struct ExportPtrs {
 __device__ __constant__ int kMidSensorIdx[5] = {1, 3, 11, 6, 8};
 constexpr int kFoot0Sensor = 9, kFoot1Sensor = 10;
 
+// kExport flavours: write the articulation / contact-sensor view the MDP phase of THIS launch saw (test hook: the
+// reference-pinned MDP oracle is evaluated on it).  Layouts = the reference's robot.data / contact_sensor.data tensors.
+__device__ __noinline__ void step_export_store(const StepExport<float>& ex, const ExportPtrs& xp, int e) {
+  for (int i = 0; i < 36; ++i) { xp.pos0[(size_t)e * 36 + i] = ex.pos0[i]; xp.vel0[(size_t)e * 36 + i] = ex.vel0[i];
+                                 xp.pos1[(size_t)e * 36 + i] = ex.pos1[i]; xp.vel1[(size_t)e * 36 + i] = ex.vel1[i]; }
+  for (int i = 0; i < 48; ++i) { xp.quat0[(size_t)e * 48 + i] = ex.quat0[i]; xp.quat1[(size_t)e * 48 + i] = ex.quat1[i]; }
+  for (int i = 0; i < 6; ++i) { xp.q1[(size_t)e * 6 + i] = ex.q1[i]; xp.qd1[(size_t)e * 6 + i] = ex.qd1[i];
+                                xp.tau1[(size_t)e * 6 + i] = ex.applied_torque[i]; }
+  float* h = xp.hist1 + (size_t)e * (5 * 12 * 3);
+  for (int i = 0; i < 5 * 12 * 3; ++i) h[i] = 0.f;
+  for (int t = 0; t < 5; ++t) {
+    for (int i = 0; i < 3; ++i) {
+      h[(t * 12 + kFoot0Sensor) * 3 + i] = ex.feet_force_hist[t][0][i];
+      h[(t * 12 + kFoot1Sensor) * 3 + i] = ex.feet_force_hist[t][1][i];
+      for (int b = 0; b < 5; ++b) h[(t * 12 + kMidSensorIdx[b]) * 3 + i] = ex.mid_force_hist[t][b][i];
+    }
+  }
+  for (int b = 0; b < 12; ++b) { xp.last_air1[(size_t)e * 12 + b] = 0.f; xp.cur_contact1[(size_t)e * 12 + b] = 0.f; }
+  xp.last_air1[(size_t)e * 12 + kFoot0Sensor] = ex.last_air[0];
+  xp.last_air1[(size_t)e * 12 + kFoot1Sensor] = ex.last_air[1];
+  xp.cur_contact1[(size_t)e * 12 + kFoot0Sensor] = ex.cur_contact[0];
+  xp.cur_contact1[(size_t)e * 12 + kFoot1Sensor] = ex.cur_contact[1];
+}
+
 // ---------------------------------------------------------------------------------------------
 // the fused control step
 // ---------------------------------------------------------------------------------------------
@@ -256,35 +304,8 @@ zbot_step_body(const Params<float>& P, const DefaultPose& dp,
     SmemScratch scr{smem + threadIdx.x * SCR_STRIDE};
     const float2* a2p = reinterpret_cast<const float2*>(actions + (size_t)e * 6);
     int64_t ep;
-    if (kExport) {
-      float w[ZBOT_STATE_WORDS];
-      load_words<ZBOT_STATE_WORDS / 4>(state, n, e, w);
-      env_state_unpack(w, es);
-      const float2 a0 = __ldg(a2p), a1 = __ldg(a2p + 1), a2v = __ldg(a2p + 2);
-      const float raw[6] = {a0.x, a0.y, a1.x, a1.y, a2v.x, a2v.y};
-      ep = ep_len_buf[e];
-      StepExport<float> ex;
-      env_step(P, es, raw, ep, dp.feet_pos, dp.base_quat, out, rs, &ex, scr);
-      for (int i = 0; i < 36; ++i) { xp.pos0[(size_t)e * 36 + i] = ex.pos0[i]; xp.vel0[(size_t)e * 36 + i] = ex.vel0[i];
-                                     xp.pos1[(size_t)e * 36 + i] = ex.pos1[i]; xp.vel1[(size_t)e * 36 + i] = ex.vel1[i]; }
-      for (int i = 0; i < 48; ++i) { xp.quat0[(size_t)e * 48 + i] = ex.quat0[i]; xp.quat1[(size_t)e * 48 + i] = ex.quat1[i]; }
-      for (int i = 0; i < 6; ++i) { xp.q1[(size_t)e * 6 + i] = ex.q1[i]; xp.qd1[(size_t)e * 6 + i] = ex.qd1[i];
-                                    xp.tau1[(size_t)e * 6 + i] = ex.applied_torque[i]; }
-      float* h = xp.hist1 + (size_t)e * (5 * 12 * 3);
-      for (int i = 0; i < 5 * 12 * 3; ++i) h[i] = 0.f;
-      for (int t = 0; t < 5; ++t) {
-        for (int i = 0; i < 3; ++i) {
-          h[(t * 12 + kFoot0Sensor) * 3 + i] = ex.feet_force_hist[t][0][i];
-          h[(t * 12 + kFoot1Sensor) * 3 + i] = ex.feet_force_hist[t][1][i];
-          for (int b = 0; b < 5; ++b) h[(t * 12 + kMidSensorIdx[b]) * 3 + i] = ex.mid_force_hist[t][b][i];
-        }
-      }
-      for (int b = 0; b < 12; ++b) { xp.last_air1[(size_t)e * 12 + b] = 0.f; xp.cur_contact1[(size_t)e * 12 + b] = 0.f; }
-      xp.last_air1[(size_t)e * 12 + kFoot0Sensor] = ex.last_air[0];
-      xp.last_air1[(size_t)e * 12 + kFoot1Sensor] = ex.last_air[1];
-      xp.cur_contact1[(size_t)e * 12 + kFoot0Sensor] = ex.cur_contact[0];
-      xp.cur_contact1[(size_t)e * 12 + kFoot1Sensor] = ex.cur_contact[1];
-    } else {
+    StepExport<float> ex;   // kExport only (dead otherwise): the articulation / sensor view the MDP phase saw
+    {
       // ---- phase A: only the 11 "early" quads (articulation state, p_delta, contact carry, timers) ----
       {
         float w[4 * EARLY_QUADS];
@@ -302,7 +323,7 @@ zbot_step_body(const Params<float>& P, const DefaultPose& dp,
 #pragma unroll
         for (int k = 0; k < 6; ++k) scr.base[SCR_RAW_ACT + k] = raw[k];
         // ---- phase B: 4 physics substeps; the MDP state is not even loaded yet (register budget) ----
-        env_step_physics<ModelWalk, kUnroll>(P, es, raw, po, scr, (StepExport<float>*)nullptr);
+        env_step_physics<ModelWalk, kUnroll>(P, es, raw, po, scr, kExport ? &ex : (StepExport<float>*)nullptr);
       }
       // ---- phase C: the 9 "late" quads, the start-of-step state S0 again (still unmodified in global
       //      memory -> L2 hit) for the one-step-stale quantities, the raw actions again, then the MDP ----
@@ -321,7 +342,8 @@ zbot_step_body(const Params<float>& P, const DefaultPose& dp,
 #pragma unroll
       for (int k = 0; k < 6; ++k) raw[k] = scr.base[SCR_RAW_ACT + k];
       ep = ep_len_buf[e];
-      env_step_finish(P, es, s0, raw, po, ep, dp.feet_pos, dp.base_quat, out, rs, (StepExport<float>*)nullptr);
+      env_step_finish(P, es, s0, raw, po, ep, dp.feet_pos, dp.base_quat, out, rs, kExport ? &ex : (StepExport<float>*)nullptr);
+      if (kExport) step_export_store(ex, xp, e);
     }
     float w[ZBOT_STATE_WORDS];
     env_state_pack(es, w);
@@ -337,7 +359,7 @@ zbot_step_body(const Params<float>& P, const DefaultPose& dp,
     }
 #pragma unroll
     for (int i = 0; i < ZBOT_NUM_OBS; ++i) obs_row[i] = out.obs[i];
-    obs_add_noise<ZBOT_NUM_OBS>(P, sc.call, e, obs_row);
+    obs_add_noise<ZBOT_NUM_OBS>(P, sc, e, obs_row);
     did_reset = out.terminated || out.time_out;
     if (did_reset) {
 #pragma unroll
@@ -451,8 +473,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) zbot_step2_kernel(ZB_
       rew[e] = out.reward;
       terminated[e] = out.terminated ? 1 : 0;
       truncated[e] = out.time_out ? 1 : 0;
-#pragma unroll
-      obs_add_noise<ZBOT_NUM_OBS>(P, sc.call, e, out.obs);
+      obs_add_noise<ZBOT_NUM_OBS>(P, sc, e, out.obs);
 #pragma unroll
       for (int i = 0; i < ZBOT_NUM_OBS; ++i) { if (l) obs_b[i] = out.obs[i]; else obs_a[i] = out.obs[i]; }
       if (out.terminated || out.time_out) {
@@ -480,6 +501,11 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) zbot_step2_kernel(ZB_
 template <int kMaxThreads, int kMinBlocks>
 __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) zbot_step_u2_kernel(ZB_STEP_ARGS) {
   zbot_step_body<false, 2>(ZB_STEP_CALL);
+}
+// export flavour of the unrolled instantiation (test hook): the SAME phased body and sweep unroll as the kernel that is
+// launched -- and benchmarked -- above 18944 envs, plus the stores of the view its MDP phase saw
+__global__ void __launch_bounds__(128, 1) zbot_step_u2_export_kernel(ZB_STEP_ARGS) {
+  zbot_step_body<true, 2>(ZB_STEP_CALL);
 }
 // unrolled sweeps under a direct register cap (single-wave experiments: 14 warps/SM hold 65536 envs at <= 146 registers)
 template <int kMaxRegs>
@@ -569,7 +595,7 @@ zbot_snake_step_kernel(const __grid_constant__ Params<float> P, const __grid_con
     truncated[e] = out.time_out ? 1 : 0;
 #pragma unroll
     for (int i = 0; i < ZBOT_NUM_OBS; ++i) obs_row[i] = out.obs[i];
-    obs_add_noise<ZBOT_NUM_OBS>(P, sc.call, e, obs_row);
+    obs_add_noise<ZBOT_NUM_OBS>(P, sc, e, obs_row);
     did_reset = out.terminated || out.time_out;
     if (did_reset) {
 #pragma unroll
@@ -598,7 +624,7 @@ static_assert(sizeof(V4Export<float>) / sizeof(float) == ZBOT_V4_EXPORT_WORDS, "
 template <bool kExport, int kUnroll = 1, int kMinBlocks = 2>
 __global__ void __launch_bounds__(128, kMinBlocks)
 zbot_v4_step_kernel(const __grid_constant__ Params<float> P, float4* __restrict__ state, int64_t* __restrict__ ep_len_buf,
-                    const float* __restrict__ actions, const float* __restrict__ rand, uint64_t seed, uint64_t call,
+                    const float* __restrict__ actions, const float* __restrict__ rand, uint64_t seed,
                     float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ terminated,
                     uint8_t* __restrict__ truncated, int n, StatsCtx sc, float* __restrict__ export_buf) {
   extern __shared__ float smem[];
@@ -650,13 +676,14 @@ zbot_v4_step_kernel(const __grid_constant__ Params<float> P, float4* __restrict_
 #pragma unroll
       for (int i = 0; i < V4_NUM_RAND / 2; ++i) { const float2 v = __ldg(rp + i); rnd[2 * i] = v.x; rnd[2 * i + 1] = v.y; }
     } else {
+      const uint64_t call = rng_position(sc);
 #pragma unroll
       for (int i = 0; i < V4_NUM_RAND; ++i) rnd[i] = v4_uniform(seed, call, (uint32_t)e, (uint32_t)i);
     }
     int64_t ep = ep_len_buf[e];
     V4Export<float> ex;
     v4_step_finish(P, es, raw, po, ep, rnd, obs_row, out, rs, kExport ? &ex : (V4Export<float>*)nullptr);
-    obs_add_noise<ZBOT_V4_NUM_OBS>(P, call, e, obs_row);
+    obs_add_noise<ZBOT_V4_NUM_OBS>(P, sc, e, obs_row);
     if (kExport) {
       const float* src = reinterpret_cast<const float*>(&ex);
       for (int i = 0; i < ZBOT_V4_EXPORT_WORDS; ++i) export_buf[(size_t)e * ZBOT_V4_EXPORT_WORDS + i] = src[i];
@@ -697,7 +724,7 @@ static_assert(M_NUM_OBS == ZBOT_M_NUM_OBS && M_NUM_RAND == ZBOT_M_NUM_RAND, "man
 template <bool kExport, int kUnroll = 1, int kMinBlocks = 2>
 __global__ void __launch_bounds__(128, kMinBlocks)
 zbot_m_step_kernel(const __grid_constant__ Params<float> P, float4* __restrict__ state, int64_t* __restrict__ ep_len_buf,
-                   const float* __restrict__ actions, const float* __restrict__ rand, uint64_t seed, uint64_t call,
+                   const float* __restrict__ actions, const float* __restrict__ rand, uint64_t seed,
                    float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ terminated,
                    uint8_t* __restrict__ truncated, int n, StatsCtx sc, float* __restrict__ export_buf) {
   extern __shared__ float smem[];
@@ -748,6 +775,7 @@ zbot_m_step_kernel(const __grid_constant__ Params<float> P, float4* __restrict__
 #pragma unroll
       for (int i = 0; i < M_NUM_RAND; ++i) rnd[i] = __ldg(rand + (size_t)e * M_NUM_RAND + i);
     } else {
+      const uint64_t call = rng_position(sc);
 #pragma unroll
       for (int i = 0; i < M_NUM_RAND; ++i) rnd[i] = v4_uniform(seed, call, (uint32_t)e, (uint32_t)i);
     }
@@ -756,6 +784,7 @@ zbot_m_step_kernel(const __grid_constant__ Params<float> P, float4* __restrict__
     m_step_finish(P, es, raw, po, ep, rnd, obs_row, out, rs, kExport ? &ex : (MExport<float>*)nullptr);
     // ObservationManager corruption (PolicyCfg: base_quat +-0.01, joint_pos +-0.01, joint_vel +-1.5); columns 0..23
     if (P.obs_noise_enable) {
+      const uint64_t call = rng_position(sc);
 #pragma unroll
       for (int i = 0; i < 24; ++i)
         obs_row[i] = fmaf(v4_uniform(P.rng_seed, call, (uint32_t)e, 32u + (uint32_t)i), P.obs_noise_w[i], obs_row[i] + P.obs_noise_lo[i]);
@@ -1113,7 +1142,10 @@ struct ZbotHandle {
   float inv_episode_s;
   int variant;      // index into kStepVariants
   int force_block;
-  uint64_t v4_calls;   // zbot_v4_step call counter (stream position of the in-kernel generator)
+  unsigned long long* rng_ctr;   // device: stream position of the in-kernel generator (see StatsCtx::rng_ctr)
+  DefaultPose* d_dp;             // device scratch of the create-time default-pose FK
+  int spread_all_reset;          // zbot_set_all_reset_spread
+  char kernel_name[96];          // zbot_step_kernel_name
   int mdp_tile;
 };
 
@@ -1169,6 +1201,28 @@ int find_variant(int threads, int ctas) {
   return -1;
 }
 
+// Makes the handle's device current for the duration of an entry point and restores the caller's device afterwards
+// (a handle used while another device is current would otherwise launch on a foreign device / stream).
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != device) switched = (cudaSetDevice(device) == cudaSuccess);
+  }
+  ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
+template <typename H>
+void ctx_spread(StatsCtx& sc, const H* h) {
+  if (!h->spread_all_reset) return;
+  sc.spread_ep_len = h->ep_len;
+  sc.spread_n = h->cfg.num_envs;
+  sc.spread_high = h->cfg.max_episode_length;
+  sc.spread_seed = h->cfg.rng_seed ^ 0xA11E5E7ull;
+}
+
 int check_slot(int slot, int prev, int slots) {
   if (slot < 0 || slot >= slots) return fail(ZBOT_E_INVALID, "stats_slot out of range%s");
   if (prev >= slots) return fail(ZBOT_E_INVALID, "prev_slot out of range%s");
@@ -1192,6 +1246,8 @@ int zbot_default_cfg(ZbotCfg* cfg, int32_t num_envs) {
 int zbot_state_word(const char* f) { return find_word(kStateFields, (int)(sizeof(kStateFields) / sizeof(kStateFields[0])), f); }
 int zbot_mdp_state_word(const char* f) { return find_word(kMdpFields, (int)(sizeof(kMdpFields) / sizeof(kMdpFields[0])), f); }
 
+static int create_impl(const ZbotCfg* cfg, int device, ZbotHandle* h);
+
 int zbot_create(const ZbotCfg* cfg, int device, ZbotHandle** out) {
   if (!cfg || !out) return fail(ZBOT_E_INVALID, "cfg/out is NULL%s");
   const char* why = "";
@@ -1199,10 +1255,21 @@ int zbot_create(const ZbotCfg* cfg, int device, ZbotHandle** out) {
   int ndev = 0;
   ZB_CUDA(cudaGetDeviceCount(&ndev));
   if (device < 0 || device >= ndev) return fail(ZBOT_E_INVALID, "no such CUDA device%s");
-  ZB_CUDA(cudaSetDevice(device));
+  DeviceGuard guard(device);             // the caller's current device is restored on every path
   ZbotHandle* h = new (std::nothrow) ZbotHandle();
   if (!h) return fail(ZBOT_E_INVALID, "out of host memory%s");
   memset(h, 0, sizeof(*h));
+  h->device = device;
+  const int rc = create_impl(cfg, device, h);
+  if (rc != ZBOT_OK) {                   // nothing leaks on an early CUDA error: the handle owns every allocation
+    zbot_destroy(h);
+    return rc;
+  }
+  *out = h;
+  return ZBOT_OK;
+}
+
+static int create_impl(const ZbotCfg* cfg, int device, ZbotHandle* h) {
   h->cfg = *cfg;
   params_from_cfg(*cfg, h->P);
   h->device = device;
@@ -1213,17 +1280,18 @@ int zbot_create(const ZbotCfg* cfg, int device, ZbotHandle** out) {
   h->num_sms = prop.multiProcessorCount;
   h->max_blocks = (cfg->num_envs + 31) / 32 + 1;
   ZB_CUDA(cudaMalloc(&h->partials, (size_t)h->max_blocks * kStats * sizeof(float)));
-  DefaultPose* d_dp = nullptr;
-  ZB_CUDA(cudaMalloc(&d_dp, sizeof(DefaultPose)));
-  zbot_default_pose_kernel<<<1, 1>>>(d_dp, cfg->task);
+  ZB_CUDA(cudaMalloc(&h->rng_ctr, sizeof(unsigned long long)));
+  ZB_CUDA(cudaMemset(h->rng_ctr, 0, sizeof(unsigned long long)));
+  ZB_CUDA(cudaMalloc(&h->d_dp, sizeof(DefaultPose)));          // scratch of the default-pose FK; freed by zbot_destroy
+  zbot_default_pose_kernel<<<1, 1>>>(h->d_dp, cfg->task);
   ZB_CUDA(cudaGetLastError());
-  ZB_CUDA(cudaMemcpy(&h->dp, d_dp, sizeof(DefaultPose), cudaMemcpyDeviceToHost));
-  ZB_CUDA(cudaFree(d_dp));
+  ZB_CUDA(cudaMemcpy(&h->dp, h->d_dp, sizeof(DefaultPose), cudaMemcpyDeviceToHost));
   ZB_CUDA(cudaFuncSetAttribute(zbot_mdp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * kHistRow * 4));
   for (int v = 0; v < kNumStepVariants; ++v)
     ZB_CUDA(cudaFuncSetAttribute((const void*)kStepVariants[v].fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  128 * SCR_STRIDE * 4 * kStepVariants[v].envs_per_thread));
-  ZB_CUDA(cudaFuncSetAttribute(zbot_step_kernel<true, 128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
+  ZB_CUDA(cudaFuncSetAttribute(zbot_step_kernel<true, 128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
+  ZB_CUDA(cudaFuncSetAttribute(zbot_step_u2_export_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
   ZB_CUDA(cudaFuncSetAttribute(zbot_snake_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
   ZB_CUDA(cudaFuncSetAttribute(zbot_snake_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
   ZB_CUDA(cudaFuncSetAttribute(zbot_v4_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
@@ -1234,6 +1302,9 @@ int zbot_create(const ZbotCfg* cfg, int device, ZbotHandle** out) {
   ZB_CUDA(cudaFuncSetAttribute(zbot_m_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
   ZB_CUDA(cudaFuncSetAttribute(zbot_m_step_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
   ZB_CUDA(cudaFuncSetAttribute(zbot_snake_step_kernel<false, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
+  ZB_CUDA(cudaFuncSetAttribute(zbot_snake_step_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
+  ZB_CUDA(cudaFuncSetAttribute(zbot_v4_step_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
+  ZB_CUDA(cudaFuncSetAttribute(zbot_m_step_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
   ZB_CUDA(cudaFuncSetAttribute(zbot_v4_step_kernel<false, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
   ZB_CUDA(cudaFuncSetAttribute(zbot_m_step_kernel<false, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
   {
@@ -1272,14 +1343,30 @@ int zbot_create(const ZbotCfg* cfg, int device, ZbotHandle** out) {
     const char* bs = getenv("ZBOT_STEP_BLOCK");
     h->force_block = bs ? atoi(bs) : 0;
   }
-  *out = h;
+  {
+    const StepVariant& v = kStepVariants[h->variant];
+    const int u = h->unroll2 ? 2 : 1, c = h->ctas3 ? 3 : 2;
+    switch (cfg->task) {
+      case ZBOT_TASK_SNAKE_V0: snprintf(h->kernel_name, sizeof(h->kernel_name), "zbot_snake_step_kernel<false,%d,%d>", u, u == 2 ? c : 2); break;
+      case ZBOT_TASK_WALKING_V4: snprintf(h->kernel_name, sizeof(h->kernel_name), "zbot_v4_step_kernel<false,%d,%d>", u, u == 2 ? c : 2); break;
+      case ZBOT_TASK_WALKING_M: snprintf(h->kernel_name, sizeof(h->kernel_name), "zbot_m_step_kernel<false,%d,%d>", u, u == 2 ? c : 2); break;
+      default:
+        if (v.threads >= 2000) snprintf(h->kernel_name, sizeof(h->kernel_name), "zbot_step_u2_kernel<%d,%d>", v.threads % 1000, v.ctas);
+        else if (v.threads >= 1000) snprintf(h->kernel_name, sizeof(h->kernel_name), "zbot_step2_kernel<%d,%d>", v.threads % 1000, v.ctas);
+        else snprintf(h->kernel_name, sizeof(h->kernel_name), "zbot_step_kernel<false,%d,%d>", v.threads, v.ctas);
+    }
+  }
   return ZBOT_OK;
 }
 
 int zbot_destroy(ZbotHandle* h) {
   if (!h) return ZBOT_OK;
-  cudaSetDevice(h->device);
-  cudaFree(h->partials);
+  {
+    DeviceGuard guard(h->device);
+    cudaFree(h->partials);
+    cudaFree(h->rng_ctr);
+    cudaFree(h->d_dp);
+  }
   delete h;
   return ZBOT_OK;
 }
@@ -1297,6 +1384,7 @@ int zbot_bind(ZbotHandle* h, float* state, int64_t* episode_length, float* stats
 static int step_impl(ZbotHandle* h, const float* actions, float* obs, float* rew, uint8_t* terminated, uint8_t* truncated,
                      int32_t slot, int32_t prev, const ZbotExport* ex, void* stream, float* snake_export = nullptr) {
   if (!h) return fail(ZBOT_E_INVALID, "handle is NULL%s");
+  DeviceGuard guard(h->device);
   if (!h->state) return fail(ZBOT_E_UNBOUND, "zbot_bind has not been called%s");
   if (!actions || !obs || !rew || !terminated || !truncated) return fail(ZBOT_E_INVALID, "zbot_step: NULL buffer%s");
   if (((uintptr_t)actions & 7) != 0) return fail(ZBOT_E_INVALID, "actions must be 8-byte aligned%s");
@@ -1308,14 +1396,18 @@ static int step_impl(ZbotHandle* h, const float* actions, float* obs, float* rew
   if (!walk) { block = 128; while (block > 32 && (n + block - 1) / block < 2 * h->num_sms) block >>= 1; }
   const int grid = (n + block * ept - 1) / (block * ept);
   const size_t smem = (size_t)block * SCR_STRIDE * sizeof(float) * ept;   // >= obs rows (23/thread) and stats (704 floats)
-  StatsCtx sc{h->partials, h->ring, slot, prev, h->inv_episode_s, 0, (unsigned long long)h->launches, 0};
+  StatsCtx sc{h->partials, h->ring, slot, prev, h->inv_episode_s, 0, h->rng_ctr, 0};
+  ctx_spread(sc, h);
   cudaStream_t s = (cudaStream_t)stream;
   ExportPtrs xp{};
   if (h->cfg.task == ZBOT_TASK_WALKING_V4) return fail(ZBOT_E_INVALID, "task zbot-6b-walking-v4 steps through zbot_v4_step%s");
   if (h->cfg.task == ZBOT_TASK_WALKING_M) return fail(ZBOT_E_INVALID, "task zbot-6b-walking-m-v0 steps through zbot_m_step%s");
   if (h->cfg.task == ZBOT_TASK_SNAKE_V0) {
     if (ex) return fail(ZBOT_E_INVALID, "zbot_step_export is a walking-task hook; use zbot_snake_step_export%s");
-    if (snake_export)
+    if (snake_export && h->unroll2)   // export flavour of the SAME sweep unroll the product launch uses at this N
+      ZB_CUDA_LAUNCH((zbot_snake_step_kernel<true, 2>), h->P, h->dp, h->state, h->ep_len, actions, obs, rew, terminated,
+                                                         truncated, n, sc, snake_export);
+    else if (snake_export)
       ZB_CUDA_LAUNCH(zbot_snake_step_kernel<true>, h->P, h->dp, h->state, h->ep_len, actions, obs, rew, terminated,
                                                          truncated, n, sc, snake_export);
     else if (h->unroll2 && h->ctas3)   // more than one warp per scheduler: sweeps unrolled by two (see zbot_create)
@@ -1336,7 +1428,12 @@ static int step_impl(ZbotHandle* h, const float* actions, float* obs, float* rew
     const float* const* pp = reinterpret_cast<const float* const*>(&xp);
     for (int i = 0; i < 12; ++i)
       if (!pp[i]) return fail(ZBOT_E_INVALID, "zbot_step_export: NULL export buffer%s");
-    zbot_step_kernel<true, 128, 2><<<grid, block, smem, s>>>(h->P, h->dp, h->state, h->ep_len, actions, obs, rew, terminated,
+    // the export flavour of the instantiation `zbot_step` launches for this handle (same phased body, same sweep unroll)
+    if (h->unroll2)
+      zbot_step_u2_export_kernel<<<grid, block, smem, s>>>(h->P, h->dp, h->state, h->ep_len, actions, obs, rew, terminated,
+                                                         truncated, n, 0, n, sc, xp);
+    else
+      zbot_step_kernel<true, 128, 1><<<grid, block, smem, s>>>(h->P, h->dp, h->state, h->ep_len, actions, obs, rew, terminated,
                                                          truncated, n, 0, n, sc, xp);
   } else if (h->pdl) {
     ZB_CUDA(launch_pdl(kStepVariants[h->variant].fn, dim3(grid), dim3(block), smem, s, true, h->P, h->dp, h->state, h->ep_len,
@@ -1378,6 +1475,7 @@ int zbot_step_export(ZbotHandle* h, const float* actions, float* obs, float* rew
 int zbot_step_host(ZbotHandle* h, const float* host_actions, float* host_rows, int32_t stats_slot, int32_t prev_slot,
                    void* stream) {
   if (!h) return fail(ZBOT_E_INVALID, "handle is NULL%s");
+  DeviceGuard guard(h->device);
   if (!h->state) return fail(ZBOT_E_UNBOUND, "zbot_bind has not been called%s");
   if (h->cfg.task != ZBOT_TASK_WALKING_V2) return fail(ZBOT_E_INVALID, "zbot_step_host: walking task only%s");
   if (!host_actions || !host_rows) return fail(ZBOT_E_INVALID, "zbot_step_host: NULL buffer%s");
@@ -1403,7 +1501,8 @@ int zbot_step_host(ZbotHandle* h, const float* host_actions, float* host_rows, i
   const int grid = (n + block - 1) / block;
   const size_t smem = (size_t)block * SCR_STRIDE * sizeof(float);
   cudaStream_t s = (cudaStream_t)stream;
-  StatsCtx sc{h->partials, h->ring, stats_slot, prev_slot, h->inv_episode_s, 0, (unsigned long long)h->launches, 1};
+  StatsCtx sc{h->partials, h->ring, stats_slot, prev_slot, h->inv_episode_s, 0, h->rng_ctr, 1};
+  ctx_spread(sc, h);
   ExportPtrs xp{};
   kStepVariants[vi].fn<<<grid, block, smem, s>>>(h->P, h->dp, h->state, h->ep_len, host_actions, host_rows, nullptr, nullptr,
                                                    nullptr, n, 0, n, sc, xp);
@@ -1418,6 +1517,7 @@ int zbot_step_host(ZbotHandle* h, const float* host_actions, float* host_rows, i
 static int v4_step_impl(ZbotHandle* h, const float* actions, const float* rand, float* obs, float* rew, uint8_t* terminated,
                         uint8_t* truncated, int32_t slot, int32_t prev, float* export_buf, void* stream) {
   if (!h) return fail(ZBOT_E_INVALID, "handle is NULL%s");
+  DeviceGuard guard(h->device);
   if (h->cfg.task != ZBOT_TASK_WALKING_V4) return fail(ZBOT_E_INVALID, "zbot_v4_step needs task = ZBOT_TASK_WALKING_V4%s");
   if (!h->state) return fail(ZBOT_E_UNBOUND, "zbot_bind has not been called%s");
   if (!actions || !obs || !rew || !terminated || !truncated) return fail(ZBOT_E_INVALID, "zbot_v4_step: NULL buffer%s");
@@ -1429,20 +1529,23 @@ static int v4_step_impl(ZbotHandle* h, const float* actions, const float* rand, 
   while (block > 32 && (n + block - 1) / block < 2 * h->num_sms) block >>= 1;
   const int grid = (n + block - 1) / block;
   const size_t smem = (size_t)block * SCR_STRIDE * sizeof(float);
-  StatsCtx sc{h->partials, h->ring, slot, prev, h->inv_episode_s, 0, (unsigned long long)h->launches, 0};
+  StatsCtx sc{h->partials, h->ring, slot, prev, h->inv_episode_s, 0, h->rng_ctr, 0};
+  ctx_spread(sc, h);
   cudaStream_t s = (cudaStream_t)stream;
-  const uint64_t call = h->v4_calls++;
-  if (export_buf)
-    ZB_CUDA_LAUNCH(zbot_v4_step_kernel<true>, h->P, h->state, h->ep_len, actions, rand, h->cfg.rng_seed, call, obs, rew,
+  if (export_buf && h->unroll2)
+    ZB_CUDA_LAUNCH((zbot_v4_step_kernel<true, 2>), h->P, h->state, h->ep_len, actions, rand, h->cfg.rng_seed, obs, rew,
+                                                    terminated, truncated, n, sc, export_buf);
+  else if (export_buf)
+    ZB_CUDA_LAUNCH(zbot_v4_step_kernel<true>, h->P, h->state, h->ep_len, actions, rand, h->cfg.rng_seed, obs, rew,
                                                     terminated, truncated, n, sc, export_buf);
   else if (h->unroll2 && h->ctas3)
-    ZB_CUDA_LAUNCH((zbot_v4_step_kernel<false, 2, 3>), h->P, h->state, h->ep_len, actions, rand, h->cfg.rng_seed, call, obs,
+    ZB_CUDA_LAUNCH((zbot_v4_step_kernel<false, 2, 3>), h->P, h->state, h->ep_len, actions, rand, h->cfg.rng_seed, obs,
                                                         rew, terminated, truncated, n, sc, nullptr);
   else if (h->unroll2)
-    ZB_CUDA_LAUNCH((zbot_v4_step_kernel<false, 2>), h->P, h->state, h->ep_len, actions, rand, h->cfg.rng_seed, call, obs,
+    ZB_CUDA_LAUNCH((zbot_v4_step_kernel<false, 2>), h->P, h->state, h->ep_len, actions, rand, h->cfg.rng_seed, obs,
                                                         rew, terminated, truncated, n, sc, nullptr);
   else
-    ZB_CUDA_LAUNCH(zbot_v4_step_kernel<false>, h->P, h->state, h->ep_len, actions, rand, h->cfg.rng_seed, call, obs, rew,
+    ZB_CUDA_LAUNCH(zbot_v4_step_kernel<false>, h->P, h->state, h->ep_len, actions, rand, h->cfg.rng_seed, obs, rew,
                                                      terminated, truncated, n, sc, nullptr);
   ZB_CUDA(cudaGetLastError());
   h->launches += 1;
@@ -1465,6 +1568,7 @@ int zbot_v4_step_export(ZbotHandle* h, const float* actions, const float* rand, 
 static int m_step_impl(ZbotHandle* h, const float* actions, const float* rand, float* obs, float* rew, uint8_t* terminated,
                        uint8_t* truncated, int32_t slot, int32_t prev, float* export_buf, void* stream) {
   if (!h) return fail(ZBOT_E_INVALID, "handle is NULL%s");
+  DeviceGuard guard(h->device);
   if (h->cfg.task != ZBOT_TASK_WALKING_M) return fail(ZBOT_E_INVALID, "zbot_m_step needs task = ZBOT_TASK_WALKING_M%s");
   if (!h->state) return fail(ZBOT_E_UNBOUND, "zbot_bind has not been called%s");
   if (!actions || !obs || !rew || !terminated || !truncated) return fail(ZBOT_E_INVALID, "zbot_m_step: NULL buffer%s");
@@ -1475,21 +1579,24 @@ static int m_step_impl(ZbotHandle* h, const float* actions, const float* rand, f
   while (block > 32 && (n + block - 1) / block < 2 * h->num_sms) block >>= 1;
   const int grid = (n + block - 1) / block;
   const size_t smem = (size_t)block * SCR_STRIDE * sizeof(float);
-  StatsCtx sc{h->partials, h->ring, slot, prev, h->inv_episode_s, 0, (unsigned long long)h->launches, 0,
+  StatsCtx sc{h->partials, h->ring, slot, prev, h->inv_episode_s, 0, h->rng_ctr, 0,
               (h->cfg.num_terms <= MAX_TERMS - 3) ? 2 : 0};
+  ctx_spread(sc, h);
   cudaStream_t s = (cudaStream_t)stream;
-  const uint64_t call = h->v4_calls++;
-  if (export_buf)
-    ZB_CUDA_LAUNCH(zbot_m_step_kernel<true>, h->P, h->state, h->ep_len, actions, rand, h->cfg.rng_seed, call, obs, rew,
+  if (export_buf && h->unroll2)
+    ZB_CUDA_LAUNCH((zbot_m_step_kernel<true, 2>), h->P, h->state, h->ep_len, actions, rand, h->cfg.rng_seed, obs, rew,
+                                                   terminated, truncated, n, sc, export_buf);
+  else if (export_buf)
+    ZB_CUDA_LAUNCH(zbot_m_step_kernel<true>, h->P, h->state, h->ep_len, actions, rand, h->cfg.rng_seed, obs, rew,
                                                    terminated, truncated, n, sc, export_buf);
   else if (h->unroll2 && h->ctas3)
-    ZB_CUDA_LAUNCH((zbot_m_step_kernel<false, 2, 3>), h->P, h->state, h->ep_len, actions, rand, h->cfg.rng_seed, call, obs,
+    ZB_CUDA_LAUNCH((zbot_m_step_kernel<false, 2, 3>), h->P, h->state, h->ep_len, actions, rand, h->cfg.rng_seed, obs,
                                                        rew, terminated, truncated, n, sc, nullptr);
   else if (h->unroll2)
-    ZB_CUDA_LAUNCH((zbot_m_step_kernel<false, 2>), h->P, h->state, h->ep_len, actions, rand, h->cfg.rng_seed, call, obs,
+    ZB_CUDA_LAUNCH((zbot_m_step_kernel<false, 2>), h->P, h->state, h->ep_len, actions, rand, h->cfg.rng_seed, obs,
                                                        rew, terminated, truncated, n, sc, nullptr);
   else
-    ZB_CUDA_LAUNCH(zbot_m_step_kernel<false>, h->P, h->state, h->ep_len, actions, rand, h->cfg.rng_seed, call, obs, rew,
+    ZB_CUDA_LAUNCH(zbot_m_step_kernel<false>, h->P, h->state, h->ep_len, actions, rand, h->cfg.rng_seed, obs, rew,
                                                     terminated, truncated, n, sc, nullptr);
   ZB_CUDA(cudaGetLastError());
   h->launches += 1;
@@ -1507,6 +1614,12 @@ int zbot_m_step_export(ZbotHandle* h, const float* actions, const float* rand, f
                        uint8_t* truncated, int32_t stats_slot, int32_t prev_slot, float* export_buf, void* stream) {
   if (!export_buf) return fail(ZBOT_E_INVALID, "zbot_m_step_export: export_buf is NULL%s");
   return m_step_impl(h, actions, rand, obs, rew, terminated, truncated, stats_slot, prev_slot, export_buf, stream);
+}
+
+int zbot_set_all_reset_spread(ZbotHandle* h, int32_t enable) {
+  if (!h) return fail(ZBOT_E_INVALID, "handle is NULL%s");
+  h->spread_all_reset = enable ? 1 : 0;
+  return ZBOT_OK;
 }
 
 int zbot_update_cfg(ZbotHandle* h, const ZbotCfg* cfg) {
@@ -1530,6 +1643,7 @@ int zbot_snake_step_export(ZbotHandle* h, const float* actions, float* obs, floa
 int zbot_reset_idx(ZbotHandle* h, const int64_t* env_ids, int64_t nids, const uint8_t* terminated, const uint8_t* truncated,
                    int32_t stats_slot, void* stream) {
   if (!h) return fail(ZBOT_E_INVALID, "handle is NULL%s");
+  DeviceGuard guard(h->device);
   if (!h->state) return fail(ZBOT_E_UNBOUND, "zbot_bind has not been called%s");
   if (int rc = check_slot(stats_slot, -1, h->ring_slots)) return rc;
   if (h->cfg.task == ZBOT_TASK_WALKING_V4 || h->cfg.task == ZBOT_TASK_WALKING_M)
@@ -1540,7 +1654,7 @@ int zbot_reset_idx(ZbotHandle* h, const int64_t* env_ids, int64_t nids, const ui
   if (nids > n) return fail(ZBOT_E_INVALID, "more env ids than envs%s");
   const int block = 64;
   const int grid = (int)((nids + block - 1) / block);
-  StatsCtx sc{h->partials, h->ring, stats_slot, -1, h->inv_episode_s, 0, (unsigned long long)h->launches, 0};
+  StatsCtx sc{h->partials, h->ring, stats_slot, -1, h->inv_episode_s, 0, h->rng_ctr, 0};
   if (h->cfg.task == ZBOT_TASK_SNAKE_V0)
     zbot_reset_kernel<true><<<grid, block, 32 * kStatUsed * sizeof(float), (cudaStream_t)stream>>>(
         h->P, h->dp, h->state, h->ep_len, env_ids, nids, terminated, truncated, n, sc);
@@ -1557,6 +1671,7 @@ int zbot_reset_idx(ZbotHandle* h, const int64_t* env_ids, int64_t nids, const ui
 
 int zbot_observe(ZbotHandle* h, float* obs, void* stream) {
   if (!h || !obs) return fail(ZBOT_E_INVALID, "zbot_observe: NULL argument%s");
+  DeviceGuard guard(h->device);
   if (h->cfg.task == ZBOT_TASK_WALKING_V4 || h->cfg.task == ZBOT_TASK_WALKING_M)
     return fail(ZBOT_E_INVALID, "zbot_observe: v2 / snake observation layout only%s");
   if (!h->state) return fail(ZBOT_E_UNBOUND, "zbot_bind has not been called%s");
@@ -1572,6 +1687,7 @@ int zbot_observe(ZbotHandle* h, float* obs, void* stream) {
 
 int zbot_articulation_view(ZbotHandle* h, float* pos, float* quat, float* vel, void* stream) {
   if (!h) return fail(ZBOT_E_INVALID, "handle is NULL%s");
+  DeviceGuard guard(h->device);
   if (!h->state) return fail(ZBOT_E_UNBOUND, "zbot_bind has not been called%s");
   if (h->cfg.task == ZBOT_TASK_SNAKE_V0) return fail(ZBOT_E_INVALID, "zbot_articulation_view: walking tasks only%s");
   const int n = h->cfg.num_envs, block = 64, grid = (n + block - 1) / block;
@@ -1607,11 +1723,12 @@ static int mdp_check(const ZbotHandle* h, const ZbotMdpInputs* in, bool step) {
 
 int zbot_mdp_observe(ZbotHandle* h, const ZbotMdpInputs* in, float* obs, void* stream) {
   if (int rc = mdp_check(h, in, false)) return rc;
+  DeviceGuard guard(h->device);
   if (!obs) return fail(ZBOT_E_INVALID, "obs is NULL%s");
   const int n = h->cfg.num_envs, block = 128, grid = (n + block - 1) / block;
   MdpIn mi{in->body_link_pos_w, in->body_link_quat_w, in->body_com_lin_vel_w, in->joint_pos, in->joint_vel,
            in->applied_torque, in->net_forces_w_history, in->last_air_time, in->env_origins};
-  StatsCtx sc{h->partials, h->m_ring, 0, -1, h->inv_episode_s, 0, (unsigned long long)h->launches, 0};
+  StatsCtx sc{h->partials, h->m_ring, 0, -1, h->inv_episode_s, 0, h->rng_ctr, 0};
   zbot_mdp_kernel<false><<<grid, block, block * ZBOT_NUM_OBS * sizeof(float), (cudaStream_t)stream>>>(
       h->P, h->dp, mi, h->mstate, h->m_ep_len, nullptr, obs, nullptr, nullptr, nullptr, n, sc);
   ZB_CUDA(cudaGetLastError());
@@ -1622,12 +1739,13 @@ int zbot_mdp_observe(ZbotHandle* h, const ZbotMdpInputs* in, float* obs, void* s
 int zbot_mdp_step(ZbotHandle* h, const ZbotMdpInputs* in, const float* actions, float* obs, float* rew, uint8_t* terminated,
                   uint8_t* truncated, int32_t stats_slot, int32_t prev_slot, void* stream) {
   if (int rc = mdp_check(h, in, true)) return rc;
+  DeviceGuard guard(h->device);
   if (!actions || !obs || !rew || !terminated || !truncated) return fail(ZBOT_E_INVALID, "zbot_mdp_step: NULL buffer%s");
   if (int rc = check_slot(stats_slot, prev_slot, h->m_ring_slots)) return rc;
   const int n = h->cfg.num_envs, block = h->mdp_tile, grid = (n + block - 1) / block;
   MdpIn mi{in->body_link_pos_w, in->body_link_quat_w, in->body_com_lin_vel_w, in->joint_pos, in->joint_vel,
            in->applied_torque, in->net_forces_w_history, in->last_air_time, in->env_origins};
-  StatsCtx sc{h->partials, h->m_ring, stats_slot, prev_slot, h->inv_episode_s, 0, (unsigned long long)h->launches, 0};
+  StatsCtx sc{h->partials, h->m_ring, stats_slot, prev_slot, h->inv_episode_s, 0, h->rng_ctr, 0};
   ZB_CUDA(launch_pdl(zbot_mdp_kernel<true>, dim3(grid), dim3(block), (size_t)block * kHistRow * sizeof(float), (cudaStream_t)stream,
                      h->pdl, h->P, h->dp, mi, h->mstate, h->m_ep_len, actions, obs, rew, terminated, truncated, n, sc));
   h->launches += 1;
@@ -1637,5 +1755,7 @@ int zbot_mdp_step(ZbotHandle* h, const ZbotMdpInputs* in, const float* actions, 
 }
 
 int64_t zbot_launch_count(const ZbotHandle* h) { return h ? h->launches : 0; }
+
+const char* zbot_step_kernel_name(const ZbotHandle* h) { return h ? h->kernel_name : ""; }
 
 }  // extern "C"

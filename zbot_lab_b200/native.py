@@ -199,6 +199,7 @@ def _declare(lib):
     lib.zbot_m_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, vp]
     lib.zbot_m_step_export.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp]
     lib.zbot_update_cfg.argtypes = [vp, P(ZbotCfg)]
+    lib.zbot_set_all_reset_spread.argtypes = [vp, i32]
     lib.zbot_reset_idx.argtypes = [vp, vp, i64, vp, vp, i32, vp]
     lib.zbot_observe.argtypes = [vp, vp, vp]
     lib.zbot_articulation_view.argtypes = [vp, vp, vp, vp, vp]
@@ -207,10 +208,12 @@ def _declare(lib):
     lib.zbot_mdp_step.argtypes = [vp, P(ZbotMdpInputs), vp, vp, vp, vp, vp, i32, i32, vp]
     lib.zbot_launch_count.argtypes = [vp]
     lib.zbot_launch_count.restype = i64
+    lib.zbot_step_kernel_name.argtypes = [vp]
+    lib.zbot_step_kernel_name.restype = C.c_char_p
     for name in ("zbot_default_cfg", "zbot_state_word", "zbot_mdp_state_word", "zbot_create", "zbot_destroy",
                  "zbot_bind", "zbot_step", "zbot_step_export", "zbot_snake_step_export", "zbot_step_host", "zbot_v4_step",
                  "zbot_v4_step_export", "zbot_m_step", "zbot_m_step_export", "zbot_update_cfg", "zbot_reset_idx",
-                 "zbot_observe",
+                 "zbot_observe", "zbot_set_all_reset_spread",
                  "zbot_articulation_view", "zbot_mdp_bind", "zbot_mdp_observe", "zbot_mdp_step"):
         getattr(lib, name).restype = C.c_int
 
@@ -220,7 +223,7 @@ EXPORTED_SYMBOLS = (
     "zbot_mdp_state_word", "zbot_create", "zbot_destroy", "zbot_bind", "zbot_step", "zbot_step_export",
     "zbot_snake_step_export", "zbot_step_host", "zbot_v4_step", "zbot_v4_step_export", "zbot_m_step", "zbot_m_step_export",
     "zbot_update_cfg", "zbot_reset_idx", "zbot_observe", "zbot_articulation_view", "zbot_mdp_bind", "zbot_mdp_observe",
-    "zbot_mdp_step", "zbot_launch_count",
+    "zbot_mdp_step", "zbot_launch_count", "zbot_set_all_reset_spread", "zbot_step_kernel_name",
 )
 
 

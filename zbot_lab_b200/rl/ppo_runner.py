@@ -93,6 +93,18 @@ class OnPolicyRunner:
         # into ONE CUDA graph and replayed per iteration (no Python / launch overhead between the kernels)
         self.use_cuda_graph = bool(train_cfg.get("use_cuda_graph", self.device.type == "cuda"))
         self._graph = None
+        # extras["log"] values are 0-dim VIEWS into the env's statistics ring (one slot per step): the per-step dicts of a
+        # rollout stay valid only while the ring does not wrap.  Longer rollouts clone the scalars; the captured graph
+        # additionally needs slots T..2T-1 (`_pin_env_cursors`), so it is only used when 2T fits.
+        st = getattr(getattr(env, "unwrapped", env), "_stepper", None)
+        ring = getattr(st, "stats_ring", None)
+        self._ring_slots = int(ring.shape[0]) if ring is not None else None
+        self._clone_logs = self._ring_slots is not None and self.num_steps > self._ring_slots
+        if self.use_cuda_graph and self._ring_slots is not None and 2 * self.num_steps > self._ring_slots:
+            import warnings
+            warnings.warn(f"num_steps_per_env = {self.num_steps} needs {2 * self.num_steps} statistics slots for the captured "
+                          f"rollout graph, the ring has {self._ring_slots}: running the rollout eagerly")
+            self.use_cuda_graph = False
         self.current_learning_iteration = 0
         self.history: list[dict] = []
         self.git_status_repos: list[str] = []
@@ -146,7 +158,10 @@ class OnPolicyRunner:
                 rew += self.gamma * b["val"][t] * infos["time_outs"].to(rew.dtype)
             b["rew"][t], b["done"][t] = rew, dones.to(rew.dtype)
             if "log" in infos:
-                ep_infos.append(infos["log"])
+                log = infos["log"]
+                if self._clone_logs:   # the ring wraps within this rollout: detach the scalars from their slots
+                    log = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in log.items()}
+                ep_infos.append(log)
         return obs, ep_infos
 
     # ------------------------------------------------------------------ CUDA-graph rollout
@@ -180,9 +195,23 @@ class OnPolicyRunner:
         return self._obs_in
 
     def replay_rollout(self):
+        """Replay the captured rollout.  `env.step`'s Python does not run during a replay, so what it does on the host is
+        done here: the global step counter advances, and the env's HOST curricula (v4 `my_curriculum` / `range_curriculum`,
+        …env_v4.py:138-265; manager `lin_vel_cmd_levels`, mdp/curriculums.py:57-83) are evaluated for the replayed steps.
+        The kernel parameters are by-value arguments baked into the graph, so when a curriculum changed them the graph
+        is dropped and re-captured before the next rollout (a few times per training run)."""
         self._graph.replay()
         u = self.env.unwrapped
-        u.common_step_counter += self.num_steps
+        adv = getattr(u, "advance_host_curricula", None)
+        if adv is None:
+            u.common_step_counter += self.num_steps
+        elif adv(self.num_steps):
+            self._graph = None                      # stale parameters inside the captured launches: re-capture
+        cur = getattr(u, "curriculum_log", None)
+        if cur is not None:                         # python-float log entries were frozen at capture time
+            fresh = cur()
+            for e in self._graph_ep_infos:
+                e.update(fresh)
         return self._obs_in, self._graph_ep_infos
 
     def _returns(self, last_obs):
@@ -268,9 +297,9 @@ class OnPolicyRunner:
             os.makedirs(self.log_dir, exist_ok=True)
         start = self.current_learning_iteration
         graphed = self.use_cuda_graph and self.device.type == "cuda"
-        if graphed and self._graph is None:
-            obs = self.capture_rollout(obs)
         for it in range(start, start + num_learning_iterations):
+            if graphed and self._graph is None:     # first iteration, or a host curriculum changed the kernel parameters
+                obs = self.capture_rollout(obs)
             t0 = time.perf_counter()
             if graphed:
                 obs, ep_infos = self.replay_rollout()

@@ -135,6 +135,11 @@ class NativeStepper:
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     @property
+    def kernel_name(self) -> str:
+        """The step-kernel instantiation this handle launches (as in an ncu launch list)."""
+        return self.lib.zbot_step_kernel_name(self._h).decode()
+
+    @property
     def launch_count(self) -> int:
         return int(self.lib.zbot_launch_count(self._h))
 
@@ -232,6 +237,11 @@ class NativeStepper:
             "joint_pos1": z(n, 6), "joint_vel1": z(n, 6), "applied_torque1": z(n, 6),
             "net_forces_w_history1": z(n, 5, 12, 3), "last_air_time1": z(n, 12), "current_contact_time1": z(n, 12),
         }
+
+    def set_all_reset_spread(self, enable: bool):
+        """Device-side `episode_length_buf[:] = randint(0, max_episode_length)` when every env reset in one step
+        (…env_v2.py:418-422), decided and written by the statistics kernel: no host sync (include/zbot_b200.h)."""
+        native.check(self.lib.zbot_set_all_reset_spread(self._h, 1 if enable else 0), "zbot_set_all_reset_spread")
 
     def update_cfg(self):
         """Push the (mutated) ``self.cfg`` reward weights / event parameters to the live handle (host curricula)."""

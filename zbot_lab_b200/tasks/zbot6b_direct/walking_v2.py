@@ -135,8 +135,15 @@ class ZbotDirectEnvV2:
         self.reset_terminated = torch.zeros(n, dtype=torch.bool, device=dev)
         self.reset_time_outs = torch.zeros(n, dtype=torch.bool, device=dev)
         self.reset_buf = torch.zeros(n, dtype=torch.bool, device=dev)
+        # all-envs-reset spread of the episode counters (…env_v2.py:418-422).  `check_all_envs_reset`:
+        #   True  -> host sync on the reset count + torch.randint_like on the torch generator (bit-exact against the
+        #            reference's call); None (default) picks this for N <= 256;
+        #   None  -> N > 256: the statistics kernel decides and writes the counters ON THE DEVICE (in-kernel generator;
+        #            no sync, no work unless the event fires, also inside a captured rollout graph);
+        #   False -> no spread at all (deterministic counters, tests).
         chk = self.cfg.check_all_envs_reset
         self._check_all_reset = (self.num_envs <= 256) if chk is None else bool(chk)
+        self._stepper.set_all_reset_spread(chk is None and not self._check_all_reset)
         self._initial_reset()
         self._sim_step_counter = 0
 
@@ -269,6 +276,14 @@ class ZbotDirectEnvV2:
                 self.episode_length_buf = torch.randint_like(st.episode_length_buf, high=int(self.max_episode_length))
         self.extras["log"] = self._log_from_slot()
         return {"policy": obs}, rew, self.reset_terminated, self.reset_time_outs, self.extras
+
+    def advance_host_curricula(self, steps: int) -> bool:
+        """Host-side bookkeeping of `steps` control steps that ran WITHOUT `step()`'s Python (replay of a captured
+        rollout graph, `rl/ppo_runner.py`): advances the global step counter and evaluates the task's host curricula.
+        Returns True when kernel parameters changed (the caller must re-capture its graph).  v2 has no curriculum."""
+        self.common_step_counter += int(steps)
+        self._sim_step_counter += int(steps) * int(self.cfg.decimation)
+        return False
 
     def alloc_host_buffers(self):
         """Pinned host buffers for ``step_host``: ``(actions (N,6) f32, rows (N,25) f32)``."""

@@ -79,7 +79,7 @@ class ZbotDirectEnvCfgV2(Cfg):
     # (ObservationManager `Unoise` semantics of the manager-based task, zbotlab_manager/zbotlab_env_cfg.py PolicyCfg:
     # base_quat +-0.01, joint_pos +-0.01, joint_vel +-1.5); None = the direct tasks' behaviour (no corruption)
     observation_noise = None
-    check_all_envs_reset = None   # None: sync-check only when num_envs <= 256 (…env_v2.py:418-422)
+    check_all_envs_reset = None   # None: host sync-check when num_envs <= 256, device-side spread above; True / False: force host path / off (…env_v2.py:418-422)
     output_ring = 4               # step() outputs rotate through this many buffers
 
 

@@ -156,13 +156,31 @@ class Zbot6SEnvV4(ZbotDirectEnvV2):
                 changed = True
         return changed
 
+    def advance_host_curricula(self, steps: int) -> bool:
+        """The curricula of `steps` control steps that ran inside a replayed rollout graph (no Python per step): the
+        step-count thresholds of `my_curriculum` / `range_curriculum` are checked for every replayed step; a change takes
+        effect from the next rollout (<= steps - 1 control steps later than in the eager loop)."""
+        changed = False
+        for _ in range(int(steps)):
+            self.common_step_counter += 1
+            if self.cfg.events.my_curric:
+                changed |= bool(self._my_curriculum() | self._range_curriculum())
+        self._sim_step_counter += int(steps) * int(self.cfg.decimation)
+        if changed:
+            self._push_cfg()
+            self._log_cache.clear()
+        return changed
+
     # ------------------------------------------------------------------ log
+    def curriculum_log(self) -> dict:
+        return {"Curriculum/curriculum_stage": self.curriculum_stage,                  # …env_v4.py:925-933
+                "Curriculum/vel_lower_bound": self.event_params["velocity_range"][0],
+                "Curriculum/vel_upper_bound": self.event_params["velocity_range"][1],
+                "Curriculum/yaw_bound": self.event_params["yaw_range"][0]}
+
     def _log_from_slot(self) -> dict:
         log = dict(super()._log_from_slot())
-        log["Curriculum/curriculum_stage"] = self.curriculum_stage                     # …env_v4.py:925-933
-        log["Curriculum/vel_lower_bound"] = self.event_params["velocity_range"][0]
-        log["Curriculum/vel_upper_bound"] = self.event_params["velocity_range"][1]
-        log["Curriculum/yaw_bound"] = self.event_params["yaw_range"][0]
+        log.update(self.curriculum_log())
         return log
 
     # ------------------------------------------------------------------ gym API

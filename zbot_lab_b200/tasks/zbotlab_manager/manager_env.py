@@ -214,16 +214,19 @@ class ManagerBasedRLEnv(ZbotDirectEnvV2):
         raise AttributeError(name)
 
     # ------------------------------------------------------------------ curriculum (host), mdp/curriculums.py:57-83
-    def _lin_vel_cmd_levels(self):
+    def _lin_vel_cmd_levels(self, slot: int | None = None) -> bool:
+        """Returns True when the command ranges (hence the kernel parameters) changed.  `slot`: statistics slot of the
+        step the curriculum is evaluated for (default: the most recent one)."""
         if not self._curr_lin_vel or self.common_step_counter % self.max_episode_length != 0:
-            return
+            return False
         names = self._term_names
         if "track_lin_vel_xy_exp" not in names:
-            return
+            return False
         i = names.index("track_lin_vel_xy_exp")
-        s = self._stepper.stats_ring[max(self._stepper._slot, 0)].cpu()       # one host read per max_episode_length steps
+        slot = max(self._stepper._slot, 0) if slot is None else slot
+        s = self._stepper.stats_ring[slot].cpu()                 # one host read per max_episode_length steps
         if float(s[native.STAT_NUM_RESET]) == 0:                 # CurriculumManager.compute runs inside _reset_idx: no reset, no update
-            return
+            return False
         reward = float(s[i])                                     # mean episodic sum of the reset envs / episode seconds
         weight = self._reward_terms[i][2]
         if reward > weight * 0.8:
@@ -235,6 +238,24 @@ class ManagerBasedRLEnv(ZbotDirectEnvV2):
             for f, _ in native.ZbotCfg._fields_:
                 setattr(self._stepper.cfg, f, getattr(new, f))
             self._stepper.update_cfg()
+            return True
+        return False
+
+    def advance_host_curricula(self, steps: int) -> bool:
+        """`steps` control steps ran inside a replayed rollout graph (no Python per step; `rl/ppo_runner.py`): advance the
+        global step counter and evaluate `lin_vel_cmd_levels` for the replayed step that crossed a multiple of
+        max_episode_length, on that step's own statistics slot.  True = kernel parameters changed (re-capture)."""
+        changed = False
+        last = self._stepper._slot                              # slot of the LAST replayed step
+        slots = self._stepper.stats_ring.shape[0]
+        for t in range(int(steps)):
+            self.common_step_counter += 1
+            changed |= self._lin_vel_cmd_levels((last - (int(steps) - 1 - t)) % slots)
+        self._sim_step_counter += int(steps) * int(self.cfg.decimation)
+        return changed
+
+    def curriculum_log(self) -> dict:
+        return {"Curriculum/lin_vel_cmd_levels": float(self._cmd.ranges.lin_vel_x[1])}
 
     # ------------------------------------------------------------------ log (managers' reset logs [IL-upstream])
     def _log_from_slot(self) -> dict:
