@@ -58,7 +58,8 @@ def csrc_hash() -> str:
     import hashlib
     h = hashlib.sha256()
     for f in sorted(glob.glob(os.path.join(ROOT, "zbot_lab_b200", "csrc", "*.cu")) +
-                    glob.glob(os.path.join(ROOT, "zbot_lab_b200", "csrc", "*.h"))) + [os.path.join(ROOT, "include", "zbot_b200.h")]:
+                    glob.glob(os.path.join(ROOT, "zbot_lab_b200", "csrc", "*.h")) +
+                    glob.glob(os.path.join(ROOT, "zbot_lab_b200", "csrc", "*.cuh"))) + [os.path.join(ROOT, "include", "zbot_b200.h")]:
         h.update(os.path.basename(f).encode())
         h.update(open(f, "rb").read())
     return h.hexdigest()[:16]

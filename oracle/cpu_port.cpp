@@ -16,6 +16,7 @@
 
 #include "../zbot_lab_b200/csrc/zbot_layout.h"
 #include "../zbot_lab_b200/csrc/zbot_pair.h"
+#include "../zbot_lab_b200/csrc/zbot_halves.h"
 
 using namespace zbot;
 
@@ -183,6 +184,7 @@ static int port_substeps(const ZbotCfg* cfg, T* sim, const T* target, T* forces,
     for (int k = 0; k < nsub; ++k) {
       if (snake) physics_substep<ModelSnake>(P, s, tgt7, so, scr, midf);
       else if (model == 2) physics_substep<ModelWalkM>(P, s, tgt7, so, scr, midf);
+      else if (model == 3) physics_substep_halves<ModelWalk>(P, s, tgt7, so, midf);   // two-halves elimination (csrc/zbot_halves.h)
       else physics_substep<ModelWalk>(P, s, tgt7, so, scr, midf);
     }
     for (int i = 0; i < 3; ++i) { w[i] = s.p[i]; w[7 + i] = s.v[i]; w[10 + i] = s.w[i]; }
@@ -289,6 +291,12 @@ int zbot_port_substeps_f32(const ZbotCfg* cfg, float* sim, const float* target, 
 }
 int zbot_port_substeps_f64(const ZbotCfg* cfg, double* sim, const double* target, double* forces, double* tau, int n, int nsub) {
   return port_substeps<double>(cfg, sim, target, forces, tau, n, nsub);
+}
+int zbot_port_substeps_halves_f32(const ZbotCfg* cfg, float* sim, const float* target, float* forces, float* tau, int n, int nsub) {
+  return port_substeps<float>(cfg, sim, target, forces, tau, n, nsub, 3);
+}
+int zbot_port_substeps_halves_f64(const ZbotCfg* cfg, double* sim, const double* target, double* forces, double* tau, int n, int nsub) {
+  return port_substeps<double>(cfg, sim, target, forces, tau, n, nsub, 3);
 }
 int zbot_port_substeps_snake_f32(const ZbotCfg* cfg, float* sim, const float* target, float* forces, float* tau, int n, int nsub) {
   return port_substeps<float>(cfg, sim, target, forces, tau, n, nsub, 1);

@@ -21,6 +21,8 @@ SRCS = [os.path.join(HERE, "cpu_port.cpp"),
         os.path.join(ROOT, "zbot_lab_b200", "csrc", "zbot_core.h"),
         os.path.join(ROOT, "zbot_lab_b200", "csrc", "zbot_layout.h"),
         os.path.join(ROOT, "zbot_lab_b200", "csrc", "zbot_model_constants.h"),
+        os.path.join(ROOT, "zbot_lab_b200", "csrc", "zbot_pair.h"),
+        os.path.join(ROOT, "zbot_lab_b200", "csrc", "zbot_halves.h"),
         os.path.join(ROOT, "include", "zbot_b200.h")]
 
 
@@ -169,7 +171,8 @@ def substeps(sim: np.ndarray, target: np.ndarray, nsub: int, cfg: ZbotCfg | None
     forces = np.zeros((n, 7, 3), dt)
     tau = np.zeros((n, 6), dt)
     target = np.ascontiguousarray(target, dt)
-    name = "zbot_port_substeps_m_" if model == "m" else "zbot_port_substeps_snake_" if snake else "zbot_port_substeps_"
+    name = ("zbot_port_substeps_m_" if model == "m" else "zbot_port_substeps_halves_" if model == "halves" else
+            "zbot_port_substeps_snake_" if snake else "zbot_port_substeps_")
     rc = getattr(lib(), name + sfx)(C.byref(cfg), _p(sim), _p(target), _p(forces), _p(tau),
                                                      C.c_int(n), C.c_int(nsub))
     assert rc == 0

@@ -569,3 +569,36 @@ def test_sole_geometry_matches_the_collision_meshes():
         assert len(faces) == 1, (fname, link, faces)                 # each half-module has exactly one flat circular end
         a, v, r = faces[0]
         assert a == ax and abs(v - pos) < 2e-4 and abs(r - Z.FOOT_DISC_RADIUS) < 1.5e-3, (fname, link, faces)
+
+
+def test_halves_elimination_equals_the_one_chain_substep():
+    """csrc/zbot_halves.h (the arithmetic of the two-warps-per-32-envs GPU kernel): the articulated-body elimination run from
+    BOTH feet towards body 3 -- side A through the reversed joints 0..2, side B through joints 5..3, one 6x6 solve at body
+    3 -- is the same substep as the one-chain `physics_substep`: identical model, identical discretisation.  In float64 the
+    two agree to round-off over 8 substeps with contact, PD saturation and random targets; in float32 both sit at the same
+    distance from the float64 result."""
+    from oracle import cpu_port
+    from zbot_lab_b200.utils import synthetic as syn
+    n = 600
+    rng = np.random.default_rng(3)
+    st = syn.synth_sim_state(rng, n)
+    keys = ("root_pos", "root_quat", "root_lin_vel", "root_ang_vel", "joint_pos", "joint_vel")
+    sim = np.concatenate([st[k].reshape(n, -1) for k in keys], 1).astype(np.float64)
+    tgt = st["joint_pos"].astype(np.float64) + rng.normal(0, 0.6, (n, 6))     # large errors: the +-20 N m clamp is active
+    a, b = sim.copy(), sim.copy()
+    touched = 0
+    for k in range(8):
+        fa, ta = cpu_port.substeps(a, tgt, 1)
+        fb, tb = cpu_port.substeps(b, tgt, 1, model="halves")
+        assert np.abs(a - b).max() <= 1e-9 * (k + 1) and np.abs(ta - tb).max() <= 1e-9
+        assert np.abs(fa - fb).max() <= 1e-7          # contact forces (hundreds of newtons), feet applied + merged-body predictor
+        touched += int((np.abs(fa[:, 0, 2]) > 1.0).sum() + (np.abs(fa[:, 6, 2]) > 1.0).sum())
+        b[:] = a                                      # one-step comparison each time
+    assert touched > n                                # the feet were actually on the ground
+    ref = sim.copy()
+    cpu_port.substeps(ref, tgt, 4)
+    x32, h32 = sim.astype(np.float32), sim.astype(np.float32)
+    cpu_port.substeps(x32, tgt.astype(np.float32), 4)
+    cpu_port.substeps(h32, tgt.astype(np.float32), 4, model="halves")
+    dx, dh = np.abs(x32 - ref).max(1), np.abs(h32 - ref).max(1)
+    assert np.median(dh) <= 2.0 * np.median(dx) + 1e-7 and np.quantile(dh, 0.99) <= 3.0 * np.quantile(dx, 0.99) + 1e-6

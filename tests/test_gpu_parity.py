@@ -986,6 +986,7 @@ def test_unrolled_chain_sweeps_agree_with_the_rolled_kernel(monkeypatch, task):
     res = []
     # rolled; unrolled with 2 CTAs/SM; unrolled with 3 CTAs/SM (168 registers: the instantiation the wave rule picks e.g. at
     # 49152 or 131072 envs; for the walking task that is ZBOT_STEP_VARIANT=u128x3)
+    monkeypatch.setenv("ZBOT_W2", "0")       # the one-thread-per-env kernels (at this N the walking default is the two-warp kernel)
     for unroll, ctas3 in (("1", "0"), ("2", "0"), ("2", "1")):
         monkeypatch.setenv("ZBOT_SWEEP_UNROLL", unroll)
         monkeypatch.setenv("ZBOT_CTAS3", ctas3)
@@ -1033,6 +1034,64 @@ def test_unrolled_chain_sweeps_agree_with_the_rolled_kernel(monkeypatch, task):
         assert float((r0[same] - r1[same]).abs().max()) <= 2e-3
         worst = max(worst, float(d.max()))
     print(f"unroll-2 vs rolled ({task}): worst one-step observation difference {worst:.3e}")
+
+
+def test_two_warp_kernel_agrees_with_the_one_thread_kernel_and_selection_rule(monkeypatch):
+    """The walking step as two warps per 32 envs (csrc/zbot_w2_kernel.cuh: elimination from both feet towards body 3, the
+    library's choice while an SM holds at most two warp pairs) and the one-thread-per-env kernel integrate the SAME model
+    with the SAME discretisation; they differ by float32 round-off only.  ONE step from identical states (ragged N, so a
+    CTA with dead lanes is covered), at every register-budget variant: time-outs / counters equal, observations within
+    the one-step bounds of DESIGN.md §6, termination flags equal on >= 99.5 % of the envs.  Plus the selection rule."""
+    from zbot_lab_b200.utils import synthetic as syn
+    n = 2048 + 37
+    rng = np.random.default_rng(33)
+    a = rng.normal(0, 0.7, (4, n, 6)).astype(np.float32)
+    res, names = [], []
+    for env in ({"ZBOT_W2": "0"}, {}, {"ZBOT_W2_CTAS": "6"}, {"ZBOT_W2_CTAS": "8"}, {"ZBOT_W2_CTAS": "10"}):
+        for k in ("ZBOT_W2", "ZBOT_W2_CTAS"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        r = np.random.default_rng(5)
+        st = _stepper(n)
+        names.append(st.kernel_name)
+        st.reset_idx(None)
+        st.set_sim_state({k: _t(v) for k, v in syn.synth_sim_state(r, n).items()})
+        st.episode_length_buf[:] = _t(r.integers(0, 1000, n).astype(np.int64))
+        outs = []
+        for t in range(4):
+            o = st.step(_t(a[t]))
+            outs.append([x.clone() for x in o] + [st.state.buf.clone(), st.episode_length_buf.clone()])
+            if res:                       # re-synchronise to the one-thread kernel's state: a ONE-step comparison each time
+                st.state.buf.copy_(res[0][t][4])
+                st.episode_length_buf.copy_(res[0][t][5])
+        res.append(outs)
+        st.close()
+    assert names[0].startswith("zbot_step_kernel<false") and names[1] == "zbot_step_w2_kernel<3>" and names[3] == "zbot_step_w2_kernel<8>"
+    worst = 0.0
+    for other in range(1, len(res)):
+        for t in range(4):
+            o0, r0, te0, tr0, s0, ep0 = res[0][t]
+            o1, r1, te1, tr1, s1, ep1 = res[other][t]
+            same = te0 == te1
+            assert torch.equal(tr0, tr1) and float(same.float().mean()) >= 0.995, (names[other], t)
+            assert torch.equal(ep0[same], ep1[same])
+            d = (o0[same] - o1[same]).abs()
+            assert float(d[:, :10].max()) <= 2e-4 and float(d[:, 10:16].max()) <= 2e-2, (names[other], t)
+            assert float(d[:, 16:23].max()) <= 1e-6
+            # rewards: round-off, except where a thresholded term (touchdown at 10 N, slide gate at 1 N) flips
+            dr = (r0[same] - r1[same]).abs()
+            assert float(torch.quantile(dr, 0.999)) <= 2e-3 and float(dr.max()) <= 5e-2, (names[other], t)
+            worst = max(worst, float(d.max()))
+    print(f"two-warp vs one-thread kernel: worst one-step observation difference {worst:.3e}")
+    # selection rule: two warps per 32 envs while an SM holds at most two pairs (148 SMs -> 9472 envs), one thread per env beyond
+    for k in ("ZBOT_W2", "ZBOT_W2_CTAS"):
+        monkeypatch.delenv(k, raising=False)
+    for nn, want in ((4096, "zbot_step_w2_kernel<3>"), (9472, "zbot_step_w2_kernel<3>"), (9473, "zbot_step_kernel<false,128,2>"),
+                     (65536, "zbot_step_u2_kernel<128,2>")):
+        st = _stepper(nn)
+        assert st.kernel_name == want, (nn, st.kernel_name)
+        st.close()
 
 
 # ---------------------------------------------------------------------------------------------

@@ -20,7 +20,7 @@ def deps() -> list:
     """Every source the library is built from: all of csrc/*.cu|*.h (globbed, so a new header cannot be forgotten)
     plus the C-ABI header."""
     import glob
-    return sorted(glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.h"))) + [
+    return sorted(glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.h")) + glob.glob(os.path.join(CSRC, "*.cuh"))) + [
         os.path.join(HERE, "..", "include", "zbot_b200.h")]
 
 

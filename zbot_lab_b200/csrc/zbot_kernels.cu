@@ -23,6 +23,7 @@
 
 #include "zbot_layout.h"
 #include "zbot_pair.h"
+#include "zbot_halves.h"
 
 using namespace zbot;
 
@@ -507,6 +508,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) zbot_step_u2_kernel(Z
 __global__ void __launch_bounds__(128, 1) zbot_step_u2_export_kernel(ZB_STEP_ARGS) {
   zbot_step_body<true, 2>(ZB_STEP_CALL);
 }
+#include "zbot_w2_kernel.cuh"   // two warps per 32 envs (the default walking-v2 step kernel)
 // unrolled sweeps under a direct register cap (single-wave experiments: 14 warps/SM hold 65536 envs at <= 146 registers)
 template <int kMaxRegs>
 __global__ void __maxnreg__(kMaxRegs) zbot_step_u2_kernel_r(ZB_STEP_ARGS) {
@@ -1145,6 +1147,8 @@ struct ZbotHandle {
   unsigned long long* rng_ctr;   // device: stream position of the in-kernel generator (see StatsCtx::rng_ctr)
   DefaultPose* d_dp;             // device scratch of the create-time default-pose FK
   int spread_all_reset;          // zbot_set_all_reset_spread
+  int w2_ctas;                   // resident 64-thread CTAs per SM the w2 kernel is compiled for (register budget); ZBOT_W2_CTAS
+  bool w2;                       // walking-v2: the two-warps-per-32-envs kernel (zbot_w2_kernel.cuh); ZBOT_W2=0 / a ZBOT_STEP_VARIANT restore the one-thread-per-env kernels
   char kernel_name[96];          // zbot_step_kernel_name
   int mdp_tile;
 };
@@ -1184,6 +1188,15 @@ cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+StepFn w2_fn(int ctas) {
+  switch (ctas) {
+    case 3: return zbot_step_w2_kernel<3>;
+    case 6: return zbot_step_w2_kernel<6>;
+    case 10: return zbot_step_w2_kernel<10>;
+    default: return zbot_step_w2_kernel<8>;
+  }
 }
 
 int pick_block(const ZbotHandle* h, int n) {
@@ -1342,6 +1355,15 @@ static int create_impl(const ZbotCfg* cfg, int device, ZbotHandle* h) {
     if (h->mdp_tile != 32 && h->mdp_tile != 64 && h->mdp_tile != 128) h->mdp_tile = kMdpTile;
     const char* bs = getenv("ZBOT_STEP_BLOCK");
     h->force_block = bs ? atoi(bs) : 0;
+    // Two warps per 32 envs (zbot_w2_kernel.cuh) while an SM holds at most two warp pairs, i.e. while the step is bound by
+    // the dependent-issue latency of one env's chain: 24.8 vs 31.2 us per step at 4096 envs, 25.4 vs 31.7 at 8192.  Beyond
+    // that the one-thread-per-env kernels win on instruction count (the split costs ~27 % more warp instructions: loop /
+    // select overhead of the side-generic sweep, the redundant 6x6 solve, the exchanges): 102 vs 77 us at 65536 envs
+    // (profiles/r2_notes.md).  ZBOT_W2=0 / 1 forces the choice.
+    h->w2 = (cfg->task == ZBOT_TASK_WALKING_V2) && !sv && cfg->num_envs <= 2 * 32 * h->num_sms;
+    if (const char* sw = getenv("ZBOT_W2")) h->w2 = (cfg->task == ZBOT_TASK_WALKING_V2) && !sv && (atoi(sw) != 0);
+    h->w2_ctas = 3;      // register budget: uncapped (<= 2 pairs per SM where this kernel is the default); 6 / 8 / 10 = tuning variants
+    if (const char* sc2 = getenv("ZBOT_W2_CTAS")) { const int c = atoi(sc2); if (c == 3 || c == 6 || c == 8 || c == 10) h->w2_ctas = c; }
   }
   {
     const StepVariant& v = kStepVariants[h->variant];
@@ -1351,7 +1373,8 @@ static int create_impl(const ZbotCfg* cfg, int device, ZbotHandle* h) {
       case ZBOT_TASK_WALKING_V4: snprintf(h->kernel_name, sizeof(h->kernel_name), "zbot_v4_step_kernel<false,%d,%d>", u, u == 2 ? c : 2); break;
       case ZBOT_TASK_WALKING_M: snprintf(h->kernel_name, sizeof(h->kernel_name), "zbot_m_step_kernel<false,%d,%d>", u, u == 2 ? c : 2); break;
       default:
-        if (v.threads >= 2000) snprintf(h->kernel_name, sizeof(h->kernel_name), "zbot_step_u2_kernel<%d,%d>", v.threads % 1000, v.ctas);
+        if (h->w2) snprintf(h->kernel_name, sizeof(h->kernel_name), "zbot_step_w2_kernel<%d>", h->w2_ctas);
+        else if (v.threads >= 2000) snprintf(h->kernel_name, sizeof(h->kernel_name), "zbot_step_u2_kernel<%d,%d>", v.threads % 1000, v.ctas);
         else if (v.threads >= 1000) snprintf(h->kernel_name, sizeof(h->kernel_name), "zbot_step2_kernel<%d,%d>", v.threads % 1000, v.ctas);
         else snprintf(h->kernel_name, sizeof(h->kernel_name), "zbot_step_kernel<false,%d,%d>", v.threads, v.ctas);
     }
@@ -1391,10 +1414,11 @@ static int step_impl(ZbotHandle* h, const float* actions, float* obs, float* rew
   if (int rc = check_slot(slot, prev, h->ring_slots)) return rc;
   const int n = h->cfg.num_envs;
   const bool walk = (h->cfg.task == ZBOT_TASK_WALKING_V2) && !ex;
+  const bool walk_any = (h->cfg.task == ZBOT_TASK_WALKING_V2);
   const int ept = walk ? kStepVariants[h->variant].envs_per_thread : 1;
   int block = pick_block(h, n);
   if (!walk) { block = 128; while (block > 32 && (n + block - 1) / block < 2 * h->num_sms) block >>= 1; }
-  const int grid = (n + block * ept - 1) / (block * ept);
+  const int grid = (walk_any && h->w2) ? (n + 31) / 32 : (n + block * ept - 1) / (block * ept);
   const size_t smem = (size_t)block * SCR_STRIDE * sizeof(float) * ept;   // >= obs rows (23/thread) and stats (704 floats)
   StatsCtx sc{h->partials, h->ring, slot, prev, h->inv_episode_s, 0, h->rng_ctr, 0};
   ctx_spread(sc, h);
@@ -1429,12 +1453,31 @@ static int step_impl(ZbotHandle* h, const float* actions, float* obs, float* rew
     for (int i = 0; i < 12; ++i)
       if (!pp[i]) return fail(ZBOT_E_INVALID, "zbot_step_export: NULL export buffer%s");
     // the export flavour of the instantiation `zbot_step` launches for this handle (same phased body, same sweep unroll)
-    if (h->unroll2)
+    if (h->w2) {
+      // The two-warp kernel exports from the PRODUCT instantiation itself (run-time hook: plain stores behind uniform
+      // branches), so the launch the oracle tests read is bit for bit the launch that is benchmarked.  Around it: the
+      // start-of-step 12-link view and history slot 4 from the state before the step, the end-of-physics view from the
+      // exported state after it.
+      const int vb = 64, vg = (n + vb - 1) / vb;
+      zbot_view_kernel<<<vg, vb, 0, s>>>(h->state, xp.pos0, xp.quat0, xp.vel0, n);
+      zbot_w2_export_pre_kernel<<<vg, vb, 0, s>>>(h->state, xp, n);
+      w2_fn(h->w2_ctas)<<<(n + 31) / 32, 64, kW2Smem, s>>>(h->P, h->dp, h->state, h->ep_len, actions, obs, rew, terminated,
+                                                          truncated, n, 0, n, sc, xp);
+      zbot_w2_export_view_kernel<<<vg, vb, 0, s>>>(xp, n);
+    } else if (h->unroll2)
       zbot_step_u2_export_kernel<<<grid, block, smem, s>>>(h->P, h->dp, h->state, h->ep_len, actions, obs, rew, terminated,
                                                          truncated, n, 0, n, sc, xp);
     else
       zbot_step_kernel<true, 128, 1><<<grid, block, smem, s>>>(h->P, h->dp, h->state, h->ep_len, actions, obs, rew, terminated,
                                                          truncated, n, 0, n, sc, xp);
+  } else if (h->w2) {
+    const int g2 = (n + 31) / 32;
+    ZB_CUDA(launch_pdl(w2_fn(h->w2_ctas), dim3(g2), dim3(64), kW2Smem, s, h->pdl, h->P, h->dp, h->state, h->ep_len,
+                       actions, obs, rew, terminated, truncated, n, 0, n, sc, xp));
+    h->launches += 1;
+    ZB_CUDA(launch_pdl(zbot_stats_finalize_kernel, dim3(1), dim3(1024), 0, s, h->pdl, sc, (unsigned int)g2));
+    h->launches += 1;
+    return ZBOT_OK;
   } else if (h->pdl) {
     ZB_CUDA(launch_pdl(kStepVariants[h->variant].fn, dim3(grid), dim3(block), smem, s, true, h->P, h->dp, h->state, h->ep_len,
                        actions, obs, rew, terminated, truncated, n, 0, n, sc, xp));
@@ -1504,11 +1547,16 @@ int zbot_step_host(ZbotHandle* h, const float* host_actions, float* host_rows, i
   StatsCtx sc{h->partials, h->ring, stats_slot, prev_slot, h->inv_episode_s, 0, h->rng_ctr, 1};
   ctx_spread(sc, h);
   ExportPtrs xp{};
-  kStepVariants[vi].fn<<<grid, block, smem, s>>>(h->P, h->dp, h->state, h->ep_len, host_actions, host_rows, nullptr, nullptr,
+  const int grid_used = h->w2 ? (n + 31) / 32 : grid;
+  if (h->w2)
+    w2_fn(h->w2_ctas)<<<grid_used, 64, kW2Smem, s>>>(h->P, h->dp, h->state, h->ep_len, host_actions, host_rows, nullptr,
+                                                    nullptr, nullptr, n, 0, n, sc, xp);
+  else
+    kStepVariants[vi].fn<<<grid, block, smem, s>>>(h->P, h->dp, h->state, h->ep_len, host_actions, host_rows, nullptr, nullptr,
                                                    nullptr, n, 0, n, sc, xp);
   ZB_CUDA(cudaGetLastError());
   h->launches += 1;
-  ZB_CUDA(launch_pdl(zbot_stats_finalize_kernel, dim3(1), dim3(1024), 0, s, h->pdl, sc, (unsigned int)grid));
+  ZB_CUDA(launch_pdl(zbot_stats_finalize_kernel, dim3(1), dim3(1024), 0, s, h->pdl, sc, (unsigned int)grid_used));
   h->launches += 1;
   ZB_CUDA(cudaStreamSynchronize(s));
   return ZBOT_OK;
