@@ -277,6 +277,12 @@ class DynOracle:
         nu = nu + dt * nud
         self.root_lin_vel, self.root_ang_vel, self.qd = nu[:, 0:3], nu[:, 3:6], nu[:, 6:]
         self.q = self.q + dt * self.qd
+        # PhysX wraps revolute joints WITHOUT limits into [-2 pi, 2 pi] by shifting 4 pi (reference note
+        # assets/test_articulation.py:18-20): all six joints of zbot_6s_new.usd, joints 1-5 of zbot_6s_v03.usd (joint6 has
+        # +-720 deg limits), none of zbot_6s_v09.usd (+-360 deg limits)
+        wrap = {"zbot_6s_new": np.ones(6, bool), "zbot_6s_v03": np.arange(6) != 5}.get(self.m.name, np.zeros(6, bool))
+        hi, lo = (self.q > 2 * np.pi) & wrap, (self.q < -2 * np.pi) & wrap
+        self.q = self.q - 4 * np.pi * hi + 4 * np.pi * lo
         self.root_pos = self.root_pos + dt * self.root_lin_vel
         wq = np.concatenate([np.zeros((n, 1)), self.root_ang_vel], -1)
         Q = self.root_quat + 0.5 * dt * Z.quat_mul(wq, self.root_quat)

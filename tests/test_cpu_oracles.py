@@ -602,3 +602,50 @@ def test_halves_elimination_equals_the_one_chain_substep():
     cpu_port.substeps(h32, tgt.astype(np.float32), 4, model="halves")
     dx, dh = np.abs(x32 - ref).max(1), np.abs(h32 - ref).max(1)
     assert np.median(dh) <= 2.0 * np.median(dx) + 1e-7 and np.quantile(dh, 0.99) <= 3.0 * np.quantile(dx, 0.99) + 1e-6
+
+
+def test_unlimited_revolute_joints_wrap_at_two_pi_like_physx():
+    """PhysX keeps the position of a revolute joint without limits inside [-2 pi, 2 pi] (the reference's own note,
+    assets/test_articulation.py:18-20): a joint spinning past +2 pi re-enters at -2 pi (shift by 4 pi, same physical angle).
+    Kernel arithmetic (one-chain and two-halves formulations) and the float64 oracle agree, the pose of every link is
+    continuous across the wrap, and the snake robot's limited joint6 does not wrap."""
+    from oracle import cpu_port
+    from zbot_lab_b200.assets import zbot_6s as Z
+    n = 4
+    two_pi = 2 * np.pi
+    st = {"root_pos": np.tile([0.0, 0.0, 1.0], (n, 1)), "root_quat": np.tile([1.0, 0.0, 0.0, 0.0], (n, 1)),
+          "root_lin_vel": np.zeros((n, 3)), "root_ang_vel": np.zeros((n, 3)),
+          "joint_pos": np.zeros((n, 6)), "joint_vel": np.zeros((n, 6))}
+    st["joint_pos"][:, 1] = two_pi - 0.01          # joint 2 about to cross +2 pi
+    st["joint_pos"][:, 4] = -two_pi + 0.01         # joint 5 about to cross -2 pi
+    st["joint_vel"][:, 1], st["joint_vel"][:, 4] = 4.0, -4.0
+    tgt = st["joint_pos"] + 2.0 * np.sign(st["joint_vel"])       # drive pushes further the same way
+    o = DynOracle(n)
+    o.set_state(st)
+    a, b = cpu_port.pack_sim(st, np.float64), cpu_port.pack_sim(st, np.float64)
+    lp0, lq0 = Z.fk_links(a[0, :3], a[0, 3:7], a[0, 13:19], o.m)
+    for i in range(6):
+        cpu_port.substeps(a, tgt, 1)
+        cpu_port.substeps(b, tgt, 1, model="halves")
+        o.substep(tgt)
+        ref = np.concatenate([o.root_pos, o.root_quat, o.root_lin_vel, o.root_ang_vel, o.q, o.qd], -1)
+        assert np.abs(a - ref).max() < 1e-9 and np.abs(b - ref).max() < 1e-9, i
+    assert np.all(a[:, 13 + 1] < -two_pi + 1.0) and np.all(a[:, 13 + 4] > two_pi - 1.0)          # wrapped to the other end
+    assert np.all(np.abs(a[:, 13:19]) <= two_pi)
+    lp1, lq1 = Z.fk_links(a[0, :3], a[0, 3:7], a[0, 13:19], o.m)
+    unwrapped = a[0, 13:19].copy()
+    unwrapped[1] += 2 * two_pi
+    unwrapped[4] -= 2 * two_pi
+    lp2, lq2 = Z.fk_links(a[0, :3], a[0, 3:7], unwrapped, o.m)
+    assert np.abs(lp1 - lp2).max() < 1e-12 and np.abs(np.abs(np.sum(lq1 * lq2, -1)) - 1).max() < 1e-12   # same link poses
+    # snake robot: joint6 carries +-720 deg limits in zbot_6s_v03.usd -> not wrapped; joint 2 is
+    from zbot_lab_b200.assets import zbot_d_6s as S
+    ms = S.model_f32()
+    sims = np.zeros((1, 25))
+    sims[0, :3], sims[0, 3:7] = [0, 0, 1.0], ms.default_root_quat
+    sims[0, 13 + 5], sims[0, 19 + 5] = two_pi - 0.005, 4.0
+    sims[0, 13 + 1], sims[0, 19 + 1] = two_pi - 0.005, 4.0
+    tg = sims[:, 13:19] + 1.0
+    for i in range(4):
+        cpu_port.substeps(sims, tg, 1, cfg=cpu_port.make_cfg(1, task=cpu_port.TASK_SNAKE_V0) if hasattr(cpu_port, "TASK_SNAKE_V0") else None, snake=True)
+    assert sims[0, 13 + 5] > two_pi and sims[0, 13 + 1] < -two_pi + 1.0

@@ -75,7 +75,7 @@ def test_env_matches_bare_stepper_and_cfg_weights_drive_the_kernel():
     assert set(ex["log"]) == {"Episode_Reward/torques", "Episode_Reward/base_vel_forward",
                               "Episode_Termination/body_contact", "Episode_Termination/time_out"}
     assert torch.isfinite(r).all()
-    with pytest.raises(KeyError):
+    with pytest.raises(AttributeError):        # the reference's getattr(self, "_reward_" + name) (…env_v2.py:252)
         _make(4, reward_cfg={"reward_scales": {"no_such_term": 1.0}})
     env.close(); env2.close(); st.close()
 
@@ -425,3 +425,102 @@ def test_manager_env_registry_protocol_noise_friction_curriculum_and_ppo(tmp_pat
     assert len(hist) == 2 and all(np.isfinite(h["value_loss"]) for h in hist)
     assert "Episode_Reward/foot_step_length" in hist[-1]
     w.close()
+
+
+def _make_cls(cls, n, scales=None, **over):
+    import zbot_lab_b200.tasks  # noqa: F401
+    from zbot_lab_b200.compat import gym_registry as gym
+    cfg = gym.load_cfg_from_registry("zbot-6b-walking-v2", "env_cfg_entry_point")
+    cfg.scene.num_envs, cfg.sim.device, cfg.seed = n, "cuda:0", 3
+    cfg.check_all_envs_reset = False
+    if scales is not None:
+        cfg.reward_cfg = {"reward_scales": dict(scales)}
+    for k, v in over.items():
+        setattr(cfg, k, v)
+    return cls(cfg=cfg, render_mode=None)
+
+
+def test_subclass_reward_hooks_host_terms_and_step_view():
+    """SURVEY §8b "subclass hooks": reward terms are discovered by `getattr(self, "_reward_" + name)` over the cfg dict
+    (…env_v2.py:246-252).  (1) a subclass ADDS a term -> evaluated on the host after the kernel on the step view (end of
+    physics, before the reset), weight * step_dt, with its own episode sum / log entry; (2) a subclass OVERRIDES every
+    built-in term with the torch view of it -> the host-evaluated total equals the fused kernel's reward, which checks the
+    15 `_reward_<name>` views against the kernel term by term; (3) an unknown key without a method raises like the reference;
+    (4) `_contact_sensor.data`, `_get_dones / _get_rewards / _get_observations / _reset_idx` views."""
+    import warnings
+    from zbot_lab_b200.tasks.zbot6b_direct.host_terms import RewardTermViews
+    from zbot_lab_b200.tasks.zbot6b_direct.walking_v2 import ZbotDirectEnvV2
+    from zbot_lab_b200.tasks.zbot6b_direct.walking_v2_cfg import REWARD_SCALES_V2
+    n = 512
+
+    class WithHeight(ZbotDirectEnvV2):
+        def _reward_base_height(self):
+            return self._robot.data.body_link_pos_w[:, self.base_body_idx[0], 2]
+
+    class AllOnHost(ZbotDirectEnvV2):
+        pass
+    # the three stateful terms stay in the kernel: their integrators / touchdown memory are advanced BY the kernel's term
+    # evaluation, the built-in methods only view them
+    stateful = {"base_heading_x_sum", "step_length", "base_pos_y_err_sum"}
+    moved = [k for k in REWARD_SCALES_V2 if k not in stateful]
+    for name in moved:
+        setattr(AllOnHost, "_reward_" + name, (lambda nm: lambda self: getattr(RewardTermViews, "_reward_" + nm)(self))(name))
+
+    plain = _make_cls(ZbotDirectEnvV2, n, capture_step_view=True)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        plus = _make_cls(WithHeight, n, {**REWARD_SCALES_V2, "base_height": 0.5})
+        host = _make_cls(AllOnHost, n)
+    assert sum("evaluated on the HOST" in str(x.message) for x in w) == 1 + len(moved)
+    assert plus._stepper.cfg.num_terms == 13 and host._stepper.cfg.num_terms == 3
+    with pytest.raises(AttributeError):
+        _make_cls(ZbotDirectEnvV2, 64, {**REWARD_SCALES_V2, "no_such_term": 1.0})
+    for e in (plain, plus, host):
+        e.reset()
+        e.episode_length_buf = torch.randint(0, 990, (n,), device="cuda:0", generator=torch.Generator("cuda:0").manual_seed(1))
+    g = torch.Generator("cuda:0").manual_seed(5)
+    resets = 0
+    for t in range(40):
+        a = torch.randn(n, 6, device="cuda:0", generator=g) * (2.0 if t % 10 == 9 else 0.7)
+        eps0 = {k: v.clone() for k, v in plain._episode_sums.items()}
+        o0, r0, te0, tr0, x0 = plain.step(a)
+        # term by term: the kernel's contribution of this step (increment of the episode sum) == the torch view x scale
+        keep = ~(te0 | tr0)
+        plain._active_view = plain._view
+        for name, wgt in REWARD_SCALES_V2.items():
+            view = getattr(RewardTermViews, "_reward_" + name)(plain) * (wgt * 0.02)
+            kern = plain._episode_sums[name] - eps0[name]
+            assert float((view - kern)[keep].abs().max()) <= 2e-6, (t, name)
+        plain._active_view = None
+        o1, r1, te1, tr1, x1 = plus.step(a)
+        o2, r2, te2, tr2, x2 = host.step(a)
+        o0, o1, o2 = o0["policy"], o1["policy"], o2["policy"]
+        assert torch.equal(o0, o1) and torch.equal(te0, te1) and torch.equal(tr0, tr1) and torch.equal(o0, o2) and torch.equal(te0, te2)
+        base_z = plain._view.robot.body_link_pos_w[:, plain.base_body_idx[0], 2]          # end of physics, before the reset
+        assert torch.allclose(r1 - r0, 0.5 * 0.02 * base_z, atol=2e-6)
+        done = te0 | tr0
+        resets += int(done.sum())
+        # ten terms on the host + three in the kernel == thirteen in the kernel
+        assert torch.allclose(r2, r0, rtol=1e-5, atol=3e-6), float((r2 - r0).abs().max())
+    assert resets > 0
+    log = x1["log"]
+    assert "Episode_Reward/base_height" in log and float(log["Episode_Reward/base_height"]) > 0.0
+    assert set(x2["log"]) >= {"Episode_Reward/" + k for k in REWARD_SCALES_V2}
+    # contact sensor / hook views
+    d = plain._contact_sensor.data
+    assert d.net_forces_w_history.shape == (n, 5, 12, 3) and d.last_air_time.shape == (n, 12) and d.current_contact_time.shape == (n, 12)
+    feet, _ = plain._contact_sensor.find_bodies("foot.*")
+    assert float(d.net_forces_w_history[:, 0, feet, 2].max()) > 1.0
+    te, tr = plain._get_dones()
+    assert torch.equal(te, te0) and torch.equal(tr, tr0) and torch.equal(plain._get_rewards(), r0)
+    assert torch.equal(plain._get_observations()["policy"], o0)
+    ids = torch.tensor([3, 5, 100], device="cuda:0")
+    plain._reset_idx(ids)
+    assert torch.all(plain.episode_length_buf[ids] == 0) and float(plain._stepper.state.get("joint_vel")[ids].abs().max()) == 0.0
+    fresh = _make_cls(ZbotDirectEnvV2, 64)
+    fresh.reset()
+    fresh.step(torch.zeros(64, 6, device="cuda:0"))
+    with pytest.raises(RuntimeError):
+        fresh._contact_sensor.data
+    for e in (plain, plus, host, fresh):
+        e.close()

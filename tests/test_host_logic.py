@@ -62,7 +62,7 @@ def test_product_never_imports_oracle():
     pkg = os.path.join(ROOT, "zbot_lab_b200")
     for d, _, files in os.walk(pkg):
         for f in files:
-            if f.endswith((".py", ".cu", ".h")):
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(d, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), os.path.join(d, f)
                 assert "cpu_port" not in src or f.endswith(".h") is False and "cpu_port" not in src, f

@@ -225,6 +225,19 @@ ZB_HD T zb_clamp(T x, T lo, T hi) {
   return zb_min(zb_max(x, lo), hi);
 }
 
+// PhysX keeps the position of a revolute joint WITHOUT limits inside [-2 pi, 2 pi]: past either end it re-enters from
+// the other one, i.e. shifts by 4 pi (two full turns: the same physical angle, and the same half-angle quaternion).
+// The reference's author checked it on these robots: "joint_pos is normalised into [-2pi, 2pi] by default even without
+// joint limits; only with limits set is it kept inside the limits" (assets/test_articulation.py:18-20).  Targets are
+// p_delta (clipped to +-pi) + the default pose, |target| <= 5.16 rad, so a tracked joint never gets there; a free-spinning
+// one (saturated drive after a fall) does, and then the PD error jumps by 4 pi exactly as it does in the reference.
+template <typename T>
+ZB_HD T zb_wrap_joint(T q) {
+  const T two_pi = T(6.283185307179586476925286766559);
+  const T four_pi = T(12.566370614359172953850573533118);
+  return zb_sel(zb_gt(q, two_pi), q - four_pi, zb_sel(zb_gt(-two_pi, q), q + four_pi, q));
+}
+
 template <typename T>
 ZB_HD void cross3(const T* a, const T* b, T* o) {
   T x = a[1] * b[2] - a[2] * b[1];
@@ -568,6 +581,7 @@ struct ModelWalk {   // ZBOT_6S_CFG + zbot_6s_new.usd (zbot-6b-walking-*): stand
   static constexpr bool kPerEnvFriction = false;
   static constexpr bool kFresh = false;            // MDP reads one-step-stale quantities, 5-deep force history
   static constexpr bool kGroundForceSensor = true;   // feet: applied force; merged bodies: predictor force
+  static ZB_HD bool wraps(int) { return true; }      // zbot_6s_new.usd: no joint has limits -> PhysX wraps all six at +-2 pi
   template <typename T>
   static ZB_HD void body(int k, T& mass, T& cx, T& cz, T& ixx, T& iyy, T& izz, T& ixz) {
     using namespace model;
@@ -614,6 +628,7 @@ struct ModelSnake {  // ZBOT_D_6S_CFG + zbot_6s_v03.usd (zbot-6s-snake-v0): lies
   static constexpr bool kPerEnvFriction = false;
   static constexpr bool kFresh = false;
   static constexpr bool kGroundForceSensor = false;  // the task only senses filtered SELF contacts
+  static ZB_HD bool wraps(int k) { return k != 5; }  // zbot_6s_v03.usd: only joint6 has limits (+-720 deg): it is not wrapped
   template <typename T>
   static ZB_HD void body(int k, T& mass, T& cx, T& cz, T& ixx, T& iyy, T& izz, T& ixz) {
     using namespace model_snake;
@@ -650,6 +665,7 @@ struct ModelWalkM : ModelWalk {   // ZBOT_6S_V2_CFG + zbot_6s_v09.usd (zbot-6b-w
   static constexpr bool kFullInertia = true;       // CoM / inertia sit off the chain's plane (assets/zbot_6s_v2.py)
   static constexpr bool kPerEnvFriction = true;    // EventCfg.physics_material: per-env friction drawn at startup
   static constexpr bool kFresh = true;             // ManagerBasedRLEnv: every term reads end-of-physics data; history_length = 3
+  static ZB_HD bool wraps(int) { return false; }   // zbot_6s_v09.usd: all six joints carry +-360 deg limits (hard stops in PhysX; not modelled)
   template <typename T>
   static ZB_HD void body_full(int k, T& mass, T* c, T* I) {
     using namespace model_m;
@@ -1055,7 +1071,11 @@ ZB_PRAGMA_UNROLL(ZB_UNROLL_FWD)
   }
   if (Model::kGroundForceSensor) contact_agg_force(agg1, dt, At, Ab, out.foot_force[1]);
   out.mid_force2_max = mid2;
-  ZB_UNROLL for (int k = 0; k < 6; ++k) { s.qd[k] = scr(k, SC_QD); s.q[k] += dt * s.qd[k]; }
+  ZB_UNROLL for (int k = 0; k < 6; ++k) {
+    s.qd[k] = scr(k, SC_QD);
+    s.q[k] += dt * s.qd[k];
+    if (Model::wraps(k)) s.q[k] = zb_wrap_joint(s.q[k]);
+  }
   // ---- root pose ----
   ZB_UNROLL for (int i = 0; i < 3; ++i) s.p[i] += dt * s.v[i];
   {

@@ -15,7 +15,7 @@
 // in between; zbot_kernels.cu: zbot_step_w2_kernel).  A warp carries half the per-env state and half the dependent chain
 // of the one-thread-per-env kernel, so twice as many warps fit a scheduler at the same register file, and no instruction
 // is issued twice (a lane-pair split would execute the serial kinematics chain redundantly).
-// On the CPU (oracle/cpu_port.cpp, tests) the same functions run one after the other: `physics_substep_halves`.
+// On a CPU (the host build used by the tests) the same functions run one after the other: `physics_substep_halves`.
 //
 // Derivation of the reversed joint (side A).  Joint k: V_{k+1} = V_k + S qd,  a_{k+1} = a_k + S qdd + V_{k+1} x S qd,
 // tau = S^T f_{k+1} (f = force the joint transmits to the child).  Seen from the child: a_k = a_{k+1} + S' qdd + c' with
@@ -259,7 +259,7 @@ ZB_HD void half_forward(const Params<PS>& P, int side, Scr& scr, const T* w3, co
 template <typename PS, typename T, typename Scr>
 ZB_HD void half_integrate(const Params<PS>& P, int side, HalfState<T>& h, Scr& scr, const T* At, const T* Ab) {
   const T dt = T(P.dt);
-  ZB_UNROLL for (int t = 0; t < 3; ++t) { h.qd[t] = scr(t, SC_QD); h.q[t] += dt * h.qd[t]; }
+  ZB_UNROLL for (int t = 0; t < 3; ++t) { h.qd[t] = scr(t, SC_QD); h.q[t] = zb_wrap_joint(h.q[t] + dt * h.qd[t]); }   // walking robot: all six joints wrap
   if (side == 0) {
     T wxv[3];
     cross3(h.w, h.v, wxv);
@@ -280,7 +280,7 @@ ZB_HD void half_integrate(const Params<PS>& P, int side, HalfState<T>& h, Scr& s
 }
 
 // ------------------------------------------------------------------------------------
-// the same substep, both sides one after the other (CPU port, tests): drop-in for physics_substep<Model>
+// the same substep, both sides one after the other (host build, tests): drop-in for physics_substep<Model>
 // ------------------------------------------------------------------------------------
 template <typename T>
 struct HalfArrayScratch {

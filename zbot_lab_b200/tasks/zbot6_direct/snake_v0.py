@@ -63,6 +63,8 @@ class ZbotDirectEnvV0(ZbotDirectEnvV2):
     cfg: ZbotDirectEnvCfgV0
 
     _TASK = native.TASK_SNAKE_V0
+    _TERM_IDS = native.SNAKE_TERM_IDS
+    _HOST_TERMS_SUPPORTED = False
     _DIED_LOG_KEY = "Episode_Termination/died"      # snake_v0.py:289
 
     def __init__(self, cfg: ZbotDirectEnvCfgV0 | None = None, render_mode: str | None = None, **kwargs):

@@ -15,6 +15,7 @@ from ... import native
 from ...assets import zbot_6s as Z
 from ...stepper import NativeStepper
 from ...utils import synthetic as syn
+from .host_terms import ContactSensor, RewardTermViews, StepView
 from .walking_v2_cfg import ZbotDirectEnvCfgV2
 
 
@@ -46,8 +47,16 @@ class _ArticulationData:
         self.GRAVITY_VEC_W = torch.tensor([0.0, 0.0, -1.0], device=dev).repeat(n, 1)
 
     def _view(self):
+        v = self._env.__dict__.get("_active_view")
+        if v is not None:       # host reward terms are being evaluated: END of physics of this step, before any reset
+            return v.robot.body_link_pos_w, v.robot.body_link_quat_w, v.robot.body_com_lin_vel_w
         pos, quat, vel = self._env._stepper.articulation_view()
         return pos + self._env._terrain.env_origins.unsqueeze(1), quat, vel
+
+    @property
+    def applied_torque(self):
+        """ImplicitActuator bookkeeping before the last substep of the most recent step (…env_v2.py:560); needs a step view."""
+        return self._env._need_view().robot.applied_torque
 
     @property
     def body_link_pos_w(self):
@@ -63,11 +72,13 @@ class _ArticulationData:
 
     @property
     def joint_pos(self):
-        return self._env._stepper.state.get("joint_pos")
+        v = self._env.__dict__.get("_active_view")
+        return v.robot.joint_pos if v is not None else self._env._stepper.state.get("joint_pos")
 
     @property
     def joint_vel(self):
-        return self._env._stepper.state.get("joint_vel")
+        v = self._env.__dict__.get("_active_view")
+        return v.robot.joint_vel if v is not None else self._env._stepper.state.get("joint_vel")
 
 
 class _Robot:
@@ -86,8 +97,13 @@ class _Terrain:
         self.env_origins = torch.from_numpy(syn.env_origins_grid(n, spacing)).to(device)
 
 
-class ZbotDirectEnvV2:
-    """``DirectRLEnv``-shaped vectorised env; all tensors live on ``cfg.sim.device``."""
+class ZbotDirectEnvV2(RewardTermViews):
+    """``DirectRLEnv``-shaped vectorised env; all tensors live on ``cfg.sim.device``.
+
+    Subclass hooks: the reward table is ``cfg.reward_cfg["reward_scales"]``; a name the fused kernel knows
+    and that the subclass does not override is evaluated IN the kernel, any other name must have a ``_reward_<name>``
+    method and is evaluated on the host after the kernel (``host_terms.py``).  ``_get_dones / _get_rewards /
+    _get_observations / _reset_idx`` are host-side views of the fused step's results."""
 
     metadata = {"render_modes": [None]}
     cfg: ZbotDirectEnvCfgV2
@@ -108,6 +124,7 @@ class ZbotDirectEnvV2:
         self.max_episode_length = math.ceil(self.max_episode_length_s / self.step_dt)
         # reward table: a COPY scaled once by step_dt (the reference scales its class dict in place, C-3)
         self.reward_scales = {k: v * self.step_dt for k, v in self.cfg.reward_cfg["reward_scales"].items()}
+        self._split_reward_terms()
         self._stepper = NativeStepper(self.num_envs, self.device, self._native_cfg())
         self._terrain = _Terrain(self.num_envs, self.cfg.scene.env_spacing, self.device)
         self._setup_scene()
@@ -119,8 +136,13 @@ class ZbotDirectEnvV2:
         # buffers the scripts / wrappers read
         self.common_step_counter = 0
         self.extras: dict = {}
-        self._term_names = list(self.cfg.reward_cfg["reward_scales"].keys())
+        self._term_names = list(self._fused_scales.keys())
         self._log_cache: dict = {}
+        self._view: StepView | None = None
+        self._active_view = None
+        self.capture_step_view = bool(getattr(self.cfg, "capture_step_view", False)) or bool(self._host_terms)
+        self._host_sums = {k: torch.zeros(self.num_envs, device=self.device) for k, _ in self._host_terms}
+        self._host_log = {"Episode_Reward/" + k: torch.zeros((), device=self.device) for k, _ in self._host_terms}
         self._host_views: dict = {}
         ring = max(2, int(self.cfg.output_ring))
         n, dev = self.num_envs, self.device
@@ -150,6 +172,29 @@ class ZbotDirectEnvV2:
     # ------------------------------------------------------------------ task hooks (overridden by the snake task)
     _TASK = native.TASK_WALKING_V2
     _DIED_LOG_KEY = "Episode_Termination/body_contact"     # …env_v2.py:453
+    _TERM_IDS = native.TERM_IDS                            # names the fused kernel evaluates for this task
+    _HOST_TERMS_SUPPORTED = True                           # step view + host reward terms (walking-v2 export layout)
+
+    def _split_reward_terms(self):
+        """The reference resolves every key of ``reward_scales`` with ``getattr(self, "_reward_" + name)``
+        (…env_v2.py:246-252).  Here: fused (kernel term table) unless the subclass defines / overrides the method."""
+        self._fused_scales, self._host_terms = {}, []
+        for name, w in self.cfg.reward_cfg["reward_scales"].items():
+            meth = getattr(type(self), "_reward_" + name, None)
+            builtin = getattr(RewardTermViews, "_reward_" + name, None)
+            if name in self._TERM_IDS and (meth is None or meth is builtin):
+                self._fused_scales[name] = w
+            elif meth is not None:
+                if not self._HOST_TERMS_SUPPORTED:
+                    raise NotImplementedError(f"{type(self).__name__}: host-side reward terms ({name!r}) are implemented for "
+                                              "zbot-6b-walking-v2 only; this task's terms are the kernel's")
+                import warnings
+                warnings.warn(f"reward term {name!r} is evaluated on the HOST ({type(self).__name__}._reward_{name}): off the fused "
+                              "path -- the step runs through the export hook plus a few torch launches per such term")
+                self._host_terms.append((name, float(w) * self.step_dt))
+            else:
+                raise AttributeError(f"{type(self).__name__} has no reward method '_reward_{name}' for the key {name!r} of "
+                                     f"cfg.reward_cfg['reward_scales'] (the fused kernel knows {sorted(self._TERM_IDS)})")
 
     def _native_cfg(self) -> native.ZbotCfg:
         c, a = self.cfg.contact, self.cfg.actuator
@@ -157,7 +202,7 @@ class ZbotDirectEnvV2:
         if getattr(self.cfg, "observation_noise", None):
             extra["rng_seed"] = int(self.cfg.seed if self.cfg.seed is not None else torch.initial_seed() & 0x7FFFFFFF)
         return native.set_obs_noise(native.make_cfg(
-            self.num_envs, reward_scales=self.cfg.reward_cfg["reward_scales"], step_dt=self.step_dt, task=self._TASK,
+            self.num_envs, reward_scales=self._fused_scales, step_dt=self.step_dt, task=self._TASK,
             sim_dt=self.physics_dt, decimation=int(self.cfg.decimation),
             max_episode_length=int(self.max_episode_length),
             kp=a.stiffness, kd=a.damping, effort_limit=a.effort_limit,
@@ -171,6 +216,7 @@ class ZbotDirectEnvV2:
 
     def _setup_scene(self):
         self._robot = _Robot(self)
+        self._contact_sensor = ContactSensor(self)
         # index sets, resolved by name exactly as …env_v2.py:227-230
         self._feet_ids, _ = Z.find_bodies("foot.*", Z.SENSOR_BODY_NAMES)
         self._undesired_contact_body_ids, _ = Z.find_bodies("base|a.*|b.*", Z.SENSOR_BODY_NAMES)
@@ -224,7 +270,70 @@ class ZbotDirectEnvV2:
             return v if fields[name] > 1 else v[:, 0]
         if name == "feet_down_pos_last" and "_stepper" in self.__dict__:
             return self._stepper.state.get(name).view(self.num_envs, 2, 3) + self._terrain.env_origins.unsqueeze(1)
+        # the tensors the reference's _get_observations caches (…env_v2.py:315-345): start-of-step values of the step view
+        view = self.__dict__.get("_view")
+        if view is not None and name in view.stale:
+            return self._need_view().stale[name]
         raise AttributeError(name)
+
+    # ------------------------------------------------------------------ step view / host terms (host_terms.py)
+    def _need_view(self) -> StepView:
+        v = self.__dict__.get("_view")
+        if v is None or not v.valid:
+            raise RuntimeError("no step view: the articulation / contact-sensor tensors of a step are only exported when asked for -- "
+                               "set `env.capture_step_view = True` (or cfg.capture_step_view) before stepping; envs with host "
+                               "reward terms do it automatically")
+        return v
+
+    def _eval_host_terms(self, rew, term, trunc):
+        """``reward += f() * scale`` for the terms the kernel does not evaluate, their episode sums and log entries
+        (…env_v2.py:371-382, 441-447).  Runs on the step view: end-of-physics data, before the reset the kernel applied."""
+        self._active_view = self._view
+        try:
+            done = (term.view(torch.bool) | trunc.view(torch.bool))
+            cnt = done.sum()
+            for name, scale in self._host_terms:
+                r = getattr(self, "_reward_" + name)() * scale
+                rew += r
+                sums = self._host_sums[name]
+                sums += r
+                mean = (sums * done).sum() / cnt.clamp(min=1) / self.max_episode_length_s
+                key = "Episode_Reward/" + name
+                self._host_log[key].copy_(torch.where(cnt > 0, mean, self._host_log[key]))     # kept while nothing resets (:450)
+                sums.masked_fill_(done, 0.0)
+        finally:
+            self._active_view = None
+
+    # ------------------------------------------------------------------ DirectRLEnv hook names (views of the fused step)
+    def _pre_physics_step(self, actions):
+        """…env_v2.py:276-287 happens inside the kernel (``mdp_pre_physics``); kept so callers of the hook do not break."""
+
+    def _apply_action(self):
+        """…env_v2.py:309-310: the joint targets are handed to the actuator model inside the kernel, every substep."""
+
+    def _get_dones(self):
+        """(terminated, time_outs) of the most recent step (…env_v2.py:384-411, evaluated in the kernel)."""
+        return self.reset_terminated, self.reset_time_outs
+
+    def _get_rewards(self):
+        """Reward of the most recent step (…env_v2.py:371-382; fused terms in the kernel + host terms)."""
+        return self._out[self._out_i][1]
+
+    def _get_observations(self):
+        """{"policy": (N, 23)} of the current state (…env_v2.py:312-369, evaluated by the observe kernel)."""
+        return {"policy": self._stepper.observe().clone()}
+
+    def _reset_idx(self, env_ids):
+        """…env_v2.py:413-459 for an explicit id list (the per-step partial reset happens inside the step kernel)."""
+        if env_ids is None:
+            env_ids = self._robot._ALL_INDICES
+        env_ids = torch.as_tensor(env_ids, device=self.device, dtype=torch.int64)
+        self._stepper.reset_idx(env_ids, self._out[self._out_i][2], self._out[self._out_i][3])
+        if env_ids.numel() == self.num_envs:
+            self.episode_length_buf = torch.randint_like(self._stepper.episode_length_buf, high=int(self.max_episode_length))
+        for k, _ in self._host_terms:
+            self._host_sums[k][env_ids] = 0.0
+        self.extras["log"] = self._log_from_slot()
 
     def seed(self, seed: int = -1) -> int:
         if seed == -1:
@@ -245,6 +354,7 @@ class ZbotDirectEnvV2:
             log = {"Episode_Reward/" + k: s[i] for i, k in enumerate(self._term_names)}
             log[self._DIED_LOG_KEY] = s[native.STAT_NUM_TERMINATED_RESET]
             log["Episode_Termination/time_out"] = s[native.STAT_NUM_TIMEOUT_RESET]
+            log.update(self._host_log)
             self._log_cache[slot] = log
         return log
 
@@ -265,7 +375,20 @@ class ZbotDirectEnvV2:
         st = self._stepper
         self._out_i = (self._out_i + 1) % len(self._out)
         st.obs, st.rew, st.terminated, st.truncated = self._out[self._out_i]
-        obs, rew, term, trunc = st.step(actions.to(self.device))
+        if self.capture_step_view:
+            # off the fused fast path: the same kernel through the export hook, so host reward terms / callers of
+            # `_robot.data`, `_contact_sensor.data` see this step's end-of-physics tensors
+            if self._view is None:
+                self._view = StepView(self)
+            v = self._view
+            v.actions_prev = st.state.get("actions")
+            obs, rew, term, trunc = st.step(actions.to(self.device), export=v.export)
+            v.actions_now = torch.tanh(actions.to(self.device))
+            v.refresh()
+            if self._host_terms:
+                self._eval_host_terms(rew, term, trunc)
+        else:
+            obs, rew, term, trunc = st.step(actions.to(self.device))
         self.common_step_counter += 1
         self._sim_step_counter += self.cfg.decimation
         self.reset_terminated = term.view(torch.bool)

@@ -23,6 +23,8 @@ class Zbot6SEnvV4(ZbotDirectEnvV2):
     cfg: Zbot6SEnvV4Cfg
 
     _TASK = native.TASK_WALKING_V4
+    _TERM_IDS = native.V4_TERM_IDS
+    _HOST_TERMS_SUPPORTED = False
     _DIED_LOG_KEY = "Episode_Termination/died"          # …env_v4.py:918
 
     def __init__(self, cfg: Zbot6SEnvV4Cfg | None = None, render_mode: str | None = None, **kwargs):
