@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define ZBOT_ABI_VERSION 5
+#define ZBOT_ABI_VERSION 6
 
 #define ZBOT_OK 0
 #define ZBOT_E_INVALID (-1) /* bad argument / unsupported configuration */
@@ -103,8 +103,8 @@ enum ZbotTerm {
 #define ZBOT_TASK_WALKING_V4 2 /* zbot-6b-walking-v4: Zbot6SEnvV4 + ZBOT_6S_CFG, commands + events */
 #define ZBOT_TASK_WALKING_M 3  /* zbot-6b-walking-m-v0: ManagerBasedRLEnv + Zbot6BFlatEnvCfg + ZBOT_6S_V2_CFG */
 #define ZBOT_M_NUM_OBS 25
-#define ZBOT_M_NUM_RAND 13     /* uniforms per env-step, see zbot_m_step */
-#define ZBOT_M_EXPORT_WORDS 67
+#define ZBOT_M_NUM_RAND 22     /* uniforms per env-step, see zbot_m_step */
+#define ZBOT_M_EXPORT_WORDS 72
 #define ZBOT_V4_NUM_OBS 24
 #define ZBOT_V4_NUM_RAND 10    /* uniforms per env-step, see zbot_v4_step */
 #define ZBOT_V4_EXPORT_WORDS 69
@@ -161,6 +161,18 @@ typedef struct ZbotCfg {
   float act_scale, act_clip;
   float feet_close_min;
   float is_terminated_weight;
+  /* ... continued: the cfg features the reference's registered manager cfgs switch off but its cfg classes define
+   * (zbotlab_env_cfg.py).  DoneTerm `base_contact` = mdp.illegal_contact (:385-388): threshold (<= 0: absent) and the set of
+   * MERGED bodies 1..5 its body_names select (bit b-1; a merged body senses on its "a" link).  `heading_command=True`
+   * (:91-97): ang_vel_z = clip(stiffness * wrap(heading_target - heading), ang_vel_z range) for the heading envs.
+   * EventTerm `push_robot` = push_by_setting_velocity in interval mode (:253-258): interval range in seconds
+   * (hi <= 0: absent), x / y velocity ranges. */
+  float illegal_contact_threshold;
+  int32_t illegal_contact_mask;
+  int32_t cmd_heading;
+  float cmd_heading_lo, cmd_heading_hi, cmd_heading_stiffness, cmd_rel_heading;
+  float push_interval_lo, push_interval_hi;
+  float push_lo[2], push_hi[2];
 } ZbotCfg;
 
 typedef struct ZbotHandle ZbotHandle;
@@ -264,18 +276,34 @@ int zbot_v4_step_export(ZbotHandle* h, const float* actions, const float* rand, 
  *   actions float [N][6]   raw policy output, Isaac Lab joint order (joint1, joint7, joint2, joint8, joint3, joint9)
  *   obs     float [N][25]  [root_quat_w 4, velocity_commands 3, joint_pos_rel 6, joint_vel_rel 6, last_action 6]
  *   rand    float [N][ZBOT_M_NUM_RAND] uniforms in [0,1) or NULL = in-kernel generator.  Slots: 0..2 reset pose x / y /
- *           yaw, 3..7 command resample at reset (time, vx, vy, wz, standing), 8..12 the same at timer expiry.
+ *           yaw, 3..7 command resample at reset (time, vx, vy, wz, standing), 8..12 the same at timer expiry, 13..14 /
+ *           15..16 heading target + is_heading_env at reset / at timer expiry (heading_command), 17 push timer at reset,
+ *           18..20 push timer re-arm + x / y velocity when the push_robot interval event fires, 21 the random restart
+ *           level of the terrain curriculum.
  * State slots reused (zbot_state_word names): carry_feet_fz = command lin_vel x / y, carry_mid_max = command ang_vel z,
  * base_heading_x_sum = is_standing_env, base_pos_y_err_sum = command time_left, joint_speed_limit = friction
- * coefficient of the env, actions = last raw action.  Statistics words 0..num_terms-1 = Episode_Reward/<term>; when
- * num_terms <= 13, word 13 = Episode_Reward of the is_terminated term and words 14 / 15 = the number of reset envs that
- * tripped base_height / feet_close (raw counts).
+ * coefficient of the env, actions = last raw action, p_delta[0..2] = heading target / is_heading_env / push_robot timer.
+ * Statistics words 0..num_terms-1 = Episode_Reward/<term>; word 22 = Episode_Reward of the is_terminated term, words 23 / 24
+ * / 25 = the number of reset envs that tripped base_height / feet_close / illegal_contact (raw counts); with num_terms <=
+ * 13 the first three are also mirrored in words 13..15.
  * `export` (zbot_m_step_export, test hook): [N][ZBOT_M_EXPORT_WORDS] view the terms saw (MExport). */
 int zbot_m_step(ZbotHandle* h, const float* actions, const float* rand, float* obs, float* rew, uint8_t* terminated,
                 uint8_t* truncated, int32_t stats_slot, int32_t prev_slot, void* stream);
 int zbot_m_step_export(ZbotHandle* h, const float* actions, const float* rand, float* obs, float* rew,
                        uint8_t* terminated, uint8_t* truncated, int32_t stats_slot, int32_t prev_slot,
                        float* export_buf, void* stream);
+/* Rough ground of the manager-based task (`zbot-6b-walking-m-rough-v0`: TerrainImporterCfg(terrain_type="generator",
+ * ROUGH_TERRAINS_CFG), zbotlab_env_cfg.py:44-48, and CurrTerm terrain_levels_vel, mdp/curriculums.py:26-55).  Caller-owned
+ * device buffers: `heights` float [nx][ny] = the height field over the whole tile grid in the WORLD frame (H[0][0] at
+ * (x0, y0), `cell` metres per cell; sampled bilinearly under every ground-contact candidate, normals vertical),
+ * `tile_origins` float [rows][cols][3] = spawn point of every (level, type) tile, `env_origins` float [N][4] = each env's
+ * current origin (x, y, z, unused; the state's root position is relative to it) -- READ every step and REWRITTEN by the
+ * kernel when `curriculum` is set and a reset moves the env to another level (state words p_delta[3] = level,
+ * p_delta[4] = type).  heights == NULL returns the handle to the flat plane. */
+int zbot_bind_terrain(ZbotHandle* h, const float* heights, int32_t nx, int32_t ny, float x0, float y0, float cell,
+                      const float* tile_origins, int32_t rows, int32_t cols, float tile_size, float* env_origins,
+                      int32_t curriculum);
+
 /* All-envs-reset spread of the episode counters, on the device.  The reference's `_reset_idx` does
  * `episode_length_buf[:] = torch.randint_like(episode_length_buf, high=max_episode_length)` when EVERY env resets in one
  * step (zbot_direct_6dof_bipedal_env_v2.py:418-422, ..._env_v4.py:972, zbot_direct_6dof_snake_v0.py:275) -- a host

@@ -131,10 +131,22 @@ static int port_v4_step(const ZbotCfg* cfg, T* state, int64_t* ep_len, const T* 
   return ZBOT_OK;
 }
 
+// rough ground of the manager task (host twin of zbot_bind_terrain); heights == nullptr / t == nullptr: flat
+struct PortTerrain {
+  const float* heights;
+  int nx, ny;
+  float x0, y0, cell;
+  const float* tile_origins;
+  int rows, cols;
+  float tile_size;
+  float* env_origins;     // [N][4]
+  int curriculum;
+};
+
 // zbot-6b-walking-m-v0: whole control step; rnd [N][M_NUM_RAND] uniforms, obs [N][25] (no observation noise here)
 template <typename T>
 static int port_m_step(const ZbotCfg* cfg, T* state, int64_t* ep_len, const T* actions, const T* rnd, T* obs, T* rew,
-                       uint8_t* term, uint8_t* trunc, T* reset_sums, T* export_buf, int n) {
+                       uint8_t* term, uint8_t* trunc, T* reset_sums, T* export_buf, int n, const PortTerrain* pt = nullptr) {
   const char* why = nullptr;
   if (cfg_validate(*cfg, &why) != ZBOT_OK || cfg->task != ZBOT_TASK_WALKING_M) return ZBOT_E_INVALID;
   Params<T> P;
@@ -144,18 +156,30 @@ static int port_m_step(const ZbotCfg* cfg, T* state, int64_t* ep_len, const T* a
     EnvState<T> es;
     env_state_unpack(state + (size_t)e * ZBOT_STATE_WORDS, es);
     StepOut<T> out;
-    T rs[MAX_TERMS];
-    for (int i = 0; i < MAX_TERMS; ++i) rs[i] = T(0);
+    T rs[MAX_TERMS + 4];      // + is_terminated sum, base_height / feet_close / illegal_contact counts (statistics words 22..25)
+    for (int i = 0; i < MAX_TERMS + 4; ++i) rs[i] = T(0);
     MExport<T> ex;
     ArrayScratch<T> scr;
-    m_env_step(P, es, actions + (size_t)e * 6, ep_len[e], rnd + (size_t)e * M_NUM_RAND, obs + (size_t)e * M_NUM_OBS, out,
-               rs, export_buf ? &ex : (MExport<T>*)nullptr, scr);
+    if (pt && pt->heights) {
+      float* o = pt->env_origins + (size_t)e * 4;
+      const TerrainGround<T> ground{pt->heights, pt->nx, pt->ny, T(pt->x0), T(pt->y0), T(1.0f / pt->cell), T(o[0]), T(o[1]), T(o[2])};
+      MTerrainCtx<T> tc{{T(o[0]), T(o[1]), T(o[2])}, pt->tile_origins, pt->rows, pt->cols, T(pt->tile_size),
+                        T((float)cfg->max_episode_length * cfg->sim_dt * (float)cfg->decimation), pt->curriculum};
+      PhysOut<T> po;
+      env_step_physics<ModelWalkM>(P, es, actions + (size_t)e * 6, po, scr, (StepExport<T>*)nullptr, ground);
+      m_step_finish(P, es, actions + (size_t)e * 6, po, ep_len[e], rnd + (size_t)e * M_NUM_RAND, obs + (size_t)e * M_NUM_OBS, out,
+                    rs, export_buf ? &ex : (MExport<T>*)nullptr, &tc);
+      if (out.terminated || out.time_out) { o[0] = (float)tc.origin[0]; o[1] = (float)tc.origin[1]; o[2] = (float)tc.origin[2]; }
+    } else {
+      m_env_step(P, es, actions + (size_t)e * 6, ep_len[e], rnd + (size_t)e * M_NUM_RAND, obs + (size_t)e * M_NUM_OBS, out,
+                 rs, export_buf ? &ex : (MExport<T>*)nullptr, scr);
+    }
     env_state_pack(es, state + (size_t)e * ZBOT_STATE_WORDS);
     rew[e] = out.reward;
     term[e] = out.terminated ? 1 : 0;
     trunc[e] = out.time_out ? 1 : 0;
-    if (reset_sums)
-      for (int i = 0; i < MAX_TERMS; ++i) reset_sums[(size_t)e * MAX_TERMS + i] = rs[i];
+    if (reset_sums)      // manager task: [N][MAX_TERMS + 4]
+      for (int i = 0; i < MAX_TERMS + 4; ++i) reset_sums[(size_t)e * (MAX_TERMS + 4) + i] = rs[i];
     if (export_buf) memcpy(export_buf + (size_t)e * ZBOT_M_EXPORT_WORDS, &ex, sizeof(ex));
   }
   return ZBOT_OK;
@@ -164,7 +188,8 @@ static int port_m_step(const ZbotCfg* cfg, T* state, int64_t* ep_len, const T* a
 // dynamics only: sim [N][25] (root_pos3 quat4 lin3 ang3 q6 qd6), target [N][6]
 // forces [N][7][3] (body 0 and 6 = applied foot forces, 1..5 = predictor), tau [N][6]
 template <typename T>
-static int port_substeps(const ZbotCfg* cfg, T* sim, const T* target, T* forces, T* tau, int n, int nsub, int model = 0) {
+static int port_substeps(const ZbotCfg* cfg, T* sim, const T* target, T* forces, T* tau, int n, int nsub, int model = 0,
+                         const PortTerrain* pt = nullptr) {
   const bool snake = (model == 1);
   Params<T> P;
   params_from_cfg(*cfg, P);
@@ -183,6 +208,11 @@ static int port_substeps(const ZbotCfg* cfg, T* sim, const T* target, T* forces,
     tgt7[6] = T(cfg->contact_mu);     // ModelWalkM reads its friction coefficient per env
     for (int k = 0; k < nsub; ++k) {
       if (snake) physics_substep<ModelSnake>(P, s, tgt7, so, scr, midf);
+      else if (model == 2 && pt && pt->heights) {
+        const float* o = pt->env_origins + (size_t)e * 4;
+        const TerrainGround<T> ground{pt->heights, pt->nx, pt->ny, T(pt->x0), T(pt->y0), T(1.0f / pt->cell), T(o[0]), T(o[1]), T(o[2])};
+        physics_substep<ModelWalkM>(P, s, tgt7, so, scr, midf, ground);
+      }
       else if (model == 2) physics_substep<ModelWalkM>(P, s, tgt7, so, scr, midf);
       else if (model == 3) physics_substep_halves<ModelWalk>(P, s, tgt7, so, midf);   // two-halves elimination (csrc/zbot_halves.h)
       else physics_substep<ModelWalk>(P, s, tgt7, so, scr, midf);
@@ -304,11 +334,29 @@ int zbot_port_substeps_snake_f32(const ZbotCfg* cfg, float* sim, const float* ta
 int zbot_port_substeps_snake_f64(const ZbotCfg* cfg, double* sim, const double* target, double* forces, double* tau, int n, int nsub) {
   return port_substeps<double>(cfg, sim, target, forces, tau, n, nsub, 1);
 }
+int zbot_port_substeps_m_terrain_f64(const ZbotCfg* cfg, double* sim, const double* target, double* forces, double* tau, int n, int nsub,
+                                     const PortTerrain* pt) {
+  return port_substeps<double>(cfg, sim, target, forces, tau, n, nsub, 2, pt);
+}
+int zbot_port_substeps_m_terrain_f32(const ZbotCfg* cfg, float* sim, const float* target, float* forces, float* tau, int n, int nsub,
+                                     const PortTerrain* pt) {
+  return port_substeps<float>(cfg, sim, target, forces, tau, n, nsub, 2, pt);
+}
 int zbot_port_substeps_m_f32(const ZbotCfg* cfg, float* sim, const float* target, float* forces, float* tau, int n, int nsub) {
   return port_substeps<float>(cfg, sim, target, forces, tau, n, nsub, 2);
 }
 int zbot_port_substeps_m_f64(const ZbotCfg* cfg, double* sim, const double* target, double* forces, double* tau, int n, int nsub) {
   return port_substeps<double>(cfg, sim, target, forces, tau, n, nsub, 2);
+}
+int zbot_port_m_step_terrain_f32(const ZbotCfg* cfg, float* state, int64_t* ep_len, const float* actions, const float* rnd,
+                                 float* obs, float* rew, uint8_t* term, uint8_t* trunc, float* reset_sums, float* export_buf, int n,
+                                 const PortTerrain* pt) {
+  return port_m_step<float>(cfg, state, ep_len, actions, rnd, obs, rew, term, trunc, reset_sums, export_buf, n, pt);
+}
+int zbot_port_m_step_terrain_f64(const ZbotCfg* cfg, double* state, int64_t* ep_len, const double* actions, const double* rnd,
+                                 double* obs, double* rew, uint8_t* term, uint8_t* trunc, double* reset_sums, double* export_buf, int n,
+                                 const PortTerrain* pt) {
+  return port_m_step<double>(cfg, state, ep_len, actions, rnd, obs, rew, term, trunc, reset_sums, export_buf, n, pt);
 }
 int zbot_port_m_step_f32(const ZbotCfg* cfg, float* state, int64_t* ep_len, const float* actions, const float* rnd,
                          float* obs, float* rew, uint8_t* term, uint8_t* trunc, float* reset_sums, float* export_buf, int n) {

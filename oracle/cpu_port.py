@@ -12,7 +12,7 @@ import subprocess
 
 import numpy as np
 
-from zbot_lab_b200.native import ZbotCfg, make_cfg  # noqa: F401  (struct definition only)
+from zbot_lab_b200.native import M_NUM_RAND, ZbotCfg, make_cfg  # noqa: F401  (struct definition / constants only)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
@@ -57,6 +57,22 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
 
 
+class PortTerrain(C.Structure):
+    """Host twin of ``zbot_bind_terrain`` (struct PortTerrain in cpu_port.cpp)."""
+    _fields_ = [("heights", C.c_void_p), ("nx", C.c_int), ("ny", C.c_int), ("x0", C.c_float), ("y0", C.c_float),
+                ("cell", C.c_float), ("tile_origins", C.c_void_p), ("rows", C.c_int), ("cols", C.c_int),
+                ("tile_size", C.c_float), ("env_origins", C.c_void_p), ("curriculum", C.c_int)]
+
+
+def make_port_terrain(terrain, env_origins4: np.ndarray, curriculum: bool):
+    """``terrain`` = zbot_lab_b200.terrain.Terrain; ``env_origins4`` (N, 4) float32, updated in place by the steps."""
+    assert env_origins4.dtype == np.float32 and env_origins4.flags.c_contiguous and env_origins4.shape[1] == 4
+    pt = PortTerrain(_p(terrain.heights), terrain.heights.shape[0], terrain.heights.shape[1], terrain.x0, terrain.y0, terrain.cell,
+                     _p(terrain.origins), terrain.rows, terrain.cols, float(terrain.cfg.size[0]), _p(env_origins4), int(bool(curriculum)))
+    pt._keep = (terrain, env_origins4)
+    return pt
+
+
 class PortEnv:
     """N envs stepped on the CPU with the kernel's own arithmetic (float32 or float64)."""
 
@@ -70,7 +86,7 @@ class PortEnv:
         self.mtask = (self.cfg.task == 3)
         self.state = np.zeros((n, 80), self.dtype)
         self.ep_len = np.zeros(n, np.int64)
-        self.export_words = (lib().zbot_port_snake_export_words() if self.snake else 69 if self.v4 else 67 if self.mtask
+        self.export_words = (lib().zbot_port_snake_export_words() if self.snake else 69 if self.v4 else 72 if self.mtask
                              else getattr(lib(), "zbot_port_export_words_" + self.sfx)())
         self.reset_all()
 
@@ -127,13 +143,19 @@ class PortEnv:
         if self.mtask:
             obs = np.zeros((n, 25), self.dtype)
             rew, term, trunc = np.zeros(n, self.dtype), np.zeros(n, np.uint8), np.zeros(n, np.uint8)
-            rs = np.zeros((n, 16), self.dtype)
+            rs = np.zeros((n, 20), self.dtype)      # 16 term slots + is_terminated sum, base_height / feet_close / illegal_contact flags
             ex = np.zeros((n, self.export_words), self.dtype) if export else None
             r = np.ascontiguousarray(rnd, self.dtype)
-            assert r.shape == (n, 13)
-            rc = getattr(lib(), "zbot_port_m_step_" + self.sfx)(
-                C.byref(self.cfg), _p(self.state), _p(self.ep_len), _p(a), _p(r), _p(obs), _p(rew), _p(term), _p(trunc),
-                _p(rs), _p(ex), C.c_int(n))
+            assert r.shape == (n, M_NUM_RAND)
+            pt = getattr(self, "terrain", None)
+            if pt is not None:
+                rc = getattr(lib(), "zbot_port_m_step_terrain_" + self.sfx)(
+                    C.byref(self.cfg), _p(self.state), _p(self.ep_len), _p(a), _p(r), _p(obs), _p(rew), _p(term), _p(trunc),
+                    _p(rs), _p(ex), C.c_int(n), C.byref(pt))
+            else:
+                rc = getattr(lib(), "zbot_port_m_step_" + self.sfx)(
+                    C.byref(self.cfg), _p(self.state), _p(self.ep_len), _p(a), _p(r), _p(obs), _p(rew), _p(term), _p(trunc),
+                    _p(rs), _p(ex), C.c_int(n))
             assert rc == 0, rc
             return obs, rew, term.astype(bool), trunc.astype(bool), rs, ex
         if self.v4:
@@ -162,7 +184,7 @@ class PortEnv:
 
 
 def substeps(sim: np.ndarray, target: np.ndarray, nsub: int, cfg: ZbotCfg | None = None, snake: bool = False,
-             model: str | None = None):
+             model: str | None = None, terrain: "PortTerrain | None" = None):
     """sim [N][25] (in/out), target [N][6] -> forces [N][7][3], applied torque [N][6]."""
     n = sim.shape[0]
     dt = sim.dtype
@@ -173,8 +195,13 @@ def substeps(sim: np.ndarray, target: np.ndarray, nsub: int, cfg: ZbotCfg | None
     target = np.ascontiguousarray(target, dt)
     name = ("zbot_port_substeps_m_" if model == "m" else "zbot_port_substeps_halves_" if model == "halves" else
             "zbot_port_substeps_snake_" if snake else "zbot_port_substeps_")
-    rc = getattr(lib(), name + sfx)(C.byref(cfg), _p(sim), _p(target), _p(forces), _p(tau),
-                                                     C.c_int(n), C.c_int(nsub))
+    if terrain is not None:
+        assert model == "m"
+        rc = getattr(lib(), "zbot_port_substeps_m_terrain_" + sfx)(C.byref(cfg), _p(sim), _p(target), _p(forces), _p(tau),
+                                                                   C.c_int(n), C.c_int(nsub), C.byref(terrain))
+    else:
+        rc = getattr(lib(), name + sfx)(C.byref(cfg), _p(sim), _p(target), _p(forces), _p(tau),
+                                        C.c_int(n), C.c_int(nsub))
     assert rc == 0
     return forces, tau
 

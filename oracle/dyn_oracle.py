@@ -241,7 +241,8 @@ class DynOracle:
                 # classical accel of the material point = J nu_dot + a_vp; the predicted velocity
                 # v + dt*a therefore carries dt*a_vp explicitly.  (w x v_c is the part of a_vp the
                 # kernel's spatial formulation does not already include -- same total.)
-                pen = -r[:, 2]
+                # ground height under the point: 0 on the plane; `self.ground(x, y)` (env-local) on a height field
+                pen = -r[:, 2] if getattr(self, "ground", None) is None else self.ground(r[:, 0], r[:, 1]) - r[:, 2]
                 s = np.clip(pen / P.ramp, 0.0, 1.0)
                 fs = np.minimum(k_n * pen, P.alpha * P.vdep)
                 gamma = k_n * dt + d_n * s

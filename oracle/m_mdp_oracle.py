@@ -21,11 +21,11 @@ import numpy as np
 
 F = np.float32
 
-#: column map of the (N, 67) export row (MExport in csrc/zbot_core.h)
+#: column map of the (N, 72) export row (MExport in csrc/zbot_core.h)
 VIEW_COLS = {"root_pos": (0, 3), "root_quat": (3, 7), "root_lin_vel": (7, 10), "root_ang_vel": (10, 13),
              "feet_pos": (13, 19), "feet_quat": (19, 27), "feet_com_vel": (27, 33), "feet_fz_hist": (33, 39),
              "feet_fnorm_max": (39, 41), "last_air": (41, 43), "last_contact": (43, 45), "cur_air": (45, 47),
-             "cur_contact": (47, 49), "q_chain": (49, 55), "tau": (55, 61), "joint_acc": (61, 67)}
+             "cur_contact": (47, 49), "q_chain": (49, 55), "tau": (55, 61), "joint_acc": (61, 67), "midb_max": (67, 72)}
 _SHAPES = {"feet_pos": (2, 3), "feet_quat": (2, 4), "feet_com_vel": (2, 3), "feet_fz_hist": (3, 2)}
 
 
@@ -173,6 +173,12 @@ class MTerms:
         s["feet_force_sum"] = (s["feet_force_sum"] + F(0.001) * (Fz[:, 0] - Fz[:, 1])).astype(F)
         return (F(0.5) * diff - F(0.1) * np.abs(s["feet_force_sum"])).astype(F)
 
+    @staticmethod
+    def undesired_contacts(v, s, cmd, p):
+        """isaaclab.envs.mdp.undesired_contacts [IL-upstream]: number of selected sensor bodies whose force norm exceeded the
+        threshold anywhere in the history (zbotlab_env_cfg.py:367-371: base|a.*|b.* -> here the five merged bodies)."""
+        return (v["midb_max"] > F(p.get("threshold", 1.0))).sum(1).astype(F)
+
 
 class MMdpOracle:
     """Manager-ordered control step on a supplied view.  ``terms`` = [(name, func_name, weight, params)] in cfg order
@@ -191,6 +197,12 @@ class MMdpOracle:
         self.cmd = z(n, 3)
         self.standing = np.zeros(n, bool)
         self.time_left = z(n)
+        self.heading_target, self.is_heading = z(n), np.zeros(n, bool)      # heading_command=True [IL-upstream]
+        self.push_left = z(n)                                               # EventTerm push_robot interval timer [IL-upstream]
+        self.push_dv = z(n, 2)                                              # velocity the last step's push added (0 if none)
+        # rough terrain (P["terrain"] = {"origins": (rows, cols, 3), "tile_size", "curriculum"}): TerrainImporter state [IL-upstream]
+        self.levels, self.types = np.zeros(n, np.int64), np.zeros(n, np.int64)
+        self.env_origins = z(n, 3)
         self.ep_sums = {name: z(n) for name, f, w, p in self.terms if float(w) != 0.0}
 
     # -- UniformVelocityCommand._resample [IL-upstream]
@@ -203,6 +215,12 @@ class MMdpOracle:
             self.cmd[ids, i] = u[:, 1 + i] * (F(b) - F(a)) + F(a)
         self.standing[ids] = u[:, 4] <= F(P["rel_standing_envs"])
 
+    def _resample_heading(self, ids, u):
+        h = self.P["heading"]
+        lo, hi = h["range"]
+        self.heading_target[ids] = u[:, 0] * (F(hi) - F(lo)) + F(lo)
+        self.is_heading[ids] = u[:, 1] <= F(h["rel_heading_envs"])
+
     def step(self, view: dict, raw_actions: np.ndarray, rnd: np.ndarray):
         n, P, s = self.n, self.P, self.s
         a = np.asarray(raw_actions, F)
@@ -210,11 +228,16 @@ class MMdpOracle:
         s["episode_length_buf"] = s["episode_length_buf"] + 1
         # TerminationManager
         time_out = s["episode_length_buf"] >= P["max_episode_length"]
-        low = view["root_pos"][:, 2] < F(P["minimum_height"])
+        low = (view["root_pos"][:, 2] + self.env_origins[:, 2]).astype(F) < F(P["minimum_height"])     # root_pos_w: world height
         close = np.zeros(n, bool)
         if P.get("feet_close_min"):
             close = np.linalg.norm(view["feet_pos"][:, 0] - view["feet_pos"][:, 1], axis=-1).astype(F) < F(P["feet_close_min"])
-        terminated = low | close
+        illegal = np.zeros(n, bool)
+        if P.get("illegal_contact"):                               # mdp.illegal_contact: any selected body with max_t |F| > threshold
+            thr, mask = P["illegal_contact"]
+            sel = np.array([(mask >> b) & 1 for b in range(5)], bool)
+            illegal = (view["midb_max"][:, sel] > F(thr)).any(1)
+        terminated = low | close | illegal
         # RewardManager
         reward = np.zeros(n, F)
         values = {}
@@ -234,6 +257,20 @@ class MMdpOracle:
         if len(ids):
             log = {name: float(np.mean(v[ids]) / F(P["max_episode_length"] * P["step_dt"])) for name, v in self.ep_sums.items()}
             log["#base_height"], log["#feet_close"], log["#time_out"] = int(low[ids].sum()), int(close[ids].sum()), int(time_out[ids].sum())
+            log["#illegal_contact"] = int(illegal[ids].sum())
+            if P.get("terrain") and P["terrain"].get("curriculum"):
+                # CurriculumManager.compute(env_ids) runs first in _reset_idx: terrain_levels_vel (mdp/curriculums.py:26-55) on
+                # the pre-reset root position / command, then TerrainImporter.update_env_origins [IL-upstream]
+                from zbot_lab_b200.terrain import terrain_levels_vel
+                tp = P["terrain"]
+                rows = tp["origins"].shape[0]
+                up, down = terrain_levels_vel(view["root_pos"][ids, :2], self.cmd[ids, :2], tp["tile_size"],
+                                              P["max_episode_length"] * P["step_dt"])
+                lv = self.levels[ids] + up.astype(np.int64) - down.astype(np.int64)
+                rand_lv = np.minimum((np.asarray(rnd, F)[ids, 21] * F(rows)).astype(np.int64), rows - 1)
+                self.levels[ids] = np.where(lv >= rows, rand_lv, np.clip(lv, 0, None))
+                self.env_origins[ids] = tp["origins"][self.levels[ids], self.types[ids]]
+                log["#move_up"], log["#move_down"] = int(up.sum()), int(down.sum())
             # reset_root_state_uniform on the root link + reset_joints_by_scale (1,1) + reset_my_data
             u = np.asarray(rnd, F)[ids]
             pr = P["pose_range"]
@@ -255,12 +292,46 @@ class MMdpOracle:
                 v[ids] = 0
             s["episode_length_buf"][ids] = 0
             self._resample(ids, u[:, 3:8])
+            if P.get("heading"):
+                self._resample_heading(ids, u[:, 13:15])
+            if P.get("push"):                                          # EventManager.reset re-draws the interval timer
+                lo, hi = P["push"]["interval_range_s"]
+                self.push_left[ids] = u[:, 17] * (F(hi) - F(lo)) + F(lo)
         # CommandManager.compute
         self.time_left = (self.time_left - dt).astype(F)
         rs = np.nonzero(self.time_left <= 0)[0]
         if len(rs):
             self._resample(rs, np.asarray(rnd, F)[rs][:, 8:13])
+            if P.get("heading"):
+                self._resample_heading(rs, np.asarray(rnd, F)[rs][:, 15:17])
+        if P.get("heading"):
+            # _update_command: ang_vel_z = clip(stiffness * wrap_to_pi(target - heading_w), ang_vel_z range) for the heading envs;
+            # heading_w = atan2 of the root x axis (post-reset root for the envs reset above)
+            rq_h = view["root_quat"].copy()
+            if len(ids):
+                rq_h[ids] = new_root["root_quat"]
+            ex_ = np.zeros((n, 3), F)
+            ex_[:, 0] = 1
+            fw = quat_apply(rq_h, ex_)
+            hw = np.arctan2(fw[:, 1], fw[:, 0]).astype(F)
+            d = (self.heading_target - hw).astype(F)
+            err = np.arctan2(np.sin(d), np.cos(d)).astype(F)
+            a_, b_ = P["cmd_ranges"][2]
+            wz = np.clip(F(P["heading"]["stiffness"]) * err, F(a_), F(b_)).astype(F)
+            self.cmd[self.is_heading, 2] = wz[self.is_heading]
         self.cmd[self.standing] = 0
+        # EventManager.apply(mode="interval"): push_by_setting_velocity
+        self.push_dv[:] = 0
+        if P.get("push"):
+            self.push_left = (self.push_left - dt).astype(F)
+            ps = np.nonzero(self.push_left < F(1e-6))[0]
+            if len(ps):
+                up = np.asarray(rnd, F)[ps]
+                lo, hi = P["push"]["interval_range_s"]
+                self.push_left[ps] = up[:, 18] * (F(hi) - F(lo)) + F(lo)
+                for i, k in enumerate(("x", "y")):
+                    a_, b_ = P["push"]["velocity_range"].get(k, (0.0, 0.0))
+                    self.push_dv[ps, i] = up[:, 19 + i] * (F(b_) - F(a_)) + F(a_)
         # observation (clean): root_quat, command, joint_pos_rel, joint_vel_rel (Isaac Lab joint order), last_action
         il = np.asarray(self.V.CHAIN_TO_IL)
         q_rel = np.zeros((n, 6), F)
@@ -276,7 +347,7 @@ class MMdpOracle:
         obs = np.concatenate([rq, self.cmd, q_rel, qd, s["action"]], axis=1).astype(F)
         return {"obs": obs, "reward": reward, "terminated": terminated, "time_outs": time_out, "reset_ids": ids,
                 "values": values, "log": log, "resample_ids": rs, "new_root": new_root,
-                "low": low, "close": close}
+                "low": low, "close": close, "illegal": illegal}
 
     def post_reset_feet_and_root_quat(self, base_pos, yaw):
         """Feet LINK positions and root quaternion right after reset_base: the default pose moved by (x, y, yaw)."""
@@ -330,5 +401,9 @@ def synth_m_views(seed: int, n: int, steps: int):
         v["cur_contact"] = np.where(inair, 0.0, v["cur_contact"])
         v["cur_air"] = np.where(inair, v["cur_air"], 0.0)
         v = {k: np.asarray(x, F) for k, x in v.items()}
-        out.append((v, rng.normal(0, 1, (n, 6)).astype(F), rng.random((n, 13)).astype(F)))
+        # 13 uniforms from the main stream (the golden fixtures were generated with exactly this draw order) + the 9 slots
+        # added later (heading command, push event) from a side stream
+        u13 = rng.normal(0, 1, (n, 6)).astype(F), rng.random((n, 13)).astype(F)
+        u8 = np.random.default_rng(100003 * seed + t).random((n, 9)).astype(F)
+        out.append((v, u13[0], np.concatenate([u13[1], u8], axis=1)))
     return out

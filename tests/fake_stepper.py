@@ -24,6 +24,9 @@ class _State:
         else:
             f[np.asarray(ids)] = v
 
+    def column(self, name, i=0):
+        return torch.from_numpy(self.port.field(name, STATE_FIELDS[name])[:, i])
+
 
 class FakeStepper:
     def __init__(self, num_envs, device, cfg=None):
@@ -135,6 +138,13 @@ class FakeMStepper(FakeStepper):
     def reset_idx(self, env_ids=None, terminated=None, truncated=None):
         return self.reset_idx_m(env_ids)
 
+    def bind_terrain(self, heights, x0, y0, cell, tile_origins, tile_size, env_origins4, curriculum):
+        h, to, eo = heights.numpy(), tile_origins.numpy(), env_origins4.numpy()      # CPU tensors: numpy shares their memory
+        pt = cpu_port.PortTerrain(h.ctypes.data, h.shape[0], h.shape[1], float(x0), float(y0), float(cell), to.ctypes.data,
+                                  to.shape[0], to.shape[1], float(tile_size), eo.ctypes.data, int(bool(curriculum)))
+        pt._keep = (heights, tile_origins, env_origins4, h, to, eo)
+        self.port.terrain = pt
+
     def update_cfg(self):
         pass          # the port reads self.cfg on every step
 
@@ -150,9 +160,16 @@ class FakeMStepper(FakeStepper):
         self.terminated.copy_(torch.from_numpy(term.astype(np.uint8)))
         self.truncated.copy_(torch.from_numpy(trunc.astype(np.uint8)))
         mask = term | trunc
-        self._write_stats(mask, rs, term, trunc, rew)
-        if mask.any() and self.cfg.num_terms <= 13:      # raw-count tail slots (include/zbot_b200.h: zbot_m_step)
-            self.stats_ring[self._slot][14] = float(rs[mask][:, 14].sum())
-            self.stats_ring[self._slot][15] = float(rs[mask][:, 15].sum())
+        prev = self._slot
+        self._write_stats(mask, rs[:, :16], term, trunc, rew)
+        s = self.stats_ring[self._slot]
+        if mask.any():
+            if self.cfg.num_terms <= 13:                 # raw-count tail slots (include/zbot_b200.h: zbot_m_step)
+                s[14], s[15] = float(rs[mask][:, 14].sum()), float(rs[mask][:, 15].sum())
+            # statistics words 22..25: is_terminated's episodic sum (normalised like a term) and the per-DoneTerm counts
+            s[22] = float(rs[mask][:, 16].sum()) / int(mask.sum()) / 20.0
+            s[23], s[24], s[25] = (float(rs[mask][:, 17 + i].sum()) for i in range(3))
+        elif prev >= 0:
+            s[22:26] = self.stats_ring[prev][22:26]
         self.launch_count += 2
         return self.obs, self.rew, self.terminated, self.truncated

@@ -123,6 +123,14 @@ M_PARAMS = {"minimum_height": 0.2, "feet_close_min": 0.12, "cmd_ranges": ((-0.3,
             "max_episode_length": 1000, "step_dt": 0.02}
 
 
+#: the cfg features the reference's registered cfgs switch off (zbotlab_env_cfg.py:86-97, 253-258, 367-371, 385-388), all on
+M_EXTRA_TERMS = [t for t in M_ALL_TERMS if t[0] != "air_time_variance2"] + [
+    ("undesired_contacts", "undesired_contacts", -1.0, {"threshold": 1.0})]
+M_PARAMS_EXTRA = dict(M_PARAMS, cmd_ranges=((-0.3, 0.3), (-0.1, 0.1), (-1.0, 1.0)), illegal_contact=(1.0, 0b00100),
+                      heading={"range": (-np.pi, np.pi), "stiffness": 0.5, "rel_heading_envs": 0.7},
+                      push={"interval_range_s": (0.1, 0.4), "velocity_range": {"x": (-0.5, 0.5), "y": (-0.5, 0.5)}})
+
+
 def m_native_cfg(n, terms, P=M_PARAMS, **kw):
     from zbot_lab_b200 import native
     slot = [(f, w, p) for _, f, w, p in terms if f != "is_terminated"]
@@ -130,7 +138,8 @@ def m_native_cfg(n, terms, P=M_PARAMS, **kw):
     return native.make_m_cfg(n, slot, is_terminated_weight=wt[0] if wt else 0.0, minimum_height=P["minimum_height"],
                              feet_close_min=kw.pop("feet_close_min", P["feet_close_min"]), cmd_ranges=P["cmd_ranges"],
                              rel_standing_envs=P["rel_standing_envs"], resampling_time_range=P["resampling_time_range"],
-                             pose_range=P["pose_range"], act_clip=0.04 * np.pi, **kw)
+                             pose_range=P["pose_range"], act_clip=0.04 * np.pi, illegal_contact=P.get("illegal_contact"),
+                             heading=P.get("heading"), push=P.get("push"), **kw)
 
 
 def m_make_oracle(n, terms, state_get, ep_len, P=M_PARAMS):
@@ -147,6 +156,8 @@ def m_make_oracle(n, terms, state_get, ep_len, P=M_PARAMS):
     o.s["feet_step_length"][:] = state_get("feet_step_length", 2)
     o.s["feet_force_sum"][:] = state_get("feet_force_sum", 1)[:, 0]
     o.s["action"][:] = state_get("actions", 6)
+    pd = state_get("p_delta", 6)
+    o.heading_target[:], o.is_heading[:], o.push_left[:] = pd[:, 0], pd[:, 1] != 0, pd[:, 2]
     return o
 
 
@@ -167,6 +178,11 @@ def m_check_step(o, a, rnd, ex, obs, rew, term, trunc, ep_len, state_get, rs=Non
     assert np.abs(cmd - o.cmd).max() <= 1e-6, "commands"
     assert np.array_equal(state_get("base_heading_x_sum", 1)[:, 0] != 0, o.standing), "standing envs"
     assert np.abs(state_get("base_pos_y_err_sum", 1)[:, 0] - o.time_left).max() <= 1e-5, "command time_left"
+    pd = state_get("p_delta", 6)
+    if o.P.get("heading"):
+        assert np.abs(pd[:, 0] - o.heading_target).max() <= 1e-6 and np.array_equal(pd[:, 1] != 0, o.is_heading), "heading command state"
+    if o.P.get("push"):
+        assert np.abs(pd[:, 2] - o.push_left).max() <= 1e-5, "push_robot interval timer"
     for k, w in (("feet_step_length", 2), ("feet_contact_forces_last", 2), ("feet_down_pos_last", 6)):
         assert np.abs(state_get(k, w).reshape(n, -1) - o.s[k].reshape(n, -1)).max() <= 2e-5, k
     assert np.abs(state_get("feet_force_sum", 1)[:, 0] - o.s["feet_force_sum"]).max() <= 1e-6
@@ -181,11 +197,16 @@ def m_check_step(o, a, rnd, ex, obs, rew, term, trunc, ep_len, state_get, rs=Non
             want = r["log"][nm] * (o.P["max_episode_length"] * o.P["step_dt"])     # mean episodic sum over the reset envs
             got = float(np.mean(np.asarray(rs)[ids, i], dtype=np.float32))
             assert abs(got - want) <= 20 * rtol * max(1e-2, abs(want)), ("log", nm, got, want)
-        if len(slot_names) <= 13:
+        rs_ = np.asarray(rs)
+        cols = [(13, 14, 15)] if len(slot_names) <= 13 else []           # mirrored in the spare term slots when there are any
+        if rs_.shape[1] >= 20:
+            cols.append((16, 17, 18))                                     # statistics words 22..24 (+ 25 = illegal_contact)
+            assert int(rs_[ids, 19].sum()) == r["log"]["#illegal_contact"]
+        for c_pen, c_low, c_close in cols:
             pen = [nm for nm, f, w, p in o.terms if f == "is_terminated"]
             if pen:
                 want = r["log"][pen[0]] * (o.P["max_episode_length"] * o.P["step_dt"])
-                assert abs(float(np.mean(np.asarray(rs)[ids, 13], dtype=np.float32)) - want) <= 1e-5 * max(1e-2, abs(want))
-            assert int(np.asarray(rs)[ids, 14].sum()) == r["log"]["#base_height"]
-            assert int(np.asarray(rs)[ids, 15].sum()) == r["log"]["#feet_close"]
+                assert abs(float(np.mean(rs_[ids, c_pen], dtype=np.float32)) - want) <= 1e-5 * max(1e-2, abs(want))
+            assert int(rs_[ids, c_low].sum()) == r["log"]["#base_height"]
+            assert int(rs_[ids, c_close].sum()) == r["log"]["#feet_close"]
     return r

@@ -310,10 +310,10 @@ def test_two_lane_instantiation_equals_scalar_bit_for_bit():
 
 
 # ------------------------------------------------------------------------------------------------ manager-based task
-def _m_port(n, dtype, rng, terms):
-    from helpers import m_native_cfg
+def _m_port(n, dtype, rng, terms, P=None):
+    from helpers import M_PARAMS, m_native_cfg
     from oracle import cpu_port
-    pe = cpu_port.PortEnv(n, dtype, m_native_cfg(n, terms))
+    pe = cpu_port.PortEnv(n, dtype, m_native_cfg(n, terms, P or M_PARAMS))
     pe.field("carry_feet_fz", 2)[:] = np.stack([rng.uniform(-0.3, 0.3, n), rng.uniform(-0.1, 0.1, n)], -1)
     pe.field("carry_mid_max", 1)[:, 0] = rng.uniform(-0.2, 0.2, n)
     pe.field("base_pos_y_err_sum", 1)[:, 0] = rng.uniform(0.05, 0.3, n)          # command time_left
@@ -342,13 +342,55 @@ def test_m_full_step_port_matches_pinned_oracle_on_exported_physics(which):
     n_reset = n_term = n_res = 0
     for t in range(40):
         a = rng.normal(0, 1.5, (n, 6)).astype(np.float32)
-        rnd = rng.random((n, 13)).astype(np.float32)
+        rnd = rng.random((n, 22)).astype(np.float32)
         obs, rew, term, trunc, rs, ex = pe.step(a, export=True, rnd=rnd)
         r = m_check_step(o, a, rnd, ex, obs, rew, term, trunc, pe.ep_len, get, rs)
         n_reset += len(r["reset_ids"])
         n_term += int(term.sum())
         n_res += len(r["resample_ids"])
     assert n_reset >= 6 and n_term > 0 and n_res >= n
+
+
+def test_m_extra_cfg_features_port_matches_oracle():
+    """The cfg features `ZbotLabRoughEnvCfg` defines and the registered cfgs switch off, all switched on: RewTerm
+    `undesired_contacts` (zbotlab_env_cfg.py:367-371), DoneTerm `base_contact` = illegal_contact on `base` (:385-388),
+    `heading_command=True` (:86-97) and the interval EventTerm `push_robot` (:253-258).  All four are Isaac Lab functions the
+    reference does not vendor ([IL-upstream], unpinned): the oracle restates them from upstream knowledge, the kernel
+    arithmetic (host build) must agree with it -- flags / masks / timers exact, floats <= 1e-5; a push adds exactly the drawn
+    velocity to the whole robot."""
+    from helpers import M_EXTRA_TERMS, M_PARAMS_EXTRA, m_check_step, m_make_oracle
+    n = 128
+    rng = np.random.default_rng(7)
+    pe = _m_port(n, np.float32, rng, M_EXTRA_TERMS, M_PARAMS_EXTRA)
+    twin = _m_port(n, np.float32, np.random.default_rng(7), M_EXTRA_TERMS, dict(M_PARAMS_EXTRA, push=None))
+    pd = pe.field("p_delta", 6)
+    pd[:, 0], pd[:, 1], pd[:, 2] = rng.uniform(-3, 3, n), rng.random(n) < 0.7, rng.uniform(0.02, 0.4, n)
+    # a third of the robots start lying on their side: merged bodies on the ground -> undesired / illegal contacts
+    lying = np.arange(n) % 3 == 0
+    pe.field("root_pos", 3)[lying, 2] = 0.0485
+    pe.field("root_quat", 4)[lying] = np.array([0.7071068, 0.0, 0.7071068, 0.0], np.float32)
+    pe.field("joint_pos", 6)[lying] = 0.0
+    ep0 = rng.integers(0, 990, n)
+    pe.ep_len[:] = ep0
+    get = lambda k, w: pe.field(k, w).copy()
+    o = m_make_oracle(n, M_EXTRA_TERMS, get, ep0, M_PARAMS_EXTRA)
+    n_ill = n_und = n_push = n_head = 0
+    for t in range(30):
+        a = rng.normal(0, 1.0, (n, 6)).astype(np.float32)
+        rnd = rng.random((n, 22)).astype(np.float32)
+        twin.state[:] = pe.state
+        twin.ep_len[:] = pe.ep_len
+        obs, rew, term, trunc, rs, ex = pe.step(a, export=True, rnd=rnd)
+        twin.step(a, rnd=rnd)
+        r = m_check_step(o, a, rnd, ex, obs, rew, term, trunc, pe.ep_len, get, rs)
+        # the push: the twin (same state, same uniforms, no push_robot term) differs by exactly the drawn velocity
+        dv = pe.field("root_lin_vel", 3) - twin.field("root_lin_vel", 3)
+        assert np.abs(dv[:, :2] - o.push_dv).max() <= 1e-6 and np.abs(dv[:, 2]).max() == 0
+        n_push += int((np.abs(o.push_dv).sum(1) > 0).sum())
+        n_ill += int(r["illegal"].sum())
+        n_und += int((r["values"]["undesired_contacts"] > 0).sum())
+        n_head += int((o.is_heading & ~o.standing & (np.abs(o.cmd[:, 2]) > 0)).sum())
+    assert n_ill > 0 and n_und > n_ill and n_push > n // 2 and n_head > n
 
 
 def test_m_port_f32_tracks_f64_and_the_robot_stands():
@@ -364,7 +406,7 @@ def test_m_port_f32_tracks_f64_and_the_robot_stands():
     alive = np.ones(n, bool)
     for t in range(50):
         a = rng.normal(0, 0.3, (n, 6)).astype(np.float32)
-        rnd = rng.random((n, 13)).astype(np.float32)
+        rnd = rng.random((n, 22)).astype(np.float32)
         _, _, t32, tr32, _, _ = e32.step(a, rnd=rnd)
         _, _, t64, tr64, _, _ = e64.step(a, rnd=rnd)
         alive &= ~(t32 | t64 | tr32 | tr64)
@@ -377,7 +419,7 @@ def test_m_port_f32_tracks_f64_and_the_robot_stands():
     pe.cfg.num_envs = 4
     pe.field("base_pos_y_err_sum", 1)[:] = 100.0
     for t in range(40):
-        obs, rew, term, trunc, rs, ex = pe.step(np.zeros((4, 6)), export=True, rnd=np.full((4, 13), 0.5))
+        obs, rew, term, trunc, rs, ex = pe.step(np.zeros((4, 6)), export=True, rnd=np.full((4, 22), 0.5))
     v = split_view(ex)
     assert abs(v["root_pos"][0, 2] - 0.2545) < 1e-3 and abs(v["root_quat"][0, 0]) > 0.99999
     assert np.abs(v["feet_fz_hist"][0] - 0.5 * 3.00504 * 9.81).max() < 0.05          # each sole carries m g / 2
@@ -649,3 +691,122 @@ def test_unlimited_revolute_joints_wrap_at_two_pi_like_physx():
     for i in range(4):
         cpu_port.substeps(sims, tg, 1, cfg=cpu_port.make_cfg(1, task=cpu_port.TASK_SNAKE_V0) if hasattr(cpu_port, "TASK_SNAKE_V0") else None, snake=True)
     assert sims[0, 13 + 5] > two_pi and sims[0, 13 + 1] < -two_pi + 1.0
+
+
+def _terrain_fixture(rows=3, cols=4, curriculum=True, seed=4):
+    from zbot_lab_b200.terrain import Terrain, rough_terrains_cfg
+    g = rough_terrains_cfg()
+    g.num_rows, g.num_cols, g.border_width, g.curriculum = rows, cols, 2.0, curriculum
+    return Terrain(g, seed=seed)
+
+
+def test_generated_terrain_and_importer_bookkeeping():
+    """zbot_lab_b200/terrain.py (restated ROUGH_TERRAINS_CFG / TerrainImporter [IL-upstream]): tile grid geometry, every
+    sub-terrain family, difficulty growing with the level, spawn points on the field, bilinear sampling, level updates; and
+    the reference's own curriculum rule (mdp/curriculums.py:26-55)."""
+    from zbot_lab_b200.terrain import rough_terrains_cfg, sub_terrain, terrain_levels_vel
+    t = _terrain_fixture(rows=4, cols=10)
+    n = t.tile_cells
+    assert n == 80 and t.heights.shape == (4 * 80 + 2 * 20 + 1, 10 * 80 + 2 * 20 + 1) and t.heights.dtype == np.float32
+    assert set(t.col_kind) == set(rough_terrains_cfg().sub_terrains) and t.col_kind.count("pyramid_stairs") == 2
+    assert np.all(t.heights[:20] == 0) and np.all(t.heights[:, -20:] == 0)                       # flat border
+    for r in range(4):
+        for c in range(10):
+            o = t.origins[r, c]
+            assert abs(float(t.height_at(o[0], o[1])) - o[2]) < 1e-6                             # spawn point sits on the field
+    # level = difficulty: the stairs' platform rises with the row; inverted ones sink
+    cs, ci = t.col_kind.index("pyramid_stairs"), t.col_kind.index("pyramid_stairs_inv")
+    assert np.all(np.diff(t.origins[:, cs, 2]) > 0) and np.all(np.diff(t.origins[:, ci, 2]) < 0)
+    rng = np.random.default_rng(0)
+    st = sub_terrain("pyramid_stairs", dict(step_height_range=(0.05, 0.23), step_width=0.3, platform_width=3.0), 1.0, 80, 0.1, rng)
+    assert abs(st.max() - 0.23 * ((80 - 30) // 2 // 3)) < 1e-9 and st[0, 0] == 0 and np.all(st == st.T)
+    sl = sub_terrain("pyramid_slope", dict(slope_range=(0.0, 0.4), platform_width=2.0), 0.5, 80, 0.1, rng)
+    assert abs(sl[40, 40] - 0.2 * 0.1 * 30) < 1e-9 and abs((sl[5, 40] - sl[4, 40]) / 0.1 - 0.2) < 1e-9
+    bx = sub_terrain("random_grid", dict(grid_width=0.45, grid_height_range=(0.05, 0.2), platform_width=2.0), 1.0, 80, 0.1, rng)
+    assert np.all(bx[30:50, 30:50] == 0) and abs(bx).max() <= 0.2 and len(np.unique(bx)) > 50
+    ru = sub_terrain("random_uniform", dict(noise_range=(0.02, 0.10), noise_step=0.02), 1.0, 80, 0.1, rng)
+    assert ru[40, 40] == 0 and 0.02 < np.ptp(ru) <= 0.16
+    # bilinear sample between four cells
+    x, y = t.x0 + 57.25 * t.cell, t.y0 + 33.5 * t.cell
+    H = t.heights.astype(np.float64)
+    want = (H[57, 33] * 0.75 + H[58, 33] * 0.25) * 0.5 + (H[57, 34] * 0.75 + H[58, 34] * 0.25) * 0.5
+    assert abs(float(t.height_at(x, y)) - want) < 1e-5
+    # TerrainImporter: initial placement and level updates
+    lv, ty = t.initial_levels_types(1000, 5, np.random.default_rng(1))
+    assert lv.min() == 0 and lv.max() == 3 and np.all(np.diff(ty) >= 0) and ty[0] == 0 and ty[-1] == 9 and np.bincount(ty).min() == 100
+    new = t.update_levels(np.array([0, 0, 3, 3, 2]), np.array([0, 1, 1, 0, 0], bool), np.array([1, 0, 0, 1, 0], bool), np.array([9, 9, 1, 9, 9]))
+    assert list(new) == [0, 1, 1, 2, 2]              # clipped at 0; solved the last level -> random restart; down; unchanged
+    up, down = terrain_levels_vel(np.array([[4.1, 0], [0.5, 0.3], [2.0, 0.0], [0.0, 0.0]]), np.array([[0.1, 0], [0.1, 0], [0.1, 0.0], [0, 0]]), 8.0, 20.0)
+    assert list(up) == [True, False, False, False] and list(down) == [False, True, False, False]
+
+
+def test_m_rough_port_matches_oracles_on_the_height_field():
+    """zbot-6b-walking-m-rough-v0 (kernel arithmetic, host build): (1) the substep with the height field under every contact
+    candidate equals the independent float64 dynamics oracle with the same ground function; (2) the full step with the
+    terrain curriculum -- world-height termination, level moves at reset, new origins -- equals the oracle on the exported
+    view: flags, levels, origins exact."""
+    from helpers import M_EXTRA_TERMS, M_PARAMS_EXTRA, m_check_step, m_make_oracle, m_native_cfg
+    from oracle import cpu_port
+    from oracle.dyn_oracle import DynOracle, DynParams
+    from zbot_lab_b200 import native
+    from zbot_lab_b200.assets import zbot_6s_v2 as V
+    t = _terrain_fixture()
+    n = 48
+    rng = np.random.default_rng(11)
+    lv, ty = t.initial_levels_types(n, 2, rng)
+    org4 = np.zeros((n, 4), np.float32)
+    org4[:, :3] = t.origins[lv, ty]
+    # (1) dynamics on slopes / boxes: robots dropped next to their spawn points (off the flat platform)
+    cfg = m_native_cfg(n, native.M_FLAT_TERMS)
+    m = V.model_f32()
+    pt = cpu_port.make_port_terrain(t, org4, False)
+    st = {"root_pos": np.tile(m.default_root_pos, (n, 1)), "root_quat": np.tile(m.default_root_quat, (n, 1)),
+          "root_lin_vel": rng.normal(0, 0.1, (n, 3)), "root_ang_vel": rng.normal(0, 0.3, (n, 3)),
+          "joint_pos": np.tile(m.default_joint_pos, (n, 1)) + rng.uniform(-0.1, 0.1, (n, 6)), "joint_vel": rng.normal(0, 0.3, (n, 6))}
+    st["root_pos"][:, 0] += rng.uniform(-2.5, 2.5, n)
+    st["root_pos"][:, 1] += rng.uniform(-2.5, 2.5, n)
+    gz = t.height_at(org4[:, 0] + st["root_pos"][:, 0], org4[:, 1] + st["root_pos"][:, 1]).astype(np.float64) - org4[:, 2]
+    st["root_pos"][:, 2] += gz + 0.004
+    o = DynOracle(n, DynParams(model=m, mu=float(cfg.contact_mu)), model=m)
+    o64 = org4.astype(np.float64)
+    o.ground = lambda x, y: t.height_at(x + o64[:, 0], y + o64[:, 1], np.float64) - o64[:, 2]
+    o.set_state(st)
+    sim = cpu_port.pack_sim(st, np.float64)
+    tgt = st["joint_pos"].copy()
+    touched = 0
+    for i in range(12):
+        f, tau = cpu_port.substeps(sim, tgt, 1, cfg=cfg, model="m", terrain=pt)
+        o.substep(tgt)
+        ref = np.concatenate([o.root_pos, o.root_quat, o.root_lin_vel, o.root_ang_vel, o.q, o.qd], -1)
+        assert np.abs(sim - ref).max() < 1e-6, i          # the height field itself is float32: its samples carry ~1e-7
+        touched += int((np.abs(f[:, [0, 6], 2]) > 1.0).sum())
+        sim[:] = ref
+    assert touched > n
+    # (2) the full step with the curriculum
+    P = dict(M_PARAMS_EXTRA, terrain={"origins": t.origins, "tile_size": 8.0, "curriculum": True}, cmd_ranges=((-0.3, 0.3), (-0.1, 0.1), (-1.0, 1.0)))
+    pe = cpu_port.PortEnv(n, np.float32, m_native_cfg(n, M_EXTRA_TERMS, P))
+    org4b = org4.copy()
+    pe.terrain = cpu_port.make_port_terrain(t, org4b, True)
+    pd = pe.field("p_delta", 6)
+    pd[:, 3], pd[:, 4] = lv, ty
+    pe.field("carry_feet_fz", 2)[:] = np.stack([rng.uniform(-0.3, 0.3, n), rng.uniform(-0.1, 0.1, n)], -1)
+    pe.field("base_pos_y_err_sum", 1)[:, 0] = rng.uniform(0.05, 0.3, n)
+    walked = np.arange(n) % 4 == 0                          # a quarter of the robots have walked more than half a tile: move up
+    pe.field("root_pos", 3)[walked, 0] += 4.3
+    ep0 = rng.integers(900, 999, n)
+    pe.ep_len[:] = ep0
+    get = lambda k, w: pe.field(k, w).copy()
+    orc = m_make_oracle(n, M_EXTRA_TERMS, get, ep0, P)
+    orc.levels[:], orc.types[:], orc.env_origins[:] = lv, ty, org4[:, :3]
+    ups = downs = resets = 0
+    for s in range(25):
+        a = rng.normal(0, 0.5, (n, 6)).astype(np.float32)
+        rnd = rng.random((n, 22)).astype(np.float32)
+        obs, rew, term, trunc, rs, ex = pe.step(a, export=True, rnd=rnd)
+        r = m_check_step(orc, a, rnd, ex, obs, rew, term, trunc, pe.ep_len, get, rs)
+        assert np.array_equal(pe.field("p_delta", 6)[:, 3].astype(np.int64), orc.levels), "terrain levels"
+        assert np.array_equal(org4b[:, :3], orc.env_origins), "env origins"
+        if r["log"]:
+            ups, downs = ups + r["log"]["#move_up"], downs + r["log"]["#move_down"]
+        resets += len(r["reset_ids"])
+    assert resets > n and ups > 0 and downs > 0

@@ -1128,11 +1128,11 @@ def test_m_fused_step_matches_pinned_oracle_on_exported_physics(which):
     st.episode_length_buf[:] = _t(ep0.astype(np.int64))
     get = lambda k, w: st.state.get(k).cpu().numpy()
     o = m_make_oracle(n, terms, get, ep0)
-    ex_t = torch.zeros(n, 67, device=DEV)
+    ex_t = torch.zeros(n, 72, device=DEV)
     n_reset = n_term = n_res = 0
     for t in range(40):
         a = rng.normal(0, 1.5, (n, 6)).astype(np.float32)
-        rnd = rng.random((n, 13)).astype(np.float32)
+        rnd = rng.random((n, 22)).astype(np.float32)
         obs, rew, term, trunc = st.step(_t(a), export=ex_t, rand=_t(rnd))
         torch.cuda.synchronize()
         r = m_check_step(o, a, rnd, ex_t.cpu().numpy(), obs.cpu().numpy(), rew.cpu().numpy(), term.cpu().numpy(),
@@ -1156,6 +1156,130 @@ def test_m_fused_step_matches_pinned_oracle_on_exported_physics(which):
     st.close()
 
 
+def test_m_extra_cfg_features_match_oracle_on_exported_physics():
+    """GPU twin of tests/test_cpu_oracles.py::test_m_extra_cfg_features_port_matches_oracle: RewTerm `undesired_contacts`,
+    DoneTerm illegal_contact on `base`, `heading_command=True` and the interval EventTerm `push_robot`
+    (zbotlab_env_cfg.py:86-97, 253-258, 367-371, 385-388; [IL-upstream] functions, oracle restated from upstream knowledge).
+    Flags / masks / timers exact, floats <= 1e-5, statistics words 22..25, a push adds exactly the drawn velocity."""
+    from helpers import M_EXTRA_TERMS, M_PARAMS_EXTRA, m_check_step, m_make_oracle
+    n = 200
+    rng = np.random.default_rng(9)
+    st = _m_stepper(n, rng, M_EXTRA_TERMS, P=M_PARAMS_EXTRA)
+    twin = _m_stepper(n, np.random.default_rng(9), M_EXTRA_TERMS, P=dict(M_PARAMS_EXTRA, push=None))
+    pd = np.zeros((n, 6), np.float32)
+    pd[:, 0], pd[:, 1], pd[:, 2] = rng.uniform(-3, 3, n), rng.random(n) < 0.7, rng.uniform(0.02, 0.4, n)
+    st.state.set("p_delta", _t(pd))
+    lying = torch.arange(n, device=DEV) % 3 == 0
+    rp, rq, jp = st.state.get("root_pos"), st.state.get("root_quat"), st.state.get("joint_pos")
+    rp[lying, 2] = 0.0485
+    rq[lying] = torch.tensor([0.7071068, 0.0, 0.7071068, 0.0], device=DEV)
+    jp[lying] = 0.0
+    st.state.set("root_pos", rp); st.state.set("root_quat", rq); st.state.set("joint_pos", jp)
+    ep0 = rng.integers(0, 990, n)
+    st.episode_length_buf[:] = _t(ep0.astype(np.int64))
+    get = lambda k, w: st.state.get(k).cpu().numpy()
+    o = m_make_oracle(n, M_EXTRA_TERMS, get, ep0, M_PARAMS_EXTRA)
+    ex_t = torch.zeros(n, 72, device=DEV)
+    n_ill = n_und = n_push = n_head = 0
+    for t in range(30):
+        a = rng.normal(0, 1.0, (n, 6)).astype(np.float32)
+        rnd = rng.random((n, 22)).astype(np.float32)
+        twin.state.buf.copy_(st.state.buf)
+        twin.episode_length_buf.copy_(st.episode_length_buf)
+        obs, rew, term, trunc = st.step(_t(a), export=ex_t, rand=_t(rnd))
+        twin.step(_t(a), rand=_t(rnd))
+        torch.cuda.synchronize()
+        r = m_check_step(o, a, rnd, ex_t.cpu().numpy(), obs.cpu().numpy(), rew.cpu().numpy(), term.cpu().numpy(),
+                         trunc.cpu().numpy(), st.episode_length_buf.cpu().numpy(), get)
+        dv = (st.state.get("root_lin_vel") - twin.state.get("root_lin_vel")).cpu().numpy()
+        assert np.abs(dv[:, :2] - o.push_dv).max() <= 1e-6 and np.abs(dv[:, 2]).max() == 0
+        ids = r["reset_ids"]
+        if len(ids):
+            s = st.stats.cpu().numpy()
+            assert s[16] == len(ids) and s[23] == r["log"]["#base_height"] and s[24] == r["log"]["#feet_close"]
+            assert s[25] == r["log"]["#illegal_contact"]
+            want = r["log"]["termination_penalty"]
+            assert abs(s[22] - want) <= 1e-5 * max(1e-2, abs(want))
+        n_push += int((np.abs(o.push_dv).sum(1) > 0).sum())
+        n_ill += int(r["illegal"].sum())
+        n_und += int((r["values"]["undesired_contacts"] > 0).sum())
+        n_head += int((o.is_heading & ~o.standing & (np.abs(o.cmd[:, 2]) > 0)).sum())
+    assert n_ill > 0 and n_und > n_ill and n_push > n // 2 and n_head > n
+    st.close()
+    twin.close()
+
+
+def test_m_rough_kernel_matches_oracle_and_host_build_on_the_height_field():
+    """zbot-6b-walking-m-rough-v0 on the GPU (`zbot_bind_terrain`, kTerrain instantiation of zbot_m_step_kernel): the full
+    step with the height field under every contact candidate, the WORLD-height termination and the terrain curriculum equals
+    (1) the oracle on the exported view -- flags, reset ids, terrain levels and env origins exact, floats <= 1e-5 -- and
+    (2) the same arithmetic compiled for the host, one step from identical states, within the manager task's one-step
+    bounds.  Robots are dropped off the spawn platforms so slopes / boxes / stair edges are under their feet."""
+    from helpers import M_EXTRA_TERMS, M_PARAMS_EXTRA, m_check_step, m_make_oracle, m_native_cfg
+    from oracle import cpu_port
+    from zbot_lab_b200.stepper import NativeStepper
+    from zbot_lab_b200.terrain import Terrain, rough_terrains_cfg
+    g = rough_terrains_cfg()
+    g.num_rows, g.num_cols, g.border_width, g.curriculum = 3, 4, 2.0, True
+    t = Terrain(g, seed=4)
+    n = 300
+    rng = np.random.default_rng(12)
+    lv, ty = t.initial_levels_types(n, 2, rng)
+    org4 = np.zeros((n, 4), np.float32)
+    org4[:, :3] = t.origins[lv, ty]
+    P = dict(M_PARAMS_EXTRA, terrain={"origins": t.origins, "tile_size": 8.0, "curriculum": True})
+    st = _m_stepper(n, rng, M_EXTRA_TERMS, P=P)
+    d_heights, d_tiles, d_org = _t(t.heights), _t(t.origins).contiguous(), _t(org4)
+    st.bind_terrain(d_heights, t.x0, t.y0, t.cell, d_tiles, 8.0, d_org, True)
+    pd = st.state.get("p_delta")
+    pd[:, 3], pd[:, 4] = _t(lv.astype(np.float32)), _t(ty.astype(np.float32))
+    st.state.set("p_delta", pd)
+    # off the platform: shift in x / y, put the feet 4 mm above the local ground
+    rp = st.state.get("root_pos").cpu().numpy()
+    rp[:, 0] += rng.uniform(-2.5, 2.5, n)
+    rp[:, 1] += rng.uniform(-2.5, 2.5, n)
+    walked = np.arange(n) % 4 == 0
+    rp[walked, 0] = 4.3 * np.sign(rp[walked, 0] + 1e-3)                    # beyond half a tile: these move UP at their reset
+    rp[:, 2] += t.height_at(org4[:, 0] + rp[:, 0], org4[:, 1] + rp[:, 1]) - org4[:, 2] + 0.004
+    st.state.set("root_pos", _t(rp.astype(np.float32)))
+    ep0 = rng.integers(900, 999, n)
+    st.episode_length_buf[:] = _t(ep0.astype(np.int64))
+    pe = cpu_port.PortEnv(n, np.float32, m_native_cfg(n, M_EXTRA_TERMS, P))
+    org4_host = org4.copy()
+    pe.terrain = cpu_port.make_port_terrain(t, org4_host, True)
+    get = lambda k, w: st.state.get(k).cpu().numpy()
+    orc = m_make_oracle(n, M_EXTRA_TERMS, get, ep0, P)
+    orc.levels[:], orc.types[:], orc.env_origins[:] = lv, ty, org4[:, :3]
+    ex_t = torch.zeros(n, 72, device=DEV)
+    ups = downs = resets = 0
+    worst = 0.0
+    for s_ in range(25):
+        a = rng.normal(0, 0.5, (n, 6)).astype(np.float32)
+        rnd = rng.random((n, 22)).astype(np.float32)
+        # host build from the SAME state (one-step comparison)
+        pe.state[:] = st.state.buf.permute(1, 0, 2).reshape(n, 80).cpu().numpy()
+        pe.ep_len[:] = st.episode_length_buf.cpu().numpy()
+        org4_host[:] = d_org.cpu().numpy()
+        obs, rew, term, trunc = st.step(_t(a), export=ex_t, rand=_t(rnd))
+        torch.cuda.synchronize()
+        o_h, r_h, te_h, tr_h, _, _ = pe.step(a, rnd=rnd)
+        r = m_check_step(orc, a, rnd, ex_t.cpu().numpy(), obs.cpu().numpy(), rew.cpu().numpy(), term.cpu().numpy(),
+                         trunc.cpu().numpy(), st.episode_length_buf.cpu().numpy(), get)
+        assert np.array_equal(st.state.get("p_delta")[:, 3].cpu().numpy().astype(np.int64), orc.levels), "terrain levels"
+        assert np.array_equal(d_org.cpu().numpy()[:, :3], orc.env_origins), "env origins"
+        same = term.cpu().numpy().astype(bool) == te_h
+        assert same.mean() >= 0.99 and np.array_equal(trunc.cpu().numpy().astype(bool), tr_h)
+        d = np.abs(obs.cpu().numpy() - o_h)[same]
+        assert d[:, :4].max() <= 1e-3 and d[:, 7:13].max() <= 1e-3 and d[:, 13:19].max() <= 5e-2
+        worst = max(worst, float(d[:, 7:13].max()))
+        if r["log"]:
+            ups, downs = ups + r["log"]["#move_up"], downs + r["log"]["#move_down"]
+        resets += len(r["reset_ids"])
+    assert resets > n and ups > 0 and downs > 0
+    print(f"rough kernel vs host build: worst one-step joint-position difference {worst:.2e}")
+    st.close()
+
+
 def test_m_kernel_equals_host_build_noise_and_internal_rng():
     """(1) GPU kernel vs the same arithmetic compiled for the host (float32): one control step from identical states and
     uniforms agrees to round-off.  (2) ObservationManager corruption (PolicyCfg: base_quat / joint_pos +-0.01, joint_vel
@@ -1174,7 +1298,7 @@ def test_m_kernel_equals_host_build_noise_and_internal_rng():
         pe.field(k, w)[:] = st.state.get(k).cpu().numpy()
     for t in range(3):
         a = rng.normal(0, 0.5, (n, 6)).astype(np.float32)
-        rnd = rng.random((n, 13)).astype(np.float32)
+        rnd = rng.random((n, 22)).astype(np.float32)
         obs, rew, term, trunc = st.step(_t(a), rand=_t(rnd))
         o2, r2, t2, tr2, _, _ = pe.step(a, rnd=rnd)
         same = (term.cpu().numpy().astype(bool) == t2)
@@ -1201,7 +1325,7 @@ def test_m_kernel_equals_host_build_noise_and_internal_rng():
         g = torch.Generator(device=DEV).manual_seed(5)
         rec = []
         for t in range(4):
-            u = torch.rand(n, 13, device=DEV, generator=g)
+            u = torch.rand(n, native.M_NUM_RAND, device=DEV, generator=g)
             o_, r_, te_, tr_ = s2.step(torch.randn(n, 6, device=DEV, generator=g) * 0.3, rand=u)
             rec.append((o_.clone(), r_.clone(), te_.clone(), tr_.clone(), s2.state.buf.clone()))
         outs.append(rec)
@@ -1239,7 +1363,7 @@ def test_m_kernel_equals_host_build_noise_and_internal_rng():
 
 def test_m_abi_error_paths_and_guard_bands():
     """zbot_m_step: wrong-task / unbound / NULL / misaligned calls return error codes with a message; guard bands around
-    every buffer the manager kernel writes stay intact at ragged N (tail blocks, export rows of 67 words, 25-wide rows)."""
+    every buffer the manager kernel writes stay intact at ragged N (tail blocks, export rows of 72 words, 25-wide rows)."""
     import ctypes as C
     from helpers import m_native_cfg
     from zbot_lab_b200 import native
@@ -1273,7 +1397,7 @@ def test_m_abi_error_paths_and_guard_bands():
         h = vp()
         native.check(lib.zbot_create(C.byref(cfg), 0, C.byref(h)))
         sizes = {"state": 80 * n * 4, "ep": 8 * n, "ring": 4 * 32 * 4, "obs": 4 * 25 * n, "rew": 4 * n, "term": n, "trunc": n,
-                 "act": 24 * n, "rand": 52 * n, "ex": 4 * 67 * n}
+                 "act": 24 * n, "rand": 4 * native.M_NUM_RAND * n, "ex": 4 * native.M_EXPORT_WORDS * n}
         gap = 1024
         total = sum((s + 255) // 256 * 256 + gap for s in sizes.values()) + gap
         arena = torch.full((total,), 0xA5, dtype=torch.uint8, device=DEV)
@@ -1328,7 +1452,7 @@ def test_m_full_size_properties_65536():
         rec = []
         for t in range(10):
             a = torch.randn(1, 6, device=DEV, generator=g).expand(n, 6).contiguous()
-            u = torch.rand(1, 13, device=DEV, generator=g).expand(n, 13).contiguous()
+            u = torch.rand(1, 22, device=DEV, generator=g).expand(n, 22).contiguous()
             obs, rew, term, trunc = st.step(a, rand=u)
             assert torch.equal(obs, obs[:1].expand_as(obs)) and torch.equal(rew, rew[:1].expand_as(rew))
             s = st.stats.clone()
@@ -1432,7 +1556,7 @@ def test_m_fused_step_50_step_horizon_vs_float64_host_build():
     alive = np.ones(n, bool)
     for t in range(50):
         a = rng.normal(0, 0.3, (n, 6)).astype(np.float32)
-        rnd = rng.random((n, 13)).astype(np.float32)
+        rnd = rng.random((n, 22)).astype(np.float32)
         obs, rew, term, trunc = st.step(_t(a), rand=_t(rnd))
         _, _, t2, tr2, _, _ = pe.step(a, rnd=rnd)
         alive &= ~(term.cpu().numpy().astype(bool) | trunc.cpu().numpy().astype(bool) | t2 | tr2)

@@ -133,13 +133,34 @@ def test_manager_cfg_compiles_into_the_kernel_term_table_and_unknown_terms_fail_
     play = gym.load_cfg_from_registry("zbot-6b-walking-m-play-v0", "env_cfg_entry_point")
     e, c = compile_(play, 64)
     assert play.scene.num_envs == 64 and c.obs_noise_enable == 0 and list(c.cmd_hi)[0] == np.float32(0.3)
-    # not built -> loud
+    # the terms ZbotLabRoughEnvCfg defines and the registered cfgs switch off (zbotlab_env_cfg.py:86-97, 253-258, 367-371, 385-388)
+    full = gym.load_cfg_from_registry("zbot-6b-walking-m-v0", "env_cfg_entry_point")
+    full.rewards.undesired_contacts = mdp.RewardTermCfg(func=mdp.undesired_contacts, weight=-1.0, params={
+        "sensor_cfg": mdp.SceneEntityCfg("contact_forces", body_names="base|a.*|b.*"), "threshold": 1.0})
+    full.terminations.base_contact = mdp.TerminationTermCfg(func=mdp.illegal_contact, params={
+        "sensor_cfg": mdp.SceneEntityCfg("contact_forces", body_names="base"), "threshold": 1.0})
+    full.events.push_robot = mdp.EventTermCfg(func=mdp.push_by_setting_velocity, mode="interval", interval_range_s=(10.0, 15.0),
+                                              params={"velocity_range": {"x": (-0.5, 0.5), "y": (-0.5, 0.5)}})
+    full.commands.base_velocity.heading_command = True
+    full.commands.base_velocity.heading_control_stiffness = 0.5
+    full.commands.base_velocity.ranges.heading = (-np.pi, np.pi)
+    full.commands.base_velocity.ranges.ang_vel_z = (-1.0, 1.0)
+    e, c = compile_(full)
+    ids = list(c.term_id)[:c.num_terms]
+    assert 43 in ids and c.term_param[ids.index(43)][0] == 1.0
+    assert c.illegal_contact_threshold == 1.0 and c.illegal_contact_mask == 0b00100            # `base` sits in merged body 3
+    assert c.cmd_heading == 1 and abs(c.cmd_heading_hi - np.pi) < 1e-6 and c.cmd_heading_stiffness == 0.5 and c.cmd_rel_heading == 1.0
+    assert (c.push_interval_lo, c.push_interval_hi) == (10.0, 15.0) and list(c.push_lo) == [-0.5, -0.5] and list(c.push_hi) == [0.5, 0.5]
+    assert ("base_contact", "illegal_contact") in e._done_names
+    # not built -> loud: the per-env mass / CoM randomisation events (None in every registered cfg, rough_env_cfg.py:38-39)
     bad = gym.load_cfg_from_registry("zbot-6b-walking-m-v0", "env_cfg_entry_point")
-    bad.rewards.undesired_contacts = mdp.RewardTermCfg(func=mdp.undesired_contacts, weight=-1.0, params={"threshold": 1.0})
+    bad.events.add_base_mass = mdp.EventTermCfg(func=mdp.randomize_rigid_body_mass, mode="startup", params={
+        "asset_cfg": mdp.SceneEntityCfg("robot", body_names="base"), "mass_distribution_params": (-1.0, 3.0), "operation": "add"})
     with pytest.raises(NotImplementedError):
         compile_(bad)
     bad = gym.load_cfg_from_registry("zbot-6b-walking-m-v0", "env_cfg_entry_point")
-    bad.terminations.base_contact = mdp.TerminationTermCfg(func=mdp.illegal_contact, params={"threshold": 1.0})
+    bad.terminations.base_contact = mdp.TerminationTermCfg(func=mdp.illegal_contact, params={
+        "sensor_cfg": mdp.SceneEntityCfg("contact_forces", body_names="foot.*"), "threshold": 1.0})
     with pytest.raises(NotImplementedError):
         compile_(bad)
     with pytest.raises(RuntimeError):

@@ -6,6 +6,7 @@ import os
 import runpy
 import sys
 
+import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -107,6 +108,54 @@ def test_reference_train_py_runs_unchanged_on_the_manager_task(shimmed, monkeypa
     import json
     recs = [json.loads(l) for l in open(run / "progress.jsonl")]
     assert len(recs) == 2 and "Episode_Reward/foot_step_length" in recs[-1] and "Curriculum/lin_vel_cmd_levels" in recs[-1]
+
+
+def test_reference_train_py_runs_unchanged_on_the_rough_manager_task(shimmed, monkeypatch):
+    """``--task zbot-6b-walking-m-rough-v0`` (config/zbot6b_manager/__init__.py:34-42): generated height field, all 16
+    weighted RewTerms of RewardsCfg incl. undesired_contacts, terrain_levels + lin_vel_cmd_levels curricula, the rough agent
+    cfg (512-256-128).  CPU double of the stepper; terrain generation, placement, logging are the shipped host code."""
+    import zbot_lab_b200.tasks.zbotlab_manager.manager_env as me
+    from fake_stepper import FakeMStepper
+    monkeypatch.setattr(me, "NativeStepper", FakeMStepper)
+    monkeypatch.setattr(sys, "argv", ["train.py", "--task", "zbot-6b-walking-m-rough-v0", "--num_envs", "16",
+                                      "--max_iterations", "1", "--headless", "--device", "cpu", "--seed", "7",
+                                      "agent.num_steps_per_env=6", "agent.device=cpu"])
+    runpy.run_path(os.path.join(REF_SCRIPTS, "train.py"), run_name="__main__")
+    root = shimmed / "logs" / "rsl_rl" / "zbot_6b_rough_mana_v1"
+    run = root / os.listdir(root)[0]
+    assert (run / "params" / "env.yaml").exists() and (run / "model_1.pt").exists()
+    import json
+    rec = [json.loads(l) for l in open(run / "progress.jsonl")][-1]
+    assert "Episode_Reward/undesired_contacts" in rec and "Curriculum/terrain_levels" in rec and 0.0 <= rec["Curriculum/terrain_levels"] <= 5.0
+
+
+def test_rough_env_places_robots_on_their_tiles(shimmed, monkeypatch):
+    """The rough play cfg on the CPU double: 5 x 5 tiles, every env standing on its (level, type) tile's spawn point (the
+    base 0.2545 m above the tile's origin), no contact termination in the first steps on any tile family."""
+    import torch
+    import zbot_lab_b200.tasks.zbotlab_manager.manager_env as me
+    from fake_stepper import FakeMStepper
+    monkeypatch.setattr(me, "NativeStepper", FakeMStepper)
+    import zbot_lab_b200.tasks  # noqa: F401
+    from zbot_lab_b200.compat import gym_registry as gym
+    cfg = gym.load_cfg_from_registry("zbot-6b-walking-m-rough-play-v0", "env_cfg_entry_point")
+    cfg.scene.num_envs, cfg.sim.device, cfg.seed = 25, "cpu", 5
+    cfg.terminations.feet_close = None
+    cfg.terminations.base_height = None      # root_height_below_minimum is a WORLD height: an inverted pyramid spawns below 0.2 m
+    env = gym.make("zbot-6b-walking-m-rough-play-v0", cfg=cfg, render_mode=None)
+    t = env._terrain_gen
+    assert t.rows == 5 and t.cols == 5 and env._terrain.env_origins.shape == (25, 3)
+    lv = env.terrain_levels.numpy()
+    ty = env._stepper.state.get("p_delta")[:, 4].numpy().astype(int)
+    assert len(set(ty)) == 5 and lv.max() <= 4 and np.allclose(env._terrain.env_origins.numpy(), t.origins[lv, ty])
+    env.reset()
+    for _ in range(15):
+        obs, rew, term, trunc, ex = env.step(torch.zeros(25, 6))
+        assert not term.any() and torch.isfinite(rew).all()
+    pos, _, _ = env._stepper.articulation_view()
+    rough = np.array([t.col_kind[c] == "random_rough" for c in ty])           # no flat platform there: the feet stand on bumps
+    dz = (pos[:, 6, 2] - 0.2545).abs().numpy()
+    assert dz[~rough].max() < 5e-3 and dz[rough].max() < 0.08 and rough.sum() == 5
 
 
 def test_manager_env_surface_on_cpu_double(shimmed, monkeypatch):

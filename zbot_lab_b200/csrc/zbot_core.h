@@ -98,7 +98,8 @@ enum TermId : int {
   TERM_M_FEET_AIR_TIME_BIPED = 40,    // feet_air_time_positive_biped (:211-230); par = {threshold}
   TERM_M_BASE_VEL_FORWARD = 41,       // base_vel_forward (:264-274); par = {which_forward}
   TERM_M_FEET_FORCE_PATTERN = 42,     // feet_force_pattern (:276-284)
-  NUM_TERM_IDS = 43
+  TERM_M_UNDESIRED_CONTACTS = 43,     // isaaclab.envs.mdp.undesired_contacts [IL-upstream] (zbotlab_env_cfg.py:367-371); par = {threshold}
+  NUM_TERM_IDS = 44
 };
 constexpr int MAX_TERMS = 16;
 
@@ -137,6 +138,12 @@ struct Params {
   T act_scale, act_clip;                // RelativeJointPositionActionCfg scale, symmetric clip of the processed action
   T feet_close_min;                     // DoneTerm feet_close minimum_distance (<= 0: term absent)
   T term_penalty_w;                     // RewTerm is_terminated: weight * step_dt (0: term absent)
+  T illegal_thr;                        // DoneTerm illegal_contact threshold (zbotlab_env_cfg.py:385-388; <= 0: term absent)
+  int illegal_mask;                     // ... over the merged bodies 1..5 (bit b-1)
+  int cmd_heading;                      // UniformVelocityCommandCfg.heading_command
+  T cmd_heading_lo, cmd_heading_hi, cmd_heading_stiffness, cmd_rel_heading;   // ranges.heading, heading_control_stiffness, rel_heading_envs
+  T push_interval_lo, push_interval_hi; // EventTerm push_robot interval_range_s (<= 0: term absent; zbotlab_env_cfg.py:253-258)
+  T push_lo[2], push_hi[2];             // push_by_setting_velocity velocity_range x / y
 };
 
 // ------------------------------------------------------------------------------------
@@ -217,6 +224,7 @@ ZB_HD double zb_rsqrt(double x) { return 1.0 / sqrt(x); }
 ZB_HD bool zb_gt(float a, float b) { return a > b; }
 ZB_HD bool zb_gt(double a, double b) { return a > b; }
 ZB_HD bool zb_any(bool m) { return m; }
+ZB_HD int zb_min_i(int a, int b) { return a < b ? a : b; }
 ZB_HD float zb_sel(bool m, float a, float b) { return m ? a : b; }
 ZB_HD double zb_sel(bool m, double a, double b) { return m ? a : b; }
 
@@ -577,6 +585,7 @@ ZB_HD void model_body_terms(const Params<PS>& P, int k, const T* R, const T* r, 
 // ------------------------------------------------------------------------------------
 struct ModelWalk {   // ZBOT_6S_CFG + zbot_6s_new.usd (zbot-6b-walking-*): stands on two foot discs
   static constexpr int kTask = 0;
+  static constexpr bool kPerBodyForces = false;    // the direct tasks only need the max over the merged bodies
   static constexpr bool kFullInertia = false;      // bodies symmetric about the chain's xz plane
   static constexpr bool kPerEnvFriction = false;
   static constexpr bool kFresh = false;            // MDP reads one-step-stale quantities, 5-deep force history
@@ -624,6 +633,7 @@ struct ModelWalkV4 : ModelWalk {   // zbot-6b-walking-v4: same robot, 3-deep for
 
 struct ModelSnake {  // ZBOT_D_6S_CFG + zbot_6s_v03.usd (zbot-6s-snake-v0): lies on the ground
   static constexpr int kTask = 1;
+  static constexpr bool kPerBodyForces = false;
   static constexpr bool kFullInertia = false;
   static constexpr bool kPerEnvFriction = false;
   static constexpr bool kFresh = false;
@@ -664,6 +674,7 @@ struct ModelWalkM : ModelWalk {   // ZBOT_6S_V2_CFG + zbot_6s_v09.usd (zbot-6b-w
   static constexpr int kTask = 3;
   static constexpr bool kFullInertia = true;       // CoM / inertia sit off the chain's plane (assets/zbot_6s_v2.py)
   static constexpr bool kPerEnvFriction = true;    // EventCfg.physics_material: per-env friction drawn at startup
+  static constexpr bool kPerBodyForces = true;     // undesired_contacts / illegal_contact need |F| of every merged body
   static constexpr bool kFresh = true;             // ManagerBasedRLEnv: every term reads end-of-physics data; history_length = 3
   static ZB_HD bool wraps(int) { return false; }   // zbot_6s_v09.usd: all six joints carry +-360 deg limits (hard stops in PhysX; not modelled)
   template <typename T>
@@ -750,6 +761,34 @@ struct SmemScratch {
 #endif
 
 // ------------------------------------------------------------------------------------
+// the ground under a contact candidate: height of the terrain at env-LOCAL (x, y), relative to the env origin's z.
+// FlatGround = the plane z = 0 of every flat task (folds away).  TerrainGround = the rough manager task's height field
+// (zbot_lab_b200/terrain.py: one float32 grid over all tiles, bilinear sample; normals stay vertical).
+// ------------------------------------------------------------------------------------
+struct FlatGround {
+  template <typename T>
+  ZB_HD T operator()(T, T) const { return T(0); }
+};
+template <typename T>
+struct TerrainGround {
+  const float* H;      // [nx][ny] heights, world frame
+  int nx, ny;
+  T x0, y0, inv_cell;  // world coordinate of H[0][0], 1 / cell size
+  T ox, oy, oz;        // this env's origin (world): local + origin = world
+  ZB_HD T operator()(T xl, T yl) const {
+    T fx = (xl + ox - x0) * inv_cell, fy = (yl + oy - y0) * inv_cell;
+    fx = zb_clamp(fx, T(0), T(nx) - T(1.001));
+    fy = zb_clamp(fy, T(0), T(ny) - T(1.001));
+    const int ix = (int)fx, iy = (int)fy;
+    const T tx = fx - T(ix), ty = fy - T(iy);
+    const float* p = H + (size_t)ix * ny + iy;
+    const T h00 = T(p[0]), h01 = T(p[1]), h10 = T(p[ny]), h11 = T(p[ny + 1]);
+    const T a = h00 + tx * (h10 - h00), b = h01 + tx * (h11 - h01);
+    return (a + ty * (b - a)) - oz;
+  }
+};
+
+// ------------------------------------------------------------------------------------
 // one physics substep (dt = P.dt): implicit PD + contact + ABA + semi-implicit Euler
 // ------------------------------------------------------------------------------------
 template <typename T>
@@ -757,6 +796,7 @@ struct SubstepOut {
   T foot_force[2][3];  // net contact force on foot_0 / foot_1 (applied, world frame)
   T mid_force2_max;    // max over bodies 1..5 of |predictor contact force|^2
   T applied_torque[6]; // ImplicitActuator bookkeeping evaluated BEFORE this substep
+  T mid_force2[5];     // Model::kPerBodyForces only: |predictor contact force|^2 of each merged body 1..5
 };
 
 // mid_force_out: optional [5][3] predictor forces of bodies 1..5 (export / debug only)
@@ -785,9 +825,10 @@ struct SubstepOut {
 #ifndef ZB_UNROLL_FWD
 #define ZB_UNROLL_FWD kUnroll
 #endif
-template <typename Model, bool kPipe = (ZB_PIPELINED_SWEEP != 0), int kUnroll = 1, typename PS, typename T, typename Scr>
+template <typename Model, bool kPipe = (ZB_PIPELINED_SWEEP != 0), int kUnroll = 1, typename PS, typename T, typename Scr,
+          typename Ground = FlatGround>
 ZB_HD void physics_substep(const Params<PS>& P, SimState<T>& s, const T* target, SubstepOut<T>& out, Scr& scr,
-                           T* mid_force_out) {
+                           T* mid_force_out, const Ground& ground = Ground()) {
   using namespace model;
   const T dt = T(P.dt);
   // friction coefficient: the uniform cfg value, or per env (`target[6]`) for models with randomised materials
@@ -839,6 +880,7 @@ ZB_PRAGMA_UNROLL(ZB_UNROLL_FK)
   ContactAgg<T> agg, agg1;   // running / foot_1 (body 6); after the sweep `agg` holds foot_0 (body 0)
   contact_agg_zero(agg1);
   T mid2 = T(0);
+  if constexpr (Model::kPerBodyForces) { ZB_UNROLL for (int b = 0; b < 5; ++b) out.mid_force2[b] = T(0); }
   if constexpr (kPipe) {
   // Software-pipelined form: the articulated-body elimination of joint k-1 is one long dependent chain
   // (IA S -> D -> 1/D -> rank-1 update); the kinematics, world inertia and bias force of the NEXT body (k-1) do not
@@ -858,7 +900,7 @@ ZB_PRAGMA_UNROLL(ZB_UNROLL_PTS)
       Model::point(6, j, lx, ly, lz, drop);
       T rho[3] = {r[0] + R[0] * lx + R[1] * ly + R[2] * lz, r[1] + R[3] * lx + R[4] * ly + R[5] * lz,
                   r[2] + R[6] * lx + R[7] * ly + R[8] * lz - drop};
-      contact_point(P, mu, rho, s.p[2] + rho[2], w, vO, IA, pAt, pAb,
+      contact_point(P, mu, rho, s.p[2] + rho[2] - ground(s.p[0] + rho[0], s.p[1] + rho[1]), w, vO, IA, pAt, pAb,
                     Model::kGroundForceSensor ? &agg : (ContactAgg<T>*)nullptr, (T*)nullptr);
     }
     if (Model::kGroundForceSensor) agg1 = agg;
@@ -938,12 +980,14 @@ ZB_PRAGMA_UNROLL(ZB_UNROLL_PTS)
       Model::point(k - 1, c, lx, ly, lz, drop);
       T rho[3] = {r[0] + Rn[0] * lx + Rn[1] * ly + Rn[2] * lz, r[1] + Rn[3] * lx + Rn[4] * ly + Rn[5] * lz,
                   r[2] + Rn[6] * lx + Rn[7] * ly + Rn[8] * lz - drop};
-      contact_point(P, mu, rho, s.p[2] + rho[2], w, vO, IA, pAt, pAb,
+      contact_point(P, mu, rho, s.p[2] + rho[2] - ground(s.p[0] + rho[0], s.p[1] + rho[1]), w, vO, IA, pAt, pAb,
                     Model::kGroundForceSensor ? &agg : (ContactAgg<T>*)nullptr, (T*)nullptr);
     }
     if (Model::kGroundForceSensor) {
       if (k - 1 != 0) {
-        mid2 = zb_max(mid2, agg.F0[0] * agg.F0[0] + agg.F0[1] * agg.F0[1] + agg.F0[2] * agg.F0[2]);
+        const T f2 = agg.F0[0] * agg.F0[0] + agg.F0[1] * agg.F0[1] + agg.F0[2] * agg.F0[2];
+        mid2 = zb_max(mid2, f2);
+        if constexpr (Model::kPerBodyForces) { ZB_UNROLL for (int b = 0; b < 5; ++b) out.mid_force2[b] = (b == k - 2) ? f2 : out.mid_force2[b]; }
         if (mid_force_out) { mid_force_out[3 * (k - 2)] = agg.F0[0]; mid_force_out[3 * (k - 2) + 1] = agg.F0[1];
                              mid_force_out[3 * (k - 2) + 2] = agg.F0[2]; }
       }
@@ -973,14 +1017,16 @@ ZB_PRAGMA_UNROLL(ZB_UNROLL_PTS)
       Model::point(k, j, lx, ly, lz, drop);
       T rho[3] = {r[0] + R[0] * lx + R[1] * ly + R[2] * lz, r[1] + R[3] * lx + R[4] * ly + R[5] * lz,
                   r[2] + R[6] * lx + R[7] * ly + R[8] * lz - drop};
-      contact_point(P, mu, rho, s.p[2] + rho[2], w, vO, IA, pAt, pAb,
+      contact_point(P, mu, rho, s.p[2] + rho[2] - ground(s.p[0] + rho[0], s.p[1] + rho[1]), w, vO, IA, pAt, pAb,
                     Model::kGroundForceSensor ? &agg : (ContactAgg<T>*)nullptr, (T*)nullptr);
     }
     if (Model::kGroundForceSensor) {
       if (foot1) {
         agg1 = agg;
       } else if (!foot0) {
-        mid2 = zb_max(mid2, agg.F0[0] * agg.F0[0] + agg.F0[1] * agg.F0[1] + agg.F0[2] * agg.F0[2]);
+        const T f2 = agg.F0[0] * agg.F0[0] + agg.F0[1] * agg.F0[1] + agg.F0[2] * agg.F0[2];
+        mid2 = zb_max(mid2, f2);
+        if constexpr (Model::kPerBodyForces) { ZB_UNROLL for (int b = 0; b < 5; ++b) out.mid_force2[b] = (b == k - 1) ? f2 : out.mid_force2[b]; }
         if (mid_force_out) { mid_force_out[3 * (k - 1)] = agg.F0[0]; mid_force_out[3 * (k - 1) + 1] = agg.F0[1];
                              mid_force_out[3 * (k - 1) + 2] = agg.F0[2]; }
       }
@@ -1531,14 +1577,15 @@ struct PhysOut {
   T mid2_h3;            // v4 (history_length = 3): max over the LAST THREE substeps only
   T qd_prev[6];         // v4: joint velocities before the last substep (joint_acc finite difference)
   T fn2_h3[2];          // manager task: max over the last three substeps of |F_foot|^2 (feet_slide, rewards.py:256)
+  T midb2_h3[5];        // manager task: the same per merged body 1..5 (undesired_contacts / illegal_contact)
 };
 
 // Phase B of the control step: _pre_physics_step (…env_v2.py:276-287) + decimation x (physics substep +
 // ContactSensor.update).  Touches only e.sim, e.mdp.p_delta / speed_limit and the contact carry /
 // timers, so a GPU thread can run it before the rest of the MDP state has even been loaded.
-template <typename Model, int kUnroll = 1, typename T, typename Scr>
+template <typename Model, int kUnroll = 1, typename T, typename Scr, typename Ground = FlatGround>
 ZB_HD void env_step_physics(const Params<T>& P, EnvState<T>& e, const T* raw_actions, PhysOut<T>& po, Scr& scr,
-                            StepExport<T>* ex) {
+                            StepExport<T>* ex, const Ground& ground = Ground()) {
   T new_actions[6], target[7], proc[6];
   if constexpr (Model::kTask == 3) {
     // RelativeJointPositionAction [IL-upstream]: processed = clip(raw * scale); applied at EVERY substep as
@@ -1549,6 +1596,7 @@ ZB_HD void env_step_physics(const Params<T>& P, EnvState<T>& e, const T* raw_act
     }
     target[6] = e.mdp.speed_limit;      // per-env friction coefficient (startup material randomisation)
     po.fn2_h3[0] = po.fn2_h3[1] = T(0);
+    ZB_UNROLL for (int b = 0; b < 5; ++b) po.midb2_h3[b] = T(0);
   } else {
     mdp_pre_physics<Model>(P, raw_actions, e.mdp, new_actions, target);
     target[6] = T(0);
@@ -1575,7 +1623,7 @@ ZB_PRAGMA_UNROLL(ZB_UNROLL_SUB)
       if (sub == P.decimation - 1) { ZB_UNROLL for (int k = 0; k < 6; ++k) po.qd_prev[k] = e.sim.qd[k]; }
     }
     if constexpr (Model::kTask == 3) { ZB_UNROLL for (int k = 0; k < 6; ++k) target[k] = proc[k] + e.sim.q[k]; }
-    physics_substep<Model, (ZB_PIPELINED_SWEEP != 0), kUnroll>(P, e.sim, target, so, scr, ex ? midf : (T*)nullptr);
+    physics_substep<Model, (ZB_PIPELINED_SWEEP != 0), kUnroll>(P, e.sim, target, so, scr, ex ? midf : (T*)nullptr, ground);
     if (!Model::kGroundForceSensor) continue;
     // ContactSensor.update
     const int slot = P.decimation - 1 - sub;  // newest first
@@ -1590,6 +1638,7 @@ ZB_PRAGMA_UNROLL(ZB_UNROLL_SUB)
     }
     if (slot < 4) po.mid2 = zb_max(po.mid2, so.mid_force2_max);
     if (Model::kFresh) { if (slot < 3) po.mid2_h3 = zb_max(po.mid2_h3, so.mid_force2_max); }
+    if constexpr (Model::kPerBodyForces) { if (slot < 3) { ZB_UNROLL for (int b = 0; b < 5; ++b) po.midb2_h3[b] = zb_max(po.midb2_h3[b], so.mid_force2[b]); } }
     if (ex && slot < 4) {
       ZB_UNROLL for (int b = 0; b < 5; ++b)
         ZB_UNROLL for (int i = 0; i < 3; ++i) ex->mid_force_hist[slot][b][i] = midf[3 * b + i];
@@ -2109,11 +2158,14 @@ ZB_HD void v4_env_step(const Params<T>& P, EnvState<T>& e, const T* raw_actions,
 // actions = last RAW action (ActionManager.action, Isaac Lab joint order); p_delta is unused.
 // ------------------------------------------------------------------------------------
 constexpr int M_NUM_OBS = 25;
-constexpr int M_NUM_RAND = 13;
+constexpr int M_NUM_RAND = 22;
 // uniforms of one env-step, in the order the reference would draw them for that env
 enum MRandSlot : int { MR_POSE_X = 0, MR_POSE_Y = 1, MR_POSE_YAW = 2,                       // reset_root_state_uniform
                        MR_RESET_TIME = 3, MR_RESET_VX = 4, MR_RESET_VY = 5, MR_RESET_WZ = 6, MR_RESET_STAND = 7,   // CommandTerm.reset
-                       MR_INT_TIME = 8, MR_INT_VX = 9, MR_INT_VY = 10, MR_INT_WZ = 11, MR_INT_STAND = 12 };        // CommandTerm.compute
+                       MR_INT_TIME = 8, MR_INT_VX = 9, MR_INT_VY = 10, MR_INT_WZ = 11, MR_INT_STAND = 12,          // CommandTerm.compute
+                       MR_RESET_HEADING = 13, MR_RESET_ISHEAD = 14, MR_INT_HEADING = 15, MR_INT_ISHEAD = 16,       // heading_command=True
+                       MR_PUSH_RESET_TIME = 17, MR_PUSH_TIME = 18, MR_PUSH_X = 19, MR_PUSH_Y = 20,                 // EventTerm push_robot
+                       MR_TERRAIN_LEVEL = 21 };                                                                    // terrain curriculum: random restart level
 
 template <typename T>
 ZB_HD void quat_mul(const T* a, const T* b, T* o) {
@@ -2215,6 +2267,12 @@ ZB_HD void m_resample_command(const Params<T>& P, T u_time, T ux, T uy, T uw, T 
   cmd2 = uw * (P.cmd_hi[2] - P.cmd_lo[2]) + P.cmd_lo[2];
   standing = (u_stand <= P.cmd_rel_standing) ? T(1) : T(0);
 }
+// ... with heading_command=True it also draws heading_target ~ U(ranges.heading) and is_heading_env ~ U(0,1) <= rel_heading_envs
+template <typename T>
+ZB_HD void m_resample_heading(const Params<T>& P, T u_heading, T u_is, T& heading_target, T& is_heading) {
+  heading_target = u_heading * (P.cmd_heading_hi - P.cmd_heading_lo) + P.cmd_heading_lo;
+  is_heading = (u_is <= P.cmd_rel_heading) ? T(1) : T(0);
+}
 
 template <typename T>
 struct MFresh {
@@ -2223,6 +2281,7 @@ struct MFresh {
   T feet_pos[2][3], feet_force[2], feet_fnorm_max[2];
   T cur_air[2], cur_contact[2];
   T phase_time;                                  // episode_length_buf * step_dt (float32 product)
+  T midb_max[5];                                 // max over the 3-deep history of |F| on each merged body 1..5
 };
 
 template <typename T>
@@ -2300,6 +2359,9 @@ ZB_HD T m_term_value(int id, const T* par, const StaleCache<T>& c, const FreshIn
       m.feet_force_sum += T(0.001) * (v.feet_force[0] - v.feet_force[1]);
       val = T(0.5) * diff - T(0.1) * zb_abs(m.feet_force_sum);
     } break;
+    case TERM_M_UNDESIRED_CONTACTS:                                              // [IL-upstream] sum_b( max_t |F_b| > threshold )
+      ZB_UNROLL for (int b = 0; b < 5; ++b) val += (v.midb_max[b] > par[0]) ? T(1) : T(0);
+      break;
     default:   // ids shared with the direct tasks (torques, joint_acc, action_rate, foot_downward / forward, air-time terms)
       val = v4_term_value(id, c, f, v4, new_actions, m, T(0));
       break;
@@ -2308,24 +2370,41 @@ ZB_HD T m_term_value(int id, const T* par, const StaleCache<T>& c, const FreshIn
 }
 
 template <typename T>
-struct MExport {   // what the manager terms saw at the end of physics (test hook), 67 words; feet_quat = LINK quaternions
+struct MExport {   // what the manager terms saw at the end of physics (test hook), 72 words; feet_quat = LINK quaternions
   T root_pos[3], root_quat[4], root_lin_vel[3], root_ang_vel[3];
   T feet_pos[2][3], feet_quat[2][4], feet_com_vel[2][3];
   T feet_fz_hist[3][2], feet_fnorm_max[2];
   T last_air[2], last_contact[2], cur_air[2], cur_contact[2];
   T q1[6], tau1[6], joint_acc1[6];     // chain joint order
+  T midb_max[5];                       // max over the 3-deep history of |F| on the merged bodies 1..5
 };
-constexpr int M_EXPORT_WORDS = 13 + 20 + 8 + 8 + 18;
+constexpr int M_EXPORT_WORDS = 13 + 20 + 8 + 8 + 18 + 5;
+
+// Rough-terrain context of one env (zbot-6b-walking-m-rough-v0): its origin on the tile grid (world frame; the state's root
+// position is relative to it) and what the `terrain_levels_vel` curriculum needs (mdp/curriculums.py:26-55 +
+// TerrainImporter.update_env_origins [IL-upstream]).  State words: p_delta[3] = terrain level, p_delta[4] = terrain type.
+template <typename T>
+struct MTerrainCtx {
+  T origin[3];                 // in: this step's origin; out: the origin after a reset moved the env to another tile
+  const float* tile_origins;   // [rows][cols][3]
+  int rows, cols;
+  T tile_size, episode_s;
+  int curriculum;              // CurriculumCfg.terrain_levels present
+};
 
 // Phase C of the manager task's control step.  `rnd` = this env-step's M_NUM_RAND uniforms; obs25 = the clean row.
 template <typename T>
 ZB_HD void m_step_finish(const Params<T>& P, EnvState<T>& e, const T* raw_actions, const PhysOut<T>& po, int64_t& ep_len,
-                         const T* rnd, T* obs25, StepOut<T>& out, T* reset_ep_sums, MExport<T>* ex) {
+                         const T* rnd, T* obs25, StepOut<T>& out, T* reset_ep_sums, MExport<T>* ex,
+                         MTerrainCtx<T>* terrain = nullptr) {
   T& cmd0 = e.carry_feet_fz[0];
   T& cmd1 = e.carry_feet_fz[1];
   T& cmd2 = e.carry_mid_max;
   T& standing = e.mdp.heading_sum;
   T& time_left = e.mdp.y_err_sum;
+  T& heading_target = e.mdp.p_delta[0];     // p_delta is unused by this task's action term: four of its words carry
+  T& is_heading = e.mdp.p_delta[1];         // the heading command state and the push_robot interval timer
+  T& push_left = e.mdp.p_delta[2];
   ep_len += 1;
   MKin<T> k1;
   m_kinematics(e.sim, k1);
@@ -2373,6 +2452,7 @@ ZB_HD void m_step_finish(const Params<T>& P, EnvState<T>& e, const T* raw_action
     c.v_fwd = T(0); c.aux = T(0);
     f.undesired_force_max = zb_sqrt(po.mid2_h3);
     f.origin_y = T(0); f.com_x_sum = T(0);
+    ZB_UNROLL for (int b = 0; b < 5; ++b) v.midb_max[b] = zb_sqrt(po.midb2_h3[b]);
   }
   if (ex) {
     ZB_UNROLL for (int i = 0; i < 3; ++i) { ex->root_pos[i] = k1.root_pos[i]; ex->root_lin_vel[i] = k1.root_lin_vel[i]; ex->root_ang_vel[i] = k1.root_ang_vel[i]; }
@@ -2388,16 +2468,22 @@ ZB_HD void m_step_finish(const Params<T>& P, EnvState<T>& e, const T* raw_action
     }
     ZB_UNROLL for (int k = 0; k < 6; ++k) { ex->q1[k] = e.sim.q[k]; ex->tau1[k] = po.applied_torque[k];
                                             ex->joint_acc1[k] = (e.sim.qd[k] - po.qd_prev[k]) * (T(1) / P.dt); }
+    ZB_UNROLL for (int b = 0; b < 5; ++b) ex->midb_max[b] = v.midb_max[b];
   }
   // ---- TerminationManager.compute (TerminationsCfg, zbotlab_env_cfg.py:371-393; base_contact is None for this robot) ----
   const bool time_out = ep_len >= (int64_t)P.max_episode_length;                 // mdp.time_out [IL-upstream]: >= max_episode_length
-  const bool low = k1.root_pos[2] < P.termination_height;                        // root_height_below_minimum
+  // root_height_below_minimum reads root_pos_w: the WORLD height (on a rough tile the origin's z is not 0)
+  const bool low = (k1.root_pos[2] + (terrain ? terrain->origin[2] : T(0))) < P.termination_height;
   bool close = false;
   if (P.feet_close_min > T(0)) {                                                 // terminations.py:55-60
     const T dx = k1.feet_pos[0][0] - k1.feet_pos[1][0], dy = k1.feet_pos[0][1] - k1.feet_pos[1][1], dz = k1.feet_pos[0][2] - k1.feet_pos[1][2];
     close = zb_sqrt(dx * dx + dy * dy + dz * dz) < P.feet_close_min;
   }
-  const bool died = low || close;
+  bool illegal = false;                                                          // mdp.illegal_contact [IL-upstream]: any selected body with max_t |F| > threshold
+  if (P.illegal_thr > T(0)) {
+    ZB_UNROLL for (int b = 0; b < 5; ++b) illegal |= ((P.illegal_mask >> b) & 1) && (v.midb_max[b] > P.illegal_thr);
+  }
+  const bool died = low || close || illegal;
   // ---- RewardManager.compute: value = func(env) * weight * dt, in cfg order; raw actions are the action term's `action` ----
   T reward = T(0);
   for (int i = 0; i < P.num_terms; ++i) {
@@ -2419,6 +2505,24 @@ ZB_HD void m_step_finish(const Params<T>& P, EnvState<T>& e, const T* raw_action
       reset_ep_sums[MAX_TERMS - 2] = low ? T(1) : T(0);
       reset_ep_sums[MAX_TERMS - 1] = close ? T(1) : T(0);
     }
+    // the same four, always, for the statistics words 22..25 (a cfg with more than 13 terms has no spare term slots)
+    reset_ep_sums[MAX_TERMS + 0] = died ? P.term_penalty_w : T(0);
+    reset_ep_sums[MAX_TERMS + 1] = low ? T(1) : T(0);
+    reset_ep_sums[MAX_TERMS + 2] = close ? T(1) : T(0);
+    reset_ep_sums[MAX_TERMS + 3] = illegal ? T(1) : T(0);
+    if (terrain && terrain->curriculum) {
+      // CurriculumManager.compute runs first in _reset_idx: terrain_levels_vel (mdp/curriculums.py:26-55) on the pre-reset
+      // root position and command, then TerrainImporter.update_env_origins [IL-upstream]
+      const T dist = zb_sqrt(k1.root_pos[0] * k1.root_pos[0] + k1.root_pos[1] * k1.root_pos[1]);   // |root_pos_w.xy - env_origin.xy|
+      const bool up = dist > terrain->tile_size * T(0.5);
+      const bool down = !up && (dist < zb_sqrt(cmd0 * cmd0 + cmd1 * cmd1) * terrain->episode_s * T(0.5));
+      int level = (int)e.mdp.p_delta[3] + (up ? 1 : 0) - (down ? 1 : 0);
+      if (level >= terrain->rows) level = zb_min_i((int)(rnd[MR_TERRAIN_LEVEL] * T(terrain->rows)), terrain->rows - 1);
+      level = level < 0 ? 0 : level;
+      e.mdp.p_delta[3] = T(level);
+      const float* o = terrain->tile_origins + ((size_t)level * terrain->cols + (int)e.mdp.p_delta[4]) * 3;
+      terrain->origin[0] = T(o[0]); terrain->origin[1] = T(o[1]); terrain->origin[2] = T(o[2]);
+    }
     // EventManager mode "reset": reset_base (reset_root_state_uniform on the root LINK `base`), reset_robot_joints
     // (default * U(1,1)), reset_my_data (rewards.py:37-43)
     sim_state_default<ModelWalkM>(e.sim);
@@ -2436,7 +2540,7 @@ ZB_HD void m_step_finish(const Params<T>& P, EnvState<T>& e, const T* raw_action
       quat_mul(qz, q0, e.sim.Q);
     }
     ep_len = 0;
-    ZB_UNROLL for (int k = 0; k < 6; ++k) { e.mdp.p_delta[k] = T(0); e.mdp.actions[k] = T(0); }   // ActionManager.reset
+    ZB_UNROLL for (int k = 0; k < 6; ++k) e.mdp.actions[k] = T(0);                // ActionManager.reset (p_delta carries command / event / terrain state)
     ZB_UNROLL for (int j = 0; j < 2; ++j) {
       e.timers[j].cur_air = e.timers[j].cur_contact = e.timers[j].last_air = e.timers[j].last_contact = T(0);
       e.mdp.feet_force_last[j] = T(0);
@@ -2450,13 +2554,37 @@ ZB_HD void m_step_finish(const Params<T>& P, EnvState<T>& e, const T* raw_action
     // CommandManager.reset -> UniformVelocityCommand._resample
     m_resample_command(P, rnd[MR_RESET_TIME], rnd[MR_RESET_VX], rnd[MR_RESET_VY], rnd[MR_RESET_WZ], rnd[MR_RESET_STAND],
                        cmd0, cmd1, cmd2, standing, time_left);
+    if (P.cmd_heading) m_resample_heading(P, rnd[MR_RESET_HEADING], rnd[MR_RESET_ISHEAD], heading_target, is_heading);
+    // EventManager.reset: the interval term's per-env timer is re-drawn
+    if (P.push_interval_hi > T(0)) push_left = rnd[MR_PUSH_RESET_TIME] * (P.push_interval_hi - P.push_interval_lo) + P.push_interval_lo;
   }
   // ---- CommandManager.compute(dt): timer, resample, standing envs get a zero command ----
   time_left -= P.step_dt;
-  if (time_left <= T(0))
+  if (time_left <= T(0)) {
     m_resample_command(P, rnd[MR_INT_TIME], rnd[MR_INT_VX], rnd[MR_INT_VY], rnd[MR_INT_WZ], rnd[MR_INT_STAND],
                        cmd0, cmd1, cmd2, standing, time_left);
+    if (P.cmd_heading) m_resample_heading(P, rnd[MR_INT_HEADING], rnd[MR_INT_ISHEAD], heading_target, is_heading);
+  }
+  if (P.cmd_heading && is_heading != T(0)) {
+    // UniformVelocityCommand._update_command [IL-upstream]: ang_vel_z = clip(stiffness * wrap_to_pi(target - heading_w), range),
+    // heading_w = atan2 of the root's x axis in the world (ArticulationData.heading_w)
+    const T qw = k1.root_quat[0], qx = k1.root_quat[1], qy = k1.root_quat[2], qz = k1.root_quat[3];
+    const T fx = T(1) - T(2) * (qy * qy + qz * qz), fy = T(2) * (qx * qy + qw * qz);
+    const T d = heading_target - zb_atan2(fy, fx);
+    const T err = zb_atan2(zb_sin(d), zb_cos(d));
+    cmd2 = zb_clamp(P.cmd_heading_stiffness * err, P.cmd_lo[2], P.cmd_hi[2]);
+  }
   if (standing != T(0)) { cmd0 = T(0); cmd1 = T(0); cmd2 = T(0); }
+  // ---- EventManager.apply(mode="interval"): push_robot = push_by_setting_velocity [IL-upstream]: root velocity += U(range),
+  //      i.e. every link of the robot gains the same linear velocity ----
+  if (P.push_interval_hi > T(0)) {
+    push_left -= P.step_dt;
+    if (push_left < T(1e-6)) {
+      push_left = rnd[MR_PUSH_TIME] * (P.push_interval_hi - P.push_interval_lo) + P.push_interval_lo;
+      e.sim.v[0] += rnd[MR_PUSH_X] * (P.push_hi[0] - P.push_lo[0]) + P.push_lo[0];
+      e.sim.v[1] += rnd[MR_PUSH_Y] * (P.push_hi[1] - P.push_lo[1]) + P.push_lo[1];
+    }
+  }
   // ---- ObservationManager: base_quat, velocity_commands, joint_pos_rel, joint_vel_rel, last_action (Isaac Lab joint order) ----
   ZB_UNROLL for (int i = 0; i < 4; ++i) obs25[i] = k1.root_quat[i];
   obs25[4] = cmd0; obs25[5] = cmd1; obs25[6] = cmd2;

@@ -55,6 +55,9 @@ constexpr int kStats = ZBOT_STATS_WORDS;   // 32
 constexpr int kStatUsed = 22;
 constexpr int S_NUM_RESET = 16, S_NUM_TERM_RESET = 17, S_NUM_TO_RESET = 18, S_REW_SUM = 19, S_NUM_TERM = 20,
               S_NUM_TRUNC = 21;
+// manager task: words 22..25 = episodic sum of the is_terminated RewTerm (normalised like a term) and the number of reset
+// envs that tripped base_height / feet_close / illegal_contact (raw counts)
+constexpr int kStatUsedM = 26, S_M_TERM_PENALTY = 22;
 
 struct StatsCtx {
   float* partials;        // [max_blocks][32]
@@ -75,6 +78,7 @@ struct StatsCtx {
   int64_t* spread_ep_len;  // nullptr: off
   int spread_n, spread_high;
   unsigned long long spread_seed;
+  int norm_word22;         // manager task: word 22 is an Episode_Reward value (normalised), not a raw count
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -137,7 +141,7 @@ __global__ void __launch_bounds__(1024) zbot_stats_finalize_kernel(StatsCtx sc, 
     float acc = 0.f;
 #pragma unroll
     for (int g = 0; g < 32; ++g) acc += red[g][threadIdx.x];
-    red[0][threadIdx.x] = (threadIdx.x < kStatUsed) ? acc : 0.f;
+    red[0][threadIdx.x] = acc;           // words a kernel does not produce are zero in every partial row
   }
   __syncthreads();
   if (threadIdx.x < kStats) {
@@ -145,10 +149,11 @@ __global__ void __launch_bounds__(1024) zbot_stats_finalize_kernel(StatsCtx sc, 
     float v = red[0][threadIdx.x];
     // words 0..15 leave the kernel as the reference's `Episode_Reward/<term>` values:
     // mean over the reset envs of the episodic sum, divided by max_episode_length_s
-    if (threadIdx.x < MAX_TERMS - sc.raw_tail && nreset > 0.f) v = (v / nreset) * sc.inv_episode_s;
+    if ((threadIdx.x < MAX_TERMS - sc.raw_tail || (sc.norm_word22 && threadIdx.x == S_M_TERM_PENALTY)) && nreset > 0.f)
+      v = (v / nreset) * sc.inv_episode_s;
     // the reference only rewrites extras["log"] when something reset (…env_v2.py:450): keep the previous log
     // (word 16, the number of envs reset THIS step, is always the live count)
-    if (threadIdx.x < S_REW_SUM && threadIdx.x != S_NUM_RESET && !(nreset > 0.f))
+    if ((threadIdx.x < S_REW_SUM || threadIdx.x >= kStatUsed) && threadIdx.x != S_NUM_RESET && !(nreset > 0.f))
       v = (sc.prev_slot >= 0) ? sc.ring[(size_t)sc.prev_slot * kStats + threadIdx.x] : 0.f;
     sc.ring[(size_t)sc.slot * kStats + threadIdx.x] = v;
   }
@@ -167,19 +172,22 @@ __global__ void __launch_bounds__(1024) zbot_stats_finalize_kernel(StatsCtx sc, 
 
 // warp shuffles -> shared memory -> this block's partial row.  `vals[0..18]` are non-zero only for
 // threads that reset this step; 19..21 for every thread.
-__device__ __forceinline__ void stats_block_partial(float (&vals)[kStatUsed], bool did_reset, float* smem, const StatsCtx& sc) {
+// kN = statistics words this kernel produces (22 for the direct tasks, 26 for the manager task: words 22..25 are reset-only)
+template <int kN>
+__device__ __forceinline__ void stats_block_partial(float (&vals)[kN], bool did_reset, float* smem, const StatsCtx& sc) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
   const bool any_reset = __any_sync(0xffffffffu, did_reset);
 #pragma unroll
-  for (int j = 0; j < kStatUsed; ++j) {
+  for (int j = 0; j < kN; ++j) {
     float v = 0.f;
-    if (j >= S_REW_SUM || any_reset) v = warp_sum(vals[j]);   // any_reset is warp-uniform
-    if (lane == 0) smem[warp * kStatUsed + j] = v;
+    if ((j >= S_REW_SUM && j < kStatUsed) || any_reset) v = warp_sum(vals[j]);   // any_reset is warp-uniform
+    if (lane == 0) smem[warp * kN + j] = v;
   }
   __syncthreads();
-  if (threadIdx.x < kStatUsed) {
+  if (threadIdx.x < kStats) {            // a whole 32-word row: the words this kernel does not produce are written as zeros
     float acc = 0.f;
-    for (int w = 0; w < nwarps; ++w) acc += smem[w * kStatUsed + threadIdx.x];
+    if (threadIdx.x < kN)
+      for (int w = 0; w < nwarps; ++w) acc += smem[w * kN + threadIdx.x];
     sc.partials[(size_t)(blockIdx.x + sc.block_offset) * kStats + threadIdx.x] = acc;
   }
 }
@@ -723,20 +731,32 @@ zbot_v4_step_kernel(const __grid_constant__ Params<float> P, float4* __restrict_
 static_assert(sizeof(MExport<float>) / sizeof(float) == ZBOT_M_EXPORT_WORDS && M_EXPORT_WORDS == ZBOT_M_EXPORT_WORDS, "MExport layout");
 static_assert(M_NUM_OBS == ZBOT_M_NUM_OBS && M_NUM_RAND == ZBOT_M_NUM_RAND, "manager task widths");
 
-template <bool kExport, int kUnroll = 1, int kMinBlocks = 2>
+// rough-terrain arguments of the manager kernel (zbot_bind_terrain); heights == nullptr: flat ground
+struct TerrainArgs {
+  const float* heights;        // [nx][ny] world-frame height field
+  int nx, ny;
+  float x0, y0, inv_cell;
+  float4* env_origins;         // [N] (x, y, z, unused): read every step, rewritten when the curriculum moves an env
+  const float* tile_origins;   // [rows][cols][3]
+  int rows, cols;
+  float tile_size, episode_s;
+  int curriculum;
+};
+
+template <bool kExport, int kUnroll = 1, int kMinBlocks = 2, bool kTerrain = false>
 __global__ void __launch_bounds__(128, kMinBlocks)
 zbot_m_step_kernel(const __grid_constant__ Params<float> P, float4* __restrict__ state, int64_t* __restrict__ ep_len_buf,
                    const float* __restrict__ actions, const float* __restrict__ rand, uint64_t seed,
                    float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ terminated,
-                   uint8_t* __restrict__ truncated, int n, StatsCtx sc, float* __restrict__ export_buf) {
+                   uint8_t* __restrict__ truncated, int n, StatsCtx sc, float* __restrict__ export_buf, TerrainArgs ta) {
   extern __shared__ float smem[];
   pdl_wait();
   const int e0 = blockIdx.x * blockDim.x;
   const int e = e0 + threadIdx.x;
   const bool live = e < n;
-  float stat[kStatUsed];
+  float stat[kStatUsedM];
 #pragma unroll
-  for (int j = 0; j < kStatUsed; ++j) stat[j] = 0.f;
+  for (int j = 0; j < kStatUsedM; ++j) stat[j] = 0.f;
   float obs_row[M_NUM_OBS];
 #pragma unroll
   for (int i = 0; i < M_NUM_OBS; ++i) obs_row[i] = 0.f;
@@ -744,9 +764,9 @@ zbot_m_step_kernel(const __grid_constant__ Params<float> P, float4* __restrict__
   if (live) {
     EnvState<float> es;
     StepOut<float> out;
-    float rs[MAX_TERMS];
+    float rs[MAX_TERMS + 4];
 #pragma unroll
-    for (int i = 0; i < MAX_TERMS; ++i) rs[i] = 0.f;
+    for (int i = 0; i < MAX_TERMS + 4; ++i) rs[i] = 0.f;
     SmemScratch scr{smem + threadIdx.x * SCR_STRIDE};
     const float2* a2p = reinterpret_cast<const float2*>(actions + (size_t)e * 6);
     {
@@ -757,12 +777,19 @@ zbot_m_step_kernel(const __grid_constant__ Params<float> P, float4* __restrict__
       env_early_unpack(w, es);
     }
     PhysOut<float> po;
+    float4 org = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (kTerrain) org = ta.env_origins[e];
     {
       const float2 a0 = __ldg(a2p), a1 = __ldg(a2p + 1), a2v = __ldg(a2p + 2);
       const float raw[6] = {a0.x, a0.y, a1.x, a1.y, a2v.x, a2v.y};
 #pragma unroll
       for (int k = 0; k < 6; ++k) scr.base[SCR_RAW_ACT + k] = raw[k];
-      env_step_physics<ModelWalkM, kUnroll>(P, es, raw, po, scr, (StepExport<float>*)nullptr);
+      if (kTerrain) {
+        const TerrainGround<float> ground{ta.heights, ta.nx, ta.ny, ta.x0, ta.y0, ta.inv_cell, org.x, org.y, org.z};
+        env_step_physics<ModelWalkM, kUnroll>(P, es, raw, po, scr, (StepExport<float>*)nullptr, ground);
+      } else {
+        env_step_physics<ModelWalkM, kUnroll>(P, es, raw, po, scr, (StepExport<float>*)nullptr);
+      }
     }
     {
       float w[ZBOT_STATE_WORDS - 4 * EARLY_QUADS];
@@ -783,7 +810,13 @@ zbot_m_step_kernel(const __grid_constant__ Params<float> P, float4* __restrict__
     }
     int64_t ep = ep_len_buf[e];
     MExport<float> ex;
-    m_step_finish(P, es, raw, po, ep, rnd, obs_row, out, rs, kExport ? &ex : (MExport<float>*)nullptr);
+    if (kTerrain) {
+      MTerrainCtx<float> tc{{org.x, org.y, org.z}, ta.tile_origins, ta.rows, ta.cols, ta.tile_size, ta.episode_s, ta.curriculum};
+      m_step_finish(P, es, raw, po, ep, rnd, obs_row, out, rs, kExport ? &ex : (MExport<float>*)nullptr, &tc);
+      if (out.terminated || out.time_out) ta.env_origins[e] = make_float4(tc.origin[0], tc.origin[1], tc.origin[2], 0.f);
+    } else {
+      m_step_finish(P, es, raw, po, ep, rnd, obs_row, out, rs, kExport ? &ex : (MExport<float>*)nullptr);
+    }
     // ObservationManager corruption (PolicyCfg: base_quat +-0.01, joint_pos +-0.01, joint_vel +-1.5); columns 0..23
     if (P.obs_noise_enable) {
       const uint64_t call = rng_position(sc);
@@ -806,6 +839,8 @@ zbot_m_step_kernel(const __grid_constant__ Params<float> P, float4* __restrict__
     if (did_reset) {
 #pragma unroll
       for (int i = 0; i < MAX_TERMS; ++i) stat[i] = rs[i];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) stat[kStatUsed + i] = rs[MAX_TERMS + i];
       stat[S_NUM_RESET] = 1.f;
       stat[S_NUM_TERM_RESET] = out.terminated ? 1.f : 0.f;
       stat[S_NUM_TO_RESET] = out.time_out ? 1.f : 0.f;
@@ -1150,6 +1185,7 @@ struct ZbotHandle {
   int w2_ctas;                   // resident 64-thread CTAs per SM the w2 kernel is compiled for (register budget); ZBOT_W2_CTAS
   bool w2;                       // walking-v2: the two-warps-per-32-envs kernel (zbot_w2_kernel.cuh); ZBOT_W2=0 / a ZBOT_STEP_VARIANT restore the one-thread-per-env kernels
   char kernel_name[96];          // zbot_step_kernel_name
+  TerrainArgs terrain;           // zbot_bind_terrain (heights == nullptr: flat)
   int mdp_tile;
 };
 
@@ -1318,6 +1354,11 @@ static int create_impl(const ZbotCfg* cfg, int device, ZbotHandle* h) {
   ZB_CUDA(cudaFuncSetAttribute(zbot_snake_step_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
   ZB_CUDA(cudaFuncSetAttribute(zbot_v4_step_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
   ZB_CUDA(cudaFuncSetAttribute(zbot_m_step_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
+  ZB_CUDA(cudaFuncSetAttribute((zbot_m_step_kernel<true, 2, 2, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
+  ZB_CUDA(cudaFuncSetAttribute((zbot_m_step_kernel<true, 1, 2, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
+  ZB_CUDA(cudaFuncSetAttribute((zbot_m_step_kernel<false, 2, 3, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
+  ZB_CUDA(cudaFuncSetAttribute((zbot_m_step_kernel<false, 2, 2, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
+  ZB_CUDA(cudaFuncSetAttribute((zbot_m_step_kernel<false, 1, 2, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
   ZB_CUDA(cudaFuncSetAttribute(zbot_v4_step_kernel<false, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
   ZB_CUDA(cudaFuncSetAttribute(zbot_m_step_kernel<false, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
   {
@@ -1630,22 +1671,25 @@ static int m_step_impl(ZbotHandle* h, const float* actions, const float* rand, f
   StatsCtx sc{h->partials, h->ring, slot, prev, h->inv_episode_s, 0, h->rng_ctr, 0,
               (h->cfg.num_terms <= MAX_TERMS - 3) ? 2 : 0};
   ctx_spread(sc, h);
+  sc.norm_word22 = 1;
   cudaStream_t s = (cudaStream_t)stream;
-  if (export_buf && h->unroll2)
-    ZB_CUDA_LAUNCH((zbot_m_step_kernel<true, 2>), h->P, h->state, h->ep_len, actions, rand, h->cfg.rng_seed, obs, rew,
-                                                   terminated, truncated, n, sc, export_buf);
-  else if (export_buf)
-    ZB_CUDA_LAUNCH(zbot_m_step_kernel<true>, h->P, h->state, h->ep_len, actions, rand, h->cfg.rng_seed, obs, rew,
-                                                   terminated, truncated, n, sc, export_buf);
-  else if (h->unroll2 && h->ctas3)
-    ZB_CUDA_LAUNCH((zbot_m_step_kernel<false, 2, 3>), h->P, h->state, h->ep_len, actions, rand, h->cfg.rng_seed, obs,
-                                                       rew, terminated, truncated, n, sc, nullptr);
-  else if (h->unroll2)
-    ZB_CUDA_LAUNCH((zbot_m_step_kernel<false, 2>), h->P, h->state, h->ep_len, actions, rand, h->cfg.rng_seed, obs,
-                                                       rew, terminated, truncated, n, sc, nullptr);
-  else
-    ZB_CUDA_LAUNCH(zbot_m_step_kernel<false>, h->P, h->state, h->ep_len, actions, rand, h->cfg.rng_seed, obs, rew,
-                                                    terminated, truncated, n, sc, nullptr);
+#define ZB_M_LAUNCH(...) ZB_CUDA_LAUNCH((zbot_m_step_kernel<__VA_ARGS__>), h->P, h->state, h->ep_len, actions, rand, h->cfg.rng_seed, obs, rew, \
+                                      terminated, truncated, n, sc, export_buf, h->terrain)
+  const bool rough = h->terrain.heights != nullptr;
+  if (rough) {     // height-field ground + terrain curriculum (zbot_bind_terrain)
+    if (export_buf && h->unroll2) ZB_M_LAUNCH(true, 2, 2, true);
+    else if (export_buf) ZB_M_LAUNCH(true, 1, 2, true);
+    else if (h->unroll2 && h->ctas3) ZB_M_LAUNCH(false, 2, 3, true);
+    else if (h->unroll2) ZB_M_LAUNCH(false, 2, 2, true);
+    else ZB_M_LAUNCH(false, 1, 2, true);
+  } else {
+    if (export_buf && h->unroll2) ZB_M_LAUNCH(true, 2);
+    else if (export_buf) ZB_M_LAUNCH(true);
+    else if (h->unroll2 && h->ctas3) ZB_M_LAUNCH(false, 2, 3);
+    else if (h->unroll2) ZB_M_LAUNCH(false, 2);
+    else ZB_M_LAUNCH(false);
+  }
+#undef ZB_M_LAUNCH
   ZB_CUDA(cudaGetLastError());
   h->launches += 1;
   ZB_CUDA(launch_pdl(zbot_stats_finalize_kernel, dim3(1), dim3(1024), 0, s, h->pdl, sc, (unsigned int)grid));
@@ -1662,6 +1706,20 @@ int zbot_m_step_export(ZbotHandle* h, const float* actions, const float* rand, f
                        uint8_t* truncated, int32_t stats_slot, int32_t prev_slot, float* export_buf, void* stream) {
   if (!export_buf) return fail(ZBOT_E_INVALID, "zbot_m_step_export: export_buf is NULL%s");
   return m_step_impl(h, actions, rand, obs, rew, terminated, truncated, stats_slot, prev_slot, export_buf, stream);
+}
+
+int zbot_bind_terrain(ZbotHandle* h, const float* heights, int32_t nx, int32_t ny, float x0, float y0, float cell,
+                      const float* tile_origins, int32_t rows, int32_t cols, float tile_size, float* env_origins,
+                      int32_t curriculum) {
+  if (!h) return fail(ZBOT_E_INVALID, "handle is NULL%s");
+  if (h->cfg.task != ZBOT_TASK_WALKING_M) return fail(ZBOT_E_INVALID, "zbot_bind_terrain: manager task only%s");
+  if (!heights) { memset(&h->terrain, 0, sizeof(h->terrain)); return ZBOT_OK; }     // back to the flat ground
+  if (!tile_origins || !env_origins || nx < 2 || ny < 2 || rows < 1 || cols < 1 || !(cell > 0.f))
+    return fail(ZBOT_E_INVALID, "zbot_bind_terrain: bad argument%s");
+  if (((uintptr_t)env_origins & 15) != 0) return fail(ZBOT_E_INVALID, "env_origins must be 16-byte aligned ([N][4] floats)%s");
+  h->terrain = TerrainArgs{heights, nx, ny, x0, y0, 1.0f / cell, reinterpret_cast<float4*>(env_origins), tile_origins, rows, cols,
+                           tile_size, (float)h->cfg.max_episode_length * h->cfg.sim_dt * (float)h->cfg.decimation, curriculum ? 1 : 0};
+  return ZBOT_OK;
 }
 
 int zbot_set_all_reset_spread(ZbotHandle* h, int32_t enable) {

@@ -200,6 +200,12 @@ inline void params_from_cfg(const ZbotCfg& c, Params<T>& P) {
   P.act_scale = T(c.act_scale); P.act_clip = T(c.act_clip);
   P.feet_close_min = T(c.feet_close_min);
   P.term_penalty_w = T(c.is_terminated_weight) * P.step_dt;       // value * weight * dt with value = 1 (RewardManager)
+  P.illegal_thr = T(c.illegal_contact_threshold); P.illegal_mask = c.illegal_contact_mask;
+  P.cmd_heading = c.cmd_heading;
+  P.cmd_heading_lo = T(c.cmd_heading_lo); P.cmd_heading_hi = T(c.cmd_heading_hi);
+  P.cmd_heading_stiffness = T(c.cmd_heading_stiffness); P.cmd_rel_heading = T(c.cmd_rel_heading);
+  P.push_interval_lo = T(c.push_interval_lo); P.push_interval_hi = T(c.push_interval_hi);
+  for (int i = 0; i < 2; ++i) { P.push_lo[i] = T(c.push_lo[i]); P.push_hi[i] = T(c.push_hi[i]); }
   P.default_terms = (c.num_terms == 13) && (c.task == ZBOT_TASK_WALKING_V2);
   for (int i = 0; i < 13 && P.default_terms; ++i) P.default_terms = (c.term_id[i] == i);
 }

@@ -13,9 +13,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # ZBOT_B200_LIB: load a tuning build of the SAME sources instead (tools/sweep_step.py); never a different implementation
 LIB_PATH = os.environ.get("ZBOT_B200_LIB") or os.path.join(HERE, "csrc", "libzbot_b200.so")
 
-ZBOT_ABI_VERSION = 5
+ZBOT_ABI_VERSION = 6
 TASK_WALKING_V2, TASK_SNAKE_V0, TASK_WALKING_V4, TASK_WALKING_M = 0, 1, 2, 3
-M_NUM_OBS, M_NUM_RAND, M_EXPORT_WORDS = 25, 13, 67
+M_NUM_OBS, M_NUM_RAND, M_EXPORT_WORDS = 25, 22, 72
 V4_NUM_OBS, V4_NUM_RAND, V4_EXPORT_WORDS = 24, 10, 69
 MAX_TERMS = 16
 HOST_ROW_WORDS = 25   # zbot_step_host result row: obs 23 | reward | flags word
@@ -74,6 +74,10 @@ class ZbotCfg(C.Structure):
         ("cmd_rel_standing", C.c_float), ("cmd_resample_lo", C.c_float), ("cmd_resample_hi", C.c_float),
         ("act_scale", C.c_float), ("act_clip", C.c_float), ("feet_close_min", C.c_float),
         ("is_terminated_weight", C.c_float),
+        ("illegal_contact_threshold", C.c_float), ("illegal_contact_mask", C.c_int32), ("cmd_heading", C.c_int32),
+        ("cmd_heading_lo", C.c_float), ("cmd_heading_hi", C.c_float), ("cmd_heading_stiffness", C.c_float),
+        ("cmd_rel_heading", C.c_float), ("push_interval_lo", C.c_float), ("push_interval_hi", C.c_float),
+        ("push_lo", C.c_float * 2), ("push_hi", C.c_float * 2),
     ]
 
 
@@ -200,6 +204,7 @@ def _declare(lib):
     lib.zbot_m_step_export.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp]
     lib.zbot_update_cfg.argtypes = [vp, P(ZbotCfg)]
     lib.zbot_set_all_reset_spread.argtypes = [vp, i32]
+    lib.zbot_bind_terrain.argtypes = [vp, vp, i32, i32, C.c_float, C.c_float, C.c_float, vp, i32, i32, C.c_float, vp, i32]
     lib.zbot_reset_idx.argtypes = [vp, vp, i64, vp, vp, i32, vp]
     lib.zbot_observe.argtypes = [vp, vp, vp]
     lib.zbot_articulation_view.argtypes = [vp, vp, vp, vp, vp]
@@ -213,7 +218,7 @@ def _declare(lib):
     for name in ("zbot_default_cfg", "zbot_state_word", "zbot_mdp_state_word", "zbot_create", "zbot_destroy",
                  "zbot_bind", "zbot_step", "zbot_step_export", "zbot_snake_step_export", "zbot_step_host", "zbot_v4_step",
                  "zbot_v4_step_export", "zbot_m_step", "zbot_m_step_export", "zbot_update_cfg", "zbot_reset_idx",
-                 "zbot_observe", "zbot_set_all_reset_spread",
+                 "zbot_observe", "zbot_set_all_reset_spread", "zbot_bind_terrain",
                  "zbot_articulation_view", "zbot_mdp_bind", "zbot_mdp_observe", "zbot_mdp_step"):
         getattr(lib, name).restype = C.c_int
 
@@ -223,7 +228,7 @@ EXPORTED_SYMBOLS = (
     "zbot_mdp_state_word", "zbot_create", "zbot_destroy", "zbot_bind", "zbot_step", "zbot_step_export",
     "zbot_snake_step_export", "zbot_step_host", "zbot_v4_step", "zbot_v4_step_export", "zbot_m_step", "zbot_m_step_export",
     "zbot_update_cfg", "zbot_reset_idx", "zbot_observe", "zbot_articulation_view", "zbot_mdp_bind", "zbot_mdp_observe",
-    "zbot_mdp_step", "zbot_launch_count", "zbot_set_all_reset_spread", "zbot_step_kernel_name",
+    "zbot_mdp_step", "zbot_launch_count", "zbot_set_all_reset_spread", "zbot_step_kernel_name", "zbot_bind_terrain",
 )
 
 
@@ -291,6 +296,7 @@ M_REWARD_FUNCS = {
     "air_time_variance_penalty": (27, lambda p: []),
     "base_vel_forward": (41, lambda p: [float(p.get("which_forward", 1))]),
     "feet_force_pattern": (42, lambda p: []),
+    "undesired_contacts": (43, lambda p: [p.get("threshold", 1.0)]),     # isaaclab.envs.mdp [IL-upstream]
 }
 
 
@@ -298,7 +304,8 @@ def make_m_cfg(num_envs: int, terms, *, is_terminated_weight: float = 0.0, minim
                feet_close_min: float = 0.12, cmd_ranges=((-0.1, 0.1), (0.0, 0.0), (0.0, 0.0)), rel_standing_envs: float = 0.02,
                resampling_time_range=(10.0, 10.0), act_scale: float = 0.04 * 3.141592653589793, act_clip: float | None = None,
                pose_range=((-0.5, 0.5), (-0.5, 0.5), (-3.14, 3.14)), episode_length_s: float = 20.0, friction: float = 1.0,
-               rng_seed: int = 0, **overrides) -> ZbotCfg:
+               rng_seed: int = 0, illegal_contact: tuple | None = None, heading: dict | None = None, push: dict | None = None,
+               **overrides) -> ZbotCfg:
     """``ZbotCfg`` of the manager-based task.  ``terms`` = [(func_name, weight, params_dict), ...] in cfg order
     (zero-weight terms are skipped, as RewardManager does); the defaults are ``Zbot6BFlatEnvCfg``
     (config/zbot6b_manager/flat_env_cfg.py) over ``ZbotLabRoughEnvCfg`` (zbotlab_env_cfg.py:99-452)."""
@@ -321,6 +328,16 @@ def make_m_cfg(num_envs: int, terms, *, is_terminated_weight: float = 0.0, minim
     cfg.act_scale = float(act_scale)
     cfg.act_clip = float(act_clip if act_clip is not None else 3.0e38)
     cfg.rng_seed = int(rng_seed)
+    if illegal_contact is not None:      # DoneTerm mdp.illegal_contact: (threshold, merged-body mask)
+        cfg.illegal_contact_threshold, cfg.illegal_contact_mask = float(illegal_contact[0]), int(illegal_contact[1])
+    if heading is not None:              # UniformVelocityCommandCfg(heading_command=True, ...)
+        cfg.cmd_heading = 1
+        cfg.cmd_heading_lo, cfg.cmd_heading_hi = float(heading["range"][0]), float(heading["range"][1])
+        cfg.cmd_heading_stiffness, cfg.cmd_rel_heading = float(heading["stiffness"]), float(heading["rel_heading_envs"])
+    if push is not None:                 # EventTerm push_by_setting_velocity, mode="interval"
+        cfg.push_interval_lo, cfg.push_interval_hi = float(push["interval_range_s"][0]), float(push["interval_range_s"][1])
+        for i, k in enumerate(("x", "y")):
+            cfg.push_lo[i], cfg.push_hi[i] = (float(v) for v in push["velocity_range"].get(k, (0.0, 0.0)))
     active = [(f, w, p) for f, w, p in terms if float(w) != 0.0]
     if len(active) > MAX_TERMS - 0:
         raise ValueError(f"at most {MAX_TERMS} weighted reward terms are supported (termination_penalty excluded)")

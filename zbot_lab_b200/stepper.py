@@ -162,7 +162,7 @@ class NativeStepper:
             raise ValueError(f"actions must be ({self.n}, 6), got {tuple(actions.shape)}")
         slot, prev = self._next_slot()
         if self.mtask:
-            # zbot-6b-walking-m-v0: `rand` = (N,13) uniforms or None (in-kernel generator); `export` = (N,67) float32 (MExport)
+            # zbot-6b-walking-m-v0: `rand` = (N,21) uniforms or None (in-kernel generator); `export` = (N,72) float32 (MExport)
             if rand is not None and (rand.dtype != torch.float32 or tuple(rand.shape) != (self.n, native.M_NUM_RAND)
                                      or not rand.is_contiguous() or rand.device != self.obs.device):
                 raise ValueError(f"rand must be a contiguous float32 ({self.n}, {native.M_NUM_RAND}) tensor on the device")
@@ -243,6 +243,17 @@ class NativeStepper:
         (…env_v2.py:418-422), decided and written by the statistics kernel: no host sync (include/zbot_b200.h)."""
         native.check(self.lib.zbot_set_all_reset_spread(self._h, 1 if enable else 0), "zbot_set_all_reset_spread")
 
+    def bind_terrain(self, heights: torch.Tensor, x0: float, y0: float, cell: float, tile_origins: torch.Tensor, tile_size: float,
+                     env_origins4: torch.Tensor, curriculum: bool):
+        """Manager task on a generated height field (``zbot_bind_terrain``); the tensors must stay alive with the stepper."""
+        for t, shape in ((heights, None), (tile_origins, None), (env_origins4, (self.n, 4))):
+            if t.dtype != torch.float32 or not t.is_contiguous() or t.device != self.device or (shape and tuple(t.shape) != shape):
+                raise ValueError("bind_terrain: contiguous float32 device tensors (env_origins (N, 4))")
+        self._terrain_keep = (heights, tile_origins, env_origins4)
+        native.check(self.lib.zbot_bind_terrain(self._h, _ptr(heights), heights.shape[0], heights.shape[1], float(x0), float(y0),
+                                                float(cell), _ptr(tile_origins), tile_origins.shape[0], tile_origins.shape[1],
+                                                float(tile_size), _ptr(env_origins4), 1 if curriculum else 0), "zbot_bind_terrain")
+
     def update_cfg(self):
         """Push the (mutated) ``self.cfg`` reward weights / event parameters to the live handle (host curricula)."""
         native.check(self.lib.zbot_update_cfg(self._h, C.byref(self.cfg)), "zbot_update_cfg")
@@ -322,10 +333,14 @@ class NativeStepper:
         st = self.state
         st.set("root_pos", pos, ids)
         st.set("root_quat", quat, ids)
-        for name, w in (("root_lin_vel", 3), ("root_ang_vel", 3), ("joint_vel", 6), ("p_delta", 6), ("actions", 6),
+        for name, w in (("root_lin_vel", 3), ("root_ang_vel", 3), ("joint_vel", 6), ("actions", 6),
                         ("current_air_time", 2), ("current_contact_time", 2), ("last_air_time", 2), ("last_contact_time", 2),
                         ("feet_step_length", 2), ("feet_contact_forces_last", 2), ("feet_force_sum", 1), ("episode_sums", 16)):
             st.set(name, z(w), ids)
+        pd0 = st.get("p_delta")[ids]                # words 3 / 4 = terrain level / type of the env: they survive a reset
+        pd0[:, :3] = 0.0
+        pd0[:, 5] = 0.0
+        st.set("p_delta", pd0, ids)
         st.set("joint_pos", f32(m.default_joint_pos).repeat(k, 1), ids)
         rng = lambda i: float(c.cmd_hi[i]) - float(c.cmd_lo[i])
         cmd = torch.stack([u[:, 4 + i] * rng(i) + float(c.cmd_lo[i]) for i in range(3)], -1)
@@ -333,6 +348,17 @@ class NativeStepper:
         st.set("carry_mid_max", cmd[:, 2:3], ids)
         st.set("base_heading_x_sum", (u[:, 7] <= c.cmd_rel_standing).float().unsqueeze(-1), ids)
         st.set("base_pos_y_err_sum", (u[:, 3] * (c.cmd_resample_hi - c.cmd_resample_lo) + c.cmd_resample_lo).unsqueeze(-1), ids)
+        # heading command / push_robot interval timer live in the (otherwise unused) p_delta words 0..2; their uniforms are the
+        # optional columns 8..10 of `rand`
+        if c.cmd_heading or c.push_interval_hi > 0:
+            ux = u[:, 8:11] if u.shape[1] >= 11 else torch.rand(k, 3, device=dev)
+            pd = st.get("p_delta")[ids]
+            if c.cmd_heading:
+                pd[:, 0] = ux[:, 0] * (c.cmd_heading_hi - c.cmd_heading_lo) + c.cmd_heading_lo
+                pd[:, 1] = (ux[:, 1] <= c.cmd_rel_heading).float()
+            if c.push_interval_hi > 0:
+                pd[:, 2] = ux[:, 2] * (c.push_interval_hi - c.push_interval_lo) + c.push_interval_lo
+            st.set("p_delta", pd, ids)
         self.episode_length_buf[ids] = 0
         posl, _, _ = self.articulation_view()         # chain view: link 1 = joint3 location = foot0 LINK origin, 11 = foot1
         st.set("feet_down_pos_last", posl[ids][:, [1, 11]].reshape(k, 6), ids)

@@ -23,8 +23,9 @@ FEET_SENSOR = {"sensor_cfg": SceneEntityCfg("contact_forces", body_names="foot.*
 
 
 class TerrainCfg(Cfg):
-    terrain_type = "plane"             # flat_env_cfg.py:107-108 (the rough cfg's "generator" is out of scope)
-    terrain_generator = None
+    terrain_type = "plane"             # flat_env_cfg.py:107-108; the rough cfg: "generator" (zbotlab_env_cfg.py:44-48)
+    terrain_generator = None           # zbot_lab_b200.terrain.TerrainGeneratorCfg (restated ROUGH_TERRAINS_CFG [IL-upstream])
+    max_init_terrain_level = 5
     static_friction = 1.0              # zbotlab_env_cfg.py:50-55, combine mode "multiply"
     dynamic_friction = 1.0
 
@@ -164,6 +165,69 @@ class Zbot6BFlatEnvCfg_PLAY(Zbot6BFlatEnvCfg):
         self.commands.base_velocity.ranges = self.commands.base_velocity.limit_ranges
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# zbot-6b-walking-m-rough-v0: ZbotLabRoughEnvCfg (zbotlab_env_cfg.py:414-452) + Zbot6BRoughEnvCfg (rough_env_cfg.py:22-56):
+# generated terrain + terrain_levels curriculum, ALL RewTerms of RewardsCfg at their base weights (:240-371), the robot
+# overrides of the rough cfg (add_base_mass / base_com / push_robot / base_contact = None)
+# ---------------------------------------------------------------------------------------------------------------------
+class RoughTerrainCfg(TerrainCfg):
+    terrain_type = "generator"
+
+    def __init__(self, **kw):
+        from ...terrain import rough_terrains_cfg
+        super().__init__(**kw)
+        if self.terrain_generator is None:
+            self.terrain_generator = rough_terrains_cfg()
+
+
+class RoughSceneCfg(MySceneCfg):
+    terrain = RoughTerrainCfg()
+
+
+class RoughRewardsCfg(RewardsCfg):                                 # zbotlab_env_cfg.py:240-371, nothing switched off
+    foot_step_length = RewTerm(func=mdp.foot_step_length, weight=2.0, params={**FEET, **FEET_SENSOR, "command_name": None})
+    gait = RewTerm(func=mdp.feet_gait, weight=0.5, params={"period": 2.0, "offset": [0.0, 0.5], "threshold": 0.55,
+                                                            "command_name": "base_velocity", **FEET_SENSOR})
+    feet_slide = RewTerm(func=mdp.feet_slide, weight=-0.2, params={**FEET, **FEET_SENSOR})
+    feet_clearance = RewTerm(func=mdp.foot_clearance_reward, weight=1.0,
+                             params={"std": 0.05, "tanh_mult": 2.0, "target_height": 0.01, **FEET})
+    feet_air_time = RewTerm(func=mdp.feet_air_time_positive_biped, weight=2.5,
+                            params={**FEET_SENSOR, "command_name": "base_velocity", "threshold": 0.3})
+    air_time_variance = RewTerm(func=mdp.air_time_balance_penalty, weight=-1.0, params=dict(FEET_SENSOR))
+    base_vel_forward = RewTerm(func=mdp.base_vel_forward, weight=1.0, params={"which_forward": 1})
+    feet_force_pattern = RewTerm(func=mdp.feet_force_pattern, weight=1.0, params=dict(FEET_SENSOR))
+    undesired_contacts = RewTerm(func=mdp.undesired_contacts, weight=-1.0, params={
+        "sensor_cfg": SceneEntityCfg("contact_forces", body_names="base|a.*|b.*"), "threshold": 1.0})
+
+
+class RoughCurriculumCfg(Cfg):                                     # :396-401
+    terrain_levels = CurrTerm(func=mdp.terrain_levels_vel)
+    lin_vel_cmd_levels = CurrTerm(func=mdp.lin_vel_cmd_levels)
+
+
+class Zbot6BRoughEnvCfg(Zbot6BFlatEnvCfg):
+    scene = RoughSceneCfg()
+    rewards = RoughRewardsCfg()
+    curriculum = RoughCurriculumCfg()
+
+
+class Zbot6BRoughEnvCfg_PLAY(Zbot6BRoughEnvCfg):
+    """rough_env_cfg.py:59-83: 64 envs, 5 x 5 tiles without the level curriculum, robots spawned on random levels,
+    forward commands, no observation corruption."""
+
+    def __init__(self, **kw):
+        super().__init__(**kw)
+        self.scene.num_envs = 64
+        self.scene.env_spacing = 2.5
+        self.scene.terrain.max_init_terrain_level = None
+        g = self.scene.terrain.terrain_generator
+        g.num_rows, g.num_cols, g.curriculum = 5, 5, False
+        self.commands.base_velocity.ranges.lin_vel_x = (0.7, 1.0)
+        self.commands.base_velocity.ranges.lin_vel_y = (0.0, 0.0)
+        self.commands.base_velocity.ranges.heading = (0.0, 0.0)
+        self.observations.policy.enable_corruption = False
+
+
 class Zbot6BFlatPPORunnerCfg(Cfg):
     """config/zbot6b_manager/agents/rsl_rl_ppo_cfg.py:11-50"""
     class_name = "OnPolicyRunner"
@@ -182,3 +246,10 @@ class Zbot6BFlatPPORunnerCfg(Cfg):
     logger = "tensorboard"
     policy = RslRlPpoActorCriticCfg(actor_hidden_dims=[128, 128, 128], critic_hidden_dims=[128, 128, 128])
     algorithm = RslRlPpoAlgorithmCfg(entropy_coef=0.01)
+
+
+class Zbot6BRoughPPORunnerCfg(Zbot6BFlatPPORunnerCfg):
+    """config/zbot6b_manager/agents/rsl_rl_ppo_cfg.py:11-38"""
+    max_iterations = 1500
+    experiment_name = "zbot_6b_rough_mana_v1"
+    policy = RslRlPpoActorCriticCfg(actor_hidden_dims=[512, 256, 128], critic_hidden_dims=[512, 256, 128])

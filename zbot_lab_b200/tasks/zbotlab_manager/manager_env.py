@@ -55,11 +55,17 @@ class ManagerBasedRLEnv(ZbotDirectEnvV2):
         self.step_dt = self.physics_dt * c.decimation
         self.max_episode_length_s = float(c.episode_length_s)
         self.max_episode_length = math.ceil(self.max_episode_length_s / self.step_dt)
-        if getattr(c.scene.terrain, "terrain_type", "plane") != "plane":
-            raise NotImplementedError("only terrain_type='plane' (Zbot6BFlatEnvCfg) is built; the generator terrain is out of scope")
+        ttype = getattr(c.scene.terrain, "terrain_type", "plane")
+        if ttype not in ("plane", "generator"):
+            raise NotImplementedError(f"terrain_type {ttype!r}: 'plane' (flat cfgs) and 'generator' (rough cfgs) are built")
         self._compile_cfg()
         self._stepper = NativeStepper(self.num_envs, self.device, self._native_cfg())
-        self._terrain = _Terrain(self.num_envs, c.scene.env_spacing, self.device)
+        if ttype == "generator":
+            self._setup_generated_terrain()
+        else:
+            if self._curr_terrain:
+                raise NotImplementedError("terrain_levels_vel needs terrain_type='generator' (mdp/curriculums.py:35-37)")
+            self._terrain = _Terrain(self.num_envs, c.scene.env_spacing, self.device)
         self.single_observation_space = {"policy": _Box((native.M_NUM_OBS,))}
         self.single_action_space = _Box((6,))
         self.observation_space = {"policy": _Box((self.num_envs, native.M_NUM_OBS))}
@@ -100,7 +106,7 @@ class ManagerBasedRLEnv(ZbotDirectEnvV2):
             self._reward_terms.append((name, fn, float(t.weight), params))
         self._term_names = [n for n, _, _, _ in self._reward_terms]
         # terminations
-        self._min_height, self._feet_close = -1.0e30, 0.0
+        self._min_height, self._feet_close, self._illegal = -1.0e30, 0.0, None
         self._done_names = []
         for name, t in _terms(c.terminations):
             fn = t.func.__name__
@@ -111,11 +117,15 @@ class ManagerBasedRLEnv(ZbotDirectEnvV2):
                 self._min_height = float(t.params["minimum_height"])
             elif fn == "feet_close":
                 self._feet_close = float(t.params["minimum_distance"])
+            elif fn == "illegal_contact":
+                # isaaclab.envs.mdp.illegal_contact [IL-upstream] (zbotlab_env_cfg.py:385-388): the sensor bodies the pattern
+                # selects -> the merged bodies of the reduced chain that sense for them (a merged body reports on its "a" link)
+                self._illegal = (float(t.params.get("threshold", 1.0)), self._merged_body_mask(t.params["sensor_cfg"].body_names))
             else:
                 raise NotImplementedError(f"termination term {fn!r} is not built into the fused step")
             self._done_names.append((name, fn))
         # events
-        self._pose_range, self._friction_range = ((0.0, 0.0),) * 3, None
+        self._pose_range, self._friction_range, self._push = ((0.0, 0.0),) * 3, None, None
         for name, t in _terms(c.events):
             fn, p = t.func.__name__, dict(t.params)
             if fn in ("init_my_data", "reset_my_data"):
@@ -128,6 +138,13 @@ class ManagerBasedRLEnv(ZbotDirectEnvV2):
                         any(k in pr and tuple(pr[k]) != (0.0, 0.0) for k in ("z", "roll", "pitch")):
                     raise NotImplementedError("reset_root_state_uniform: only x / y / yaw pose ranges are built")
                 self._pose_range = tuple(tuple(pr.get(k, (0.0, 0.0))) for k in ("x", "y", "yaw"))
+            elif fn == "push_by_setting_velocity":
+                if getattr(t, "mode", "interval") != "interval":
+                    raise NotImplementedError("push_by_setting_velocity is built as an interval-mode event")
+                vr = dict(p.get("velocity_range", {}))
+                if any(k not in ("x", "y") and tuple(v) != (0.0, 0.0) for k, v in vr.items()):
+                    raise NotImplementedError("push_by_setting_velocity: only x / y velocity ranges are built")
+                self._push = {"interval_range_s": tuple(t.interval_range_s), "velocity_range": {k: tuple(v) for k, v in vr.items()}}
             elif fn == "reset_joints_by_scale":
                 if tuple(p["position_range"]) != (1.0, 1.0) or tuple(p["velocity_range"]) != (1.0, 1.0):
                     raise NotImplementedError("reset_joints_by_scale: only the (1, 1) scale of the reference cfg is built")
@@ -135,8 +152,10 @@ class ManagerBasedRLEnv(ZbotDirectEnvV2):
                 raise NotImplementedError(f"event term {fn!r} is not built into the fused step")
         # command / action / observation terms
         cmd = c.commands.base_velocity
-        if cmd.heading_command:
-            raise NotImplementedError("heading_command=True is not built (the reference cfg uses False)")
+        self._heading = None
+        if cmd.heading_command:          # zbotlab_env_cfg.py:86-97 (the commented-out alternative of the reference cfg)
+            self._heading = {"range": tuple(cmd.ranges.heading), "stiffness": float(getattr(cmd, "heading_control_stiffness", 1.0)),
+                             "rel_heading_envs": float(cmd.rel_heading_envs)}
         self._cmd = cmd
         act = c.actions.joint_pos
         if type(act).__name__ != "RelativeJointPositionActionCfg" or not act.use_zero_offset:
@@ -159,8 +178,9 @@ class ManagerBasedRLEnv(ZbotDirectEnvV2):
                 self._obs_noise[(col, col + width)] = (float(t.noise.n_min), float(t.noise.n_max))
             col += width
         self._curr_lin_vel = any(t.func.__name__ == "lin_vel_cmd_levels" for _, t in _terms(c.curriculum))
+        self._curr_terrain = any(t.func.__name__ == "terrain_levels_vel" for _, t in _terms(c.curriculum))
         for _, t in _terms(c.curriculum):
-            if t.func.__name__ not in ("lin_vel_cmd_levels",):
+            if t.func.__name__ not in ("lin_vel_cmd_levels", "terrain_levels_vel"):
                 raise NotImplementedError(f"curriculum term {t.func.__name__!r} is not built")
 
     def _native_cfg(self) -> native.ZbotCfg:
@@ -177,7 +197,7 @@ class ManagerBasedRLEnv(ZbotDirectEnvV2):
             sim_dt=self.physics_dt, decimation=int(c.decimation), kp=float(r.stiffness), kd=float(r.damping),
             effort_limit=float(r.effort_limit), gravity=-float(c.sim.gravity[2]), contact_alpha=ct.alpha, contact_erp=ct.erp,
             contact_vdep=ct.max_depenetration_velocity, contact_beta_max=ct.beta_max, contact_ramp=ct.ramp,
-            contact_margin=ct.margin)
+            contact_margin=ct.margin, illegal_contact=self._illegal, heading=self._heading, push=self._push)
         for i in range(24):
             cfg.obs_noise_lo[i] = cfg.obs_noise_hi[i] = 0.0
         cfg.obs_noise_enable = 1 if self._obs_noise else 0
@@ -185,6 +205,60 @@ class ManagerBasedRLEnv(ZbotDirectEnvV2):
             for i in range(a, min(b, 24)):
                 cfg.obs_noise_lo[i], cfg.obs_noise_hi[i] = lo, hi
         return cfg
+
+    def _setup_generated_terrain(self):
+        """TerrainImporterCfg(terrain_type="generator") (zbotlab_env_cfg.py:44-48): generate the height field
+        (``zbot_lab_b200/terrain.py``), place the envs on their (level, type) tiles as TerrainImporter does, and bind both
+        to the kernel (``zbot_bind_terrain``); the ``terrain_levels`` curriculum then runs inside the step kernel."""
+        import numpy as np
+        from ...terrain import Terrain
+        tc = self.cfg.scene.terrain
+        gen = tc.terrain_generator
+        gen.curriculum = bool(self._curr_terrain)          # ZbotLabRoughEnvCfg.__post_init__ (zbotlab_env_cfg.py:445-452)
+        seed = self.cfg.seed if self.cfg.seed is not None else 0
+        ter = Terrain(gen, seed=int(seed))
+        rng = np.random.default_rng(int(seed) + 7919)
+        levels, types = ter.initial_levels_types(self.num_envs, tc.max_init_terrain_level, rng)
+        dev = self.device
+        org4 = np.zeros((self.num_envs, 4), np.float32)
+        org4[:, :3] = ter.origins[levels, types]
+        self._terrain_gen = ter
+        self._terrain_heights = torch.from_numpy(ter.heights).to(dev)
+        self._terrain_tile_origins = torch.from_numpy(ter.origins).to(dev).contiguous()
+        self._env_origins4 = torch.from_numpy(org4).to(dev)
+        self._terrain = type("TerrainImporter", (), {})()
+        self._terrain.env_origins = self._env_origins4[:, :3]         # a VIEW: the kernel rewrites it when an env changes level
+        self._terrain.terrain_origins = self._terrain_tile_origins
+        self._terrain.cfg = tc
+        self._stepper.bind_terrain(self._terrain_heights, ter.x0, ter.y0, ter.cell, self._terrain_tile_origins, float(gen.size[0]),
+                                   self._env_origins4, bool(self._curr_terrain))
+        pd = self._stepper.state.get("p_delta")
+        pd[:, 3] = torch.from_numpy(levels.astype(np.float32)).to(dev)
+        pd[:, 4] = torch.from_numpy(types.astype(np.float32)).to(dev)
+        self._stepper.state.set("p_delta", pd)
+
+    @property
+    def terrain_levels(self) -> torch.Tensor:
+        """``scene.terrain.terrain_levels`` (generator terrains): the level of every env."""
+        return self._stepper.state.column("p_delta", 3).to(torch.int64)
+
+    @staticmethod
+    def _merged_body_mask(body_names) -> int:
+        """Bit b-1 for every merged body 1..5 of the reduced chain one of whose links matches the sensor pattern."""
+        import re
+        from ...assets import zbot_6s_v2 as V
+        pats = [body_names] if isinstance(body_names, str) else list(body_names)
+        m = V.model_f32()
+        mask = 0
+        for li, name in enumerate(V.LINK_NAMES):
+            if any(re.fullmatch(p, name) for p in pats):
+                b = int(m.link_body[li])
+                if b in (0, 6):
+                    raise NotImplementedError(f"illegal_contact on a foot link ({name!r}) is not built (feet contact is the gait)")
+                mask |= 1 << (b - 1)
+        if mask == 0:
+            raise ValueError(f"illegal_contact: no link matches {body_names!r}")
+        return mask
 
     def _startup_events(self):
         """EventManager mode "startup": per-env friction from 64 buckets (randomize_rigid_body_material), combined with
@@ -264,16 +338,16 @@ class ManagerBasedRLEnv(ZbotDirectEnvV2):
         if log is None:
             s = self._stepper.stats_ring[slot]
             log = {"Episode_Reward/" + k: s[i] for i, k in enumerate(self._term_names)}
-            aux = len(self._term_names) <= native.MAX_TERMS - 3      # spare slots 13 / 14 / 15 (include/zbot_b200.h)
-            if self._is_terminated_weight and aux:
-                log["Episode_Reward/" + self._is_terminated_name] = s[native.MAX_TERMS - 3]
+            # statistics words 22..25 (include/zbot_b200.h): is_terminated's episodic sum, per-DoneTerm reset counts
+            if self._is_terminated_weight:
+                log["Episode_Reward/" + self._is_terminated_name] = s[22]
+            word = {"root_height_below_minimum": 23, "feet_close": 24, "illegal_contact": 25}
             for name, fn in self._done_names:
-                if fn == "time_out":
-                    log["Episode_Termination/" + name] = s[native.STAT_NUM_TIMEOUT_RESET]
-                elif aux:
-                    log["Episode_Termination/" + name] = s[14 if fn == "root_height_below_minimum" else 15]
+                log["Episode_Termination/" + name] = s[native.STAT_NUM_TIMEOUT_RESET if fn == "time_out" else word[fn]]
             self._log_cache[slot] = log
         log["Curriculum/lin_vel_cmd_levels"] = float(self._cmd.ranges.lin_vel_x[1])
+        if self._curr_terrain:                                   # terrain_levels_vel returns the mean level (mdp/curriculums.py:55)
+            log["Curriculum/terrain_levels"] = self._stepper.state.column("p_delta", 3).mean()
         return log
 
     # ------------------------------------------------------------------ gym API

@@ -83,6 +83,7 @@ class UniformVelocityCommandCfg(Cfg):
     rel_standing_envs = 0.0
     rel_heading_envs = 1.0
     heading_command = False
+    heading_control_stiffness = 1.0
     debug_vis = False
     ranges = Ranges()
 
