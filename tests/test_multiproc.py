@@ -32,6 +32,9 @@ def _worker(rank, world, port, q):
     slot[18] = nreset - 1 - rank
     slot[19] = float(rank + 0.5)
     out = zd.reduce_rollout_stats(slot)
+    red = zd.RolloutStatsReducer("cpu")          # the overlapped form degrades to the synchronous call on CPU tensors
+    red.submit(slot)
+    assert torch.equal(red.result(), out) and red.submitted == 1
     q.put((rank, lo, hi, sums, out.numpy(), zd.rank_seed(42, rank)))
     dist.destroy_process_group()
 

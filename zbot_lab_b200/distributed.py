@@ -36,3 +36,34 @@ def reduce_rollout_stats(stats: torch.Tensor, group=None) -> torch.Tensor:
     tot = s[native.STAT_NUM_RESET]
     s[:native.MAX_TERMS] = torch.where(tot > 0, s[:native.MAX_TERMS] / tot.clamp(min=1), torch.zeros_like(s[:native.MAX_TERMS]))
     return s.to(stats.dtype)
+
+
+class RolloutStatsReducer:
+    """The same reduction, OFF the stepping stream: ``submit(stats)`` snapshots the slot on the caller's stream and runs the
+    all-reduce on a side stream, so the next control steps overlap it (the statistics of a rollout are only read by the
+    logger after the rollout); ``result()`` joins the side stream back and returns the last reduced slot.  On CPU tensors
+    (gloo tests) it degrades to the synchronous call."""
+
+    def __init__(self, device, group=None):
+        self.device = torch.device(device)
+        self.group = group
+        self.side = torch.cuda.Stream(self.device) if self.device.type == "cuda" else None
+        self._last = None
+        self.submitted = 0
+
+    def submit(self, stats: torch.Tensor) -> None:
+        self.submitted += 1
+        if self.side is None:
+            self._last = reduce_rollout_stats(stats, self.group)
+            return
+        cur = torch.cuda.current_stream(self.device)
+        snap = stats.detach().clone()                 # on the stepping stream: the ring slot may be rewritten 64 steps later
+        self.side.wait_stream(cur)
+        with torch.cuda.stream(self.side):
+            snap.record_stream(self.side)
+            self._last = reduce_rollout_stats(snap, self.group)
+
+    def result(self):
+        if self.side is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self.side)
+        return self._last
