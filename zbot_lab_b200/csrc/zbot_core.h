@@ -822,6 +822,18 @@ struct SubstepOut {
 #ifndef ZB_UNROLL_SUB
 #define ZB_UNROLL_SUB 1   // the decimation loop of env_step_physics
 #endif
+// Tuning experiment (profiles/r2_notes.md "instruction fetch"): CTA barriers at phase boundaries keep the warps of a CTA in the
+// same stretch of the ~70 KB substep loop, so they share instruction-cache lines.  Level 1: once per substep; 2: also before the
+// backward and forward sweeps; 3: every backward-sweep iteration.  Only legal when every thread of the CTA is live (the
+// experiment's launches are); off (0) in the product build.
+#ifndef ZB_PHASE_BAR_LEVEL
+#define ZB_PHASE_BAR_LEVEL 0
+#endif
+#if defined(__CUDA_ARCH__) && ZB_PHASE_BAR_LEVEL > 0
+#define ZB_PHASE_BAR(lvl) do { if (ZB_PHASE_BAR_LEVEL >= (lvl)) __syncthreads(); } while (0)
+#else
+#define ZB_PHASE_BAR(lvl) do { } while (0)
+#endif
 #ifndef ZB_UNROLL_FWD
 #define ZB_UNROLL_FWD kUnroll
 #endif
@@ -872,6 +884,7 @@ ZB_PRAGMA_UNROLL(ZB_UNROLL_FK)
     else { scr(k, SC_SN) = sn; scr(k, SC_CS) = cs; }
     quat_mul_joint(Q, cs, sg * sn, T(AXIS_S) * sn);
   }
+  ZB_PHASE_BAR(2);
   // ---- backward sweep over bodies 6..0: rigid + contact terms, then eliminate the joint above ----
   SpInertia<T> IA;
   ZB_UNROLL for (int i = 0; i < 6; ++i) { IA.I[i] = T(0); IA.M[i] = T(0); }
@@ -910,6 +923,7 @@ ZB_PRAGMA_UNROLL(ZB_UNROLL_BWD)
 #endif
   for (int k = 6; k >= 1; --k) {
     const int j = k - 1;          // joint between body k and body k-1
+    ZB_PHASE_BAR(3);
     const T Sa[3] = {scr(j, SC_SA), scr(j, SC_SA + 1), scr(j, SC_SA + 2)};
     const T Sm[3] = {scr(j, SC_SM), scr(j, SC_SM + 1), scr(j, SC_SM + 2)};
     const T qd = scr(j, SC_QD);
@@ -1092,6 +1106,7 @@ ZB_PRAGMA_UNROLL(ZB_UNROLL_PTS)
     s.w[i] += dt * At[i];
     s.v[i] += dt * (Ab[i] + wxv[i]);
   }
+  ZB_PHASE_BAR(2);
   // ---- forward sweep: joint accelerations ----
 #if defined(__CUDACC__)
 ZB_PRAGMA_UNROLL(ZB_UNROLL_FWD)
@@ -1619,6 +1634,7 @@ ZB_PRAGMA_UNROLL(ZB_UNROLL_SUB)
 #endif
   for (int sub = 0; sub < P.decimation; ++sub) {
     T midf[15];
+    ZB_PHASE_BAR(1);
     if (Model::kFresh) {
       if (sub == P.decimation - 1) { ZB_UNROLL for (int k = 0; k < 6; ++k) po.qd_prev[k] = e.sim.qd[k]; }
     }

@@ -1207,6 +1207,8 @@ const StepVariant kStepVariants[] = {
     // chain sweeps unrolled by two: "u128x2" / "u128x3"
     {2128, 2, zbot_step_u2_kernel<128, 2>, 1}, {2128, 3, zbot_step_u2_kernel<128, 3>, 1},
     {2064, 7, zbot_step_u2_kernel_r<144>, 1}, {2032, 14, zbot_step_u2_kernel_r<144>, 1},   // "u64x7" / "u32x14": one wave at 65536 envs
+    // (nine warps per SM at the full budget -- 3 x 96 or 9 x 32 threads -- do not exist: the register file is per scheduler,
+    //  16384 words each, and the ninth warp puts three on one of them: ptxas caps such a shape at 168 registers and spills)
     // EXPERIMENTAL, opt-in (ZBOT_STEP_VARIANT=p128x2): two envs per thread, packed FP32 (zbot_step2_kernel).  31 % fewer
     // warp instructions per env, but 255 registers + spills at 1.7 warps per sub-partition: 84.0 vs 86.4 us at 65536 envs,
     // 59 vs 35 us at 4096 (profiles/r1_notes.md).
