@@ -17,6 +17,8 @@
 #include "../zbot_lab_b200/csrc/zbot_layout.h"
 #include "../zbot_lab_b200/csrc/zbot_pair.h"
 #include "../zbot_lab_b200/csrc/zbot_halves.h"
+#include "../zbot_lab_b200/csrc/zbot_h2.h"
+#include <type_traits>
 
 using namespace zbot;
 
@@ -215,6 +217,10 @@ static int port_substeps(const ZbotCfg* cfg, T* sim, const T* target, T* forces,
       }
       else if (model == 2) physics_substep<ModelWalkM>(P, s, tgt7, so, scr, midf);
       else if (model == 3) physics_substep_halves<ModelWalk>(P, s, tgt7, so, midf);   // two-halves elimination (csrc/zbot_halves.h)
+      else if (model == 4) {    // both halves packed in the two FP32 lanes of one thread (csrc/zbot_h2.h); float only
+        if constexpr (std::is_same<T, float>::value) physics_substep_h2_sim<ModelWalk>(P, s, tgt7, so, midf);
+        else physics_substep_halves<ModelWalk>(P, s, tgt7, so, midf);
+      }
       else physics_substep<ModelWalk>(P, s, tgt7, so, scr, midf);
     }
     for (int i = 0; i < 3; ++i) { w[i] = s.p[i]; w[7 + i] = s.v[i]; w[10 + i] = s.w[i]; }
@@ -327,6 +333,9 @@ int zbot_port_substeps_halves_f32(const ZbotCfg* cfg, float* sim, const float* t
 }
 int zbot_port_substeps_halves_f64(const ZbotCfg* cfg, double* sim, const double* target, double* forces, double* tau, int n, int nsub) {
   return port_substeps<double>(cfg, sim, target, forces, tau, n, nsub, 3);
+}
+int zbot_port_substeps_h2_f32(const ZbotCfg* cfg, float* sim, const float* target, float* forces, float* tau, int n, int nsub) {
+  return port_substeps<float>(cfg, sim, target, forces, tau, n, nsub, 4);
 }
 int zbot_port_substeps_snake_f32(const ZbotCfg* cfg, float* sim, const float* target, float* forces, float* tau, int n, int nsub) {
   return port_substeps<float>(cfg, sim, target, forces, tau, n, nsub, 1);

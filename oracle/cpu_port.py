@@ -23,6 +23,7 @@ SRCS = [os.path.join(HERE, "cpu_port.cpp"),
         os.path.join(ROOT, "zbot_lab_b200", "csrc", "zbot_model_constants.h"),
         os.path.join(ROOT, "zbot_lab_b200", "csrc", "zbot_pair.h"),
         os.path.join(ROOT, "zbot_lab_b200", "csrc", "zbot_halves.h"),
+        os.path.join(ROOT, "zbot_lab_b200", "csrc", "zbot_h2.h"),
         os.path.join(ROOT, "include", "zbot_b200.h")]
 
 
@@ -194,6 +195,7 @@ def substeps(sim: np.ndarray, target: np.ndarray, nsub: int, cfg: ZbotCfg | None
     tau = np.zeros((n, 6), dt)
     target = np.ascontiguousarray(target, dt)
     name = ("zbot_port_substeps_m_" if model == "m" else "zbot_port_substeps_halves_" if model == "halves" else
+            "zbot_port_substeps_h2_" if model == "h2" else
             "zbot_port_substeps_snake_" if snake else "zbot_port_substeps_")
     if terrain is not None:
         assert model == "m"

@@ -646,6 +646,38 @@ def test_halves_elimination_equals_the_one_chain_substep():
     assert np.median(dh) <= 2.0 * np.median(dx) + 1e-7 and np.quantile(dh, 0.99) <= 3.0 * np.quantile(dx, 0.99) + 1e-6
 
 
+def test_packed_halves_substep_is_the_halves_substep_lane_by_lane():
+    """csrc/zbot_h2.h (the arithmetic of the default GPU kernel beyond 9472 envs): both halves of the chain in the two FP32
+    lanes of one thread -- lane x eliminates bodies 0, 1, 2, lane y bodies 6, 5, 4, body 3 and the kinematics sweep stay
+    scalar.  On the host a lane pair is two plain floats, so without multiply-add contraction (the port's build) the packed
+    substep must reproduce the float32 halves form BIT FOR BIT: state, applied torques, foot and merged-body contact forces,
+    over 8 substeps with contact, PD saturation and joint wrap.  (And the halves form equals the one-chain substep:
+    test_halves_elimination_equals_the_one_chain_substep.)"""
+    from oracle import cpu_port
+    from zbot_lab_b200.utils import synthetic as syn
+    n = 700
+    rng = np.random.default_rng(9)
+    st = syn.synth_sim_state(rng, n)
+    keys = ("root_pos", "root_quat", "root_lin_vel", "root_ang_vel", "joint_pos", "joint_vel")
+    sim = np.concatenate([st[k].reshape(n, -1) for k in keys], 1).astype(np.float32)
+    sim[:40, 13:19] += np.float32(2 * np.pi - 0.05) * np.sign(rng.normal(size=(40, 6))).astype(np.float32)   # joints near the +-2 pi wrap
+    tgt = (sim[:, 13:19] + rng.normal(0, 0.6, (n, 6))).astype(np.float32)
+    a, b = sim.copy(), sim.copy()
+    touched = 0
+    for k in range(8):
+        fa, ta = cpu_port.substeps(a, tgt, 1, model="halves")
+        fb, tb = cpu_port.substeps(b, tgt, 1, model="h2")
+        assert np.array_equal(a, b) and np.array_equal(ta, tb) and np.array_equal(fa, fb), k
+        touched += int((np.abs(fa[:, 0, 2]) > 1.0).sum() + (np.abs(fa[:, 6, 2]) > 1.0).sum() + (np.abs(fa[:, 1:6]).max((1, 2)) > 0.1).sum())
+    assert touched > n
+    # four substeps in one call (the state stays packed across substeps) == four calls
+    c, d = sim.copy(), sim.copy()
+    cpu_port.substeps(c, tgt, 4, model="h2")
+    for k in range(4):
+        cpu_port.substeps(d, tgt, 1, model="h2")
+    assert np.array_equal(c, d)
+
+
 def test_unlimited_revolute_joints_wrap_at_two_pi_like_physx():
     """PhysX keeps the position of a revolute joint without limits inside [-2 pi, 2 pi] (the reference's own note,
     assets/test_articulation.py:18-20): a joint spinning past +2 pi re-enters at -2 pi (shift by 4 pi, same physical angle).

@@ -987,6 +987,7 @@ def test_unrolled_chain_sweeps_agree_with_the_rolled_kernel(monkeypatch, task):
     # rolled; unrolled with 2 CTAs/SM; unrolled with 3 CTAs/SM (168 registers: the instantiation the wave rule picks e.g. at
     # 49152 or 131072 envs; for the walking task that is ZBOT_STEP_VARIANT=u128x3)
     monkeypatch.setenv("ZBOT_W2", "0")       # the one-thread-per-env kernels (at this N the walking default is the two-warp kernel)
+    monkeypatch.setenv("ZBOT_H2", "0")       # ... with ONE chain per thread (the packed-halves kernel has no sweep-unroll variants)
     for unroll, ctas3 in (("1", "0"), ("2", "0"), ("2", "1")):
         monkeypatch.setenv("ZBOT_SWEEP_UNROLL", unroll)
         monkeypatch.setenv("ZBOT_CTAS3", ctas3)
@@ -1039,16 +1040,18 @@ def test_unrolled_chain_sweeps_agree_with_the_rolled_kernel(monkeypatch, task):
 def test_two_warp_kernel_agrees_with_the_one_thread_kernel_and_selection_rule(monkeypatch):
     """The walking step as two warps per 32 envs (csrc/zbot_w2_kernel.cuh: elimination from both feet towards body 3, the
     library's choice while an SM holds at most two warp pairs) and the one-thread-per-env kernel integrate the SAME model
-    with the SAME discretisation; they differ by float32 round-off only.  ONE step from identical states (ragged N, so a
-    CTA with dead lanes is covered), at every register-budget variant: time-outs / counters equal, observations within
+    with the SAME discretisation -- and so does the packed-halves kernel (csrc/zbot_h2.h: both halves of the chain in the two
+    FP32 lanes of one thread, the library's choice beyond 9472 envs); they differ by float32 round-off only.  ONE step from
+    identical states (ragged N, so a CTA with dead lanes is covered), at every register-budget variant: time-outs / counters equal, observations within
     the one-step bounds of DESIGN.md §6, termination flags equal on >= 99.5 % of the envs.  Plus the selection rule."""
     from zbot_lab_b200.utils import synthetic as syn
     n = 2048 + 37
     rng = np.random.default_rng(33)
     a = rng.normal(0, 0.7, (4, n, 6)).astype(np.float32)
     res, names = [], []
-    for env in ({"ZBOT_W2": "0"}, {}, {"ZBOT_W2_CTAS": "6"}, {"ZBOT_W2_CTAS": "8"}, {"ZBOT_W2_CTAS": "10"}):
-        for k in ("ZBOT_W2", "ZBOT_W2_CTAS"):
+    for env in ({"ZBOT_W2": "0", "ZBOT_H2": "0"}, {}, {"ZBOT_W2_CTAS": "6"}, {"ZBOT_W2_CTAS": "8"}, {"ZBOT_W2_CTAS": "10"},
+                {"ZBOT_W2": "0"}):        # last: the packed-halves kernel (csrc/zbot_h2.h), the default beyond 9472 envs
+        for k in ("ZBOT_W2", "ZBOT_W2_CTAS", "ZBOT_H2"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
@@ -1068,6 +1071,7 @@ def test_two_warp_kernel_agrees_with_the_one_thread_kernel_and_selection_rule(mo
         res.append(outs)
         st.close()
     assert names[0].startswith("zbot_step_kernel<false") and names[1] == "zbot_step_w2_kernel<3>" and names[3] == "zbot_step_w2_kernel<8>"
+    assert names[5].startswith("zbot_step_h2_kernel<")
     worst = 0.0
     for other in range(1, len(res)):
         for t in range(4):
@@ -1085,10 +1089,13 @@ def test_two_warp_kernel_agrees_with_the_one_thread_kernel_and_selection_rule(mo
             worst = max(worst, float(d.max()))
     print(f"two-warp vs one-thread kernel: worst one-step observation difference {worst:.3e}")
     # selection rule: two warps per 32 envs while an SM holds at most two pairs (148 SMs -> 9472 envs), one thread per env beyond
-    for k in ("ZBOT_W2", "ZBOT_W2_CTAS"):
+    # ... beyond that both halves in the two FP32 lanes of one thread, except where three CTAs/SM of the one-chain kernel hold
+    # every env in ONE wave and two do not (37888 < N <= 56832)
+    for k in ("ZBOT_W2", "ZBOT_W2_CTAS", "ZBOT_H2"):
         monkeypatch.delenv(k, raising=False)
-    for nn, want in ((4096, "zbot_step_w2_kernel<3>"), (9472, "zbot_step_w2_kernel<3>"), (9473, "zbot_step_kernel<false,128,2>"),
-                     (65536, "zbot_step_u2_kernel<128,2>")):
+    for nn, want in ((4096, "zbot_step_w2_kernel<3>"), (9472, "zbot_step_w2_kernel<3>"), (9473, "zbot_step_h2_kernel<128,2>"),
+                     (37888, "zbot_step_h2_kernel<128,2>"), (49152, "zbot_step_u2_kernel<128,3>"),
+                     (65536, "zbot_step_h2_kernel<128,2>"), (131072, "zbot_step_h2_kernel<128,2>")):
         st = _stepper(nn)
         assert st.kernel_name == want, (nn, st.kernel_name)
         st.close()

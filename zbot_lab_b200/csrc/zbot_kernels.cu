@@ -23,6 +23,7 @@
 
 #include "zbot_layout.h"
 #include "zbot_pair.h"
+#include "zbot_h2.h"
 #include "zbot_halves.h"
 
 using namespace zbot;
@@ -283,7 +284,11 @@ __device__ __noinline__ void step_export_store(const StepExport<float>& ex, cons
 // sc.packed_rows: host-facing output layout -- ONE row of 25 words per env [obs 23 | reward | flags word
 // (terminated | truncated << 8)] written to `obs` ([N][25]); `rew` / `terminated` / `truncated` are not touched.
 // A run-time flag of the SAME kernel (not a second instantiation), so step_host and step are bit-identical.
-template <bool kExport, int kUnroll = 1>
+// kPhys: 0 = one chain per thread (physics_substep), 1 = both halves of the chain in the two FP32 lanes (zbot_h2.h)
+constexpr int kH2RowF2 = HALF_SCR_WORDS + 4;   // 55 float2 per thread (odd: conflict-free 64-bit rows): 51 scratch words + the raw actions
+static_assert((kH2RowF2 & 1) == 1 && 2 * kH2RowF2 <= SCR_STRIDE + 1, "h2 scratch row");
+constexpr int kStepRowWords = SCR_STRIDE + 1;  // floats of dynamic shared memory per thread of a walking step kernel
+template <bool kExport, int kUnroll = 1, int kPhys = 0>
 __device__ __forceinline__ void
 zbot_step_body(const Params<float>& P, const DefaultPose& dp,
                  float4* __restrict__ state, int64_t* __restrict__ ep_len_buf,
@@ -310,7 +315,8 @@ zbot_step_body(const Params<float>& P, const DefaultPose& dp,
     float rs[MAX_TERMS];
 #pragma unroll
     for (int i = 0; i < MAX_TERMS; ++i) rs[i] = 0.f;
-    SmemScratch scr{smem + threadIdx.x * SCR_STRIDE};
+    float* const row = smem + threadIdx.x * (kPhys == 1 ? 2 * kH2RowF2 : SCR_STRIDE);
+    float* const raw_park = row + (kPhys == 1 ? 2 * HALF_SCR_WORDS : SCR_RAW_ACT);
     const float2* a2p = reinterpret_cast<const float2*>(actions + (size_t)e * 6);
     int64_t ep;
     StepExport<float> ex;   // kExport only (dead otherwise): the articulation / sensor view the MDP phase saw
@@ -330,9 +336,15 @@ zbot_step_body(const Params<float>& P, const DefaultPose& dp,
         // read ONCE (the buffer may be pinned host memory: zero-copy over PCIe) and parked in this thread's
         // shared-memory row for phase C
 #pragma unroll
-        for (int k = 0; k < 6; ++k) scr.base[SCR_RAW_ACT + k] = raw[k];
+        for (int k = 0; k < 6; ++k) raw_park[k] = raw[k];
         // ---- phase B: 4 physics substeps; the MDP state is not even loaded yet (register budget) ----
-        env_step_physics<ModelWalk, kUnroll>(P, es, raw, po, scr, kExport ? &ex : (StepExport<float>*)nullptr);
+        if constexpr (kPhys == 1) {
+          SmemScratch2 scr{reinterpret_cast<float2*>(row)};
+          env_step_physics_h2<ModelWalk>(P, es, raw, po, scr, kExport ? &ex : (StepExport<float>*)nullptr);
+        } else {
+          SmemScratch scr{row};
+          env_step_physics<ModelWalk, kUnroll>(P, es, raw, po, scr, kExport ? &ex : (StepExport<float>*)nullptr);
+        }
       }
       // ---- phase C: the 9 "late" quads, the start-of-step state S0 again (still unmodified in global
       //      memory -> L2 hit) for the one-step-stale quantities, the raw actions again, then the MDP ----
@@ -349,7 +361,7 @@ zbot_step_body(const Params<float>& P, const DefaultPose& dp,
       }
       float raw[6];
 #pragma unroll
-      for (int k = 0; k < 6; ++k) raw[k] = scr.base[SCR_RAW_ACT + k];
+      for (int k = 0; k < 6; ++k) raw[k] = raw_park[k];
       ep = ep_len_buf[e];
       env_step_finish(P, es, s0, raw, po, ep, dp.feet_pos, dp.base_quat, out, rs, kExport ? &ex : (StepExport<float>*)nullptr);
       if (kExport) step_export_store(ex, xp, e);
@@ -515,6 +527,14 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) zbot_step_u2_kernel(Z
 // launched -- and benchmarked -- above 18944 envs, plus the stores of the view its MDP phase saw
 __global__ void __launch_bounds__(128, 1) zbot_step_u2_export_kernel(ZB_STEP_ARGS) {
   zbot_step_body<true, 2>(ZB_STEP_CALL);
+}
+// both halves of the chain in the two FP32 lanes of one thread (zbot_h2.h): "h128x2"
+template <int kMaxThreads, int kMinBlocks>
+__global__ void __launch_bounds__(kMaxThreads, kMinBlocks) zbot_step_h2_kernel(ZB_STEP_ARGS) {
+  zbot_step_body<false, 1, 1>(ZB_STEP_CALL);
+}
+__global__ void __launch_bounds__(128, 1) zbot_step_h2_export_kernel(ZB_STEP_ARGS) {
+  zbot_step_body<true, 1, 1>(ZB_STEP_CALL);
 }
 #include "zbot_w2_kernel.cuh"   // two warps per 32 envs (the default walking-v2 step kernel)
 // unrolled sweeps under a direct register cap (single-wave experiments: 14 warps/SM hold 65536 envs at <= 146 registers)
@@ -1213,6 +1233,8 @@ const StepVariant kStepVariants[] = {
     // warp instructions per env, but 255 registers + spills at 1.7 warps per sub-partition: 84.0 vs 86.4 us at 65536 envs,
     // 59 vs 35 us at 4096 (profiles/r1_notes.md).
     {1128, 2, zbot_step2_kernel<128, 2>, 2},
+    // both halves of one env packed in the two FP32 lanes of one thread (zbot_h2.h): "h128x2"
+    {3128, 2, zbot_step_h2_kernel<128, 2>, 1},
 };
 constexpr int kNumStepVariants = (int)(sizeof(kStepVariants) / sizeof(kStepVariants[0]));
 
@@ -1340,9 +1362,10 @@ static int create_impl(const ZbotCfg* cfg, int device, ZbotHandle* h) {
   ZB_CUDA(cudaFuncSetAttribute(zbot_mdp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * kHistRow * 4));
   for (int v = 0; v < kNumStepVariants; ++v)
     ZB_CUDA(cudaFuncSetAttribute((const void*)kStepVariants[v].fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 128 * SCR_STRIDE * 4 * kStepVariants[v].envs_per_thread));
-  ZB_CUDA(cudaFuncSetAttribute(zbot_step_kernel<true, 128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
-  ZB_CUDA(cudaFuncSetAttribute(zbot_step_u2_export_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
+                                 128 * kStepRowWords * 4 * kStepVariants[v].envs_per_thread));
+  ZB_CUDA(cudaFuncSetAttribute(zbot_step_kernel<true, 128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * kStepRowWords * 4));
+  ZB_CUDA(cudaFuncSetAttribute(zbot_step_u2_export_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * kStepRowWords * 4));
+  ZB_CUDA(cudaFuncSetAttribute(zbot_step_h2_export_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * kStepRowWords * 4));
   ZB_CUDA(cudaFuncSetAttribute(zbot_snake_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
   ZB_CUDA(cudaFuncSetAttribute(zbot_snake_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
   ZB_CUDA(cudaFuncSetAttribute(zbot_v4_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
@@ -1371,6 +1394,7 @@ static int create_impl(const ZbotCfg* cfg, int device, ZbotHandle* h) {
     int vt = 0, vc = 0;
     h->variant = -1;
     if (sv && sv[0] == 'p' && sscanf(sv + 1, "%dx%d", &vt, &vc) == 2) h->variant = find_variant(1000 + vt, vc);
+    else if (sv && sv[0] == 'h' && sscanf(sv + 1, "%dx%d", &vt, &vc) == 2) h->variant = find_variant(3000 + vt, vc);
     else if (sv && sv[0] == 'u' && sscanf(sv + 1, "%dx%d", &vt, &vc) == 2) h->variant = find_variant(2000 + vt, vc);
     else if (sv && sscanf(sv, "%dx%d", &vt, &vc) == 2) h->variant = find_variant(vt, vc);
     // default register budget: by wave count, below; the sweeps unrolled by two as soon as a
@@ -1387,6 +1411,15 @@ static int create_impl(const ZbotCfg* cfg, int device, ZbotHandle* h) {
       const int cap2 = 2 * h->num_sms * 128, cap3 = 3 * h->num_sms * 128;
       const int w2 = (cfg->num_envs + cap2 - 1) / cap2, w3 = (cfg->num_envs + cap3 - 1) / cap3;
       h->variant = find_variant((h->unroll2 ? 2000 : 0) + 128, (w3 < w2) ? 3 : 2);
+      // Round 2: both halves of the chain in the two FP32 lanes of one thread (zbot_h2.h, "h128x2": 250 registers, no spill,
+      // 27 % fewer warp instructions).  Back to back on B200 (tools/time_h2.py): 31.6 vs 32.2 us at 16384 envs, 39.9 vs 41.4
+      // at 32768, 73.2 vs 77.8 at 65536, 125.2 vs 139.6 at 131072, 241.8 vs 248.0 at 262144.  The one window it loses is
+      // where three CTAs/SM of the 168-register kernel hold ALL envs in one wave and two CTAs/SM do not
+      // (37888 < N <= 56832: 55.2 vs 59.2 us at 49152).  ZBOT_H2=0 restores the one-chain kernels.
+      const char* sh = getenv("ZBOT_H2");
+      const bool h2_on = sh ? (atoi(sh) != 0) : true;
+      const bool one_wave_of_three = cfg->num_envs > cap2 && cfg->num_envs <= cap3;
+      if (h2_on && cfg->task == ZBOT_TASK_WALKING_V2 && !one_wave_of_three) h->variant = find_variant(3128, 2);
     }
     {
       const int cap2 = 2 * h->num_sms * 128, cap3 = 3 * h->num_sms * 128;
@@ -1417,6 +1450,7 @@ static int create_impl(const ZbotCfg* cfg, int device, ZbotHandle* h) {
       case ZBOT_TASK_WALKING_M: snprintf(h->kernel_name, sizeof(h->kernel_name), "zbot_m_step_kernel<false,%d,%d>", u, u == 2 ? c : 2); break;
       default:
         if (h->w2) snprintf(h->kernel_name, sizeof(h->kernel_name), "zbot_step_w2_kernel<%d>", h->w2_ctas);
+        else if (v.threads >= 3000) snprintf(h->kernel_name, sizeof(h->kernel_name), "zbot_step_h2_kernel<%d,%d>", v.threads % 1000, v.ctas);
         else if (v.threads >= 2000) snprintf(h->kernel_name, sizeof(h->kernel_name), "zbot_step_u2_kernel<%d,%d>", v.threads % 1000, v.ctas);
         else if (v.threads >= 1000) snprintf(h->kernel_name, sizeof(h->kernel_name), "zbot_step2_kernel<%d,%d>", v.threads % 1000, v.ctas);
         else snprintf(h->kernel_name, sizeof(h->kernel_name), "zbot_step_kernel<false,%d,%d>", v.threads, v.ctas);
@@ -1462,7 +1496,7 @@ static int step_impl(ZbotHandle* h, const float* actions, float* obs, float* rew
   int block = pick_block(h, n);
   if (!walk) { block = 128; while (block > 32 && (n + block - 1) / block < 2 * h->num_sms) block >>= 1; }
   const int grid = (walk_any && h->w2) ? (n + 31) / 32 : (n + block * ept - 1) / (block * ept);
-  const size_t smem = (size_t)block * SCR_STRIDE * sizeof(float) * ept;   // >= obs rows (23/thread) and stats (704 floats)
+  const size_t smem = (size_t)block * kStepRowWords * sizeof(float) * ept;   // >= obs rows (23/thread) and stats (704 floats)
   StatsCtx sc{h->partials, h->ring, slot, prev, h->inv_episode_s, 0, h->rng_ctr, 0};
   ctx_spread(sc, h);
   cudaStream_t s = (cudaStream_t)stream;
@@ -1507,7 +1541,10 @@ static int step_impl(ZbotHandle* h, const float* actions, float* obs, float* rew
       w2_fn(h->w2_ctas)<<<(n + 31) / 32, 64, kW2Smem, s>>>(h->P, h->dp, h->state, h->ep_len, actions, obs, rew, terminated,
                                                           truncated, n, 0, n, sc, xp);
       zbot_w2_export_view_kernel<<<vg, vb, 0, s>>>(xp, n);
-    } else if (h->unroll2)
+    } else if (kStepVariants[h->variant].threads >= 3000)
+      zbot_step_h2_export_kernel<<<grid, block, smem, s>>>(h->P, h->dp, h->state, h->ep_len, actions, obs, rew, terminated,
+                                                         truncated, n, 0, n, sc, xp);
+    else if (h->unroll2)
       zbot_step_u2_export_kernel<<<grid, block, smem, s>>>(h->P, h->dp, h->state, h->ep_len, actions, obs, rew, terminated,
                                                          truncated, n, 0, n, sc, xp);
     else
@@ -1585,7 +1622,7 @@ int zbot_step_host(ZbotHandle* h, const float* host_actions, float* host_rows, i
   int block = kStepVariants[vi].threads % 1000;
   while (block > 32 && (n + block - 1) / block < 2 * h->num_sms) block >>= 1;
   const int grid = (n + block - 1) / block;
-  const size_t smem = (size_t)block * SCR_STRIDE * sizeof(float);
+  const size_t smem = (size_t)block * kStepRowWords * sizeof(float);
   cudaStream_t s = (cudaStream_t)stream;
   StatsCtx sc{h->partials, h->ring, stats_slot, prev_slot, h->inv_episode_s, 0, h->rng_ctr, 1};
   ctx_spread(sc, h);
