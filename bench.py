@@ -557,10 +557,15 @@ def main():
             # the bound that actually applies: warp instructions issued per clock per SM sub-partition, and the FP32 FLOP rate
             # (2 x FFMA + FMUL + FADD thread instructions of the committed capture / live kernel time) against the FP32 peak
             inst = float(prof["smsp_inst_executed"])
-            flop = 32.0 * (2.0 * prof["ffma"] + prof["fmul"] + prof["fadd"])
+            # scalar FP32 from the sass_thread_inst counters; the packed forms (FFMA2 / FMUL2 / FADD2: two FP32 operations per
+            # lane, the packed-halves kernel) only appear in the per-opcode counts of the source page
+            packed = [float(prof.get(k, 0.0)) for k in ("op_ffma2", "op_fmul2", "op_fadd2")]
+            flop = 32.0 * (2.0 * prof["ffma"] + prof["fmul"] + prof["fadd"] + 2.0 * (2.0 * packed[0] + packed[1] + packed[2]))
             line["fp32_issue"] = {
                 "achieved_inst_per_clk_per_smsp": inst / (148 * 4) / (kern_ms * 1e-3 * clk_hz), "nominal": 1.0,
-                "warp_instructions_per_launch": inst, "fp32_share_of_instructions": (prof["ffma"] + prof["fmul"] + prof["fadd"]) / inst,
+                "warp_instructions_per_launch": inst,
+                "fp32_share_of_instructions": (prof["ffma"] + prof["fmul"] + prof["fadd"] + sum(packed)) / inst,
+                "packed_fp32_share_of_instructions": sum(packed) / inst,
                 "fp32_tflops": flop / (kern_ms * 1e-3) / 1e12, "fp32_peak_tflops": FP32_PEAK_TFLOPS,
                 "fp32_peak_frac": flop / (kern_ms * 1e-3) / 1e12 / FP32_PEAK_TFLOPS, "sm_clock_mhz": clk_hz / 1e6,
                 "registers_per_thread": prof.get("registers"), "warps_per_scheduler": prof.get("warps_per_scheduler"),

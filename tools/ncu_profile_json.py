@@ -1,7 +1,12 @@
 """Turn one `ncu --set full --clock-control none` capture of the step kernel into the tracked summary bench.py reads.
 
-    python tools/ncu_profile_json.py gpurun_out/prof_step65536.ncu-rep 65536 [kernel-name-substring]
+    python tools/ncu_profile_json.py <capture.ncu-rep | raw-page.csv> 65536 [kernel-name-substring] [source-page.csv[.gz]]
         -> profiles/step_65536.json
+
+(`tools/capture_profiles.sh` reduces a capture to its raw / source CSV pages on the GPU box -- the .ncu-rep is 25 MB -- so the
+summary can be rebuilt from those.)  The optional source page supplies the executed-instruction counts per SASS opcode: the
+`smsp__sass_thread_inst_executed_op_f*` metrics count the scalar FFMA / FMUL / FADD only, not the packed FFMA2 / FMUL2 / FADD2
+the packed-halves kernel issues.
 
 The summary carries the source hash of the kernel sources (bench.csrc_hash), so bench.py refuses it when the kernel has
 changed since the capture (VERDICT r1 "measurement hygiene": no typed-in profile constants).  Per-launch values are the
@@ -23,9 +28,35 @@ _SCALE = {"": 1.0, "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte
 
 
 def raw_rows(rep):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    if rep.endswith(".csv"):
+        out = open(rep).read()
+    else:
+        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(out.splitlines()))
     return rows[0], rows[1], rows[2:]
+
+
+def opcode_counts(path):
+    """Executed warp instructions per SASS opcode and per launch, from `ncu --page source --csv` (one table per launch)."""
+    import collections
+    import gzip
+    import re
+    fh = gzip.open(path, "rt") if path.endswith(".gz") else open(path)
+    ops, tables, col = collections.Counter(), 0, None
+    for r in csv.reader(fh):
+        if r and r[0] == "Address":
+            tables += 1
+            col = {k: i for i, k in enumerate(r)}
+            continue
+        if col is None or len(r) <= col["Instructions Executed"]:
+            continue
+        try:
+            n = int(r[col["Instructions Executed"]])
+        except ValueError:
+            continue
+        m = re.match(r"\s*(@!?U?P\d+\s+)?([A-Z0-9_]+)", r[col["Source"]])
+        ops[m.group(2) if m else "?"] += n
+    return {k: v / max(tables, 1) for k, v in ops.items()}, tables
 
 
 def main():
@@ -69,6 +100,13 @@ def main():
         "stall_long_scoreboard_per_issue": med("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio"),
         "stall_not_selected_per_issue": med("smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio"),
     }
+    if len(sys.argv) > 4:
+        ops, tables = opcode_counts(sys.argv[4])
+        tot = sum(ops.values())
+        prof["opcode_source"] = f"{os.path.basename(sys.argv[4])}: ncu source page, {tables} launch(es), executed warp instructions per launch"
+        prof["opcodes_total"] = tot
+        for k in ("FFMA", "FMUL", "FADD", "FFMA2", "FMUL2", "FADD2", "MOV", "LDS", "STS", "MUFU", "FSEL", "BRA"):
+            prof["op_" + k.lower()] = ops.get(k, 0.0)
     out = os.path.join(ROOT, "profiles", f"step_{n_envs}.json")
     with open(out, "w") as f:
         json.dump(prof, f, indent=1)
