@@ -234,9 +234,10 @@ def _gpu_state_vec(st):
                                                  "joint_pos", "joint_vel")], -1).cpu().numpy().astype(np.float64)
 
 
-def test_fused_step_dynamics_one_step_vs_float64_oracle():
+def test_fused_step_dynamics_one_step_vs_float64_oracle(walk_kernel):
     """Teacher forcing: from identical states, ONE control step (4 substeps) of the float32 kernel
-    stays within 2e-4 (positions / angles) and 2e-2 (velocities) of the independent float64 oracle."""
+    stays within 2e-4 (positions / angles) and 2e-2 (velocities) of the independent float64 oracle --
+    for each of the three step kernels (two warps per 32 envs, packed halves, one chain)."""
     from oracle.full_step_oracle import FullStepOracle
     from zbot_lab_b200.utils import synthetic as syn
     n = 256
@@ -244,6 +245,7 @@ def test_fused_step_dynamics_one_step_vs_float64_oracle():
     fo = FullStepOracle(n)
     fo.reset_all()
     st = _stepper(n)
+    assert st.kernel_name.startswith(walk_kernel), st.kernel_name
     st.reset_idx(None)
     worst_q = worst_v = 0.0
     for t in range(12):
@@ -271,16 +273,17 @@ def test_fused_step_dynamics_one_step_vs_float64_oracle():
     st.close()
 
 
-def test_fused_step_50_step_horizon_vs_float64_oracle():
+def test_fused_step_50_step_horizon_vs_float64_oracle(walk_kernel):
     """north_star: dynamics within a STATED tolerance over a fixed 50-step horizon from identical
     initial states.  Stated tolerance: joint positions 5e-3 rad and base position
-    5e-3 m (max over envs that neither side terminated), median <= 1e-4."""
+    5e-3 m (max over envs that neither side terminated), median <= 1e-4.  Each of the three step kernels."""
     from oracle.full_step_oracle import FullStepOracle
     n = 256
     rng = np.random.default_rng(9)
     fo = FullStepOracle(n)
     fo.reset_all()
     st = _stepper(n)
+    assert st.kernel_name.startswith(walk_kernel), st.kernel_name
     st.reset_idx(None)
     alive = np.ones(n, bool)
     for t in range(50):

@@ -38,11 +38,13 @@ def _momentum(state, model=None):
     return o.energy_momentum()
 
 
-def test_free_fall_is_exact_and_leaves_the_joints_alone():
+def test_free_fall_is_exact_and_leaves_the_joints_alone(walk_kernel):
     """No contact, no drive: every body accelerates at -g, so v_z = -g t exactly for semi-implicit Euler, the fall
-    distance is g dt^2 k (k + 1) / 2, and the joints of a uniformly accelerated articulated body do not move."""
+    distance is g dt^2 k (k + 1) / 2, and the joints of a uniformly accelerated articulated body do not move.
+    (Each of the three walking step kernels.)"""
     n, steps = 256, 10
     st = _stepper(n, kp=0.0, kd=0.0, contact_alpha=0.0)
+    assert st.kernel_name.startswith(walk_kernel), st.kernel_name
     rp = st.state.get("root_pos")
     rp[:, 2] += 2.0
     st.state.set("root_pos", rp)
@@ -61,7 +63,7 @@ def test_free_fall_is_exact_and_leaves_the_joints_alone():
     st.close()
 
 
-def test_momentum_and_energy_drift_is_first_order_in_free_flight():
+def test_momentum_and_energy_drift_is_first_order_in_free_flight(walk_kernel):
     """g = 0, no contact, no drive, random spin and joint velocities.  Semi-implicit Euler in generalised coordinates
     conserves momentum and energy only to first order in dt: over the same 0.2 s the drift with dt = 2.5 ms must be
     about half the drift with dt = 5 ms (a wrong bias / Coriolis term would give an O(1), dt-independent error), and
@@ -71,6 +73,7 @@ def test_momentum_and_energy_drift_is_first_order_in_free_flight():
     for sim_dt, steps in ((0.005, 10), (0.0025, 20)):
         rng = np.random.default_rng(0)
         st = _stepper(n, kp=0.0, kd=0.0, contact_alpha=0.0, gravity=0.0, sim_dt=sim_dt)
+        assert st.kernel_name.startswith(walk_kernel), st.kernel_name
         rp = st.state.get("root_pos")
         rp[:, 2] += 2.0
         st.state.set("root_pos", rp)
@@ -88,13 +91,15 @@ def test_momentum_and_energy_drift_is_first_order_in_free_flight():
     assert p5 < 0.01 and l5 < 0.01 and e5 < 0.02, drifts
 
 
-def test_static_stand_carries_the_weight():
+def test_static_stand_carries_the_weight(walk_kernel):
     """Zero actions from the default pose: the PD drive holds the pose, the two feet carry m g between them, the base
-    stays at the reference's printed height 0.2545 m (…env_v2.py:403), nothing terminates."""
+    stays at the reference's printed height 0.2545 m (…env_v2.py:403), nothing terminates.  (Each of the three kernels,
+    through its own export hook.)"""
     from zbot_lab_b200 import native
     from zbot_lab_b200.stepper import NativeStepper
     n = 64
     st = NativeStepper(n, DEV)
+    assert st.kernel_name.startswith(walk_kernel), st.kernel_name
     st.reset_idx(None)
     ex = st.alloc_export()
     for t in range(100):
@@ -135,11 +140,12 @@ def test_sliding_snake_decelerates_at_mu_g():
     st.close()
 
 
-def test_long_random_rollout_stays_bounded():
+def test_long_random_rollout_stays_bounded(walk_kernel):
     """2000 control steps of random actions with every termination disabled: contact + stiff implicit drive never blow
-    up (velocities bounded, quaternion normalised, no NaN)."""
+    up (velocities bounded, quaternion normalised, no NaN).  (Each of the three walking step kernels.)"""
     n = 512
     st = _stepper(n)
+    assert st.kernel_name.startswith(walk_kernel), st.kernel_name
     g = torch.Generator(device=DEV).manual_seed(3)
     for t in range(2000):
         st.step(torch.randn(n, 6, device=DEV, generator=g) * 2.0)
