@@ -1281,6 +1281,7 @@ def test_m_rough_kernel_matches_oracle_and_host_build_on_the_height_field():
         assert same.mean() >= 0.99 and np.array_equal(trunc.cpu().numpy().astype(bool), tr_h)
         d = np.abs(obs.cpu().numpy() - o_h)[same]
         assert d[:, :4].max() <= 1e-3 and d[:, 7:13].max() <= 1e-3 and d[:, 13:19].max() <= 5e-2
+        assert np.quantile(d[:, 7:13].max(1), 0.99) <= 1e-4 and np.quantile(d[:, 13:19].max(1), 0.99) <= 1e-2    # the bulk sits at round-off
         worst = max(worst, float(d[:, 7:13].max()))
         if r["log"]:
             ups, downs = ups + r["log"]["#move_up"], downs + r["log"]["#move_down"]
@@ -1314,9 +1315,16 @@ def test_m_kernel_equals_host_build_noise_and_internal_rng():
         same = (term.cpu().numpy().astype(bool) == t2)
         assert np.array_equal(trunc.cpu().numpy().astype(bool), tr2) and same.mean() >= 0.995
         d = np.abs(obs.cpu().numpy() - o2)[same]
-        # one-step bounds: 1e-3 on quaternion / joint positions, 5e-2 rad/s on joint velocities (kp 20 / kd 0.5 drive)
-        assert d[:, :13].max() < 1e-3 and d[:, 13:19].max() < 5e-2 and d[:, 19:].max() == 0
-        assert np.abs(rew.cpu().numpy() - r2)[same].max() < 2e-3
+        # teacher-forced ONE-step bounds (the state is re-synchronised below): quaternion / command / joint positions
+        # max 3e-4, 99 % <= 5e-5, median <= 3e-6 (observed 9.6e-5 / 1.7e-5 / 7e-7); joint velocities (kp 20 / kd 0.5 drive,
+        # contact thresholds can flip) max 5e-2, 99 % <= 5e-3, median <= 2e-4 (observed 1.8e-2 / 1.8e-3 / 5e-5)
+        assert same.all()
+        pos_d, vel_d = d[:, :13].max(1), d[:, 13:19].max(1)
+        assert pos_d.max() < 3e-4 and np.quantile(pos_d, 0.99) < 5e-5 and np.median(pos_d) < 3e-6, (pos_d.max(), np.quantile(pos_d, 0.99))
+        assert vel_d.max() < 5e-2 and np.quantile(vel_d, 0.99) < 5e-3 and np.median(vel_d) < 2e-4, (vel_d.max(), np.quantile(vel_d, 0.99))
+        assert d[:, 19:].max() == 0
+        dr = np.abs(rew.cpu().numpy() - r2)[same]
+        assert np.quantile(dr, 0.99) < 1e-4 and dr.max() < 1e-2, (np.quantile(dr, 0.99), dr.max())
         for k, w in STATE_FIELDS.items():
             pe.field(k, w)[:] = st.state.get(k).cpu().numpy()
         pe.ep_len[:] = st.episode_length_buf.cpu().numpy()

@@ -651,7 +651,8 @@ zbot_snake_step_kernel(const __grid_constant__ Params<float> P, const __grid_con
 // ---------------------------------------------------------------------------------------------
 static_assert(sizeof(V4Export<float>) / sizeof(float) == ZBOT_V4_EXPORT_WORDS, "V4Export layout");
 
-template <bool kExport, int kUnroll = 1, int kMinBlocks = 2>
+// kH2: the physics phase as packed halves (zbot_h2.h), like zbot_step_h2_kernel
+template <bool kExport, int kUnroll = 1, int kMinBlocks = 2, bool kH2 = false>
 __global__ void __launch_bounds__(128, kMinBlocks)
 zbot_v4_step_kernel(const __grid_constant__ Params<float> P, float4* __restrict__ state, int64_t* __restrict__ ep_len_buf,
                     const float* __restrict__ actions, const float* __restrict__ rand, uint64_t seed,
@@ -675,7 +676,8 @@ zbot_v4_step_kernel(const __grid_constant__ Params<float> P, float4* __restrict_
     float rs[MAX_TERMS];
 #pragma unroll
     for (int i = 0; i < MAX_TERMS; ++i) rs[i] = 0.f;
-    SmemScratch scr{smem + threadIdx.x * SCR_STRIDE};
+    float* const row = smem + threadIdx.x * (kH2 ? 2 * kH2RowF2 : SCR_STRIDE);
+    float* const raw_park = row + (kH2 ? 2 * HALF_SCR_WORDS : SCR_RAW_ACT);
     const float2* a2p = reinterpret_cast<const float2*>(actions + (size_t)e * 6);
     {
       float w[4 * EARLY_QUADS];
@@ -689,8 +691,14 @@ zbot_v4_step_kernel(const __grid_constant__ Params<float> P, float4* __restrict_
       const float2 a0 = __ldg(a2p), a1 = __ldg(a2p + 1), a2v = __ldg(a2p + 2);
       const float raw[6] = {a0.x, a0.y, a1.x, a1.y, a2v.x, a2v.y};
 #pragma unroll
-      for (int k = 0; k < 6; ++k) scr.base[SCR_RAW_ACT + k] = raw[k];
-      env_step_physics<ModelWalkV4, kUnroll>(P, es, raw, po, scr, (StepExport<float>*)nullptr);
+      for (int k = 0; k < 6; ++k) raw_park[k] = raw[k];
+      if constexpr (kH2) {
+        SmemScratch2 scr{reinterpret_cast<float2*>(row)};
+        env_step_physics_h2<ModelWalkV4>(P, es, raw, po, scr, (StepExport<float>*)nullptr);
+      } else {
+        SmemScratch scr{row};
+        env_step_physics<ModelWalkV4, kUnroll>(P, es, raw, po, scr, (StepExport<float>*)nullptr);
+      }
     }
     {
       float w[ZBOT_STATE_WORDS - 4 * EARLY_QUADS];
@@ -699,7 +707,7 @@ zbot_v4_step_kernel(const __grid_constant__ Params<float> P, float4* __restrict_
     }
     float raw[6];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) raw[k] = scr.base[SCR_RAW_ACT + k];
+    for (int k = 0; k < 6; ++k) raw[k] = raw_park[k];
     float rnd[V4_NUM_RAND];
     if (rand) {
       const float2* rp = reinterpret_cast<const float2*>(rand + (size_t)e * V4_NUM_RAND);
@@ -1204,6 +1212,7 @@ struct ZbotHandle {
   int spread_all_reset;          // zbot_set_all_reset_spread
   int w2_ctas;                   // resident 64-thread CTAs per SM the w2 kernel is compiled for (register budget); ZBOT_W2_CTAS
   bool w2;                       // walking-v2: the two-warps-per-32-envs kernel (zbot_w2_kernel.cuh); ZBOT_W2=0 / a ZBOT_STEP_VARIANT restore the one-thread-per-env kernels
+  bool v4_h2;                    // walking-v4: physics phase as packed halves (same rule as the walking-v2 kernel)
   char kernel_name[96];          // zbot_step_kernel_name
   TerrainArgs terrain;           // zbot_bind_terrain (heights == nullptr: flat)
   int mdp_tile;
@@ -1368,23 +1377,25 @@ static int create_impl(const ZbotCfg* cfg, int device, ZbotHandle* h) {
   ZB_CUDA(cudaFuncSetAttribute(zbot_step_h2_export_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * kStepRowWords * 4));
   ZB_CUDA(cudaFuncSetAttribute(zbot_snake_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
   ZB_CUDA(cudaFuncSetAttribute(zbot_snake_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
-  ZB_CUDA(cudaFuncSetAttribute(zbot_v4_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
-  ZB_CUDA(cudaFuncSetAttribute(zbot_v4_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
+  ZB_CUDA(cudaFuncSetAttribute(zbot_v4_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * kStepRowWords * 4));
+  ZB_CUDA(cudaFuncSetAttribute(zbot_v4_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * kStepRowWords * 4));
   ZB_CUDA(cudaFuncSetAttribute(zbot_snake_step_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
-  ZB_CUDA(cudaFuncSetAttribute(zbot_v4_step_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
+  ZB_CUDA(cudaFuncSetAttribute(zbot_v4_step_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * kStepRowWords * 4));
   ZB_CUDA(cudaFuncSetAttribute(zbot_m_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
   ZB_CUDA(cudaFuncSetAttribute(zbot_m_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
   ZB_CUDA(cudaFuncSetAttribute(zbot_m_step_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
   ZB_CUDA(cudaFuncSetAttribute(zbot_snake_step_kernel<false, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
   ZB_CUDA(cudaFuncSetAttribute(zbot_snake_step_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
-  ZB_CUDA(cudaFuncSetAttribute(zbot_v4_step_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
+  ZB_CUDA(cudaFuncSetAttribute(zbot_v4_step_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * kStepRowWords * 4));
   ZB_CUDA(cudaFuncSetAttribute(zbot_m_step_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
   ZB_CUDA(cudaFuncSetAttribute((zbot_m_step_kernel<true, 2, 2, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
   ZB_CUDA(cudaFuncSetAttribute((zbot_m_step_kernel<true, 1, 2, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
   ZB_CUDA(cudaFuncSetAttribute((zbot_m_step_kernel<false, 2, 3, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
   ZB_CUDA(cudaFuncSetAttribute((zbot_m_step_kernel<false, 2, 2, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
   ZB_CUDA(cudaFuncSetAttribute((zbot_m_step_kernel<false, 1, 2, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
-  ZB_CUDA(cudaFuncSetAttribute(zbot_v4_step_kernel<false, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
+  ZB_CUDA(cudaFuncSetAttribute(zbot_v4_step_kernel<false, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * kStepRowWords * 4));
+  ZB_CUDA(cudaFuncSetAttribute((zbot_v4_step_kernel<false, 2, 2, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * kStepRowWords * 4));
+  ZB_CUDA(cudaFuncSetAttribute((zbot_v4_step_kernel<true, 2, 2, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * kStepRowWords * 4));
   ZB_CUDA(cudaFuncSetAttribute(zbot_m_step_kernel<false, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * SCR_STRIDE * 4));
   {
     // register-budget variant of the step kernel = resident 128-thread CTAs per SM it is compiled for.
@@ -1423,6 +1434,9 @@ static int create_impl(const ZbotCfg* cfg, int device, ZbotHandle* h) {
     }
     {
       const int cap2 = 2 * h->num_sms * 128, cap3 = 3 * h->num_sms * 128;
+      const char* sh = getenv("ZBOT_H2");
+      h->v4_h2 = (sh ? (atoi(sh) != 0) : true) && cfg->task == ZBOT_TASK_WALKING_V4 && h->unroll2 &&
+                 !(cfg->num_envs > cap2 && cfg->num_envs <= cap3);
       h->ctas3 = (cfg->num_envs + cap3 - 1) / cap3 < (cfg->num_envs + cap2 - 1) / cap2;
       if (const char* sc3 = getenv("ZBOT_CTAS3")) h->ctas3 = (atoi(sc3) != 0);   // tuning override (snake / v4 / manager kernels)
     }
@@ -1446,7 +1460,10 @@ static int create_impl(const ZbotCfg* cfg, int device, ZbotHandle* h) {
     const int u = h->unroll2 ? 2 : 1, c = h->ctas3 ? 3 : 2;
     switch (cfg->task) {
       case ZBOT_TASK_SNAKE_V0: snprintf(h->kernel_name, sizeof(h->kernel_name), "zbot_snake_step_kernel<false,%d,%d>", u, u == 2 ? c : 2); break;
-      case ZBOT_TASK_WALKING_V4: snprintf(h->kernel_name, sizeof(h->kernel_name), "zbot_v4_step_kernel<false,%d,%d>", u, u == 2 ? c : 2); break;
+      case ZBOT_TASK_WALKING_V4:
+        if (h->v4_h2) snprintf(h->kernel_name, sizeof(h->kernel_name), "zbot_v4_step_kernel<false,2,2,h2>");
+        else snprintf(h->kernel_name, sizeof(h->kernel_name), "zbot_v4_step_kernel<false,%d,%d>", u, u == 2 ? c : 2);
+        break;
       case ZBOT_TASK_WALKING_M: snprintf(h->kernel_name, sizeof(h->kernel_name), "zbot_m_step_kernel<false,%d,%d>", u, u == 2 ? c : 2); break;
       default:
         if (h->w2) snprintf(h->kernel_name, sizeof(h->kernel_name), "zbot_step_w2_kernel<%d>", h->w2_ctas);
@@ -1656,11 +1673,17 @@ static int v4_step_impl(ZbotHandle* h, const float* actions, const float* rand, 
   int block = 128;
   while (block > 32 && (n + block - 1) / block < 2 * h->num_sms) block >>= 1;
   const int grid = (n + block - 1) / block;
-  const size_t smem = (size_t)block * SCR_STRIDE * sizeof(float);
+  const size_t smem = (size_t)block * kStepRowWords * sizeof(float);
   StatsCtx sc{h->partials, h->ring, slot, prev, h->inv_episode_s, 0, h->rng_ctr, 0};
   ctx_spread(sc, h);
   cudaStream_t s = (cudaStream_t)stream;
-  if (export_buf && h->unroll2)
+  if (export_buf && h->v4_h2)
+    ZB_CUDA_LAUNCH((zbot_v4_step_kernel<true, 2, 2, true>), h->P, h->state, h->ep_len, actions, rand, h->cfg.rng_seed, obs, rew,
+                                                    terminated, truncated, n, sc, export_buf);
+  else if (h->v4_h2)
+    ZB_CUDA_LAUNCH((zbot_v4_step_kernel<false, 2, 2, true>), h->P, h->state, h->ep_len, actions, rand, h->cfg.rng_seed, obs, rew,
+                                                    terminated, truncated, n, sc, nullptr);
+  else if (export_buf && h->unroll2)
     ZB_CUDA_LAUNCH((zbot_v4_step_kernel<true, 2>), h->P, h->state, h->ep_len, actions, rand, h->cfg.rng_seed, obs, rew,
                                                     terminated, truncated, n, sc, export_buf);
   else if (export_buf)
