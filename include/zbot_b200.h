@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define ZBOT_ABI_VERSION 6
+#define ZBOT_ABI_VERSION 7
 
 #define ZBOT_OK 0
 #define ZBOT_E_INVALID (-1) /* bad argument / unsupported configuration */
@@ -365,6 +365,35 @@ int zbot_mdp_observe(ZbotHandle* h, const ZbotMdpInputs* in, float* obs, void* s
 int zbot_mdp_step(ZbotHandle* h, const ZbotMdpInputs* in, const float* actions, float* obs, float* rew,
                   uint8_t* terminated, uint8_t* truncated, int32_t stats_slot, int32_t prev_slot,
                   void* stream);
+
+/* ---- the act half of the PPO rollout (BASELINE configs[4]) -------------------------------
+ * Replaces what rsl_rl's `OnPolicyRunner` runs between two env steps of a rollout (`scripts/rsl_rl/train.py:185-205` ->
+ * `runner.learn`; networks per `tasks/zbot6b_direct/agents/rsl_rl_ppo_cfg.py:65-91`: actor and critic MLP
+ * num_obs -> 128 -> 128 -> 128 -> {num_actions | 1}, ELU, state-independent std): actor forward, Gaussian sample,
+ * log-probability, critic forward and the stores into the rollout buffer, as ONE launch.  Weights are torch nn.Linear
+ * layout (W[out][in] row-major, b[out]) read in place each call, so an optimizer updating them in place is seen by a
+ * captured graph.  FP32 on the CUDA cores (the update differentiates the same weights in FP32). */
+typedef struct ZbotPolicy {
+  const float* actor_w[4];   /* [128][num_obs], [128][128], [128][128], [num_actions][128] */
+  const float* actor_b[4];
+  const float* critic_w[4];  /* ..., [1][128] */
+  const float* critic_b[4];
+  const float* std;          /* [num_actions], clamped at 1e-6 */
+  int32_t num_obs;           /* <= 64 */
+  int32_t num_actions;       /* <= 8 */
+  int32_t hidden;            /* must be 128 */
+  int32_t activation;        /* 0 = ELU (the only one built) */
+} ZbotPolicy;
+/* obs float [N][num_obs] -> act / mu / sigma float [N][num_actions], logp / value float [N]; obs_out (may be NULL)
+ * receives a copy of obs (the rollout buffer's slot).  The normal draws come from the handle's counter-based generator
+ * (`seed`, the device stream position the step kernels advance, env, output index): a replayed graph draws fresh
+ * numbers, two calls between the same pair of env steps draw the same ones. */
+int zbot_policy_act(ZbotHandle* h, const ZbotPolicy* p, const float* obs, float* obs_out, float* act, float* logp,
+                    float* value, float* mu, float* sigma, uint64_t seed, void* stream);
+/* The store half: rew_out = rew + gamma * value * truncated (time-out bootstrap), done_out = float(terminated
+ * | truncated).  All arrays [N]. */
+int zbot_rollout_store(ZbotHandle* h, const float* rew, const uint8_t* terminated, const uint8_t* truncated,
+                       const float* value, float gamma, float* rew_out, float* done_out, void* stream);
 
 /* Number of kernel launches issued through this handle so far (host counter). */
 int64_t zbot_launch_count(const ZbotHandle* h);

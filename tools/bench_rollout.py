@@ -17,13 +17,14 @@ from zbot_lab_b200.envs.rsl_rl_wrapper import RslRlVecEnvWrapper  # noqa: E402
 from zbot_lab_b200.rl.ppo_runner import OnPolicyRunner  # noqa: E402
 
 
-def make(n, device, graph):
+def make(n, device, graph, fused=True):
     cfg = gym.load_cfg_from_registry("zbot-6b-walking-v2", "env_cfg_entry_point")
     cfg.scene.num_envs, cfg.sim.device, cfg.seed = n, device, 1
     cfg.check_all_envs_reset = False
     env = RslRlVecEnvWrapper(gym.make("zbot-6b-walking-v2", cfg=cfg, render_mode=None))
     acfg = gym.load_cfg_from_registry("zbot-6b-walking-v2", "rsl_rl_cfg_entry_point").to_dict()
     acfg["use_cuda_graph"] = graph
+    acfg["fused_policy"] = fused      # zbot_policy_act / zbot_rollout_store instead of the torch act / store (CUDA envs only)
     return OnPolicyRunner(env, acfg, log_dir=None, device=device)
 
 
@@ -47,11 +48,29 @@ if __name__ == "__main__":
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
     iters = int(sys.argv[2]) if len(sys.argv) > 2 else 30
     out = {"config": f"PPO rollout 24 steps x {n} envs (policy+critic MLP 3x128 ELU, env step, storage)"}
-    for name, graph in (("eager", False), ("cuda_graph", True)):
-        r = make(n, "cuda:0", graph)
+    for name, graph, fused in (("torch_policy_eager", False, False), ("torch_policy_cuda_graph", True, False),
+                               ("fused_policy_eager", False, True), ("fused_policy_cuda_graph", True, True)):
+        r = make(n, "cuda:0", graph, fused)
+        assert (r._fused is not None) == fused
         s = time_rollouts(r, iters)
-        out[name] = {"ms_per_rollout": 1e3 * s, "env_steps_per_s": 24 * n / s}
+        out[name] = {"ms_per_rollout": 1e3 * s, "us_per_step": 1e6 * s / 24, "env_steps_per_s": 24 * n / s}
         r.env.close()
+    # the act launch alone, CUDA events, back to back
+    r = make(n, "cuda:0", False, True)
+    st, b, pol = r._fused, r.buf, r._policy_struct()
+    obs = r.env.get_observations()["policy"]
+    for _ in range(5):
+        st.policy_act(pol, obs, b["obs"][0], b["act"][0], b["logp"][0], b["val"][0], b["mu"][0], b["sigma"][0])
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(200):
+        st.policy_act(pol, obs, b["obs"][0], b["act"][0], b["logp"][0], b["val"][0], b["mu"][0], b["sigma"][0])
+    e1.record()
+    torch.cuda.synchronize()
+    us = 1e3 * e0.elapsed_time(e1) / 200
+    flop = 2.0 * n * 2 * (r.num_obs * 128 + 2 * 128 * 128) + 2.0 * n * 128 * (r.num_actions + 1)
+    out["zbot_policy_act_kernel"] = {"us": us, "fp32_tflops": flop / us * 1e-6}
+    r.env.close()
     # CPU path: CPU port of the env step (tests/fake_stepper.py double) + the same MLP on the host cores
     if "--no-cpu" not in sys.argv:
         import zbot_lab_b200.tasks.zbot6b_direct.walking_v2 as w2

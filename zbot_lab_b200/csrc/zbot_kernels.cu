@@ -537,6 +537,7 @@ __global__ void __launch_bounds__(128, 1) zbot_step_h2_export_kernel(ZB_STEP_ARG
   zbot_step_body<true, 1, 1>(ZB_STEP_CALL);
 }
 #include "zbot_w2_kernel.cuh"   // two warps per 32 envs (the default walking-v2 step kernel)
+#include "zbot_policy.cuh"      // the act / store halves of the PPO rollout (f4)
 // unrolled sweeps under a direct register cap (single-wave experiments: 14 warps/SM hold 65536 envs at <= 146 registers)
 template <int kMaxRegs>
 __global__ void __maxnreg__(kMaxRegs) zbot_step_u2_kernel_r(ZB_STEP_ARGS) {
@@ -1918,6 +1919,49 @@ int zbot_mdp_step(ZbotHandle* h, const ZbotMdpInputs* in, const float* actions, 
                      h->pdl, h->P, h->dp, mi, h->mstate, h->m_ep_len, actions, obs, rew, terminated, truncated, n, sc));
   h->launches += 1;
   ZB_CUDA(launch_pdl(zbot_stats_finalize_kernel, dim3(1), dim3(1024), 0, (cudaStream_t)stream, h->pdl, sc, (unsigned int)grid));
+  h->launches += 1;
+  return ZBOT_OK;
+}
+
+int zbot_policy_act(ZbotHandle* h, const ZbotPolicy* p, const float* obs, float* obs_out, float* act, float* logp,
+                    float* value, float* mu, float* sigma, uint64_t seed, void* stream) {
+  if (!h || !p || !obs || !act || !logp || !value || !mu || !sigma) return fail(ZBOT_E_INVALID, "zbot_policy_act: NULL argument%s");
+  if (p->hidden != kPolHid || p->activation != 0)
+    return fail(ZBOT_E_INVALID, "zbot_policy_act: only 3 x 128 ELU networks are built%s");
+  if (p->num_obs < 1 || p->num_obs > kPolMaxObs || p->num_actions < 1 || p->num_actions > kPolMaxAct)
+    return fail(ZBOT_E_INVALID, "zbot_policy_act: num_obs must be 1..64 and num_actions 1..8%s");
+  if (!p->std) return fail(ZBOT_E_INVALID, "zbot_policy_act: std is NULL%s");
+  PolicyArgs a{};
+  for (int l = 0; l < 4; ++l) {
+    a.w[0][l] = p->actor_w[l]; a.b[0][l] = p->actor_b[l];
+    a.w[1][l] = p->critic_w[l]; a.b[1][l] = p->critic_b[l];
+    if (!a.w[0][l] || !a.b[0][l] || !a.w[1][l] || !a.b[1][l]) return fail(ZBOT_E_INVALID, "zbot_policy_act: NULL weight%s");
+  }
+  DeviceGuard guard(h->device);
+  a.std = p->std; a.obs = obs; a.obs_out = obs_out; a.act = act; a.logp = logp; a.value = value; a.mu = mu; a.sigma = sigma;
+  a.ctr = h->rng_ctr; a.seed = seed; a.call = 0;
+  a.n = h->cfg.num_envs; a.num_obs = p->num_obs; a.num_actions = p->num_actions;
+  static bool attr_set[64] = {};
+  if (h->device < 64 && !attr_set[h->device]) {
+    ZB_CUDA(cudaFuncSetAttribute(zbot_policy_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPolSmem));
+    attr_set[h->device] = true;
+  }
+  const dim3 grid((a.n + kPolTile - 1) / kPolTile, 2);
+  zbot_policy_act_kernel<<<grid, kPolHid, kPolSmem, (cudaStream_t)stream>>>(a);
+  ZB_CUDA(cudaGetLastError());
+  h->launches += 1;
+  return ZBOT_OK;
+}
+
+int zbot_rollout_store(ZbotHandle* h, const float* rew, const uint8_t* terminated, const uint8_t* truncated,
+                       const float* value, float gamma, float* rew_out, float* done_out, void* stream) {
+  if (!h || !rew || !terminated || !truncated || !value || !rew_out || !done_out)
+    return fail(ZBOT_E_INVALID, "zbot_rollout_store: NULL argument%s");
+  DeviceGuard guard(h->device);
+  const int n = h->cfg.num_envs, block = 256;
+  zbot_rollout_store_kernel<<<(n + block - 1) / block, block, 0, (cudaStream_t)stream>>>(rew, terminated, truncated, value, gamma,
+                                                                                         rew_out, done_out, n);
+  ZB_CUDA(cudaGetLastError());
   h->launches += 1;
   return ZBOT_OK;
 }

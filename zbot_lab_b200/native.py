@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # ZBOT_B200_LIB: load a tuning build of the SAME sources instead (tools/sweep_step.py); never a different implementation
 LIB_PATH = os.environ.get("ZBOT_B200_LIB") or os.path.join(HERE, "csrc", "libzbot_b200.so")
 
-ZBOT_ABI_VERSION = 6
+ZBOT_ABI_VERSION = 7
 TASK_WALKING_V2, TASK_SNAKE_V0, TASK_WALKING_V4, TASK_WALKING_M = 0, 1, 2, 3
 M_NUM_OBS, M_NUM_RAND, M_EXPORT_WORDS = 25, 22, 72
 V4_NUM_OBS, V4_NUM_RAND, V4_EXPORT_WORDS = 24, 10, 69
@@ -93,6 +93,13 @@ class ZbotMdpInputs(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "body_link_pos_w", "body_link_quat_w", "body_com_lin_vel_w", "joint_pos", "joint_vel",
         "applied_torque", "net_forces_w_history", "last_air_time", "env_origins")]
+
+
+class ZbotPolicy(C.Structure):
+    """include/zbot_b200.h ``ZbotPolicy``: nn.Linear-layout weight pointers of the 3 x 128 ELU actor / critic."""
+    _fields_ = [("actor_w", C.c_void_p * 4), ("actor_b", C.c_void_p * 4), ("critic_w", C.c_void_p * 4),
+                ("critic_b", C.c_void_p * 4), ("std", C.c_void_p), ("num_obs", C.c_int32), ("num_actions", C.c_int32),
+                ("hidden", C.c_int32), ("activation", C.c_int32)]
 
 
 #: observation columns per term, in concatenation order (…env_v2.py:351-366 / …env_v4.py:835-847 / snake_v0.py:189-206)
@@ -211,6 +218,8 @@ def _declare(lib):
     lib.zbot_mdp_bind.argtypes = [vp, vp, vp, vp, i32]
     lib.zbot_mdp_observe.argtypes = [vp, P(ZbotMdpInputs), vp, vp]
     lib.zbot_mdp_step.argtypes = [vp, P(ZbotMdpInputs), vp, vp, vp, vp, vp, i32, i32, vp]
+    lib.zbot_policy_act.argtypes = [vp, P(ZbotPolicy), vp, vp, vp, vp, vp, vp, vp, C.c_uint64, vp]
+    lib.zbot_rollout_store.argtypes = [vp, vp, vp, vp, vp, C.c_float, vp, vp, vp]
     lib.zbot_launch_count.argtypes = [vp]
     lib.zbot_launch_count.restype = i64
     lib.zbot_step_kernel_name.argtypes = [vp]
@@ -218,8 +227,8 @@ def _declare(lib):
     for name in ("zbot_default_cfg", "zbot_state_word", "zbot_mdp_state_word", "zbot_create", "zbot_destroy",
                  "zbot_bind", "zbot_step", "zbot_step_export", "zbot_snake_step_export", "zbot_step_host", "zbot_v4_step",
                  "zbot_v4_step_export", "zbot_m_step", "zbot_m_step_export", "zbot_update_cfg", "zbot_reset_idx",
-                 "zbot_observe", "zbot_set_all_reset_spread", "zbot_bind_terrain",
-                 "zbot_articulation_view", "zbot_mdp_bind", "zbot_mdp_observe", "zbot_mdp_step"):
+                 "zbot_observe", "zbot_set_all_reset_spread", "zbot_bind_terrain", "zbot_policy_act",
+                 "zbot_rollout_store", "zbot_articulation_view", "zbot_mdp_bind", "zbot_mdp_observe", "zbot_mdp_step"):
         getattr(lib, name).restype = C.c_int
 
 
@@ -229,6 +238,7 @@ EXPORTED_SYMBOLS = (
     "zbot_snake_step_export", "zbot_step_host", "zbot_v4_step", "zbot_v4_step_export", "zbot_m_step", "zbot_m_step_export",
     "zbot_update_cfg", "zbot_reset_idx", "zbot_observe", "zbot_articulation_view", "zbot_mdp_bind", "zbot_mdp_observe",
     "zbot_mdp_step", "zbot_launch_count", "zbot_set_all_reset_spread", "zbot_step_kernel_name", "zbot_bind_terrain",
+    "zbot_policy_act", "zbot_rollout_store",
 )
 
 

@@ -6,7 +6,12 @@ from-scratch restatement of standard PPO with the hyper-parameters of ``PPORunne
 (``agents/rsl_rl_ppo_cfg.py:65-91``): 24 steps/env, 3x128 ELU actor and critic, GAE(0.99, 0.95),
 clip 0.2, 5 epochs x 4 mini-batches, adaptive learning rate on KL 0.01, grad-norm 1.0.
 
-The policy network is plain PyTorch (cuBLAS GEMMs): it is not the hot path this repo accelerates.
+The UPDATE phase is plain PyTorch (autograd over cuBLAS GEMMs).  The ROLLOUT phase (BASELINE
+configs[4]) runs, per step, three launches of the repo's own library: ``zbot_policy_act`` (actor + Gaussian sample +
+log-prob + critic + rollout-buffer stores, reading the live nn.Linear weights in place), the fused env step, and
+``zbot_rollout_store`` (time-out bootstrap + done flag) -- captured as one CUDA graph.  The torch formulation of the
+same rollout (``fused_policy: False`` in the train cfg, and automatically for network shapes the kernel is not built
+for or envs that are not this repo's) is kept as the semantic reference the tests compare with.
 Multi-GPU: when ``torch.distributed`` is initialised, parameters are broadcast from rank 0 and the
 flattened gradients are all-reduced once per mini-batch (what rsl_rl does under ``--distributed``).
 """
@@ -105,6 +110,8 @@ class OnPolicyRunner:
             warnings.warn(f"num_steps_per_env = {self.num_steps} needs {2 * self.num_steps} statistics slots for the captured "
                           f"rollout graph, the ring has {self._ring_slots}: running the rollout eagerly")
             self.use_cuda_graph = False
+        self._fused = self._fused_policy_supported() if bool(train_cfg.get("fused_policy", True)) else None
+        self._seed = int(train_cfg.get("seed", 0) or 0)
         self.current_learning_iteration = 0
         self.history: list[dict] = []
         self.git_status_repos: list[str] = []
@@ -139,9 +146,67 @@ class OnPolicyRunner:
         return d.get("infos")
 
     # ------------------------------------------------------------------ rollout + update
+    def _fused_policy_supported(self):
+        """The native stepper when the act / store halves of the rollout can run as the library's own kernels
+        (``zbot_policy_act`` / ``zbot_rollout_store``): a CUDA env of this repo, 3 x 128 ELU actor and critic,
+        num_obs <= 64, num_actions <= 8.  None otherwise (the torch formulation runs)."""
+        if self.device.type != "cuda":
+            return None
+        st = getattr(getattr(self.env, "unwrapped", self.env), "_stepper", None)
+        if st is None or not hasattr(st, "policy_act") or not hasattr(self.env, "env"):
+            return None
+        pc = self.policy_cfg
+        if (list(pc.get("actor_hidden_dims", (128, 128, 128))) != [128, 128, 128]
+                or list(pc.get("critic_hidden_dims", (128, 128, 128))) != [128, 128, 128]
+                or pc.get("activation", "elu") != "elu" or self.num_obs > 64 or self.num_actions > 8):
+            return None
+        return st
+
+    def _policy_struct(self):
+        """``ZbotPolicy`` over the LIVE parameter storage (Adam and ``load_state_dict`` update it in place, so the
+        pointers -- also those baked into a captured graph -- stay valid)."""
+        from .. import native
+        import ctypes as C
+        pol = native.ZbotPolicy()
+        for net, wn, bn in ((self.policy.actor, "actor_w", "actor_b"), (self.policy.critic, "critic_w", "critic_b")):
+            lin = [m for m in net if isinstance(m, nn.Linear)]
+            assert len(lin) == 4
+            for i, m in enumerate(lin):
+                assert m.weight.is_contiguous() and m.weight.dtype == torch.float32 and m.weight.device == self.device
+                getattr(pol, wn)[i] = m.weight.data_ptr()
+                getattr(pol, bn)[i] = m.bias.data_ptr()
+        pol.std = self.policy.std.data_ptr()
+        pol.num_obs, pol.num_actions, pol.hidden, pol.activation = self.num_obs, self.num_actions, 128, 0
+        return pol
+
+    @torch.no_grad()
+    def _collect_rollout_fused(self, obs):
+        """Per step: ``zbot_policy_act`` -> the fused env step (+ its statistics pass) -> ``zbot_rollout_store``."""
+        b, ep_infos, st, T = self.buf, [], self._fused, self.num_steps
+        pol = self._policy_struct()
+        inner, clip = self.env.env, getattr(self.env, "clip_actions", None)
+        gamma = 0.0 if getattr(self.env.unwrapped.cfg, "is_finite_horizon", False) else self.gamma
+        if obs.dtype != torch.float32 or not obs.is_contiguous():
+            obs = obs.float().contiguous()
+        for t in range(T):
+            st.policy_act(pol, obs, b["obs"][t], b["act"][t], b["logp"][t], b["val"][t], b["mu"][t], b["sigma"][t],
+                          seed=self._seed)
+            act = b["act"][t] if clip is None else torch.clamp(b["act"][t], -clip, clip)
+            obs_dict, rew, term, trunc, infos = inner.step(act)
+            obs = policy_obs(obs_dict)
+            st.rollout_store(rew, term, trunc, b["val"][t], gamma, b["rew"][t], b["done"][t])
+            if "log" in infos:
+                log = infos["log"]
+                if self._clone_logs:
+                    log = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in log.items()}
+                ep_infos.append(log)
+        return obs, ep_infos
+
     @torch.no_grad()
     def collect_rollout(self, obs):
         """``num_steps`` x (act -> env.step -> store); returns the last observation and episode infos."""
+        if self._fused is not None:
+            return self._collect_rollout_fused(obs)
         b, ep_infos = self.buf, []
         for t in range(self.num_steps):
             d = self.policy.dist(obs)

@@ -206,6 +206,33 @@ class NativeStepper:
         native.check(rc, "zbot_step")
         return self.obs, self.rew, self.terminated, self.truncated
 
+    # ------------------------------------------------------------------ rollout halves
+    def policy_act(self, pol: "native.ZbotPolicy", obs, obs_out, act, logp, value, mu, sigma, seed: int = 0):
+        """Actor + Gaussian sample + log-prob + critic + rollout-buffer stores as one launch (``zbot_policy_act``).
+        All tensors float32, contiguous, on this device; ``obs_out`` may be None."""
+        for name, x, cols in (("obs", obs, pol.num_obs), ("act", act, pol.num_actions), ("mu", mu, pol.num_actions),
+                              ("sigma", sigma, pol.num_actions), ("logp", logp, None), ("value", value, None),
+                              ("obs_out", obs_out, pol.num_obs)):
+            if x is None and name == "obs_out":
+                continue
+            want = (self.n,) if cols is None else (self.n, cols)
+            if x.dtype != torch.float32 or tuple(x.shape) != want or not x.is_contiguous() or x.device != self.obs.device:
+                raise ValueError(f"policy_act: {name} must be a contiguous float32 {want} tensor on {self.device}")
+        native.check(self.lib.zbot_policy_act(self._h, C.byref(pol), _ptr(obs), _ptr(obs_out), _ptr(act), _ptr(logp),
+                                              _ptr(value), _ptr(mu), _ptr(sigma), int(seed) & (2 ** 64 - 1),
+                                              _stream(self.device)), "zbot_policy_act")
+
+    def rollout_store(self, rew, terminated, truncated, value, gamma: float, rew_out, done_out):
+        """rew_out = rew + gamma * value * truncated, done_out = float(terminated | truncated) (``zbot_rollout_store``)."""
+        for name, x, dt in (("rew", rew, torch.float32), ("value", value, torch.float32), ("rew_out", rew_out, torch.float32),
+                            ("done_out", done_out, torch.float32), ("terminated", terminated, None), ("truncated", truncated, None)):
+            ok = x.dtype == dt if dt is not None else x.dtype in (torch.uint8, torch.bool)
+            if not ok or tuple(x.shape) != (self.n,) or not x.is_contiguous() or x.device != self.obs.device:
+                raise ValueError(f"rollout_store: {name} has the wrong dtype / shape / device")
+        native.check(self.lib.zbot_rollout_store(self._h, _ptr(rew), _ptr(terminated), _ptr(truncated), _ptr(value),
+                                                 float(gamma), _ptr(rew_out), _ptr(done_out), _stream(self.device)),
+                     "zbot_rollout_store")
+
     def step_host(self, host_actions: torch.Tensor, host_rows: torch.Tensor):
         """One control step for HOST buffers (``zbot_step_host``): ``host_actions`` pinned (N,6) f32 in, one
         25-word row per env ``[obs 23 | reward | flags]`` into the pinned ``host_rows`` ((N,25) f32).  One kernel
