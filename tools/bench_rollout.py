@@ -59,15 +59,25 @@ if __name__ == "__main__":
     r = make(n, "cuda:0", False, True)
     st, b, pol = r._fused, r.buf, r._policy_struct()
     obs = r.env.get_observations()["policy"]
-    for _ in range(5):
+    def act():
         st.policy_act(pol, obs, b["obs"][0], b["act"][0], b["logp"][0], b["val"][0], b["mu"][0], b["sigma"][0])
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        for _ in range(5):
+            act()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()          # 50 launches per replay: the Python around one ctypes call is longer than the kernel
+    with torch.cuda.graph(g):
+        for _ in range(50):
+            act()
+    g.replay()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(200):
-        st.policy_act(pol, obs, b["obs"][0], b["act"][0], b["logp"][0], b["val"][0], b["mu"][0], b["sigma"][0])
+    for _ in range(10):
+        g.replay()
     e1.record()
     torch.cuda.synchronize()
-    us = 1e3 * e0.elapsed_time(e1) / 200
+    us = 1e3 * e0.elapsed_time(e1) / 500
     flop = 2.0 * n * 2 * (r.num_obs * 128 + 2 * 128 * 128) + 2.0 * n * 128 * (r.num_actions + 1)
     out["zbot_policy_act_kernel"] = {"us": us, "fp32_tflops": flop / us * 1e-6}
     r.env.close()

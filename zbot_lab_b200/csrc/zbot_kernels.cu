@@ -1947,7 +1947,7 @@ int zbot_policy_act(ZbotHandle* h, const ZbotPolicy* p, const float* obs, float*
     attr_set[h->device] = true;
   }
   const dim3 grid((a.n + kPolTile - 1) / kPolTile, 2);
-  zbot_policy_act_kernel<<<grid, kPolHid, kPolSmem, (cudaStream_t)stream>>>(a);
+  zbot_policy_act_kernel<<<grid, kPolThreads, kPolSmem, (cudaStream_t)stream>>>(a);
   ZB_CUDA(cudaGetLastError());
   h->launches += 1;
   return ZBOT_OK;

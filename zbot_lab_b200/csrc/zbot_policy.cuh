@@ -4,26 +4,31 @@
 // MLP num_obs -> 128 -> 128 -> 128 -> {num_actions | 1}, ELU, state-independent std) evaluates the actor, samples a Gaussian
 // action, evaluates its log-probability and the critic, and stores everything in the rollout buffer: ~45 small torch launches
 // per step even inside a CUDA graph (115 us of a 140 us step at 4096 envs; the fused env step is 25 us of it).  Here it is one
-// kernel: blockIdx.y = 0 runs the actor on a tile of 32 envs (+ sampling, log-prob, stores), blockIdx.y = 1 the critic.
+// kernel: blockIdx.y = 0 runs the actor on a tile of 64 envs (+ sampling, log-prob, stores), blockIdx.y = 1 the critic.
 //
 // GEMM layout (FP32 on the CUDA cores -- the update phase differentiates the same weights in FP32 through torch, so the
-// rollout must see the same numbers to round-off; TF32 / BF16 tensor cores would not): a CTA of 128 threads owns a 32-env x
-// 128-neuron output tile per layer.  Thread (cg = t % 32, rg = t / 32) accumulates rows 8 rg .. 8 rg + 7 x columns
-// {cg, cg + 32, cg + 64, cg + 96}.  Activations live K-major in shared memory (`xs[k][m]`, row stride 36 floats: the two
-// 128-bit reads of a k-step are warp-wide broadcasts, the epilogue's 128-bit stores are conflict-free); the layer's weights
-// stream through shared memory transposed in chunks of 32 input neurons (`ws[kk][j]`), the next chunk prefetched into
-// registers while the current one is consumed.  Weights stay in torch's nn.Linear layout (W[out][in], b[out]) -- the
-// optimizer updates them in place, so a captured graph keeps seeing the live parameters.
+// rollout must see the same numbers to round-off; TF32 / BF16 tensor cores would not).  Packed FP32 (FFMA2: the FMA pipe of
+// sm_100a retires a scalar FFMA every other cycle per sub-partition, tools/micro/ffma2_probe.cu -- 39 TFLOP/s scalar against
+// 57.5 packed at two warps per sub-partition).  A CTA of 256 threads owns a 64-env x 128-neuron output tile per layer.  Thread
+// (cg = t % 16, rg = t / 16) accumulates rows 4 rg .. 4 rg + 3 x columns {cg + 16 c, c = 0..7} as 4 x 4 register pairs:
+//     (acc[r][2p], acc[r][2p+1]) += x[r] (scalar, broadcast operand form) * (w[2p], w[2p+1])        one FFMA2
+// Activations live K-major in shared memory (`xs[k][m]`, row stride 68 floats: the 128-bit read of a k-step is two addresses
+// per warp, the epilogue's 128-bit stores spread evenly over the banks); the layer's weights stream through shared memory
+// transposed in chunks of 32 input neurons (`ws[kk][pos]`), column j = cg + 16 c parked at pos = 4 cg + (c & 3) + 64 (c >> 2) so a
+// thread's eight weights of a k-step are two 128-bit reads and the register pairs are the natural ones.  The next chunk is
+// prefetched into registers while the current one is consumed.  Weights stay in torch's nn.Linear layout (W[out][in], b[out])
+// -- the optimizer updates them in place, so a captured graph keeps seeing the live parameters.
 #pragma once
 // (included inside zbot_kernels.cu's anonymous namespace, after v4_uniform)
 
-constexpr int kPolTile = 32;      // envs per CTA
-constexpr int kPolHid = 128;      // hidden width = threads per CTA
+constexpr int kPolTile = 64;      // envs per CTA
+constexpr int kPolHid = 128;      // hidden width
+constexpr int kPolThreads = 256;
 constexpr int kPolChunk = 32;     // input neurons per weight chunk
-constexpr int kPolXS = 36;        // row stride of xs (floats)
+constexpr int kPolXS = 68;        // row stride of xs (floats)
 constexpr int kPolMaxObs = 64;
 constexpr int kPolMaxAct = 8;
-constexpr size_t kPolSmem = (size_t)(2 * kPolHid * kPolXS + 2 * kPolChunk * kPolHid + kPolTile * kPolMaxAct) * sizeof(float);
+constexpr size_t kPolSmem = (size_t)(2 * kPolHid * kPolXS + 2 * kPolChunk * kPolHid + kPolTile * kPolMaxAct + kPolMaxAct * kPolHid + kPolMaxAct) * sizeof(float);
 
 struct PolicyArgs {
   const float* w[2][4];        // [net: 0 actor, 1 critic][layer]  W[out][in]
@@ -41,113 +46,145 @@ struct PolicyArgs {
   int n, num_obs, num_actions;
 };
 
-__device__ __forceinline__ float pol_elu(float x) { return x > 0.f ? x : expm1f(x); }
+// torch.nn.ELU(alpha = 1) as ATen evaluates it: x > 0 ? x : exp(x) - 1.  Branch-free; ex2.approx on the clamped argument
+// (absolute error <= 2^-22 on (-1, 0], the branch that is taken there)
+__device__ __forceinline__ float pol_elu(float x) {
+  const float e = __expf(fminf(x, 0.f)) - 1.f;
+  return x > 0.f ? x : e;
+}
 
-// one hidden layer: xs_in[K][36] -> xs_out[128][36], ELU
+// one hidden layer: xs_in[K][68] -> xs_out[128][68], ELU.  kFull: K is a multiple of the chunk (the 128-wide layers) -- the 32
+// k-steps of a chunk are unrolled completely so the shared-memory reads of the steps ahead are in flight under the FFMA2s
+template <bool kFull>
 __device__ __forceinline__ void pol_hidden_layer(const float* __restrict__ W, const float* __restrict__ bias, int K,
                                                  const float* xs_in, float* xs_out, float* ws) {
-  const int t = threadIdx.x, cg = t & 31, rg = t >> 5;
-  float acc[8][4];
+  const int t = threadIdx.x, cg = t & 15, rg = t >> 4;
+  float2 acc[4][4];
 #pragma unroll
-  for (int r = 0; r < 8; ++r)
+  for (int r = 0; r < 4; ++r)
 #pragma unroll
-    for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+    for (int p = 0; p < 4; ++p) acc[r][p] = make_float2(0.f, 0.f);
   const int nchunk = (K + kPolChunk - 1) / kPolChunk;
   const bool vec = (K & 3) == 0;
-  float wreg[kPolChunk];
-  auto prefetch = [&](int c) {      // this thread's output neuron t: W[t][c*32 .. c*32+31]
-    const int k0 = c * kPolChunk;
-    const float* row = W + (size_t)t * K + k0;
-    if (vec && k0 + kPolChunk <= K) {
+  // staging role of this thread: shared-memory position sp of the chunk row (-> weight row sj), k-half sh of the chunk
+  const int sp = t & 127, sh = t >> 7;
+  const int sj = ((sp & 63) >> 2) + 16 * ((sp & 3) + 4 * (sp >> 6));
+  float wreg[kPolChunk / 2];
+  auto prefetch = [&](int c) {      // W[sj][c*32 + 16 sh .. + 15]
+    const int k0 = c * kPolChunk + 16 * sh;
+    const float* row = W + (size_t)sj * K + k0;
+    if (vec && k0 + 16 <= K) {
 #pragma unroll
-      for (int i = 0; i < kPolChunk / 4; ++i) {
+      for (int i = 0; i < 4; ++i) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(row) + i);
         wreg[4 * i] = v.x; wreg[4 * i + 1] = v.y; wreg[4 * i + 2] = v.z; wreg[4 * i + 3] = v.w;
       }
     } else {
 #pragma unroll
-      for (int i = 0; i < kPolChunk; ++i) wreg[i] = (k0 + i < K) ? __ldg(row + i) : 0.f;
+      for (int i = 0; i < 16; ++i) wreg[i] = (k0 + i < K) ? __ldg(row + i) : 0.f;
     }
   };
   auto stash = [&](int buf) {
-    float* dst = ws + buf * kPolChunk * kPolHid + t;
+    float* dst = ws + buf * kPolChunk * kPolHid + 16 * sh * kPolHid + sp;
 #pragma unroll
-    for (int i = 0; i < kPolChunk; ++i) dst[i * kPolHid] = wreg[i];
+    for (int i = 0; i < 16; ++i) dst[i * kPolHid] = wreg[i];
   };
   prefetch(0);
   stash(0);
   __syncthreads();
   for (int c = 0; c < nchunk; ++c) {
     if (c + 1 < nchunk) prefetch(c + 1);
-    const float* wb = ws + (c & 1) * kPolChunk * kPolHid;
-    const float* xb = xs_in + (size_t)c * kPolChunk * kPolXS + 8 * rg;
-    const int kc = min(kPolChunk, K - c * kPolChunk);
-#pragma unroll 4
-    for (int kk = 0; kk < kc; ++kk) {
+    const float* wb = ws + (c & 1) * kPolChunk * kPolHid + 4 * cg;
+    const float* xb = xs_in + (size_t)c * kPolChunk * kPolXS + 4 * rg;
+    auto kstep = [&](int kk) {
       const float4 xa = *reinterpret_cast<const float4*>(xb + kk * kPolXS);
-      const float4 xc = *reinterpret_cast<const float4*>(xb + kk * kPolXS + 4);
-      const float x[8] = {xa.x, xa.y, xa.z, xa.w, xc.x, xc.y, xc.z, xc.w};
-      float w4[4];
+      const float4 w0 = *reinterpret_cast<const float4*>(wb + kk * kPolHid);
+      const float4 w1 = *reinterpret_cast<const float4*>(wb + kk * kPolHid + 64);
+      const float x[4] = {xa.x, xa.y, xa.z, xa.w};
+      const float2 wp[4] = {make_float2(w0.x, w0.y), make_float2(w0.z, w0.w), make_float2(w1.x, w1.y), make_float2(w1.z, w1.w)};
 #pragma unroll
-      for (int cc = 0; cc < 4; ++cc) w4[cc] = wb[kk * kPolHid + cg + 32 * cc];
+      for (int r = 0; r < 4; ++r)
 #pragma unroll
-      for (int r = 0; r < 8; ++r)
+        for (int p = 0; p < 4; ++p) acc[r][p] = __ffma2_rn(make_float2(x[r], x[r]), wp[p], acc[r][p]);
+    };
+    if (kFull) {
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) acc[r][cc] = fmaf(x[r], w4[cc], acc[r][cc]);
+      for (int kk = 0; kk < kPolChunk; ++kk) kstep(kk);
+    } else {
+      const int kc = min(kPolChunk, K - c * kPolChunk);
+#pragma unroll 4
+      for (int kk = 0; kk < kc; ++kk) kstep(kk);
     }
     if (c + 1 < nchunk) stash((c + 1) & 1);
     __syncthreads();
   }
 #pragma unroll
-  for (int cc = 0; cc < 4; ++cc) {
-    const int j = cg + 32 * cc;
+  for (int c = 0; c < 8; ++c) {
+    const int j = cg + 16 * c;
     const float bj = __ldg(bias + j);
-    float o[8];
+    float o[4];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) o[r] = pol_elu(acc[r][cc] + bj);
-    float* dst = xs_out + (size_t)j * kPolXS + 8 * rg;
-    *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
-    *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
+    for (int r = 0; r < 4; ++r) o[r] = pol_elu(((c & 1) ? acc[r][c >> 1].y : acc[r][c >> 1].x) + bj);
+    *reinterpret_cast<float4*>(xs_out + (size_t)j * kPolXS + 4 * rg) = make_float4(o[0], o[1], o[2], o[3]);
   }
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(kPolHid) zbot_policy_act_kernel(const PolicyArgs a) {
+__global__ void __launch_bounds__(kPolThreads, 1) zbot_policy_act_kernel(const PolicyArgs a) {
   extern __shared__ __align__(16) float psm[];
   float* xs0 = psm;
   float* xs1 = psm + kPolHid * kPolXS;
   float* ws = psm + 2 * kPolHid * kPolXS;
-  float* outs = ws + 2 * kPolChunk * kPolHid;          // [32][8] head outputs
+  float* outs = ws + 2 * kPolChunk * kPolHid;          // [64][8] head outputs
+  float* hws = outs + kPolTile * kPolMaxAct;           // [8][128] head weights, [8] head bias
   const int net = blockIdx.y;
   const int e0 = blockIdx.x * kPolTile;
   const int valid = min(kPolTile, a.n - e0);
   const int t = threadIdx.x;
-  // observation tile -> xs0[k][m] (rows of dead envs are zero); the actor CTA also writes the rollout buffer's copy
-  for (int idx = t; idx < kPolTile * a.num_obs; idx += kPolHid) {
-    const int m = idx / a.num_obs, k = idx - m * a.num_obs;
-    float v = 0.f;
-    if (m < valid) {
-      v = __ldg(a.obs + (size_t)e0 * a.num_obs + idx);
-      if (net == 0 && a.obs_out) a.obs_out[(size_t)e0 * a.num_obs + idx] = v;
+  // head weights + bias -> shared memory now (consumed after the third layer; nothing waits for them there)
+  const int nout = net == 0 ? a.num_actions : 1;
+  for (int i = t; i < nout * (kPolHid / 4); i += kPolThreads)
+    reinterpret_cast<float4*>(hws)[i] = __ldg(reinterpret_cast<const float4*>(a.w[net][3]) + i);
+  if (t < nout) hws[kPolMaxAct * kPolHid + t] = __ldg(a.b[net][3] + t);
+  // observation tile -> xs0[k][m] (rows of dead envs are zero): warp w takes envs w, w + 8, ..., lane = column (+ 32); the
+  // actor CTA also writes the rollout buffer's copy
+  {
+    const int lane = t & 31, wid = t >> 5;
+#pragma unroll
+    for (int i = 0; i < kPolTile / 8; ++i) {
+      const int m = wid + 8 * i;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int k = lane + 32 * h;
+        if (k < a.num_obs) {
+          float v = 0.f;
+          if (m < valid) {
+            v = __ldg(a.obs + (size_t)(e0 + m) * a.num_obs + k);
+            if (net == 0 && a.obs_out) a.obs_out[(size_t)(e0 + m) * a.num_obs + k] = v;
+          }
+          xs0[k * kPolXS + m] = v;
+        }
+      }
     }
-    xs0[k * kPolXS + m] = v;
   }
   __syncthreads();
-  pol_hidden_layer(a.w[net][0], a.b[net][0], a.num_obs, xs0, xs1, ws);
-  pol_hidden_layer(a.w[net][1], a.b[net][1], kPolHid, xs1, xs0, ws);
-  pol_hidden_layer(a.w[net][2], a.b[net][2], kPolHid, xs0, xs1, ws);
-  // head: num_actions (actor) or 1 (critic) outputs per env; thread (m = t % 32, o = t / 32 [+ 4])
-  const int nout = net == 0 ? a.num_actions : 1;
-  const int m = t & 31;
-  for (int o = t >> 5; o < nout; o += 4) {
-    const float* wrow = a.w[net][3] + (size_t)o * kPolHid;
-    float s0 = 0.f, s1 = 0.f;
+  pol_hidden_layer<false>(a.w[net][0], a.b[net][0], a.num_obs, xs0, xs1, ws);
+  pol_hidden_layer<true>(a.w[net][1], a.b[net][1], kPolHid, xs1, xs0, ws);
+  pol_hidden_layer<true>(a.w[net][2], a.b[net][2], kPolHid, xs0, xs1, ws);
+  // head: num_actions (actor) or 1 (critic) outputs per env; thread (m = t % 64, o = t / 64 [+ 4])
+  const int m = t & 63;
+  for (int o = t >> 6; o < nout; o += 4) {
+    const float* wrow = hws + o * kPolHid;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll 8
-    for (int k = 0; k < kPolHid; k += 2) {
-      s0 = fmaf(xs1[k * kPolXS + m], __ldg(wrow + k), s0);
-      s1 = fmaf(xs1[(k + 1) * kPolXS + m], __ldg(wrow + k + 1), s1);
+    for (int k = 0; k < kPolHid; k += 4) {
+      const float4 wv = *reinterpret_cast<const float4*>(wrow + k);
+      s0 = fmaf(xs1[k * kPolXS + m], wv.x, s0);
+      s1 = fmaf(xs1[(k + 1) * kPolXS + m], wv.y, s1);
+      s2 = fmaf(xs1[(k + 2) * kPolXS + m], wv.z, s2);
+      s3 = fmaf(xs1[(k + 3) * kPolXS + m], wv.w, s3);
     }
-    outs[m * kPolMaxAct + o] = s0 + s1 + __ldg(a.b[net][3] + o);
+    outs[m * kPolMaxAct + o] = ((s0 + s1) + (s2 + s3)) + hws[kPolMaxAct * kPolHid + o];
   }
   __syncthreads();
   if (t >= valid) return;
