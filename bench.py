@@ -518,9 +518,15 @@ def main():
             r = bench_rollout.make(4096, str(dev), True)
             sec = bench_rollout.time_rollouts(r, 30)
             other_tasks["ppo_rollout_24x4096"] = {
-                "workload": "BASELINE.json configs[4]: rollout of 24 steps x 4096 envs (actor + critic MLP 3x128 ELU, "
-                            "fused env step, storage) replayed as one CUDA graph",
-                "ms_per_rollout": 1e3 * sec, "value": 24 * 4096 / sec, "unit": UNIT}
+                "workload": "BASELINE.json configs[4]: rollout of 24 steps x 4096 envs (actor + critic MLP 3x128 ELU + Gaussian "
+                            "sample + log-prob as ONE launch of zbot_policy_act_kernel, fused env step, zbot_rollout_store) replayed "
+                            "as one CUDA graph",
+                "ms_per_rollout": 1e3 * sec, "value": 24 * 4096 / sec, "unit": UNIT,
+                "policy": "zbot_policy_act (this library)" if r._fused is not None else "torch"}
+            r.env.close()
+            r = bench_rollout.make(4096, str(dev), True, fused=False)      # the same rollout with the torch policy / storage ops
+            sec_t = bench_rollout.time_rollouts(r, 10)
+            other_tasks["ppo_rollout_24x4096"]["torch_policy_same_graph_ms"] = 1e3 * sec_t
             r.env.close()
         except Exception as exc:   # the side measurement must never break the headline line
             other_tasks["ppo_rollout_24x4096"] = {"error": repr(exc)}

@@ -1936,18 +1936,25 @@ int zbot_policy_act(ZbotHandle* h, const ZbotPolicy* p, const float* obs, float*
     a.w[0][l] = p->actor_w[l]; a.b[0][l] = p->actor_b[l];
     a.w[1][l] = p->critic_w[l]; a.b[1][l] = p->critic_b[l];
     if (!a.w[0][l] || !a.b[0][l] || !a.w[1][l] || !a.b[1][l]) return fail(ZBOT_E_INVALID, "zbot_policy_act: NULL weight%s");
+    if (((uintptr_t)a.w[0][l] | (uintptr_t)a.w[1][l]) & 15) return fail(ZBOT_E_INVALID, "zbot_policy_act: weights must be 16-byte aligned%s");
   }
   DeviceGuard guard(h->device);
   a.std = p->std; a.obs = obs; a.obs_out = obs_out; a.act = act; a.logp = logp; a.value = value; a.mu = mu; a.sigma = sigma;
   a.ctr = h->rng_ctr; a.seed = seed; a.call = 0;
   a.n = h->cfg.num_envs; a.num_obs = p->num_obs; a.num_actions = p->num_actions;
+  // rows per thread: 4 (256 threads per 64-env tile; default) or 8 (128 threads) -- ZBOT_POLICY_ROWS, tuning switch
+  static const int rows = [] { const char* e = getenv("ZBOT_POLICY_ROWS"); return (e && atoi(e) == 8) ? 8 : 4; }();
   static bool attr_set[64] = {};
   if (h->device < 64 && !attr_set[h->device]) {
-    ZB_CUDA(cudaFuncSetAttribute(zbot_policy_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPolSmem));
+    ZB_CUDA(cudaFuncSetAttribute(zbot_policy_act_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPolSmem));
+    ZB_CUDA(cudaFuncSetAttribute(zbot_policy_act_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPolSmem));
     attr_set[h->device] = true;
   }
   const dim3 grid((a.n + kPolTile - 1) / kPolTile, 2);
-  zbot_policy_act_kernel<<<grid, kPolThreads, kPolSmem, (cudaStream_t)stream>>>(a);
+  if (rows == 8)
+    zbot_policy_act_kernel<8><<<grid, 128, kPolSmem, (cudaStream_t)stream>>>(a);
+  else
+    zbot_policy_act_kernel<4><<<grid, 256, kPolSmem, (cudaStream_t)stream>>>(a);
   ZB_CUDA(cudaGetLastError());
   h->launches += 1;
   return ZBOT_OK;

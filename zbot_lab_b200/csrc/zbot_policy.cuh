@@ -23,12 +23,11 @@
 
 constexpr int kPolTile = 64;      // envs per CTA
 constexpr int kPolHid = 128;      // hidden width
-constexpr int kPolThreads = 256;
 constexpr int kPolChunk = 32;     // input neurons per weight chunk
 constexpr int kPolXS = 68;        // row stride of xs (floats)
 constexpr int kPolMaxObs = 64;
 constexpr int kPolMaxAct = 8;
-constexpr size_t kPolSmem = (size_t)(2 * kPolHid * kPolXS + 2 * kPolChunk * kPolHid + kPolTile * kPolMaxAct + kPolMaxAct * kPolHid + kPolMaxAct) * sizeof(float);
+constexpr size_t kPolSmem = (size_t)(2 * kPolHid * kPolXS + 2 * kPolChunk * kPolHid + 4 * kPolTile * kPolMaxAct + kPolMaxAct * kPolHid + kPolMaxAct) * sizeof(float);
 
 struct PolicyArgs {
   const float* w[2][4];        // [net: 0 actor, 1 critic][layer]  W[out][in]
@@ -54,56 +53,75 @@ __device__ __forceinline__ float pol_elu(float x) {
 }
 
 // one hidden layer: xs_in[K][68] -> xs_out[128][68], ELU.  kFull: K is a multiple of the chunk (the 128-wide layers) -- the 32
-// k-steps of a chunk are unrolled completely so the shared-memory reads of the steps ahead are in flight under the FFMA2s
-template <bool kFull>
-__device__ __forceinline__ void pol_hidden_layer(const float* __restrict__ W, const float* __restrict__ bias, int K,
-                                                 const float* xs_in, float* xs_out, float* ws) {
-  const int t = threadIdx.x, cg = t & 15, rg = t >> 4;
-  float2 acc[4][4];
+// k-steps of a chunk are unrolled completely so the shared-memory reads of the steps ahead are in flight under the FFMA2s.
+// kRows = rows per thread (4: 256 threads, 8: 128 threads).  A 128-bit shared-memory read is served per HALF-warp, one
+// wavefront per 128 distinct bytes (ncu: the 16-column-groups-per-half-warp mapping cost 4 + 4 + 2 wavefronts per k-step), so a
+// half-warp is 8 column groups x 2 row groups: 1 + 1 wavefronts for the weights, 1 per four rows for the activations.
+// Measured (profiles/r2_notes.md section 7): the k-loop runs at ~105 clocks per k-step and SM = 78 FMA / clock / SM against the
+// 110 a pure FFMA2 stream reaches (tools/micro/ffma2_bcast_probe.cu); what bounds it is the shared-memory -> register return
+// path (128 B / clock / SM: 256 threads x 48 B per k-step = 96 clocks), not wavefronts and not the FMA pipe.
+// weight staging: thread t parks weight row sj (shared-memory position sp = t % 128) of a chunk, k-part sh = t / 128
+template <int kStage>
+__device__ __forceinline__ void pol_prefetch(const float* __restrict__ W, int K, int c, float (&wreg)[kStage]) {
+  const int sp = threadIdx.x & 127, sh = threadIdx.x >> 7;
+  const int sj = ((sp & 63) >> 2) + 16 * ((sp & 3) + 4 * (sp >> 6));
+  const int k0 = c * kPolChunk + kStage * sh;
+  const float* row = W + (size_t)sj * K + k0;
+  if ((K & 3) == 0 && k0 + kStage <= K) {
 #pragma unroll
-  for (int r = 0; r < 4; ++r)
+    for (int i = 0; i < kStage / 4; ++i) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(row) + i);
+      wreg[4 * i] = v.x; wreg[4 * i + 1] = v.y; wreg[4 * i + 2] = v.z; wreg[4 * i + 3] = v.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < kStage; ++i) wreg[i] = (k0 + i < K) ? __ldg(row + i) : 0.f;
+  }
+}
+template <int kStage>
+__device__ __forceinline__ void pol_stash(float* ws, int buf, const float (&wreg)[kStage]) {
+  const int sp = threadIdx.x & 127, sh = threadIdx.x >> 7;
+  float* dst = ws + buf * kPolChunk * kPolHid + kStage * sh * kPolHid + sp;
+#pragma unroll
+  for (int i = 0; i < kStage; ++i) dst[i * kPolHid] = wreg[i];
+}
+
+// On entry chunk 0 of this layer is already in ws[buf] (staged by the caller / the previous layer, a barrier has passed); during
+// the last chunk the first chunk of the NEXT layer (Wn, Kn; null: none) is fetched and parked in the other buffer, so no layer
+// starts with an exposed L2 round trip.  On exit `buf` names the buffer holding the next layer's chunk 0.
+template <bool kFull, int kRows>
+__device__ __forceinline__ void pol_hidden_layer(const float* __restrict__ W, const float* __restrict__ bias, int K,
+                                                 const float* xs_in, float* xs_out, float* ws, int& buf,
+                                                 const float* __restrict__ Wn, int Kn) {
+  constexpr int kThreads = (kPolTile / kRows) * 16;
+  constexpr int kStage = kPolChunk * kPolHid / kThreads;     // weights of a chunk staged per thread (16 or 32)
+  const int t = threadIdx.x, hw = t >> 4;
+  const int cg = (t & 7) + 8 * (hw & 1), rg = ((t >> 3) & 1) + 2 * (hw >> 1);
+  float2 acc[kRows][4];
+#pragma unroll
+  for (int r = 0; r < kRows; ++r)
 #pragma unroll
     for (int p = 0; p < 4; ++p) acc[r][p] = make_float2(0.f, 0.f);
   const int nchunk = (K + kPolChunk - 1) / kPolChunk;
-  const bool vec = (K & 3) == 0;
-  // staging role of this thread: shared-memory position sp of the chunk row (-> weight row sj), k-half sh of the chunk
-  const int sp = t & 127, sh = t >> 7;
-  const int sj = ((sp & 63) >> 2) + 16 * ((sp & 3) + 4 * (sp >> 6));
-  float wreg[kPolChunk / 2];
-  auto prefetch = [&](int c) {      // W[sj][c*32 + 16 sh .. + 15]
-    const int k0 = c * kPolChunk + 16 * sh;
-    const float* row = W + (size_t)sj * K + k0;
-    if (vec && k0 + 16 <= K) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(row) + i);
-        wreg[4 * i] = v.x; wreg[4 * i + 1] = v.y; wreg[4 * i + 2] = v.z; wreg[4 * i + 3] = v.w;
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) wreg[i] = (k0 + i < K) ? __ldg(row + i) : 0.f;
-    }
-  };
-  auto stash = [&](int buf) {
-    float* dst = ws + buf * kPolChunk * kPolHid + 16 * sh * kPolHid + sp;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) dst[i * kPolHid] = wreg[i];
-  };
-  prefetch(0);
-  stash(0);
-  __syncthreads();
+  float wreg[kStage];
   for (int c = 0; c < nchunk; ++c) {
-    if (c + 1 < nchunk) prefetch(c + 1);
-    const float* wb = ws + (c & 1) * kPolChunk * kPolHid + 4 * cg;
-    const float* xb = xs_in + (size_t)c * kPolChunk * kPolXS + 4 * rg;
+    const bool last = c + 1 == nchunk;
+    if (!last) pol_prefetch<kStage>(W, K, c + 1, wreg);
+    else if (Wn) pol_prefetch<kStage>(Wn, Kn, 0, wreg);
+    const float* wb = ws + buf * kPolChunk * kPolHid + 4 * cg;
+    const float* xb = xs_in + (size_t)c * kPolChunk * kPolXS + kRows * rg;
     auto kstep = [&](int kk) {
-      const float4 xa = *reinterpret_cast<const float4*>(xb + kk * kPolXS);
+      float x[kRows];
+#pragma unroll
+      for (int q = 0; q < kRows / 4; ++q) {
+        const float4 xa = *reinterpret_cast<const float4*>(xb + kk * kPolXS + 4 * q);
+        x[4 * q] = xa.x; x[4 * q + 1] = xa.y; x[4 * q + 2] = xa.z; x[4 * q + 3] = xa.w;
+      }
       const float4 w0 = *reinterpret_cast<const float4*>(wb + kk * kPolHid);
       const float4 w1 = *reinterpret_cast<const float4*>(wb + kk * kPolHid + 64);
-      const float x[4] = {xa.x, xa.y, xa.z, xa.w};
       const float2 wp[4] = {make_float2(w0.x, w0.y), make_float2(w0.z, w0.w), make_float2(w1.x, w1.y), make_float2(w1.z, w1.w)};
 #pragma unroll
-      for (int r = 0; r < 4; ++r)
+      for (int r = 0; r < kRows; ++r)
 #pragma unroll
         for (int p = 0; p < 4; ++p) acc[r][p] = __ffma2_rn(make_float2(x[r], x[r]), wp[p], acc[r][p]);
     };
@@ -115,32 +133,48 @@ __device__ __forceinline__ void pol_hidden_layer(const float* __restrict__ W, co
 #pragma unroll 4
       for (int kk = 0; kk < kc; ++kk) kstep(kk);
     }
-    if (c + 1 < nchunk) stash((c + 1) & 1);
-    __syncthreads();
+    if (!last || Wn) pol_stash<kStage>(ws, buf ^ 1, wreg);     // the other buffer was last read before the previous barrier
+    if (!last) {
+      __syncthreads();
+      buf ^= 1;
+    }
   }
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
     const int j = cg + 16 * c;
     const float bj = __ldg(bias + j);
-    float o[4];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) o[r] = pol_elu(((c & 1) ? acc[r][c >> 1].y : acc[r][c >> 1].x) + bj);
-    *reinterpret_cast<float4*>(xs_out + (size_t)j * kPolXS + 4 * rg) = make_float4(o[0], o[1], o[2], o[3]);
+    for (int q = 0; q < kRows / 4; ++q) {
+      float o[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) o[r] = pol_elu(((c & 1) ? acc[4 * q + r][c >> 1].y : acc[4 * q + r][c >> 1].x) + bj);
+      *reinterpret_cast<float4*>(xs_out + (size_t)j * kPolXS + kRows * rg + 4 * q) = make_float4(o[0], o[1], o[2], o[3]);
+    }
   }
   __syncthreads();
+  buf ^= 1;
 }
 
-__global__ void __launch_bounds__(kPolThreads, 1) zbot_policy_act_kernel(const PolicyArgs a) {
+template <int kRows>
+__global__ void __launch_bounds__((kPolTile / kRows) * 16, 1) zbot_policy_act_kernel(const PolicyArgs a) {
+  constexpr int kPolThreads = (kPolTile / kRows) * 16;
   extern __shared__ __align__(16) float psm[];
   float* xs0 = psm;
   float* xs1 = psm + kPolHid * kPolXS;
   float* ws = psm + 2 * kPolHid * kPolXS;
-  float* outs = ws + 2 * kPolChunk * kPolHid;          // [64][8] head outputs
-  float* hws = outs + kPolTile * kPolMaxAct;           // [8][128] head weights, [8] head bias
+  float* outs = ws + 2 * kPolChunk * kPolHid;          // [4][64][8] partial head outputs
+  float* hws = outs + 4 * kPolTile * kPolMaxAct;       // [8][128] head weights, [8] head bias
   const int net = blockIdx.y;
   const int e0 = blockIdx.x * kPolTile;
   const int valid = min(kPolTile, a.n - e0);
   const int t = threadIdx.x;
+  // first weight chunk of the first layer: in flight while the observation tile is loaded
+  constexpr int kStage = kPolChunk * kPolHid / kPolThreads;
+  {
+    float wreg[kStage];
+    pol_prefetch<kStage>(a.w[net][0], a.num_obs, 0, wreg);
+    pol_stash<kStage>(ws, 0, wreg);
+  }
   // head weights + bias -> shared memory now (consumed after the third layer; nothing waits for them there)
   const int nout = net == 0 ? a.num_actions : 1;
   for (int i = t; i < nout * (kPolHid / 4); i += kPolThreads)
@@ -151,8 +185,8 @@ __global__ void __launch_bounds__(kPolThreads, 1) zbot_policy_act_kernel(const P
   {
     const int lane = t & 31, wid = t >> 5;
 #pragma unroll
-    for (int i = 0; i < kPolTile / 8; ++i) {
-      const int m = wid + 8 * i;
+    for (int i = 0; i < kPolTile / (kPolThreads / 32); ++i) {
+      const int m = wid + (kPolThreads / 32) * i;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int k = lane + 32 * h;
@@ -168,51 +202,70 @@ __global__ void __launch_bounds__(kPolThreads, 1) zbot_policy_act_kernel(const P
     }
   }
   __syncthreads();
-  pol_hidden_layer<false>(a.w[net][0], a.b[net][0], a.num_obs, xs0, xs1, ws);
-  pol_hidden_layer<true>(a.w[net][1], a.b[net][1], kPolHid, xs1, xs0, ws);
-  pol_hidden_layer<true>(a.w[net][2], a.b[net][2], kPolHid, xs0, xs1, ws);
-  // head: num_actions (actor) or 1 (critic) outputs per env; thread (m = t % 64, o = t / 64 [+ 4])
-  const int m = t & 63;
-  for (int o = t >> 6; o < nout; o += 4) {
-    const float* wrow = hws + o * kPolHid;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll 8
-    for (int k = 0; k < kPolHid; k += 4) {
-      const float4 wv = *reinterpret_cast<const float4*>(wrow + k);
-      s0 = fmaf(xs1[k * kPolXS + m], wv.x, s0);
-      s1 = fmaf(xs1[(k + 1) * kPolXS + m], wv.y, s1);
-      s2 = fmaf(xs1[(k + 2) * kPolXS + m], wv.z, s2);
-      s3 = fmaf(xs1[(k + 3) * kPolXS + m], wv.w, s3);
+  int buf = 0;
+  pol_hidden_layer<false, kRows>(a.w[net][0], a.b[net][0], a.num_obs, xs0, xs1, ws, buf, a.w[net][1], kPolHid);
+  pol_hidden_layer<true, kRows>(a.w[net][1], a.b[net][1], kPolHid, xs1, xs0, ws, buf, a.w[net][2], kPolHid);
+  pol_hidden_layer<true, kRows>(a.w[net][2], a.b[net][2], kPolHid, xs0, xs1, ws, buf, nullptr, 0);
+  // head: num_actions (actor) or 1 (critic) outputs per env.  Thread (m = t % 64, kq = t / 64) sums its quarter (half) of the
+  // 128 inputs for every output; the partial sums meet in shared memory and are added in a fixed order.
+  constexpr int kG = kPolThreads / 64;
+  const int m = t & 63, kq = t >> 6;
+  {
+    float part[kPolMaxAct];
+#pragma unroll
+    for (int o = 0; o < kPolMaxAct; ++o) part[o] = 0.f;
+    const int kb = kq * (kPolHid / kG);
+#pragma unroll 4
+    for (int k = kb; k < kb + kPolHid / kG; ++k) {
+      const float x = xs1[k * kPolXS + m];
+#pragma unroll
+      for (int o = 0; o < kPolMaxAct; ++o)
+        if (o < nout) part[o] = fmaf(x, hws[o * kPolHid + k], part[o]);
     }
-    outs[m * kPolMaxAct + o] = ((s0 + s1) + (s2 + s3)) + hws[kPolMaxAct * kPolHid + o];
+#pragma unroll
+    for (int o = 0; o < kPolMaxAct; ++o)
+      if (o < nout) outs[(kq * kPolTile + m) * kPolMaxAct + o] = part[o];
   }
   __syncthreads();
-  if (t >= valid) return;
-  const int e = e0 + t;
+  auto head_out = [&](int mm, int o) {
+    float v = outs[mm * kPolMaxAct + o];
+#pragma unroll
+    for (int g = 1; g < kG; ++g) v += outs[(g * kPolTile + mm) * kPolMaxAct + o];
+    return v + hws[kPolMaxAct * kPolHid + o];
+  };
   if (net == 1) {
-    a.value[e] = outs[t * kPolMaxAct];
+    if (t < valid) a.value[e0 + t] = head_out(t, 0);
     return;
   }
-  // Gaussian sample (Box-Muller on the counter-based uniforms of the step kernels: seed / stream position / env / slot),
-  // log-probability evaluated from the stored action exactly as torch.distributions.Normal.log_prob does
+  // Gaussian sample (Box-Muller on the counter-based uniforms of the step kernels: seed / stream position / env / slot), one
+  // (env, action) pair per thread and round; the log-probability terms are evaluated from the stored action exactly as
+  // torch.distributions.Normal.log_prob does and summed over the actions in index order
   const unsigned long long call = a.ctr ? __ldcg(a.ctr) : a.call;
-  float lp = 0.f;
-  for (int o = 0; o < a.num_actions; ++o) {
-    const float mean = outs[t * kPolMaxAct + o];
-    const float sd = fmaxf(__ldg(a.std + o), 1e-6f);
-    const float u1 = 1.0f - v4_uniform(a.seed, call, (uint32_t)e, 128u + 2u * (uint32_t)o);       // (0, 1]
-    const float u2 = v4_uniform(a.seed, call, (uint32_t)e, 129u + 2u * (uint32_t)o);
-    float sn, cs;
-    sincospif(2.0f * u2, &sn, &cs);
-    const float z = sqrtf(-2.0f * logf(u1)) * cs;
-    const float act = fmaf(sd, z, mean);
-    const float d = act - mean;
-    lp += -(d * d) / (2.0f * sd * sd) - logf(sd) - 0.91893853320467274178f;
-    a.act[(size_t)e * a.num_actions + o] = act;
-    a.mu[(size_t)e * a.num_actions + o] = mean;
-    a.sigma[(size_t)e * a.num_actions + o] = sd;
+  float* lpc = xs0;                                    // [64][8] log-prob terms (xs0 is dead after the third layer)
+  for (int o = kq; o < a.num_actions; o += kG) {
+    if (m < valid) {
+      const int e = e0 + m;
+      const float mean = head_out(m, o);
+      const float sd = fmaxf(__ldg(a.std + o), 1e-6f);
+      const float u1 = 1.0f - v4_uniform(a.seed, call, (uint32_t)e, 128u + 2u * (uint32_t)o);       // (0, 1]
+      const float u2 = v4_uniform(a.seed, call, (uint32_t)e, 129u + 2u * (uint32_t)o);
+      float sn, cs;
+      sincospif(2.0f * u2, &sn, &cs);
+      const float z = sqrtf(-2.0f * logf(u1)) * cs;
+      const float act = fmaf(sd, z, mean);
+      const float d = act - mean;
+      lpc[m * kPolMaxAct + o] = -(d * d) / (2.0f * sd * sd) - logf(sd) - 0.91893853320467274178f;
+      a.act[(size_t)e * a.num_actions + o] = act;
+      a.mu[(size_t)e * a.num_actions + o] = mean;
+      a.sigma[(size_t)e * a.num_actions + o] = sd;
+    }
   }
-  a.logp[e] = lp;
+  __syncthreads();
+  if (t < valid) {
+    float lp = 0.f;
+    for (int o = 0; o < a.num_actions; ++o) lp += lpc[t * kPolMaxAct + o];
+    a.logp[e0 + t] = lp;
+  }
 }
 
 // the store half of a rollout step: reward with the time-out bootstrap (rew + gamma * V(s_t) * time_out) and the
