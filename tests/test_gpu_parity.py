@@ -101,6 +101,40 @@ def test_mdp_kernel_matches_oracle_random_sizes():
         st.close()
 
 
+@pytest.mark.parametrize("shape", ["42", "43", "33", "41", "42+fused-stats"])
+@pytest.mark.parametrize("n", [37, 4096, 20013])
+def test_mdp_pipelined_kernel_is_bit_identical_to_the_one_shot_kernel(n, shape, monkeypatch):
+    """`zbot_mdp_pipe_kernel` (persistent, every input by bulk async copy; the default from 131072 envs, forced here with
+    ZBOT_MDP_PIPE=<stages><warps per stage>) against `zbot_mdp_kernel<true>` (ZBOT_MDP_PIPE=0) on the same inputs: the per-env
+    arithmetic is the same device code, so observations, rewards, flags, counters and every state word are bit-identical; only
+    the grid-level statistics are summed in another order (also with the pass fused into the last CTA)."""
+    from zbot_lab_b200.utils import synthetic as syn
+    case = syn.synth_mdp_case(5, n, 4)
+    outs = []
+    for pipe in (shape, "0"):
+        monkeypatch.setenv("ZBOT_MDP_PIPE", pipe.split("+")[0])
+        monkeypatch.setenv("ZBOT_MDP_FUSE_STATS", "1" if "fused" in pipe else "0")
+        st = _stepper(n)
+        st.mdp_init()
+        org = _t(case["origins"])
+        st.mdp_episode_length_buf[:] = _t(case["episode_length_buf0"])
+        st.mdp_observe(_S(case["S0"]), org)
+        rec = []
+        for a, S1 in case["steps"]:
+            obs, rew, term, trunc = st.mdp_step(_S(S1), org, _t(a))
+            torch.cuda.synchronize()
+            rec.append((obs.clone(), rew.clone(), term.clone(), trunc.clone(), st.mdp_episode_length_buf.clone(),
+                        st.mdp_state.buf.clone(), st.mdp_stats_ring[st._mdp_slot].clone()))
+        outs.append(rec)
+        st.close()
+    for a, b in zip(*outs):
+        for x, y in zip(a[:6], b[:6]):
+            assert torch.equal(x, y)
+        sa, sb = a[6].cpu().numpy(), b[6].cpu().numpy()
+        assert np.array_equal(sa[16:19], sb[16:19]) and np.array_equal(sa[20:22], sb[20:22])       # counts
+        assert np.allclose(sa, sb, rtol=1e-5, atol=1e-6)
+
+
 # ---------------------------------------------------------------------------------------------
 def _export_to_S(ex, which):
     if which == 0:

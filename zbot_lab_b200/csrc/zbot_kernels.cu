@@ -19,6 +19,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <new>
 
 #include "zbot_layout.h"
@@ -80,6 +81,8 @@ struct StatsCtx {
   int spread_n, spread_high;
   unsigned long long spread_seed;
   int norm_word22;         // manager task: word 22 is an Episode_Reward value (normalised), not a raw count
+  unsigned int* ticket;    // non-null: the producing kernel runs the grid-level pass itself in its LAST CTA to finish (a device
+                           // counter, left at zero); no separate statistics launch follows (zbot_mdp_pipe_kernel)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -122,26 +125,24 @@ __device__ __forceinline__ void obs_add_noise(const Params<float>& P, const Stat
 // b = w, w+32, ... (a row is 128 contiguous bytes: one coalesced load per warp) with four independent
 // accumulators so four L2 loads are in flight per thread; everything is combined in a fixed order, so the
 // result is bit-reproducible (no float atomics).
-__global__ void __launch_bounds__(1024) zbot_stats_finalize_kernel(StatsCtx sc, unsigned int nblocks) {
-  __shared__ float red[32][33];
-  pdl_trigger();   // the next step kernel may be scheduled behind this one-block kernel
-  pdl_wait();      // the step kernel's partial rows are complete and visible
+// (any block size that is a multiple of 32; with 1024 threads the summation order is the one-block kernel's)
+__device__ __forceinline__ void stats_finalize_body(const StatsCtx& sc, unsigned int nblocks, float (*red)[33]) {
   const int j = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const unsigned int nw = blockDim.x >> 5;
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
   const float* p = sc.partials + j;
   unsigned int b = w;
-  for (; b + 96 < nblocks; b += 128) {
-    const float v0 = __ldcg(p + (size_t)b * kStats), v1 = __ldcg(p + (size_t)(b + 32) * kStats),
-                v2 = __ldcg(p + (size_t)(b + 64) * kStats), v3 = __ldcg(p + (size_t)(b + 96) * kStats);
+  for (; b + 3 * nw < nblocks; b += 4 * nw) {
+    const float v0 = __ldcg(p + (size_t)b * kStats), v1 = __ldcg(p + (size_t)(b + nw) * kStats),
+                v2 = __ldcg(p + (size_t)(b + 2 * nw) * kStats), v3 = __ldcg(p + (size_t)(b + 3 * nw) * kStats);
     a0 += v0; a1 += v1; a2 += v2; a3 += v3;
   }
-  for (; b < nblocks; b += 32) a0 += __ldcg(p + (size_t)b * kStats);
+  for (; b < nblocks; b += nw) a0 += __ldcg(p + (size_t)b * kStats);
   red[w][j] = (a0 + a1) + (a2 + a3);
   __syncthreads();
   if (threadIdx.x < kStats) {
     float acc = 0.f;
-#pragma unroll
-    for (int g = 0; g < 32; ++g) acc += red[g][threadIdx.x];
+    for (unsigned int g = 0; g < nw; ++g) acc += red[g][threadIdx.x];
     red[0][threadIdx.x] = acc;           // words a kernel does not produce are zero in every partial row
   }
   __syncthreads();
@@ -169,6 +170,13 @@ __global__ void __launch_bounds__(1024) zbot_stats_finalize_kernel(StatsCtx sc, 
   // advance the in-kernel generator's stream position: the step kernel of this control step has completed (pdl_wait
   // above), the next one reads it only after this grid has completed (its own pdl_wait / stream order)
   if (threadIdx.x == 0 && sc.rng_ctr) *const_cast<unsigned long long*>(sc.rng_ctr) = *sc.rng_ctr + 1ull;
+}
+
+__global__ void __launch_bounds__(1024) zbot_stats_finalize_kernel(StatsCtx sc, unsigned int nblocks) {
+  __shared__ float red[32][33];
+  pdl_trigger();   // the next step kernel may be scheduled behind this one-block kernel
+  pdl_wait();      // the step kernel's partial rows are complete and visible
+  stats_finalize_body(sc, nblocks, red);
 }
 
 // warp shuffles -> shared memory -> this block's partial row.  `vals[0..18]` are non-zero only for
@@ -1180,6 +1188,8 @@ zbot_mdp_kernel(const __grid_constant__ Params<float> P, const __grid_constant__
   }
 }
 
+#include "zbot_mdp_pipe.cuh"    // the same step as a persistent, TMA-fed kernel (the default; ZBOT_MDP_PIPE=0 restores the one above)
+
 }  // namespace
 
 // =============================================================================================
@@ -1363,13 +1373,17 @@ static int create_impl(const ZbotCfg* cfg, int device, ZbotHandle* h) {
   h->num_sms = prop.multiProcessorCount;
   h->max_blocks = (cfg->num_envs + 31) / 32 + 1;
   ZB_CUDA(cudaMalloc(&h->partials, (size_t)h->max_blocks * kStats * sizeof(float)));
-  ZB_CUDA(cudaMalloc(&h->rng_ctr, sizeof(unsigned long long)));
-  ZB_CUDA(cudaMemset(h->rng_ctr, 0, sizeof(unsigned long long)));
+  ZB_CUDA(cudaMalloc(&h->rng_ctr, 2 * sizeof(unsigned long long)));          // [0] stream position, [1] last-CTA ticket (StatsCtx::ticket)
+  ZB_CUDA(cudaMemset(h->rng_ctr, 0, 2 * sizeof(unsigned long long)));
   ZB_CUDA(cudaMalloc(&h->d_dp, sizeof(DefaultPose)));          // scratch of the default-pose FK; freed by zbot_destroy
   zbot_default_pose_kernel<<<1, 1>>>(h->d_dp, cfg->task);
   ZB_CUDA(cudaGetLastError());
   ZB_CUDA(cudaMemcpy(&h->dp, h->d_dp, sizeof(DefaultPose), cudaMemcpyDeviceToHost));
   ZB_CUDA(cudaFuncSetAttribute(zbot_mdp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * kHistRow * 4));
+  ZB_CUDA(cudaFuncSetAttribute(zbot_mdp_pipe_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pipe_smem(4, 2)));
+  ZB_CUDA(cudaFuncSetAttribute(zbot_mdp_pipe_kernel<4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pipe_smem(4, 3)));
+  ZB_CUDA(cudaFuncSetAttribute(zbot_mdp_pipe_kernel<3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pipe_smem(3, 3)));
+  ZB_CUDA(cudaFuncSetAttribute(zbot_mdp_pipe_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pipe_smem(4, 1)));
   for (int v = 0; v < kNumStepVariants; ++v)
     ZB_CUDA(cudaFuncSetAttribute((const void*)kStepVariants[v].fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  128 * kStepRowWords * 4 * kStepVariants[v].envs_per_thread));
@@ -1911,15 +1925,44 @@ int zbot_mdp_step(ZbotHandle* h, const ZbotMdpInputs* in, const float* actions, 
   DeviceGuard guard(h->device);
   if (!actions || !obs || !rew || !terminated || !truncated) return fail(ZBOT_E_INVALID, "zbot_mdp_step: NULL buffer%s");
   if (int rc = check_slot(stats_slot, prev_slot, h->m_ring_slots)) return rc;
-  const int n = h->cfg.num_envs, block = h->mdp_tile, grid = (n + block - 1) / block;
+  const int n = h->cfg.num_envs, block = h->mdp_tile;
+  int grid = (n + block - 1) / block;
   MdpIn mi{in->body_link_pos_w, in->body_link_quat_w, in->body_com_lin_vel_w, in->joint_pos, in->joint_vel,
            in->applied_torque, in->net_forces_w_history, in->last_air_time, in->env_origins};
   StatsCtx sc{h->partials, h->m_ring, stats_slot, prev_slot, h->inv_episode_s, 0, h->rng_ctr, 0};
-  ZB_CUDA(launch_pdl(zbot_mdp_kernel<true>, dim3(grid), dim3(block), (size_t)block * kHistRow * sizeof(float), (cudaStream_t)stream,
-                     h->pdl, h->P, h->dp, mi, h->mstate, h->m_ep_len, actions, obs, rew, terminated, truncated, n, sc));
+  // persistent TMA-fed kernel (zbot_mdp_pipe.cuh) whenever every tensor can be a bulk-copy source (16-byte aligned base)
+  const char* pipe_env = getenv("ZBOT_MDP_PIPE");      // read per call: tests A/B the two kernels in one process
+  const bool pipe_off = pipe_env && atoi(pipe_env) == 0;
+  const uintptr_t align_or = (uintptr_t)mi.pos | (uintptr_t)mi.quat | (uintptr_t)mi.vel | (uintptr_t)mi.q | (uintptr_t)mi.qd |
+                             (uintptr_t)mi.tau | (uintptr_t)mi.hist | (uintptr_t)mi.last_air | (uintptr_t)mi.origins |
+                             (uintptr_t)actions | (uintptr_t)h->m_ep_len | (uintptr_t)h->mstate;
+  // measured (profiles/r2_notes.md section 8, CUDA-graph replay over rotating input sets): 65536 envs 28.4 us one-shot vs 29.2 us
+  // persistent; 262144 envs 96.5 vs 91.9 us -- the persistent kernel is the default from 131072 envs, ZBOT_MDP_PIPE forces either
+  if (!pipe_off && (align_or & 15) == 0 && (pipe_env || n >= 131072)) {
+    const int ntiles = (n + kPT - 1) / kPT;
+    // ZBOT_MDP_PIPE = <stages><warps per stage> (tuning switch): 42 (default), 43, 33, 41
+    const int shape = pipe_env ? atoi(pipe_env) : 0;
+    const int stages = (shape == 33) ? 3 : 4;
+    const char* fuse_env = getenv("ZBOT_MDP_FUSE_STATS");               // 1: grid-level statistics in the last CTA instead of a
+    if (fuse_env && atoi(fuse_env) == 1) sc.ticket = reinterpret_cast<unsigned int*>(h->rng_ctr + 1);   // second launch (A/B switch)
+    grid = std::min(h->num_sms, (ntiles + stages - 1) / stages);
+#define ZB_PIPE_LAUNCH(ST, SH)                                                                                             \
+  ZB_CUDA(launch_pdl(zbot_mdp_pipe_kernel<ST, SH>, dim3(grid), dim3(ST * SH * 32), pipe_smem(ST, SH), (cudaStream_t)stream, \
+                     h->pdl, h->P, h->dp, mi, h->mstate, h->m_ep_len, actions, obs, rew, terminated, truncated, n, sc))
+    if (shape == 43) { ZB_PIPE_LAUNCH(4, 3); }
+    else if (shape == 33) { ZB_PIPE_LAUNCH(3, 3); }
+    else if (shape == 41) { ZB_PIPE_LAUNCH(4, 1); }
+    else { ZB_PIPE_LAUNCH(4, 2); }
+#undef ZB_PIPE_LAUNCH
+  } else {
+    ZB_CUDA(launch_pdl(zbot_mdp_kernel<true>, dim3(grid), dim3(block), (size_t)block * kHistRow * sizeof(float), (cudaStream_t)stream,
+                       h->pdl, h->P, h->dp, mi, h->mstate, h->m_ep_len, actions, obs, rew, terminated, truncated, n, sc));
+  }
   h->launches += 1;
-  ZB_CUDA(launch_pdl(zbot_stats_finalize_kernel, dim3(1), dim3(1024), 0, (cudaStream_t)stream, h->pdl, sc, (unsigned int)grid));
-  h->launches += 1;
+  if (!sc.ticket) {
+    ZB_CUDA(launch_pdl(zbot_stats_finalize_kernel, dim3(1), dim3(1024), 0, (cudaStream_t)stream, h->pdl, sc, (unsigned int)grid));
+    h->launches += 1;
+  }
   return ZBOT_OK;
 }
 
