@@ -9,7 +9,8 @@
 
 One "step" = one control step of every env (4 physics substeps + MDP + partial reset) = ONE
 kernel launch.  Prints one JSON line (rank 0).  Timing: CUDA events on the launching stream
-around every step, an L2 flush (256 MiB write) between timed steps, max over ranks.
+around every block of 50 control steps, inputs larger than L2 (the steps cycle through independent env sets that together
+exceed 2 x the L2; `--l2 flush` = the round-1 method, a 256 MiB write fill before every step), max over ranks.
 """
 from __future__ import annotations
 
@@ -40,10 +41,11 @@ FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12     # 148 SMs x 128 FP32 lanes
 # and reported under "envs_4096".
 DEFAULT_ENVS_PER_GPU = 65536
 ROLLOUT_STEPS = 24  # agents/rsl_rl_ppo_cfg.py:67 -- statistics are reduced once per rollout
-# One bench "step" = a BLOCK of this many control steps (each one launch of the fused kernel; the L2 is flushed before
-# every one of them, outside the timed events), so the driver's `--steps 20` times 1000 control steps (>= 50 ms of
+# One bench "step" = a BLOCK of this many control steps (each one launch of the fused kernel on the next env set of the
+# rotation: inputs larger than L2), so the driver's `--steps 20` times 1000 control steps (>= 50 ms of
 # kernel time) instead of 1.7 ms.  `value` counts every control step: env-steps/s is unaffected by the block size.
 CONTROL_STEPS_PER_STEP = 50
+L2_BYTES = 126 << 20
 
 
 def workload_name(n_envs: int) -> str:
@@ -81,6 +83,17 @@ def load_step_profile(n_envs: int):
     return prof, "profiles/step_%d.json (%s)" % (n_envs, prof.get("captured_with", "ncu"))
 
 
+def l2_note(m) -> str:
+    if m["l2_mode"] == "rotate":
+        return ("inputs larger than L2: %d independent env sets of %d envs (%.0f MB of state, counters and outputs in all = %.1f x "
+                "the 126 MB L2; 16 rotating action buffers) stepped in turn, back to back, no flush; one CUDA-event pair per "
+                "block of %d control steps" % (m["n_sets"], m["n_envs"], m["n_sets"] * m["set_bytes"] / 1e6,
+                                                m["n_sets"] * m["set_bytes"] / L2_BYTES, CONTROL_STEPS_PER_STEP))
+    if m["l2_mode"] == "flush":
+        return "flushed before every control step (256 MiB write, outside the timed events, events around every control step)"
+    return "not flushed: one env set back to back (state stays in L2)"
+
+
 def parse():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
@@ -88,14 +101,20 @@ def parse():
     p.add_argument("--warmup", type=int, default=20)
     p.add_argument("--envs", type=int, default=None, help="envs per GPU (default 65536 at every N)")
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    p.add_argument("--no-flush", action="store_true", help="back-to-back steps (state stays in L2)")
+    p.add_argument("--l2", default="rotate", choices=["rotate", "flush", "none"],
+                   help="rotate: cycle through env sets that together exceed 2 x L2 (default); flush: 256 MiB write fill before "
+                        "every control step; none: one env set back to back (state stays in L2)")
+    p.add_argument("--no-flush", action="store_true", help="alias of --l2 none")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-mdp", action="store_true", help="skip the MDP-only kernel side measurement")
     p.add_argument("--no-small", action="store_true", help="skip the additional 4096-env measurement at N=1")
     p.add_argument("--no-tasks", action="store_true", help="skip the snake / v4 / PPO-rollout side measurements at N=1")
     p.add_argument("--cpu-sample-steps", type=int, default=None)
-    return p.parse_args()
+    a = p.parse_args()
+    if a.no_flush:
+        a.l2 = "none"
+    return a
 
 
 # ------------------------------------------------------------------------------------------------
@@ -246,73 +265,95 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def measure(n_envs, steps, warmup, with_e2e):
+    def measure(n_envs, steps, warmup, with_e2e, mode=None):
         """Time `steps` control steps of `n_envs` envs on this rank; returns a dict (rank-local + max-reduced)."""
 
         # the public API: gym.make(task, cfg=...) exactly as scripts/rsl_rl/train.py:158
-        cfg = gym.load_cfg_from_registry("zbot-6b-walking-v2", "env_cfg_entry_point")
-        cfg.scene.num_envs = n_envs
-        cfg.sim.device = str(dev)
-        cfg.seed = zdist.rank_seed(1234, rank)
-        env = gym.make("zbot-6b-walking-v2", cfg=cfg, render_mode=None)
-        st = env.unwrapped._stepper
-        env.reset()
-        rng = np.random.default_rng(1234 + rank)
-        st.set_sim_state({k: torch.from_numpy(v).to(dev) for k, v in syn.synth_sim_state(rng, n_envs).items()})
+        def make_set(k):
+            cfg = gym.load_cfg_from_registry("zbot-6b-walking-v2", "env_cfg_entry_point")
+            cfg.scene.num_envs = n_envs
+            cfg.sim.device = str(dev)
+            cfg.seed = zdist.rank_seed(1234 + 7919 * k, rank)
+            env_k = gym.make("zbot-6b-walking-v2", cfg=cfg, render_mode=None)
+            st_k = env_k.unwrapped._stepper
+            env_k.reset()
+            rng = np.random.default_rng(1234 + rank + 7919 * k)
+            st_k.set_sim_state({kk: torch.from_numpy(v).to(dev) for kk, v in syn.synth_sim_state(rng, n_envs).items()})
+            g_k = torch.Generator(device=dev).manual_seed(1234 + rank + 7919 * k)
+            env_k.episode_length_buf = torch.randint(0, 1000, (n_envs,), device=dev, generator=g_k)
+            return env_k, st_k
+
+        # L2 policy (bench contract: flush between timed iterations OR inputs larger than L2).  "rotate" (default): the control
+        # steps cycle through `n_sets` independent env sets whose state + outputs together are >= 2 x the 126 MB L2, so every
+        # step finds its state in DRAM and the steps still run back to back on the stream (one CUDA-event pair per block of
+        # 50 control steps).  "flush": ONE env set, a 256 MiB write fill before every control step, events around each step
+        # (the round-1 method; the fill leaves the L2 full of dirty lines that the step then has to write back).
+        mode = mode or args.l2
+        set_bytes = n_envs * (LAYOUT_BYTES_PER_ENV_STEP - 320)       # state + counters + actions + outputs of one env set
+        n_sets = min(96, max(2, -(-2 * L2_BYTES // set_bytes))) if mode == "rotate" else 1
+        sets = [make_set(k) for k in range(n_sets)]
+        env, st = sets[0]
         g = torch.Generator(device=dev).manual_seed(1234 + rank)
-        env.episode_length_buf = torch.randint(0, 1000, (n_envs,), device=dev, generator=g)
         n_act = 16
         actions = torch.randn(n_act, n_envs, 6, device=dev, generator=g)            # resident in HBM
-        flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if mode == "flush" else None
         stats_acc = torch.zeros(32, device=dev)
         reducer = zdist.RolloutStatsReducer(dev)
 
         def one_step(i):
-            st.step(actions[i % n_act])
+            sets[i % n_sets][1].step(actions[i % n_act])
+
+        def launch_count():
+            return sum(s_k.launch_count for _, s_k in sets)
 
         blk = CONTROL_STEPS_PER_STEP
         ctrl_steps, ctrl_warm = steps * blk, warmup * blk
         for i in range(ctrl_warm):
             one_step(i)
             if world > 1 and (i + 1) % ROLLOUT_STEPS == 0:
-                reducer.submit(st.stats)                             # warm-up covers the collective too (NCCL channel set-up)
+                reducer.submit(sets[i % n_sets][1].stats)            # warm-up covers the collective too (NCCL channel set-up)
         barrier()
         sampler = ClockSampler(local)
         sampler.sample_once()
         sampler.start()
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(ctrl_steps)]
+        per = 1 if flush is not None else blk                        # control steps per CUDA-event pair
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(ctrl_steps // per)]
         # the only collective on the path: the rollout statistics, all-reduced once per rollout (24 control steps) -- inside
         # the timed region, with its own events (N > 1 only)
         n_red = ctrl_steps // ROLLOUT_STEPS if world > 1 else 0
         ev_red = [torch.cuda.Event(enable_timing=True) for _ in range(n_red)]
-        launches0 = st.launch_count
+        ev_sub = [torch.cuda.Event(enable_timing=True) for _ in range(n_red)]
+        launches0 = launch_count()
         barrier()
         t_wall0 = time.perf_counter()
         k_red = 0
         for i in range(ctrl_steps):
             if flush is not None:
                 flush.fill_(i & 0xFF)                      # evict L2 (126 MB) -- outside the timed events
-            ev[i][0].record()
+            if i % per == 0:
+                ev[i // per][0].record()
             one_step(i)
             if k_red < n_red and (i + 1) % ROLLOUT_STEPS == 0:
                 # on a side stream, overlapped with the next control steps (the logger reads it after the rollout); its own
                 # events are recorded on that stream, and whatever of the LAST one outlives the last step is added below
-                reducer.submit(st.stats)
+                ev_sub[k_red].record()
+                reducer.submit(sets[i % n_sets][1].stats)
                 with torch.cuda.stream(reducer.side):
                     ev_red[k_red].record()
                 k_red += 1
-            ev[i][1].record()                               # after the submit: its 128-byte snapshot copy is inside the step's events
+            if (i + 1) % per == 0:
+                ev[i // per][1].record()                    # after the submit: its 128-byte snapshot copy is inside the timed events
         ev_tail = torch.cuda.Event(enable_timing=True)
         if n_red:
             stats_acc = reducer.result()                   # joins the side stream into the stepping stream
         ev_tail.record()
         barrier()
         t_wall = time.perf_counter() - t_wall0
-        launches = st.launch_count - launches0
+        launches = launch_count() - launches0
         sampler.stop()
         step_ms = [a.elapsed_time(b) for a, b in ev]
-        # all-reduce k is submitted right after control step 24(k+1)-1: its latency = end of that step -> its own end event
-        red_ms = [ev[(k + 1) * ROLLOUT_STEPS - 1][1].elapsed_time(ev_red[k]) for k in range(n_red)]
+        # all-reduce k is submitted right after control step 24(k+1)-1: its latency = that point of the stepping stream -> its end
+        red_ms = [ev_sub[k].elapsed_time(ev_red[k]) for k in range(n_red)]
         tail_ms = max(0.0, ev[-1][1].elapsed_time(ev_tail)) if n_red else 0.0
         total_ms = float(sum(step_ms)) + tail_ms
         t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
@@ -395,17 +436,19 @@ def main():
 
 
         kernel_name = st.kernel_name
-        env.close()
+        for env_k, _ in sets:
+            env_k.close()
         return {"n_envs": n_envs, "value": value, "total_ms": total_ms, "ctrl_steps": ctrl_steps, "kernel": kernel_name,
                 "local_ms_per_ctrl_step": float(sum(step_ms)) / ctrl_steps,
                 "stats_allreduce": ({"count": len(red_ms), "avg_us": 1e3 * float(sum(red_ms)) / len(red_ms),
                                      "median_us": 1e3 * float(sorted(red_ms)[len(red_ms) // 2]), "max_us": 1e3 * float(max(red_ms)),
                                      "every_control_steps": ROLLOUT_STEPS, "words": int(stats_acc.numel()),
                                      "overlapped": "side stream, concurrent with the following control steps; latency = end of the "
-                                                   "submitting step -> end of the all-reduce (includes the L2 flush between steps)",
+                                                   "submitting step -> end of the all-reduce",
                                      "tail_ms_added_to_timed_region": tail_ms,
                                      "included_in_value": True} if red_ms else None),
-                "launches": int(launches), "e2e": e2e, "clocks": sampler.summary(), "wall": t_wall, "flushed": flush is not None}
+                "launches": int(launches), "e2e": e2e, "clocks": sampler.summary(), "wall": t_wall, "l2_mode": mode, "n_sets": n_sets,
+                "set_bytes": set_bytes}
 
     main_m = measure(n_envs, args.steps, args.warmup, not args.no_e2e)
     step_kernel_name = main_m["kernel"]
@@ -413,6 +456,10 @@ def main():
     if world == 1 and args.envs is None and not args.no_small:
         small_m = measure(4096, args.steps, args.warmup, not args.no_e2e)     # BASELINE.json configs[1]
     value, total_ms, launches, e2e = main_m["value"], main_m["total_ms"], main_m["launches"], main_m["e2e"]
+    flush_m = None
+    if world == 1 and args.l2 == "rotate" and not args.no_small:
+        # the round-1 / early round-2 method beside it, for continuity: one env set, 256 MiB write fill before every control step
+        flush_m = measure(n_envs, max(2, min(4, args.steps)), 1, False, mode="flush")
 
     mdp_only = None
     if rank == 0 and world == 1 and not args.no_mdp:
@@ -555,7 +602,7 @@ def main():
             "timing": {"control_steps_per_step": CONTROL_STEPS_PER_STEP, "ms_per_control_step": total_ms / main_m["ctrl_steps"],
                        "timed_control_steps": main_m["ctrl_steps"], "timed_region_ms": total_ms,
                        "parallelism": f"env-sharded x{world}, no collective in the step",
-                       "l2": "flushed before every control step (256 MiB write, outside the timed events)" if main_m["flushed"] else "not flushed",
+                       "l2": l2_note(main_m),
                        "wall_s_incl_flush": main_m["wall"], "stats_allreduce": main_m["stats_allreduce"]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (prof["dram_bytes_read"] + prof["dram_bytes_write"]) if prof else None,
@@ -587,6 +634,12 @@ def main():
                 "source": prof_note + ": instruction counts of the committed capture / live CUDA-event kernel time"}
         else:
             line["fp32_issue"] = {"unavailable": prof_note}
+        if flush_m is not None:
+            line["timing"]["after_256MB_write_flush"] = {
+                "value": flush_m["value"], "unit": UNIT, "ms_per_control_step": flush_m["total_ms"] / flush_m["ctrl_steps"],
+                "timed_control_steps": flush_m["ctrl_steps"], "l2": l2_note(flush_m),
+                "note": "the fill leaves the L2 full of dirty lines; their write-back (126 MB) shares the DRAM with the step, and the "
+                        "fill between two steps removes the launch overlap (PDL) the back-to-back stream has"}
         if small_m is not None:
             a4 = ALGO_BYTES_PER_ENV_STEP * 4096 / (small_m["local_ms_per_ctrl_step"] * 1e-3) / 1e9
             line["envs_4096"] = {"workload": "BASELINE.json configs[1]: full fused step, 4096 envs, 1 x B200",

@@ -1,4 +1,5 @@
-"""Step time with and without programmatic dependent launch (ZBOT_PDL), back to back and with a gap kernel in between:
+"""Step time with and without programmatic dependent launch (ZBOT_PDL; ZBOT_PDL_EARLY = the step kernel releases its
+dependents at its start), back to back:
    python tools/time_pdl.py [envs ...]"""
 import os
 import sys
@@ -12,8 +13,10 @@ from zbot_lab_b200.stepper import NativeStepper  # noqa: E402
 from zbot_lab_b200.utils import synthetic as syn  # noqa: E402
 
 
-def run(n, pdl, steps=300):
+def run(n, pdl, steps=300, early=False, fused=False):
     os.environ["ZBOT_PDL"] = "1" if pdl else "0"
+    os.environ["ZBOT_FUSED_STATS"] = "1" if fused else "0"
+    os.environ["ZBOT_PDL_EARLY"] = "1" if early else "0"
     st = NativeStepper(n, "cuda:0")
     st.reset_idx(None)
     rng = np.random.default_rng(0)
@@ -43,4 +46,11 @@ if __name__ == "__main__":
     for n in [int(x) for x in sys.argv[1:]] or [4096, 65536]:
         t0, c0 = run(n, False)
         t1, c1 = run(n, True)
-        print(f"envs {n:6d}: plain {t0:7.2f} us/step   PDL {t1:7.2f} us/step   same result: {c0 == c1}", flush=True)
+        t2, c2 = run(n, True, early=True)
+        t3, c3 = run(n, True, fused=True)
+        t4, c4 = run(n, True, early=True, fused=True)
+        t5, c5 = run(n, False, fused=True)
+        print(f"envs {n:6d}: separate statistics kernel: plain {t0:7.2f} us/step   PDL {t1:7.2f}   PDL + early trigger {t2:7.2f}   "
+              f"same result: {c0 == c1 == c2}", flush=True)
+        print(f"envs {n:6d}: fused statistics:           plain {t5:7.2f} us/step   PDL {t3:7.2f}   PDL + early trigger {t4:7.2f}   "
+              f"same state: {c0[0] == c3[0] == c4[0] == c5[0]}  stats sums {c0[1]!r} vs {c3[1]!r}", flush=True)

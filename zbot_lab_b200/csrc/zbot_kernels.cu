@@ -83,6 +83,14 @@ struct StatsCtx {
   int norm_word22;         // manager task: word 22 is an Episode_Reward value (normalised), not a raw count
   unsigned int* ticket;    // non-null: the producing kernel runs the grid-level pass itself in its LAST CTA to finish (a device
                            // counter, left at zero); no separate statistics launch follows (zbot_mdp_pipe_kernel)
+  unsigned long long* acc; // non-null: FUSED statistics.  Every CTA adds its partial row to 32 fixed-point (2^-30) 64-bit accumulators
+                           // with integer atomics -- integer addition commutes, so the totals are bit-reproducible whatever the
+                           // order the CTAs finish in -- and the LAST CTA to finish (`ticket`) converts them, writes the ring slot,
+                           // does the all-env-reset spread, bumps the generator position and clears the accumulators: the
+                           // control step is ONE launch, and the next step's kernel follows it directly
+  int pdl_early;           // 1: the step kernel releases its dependents (the statistics CTA, and through it the next step's CTAs)
+                           // as soon as every one of its CTAs is running, so they are RESIDENT -- parked at their own
+                           // griddepcontrol.wait -- when this grid completes, instead of being launched then
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -126,6 +134,35 @@ __device__ __forceinline__ void obs_add_noise(const Params<float>& P, const Stat
 // accumulators so four L2 loads are in flight per thread; everything is combined in a fixed order, so the
 // result is bit-reproducible (no float atomics).
 // (any block size that is a multiple of 32; with 1024 threads the summation order is the one-block kernel's)
+// The part after the totals (`tot[0..31]`, shared memory, visible to the block): normalisation, ring slot, all-env-reset spread,
+// generator position.  Any block size that is a multiple of 32.
+__device__ __forceinline__ void stats_finalize_tail(const StatsCtx& sc, const float* tot) {
+  if (threadIdx.x < kStats) {
+    const float nreset = tot[S_NUM_RESET];
+    float v = tot[threadIdx.x];
+    // words 0..15 leave the kernel as the reference's `Episode_Reward/<term>` values:
+    // mean over the reset envs of the episodic sum, divided by max_episode_length_s
+    if ((threadIdx.x < MAX_TERMS - sc.raw_tail || (sc.norm_word22 && threadIdx.x == S_M_TERM_PENALTY)) && nreset > 0.f)
+      v = (v / nreset) * sc.inv_episode_s;
+    // the reference only rewrites extras["log"] when something reset (…env_v2.py:450): keep the previous log
+    // (word 16, the number of envs reset THIS step, is always the live count)
+    if ((threadIdx.x < S_REW_SUM || threadIdx.x >= kStatUsed) && threadIdx.x != S_NUM_RESET && !(nreset > 0.f))
+      v = (sc.prev_slot >= 0) ? sc.ring[(size_t)sc.prev_slot * kStats + threadIdx.x] : 0.f;
+    sc.ring[(size_t)sc.slot * kStats + threadIdx.x] = v;
+  }
+  if (sc.spread_ep_len && tot[S_NUM_RESET] == (float)sc.spread_n) {   // block-uniform: every env reset in this step
+    const uint64_t call = rng_position(sc);
+    for (int i = threadIdx.x; i < sc.spread_n; i += blockDim.x) {
+      const float u = v4_uniform(sc.spread_seed, call, (uint32_t)i, 64u);
+      sc.spread_ep_len[i] = min((int)(u * (float)sc.spread_high), sc.spread_high - 1);
+    }
+    __syncthreads();                                                     // all reads of the position precede the bump
+  }
+  // advance the in-kernel generator's stream position: every CTA of this control step's kernel has finished (the separate
+  // statistics kernel: pdl_wait; the fused pass: the ticket), the next one reads it only after this grid has completed
+  if (threadIdx.x == 0 && sc.rng_ctr) *const_cast<unsigned long long*>(sc.rng_ctr) = *sc.rng_ctr + 1ull;
+}
+
 __device__ __forceinline__ void stats_finalize_body(const StatsCtx& sc, unsigned int nblocks, float (*red)[33]) {
   const int j = threadIdx.x & 31, w = threadIdx.x >> 5;
   const unsigned int nw = blockDim.x >> 5;
@@ -146,30 +183,30 @@ __device__ __forceinline__ void stats_finalize_body(const StatsCtx& sc, unsigned
     red[0][threadIdx.x] = acc;           // words a kernel does not produce are zero in every partial row
   }
   __syncthreads();
+  stats_finalize_tail(sc, red[0]);
+}
+
+// FUSED statistics (StatsCtx::acc): this CTA's total of word `threadIdx.x` (threads 0..31 carry one each, the others pass 0)
+// goes to the fixed-point accumulators; the last CTA of the grid to get here runs the tail.  `tot`: >= 32 floats of shared
+// memory nobody else uses any more.  Must be reached by every thread of every CTA of the grid.
+constexpr float kStatFix = 1073741824.f;          // 2^30: a float32 partial of magnitude >= 2^-7 is represented exactly
+__device__ __forceinline__ void stats_fused_commit(const StatsCtx& sc, float cta_total, float* tot) {
+  __shared__ int s_last;
+  if (threadIdx.x < kStats && cta_total != 0.f)
+    atomicAdd(sc.acc + threadIdx.x, (unsigned long long)__float2ll_rn(cta_total * kStatFix));   // two's complement: signed add
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(sc.ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
   if (threadIdx.x < kStats) {
-    const float nreset = red[0][S_NUM_RESET];
-    float v = red[0][threadIdx.x];
-    // words 0..15 leave the kernel as the reference's `Episode_Reward/<term>` values:
-    // mean over the reset envs of the episodic sum, divided by max_episode_length_s
-    if ((threadIdx.x < MAX_TERMS - sc.raw_tail || (sc.norm_word22 && threadIdx.x == S_M_TERM_PENALTY)) && nreset > 0.f)
-      v = (v / nreset) * sc.inv_episode_s;
-    // the reference only rewrites extras["log"] when something reset (…env_v2.py:450): keep the previous log
-    // (word 16, the number of envs reset THIS step, is always the live count)
-    if ((threadIdx.x < S_REW_SUM || threadIdx.x >= kStatUsed) && threadIdx.x != S_NUM_RESET && !(nreset > 0.f))
-      v = (sc.prev_slot >= 0) ? sc.ring[(size_t)sc.prev_slot * kStats + threadIdx.x] : 0.f;
-    sc.ring[(size_t)sc.slot * kStats + threadIdx.x] = v;
+    const long long raw = (long long)atomicExch(sc.acc + threadIdx.x, 0ull);      // read and clear for the next control step
+    tot[threadIdx.x] = (float)((double)raw * (1.0 / (double)kStatFix));
   }
-  if (sc.spread_ep_len && red[0][S_NUM_RESET] == (float)sc.spread_n) {   // block-uniform: every env reset in this step
-    const uint64_t call = rng_position(sc);
-    for (int i = threadIdx.x; i < sc.spread_n; i += blockDim.x) {
-      const float u = v4_uniform(sc.spread_seed, call, (uint32_t)i, 64u);
-      sc.spread_ep_len[i] = min((int)(u * (float)sc.spread_high), sc.spread_high - 1);
-    }
-    __syncthreads();                                                     // all reads of the position precede the bump
-  }
-  // advance the in-kernel generator's stream position: the step kernel of this control step has completed (pdl_wait
-  // above), the next one reads it only after this grid has completed (its own pdl_wait / stream order)
-  if (threadIdx.x == 0 && sc.rng_ctr) *const_cast<unsigned long long*>(sc.rng_ctr) = *sc.rng_ctr + 1ull;
+  if (threadIdx.x == 0) *sc.ticket = 0u;
+  __syncthreads();
+  stats_finalize_tail(sc, tot);
 }
 
 __global__ void __launch_bounds__(1024) zbot_stats_finalize_kernel(StatsCtx sc, unsigned int nblocks) {
@@ -193,11 +230,15 @@ __device__ __forceinline__ void stats_block_partial(float (&vals)[kN], bool did_
     if (lane == 0) smem[warp * kN + j] = v;
   }
   __syncthreads();
+  float acc = 0.f;
   if (threadIdx.x < kStats) {            // a whole 32-word row: the words this kernel does not produce are written as zeros
-    float acc = 0.f;
     if (threadIdx.x < kN)
       for (int w = 0; w < nwarps; ++w) acc += smem[w * kN + threadIdx.x];
-    sc.partials[(size_t)(blockIdx.x + sc.block_offset) * kStats + threadIdx.x] = acc;
+    if (!sc.acc) sc.partials[(size_t)(blockIdx.x + sc.block_offset) * kStats + threadIdx.x] = acc;
+  }
+  if (sc.acc) {                          // grid-uniform
+    __syncthreads();                     // the warp rows have been read: smem is free for the totals
+    stats_fused_commit(sc, acc, smem);
   }
 }
 
@@ -305,6 +346,7 @@ zbot_step_body(const Params<float>& P, const DefaultPose& dp,
                  StatsCtx sc, ExportPtrs xp) {
   extern __shared__ float smem[];   // blockDim*SCR_STRIDE floats: substep scratch, then obs rows, then stats
   pdl_wait();                       // ordered after the previous kernel of the stream (no-op unless launched with PDL)
+  if (sc.pdl_early) pdl_trigger();
   // this launch covers envs [e_begin, e_end) of the n-env state (whole range: 0, n)
   const int e0 = e_begin + blockIdx.x * blockDim.x;
   const int e = e0 + threadIdx.x;
@@ -1203,6 +1245,8 @@ struct ZbotHandle {
   int num_sms;
   bool unroll2;    // chain sweeps unrolled by two (more than one warp per scheduler)
   bool pdl;        // launch the step / statistics kernels with programmatic stream serialization
+  bool fused_stats;  // the grid-level statistics pass runs in the last CTA of the producing kernel (StatsCtx::acc): no second launch
+  bool pdl_early;  // ... and let the step kernel release its dependents at its start (StatsCtx::pdl_early; ZBOT_PDL_EARLY=0/1)
   bool ctas3;      // 3 CTAs/SM need fewer waves than 2 at this N (the register-budget rule of zbot_create)
   float4* state;
   int64_t* ep_len;
@@ -1308,7 +1352,15 @@ struct DeviceGuard {
 };
 
 template <typename H>
+void ctx_fuse(StatsCtx& sc, const H* h) {
+  if (!h->fused_stats) return;
+  sc.acc = h->rng_ctr + 2;
+  sc.ticket = reinterpret_cast<unsigned int*>(h->rng_ctr + 1);
+}
+
+template <typename H>
 void ctx_spread(StatsCtx& sc, const H* h) {
+  sc.pdl_early = (h->pdl && h->pdl_early) ? 1 : 0;
   if (!h->spread_all_reset) return;
   sc.spread_ep_len = h->ep_len;
   sc.spread_n = h->cfg.num_envs;
@@ -1373,8 +1425,9 @@ static int create_impl(const ZbotCfg* cfg, int device, ZbotHandle* h) {
   h->num_sms = prop.multiProcessorCount;
   h->max_blocks = (cfg->num_envs + 31) / 32 + 1;
   ZB_CUDA(cudaMalloc(&h->partials, (size_t)h->max_blocks * kStats * sizeof(float)));
-  ZB_CUDA(cudaMalloc(&h->rng_ctr, 2 * sizeof(unsigned long long)));          // [0] stream position, [1] last-CTA ticket (StatsCtx::ticket)
-  ZB_CUDA(cudaMemset(h->rng_ctr, 0, 2 * sizeof(unsigned long long)));
+  // [0] stream position, [1] last-CTA ticket (StatsCtx::ticket), [2..33] fixed-point statistics accumulators (StatsCtx::acc)
+  ZB_CUDA(cudaMalloc(&h->rng_ctr, (2 + kStats) * sizeof(unsigned long long)));
+  ZB_CUDA(cudaMemset(h->rng_ctr, 0, (2 + kStats) * sizeof(unsigned long long)));
   ZB_CUDA(cudaMalloc(&h->d_dp, sizeof(DefaultPose)));          // scratch of the default-pose FK; freed by zbot_destroy
   zbot_default_pose_kernel<<<1, 1>>>(h->d_dp, cfg->task);
   ZB_CUDA(cudaGetLastError());
@@ -1428,6 +1481,10 @@ static int create_impl(const ZbotCfg* cfg, int device, ZbotHandle* h) {
     // programmatic dependent launch: the statistics kernel and the next step kernel are scheduled while their predecessor
     // drains (34.9 -> 30.9 us per step at 4096 envs, 80.0 -> 76.7 at 65536); ZBOT_PDL=0 restores plain launches
     { const char* sp = getenv("ZBOT_PDL"); h->pdl = sp ? (atoi(sp) != 0) : true; }
+    // statistics fused into the producing kernel (fixed-point accumulators + last-CTA pass); ZBOT_FUSED_STATS=0 restores the
+    // separate one-block zbot_stats_finalize_kernel behind every step
+    { const char* sp = getenv("ZBOT_FUSED_STATS"); h->fused_stats = sp ? (atoi(sp) != 0) : true; }
+    { const char* sp = getenv("ZBOT_PDL_EARLY"); h->pdl_early = sp ? (atoi(sp) != 0) : false; }
     h->unroll2 = cfg->num_envs > 4 * 32 * h->num_sms;
     if (const char* su = getenv("ZBOT_SWEEP_UNROLL")) h->unroll2 = (atoi(su) == 2);   // test / tuning override, all tasks
     if (h->variant < 0) {
@@ -1530,6 +1587,7 @@ static int step_impl(ZbotHandle* h, const float* actions, float* obs, float* rew
   const int grid = (walk_any && h->w2) ? (n + 31) / 32 : (n + block * ept - 1) / (block * ept);
   const size_t smem = (size_t)block * kStepRowWords * sizeof(float) * ept;   // >= obs rows (23/thread) and stats (704 floats)
   StatsCtx sc{h->partials, h->ring, slot, prev, h->inv_episode_s, 0, h->rng_ctr, 0};
+  ctx_fuse(sc, h);
   ctx_spread(sc, h);
   cudaStream_t s = (cudaStream_t)stream;
   ExportPtrs xp{};
@@ -1587,15 +1645,19 @@ static int step_impl(ZbotHandle* h, const float* actions, float* obs, float* rew
     ZB_CUDA(launch_pdl(w2_fn(h->w2_ctas), dim3(g2), dim3(64), kW2Smem, s, h->pdl, h->P, h->dp, h->state, h->ep_len,
                        actions, obs, rew, terminated, truncated, n, 0, n, sc, xp));
     h->launches += 1;
-    ZB_CUDA(launch_pdl(zbot_stats_finalize_kernel, dim3(1), dim3(1024), 0, s, h->pdl, sc, (unsigned int)g2));
-    h->launches += 1;
+    if (!sc.acc) {
+      ZB_CUDA(launch_pdl(zbot_stats_finalize_kernel, dim3(1), dim3(1024), 0, s, h->pdl, sc, (unsigned int)g2));
+      h->launches += 1;
+    }
     return ZBOT_OK;
   } else if (h->pdl) {
     ZB_CUDA(launch_pdl(kStepVariants[h->variant].fn, dim3(grid), dim3(block), smem, s, true, h->P, h->dp, h->state, h->ep_len,
                        actions, obs, rew, terminated, truncated, n, 0, n, sc, xp));
     h->launches += 1;
-    ZB_CUDA(launch_pdl(zbot_stats_finalize_kernel, dim3(1), dim3(1024), 0, s, true, sc, (unsigned int)grid));
-    h->launches += 1;
+    if (!sc.acc) {
+      ZB_CUDA(launch_pdl(zbot_stats_finalize_kernel, dim3(1), dim3(1024), 0, s, true, sc, (unsigned int)grid));
+      h->launches += 1;
+    }
     return ZBOT_OK;
   } else {
     kStepVariants[h->variant].fn<<<grid, block, smem, s>>>(h->P, h->dp, h->state, h->ep_len, actions, obs, rew, terminated,
@@ -1603,8 +1665,10 @@ static int step_impl(ZbotHandle* h, const float* actions, float* obs, float* rew
   }
   ZB_CUDA(cudaGetLastError());
   h->launches += 1;
-  ZB_CUDA(launch_pdl(zbot_stats_finalize_kernel, dim3(1), dim3(1024), 0, s, h->pdl, sc, (unsigned int)grid));
-  h->launches += 1;
+  if (!sc.acc) {
+    ZB_CUDA(launch_pdl(zbot_stats_finalize_kernel, dim3(1), dim3(1024), 0, s, h->pdl, sc, (unsigned int)grid));
+    h->launches += 1;
+  }
   return ZBOT_OK;
 }
 
@@ -1657,6 +1721,7 @@ int zbot_step_host(ZbotHandle* h, const float* host_actions, float* host_rows, i
   const size_t smem = (size_t)block * kStepRowWords * sizeof(float);
   cudaStream_t s = (cudaStream_t)stream;
   StatsCtx sc{h->partials, h->ring, stats_slot, prev_slot, h->inv_episode_s, 0, h->rng_ctr, 1};
+  ctx_fuse(sc, h);
   ctx_spread(sc, h);
   ExportPtrs xp{};
   const int grid_used = h->w2 ? (n + 31) / 32 : grid;
@@ -1668,8 +1733,10 @@ int zbot_step_host(ZbotHandle* h, const float* host_actions, float* host_rows, i
                                                    nullptr, n, 0, n, sc, xp);
   ZB_CUDA(cudaGetLastError());
   h->launches += 1;
-  ZB_CUDA(launch_pdl(zbot_stats_finalize_kernel, dim3(1), dim3(1024), 0, s, h->pdl, sc, (unsigned int)grid_used));
-  h->launches += 1;
+  if (!sc.acc) {
+    ZB_CUDA(launch_pdl(zbot_stats_finalize_kernel, dim3(1), dim3(1024), 0, s, h->pdl, sc, (unsigned int)grid_used));
+    h->launches += 1;
+  }
   ZB_CUDA(cudaStreamSynchronize(s));
   return ZBOT_OK;
 }
@@ -1690,6 +1757,7 @@ static int v4_step_impl(ZbotHandle* h, const float* actions, const float* rand, 
   const int grid = (n + block - 1) / block;
   const size_t smem = (size_t)block * kStepRowWords * sizeof(float);
   StatsCtx sc{h->partials, h->ring, slot, prev, h->inv_episode_s, 0, h->rng_ctr, 0};
+  ctx_fuse(sc, h);
   ctx_spread(sc, h);
   cudaStream_t s = (cudaStream_t)stream;
   if (export_buf && h->v4_h2)
@@ -1715,8 +1783,10 @@ static int v4_step_impl(ZbotHandle* h, const float* actions, const float* rand, 
                                                      terminated, truncated, n, sc, nullptr);
   ZB_CUDA(cudaGetLastError());
   h->launches += 1;
-  ZB_CUDA(launch_pdl(zbot_stats_finalize_kernel, dim3(1), dim3(1024), 0, s, h->pdl, sc, (unsigned int)grid));
-  h->launches += 1;
+  if (!sc.acc) {
+    ZB_CUDA(launch_pdl(zbot_stats_finalize_kernel, dim3(1), dim3(1024), 0, s, h->pdl, sc, (unsigned int)grid));
+    h->launches += 1;
+  }
   return ZBOT_OK;
 }
 
@@ -1747,6 +1817,7 @@ static int m_step_impl(ZbotHandle* h, const float* actions, const float* rand, f
   const size_t smem = (size_t)block * SCR_STRIDE * sizeof(float);
   StatsCtx sc{h->partials, h->ring, slot, prev, h->inv_episode_s, 0, h->rng_ctr, 0,
               (h->cfg.num_terms <= MAX_TERMS - 3) ? 2 : 0};
+  ctx_fuse(sc, h);
   ctx_spread(sc, h);
   sc.norm_word22 = 1;
   cudaStream_t s = (cudaStream_t)stream;
@@ -1769,8 +1840,10 @@ static int m_step_impl(ZbotHandle* h, const float* actions, const float* rand, f
 #undef ZB_M_LAUNCH
   ZB_CUDA(cudaGetLastError());
   h->launches += 1;
-  ZB_CUDA(launch_pdl(zbot_stats_finalize_kernel, dim3(1), dim3(1024), 0, s, h->pdl, sc, (unsigned int)grid));
-  h->launches += 1;
+  if (!sc.acc) {
+    ZB_CUDA(launch_pdl(zbot_stats_finalize_kernel, dim3(1), dim3(1024), 0, s, h->pdl, sc, (unsigned int)grid));
+    h->launches += 1;
+  }
   return ZBOT_OK;
 }
 
@@ -1838,6 +1911,7 @@ int zbot_reset_idx(ZbotHandle* h, const int64_t* env_ids, int64_t nids, const ui
   const int block = 64;
   const int grid = (int)((nids + block - 1) / block);
   StatsCtx sc{h->partials, h->ring, stats_slot, -1, h->inv_episode_s, 0, h->rng_ctr, 0};
+  ctx_fuse(sc, h);
   if (h->cfg.task == ZBOT_TASK_SNAKE_V0)
     zbot_reset_kernel<true><<<grid, block, 32 * kStatUsed * sizeof(float), (cudaStream_t)stream>>>(
         h->P, h->dp, h->state, h->ep_len, env_ids, nids, terminated, truncated, n, sc);
@@ -1846,9 +1920,11 @@ int zbot_reset_idx(ZbotHandle* h, const int64_t* env_ids, int64_t nids, const ui
         h->P, h->dp, h->state, h->ep_len, env_ids, nids, terminated, truncated, n, sc);
   ZB_CUDA(cudaGetLastError());
   h->launches += 1;
-  zbot_stats_finalize_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(sc, (unsigned int)grid);
-  ZB_CUDA(cudaGetLastError());
-  h->launches += 1;
+  if (!sc.acc) {
+    zbot_stats_finalize_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(sc, (unsigned int)grid);
+    ZB_CUDA(cudaGetLastError());
+    h->launches += 1;
+  }
   return ZBOT_OK;
 }
 
@@ -1930,6 +2006,7 @@ int zbot_mdp_step(ZbotHandle* h, const ZbotMdpInputs* in, const float* actions, 
   MdpIn mi{in->body_link_pos_w, in->body_link_quat_w, in->body_com_lin_vel_w, in->joint_pos, in->joint_vel,
            in->applied_torque, in->net_forces_w_history, in->last_air_time, in->env_origins};
   StatsCtx sc{h->partials, h->m_ring, stats_slot, prev_slot, h->inv_episode_s, 0, h->rng_ctr, 0};
+  ctx_fuse(sc, h);
   // persistent TMA-fed kernel (zbot_mdp_pipe.cuh) whenever every tensor can be a bulk-copy source (16-byte aligned base)
   const char* pipe_env = getenv("ZBOT_MDP_PIPE");      // read per call: tests A/B the two kernels in one process
   const bool pipe_off = pipe_env && atoi(pipe_env) == 0;
@@ -1960,8 +2037,10 @@ int zbot_mdp_step(ZbotHandle* h, const ZbotMdpInputs* in, const float* actions, 
   }
   h->launches += 1;
   if (!sc.ticket) {
-    ZB_CUDA(launch_pdl(zbot_stats_finalize_kernel, dim3(1), dim3(1024), 0, (cudaStream_t)stream, h->pdl, sc, (unsigned int)grid));
-    h->launches += 1;
+    {
+      ZB_CUDA(launch_pdl(zbot_stats_finalize_kernel, dim3(1), dim3(1024), 0, (cudaStream_t)stream, h->pdl, sc, (unsigned int)grid));
+      h->launches += 1;
+    }
   }
   return ZBOT_OK;
 }

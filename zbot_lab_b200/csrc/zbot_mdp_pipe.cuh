@@ -320,11 +320,16 @@ zbot_mdp_pipe_kernel(const __grid_constant__ Params<float> P, const __grid_const
       if (lane == 0) stat_sm[w * kStats + j] = v;
     }
     __syncthreads();
+    float acc = 0.f;
     if (threadIdx.x < kStats) {
-      float acc = 0.f;
       if (threadIdx.x < kStatUsed)
         for (int ww = 0; ww < kWarps; ++ww) acc += stat_sm[ww * kStats + threadIdx.x];
-      sc.partials[(size_t)(blockIdx.x + sc.block_offset) * kStats + threadIdx.x] = acc;
+      if (!sc.acc) sc.partials[(size_t)(blockIdx.x + sc.block_offset) * kStats + threadIdx.x] = acc;
+    }
+    if (sc.acc) {      // fused statistics (fixed-point accumulators + ticket): see stats_fused_commit
+      __syncthreads();
+      stats_fused_commit(sc, acc, stat_sm);
+      return;
     }
   }
   // ---- grid-level pass in the last CTA to finish (no second launch): ticket, then the one-block finalize body -----------------

@@ -86,6 +86,7 @@ zbot_step_w2_body(const Params<float>& P, const DefaultPose& dp, float4* __restr
                   StatsCtx sc, ExportPtrs xp) {
   extern __shared__ float smem[];   // 64 rows of W2_STRIDE words, then the pair's exchange buffer
   pdl_wait();
+  if (sc.pdl_early) pdl_trigger();
   const int side = threadIdx.x >> 5, lane = threadIdx.x & 31;     // warp-uniform side
   const int e0 = e_begin + blockIdx.x * 32;
   const int e = e0 + lane;
