@@ -482,8 +482,8 @@ def main():
                                   "l2": "inputs larger than L2 (6 rotating input sets), CUDA-graph replay of 12 steps, no flush",
                                   "after_256MB_write_flush": {"ms_per_step": ms_w, "achieved_gbs": gbs_w,
                                                               "frac_of_measured_hbm_peak": gbs_w / peak_m}}
-        mdp_only["kernel"] = ("zbot_mdp_kernel<true> + zbot_stats_finalize_kernel below 131072 envs, "
-                              "zbot_mdp_pipe_kernel<4,2> (persistent, TMA-fed) + zbot_stats_finalize_kernel from there")
+        mdp_only["kernel"] = ("zbot_mdp_kernel<true>, 112-env tiles (65536 envs = two full waves of 2 x 148 CTAs), statistics fused "
+                              "into its last CTA: one launch per step")
         mdp_only["algorithmic_bytes_per_env_step"] = bench_mdp.MDP_ALGO_BYTES
 
     other_tasks = None

@@ -104,7 +104,7 @@ def test_mdp_kernel_matches_oracle_random_sizes():
 @pytest.mark.parametrize("shape", ["42", "43", "33", "41", "42+fused-stats"])
 @pytest.mark.parametrize("n", [37, 4096, 20013])
 def test_mdp_pipelined_kernel_is_bit_identical_to_the_one_shot_kernel(n, shape, monkeypatch):
-    """`zbot_mdp_pipe_kernel` (persistent, every input by bulk async copy; the default from 131072 envs, forced here with
+    """`zbot_mdp_pipe_kernel` (persistent, every input by bulk async copy; selected with
     ZBOT_MDP_PIPE=<stages><warps per stage>) against `zbot_mdp_kernel<true>` (ZBOT_MDP_PIPE=0) on the same inputs: the per-env
     arithmetic is the same device code, so observations, rewards, flags, counters and every state word are bit-identical; only
     the grid-level statistics are summed in another order (also with the pass fused into the last CTA)."""
@@ -1618,3 +1618,78 @@ def test_m_fused_step_50_step_horizon_vs_float64_host_build():
     assert np.median(dq) <= 1e-4 and np.quantile(dq, 0.9) <= 2e-3 and dq.max() <= 5e-2, (np.median(dq), np.quantile(dq, 0.9), dq.max())
     assert np.median(dp) <= 1e-4 and dp.max() <= 2e-2, (np.median(dp), dp.max())
     st.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# statistics fused into the producing kernel (fixed-point accumulators + last-CTA pass) vs the separate one-block kernel
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [37, 4096, 20013, 65536])
+def test_fused_statistics_equal_the_separate_statistics_kernel(n, monkeypatch):
+    """ZBOT_FUSED_STATS=1 (default: every CTA adds its partial row to 64-bit fixed-point accumulators with integer atomics, the
+    last CTA to finish writes the ring slot, bumps the generator position and clears them -- ONE launch per control step)
+    against ZBOT_FUSED_STATS=0 (partial rows + `zbot_stats_finalize_kernel`) from identical states: the step itself is the
+    same code, so every per-env output and state word is bit-identical; counts are exact; the float words agree to float32
+    round-off (a fixed-point sum of the SAME per-CTA float partials: closer to the exact sum than the float tree).  Fused twice
+    = bit-identical (integer addition commutes: the order the CTAs finish in does not matter).  Launches: 1 vs 2 per step."""
+    from zbot_lab_b200.utils import synthetic as syn
+    rng = np.random.default_rng(11)
+    acts = _t(rng.normal(0, 1.0, (6, n, 6)).astype(np.float32))
+    sim = syn.synth_sim_state(np.random.default_rng(12), n)
+    ep0 = _t(np.random.default_rng(13).integers(0, 1000, n).astype(np.int64))
+    runs = []
+    for fused in ("1", "0", "1"):
+        monkeypatch.setenv("ZBOT_FUSED_STATS", fused)
+        st = _stepper(n)
+        st.reset_idx(None)
+        st.set_sim_state({k: _t(v) for k, v in sim.items()})
+        st.episode_length_buf[:] = ep0
+        l0 = st.launch_count
+        rec = []
+        for t in range(6):
+            o = st.step(acts[t])
+            torch.cuda.synchronize()
+            rec.append([x.clone() for x in o] + [st.state.buf.clone(), st.episode_length_buf.clone(), st.stats.clone()])
+        runs.append((rec, st.launch_count - l0))
+        st.close()
+    (fa, la), (sb, lb), (fc, lc) = runs
+    assert la == 6 and lb == 12 and lc == 6
+    saw_reset = False
+    for a, b, c in zip(fa, sb, fc):
+        for x, y, z in zip(a[:6], b[:6], c[:6]):
+            assert torch.equal(x, y) and torch.equal(x, z)
+        assert torch.equal(a[6], c[6])                                   # fused statistics are run-to-run bit-identical
+        s1, s0 = a[6].cpu().numpy(), b[6].cpu().numpy()
+        assert np.array_equal(s1[16:19], s0[16:19]) and np.array_equal(s1[20:22], s0[20:22])       # counts
+        assert np.allclose(s1, s0, rtol=2e-6, atol=1e-6)
+        saw_reset |= bool(s1[16] > 0)
+    assert saw_reset or n < 1000      # the reset-only words were exercised (a few dozen envs may see no reset in six steps)
+
+
+def test_mdp_kernel_tile_size_does_not_change_results(monkeypatch):
+    """The MDP-only kernel's envs-per-CTA (ZBOT_MDP_TILE; default 112 of 128 threads so that 65536 envs are two FULL waves of
+    2 x 148 CTAs) only changes which CTA owns an env: per-env outputs and state are bit-identical, statistics to round-off."""
+    from zbot_lab_b200.utils import synthetic as syn
+    n = 20013
+    case = syn.synth_mdp_case(5, n, 3)
+    outs = []
+    for tile in ("112", "128", "40"):
+        monkeypatch.setenv("ZBOT_MDP_TILE", tile)
+        monkeypatch.setenv("ZBOT_MDP_PIPE", "0")
+        st = _stepper(n)
+        st.mdp_init()
+        org = _t(case["origins"])
+        st.mdp_episode_length_buf[:] = _t(case["episode_length_buf0"])
+        st.mdp_observe(_S(case["S0"]), org)
+        rec = []
+        for a, S1 in case["steps"]:
+            o = st.mdp_step(_S(S1), org, _t(a))
+            torch.cuda.synchronize()
+            rec.append([x.clone() for x in o] + [st.mdp_episode_length_buf.clone(), st.mdp_state.buf.clone(),
+                                                 st.mdp_stats_ring[st._mdp_slot].clone()])
+        outs.append(rec)
+        st.close()
+    for a, b, c in zip(*outs):
+        for x, y, z in zip(a[:6], b[:6], c[:6]):
+            assert torch.equal(x, y) and torch.equal(x, z)
+        assert np.allclose(a[6].cpu().numpy(), b[6].cpu().numpy(), rtol=1e-5, atol=1e-6)
+        assert np.allclose(a[6].cpu().numpy(), c[6].cpu().numpy(), rtol=1e-5, atol=1e-6)

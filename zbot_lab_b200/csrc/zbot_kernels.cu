@@ -275,12 +275,12 @@ __device__ __forceinline__ void store_words(float4* __restrict__ st, int n, int 
 // stage per-thread rows of ROW floats through shared memory, write the block's rows contiguously
 template <int ROW>
 __device__ __forceinline__ void store_rows_coalesced(float* __restrict__ dst, const float* row, int n, int e0,
-                                                     float* smem /*blockDim*ROW*/) {
+                                                     float* smem /*blockDim*ROW*/, int tile = 0 /*envs of this CTA; 0: blockDim*/) {
   const int e = e0 + threadIdx.x;
 #pragma unroll
   for (int i = 0; i < ROW; ++i) smem[threadIdx.x * ROW + i] = row[i];   // ROW odd -> conflict-free
   __syncthreads();
-  const int valid = min((int)blockDim.x, n - e0);
+  const int valid = min(tile ? tile : (int)blockDim.x, n - e0);
   const int total = valid * ROW;
   float* base = dst + (size_t)e0 * ROW;
   if ((((size_t)e0 * ROW) & 3) == 0 && ((uintptr_t)dst & 15) == 0) {
@@ -1091,7 +1091,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
-constexpr int kMdpTile = 128;  // envs (= threads) per CTA of the MDP step kernel: 90 KB history tile, 2 CTAs / SM (tile sweep: profiles/r1_notes.md)
+// envs per CTA of the MDP step kernel (128 threads, the last 16 idle): 79 KB history tile, 2 CTAs / SM, and 65536 / 131072 / 262144
+// envs are 1.98 / 3.95 / 7.9 waves of 296 CTAs instead of 1.73 / 3.46 / 6.9 (tile sweep: profiles/r2_notes.md section 9; the
+// per-thread row loads lean on the L1, so the tile sizes for which the driver picks a large shared-memory carve-out -- 96, 72, 56,
+// 48, 32 -- and an explicit maximum carve-out are 25 % slower)
+constexpr int kMdpTile = 112;
 
 // kStep = false: `_get_observations` only (fills the stale cache)
 template <bool kStep>
@@ -1099,13 +1103,14 @@ __global__ void __launch_bounds__(128)
 zbot_mdp_kernel(const __grid_constant__ Params<float> P, const __grid_constant__ DefaultPose dp, MdpIn in,
                 float4* __restrict__ mstate, int64_t* __restrict__ ep_len_buf, const float* __restrict__ actions,
                 float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ terminated,
-                uint8_t* __restrict__ truncated, int n, StatsCtx sc) {
+                uint8_t* __restrict__ truncated, int n, StatsCtx sc, int tile) {
   extern __shared__ __align__(128) float smem[];   // [blockDim][180] history tile, reused for obs rows / stats
   pdl_wait();
-  const int e0 = blockIdx.x * blockDim.x;
+  // `tile` envs per CTA (<= blockDim, a multiple of 4): chosen by the host so that the grid is a whole number of full waves
+  const int e0 = blockIdx.x * tile;
   const int e = e0 + threadIdx.x;
-  const bool live = e < n;
-  const int valid = min((int)blockDim.x, n - e0);
+  const bool live = (int)threadIdx.x < tile && e < n;
+  const int valid = min(tile, n - e0);
   float stat[kStatUsed];
 #pragma unroll
   for (int j = 0; j < kStatUsed; ++j) stat[j] = 0.f;
@@ -1223,7 +1228,7 @@ zbot_mdp_kernel(const __grid_constant__ Params<float> P, const __grid_constant__
     store_words<ZBOT_MDP_STATE_WORDS / 4>(mstate, n, e, w);
   }
   if (kStep) __syncthreads();   // every thread has consumed its history row: the tile is dead, smem is reused
-  store_rows_coalesced<ZBOT_NUM_OBS>(obs, obs_row, n, e0, smem);
+  store_rows_coalesced<ZBOT_NUM_OBS>(obs, obs_row, n, e0, smem, tile);
   if (kStep) {
     __syncthreads();
     stats_block_partial(stat, did_reset, smem, sc);
@@ -1514,7 +1519,7 @@ static int create_impl(const ZbotCfg* cfg, int device, ZbotHandle* h) {
     }
     const char* mt = getenv("ZBOT_MDP_TILE");          // envs (= threads) per CTA of the MDP-only step kernel
     h->mdp_tile = mt ? atoi(mt) : kMdpTile;
-    if (h->mdp_tile != 32 && h->mdp_tile != 64 && h->mdp_tile != 128) h->mdp_tile = kMdpTile;
+    if (h->mdp_tile < 32 || h->mdp_tile > 128 || (h->mdp_tile & 3)) h->mdp_tile = kMdpTile;
     const char* bs = getenv("ZBOT_STEP_BLOCK");
     h->force_block = bs ? atoi(bs) : 0;
     // Two warps per 32 envs (zbot_w2_kernel.cuh) while an SM holds at most two warp pairs, i.e. while the step is bound by
@@ -1989,7 +1994,7 @@ int zbot_mdp_observe(ZbotHandle* h, const ZbotMdpInputs* in, float* obs, void* s
            in->applied_torque, in->net_forces_w_history, in->last_air_time, in->env_origins};
   StatsCtx sc{h->partials, h->m_ring, 0, -1, h->inv_episode_s, 0, h->rng_ctr, 0};
   zbot_mdp_kernel<false><<<grid, block, block * ZBOT_NUM_OBS * sizeof(float), (cudaStream_t)stream>>>(
-      h->P, h->dp, mi, h->mstate, h->m_ep_len, nullptr, obs, nullptr, nullptr, nullptr, n, sc);
+      h->P, h->dp, mi, h->mstate, h->m_ep_len, nullptr, obs, nullptr, nullptr, nullptr, n, sc, block);
   ZB_CUDA(cudaGetLastError());
   h->launches += 1;
   return ZBOT_OK;
@@ -2001,8 +2006,8 @@ int zbot_mdp_step(ZbotHandle* h, const ZbotMdpInputs* in, const float* actions, 
   DeviceGuard guard(h->device);
   if (!actions || !obs || !rew || !terminated || !truncated) return fail(ZBOT_E_INVALID, "zbot_mdp_step: NULL buffer%s");
   if (int rc = check_slot(stats_slot, prev_slot, h->m_ring_slots)) return rc;
-  const int n = h->cfg.num_envs, block = h->mdp_tile;
-  int grid = (n + block - 1) / block;
+  const int n = h->cfg.num_envs, tile = h->mdp_tile, block = (tile + 31) & ~31;
+  int grid = (n + tile - 1) / tile;
   MdpIn mi{in->body_link_pos_w, in->body_link_quat_w, in->body_com_lin_vel_w, in->joint_pos, in->joint_vel,
            in->applied_torque, in->net_forces_w_history, in->last_air_time, in->env_origins};
   StatsCtx sc{h->partials, h->m_ring, stats_slot, prev_slot, h->inv_episode_s, 0, h->rng_ctr, 0};
@@ -2013,9 +2018,10 @@ int zbot_mdp_step(ZbotHandle* h, const ZbotMdpInputs* in, const float* actions, 
   const uintptr_t align_or = (uintptr_t)mi.pos | (uintptr_t)mi.quat | (uintptr_t)mi.vel | (uintptr_t)mi.q | (uintptr_t)mi.qd |
                              (uintptr_t)mi.tau | (uintptr_t)mi.hist | (uintptr_t)mi.last_air | (uintptr_t)mi.origins |
                              (uintptr_t)actions | (uintptr_t)h->m_ep_len | (uintptr_t)h->mstate;
-  // measured (profiles/r2_notes.md section 8, CUDA-graph replay over rotating input sets): 65536 envs 28.4 us one-shot vs 29.2 us
-  // persistent; 262144 envs 96.5 vs 91.9 us -- the persistent kernel is the default from 131072 envs, ZBOT_MDP_PIPE forces either
-  if (!pipe_off && (align_or & 15) == 0 && (pipe_env || n >= 131072)) {
+  // measured (profiles/r2_notes.md sections 8, 9; CUDA-graph replay over rotating input sets): with 112-env tiles the one-shot
+  // kernel is ahead at every size (65536 envs 27.0 us vs 28.6 persistent, 131072: 49.0 vs 49.1, 262144: 87.0 vs 89.7) and is the
+  // default; ZBOT_MDP_PIPE=<shape> selects the persistent kernel
+  if (!pipe_off && (align_or & 15) == 0 && pipe_env) {
     const int ntiles = (n + kPT - 1) / kPT;
     // ZBOT_MDP_PIPE = <stages><warps per stage> (tuning switch): 42 (default), 43, 33, 41
     const int shape = pipe_env ? atoi(pipe_env) : 0;
@@ -2032,8 +2038,8 @@ int zbot_mdp_step(ZbotHandle* h, const ZbotMdpInputs* in, const float* actions, 
     else { ZB_PIPE_LAUNCH(4, 2); }
 #undef ZB_PIPE_LAUNCH
   } else {
-    ZB_CUDA(launch_pdl(zbot_mdp_kernel<true>, dim3(grid), dim3(block), (size_t)block * kHistRow * sizeof(float), (cudaStream_t)stream,
-                       h->pdl, h->P, h->dp, mi, h->mstate, h->m_ep_len, actions, obs, rew, terminated, truncated, n, sc));
+    ZB_CUDA(launch_pdl(zbot_mdp_kernel<true>, dim3(grid), dim3(block), (size_t)tile * kHistRow * sizeof(float), (cudaStream_t)stream,
+                       h->pdl, h->P, h->dp, mi, h->mstate, h->m_ep_len, actions, obs, rew, terminated, truncated, n, sc, tile));
   }
   h->launches += 1;
   if (!sc.ticket) {
