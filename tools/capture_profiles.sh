@@ -1,13 +1,12 @@
 #!/bin/bash
 # Round-end measurement recipe (run on the GPU box from the repo root):  bash tools/capture_profiles.sh <tag>
-#   1. the bench lines, WITHOUT a profiler (default run, the driver's --steps 20 --warmup 3 run, the reference arm);
+#   1. the bench lines, WITHOUT a profiler (the driver's --steps 20 --warmup 3 run, the reference arm);
 #   2. the ncu launch list of the same bench command (--metrics gpu__time_duration.sum --clock-control none);
 #   3. one `ncu --set full --clock-control none --import-source on` capture per kernel, reduced ON THE BOX to raw / details /
 #      source CSV pages and to profiles/step_<N>.json (tools/ncu_profile_json.py) -- the .ncu-rep files (25 MB each) stay in /tmp.
 # Everything lands in gpurun_out/<tag>_*; copy what is to be judged into profiles/.
 T=${1:-cap}
 set -x
-python bench.py > gpurun_out/${T}_bench_default.json 2> gpurun_out/${T}_bench_default.err; echo bench_default=$?
 python bench.py --steps 20 --warmup 3 > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err; echo bench=$?
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${T}_bench_ref.json 2> gpurun_out/${T}_bench_ref.err; echo ref=$?
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/${T}_launches_bench_65536.csv \
@@ -20,9 +19,9 @@ cap() {  # name envs task kernel-regex
   ncu -i /tmp/rep/$1.ncu-rep --page source --csv --kernel-id :::1 2>/dev/null | gzip > gpurun_out/${T}_$1_source.csv.gz
 }
 cap step65536 65536 walk zbot_step
-python tools/ncu_profile_json.py /tmp/rep/step65536.ncu-rep 65536 > gpurun_out/${T}_profjson65536.log 2>&1 && cp profiles/step_65536.json gpurun_out/
+python tools/ncu_profile_json.py gpurun_out/${T}_step65536_raw.csv 65536 zbot_step gpurun_out/${T}_step65536_source.csv.gz > gpurun_out/${T}_profjson65536.log 2>&1 && cp profiles/step_65536.json gpurun_out/
 cap step4096 4096 walk zbot_step
-python tools/ncu_profile_json.py /tmp/rep/step4096.ncu-rep 4096 > gpurun_out/${T}_profjson4096.log 2>&1 && cp profiles/step_4096.json gpurun_out/
+python tools/ncu_profile_json.py gpurun_out/${T}_step4096_raw.csv 4096 zbot_step gpurun_out/${T}_step4096_source.csv.gz > gpurun_out/${T}_profjson4096.log 2>&1 && cp profiles/step_4096.json gpurun_out/
 cap m65536 65536 m zbot_m_step
 # the bench again, now that profiles/step_65536.json matches the sources: its line carries traffic / fp32_issue
 python bench.py --steps 20 --warmup 3 > gpurun_out/${T}_bench_with_profile.json 2> gpurun_out/${T}_bench_with_profile.err; echo bench_with_profile=$?
