@@ -44,8 +44,14 @@ def _act(st, pol, obs, b, seed=11):
     torch.cuda.synchronize()
 
 
+@pytest.mark.parametrize("kernel", ["tensor-core (3 x TF32 split products, default)", "cuda-core FFMA2"])
 @pytest.mark.parametrize("n,num_obs,num_actions", [(4096, 23, 6), (1000 + 17, 23, 6), (300, 48, 6), (33, 64, 8), (5, 7, 1)])
-def test_policy_act_matches_torch_fp32(n, num_obs, num_actions):
+def test_policy_act_matches_torch_fp32(n, num_obs, num_actions, kernel, monkeypatch):
+    """Both builds of the act kernel -- `zbot_policy_act_tc_kernel` (mma.sync TF32 with every product split into
+    lo*hi + hi*lo + hi*hi, FP32 accumulate: csrc/zbot_policy_tc.cuh) and `zbot_policy_act_kernel<4>` (packed FP32 on the CUDA
+    cores, ZBOT_POLICY_TC=0) -- against torch FP32 and float64: the same bounds for both, i.e. the tensor-core kernel is FP32
+    to round-off, not TF32."""
+    monkeypatch.setenv("ZBOT_POLICY_TC", "1" if kernel.startswith("tensor") else "0")
     st, ac, pol, b = _setup(n, num_obs, num_actions, seed=n)
     obs = (torch.randn(n, num_obs, device=DEV) * 1.5).contiguous()
     _act(st, pol, obs, b)
@@ -98,6 +104,24 @@ def test_policy_act_draws_are_standard_normal_and_follow_the_device_stream_posit
     _act(st, pol, obs, b)
     assert float((b["act"] - a0).abs().min()) >= 0 and float(((b["act"] - a0).abs() > 1e-6).float().mean()) > 0.999
     st.close()
+
+
+def test_tensor_core_and_cuda_core_act_kernels_draw_the_same_actions(monkeypatch):
+    """Same generator, same slots: the two kernels differ only in the rounding of the network outputs, so means, values, actions
+    and log-probabilities agree to FP32 round-off on the same observations and stream position."""
+    n = 4096 + 33
+    outs = []
+    for tc in ("1", "0"):
+        monkeypatch.setenv("ZBOT_POLICY_TC", tc)
+        st, ac, pol, b = _setup(n, seed=3)
+        obs = torch.randn(n, 23, device=DEV)
+        _act(st, pol, obs, b)
+        outs.append({k: v.clone() for k, v in b.items()})
+        st.close()
+    a, c = outs
+    assert torch.equal(a["obs_out"], c["obs_out"]) and torch.equal(a["sigma"], c["sigma"])
+    for k, tol in (("mu", 5e-6), ("value", 5e-6), ("act", 5e-6), ("logp", 5e-5)):
+        assert float((a[k] - c[k]).abs().max()) < tol, (k, float((a[k] - c[k]).abs().max()))
 
 
 def test_policy_act_reads_the_live_weights_and_rejects_bad_shapes():

@@ -588,6 +588,7 @@ __global__ void __launch_bounds__(128, 1) zbot_step_h2_export_kernel(ZB_STEP_ARG
 }
 #include "zbot_w2_kernel.cuh"   // two warps per 32 envs (the default walking-v2 step kernel)
 #include "zbot_policy.cuh"      // the act / store halves of the PPO rollout (f4)
+#include "zbot_policy_tc.cuh"   // the act half on the tensor cores (3 x TF32 split products: FP32 accuracy), the default
 // unrolled sweeps under a direct register cap (single-wave experiments: 14 warps/SM hold 65536 envs at <= 146 registers)
 template <int kMaxRegs>
 __global__ void __maxnreg__(kMaxRegs) zbot_step_u2_kernel_r(ZB_STEP_ARGS) {
@@ -2079,7 +2080,17 @@ int zbot_policy_act(ZbotHandle* h, const ZbotPolicy* p, const float* obs, float*
     attr_set[h->device] = true;
   }
   const dim3 grid((a.n + kPolTile - 1) / kPolTile, 2);
-  if (rows == 8)
+  // tensor-core kernel (zbot_policy_tc.cuh) by default; ZBOT_POLICY_TC=0 selects the CUDA-core FFMA2 kernels (read per call:
+  // tests compare the two in one process)
+  const char* tc_env = getenv("ZBOT_POLICY_TC");
+  if (!tc_env || atoi(tc_env) != 0) {
+    static bool tc_attr_set[64] = {};
+    if (h->device < 64 && !tc_attr_set[h->device]) {
+      ZB_CUDA(cudaFuncSetAttribute(zbot_policy_act_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPolTcSmem));
+      tc_attr_set[h->device] = true;
+    }
+    zbot_policy_act_tc_kernel<<<grid, kTcThreads, kPolTcSmem, (cudaStream_t)stream>>>(a);
+  } else if (rows == 8)
     zbot_policy_act_kernel<8><<<grid, 128, kPolSmem, (cudaStream_t)stream>>>(a);
   else
     zbot_policy_act_kernel<4><<<grid, 256, kPolSmem, (cudaStream_t)stream>>>(a);

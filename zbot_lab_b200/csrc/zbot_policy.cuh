@@ -6,8 +6,11 @@
 // per step even inside a CUDA graph (115 us of a 140 us step at 4096 envs; the fused env step is 25 us of it).  Here it is one
 // kernel: blockIdx.y = 0 runs the actor on a tile of 64 envs (+ sampling, log-prob, stores), blockIdx.y = 1 the critic.
 //
+// (This file: the CUDA-core build, ZBOT_POLICY_TC=0.  The default since the end of round 2 is zbot_policy_tc.cuh -- the same
+// kernel with the three hidden layers on the tensor cores as 3 x TF32 split products, FP32 to round-off: 19.3 vs 27.7 us.)
+//
 // GEMM layout (FP32 on the CUDA cores -- the update phase differentiates the same weights in FP32 through torch, so the
-// rollout must see the same numbers to round-off; TF32 / BF16 tensor cores would not).  Packed FP32 (FFMA2: the FMA pipe of
+// rollout must see the same numbers to round-off; plain TF32 / BF16 tensor-core products would not).  Packed FP32 (FFMA2: the FMA pipe of
 // sm_100a retires a scalar FFMA every other cycle per sub-partition, tools/micro/ffma2_probe.cu -- 39 TFLOP/s scalar against
 // 57.5 packed at two warps per sub-partition).  A CTA of 256 threads owns a 64-env x 128-neuron output tile per layer.  Thread
 // (cg = t % 16, rg = t / 16) accumulates rows 4 rg .. 4 rg + 3 x columns {cg + 16 c, c = 0..7} as 4 x 4 register pairs:
