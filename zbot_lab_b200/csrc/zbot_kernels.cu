@@ -1236,6 +1236,7 @@ zbot_mdp_kernel(const __grid_constant__ Params<float> P, const __grid_constant__
   }
 }
 
+#include "zbot_policy_tc5.cuh"  // the act half on tcgen05.mma / TMEM (uses the mbarrier helpers above)
 #include "zbot_mdp_pipe.cuh"    // the same step as a persistent, TMA-fed kernel (the default; ZBOT_MDP_PIPE=0 restores the one above)
 
 }  // namespace
@@ -2083,7 +2084,14 @@ int zbot_policy_act(ZbotHandle* h, const ZbotPolicy* p, const float* obs, float*
   // tensor-core kernel (zbot_policy_tc.cuh) by default; ZBOT_POLICY_TC=0 selects the CUDA-core FFMA2 kernels (read per call:
   // tests compare the two in one process)
   const char* tc_env = getenv("ZBOT_POLICY_TC");
-  if (!tc_env || atoi(tc_env) != 0) {
+  if (tc_env && atoi(tc_env) == 2) {               // tcgen05.mma / TMEM build (zbot_policy_tc5.cuh)
+    static bool t5_attr_set[64] = {};
+    if (h->device < 64 && !t5_attr_set[h->device]) {
+      ZB_CUDA(cudaFuncSetAttribute(zbot_policy_act_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPolT5Smem));
+      t5_attr_set[h->device] = true;
+    }
+    zbot_policy_act_tc5_kernel<<<grid, kT5Threads, kPolT5Smem, (cudaStream_t)stream>>>(a);
+  } else if (!tc_env || atoi(tc_env) != 0) {
     static bool tc_attr_set[64] = {};
     if (h->device < 64 && !tc_attr_set[h->device]) {
       ZB_CUDA(cudaFuncSetAttribute(zbot_policy_act_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPolTcSmem));
