@@ -44,14 +44,16 @@ def _act(st, pol, obs, b, seed=11):
     torch.cuda.synchronize()
 
 
-@pytest.mark.parametrize("kernel", ["tensor-core (3 x TF32 split products, default)", "cuda-core FFMA2"])
+@pytest.mark.parametrize("kernel", ["tcgen05 (TMEM accumulators, 3 x TF32 split products, default)", "mma.sync (3 x TF32 split products)",
+                                    "cuda-core FFMA2"])
 @pytest.mark.parametrize("n,num_obs,num_actions", [(4096, 23, 6), (1000 + 17, 23, 6), (300, 48, 6), (33, 64, 8), (5, 7, 1)])
 def test_policy_act_matches_torch_fp32(n, num_obs, num_actions, kernel, monkeypatch):
-    """Both builds of the act kernel -- `zbot_policy_act_tc_kernel` (mma.sync TF32 with every product split into
-    lo*hi + hi*lo + hi*hi, FP32 accumulate: csrc/zbot_policy_tc.cuh) and `zbot_policy_act_kernel<4>` (packed FP32 on the CUDA
-    cores, ZBOT_POLICY_TC=0) -- against torch FP32 and float64: the same bounds for both, i.e. the tensor-core kernel is FP32
-    to round-off, not TF32."""
-    monkeypatch.setenv("ZBOT_POLICY_TC", "1" if kernel.startswith("tensor") else "0")
+    """The three builds of the act kernel -- `zbot_policy_act_tc5_kernel` (tcgen05.mma kind::tf32 with the accumulators in TMEM:
+    csrc/zbot_policy_tc5.cuh, the default), `zbot_policy_act_tc_kernel` (mma.sync TF32: csrc/zbot_policy_tc.cuh,
+    ZBOT_POLICY_TC=1) -- both with every product split into lo*hi + hi*lo + hi*hi, FP32 accumulate -- and
+    `zbot_policy_act_kernel<4>` (packed FP32 on the CUDA cores, ZBOT_POLICY_TC=0) against torch FP32 and float64: the same
+    bounds for all, i.e. the tensor-core kernels are FP32 to round-off, not TF32."""
+    monkeypatch.setenv("ZBOT_POLICY_TC", "2" if kernel.startswith("tcgen05") else "1" if kernel.startswith("mma") else "0")
     st, ac, pol, b = _setup(n, num_obs, num_actions, seed=n)
     obs = (torch.randn(n, num_obs, device=DEV) * 1.5).contiguous()
     _act(st, pol, obs, b)
@@ -111,17 +113,21 @@ def test_tensor_core_and_cuda_core_act_kernels_draw_the_same_actions(monkeypatch
     and log-probabilities agree to FP32 round-off on the same observations and stream position."""
     n = 4096 + 33
     outs = []
-    for tc in ("1", "0"):
+    for tc in ("2", "0", "1"):
         monkeypatch.setenv("ZBOT_POLICY_TC", tc)
         st, ac, pol, b = _setup(n, seed=3)
         obs = torch.randn(n, 23, device=DEV)
         _act(st, pol, obs, b)
         outs.append({k: v.clone() for k, v in b.items()})
         st.close()
-    a, c = outs
-    assert torch.equal(a["obs_out"], c["obs_out"]) and torch.equal(a["sigma"], c["sigma"])
-    for k, tol in (("mu", 5e-6), ("value", 5e-6), ("act", 5e-6), ("logp", 5e-5)):
-        assert float((a[k] - c[k]).abs().max()) < tol, (k, float((a[k] - c[k]).abs().max()))
+    a, c, m = outs
+    for x in (a, m):
+        assert torch.equal(x["obs_out"], c["obs_out"]) and torch.equal(x["sigma"], c["sigma"])
+        for k, tol in (("mu", 5e-6), ("value", 5e-6), ("act", 5e-6), ("logp", 5e-5)):
+            assert float((x[k] - c[k]).abs().max()) < tol, (k, float((x[k] - c[k]).abs().max()))
+    # the two tensor-core kernels evaluate the same split products in the same k order: their hidden layers agree to the last
+    # few bits (the accumulation inside one MMA may differ), far below the tolerance against the CUDA-core kernel
+    assert float((a["mu"] - m["mu"]).abs().max()) < 2e-6
 
 
 def test_policy_act_reads_the_live_weights_and_rejects_bad_shapes():

@@ -2081,17 +2081,17 @@ int zbot_policy_act(ZbotHandle* h, const ZbotPolicy* p, const float* obs, float*
     attr_set[h->device] = true;
   }
   const dim3 grid((a.n + kPolTile - 1) / kPolTile, 2);
-  // tensor-core kernel (zbot_policy_tc.cuh) by default; ZBOT_POLICY_TC=0 selects the CUDA-core FFMA2 kernels (read per call:
-  // tests compare the two in one process)
+  // tcgen05 kernel (zbot_policy_tc5.cuh) by default; ZBOT_POLICY_TC=1 selects the mma.sync kernel (zbot_policy_tc.cuh), =0 the
+  // CUDA-core FFMA2 kernels (read per call: tests compare the three in one process)
   const char* tc_env = getenv("ZBOT_POLICY_TC");
-  if (tc_env && atoi(tc_env) == 2) {               // tcgen05.mma / TMEM build (zbot_policy_tc5.cuh)
+  if (!tc_env || atoi(tc_env) == 2) {              // tcgen05.mma / TMEM build (zbot_policy_tc5.cuh): the default
     static bool t5_attr_set[64] = {};
     if (h->device < 64 && !t5_attr_set[h->device]) {
       ZB_CUDA(cudaFuncSetAttribute(zbot_policy_act_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPolT5Smem));
       t5_attr_set[h->device] = true;
     }
     zbot_policy_act_tc5_kernel<<<grid, kT5Threads, kPolT5Smem, (cudaStream_t)stream>>>(a);
-  } else if (!tc_env || atoi(tc_env) != 0) {
+  } else if (atoi(tc_env) != 0) {                  // ZBOT_POLICY_TC=1: mma.sync build (zbot_policy_tc.cuh)
     static bool tc_attr_set[64] = {};
     if (h->device < 64 && !tc_attr_set[h->device]) {
       ZB_CUDA(cudaFuncSetAttribute(zbot_policy_act_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPolTcSmem));
