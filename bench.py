@@ -575,7 +575,7 @@ def main():
             sec = bench_rollout.time_rollouts(r, 30)
             other_tasks["ppo_rollout_24x4096"] = {
                 "workload": "BASELINE.json configs[4]: rollout of 24 steps x 4096 envs (actor + critic MLP 3x128 ELU + Gaussian "
-                            "sample + log-prob as ONE launch of zbot_policy_act_tc_kernel (tensor cores, 3 x TF32 split products = FP32 accuracy), fused env step, zbot_rollout_store) replayed "
+                            "sample + log-prob as ONE launch of zbot_policy_act_tc5_kernel (tcgen05.mma kind::tf32, accumulators in TMEM, 3 x TF32 split products = FP32 accuracy), fused env step, zbot_rollout_store) replayed "
                             "as one CUDA graph",
                 "ms_per_rollout": 1e3 * sec, "value": 24 * 4096 / sec, "unit": UNIT,
                 "policy": "zbot_policy_act (this library)" if r._fused is not None else "torch"}

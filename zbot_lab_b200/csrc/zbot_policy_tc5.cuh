@@ -22,13 +22,19 @@
 // Order of events per layer: [all] next layer's weights -> registers (global loads in flight) | wait for the MMAs of this layer
 // (mbarrier armed by tcgen05.commit) | epilogue TMEM -> A tiles | weights registers -> B tiles | fence.proxy.async, barrier |
 // [thread 0] 48 x tcgen05.mma, tcgen05.commit.
+//
+// Measured (profiles/r2_notes.md section 12): 17.0 us at 4096 envs and 16.4 us for a dozen CTAs -- the kernel is a chain of
+// dependent latencies (L2 round trips of the operand loads, MMA phase, TMEM read-back, barriers), not a throughput problem.
+// Requesting the weights a whole layer ahead, or all prologue loads before the first dependent store, or the biases through shared
+// memory each made it SLOWER (17.7 / 19.0 / 18.5 us): loads that are still in flight hold the scoreboards the next dependent
+// instruction waits on.
 #pragma once
 // (included inside zbot_kernels.cu's anonymous namespace, after zbot_policy_tc.cuh)
 
 constexpr int kT5Threads = 256;
 constexpr int kT5TileA = kPolTile * kPolHid;                 // floats per A tile (64 x 128)
 constexpr int kT5TileB = kPolHid * kPolHid;                  // floats per B tile (128 x 128)
-constexpr size_t kPolT5Smem = (size_t)(2 * kT5TileA + 2 * kT5TileB) * sizeof(float) + 1024;   // + alignment slack
+constexpr size_t kPolT5Smem = (size_t)(2 * kT5TileA + 2 * kT5TileB) * sizeof(float);
 
 __device__ __forceinline__ int t5_off(int r, int k) { return (r >> 3) * 1024 + (k >> 2) * 32 + (r & 7) * 4 + (k & 3); }   // in floats
 
@@ -117,9 +123,8 @@ __device__ __forceinline__ void t5_issue_layer(uint32_t tmem_d, const float* a_h
 }
 
 __global__ void __launch_bounds__(kT5Threads, 1) zbot_policy_act_tc5_kernel(const PolicyArgs a) {
-  extern __shared__ __align__(16) uint8_t t5_raw[];
-  float* base = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(t5_raw) + 1023) & ~(uintptr_t)1023);
-  float* a_hi = base;
+  extern __shared__ __align__(1024) uint8_t t5_raw[];   // (the no-swizzle descriptors only need 16-byte alignment)
+  float* a_hi = reinterpret_cast<float*>(t5_raw);        // no integer round trip: the compiler keeps the shared address space (STS / LDS)
   float* a_lo = a_hi + kT5TileA;
   float* b_hi = a_lo + kT5TileA;
   float* b_lo = b_hi + kT5TileB;
