@@ -588,7 +588,7 @@ __global__ void __launch_bounds__(128, 1) zbot_step_h2_export_kernel(ZB_STEP_ARG
 }
 #include "zbot_w2_kernel.cuh"   // two warps per 32 envs (the default walking-v2 step kernel)
 #include "zbot_policy.cuh"      // the act / store halves of the PPO rollout (f4)
-#include "zbot_policy_tc.cuh"   // the act half on the tensor cores (3 x TF32 split products: FP32 accuracy), the default
+#include "zbot_policy_tc.cuh"   // the act half on the tensor cores, mma.sync build (3 x TF32 split products: FP32 accuracy)
 // unrolled sweeps under a direct register cap (single-wave experiments: 14 warps/SM hold 65536 envs at <= 146 registers)
 template <int kMaxRegs>
 __global__ void __maxnreg__(kMaxRegs) zbot_step_u2_kernel_r(ZB_STEP_ARGS) {
@@ -1236,7 +1236,7 @@ zbot_mdp_kernel(const __grid_constant__ Params<float> P, const __grid_constant__
   }
 }
 
-#include "zbot_policy_tc5.cuh"  // the act half on tcgen05.mma / TMEM (uses the mbarrier helpers above)
+#include "zbot_policy_tc5.cuh"  // the act half on tcgen05.mma / TMEM, the default (uses the mbarrier helpers above)
 #include "zbot_mdp_pipe.cuh"    // the same step as a persistent, TMA-fed kernel (the default; ZBOT_MDP_PIPE=0 restores the one above)
 
 }  // namespace

@@ -6,8 +6,10 @@
 // per step even inside a CUDA graph (115 us of a 140 us step at 4096 envs; the fused env step is 25 us of it).  Here it is one
 // kernel: blockIdx.y = 0 runs the actor on a tile of 64 envs (+ sampling, log-prob, stores), blockIdx.y = 1 the critic.
 //
-// (This file: the CUDA-core build, ZBOT_POLICY_TC=0.  The default since the end of round 2 is zbot_policy_tc.cuh -- the same
-// kernel with the three hidden layers on the tensor cores as 3 x TF32 split products, FP32 to round-off: 19.3 vs 27.7 us.)
+// (This file: the CUDA-core build, ZBOT_POLICY_TC=0, 27.1 us at 4096 envs.  The default since the end of round 2 is
+// zbot_policy_tc5.cuh -- the same kernel with the three hidden layers as tcgen05.mma kind::tf32 (accumulators in TMEM), every
+// product split three ways so the result is FP32 to round-off: 16.9 us; zbot_policy_tc.cuh is the mma.sync build of that
+// arithmetic, ZBOT_POLICY_TC=1, 19.2 us.)
 //
 // GEMM layout (FP32 on the CUDA cores -- the update phase differentiates the same weights in FP32 through torch, so the
 // rollout must see the same numbers to round-off; plain TF32 / BF16 tensor-core products would not).  Packed FP32 (FFMA2: the FMA pipe of

@@ -1,4 +1,5 @@
-// zbot_policy_tc.cuh -- the act half of the PPO rollout on the tensor cores, at FP32 accuracy (3 x TF32 split products).
+// zbot_policy_tc.cuh -- the act half of the PPO rollout on the tensor cores through the legacy warp-level path (mma.sync), at
+// FP32 accuracy (3 x TF32 split products).  ZBOT_POLICY_TC=1; the default is the tcgen05 / TMEM build, zbot_policy_tc5.cuh.
 //
 // Same contract as zbot_policy_act_kernel (zbot_policy.cuh): blockIdx.y = 0 actor (+ Gaussian sample, log-prob, stores),
 // blockIdx.y = 1 critic, a tile of 64 envs per CTA, weights read live in torch's nn.Linear layout (W[out][in]).  The three
